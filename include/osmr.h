@@ -1,0 +1,168 @@
+/*
+ * osmr.h -- C ABI of the B200-native tile rasteriser (libosmr_b200.so).
+ *
+ * Drop-in boundary for ONE path of dfyz/osm-renderer: everything between "ordered styled areas" and
+ * "RGB triples" inside `Drawer::draw_to_pixels` (reference src/draw/drawer.rs:60-131), i.e.
+ *   a1 Web-Mercator lon/lat -> integer tile pixel ... src/tile.rs:88-106, src/draw/point.rs:11-19
+ *   a2/a3 even-odd polygon scanline fill ............. src/draw/fill.rs:16-104
+ *   a4/a5 thick anti-aliased lines, dashes, caps ...... src/draw/line.rs:9-158, opacity_calculator.rs:16-185
+ *   a6/a7 generation compositor, alpha-over, export .... src/draw/tile_pixels.rs:89-129,164-181,205-223
+ *   a8 Fill -> Casing -> Stroke pass ordering ........... src/draw/drawer.rs:94-100,133-219
+ * The styler (string matching, reference src/mapcss/styler.rs) stays on the host and hands over its
+ * output unchanged: an ordered list of (area, style) pairs per tile.  Batching many tiles per call is the
+ * only semantic extension; n_tiles == 1 reproduces one reference call.
+ *
+ * Conventions: every function returns 0 on success or a negative OSMR_E_* code and never aborts or throws
+ * across the boundary; the message of the last failure on a context is osmr_last_error(ctx).  A context is
+ * NOT thread-safe (one per host worker thread, the analogue of the reference's per-thread TilePixels,
+ * src/http_server.rs:69-72).  No pointer argument is retained after a call returns (data is copied to the
+ * device).  There is no CPU fallback: without a usable CUDA device osmr_ctx_create fails.
+ */
+#ifndef OSMR_H
+#define OSMR_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OSMR_OK 0
+#define OSMR_E_INVALID (-1)  /* bad argument / malformed geodata image */
+#define OSMR_E_CUDA (-2)     /* CUDA runtime error (see osmr_last_error) */
+#define OSMR_E_NOMEM (-3)
+#define OSMR_E_STATE (-4)    /* call sequence error (e.g. draw before osmr_set_geodata) */
+
+/* reference: struct Tile {zoom: u8, x: u32, y: u32} (src/tile.rs:8-13) + the `scale: usize` argument of
+ * Drawer::draw_to_pixels (src/draw/drawer.rs:65).  Output dimension D = 256 * scale. */
+typedef struct osmr_tile {
+    uint32_t zoom;
+    uint32_t x;
+    uint32_t y;
+    uint32_t scale;
+} osmr_tile;
+
+/* Option<...> presence bits of osmr_style.flags */
+#define OSMR_STYLE_COLOR (1u << 0)
+#define OSMR_STYLE_FILL_COLOR (1u << 1)
+#define OSMR_STYLE_FILL_IMAGE (1u << 2)
+#define OSMR_STYLE_CASING_COLOR (1u << 3)
+#define OSMR_STYLE_CASING_WIDTH (1u << 4)
+#define OSMR_STYLE_WIDTH (1u << 5)
+#define OSMR_STYLE_OPACITY (1u << 6)
+#define OSMR_STYLE_FILL_OPACITY (1u << 7)
+#define OSMR_STYLE_DASHES (1u << 8)
+#define OSMR_STYLE_CASING_DASHES (1u << 9)
+
+/* reference: enum LineCap (src/mapcss/styler.rs:11-16); 0 encodes Option::None */
+#define OSMR_CAP_NONE 0
+#define OSMR_CAP_BUTT 1
+#define OSMR_CAP_ROUND 2
+#define OSMR_CAP_SQUARE 3
+
+/* The draw-relevant fields of reference `struct Style` (src/mapcss/styler.rs:49-72).  Widths and dashes are
+ * UNSCALED (the library multiplies by tile.scale exactly as drawer.rs:163-164,193,207 does).
+ * fill_image is an index into the icon table of osmr_set_icons, or -1 when the icon failed to load
+ * (the reference then silently skips the area: drawer.rs:179-184, icon_cache.rs:32-41). */
+typedef struct osmr_style {
+    uint32_t flags;
+    uint8_t color[3];
+    uint8_t line_cap;
+    uint8_t fill_color[3];
+    uint8_t casing_line_cap;
+    uint8_t casing_color[3];
+    uint8_t reserved0;
+    int32_t fill_image;
+    double width;
+    double opacity;
+    double fill_opacity;
+    double casing_width;
+    uint32_t dashes_off; /* into the `dashes` array of osmr_set_styles */
+    uint32_t dashes_len;
+    uint32_t casing_dashes_off;
+    uint32_t casing_dashes_len;
+} osmr_style;
+
+/* One element of the styler's output Vec<(StyledArea, Arc<Style>)> (src/mapcss/styler.rs:168-203).
+ * entity: local index into the `.bin` way table, or OSMR_AREA_MULTIPOLYGON | index into the multipolygon
+ * table (reference enum StyledArea, styler.rs:85-92). */
+#define OSMR_AREA_MULTIPOLYGON 0x80000000u
+typedef struct osmr_styled_area {
+    uint32_t entity;
+    uint32_t style;
+} osmr_styled_area;
+
+/* reference: struct Icon (src/draw/icon.rs:8-12) before premultiplication: 8-bit RGBA rows, as produced by
+ * png `normalize_to_color8` + the colour-type switch of icon.rs:29-49. */
+typedef struct osmr_icon {
+    uint32_t width;
+    uint32_t height;
+    const uint8_t* rgba; /* width*height*4 bytes */
+} osmr_icon;
+
+/* draw flags */
+#define OSMR_DRAW_USE_CAPS_FOR_DASHES (1u << 0) /* Styler.use_caps_for_dashes (styler.rs:95) */
+#define OSMR_DRAW_HAS_CANVAS_COLOR (1u << 1)    /* Styler.canvas_fill_color is Some (styler.rs:96) */
+#define OSMR_DRAW_OUT_RGBA (1u << 2)            /* 4 bytes/pixel, A=255; default is the reference's RGB triples */
+#define OSMR_DRAW_OUT_DEVICE (1u << 3)          /* `out` is a device pointer (stays in HBM) */
+
+typedef struct osmr_ctx osmr_ctx;
+
+/* replaces Drawer::new + TilePixels::new (drawer.rs:33, tile_pixels.rs:57): scratch + CUDA stream on `device` */
+int osmr_ctx_create(int device, osmr_ctx** out_ctx);
+void osmr_ctx_destroy(osmr_ctx* ctx);
+const char* osmr_last_error(const osmr_ctx* ctx);
+
+/* replaces GeodataReader::load (src/geodata/reader.rs:44-58): `bin` is the geodata file image in the
+ * reference's on-disk format (saver.rs:21-165).  Node coordinates are projected on the device once
+ * (a1, transcendental part) and kept resident together with the way/polygon/multipolygon tables. */
+int osmr_set_geodata(osmr_ctx* ctx, const void* bin, size_t bin_len);
+
+/* replaces IconCache for `fill-image` patterns (src/draw/icon_cache.rs:21-45, icon.rs:14-58) */
+int osmr_set_icons(osmr_ctx* ctx, const osmr_icon* icons, uint32_t n_icons);
+
+/* the interned Arc<Style> table (styler.rs:49-72) + flat dash storage */
+int osmr_set_styles(osmr_ctx* ctx, const osmr_style* styles, uint32_t n_styles, const double* dashes, uint32_t n_dashes);
+
+/* replaces Drawer::draw_to_pixels for the area passes (drawer.rs:60-104,128): for tile t the styled areas are
+ * areas[area_begin[t] .. area_begin[t+1]) in styler order.  canvas_rgb = Styler.canvas_fill_color when
+ * OSMR_DRAW_HAS_CANVAS_COLOR is set.  `out` receives n_tiles images of D*D*3 (or *4) bytes, tightly packed in
+ * tile order, D = 256*scale; all tiles of one call must share one scale. Host pointers unless OUT_DEVICE. */
+int osmr_draw_tiles(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, const uint32_t* area_begin,
+                    const osmr_styled_area* areas, const uint8_t canvas_rgb[3], uint32_t flags, uint8_t* out);
+
+/* Same work with the batch description already resident in HBM (benchmark "value" leg): upload once ... */
+int osmr_batch_upload(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, const uint32_t* area_begin,
+                      const osmr_styled_area* areas);
+/* ... then draw any number of times; `out` as in osmr_draw_tiles (NULL = keep the result in the context's
+ * own device buffer).  gpu_ms (optional) receives the device time of this call measured with CUDA events
+ * on the context's stream. */
+int osmr_batch_draw(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t flags, uint8_t* out, float* gpu_ms);
+
+/* device pointer + byte size of the context-owned output of the last draw (RGB or RGBA as drawn) */
+int osmr_batch_output(osmr_ctx* ctx, const uint8_t** dev_ptr, size_t* n_bytes);
+
+/* counters of the last draw, for the roofline arithmetic of bench.py */
+typedef struct osmr_stats {
+    uint64_t n_tiles;
+    uint64_t n_areas;        /* styled areas in the batch (G/3 generations per pass) */
+    uint64_t n_visible_ops;  /* generations whose reach intersects their tile */
+    uint64_t n_node_refs;    /* R: node references of all styled areas */
+    uint64_t kernel_launches;
+    float ms_plan;           /* per-stage device times of the last draw (CUDA events) */
+    float ms_raster;
+    float ms_total;
+} osmr_stats;
+int osmr_get_stats(osmr_ctx* ctx, osmr_stats* out);
+
+/* a1 in isolation (parity tests): integer pixel of every node for one tile, exactly
+ * Point::from_node (point.rs:11-19).  out_xy: n_nodes * 2 int32 (host). */
+int osmr_project_nodes(osmr_ctx* ctx, const osmr_tile* tile, int32_t* out_xy);
+
+uint32_t osmr_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OSMR_H */

@@ -1,0 +1,230 @@
+"""Wire structures of the C ABI (include/osmr.h) as numpy dtypes + ctypes mirrors, and the host-side
+interning of styler output (`Arc<Style>` -> table index, icon name -> icon index).
+
+Shared by the product binding (osm_renderer_b200/drawer.py) and by the test-only oracle binding
+(oracle/__init__.py) so both sides receive byte-identical inputs.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+OSMR_STYLE_COLOR = 1 << 0
+OSMR_STYLE_FILL_COLOR = 1 << 1
+OSMR_STYLE_FILL_IMAGE = 1 << 2
+OSMR_STYLE_CASING_COLOR = 1 << 3
+OSMR_STYLE_CASING_WIDTH = 1 << 4
+OSMR_STYLE_WIDTH = 1 << 5
+OSMR_STYLE_OPACITY = 1 << 6
+OSMR_STYLE_FILL_OPACITY = 1 << 7
+OSMR_STYLE_DASHES = 1 << 8
+OSMR_STYLE_CASING_DASHES = 1 << 9
+
+OSMR_AREA_MULTIPOLYGON = 0x80000000
+
+OSMR_DRAW_USE_CAPS_FOR_DASHES = 1 << 0
+OSMR_DRAW_HAS_CANVAS_COLOR = 1 << 1
+OSMR_DRAW_OUT_RGBA = 1 << 2
+OSMR_DRAW_OUT_DEVICE = 1 << 3
+
+TILE_DTYPE = np.dtype([("zoom", "<u4"), ("x", "<u4"), ("y", "<u4"), ("scale", "<u4")])
+
+STYLE_DTYPE = np.dtype(
+    [
+        ("flags", "<u4"),
+        ("color", "u1", (3,)),
+        ("line_cap", "u1"),
+        ("fill_color", "u1", (3,)),
+        ("casing_line_cap", "u1"),
+        ("casing_color", "u1", (3,)),
+        ("reserved0", "u1"),
+        ("fill_image", "<i4"),
+        ("width", "<f8"),
+        ("opacity", "<f8"),
+        ("fill_opacity", "<f8"),
+        ("casing_width", "<f8"),
+        ("dashes_off", "<u4"),
+        ("dashes_len", "<u4"),
+        ("casing_dashes_off", "<u4"),
+        ("casing_dashes_len", "<u4"),
+    ],
+    align=True,
+)
+assert STYLE_DTYPE.itemsize == 72, STYLE_DTYPE.itemsize
+
+AREA_DTYPE = np.dtype([("entity", "<u4"), ("style", "<u4")])
+
+
+class IconStruct(C.Structure):
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("rgba", C.c_void_p)]
+
+
+class StatsStruct(C.Structure):
+    _fields_ = [
+        ("n_tiles", C.c_uint64),
+        ("n_areas", C.c_uint64),
+        ("n_visible_ops", C.c_uint64),
+        ("n_node_refs", C.c_uint64),
+        ("kernel_launches", C.c_uint64),
+        ("ms_plan", C.c_float),
+        ("ms_raster", C.c_float),
+        ("ms_total", C.c_float),
+    ]
+
+
+def load_icon_rgba(path: str):
+    """Decode a PNG the way reference src/draw/icon.rs:14-58 does (png crate, `normalize_to_color8`):
+    palette -> RGB (RGBA with tRNS), 16-bit -> 8-bit, grey+tRNS -> grey+alpha; then only RGB, RGBA and
+    GrayscaleAlpha are accepted -- plain Grayscale makes Icon::load fail (icon.rs:46).
+    Returns (width, height, uint8[h, w, 4]) or None when the reference would fail to load the icon.
+    """
+    from PIL import Image
+
+    try:
+        im = Image.open(path)
+        im.load()
+    except Exception:
+        return None
+    mode = im.mode
+    has_trns = "transparency" in im.info
+    if mode == "P":
+        im = im.convert("RGBA" if has_trns else "RGB")
+    elif mode in ("L", "1", "I;16", "I"):
+        if not has_trns:
+            return None  # ColorType::Grayscale -> "Unknown color type"
+        im = im.convert("LA")
+    elif mode == "RGB" and has_trns:
+        im = im.convert("RGBA")
+    mode = im.mode
+    arr = np.asarray(im)
+    h, w = arr.shape[0], arr.shape[1]
+    out = np.empty((h, w, 4), dtype=np.uint8)
+    if mode == "RGB":
+        out[..., :3] = arr
+        out[..., 3] = 255
+    elif mode == "RGBA":
+        out[...] = arr
+    elif mode == "LA":
+        out[..., 0] = out[..., 1] = out[..., 2] = arr[..., 0]
+        out[..., 3] = arr[..., 1]
+    else:
+        return None
+    return w, h, np.ascontiguousarray(out)
+
+
+class StyleTable:
+    """Interns styler.Style objects (the reference's Arc<Style>) into the flat table of osmr_set_styles and
+    icon names into the icon table of osmr_set_icons (reference IconCache, src/draw/icon_cache.rs:21-45:
+    lazily loaded relative to the stylesheet directory, failures cached as None)."""
+
+    def __init__(self, icon_base_path: str | None = None):
+        self.icon_base_path = icon_base_path
+        self._style_ids: dict[int, int] = {}
+        self._styles_keepalive: list = []
+        self.rows: list = []
+        self.dashes: list[float] = []
+        self._icon_ids: dict[str, int] = {}
+        self.icons: list = []  # (w, h, rgba ndarray)
+
+    def icon_id(self, name: str) -> int:
+        i = self._icon_ids.get(name)
+        if i is None:
+            ic = None
+            if self.icon_base_path is not None:
+                ic = load_icon_rgba(os.path.join(self.icon_base_path, name))
+            if ic is None:
+                i = -1
+            else:
+                i = len(self.icons)
+                self.icons.append(ic)
+            self._icon_ids[name] = i
+        return i
+
+    def add_raw_icon(self, name: str, rgba: np.ndarray) -> int:
+        rgba = np.ascontiguousarray(rgba, dtype=np.uint8)
+        i = len(self.icons)
+        self.icons.append((rgba.shape[1], rgba.shape[0], rgba))
+        self._icon_ids[name] = i
+        return i
+
+    def style_id(self, s) -> int:
+        k = id(s)
+        i = self._style_ids.get(k)
+        if i is not None:
+            return i
+        row = np.zeros((), dtype=STYLE_DTYPE)
+        flags = 0
+        if s.color is not None:
+            flags |= OSMR_STYLE_COLOR
+            row["color"] = s.color
+        if s.fill_color is not None:
+            flags |= OSMR_STYLE_FILL_COLOR
+            row["fill_color"] = s.fill_color
+        row["fill_image"] = -1
+        if s.fill_image is not None:
+            flags |= OSMR_STYLE_FILL_IMAGE
+            # the reference only consults the icon cache when there is no fill colour (drawer.rs:176-184)
+            row["fill_image"] = self.icon_id(s.fill_image) if s.fill_color is None else -1
+        if s.casing_color is not None:
+            flags |= OSMR_STYLE_CASING_COLOR
+            row["casing_color"] = s.casing_color
+        if s.casing_width is not None:
+            flags |= OSMR_STYLE_CASING_WIDTH
+            row["casing_width"] = s.casing_width
+        if s.width is not None:
+            flags |= OSMR_STYLE_WIDTH
+            row["width"] = s.width
+        if s.opacity is not None:
+            flags |= OSMR_STYLE_OPACITY
+            row["opacity"] = s.opacity
+        if s.fill_opacity is not None:
+            flags |= OSMR_STYLE_FILL_OPACITY
+            row["fill_opacity"] = s.fill_opacity
+        if s.dashes is not None:
+            flags |= OSMR_STYLE_DASHES
+            row["dashes_off"] = len(self.dashes)
+            row["dashes_len"] = len(s.dashes)
+            self.dashes.extend(s.dashes)
+        if s.casing_dashes is not None:
+            flags |= OSMR_STYLE_CASING_DASHES
+            row["casing_dashes_off"] = len(self.dashes)
+            row["casing_dashes_len"] = len(s.casing_dashes)
+            self.dashes.extend(s.casing_dashes)
+        row["line_cap"] = s.line_cap
+        row["casing_line_cap"] = s.casing_line_cap
+        row["flags"] = flags
+        i = len(self.rows)
+        self.rows.append(row)
+        self._style_ids[k] = i
+        self._styles_keepalive.append(s)
+        return i
+
+    def styles_array(self) -> np.ndarray:
+        if not self.rows:
+            return np.zeros(0, dtype=STYLE_DTYPE)
+        return np.array(self.rows, dtype=STYLE_DTYPE)
+
+    def dashes_array(self) -> np.ndarray:
+        return np.asarray(self.dashes, dtype=np.float64)
+
+    def icon_structs(self):
+        """(ctypes array of osmr_icon, keepalive list)"""
+        arr = (IconStruct * max(1, len(self.icons)))()
+        for i, (w, h, px) in enumerate(self.icons):
+            arr[i].width = w
+            arr[i].height = h
+            arr[i].rgba = px.ctypes.data
+        return arr, list(self.icons)
+
+
+def styled_areas_to_array(styled, table: StyleTable) -> np.ndarray:
+    """[(entity tuple (kind, local_id, global_id, tags), Style)] -> AREA_DTYPE array in styler order."""
+    from .upstream.styler import KIND_MULTIPOLYGON
+
+    out = np.empty(len(styled), dtype=AREA_DTYPE)
+    for i, (ent, s) in enumerate(styled):
+        e = ent[1] | (OSMR_AREA_MULTIPOLYGON if ent[0] == KIND_MULTIPOLYGON else 0)
+        out[i] = (e, table.style_id(s))
+    return out
