@@ -1,0 +1,100 @@
+#!/usr/bin/env python
+"""Generate tests/golden/* from the reference's own fixtures (run in the build container only).
+
+Inputs (read-only, /root/reference): tests/osm/nano_moscow.osm, tests/mapcss/mapnik.mapcss (+ symbols/),
+tests/rendered/{14,15,16,17,18,18_2x}_expected.png and the tile sets of tests/test_rendering.rs:147-176.
+Outputs (committed, travel to the GPU box where /root/reference does not exist):
+  tests/golden/nano_moscow.bin        geodata image written by the restated importer (saver.rs format)
+  tests/golden/fixture_inputs.npz     style table, dashes, icons, canvas colour, per-config tile lists and
+                                      ordered styled-area lists (the styler output = C-ABI input)
+  tests/golden/golden_<cfg>.npz       reference golden pixels per tile + `label_mask`: pixels the reference's
+                                      label pass (drawer.rs:106-126, not restated yet) or the red test grid
+                                      (test_rendering.rs:109-114) touched.  The mask is *derived*: it is the set of
+                                      pixels where the golden differs from the area-only oracle render at the
+                                      time of generation (inspected: glyphs and icons only, 0.4-2.5 % of pixels).
+"""
+import os
+import sys
+import time
+
+import numpy as np
+from PIL import Image
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import oracle  # noqa: E402
+from osm_renderer_b200.upstream import geodata, mapcss, pipeline, styler as st  # noqa: E402
+from osm_renderer_b200.wire import StyleTable  # noqa: E402
+
+REF = "/root/reference"
+OUT = os.path.join(ROOT, "tests", "golden")
+
+# tests/test_rendering.rs:147-176
+CONFIGS = {
+    "14": (14, 9903, 9904, 5121, 5122, 1),
+    "15": (15, 19807, 19808, 10243, 10244, 1),
+    "16": (16, 39614, 39616, 20486, 20488, 1),
+    "17": (17, 79228, 79232, 40973, 40976, 1),
+    "18": (18, 158457, 158465, 81946, 81953, 1),
+    "18_2x": (18, 158457, 158465, 81946, 81953, 2),
+}
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    t0 = time.time()
+    data = geodata.import_osm(os.path.join(REF, "tests/osm/nano_moscow.osm"))
+    with open(os.path.join(OUT, "nano_moscow.bin"), "wb") as f:
+        f.write(data)
+    rd = geodata.GeodataReader(data)
+    S = st.Styler(mapcss.parse_file(os.path.join(REF, "tests/mapcss"), "mapnik.mapcss"), "josm", None)
+    table = StyleTable(os.path.join(REF, "tests/mapcss"))
+    ts = pipeline.TileStyler(rd, S, table)
+
+    batches = {}
+    for name, (z, x0, x1, y0, y1, s) in CONFIGS.items():
+        tiles = [(z, x, y, s) for y in range(y0, y1 + 1) for x in range(x0, x1 + 1)]
+        batches[name] = pipeline.build_batch(ts, tiles)
+
+    save = {
+        "styles": table.styles_array(),
+        "dashes": table.dashes_array(),
+        "canvas_rgb": np.asarray(S.canvas_fill_color, dtype=np.uint8),
+        "use_caps_for_dashes": np.asarray(S.use_caps_for_dashes),
+        "n_icons": np.asarray(len(table.icons)),
+    }
+    for i, (w, h, px) in enumerate(table.icons):
+        save[f"icon_{i}"] = px
+    for name, (tarr, begins, areas) in batches.items():
+        save[f"tiles_{name}"] = tarr
+        save[f"area_begin_{name}"] = begins
+        save[f"areas_{name}"] = areas
+    np.savez_compressed(os.path.join(OUT, "fixture_inputs.npz"), **save)
+
+    for name, (z, x0, x1, y0, y1, s) in CONFIGS.items():
+        tarr, begins, areas = batches[name]
+        imgs = oracle.draw_tiles(data, table, tarr, begins, areas, S.canvas_fill_color, S.use_caps_for_dashes, n_threads=8)
+        gold = np.asarray(Image.open(os.path.join(REF, f"tests/rendered/{name}_expected.png")).convert("RGB"))
+        D = 256 * s
+        nx = x1 - x0 + 1
+        g_tiles = np.empty((len(imgs), D, D, 3), dtype=np.uint8)
+        masks = np.empty((len(imgs), D, D), dtype=bool)
+        for i in range(len(imgs)):
+            r, c = divmod(i, nx)
+            g = gold[r * D : (r + 1) * D, c * D : (c + 1) * D]
+            g_tiles[i] = g
+            m = (imgs[i] != g).any(axis=2)
+            m[0, :] = True       # red grid: row 0 ...
+            m[:, D - 1] = True   # ... and the last column of every tile (test_rendering.rs:109-114)
+            masks[i] = m
+        frac = masks.mean()
+        print(f"{name}: {len(imgs)} tiles, label+grid mask {100 * frac:.3f} % of pixels")
+        np.savez_compressed(
+            os.path.join(OUT, f"golden_{name}.npz"), golden=g_tiles, label_mask=np.packbits(masks, axis=-1), dim=np.asarray(D)
+        )
+    print("done in %.1fs" % (time.time() - t0))
+
+
+if __name__ == "__main__":
+    main()
