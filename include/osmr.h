@@ -160,6 +160,15 @@ int osmr_get_stats(osmr_ctx* ctx, osmr_stats* out);
  * Point::from_node (point.rs:11-19).  out_xy: n_nodes * 2 int32 (host). */
 int osmr_project_nodes(osmr_ctx* ctx, const osmr_tile* tile, int32_t* out_xy);
 
+/* Optional page-locked host memory for callers that want full-speed host<->device copies of `out` / batch
+ * arrays (plain malloc'ed buffers work too, at pageable-copy speed). */
+void* osmr_alloc_pinned(size_t bytes);
+void osmr_free_pinned(void* p);
+
+/* Test hook: "fill_cap" (0..128) lowers the number of row spans ranked in shared memory so that the
+ * order-free streaming form of the even-odd rule is exercised on ordinary data. */
+int osmr_debug_set(osmr_ctx* ctx, const char* key, int value);
+
 uint32_t osmr_abi_version(void);
 
 #ifdef __cplusplus

@@ -1,0 +1,541 @@
+// osmr_capi.cu -- C ABI (include/osmr.h) of libosmr_b200.so: context, dataset residency, batch launch.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo ...  (osm_renderer_b200/build.py)
+// There is deliberately no CPU code path for any part of the draw path in this library.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "osmr.h"
+#include "osmr_kernels.cuh"
+
+using namespace osmr;
+
+namespace {
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;  // elements
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = n + n / 4 + 64;
+        cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+}  // namespace
+
+struct osmr_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::string err;
+    int num_sms = 0;
+
+    // dataset
+    bool has_geo = false;
+    unsigned n_nodes = 0, n_ways = 0, n_polys = 0, n_mps = 0, n_ints = 0;
+    DevBuf<double2> merc;
+    DevBuf<uint2> ways, polys, mps;
+    DevBuf<unsigned> ints;
+    std::vector<unsigned> h_way_len, h_mp_pts;  // node counts per entity (host copy, for scratch sizing)
+    // styles / icons
+    unsigned n_styles = 0, n_dashes = 0, n_icons = 0;
+    DevBuf<osmr_style> styles;
+    DevBuf<double> dashes;
+    DevBuf<DevIcon> icons;
+    DevBuf<double4> icon_px;
+    // batch
+    bool has_batch = false;
+    unsigned n_tiles = 0, n_areas = 0;
+    int scale = 1;
+    DevBuf<osmr_tile> tiles;
+    DevBuf<unsigned> area_begin;
+    DevBuf<osmr_styled_area> areas;
+    // scratch
+    DevBuf<AreaInfo> area_info;
+    DevBuf<VisOp> vis;
+    DevBuf<unsigned> vis_count, work, fill_work, counters, mask;
+    DevBuf<uint4> geom;
+    size_t geom_cap_units = 0, mask_cap_words = 0;
+    DevBuf<unsigned char> out;
+    size_t out_bytes = 0;
+    int fill_cap = kFillCap;
+    osmr_stats stats{};
+
+    int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
+        char buf[512];
+        if (e != cudaSuccess)
+            snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+        else
+            snprintf(buf, sizeof buf, "%s", what);
+        err = buf;
+        return code;
+    }
+};
+
+#define CK(call)                                                       \
+    do {                                                               \
+        cudaError_t e_ = (call);                                       \
+        if (e_ != cudaSuccess) return ctx->fail(OSMR_E_CUDA, #call, e_); \
+    } while (0)
+
+static inline uint32_t rd_u32(const uint8_t* p) {
+    uint32_t v;
+    memcpy(&v, p, 4);
+    return v;
+}
+
+extern "C" {
+
+uint32_t osmr_abi_version(void) { return 1; }
+
+int osmr_ctx_create(int device, osmr_ctx** out_ctx) {
+    if (!out_ctx) return OSMR_E_INVALID;
+    *out_ctx = nullptr;
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || device < 0 || device >= n_dev) return OSMR_E_CUDA;
+    osmr_ctx* ctx = new (std::nothrow) osmr_ctx();
+    if (!ctx) return OSMR_E_NOMEM;
+    ctx->device = device;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(raster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RasterSmem));
+    if (e != cudaSuccess) {
+        osmr_ctx_destroy(ctx);
+        return OSMR_E_CUDA;
+    }
+    *out_ctx = ctx;
+    return OSMR_OK;
+}
+
+void osmr_ctx_destroy(osmr_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    ctx->merc.release();
+    ctx->ways.release();
+    ctx->polys.release();
+    ctx->mps.release();
+    ctx->ints.release();
+    ctx->styles.release();
+    ctx->dashes.release();
+    ctx->icons.release();
+    ctx->icon_px.release();
+    ctx->tiles.release();
+    ctx->area_begin.release();
+    ctx->areas.release();
+    ctx->area_info.release();
+    ctx->vis.release();
+    ctx->vis_count.release();
+    ctx->work.release();
+    ctx->fill_work.release();
+    ctx->counters.release();
+    ctx->mask.release();
+    ctx->geom.release();
+    ctx->out.release();
+    for (auto& e : ctx->ev)
+        if (e) cudaEventDestroy(e);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* osmr_last_error(const osmr_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int osmr_debug_set(osmr_ctx* ctx, const char* key, int value) {
+    if (!ctx || !key) return OSMR_E_INVALID;
+    if (strcmp(key, "fill_cap") == 0) {
+        if (value < 0 || value > kFillCap) return ctx->fail(OSMR_E_INVALID, "fill_cap out of range");
+        ctx->fill_cap = value;
+        return OSMR_OK;
+    }
+    return ctx->fail(OSMR_E_INVALID, "unknown debug key");
+}
+
+// ---------------------------------------------------------------------------------------------------------
+int osmr_set_geodata(osmr_ctx* ctx, const void* bin, size_t len) {
+    if (!ctx) return OSMR_E_INVALID;
+    if (!bin) return ctx->fail(OSMR_E_INVALID, "null geodata image");
+    cudaSetDevice(ctx->device);
+    const uint8_t* p = (const uint8_t*)bin;
+    size_t pos = 0;
+    const uint8_t* base[6];
+    uint32_t cnt[6];
+    const size_t rec[6] = {32, 24, 8, 24, 32, 4};  // nodes, ways, polygons, multipolygons, tiles, ints (reader.rs:301-305)
+    for (int i = 0; i < 6; ++i) {
+        if (pos + 4 > len) return ctx->fail(OSMR_E_INVALID, "geodata image truncated");
+        cnt[i] = rd_u32(p + pos);
+        pos += 4;
+        if ((size_t)cnt[i] * rec[i] > len - pos) return ctx->fail(OSMR_E_INVALID, "geodata image truncated");
+        base[i] = p + pos;
+        pos += (size_t)cnt[i] * rec[i];
+    }
+    const uint32_t n_nodes = cnt[0], n_ways = cnt[1], n_polys = cnt[2], n_mps = cnt[3], n_ints = cnt[5];
+    std::vector<uint32_t> ints(n_ints);
+    if (n_ints) memcpy(ints.data(), base[5], (size_t)n_ints * 4);
+    std::vector<uint2> ways(n_ways), polys(n_polys), mps(n_mps);
+    ctx->h_way_len.assign(n_ways, 0);
+    ctx->h_mp_pts.assign(n_mps, 0);
+    auto range_ok = [&](uint32_t off, uint32_t l) { return (uint64_t)off + l <= n_ints; };
+    for (uint32_t i = 0; i < n_ways; ++i) {
+        ways[i] = make_uint2(rd_u32(base[1] + (size_t)i * 24 + 8), rd_u32(base[1] + (size_t)i * 24 + 12));
+        if (!range_ok(ways[i].x, ways[i].y)) return ctx->fail(OSMR_E_INVALID, "way node list out of range");
+        for (uint32_t k = 0; k < ways[i].y; ++k)
+            if (ints[ways[i].x + k] >= n_nodes) return ctx->fail(OSMR_E_INVALID, "way references a missing node");
+        ctx->h_way_len[i] = ways[i].y;
+    }
+    for (uint32_t i = 0; i < n_polys; ++i) {
+        polys[i] = make_uint2(rd_u32(base[2] + (size_t)i * 8), rd_u32(base[2] + (size_t)i * 8 + 4));
+        if (!range_ok(polys[i].x, polys[i].y)) return ctx->fail(OSMR_E_INVALID, "polygon node list out of range");
+        for (uint32_t k = 0; k < polys[i].y; ++k)
+            if (ints[polys[i].x + k] >= n_nodes) return ctx->fail(OSMR_E_INVALID, "polygon references a missing node");
+    }
+    for (uint32_t i = 0; i < n_mps; ++i) {
+        mps[i] = make_uint2(rd_u32(base[3] + (size_t)i * 24 + 8), rd_u32(base[3] + (size_t)i * 24 + 12));
+        if (!range_ok(mps[i].x, mps[i].y)) return ctx->fail(OSMR_E_INVALID, "multipolygon polygon list out of range");
+        for (uint32_t k = 0; k < mps[i].y; ++k) {
+            uint32_t pid = ints[mps[i].x + k];
+            if (pid >= n_polys) return ctx->fail(OSMR_E_INVALID, "multipolygon references a missing polygon");
+            ctx->h_mp_pts[i] += polys[pid].y;
+        }
+    }
+    ctx->has_geo = false;
+    DevBuf<unsigned char> raw_nodes;
+    CK(raw_nodes.reserve((size_t)n_nodes * 32 + 16));
+    CK(ctx->merc.reserve(n_nodes + 1));
+    CK(ctx->ways.reserve(n_ways + 1));
+    CK(ctx->polys.reserve(n_polys + 1));
+    CK(ctx->mps.reserve(n_mps + 1));
+    CK(ctx->ints.reserve(n_ints + 1));
+    if (n_nodes) CK(cudaMemcpyAsync(raw_nodes.p, base[0], (size_t)n_nodes * 32, cudaMemcpyHostToDevice, ctx->stream));
+    if (n_ways) CK(cudaMemcpyAsync(ctx->ways.p, ways.data(), (size_t)n_ways * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (n_polys) CK(cudaMemcpyAsync(ctx->polys.p, polys.data(), (size_t)n_polys * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (n_mps) CK(cudaMemcpyAsync(ctx->mps.p, mps.data(), (size_t)n_mps * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (n_ints) CK(cudaMemcpyAsync(ctx->ints.p, ints.data(), (size_t)n_ints * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (n_nodes) {
+        project_nodes_kernel<<<(n_nodes + 255) / 256, 256, 0, ctx->stream>>>(raw_nodes.p, n_nodes, ctx->merc.p);
+        CK(cudaGetLastError());
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    raw_nodes.release();
+    ctx->n_nodes = n_nodes;
+    ctx->n_ways = n_ways;
+    ctx->n_polys = n_polys;
+    ctx->n_mps = n_mps;
+    ctx->n_ints = n_ints;
+    ctx->has_geo = true;
+    ctx->has_batch = false;
+    return OSMR_OK;
+}
+
+int osmr_set_icons(osmr_ctx* ctx, const osmr_icon* icons, uint32_t n_icons) {
+    if (!ctx) return OSMR_E_INVALID;
+    if (n_icons && !icons) return ctx->fail(OSMR_E_INVALID, "null icon table");
+    cudaSetDevice(ctx->device);
+    std::vector<DevIcon> meta(n_icons);
+    std::vector<double4> px;
+    for (uint32_t i = 0; i < n_icons; ++i) {
+        if (!icons[i].rgba || icons[i].width == 0 || icons[i].height == 0) return ctx->fail(OSMR_E_INVALID, "empty icon");
+        meta[i].w = icons[i].width;
+        meta[i].h = icons[i].height;
+        meta[i].off = (unsigned)px.size();
+        meta[i].pad = 0;
+        size_t n = (size_t)icons[i].width * icons[i].height;
+        for (size_t k = 0; k < n; ++k) {
+            const uint8_t* c = icons[i].rgba + 4 * k;
+            // RgbaColor::from_components (tile_pixels.rs:24-26): opacity = a/255; channel = opacity * (c/255).
+            // Plain IEEE divisions and multiplications: host and device agree bit for bit.
+            volatile double opacity = (double)c[3] / 255.0;
+            double4 v;
+            volatile double r = (double)c[0] / 255.0, g = (double)c[1] / 255.0, b = (double)c[2] / 255.0;
+            volatile double pr = opacity * r, pg = opacity * g, pb = opacity * b;
+            v.x = pr;
+            v.y = pg;
+            v.z = pb;
+            v.w = opacity;
+            px.push_back(v);
+        }
+    }
+    CK(ctx->icons.reserve(n_icons + 1));
+    CK(ctx->icon_px.reserve(px.size() + 1));
+    if (n_icons) CK(cudaMemcpyAsync(ctx->icons.p, meta.data(), n_icons * sizeof(DevIcon), cudaMemcpyHostToDevice, ctx->stream));
+    if (!px.empty()) CK(cudaMemcpyAsync(ctx->icon_px.p, px.data(), px.size() * sizeof(double4), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->n_icons = n_icons;
+    return OSMR_OK;
+}
+
+int osmr_set_styles(osmr_ctx* ctx, const osmr_style* styles, uint32_t n_styles, const double* dashes, uint32_t n_dashes) {
+    if (!ctx) return OSMR_E_INVALID;
+    if ((n_styles && !styles) || (n_dashes && !dashes)) return ctx->fail(OSMR_E_INVALID, "null style table");
+    cudaSetDevice(ctx->device);
+    for (uint32_t i = 0; i < n_styles; ++i) {
+        const osmr_style& s = styles[i];
+        if ((s.flags & OSMR_STYLE_DASHES) && ((uint64_t)s.dashes_off + s.dashes_len > n_dashes || s.dashes_len > 64))
+            return ctx->fail(OSMR_E_INVALID, "style dashes out of range (at most 64 numbers)");
+        if ((s.flags & OSMR_STYLE_CASING_DASHES) &&
+            ((uint64_t)s.casing_dashes_off + s.casing_dashes_len > n_dashes || s.casing_dashes_len > 64))
+            return ctx->fail(OSMR_E_INVALID, "style casing dashes out of range (at most 64 numbers)");
+        if (s.line_cap > OSMR_CAP_SQUARE || s.casing_line_cap > OSMR_CAP_SQUARE) return ctx->fail(OSMR_E_INVALID, "bad line cap");
+    }
+    CK(ctx->styles.reserve(n_styles + 1));
+    CK(ctx->dashes.reserve(n_dashes + 1));
+    if (n_styles) CK(cudaMemcpyAsync(ctx->styles.p, styles, (size_t)n_styles * sizeof(osmr_style), cudaMemcpyHostToDevice, ctx->stream));
+    if (n_dashes) CK(cudaMemcpyAsync(ctx->dashes.p, dashes, (size_t)n_dashes * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->n_styles = n_styles;
+    ctx->n_dashes = n_dashes;
+    return OSMR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+static int validate_batch(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, const uint32_t* area_begin) {
+    if (!ctx->has_geo) return ctx->fail(OSMR_E_STATE, "osmr_set_geodata has not been called");
+    if (n_tiles == 0) return ctx->fail(OSMR_E_INVALID, "empty batch");
+    if (!tiles || !area_begin) return ctx->fail(OSMR_E_INVALID, "null batch arrays");
+    uint32_t scale = tiles[0].scale;
+    if (scale < 1 || scale > 8) return ctx->fail(OSMR_E_INVALID, "scale must be 1..8");
+    if (area_begin[0] != 0) return ctx->fail(OSMR_E_INVALID, "area_begin[0] must be 0");
+    for (uint32_t t = 0; t < n_tiles; ++t) {
+        if (tiles[t].scale != scale) return ctx->fail(OSMR_E_INVALID, "all tiles of a batch must share one scale");
+        if (tiles[t].zoom > 22) return ctx->fail(OSMR_E_INVALID, "zoom must be <= 22");
+        if (area_begin[t + 1] < area_begin[t]) return ctx->fail(OSMR_E_INVALID, "area_begin must be non-decreasing");
+    }
+    if ((uint64_t)area_begin[n_tiles] * 3ull >= 0xffffffffull) return ctx->fail(OSMR_E_INVALID, "batch too large");
+    return OSMR_OK;
+}
+
+int osmr_batch_upload(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, const uint32_t* area_begin,
+                      const osmr_styled_area* areas) {
+    if (!ctx) return OSMR_E_INVALID;
+    int rc = validate_batch(ctx, tiles, n_tiles, area_begin);
+    if (rc) return rc;
+    cudaSetDevice(ctx->device);
+    uint32_t n_areas = area_begin[n_tiles];
+    if (n_areas && !areas) return ctx->fail(OSMR_E_INVALID, "null area list");
+    ctx->has_batch = false;
+    CK(ctx->tiles.reserve(n_tiles));
+    CK(ctx->area_begin.reserve(n_tiles + 1));
+    CK(ctx->areas.reserve(n_areas + 1));
+    CK(cudaMemcpyAsync(ctx->tiles.p, tiles, (size_t)n_tiles * sizeof(osmr_tile), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->area_begin.p, area_begin, (size_t)(n_tiles + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (n_areas) CK(cudaMemcpyAsync(ctx->areas.p, areas, (size_t)n_areas * sizeof(osmr_styled_area), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->n_tiles = n_tiles;
+    ctx->n_areas = n_areas;
+    ctx->scale = (int)tiles[0].scale;
+    // scratch that scales with the batch
+    CK(ctx->area_info.reserve(n_areas + 1));
+    CK(ctx->vis.reserve(3ull * n_areas + 1));
+    CK(ctx->work.reserve(3ull * n_areas + 1));
+    CK(ctx->fill_work.reserve((size_t)n_areas + 1));
+    CK(ctx->vis_count.reserve(n_tiles));
+    CK(ctx->counters.reserve(CNT_COUNT));
+    // the caller's arrays may be reused as soon as we return
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->has_batch = true;
+    return OSMR_OK;
+}
+
+static int run_pipeline(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t flags, unsigned char* dev_out) {
+    const int D = 256 * ctx->scale;
+    for (int attempt = 0; attempt < 6; ++attempt) {
+        if (ctx->geom_cap_units == 0) {
+            size_t units = (size_t)ctx->n_areas * 8 + (1u << 20);  // first guess; grown on overflow
+            CK(ctx->geom.reserve(units));
+            ctx->geom_cap_units = ctx->geom.cap;
+        }
+        if (ctx->mask_cap_words == 0) {
+            size_t words = (size_t)ctx->n_tiles * (size_t)D * (D / 32) * 4 + (1u << 20);
+            CK(ctx->mask.reserve(words));
+            ctx->mask_cap_words = ctx->mask.cap;
+        }
+        Scene s{};
+        s.merc = ctx->merc.p;
+        s.ways = ctx->ways.p;
+        s.polys = ctx->polys.p;
+        s.mps = ctx->mps.p;
+        s.ints = ctx->ints.p;
+        s.n_nodes = ctx->n_nodes;
+        s.n_ways = ctx->n_ways;
+        s.n_polys = ctx->n_polys;
+        s.n_mps = ctx->n_mps;
+        s.n_ints = ctx->n_ints;
+        s.styles = ctx->styles.p;
+        s.dashes = ctx->dashes.p;
+        s.n_styles = ctx->n_styles;
+        s.n_dashes = ctx->n_dashes;
+        s.icons = ctx->icons.p;
+        s.icon_px = ctx->icon_px.p;
+        s.n_icons = ctx->n_icons;
+        s.tiles = ctx->tiles.p;
+        s.area_begin = ctx->area_begin.p;
+        s.areas = ctx->areas.p;
+        s.n_tiles = ctx->n_tiles;
+        s.n_areas = ctx->n_areas;
+        s.D = D;
+        s.scale = ctx->scale;
+        s.flags = flags;
+        if (flags & OSMR_DRAW_HAS_CANVAS_COLOR) memcpy(s.canvas, canvas_rgb, 3);
+        s.area_info = ctx->area_info.p;
+        s.vis = ctx->vis.p;
+        s.vis_count = ctx->vis_count.p;
+        s.work = ctx->work.p;
+        s.fill_work = ctx->fill_work.p;
+        s.geom = ctx->geom.p;
+        s.geom_cap = (unsigned)std::min<size_t>(ctx->geom_cap_units, 0xffffffffu);
+        s.mask = ctx->mask.p;
+        s.mask_cap = (unsigned)std::min<size_t>(ctx->mask_cap_words, 0xffffffffu);
+        s.counters = ctx->counters.p;
+        s.fill_cap = ctx->fill_cap;
+        s.out = dev_out;
+
+        cudaStream_t st = ctx->stream;
+        CK(cudaEventRecord(ctx->ev[0], st));
+        CK(cudaMemsetAsync(ctx->counters.p, 0, CNT_COUNT * sizeof(unsigned), st));
+        unsigned launches = 0;
+        if (ctx->n_areas) {
+            area_bbox_kernel<<<(ctx->n_areas + 255) / 256, 256, 0, st>>>(s);
+            ++launches;
+        }
+        plan_ops_kernel<<<ctx->n_tiles, kPlanThreads, 0, st>>>(s);
+        build_geometry_kernel<<<ctx->num_sms * 8, kGeomThreads, 0, st>>>(s);
+        fill_rows_kernel<<<ctx->num_sms * 4, kFillThreads, 0, st>>>(s);
+        launches += 3;
+        CK(cudaEventRecord(ctx->ev[1], st));
+        const unsigned regions = (unsigned)((D / kRW) * (D / kRH));
+        raster_kernel<<<ctx->n_tiles * regions, kRasterThreads, sizeof(RasterSmem), st>>>(s);
+        ++launches;
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(ctx->ev[2], st));
+        unsigned h_cnt[CNT_COUNT];
+        CK(cudaMemcpyAsync(h_cnt, ctx->counters.p, sizeof h_cnt, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (h_cnt[CNT_BAD_INPUT]) return ctx->fail(OSMR_E_INVALID, "styled area references an entity or style that does not exist");
+        if (h_cnt[CNT_OVERFLOW]) {  // grow the scratch that ran out and redo the batch
+            if (h_cnt[CNT_OVERFLOW] & 1u) {
+                size_t need = (size_t)h_cnt[CNT_GEOM_USED] + (size_t)h_cnt[CNT_GEOM_USED] / 2 + 1024;
+                if (need <= ctx->geom_cap_units) need = ctx->geom_cap_units * 2;
+                if (need >= 0xffffffffull) return ctx->fail(OSMR_E_NOMEM, "geometry scratch exceeds 64 GiB; split the batch");
+                CK(ctx->geom.reserve(need));
+                ctx->geom_cap_units = ctx->geom.cap;
+            }
+            if (h_cnt[CNT_OVERFLOW] & 2u) {
+                size_t need = (size_t)h_cnt[CNT_MASK_USED] + (size_t)h_cnt[CNT_MASK_USED] / 2 + 1024;
+                if (need <= ctx->mask_cap_words) need = ctx->mask_cap_words * 2;
+                if (need >= 0xffffffffull) return ctx->fail(OSMR_E_NOMEM, "mask scratch exceeds 16 GiB; split the batch");
+                CK(ctx->mask.reserve(need));
+                ctx->mask_cap_words = ctx->mask.cap;
+            }
+            continue;
+        }
+        float ms_plan = 0, ms_raster = 0;
+        cudaEventElapsedTime(&ms_plan, ctx->ev[0], ctx->ev[1]);
+        cudaEventElapsedTime(&ms_raster, ctx->ev[1], ctx->ev[2]);
+        ctx->stats.n_tiles = ctx->n_tiles;
+        ctx->stats.n_areas = ctx->n_areas;
+        ctx->stats.n_visible_ops = h_cnt[CNT_VISIBLE];
+        ctx->stats.n_node_refs = ((uint64_t)h_cnt[CNT_NODE_REFS_HI] << 32) | h_cnt[CNT_NODE_REFS_LO];
+        ctx->stats.kernel_launches = launches;
+        ctx->stats.ms_plan = ms_plan;
+        ctx->stats.ms_raster = ms_raster;
+        ctx->stats.ms_total = ms_plan + ms_raster;
+        return OSMR_OK;
+    }
+    return ctx->fail(OSMR_E_NOMEM, "scratch kept overflowing");
+}
+
+int osmr_batch_draw(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t flags, uint8_t* out, float* gpu_ms) {
+    if (!ctx) return OSMR_E_INVALID;
+    if (!ctx->has_batch) return ctx->fail(OSMR_E_STATE, "no batch uploaded");
+    if ((flags & OSMR_DRAW_HAS_CANVAS_COLOR) && !canvas_rgb) return ctx->fail(OSMR_E_INVALID, "null canvas colour");
+    cudaSetDevice(ctx->device);
+    const size_t D = 256 * (size_t)ctx->scale;
+    const size_t bytes = (size_t)ctx->n_tiles * D * D * ((flags & OSMR_DRAW_OUT_RGBA) ? 4 : 3);
+    unsigned char* dev_out;
+    if (out && (flags & OSMR_DRAW_OUT_DEVICE)) {
+        dev_out = out;
+    } else {
+        CK(ctx->out.reserve(bytes));
+        dev_out = ctx->out.p;
+    }
+    ctx->out_bytes = bytes;
+    CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+    int rc = run_pipeline(ctx, canvas_rgb, flags, dev_out);
+    if (rc) return rc;
+    if (out && !(flags & OSMR_DRAW_OUT_DEVICE)) {
+        CK(cudaMemcpyAsync(out, dev_out, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    if (gpu_ms) *gpu_ms = ctx->stats.ms_total;
+    return OSMR_OK;
+}
+
+int osmr_batch_output(osmr_ctx* ctx, const uint8_t** dev_ptr, size_t* n_bytes) {
+    if (!ctx || !dev_ptr || !n_bytes) return OSMR_E_INVALID;
+    *dev_ptr = ctx->out.p;
+    *n_bytes = ctx->out_bytes;
+    return OSMR_OK;
+}
+
+int osmr_draw_tiles(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, const uint32_t* area_begin,
+                    const osmr_styled_area* areas, const uint8_t canvas_rgb[3], uint32_t flags, uint8_t* out) {
+    if (!ctx) return OSMR_E_INVALID;
+    if (!out) return ctx->fail(OSMR_E_INVALID, "null output buffer");
+    int rc = osmr_batch_upload(ctx, tiles, n_tiles, area_begin, areas);
+    if (rc) return rc;
+    return osmr_batch_draw(ctx, canvas_rgb, flags, out, nullptr);
+}
+
+int osmr_get_stats(osmr_ctx* ctx, osmr_stats* out) {
+    if (!ctx || !out) return OSMR_E_INVALID;
+    *out = ctx->stats;
+    return OSMR_OK;
+}
+
+int osmr_project_nodes(osmr_ctx* ctx, const osmr_tile* tile, int32_t* out_xy) {
+    if (!ctx) return OSMR_E_INVALID;
+    if (!ctx->has_geo) return ctx->fail(OSMR_E_STATE, "osmr_set_geodata has not been called");
+    if (!tile || !out_xy) return ctx->fail(OSMR_E_INVALID, "null argument");
+    if (tile->scale < 1 || tile->scale > 8 || tile->zoom > 22) return ctx->fail(OSMR_E_INVALID, "bad tile");
+    cudaSetDevice(ctx->device);
+    if (ctx->n_nodes == 0) return OSMR_OK;
+    DevBuf<int2> tmp;
+    CK(tmp.reserve(ctx->n_nodes));
+    project_all_kernel<<<(ctx->n_nodes + 255) / 256, 256, 0, ctx->stream>>>(ctx->merc.p, ctx->n_nodes, *tile, tmp.p);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out_xy, tmp.p, (size_t)ctx->n_nodes * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    tmp.release();
+    return OSMR_OK;
+}
+
+// pinned host memory for callers that want full-speed transfers (optional)
+void* osmr_alloc_pinned(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
+    return p;
+}
+void osmr_free_pinned(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+}  // extern "C"

@@ -1,0 +1,269 @@
+// osmr_device.cuh -- device-side arithmetic shared by the kernels of libosmr_b200.so.
+//
+// Everything here reproduces the reference's scalar arithmetic bit-for-bit (f64 / i32 / i64, IEEE basic
+// operations in the reference's order).  The translation unit MUST be compiled with -fmad=false: the
+// reference has no fused multiply-adds, and e.g. `src + (1-a)*dst` contracted to an FMA changes the
+// truncated 8-bit result.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "osmr.h"
+
+namespace osmr {
+
+constexpr double kPi = 3.14159265358979323846264338327950288;
+
+// ------------------------------------------------------------------------------------------------------
+// Rust cast semantics
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int f64_as_i32(double v) {
+    // `as i32`: round toward zero, saturate, NaN -> 0.  cvt.rzi.s32.f64 has exactly these semantics.
+    return __double2int_rz(v);
+}
+__device__ __forceinline__ unsigned f64_as_u8(double v) {
+    // `as u8`
+    if (!(v > 0.0)) return 0u;  // negatives, -0, NaN
+    if (v >= 255.0) return 255u;
+    return (unsigned)__double2int_rz(v);
+}
+__device__ __forceinline__ int wsub(int a, int b) { return (int)((unsigned)a - (unsigned)b); }
+__device__ __forceinline__ int wadd(int a, int b) { return (int)((unsigned)a + (unsigned)b); }
+
+// ------------------------------------------------------------------------------------------------------
+// a1: projection.  reference src/tile.rs:88-106 + src/draw/point.rs:11-19.
+//
+// coords_to_xy(z) = factor * (256 * 2^z) where factor = x/(2*pi) depends only on the node.  The second
+// factor is a power of two, so the product is exact and `merc` (the per-node factor pair, computed once per
+// dataset by project_nodes_kernel) reproduces coords_to_xy for every zoom with one multiplication.
+// ------------------------------------------------------------------------------------------------------
+struct TileXform {
+    double dim;    // 256 * 2^zoom
+    double tx256;  // f64::from(tile.x * TILE_SIZE) (u32 multiply, wrapping)
+    double ty256;
+    double scale;
+};
+
+__device__ __forceinline__ TileXform make_xform(const osmr_tile& t) {
+    TileXform x;
+    x.dim = (double)(unsigned)(256u * (1u << (t.zoom & 31u)));
+    x.tx256 = (double)(unsigned)(t.x * 256u);
+    x.ty256 = (double)(unsigned)(t.y * 256u);
+    x.scale = (double)t.scale;
+    return x;
+}
+
+__device__ __forceinline__ int2 project_point(const double2 m, const TileXform& t) {
+    double x = m.x * t.dim - t.tx256;  // -fmad=false keeps mul and sub separate
+    double y = m.y * t.dim - t.ty256;
+    int2 p;
+    p.x = f64_as_i32(round(x * t.scale));  // f64::round: half away from zero == CUDA round()
+    p.y = f64_as_i32(round(y * t.scale));
+    return p;
+}
+
+// Point::dist (point.rs:21-25)
+__device__ __forceinline__ double point_dist(int ax, int ay, int bx, int by) {
+    double dx = (double)wsub(ax, bx);
+    double dy = (double)wsub(ay, by);
+    return sqrt(dx * dx + dy * dy);
+}
+
+// Point::push_away_from (point.rs:27-35)
+__device__ __forceinline__ int2 push_away_from(int sx, int sy, int ox, int oy, double by) {
+    double dist = point_dist(sx, sy, ox, oy);
+    double push = by / dist;
+    int2 r;
+    r.x = wadd(sx, f64_as_i32(round((double)wsub(sx, ox) * push)));
+    r.y = wadd(sy, f64_as_i32(round((double)wsub(sy, oy) * push)));
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// a2: fill edge -> row span in O(1).  Closed form of the all-octant Bresenham walk of fill.rs:51-104
+// (pinned against the step-by-step oracle by tests/test_closed_forms.py).
+// Returns false when row y is not visited by the edge.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ long long floor_div(long long a, long long b) {  // b > 0
+    long long q = a / b;
+    return (a % b != 0 && a < 0) ? q - 1 : q;
+}
+__device__ __forceinline__ long long ceil_div(long long a, long long b) {  // b > 0
+    long long q = a / b;
+    return (a % b != 0 && a > 0) ? q + 1 : q;
+}
+
+__device__ __forceinline__ long long fill_hi(long long jj, long long a, long long b) {
+    if (jj == b) return a;
+    long long Y = ceil_div(a - 2 * b + 2 * jj * a, 2 * b);
+    Y = Y < 0 ? 0 : Y;
+    return Y < a ? Y : a;
+}
+
+__device__ __forceinline__ bool fill_edge_row_span(int x1, int y1, int x2, int y2, int y, int& xmin, int& xmax,
+                                                   bool& poisoned) {
+    long long a = llabs((long long)x2 - (long long)x1);
+    long long b = llabs((long long)y2 - (long long)y1);
+    int sx = (x1 < x2) ? 1 : -1;
+    int sy = (y1 < y2) ? 1 : -1;
+    long long j = ((long long)y - (long long)y1) * sy;
+    if (j < 0 || j > b) return false;
+    if (b == 0) {
+        xmin = min(x1, x2);
+        xmax = max(x1, x2);
+        poisoned = true;
+        return true;
+    }
+    long long lo;
+    if (j == 0) {
+        lo = 0;
+    } else {
+        long long h = fill_hi(j - 1, a, b);
+        long long X = floor_div(2 * a - b + 2 * (j - 1) * a, 2 * b);
+        lo = h + ((h <= X) ? 1 : 0);
+        lo = lo < a ? lo : a;
+    }
+    long long h = fill_hi(j, a, b);
+    long long e = lo > h ? lo : h;
+    int xa = x1 + sx * (int)lo;
+    int xb = x1 + sx * (int)e;
+    xmin = min(xa, xb);
+    xmax = max(xa, xb);
+    poisoned = (j == 0 && y1 <= y2) || (j == b && y2 <= y1);
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// a4: thick-line traversal with random access (closed form of line.rs:65-158).
+// Number of Bresenham corrections after n calls of `update_error` starting from error e0.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ long long ncorr(long long e0, long long n, long long mn_d, long long mx_d) {
+    long long num = e0 + 2 * mn_d * n - mx_d;
+    if (num <= 0) return 0;
+    long long den = 2 * mx_d;
+    if (num < 0x7fffffffLL && den < 0x7fffffffLL) return (long long)(((unsigned)num + (unsigned)den - 1u) / (unsigned)den);
+    return (num + den - 1) / den;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// a5: opacity calculator (opacity_calculator.rs).  Built once per line op in shared memory.
+// ------------------------------------------------------------------------------------------------------
+constexpr int kMaxDashSegs = 33;  // dash lists of up to 64 numbers -> <= 33 "on" segments
+
+struct DashSeg {
+    double start_from, start_to, end_from, end_to, opacity_mul;
+    double orig_a, orig_b;  // valid when OpacityCalc::round_caps
+};
+
+struct OpacityCalc {
+    double half_line_width;
+    double total_dash_len;
+    // per-op constants of get_opacity_by_center_distance for cap_dist == 0 (the only case unless round_caps)
+    double feather_from, feather_to, feather_dist, opacity_mul;
+    int n_segs;       // 0 == "dashes: None"
+    int round_caps;   // original_endpoints is Some(..)  (LineCap::Round)
+    DashSeg segs[kMaxDashSegs];
+};
+
+__device__ __forceinline__ bool is_non_trivial_cap(unsigned cap) { return cap == OSMR_CAP_SQUARE || cap == OSMR_CAP_ROUND; }
+
+__device__ __forceinline__ void center_feather(double hw, double& from, double& to, double& dist, double& mul) {
+    from = fmax(hw - 0.5, 0.0);  // f64::max ignores NaN, like fmax
+    to = fmax(hw + 0.5, 1.0);
+    dist = to - from;
+    mul = fmin(2.0 * hw, 1.0);
+}
+
+// OpacityCalculator::new + compute_segments (opacity_calculator.rs:16-30, 98-143)
+__device__ inline void build_calc(OpacityCalc& c, double hw, const double* dashes, int n, double dash_scale, bool has_dashes,
+                                  unsigned cap) {
+    c.half_line_width = hw;
+    c.n_segs = 0;
+    c.round_caps = (cap == OSMR_CAP_ROUND) ? 1 : 0;
+    double len_before = 0.0;
+    if (has_dashes && n > 0) {
+        for (int k = 0; k < n + 1; ++k) {
+            int idx = (k < n) ? k : 0;
+            double dash = dashes[idx] * dash_scale;  // drawer.rs:163-164 scale_dashes
+            double start = len_before;
+            if (idx != 0 || c.n_segs == 0) len_before += dash;
+            if (idx % 2 != 0) continue;
+            double end = start + dash;
+            double oa = start, ob = end;
+            if (is_non_trivial_cap(cap)) {
+                start -= hw;
+                end += hw;
+            }
+            double mid = (start + end) / 2.0;
+            if (c.n_segs < kMaxDashSegs) {
+                DashSeg& s = c.segs[c.n_segs++];
+                s.start_from = fmin(start - 0.5, mid - 1.0);
+                s.start_to = fmin(start + 0.5, mid);
+                s.end_from = fmax(end - 0.5, mid);
+                s.end_to = fmax(end + 0.5, mid + 1.0);
+                s.opacity_mul = fmin(end - start, 1.0);
+                s.orig_a = oa;
+                s.orig_b = ob;
+            }
+        }
+    }
+    c.total_dash_len = len_before;
+    double hw0 = sqrt(hw * hw - 0.0 * 0.0);  // calculate() with cap_dist == 0
+    center_feather(hw0, c.feather_from, c.feather_to, c.feather_dist, c.opacity_mul);
+}
+
+// OpacityCalculator::calculate (opacity_calculator.rs:32-43) with traveled distance supplied per segment.
+__device__ __forceinline__ void calc_opacity(const OpacityCalc& c, double traveled, double center_distance, double start_distance,
+                                             double& opacity, bool& is_in_line) {
+    double sd_opacity = 1.0;
+    double ff = c.feather_from, ft = c.feather_to, fd = c.feather_dist, fm = c.opacity_mul;
+    if (c.n_segs != 0) {
+        double dist_rem = traveled + start_distance;
+        if (c.total_dash_len > 0.0) dist_rem = fmod(dist_rem, c.total_dash_len);
+        double acc = 0.0;
+        bool has_cap = false;
+        double cap = 0.0;
+        for (int i = 0; i < c.n_segs; ++i) {
+            const DashSeg& s = c.segs[i];
+            if (dist_rem < s.start_from || dist_rem > s.end_to) continue;  // NaN falls through to the last branch, as in the reference
+            double base;
+            if (dist_rem <= s.start_to)
+                base = (dist_rem - s.start_from) / (s.start_to - s.start_from);
+            else if (dist_rem < s.end_from)
+                base = 1.0;
+            else
+                base = (s.end_to - dist_rem) / (s.end_to - s.end_from);
+            acc = fmax(acc, s.opacity_mul * base);
+            if (c.round_caps) {
+                double dcap;
+                if (dist_rem < s.orig_a)
+                    dcap = s.orig_a - dist_rem;
+                else if (dist_rem <= s.orig_b)
+                    dcap = 0.0;
+                else
+                    dcap = dist_rem - s.orig_b;
+                if (!has_cap || dcap < cap) {
+                    has_cap = true;
+                    cap = dcap;
+                }
+            }
+        }
+        sd_opacity = acc;
+        if (has_cap && cap != 0.0) {
+            double hw = sqrt(c.half_line_width * c.half_line_width - cap * cap);  // may be NaN on purpose
+            center_feather(hw, ff, ft, fd, fm);
+        }
+    }
+    double v;
+    if (center_distance < ff)
+        v = 1.0;
+    else if (center_distance < ft)
+        v = (ft - center_distance) / fd;
+    else
+        v = 0.0;
+    double cd = fm * v;
+    opacity = fmin(sd_opacity, cd);
+    is_in_line = cd > 0.0;
+}
+
+}  // namespace osmr

@@ -1,0 +1,221 @@
+"""Host-side mirror of the reference's draw interface on top of the C ABI.
+
+Same names, argument meaning and error behaviour as the reference (file:line in /root/reference):
+    Tile ................ src/tile.rs:8-13
+    TilePixels(scale) ... src/draw/tile_pixels.rs:57   per-worker scratch; here it owns the GPU context
+    Drawer(base_path) ... src/draw/drawer.rs:33        owns the icon cache (fill-image patterns)
+    Drawer.draw_to_pixels(entities, tile, pixels, scale, styler) -> TileRenderedPixels   drawer.rs:60-131
+plus the batched extension Drawer.draw_tiles_to_pixels (many tiles per launch).
+
+Everything numeric happens in libosmr_b200.so (hand-written CUDA); this file only marshals the styler's
+output.  The label pass (drawer.rs:106-126) is not part of the accelerated path yet: like the C ABI this
+returns the tile after the area passes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from .wire import (
+    AREA_DTYPE,
+    OSMR_DRAW_HAS_CANVAS_COLOR,
+    OSMR_DRAW_OUT_RGBA,
+    OSMR_DRAW_USE_CAPS_FOR_DASHES,
+    TILE_DTYPE,
+    StatsStruct,
+    StyleTable,
+    styled_areas_to_array,
+)
+
+
+@dataclass(frozen=True)
+class Tile:
+    zoom: int
+    x: int
+    y: int
+
+
+@dataclass
+class TileRenderedPixels:
+    triples: np.ndarray  # uint8 [dimension, dimension, 3]  (reference: Vec<(u8,u8,u8)>)
+    dimension: int
+
+
+@dataclass
+class OsmEntities:
+    """reader.rs:21-25: what get_entities_in_tile_with_neighbors returns (local ids into the `.bin`)."""
+
+    reader: object
+    nodes: np.ndarray
+    ways: np.ndarray
+    multipolygons: np.ndarray
+
+
+class GpuContext:
+    """Thin RAII wrapper of osmr_ctx."""
+
+    def __init__(self, device: int = 0):
+        self.L = _lib.load()
+        h = C.c_void_p()
+        rc = self.L.osmr_ctx_create(device, C.byref(h))
+        if rc != 0:
+            raise _lib.OsmrError(f"osmr_ctx_create(device={device}) failed with {rc}: no usable CUDA device (no CPU fallback)")
+        self.h = h
+        self._geodata_id = None
+        self._n_styles = -1
+        self._n_icons = -1
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.osmr_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            msg = self.L.osmr_last_error(self.h)
+            raise _lib.OsmrError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+    # ---- residency ------------------------------------------------------------------------------------------
+    def set_geodata(self, image: bytes):
+        buf = np.frombuffer(image, dtype=np.uint8)
+        self._check(self.L.osmr_set_geodata(self.h, buf.ctypes.data, len(image)), "osmr_set_geodata")
+        self._geodata_id = id(image)
+        self.n_nodes = int(np.frombuffer(image, dtype="<u4", count=1)[0])
+
+    def set_table(self, table: StyleTable):
+        if len(table.icons) != self._n_icons:
+            icons, keep = table.icon_structs()
+            self._check(self.L.osmr_set_icons(self.h, C.addressof(icons), len(table.icons)), "osmr_set_icons")
+            self._n_icons = len(table.icons)
+        if len(table.rows) != self._n_styles:
+            styles = table.styles_array()
+            dashes = table.dashes_array()
+            self._check(
+                self.L.osmr_set_styles(self.h, styles.ctypes.data, len(styles), dashes.ctypes.data, len(dashes)),
+                "osmr_set_styles",
+            )
+            self._n_styles = len(table.rows)
+
+    # ---- drawing ------------------------------------------------------------------------------------------------
+    @staticmethod
+    def _flags(canvas_rgb, use_caps_for_dashes: bool, rgba: bool):
+        flags = OSMR_DRAW_USE_CAPS_FOR_DASHES if use_caps_for_dashes else 0
+        canvas = np.zeros(3, dtype=np.uint8)
+        if canvas_rgb is not None:
+            flags |= OSMR_DRAW_HAS_CANVAS_COLOR
+            canvas[:] = canvas_rgb
+        if rgba:
+            flags |= OSMR_DRAW_OUT_RGBA
+        return flags, canvas
+
+    def draw_tiles(self, tiles, area_begin, areas, canvas_rgb, use_caps_for_dashes=True, rgba=False, out=None):
+        """osmr_draw_tiles with host buffers: returns uint8 [n_tiles, D, D, 3|4]."""
+        tiles = np.ascontiguousarray(tiles, dtype=TILE_DTYPE)
+        area_begin = np.ascontiguousarray(area_begin, dtype=np.uint32)
+        areas = np.ascontiguousarray(areas, dtype=AREA_DTYPE)
+        n = len(tiles)
+        d = 256 * int(tiles["scale"][0]) if n else 256
+        ch = 4 if rgba else 3
+        if out is None:
+            out = np.empty((n, d, d, ch), dtype=np.uint8)
+        flags, canvas = self._flags(canvas_rgb, use_caps_for_dashes, rgba)
+        self._check(
+            self.L.osmr_draw_tiles(
+                self.h, tiles.ctypes.data, n, area_begin.ctypes.data, areas.ctypes.data, canvas.ctypes.data, flags, out.ctypes.data
+            ),
+            "osmr_draw_tiles",
+        )
+        return out
+
+    def batch_upload(self, tiles, area_begin, areas):
+        tiles = np.ascontiguousarray(tiles, dtype=TILE_DTYPE)
+        area_begin = np.ascontiguousarray(area_begin, dtype=np.uint32)
+        areas = np.ascontiguousarray(areas, dtype=AREA_DTYPE)
+        self._check(
+            self.L.osmr_batch_upload(self.h, tiles.ctypes.data, len(tiles), area_begin.ctypes.data, areas.ctypes.data),
+            "osmr_batch_upload",
+        )
+        self._batch_shape = (len(tiles), 256 * int(tiles["scale"][0]))
+
+    def batch_draw(self, canvas_rgb, use_caps_for_dashes=True, rgba=False, out=None) -> float:
+        """Draw the resident batch; returns device milliseconds (CUDA events on the context stream)."""
+        flags, canvas = self._flags(canvas_rgb, use_caps_for_dashes, rgba)
+        ms = C.c_float(0.0)
+        ptr = out.ctypes.data if out is not None else None
+        self._check(self.L.osmr_batch_draw(self.h, canvas.ctypes.data, flags, ptr, C.byref(ms)), "osmr_batch_draw")
+        return float(ms.value)
+
+    def stats(self) -> dict:
+        st = StatsStruct()
+        self._check(self.L.osmr_get_stats(self.h, C.byref(st)), "osmr_get_stats")
+        return {k: getattr(st, k) for k, _ in StatsStruct._fields_}
+
+    def project_nodes(self, tile) -> np.ndarray:
+        t = np.array([tuple(tile)], dtype=TILE_DTYPE)
+        out = np.zeros((self.n_nodes, 2), dtype=np.int32)
+        self._check(self.L.osmr_project_nodes(self.h, t.ctypes.data, out.ctypes.data), "osmr_project_nodes")
+        return out
+
+    def debug_set(self, key: str, value: int):
+        self._check(self.L.osmr_debug_set(self.h, key.encode(), value), "osmr_debug_set")
+
+
+class TilePixels:
+    """Per-worker scratch (tile_pixels.rs:57).  Reallocated by the caller when the scale changes, exactly like
+    the reference server does (http_server.rs:156-160); here it owns the GPU context and its device buffers."""
+
+    def __init__(self, scale: int, device: int = 0):
+        self.scale = int(scale)
+        self.ctx = GpuContext(device)
+
+    def dimension(self) -> int:
+        return 256 * self.scale
+
+
+class Drawer:
+    def __init__(self, base_path: str | None):
+        self.table = StyleTable(base_path)  # icon cache + interned styles
+
+    def _areas_for(self, entities: OsmEntities, tile: Tile, styler):
+        from .upstream.pipeline import TileStyler
+
+        ts = getattr(entities.reader, "_tile_styler", None)
+        if ts is None or ts.styler is not styler or ts.table is not self.table:
+            ts = TileStyler(entities.reader, styler, self.table)
+            entities.reader._tile_styler = ts
+        way_ents = [ts.way_entity(int(w)) for w in entities.ways]
+        mp_ents = [ts.mp_entity(int(m)) for m in entities.multipolygons]
+        styled = styler.style_areas(way_ents, mp_ents, tile.zoom, False)  # drawer.rs:75-78
+        return styled_areas_to_array(styled, self.table)
+
+    def draw_to_pixels(self, entities: OsmEntities, tile: Tile, pixels: TilePixels, scale: int, styler) -> TileRenderedPixels:
+        out = self.draw_tiles_to_pixels([entities], [tile], pixels, scale, styler)
+        return out[0]
+
+    def draw_tiles_to_pixels(self, entities_list, tiles, pixels: TilePixels, scale: int, styler):
+        """Batched form: one launch for many (entities, tile) pairs sharing a reader, scale and styler."""
+        if scale != pixels.scale:
+            raise ValueError("TilePixels was created for another scale (reference: http_server.rs:156-160)")
+        ctx = pixels.ctx
+        reader = entities_list[0].reader
+        if ctx._geodata_id != id(reader.data):
+            ctx.set_geodata(reader.data)
+        parts = [self._areas_for(e, t, styler) for e, t in zip(entities_list, tiles)]
+        ctx.set_table(self.table)
+        begins = np.zeros(len(parts) + 1, dtype=np.uint32)
+        begins[1:] = np.cumsum([len(p) for p in parts])
+        areas = np.concatenate(parts) if parts else np.zeros(0, dtype=AREA_DTYPE)
+        tarr = np.array([(t.zoom, t.x, t.y, scale) for t in tiles], dtype=TILE_DTYPE)
+        img = ctx.draw_tiles(tarr, begins, areas, styler.canvas_fill_color, styler.use_caps_for_dashes)
+        d = 256 * scale
+        return [TileRenderedPixels(img[i], d) for i in range(len(tiles))]

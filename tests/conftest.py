@@ -1,0 +1,57 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+CONFIG_NAMES = ["14", "15", "16", "17", "18", "18_2x"]
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+class FixtureInputs:
+    """tests/golden/fixture_inputs.npz + nano_moscow.bin (made by tools/make_fixtures.py)."""
+
+    def __init__(self):
+        from osm_renderer_b200.wire import StyleTable
+
+        with open(os.path.join(GOLDEN, "nano_moscow.bin"), "rb") as f:
+            self.bin = f.read()
+        z = np.load(os.path.join(GOLDEN, "fixture_inputs.npz"))
+        self.canvas_rgb = tuple(int(v) for v in z["canvas_rgb"])
+        self.use_caps_for_dashes = bool(z["use_caps_for_dashes"])
+        self.table = StyleTable(None)
+        self.table.rows = list(z["styles"])
+        self.table.dashes = list(z["dashes"])
+        for i in range(int(z["n_icons"])):
+            self.table.add_raw_icon(f"icon_{i}", z[f"icon_{i}"])
+        self.batches = {n: (z[f"tiles_{n}"], z[f"area_begin_{n}"], z[f"areas_{n}"]) for n in CONFIG_NAMES}
+
+    def golden(self, name):
+        g = np.load(os.path.join(GOLDEN, f"golden_{name}.npz"))
+        d = int(g["dim"])
+        mask = np.unpackbits(g["label_mask"], axis=-1)[..., :d].astype(bool)
+        return g["golden"], mask
+
+
+@pytest.fixture(scope="session")
+def fx():
+    return FixtureInputs()
+
+
+@pytest.fixture(scope="session")
+def gpu_ctx(fx):
+    from osm_renderer_b200.drawer import GpuContext
+
+    ctx = GpuContext(0)
+    ctx.set_geodata(fx.bin)
+    ctx.set_table(fx.table)
+    yield ctx
+    ctx.close()
