@@ -150,6 +150,8 @@ typedef struct osmr_stats {
     uint64_t n_visible_ops;  /* generations whose reach intersects their tile */
     uint64_t n_node_refs;    /* R: node references of all styled areas */
     uint64_t kernel_launches;
+    uint64_t geom_bytes;     /* edge/segment records written for the visible ops */
+    uint64_t mask_bytes;     /* fill row masks written (1 bit per pixel of every fill row) */
     float ms_plan;           /* per-stage device times of the last draw (CUDA events) */
     float ms_raster;
     float ms_total;

@@ -455,6 +455,8 @@ static int run_pipeline(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t fla
         ctx->stats.n_visible_ops = h_cnt[CNT_VISIBLE];
         ctx->stats.n_node_refs = ((uint64_t)h_cnt[CNT_NODE_REFS_HI] << 32) | h_cnt[CNT_NODE_REFS_LO];
         ctx->stats.kernel_launches = launches;
+        ctx->stats.geom_bytes = (uint64_t)h_cnt[CNT_GEOM_USED] * 16ull;
+        ctx->stats.mask_bytes = (uint64_t)h_cnt[CNT_MASK_USED] * 4ull;
         ctx->stats.ms_plan = ms_plan;
         ctx->stats.ms_raster = ms_raster;
         ctx->stats.ms_total = ms_plan + ms_raster;

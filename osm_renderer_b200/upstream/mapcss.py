@@ -595,3 +595,64 @@ def parse_file(base_path: str, file_name: str) -> list:
 
 def rules_to_string(rules: list) -> str:
     return "\n\n".join(str(r) for r in rules)
+
+
+# ------------------------------------------------------------------------------------------------
+# (de)serialisation of parsed rules: lets the benchmark style synthetic data on a machine that does not have
+# the reference's stylesheet files (tests/golden/*_rules.json.gz are produced by tools/make_fixtures.py).
+# ------------------------------------------------------------------------------------------------
+def rules_to_json(rules: list) -> list:
+    out = []
+    for r in rules:
+        out.append(
+            {
+                "selectors": [
+                    {
+                        "object_type": s.object_type,
+                        "min_zoom": s.min_zoom,
+                        "max_zoom": s.max_zoom,
+                        "layer_id": s.layer_id,
+                        "tests": [{"kind": t.kind, "tag": t.tag, "op": t.op, "value": t.value} for t in s.tests],
+                    }
+                    for s in r.selectors
+                ],
+                "properties": [
+                    {"name": p.name, "kind": p.kind, "value": list(p.value) if isinstance(p.value, (tuple, list)) else p.value}
+                    for p in r.properties
+                ],
+            }
+        )
+    return out
+
+
+def rules_from_json(data: list) -> list:
+    rules = []
+    for r in data:
+        sels = [
+            Selector(s["object_type"], s["min_zoom"], s["max_zoom"], [Test(t["kind"], t["tag"], t["op"], t["value"]) for t in s["tests"]], s["layer_id"])
+            for s in r["selectors"]
+        ]
+        props = []
+        for p in r["properties"]:
+            v = p["value"]
+            if p["kind"] == "color":
+                v = tuple(v)
+            props.append(Property(p["name"], p["kind"], v))
+        rules.append(Rule(sels, props))
+    return rules
+
+
+def load_rules_json(path: str) -> list:
+    import gzip
+    import json
+
+    with gzip.open(path, "rt", encoding="utf-8") as f:
+        return rules_from_json(json.load(f))
+
+
+def save_rules_json(rules: list, path: str):
+    import gzip
+    import json
+
+    with gzip.open(path, "wt", encoding="utf-8") as f:
+        json.dump(rules_to_json(rules), f)

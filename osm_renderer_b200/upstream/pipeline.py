@@ -66,3 +66,130 @@ def build_batch(ts: TileStyler, tiles):
         begins.append(begins[-1] + len(a))
     areas = np.concatenate(parts) if parts else np.zeros(0, dtype=AREA_DTYPE)
     return tarr, np.asarray(begins, dtype=np.uint32), areas
+
+
+class FastBatchBuilder:
+    """Vectorised equivalent of TileStyler.areas_array for large datasets (the synthetic metro).
+
+    Same semantics as reader.rs:60-100 + styler.rs:115-203; per distinct (closedness, tag list) the styles are
+    computed once through Styler.styles_for, the per-tile work is numpy (candidate selection, expansion, and
+    the painter's-order sort of styler.rs:246-272).  tests/test_upstream.py checks it against TileStyler.
+    """
+
+    def __init__(self, reader: GeodataReader, styler: Styler, table: StyleTable):
+        self.rd = reader
+        self.styler = styler
+        self.table = table
+        rd = reader
+        ints = rd.ints
+        w = rd.ways
+        wlen = w["len"].astype(np.int64)
+        woff = w["off"].astype(np.int64)
+        first = ints[np.minimum(woff, max(len(ints) - 1, 0))] if len(ints) else np.zeros(len(w), dtype=np.uint32)
+        last = ints[np.clip(woff + wlen - 1, 0, max(len(ints) - 1, 0))] if len(ints) else first
+        nlat, nlon = rd.nodes["lat"], rd.nodes["lon"]
+        closed = (wlen > 2) & (nlat[first] == nlat[last]) & (nlon[first] == nlon[last])
+        self.way_kind = np.where(closed, KIND_WAY_CLOSED, KIND_WAY_OPEN).astype(np.int64)
+        self.way_gid = w["id"].astype(np.int64)
+        self.way_tagkey = (w["tags_off"].astype(np.int64) << 32) | w["tags_len"].astype(np.int64)
+        m = rd.multipolygons
+        self.mp_gid = m["id"].astype(np.int64)
+        self.mp_tagkey = (m["tags_off"].astype(np.int64) << 32) | m["tags_len"].astype(np.int64)
+        self._tx = rd.tiles["x"].astype(np.int64)
+        self._ty = rd.tiles["y"].astype(np.int64)
+        self._cache: dict = {}
+
+    def _candidates(self, zoom, x, y):
+        rd = self.rd
+        mul = 1 << (18 - zoom)
+        xa, xb = (x - 1) * mul, (x + 2) * mul - 1
+        ya, yb = (y - 1) * mul, (y + 2) * mul - 1
+        lo = np.searchsorted(self._tx, max(xa, 0), side="left")
+        hi = np.searchsorted(self._tx, xb, side="right")
+        sel = np.nonzero((self._ty[lo:hi] >= ya) & (self._ty[lo:hi] <= yb))[0] + lo
+        recs = rd.tiles[sel]
+
+        def gather(off_name, len_name):
+            offs = recs[off_name].astype(np.int64)
+            lens = recs[len_name].astype(np.int64)
+            tot = int(lens.sum())
+            if tot == 0:
+                return np.zeros(0, dtype=np.int64)
+            rep = np.repeat(np.arange(len(offs)), lens)
+            start = np.concatenate([[0], np.cumsum(lens)[:-1]])
+            idx = offs[rep] + (np.arange(tot) - start[rep])
+            return np.unique(rd.ints[idx]).astype(np.int64)
+
+        ways = gather("w_off", "w_len")
+        mps = gather("m_off", "m_len")
+        if len(mps):
+            mps = mps[rd.multipolygons["len"][mps] > 0]
+        return ways, mps
+
+    def _styles_csr(self, zoom, kind, tagkeys):
+        """for an array of tag keys: CSR (ptr, style ids, layer, fg, z) through the memo."""
+        uniq, inv = np.unique(tagkeys, return_inverse=True)
+        lists = []
+        for k in uniq:
+            ck = (zoom, kind, int(k))
+            ent = self._cache.get(ck)
+            if ent is None:
+                tags = self.rd.tags_of(int(k) >> 32, int(k) & 0xFFFFFFFF)
+                styles = self.styler.styles_for(tags, zoom, kind)
+                ent = (
+                    np.array([self.table.style_id(s) for s in styles], dtype=np.int64),
+                    np.array([s.layer or 0 for s in styles], dtype=np.int64),
+                    np.array([1 if s.is_foreground_fill else 0 for s in styles], dtype=np.int64),
+                    np.array([s.z_index for s in styles], dtype=np.float64),
+                )
+                self._cache[ck] = ent
+            lists.append(ent)
+        return inv, lists
+
+    def _expand(self, zoom, ids, kinds, gids, tagkeys, is_way):
+        if len(ids) == 0:
+            z = np.zeros(0, dtype=np.int64)
+            return z, z, z, z, np.zeros(0), z, z
+        out = []
+        for kind in np.unique(kinds):
+            m = kinds == kind
+            inv, lists = self._styles_csr(zoom, int(kind), tagkeys[m])
+            cnt = np.array([len(l[0]) for l in lists], dtype=np.int64)[inv]
+            tot = int(cnt.sum())
+            if tot == 0:
+                continue
+            rep = np.repeat(np.arange(len(inv)), cnt)
+            start = np.concatenate([[0], np.cumsum(cnt)[:-1]])
+            within = np.arange(tot) - start[rep]
+            # ragged gather through a padded table
+            width = max(len(l[0]) for l in lists)
+            pad = lambda j, dt: np.array([np.pad(l[j], (0, width - len(l[j]))) for l in lists], dtype=dt)
+            sid, lay, fg, zi = pad(0, np.int64), pad(1, np.int64), pad(2, np.int64), pad(3, np.float64)
+            u = inv[rep]
+            ent_ids = ids[m][rep]
+            out.append((ent_ids, sid[u, within], lay[u, within], fg[u, within], zi[u, within], gids[m][rep], within))
+        if not out:
+            z = np.zeros(0, dtype=np.int64)
+            return z, z, z, z, np.zeros(0), z, z
+        return tuple(np.concatenate([o[i] for o in out]) for i in range(7))
+
+    def areas_array(self, zoom, x, y) -> np.ndarray:
+        from ..wire import OSMR_AREA_MULTIPOLYGON
+
+        ways, mps = self._candidates(zoom, x, y)
+        we = self._expand(zoom, ways, self.way_kind[ways], self.way_gid[ways], self.way_tagkey[ways], True)
+        me = self._expand(zoom, mps, np.full(len(mps), KIND_MULTIPOLYGON), self.mp_gid[mps], self.mp_tagkey[mps], False)
+        ent = np.concatenate([me[0] | OSMR_AREA_MULTIPOLYGON, we[0]])
+        sid = np.concatenate([me[1], we[1]])
+        lay = np.concatenate([me[2], we[2]])
+        fg = np.concatenate([me[3], we[3]])
+        zi = np.concatenate([me[4], we[4]])
+        gid = np.concatenate([me[5], we[5]])
+        is_way = np.concatenate([np.zeros(len(me[0]), dtype=np.int64), np.ones(len(we[0]), dtype=np.int64)])
+        loc = np.concatenate([me[0], we[0]])  # local id: entities are visited in local-id order (stable sort)
+        within = np.concatenate([me[6], we[6]])
+        order = np.lexsort((within, loc, is_way, gid, zi, fg, lay))
+        out = np.empty(len(order), dtype=AREA_DTYPE)
+        out["entity"] = ent[order]
+        out["style"] = sid[order]
+        return out

@@ -68,6 +68,8 @@ class StatsStruct(C.Structure):
         ("n_visible_ops", C.c_uint64),
         ("n_node_refs", C.c_uint64),
         ("kernel_launches", C.c_uint64),
+        ("geom_bytes", C.c_uint64),
+        ("mask_bytes", C.c_uint64),
         ("ms_plan", C.c_float),
         ("ms_raster", C.c_float),
         ("ms_total", C.c_float),

@@ -7,6 +7,7 @@ Outputs (committed, travel to the GPU box where /root/reference does not exist):
   tests/golden/nano_moscow.bin        geodata image written by the restated importer (saver.rs format)
   tests/golden/fixture_inputs.npz     style table, dashes, icons, canvas colour, per-config tile lists and
                                       ordered styled-area lists (the styler output = C-ABI input)
+  tests/golden/*_rules.json.gz        parsed rule lists of tests/mapcss/mapnik.mapcss and mapcss/osmosnimki-minimal.mapcss
   tests/golden/golden_<cfg>.npz       reference golden pixels per tile + `label_mask`: pixels the reference's
                                       label pass (drawer.rs:106-126, not restated yet) or the red test grid
                                       (test_rendering.rs:109-114) touched.  The mask is *derived*: it is the set of
@@ -50,6 +51,11 @@ def main():
     rd = geodata.GeodataReader(data)
     S = st.Styler(mapcss.parse_file(os.path.join(REF, "tests/mapcss"), "mapnik.mapcss"), "josm", None)
     table = StyleTable(os.path.join(REF, "tests/mapcss"))
+    # parsed stylesheets for the benchmark's synthetic data (the .mapcss files do not exist on the GPU box)
+    mapcss.save_rules_json(S.rules, os.path.join(OUT, "mapnik_rules.json.gz"))
+    mapcss.save_rules_json(
+        mapcss.parse_file(os.path.join(REF, "mapcss"), "osmosnimki-minimal.mapcss"), os.path.join(OUT, "osmosnimki_rules.json.gz")
+    )
     ts = pipeline.TileStyler(rd, S, table)
 
     batches = {}
