@@ -71,6 +71,7 @@ struct osmr_ctx {
     // scratch
     DevBuf<AreaInfo> area_info;
     DevBuf<VisOp> vis;
+    DevBuf<short4> vis_bbox;
     DevBuf<unsigned> vis_count, work, fill_work, counters, mask;
     DevBuf<uint4> geom;
     size_t geom_cap_units = 0, mask_cap_words = 0;
@@ -118,8 +119,6 @@ int osmr_ctx_create(int device, osmr_ctx** out_ctx) {
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device);
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(raster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RasterSmem));
     if (e != cudaSuccess) {
         osmr_ctx_destroy(ctx);
         return OSMR_E_CUDA;
@@ -146,6 +145,7 @@ void osmr_ctx_destroy(osmr_ctx* ctx) {
     ctx->areas.release();
     ctx->area_info.release();
     ctx->vis.release();
+    ctx->vis_bbox.release();
     ctx->vis_count.release();
     ctx->work.release();
     ctx->fill_work.release();
@@ -290,11 +290,11 @@ int osmr_set_styles(osmr_ctx* ctx, const osmr_style* styles, uint32_t n_styles, 
     cudaSetDevice(ctx->device);
     for (uint32_t i = 0; i < n_styles; ++i) {
         const osmr_style& s = styles[i];
-        if ((s.flags & OSMR_STYLE_DASHES) && ((uint64_t)s.dashes_off + s.dashes_len > n_dashes || s.dashes_len > 64))
-            return ctx->fail(OSMR_E_INVALID, "style dashes out of range (at most 64 numbers)");
+        if ((s.flags & OSMR_STYLE_DASHES) && ((uint64_t)s.dashes_off + s.dashes_len > n_dashes || s.dashes_len > 32))
+            return ctx->fail(OSMR_E_INVALID, "style dashes out of range (at most 32 numbers)");
         if ((s.flags & OSMR_STYLE_CASING_DASHES) &&
-            ((uint64_t)s.casing_dashes_off + s.casing_dashes_len > n_dashes || s.casing_dashes_len > 64))
-            return ctx->fail(OSMR_E_INVALID, "style casing dashes out of range (at most 64 numbers)");
+            ((uint64_t)s.casing_dashes_off + s.casing_dashes_len > n_dashes || s.casing_dashes_len > 32))
+            return ctx->fail(OSMR_E_INVALID, "style casing dashes out of range (at most 32 numbers)");
         if (s.line_cap > OSMR_CAP_SQUARE || s.casing_line_cap > OSMR_CAP_SQUARE) return ctx->fail(OSMR_E_INVALID, "bad line cap");
     }
     CK(ctx->styles.reserve(n_styles + 1));
@@ -345,6 +345,7 @@ int osmr_batch_upload(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, c
     // scratch that scales with the batch
     CK(ctx->area_info.reserve(n_areas + 1));
     CK(ctx->vis.reserve(3ull * n_areas + 1));
+    CK(ctx->vis_bbox.reserve(3ull * n_areas + 1));
     CK(ctx->work.reserve(3ull * n_areas + 1));
     CK(ctx->fill_work.reserve((size_t)n_areas + 1));
     CK(ctx->vis_count.reserve(n_tiles));
@@ -397,6 +398,7 @@ static int run_pipeline(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t fla
         if (flags & OSMR_DRAW_HAS_CANVAS_COLOR) memcpy(s.canvas, canvas_rgb, 3);
         s.area_info = ctx->area_info.p;
         s.vis = ctx->vis.p;
+        s.vis_bbox = ctx->vis_bbox.p;
         s.vis_count = ctx->vis_count.p;
         s.work = ctx->work.p;
         s.fill_work = ctx->fill_work.p;
@@ -421,8 +423,8 @@ static int run_pipeline(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t fla
         fill_rows_kernel<<<ctx->num_sms * 4, kFillThreads, 0, st>>>(s);
         launches += 3;
         CK(cudaEventRecord(ctx->ev[1], st));
-        const unsigned regions = (unsigned)((D / kRW) * (D / kRH));
-        raster_kernel<<<ctx->n_tiles * regions, kRasterThreads, sizeof(RasterSmem), st>>>(s);
+        const unsigned blocks = (unsigned)((D / kSB) * (D / kSB));
+        raster_kernel<<<ctx->n_tiles * blocks, kRasterThreads, 0, st>>>(s);
         ++launches;
         CK(cudaGetLastError());
         CK(cudaEventRecord(ctx->ev[2], st));

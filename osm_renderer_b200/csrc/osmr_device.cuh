@@ -148,7 +148,7 @@ __device__ __forceinline__ long long ncorr(long long e0, long long n, long long 
 // ------------------------------------------------------------------------------------------------------
 // a5: opacity calculator (opacity_calculator.rs).  Built once per line op in shared memory.
 // ------------------------------------------------------------------------------------------------------
-constexpr int kMaxDashSegs = 33;  // dash lists of up to 64 numbers -> <= 33 "on" segments
+constexpr int kMaxDashSegs = 17;  // dash lists of up to 32 numbers -> <= 17 "on" segments
 
 struct DashSeg {
     double start_from, start_to, end_from, end_to, opacity_mul;

@@ -86,6 +86,7 @@ struct Scene {
     // scratch
     AreaInfo* area_info;
     VisOp* vis;            // tile t owns vis[3*area_begin[t] ...)
+    short4* vis_bbox;      // reach bbox of vis[i] (8 bytes; what the raster warps scan)
     unsigned* vis_count;   // per tile
     unsigned* work;        // global indices into vis (all visible ops)
     unsigned* fill_work;   // global indices into vis (fills)
@@ -367,6 +368,7 @@ __global__ void __launch_bounds__(kPlanThreads) plan_ops_kernel(Scene s) {
         pos += __popc(bal & ((1u << lane_id()) - 1u));
         if (visible) {
             vis[pos] = op;
+            s.vis_bbox[3ull * base + pos] = make_short4(op.x0, op.y0, op.x1, op.y1);
             unsigned gi = (unsigned)(3ull * base + pos);
             s.work[atomicAdd(&s.counters[CNT_N_WORK], 1u)] = gi;
             if (op.kind != OP_LINE) s.fill_work[atomicAdd(&s.counters[CNT_N_FILL_WORK], 1u)] = gi;
@@ -705,96 +707,136 @@ __global__ void __launch_bounds__(kFillThreads) fill_rows_kernel(Scene s) {
 }
 
 // ------------------------------------------------------------------------------------------------------
-// raster_kernel (a3 blend, a4/a5, a6, a7): one CTA per 64x32-pixel region of a tile.
+// raster_kernel (a3 blend, a4/a5, a6, a7): ONE WARP (= one 32-thread CTA) per 16x16-pixel block of a tile.
 //
 // Compositor invariants used (tile_pixels.rs:107-129,205-223): inside one generation the
 // surviving source of a pixel is the contribution with the largest alpha; generations blend in order with
 // premultiplied over; canvas alpha stays exactly 1.0, so only RGB is kept and export is trunc(255*c).
-// The canvas lives in shared memory as f64 for the whole op list; line coverage is an f64 alpha plane updated
-// with 64-bit atomicMax (non-negative doubles order like their bit patterns).
-// Warp w owns rows 4w..4w+3 of the region for every blend, so fill ops need no CTA barrier at all.
+//
+// The warp owns its block for the whole ordered op list of the tile: f64 canvas + f64 alpha plane in shared
+// memory, it culls ops and segments against its own block and walks every perpendicular that can reach it.
+// There is no CTA barrier anywhere (v1 shared a 64x32 region between 8 warps and was barrier-bound, v2 kept a
+// per-chunk barrier and lost to load imbalance: profiles/r01_raster_v{1,2}_ncu_summary.txt); the hardware block
+// scheduler balances the 16x16 blocks.
 // ------------------------------------------------------------------------------------------------------
-constexpr int kRW = 64;
-constexpr int kRH = 32;
-constexpr int kRasterThreads = 256;
-constexpr int kRasterWarps = kRasterThreads / 32;
-constexpr int kRowsPerWarp = kRH / kRasterWarps;
+constexpr int kSB = 16;  // block edge owned by one warp
+constexpr int kRasterThreads = 32;
 
 struct SegHit {
     int x1, y1, x2, y2;
     double traveled;
     int k0;
-    unsigned is_cap;
+    unsigned flags;            // bit0 outer cap, bit1 32-bit fast path valid
+    unsigned long long magic;  // floor(2^64 / (2*mx_d)) + 1 (exact quotients for numerators < 2^32)
+    double denom;              // center_dist_denom (line.rs:106)
 };
 
 struct RasterSmem {
-    double canvas[3][kRH][kRW];
-    unsigned long long plane[kRH][kRW];
+    double canvas[3][kSB * kSB];
+    unsigned long long plane[kSB * kSB];
     OpacityCalc calc[2];  // [0] dashes of the op, [1] outer caps
-    SegHit hits[kRasterThreads];
-    unsigned item_local[kRasterThreads];  // exclusive scan of walker items inside the owning warp
-    unsigned warp_items[kRasterWarps];
-    unsigned queue[kRasterThreads];
-    unsigned warp_cnt[kRasterWarps];
-    unsigned n_queue;
+    SegHit hits[32];
+    unsigned pre[32];
 };
 
-__device__ __forceinline__ void walk_perpendicular(const RasterSmem& sm, unsigned long long (*plane)[kRW], const SegHit& h,
-                                                   const OpacityCalc& calc, bool swap, int mn, int mx, long long p_error,
-                                                   int mul, int mn_inc, int mx_inc, long long mn_d, long long mx_d,
-                                                   long long numer_const, long long sdx, long long sdy, double denom,
-                                                   double opacity0, int rx0, int ry0) {
-    // draw_one_perpendicular (line.rs:89-131)
+// per-segment constants of line.rs:65-118
+struct SegConst {
+    int x1, y1;
+    bool swap;
+    int mn_inc, mx_inc;
+    int mn_d, mx_d;
+    long long numer_const, sdx, sdy;
+    double denom;
+    double traveled;
+    bool small;  // all coordinates < 2^24: `raw as f64` can be carried exactly in f64
+};
+
+// draw_one_perpendicular (line.rs:89-131) restricted to one 16x16 block.
+__device__ __forceinline__ void walk_perpendicular(unsigned long long* plane, const SegConst& sc, const OpacityCalc& calc,
+                                                   int mn, int mx, int p_error, int mul, double opacity0, int bx0, int by0) {
     int p_mn = mx;
     int p_mx = mn;
-    long long err = (long long)mul * p_error;
-    // p_mx moves by mul*mn_inc every step: once it leaves the region on that side it never comes back
-    const int step = mul * mn_inc;
-    const int lo = swap ? ry0 : rx0;
-    const int hi = swap ? ry0 + kRH - 1 : rx0 + kRW - 1;
+    int err = mul * p_error;  // i32 like the reference (line.rs:80-91)
+    // p_mx moves by mul*mn_inc every step: once it leaves the block on that side it never comes back
+    const int step = mul * sc.mn_inc;
+    const int corr = -mul * sc.mx_inc;
+    const int lo = sc.swap ? by0 : bx0;
+    const int hi = lo + kSB - 1;
+    // raw = numer_const + sdy*px - sdx*py (i64, line.rs:102-103); its per-step increments are integers
+    const long long d_step = sc.swap ? -sc.sdx * step : sc.sdy * step;
+    const long long d_corr = sc.swap ? sc.sdy * corr : -sc.sdx * corr;
+    long long raw;
+    {
+        int px = sc.swap ? p_mn : p_mx, py = sc.swap ? p_mx : p_mn;
+        raw = sc.numer_const + (sc.sdy * (long long)px - sc.sdx * (long long)py);
+    }
+    // `raw as f64` (line.rs:104): when every coordinate is below 2^24 the value is an integer below 2^53 and is
+    // carried in f64 exactly, which keeps 64-bit integer maths and the i64->f64 conversion out of the loop
+    double fraw = (double)raw;
+    const double f_step = (double)d_step, f_corr = (double)d_corr;
+    const bool dashed = calc.n_segs != 0;
+    // conservative thresholds that classify a pixel without the division (only when the feather is a per-op
+    // constant, i.e. no round dash cap can change the half width):  |raw| < from*denom*(1-1e-12)  =>  cd = mul*1
+    const bool quick = !(dashed && calc.round_caps);
+    const double t_in = calc.feather_from * sc.denom * (1.0 - 9.0e-13);
+    const double t_out = calc.feather_to * sc.denom * (1.0 + 9.0e-13);
     for (;;) {
         if (step > 0 ? (p_mx > hi) : (p_mx < lo)) break;
-        int px = swap ? p_mn : p_mx;
-        int py = swap ? p_mx : p_mn;
-        long long raw = numer_const + (sdy * (long long)px - sdx * (long long)py);
-        double center_dist = fabs((double)raw) / denom;
-        double long_start = point_dist(px, py, h.x1, h.y1);
-        double short_start = sqrt(fmax(long_start * long_start - center_dist * center_dist, 0.0));
+        const double araw = fabs(sc.small ? fraw : (double)raw);
         double opacity;
         bool in_line;
-        calc_opacity(calc, h.traveled, center_dist, short_start, opacity, in_line);
+        if (quick && !dashed && araw < t_in) {
+            opacity = fmin(1.0, calc.opacity_mul * 1.0);  // sd = 1.0, cd = mul * 1.0
+            in_line = calc.opacity_mul * 1.0 > 0.0;
+        } else if (quick && araw > t_out) {
+            in_line = false;  // cd = mul * 0.0
+            opacity = 0.0;
+        } else {
+            double center_dist = araw / sc.denom;
+            double short_start = 0.0;
+            if (dashed) {
+                int px = sc.swap ? p_mn : p_mx, py = sc.swap ? p_mx : p_mn;
+                double long_start = point_dist(px, py, sc.x1, sc.y1);
+                short_start = sqrt(fmax(long_start * long_start - center_dist * center_dist, 0.0));
+            }
+            calc_opacity(calc, sc.traveled, center_dist, short_start, opacity, in_line);
+        }
         if (!in_line) break;
-        int lx = px - rx0, ly = py - ry0;
-        if ((unsigned)lx < (unsigned)kRW && (unsigned)ly < (unsigned)kRH) {
+        const int lx = (sc.swap ? p_mn : p_mx) - bx0, ly = (sc.swap ? p_mx : p_mn) - by0;
+        if ((unsigned)lx < (unsigned)kSB && (unsigned)ly < (unsigned)kSB) {
             double a = opacity0 * opacity;  // RgbaColor::from_color(color, initial_opacity * opacity).a
             unsigned long long bits = (unsigned long long)__double_as_longlong(a);
-            if (a > 0.0) atomicMax(&plane[ly][lx], bits);
+            unsigned long long* cell = &plane[ly * kSB + lx];
+            if (a > 0.0 && bits > *cell) atomicMax(cell, bits);
         }
-        // update_error (line.rs:82-91)
-        if (err + 2 * mn_d > mx_d) {
-            err -= 2 * mx_d;
-            p_mn -= mul * mx_inc;
+        // update_error (line.rs:82-91), wrapping i32 arithmetic
+        if (wadd(err, 2 * sc.mn_d) > sc.mx_d) {
+            err = wsub(err, 2 * sc.mx_d);
+            p_mn += corr;
+            if (sc.small) fraw += f_corr; else raw += d_corr;
         }
-        err += 2 * mn_d;
+        err = wadd(err, 2 * sc.mn_d);
         p_mx += step;
+        if (sc.small) fraw += f_step; else raw += d_step;
     }
-    (void)sm;
 }
 
-__global__ void __launch_bounds__(kRasterThreads) raster_kernel(Scene s) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    RasterSmem& sm = *reinterpret_cast<RasterSmem*>(smem_raw);
+__global__ void __launch_bounds__(kRasterThreads, 16) raster_kernel(Scene s) {
+    __shared__ RasterSmem sm;
     const int D = s.D;
-    const int regs_x = D / kRW, regs_y = D / kRH;
-    const unsigned tile = blockIdx.x / (unsigned)(regs_x * regs_y);
-    const unsigned reg = blockIdx.x % (unsigned)(regs_x * regs_y);
-    const int rx0 = (int)(reg % regs_x) * kRW;
-    const int ry0 = (int)(reg / regs_x) * kRH;
-    const unsigned lane = lane_id();
-    const unsigned w = threadIdx.x >> 5;
+    const int bpr = D / kSB;  // blocks per tile row
+    const unsigned tile = blockIdx.x / (unsigned)(bpr * bpr);
+    const unsigned blk = blockIdx.x % (unsigned)(bpr * bpr);
+    // consecutive CTAs tile a 64x32 area (4x2 blocks) before moving on, so neighbours share op lists in L1/L2
+    const unsigned grp = blk / 8u, in_grp = blk % 8u;
+    const unsigned grp_per_row = (unsigned)bpr / 4u;
+    const int bx0 = (int)((grp % grp_per_row) * 4u + (in_grp % 4u)) * kSB;
+    const int by0 = (int)((grp / grp_per_row) * 2u + (in_grp / 4u)) * kSB;
+    const unsigned lane = threadIdx.x;
     const unsigned base = s.area_begin[tile];
     const unsigned n_areas = s.area_begin[tile + 1] - base;
     const VisOp* vis = s.vis + 3ull * base;
+    const short4* vbb = s.vis_bbox + 3ull * base;
     const unsigned n_vis = s.vis_count[tile];
     const double scale = (double)s.scale;
 
@@ -803,49 +845,34 @@ __global__ void __launch_bounds__(kRasterThreads) raster_kernel(Scene s) {
         double c[3] = {0.0, 0.0, 0.0};
         if (s.flags & OSMR_DRAW_HAS_CANVAS_COLOR)
             for (int k = 0; k < 3; ++k) c[k] = 1.0 * ((double)s.canvas[k] / 255.0);
-        for (int i = threadIdx.x; i < kRH * kRW; i += kRasterThreads) {
-            int r = i / kRW, x = i % kRW;
-            sm.canvas[0][r][x] = c[0];
-            sm.canvas[1][r][x] = c[1];
-            sm.canvas[2][r][x] = c[2];
-            sm.plane[r][x] = 0ull;
+        for (int i = (int)lane; i < kSB * kSB; i += 32) {
+            sm.canvas[0][i] = c[0];
+            sm.canvas[1][i] = c[1];
+            sm.canvas[2][i] = c[2];
+            sm.plane[i] = 0ull;
         }
     }
-    __syncthreads();
+    __syncwarp();
 
-    for (unsigned chunk = 0; chunk < n_vis; chunk += kRasterThreads) {
-        // ---- ordered queue of the ops whose reach bbox meets this region ----
-        unsigned vi = chunk + threadIdx.x;
+    for (unsigned chunk = 0; chunk < n_vis; chunk += 32) {
+        // ---- the ops of this chunk whose reach bbox meets my block, in order ----
+        unsigned vi = chunk + lane;
         bool hit = false;
         if (vi < n_vis) {
-            const VisOp& o = vis[vi];
-            hit = o.x0 <= rx0 + kRW - 1 && o.x1 >= rx0 && o.y0 <= ry0 + kRH - 1 && o.y1 >= ry0;
+            const short4 o = vbb[vi];
+            hit = o.x <= bx0 + kSB - 1 && o.z >= bx0 && o.y <= by0 + kSB - 1 && o.w >= by0;
         }
-        unsigned bal = __ballot_sync(0xffffffffu, hit);
-        if (lane == 0) sm.warp_cnt[w] = __popc(bal);
-        __syncthreads();
-        {
-            unsigned pos = 0;
-            for (unsigned k = 0; k < w; ++k) pos += sm.warp_cnt[k];
-            pos += __popc(bal & ((1u << lane) - 1u));
-            if (hit) sm.queue[pos] = vi;
-            if (threadIdx.x == 0) {
-                unsigned tot = 0;
-                for (unsigned k = 0; k < kRasterWarps; ++k) tot += sm.warp_cnt[k];
-                sm.n_queue = tot;
-            }
-        }
-        __syncthreads();
-        const unsigned nq = sm.n_queue;
-
-        for (unsigned q = 0; q < nq; ++q) {
-            const VisOp op = vis[sm.queue[q]];
+        unsigned todo = __ballot_sync(0xffffffffu, hit);
+        while (todo) {
+            const unsigned qi = chunk + (unsigned)(__ffs(todo) - 1);
+            todo &= todo - 1;
+            const VisOp op = vis[qi];
             const unsigned pass = op.g / n_areas;
             const osmr_styled_area ar = s.areas[base + (op.g - pass * n_areas)];
             const osmr_style& st = s.styles[ar.style];
 
             if (op.kind != OP_LINE) {
-                // ---------------- fill: blend own rows straight from the row masks ----------------
+                // ---------------- fill: blend straight from the row masks ----------------
                 const int ya = max((int)op.y0, 0);
                 const int wpr = D / 32;
                 double src[4];
@@ -857,38 +884,35 @@ __global__ void __launch_bounds__(kRasterThreads) raster_kernel(Scene s) {
                 } else {
                     icon = &s.icons[st.fill_image];
                 }
+                const int col = (int)(lane & 15u);
 #pragma unroll
-                for (int rr = 0; rr < kRowsPerWarp; ++rr) {
-                    int r = (int)w * kRowsPerWarp + rr;
-                    int y = ry0 + r;
+                for (int j = 0; j < kSB * kSB / 32; ++j) {
+                    const int r = 2 * j + (int)(lane >> 4);
+                    const int y = by0 + r;
                     if (y < (int)op.y0 || y > (int)op.y1) continue;
-                    const unsigned* mrow = s.mask + op.mask_off + (size_t)(y - ya) * wpr + (rx0 >> 5);
-                    unsigned m0 = mrow[0], m1 = mrow[1];
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        unsigned mm = h ? m1 : m0;
-                        if (!((mm >> lane) & 1u)) continue;
-                        int xl = (int)lane + 32 * h;
-                        double c0, c1, c2, a;
-                        if (icon) {  // Filler::Image (fill.rs:36-40): texel (x mod w, y mod h), already premultiplied
-                            unsigned ix = (unsigned)(rx0 + xl) % icon->w, iy = (unsigned)y % icon->h;
-                            double4 t = s.icon_px[icon->off + iy * icon->w + ix];
-                            c0 = t.x;
-                            c1 = t.y;
-                            c2 = t.z;
-                            a = t.w;
-                        } else {
-                            c0 = src[0];
-                            c1 = src[1];
-                            c2 = src[2];
-                            a = src[3];
-                        }
-                        double inv = 1.0 - a;  // blend_pixel (tile_pixels.rs:211-216)
-                        sm.canvas[0][r][xl] = c0 + inv * sm.canvas[0][r][xl];
-                        sm.canvas[1][r][xl] = c1 + inv * sm.canvas[1][r][xl];
-                        sm.canvas[2][r][xl] = c2 + inv * sm.canvas[2][r][xl];
+                    const unsigned mword = s.mask[op.mask_off + (size_t)(y - ya) * wpr + (bx0 >> 5)];
+                    if (!((mword >> ((bx0 & 31) + col)) & 1u)) continue;
+                    const int idx = r * kSB + col;
+                    double c0, c1, c2, a;
+                    if (icon) {  // Filler::Image (fill.rs:36-40): texel (x mod w, y mod h), already premultiplied
+                        unsigned ix = (unsigned)(bx0 + col) % icon->w, iy = (unsigned)y % icon->h;
+                        double4 t = s.icon_px[icon->off + iy * icon->w + ix];
+                        c0 = t.x;
+                        c1 = t.y;
+                        c2 = t.z;
+                        a = t.w;
+                    } else {
+                        c0 = src[0];
+                        c1 = src[1];
+                        c2 = src[2];
+                        a = src[3];
                     }
+                    double inv = 1.0 - a;  // blend_pixel (tile_pixels.rs:211-216)
+                    sm.canvas[0][idx] = c0 + inv * sm.canvas[0][idx];
+                    sm.canvas[1][idx] = c1 + inv * sm.canvas[1][idx];
+                    sm.canvas[2][idx] = c2 + inv * sm.canvas[2][idx];
                 }
+                __syncwarp();
                 continue;
             }
 
@@ -897,32 +921,27 @@ __global__ void __launch_bounds__(kRasterThreads) raster_kernel(Scene s) {
             line_params(s, st, (int)pass, lp);
             const double hw = lp.width / 2.0;
             const int reach = line_reach(hw);
-            if (threadIdx.x == 0) {
-                unsigned cap_for_dashes = (s.flags & OSMR_DRAW_USE_CAPS_FOR_DASHES) ? lp.cap : (unsigned)OSMR_CAP_NONE;
-                build_calc(sm.calc[0], hw, lp.dashes, lp.n_dashes, scale, lp.has_dashes, cap_for_dashes);
-            } else if (threadIdx.x == 32) {
-                const double zero = 0.0;
-                build_calc(sm.calc[1], hw, &zero, 1, 1.0, true, lp.cap);
-            }
             const SegRec* segs = reinterpret_cast<const SegRec*>(s.geom + op.geom_off);
             const unsigned n_seg = op.geom_cnt;
-            for (unsigned sb = 0; sb < n_seg; sb += kRasterThreads) {
-                // one segment per thread: does any of its perpendiculars reach the region?
-                unsigned si = sb + threadIdx.x;
+            bool any = false;
+            for (unsigned sb = 0; sb < n_seg; sb += 32) {
+                // one segment per lane: can any of its perpendiculars reach my block?
+                unsigned si = sb + lane;
                 unsigned items = 0;
+                SegHit hrec;
                 if (si < n_seg) {
                     SegRec sr = segs[si];
                     int mnx = min(sr.x1, sr.x2), mxx = max(sr.x1, sr.x2), mny = min(sr.y1, sr.y2), mxy = max(sr.y1, sr.y2);
-                    if ((long long)mnx - reach <= rx0 + kRW - 1 && (long long)mxx + reach >= rx0 &&
-                        (long long)mny - reach <= ry0 + kRH - 1 && (long long)mxy + reach >= ry0) {
+                    if ((long long)mnx - reach <= bx0 + kSB - 1 && (long long)mxx + reach >= bx0 &&
+                        (long long)mny - reach <= by0 + kSB - 1 && (long long)mxy + reach >= by0) {
                         int dx = abs(wsub(sr.x2, sr.x1)), dy = abs(wsub(sr.y2, sr.y1));
                         bool swap = dx > dy;
                         int mx0 = swap ? sr.x1 : sr.y1;
                         int mxd = swap ? dx : dy;
                         int mx_inc = swap ? (sr.x1 <= sr.x2 ? 1 : -1) : (sr.y1 <= sr.y2 ? 1 : -1);
-                        // main steps whose major coordinate lies within `reach` of the region
-                        long long lo = (long long)(swap ? rx0 : ry0) - reach;
-                        long long hi = (long long)(swap ? rx0 + kRW - 1 : ry0 + kRH - 1) + reach;
+                        // main steps whose major coordinate lies within `reach` of the block
+                        long long lo = (long long)(swap ? bx0 : by0) - reach;
+                        long long hi = (long long)(swap ? bx0 : by0) + kSB - 1 + reach;
                         long long ka, kb;
                         if (mx_inc > 0) {
                             ka = lo - mx0;
@@ -935,148 +954,158 @@ __global__ void __launch_bounds__(kRasterThreads) raster_kernel(Scene s) {
                         if (kb > mxd) kb = mxd;
                         if (kb >= ka) {
                             items = 2u * (unsigned)(kb - ka + 1);
-                            SegHit& hrec = sm.hits[threadIdx.x];
                             hrec.x1 = sr.x1;
                             hrec.y1 = sr.y1;
                             hrec.x2 = sr.x2;
                             hrec.y2 = sr.y2;
                             hrec.traveled = sr.traveled;
                             hrec.k0 = (int)ka;
-                            hrec.is_cap = sr.is_cap;
+                            bool fast = mxd < 32768;  // numerators 2*mn_d*n stay below 2^31
+                            hrec.flags = (sr.is_cap ? 1u : 0u) | (fast ? 2u : 0u);
+                            hrec.magic = fast ? (0xffffffffffffffffull / (unsigned long long)(2 * mxd)) + 1ull : 0ull;
+                            const double dxf = (double)dx, dyf = (double)dy;
+                            hrec.denom = sqrt(dyf * dyf + dxf * dxf);
                         }
                     }
                 }
-                // exclusive scan of item counts inside the warp + warp totals
+                unsigned hb = __ballot_sync(0xffffffffu, items != 0);
+                if (!hb) continue;
+                if (!any) {  // first segment that reaches my block: build the op's opacity calculators now
+                    if (lane == 0) {
+                        unsigned cap_for_dashes = (s.flags & OSMR_DRAW_USE_CAPS_FOR_DASHES) ? lp.cap : (unsigned)OSMR_CAP_NONE;
+                        build_calc(sm.calc[0], hw, lp.dashes, lp.n_dashes, scale, lp.has_dashes, cap_for_dashes);
+                    } else if (lane == 1 && is_non_trivial_cap(lp.cap)) {
+                        const double zero = 0.0;
+                        build_calc(sm.calc[1], hw, &zero, 1, 1.0, true, lp.cap);
+                    }
+                }
+                any = true;
+                // exclusive scan of the item counts
                 unsigned incl = items;
                 for (int o = 1; o < 32; o <<= 1) {
                     unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
                     if ((int)lane >= o) incl += v;
                 }
-                sm.item_local[threadIdx.x] = incl - items;
-                if (lane == 31) sm.warp_items[w] = incl;
-                __syncthreads();  // hits, scans and calculators visible; previous blend/clear finished
-                unsigned wbase[kRasterWarps + 1];
-                wbase[0] = 0;
-#pragma unroll
-                for (int k = 0; k < kRasterWarps; ++k) wbase[k + 1] = wbase[k] + sm.warp_items[k];
-                const unsigned total = wbase[kRasterWarps];
-                for (unsigned item = threadIdx.x; item < total; item += kRasterThreads) {
-                    // owning warp, then owning thread slot
-                    int ww = 0;
-#pragma unroll
-                    for (int k = 1; k < kRasterWarps; ++k) ww += (item >= wbase[k]) ? 1 : 0;
-                    unsigned rel = item - wbase[ww];
-                    int lo = 0, hi = 32;  // largest slot with item_local <= rel
+                const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+                __syncwarp();
+                sm.pre[lane] = incl - items;
+                if (items) sm.hits[lane] = hrec;
+                __syncwarp();
+                for (unsigned item = lane; item < total; item += 32) {
+                    int lo = 0, hi = 32;  // largest slot with pre <= item
                     while (hi - lo > 1) {
                         int mid = (lo + hi) >> 1;
-                        if (sm.item_local[ww * 32 + mid] <= rel)
+                        if (sm.pre[mid] <= item)
                             lo = mid;
                         else
                             hi = mid;
                     }
-                    const int slot = ww * 32 + lo;
-                    const SegHit h = sm.hits[slot];
-                    const unsigned local = rel - sm.item_local[slot];
-                    const long long k = (long long)h.k0 + (local >> 1);
+                    const SegHit& h = sm.hits[lo];
+                    const unsigned local = item - sm.pre[lo];
+                    const int k = h.k0 + (int)(local >> 1);
                     const int mul = (local & 1u) ? -1 : 1;
-                    const OpacityCalc& calc = sm.calc[h.is_cap ? 1 : 0];
+                    const OpacityCalc& calc = sm.calc[h.flags & 1u];
 
                     // line.rs:65-118 set-up
+                    SegConst sc;
                     const int dx = abs(wsub(h.x2, h.x1)), dy = abs(wsub(h.y2, h.y1));
-                    const bool swap = dx > dy;
-                    const int mn0 = swap ? h.y1 : h.x1, mx0 = swap ? h.x1 : h.y1;
-                    const long long mn_d = swap ? dy : dx, mx_d = swap ? dx : dy;
+                    sc.x1 = h.x1;
+                    sc.y1 = h.y1;
+                    sc.swap = dx > dy;
+                    const int mn0 = sc.swap ? h.y1 : h.x1, mx0 = sc.swap ? h.x1 : h.y1;
+                    sc.mn_d = sc.swap ? dy : dx;
+                    sc.mx_d = sc.swap ? dx : dy;
                     const int inc_x = (h.x1 <= h.x2) ? 1 : -1, inc_y = (h.y1 <= h.y2) ? 1 : -1;
-                    const int mn_inc = swap ? inc_y : inc_x, mx_inc = swap ? inc_x : inc_y;
-                    const long long numer_const = (long long)h.x2 * (long long)h.y1 - (long long)h.y2 * (long long)h.x1;
-                    const long long sdx = (long long)h.x2 - (long long)h.x1, sdy = (long long)h.y2 - (long long)h.y1;
-                    const double dxf = (double)dx, dyf = (double)dy;
-                    const double denom = sqrt(dyf * dyf + dxf * dxf);
+                    sc.mn_inc = sc.swap ? inc_y : inc_x;
+                    sc.mx_inc = sc.swap ? inc_x : inc_y;
+                    sc.numer_const = (long long)h.x2 * (long long)h.y1 - (long long)h.y2 * (long long)h.x1;
+                    sc.sdx = (long long)h.x2 - (long long)h.x1;
+                    sc.sdy = (long long)h.y2 - (long long)h.y1;
+                    sc.denom = h.denom;
+                    sc.traveled = h.traveled;
+                    const int big = 1 << 24;
+                    sc.small = h.x1 > -big && h.x1 < big && h.y1 > -big && h.y1 < big && h.x2 > -big && h.x2 < big &&
+                               h.y2 > -big && h.y2 < big;
 
-                    const long long c = ncorr(0, k, mn_d, mx_d);
-                    const long long pc = ncorr(0, c, mn_d, mx_d);
-                    const int mx = mx0 + mx_inc * (int)k;
-                    {
-                        int mn = mn0 + mn_inc * (int)c;
-                        // minor-axis cull: the walk starts at mn and never gets closer than that on this side
-                        int rlo = (swap ? ry0 : rx0) - reach, rhi = (swap ? ry0 + kRH - 1 : rx0 + kRW - 1) + reach;
-                        if (mn >= rlo && mn <= rhi)
-                            walk_perpendicular(sm, sm.plane, h, calc, swap, mn, mx, 2 * mn_d * c - 2 * mx_d * pc, mul, mn_inc,
-                                               mx_inc, mn_d, mx_d, numer_const, sdx, sdy, denom, lp.opacity, rx0, ry0);
+                    // Bresenham state at main step k (closed form; exact quotients via the per-segment magic)
+                    long long c, pc;
+                    if (h.flags & 2u) {
+                        int num = 2 * sc.mn_d * k - sc.mx_d;
+                        c = num <= 0 ? 0 : (long long)__umul64hi((unsigned long long)(unsigned)(num + 2 * sc.mx_d - 1), h.magic);
+                        int num2 = 2 * sc.mn_d * (int)c - sc.mx_d;
+                        pc = num2 <= 0 ? 0 : (long long)__umul64hi((unsigned long long)(unsigned)(num2 + 2 * sc.mx_d - 1), h.magic);
+                    } else {
+                        c = ncorr(0, k, sc.mn_d, sc.mx_d);
+                        pc = ncorr(0, c, sc.mn_d, sc.mx_d);
                     }
-                    if (k < mx_d) {  // extra perpendicular on a double correction (line.rs:150-155)
-                        const long long c2 = ncorr(0, k + 1, mn_d, mx_d);
-                        if (c2 > c) {
-                            const long long pc2 = ncorr(0, c2, mn_d, mx_d);
-                            if (pc2 > pc) {
-                                int mn = mn0 + mn_inc * (int)c2;
-                                walk_perpendicular(sm, sm.plane, h, calc, swap, mn, mx, 2 * mn_d * c2 - 2 * mx_d * pc2, mul,
-                                                   mn_inc, mx_inc, mn_d, mx_d, numer_const, sdx, sdy, denom, lp.opacity, rx0,
-                                                   ry0);
-                            }
+                    const int mx = mx0 + sc.mx_inc * k;
+                    int mn = mn0 + sc.mn_inc * (int)c;
+                    // i32 (wrapping) like the reference's `error` / `p_error`
+                    int p_error = (int)(2ll * sc.mn_d * c - 2ll * sc.mx_d * pc);
+                    const int e_main = (int)(2ll * sc.mn_d * k - 2ll * sc.mx_d * c);  // main error before step k
+                    // the walk of step k, then the extra one of a double correction (line.rs:150-155)
+                    const bool extra = k < sc.mx_d && wadd(e_main, 2 * sc.mn_d) > sc.mx_d && wadd(p_error, 2 * sc.mn_d) > sc.mx_d;
+                    const int rlo = (sc.swap ? by0 : bx0) - reach, rhi = (sc.swap ? by0 : bx0) + kSB - 1 + reach;
+                    for (int v = 0; v < (extra ? 2 : 1); ++v) {
+                        if (v == 1) {
+                            p_error = wadd(wsub(p_error, 2 * sc.mx_d), 2 * sc.mn_d);
+                            mn += sc.mn_inc;
                         }
+                        // minor-axis cull: a walk starts at mn and moves away from it
+                        if (mn >= rlo && mn <= rhi) walk_perpendicular(sm.plane, sc, calc, mn, mx, p_error, mul, lp.opacity, bx0, by0);
                     }
                 }
-                __syncthreads();  // coverage complete (and hits[] free for the next window)
             }
-            // blend own rows: pending pixel = from_color(color, alpha_max) (tile_pixels.rs:13-22), then over
-            {
+            __syncwarp();
+            if (any) {
+                // blend: pending pixel = from_color(color, alpha_max) (tile_pixels.rs:13-22), then over
                 double cn[3];
                 for (int k = 0; k < 3; ++k) cn[k] = (double)lp.rgb[k] / 255.0;
 #pragma unroll
-                for (int rr = 0; rr < kRowsPerWarp; ++rr) {
-                    int r = (int)w * kRowsPerWarp + rr;
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        int xl = (int)lane + 32 * h;
-                        unsigned long long bits = sm.plane[r][xl];
-                        if (bits) {
-                            double a = __longlong_as_double((long long)bits);
-                            double inv = 1.0 - a;
-                            sm.canvas[0][r][xl] = a * cn[0] + inv * sm.canvas[0][r][xl];
-                            sm.canvas[1][r][xl] = a * cn[1] + inv * sm.canvas[1][r][xl];
-                            sm.canvas[2][r][xl] = a * cn[2] + inv * sm.canvas[2][r][xl];
-                            sm.plane[r][xl] = 0ull;
-                        }
+                for (int j = 0; j < kSB * kSB / 32; ++j) {
+                    const int idx = j * 32 + (int)lane;
+                    unsigned long long bits = sm.plane[idx];
+                    if (bits) {
+                        double a = __longlong_as_double((long long)bits);
+                        double inv = 1.0 - a;
+                        sm.canvas[0][idx] = a * cn[0] + inv * sm.canvas[0][idx];
+                        sm.canvas[1][idx] = a * cn[1] + inv * sm.canvas[1][idx];
+                        sm.canvas[2][idx] = a * cn[2] + inv * sm.canvas[2][idx];
+                        sm.plane[idx] = 0ull;
                     }
                 }
             }
+            __syncwarp();
         }
-        __syncthreads();  // queue[] is rebuilt by the next chunk
     }
 
     // ---- export (tile_pixels.rs:164-181): alpha == 1.0, so postdivide is the identity ----
-    __syncthreads();
-    const bool rgba = (s.flags & OSMR_DRAW_OUT_RGBA) != 0;
-    if (rgba) {
+    __syncwarp();
+    auto texel = [&](int ch, int idx) -> unsigned { return f64_as_u8(255.0 * (sm.canvas[ch][idx] / 1.0)); };
+    if (s.flags & OSMR_DRAW_OUT_RGBA) {
         uchar4* out = reinterpret_cast<uchar4*>(s.out) + (size_t)tile * D * D;
-        for (int i = threadIdx.x; i < kRH * kRW; i += kRasterThreads) {
-            int r = i / kRW, x = i % kRW;
+        for (int i = (int)lane; i < kSB * kSB; i += 32) {
+            int r = i / kSB, x = i % kSB;
             uchar4 v;
-            v.x = (unsigned char)f64_as_u8(255.0 * (sm.canvas[0][r][x] / 1.0));
-            v.y = (unsigned char)f64_as_u8(255.0 * (sm.canvas[1][r][x] / 1.0));
-            v.z = (unsigned char)f64_as_u8(255.0 * (sm.canvas[2][r][x] / 1.0));
+            v.x = (unsigned char)texel(0, i);
+            v.y = (unsigned char)texel(1, i);
+            v.z = (unsigned char)texel(2, i);
             v.w = 255;
-            out[(size_t)(ry0 + r) * D + rx0 + x] = v;
+            out[(size_t)(by0 + r) * D + bx0 + x] = v;
         }
     } else {
-        // stage the 192 bytes of every region row in the (now idle) alpha plane, then store 32-bit words
-        unsigned char* stage = reinterpret_cast<unsigned char*>(&sm.plane[0][0]);
-        for (int i = threadIdx.x; i < kRH * kRW; i += kRasterThreads) {
-            int r = i / kRW, x = i % kRW;
-            unsigned char* p = stage + (r * kRW + x) * 3;
-            p[0] = (unsigned char)f64_as_u8(255.0 * (sm.canvas[0][r][x] / 1.0));
-            p[1] = (unsigned char)f64_as_u8(255.0 * (sm.canvas[1][r][x] / 1.0));
-            p[2] = (unsigned char)f64_as_u8(255.0 * (sm.canvas[2][r][x] / 1.0));
-        }
-        __syncthreads();
-        const unsigned* sw = reinterpret_cast<const unsigned*>(stage);
+        // 16 rows of 48 bytes = 12 aligned words each
         unsigned char* tile_out = s.out + (size_t)tile * D * D * 3;
-        const int words_per_row = kRW * 3 / 4;
-        for (int i = threadIdx.x; i < kRH * words_per_row; i += kRasterThreads) {
-            int r = i / words_per_row, j = i % words_per_row;
-            unsigned* dst = reinterpret_cast<unsigned*>(tile_out + ((size_t)(ry0 + r) * D + rx0) * 3);
-            dst[j] = sw[r * words_per_row + j];
+        for (int i = (int)lane; i < kSB * 12; i += 32) {
+            int r = i / 12, j = i % 12;
+            unsigned word = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                int byte = 4 * j + b;
+                word |= texel(byte % 3, r * kSB + byte / 3) << (8 * b);
+            }
+            unsigned* dst = reinterpret_cast<unsigned*>(tile_out + ((size_t)(by0 + r) * D + bx0) * 3);
+            dst[j] = word;
         }
     }
 }
