@@ -262,11 +262,18 @@ def main():
 
     from osm_renderer_b200.drawer import GpuContext
 
+    from osm_renderer_b200 import sharding
+
     w = build_workload(args.workload)
+    # weak scaling: the global request list is `world` interleaved copies of the batch; rank r renders the requests
+    # i with i % world == r, i.e. exactly one full batch per GPU over the replicated dataset
+    req = sharding.weak_scaling_request_list(len(w["tiles"]), world)
+    mine = req[sharding.shard_indices(len(req), rank, world)]
+    assert (mine == np.arange(len(w["tiles"]))).all()
     ctx = GpuContext(local_rank)
     ctx.set_geodata(w["bin"])
     ctx.set_table(w["table"])
-    n_tiles = len(w["tiles"])
+    n_tiles = len(mine)
 
     def barrier():
         torch.cuda.synchronize()
@@ -324,18 +331,18 @@ def main():
     e2e_wall = time.perf_counter() - t1
     checksum = int(np.frombuffer((C.c_uint8 * 4096).from_address(pin_out), dtype=np.uint8).sum())
 
-    # ---- max over ranks ----
-    times = torch.tensor([dev_s, wall, e2e_wall, float(np.mean(raster_ms))], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dev_s, wall, e2e_wall, raster_mean_ms = (float(v) for v in times.cpu())
+    # ---- max over ranks (time), sum over ranks (tiles): the only collectives of the whole job ----
+    job_tiles = n_tiles * args.steps
+    dev_s, total_tiles = sharding.reduce_job(dist, dev_s, job_tiles, device="cuda")
+    wall, _ = sharding.reduce_job(dist, wall, job_tiles, device="cuda")
+    e2e_wall, _ = sharding.reduce_job(dist, e2e_wall, job_tiles, device="cuda")
+    raster_mean_ms, _ = sharding.reduce_job(dist, float(np.mean(raster_ms)), job_tiles, device="cuda")
 
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
 
-    total_tiles = n_tiles * world * args.steps
     value = total_tiles / dev_s
     e2e_value = total_tiles / e2e_wall
 
