@@ -150,20 +150,23 @@ __device__ __forceinline__ long long ncorr(long long e0, long long n, long long 
 // ------------------------------------------------------------------------------------------------------
 constexpr int kMaxDashSegs = 17;  // dash lists of up to 32 numbers -> <= 17 "on" segments
 
-struct DashSeg {
+struct DashSeg {  // 64 bytes
     double start_from, start_to, end_from, end_to, opacity_mul;
     double orig_a, orig_b;  // valid when OpacityCalc::round_caps
+    double pad;
 };
 
-struct OpacityCalc {
+struct alignas(16) OpacityCalc {  // 64-byte header + 64 bytes per dash segment (same layout in HBM and smem)
     double half_line_width;
     double total_dash_len;
     // per-op constants of get_opacity_by_center_distance for cap_dist == 0 (the only case unless round_caps)
     double feather_from, feather_to, feather_dist, opacity_mul;
     int n_segs;       // 0 == "dashes: None"
     int round_caps;   // original_endpoints is Some(..)  (LineCap::Round)
+    double pad;
     DashSeg segs[kMaxDashSegs];
 };
+static_assert(sizeof(DashSeg) == 64 && sizeof(OpacityCalc) == 64 + 64 * kMaxDashSegs, "calculator wire layout");
 
 __device__ __forceinline__ bool is_non_trivial_cap(unsigned cap) { return cap == OSMR_CAP_SQUARE || cap == OSMR_CAP_ROUND; }
 
@@ -176,7 +179,7 @@ __device__ __forceinline__ void center_feather(double hw, double& from, double& 
 
 // OpacityCalculator::new + compute_segments (opacity_calculator.rs:16-30, 98-143)
 __device__ inline void build_calc(OpacityCalc& c, double hw, const double* dashes, int n, double dash_scale, bool has_dashes,
-                                  unsigned cap) {
+                                  unsigned cap, int max_segs) {
     c.half_line_width = hw;
     c.n_segs = 0;
     c.round_caps = (cap == OSMR_CAP_ROUND) ? 1 : 0;
@@ -186,7 +189,7 @@ __device__ inline void build_calc(OpacityCalc& c, double hw, const double* dashe
             int idx = (k < n) ? k : 0;
             double dash = dashes[idx] * dash_scale;  // drawer.rs:163-164 scale_dashes
             double start = len_before;
-            if (idx != 0 || c.n_segs == 0) len_before += dash;
+            if (idx != 0 || k == 0) len_before += dash;  // `segments.is_empty()` <=> first iteration
             if (idx % 2 != 0) continue;
             double end = start + dash;
             double oa = start, ob = end;
@@ -195,7 +198,7 @@ __device__ inline void build_calc(OpacityCalc& c, double hw, const double* dashe
                 end += hw;
             }
             double mid = (start + end) / 2.0;
-            if (c.n_segs < kMaxDashSegs) {
+            if (c.n_segs < max_segs) {
                 DashSeg& s = c.segs[c.n_segs++];
                 s.start_from = fmin(start - 0.5, mid - 1.0);
                 s.start_to = fmin(start + 0.5, mid);
@@ -212,6 +215,25 @@ __device__ inline void build_calc(OpacityCalc& c, double hw, const double* dashe
     center_feather(hw0, c.feather_from, c.feather_to, c.feather_dist, c.opacity_mul);
 }
 
+// f64 `%` for x >= 0, y > 0.  fmod's result x - n*y (n = floor(x/y)) is always representable, so one FMA with the
+// right integer n yields it exactly; a quotient that rounded across an integer is repaired by the sign test.
+// Much smaller than libdevice's general fmod, which matters for the instruction cache of raster_kernel.
+__device__ __noinline__ double fmod_general(double x, double y) { return fmod(x, y); }
+__device__ __forceinline__ double fmod_exact(double x, double y) {
+    double qf = x / y;
+    if (!(x >= 0.0) || !(qf < 4.0e15)) return fmod_general(x, y);
+    double q = floor(qf);
+    double r = __fma_rn(-q, y, x);
+    if (r < 0.0) {
+        q -= 1.0;
+        r = __fma_rn(-q, y, x);
+    } else if (r >= y) {
+        q += 1.0;
+        r = __fma_rn(-q, y, x);
+    }
+    return r;
+}
+
 // OpacityCalculator::calculate (opacity_calculator.rs:32-43) with traveled distance supplied per segment.
 __device__ __forceinline__ void calc_opacity(const OpacityCalc& c, double traveled, double center_distance, double start_distance,
                                              double& opacity, bool& is_in_line) {
@@ -219,7 +241,7 @@ __device__ __forceinline__ void calc_opacity(const OpacityCalc& c, double travel
     double ff = c.feather_from, ft = c.feather_to, fd = c.feather_dist, fm = c.opacity_mul;
     if (c.n_segs != 0) {
         double dist_rem = traveled + start_distance;
-        if (c.total_dash_len > 0.0) dist_rem = fmod(dist_rem, c.total_dash_len);
+        if (c.total_dash_len > 0.0) dist_rem = fmod_exact(dist_rem, c.total_dash_len);  // `%=` (opacity_calculator.rs:59)
         double acc = 0.0;
         bool has_cap = false;
         double cap = 0.0;

@@ -33,16 +33,25 @@ struct VisOp {
     unsigned geom_cnt;     // records written by build_geometry_kernel
     unsigned mask_off;     // fills: first word of its row masks
     unsigned kind;         // OP_*
-    unsigned pad[2];
+    unsigned calc_units;   // lines: 16-byte units of the main calculator block at geom_off (cap block follows, then SegRecs)
+    unsigned pad;
 };
 enum { OP_FILL_COLOR = 0, OP_FILL_IMAGE = 1, OP_LINE = 2 };
 
-struct SegRec {  // 32 bytes: one line segment (or outer cap line) that can touch the tile
+struct SegRec {  // 48 bytes: one line segment (or outer cap line) that can touch the tile
     int x1, y1, x2, y2;
-    double traveled;  // OpacityCalculator.traveled_distance when this segment is drawn (line.rs:31)
-    unsigned is_cap;  // drawn with the outer-cap calculator (line.rs:22,33-57)
+    double traveled;           // OpacityCalculator.traveled_distance when this segment is drawn (line.rs:31)
+    double denom;              // center_dist_denom (line.rs:106)
+    unsigned long long magic;  // floor(2^64 / (2*mx_d)) + 1: exact quotients for numerators < 2^32 (flags bit1)
+    unsigned flags;            // bit0: outer cap calculator (line.rs:22,33-57); bit1: 32-bit fast path valid
     unsigned pad;
 };
+constexpr unsigned kCapCalcUnits = 8;  // header + one dash segment
+
+__device__ __forceinline__ unsigned main_calc_units(bool has_dashes, int n_dashes) {
+    int n = (has_dashes && n_dashes > 0) ? min(n_dashes / 2 + 2, kMaxDashSegs) : 0;
+    return 4u + 4u * (unsigned)n;
+}
 
 enum {
     CNT_GEOM_USED = 0,   // 16-byte units
@@ -56,6 +65,7 @@ enum {
     CNT_NODE_REFS_LO = 8,
     CNT_NODE_REFS_HI = 9,
     CNT_VISIBLE = 10,
+    CNT_BIG_COORDS = 11,  // some visible segment has a coordinate >= 2^24 (raster uses exact i64 cross products)
     CNT_COUNT = 16
 };
 
@@ -295,6 +305,7 @@ __global__ void __launch_bounds__(kPlanThreads) plan_ops_kernel(Scene s) {
                 const osmr_style& st = s.styles[ar.style];
                 int x0 = info.x0, y0 = info.y0, x1 = info.x1, y1 = info.y1;
                 bool active = false;
+                op.calc_units = 0;
                 if (pass == 0) {  // drawer.rs:172-185
                     if (st.flags & OSMR_STYLE_FILL_COLOR) {
                         active = true;
@@ -322,7 +333,9 @@ __global__ void __launch_bounds__(kPlanThreads) plan_ops_kernel(Scene s) {
                         y0 = (int)max(ly0, -2147483647LL);
                         x1 = (int)min(lx1, 2147483647LL);
                         y1 = (int)min(ly1, 2147483647LL);
-                        geom_units = 2u * (info.npts + 1u);  // <= npts-1 segments + 2 caps, 32 bytes each
+                        op.calc_units = main_calc_units(lp.has_dashes, lp.n_dashes);
+                        // calculators + (<= npts-1 segments + 2 caps) of 48 bytes
+                        geom_units = op.calc_units + kCapCalcUnits + 3u * (info.npts + 1u);
                     }
                 }
                 if (active && x0 <= D - 1 && x1 >= 0 && y0 <= D - 1 && y1 >= 0) {
@@ -335,7 +348,7 @@ __global__ void __launch_bounds__(kPlanThreads) plan_ops_kernel(Scene s) {
                     op.geom_cnt = 0;
                     op.geom_off = 0;
                     op.mask_off = 0;
-                    op.pad[0] = op.pad[1] = 0;
+                    op.pad = 0;
                 }
             }
         }
@@ -456,10 +469,41 @@ __global__ void __launch_bounds__(kGeomThreads) build_geometry_kernel(Scene s) {
             int reach = line_reach(hw);
             bool caps = is_non_trivial_cap(lp.cap);
             bool dashed = lp.has_dashes && lp.n_dashes > 0;
-            SegRec* out = reinterpret_cast<SegRec*>(s.geom + op.geom_off);
+            // opacity calculators of the op (OpacityCalculator::new, line.rs:21-22), built once per (tile, op)
+            OpacityCalc* cmain = reinterpret_cast<OpacityCalc*>(s.geom + op.geom_off);
+            OpacityCalc* ccap = reinterpret_cast<OpacityCalc*>(s.geom + op.geom_off + op.calc_units);
+            if (lane == 0) {
+                unsigned cap_for_dashes = (s.flags & OSMR_DRAW_USE_CAPS_FOR_DASHES) ? lp.cap : (unsigned)OSMR_CAP_NONE;
+                build_calc(*cmain, hw, lp.dashes, lp.n_dashes, (double)s.scale, lp.has_dashes, cap_for_dashes,
+                           (int)(op.calc_units - 4u) / 4);
+            } else if (lane == 1) {
+                const double zero = 0.0;
+                build_calc(*ccap, hw, &zero, 1, 1.0, true, lp.cap, 1);
+            }
+            SegRec* out = reinterpret_cast<SegRec*>(s.geom + op.geom_off + op.calc_units + kCapCalcUnits);
             uint2 r = it.ring(0);
             double acc = 0.0;  // traveled_distance
             unsigned n_pairs = r.y ? r.y - 1 : 0;
+            auto make_rec = [&](int ax, int ay, int bx, int by, double trav, unsigned is_cap) {
+                SegRec rec;
+                rec.x1 = ax;
+                rec.y1 = ay;
+                rec.x2 = bx;
+                rec.y2 = by;
+                rec.traveled = trav;
+                int dx = abs(wsub(bx, ax)), dy = abs(wsub(by, ay));
+                int mxd = max(dx, dy);
+                const double dxf = (double)dx, dyf = (double)dy;
+                rec.denom = sqrt(dyf * dyf + dxf * dxf);
+                const int big = 1 << 24;
+                bool small = ax > -big && ax < big && ay > -big && ay < big && bx > -big && bx < big && by > -big && by < big;
+                bool fast = mxd < 32768 && mxd > 0;  // numerators 2*mn_d*n stay below 2^31
+                rec.magic = fast ? (0xffffffffffffffffull / (unsigned long long)(2 * mxd)) + 1ull : 0ull;
+                rec.flags = (is_cap ? 1u : 0u) | (fast ? 2u : 0u) | (small ? 4u : 0u);
+                rec.pad = 0;
+                if (!small) atomicOr(&s.counters[CNT_BIG_COORDS], 1u);
+                return rec;
+            };
             for (unsigned b = 0; b < n_pairs; b += 32) {
                 unsigned e = b + lane;
                 bool valid = e < n_pairs;
@@ -486,17 +530,7 @@ __global__ void __launch_bounds__(kGeomThreads) build_geometry_kernel(Scene s) {
                 };
                 bool keep = nondeg && touches(p1.x, p1.y, p2.x, p2.y);
                 unsigned bal = __ballot_sync(0xffffffffu, keep);
-                if (keep) {
-                    SegRec rec;
-                    rec.x1 = p1.x;
-                    rec.y1 = p1.y;
-                    rec.x2 = p2.x;
-                    rec.y2 = p2.y;
-                    rec.traveled = trav;
-                    rec.is_cap = 0;
-                    rec.pad = 0;
-                    out[count + __popc(bal & ((1u << lane) - 1u))] = rec;
-                }
+                if (keep) out[count + __popc(bal & ((1u << lane) - 1u))] = make_rec(p1.x, p1.y, p2.x, p2.y, trav, 0u);
                 count += __popc(bal);
                 // outer caps: only for a non-degenerate first / last pair (line.rs:33-57)
                 bool first_cap = caps && nondeg && e == 0;
@@ -513,15 +547,9 @@ __global__ void __launch_bounds__(kGeomThreads) build_geometry_kernel(Scene s) {
                 }
                 unsigned b1 = __ballot_sync(0xffffffffu, k1);
                 unsigned b2 = __ballot_sync(0xffffffffu, k2);
-                if (k1) {
-                    SegRec rec = {p1.x, p1.y, c1.x, c1.y, 0.0, 1u, 0u};
-                    out[count] = rec;
-                }
+                if (k1) out[count] = make_rec(p1.x, p1.y, c1.x, c1.y, 0.0, 1u);
                 count += b1 ? 1u : 0u;
-                if (k2) {
-                    SegRec rec = {p2.x, p2.y, c2.x, c2.y, 0.0, 1u, 0u};
-                    out[count] = rec;
-                }
+                if (k2) out[count] = make_rec(p2.x, p2.y, c2.x, c2.y, 0.0, 1u);
                 count += b2 ? 1u : 0u;
             }
         }
@@ -726,7 +754,7 @@ struct SegHit {
     int x1, y1, x2, y2;
     double traveled;
     int k0;
-    unsigned flags;            // bit0 outer cap, bit1 32-bit fast path valid
+    unsigned flags;            // SegRec.flags: bit0 outer cap, bit1 32-bit fast path valid, bit2 all coordinates < 2^24
     unsigned long long magic;  // floor(2^64 / (2*mx_d)) + 1 (exact quotients for numerators < 2^32)
     double denom;              // center_dist_denom (line.rs:106)
 };
@@ -885,7 +913,7 @@ __global__ void __launch_bounds__(kRasterThreads, 16) raster_kernel(Scene s) {
                     icon = &s.icons[st.fill_image];
                 }
                 const int col = (int)(lane & 15u);
-#pragma unroll
+#pragma unroll 1
                 for (int j = 0; j < kSB * kSB / 32; ++j) {
                     const int r = 2 * j + (int)(lane >> 4);
                     const int y = by0 + r;
@@ -921,7 +949,7 @@ __global__ void __launch_bounds__(kRasterThreads, 16) raster_kernel(Scene s) {
             line_params(s, st, (int)pass, lp);
             const double hw = lp.width / 2.0;
             const int reach = line_reach(hw);
-            const SegRec* segs = reinterpret_cast<const SegRec*>(s.geom + op.geom_off);
+            const SegRec* segs = reinterpret_cast<const SegRec*>(s.geom + op.geom_off + op.calc_units + kCapCalcUnits);
             const unsigned n_seg = op.geom_cnt;
             bool any = false;
             for (unsigned sb = 0; sb < n_seg; sb += 32) {
@@ -930,15 +958,15 @@ __global__ void __launch_bounds__(kRasterThreads, 16) raster_kernel(Scene s) {
                 unsigned items = 0;
                 SegHit hrec;
                 if (si < n_seg) {
-                    SegRec sr = segs[si];
-                    int mnx = min(sr.x1, sr.x2), mxx = max(sr.x1, sr.x2), mny = min(sr.y1, sr.y2), mxy = max(sr.y1, sr.y2);
+                    const int4 sr = *reinterpret_cast<const int4*>(&segs[si]);  // x1, y1, x2, y2
+                    int mnx = min(sr.x, sr.z), mxx = max(sr.x, sr.z), mny = min(sr.y, sr.w), mxy = max(sr.y, sr.w);
                     if ((long long)mnx - reach <= bx0 + kSB - 1 && (long long)mxx + reach >= bx0 &&
                         (long long)mny - reach <= by0 + kSB - 1 && (long long)mxy + reach >= by0) {
-                        int dx = abs(wsub(sr.x2, sr.x1)), dy = abs(wsub(sr.y2, sr.y1));
+                        int dx = abs(wsub(sr.z, sr.x)), dy = abs(wsub(sr.w, sr.y));
                         bool swap = dx > dy;
-                        int mx0 = swap ? sr.x1 : sr.y1;
+                        int mx0 = swap ? sr.x : sr.y;
                         int mxd = swap ? dx : dy;
-                        int mx_inc = swap ? (sr.x1 <= sr.x2 ? 1 : -1) : (sr.y1 <= sr.y2 ? 1 : -1);
+                        int mx_inc = swap ? (sr.x <= sr.z ? 1 : -1) : (sr.y <= sr.w ? 1 : -1);
                         // main steps whose major coordinate lies within `reach` of the block
                         long long lo = (long long)(swap ? bx0 : by0) - reach;
                         long long hi = (long long)(swap ? bx0 : by0) + kSB - 1 + reach;
@@ -954,30 +982,28 @@ __global__ void __launch_bounds__(kRasterThreads, 16) raster_kernel(Scene s) {
                         if (kb > mxd) kb = mxd;
                         if (kb >= ka) {
                             items = 2u * (unsigned)(kb - ka + 1);
-                            hrec.x1 = sr.x1;
-                            hrec.y1 = sr.y1;
-                            hrec.x2 = sr.x2;
-                            hrec.y2 = sr.y2;
-                            hrec.traveled = sr.traveled;
+                            const SegRec& full = segs[si];
+                            hrec.x1 = sr.x;
+                            hrec.y1 = sr.y;
+                            hrec.x2 = sr.z;
+                            hrec.y2 = sr.w;
+                            hrec.traveled = full.traveled;
                             hrec.k0 = (int)ka;
-                            bool fast = mxd < 32768;  // numerators 2*mn_d*n stay below 2^31
-                            hrec.flags = (sr.is_cap ? 1u : 0u) | (fast ? 2u : 0u);
-                            hrec.magic = fast ? (0xffffffffffffffffull / (unsigned long long)(2 * mxd)) + 1ull : 0ull;
-                            const double dxf = (double)dx, dyf = (double)dy;
-                            hrec.denom = sqrt(dyf * dyf + dxf * dxf);
+                            hrec.flags = full.flags;
+                            hrec.magic = full.magic;
+                            hrec.denom = full.denom;
                         }
                     }
                 }
                 unsigned hb = __ballot_sync(0xffffffffu, items != 0);
                 if (!hb) continue;
-                if (!any) {  // first segment that reaches my block: build the op's opacity calculators now
-                    if (lane == 0) {
-                        unsigned cap_for_dashes = (s.flags & OSMR_DRAW_USE_CAPS_FOR_DASHES) ? lp.cap : (unsigned)OSMR_CAP_NONE;
-                        build_calc(sm.calc[0], hw, lp.dashes, lp.n_dashes, scale, lp.has_dashes, cap_for_dashes);
-                    } else if (lane == 1 && is_non_trivial_cap(lp.cap)) {
-                        const double zero = 0.0;
-                        build_calc(sm.calc[1], hw, &zero, 1, 1.0, true, lp.cap);
-                    }
+                if (!any) {  // first segment that reaches my block: fetch the op's opacity calculators (built by
+                             // build_geometry_kernel) into shared memory, 16 bytes per lane and step
+                    const uint4* src = s.geom + op.geom_off;
+                    uint4* dst0 = reinterpret_cast<uint4*>(&sm.calc[0]);
+                    uint4* dst1 = reinterpret_cast<uint4*>(&sm.calc[1]);
+                    for (unsigned u = lane; u < op.calc_units; u += 32) dst0[u] = src[u];
+                    if (lane < kCapCalcUnits) dst1[lane] = src[op.calc_units + lane];
                 }
                 any = true;
                 // exclusive scan of the item counts
@@ -1023,9 +1049,7 @@ __global__ void __launch_bounds__(kRasterThreads, 16) raster_kernel(Scene s) {
                     sc.sdy = (long long)h.y2 - (long long)h.y1;
                     sc.denom = h.denom;
                     sc.traveled = h.traveled;
-                    const int big = 1 << 24;
-                    sc.small = h.x1 > -big && h.x1 < big && h.y1 > -big && h.y1 < big && h.x2 > -big && h.x2 < big &&
-                               h.y2 > -big && h.y2 < big;
+                    sc.small = (h.flags & 4u) != 0;
 
                     // Bresenham state at main step k (closed form; exact quotients via the per-segment magic)
                     long long c, pc;
@@ -1061,7 +1085,7 @@ __global__ void __launch_bounds__(kRasterThreads, 16) raster_kernel(Scene s) {
                 // blend: pending pixel = from_color(color, alpha_max) (tile_pixels.rs:13-22), then over
                 double cn[3];
                 for (int k = 0; k < 3; ++k) cn[k] = (double)lp.rgb[k] / 255.0;
-#pragma unroll
+#pragma unroll 2
                 for (int j = 0; j < kSB * kSB / 32; ++j) {
                     const int idx = j * 32 + (int)lane;
                     unsigned long long bits = sm.plane[idx];

@@ -32,7 +32,7 @@ hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 cols = {n: i for i, n in enumerate(rows[hi])}
 data = [r for r in rows[hi + 1 :] if len(r) > cols["Instructions Executed"]]
 base = min(int(r[0], 16) for r in data)
-by_line = defaultdict(lambda: [0, 0])
+by_line = defaultdict(lambda: [0, 0, 0.0])
 tot_s = tot_e = 0
 for r in data:
     off = int(r[0], 16) - base
@@ -41,6 +41,7 @@ for r in data:
     e_ = int(float(r[cols["Instructions Executed"]] or 0))
     by_line[key][0] += s_
     by_line[key][1] += e_
+    by_line[key][2] += float(r[cols["Predicated-On Thread Instructions Executed"]] or 0)
     tot_s += s_
     tot_e += e_
 srcs = {}
@@ -56,6 +57,6 @@ def text(key):
             if l - 1 < len(srcs[p]):
                 return srcs[p][l - 1].strip()[:100]
     return ""
-print(f"# {rep}: samples {tot_s}, warp instructions {tot_e}; share of samples / share of instructions per source line")
-for key, (s_, e_) in sorted(by_line.items(), key=lambda kv: -kv[1][0])[:topn]:
-    print(f"{100*s_/max(tot_s,1):6.2f}% {100*e_/max(tot_e,1):6.2f}%  {key[0] if key else '?'}:{key[1] if key else 0:<5d} {text(key)}")
+print(f"# {rep}: samples {tot_s}, warp instructions {tot_e}; share of samples / share of warp instructions / avg active threads per source line")
+for key, (s_, e_, t_) in sorted(by_line.items(), key=lambda kv: -kv[1][0])[:topn]:
+    print(f"{100*s_/max(tot_s,1):6.2f}% {100*e_/max(tot_e,1):6.2f}% thr {t_/max(e_,1):5.1f}  {key[0] if key else '?'}:{key[1] if key else 0:<5d} {text(key)}")
