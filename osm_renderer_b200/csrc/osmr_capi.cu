@@ -119,6 +119,14 @@ int osmr_ctx_create(int device, osmr_ctx** out_ctx) {
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device);
+    if (e == cudaSuccess) {
+        double lut[256];
+        for (int i = 0; i < 256; ++i) {
+            volatile double num = (double)i, den = 255.0;
+            lut[i] = num / den;  // IEEE division, identical to the device's `(double)c / 255.0`
+        }
+        e = cudaMemcpyToSymbol(osmr::kUnitOfU8, lut, sizeof lut);
+    }
     if (e != cudaSuccess) {
         osmr_ctx_destroy(ctx);
         return OSMR_E_CUDA;

@@ -14,6 +14,12 @@ namespace osmr {
 
 constexpr double kPi = 3.14159265358979323846264338327950288;
 
+// component_to_opacity (tile_pixels.rs:226-228): f64::from(c) / 255.0 for every u8, filled by the host with the same
+// IEEE division (osmr_ctx_create).  A table look-up instead of an inline f64 division keeps ~4 KB of code out of
+// raster_kernel.
+__constant__ double kUnitOfU8[256];
+__device__ __forceinline__ double unit_of_u8(unsigned char c) { return kUnitOfU8[c]; }
+
 // ------------------------------------------------------------------------------------------------------
 // Rust cast semantics
 // ------------------------------------------------------------------------------------------------------
@@ -27,6 +33,20 @@ __device__ __forceinline__ unsigned f64_as_u8(double v) {
     if (v >= 255.0) return 255u;
     return (unsigned)__double2int_rz(v);
 }
+// sqrt / division with the operand classes that send CUDA's inline f64 sequences to their (long, out-of-line)
+// special-case subroutines peeled off first: a zero or negative radicand, a zero dividend.  Those are everyday
+// inputs here (pixels exactly on a centre line, the first pixel of a segment, points beyond a round cap), and
+// results are identical: sqrt(+-0) = +-0, sqrt(x<0) = NaN, +-0 / positive = +-0.
+__device__ __forceinline__ double sqrt_peeled(double x) {
+    if (x == 0.0) return x;
+    if (x < 0.0) return __longlong_as_double(0x7ff8000000000000LL);
+    return sqrt(x);
+}
+__device__ __forceinline__ double div_pos_peeled(double a, double b) {  // b > 0 and finite
+    if (a == 0.0) return a;
+    return a / b;
+}
+
 __device__ __forceinline__ int wsub(int a, int b) { return (int)((unsigned)a - (unsigned)b); }
 __device__ __forceinline__ int wadd(int a, int b) { return (int)((unsigned)a + (unsigned)b); }
 
@@ -66,7 +86,7 @@ __device__ __forceinline__ int2 project_point(const double2 m, const TileXform& 
 __device__ __forceinline__ double point_dist(int ax, int ay, int bx, int by) {
     double dx = (double)wsub(ax, bx);
     double dy = (double)wsub(ay, by);
-    return sqrt(dx * dx + dy * dy);
+    return sqrt_peeled(dx * dx + dy * dy);
 }
 
 // Point::push_away_from (point.rs:27-35)
@@ -220,6 +240,7 @@ __device__ inline void build_calc(OpacityCalc& c, double hw, const double* dashe
 // Much smaller than libdevice's general fmod, which matters for the instruction cache of raster_kernel.
 __device__ __noinline__ double fmod_general(double x, double y) { return fmod(x, y); }
 __device__ __forceinline__ double fmod_exact(double x, double y) {
+    if (x >= 0.0 && x < y) return x;
     double qf = x / y;
     if (!(x >= 0.0) || !(qf < 4.0e15)) return fmod_general(x, y);
     double q = floor(qf);
@@ -250,11 +271,11 @@ __device__ __forceinline__ void calc_opacity(const OpacityCalc& c, double travel
             if (dist_rem < s.start_from || dist_rem > s.end_to) continue;  // NaN falls through to the last branch, as in the reference
             double base;
             if (dist_rem <= s.start_to)
-                base = (dist_rem - s.start_from) / (s.start_to - s.start_from);
+                base = div_pos_peeled(dist_rem - s.start_from, s.start_to - s.start_from);
             else if (dist_rem < s.end_from)
                 base = 1.0;
             else
-                base = (s.end_to - dist_rem) / (s.end_to - s.end_from);
+                base = div_pos_peeled(s.end_to - dist_rem, s.end_to - s.end_from);
             acc = fmax(acc, s.opacity_mul * base);
             if (c.round_caps) {
                 double dcap;
@@ -272,7 +293,7 @@ __device__ __forceinline__ void calc_opacity(const OpacityCalc& c, double travel
         }
         sd_opacity = acc;
         if (has_cap && cap != 0.0) {
-            double hw = sqrt(c.half_line_width * c.half_line_width - cap * cap);  // may be NaN on purpose
+            double hw = sqrt_peeled(c.half_line_width * c.half_line_width - cap * cap);  // may be NaN on purpose
             center_feather(hw, ff, ft, fd, fm);
         }
     }
@@ -280,7 +301,7 @@ __device__ __forceinline__ void calc_opacity(const OpacityCalc& c, double travel
     if (center_distance < ff)
         v = 1.0;
     else if (center_distance < ft)
-        v = (ft - center_distance) / fd;
+        v = div_pos_peeled(ft - center_distance, fd);
     else
         v = 0.0;
     double cd = fm * v;

@@ -820,12 +820,12 @@ __device__ __forceinline__ void walk_perpendicular(unsigned long long* plane, co
             in_line = false;  // cd = mul * 0.0
             opacity = 0.0;
         } else {
-            double center_dist = araw / sc.denom;
+            double center_dist = div_pos_peeled(araw, sc.denom);
             double short_start = 0.0;
             if (dashed) {
                 int px = sc.swap ? p_mn : p_mx, py = sc.swap ? p_mx : p_mn;
                 double long_start = point_dist(px, py, sc.x1, sc.y1);
-                short_start = sqrt(fmax(long_start * long_start - center_dist * center_dist, 0.0));
+                short_start = sqrt_peeled(fmax(long_start * long_start - center_dist * center_dist, 0.0));
             }
             calc_opacity(calc, sc.traveled, center_dist, short_start, opacity, in_line);
         }
@@ -872,7 +872,7 @@ __global__ void __launch_bounds__(kRasterThreads, 16) raster_kernel(Scene s) {
     {
         double c[3] = {0.0, 0.0, 0.0};
         if (s.flags & OSMR_DRAW_HAS_CANVAS_COLOR)
-            for (int k = 0; k < 3; ++k) c[k] = 1.0 * ((double)s.canvas[k] / 255.0);
+            for (int k = 0; k < 3; ++k) c[k] = 1.0 * unit_of_u8(s.canvas[k]);
         for (int i = (int)lane; i < kSB * kSB; i += 32) {
             sm.canvas[0][i] = c[0];
             sm.canvas[1][i] = c[1];
@@ -907,7 +907,7 @@ __global__ void __launch_bounds__(kRasterThreads, 16) raster_kernel(Scene s) {
                 const DevIcon* icon = nullptr;
                 if (op.kind == OP_FILL_COLOR) {
                     double opacity = (st.flags & OSMR_STYLE_FILL_OPACITY) ? st.fill_opacity : 1.0;
-                    for (int k = 0; k < 3; ++k) src[k] = opacity * ((double)st.fill_color[k] / 255.0);
+                    for (int k = 0; k < 3; ++k) src[k] = opacity * unit_of_u8(st.fill_color[k]);
                     src[3] = opacity;
                 } else {
                     icon = &s.icons[st.fill_image];
@@ -1084,7 +1084,7 @@ __global__ void __launch_bounds__(kRasterThreads, 16) raster_kernel(Scene s) {
             if (any) {
                 // blend: pending pixel = from_color(color, alpha_max) (tile_pixels.rs:13-22), then over
                 double cn[3];
-                for (int k = 0; k < 3; ++k) cn[k] = (double)lp.rgb[k] / 255.0;
+                for (int k = 0; k < 3; ++k) cn[k] = unit_of_u8(lp.rgb[k]);
 #pragma unroll 2
                 for (int j = 0; j < kSB * kSB / 32; ++j) {
                     const int idx = j * 32 + (int)lane;
