@@ -44,6 +44,8 @@ struct DevBuf {
 struct osmr_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t chunk_done[2] = {nullptr, nullptr};
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::string err;
     int num_sms = 0;
@@ -68,6 +70,7 @@ struct osmr_ctx {
     DevBuf<osmr_tile> tiles;
     DevBuf<unsigned> area_begin;
     DevBuf<osmr_styled_area> areas;
+    std::vector<uint32_t> h_area_begin;
     // scratch
     DevBuf<AreaInfo> area_info;
     DevBuf<VisOp> vis;
@@ -117,6 +120,8 @@ int osmr_ctx_create(int device, osmr_ctx** out_ctx) {
     ctx->device = device;
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->chunk_done[i], cudaEventDisableTiming);
     for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) {
@@ -163,6 +168,9 @@ void osmr_ctx_destroy(osmr_ctx* ctx) {
     ctx->out.release();
     for (auto& e : ctx->ev)
         if (e) cudaEventDestroy(e);
+    for (auto& e : ctx->chunk_done)
+        if (e) cudaEventDestroy(e);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -350,6 +358,7 @@ int osmr_batch_upload(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, c
     ctx->n_tiles = n_tiles;
     ctx->n_areas = n_areas;
     ctx->scale = (int)tiles[0].scale;
+    ctx->h_area_begin.assign(area_begin, area_begin + n_tiles + 1);
     // scratch that scales with the batch
     CK(ctx->area_info.reserve(n_areas + 1));
     CK(ctx->vis.reserve(3ull * n_areas + 1));
@@ -364,8 +373,12 @@ int osmr_batch_upload(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, c
     return OSMR_OK;
 }
 
-static int run_pipeline(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t flags, unsigned char* dev_out) {
+// Draws tiles [tb, tb+tc) of the uploaded batch into dev_out (which points at tile tb's image).  Synchronises the
+// compute stream (the scratch-overflow check needs the counters) and adds to ctx->stats.
+static int run_pipeline(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t flags, unsigned char* dev_out, unsigned tb, unsigned tc) {
     const int D = 256 * ctx->scale;
+    const unsigned area_base = ctx->h_area_begin[tb];
+    const unsigned n_areas = ctx->h_area_begin[tb + tc] - area_base;
     for (int attempt = 0; attempt < 6; ++attempt) {
         if (ctx->geom_cap_units == 0) {
             size_t units = (size_t)ctx->n_areas * 8 + (1u << 20);  // first guess; grown on overflow
@@ -395,11 +408,12 @@ static int run_pipeline(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t fla
         s.icons = ctx->icons.p;
         s.icon_px = ctx->icon_px.p;
         s.n_icons = ctx->n_icons;
-        s.tiles = ctx->tiles.p;
-        s.area_begin = ctx->area_begin.p;
+        s.tiles = ctx->tiles.p + tb;
+        s.area_begin = ctx->area_begin.p + tb;
         s.areas = ctx->areas.p;
-        s.n_tiles = ctx->n_tiles;
-        s.n_areas = ctx->n_areas;
+        s.n_tiles = tc;
+        s.n_areas = n_areas;
+        s.area_base = area_base;
         s.D = D;
         s.scale = ctx->scale;
         s.flags = flags;
@@ -422,17 +436,17 @@ static int run_pipeline(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t fla
         CK(cudaEventRecord(ctx->ev[0], st));
         CK(cudaMemsetAsync(ctx->counters.p, 0, CNT_COUNT * sizeof(unsigned), st));
         unsigned launches = 0;
-        if (ctx->n_areas) {
-            area_bbox_kernel<<<(ctx->n_areas + 255) / 256, 256, 0, st>>>(s);
+        if (n_areas) {
+            area_bbox_kernel<<<(n_areas + 255) / 256, 256, 0, st>>>(s);
             ++launches;
         }
-        plan_ops_kernel<<<ctx->n_tiles, kPlanThreads, 0, st>>>(s);
+        plan_ops_kernel<<<tc, kPlanThreads, 0, st>>>(s);
         build_geometry_kernel<<<ctx->num_sms * 8, kGeomThreads, 0, st>>>(s);
-        fill_rows_kernel<<<ctx->num_sms * 4, kFillThreads, 0, st>>>(s);
+        fill_rows_kernel<<<ctx->num_sms * 16, kFillThreads, 0, st>>>(s);
         launches += 3;
         CK(cudaEventRecord(ctx->ev[1], st));
         const unsigned blocks = (unsigned)((D / kSB) * (D / kSB));
-        raster_kernel<<<ctx->n_tiles * blocks, kRasterThreads, 0, st>>>(s);
+        raster_kernel<<<tc * blocks, kRasterThreads, 0, st>>>(s);
         ++launches;
         CK(cudaGetLastError());
         CK(cudaEventRecord(ctx->ev[2], st));
@@ -460,16 +474,16 @@ static int run_pipeline(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t fla
         float ms_plan = 0, ms_raster = 0;
         cudaEventElapsedTime(&ms_plan, ctx->ev[0], ctx->ev[1]);
         cudaEventElapsedTime(&ms_raster, ctx->ev[1], ctx->ev[2]);
-        ctx->stats.n_tiles = ctx->n_tiles;
-        ctx->stats.n_areas = ctx->n_areas;
-        ctx->stats.n_visible_ops = h_cnt[CNT_VISIBLE];
-        ctx->stats.n_node_refs = ((uint64_t)h_cnt[CNT_NODE_REFS_HI] << 32) | h_cnt[CNT_NODE_REFS_LO];
-        ctx->stats.kernel_launches = launches;
-        ctx->stats.geom_bytes = (uint64_t)h_cnt[CNT_GEOM_USED] * 16ull;
-        ctx->stats.mask_bytes = (uint64_t)h_cnt[CNT_MASK_USED] * 4ull;
-        ctx->stats.ms_plan = ms_plan;
-        ctx->stats.ms_raster = ms_raster;
-        ctx->stats.ms_total = ms_plan + ms_raster;
+        ctx->stats.n_tiles += tc;
+        ctx->stats.n_areas += n_areas;
+        ctx->stats.n_visible_ops += h_cnt[CNT_VISIBLE];
+        ctx->stats.n_node_refs += ((uint64_t)h_cnt[CNT_NODE_REFS_HI] << 32) | h_cnt[CNT_NODE_REFS_LO];
+        ctx->stats.kernel_launches += launches;
+        ctx->stats.geom_bytes += (uint64_t)h_cnt[CNT_GEOM_USED] * 16ull;
+        ctx->stats.mask_bytes += (uint64_t)h_cnt[CNT_MASK_USED] * 4ull;
+        ctx->stats.ms_plan += ms_plan;
+        ctx->stats.ms_raster += ms_raster;
+        ctx->stats.ms_total += ms_plan + ms_raster;
         return OSMR_OK;
     }
     return ctx->fail(OSMR_E_NOMEM, "scratch kept overflowing");
@@ -490,13 +504,25 @@ int osmr_batch_draw(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t flags, 
         dev_out = ctx->out.p;
     }
     ctx->out_bytes = bytes;
-    CK(cudaEventRecord(ctx->ev[3], ctx->stream));
-    int rc = run_pipeline(ctx, canvas_rgb, flags, dev_out);
-    if (rc) return rc;
-    if (out && !(flags & OSMR_DRAW_OUT_DEVICE)) {
-        CK(cudaMemcpyAsync(out, dev_out, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+    ctx->stats = osmr_stats{};
+    const size_t tile_bytes = D * D * ((flags & OSMR_DRAW_OUT_RGBA) ? 4 : 3);
+    const bool to_host = out && !(flags & OSMR_DRAW_OUT_DEVICE);
+    // Host output: draw in chunks and copy chunk i back on a second stream while chunk i+1 is being drawn
+    // (the copy really overlaps only when `out` is page-locked, e.g. from osmr_alloc_pinned).
+    const unsigned chunk = (to_host && ctx->n_tiles >= 128) ? std::max(64u, (ctx->n_tiles + 3) / 4) : ctx->n_tiles;
+    unsigned k = 0;
+    for (unsigned tb = 0; tb < ctx->n_tiles; tb += chunk, ++k) {
+        const unsigned tc = std::min(chunk, ctx->n_tiles - tb);
+        int rc = run_pipeline(ctx, canvas_rgb, flags, dev_out + (size_t)tb * tile_bytes, tb, tc);
+        if (rc) {
+            cudaStreamSynchronize(ctx->copy_stream);
+            return rc;
+        }
+        if (to_host)  // the compute stream is idle here (run_pipeline synchronised it), so the slice is complete
+            CK(cudaMemcpyAsync(out + (size_t)tb * tile_bytes, dev_out + (size_t)tb * tile_bytes, (size_t)tc * tile_bytes,
+                               cudaMemcpyDeviceToHost, ctx->copy_stream));
     }
+    if (to_host) CK(cudaStreamSynchronize(ctx->copy_stream));
     if (gpu_ms) *gpu_ms = ctx->stats.ms_total;
     return OSMR_OK;
 }

@@ -88,7 +88,8 @@ struct Scene {
     const osmr_tile* tiles;
     const unsigned* area_begin;
     const osmr_styled_area* areas;
-    unsigned n_tiles, n_areas;
+    unsigned n_tiles, n_areas;  // of the tile range being drawn (tiles/area_begin point at its first tile)
+    unsigned area_base;         // absolute index of the range's first styled area (area_begin values are absolute)
     int D;      // 256 * scale
     int scale;
     unsigned flags;
@@ -185,9 +186,10 @@ __device__ __forceinline__ bool entity_valid(const Scene& s, unsigned entity) {
 // area_bbox_kernel: one thread per (tile, styled area)
 // ------------------------------------------------------------------------------------------------------
 __global__ void area_bbox_kernel(Scene s) {
-    unsigned a = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned rel = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned a = s.area_base + rel;
     unsigned long long refs = 0;
-    if (a < s.n_areas) {
+    if (rel < s.n_areas) {
         AreaInfo info;
         info.x0 = info.y0 = 0x7fffffff;
         info.x1 = info.y1 = (int)0x80000000;
@@ -567,7 +569,7 @@ __global__ void __launch_bounds__(kGeomThreads) build_geometry_kernel(Scene s) {
 //   covered(x) = [c(x) odd and c(x) < m]  or  [x in span(e) for some e of odd rank]
 // with c(x) = #{spans with x_min <= x}, rank(e) = #{e' : (x_min', idx') < (x_min, idx)}.
 // ------------------------------------------------------------------------------------------------------
-constexpr int kFillThreads = 256;
+constexpr int kFillThreads = 128;
 constexpr int kFillWarps = kFillThreads / 32;
 constexpr int kMaxD = 2048;  // scale <= 8
 
@@ -584,23 +586,22 @@ __global__ void __launch_bounds__(kFillThreads) fill_rows_kernel(Scene s) {
     __shared__ int2 act[kFillWarps][kFillCap];
     __shared__ int2 sorted[kFillWarps][kFillCap];
     __shared__ unsigned hist[kFillWarps][kMaxD / 8 + 1];  // slow path: x_min histogram in 8 passes of D/8 columns
-    __shared__ unsigned cur_work;
     const unsigned lane = lane_id();
     const unsigned w = threadIdx.x >> 5;
     const int D = s.D;
     const int wpr = D / 32;
     const int cap = s.fill_cap;
+    // every warp is an independent worker: fetch one fill op, produce all its rows, repeat (no CTA barrier)
     for (;;) {
-        __syncthreads();
-        if (threadIdx.x == 0) cur_work = atomicAdd(&s.counters[CNT_FILL_CURSOR], 1u);
-        __syncthreads();
-        unsigned wi = cur_work;
+        unsigned wi = 0;
+        if (lane == 0) wi = atomicAdd(&s.counters[CNT_FILL_CURSOR], 1u);
+        wi = __shfl_sync(0xffffffffu, wi, 0);
         if (wi >= s.counters[CNT_N_FILL_WORK]) break;
         const VisOp op = s.vis[s.fill_work[wi]];
         const int4* edges = reinterpret_cast<const int4*>(s.geom + op.geom_off);
         const int ne = (int)op.geom_cnt;
         const int ya = max((int)op.y0, 0), yb = min((int)op.y1, D - 1);
-        for (int y = ya + (int)w; y <= yb; y += kFillWarps) {
+        for (int y = ya; y <= yb; ++y) {
             unsigned* mrow = s.mask + op.mask_off + (size_t)(y - ya) * wpr;
             // ---- gather the non-poisoned spans of this row, in edge order ----
             int m = 0;
