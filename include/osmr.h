@@ -168,7 +168,8 @@ void* osmr_alloc_pinned(size_t bytes);
 void osmr_free_pinned(void* p);
 
 /* Test hook: "fill_cap" (0..128) lowers the number of row spans ranked in shared memory so that the
- * order-free streaming form of the even-odd rule is exercised on ordinary data. */
+ * order-free streaming form of the even-odd rule is exercised on ordinary data; "scratch_units" restarts the
+ * bump-allocated geometry / mask scratch at that many units so the grow-and-redo path runs. */
 int osmr_debug_set(osmr_ctx* ctx, const char* key, int value);
 
 uint32_t osmr_abi_version(void);

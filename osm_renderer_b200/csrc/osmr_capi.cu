@@ -184,6 +184,17 @@ int osmr_debug_set(osmr_ctx* ctx, const char* key, int value) {
         ctx->fill_cap = value;
         return OSMR_OK;
     }
+    if (strcmp(key, "scratch_units") == 0) {  // (re)start with a tiny geometry / mask scratch to exercise the grow-and-redo path
+        if (value < 1) return ctx->fail(OSMR_E_INVALID, "scratch_units must be positive");
+        ctx->geom.release();
+        ctx->mask.release();
+        cudaError_t e1 = ctx->geom.reserve((size_t)value);
+        cudaError_t e2 = ctx->mask.reserve((size_t)value);
+        if (e1 != cudaSuccess || e2 != cudaSuccess) return ctx->fail(OSMR_E_CUDA, "scratch_units", e1 != cudaSuccess ? e1 : e2);
+        ctx->geom_cap_units = (size_t)value;
+        ctx->mask_cap_words = (size_t)value;
+        return OSMR_OK;
+    }
     return ctx->fail(OSMR_E_INVALID, "unknown debug key");
 }
 

@@ -235,7 +235,9 @@ def make_metro(seed: int = SEED, zoom: int = 14, x0: int = 9888, y0: int = 5104,
     return _serialise(b)
 
 
-def _serialise(b: _Builder) -> bytes:
+def _serialise(b: _Builder, with_index: bool = True) -> bytes:
+    """with_index=False leaves the z18 tile index empty (the draw path never reads it; tests with planet-sized
+    ways would otherwise enumerate billions of index cells)."""
     px = np.concatenate(b.px)
     py = np.concatenate(b.py)
     lat, lon = _px18_to_latlon(px, py)
@@ -304,12 +306,16 @@ def _serialise(b: _Builder) -> bytes:
 
     # ---- z18 tile index (saver.rs:167-226) ----
     tx, ty = _latlon_to_tile18(lat, lon)
-    ent_x, ent_y, ent_id, ent_kind = [tx], [ty], [np.arange(n_nodes, dtype=np.int64)], [np.zeros(n_nodes, dtype=np.int8)]
+    if not with_index:
+        tx, ty = tx[:0], ty[:0]
+    ent_x, ent_y, ent_id, ent_kind = [tx], [ty], [np.arange(len(tx), dtype=np.int64)], [np.zeros(len(tx), dtype=np.int8)]
 
     def add_bbox_entries(x0, x1, y0, y1, ids, kind):
         wx = (x1 - x0 + 1).astype(np.int64)
         wy = (y1 - y0 + 1).astype(np.int64)
         cnt = wx * wy
+        if int(cnt.sum()) > 200_000_000:
+            raise MemoryError("tile index would need %d cells; build this image with with_index=False" % int(cnt.sum()))
         rep = np.repeat(np.arange(len(ids)), cnt)
         start = np.concatenate([[0], np.cumsum(cnt)[:-1]])
         local = np.arange(cnt.sum()) - start[rep]
@@ -318,7 +324,7 @@ def _serialise(b: _Builder) -> bytes:
         ent_id.append(ids[rep])
         ent_kind.append(np.full(len(rep), kind, dtype=np.int8))
 
-    if n_ways:
+    if n_ways and with_index:
         seg = np.repeat(np.arange(n_ways), way_len)
         wx0 = np.full(n_ways, 2**32 - 1, dtype=np.int64)
         wx1 = np.zeros(n_ways, dtype=np.int64)
@@ -331,7 +337,7 @@ def _serialise(b: _Builder) -> bytes:
         np.minimum.at(wy0, seg, ny_)
         np.maximum.at(wy1, seg, ny_)
         add_bbox_entries(wx0, wx1, wy0, wy1, np.arange(n_ways, dtype=np.int64), 1)
-    for i, (pids, _) in enumerate(b.mps):
+    for i, (pids, _) in enumerate(b.mps if with_index else []):
         nn = np.concatenate([b.polys[p] for p in pids])
         add_bbox_entries(
             np.array([tx[nn].min()], dtype=np.int64), np.array([tx[nn].max()], dtype=np.int64),
@@ -345,9 +351,9 @@ def _serialise(b: _Builder) -> bytes:
     order = np.lexsort((eid, ek, ey, ex))
     ex, ey, eid, ek = ex[order], ey[order], eid[order], ek[order]
     key = (ex << 32) | ey
-    tile_start = np.concatenate([[0], np.nonzero(np.diff(key))[0] + 1])
+    tile_start = np.concatenate([[0], np.nonzero(np.diff(key))[0] + 1]) if len(key) else np.zeros(0, dtype=np.int64)
     n_tiles = len(tile_start)
-    tile_end = np.concatenate([tile_start[1:], [len(key)]])
+    tile_end = np.concatenate([tile_start[1:], [len(key)]]).astype(np.int64) if n_tiles else tile_start
     idx_off = n_ints
     push(eid)
     tiles = np.zeros(n_tiles, dtype=[("x", "<u4"), ("y", "<u4"), ("no", "<u4"), ("nl", "<u4"), ("wo", "<u4"), ("wl", "<u4"), ("mo", "<u4"), ("ml", "<u4")])

@@ -1,0 +1,110 @@
+"""-m gpu: edge cases of the C-ABI path (empty tiles, scratch overflow + redo, huge coordinates, resident batch API,
+argument validation)."""
+import numpy as np
+import pytest
+
+import oracle
+from osm_renderer_b200.wire import AREA_DTYPE, OSMR_STYLE_COLOR, OSMR_STYLE_DASHES, OSMR_STYLE_WIDTH, STYLE_DTYPE, TILE_DTYPE, StyleTable
+
+pytestmark = pytest.mark.gpu
+
+
+def test_tiles_without_areas_are_canvas_colour(fx, gpu_ctx):
+    tiles, begins, areas = fx.batches["16"]
+    # tile 0 keeps its areas, tiles 1 and 2 get none
+    b = np.array([0, begins[1], begins[1], begins[1]], dtype=np.uint32)
+    got = gpu_ctx.draw_tiles(tiles[:3], b, areas[: begins[1]], fx.canvas_rgb, True)
+    want = oracle.draw_tiles(fx.bin, fx.table, tiles[:3], b, areas[: begins[1]], fx.canvas_rgb, True)
+    assert (got == np.stack(want)).all()
+    assert (got[1] == np.array(fx.canvas_rgb, dtype=np.uint8)).all() and (got[2] == got[1]).all()
+
+
+def test_scratch_overflow_grows_and_redoes_the_batch(fx):
+    from osm_renderer_b200.drawer import GpuContext
+
+    tiles, begins, areas = fx.batches["17"]
+    want = np.stack(oracle.draw_tiles(fx.bin, fx.table, tiles, begins, areas, fx.canvas_rgb, True, n_threads=8))
+    ctx = GpuContext(0)
+    try:
+        ctx.set_geodata(fx.bin)
+        ctx.set_table(fx.table)
+        ctx.debug_set("scratch_units", 64)  # far too small: both allocators overflow, the library must grow and redo
+        got = ctx.draw_tiles(tiles, begins, areas, fx.canvas_rgb, True)
+    finally:
+        ctx.close()
+    assert (got == want).all()
+
+
+def test_resident_batch_api_equals_one_shot(fx, gpu_ctx):
+    tiles, begins, areas = fx.batches["16"]
+    one = gpu_ctx.draw_tiles(tiles, begins, areas, fx.canvas_rgb, True)
+    gpu_ctx.batch_upload(tiles, begins, areas)
+    out = np.empty_like(one)
+    ms1 = gpu_ctx.batch_draw(fx.canvas_rgb, True, out=out)
+    ms2 = gpu_ctx.batch_draw(fx.canvas_rgb, True)  # output stays in HBM
+    assert (out == one).all() and ms1 > 0 and ms2 > 0
+    st = gpu_ctx.stats()
+    assert st["n_tiles"] == len(tiles) and st["n_areas"] == len(areas) and st["kernel_launches"] == 5
+
+
+def test_huge_coordinates_take_the_exact_i64_path():
+    """A way whose far end lies a quarter of the planet away: tile-relative coordinates beyond 2^24 at z18 @2x."""
+    from osm_renderer_b200.drawer import GpuContext
+    from osm_renderer_b200.upstream import synth
+    from synthgeom import TX, TY
+
+    b = synth._Builder()
+    ts = b.tagset({"k": "v"})
+    ox, oy = TX * 256, TY * 256
+    for (x0, y0, x1, y1) in [(100, 40, 100 + 17_000_000, 40 + 6_000_000), (10, 200, 10 - 17_500_000, 200 - 9_000_000), (5, 5, 250, 240)]:
+        ids = b.add_nodes([x0 + ox, x1 + ox], [y0 + oy, y1 + oy])
+        b.way_nodes.append(ids)
+        b.way_tags.append(ts)
+    image = synth._serialise(b, with_index=False)  # a planet-sized bbox must not be enumerated into a tile index
+    table = StyleTable(None)
+    rows = np.zeros(2, dtype=STYLE_DTYPE)
+    rows[0]["flags"] = OSMR_STYLE_COLOR | OSMR_STYLE_WIDTH
+    rows[0]["color"] = (200, 30, 30)
+    rows[0]["width"] = 5.0
+    rows[0]["line_cap"] = 2
+    rows[1]["flags"] = OSMR_STYLE_COLOR | OSMR_STYLE_WIDTH | OSMR_STYLE_DASHES
+    rows[1]["color"] = (20, 60, 220)
+    rows[1]["width"] = 2.0
+    rows[1]["dashes_off"], rows[1]["dashes_len"] = 0, 2
+    rows[1]["line_cap"] = 3
+    table.rows = list(rows)
+    table.dashes = [6.0, 3.0]
+    areas = np.array([(0, 0), (1, 1), (2, 0), (0, 1)], dtype=AREA_DTYPE)
+    for scale in (1, 2):
+        tiles = np.array([(18, TX, TY, scale)], dtype=TILE_DTYPE)
+        begins = np.array([0, len(areas)], dtype=np.uint32)
+        ctx = GpuContext(0)
+        try:
+            ctx.set_geodata(image)
+            ctx.set_table(table)
+            got = ctx.draw_tiles(tiles, begins, areas, (255, 255, 255), True)
+        finally:
+            ctx.close()
+        want = np.stack(oracle.draw_tiles(image, table, tiles, begins, areas, (255, 255, 255), True))
+        assert (got == want).all(), scale
+        assert (want != 255).any()
+
+
+def test_argument_validation(fx, gpu_ctx):
+    from osm_renderer_b200._lib import OsmrError
+
+    tiles, begins, areas = fx.batches["14"]
+    bad = tiles.copy()
+    bad["scale"][1] = 2
+    with pytest.raises(OsmrError):
+        gpu_ctx.draw_tiles(bad, begins, areas, fx.canvas_rgb, True)
+    bad = tiles.copy()
+    bad["zoom"][0] = 40
+    with pytest.raises(OsmrError):
+        gpu_ctx.draw_tiles(bad, begins, areas, fx.canvas_rgb, True)
+    badb = begins.copy()
+    badb[2] = 1
+    with pytest.raises(OsmrError):
+        gpu_ctx.draw_tiles(tiles, badb, areas, fx.canvas_rgb, True)
+    with pytest.raises(OsmrError):
+        gpu_ctx.debug_set("fill_cap", 9999)
