@@ -57,6 +57,8 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
         "-o",
         LIB_PATH,
     ] + SOURCES
+    extra = os.environ.get("OSMR_EXTRA_NVCC_FLAGS", "").split()  # experiments only, e.g. -DOSMR_BW=32
+    cmd[1:1] = extra
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

@@ -456,7 +456,7 @@ static int run_pipeline(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t fla
         fill_rows_kernel<<<ctx->num_sms * 16, kFillThreads, 0, st>>>(s);
         launches += 3;
         CK(cudaEventRecord(ctx->ev[1], st));
-        const unsigned blocks = (unsigned)((D / kSB) * (D / kSB));
+        const unsigned blocks = (unsigned)((D / kBW) * (D / kBH));
         raster_kernel<<<tc * blocks, kRasterThreads, 0, st>>>(s);
         ++launches;
         CK(cudaGetLastError());

@@ -271,7 +271,9 @@ __device__ __forceinline__ bool line_params(const Scene& s, const osmr_style& st
 __device__ __forceinline__ int line_reach(double half_width) {
     double hw = (half_width > 0.0) ? half_width : 0.0;  // NaN -> 0
     if (hw > 1.0e6) hw = 1.0e6;
-    return (int)ceil(hw) + 4;
+    // proven bound: a drawn pixel is < hw + 1.21 minor steps and <= that + 1 major corrections away from its main
+    // pixel, an extra perpendicular starts one pixel off: ceil(hw) + 2 (tests/test_closed_forms.py); + 1 spare
+    return (int)ceil(hw) + 3;
 }
 
 __device__ __forceinline__ short clamp_s(int v, int lo, int hi) { return (short)(v < lo ? lo : (v > hi ? hi : v)); }
@@ -748,7 +750,16 @@ __global__ void __launch_bounds__(kFillThreads) fill_rows_kernel(Scene s) {
 // per-chunk barrier and lost to load imbalance: profiles/r01_raster_v{1,2}_ncu_summary.txt); the hardware block
 // scheduler balances the 16x16 blocks.
 // ------------------------------------------------------------------------------------------------------
-constexpr int kSB = 16;  // block edge owned by one warp
+#ifndef OSMR_BW
+#define OSMR_BW 16
+#endif
+#ifndef OSMR_BH
+#define OSMR_BH 16
+#endif
+constexpr int kBW = OSMR_BW;  // block owned by one warp: kBW x kBH pixels (kBW 16 or 32)
+constexpr int kBH = OSMR_BH;
+constexpr int kBP = kBW * kBH;
+static_assert((kBW == 16 || kBW == 32) && kBP % 32 == 0 && 256 % kBW == 0 && 256 % kBH == 0, "block shape");
 constexpr int kRasterThreads = 32;
 
 struct SegHit {
@@ -761,8 +772,8 @@ struct SegHit {
 };
 
 struct RasterSmem {
-    double canvas[3][kSB * kSB];
-    unsigned long long plane[kSB * kSB];
+    double canvas[3][kBP];
+    unsigned long long plane[kBP];
     OpacityCalc calc[2];  // [0] dashes of the op, [1] outer caps
     SegHit hits[32];
     unsigned pre[32];
@@ -790,7 +801,7 @@ __device__ __forceinline__ void walk_perpendicular(unsigned long long* plane, co
     const int step = mul * sc.mn_inc;
     const int corr = -mul * sc.mx_inc;
     const int lo = sc.swap ? by0 : bx0;
-    const int hi = lo + kSB - 1;
+    const int hi = lo + (sc.swap ? kBH : kBW) - 1;
     // raw = numer_const + sdy*px - sdx*py (i64, line.rs:102-103); its per-step increments are integers
     const long long d_step = sc.swap ? -sc.sdx * step : sc.sdy * step;
     const long long d_corr = sc.swap ? sc.sdy * corr : -sc.sdx * corr;
@@ -832,10 +843,10 @@ __device__ __forceinline__ void walk_perpendicular(unsigned long long* plane, co
         }
         if (!in_line) break;
         const int lx = (sc.swap ? p_mn : p_mx) - bx0, ly = (sc.swap ? p_mx : p_mn) - by0;
-        if ((unsigned)lx < (unsigned)kSB && (unsigned)ly < (unsigned)kSB) {
+        if ((unsigned)lx < (unsigned)kBW && (unsigned)ly < (unsigned)kBH) {
             double a = opacity0 * opacity;  // RgbaColor::from_color(color, initial_opacity * opacity).a
             unsigned long long bits = (unsigned long long)__double_as_longlong(a);
-            unsigned long long* cell = &plane[ly * kSB + lx];
+            unsigned long long* cell = &plane[ly * kBW + lx];
             if (a > 0.0 && bits > *cell) atomicMax(cell, bits);
         }
         // update_error (line.rs:82-91), wrapping i32 arithmetic
@@ -853,14 +864,14 @@ __device__ __forceinline__ void walk_perpendicular(unsigned long long* plane, co
 __global__ void __launch_bounds__(kRasterThreads, 16) raster_kernel(Scene s) {
     __shared__ RasterSmem sm;
     const int D = s.D;
-    const int bpr = D / kSB;  // blocks per tile row
-    const unsigned tile = blockIdx.x / (unsigned)(bpr * bpr);
-    const unsigned blk = blockIdx.x % (unsigned)(bpr * bpr);
-    // consecutive CTAs tile a 64x32 area (4x2 blocks) before moving on, so neighbours share op lists in L1/L2
-    const unsigned grp = blk / 8u, in_grp = blk % 8u;
-    const unsigned grp_per_row = (unsigned)bpr / 4u;
-    const int bx0 = (int)((grp % grp_per_row) * 4u + (in_grp % 4u)) * kSB;
-    const int by0 = (int)((grp / grp_per_row) * 2u + (in_grp / 4u)) * kSB;
+    const int bpr = D / kBW, bpc = D / kBH;  // blocks per tile row / column
+    const unsigned tile = blockIdx.x / (unsigned)(bpr * bpc);
+    const unsigned blk = blockIdx.x % (unsigned)(bpr * bpc);
+    // consecutive CTAs cover a 2x2 group of blocks before moving on, so neighbours share op lists in L1/L2
+    const unsigned grp = blk / 4u, in_grp = blk % 4u;
+    const unsigned grp_per_row = (unsigned)bpr / 2u;
+    const int bx0 = (int)((grp % grp_per_row) * 2u + (in_grp % 2u)) * kBW;
+    const int by0 = (int)((grp / grp_per_row) * 2u + (in_grp / 2u)) * kBH;
     const unsigned lane = threadIdx.x;
     const unsigned base = s.area_begin[tile];
     const unsigned n_areas = s.area_begin[tile + 1] - base;
@@ -874,7 +885,7 @@ __global__ void __launch_bounds__(kRasterThreads, 16) raster_kernel(Scene s) {
         double c[3] = {0.0, 0.0, 0.0};
         if (s.flags & OSMR_DRAW_HAS_CANVAS_COLOR)
             for (int k = 0; k < 3; ++k) c[k] = 1.0 * unit_of_u8(s.canvas[k]);
-        for (int i = (int)lane; i < kSB * kSB; i += 32) {
+        for (int i = (int)lane; i < kBP; i += 32) {
             sm.canvas[0][i] = c[0];
             sm.canvas[1][i] = c[1];
             sm.canvas[2][i] = c[2];
@@ -889,7 +900,7 @@ __global__ void __launch_bounds__(kRasterThreads, 16) raster_kernel(Scene s) {
         bool hit = false;
         if (vi < n_vis) {
             const short4 o = vbb[vi];
-            hit = o.x <= bx0 + kSB - 1 && o.z >= bx0 && o.y <= by0 + kSB - 1 && o.w >= by0;
+            hit = o.x <= bx0 + kBW - 1 && o.z >= bx0 && o.y <= by0 + kBH - 1 && o.w >= by0;
         }
         unsigned todo = __ballot_sync(0xffffffffu, hit);
         while (todo) {
@@ -913,15 +924,15 @@ __global__ void __launch_bounds__(kRasterThreads, 16) raster_kernel(Scene s) {
                 } else {
                     icon = &s.icons[st.fill_image];
                 }
-                const int col = (int)(lane & 15u);
+                const int col = (int)(lane % (unsigned)kBW);
 #pragma unroll 1
-                for (int j = 0; j < kSB * kSB / 32; ++j) {
-                    const int r = 2 * j + (int)(lane >> 4);
+                for (int j = 0; j < kBP / 32; ++j) {
+                    const int r = (j * 32 + (int)lane) / kBW;
                     const int y = by0 + r;
                     if (y < (int)op.y0 || y > (int)op.y1) continue;
                     const unsigned mword = s.mask[op.mask_off + (size_t)(y - ya) * wpr + (bx0 >> 5)];
                     if (!((mword >> ((bx0 & 31) + col)) & 1u)) continue;
-                    const int idx = r * kSB + col;
+                    const int idx = r * kBW + col;
                     double c0, c1, c2, a;
                     if (icon) {  // Filler::Image (fill.rs:36-40): texel (x mod w, y mod h), already premultiplied
                         unsigned ix = (unsigned)(bx0 + col) % icon->w, iy = (unsigned)y % icon->h;
@@ -961,8 +972,8 @@ __global__ void __launch_bounds__(kRasterThreads, 16) raster_kernel(Scene s) {
                 if (si < n_seg) {
                     const int4 sr = *reinterpret_cast<const int4*>(&segs[si]);  // x1, y1, x2, y2
                     int mnx = min(sr.x, sr.z), mxx = max(sr.x, sr.z), mny = min(sr.y, sr.w), mxy = max(sr.y, sr.w);
-                    if ((long long)mnx - reach <= bx0 + kSB - 1 && (long long)mxx + reach >= bx0 &&
-                        (long long)mny - reach <= by0 + kSB - 1 && (long long)mxy + reach >= by0) {
+                    if ((long long)mnx - reach <= bx0 + kBW - 1 && (long long)mxx + reach >= bx0 &&
+                        (long long)mny - reach <= by0 + kBH - 1 && (long long)mxy + reach >= by0) {
                         int dx = abs(wsub(sr.z, sr.x)), dy = abs(wsub(sr.w, sr.y));
                         bool swap = dx > dy;
                         int mx0 = swap ? sr.x : sr.y;
@@ -970,7 +981,7 @@ __global__ void __launch_bounds__(kRasterThreads, 16) raster_kernel(Scene s) {
                         int mx_inc = swap ? (sr.x <= sr.z ? 1 : -1) : (sr.y <= sr.w ? 1 : -1);
                         // main steps whose major coordinate lies within `reach` of the block
                         long long lo = (long long)(swap ? bx0 : by0) - reach;
-                        long long hi = (long long)(swap ? bx0 : by0) + kSB - 1 + reach;
+                        long long hi = (long long)(swap ? bx0 + kBW : by0 + kBH) - 1 + reach;
                         long long ka, kb;
                         if (mx_inc > 0) {
                             ka = lo - mx0;
@@ -1070,7 +1081,7 @@ __global__ void __launch_bounds__(kRasterThreads, 16) raster_kernel(Scene s) {
                     const int e_main = (int)(2ll * sc.mn_d * k - 2ll * sc.mx_d * c);  // main error before step k
                     // the walk of step k, then the extra one of a double correction (line.rs:150-155)
                     const bool extra = k < sc.mx_d && wadd(e_main, 2 * sc.mn_d) > sc.mx_d && wadd(p_error, 2 * sc.mn_d) > sc.mx_d;
-                    const int rlo = (sc.swap ? by0 : bx0) - reach, rhi = (sc.swap ? by0 : bx0) + kSB - 1 + reach;
+                    const int rlo = (sc.swap ? by0 : bx0) - reach, rhi = (sc.swap ? by0 + kBH : bx0 + kBW) - 1 + reach;
                     for (int v = 0; v < (extra ? 2 : 1); ++v) {
                         if (v == 1) {
                             p_error = wadd(wsub(p_error, 2 * sc.mx_d), 2 * sc.mn_d);
@@ -1087,7 +1098,7 @@ __global__ void __launch_bounds__(kRasterThreads, 16) raster_kernel(Scene s) {
                 double cn[3];
                 for (int k = 0; k < 3; ++k) cn[k] = unit_of_u8(lp.rgb[k]);
 #pragma unroll 2
-                for (int j = 0; j < kSB * kSB / 32; ++j) {
+                for (int j = 0; j < kBP / 32; ++j) {
                     const int idx = j * 32 + (int)lane;
                     unsigned long long bits = sm.plane[idx];
                     if (bits) {
@@ -1109,8 +1120,8 @@ __global__ void __launch_bounds__(kRasterThreads, 16) raster_kernel(Scene s) {
     auto texel = [&](int ch, int idx) -> unsigned { return f64_as_u8(255.0 * (sm.canvas[ch][idx] / 1.0)); };
     if (s.flags & OSMR_DRAW_OUT_RGBA) {
         uchar4* out = reinterpret_cast<uchar4*>(s.out) + (size_t)tile * D * D;
-        for (int i = (int)lane; i < kSB * kSB; i += 32) {
-            int r = i / kSB, x = i % kSB;
+        for (int i = (int)lane; i < kBP; i += 32) {
+            int r = i / kBW, x = i % kBW;
             uchar4 v;
             v.x = (unsigned char)texel(0, i);
             v.y = (unsigned char)texel(1, i);
@@ -1119,15 +1130,16 @@ __global__ void __launch_bounds__(kRasterThreads, 16) raster_kernel(Scene s) {
             out[(size_t)(by0 + r) * D + bx0 + x] = v;
         }
     } else {
-        // 16 rows of 48 bytes = 12 aligned words each
+        // kBH rows of 3*kBW bytes = 3*kBW/4 aligned words each
+        constexpr int wpb = 3 * kBW / 4;
         unsigned char* tile_out = s.out + (size_t)tile * D * D * 3;
-        for (int i = (int)lane; i < kSB * 12; i += 32) {
-            int r = i / 12, j = i % 12;
+        for (int i = (int)lane; i < kBH * wpb; i += 32) {
+            int r = i / wpb, j = i % wpb;
             unsigned word = 0;
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
                 int byte = 4 * j + b;
-                word |= texel(byte % 3, r * kSB + byte / 3) << (8 * b);
+                word |= texel(byte % 3, r * kBW + byte / 3) << (8 * b);
             }
             unsigned* dst = reinterpret_cast<unsigned*>(tile_out + ((size_t)(by0 + r) * D + bx0) * 3);
             dst[j] = word;
