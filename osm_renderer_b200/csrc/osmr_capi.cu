@@ -76,7 +76,7 @@ struct osmr_ctx {
     DevBuf<VisOp> vis;
     DevBuf<short4> vis_bbox;
     DevBuf<unsigned> vis_count, work, fill_work, counters, mask;
-    DevBuf<uint4> geom;
+    DevBuf<uint4> geom, calc_table;
     size_t geom_cap_units = 0, mask_cap_words = 0;
     DevBuf<unsigned char> out;
     size_t out_bytes = 0;
@@ -165,6 +165,7 @@ void osmr_ctx_destroy(osmr_ctx* ctx) {
     ctx->counters.release();
     ctx->mask.release();
     ctx->geom.release();
+    ctx->calc_table.release();
     ctx->out.release();
     for (auto& e : ctx->ev)
         if (e) cudaEventDestroy(e);
@@ -435,6 +436,8 @@ static int run_pipeline(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t fla
         s.vis_count = ctx->vis_count.p;
         s.work = ctx->work.p;
         s.fill_work = ctx->fill_work.p;
+        CK(ctx->calc_table.reserve((size_t)2 * ctx->n_styles * kCalcEntryUnits + 1));
+        s.calc_table = ctx->calc_table.p;
         s.geom = ctx->geom.p;
         s.geom_cap = (unsigned)std::min<size_t>(ctx->geom_cap_units, 0xffffffffu);
         s.mask = ctx->mask.p;
@@ -447,6 +450,10 @@ static int run_pipeline(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t fla
         CK(cudaEventRecord(ctx->ev[0], st));
         CK(cudaMemsetAsync(ctx->counters.p, 0, CNT_COUNT * sizeof(unsigned), st));
         unsigned launches = 0;
+        if (ctx->n_styles) {
+            style_calc_kernel<<<(2 * ctx->n_styles + 127) / 128, 128, 0, st>>>(s, ctx->calc_table.p);
+            ++launches;
+        }
         if (n_areas) {
             area_bbox_kernel<<<(n_areas + 255) / 256, 256, 0, st>>>(s);
             ++launches;

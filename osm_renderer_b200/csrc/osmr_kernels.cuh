@@ -33,8 +33,8 @@ struct VisOp {
     unsigned geom_cnt;     // records written by build_geometry_kernel
     unsigned mask_off;     // fills: first word of its row masks
     unsigned kind;         // OP_*
-    unsigned calc_units;   // lines: 16-byte units of the main calculator block at geom_off (cap block follows, then SegRecs)
-    unsigned pad;
+    unsigned area;         // index of the styled area inside its tile (g = pass * n + area)
+    unsigned pass;         // 0 Fill, 1 Casing, 2 Stroke
 };
 enum { OP_FILL_COLOR = 0, OP_FILL_IMAGE = 1, OP_LINE = 2 };
 
@@ -46,12 +46,12 @@ struct SegRec {  // 48 bytes: one line segment (or outer cap line) that can touc
     unsigned flags;            // bit0: outer cap calculator (line.rs:22,33-57); bit1: 32-bit fast path valid
     unsigned pad;
 };
-constexpr unsigned kCapCalcUnits = 8;  // header + one dash segment
-
-__device__ __forceinline__ unsigned main_calc_units(bool has_dashes, int n_dashes) {
-    int n = (has_dashes && n_dashes > 0) ? min(n_dashes / 2 + 2, kMaxDashSegs) : 0;
-    return 4u + 4u * (unsigned)n;
-}
+// Opacity calculators depend only on (style, pass, scale, use_caps_for_dashes): style_calc_kernel builds them once per
+// draw into a table; entry (style, pass) = one full OpacityCalc (dashes of the op) + header and first segment of the
+// outer-cap calculator.
+constexpr unsigned kCapCalcUnits = 8;                                      // header + one dash segment
+constexpr unsigned kMainCalcUnits = (unsigned)(sizeof(OpacityCalc) / 16);  // 4 + 4 * kMaxDashSegs
+constexpr unsigned kCalcEntryUnits = kMainCalcUnits + kCapCalcUnits;
 
 enum {
     CNT_GEOM_USED = 0,   // 16-byte units
@@ -101,6 +101,7 @@ struct Scene {
     unsigned* vis_count;   // per tile
     unsigned* work;        // global indices into vis (all visible ops)
     unsigned* fill_work;   // global indices into vis (fills)
+    const uint4* calc_table;  // kCalcEntryUnits per (style, pass-1), built by style_calc_kernel
     uint4* geom;           // geometry scratch, 16-byte units
     unsigned geom_cap;
     unsigned* mask;        // fill row masks
@@ -279,6 +280,25 @@ __device__ __forceinline__ int line_reach(double half_width) {
 __device__ __forceinline__ short clamp_s(int v, int lo, int hi) { return (short)(v < lo ? lo : (v > hi ? hi : v)); }
 
 // ------------------------------------------------------------------------------------------------------
+// style_calc_kernel: one thread per (style, line pass): OpacityCalculator::new for the op's dashes and for the outer
+// caps (line.rs:21-22, opacity_calculator.rs:16-30,98-143)
+// ------------------------------------------------------------------------------------------------------
+__global__ void style_calc_kernel(Scene s, uint4* table) {
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2u * s.n_styles) return;
+    const osmr_style& st = s.styles[i >> 1];
+    LineParams lp;
+    if (!line_params(s, st, 1 + (int)(i & 1u), lp)) return;
+    const double hw = lp.width / 2.0;
+    OpacityCalc* cmain = reinterpret_cast<OpacityCalc*>(table + (size_t)i * kCalcEntryUnits);
+    OpacityCalc* ccap = reinterpret_cast<OpacityCalc*>(table + (size_t)i * kCalcEntryUnits + kMainCalcUnits);
+    unsigned cap_for_dashes = (s.flags & OSMR_DRAW_USE_CAPS_FOR_DASHES) ? lp.cap : (unsigned)OSMR_CAP_NONE;
+    build_calc(*cmain, hw, lp.dashes, lp.n_dashes, (double)s.scale, lp.has_dashes, cap_for_dashes, kMaxDashSegs);
+    const double zero = 0.0;
+    build_calc(*ccap, hw, &zero, 1, 1.0, true, lp.cap, 1);
+}
+
+// ------------------------------------------------------------------------------------------------------
 // plan_ops_kernel: one CTA per tile; ordered compaction of the visible generations (a8)
 // ------------------------------------------------------------------------------------------------------
 constexpr int kPlanThreads = 256;
@@ -309,7 +329,6 @@ __global__ void __launch_bounds__(kPlanThreads) plan_ops_kernel(Scene s) {
                 const osmr_style& st = s.styles[ar.style];
                 int x0 = info.x0, y0 = info.y0, x1 = info.x1, y1 = info.y1;
                 bool active = false;
-                op.calc_units = 0;
                 if (pass == 0) {  // drawer.rs:172-185
                     if (st.flags & OSMR_STYLE_FILL_COLOR) {
                         active = true;
@@ -337,9 +356,7 @@ __global__ void __launch_bounds__(kPlanThreads) plan_ops_kernel(Scene s) {
                         y0 = (int)max(ly0, -2147483647LL);
                         x1 = (int)min(lx1, 2147483647LL);
                         y1 = (int)min(ly1, 2147483647LL);
-                        op.calc_units = main_calc_units(lp.has_dashes, lp.n_dashes);
-                        // calculators + (<= npts-1 segments + 2 caps) of 48 bytes
-                        geom_units = op.calc_units + kCapCalcUnits + 3u * (info.npts + 1u);
+                        geom_units = 3u * (info.npts + 1u);  // <= npts-1 segments + 2 caps of 48 bytes
                     }
                 }
                 if (active && x0 <= D - 1 && x1 >= 0 && y0 <= D - 1 && y1 >= 0) {
@@ -352,7 +369,8 @@ __global__ void __launch_bounds__(kPlanThreads) plan_ops_kernel(Scene s) {
                     op.geom_cnt = 0;
                     op.geom_off = 0;
                     op.mask_off = 0;
-                    op.pad = 0;
+                    op.area = i;
+                    op.pass = pass;
                 }
             }
         }
@@ -473,18 +491,7 @@ __global__ void __launch_bounds__(kGeomThreads) build_geometry_kernel(Scene s) {
             int reach = line_reach(hw);
             bool caps = is_non_trivial_cap(lp.cap);
             bool dashed = lp.has_dashes && lp.n_dashes > 0;
-            // opacity calculators of the op (OpacityCalculator::new, line.rs:21-22), built once per (tile, op)
-            OpacityCalc* cmain = reinterpret_cast<OpacityCalc*>(s.geom + op.geom_off);
-            OpacityCalc* ccap = reinterpret_cast<OpacityCalc*>(s.geom + op.geom_off + op.calc_units);
-            if (lane == 0) {
-                unsigned cap_for_dashes = (s.flags & OSMR_DRAW_USE_CAPS_FOR_DASHES) ? lp.cap : (unsigned)OSMR_CAP_NONE;
-                build_calc(*cmain, hw, lp.dashes, lp.n_dashes, (double)s.scale, lp.has_dashes, cap_for_dashes,
-                           (int)(op.calc_units - 4u) / 4);
-            } else if (lane == 1) {
-                const double zero = 0.0;
-                build_calc(*ccap, hw, &zero, 1, 1.0, true, lp.cap, 1);
-            }
-            SegRec* out = reinterpret_cast<SegRec*>(s.geom + op.geom_off + op.calc_units + kCapCalcUnits);
+            SegRec* out = reinterpret_cast<SegRec*>(s.geom + op.geom_off);
             uint2 r = it.ring(0);
             double acc = 0.0;  // traveled_distance
             unsigned n_pairs = r.y ? r.y - 1 : 0;
@@ -874,11 +881,9 @@ __global__ void __launch_bounds__(kRasterThreads, 16) raster_kernel(Scene s) {
     const int by0 = (int)((grp / grp_per_row) * 2u + (in_grp / 2u)) * kBH;
     const unsigned lane = threadIdx.x;
     const unsigned base = s.area_begin[tile];
-    const unsigned n_areas = s.area_begin[tile + 1] - base;
     const VisOp* vis = s.vis + 3ull * base;
     const short4* vbb = s.vis_bbox + 3ull * base;
     const unsigned n_vis = s.vis_count[tile];
-    const double scale = (double)s.scale;
 
     // TilePixels::reset (tile_pixels.rs:89-105): canvas colour premultiplied with opacity 1.0, or (0,0,0,1)
     {
@@ -907,8 +912,8 @@ __global__ void __launch_bounds__(kRasterThreads, 16) raster_kernel(Scene s) {
             const unsigned qi = chunk + (unsigned)(__ffs(todo) - 1);
             todo &= todo - 1;
             const VisOp op = vis[qi];
-            const unsigned pass = op.g / n_areas;
-            const osmr_styled_area ar = s.areas[base + (op.g - pass * n_areas)];
+            const unsigned pass = op.pass;
+            const osmr_styled_area ar = s.areas[base + op.area];
             const osmr_style& st = s.styles[ar.style];
 
             if (op.kind != OP_LINE) {
@@ -961,7 +966,7 @@ __global__ void __launch_bounds__(kRasterThreads, 16) raster_kernel(Scene s) {
             line_params(s, st, (int)pass, lp);
             const double hw = lp.width / 2.0;
             const int reach = line_reach(hw);
-            const SegRec* segs = reinterpret_cast<const SegRec*>(s.geom + op.geom_off + op.calc_units + kCapCalcUnits);
+            const SegRec* segs = reinterpret_cast<const SegRec*>(s.geom + op.geom_off);
             const unsigned n_seg = op.geom_cnt;
             bool any = false;
             for (unsigned sb = 0; sb < n_seg; sb += 32) {
@@ -1010,12 +1015,13 @@ __global__ void __launch_bounds__(kRasterThreads, 16) raster_kernel(Scene s) {
                 unsigned hb = __ballot_sync(0xffffffffu, items != 0);
                 if (!hb) continue;
                 if (!any) {  // first segment that reaches my block: fetch the op's opacity calculators (built by
-                             // build_geometry_kernel) into shared memory, 16 bytes per lane and step
-                    const uint4* src = s.geom + op.geom_off;
+                             // style_calc_kernel) into shared memory, 16 bytes per lane and step
+                    const uint4* src = s.calc_table + (size_t)(2u * ar.style + (pass - 1u)) * kCalcEntryUnits;
                     uint4* dst0 = reinterpret_cast<uint4*>(&sm.calc[0]);
                     uint4* dst1 = reinterpret_cast<uint4*>(&sm.calc[1]);
-                    for (unsigned u = lane; u < op.calc_units; u += 32) dst0[u] = src[u];
-                    if (lane < kCapCalcUnits) dst1[lane] = src[op.calc_units + lane];
+                    const unsigned n_main = 4u + 4u * (unsigned)reinterpret_cast<const OpacityCalc*>(src)->n_segs;
+                    for (unsigned u = lane; u < n_main; u += 32) dst0[u] = src[u];
+                    if (lane < kCapCalcUnits) dst1[lane] = src[kMainCalcUnits + lane];
                 }
                 any = true;
                 // exclusive scan of the item counts
