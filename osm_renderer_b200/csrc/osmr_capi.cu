@@ -46,6 +46,8 @@ struct osmr_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t chunk_done[2] = {nullptr, nullptr};
+    cudaEvent_t areas_ready = nullptr;
+    bool areas_deferred = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::string err;
     int num_sms = 0;
@@ -122,6 +124,7 @@ int osmr_ctx_create(int device, osmr_ctx** out_ctx) {
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->chunk_done[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->areas_ready, cudaEventDisableTiming);
     for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) {
@@ -171,6 +174,7 @@ void osmr_ctx_destroy(osmr_ctx* ctx) {
         if (e) cudaEventDestroy(e);
     for (auto& e : ctx->chunk_done)
         if (e) cudaEventDestroy(e);
+    if (ctx->areas_ready) cudaEventDestroy(ctx->areas_ready);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -352,8 +356,16 @@ static int validate_batch(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tile
     return OSMR_OK;
 }
 
-int osmr_batch_upload(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, const uint32_t* area_begin,
-                      const osmr_styled_area* areas) {
+// defer_tail: copy only the styled areas of the first draw chunk on the compute stream and send the rest on the copy
+// stream (event ctx->areas_ready), so that the upload overlaps the drawing of the first chunk (osmr_draw_tiles only:
+// the caller's arrays stay valid until that call returns).
+static unsigned draw_chunk_tiles(const osmr_ctx* ctx, unsigned n_tiles, bool to_host) {
+    (void)ctx;
+    return (to_host && n_tiles >= 128) ? std::max(64u, (n_tiles + 3) / 4) : n_tiles;
+}
+
+static int batch_upload_impl(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, const uint32_t* area_begin,
+                             const osmr_styled_area* areas, bool defer_tail) {
     if (!ctx) return OSMR_E_INVALID;
     int rc = validate_batch(ctx, tiles, n_tiles, area_begin);
     if (rc) return rc;
@@ -366,7 +378,19 @@ int osmr_batch_upload(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, c
     CK(ctx->areas.reserve(n_areas + 1));
     CK(cudaMemcpyAsync(ctx->tiles.p, tiles, (size_t)n_tiles * sizeof(osmr_tile), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->area_begin.p, area_begin, (size_t)(n_tiles + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
-    if (n_areas) CK(cudaMemcpyAsync(ctx->areas.p, areas, (size_t)n_areas * sizeof(osmr_styled_area), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->areas_deferred = false;
+    size_t head = n_areas;
+    if (defer_tail) {
+        unsigned chunk = draw_chunk_tiles(ctx, n_tiles, true);
+        if (chunk < n_tiles) head = area_begin[chunk];
+    }
+    if (head) CK(cudaMemcpyAsync(ctx->areas.p, areas, head * sizeof(osmr_styled_area), cudaMemcpyHostToDevice, ctx->stream));
+    if (head < n_areas) {
+        CK(cudaMemcpyAsync(ctx->areas.p + head, areas + head, (n_areas - head) * sizeof(osmr_styled_area), cudaMemcpyHostToDevice,
+                           ctx->copy_stream));
+        CK(cudaEventRecord(ctx->areas_ready, ctx->copy_stream));
+        ctx->areas_deferred = true;
+    }
     ctx->n_tiles = n_tiles;
     ctx->n_areas = n_areas;
     ctx->scale = (int)tiles[0].scale;
@@ -383,6 +407,11 @@ int osmr_batch_upload(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, c
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->has_batch = true;
     return OSMR_OK;
+}
+
+int osmr_batch_upload(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, const uint32_t* area_begin,
+                      const osmr_styled_area* areas) {
+    return batch_upload_impl(ctx, tiles, n_tiles, area_begin, areas, false);
 }
 
 // Draws tiles [tb, tb+tc) of the uploaded batch into dev_out (which points at tile tb's image).  Synchronises the
@@ -527,10 +556,13 @@ int osmr_batch_draw(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t flags, 
     const bool to_host = out && !(flags & OSMR_DRAW_OUT_DEVICE);
     // Host output: draw in chunks and copy chunk i back on a second stream while chunk i+1 is being drawn
     // (the copy really overlaps only when `out` is page-locked, e.g. from osmr_alloc_pinned).
-    const unsigned chunk = (to_host && ctx->n_tiles >= 128) ? std::max(64u, (ctx->n_tiles + 3) / 4) : ctx->n_tiles;
-    unsigned k = 0;
-    for (unsigned tb = 0; tb < ctx->n_tiles; tb += chunk, ++k) {
+    const unsigned chunk = draw_chunk_tiles(ctx, ctx->n_tiles, to_host);
+    for (unsigned tb = 0; tb < ctx->n_tiles; tb += chunk) {
         const unsigned tc = std::min(chunk, ctx->n_tiles - tb);
+        if (tb > 0 && ctx->areas_deferred) {  // the tail of the styled-area list was uploaded on the copy stream
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->areas_ready, 0));
+            ctx->areas_deferred = false;
+        }
         int rc = run_pipeline(ctx, canvas_rgb, flags, dev_out + (size_t)tb * tile_bytes, tb, tc);
         if (rc) {
             cudaStreamSynchronize(ctx->copy_stream);
@@ -556,9 +588,14 @@ int osmr_draw_tiles(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, con
                     const osmr_styled_area* areas, const uint8_t canvas_rgb[3], uint32_t flags, uint8_t* out) {
     if (!ctx) return OSMR_E_INVALID;
     if (!out) return ctx->fail(OSMR_E_INVALID, "null output buffer");
-    int rc = osmr_batch_upload(ctx, tiles, n_tiles, area_begin, areas);
+    int rc = batch_upload_impl(ctx, tiles, n_tiles, area_begin, areas, !(flags & OSMR_DRAW_OUT_DEVICE));
     if (rc) return rc;
-    return osmr_batch_draw(ctx, canvas_rgb, flags, out, nullptr);
+    rc = osmr_batch_draw(ctx, canvas_rgb, flags, out, nullptr);
+    if (ctx->areas_deferred) {  // error path before the tail was consumed: do not leave a copy of the caller's memory in flight
+        cudaStreamSynchronize(ctx->copy_stream);
+        ctx->areas_deferred = false;
+    }
+    return rc;
 }
 
 int osmr_get_stats(osmr_ctx* ctx, osmr_stats* out) {

@@ -37,14 +37,18 @@ __device__ __forceinline__ unsigned f64_as_u8(double v) {
 // special-case subroutines peeled off first: a zero or negative radicand, a zero dividend.  Those are everyday
 // inputs here (pixels exactly on a centre line, the first pixel of a segment, points beyond a round cap), and
 // results are identical: sqrt(+-0) = +-0, sqrt(x<0) = NaN, +-0 / positive = +-0.
+// (The special operand is replaced by 1.0 *before* the operation and the result selected afterwards: a plain
+// `if (x == 0) return x;` is if-converted by the compiler, which then still sends those lanes down the slow path.)
 __device__ __forceinline__ double sqrt_peeled(double x) {
-    if (x == 0.0) return x;
-    if (x < 0.0) return __longlong_as_double(0x7ff8000000000000LL);
-    return sqrt(x);
+    const bool special = !(x > 0.0);  // zero, negative or NaN
+    const double r = sqrt(special ? 1.0 : x);
+    if (!special) return r;
+    return (x == 0.0) ? x : __longlong_as_double(0x7ff8000000000000LL);
 }
 __device__ __forceinline__ double div_pos_peeled(double a, double b) {  // b > 0 and finite
-    if (a == 0.0) return a;
-    return a / b;
+    const bool zero = (a == 0.0);
+    const double q = (zero ? 1.0 : a) / b;
+    return zero ? a : q;
 }
 
 __device__ __forceinline__ int wsub(int a, int b) { return (int)((unsigned)a - (unsigned)b); }
