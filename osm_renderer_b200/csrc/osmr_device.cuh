@@ -201,7 +201,7 @@ constexpr int kMaxDashSegs = 17;  // dash lists of up to 32 numbers -> <= 17 "on
 struct DashSeg {  // 64 bytes
     double start_from, start_to, end_from, end_to, opacity_mul;
     double orig_a, orig_b;  // valid when OpacityCalc::round_caps
-    double pad;
+    double unit_ramps;      // 1.0 when both ramp lengths (start_to-start_from, end_to-end_from) are exactly 1.0
 };
 
 struct alignas(16) OpacityCalc {  // 64-byte header + 64 bytes per dash segment (same layout in HBM and smem)
@@ -211,7 +211,7 @@ struct alignas(16) OpacityCalc {  // 64-byte header + 64 bytes per dash segment 
     double feather_from, feather_to, feather_dist, opacity_mul;
     int n_segs;       // 0 == "dashes: None"
     int round_caps;   // original_endpoints is Some(..)  (LineCap::Round)
-    double pad;
+    double inv_total;  // 1 / total_dash_len: quotient estimate of the exact fmod below
     DashSeg segs[kMaxDashSegs];
 };
 static_assert(sizeof(DashSeg) == 64 && sizeof(OpacityCalc) == 64 + 64 * kMaxDashSegs, "calculator wire layout");
@@ -255,10 +255,12 @@ __device__ inline void build_calc(OpacityCalc& c, double hw, const double* dashe
                 s.opacity_mul = fmin(end - start, 1.0);
                 s.orig_a = oa;
                 s.orig_b = ob;
+                s.unit_ramps = (s.start_to - s.start_from == 1.0 && s.end_to - s.end_from == 1.0) ? 1.0 : 0.0;
             }
         }
     }
     c.total_dash_len = len_before;
+    c.inv_total = (len_before > 0.0) ? 1.0 / len_before : 0.0;
     double hw0 = sqrt(hw * hw - 0.0 * 0.0);  // calculate() with cap_dist == 0
     center_feather(hw0, c.feather_from, c.feather_to, c.feather_dist, c.opacity_mul);
 }
@@ -267,12 +269,13 @@ __device__ inline void build_calc(OpacityCalc& c, double hw, const double* dashe
 // right integer n yields it exactly; a quotient that rounded across an integer is repaired by the sign test.
 // Much smaller than libdevice's general fmod, which matters for the instruction cache of raster_kernel.
 __device__ __noinline__ double fmod_general(double x, double y) { return fmod(x, y); }
-__device__ __forceinline__ double fmod_exact(double x, double y) {
+__device__ __noinline__ double div_general(double a, double b) { return a / b; }
+__device__ __forceinline__ double fmod_exact(double x, double y, double inv_y) {
     if (x >= 0.0 && x < y) return x;
-    double qf = x / y;
-    if (!(x >= 0.0) || !(qf < 4.0e15)) return fmod_general(x, y);
+    double qf = x * inv_y;  // estimate of x / y, off by far less than one for quotients below 2^50
+    if (!(x >= 0.0) || !(qf < 1.0e15)) return fmod_general(x, y);
     double q = floor(qf);
-    double r = __fma_rn(-q, y, x);
+    double r = __fma_rn(-q, y, x);  // exact: x - q*y is representable for q within one of floor(x/y)
     if (r < 0.0) {
         q -= 1.0;
         r = __fma_rn(-q, y, x);
@@ -280,6 +283,7 @@ __device__ __forceinline__ double fmod_exact(double x, double y) {
         q += 1.0;
         r = __fma_rn(-q, y, x);
     }
+    if (!(r >= 0.0 && r < y)) return fmod_general(x, y);  // cannot happen for sane dash lengths; stay exact anyway
     return r;
 }
 
@@ -290,7 +294,7 @@ __device__ __forceinline__ void calc_opacity(const OpacityCalc& c, double travel
     double ff = c.feather_from, ft = c.feather_to, fd = c.feather_dist, fm = c.opacity_mul;
     if (c.n_segs != 0) {
         double dist_rem = traveled + start_distance;
-        if (c.total_dash_len > 0.0) dist_rem = fmod_exact(dist_rem, c.total_dash_len);  // `%=` (opacity_calculator.rs:59)
+        if (c.total_dash_len > 0.0) dist_rem = fmod_exact(dist_rem, c.total_dash_len, c.inv_total);  // `%=` (opacity_calculator.rs:59)
         double acc = 0.0;
         bool has_cap = false;
         double cap = 0.0;
@@ -299,11 +303,11 @@ __device__ __forceinline__ void calc_opacity(const OpacityCalc& c, double travel
             if (dist_rem < s.start_from || dist_rem > s.end_to) continue;  // NaN falls through to the last branch, as in the reference
             double base;
             if (dist_rem <= s.start_to)
-                base = div_pos_peeled(dist_rem - s.start_from, s.start_to - s.start_from);
+                base = (s.unit_ramps != 0.0) ? (dist_rem - s.start_from) : div_general(dist_rem - s.start_from, s.start_to - s.start_from);  // x / 1.0 == x
             else if (dist_rem < s.end_from)
                 base = 1.0;
             else
-                base = div_pos_peeled(s.end_to - dist_rem, s.end_to - s.end_from);
+                base = (s.unit_ramps != 0.0) ? (s.end_to - dist_rem) : div_general(s.end_to - dist_rem, s.end_to - s.end_from);
             acc = fmax(acc, s.opacity_mul * base);
             if (c.round_caps) {
                 double dcap;
@@ -329,7 +333,7 @@ __device__ __forceinline__ void calc_opacity(const OpacityCalc& c, double travel
     if (center_distance < ff)
         v = 1.0;
     else if (center_distance < ft)
-        v = div_pos_peeled(ft - center_distance, fd);
+        v = (fd == 1.0) ? (ft - center_distance) : div_general(ft - center_distance, fd);
     else
         v = 0.0;
     double cd = fm * v;
