@@ -103,3 +103,63 @@ def fill_edge_rows(x1, y1, x2, y2, min_y, max_y) -> np.ndarray:
     out = np.zeros((max_y - min_y + 1, 3), dtype=np.int32)
     lib().osmr_oracle_fill_edge_rows(x1, y1, x2, y2, min_y, max_y, out.ctypes.data)
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# label pass (oracle only)
+# ---------------------------------------------------------------------------------------------------------------
+LABEL_DTYPE = np.dtype(
+    [
+        ("kind", "<u4"), ("entity", "<u4"), ("icon", "<i4"), ("has_text_style", "<u4"), ("has_font_size", "<u4"),
+        ("has_text", "<u4"), ("text_off", "<u4"), ("text_len", "<u4"), ("text_pos", "<u4"),
+        ("text_color", "u1", (3,)), ("has_text_color", "u1"), ("font_size", "<f8"),
+    ],
+    align=True,
+)
+assert LABEL_DTYPE.itemsize == 48
+
+
+def draw_tiles_with_labels(bin_image, table, tiles, area_begin, areas, canvas_rgb, use_caps_for_dashes, font_bytes,
+                           label_icons, label_begin, labels, texts: bytes, n_threads: int = 1):
+    """Full draw_to_pixels (area passes + label pass).  label_icons: list of (w, h, rgba ndarray)."""
+    from osm_renderer_b200.wire import OSMR_DRAW_HAS_CANVAS_COLOR, OSMR_DRAW_USE_CAPS_FOR_DASHES, IconStruct
+
+    L = lib()
+    L.osmr_oracle_draw_tiles_labels.restype = C.c_int
+    L.osmr_oracle_draw_tiles_labels.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p,
+                                                 C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
+                                                 C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_char_p,
+                                                 C.c_int, C.c_void_p]
+    styles = table.styles_array()
+    dashes = table.dashes_array()
+    icons, _keep = table.icon_structs()
+    licons = (IconStruct * max(1, len(label_icons)))()
+    for i, (w, h, px) in enumerate(label_icons):
+        licons[i].width, licons[i].height, licons[i].rgba = w, h, px.ctypes.data
+    tiles = np.ascontiguousarray(tiles)
+    area_begin = np.ascontiguousarray(area_begin, dtype=np.uint32)
+    areas = np.ascontiguousarray(areas)
+    label_begin = np.ascontiguousarray(label_begin, dtype=np.uint32)
+    labels = np.ascontiguousarray(labels, dtype=LABEL_DTYPE)
+    sizes = [(256 * int(s)) ** 2 * 3 for s in tiles["scale"]]
+    out = np.zeros(int(sum(sizes)), dtype=np.uint8)
+    flags = OSMR_DRAW_USE_CAPS_FOR_DASHES if use_caps_for_dashes else 0
+    canvas = np.zeros(3, dtype=np.uint8)
+    if canvas_rgb is not None:
+        flags |= OSMR_DRAW_HAS_CANVAS_COLOR
+        canvas[:] = canvas_rgb
+    buf = np.frombuffer(bin_image, dtype=np.uint8)
+    fbuf = np.frombuffer(font_bytes, dtype=np.uint8)
+    rc = L.osmr_oracle_draw_tiles_labels(
+        buf.ctypes.data, len(bin_image), styles.ctypes.data, len(styles), dashes.ctypes.data, len(dashes), C.addressof(icons),
+        len(table.icons), tiles.ctypes.data, len(tiles), area_begin.ctypes.data, areas.ctypes.data, canvas.ctypes.data, flags,
+        fbuf.ctypes.data, len(font_bytes), C.addressof(licons), len(label_icons), label_begin.ctypes.data, labels.ctypes.data, texts,
+        n_threads, out.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"osmr_oracle_draw_tiles_labels failed: {rc}")
+    res, off = [], 0
+    for s, n in zip(tiles["scale"], sizes):
+        d = 256 * int(s)
+        res.append(out[off : off + n].reshape(d, d, 3))
+        off += n
+    return res

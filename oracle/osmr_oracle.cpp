@@ -18,7 +18,7 @@
 //   .bin views: src/geodata/reader.rs:264-335,444-483
 // Parity pin: the reference's golden renders tests/rendered/*_expected.png (exact RGB outside the label
 // pass, see tests/test_golden_tiles.py) and the doc-test vectors of src/tile.rs:23-29,77-87.
-// The label pass (drawer.rs:106-126) is not restated here.
+// The label pass (drawer.rs:106-126) lives in osmr_oracle_labels.inc (oracle only; the CUDA library has none yet).
 
 #include <algorithm>
 #include <atomic>
@@ -26,6 +26,7 @@
 #include <cstdint>
 #include <cstring>
 #include <limits>
+#include <map>
 #include <thread>
 #include <vector>
 
@@ -683,8 +684,8 @@ void draw_one_area(const World& w, TilePixels& px, const osmr_tile& t, double sc
     px.bump_generation();
 }
 
-void draw_to_pixels(const World& w, TilePixels& px, const osmr_tile& t, const osmr_styled_area* areas,
-                    uint32_t n_areas, const uint8_t canvas[3], uint32_t flags, uint32_t gen_limit, uint8_t* out) {
+void draw_area_passes(const World& w, TilePixels& px, const osmr_tile& t, const osmr_styled_area* areas, uint32_t n_areas,
+                      const uint8_t canvas[3], uint32_t flags, uint32_t gen_limit) {
     px.reset((flags & OSMR_DRAW_HAS_CANVAS_COLOR) != 0, canvas);  // drawer.rs:70
     double scale = (double)t.scale;
     bool caps = (flags & OSMR_DRAW_USE_CAPS_FOR_DASHES) != 0;
@@ -700,8 +701,15 @@ void draw_to_pixels(const World& w, TilePixels& px, const osmr_tile& t, const os
         }
     }
     px.blend_unfinished_pixels();  // drawer.rs:104
-    px.to_rgb(out);                // drawer.rs:128 (label pass not restated)
 }
+
+void draw_to_pixels(const World& w, TilePixels& px, const osmr_tile& t, const osmr_styled_area* areas,
+                    uint32_t n_areas, const uint8_t canvas[3], uint32_t flags, uint32_t gen_limit, uint8_t* out) {
+    draw_area_passes(w, px, t, areas, n_areas, canvas, flags, gen_limit);
+    px.to_rgb(out);  // drawer.rs:128 (label pass: see osmr_oracle_draw_tiles_labels)
+}
+
+#include "osmr_oracle_labels.inc"
 
 bool build_world(World& w, const void* bin, size_t bin_len, const osmr_style* styles, uint32_t n_styles,
                  const double* dashes, uint32_t n_dashes, const osmr_icon* icons, uint32_t n_icons) {
@@ -811,6 +819,60 @@ void osmr_oracle_fill_edge_rows(int32_t x1, int32_t y1, int32_t x2, int32_t y2, 
     }
 }
 
-uint32_t osmr_oracle_abi_version(void) { return 1; }
+// Full Drawer::draw_to_pixels including the label pass (drawer.rs:106-126).  labels of tile t:
+// labels[label_begin[t] .. label_begin[t+1]) in label-generation order.  CPU only; pins the oracle (and the upstream
+// restatement) to the reference goldens on EVERY pixel.
+int osmr_oracle_draw_tiles_labels(const void* bin, size_t bin_len, const osmr_style* styles, uint32_t n_styles,
+                                  const double* dashes, uint32_t n_dashes, const osmr_icon* icons, uint32_t n_icons,
+                                  const osmr_tile* tiles, uint32_t n_tiles, const uint32_t* area_begin,
+                                  const osmr_styled_area* areas, const uint8_t canvas_rgb[3], uint32_t flags,
+                                  const void* font, size_t font_len, const osmr_icon* label_icons, uint32_t n_label_icons,
+                                  const uint32_t* label_begin, const LabelRec* labels, const char* texts, int n_threads,
+                                  uint8_t* out_rgb) {
+    World w;
+    if (!build_world(w, bin, bin_len, styles, n_styles, dashes, n_dashes, icons, n_icons)) return OSMR_E_INVALID;
+    LabelWorld lw;
+    lw.w = &w;
+    lw.texts = texts;
+    if (!lw.font.init((const uint8_t*)font, font_len)) return OSMR_E_INVALID;
+    lw.icons.resize(n_label_icons);
+    for (uint32_t i = 0; i < n_label_icons; ++i) {
+        Icon& ic = lw.icons[i];
+        ic.width = label_icons[i].width;
+        ic.height = label_icons[i].height;
+        ic.px.resize(ic.width * ic.height);
+        for (size_t k = 0; k < ic.px.size(); ++k) {
+            const uint8_t* p = label_icons[i].rgba + 4 * k;
+            ic.px[k] = from_components(p[0], p[1], p[2], p[3]);
+        }
+    }
+    if (n_threads < 1) n_threads = 1;
+    std::vector<size_t> out_off(n_tiles + 1, 0);
+    for (uint32_t t = 0; t < n_tiles; ++t) {
+        size_t d = 256 * (size_t)tiles[t].scale;
+        out_off[t + 1] = out_off[t] + d * d * 3;
+    }
+    auto worker = [&](int tid) {
+        TilePixels* px = nullptr;
+        size_t cur_scale = 0;
+        for (uint32_t t = (uint32_t)tid; t < n_tiles; t += (uint32_t)n_threads) {
+            if (!px || cur_scale != tiles[t].scale) {
+                delete px;
+                px = new TilePixels(tiles[t].scale);
+                cur_scale = tiles[t].scale;
+            }
+            draw_area_passes(w, *px, tiles[t], areas + area_begin[t], area_begin[t + 1] - area_begin[t], canvas_rgb, flags, 0xffffffffu);
+            draw_labels(lw, *px, tiles[t], labels + label_begin[t], label_begin[t + 1] - label_begin[t]);
+            px->to_rgb(out_rgb + out_off[t]);
+        }
+        delete px;
+    };
+    std::vector<std::thread> th;
+    for (int i = 0; i < n_threads; ++i) th.emplace_back(worker, i);
+    for (auto& x : th) x.join();
+    return OSMR_OK;
+}
+
+uint32_t osmr_oracle_abi_version(void) { return 2; }
 
 }  // extern "C"

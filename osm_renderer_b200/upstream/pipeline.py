@@ -6,6 +6,8 @@ step is `styler.style_areas(ways, multipolygons, zoom, false)`, src/draw/drawer.
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 from ..wire import AREA_DTYPE, StyleTable, styled_areas_to_array
@@ -193,3 +195,79 @@ class FastBatchBuilder:
         out["entity"] = ent[order]
         out["style"] = sid[order]
         return out
+
+
+class LabelListBuilder:
+    """The label generations of a tile in the order the reference draws them (drawer.rs:106-119, 221-262):
+    styled areas with for_labels=true (ways: text on the line, multipolygons: centred), then styled nodes.
+    Oracle-side only: the CUDA library has no label pass yet."""
+
+    def __init__(self, ts: TileStyler, icon_base_path: str | None):
+        from ..wire import load_icon_rgba
+
+        self.ts = ts
+        self._load = load_icon_rgba
+        self.icon_base_path = icon_base_path
+        self.icon_ids: dict = {}
+        self.icons: list = []
+        self.texts = bytearray()
+        self._text_off: dict = {}
+        self._node_ent: dict = {}
+
+    def _icon(self, name):
+        if name is None:
+            return -2
+        i = self.icon_ids.get(name)
+        if i is None:
+            ic = self._load(os.path.join(self.icon_base_path, name)) if self.icon_base_path else None
+            i = -1
+            if ic is not None:
+                i = len(self.icons)
+                self.icons.append(ic)
+            self.icon_ids[name] = i
+        return i
+
+    def _text(self, s: str):
+        t = self._text_off.get(s)
+        if t is None:
+            b = s.encode("utf-8")
+            t = (len(self.texts), len(b))
+            self.texts += b
+            self._text_off[s] = t
+        return t
+
+    def node_entity(self, n: int):
+        from .styler import KIND_NODE
+
+        e = self._node_ent.get(n)
+        if e is None:
+            rd = self.ts.reader
+            e = (KIND_NODE, n, int(rd.nodes[n]["id"]), rd.node_tags(n))
+            self._node_ent[n] = e
+        return e
+
+    def labels(self, zoom, x, y):
+        from .styler import KIND_MULTIPOLYGON, KIND_NODE
+
+        ts = self.ts
+        nodes, _, _ = ts.reader.get_entities_in_tile_with_neighbors(zoom, x, y)
+        styled = ts.styled_areas(zoom, x, y, for_labels=True)
+        styled_nodes = ts.styler.style_entities([self.node_entity(int(n)) for n in nodes], zoom, True)
+        rows = []
+        for ent, s in list(styled) + list(styled_nodes):
+            kind = 2 if ent[0] == KIND_NODE else (1 if ent[0] == KIND_MULTIPOLYGON else 0)
+            tstyle = s.text_style
+            has_text = False
+            toff = tlen = 0
+            if tstyle is not None and tstyle.text in ent[3]:
+                has_text = True
+                toff, tlen = self._text(ent[3][tstyle.text])
+            rows.append((
+                kind, ent[1], self._icon(s.icon_image), 1 if tstyle is not None else 0,
+                1 if (tstyle is not None and tstyle.font_size is not None) else 0, 1 if has_text else 0, toff, tlen,
+                0 if (tstyle is None or tstyle.text_position is None) else (1 if tstyle.text_position == "center" else 2),
+                tuple(tstyle.text_color) if (tstyle is not None and tstyle.text_color is not None) else (0, 0, 0),
+                1 if (tstyle is not None and tstyle.text_color is not None) else 0,
+                float(tstyle.font_size) if (tstyle is not None and tstyle.font_size is not None) else 0.0,
+            ))
+        return rows
