@@ -162,6 +162,54 @@ int osmr_get_stats(osmr_ctx* ctx, osmr_stats* out);
  * Point::from_node (point.rs:11-19).  out_xy: n_nodes * 2 int32 (host). */
 int osmr_project_nodes(osmr_ctx* ctx, const osmr_tile* tile, int32_t* out_xy);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Label pass (reference src/draw/drawer.rs:106-126,221-262; src/draw/labeler.rs:16-106; src/draw/labelable.rs;
+ * src/draw/font/{text_placer,rasterizer}.rs; src/draw/tile_pixels.rs:131-162,205-209).
+ * Host C++ inside the library does the string / font work exactly as the reference does it on the CPU (tag lookup,
+ * stb_truetype glyph outlines, glyph placement with the platform libm, polylabel); the device rasterises glyph
+ * coverage (exact-area accumulation in segment order), resolves the greedy label collisions over the 3x3 canvas and
+ * blends the surviving labels over the f64 tile canvas before the RGB export.
+ * ------------------------------------------------------------------------------------------------------------ */
+#define OSMR_LABEL_NODE 0x40000000u /* osmr_label.entity: node index | OSMR_LABEL_NODE (ways / multipolygons as in
+                                       osmr_styled_area) */
+#define OSMR_LSTYLE_TEXT (1u << 0)       /* Style.text_style is Some */
+#define OSMR_LSTYLE_FONT_SIZE (1u << 1)  /* TextStyle.font_size is Some (already multiplied by font-mul) */
+#define OSMR_LSTYLE_TEXT_COLOR (1u << 2) /* TextStyle.text_color is Some (default black, text_placer.rs:52-55) */
+#define OSMR_TEXT_POS_NONE 0
+#define OSMR_TEXT_POS_CENTER 1
+#define OSMR_TEXT_POS_LINE 2
+
+/* label-relevant fields of reference `struct Style` / `struct TextStyle` (styler.rs:42-47,69-71) */
+typedef struct osmr_label_style {
+    int32_t icon;          /* -2: no icon-image; -1: icon failed to load (labeler.rs:52-67 then continues with the
+                              text); >= 0: index into the table of osmr_set_label_icons */
+    uint32_t flags;        /* OSMR_LSTYLE_* */
+    uint32_t text_key_off; /* TextStyle.text = the tag KEY whose value is drawn; bytes in `strings` */
+    uint32_t text_key_len;
+    uint8_t text_color[3];
+    uint8_t text_position; /* OSMR_TEXT_POS_* (NONE = default: Line for ways, Center otherwise, drawer.rs:232-257) */
+    uint32_t reserved0;
+    double font_size;
+} osmr_label_style;
+
+/* one label generation: element of the styler output for labels, in the reference's order (areas styled with
+ * for_labels = true, then nodes; drawer.rs:106-119) */
+typedef struct osmr_label {
+    uint32_t entity;
+    uint32_t style; /* index into the table of osmr_set_label_styles */
+} osmr_label;
+
+/* replaces `FONT_DATA` (text_placer.rs:299): the TrueType file used for every label */
+int osmr_set_font(osmr_ctx* ctx, const void* ttf, size_t len);
+/* replaces IconCache for `icon-image` (labeler.rs:46-50); same pixel format as osmr_set_icons */
+int osmr_set_label_icons(osmr_ctx* ctx, const osmr_icon* icons, uint32_t n_icons);
+int osmr_set_label_styles(osmr_ctx* ctx, const osmr_label_style* styles, uint32_t n_styles, const char* strings, size_t strings_len);
+/* osmr_draw_tiles including the label pass: the labels of tile t are labels[label_begin[t] .. label_begin[t+1]).
+ * Requires osmr_set_font (and the label tables) first. */
+int osmr_draw_tiles_labeled(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, const uint32_t* area_begin,
+                            const osmr_styled_area* areas, const uint32_t* label_begin, const osmr_label* labels,
+                            const uint8_t canvas_rgb[3], uint32_t flags, uint8_t* out);
+
 /* Optional page-locked host memory for callers that want full-speed host<->device copies of `out` / batch
  * arrays (plain malloc'ed buffers work too, at pageable-copy speed). */
 void* osmr_alloc_pinned(size_t bytes);

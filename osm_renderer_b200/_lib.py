@@ -30,6 +30,10 @@ EXPORTS = [
     "osmr_alloc_pinned",
     "osmr_free_pinned",
     "osmr_debug_set",
+    "osmr_set_font",
+    "osmr_set_label_icons",
+    "osmr_set_label_styles",
+    "osmr_draw_tiles_labeled",
 ]
 
 _lib = None
@@ -83,5 +87,13 @@ def load():
     L.osmr_free_pinned.argtypes = [vp]
     L.osmr_debug_set.restype = C.c_int
     L.osmr_debug_set.argtypes = [vp, C.c_char_p, C.c_int]
+    L.osmr_set_font.restype = C.c_int
+    L.osmr_set_font.argtypes = [vp, vp, sz]
+    L.osmr_set_label_icons.restype = C.c_int
+    L.osmr_set_label_icons.argtypes = [vp, vp, u32]
+    L.osmr_set_label_styles.restype = C.c_int
+    L.osmr_set_label_styles.argtypes = [vp, vp, u32, C.c_char_p, sz]
+    L.osmr_draw_tiles_labeled.restype = C.c_int
+    L.osmr_draw_tiles_labeled.argtypes = [vp, vp, u32, vp, vp, vp, vp, vp, u32, vp]
     _lib = L
     return L

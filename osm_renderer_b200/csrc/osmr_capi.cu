@@ -13,6 +13,7 @@
 
 #include "osmr.h"
 #include "osmr_kernels.cuh"
+#include "osmr_labels_host.hpp"
 
 using namespace osmr;
 
@@ -59,6 +60,21 @@ struct osmr_ctx {
     DevBuf<uint2> ways, polys, mps;
     DevBuf<unsigned> ints;
     std::vector<unsigned> h_way_len, h_mp_pts;  // node counts per entity (host copy, for scratch sizing)
+    // label pass (host half: osmr_labels_host.hpp)
+    std::vector<uint8_t> h_bin;  // host copy of the geodata image: tags and coordinates for label layout
+    osmr_host::BinView h_view;
+    osmr_host::TrueType font;
+    std::vector<osmr_host::LabelStyleHost> label_styles;
+    std::vector<osmr_host::IconDim> label_icon_dims;
+    DevBuf<DevIcon> label_icons;
+    DevBuf<double4> label_icon_px;
+    DevBuf<DevLabel> d_labels;
+    DevBuf<DevSeg> d_label_segs;
+    DevBuf<unsigned> d_label_begin, label_occ;
+    DevBuf<double> label_acc;
+    DevBuf<int> label_row_keys;
+    DevBuf<LabelPix> label_plane;
+    bool label_plane_active = false;
     // styles / icons
     unsigned n_styles = 0, n_dashes = 0, n_icons = 0;
     DevBuf<osmr_style> styles;
@@ -167,6 +183,15 @@ void osmr_ctx_destroy(osmr_ctx* ctx) {
     ctx->fill_work.release();
     ctx->counters.release();
     ctx->mask.release();
+    ctx->label_icons.release();
+    ctx->label_icon_px.release();
+    ctx->d_labels.release();
+    ctx->d_label_segs.release();
+    ctx->d_label_begin.release();
+    ctx->label_occ.release();
+    ctx->label_acc.release();
+    ctx->label_row_keys.release();
+    ctx->label_plane.release();
     ctx->geom.release();
     ctx->calc_table.release();
     ctx->out.release();
@@ -269,6 +294,8 @@ int osmr_set_geodata(osmr_ctx* ctx, const void* bin, size_t len) {
     }
     CK(cudaStreamSynchronize(ctx->stream));
     raw_nodes.release();
+    ctx->h_bin.assign(p, p + len);
+    if (!ctx->h_view.parse(ctx->h_bin.data(), ctx->h_bin.size())) return ctx->fail(OSMR_E_INVALID, "geodata image truncated");
     ctx->n_nodes = n_nodes;
     ctx->n_ways = n_ways;
     ctx->n_polys = n_polys;
@@ -473,6 +500,8 @@ static int run_pipeline(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t fla
         s.mask_cap = (unsigned)std::min<size_t>(ctx->mask_cap_words, 0xffffffffu);
         s.counters = ctx->counters.p;
         s.fill_cap = ctx->fill_cap;
+        s.label_plane = ctx->label_plane_active ? ctx->label_plane.p + (size_t)tb * D * D : nullptr;
+        s.label_icon_px = ctx->label_icon_px.p;
         s.out = dev_out;
 
         cudaStream_t st = ctx->stream;
@@ -619,6 +648,137 @@ int osmr_project_nodes(osmr_ctx* ctx, const osmr_tile* tile, int32_t* out_xy) {
     CK(cudaStreamSynchronize(ctx->stream));
     tmp.release();
     return OSMR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// label pass
+// ---------------------------------------------------------------------------------------------------------
+int osmr_set_font(osmr_ctx* ctx, const void* ttf, size_t len) {
+    if (!ctx) return OSMR_E_INVALID;
+    if (!ttf || len < 64) return ctx->fail(OSMR_E_INVALID, "null or truncated font");
+    if (!ctx->font.load((const uint8_t*)ttf, len)) return ctx->fail(OSMR_E_INVALID, "not a TrueType font with a Unicode cmap and glyf outlines");
+    return OSMR_OK;
+}
+
+int osmr_set_label_icons(osmr_ctx* ctx, const osmr_icon* icons, uint32_t n_icons) {
+    if (!ctx) return OSMR_E_INVALID;
+    if (n_icons && !icons) return ctx->fail(OSMR_E_INVALID, "null icon table");
+    cudaSetDevice(ctx->device);
+    std::vector<DevIcon> meta(n_icons);
+    std::vector<double4> px;
+    ctx->label_icon_dims.assign(n_icons, osmr_host::IconDim{0, 0});
+    for (uint32_t i = 0; i < n_icons; ++i) {
+        if (!icons[i].rgba || icons[i].width == 0 || icons[i].height == 0) return ctx->fail(OSMR_E_INVALID, "empty icon");
+        meta[i].w = icons[i].width;
+        meta[i].h = icons[i].height;
+        meta[i].off = (unsigned)px.size();
+        meta[i].pad = 0;
+        ctx->label_icon_dims[i] = osmr_host::IconDim{icons[i].width, icons[i].height};
+        size_t n = (size_t)icons[i].width * icons[i].height;
+        for (size_t k = 0; k < n; ++k) {  // RgbaColor::from_components (tile_pixels.rs:24-26)
+            const uint8_t* c = icons[i].rgba + 4 * k;
+            volatile double opacity = (double)c[3] / 255.0;
+            volatile double r = (double)c[0] / 255.0, g = (double)c[1] / 255.0, b = (double)c[2] / 255.0;
+            volatile double pr = opacity * r, pg = opacity * g, pb = opacity * b;
+            double4 v;
+            v.x = pr;
+            v.y = pg;
+            v.z = pb;
+            v.w = opacity;
+            px.push_back(v);
+        }
+    }
+    if (px.size() >= 0x3fffffffu) return ctx->fail(OSMR_E_INVALID, "label icon table too large");
+    CK(ctx->label_icons.reserve(n_icons + 1));
+    CK(ctx->label_icon_px.reserve(px.size() + 1));
+    if (n_icons) CK(cudaMemcpyAsync(ctx->label_icons.p, meta.data(), n_icons * sizeof(DevIcon), cudaMemcpyHostToDevice, ctx->stream));
+    if (!px.empty()) CK(cudaMemcpyAsync(ctx->label_icon_px.p, px.data(), px.size() * sizeof(double4), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return OSMR_OK;
+}
+
+int osmr_set_label_styles(osmr_ctx* ctx, const osmr_label_style* styles, uint32_t n_styles, const char* strings, size_t strings_len) {
+    if (!ctx) return OSMR_E_INVALID;
+    if (n_styles && !styles) return ctx->fail(OSMR_E_INVALID, "null label style table");
+    std::vector<osmr_host::LabelStyleHost> tmp(n_styles);
+    for (uint32_t i = 0; i < n_styles; ++i) {
+        tmp[i].s = styles[i];
+        if (styles[i].flags & OSMR_LSTYLE_TEXT) {
+            if (!strings || (uint64_t)styles[i].text_key_off + styles[i].text_key_len > strings_len)
+                return ctx->fail(OSMR_E_INVALID, "label style text key out of range");
+            tmp[i].key.assign(strings + styles[i].text_key_off, styles[i].text_key_len);
+        }
+        if (styles[i].text_position > OSMR_TEXT_POS_LINE) return ctx->fail(OSMR_E_INVALID, "bad text position");
+    }
+    ctx->label_styles.swap(tmp);
+    return OSMR_OK;
+}
+
+int osmr_draw_tiles_labeled(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, const uint32_t* area_begin,
+                            const osmr_styled_area* areas, const uint32_t* label_begin, const osmr_label* labels,
+                            const uint8_t canvas_rgb[3], uint32_t flags, uint8_t* out) {
+    if (!ctx) return OSMR_E_INVALID;
+    if (!out) return ctx->fail(OSMR_E_INVALID, "null output buffer");
+    if (!label_begin) return ctx->fail(OSMR_E_INVALID, "null label_begin");
+    if (!ctx->font.loaded()) return ctx->fail(OSMR_E_STATE, "osmr_set_font has not been called");
+    int rc = batch_upload_impl(ctx, tiles, n_tiles, area_begin, areas, false);
+    if (rc) return rc;
+    const int D = 256 * ctx->scale, E = 3 * D;
+    // ---- host half: layout (string / font / heap work, as the reference does it on the CPU) ----
+    std::vector<osmr_host::LabelRec> recs;
+    std::vector<osmr_host::Seg> segs;
+    std::vector<unsigned> lbegin(n_tiles + 1, 0);
+    osmr_host::LayoutEnv env{&ctx->h_view, &ctx->font, &ctx->label_styles, &ctx->label_icon_dims};
+    unsigned long long max_cells = 1;
+    for (uint32_t t = 0; t < n_tiles; ++t) {
+        if (label_begin[t + 1] < label_begin[t]) return ctx->fail(OSMR_E_INVALID, "label_begin must be non-decreasing");
+        uint32_t n = label_begin[t + 1] - label_begin[t];
+        if (n && !labels) return ctx->fail(OSMR_E_INVALID, "null label list");
+        size_t first = recs.size();
+        if (!osmr_host::layout_tile(env, tiles[t], labels + label_begin[t], n, recs, segs))
+            return ctx->fail(OSMR_E_INVALID, "label references an entity, style or icon that does not exist");
+        for (size_t i = first; i < recs.size(); ++i) {
+            const osmr_host::LabelRec& r = recs[i];
+            if (r.seg_count) {
+                long long rows = (long long)std::min(r.by1, 2 * D - 1) - std::max(r.by0, -D) + 1;
+                long long cols = (long long)r.bx1 - r.bx0 + 1;
+                if (rows > 0 && cols > 0) max_cells = std::max<unsigned long long>(max_cells, (unsigned long long)rows * cols);
+            }
+        }
+        lbegin[t + 1] = (unsigned)recs.size();
+    }
+    if (max_cells * 2ull * n_tiles > (1ull << 33)) return ctx->fail(OSMR_E_NOMEM, "label scratch too large; split the batch");
+    static_assert(sizeof(osmr_host::LabelRec) == sizeof(DevLabel) && sizeof(osmr_host::Seg) == sizeof(DevSeg), "label wire layout");
+    // ---- device half ----
+    cudaSetDevice(ctx->device);
+    CK(ctx->d_labels.reserve(recs.size() + 1));
+    CK(ctx->d_label_segs.reserve(segs.size() + 1));
+    CK(ctx->d_label_begin.reserve(n_tiles + 1));
+    CK(ctx->label_occ.reserve((size_t)n_tiles * ((size_t)E * E / 32)));
+    CK(ctx->label_acc.reserve((size_t)n_tiles * 2 * max_cells));
+    CK(ctx->label_row_keys.reserve((size_t)n_tiles * 2 * E));
+    CK(ctx->label_plane.reserve((size_t)n_tiles * D * D));
+    if (!recs.empty()) CK(cudaMemcpyAsync(ctx->d_labels.p, recs.data(), recs.size() * sizeof(DevLabel), cudaMemcpyHostToDevice, ctx->stream));
+    if (!segs.empty()) CK(cudaMemcpyAsync(ctx->d_label_segs.p, segs.data(), segs.size() * sizeof(DevSeg), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_label_begin.p, lbegin.data(), (n_tiles + 1) * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
+    LabelScene ls{};
+    ls.labels = ctx->d_labels.p;
+    ls.label_begin = ctx->d_label_begin.p;
+    ls.segs = ctx->d_label_segs.p;
+    ls.icons = ctx->label_icons.p;
+    ls.occ = ctx->label_occ.p;
+    ls.acc = ctx->label_acc.p;
+    ls.row_keys = ctx->label_row_keys.p;
+    ls.plane = ctx->label_plane.p;
+    ls.cells = max_cells;
+    ls.D = D;
+    label_kernel<<<n_tiles, kLabelThreads, 0, ctx->stream>>>(ls);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));  // recs / segs live on this stack frame
+    ctx->label_plane_active = true;
+    rc = osmr_batch_draw(ctx, canvas_rgb, flags, out, nullptr);
+    ctx->label_plane_active = false;
+    return rc;
 }
 
 // pinned host memory for callers that want full-speed transfers (optional)

@@ -69,6 +69,14 @@ enum {
     CNT_COUNT = 16
 };
 
+// what the label pass leaves for a pixel of the centre tile: the pending pixel of the last successful label that
+// touched it (tile_pixels.rs:131-148,205-223)
+struct LabelPix {
+    double alpha;   // text: coverage `total`; icon: unused (texel alpha is in the icon table)
+    unsigned src;   // 0: none; 0x40000000 | 0xBBGGRR: text colour; 0x80000000 | texel index: icon texel
+    unsigned pad;
+};
+
 struct Scene {
     // dataset
     const double2* merc;
@@ -108,6 +116,8 @@ struct Scene {
     unsigned mask_cap;
     unsigned* counters;
     int fill_cap;          // <= kFillCap; lowered by tests to force the streaming path
+    const struct LabelPix* label_plane;  // per tile D*D entries written by label_kernel, or nullptr (no label pass)
+    const double4* label_icon_px;        // premultiplied texels of the label icons
     unsigned char* out;
 };
 
@@ -1123,6 +1133,32 @@ __global__ void __launch_bounds__(kRasterThreads, 16) raster_kernel(Scene s) {
 
     // ---- export (tile_pixels.rs:164-181): alpha == 1.0, so postdivide is the identity ----
     __syncwarp();
+    // label pass result (drawer.rs:124 blend_unfinished_pixels(true)): one more premultiplied over per labelled pixel
+    if (s.label_plane) {
+        const LabelPix* plane = s.label_plane + (size_t)tile * D * D;
+        for (int i = (int)lane; i < kBP; i += 32) {
+            const LabelPix lp = plane[(size_t)(by0 + i / kBW) * D + bx0 + i % kBW];
+            if (!lp.src) continue;
+            double c0, c1, c2, a;
+            if (lp.src & 0x80000000u) {
+                const double4 tx = s.label_icon_px[lp.src & 0x3fffffffu];
+                c0 = tx.x;
+                c1 = tx.y;
+                c2 = tx.z;
+                a = tx.w;
+            } else {  // RgbaColor::from_color(text_color, total)
+                a = lp.alpha;
+                c0 = a * unit_of_u8((unsigned char)(lp.src & 0xffu));
+                c1 = a * unit_of_u8((unsigned char)((lp.src >> 8) & 0xffu));
+                c2 = a * unit_of_u8((unsigned char)((lp.src >> 16) & 0xffu));
+            }
+            const double inv = 1.0 - a;
+            sm.canvas[0][i] = c0 + inv * sm.canvas[0][i];
+            sm.canvas[1][i] = c1 + inv * sm.canvas[1][i];
+            sm.canvas[2][i] = c2 + inv * sm.canvas[2][i];
+        }
+        __syncwarp();
+    }
     auto texel = [&](int ch, int idx) -> unsigned { return f64_as_u8(255.0 * (sm.canvas[ch][idx] / 1.0)); };
     if (s.flags & OSMR_DRAW_OUT_RGBA) {
         uchar4* out = reinterpret_cast<uchar4*>(s.out) + (size_t)tile * D * D;
@@ -1150,6 +1186,198 @@ __global__ void __launch_bounds__(kRasterThreads, 16) raster_kernel(Scene s) {
             unsigned* dst = reinterpret_cast<unsigned*>(tile_out + ((size_t)(by0 + r) * D + bx0) * 3);
             dst[j] = word;
         }
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------------
+// label_kernel (a9 + f1 + f2, device half): one CTA per tile walks the tile's labels in order.
+//   icon blit (labeler.rs:91-106) / glyph coverage (rasterizer.rs:27-84,109-148) -> collision test against the pixels of
+//   earlier successful labels over the 3x3 label canvas (tile_pixels.rs:131-148) -> commit.
+// Glyph coverage is the reference's exact-area accumulation: one thread per pixel row adds the contributions of the
+// label's segments IN SEGMENT ORDER into dense per-row `a` / `s` arrays (the reference's BTreeMaps), tracking the
+// smallest / largest touched key, then sweeps the row left to right.  Only IEEE basic operations are used; the
+// segments themselves come from the host (osmr_labels_host.hpp), where the reference's libm calls live.
+// ------------------------------------------------------------------------------------------------------
+struct DevLabel {  // == osmr_host::LabelRec
+    int icon, ix, iy;
+    unsigned seg_begin, seg_count;
+    int bx0, by0, bx1, by1;
+    unsigned rgb, pad;
+};
+struct DevSeg {
+    double x0, y0, x1, y1;
+};
+struct LabelScene {
+    const DevLabel* labels;
+    const unsigned* label_begin;  // per tile
+    const DevSeg* segs;
+    const DevIcon* icons;
+    unsigned* occ;        // per tile (3D)^2 bits
+    double* acc;          // per tile 2 * cells doubles
+    int* row_keys;        // per tile 2 * 3D ints (min key, max key per row)
+    LabelPix* plane;      // per tile D*D
+    unsigned long long cells;  // acc capacity per tile (cells)
+    int D;
+};
+constexpr int kLabelThreads = 256;
+
+__global__ void __launch_bounds__(kLabelThreads) label_kernel(LabelScene ls) {
+    __shared__ int fail;
+    const unsigned tile = blockIdx.x;
+    const int D = ls.D, E = 3 * D;
+    const unsigned occ_words = (unsigned)((size_t)E * E / 32);
+    unsigned* occ = ls.occ + (size_t)tile * occ_words;
+    LabelPix* plane = ls.plane + (size_t)tile * D * D;
+    double* acc_a = ls.acc + (size_t)tile * 2 * ls.cells;
+    double* acc_s = acc_a + ls.cells;
+    int* kmin = ls.row_keys + (size_t)tile * 2 * E;
+    int* kmax = kmin + E;
+    for (unsigned i = threadIdx.x; i < occ_words; i += kLabelThreads) occ[i] = 0u;
+    for (int i = threadIdx.x; i < D * D; i += kLabelThreads) plane[i].src = 0u;
+    __syncthreads();
+    auto in_canvas = [&](int x, int y) { return x >= -D && x <= 2 * D - 1 && y >= -D && y <= 2 * D - 1; };  // labels_bb
+    auto occ_index = [&](int x, int y) { return (size_t)(y + D) * E + (size_t)(x + D); };
+
+    for (unsigned li = ls.label_begin[tile]; li < ls.label_begin[tile + 1]; ++li) {
+        const DevLabel L = ls.labels[li];
+        if (threadIdx.x == 0) fail = 0;
+        __syncthreads();
+        int iw = 0, ih = 0;
+        if (L.icon >= 0) {  // labeler.rs:94-103: every texel (transparent ones too) claims its pixel
+            iw = (int)ls.icons[L.icon].w;
+            ih = (int)ls.icons[L.icon].h;
+            for (int p = threadIdx.x; p < iw * ih; p += kLabelThreads) {
+                int x = wadd(L.ix, p / ih), y = wadd(L.iy, p % ih);
+                if (in_canvas(x, y)) {
+                    size_t b = occ_index(x, y);
+                    if (occ[b >> 5] & (1u << (b & 31))) fail = 1;
+                }
+            }
+        }
+        __syncthreads();
+        const bool has_text = L.seg_count != 0 && !fail;  // a failed icon fails the label before the text is tried
+        const int W = L.bx1 - L.bx0 + 1;
+        // rows outside the label canvas cannot collide or draw; columns must stay complete (the sweep is a prefix sum)
+        const int ry0 = max(L.by0, -D), ry1 = min(L.by1, 2 * D - 1);
+        const int R = ry1 - ry0 + 1;
+        if (has_text && R > 0 && W > 0) {
+            for (size_t c = threadIdx.x; c < (size_t)R * W; c += kLabelThreads) {
+                acc_a[c] = 0.0;
+                acc_s[c] = 0.0;
+            }
+            for (int r = threadIdx.x; r < R; r += kLabelThreads) {
+                kmin[r] = 0x7fffffff;
+                kmax[r] = (int)0x80000000;
+            }
+            __syncthreads();
+            for (int r = threadIdx.x; r < R; r += kLabelThreads) {
+                const int y = ry0 + r;
+                double* a = acc_a + (size_t)r * W;
+                double* sacc = acc_s + (size_t)r * W;
+                int lo = 0x7fffffff, hi = (int)0x80000000;
+                for (unsigned k = 0; k < L.seg_count; ++k) {  // Rasterizer::draw_line for this stripe (rasterizer.rs:27-84)
+                    const DevSeg sg = ls.segs[L.seg_begin + k];
+                    const double delta = sg.y1 - sg.y0;
+                    const double y_min = fmin(sg.y0, sg.y1), y_max = fmax(sg.y0, sg.y1);
+                    if (y < f64_as_i32(floor(y_min)) || y > f64_as_i32(floor(y_max))) continue;
+                    const double sign = (sg.y0 <= sg.y1) ? 1.0 : -1.0;
+                    const double slope = (sg.x1 - sg.x0) / delta;
+                    const double rslope = 1.0 / slope;
+                    const double y_bottom = fmax((double)y, y_min);
+                    const double y_top = fmin((double)(y + 1), y_max);
+                    const double y_delta = y_top - y_bottom;
+                    const double x_at_bottom = sg.x0 + (y_bottom - sg.y0) * slope;
+                    const double x_at_top = sg.x0 + (y_top - sg.y0) * slope;
+                    const bool flip = !(x_at_bottom <= x_at_top);
+                    const double x_smallest = flip ? x_at_top : x_at_bottom;
+                    const double x_largest = flip ? x_at_bottom : x_at_top;
+                    const int x_to = f64_as_i32(floor(x_largest));
+                    for (int x = f64_as_i32(floor(x_smallest)); x <= x_to; ++x) {
+                        const double x_left = fmax((double)x, x_smallest);
+                        const double x_next = (double)(x + 1);
+                        const double x_right = fmin(x_next, x_largest);
+                        double pixel_area = (x_next - x_right) * y_delta;
+                        const double tw = x_right - x_left;
+                        if (tw > 0.0) {
+                            const double y_at_left = sg.y0 + (x_left - sg.x0) * rslope;
+                            const double y_at_right = sg.y0 + (x_right - sg.x0) * rslope;
+                            const double th = flip ? (y_top - y_at_left) + (y_top - y_at_right)
+                                                   : (y_at_left - y_bottom) + (y_at_right - y_bottom);
+                            pixel_area += tw * th / 2.0;
+                        }
+                        const int cx = x - L.bx0;
+                        if (cx >= 0 && cx < W) a[cx] += sign * pixel_area;
+                        lo = min(lo, x);
+                        hi = max(hi, x);
+                    }
+                    const int cs = x_to + 1 - L.bx0;
+                    if (cs >= 0 && cs < W) sacc[cs] += sign * y_delta;
+                    lo = min(lo, x_to + 1);
+                    hi = max(hi, x_to + 1);
+                }
+                // save_to_figure for this stripe (rasterizer.rs:109-148): sweep the touched key range left to right
+                kmin[r] = lo;
+                kmax[r] = hi;
+                if (lo <= hi) {
+                    double run = 0.0;
+                    for (int x = lo; x <= hi; ++x) {
+                        const int c = x - L.bx0;
+                        const bool inside = c >= 0 && c < W;  // the host bbox covers every key; defensive
+                        run += inside ? sacc[c] : 0.0;
+                        const double total = fmin((inside ? a[c] : 0.0) + run, 1.0);
+                        if (inside) a[c] = total;
+                        if (total > 0.0 && in_canvas(x, y)) {
+                            size_t b = occ_index(x, y);
+                            if (occ[b >> 5] & (1u << (b & 31))) fail = 1;
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (!fail) {  // bump_label_generation(true): the label's pixels become final
+            if (L.icon >= 0) {
+                const unsigned tex0 = ls.icons[L.icon].off;
+                for (int p = threadIdx.x; p < iw * ih; p += kLabelThreads) {
+                    int xo = p / ih, yo = p % ih;
+                    int x = wadd(L.ix, xo), y = wadd(L.iy, yo);
+                    if (!in_canvas(x, y)) continue;
+                    size_t b = occ_index(x, y);
+                    atomicOr(&occ[b >> 5], 1u << (b & 31));
+                    if (x >= 0 && x < D && y >= 0 && y < D) {
+                        LabelPix px;
+                        px.alpha = 0.0;
+                        px.src = 0x80000000u | (tex0 + (unsigned)(yo * iw + xo));
+                        px.pad = 0;
+                        plane[(size_t)y * D + x] = px;
+                    }
+                }
+            }
+            __syncthreads();  // text pixels overwrite icon pixels of the same label (later set_label_pixel wins)
+            if (has_text && R > 0 && W > 0) {
+                for (int r = threadIdx.x; r < R; r += kLabelThreads) {
+                    const int y = ry0 + r;
+                    const double* a = acc_a + (size_t)r * W;
+                    for (int x = kmin[r]; x <= kmax[r]; ++x) {
+                        const int c = x - L.bx0;
+                        if (c < 0 || c >= W) continue;
+                        const double total = a[c];
+                        if (!(total > 0.0) || !in_canvas(x, y)) continue;
+                        size_t b = occ_index(x, y);
+                        atomicOr(&occ[b >> 5], 1u << (b & 31));
+                        if (x >= 0 && x < D && y >= 0 && y < D) {
+                            LabelPix px;
+                            px.alpha = total;
+                            px.src = 0x40000000u | (L.rgb & 0xffffffu);
+                            px.pad = 0;
+                            plane[(size_t)y * D + x] = px;
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
     }
 }
 

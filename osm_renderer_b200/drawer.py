@@ -166,6 +166,38 @@ class GpuContext:
         self._check(self.L.osmr_project_nodes(self.h, t.ctypes.data, out.ctypes.data), "osmr_project_nodes")
         return out
 
+    # ---- label pass ---------------------------------------------------------------------------------------------
+    def set_font(self, ttf: bytes):
+        buf = np.frombuffer(ttf, dtype=np.uint8)
+        self._check(self.L.osmr_set_font(self.h, buf.ctypes.data, len(ttf)), "osmr_set_font")
+
+    def set_label_table(self, ltable):
+        icons, keep = ltable.icon_structs()
+        self._check(self.L.osmr_set_label_icons(self.h, C.addressof(icons), len(ltable.icons)), "osmr_set_label_icons")
+        styles = ltable.styles_array()
+        blob = bytes(ltable.strings)
+        self._check(self.L.osmr_set_label_styles(self.h, styles.ctypes.data, len(styles), blob, len(blob)), "osmr_set_label_styles")
+
+    def draw_tiles_labeled(self, tiles, area_begin, areas, label_begin, labels, canvas_rgb, use_caps_for_dashes=True, rgba=False):
+        """osmr_draw_tiles_labeled: area passes + label pass, host buffers."""
+        from .wire import LABEL_DTYPE
+
+        tiles = np.ascontiguousarray(tiles, dtype=TILE_DTYPE)
+        area_begin = np.ascontiguousarray(area_begin, dtype=np.uint32)
+        areas = np.ascontiguousarray(areas, dtype=AREA_DTYPE)
+        label_begin = np.ascontiguousarray(label_begin, dtype=np.uint32)
+        labels = np.ascontiguousarray(labels, dtype=LABEL_DTYPE)
+        n = len(tiles)
+        d = 256 * int(tiles["scale"][0])
+        out = np.empty((n, d, d, 4 if rgba else 3), dtype=np.uint8)
+        flags, canvas = self._flags(canvas_rgb, use_caps_for_dashes, rgba)
+        self._check(
+            self.L.osmr_draw_tiles_labeled(self.h, tiles.ctypes.data, n, area_begin.ctypes.data, areas.ctypes.data,
+                                           label_begin.ctypes.data, labels.ctypes.data, canvas.ctypes.data, flags, out.ctypes.data),
+            "osmr_draw_tiles_labeled",
+        )
+        return out
+
     def debug_set(self, key: str, value: int):
         self._check(self.L.osmr_debug_set(self.h, key.encode(), value), "osmr_debug_set")
 

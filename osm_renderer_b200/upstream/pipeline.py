@@ -246,6 +246,22 @@ class LabelListBuilder:
             self._node_ent[n] = e
         return e
 
+    def labels_abi(self, zoom, x, y, ltable):
+        """The same label generations as `labels`, as osmr_label records (entity, label-style index) for the C ABI."""
+        from ..wire import LABEL_DTYPE, OSMR_AREA_MULTIPOLYGON, OSMR_LABEL_NODE
+        from .styler import KIND_MULTIPOLYGON, KIND_NODE
+
+        ts = self.ts
+        nodes, _, _ = ts.reader.get_entities_in_tile_with_neighbors(zoom, x, y)
+        styled = ts.styled_areas(zoom, x, y, for_labels=True)
+        styled_nodes = ts.styler.style_entities([self.node_entity(int(n)) for n in nodes], zoom, True)
+        seq = list(styled) + list(styled_nodes)
+        out = np.empty(len(seq), dtype=LABEL_DTYPE)
+        for i, (ent, s) in enumerate(seq):
+            flag = OSMR_LABEL_NODE if ent[0] == KIND_NODE else (OSMR_AREA_MULTIPOLYGON if ent[0] == KIND_MULTIPOLYGON else 0)
+            out[i] = (ent[1] | flag, ltable.style_id(s))
+        return out
+
     def labels(self, zoom, x, y):
         from .styler import KIND_MULTIPOLYGON, KIND_NODE
 

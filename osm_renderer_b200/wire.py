@@ -56,6 +56,21 @@ assert STYLE_DTYPE.itemsize == 72, STYLE_DTYPE.itemsize
 
 AREA_DTYPE = np.dtype([("entity", "<u4"), ("style", "<u4")])
 
+# label pass (include/osmr.h: osmr_label_style, osmr_label)
+OSMR_LABEL_NODE = 0x40000000
+OSMR_LSTYLE_TEXT = 1 << 0
+OSMR_LSTYLE_FONT_SIZE = 1 << 1
+OSMR_LSTYLE_TEXT_COLOR = 1 << 2
+LABEL_STYLE_DTYPE = np.dtype(
+    [
+        ("icon", "<i4"), ("flags", "<u4"), ("text_key_off", "<u4"), ("text_key_len", "<u4"),
+        ("text_color", "u1", (3,)), ("text_position", "u1"), ("reserved0", "<u4"), ("font_size", "<f8"),
+    ],
+    align=True,
+)
+assert LABEL_STYLE_DTYPE.itemsize == 32, LABEL_STYLE_DTYPE.itemsize
+LABEL_DTYPE = np.dtype([("entity", "<u4"), ("style", "<u4")])
+
 
 class IconStruct(C.Structure):
     _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("rgba", C.c_void_p)]
@@ -230,3 +245,74 @@ def styled_areas_to_array(styled, table: StyleTable) -> np.ndarray:
         e = ent[1] | (OSMR_AREA_MULTIPOLYGON if ent[0] == KIND_MULTIPOLYGON else 0)
         out[i] = (e, table.style_id(s))
     return out
+
+
+class LabelStyleTable:
+    """Interns styler.Style objects into the label-style table of osmr_set_label_styles and icon names into the label
+    icon table of osmr_set_label_icons (reference IconCache for `icon-image`, labeler.rs:46-50)."""
+
+    def __init__(self, icon_base_path: str | None = None):
+        self.icon_base_path = icon_base_path
+        self._ids: dict[int, int] = {}
+        self._keep: list = []
+        self.rows: list = []
+        self.strings = bytearray()
+        self._key_off: dict[str, tuple] = {}
+        self._icon_ids: dict[str, int] = {}
+        self.icons: list = []
+
+    def icon_id(self, name) -> int:
+        if name is None:
+            return -2
+        i = self._icon_ids.get(name)
+        if i is None:
+            ic = load_icon_rgba(os.path.join(self.icon_base_path, name)) if self.icon_base_path else None
+            i = -1
+            if ic is not None:
+                i = len(self.icons)
+                self.icons.append(ic)
+            self._icon_ids[name] = i
+        return i
+
+    def style_id(self, s) -> int:
+        k = id(s)
+        i = self._ids.get(k)
+        if i is not None:
+            return i
+        row = np.zeros((), dtype=LABEL_STYLE_DTYPE)
+        row["icon"] = self.icon_id(s.icon_image)
+        ts = s.text_style
+        flags = 0
+        if ts is not None:
+            flags |= OSMR_LSTYLE_TEXT
+            ko = self._key_off.get(ts.text)
+            if ko is None:
+                b = ts.text.encode("utf-8")
+                ko = (len(self.strings), len(b))
+                self.strings += b
+                self._key_off[ts.text] = ko
+            row["text_key_off"], row["text_key_len"] = ko
+            if ts.font_size is not None:
+                flags |= OSMR_LSTYLE_FONT_SIZE
+                row["font_size"] = ts.font_size
+            if ts.text_color is not None:
+                flags |= OSMR_LSTYLE_TEXT_COLOR
+                row["text_color"] = ts.text_color
+            row["text_position"] = 0 if ts.text_position is None else (1 if ts.text_position == "center" else 2)
+        row["flags"] = flags
+        i = len(self.rows)
+        self.rows.append(row)
+        self._ids[k] = i
+        self._keep.append(s)
+        return i
+
+    def styles_array(self) -> np.ndarray:
+        return np.array(self.rows, dtype=LABEL_STYLE_DTYPE) if self.rows else np.zeros(0, dtype=LABEL_STYLE_DTYPE)
+
+    def icon_structs(self):
+        arr = (IconStruct * max(1, len(self.icons)))()
+        for i, (w, h, px) in enumerate(self.icons):
+            arr[i].width = w
+            arr[i].height = h
+            arr[i].rgba = px.ctypes.data
+        return arr, list(self.icons)

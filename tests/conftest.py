@@ -34,6 +34,26 @@ class FixtureInputs:
             self.table.add_raw_icon(f"icon_{i}", z[f"icon_{i}"])
         self.batches = {n: (z[f"tiles_{n}"], z[f"area_begin_{n}"], z[f"areas_{n}"]) for n in CONFIG_NAMES}
 
+    def labels(self):
+        """tests/golden/label_inputs.npz -> (LabelStyleTable, font bytes, {config: (label_begin, labels)})"""
+        from osm_renderer_b200.wire import LabelStyleTable
+
+        if getattr(self, "_labels", None) is None:
+            z = np.load(os.path.join(GOLDEN, "label_inputs.npz"))
+            lt = LabelStyleTable(None)
+            lt.rows = list(z["label_styles"])
+            lt.strings = bytearray(z["label_strings"].tobytes())
+            lt.icons = []
+            for i in range(int(z["n_label_icons"])):
+                px = np.ascontiguousarray(z[f"label_icon_{i}"])
+                lt.icons.append((px.shape[1], px.shape[0], px))
+            per = {}
+            for n in CONFIG_NAMES:
+                src = "18" if n == "18_2x" else n
+                per[n] = (z[f"label_begin_{src}"], z[f"labels_{src}"])
+            self._labels = (lt, z["font"].tobytes(), per)
+        return self._labels
+
     def golden(self, name):
         g = np.load(os.path.join(GOLDEN, f"golden_{name}.npz"))
         d = int(g["dim"])

@@ -1,0 +1,46 @@
+"""-m gpu: the whole Drawer::draw_to_pixels on the GPU path -- area passes AND label pass (icons, text, greedy
+collisions) -- against the REFERENCE'S OWN golden renders, every pixel, no oracle in between
+(tests/test_rendering.rs:46-51,147-176: exact RGB; only the red test grid of :109-114 is excluded)."""
+import numpy as np
+import pytest
+
+from conftest import CONFIG_NAMES
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def label_ctx(fx):
+    from osm_renderer_b200.drawer import GpuContext
+
+    ltable, font, per = fx.labels()
+    ctx = GpuContext(0)
+    ctx.set_geodata(fx.bin)
+    ctx.set_table(fx.table)
+    ctx.set_font(font)
+    ctx.set_label_table(ltable)
+    yield ctx, per
+    ctx.close()
+
+
+@pytest.mark.parametrize("name", CONFIG_NAMES)
+def test_full_tiles_equal_reference_golden_on_every_pixel(fx, label_ctx, name):
+    ctx, per = label_ctx
+    tiles, begins, areas = fx.batches[name]
+    label_begin, labels = per[name]
+    got = ctx.draw_tiles_labeled(tiles, begins, areas, label_begin, labels, fx.canvas_rgb, fx.use_caps_for_dashes)
+    golden, _ = fx.golden(name)
+    d = golden.shape[1]
+    grid = np.zeros((d, d), dtype=bool)
+    grid[0, :] = True
+    grid[:, d - 1] = True
+    diff = (got != golden).any(axis=-1) & ~grid[None]
+    assert diff.sum() == 0, f"{name}: {diff.sum()} pixels differ from the reference golden in tiles {sorted(set(np.argwhere(diff)[:, 0].tolist()))[:10]}"
+
+
+def test_label_pass_without_labels_equals_area_passes(fx, label_ctx):
+    ctx, per = label_ctx
+    tiles, begins, areas = fx.batches["16"]
+    plain = ctx.draw_tiles(tiles, begins, areas, fx.canvas_rgb, True)
+    empty = ctx.draw_tiles_labeled(tiles, begins, areas, np.zeros(len(tiles) + 1, dtype=np.uint32), per["16"][1][:0], fx.canvas_rgb, True)
+    assert (plain == empty).all()

@@ -7,6 +7,7 @@ Outputs (committed, travel to the GPU box where /root/reference does not exist):
   tests/golden/nano_moscow.bin        geodata image written by the restated importer (saver.rs format)
   tests/golden/fixture_inputs.npz     style table, dashes, icons, canvas colour, per-config tile lists and
                                       ordered styled-area lists (the styler output = C-ABI input)
+  tests/golden/label_inputs.npz       label generations per tile, label-style table, label icons, font bytes (GPU label tests)
   tests/golden/*_rules.json.gz        parsed rule lists of tests/mapcss/mapnik.mapcss and mapcss/osmosnimki-minimal.mapcss
   tests/golden/golden_<cfg>.npz       reference golden pixels per tile + `label_mask`: pixels the reference's
                                       label pass (drawer.rs:106-126, not restated yet) or the red test grid
@@ -26,7 +27,7 @@ sys.path.insert(0, ROOT)
 
 import oracle  # noqa: E402
 from osm_renderer_b200.upstream import geodata, mapcss, pipeline, styler as st  # noqa: E402
-from osm_renderer_b200.wire import StyleTable  # noqa: E402
+from osm_renderer_b200.wire import LABEL_DTYPE, LabelStyleTable, StyleTable  # noqa: E402
 
 REF = "/root/reference"
 OUT = os.path.join(ROOT, "tests", "golden")
@@ -77,6 +78,31 @@ def main():
         save[f"area_begin_{name}"] = begins
         save[f"areas_{name}"] = areas
     np.savez_compressed(os.path.join(OUT, "fixture_inputs.npz"), **save)
+
+    # label pass inputs for the GPU tests: label generations per tile (styler order), label-style table, label icons
+    # and the font the reference embeds (src/draw/font/NotoSans-Regular.ttf, SIL OFL; stored as a byte array)
+    ltable = LabelStyleTable(os.path.join(REF, "tests/mapcss"))
+    lb = pipeline.LabelListBuilder(ts, os.path.join(REF, "tests/mapcss"))
+    lsave = {}
+    for name, (z, x0, x1, y0, y1, s) in CONFIGS.items():
+        if name == "18_2x":
+            continue  # same labels as "18"
+        parts, lbeg = [], [0]
+        for y in range(y0, y1 + 1):
+            for x in range(x0, x1 + 1):
+                parts.append(lb.labels_abi(z, x, y, ltable))
+                lbeg.append(lbeg[-1] + len(parts[-1]))
+        lsave[f"labels_{name}"] = np.concatenate(parts) if parts else np.zeros(0, dtype=LABEL_DTYPE)
+        lsave[f"label_begin_{name}"] = np.asarray(lbeg, dtype=np.uint32)
+    lsave["label_styles"] = ltable.styles_array()
+    lsave["label_strings"] = np.frombuffer(bytes(ltable.strings), dtype=np.uint8)
+    lsave["n_label_icons"] = np.asarray(len(ltable.icons))
+    for i, (w, h, px) in enumerate(ltable.icons):
+        lsave[f"label_icon_{i}"] = px
+    with open(os.path.join(REF, "src/draw/font/NotoSans-Regular.ttf"), "rb") as f:
+        lsave["font"] = np.frombuffer(f.read(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(OUT, "label_inputs.npz"), **lsave)
+    print(f"label fixtures: {len(ltable.rows)} label styles, {len(ltable.icons)} icons")
 
     for name, (z, x0, x1, y0, y1, s) in CONFIGS.items():
         tarr, begins, areas = batches[name]
