@@ -7,9 +7,10 @@ Same names, argument meaning and error behaviour as the reference (file:line in 
     Drawer.draw_to_pixels(entities, tile, pixels, scale, styler) -> TileRenderedPixels   drawer.rs:60-131
 plus the batched extension Drawer.draw_tiles_to_pixels (many tiles per launch).
 
-Everything numeric happens in libosmr_b200.so (hand-written CUDA); this file only marshals the styler's
-output.  The label pass (drawer.rs:106-126) is not part of the accelerated path yet: like the C ABI this
-returns the tile after the area passes.
+Everything numeric happens in libosmr_b200.so (hand-written CUDA + its host C++); this file only marshals the
+styler's output.  With a font (`Drawer(base_path, font=...)`, the reference embeds NotoSans-Regular.ttf,
+text_placer.rs:299) draw_to_pixels is the complete reference call: area passes + label pass; without one it returns
+the tile after the area passes (osmr_draw_tiles).
 """
 from __future__ import annotations
 
@@ -215,20 +216,46 @@ class TilePixels:
 
 
 class Drawer:
-    def __init__(self, base_path: str | None):
-        self.table = StyleTable(base_path)  # icon cache + interned styles
+    def __init__(self, base_path: str | None, font: bytes | None = None, icon_loader=None):
+        from .wire import LabelStyleTable
+
+        self.table = StyleTable(base_path, icon_loader)  # icon cache (fill patterns) + interned styles
+        self.ltable = LabelStyleTable(base_path, icon_loader)  # icon cache (label icons) + interned label styles
+        self.font = font
+        self._n_lstyles = -1
+
+    def _builders(self, reader, styler):
+        from .upstream.pipeline import LabelListBuilder, TileStyler
+
+        ts = getattr(reader, "_tile_styler", None)
+        if ts is None or ts.styler is not styler or ts.table is not self.table:
+            ts = TileStyler(reader, styler, self.table)
+            reader._tile_styler = ts
+            reader._label_builder = LabelListBuilder(ts, None)
+        return ts, reader._label_builder
 
     def _areas_for(self, entities: OsmEntities, tile: Tile, styler):
-        from .upstream.pipeline import TileStyler
-
-        ts = getattr(entities.reader, "_tile_styler", None)
-        if ts is None or ts.styler is not styler or ts.table is not self.table:
-            ts = TileStyler(entities.reader, styler, self.table)
-            entities.reader._tile_styler = ts
+        ts, _ = self._builders(entities.reader, styler)
         way_ents = [ts.way_entity(int(w)) for w in entities.ways]
         mp_ents = [ts.mp_entity(int(m)) for m in entities.multipolygons]
         styled = styler.style_areas(way_ents, mp_ents, tile.zoom, False)  # drawer.rs:75-78
         return styled_areas_to_array(styled, self.table)
+
+    def _labels_for(self, entities: OsmEntities, tile: Tile, styler):
+        """drawer.rs:106-119: areas styled for labels, then nodes, as osmr_label records."""
+        from .upstream.styler import KIND_MULTIPOLYGON, KIND_NODE
+        from .wire import LABEL_DTYPE, OSMR_AREA_MULTIPOLYGON, OSMR_LABEL_NODE
+
+        ts, lb = self._builders(entities.reader, styler)
+        way_ents = [ts.way_entity(int(w)) for w in entities.ways]
+        mp_ents = [ts.mp_entity(int(m)) for m in entities.multipolygons]
+        seq = list(styler.style_areas(way_ents, mp_ents, tile.zoom, True))
+        seq += list(styler.style_entities([lb.node_entity(int(n)) for n in entities.nodes], tile.zoom, True))
+        out = np.empty(len(seq), dtype=LABEL_DTYPE)
+        for i, (ent, s) in enumerate(seq):
+            flag = OSMR_LABEL_NODE if ent[0] == KIND_NODE else (OSMR_AREA_MULTIPOLYGON if ent[0] == KIND_MULTIPOLYGON else 0)
+            out[i] = (ent[1] | flag, self.ltable.style_id(s))
+        return out
 
     def draw_to_pixels(self, entities: OsmEntities, tile: Tile, pixels: TilePixels, scale: int, styler) -> TileRenderedPixels:
         out = self.draw_tiles_to_pixels([entities], [tile], pixels, scale, styler)
@@ -248,6 +275,19 @@ class Drawer:
         begins[1:] = np.cumsum([len(p) for p in parts])
         areas = np.concatenate(parts) if parts else np.zeros(0, dtype=AREA_DTYPE)
         tarr = np.array([(t.zoom, t.x, t.y, scale) for t in tiles], dtype=TILE_DTYPE)
-        img = ctx.draw_tiles(tarr, begins, areas, styler.canvas_fill_color, styler.use_caps_for_dashes)
+        if self.font is None:
+            img = ctx.draw_tiles(tarr, begins, areas, styler.canvas_fill_color, styler.use_caps_for_dashes)
+        else:
+            lparts = [self._labels_for(e, t, styler) for e, t in zip(entities_list, tiles)]
+            lbegins = np.zeros(len(lparts) + 1, dtype=np.uint32)
+            lbegins[1:] = np.cumsum([len(p) for p in lparts])
+            labels = np.concatenate(lparts)
+            if not getattr(ctx, "_font_set", False):
+                ctx.set_font(self.font)
+                ctx._font_set = True
+            if len(self.ltable.rows) != self._n_lstyles:
+                ctx.set_label_table(self.ltable)
+                self._n_lstyles = len(self.ltable.rows)
+            img = ctx.draw_tiles_labeled(tarr, begins, areas, lbegins, labels, styler.canvas_fill_color, styler.use_caps_for_dashes)
         d = 256 * scale
         return [TileRenderedPixels(img[i], d) for i in range(len(tiles))]

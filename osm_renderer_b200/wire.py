@@ -136,8 +136,10 @@ class StyleTable:
     icon names into the icon table of osmr_set_icons (reference IconCache, src/draw/icon_cache.rs:21-45:
     lazily loaded relative to the stylesheet directory, failures cached as None)."""
 
-    def __init__(self, icon_base_path: str | None = None):
+    def __init__(self, icon_base_path: str | None = None, icon_loader=None):
         self.icon_base_path = icon_base_path
+        self.icon_loader = icon_loader  # optional: name -> (w, h, rgba) | None, instead of reading files
+        self.icon_names: list = []
         self._style_ids: dict[int, int] = {}
         self._styles_keepalive: list = []
         self.rows: list = []
@@ -149,13 +151,16 @@ class StyleTable:
         i = self._icon_ids.get(name)
         if i is None:
             ic = None
-            if self.icon_base_path is not None:
+            if self.icon_loader is not None:
+                ic = self.icon_loader(name)
+            elif self.icon_base_path is not None:
                 ic = load_icon_rgba(os.path.join(self.icon_base_path, name))
             if ic is None:
                 i = -1
             else:
                 i = len(self.icons)
                 self.icons.append(ic)
+                self.icon_names.append(name)
             self._icon_ids[name] = i
         return i
 
@@ -251,8 +256,10 @@ class LabelStyleTable:
     """Interns styler.Style objects into the label-style table of osmr_set_label_styles and icon names into the label
     icon table of osmr_set_label_icons (reference IconCache for `icon-image`, labeler.rs:46-50)."""
 
-    def __init__(self, icon_base_path: str | None = None):
+    def __init__(self, icon_base_path: str | None = None, icon_loader=None):
         self.icon_base_path = icon_base_path
+        self.icon_loader = icon_loader
+        self.icon_names: list = []
         self._ids: dict[int, int] = {}
         self._keep: list = []
         self.rows: list = []
@@ -266,11 +273,15 @@ class LabelStyleTable:
             return -2
         i = self._icon_ids.get(name)
         if i is None:
-            ic = load_icon_rgba(os.path.join(self.icon_base_path, name)) if self.icon_base_path else None
+            if self.icon_loader is not None:
+                ic = self.icon_loader(name)
+            else:
+                ic = load_icon_rgba(os.path.join(self.icon_base_path, name)) if self.icon_base_path else None
             i = -1
             if ic is not None:
                 i = len(self.icons)
                 self.icons.append(ic)
+                self.icon_names.append(name)
             self._icon_ids[name] = i
         return i
 

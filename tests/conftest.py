@@ -54,6 +54,20 @@ class FixtureInputs:
             self._labels = (lt, z["font"].tobytes(), per)
         return self._labels
 
+    def icon_loader(self):
+        """name -> (w, h, rgba) from the committed fixtures (fill patterns + label icons); None for unknown names,
+        which is what a failed Icon::load looks like."""
+        z = np.load(os.path.join(GOLDEN, "fixture_inputs.npz"))
+        lz = np.load(os.path.join(GOLDEN, "label_inputs.npz"))
+        icons = {}
+        for i, n in enumerate(z["icon_names"]):
+            px = np.ascontiguousarray(z[f"icon_{i}"])
+            icons[str(n)] = (px.shape[1], px.shape[0], px)
+        for i, n in enumerate(lz["label_icon_names"]):
+            px = np.ascontiguousarray(lz[f"label_icon_{i}"])
+            icons[str(n)] = (px.shape[1], px.shape[0], px)
+        return lambda name: icons.get(name)
+
     def golden(self, name):
         g = np.load(os.path.join(GOLDEN, f"golden_{name}.npz"))
         d = int(g["dim"])

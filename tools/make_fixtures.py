@@ -73,6 +73,7 @@ def main():
     }
     for i, (w, h, px) in enumerate(table.icons):
         save[f"icon_{i}"] = px
+    save["icon_names"] = np.array(table.icon_names)
     for name, (tarr, begins, areas) in batches.items():
         save[f"tiles_{name}"] = tarr
         save[f"area_begin_{name}"] = begins
@@ -99,6 +100,7 @@ def main():
     lsave["n_label_icons"] = np.asarray(len(ltable.icons))
     for i, (w, h, px) in enumerate(ltable.icons):
         lsave[f"label_icon_{i}"] = px
+    lsave["label_icon_names"] = np.array(ltable.icon_names)
     with open(os.path.join(REF, "src/draw/font/NotoSans-Regular.ttf"), "rb") as f:
         lsave["font"] = np.frombuffer(f.read(), dtype=np.uint8)
     np.savez_compressed(os.path.join(OUT, "label_inputs.npz"), **lsave)
