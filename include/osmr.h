@@ -155,6 +155,9 @@ typedef struct osmr_stats {
     float ms_plan;           /* per-stage device times of the last draw (CUDA events) */
     float ms_raster;
     float ms_total;
+    float ms_label_layout;   /* osmr_draw_tiles_labeled: host layout (wall clock) and label kernels (CUDA events) */
+    float ms_label_device;
+    float reserved;
 } osmr_stats;
 int osmr_get_stats(osmr_ctx* ctx, osmr_stats* out);
 

@@ -5,6 +5,9 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <thread>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -40,6 +43,34 @@ struct DevBuf {
     }
 };
 
+template <typename T>
+struct PinnedBuf {  // page-locked host staging, grown on demand and kept
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = n + n / 4 + 64;
+        cudaError_t e = cudaMallocHost(&p, want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct LabelWorkItem {  // a run of consecutive labels of one tile, laid out by one host thread
+    uint32_t tile, first, count;
+    std::vector<osmr_host::LabelRec> recs;
+    std::vector<osmr_host::Seg> segs;
+    size_t seg_base;
+};
+
 }  // namespace
 
 struct osmr_ctx {
@@ -73,6 +104,12 @@ struct osmr_ctx {
     DevBuf<unsigned> d_label_begin, label_occ;
     DevBuf<double> label_acc;
     DevBuf<int> label_row_keys;
+    DevBuf<DevRowRec> d_label_rows;
+    std::vector<LabelWorkItem> label_items;  // kept between calls: their vectors' capacity is the layout arena
+    PinnedBuf<osmr_host::Seg> h_label_segs;
+    cudaEvent_t ev_label0 = nullptr, ev_label1 = nullptr;
+    float stats_label_layout_ms = 0.f, stats_label_device_ms = 0.f;
+    unsigned label_threads = 32;
     DevBuf<LabelPix> label_plane;
     bool label_plane_active = false;
     // styles / icons
@@ -142,6 +179,8 @@ int osmr_ctx_create(int device, osmr_ctx** out_ctx) {
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->chunk_done[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->areas_ready, cudaEventDisableTiming);
     for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_label0);
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_label1);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) {
         double lut[256];
@@ -191,6 +230,8 @@ void osmr_ctx_destroy(osmr_ctx* ctx) {
     ctx->label_occ.release();
     ctx->label_acc.release();
     ctx->label_row_keys.release();
+    ctx->d_label_rows.release();
+    ctx->h_label_segs.release();
     ctx->label_plane.release();
     ctx->geom.release();
     ctx->calc_table.release();
@@ -200,6 +241,8 @@ void osmr_ctx_destroy(osmr_ctx* ctx) {
     for (auto& e : ctx->chunk_done)
         if (e) cudaEventDestroy(e);
     if (ctx->areas_ready) cudaEventDestroy(ctx->areas_ready);
+    if (ctx->ev_label0) cudaEventDestroy(ctx->ev_label0);
+    if (ctx->ev_label1) cudaEventDestroy(ctx->ev_label1);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -209,6 +252,11 @@ const char* osmr_last_error(const osmr_ctx* ctx) { return ctx ? ctx->err.c_str()
 
 int osmr_debug_set(osmr_ctx* ctx, const char* key, int value) {
     if (!ctx || !key) return OSMR_E_INVALID;
+    if (strcmp(key, "label_threads") == 0) {  // host threads of the label layout (1: serial)
+        if (value < 1 || value > 256) return ctx->fail(OSMR_E_INVALID, "label_threads must be 1..256");
+        ctx->label_threads = (unsigned)value;
+        return OSMR_OK;
+    }
     if (strcmp(key, "fill_cap") == 0) {
         if (value < 0 || value > kFillCap) return ctx->fail(OSMR_E_INVALID, "fill_cap out of range");
         ctx->fill_cap = value;
@@ -724,60 +772,147 @@ int osmr_draw_tiles_labeled(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_ti
     int rc = batch_upload_impl(ctx, tiles, n_tiles, area_begin, areas, false);
     if (rc) return rc;
     const int D = 256 * ctx->scale, E = 3 * D;
-    // ---- host half: layout (string / font / heap work, as the reference does it on the CPU) ----
-    std::vector<osmr_host::LabelRec> recs;
-    std::vector<osmr_host::Seg> segs;
-    std::vector<unsigned> lbegin(n_tiles + 1, 0);
-    osmr_host::LayoutEnv env{&ctx->h_view, &ctx->font, &ctx->label_styles, &ctx->label_icon_dims};
-    unsigned long long max_cells = 1;
+    // ---- host half: layout (string / font / heap work, as the reference does it on the CPU), tiles in parallel ----
+    const auto t_host0 = std::chrono::steady_clock::now();
     for (uint32_t t = 0; t < n_tiles; ++t) {
         if (label_begin[t + 1] < label_begin[t]) return ctx->fail(OSMR_E_INVALID, "label_begin must be non-decreasing");
-        uint32_t n = label_begin[t + 1] - label_begin[t];
-        if (n && !labels) return ctx->fail(OSMR_E_INVALID, "null label list");
-        size_t first = recs.size();
-        if (!osmr_host::layout_tile(env, tiles[t], labels + label_begin[t], n, recs, segs))
-            return ctx->fail(OSMR_E_INVALID, "label references an entity, style or icon that does not exist");
-        for (size_t i = first; i < recs.size(); ++i) {
-            const osmr_host::LabelRec& r = recs[i];
-            if (r.seg_count) {
-                long long rows = (long long)std::min(r.by1, 2 * D - 1) - std::max(r.by0, -D) + 1;
-                long long cols = (long long)r.bx1 - r.bx0 + 1;
-                if (rows > 0 && cols > 0) max_cells = std::max<unsigned long long>(max_cells, (unsigned long long)rows * cols);
-            }
-        }
-        lbegin[t + 1] = (unsigned)recs.size();
+        if (label_begin[t + 1] > label_begin[t] && !labels) return ctx->fail(OSMR_E_INVALID, "null label list");
     }
-    if (max_cells * 2ull * n_tiles > (1ull << 33)) return ctx->fail(OSMR_E_NOMEM, "label scratch too large; split the batch");
-    static_assert(sizeof(osmr_host::LabelRec) == sizeof(DevLabel) && sizeof(osmr_host::Seg) == sizeof(DevSeg), "label wire layout");
-    // ---- device half ----
+    osmr_host::LayoutEnv env{&ctx->h_view, &ctx->font, &ctx->label_styles, &ctx->label_icon_dims};
+    // work items: runs of <= kLabelRun consecutive labels of a tile (the layout of a label does not depend on the others)
+    constexpr uint32_t kLabelRun = 96;
+    std::vector<LabelWorkItem>& items = ctx->label_items;
+    size_t n_items = 0;
+    for (uint32_t t = 0; t < n_tiles; ++t)
+        for (uint32_t f = label_begin[t]; f < label_begin[t + 1]; f += kLabelRun) ++n_items;
+    if (items.size() < n_items) items.resize(n_items);
+    {
+        size_t k = 0;
+        for (uint32_t t = 0; t < n_tiles; ++t)
+            for (uint32_t f = label_begin[t]; f < label_begin[t + 1]; f += kLabelRun) {
+                items[k].tile = t;
+                items[k].first = f;
+                items[k].count = std::min(kLabelRun, label_begin[t + 1] - f);
+                ++k;
+            }
+    }
+    const unsigned hw = std::thread::hardware_concurrency();
+    const unsigned n_threads = (unsigned)std::max<size_t>(1, std::min<size_t>({hw ? hw : 1u, n_items, ctx->label_threads}));
+    auto run_parallel = [&](auto&& body) {  // body(item index), items handed out dynamically
+        std::atomic<size_t> next{0};
+        auto worker = [&]() {
+            for (size_t k; (k = next.fetch_add(1)) < n_items;) body(k);
+        };
+        std::vector<std::thread> pool;
+        for (unsigned i = 1; i < n_threads; ++i) pool.emplace_back(worker);
+        worker();
+        for (auto& th : pool) th.join();
+    };
+    std::atomic<bool> bad{false};
+    run_parallel([&](size_t k) {
+        LabelWorkItem& it = items[k];
+        it.recs.clear();
+        it.segs.clear();
+        if (bad.load(std::memory_order_relaxed)) return;
+        if (!osmr_host::layout_tile(env, tiles[it.tile], labels + it.first, it.count, it.recs, it.segs)) bad.store(true);
+    });
+    if (bad.load()) return ctx->fail(OSMR_E_INVALID, "label references an entity, style or icon that does not exist");
+    // batch assembly: global segment indices, coverage storage and the (label, row) work list of label_cover_kernel
+    std::vector<osmr_host::LabelRec> recs;
+    std::vector<osmr_host::RowRec> rowrecs;
+    std::vector<unsigned> lbegin(n_tiles + 1, 0);
+    unsigned long long cells = 0;
+    size_t n_segs = 0;
+    {
+        size_t nr = 0;
+        for (size_t k = 0; k < n_items; ++k) {
+            items[k].seg_base = n_segs;
+            nr += items[k].recs.size();
+            n_segs += items[k].segs.size();
+        }
+        if (n_segs >= 0xffffffffull || nr >= 0xffffffffull) return ctx->fail(OSMR_E_NOMEM, "label batch too large; split the batch");
+        recs.reserve(nr);
+    }
     cudaSetDevice(ctx->device);
+    CK(ctx->h_label_segs.reserve(n_segs + 1));
+    osmr_host::Seg* const seg_stage = ctx->h_label_segs.p;
+    run_parallel([&](size_t k) {
+        const LabelWorkItem& it = items[k];
+        if (!it.segs.empty()) memcpy(seg_stage + it.seg_base, it.segs.data(), it.segs.size() * sizeof(osmr_host::Seg));
+    });
+    for (size_t k = 0; k < n_items; ++k) {
+        const LabelWorkItem& it = items[k];
+        for (osmr_host::LabelRec r : it.recs) {
+            r.seg_begin += (unsigned)it.seg_base;
+            // rows outside the label canvas cannot collide or draw; columns stay complete (the sweep is a prefix sum)
+            r.ry0 = std::max(r.by0, -D);
+            long long rows = (long long)std::min(r.by1, 2 * D - 1) - r.ry0 + 1;
+            long long cols = (long long)r.bx1 - r.bx0 + 1;
+            const bool touches = r.seg_count && rows > 0 && cols > 0 && r.bx1 >= -D && r.bx0 <= 2 * D - 1;
+            r.rows = touches ? (int)rows : 0;
+            r.width = touches ? (int)cols : 0;
+            r.row_first = (unsigned)rowrecs.size();
+            r.cell_off = cells;
+            if (r.icon < 0 && !touches) continue;  // cannot draw, claim or collide
+            if (touches) {
+                if (cols > (1 << 20)) return ctx->fail(OSMR_E_NOMEM, "label text wider than 2^20 pixels");
+                for (int y = 0; y < r.rows; ++y) rowrecs.push_back({(unsigned)recs.size(), (unsigned)y});
+                cells += (unsigned long long)rows * cols;
+            }
+            recs.push_back(r);
+        }
+        lbegin[it.tile + 1] = (unsigned)recs.size();
+    }
+    for (uint32_t t = 0; t < n_tiles; ++t) lbegin[t + 1] = std::max(lbegin[t + 1], lbegin[t]);  // tiles without labels
+    if (cells > (1ull << 31) || rowrecs.size() >= 0x7fffffffull) return ctx->fail(OSMR_E_NOMEM, "label scratch too large; split the batch");
+    ctx->stats_label_layout_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_host0).count();
+    static_assert(sizeof(osmr_host::LabelRec) == sizeof(DevLabel) && sizeof(osmr_host::Seg) == sizeof(DevSeg) &&
+                      sizeof(osmr_host::RowRec) == sizeof(DevRowRec),
+                  "label wire layout");
+    // ---- device half ----
     CK(ctx->d_labels.reserve(recs.size() + 1));
-    CK(ctx->d_label_segs.reserve(segs.size() + 1));
+    CK(ctx->d_label_segs.reserve(n_segs + 1));
+    CK(ctx->d_label_rows.reserve(rowrecs.size() + 1));
     CK(ctx->d_label_begin.reserve(n_tiles + 1));
     CK(ctx->label_occ.reserve((size_t)n_tiles * ((size_t)E * E / 32)));
-    CK(ctx->label_acc.reserve((size_t)n_tiles * 2 * max_cells));
-    CK(ctx->label_row_keys.reserve((size_t)n_tiles * 2 * E));
+    CK(ctx->label_acc.reserve(2 * (size_t)cells + 2));
+    CK(ctx->label_row_keys.reserve(2 * rowrecs.size() + 2));
     CK(ctx->label_plane.reserve((size_t)n_tiles * D * D));
+    CK(cudaEventRecord(ctx->ev_label0, ctx->stream));
     if (!recs.empty()) CK(cudaMemcpyAsync(ctx->d_labels.p, recs.data(), recs.size() * sizeof(DevLabel), cudaMemcpyHostToDevice, ctx->stream));
-    if (!segs.empty()) CK(cudaMemcpyAsync(ctx->d_label_segs.p, segs.data(), segs.size() * sizeof(DevSeg), cudaMemcpyHostToDevice, ctx->stream));
+    if (n_segs) CK(cudaMemcpyAsync(ctx->d_label_segs.p, seg_stage, n_segs * sizeof(DevSeg), cudaMemcpyHostToDevice, ctx->stream));
+    if (!rowrecs.empty())
+        CK(cudaMemcpyAsync(ctx->d_label_rows.p, rowrecs.data(), rowrecs.size() * sizeof(DevRowRec), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_label_begin.p, lbegin.data(), (n_tiles + 1) * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
+    if (cells) CK(cudaMemsetAsync(ctx->label_acc.p, 0, 2 * (size_t)cells * sizeof(double), ctx->stream));
     LabelScene ls{};
     ls.labels = ctx->d_labels.p;
     ls.label_begin = ctx->d_label_begin.p;
     ls.segs = ctx->d_label_segs.p;
+    ls.rowrecs = ctx->d_label_rows.p;
+    ls.n_rowrecs = (unsigned)rowrecs.size();
     ls.icons = ctx->label_icons.p;
     ls.occ = ctx->label_occ.p;
-    ls.acc = ctx->label_acc.p;
-    ls.row_keys = ctx->label_row_keys.p;
+    ls.acc_a = ctx->label_acc.p;
+    ls.acc_s = ctx->label_acc.p + cells;
+    ls.kmin = ctx->label_row_keys.p;
+    ls.kmax = ctx->label_row_keys.p + rowrecs.size();
     ls.plane = ctx->label_plane.p;
-    ls.cells = max_cells;
     ls.D = D;
-    label_kernel<<<n_tiles, kLabelThreads, 0, ctx->stream>>>(ls);
+    if (ls.n_rowrecs) {
+        label_cover_kernel<<<(ls.n_rowrecs + 63) / 64, 64, 0, ctx->stream>>>(ls);
+        CK(cudaGetLastError());
+    }
+    label_commit_kernel<<<n_tiles, kLabelThreads, 0, ctx->stream>>>(ls);
     CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev_label1, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));  // recs / segs live on this stack frame
+    CK(cudaEventElapsedTime(&ctx->stats_label_device_ms, ctx->ev_label0, ctx->ev_label1));
     ctx->label_plane_active = true;
     rc = osmr_batch_draw(ctx, canvas_rgb, flags, out, nullptr);
     ctx->label_plane_active = false;
+    ctx->stats.ms_label_layout = ctx->stats_label_layout_ms;
+    ctx->stats.ms_label_device = ctx->stats_label_device_ms;
     return rc;
 }
 

@@ -1191,7 +1191,7 @@ __global__ void __launch_bounds__(kRasterThreads, 16) raster_kernel(Scene s) {
 
 
 // ------------------------------------------------------------------------------------------------------
-// label_kernel (a9 + f1 + f2, device half): one CTA per tile walks the tile's labels in order.
+// label pass, device half (a9 + f1 + f2): label_cover_kernel + label_commit_kernel.
 //   icon blit (labeler.rs:91-106) / glyph coverage (rasterizer.rs:27-84,109-148) -> collision test against the pixels of
 //   earlier successful labels over the 3x3 label canvas (tile_pixels.rs:131-148) -> commit.
 // Glyph coverage is the reference's exact-area accumulation: one thread per pixel row adds the contributions of the
@@ -1203,36 +1203,113 @@ struct DevLabel {  // == osmr_host::LabelRec
     int icon, ix, iy;
     unsigned seg_begin, seg_count;
     int bx0, by0, bx1, by1;
-    unsigned rgb, pad;
+    unsigned rgb;
+    int ry0, rows, width;
+    unsigned row_first, pad;
+    unsigned long long cell_off;
 };
 struct DevSeg {
     double x0, y0, x1, y1;
+};
+struct DevRowRec {
+    unsigned label, row;
 };
 struct LabelScene {
     const DevLabel* labels;
     const unsigned* label_begin;  // per tile
     const DevSeg* segs;
+    const DevRowRec* rowrecs;
+    unsigned n_rowrecs;
     const DevIcon* icons;
-    unsigned* occ;        // per tile (3D)^2 bits
-    double* acc;          // per tile 2 * cells doubles
-    int* row_keys;        // per tile 2 * 3D ints (min key, max key per row)
-    LabelPix* plane;      // per tile D*D
-    unsigned long long cells;  // acc capacity per tile (cells)
+    unsigned* occ;   // per tile (3D)^2 bits
+    double* acc_a;   // coverage: per label rows x width cells (`a` map, then the swept totals)
+    double* acc_s;   // the `s` map
+    int* kmin;       // per (label, row): smallest / largest touched key
+    int* kmax;
+    LabelPix* plane;  // per tile D*D
     int D;
 };
+
+// Glyph coverage of one pixel row of one label: Rasterizer::draw_line for this stripe over the label's segments in
+// order (rasterizer.rs:27-84), then the left-to-right sweep of save_to_figure (rasterizer.rs:109-148).
+__global__ void label_cover_kernel(LabelScene ls) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ls.n_rowrecs) return;
+    const DevRowRec rr = ls.rowrecs[i];
+    const DevLabel L = ls.labels[rr.label];
+    const int W = L.width;
+    const int y = L.ry0 + (int)rr.row;
+    double* a = ls.acc_a + L.cell_off + (size_t)rr.row * W;
+    double* sacc = ls.acc_s + L.cell_off + (size_t)rr.row * W;
+    int lo = 0x7fffffff, hi = (int)0x80000000;
+    for (unsigned k = 0; k < L.seg_count; ++k) {
+        const DevSeg sg = ls.segs[L.seg_begin + k];
+        const double y_min = fmin(sg.y0, sg.y1), y_max = fmax(sg.y0, sg.y1);
+        if (y < f64_as_i32(floor(y_min)) || y > f64_as_i32(floor(y_max))) continue;
+        const double delta = sg.y1 - sg.y0;
+        const double sign = (sg.y0 <= sg.y1) ? 1.0 : -1.0;
+        const double slope = (sg.x1 - sg.x0) / delta;
+        const double rslope = 1.0 / slope;
+        const double y_bottom = fmax((double)y, y_min);
+        const double y_top = fmin((double)(y + 1), y_max);
+        const double y_delta = y_top - y_bottom;
+        const double x_at_bottom = sg.x0 + (y_bottom - sg.y0) * slope;
+        const double x_at_top = sg.x0 + (y_top - sg.y0) * slope;
+        const bool flip = !(x_at_bottom <= x_at_top);
+        const double x_smallest = flip ? x_at_top : x_at_bottom;
+        const double x_largest = flip ? x_at_bottom : x_at_top;
+        const int x_to = f64_as_i32(floor(x_largest));
+        for (int x = f64_as_i32(floor(x_smallest)); x <= x_to; ++x) {
+            const double x_left = fmax((double)x, x_smallest);
+            const double x_next = (double)(x + 1);
+            const double x_right = fmin(x_next, x_largest);
+            double pixel_area = (x_next - x_right) * y_delta;
+            const double tw = x_right - x_left;
+            if (tw > 0.0) {
+                const double y_at_left = sg.y0 + (x_left - sg.x0) * rslope;
+                const double y_at_right = sg.y0 + (x_right - sg.x0) * rslope;
+                const double th = flip ? (y_top - y_at_left) + (y_top - y_at_right) : (y_at_left - y_bottom) + (y_at_right - y_bottom);
+                pixel_area += tw * th / 2.0;
+            }
+            const int cx = x - L.bx0;
+            if (cx >= 0 && cx < W) a[cx] += sign * pixel_area;
+            lo = min(lo, x);
+            hi = max(hi, x);
+        }
+        const int cs = x_to + 1 - L.bx0;
+        if (cs >= 0 && cs < W) sacc[cs] += sign * y_delta;
+        lo = min(lo, x_to + 1);
+        hi = max(hi, x_to + 1);
+    }
+    ls.kmin[L.row_first + rr.row] = lo;
+    ls.kmax[L.row_first + rr.row] = hi;
+    if (lo <= hi) {
+        double run = 0.0;
+        for (int x = lo; x <= hi; ++x) {
+            const int c = x - L.bx0;
+            const bool inside = c >= 0 && c < W;  // the host bbox covers every key; defensive
+            run += inside ? sacc[c] : 0.0;
+            const double total = fmin((inside ? a[c] : 0.0) + run, 1.0);
+            if (inside) a[c] = total;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// label_commit_kernel (a9 + f1): one CTA per tile walks the tile's labels IN ORDER (the collision rule is greedy):
+// icon blit (labeler.rs:91-106) and the text coverage computed by label_cover_kernel are tested against the pixels of
+// earlier successful labels over the 3x3 label canvas (tile_pixels.rs:131-148); survivors claim their pixels and
+// leave their pending pixel for the export of raster_kernel.
+// ------------------------------------------------------------------------------------------------------
 constexpr int kLabelThreads = 256;
 
-__global__ void __launch_bounds__(kLabelThreads) label_kernel(LabelScene ls) {
+__global__ void __launch_bounds__(kLabelThreads) label_commit_kernel(LabelScene ls) {
     __shared__ int fail;
     const unsigned tile = blockIdx.x;
     const int D = ls.D, E = 3 * D;
     const unsigned occ_words = (unsigned)((size_t)E * E / 32);
     unsigned* occ = ls.occ + (size_t)tile * occ_words;
     LabelPix* plane = ls.plane + (size_t)tile * D * D;
-    double* acc_a = ls.acc + (size_t)tile * 2 * ls.cells;
-    double* acc_s = acc_a + ls.cells;
-    int* kmin = ls.row_keys + (size_t)tile * 2 * E;
-    int* kmax = kmin + E;
     for (unsigned i = threadIdx.x; i < occ_words; i += kLabelThreads) occ[i] = 0u;
     for (int i = threadIdx.x; i < D * D; i += kLabelThreads) plane[i].src = 0u;
     __syncthreads();
@@ -1256,82 +1333,18 @@ __global__ void __launch_bounds__(kLabelThreads) label_kernel(LabelScene ls) {
             }
         }
         __syncthreads();
-        const bool has_text = L.seg_count != 0 && !fail;  // a failed icon fails the label before the text is tried
-        const int W = L.bx1 - L.bx0 + 1;
-        // rows outside the label canvas cannot collide or draw; columns must stay complete (the sweep is a prefix sum)
-        const int ry0 = max(L.by0, -D), ry1 = min(L.by1, 2 * D - 1);
-        const int R = ry1 - ry0 + 1;
-        if (has_text && R > 0 && W > 0) {
+        const int W = L.width, R = L.rows;
+        const bool has_text = L.seg_count != 0 && R > 0 && W > 0 && !fail;  // a failed icon fails the label before its text
+        const double* tot = ls.acc_a + L.cell_off;
+        const int* kmin = ls.kmin + L.row_first;
+        const int* kmax = ls.kmax + L.row_first;
+        if (has_text) {
             for (size_t c = threadIdx.x; c < (size_t)R * W; c += kLabelThreads) {
-                acc_a[c] = 0.0;
-                acc_s[c] = 0.0;
-            }
-            for (int r = threadIdx.x; r < R; r += kLabelThreads) {
-                kmin[r] = 0x7fffffff;
-                kmax[r] = (int)0x80000000;
-            }
-            __syncthreads();
-            for (int r = threadIdx.x; r < R; r += kLabelThreads) {
-                const int y = ry0 + r;
-                double* a = acc_a + (size_t)r * W;
-                double* sacc = acc_s + (size_t)r * W;
-                int lo = 0x7fffffff, hi = (int)0x80000000;
-                for (unsigned k = 0; k < L.seg_count; ++k) {  // Rasterizer::draw_line for this stripe (rasterizer.rs:27-84)
-                    const DevSeg sg = ls.segs[L.seg_begin + k];
-                    const double delta = sg.y1 - sg.y0;
-                    const double y_min = fmin(sg.y0, sg.y1), y_max = fmax(sg.y0, sg.y1);
-                    if (y < f64_as_i32(floor(y_min)) || y > f64_as_i32(floor(y_max))) continue;
-                    const double sign = (sg.y0 <= sg.y1) ? 1.0 : -1.0;
-                    const double slope = (sg.x1 - sg.x0) / delta;
-                    const double rslope = 1.0 / slope;
-                    const double y_bottom = fmax((double)y, y_min);
-                    const double y_top = fmin((double)(y + 1), y_max);
-                    const double y_delta = y_top - y_bottom;
-                    const double x_at_bottom = sg.x0 + (y_bottom - sg.y0) * slope;
-                    const double x_at_top = sg.x0 + (y_top - sg.y0) * slope;
-                    const bool flip = !(x_at_bottom <= x_at_top);
-                    const double x_smallest = flip ? x_at_top : x_at_bottom;
-                    const double x_largest = flip ? x_at_bottom : x_at_top;
-                    const int x_to = f64_as_i32(floor(x_largest));
-                    for (int x = f64_as_i32(floor(x_smallest)); x <= x_to; ++x) {
-                        const double x_left = fmax((double)x, x_smallest);
-                        const double x_next = (double)(x + 1);
-                        const double x_right = fmin(x_next, x_largest);
-                        double pixel_area = (x_next - x_right) * y_delta;
-                        const double tw = x_right - x_left;
-                        if (tw > 0.0) {
-                            const double y_at_left = sg.y0 + (x_left - sg.x0) * rslope;
-                            const double y_at_right = sg.y0 + (x_right - sg.x0) * rslope;
-                            const double th = flip ? (y_top - y_at_left) + (y_top - y_at_right)
-                                                   : (y_at_left - y_bottom) + (y_at_right - y_bottom);
-                            pixel_area += tw * th / 2.0;
-                        }
-                        const int cx = x - L.bx0;
-                        if (cx >= 0 && cx < W) a[cx] += sign * pixel_area;
-                        lo = min(lo, x);
-                        hi = max(hi, x);
-                    }
-                    const int cs = x_to + 1 - L.bx0;
-                    if (cs >= 0 && cs < W) sacc[cs] += sign * y_delta;
-                    lo = min(lo, x_to + 1);
-                    hi = max(hi, x_to + 1);
-                }
-                // save_to_figure for this stripe (rasterizer.rs:109-148): sweep the touched key range left to right
-                kmin[r] = lo;
-                kmax[r] = hi;
-                if (lo <= hi) {
-                    double run = 0.0;
-                    for (int x = lo; x <= hi; ++x) {
-                        const int c = x - L.bx0;
-                        const bool inside = c >= 0 && c < W;  // the host bbox covers every key; defensive
-                        run += inside ? sacc[c] : 0.0;
-                        const double total = fmin((inside ? a[c] : 0.0) + run, 1.0);
-                        if (inside) a[c] = total;
-                        if (total > 0.0 && in_canvas(x, y)) {
-                            size_t b = occ_index(x, y);
-                            if (occ[b >> 5] & (1u << (b & 31))) fail = 1;
-                        }
-                    }
+                const int r = (int)(c / W), x = L.bx0 + (int)(c % W), y = L.ry0 + r;
+                if (x < kmin[r] || x > kmax[r]) continue;  // outside the stripe's key range nothing is ever set
+                if (tot[c] > 0.0 && in_canvas(x, y)) {
+                    size_t b = occ_index(x, y);
+                    if (occ[b >> 5] & (1u << (b & 31))) fail = 1;
                 }
             }
         }
@@ -1355,24 +1368,20 @@ __global__ void __launch_bounds__(kLabelThreads) label_kernel(LabelScene ls) {
                 }
             }
             __syncthreads();  // text pixels overwrite icon pixels of the same label (later set_label_pixel wins)
-            if (has_text && R > 0 && W > 0) {
-                for (int r = threadIdx.x; r < R; r += kLabelThreads) {
-                    const int y = ry0 + r;
-                    const double* a = acc_a + (size_t)r * W;
-                    for (int x = kmin[r]; x <= kmax[r]; ++x) {
-                        const int c = x - L.bx0;
-                        if (c < 0 || c >= W) continue;
-                        const double total = a[c];
-                        if (!(total > 0.0) || !in_canvas(x, y)) continue;
-                        size_t b = occ_index(x, y);
-                        atomicOr(&occ[b >> 5], 1u << (b & 31));
-                        if (x >= 0 && x < D && y >= 0 && y < D) {
-                            LabelPix px;
-                            px.alpha = total;
-                            px.src = 0x40000000u | (L.rgb & 0xffffffu);
-                            px.pad = 0;
-                            plane[(size_t)y * D + x] = px;
-                        }
+            if (has_text) {
+                for (size_t c = threadIdx.x; c < (size_t)R * W; c += kLabelThreads) {
+                    const int r = (int)(c / W), x = L.bx0 + (int)(c % W), y = L.ry0 + r;
+                    if (x < kmin[r] || x > kmax[r]) continue;
+                    const double total = tot[c];
+                    if (!(total > 0.0) || !in_canvas(x, y)) continue;
+                    size_t b = occ_index(x, y);
+                    atomicOr(&occ[b >> 5], 1u << (b & 31));
+                    if (x >= 0 && x < D && y >= 0 && y < D) {
+                        LabelPix px;
+                        px.alpha = total;
+                        px.src = 0x40000000u | (L.rgb & 0xffffffu);
+                        px.pad = 0;
+                        plane[(size_t)y * D + x] = px;
                     }
                 }
             }

@@ -21,6 +21,8 @@
 #include <unordered_map>
 #include <utility>
 #include <vector>
+#include <shared_mutex>
+#include <mutex>
 
 #include "osmr.h"
 
@@ -36,7 +38,17 @@ struct LabelRec {
     unsigned seg_count;
     int bx0, by0, bx1, by1;   // inclusive pixel bbox of everything the text can touch; bx0 > bx1: no text geometry
     unsigned rgb;             // text colour 0x00BBGGRR
+    // filled by the batch assembler (osmr_draw_tiles_labeled): coverage storage of the rows inside the label canvas
+    int ry0;                  // first stored row (by0 clipped to the 3x3 canvas)
+    int rows;                 // stored rows (0: the text cannot touch the canvas)
+    int width;                // bx1 - bx0 + 1
+    unsigned row_first;       // index of the first (label, row) work item
     unsigned pad;
+    unsigned long long cell_off;  // first cell of this label in the coverage arrays
+};
+struct RowRec {  // one unit of work of label_cover_kernel
+    unsigned label;
+    unsigned row;  // 0 .. rows-1
 };
 struct Seg {
     double x0, y0, x1, y1;
@@ -169,6 +181,7 @@ class TrueType {
     bool load(const uint8_t* data, size_t len) {
         bytes_.assign(data, data + len);
         d_ = bytes_.data();
+        glyph_cache_.clear();
         if (len < 12) return false;
         cmap_ = table("cmap");
         loca_ = table("loca");
@@ -260,14 +273,18 @@ class TrueType {
         }
         return 0;
     }
-    // outline of a glyph (nullptr: the glyph has none); memoised, so layout is single-threaded per font
+    // outline of a glyph (nullptr: the glyph has none); memoised behind a reader/writer lock (tiles are laid out by
+    // several host threads; unordered_map nodes never move, so the returned pointer stays valid)
     const std::vector<GlyphVertex>* shape(int g) const {
-        auto it = glyph_cache_.find(g);
-        if (it == glyph_cache_.end()) {
-            std::vector<GlyphVertex> v;
-            if (!outline(g, v, 0)) v.clear();
-            it = glyph_cache_.emplace(g, std::move(v)).first;
+        {
+            std::shared_lock<std::shared_mutex> rd(glyph_mu_);
+            auto it = glyph_cache_.find(g);
+            if (it != glyph_cache_.end()) return it->second.empty() ? nullptr : &it->second;
         }
+        std::vector<GlyphVertex> v;
+        if (!outline(g, v, 0)) v.clear();
+        std::unique_lock<std::shared_mutex> wr(glyph_mu_);
+        auto it = glyph_cache_.emplace(g, std::move(v)).first;
         return it->second.empty() ? nullptr : &it->second;
     }
 
@@ -277,6 +294,7 @@ class TrueType {
     uint32_t cmap_ = 0, loca_ = 0, head_ = 0, glyf_ = 0, hhea_ = 0, hmtx_ = 0, kern_ = 0, index_map_ = 0;
     int num_glyphs_ = 0, loc_format_ = 0;
     mutable std::unordered_map<int, std::vector<GlyphVertex>> glyph_cache_;
+    mutable std::shared_mutex glyph_mu_;
 
     int be16(uint32_t o) const { return d_[o] * 256 + d_[o + 1]; }
     int sbe16(uint32_t o) const { return (int16_t)(d_[o] * 256 + d_[o + 1]); }
@@ -644,14 +662,30 @@ class SegSink {  // Rasterizer::draw_line / draw_quad call stream (rasterizer.rs
     void line(double x0, double y0, double x1, double y1) {
         if (y1 - y0 == 0.0) return;  // draw_line returns before touching anything (rasterizer.rs:30-32)
         out->push_back(Seg{x0, y0, x1, y1});
-        min_x = std::fmin(min_x, std::fmin(x0, x1));
-        max_x = std::fmax(max_x, std::fmax(x0, x1));
-        min_y = std::fmin(min_y, std::fmin(y0, y1));
-        max_y = std::fmax(max_y, std::fmax(y0, y1));
+        // NaN-ignoring min / max without the libm call
+        auto mn = [](double a, double b) { return (b < a || a != a) ? b : a; };
+        auto mx = [](double a, double b) { return (b > a || a != a) ? b : a; };
+        min_x = mn(min_x, mn(x0, x1));
+        max_x = mx(max_x, mx(x0, x1));
+        min_y = mn(min_y, mn(y0, y1));
+        max_y = mx(max_y, mx(y0, y1));
+    }
+    // The flatness test of draw_quad (rasterizer.rs:86-107) compares platform-libm hypot values.  hypot is accurate to
+    // < 1 ulp and sqrt(dx*dx + dy*dy) to < 2 ulp at pixel magnitudes, so the cheap form decides whenever the two sides
+    // differ by more than 1e-12 relative; only near-ties pay for the three hypot calls.
+    static bool flat_enough(double x0, double y0, double x1, double y1, double x2, double y2) {
+        const double ax = std::fabs(x0 - x1), ay = std::fabs(y0 - y1), bx = std::fabs(x1 - x2), by = std::fabs(y1 - y2);
+        const double cx = std::fabs(x0 - x2), cy = std::fabs(y0 - y2);
+        const double lhs = std::sqrt(ax * ax + ay * ay) + std::sqrt(bx * bx + by * by);
+        const double rhs = 1.0001 * std::sqrt(cx * cx + cy * cy);
+        const double big = 1e150, tiny = 1e-150;
+        const bool safe = lhs < big && rhs < big && lhs > tiny && rhs > tiny;  // also false for NaN
+        if (safe && lhs < rhs * (1.0 - 1e-12)) return true;
+        if (safe && lhs > rhs * (1.0 + 1e-12)) return false;
+        return std::hypot(ax, ay) + std::hypot(bx, by) <= 1.0001 * std::hypot(cx, cy);
     }
     void quad(double x0, double y0, double x1, double y1, double x2, double y2) {
-        auto dist = [](double xa, double ya, double xb, double yb) { return std::hypot(std::fabs(xa - xb), std::fabs(ya - yb)); };
-        if (dist(x0, y0, x1, y1) + dist(x1, y1, x2, y2) <= 1.0001 * dist(x0, y0, x2, y2)) {
+        if (flat_enough(x0, y0, x1, y1, x2, y2)) {
             line(x0, y0, x2, y2);
             return;
         }

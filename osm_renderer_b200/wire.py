@@ -88,6 +88,9 @@ class StatsStruct(C.Structure):
         ("ms_plan", C.c_float),
         ("ms_raster", C.c_float),
         ("ms_total", C.c_float),
+        ("ms_label_layout", C.c_float),
+        ("ms_label_device", C.c_float),
+        ("reserved", C.c_float),
     ]
 
 

@@ -44,3 +44,42 @@ def test_label_pass_without_labels_equals_area_passes(fx, label_ctx):
     plain = ctx.draw_tiles(tiles, begins, areas, fx.canvas_rgb, True)
     empty = ctx.draw_tiles_labeled(tiles, begins, areas, np.zeros(len(tiles) + 1, dtype=np.uint32), per["16"][1][:0], fx.canvas_rgb, True)
     assert (plain == empty).all()
+
+
+def test_label_layout_is_independent_of_host_threading_and_batching(fx, label_ctx):
+    """The layout is handed to host threads in runs of labels and tiles are batched: neither may change a pixel."""
+    ctx, per = label_ctx
+    tiles, begins, areas = fx.batches["17"]
+    lb, labels = per["17"]
+    ref = ctx.draw_tiles_labeled(tiles, begins, areas, lb, labels, fx.canvas_rgb, True)
+    try:
+        ctx.debug_set("label_threads", 1)
+        serial = ctx.draw_tiles_labeled(tiles, begins, areas, lb, labels, fx.canvas_rgb, True)
+    finally:
+        ctx.debug_set("label_threads", 32)
+    assert (serial == ref).all()
+    for t in (0, len(tiles) // 2, len(tiles) - 1):  # one tile at a time
+        a0, a1 = int(begins[t]), int(begins[t + 1])
+        l0, l1 = int(lb[t]), int(lb[t + 1])
+        one = ctx.draw_tiles_labeled(tiles[t:t + 1], np.array([0, a1 - a0], dtype=np.uint32), areas[a0:a1],
+                                     np.array([0, l1 - l0], dtype=np.uint32), labels[l0:l1], fx.canvas_rgb, True)
+        assert (one[0] == ref[t]).all()
+
+
+def test_label_api_rejects_bad_input(fx, label_ctx):
+    ctx, per = label_ctx
+    from osm_renderer_b200._lib import OsmrError
+
+    tiles, begins, areas = fx.batches["18"]
+    lb, labels = per["18"]
+    bad = labels.copy()
+    bad["style"][0] = 1 << 30
+    with pytest.raises(OsmrError):
+        ctx.draw_tiles_labeled(tiles, begins, areas, lb, bad, fx.canvas_rgb, True)
+    bad = labels.copy()
+    bad["entity"][0] = 0x3FFFFFFF  # way index far beyond the dataset
+    with pytest.raises(OsmrError):
+        ctx.draw_tiles_labeled(tiles, begins, areas, lb, bad, fx.canvas_rgb, True)
+    # the context stays usable
+    ok = ctx.draw_tiles_labeled(tiles[:2], begins[:3], areas[: int(begins[2])], lb[:3], labels[: int(lb[2])], fx.canvas_rgb, True)
+    assert ok.shape[0] == 2
