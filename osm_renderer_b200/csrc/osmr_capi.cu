@@ -105,6 +105,8 @@ struct osmr_ctx {
     DevBuf<double> label_acc;
     DevBuf<int> label_row_keys;
     DevBuf<DevRowRec> d_label_rows;
+    DevBuf<double2> d_seg_slope;
+    DevBuf<int2> d_seg_rows;
     std::vector<LabelWorkItem> label_items;  // kept between calls: their vectors' capacity is the layout arena
     PinnedBuf<osmr_host::Seg> h_label_segs;
     cudaEvent_t ev_label0 = nullptr, ev_label1 = nullptr;
@@ -231,6 +233,8 @@ void osmr_ctx_destroy(osmr_ctx* ctx) {
     ctx->label_acc.release();
     ctx->label_row_keys.release();
     ctx->d_label_rows.release();
+    ctx->d_seg_slope.release();
+    ctx->d_seg_rows.release();
     ctx->h_label_segs.release();
     ctx->label_plane.release();
     ctx->geom.release();
@@ -857,6 +861,7 @@ int osmr_draw_tiles_labeled(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_ti
             if (touches) {
                 if (cols > (1 << 20)) return ctx->fail(OSMR_E_NOMEM, "label text wider than 2^20 pixels");
                 for (int y = 0; y < r.rows; ++y) rowrecs.push_back({(unsigned)recs.size(), (unsigned)y});
+                while (rowrecs.size() % 32) rowrecs.push_back({(unsigned)recs.size(), 0xffffffffu});  // a warp never mixes labels
                 cells += (unsigned long long)rows * cols;
             }
             recs.push_back(r);
@@ -872,6 +877,8 @@ int osmr_draw_tiles_labeled(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_ti
     // ---- device half ----
     CK(ctx->d_labels.reserve(recs.size() + 1));
     CK(ctx->d_label_segs.reserve(n_segs + 1));
+    CK(ctx->d_seg_slope.reserve(n_segs + 1));
+    CK(ctx->d_seg_rows.reserve(n_segs + 1));
     CK(ctx->d_label_rows.reserve(rowrecs.size() + 1));
     CK(ctx->d_label_begin.reserve(n_tiles + 1));
     CK(ctx->label_occ.reserve((size_t)n_tiles * ((size_t)E * E / 32)));
@@ -891,6 +898,9 @@ int osmr_draw_tiles_labeled(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_ti
     ls.segs = ctx->d_label_segs.p;
     ls.rowrecs = ctx->d_label_rows.p;
     ls.n_rowrecs = (unsigned)rowrecs.size();
+    ls.n_segs = (unsigned)n_segs;
+    ls.seg_slope = ctx->d_seg_slope.p;
+    ls.seg_rows = ctx->d_seg_rows.p;
     ls.icons = ctx->label_icons.p;
     ls.occ = ctx->label_occ.p;
     ls.acc_a = ctx->label_acc.p;
@@ -900,7 +910,9 @@ int osmr_draw_tiles_labeled(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_ti
     ls.plane = ctx->label_plane.p;
     ls.D = D;
     if (ls.n_rowrecs) {
-        label_cover_kernel<<<(ls.n_rowrecs + 63) / 64, 64, 0, ctx->stream>>>(ls);
+        label_seg_kernel<<<(ls.n_segs + 255) / 256, 256, 0, ctx->stream>>>(ls);
+        CK(cudaGetLastError());
+        label_cover_kernel<<<ls.n_rowrecs / 32, 32, 0, ctx->stream>>>(ls);  // rowrecs are padded per label to whole warps
         CK(cudaGetLastError());
     }
     label_commit_kernel<<<n_tiles, kLabelThreads, 0, ctx->stream>>>(ls);

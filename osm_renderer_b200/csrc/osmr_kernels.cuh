@@ -1220,6 +1220,9 @@ struct LabelScene {
     const DevSeg* segs;
     const DevRowRec* rowrecs;
     unsigned n_rowrecs;
+    unsigned n_segs;
+    double2* seg_slope;  // per segment: (x1 - x0) / (y1 - y0) and its reciprocal
+    int2* seg_rows;      // per segment: first / last pixel row it crosses
     const DevIcon* icons;
     unsigned* occ;   // per tile (3D)^2 bits
     double* acc_a;   // coverage: per label rows x width cells (`a` map, then the swept totals)
@@ -1230,57 +1233,92 @@ struct LabelScene {
     int D;
 };
 
+// Per-segment constants of Rasterizer::draw_line (rasterizer.rs:27-50), one thread per segment: the two divisions and
+// the stripe range are the same for every pixel row the segment crosses.
+__global__ void label_seg_kernel(LabelScene ls) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ls.n_segs) return;
+    const DevSeg sg = ls.segs[i];
+    const double slope = (sg.x1 - sg.x0) / (sg.y1 - sg.y0);
+    ls.seg_slope[i] = make_double2(slope, 1.0 / slope);
+    ls.seg_rows[i] = make_int2(f64_as_i32(floor(fmin(sg.y0, sg.y1))), f64_as_i32(floor(fmax(sg.y0, sg.y1))));
+}
+
 // Glyph coverage of one pixel row of one label: Rasterizer::draw_line for this stripe over the label's segments in
 // order (rasterizer.rs:27-84), then the left-to-right sweep of save_to_figure (rasterizer.rs:109-148).
-__global__ void label_cover_kernel(LabelScene ls) {
-    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= ls.n_rowrecs) return;
+// A warp holds up to 32 stripes of ONE label (the host pads every label's rows to a multiple of 32 with dead entries).
+// The warp reads the segments' stripe ranges 32 at a time, each lane collects the bit mask of the segments that cross
+// its stripe, and the lanes then do the area arithmetic together, lowest bit (= earliest segment) first: per stripe the
+// additions happen in segment order, as on the CPU.
+__global__ void __launch_bounds__(32) label_cover_kernel(LabelScene ls) {
+    constexpr unsigned kFull = 0xffffffffu;
+    const unsigned i = blockIdx.x * 32u + threadIdx.x;
+    const unsigned lane = threadIdx.x;
     const DevRowRec rr = ls.rowrecs[i];
     const DevLabel L = ls.labels[rr.label];
+    const bool live = rr.row != 0xffffffffu;
     const int W = L.width;
-    const int y = L.ry0 + (int)rr.row;
-    double* a = ls.acc_a + L.cell_off + (size_t)rr.row * W;
-    double* sacc = ls.acc_s + L.cell_off + (size_t)rr.row * W;
+    const int y = L.ry0 + (int)(live ? rr.row : 0u);
+    double* a = ls.acc_a + L.cell_off + (size_t)(live ? rr.row : 0u) * W;
+    double* sacc = ls.acc_s + L.cell_off + (size_t)(live ? rr.row : 0u) * W;
+    const int2* rows = ls.seg_rows + L.seg_begin;
+    const int y_lo = __shfl_sync(kFull, y, 0);  // lane 0 is always live, live lanes are a prefix with increasing y
+    const int y_hi = y_lo + __popc(__ballot_sync(kFull, live)) - 1;
     int lo = 0x7fffffff, hi = (int)0x80000000;
-    for (unsigned k = 0; k < L.seg_count; ++k) {
-        const DevSeg sg = ls.segs[L.seg_begin + k];
-        const double y_min = fmin(sg.y0, sg.y1), y_max = fmax(sg.y0, sg.y1);
-        if (y < f64_as_i32(floor(y_min)) || y > f64_as_i32(floor(y_max))) continue;
-        const double delta = sg.y1 - sg.y0;
-        const double sign = (sg.y0 <= sg.y1) ? 1.0 : -1.0;
-        const double slope = (sg.x1 - sg.x0) / delta;
-        const double rslope = 1.0 / slope;
-        const double y_bottom = fmax((double)y, y_min);
-        const double y_top = fmin((double)(y + 1), y_max);
-        const double y_delta = y_top - y_bottom;
-        const double x_at_bottom = sg.x0 + (y_bottom - sg.y0) * slope;
-        const double x_at_top = sg.x0 + (y_top - sg.y0) * slope;
-        const bool flip = !(x_at_bottom <= x_at_top);
-        const double x_smallest = flip ? x_at_top : x_at_bottom;
-        const double x_largest = flip ? x_at_bottom : x_at_top;
-        const int x_to = f64_as_i32(floor(x_largest));
-        for (int x = f64_as_i32(floor(x_smallest)); x <= x_to; ++x) {
-            const double x_left = fmax((double)x, x_smallest);
-            const double x_next = (double)(x + 1);
-            const double x_right = fmin(x_next, x_largest);
-            double pixel_area = (x_next - x_right) * y_delta;
-            const double tw = x_right - x_left;
-            if (tw > 0.0) {
-                const double y_at_left = sg.y0 + (x_left - sg.x0) * rslope;
-                const double y_at_right = sg.y0 + (x_right - sg.x0) * rslope;
-                const double th = flip ? (y_top - y_at_left) + (y_top - y_at_right) : (y_at_left - y_bottom) + (y_at_right - y_bottom);
-                pixel_area += tw * th / 2.0;
-            }
-            const int cx = x - L.bx0;
-            if (cx >= 0 && cx < W) a[cx] += sign * pixel_area;
-            lo = min(lo, x);
-            hi = max(hi, x);
+    for (unsigned base = 0; base < L.seg_count; base += 32) {
+        const unsigned j = base + lane;
+        const int2 ry = j < L.seg_count ? rows[j] : make_int2(1, 0);
+        unsigned cand = __ballot_sync(kFull, ry.x <= ry.y && ry.y >= y_lo && ry.x <= y_hi);
+        unsigned mine = 0;
+        for (; cand; cand &= cand - 1) {
+            const int bsel = __ffs(cand) - 1;
+            const int r0 = __shfl_sync(kFull, ry.x, bsel), r1 = __shfl_sync(kFull, ry.y, bsel);
+            if (live && y >= r0 && y <= r1) mine |= 1u << bsel;
         }
-        const int cs = x_to + 1 - L.bx0;
-        if (cs >= 0 && cs < W) sacc[cs] += sign * y_delta;
-        lo = min(lo, x_to + 1);
-        hi = max(hi, x_to + 1);
+        while (__any_sync(kFull, mine != 0)) {
+            if (mine) {
+                const unsigned k = base + (unsigned)(__ffs(mine) - 1);
+                mine &= mine - 1;
+                const DevSeg sg = ls.segs[L.seg_begin + k];
+                const double2 sl = ls.seg_slope[L.seg_begin + k];
+                const double slope = sl.x, rslope = sl.y;
+                const double y_min = fmin(sg.y0, sg.y1), y_max = fmax(sg.y0, sg.y1);
+                const double sign = (sg.y0 <= sg.y1) ? 1.0 : -1.0;
+                const double y_bottom = fmax((double)y, y_min);
+                const double y_top = fmin((double)(y + 1), y_max);
+                const double y_delta = y_top - y_bottom;
+                const double x_at_bottom = sg.x0 + (y_bottom - sg.y0) * slope;
+                const double x_at_top = sg.x0 + (y_top - sg.y0) * slope;
+                const bool flip = !(x_at_bottom <= x_at_top);
+                const double x_smallest = flip ? x_at_top : x_at_bottom;
+                const double x_largest = flip ? x_at_bottom : x_at_top;
+                const int x_to = f64_as_i32(floor(x_largest));
+                for (int x = f64_as_i32(floor(x_smallest)); x <= x_to; ++x) {
+                    const double x_left = fmax((double)x, x_smallest);
+                    const double x_next = (double)(x + 1);
+                    const double x_right = fmin(x_next, x_largest);
+                    double pixel_area = (x_next - x_right) * y_delta;
+                    const double tw = x_right - x_left;
+                    if (tw > 0.0) {
+                        const double y_at_left = sg.y0 + (x_left - sg.x0) * rslope;
+                        const double y_at_right = sg.y0 + (x_right - sg.x0) * rslope;
+                        const double th =
+                            flip ? (y_top - y_at_left) + (y_top - y_at_right) : (y_at_left - y_bottom) + (y_at_right - y_bottom);
+                        pixel_area += tw * th / 2.0;
+                    }
+                    const int cx = x - L.bx0;
+                    if (cx >= 0 && cx < W) a[cx] += sign * pixel_area;
+                    lo = min(lo, x);
+                    hi = max(hi, x);
+                }
+                const int cs = x_to + 1 - L.bx0;
+                if (cs >= 0 && cs < W) sacc[cs] += sign * y_delta;
+                lo = min(lo, x_to + 1);
+                hi = max(hi, x_to + 1);
+            }
+        }
     }
+    if (!live) return;
     ls.kmin[L.row_first + rr.row] = lo;
     ls.kmax[L.row_first + rr.row] = hi;
     if (lo <= hi) {
@@ -1304,7 +1342,7 @@ __global__ void label_cover_kernel(LabelScene ls) {
 constexpr int kLabelThreads = 256;
 
 __global__ void __launch_bounds__(kLabelThreads) label_commit_kernel(LabelScene ls) {
-    __shared__ int fail;
+    __shared__ volatile int fail;
     const unsigned tile = blockIdx.x;
     const int D = ls.D, E = 3 * D;
     const unsigned occ_words = (unsigned)((size_t)E * E / 32);
@@ -1338,13 +1376,18 @@ __global__ void __launch_bounds__(kLabelThreads) label_commit_kernel(LabelScene 
         const double* tot = ls.acc_a + L.cell_off;
         const int* kmin = ls.kmin + L.row_first;
         const int* kmax = ls.kmax + L.row_first;
-        if (has_text) {
-            for (size_t c = threadIdx.x; c < (size_t)R * W; c += kLabelThreads) {
-                const int r = (int)(c / W), x = L.bx0 + (int)(c % W), y = L.ry0 + r;
-                if (x < kmin[r] || x > kmax[r]) continue;  // outside the stripe's key range nothing is ever set
-                if (tot[c] > 0.0 && in_canvas(x, y)) {
-                    size_t b = occ_index(x, y);
-                    if (occ[b >> 5] & (1u << (b & 31))) fail = 1;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        if (has_text) {  // a warp per stored row, lanes over the stripe's key range (nothing is set outside it)
+            for (int r = warp; r < R && !fail; r += kLabelThreads / 32) {
+                const int y = L.ry0 + r;
+                const int lo = max(kmin[r], max(L.bx0, -D)), hi = min(kmax[r], min(L.bx0 + W - 1, 2 * D - 1));
+                if (lo > hi) continue;  // untouched stripe (kmin = INT_MAX)
+                const double* row = tot + (size_t)r * W - L.bx0;
+                for (int x = lo + lane; x <= hi; x += 32) {
+                    if (row[x] > 0.0) {
+                        size_t b = occ_index(x, y);
+                        if (occ[b >> 5] & (1u << (b & 31))) fail = 1;
+                    }
                 }
             }
         }
@@ -1369,19 +1412,23 @@ __global__ void __launch_bounds__(kLabelThreads) label_commit_kernel(LabelScene 
             }
             __syncthreads();  // text pixels overwrite icon pixels of the same label (later set_label_pixel wins)
             if (has_text) {
-                for (size_t c = threadIdx.x; c < (size_t)R * W; c += kLabelThreads) {
-                    const int r = (int)(c / W), x = L.bx0 + (int)(c % W), y = L.ry0 + r;
-                    if (x < kmin[r] || x > kmax[r]) continue;
-                    const double total = tot[c];
-                    if (!(total > 0.0) || !in_canvas(x, y)) continue;
-                    size_t b = occ_index(x, y);
-                    atomicOr(&occ[b >> 5], 1u << (b & 31));
-                    if (x >= 0 && x < D && y >= 0 && y < D) {
-                        LabelPix px;
-                        px.alpha = total;
-                        px.src = 0x40000000u | (L.rgb & 0xffffffu);
-                        px.pad = 0;
-                        plane[(size_t)y * D + x] = px;
+                for (int r = warp; r < R; r += kLabelThreads / 32) {
+                    const int y = L.ry0 + r;
+                    const int lo = max(kmin[r], max(L.bx0, -D)), hi = min(kmax[r], min(L.bx0 + W - 1, 2 * D - 1));
+                    if (lo > hi) continue;
+                    const double* row = tot + (size_t)r * W - L.bx0;
+                    for (int x = lo + lane; x <= hi; x += 32) {
+                        const double total = row[x];
+                        if (!(total > 0.0)) continue;
+                        size_t b = occ_index(x, y);
+                        atomicOr(&occ[b >> 5], 1u << (b & 31));
+                        if (x >= 0 && x < D && y >= 0 && y < D) {
+                            LabelPix px;
+                            px.alpha = total;
+                            px.src = 0x40000000u | (L.rgb & 0xffffffu);
+                            px.pad = 0;
+                            plane[(size_t)y * D + x] = px;
+                        }
                     }
                 }
             }

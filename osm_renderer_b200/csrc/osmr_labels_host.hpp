@@ -48,7 +48,7 @@ struct LabelRec {
 };
 struct RowRec {  // one unit of work of label_cover_kernel
     unsigned label;
-    unsigned row;  // 0 .. rows-1
+    unsigned row;  // 0 .. rows-1; 0xffffffff: padding (every label's rows are padded to a multiple of 32)
 };
 struct Seg {
     double x0, y0, x1, y1;

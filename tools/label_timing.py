@@ -19,7 +19,7 @@ ctx.set_geodata(fx.bin)
 ctx.set_table(fx.table)
 ctx.set_font(font)
 ctx.set_label_table(lt)
-for name in CONFIG_NAMES:
+for name in (sys.argv[1].split(',') if len(sys.argv) > 1 else CONFIG_NAMES):
     tiles, begins, areas = fx.batches[name]
     lb, labels = per[name]
     for _ in range(2):
