@@ -14,6 +14,16 @@ CONFIG_NAMES = ["14", "15", "16", "17", "18", "18_2x"]
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # OSMR_TEST_EMU=1 python -m pytest tests -m gpu: run the GPU-marked parity tests against the kernels compiled for
+    # the host SIMT emulator (tests/emu/): a check of kernel LOGIC in the GPU-less container before a GPU box is
+    # spent.  Test infrastructure only; never set on the GPU box, where the same tests load libosmr_b200.so.
+    if os.environ.get("OSMR_TEST_EMU") == "1":
+        sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+        import build_emu
+
+        from osm_renderer_b200 import _lib
+
+        _lib.LIB_PATH = build_emu.build()
 
 
 class FixtureInputs:
