@@ -191,6 +191,9 @@ def main():
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-sample", type=int, default=0, help="tiles in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-direct", type=int, default=1, choices=[0, 1],
+                    help="e2e leg: 1 = raster_kernel stores the tiles straight into the page-locked host buffer (default), "
+                         "0 = stage them in HBM and copy back on a second stream")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -289,13 +292,14 @@ def main():
     barrier()
     sampler.start()
     t0 = time.perf_counter()
-    ev_ms, raster_ms, plan_ms = [], [], []
+    ev_ms, raster_ms, plan_ms, cover_ms = [], [], [], []
     launches = 0
     for _ in range(args.steps):
         ev_ms.append(ctx.batch_draw(w["canvas"], w["caps"]))
         st = ctx.stats()
         raster_ms.append(st["ms_raster"])
         plan_ms.append(st["ms_plan"])
+        cover_ms.append(st["ms_cover"])
         launches += st["kernel_launches"]
     barrier()
     wall = time.perf_counter() - t0
@@ -315,6 +319,7 @@ def main():
         pins.append(p)
     h2d = int(sum(a.nbytes for a in in_arrays))
     flags, canvas = ctx._flags(w["canvas"], w["caps"], False)
+    ctx.debug_set("direct_out", args.e2e_direct)
 
     def e2e_step():
         rc = L.osmr_draw_tiles(ctx.h, pins[0], n_tiles, pins[1], pins[2], canvas.ctypes.data, flags, pin_out)
@@ -337,6 +342,7 @@ def main():
     wall, _ = sharding.reduce_job(dist, wall, job_tiles, device="cuda")
     e2e_wall, _ = sharding.reduce_job(dist, e2e_wall, job_tiles, device="cuda")
     raster_mean_ms, _ = sharding.reduce_job(dist, float(np.mean(raster_ms)), job_tiles, device="cuda")
+    cover_mean_ms, _ = sharding.reduce_job(dist, float(np.mean(cover_ms)), job_tiles, device="cuda")
 
     if rank != 0:
         if dist is not None:
@@ -353,21 +359,30 @@ def main():
         peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth of this pool's B200)"
     else:
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
-    # algorithmic bytes of one raster launch: RGB written once + visible-op records, geometry records and row masks read once
-    algo_bytes = n_tiles * D * D * 3 + 32 * stats["n_visible_ops"] + stats["geom_bytes"] + stats["mask_bytes"]
-    achieved = algo_bytes / (raster_mean_ms / 1000.0) / 1e9
+    # algorithmic bytes of one launch of the dominant kernel:
+    #   raster_kernel: RGB written once + visible-op records, geometry records and row masks read once + one 8-byte alpha
+    #                  per stored walk step read once
+    #   line_cover_kernel: line records read once + one 8-byte alpha per in-line walk step and one length byte per walk written
+    raster_bytes = (n_tiles * D * D * 3 + 32 * stats["n_visible_ops"] + stats["geom_bytes"] + stats["mask_bytes"]
+                    + 8 * stats["walk_steps"])
+    cover_bytes = stats["geom_bytes"] + 8 * stats["walk_steps"] + stats["walk_bytes"] // (8 * 4)
+    if cover_mean_ms > raster_mean_ms:
+        dom, dom_ms, algo_bytes = "line_cover_kernel", cover_mean_ms, cover_bytes
+    else:
+        dom, dom_ms, algo_bytes = "raster_kernel", raster_mean_ms, raster_bytes
+    achieved = algo_bytes / (dom_ms / 1000.0) / 1e9
     traffic = None
     prof_json = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(prof_json):
         try:
             pj = json.load(open(prof_json))
             if pj.get("workload") == args.workload:
-                traffic = pj.get("raster_kernel_dram_bytes_per_launch")
+                traffic = pj.get(dom + "_dram_bytes_per_launch")
         except Exception:
             pass
     roofline = {
         "bound": "hbm",
-        "kernel": "raster_kernel",
+        "kernel": dom,
         "achieved": achieved,
         "peak": peak,
         "unit": "GB/s",
@@ -375,8 +390,8 @@ def main():
         "traffic": traffic,
         "peak_source": peak_src,
         "algorithmic_bytes_per_launch": int(algo_bytes),
-        "kernel_ms": raster_mean_ms,
-        "kernel_share_of_step": raster_mean_ms / (1000.0 * dev_s / args.steps),
+        "kernel_ms": dom_ms,
+        "kernel_share_of_step": dom_ms / (1000.0 * dev_s / args.steps),
         "note": "the path is FP64/integer-issue and shared-memory bound, not HBM bound (SURVEY.md F6); see profiles/",
     }
 
@@ -411,11 +426,15 @@ def main():
         "data": "synthetic",
         "config": cfg,
         "wall_ms_per_step": 1000.0 * wall / args.steps,
-        "stage_ms": {"plan+geometry+fill_rows": float(np.mean(plan_ms)), "raster": float(np.mean(raster_ms))},
-        "batch_stats": {k: int(stats[k]) for k in ("n_tiles", "n_areas", "n_visible_ops", "n_node_refs", "geom_bytes", "mask_bytes")},
+        "stage_ms": {"plan+geometry+fill_rows": float(np.mean(plan_ms)), "line_cover": float(np.mean(cover_ms)),
+                     "raster": float(np.mean(raster_ms))},
+        "batch_stats": {k: int(stats[k]) for k in ("n_tiles", "n_areas", "n_visible_ops", "n_node_refs", "geom_bytes", "mask_bytes",
+                                                   "walk_bytes", "walk_steps")},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "tiles/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": out_bytes,
-                "ms_per_step": 1000.0 * e2e_wall / args.steps, "api": "osmr_draw_tiles (pinned host buffers)", "checksum": checksum},
+                "ms_per_step": 1000.0 * e2e_wall / args.steps, "api": "osmr_draw_tiles (pinned host buffers; " + ("tiles stored straight into the host buffer by raster_kernel" if args.e2e_direct
+                                                                      else "tiles staged in HBM, chunked D2H on a copy stream") + ")",
+                "checksum": checksum},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": cpu,

@@ -152,12 +152,14 @@ typedef struct osmr_stats {
     uint64_t kernel_launches;
     uint64_t geom_bytes;     /* edge/segment records written for the visible ops */
     uint64_t mask_bytes;     /* fill row masks written (1 bit per pixel of every fill row) */
-    float ms_plan;           /* per-stage device times of the last draw (CUDA events) */
+    uint64_t walk_bytes;     /* walk cache handed out (8 bytes per possible step of every perpendicular walk) */
+    uint64_t walk_steps;     /* in-line walk steps actually evaluated and stored by line_cover_kernel */
+    float ms_plan;           /* per-stage device times of the last draw (CUDA events): bbox, plan, geometry, fill rows */
     float ms_raster;
     float ms_total;
     float ms_label_layout;   /* osmr_draw_tiles_labeled: host layout (wall clock) and label kernels (CUDA events) */
     float ms_label_device;
-    float reserved;
+    float ms_cover;          /* line_cover_kernel */
 } osmr_stats;
 int osmr_get_stats(osmr_ctx* ctx, osmr_stats* out);
 
@@ -223,7 +225,7 @@ void osmr_free_pinned(void* p);
  * bump-allocated geometry / mask scratch at that many units so the grow-and-redo path runs. */
 int osmr_debug_set(osmr_ctx* ctx, const char* key, int value);
 
-uint32_t osmr_abi_version(void);
+uint32_t osmr_abi_version(void); /* 2: osmr_stats gained walk_bytes / ms_cover */
 
 #ifdef __cplusplus
 }

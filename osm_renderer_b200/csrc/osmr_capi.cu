@@ -132,12 +132,16 @@ struct osmr_ctx {
     DevBuf<AreaInfo> area_info;
     DevBuf<VisOp> vis;
     DevBuf<short4> vis_bbox;
-    DevBuf<unsigned> vis_count, work, fill_work, counters, mask;
+    DevBuf<unsigned> vis_count, work, fill_work, line_work, counters, mask;
     DevBuf<uint4> geom, calc_table;
-    size_t geom_cap_units = 0, mask_cap_words = 0;
+    DevBuf<double> walk_alpha;        // walk cache (line_cover_kernel -> raster_kernel)
+    DevBuf<unsigned char> walk_len;
+    size_t geom_cap_units = 0, mask_cap_words = 0, walk_alpha_cap = 0, walk_len_cap = 0;
     DevBuf<unsigned char> out;
     size_t out_bytes = 0;
     int fill_cap = kFillCap;
+    bool direct_out = true;  // page-locked `out`: raster_kernel stores the tiles straight into host memory (no D2H stage)
+    unsigned first_chunk = 0;  // tiles in the first draw chunk of the current upload (0: one chunk)
     osmr_stats stats{};
 
     int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
@@ -165,7 +169,7 @@ static inline uint32_t rd_u32(const uint8_t* p) {
 
 extern "C" {
 
-uint32_t osmr_abi_version(void) { return 1; }
+uint32_t osmr_abi_version(void) { return 2; }
 
 int osmr_ctx_create(int device, osmr_ctx** out_ctx) {
     if (!out_ctx) return OSMR_E_INVALID;
@@ -222,6 +226,9 @@ void osmr_ctx_destroy(osmr_ctx* ctx) {
     ctx->vis_count.release();
     ctx->work.release();
     ctx->fill_work.release();
+    ctx->line_work.release();
+    ctx->walk_alpha.release();
+    ctx->walk_len.release();
     ctx->counters.release();
     ctx->mask.release();
     ctx->label_icons.release();
@@ -261,6 +268,10 @@ int osmr_debug_set(osmr_ctx* ctx, const char* key, int value) {
         ctx->label_threads = (unsigned)value;
         return OSMR_OK;
     }
+    if (strcmp(key, "direct_out") == 0) {  // 0: always stage the tiles in HBM and copy them back (A/B measurements)
+        ctx->direct_out = value != 0;
+        return OSMR_OK;
+    }
     if (strcmp(key, "fill_cap") == 0) {
         if (value < 0 || value > kFillCap) return ctx->fail(OSMR_E_INVALID, "fill_cap out of range");
         ctx->fill_cap = value;
@@ -270,11 +281,17 @@ int osmr_debug_set(osmr_ctx* ctx, const char* key, int value) {
         if (value < 1) return ctx->fail(OSMR_E_INVALID, "scratch_units must be positive");
         ctx->geom.release();
         ctx->mask.release();
+        ctx->walk_alpha.release();
+        ctx->walk_len.release();
         cudaError_t e1 = ctx->geom.reserve((size_t)value);
         cudaError_t e2 = ctx->mask.reserve((size_t)value);
+        if (e1 == cudaSuccess) e1 = ctx->walk_alpha.reserve((size_t)value);
+        if (e2 == cudaSuccess) e2 = ctx->walk_len.reserve((size_t)value);
         if (e1 != cudaSuccess || e2 != cudaSuccess) return ctx->fail(OSMR_E_CUDA, "scratch_units", e1 != cudaSuccess ? e1 : e2);
         ctx->geom_cap_units = (size_t)value;
         ctx->mask_cap_words = (size_t)value;
+        ctx->walk_alpha_cap = (size_t)value;
+        ctx->walk_len_cap = (size_t)value;
         return OSMR_OK;
     }
     return ctx->fail(OSMR_E_INVALID, "unknown debug key");
@@ -438,13 +455,35 @@ static int validate_batch(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tile
 // defer_tail: copy only the styled areas of the first draw chunk on the compute stream and send the rest on the copy
 // stream (event ctx->areas_ready), so that the upload overlaps the drawing of the first chunk (osmr_draw_tiles only:
 // the caller's arrays stay valid until that call returns).
-static unsigned draw_chunk_tiles(const osmr_ctx* ctx, unsigned n_tiles, bool to_host) {
-    (void)ctx;
-    return (to_host && n_tiles >= 128) ? std::max(64u, (n_tiles + 3) / 4) : n_tiles;
+// Device-visible alias of a page-locked host buffer (cudaMallocHost / cudaHostRegister memory is mapped under unified
+// addressing), or nullptr for pageable memory.
+static unsigned char* pinned_device_alias(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    if (a.type != cudaMemoryTypeHost) return nullptr;
+    return static_cast<unsigned char*>(a.devicePointer);
+}
+
+// Host output is drawn in chunks so that transfers overlap the drawing:
+//   staged (pageable `out`, or direct_out off): 4 equal chunks, the D2H copy of chunk i runs while chunk i+1 is drawn;
+//   direct (page-locked `out`): a small first chunk hides the upload of the remaining styled areas, the tiles themselves
+//   are written to host memory by raster_kernel as they are finished.
+static void draw_chunks(unsigned n_tiles, bool to_host, bool direct, unsigned& first, unsigned& rest) {
+    first = rest = n_tiles;
+    if (!to_host || n_tiles < 128) return;
+    if (direct) {
+        first = std::max(32u, n_tiles / 8);
+        rest = n_tiles - first;
+    } else {
+        first = rest = std::max(64u, (n_tiles + 3) / 4);
+    }
 }
 
 static int batch_upload_impl(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, const uint32_t* area_begin,
-                             const osmr_styled_area* areas, bool defer_tail) {
+                             const osmr_styled_area* areas, bool defer_tail, const void* host_out) {
     if (!ctx) return OSMR_E_INVALID;
     int rc = validate_batch(ctx, tiles, n_tiles, area_begin);
     if (rc) return rc;
@@ -459,9 +498,14 @@ static int batch_upload_impl(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_t
     CK(cudaMemcpyAsync(ctx->area_begin.p, area_begin, (size_t)(n_tiles + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
     ctx->areas_deferred = false;
     size_t head = n_areas;
+    ctx->first_chunk = 0;
     if (defer_tail) {
-        unsigned chunk = draw_chunk_tiles(ctx, n_tiles, true);
-        if (chunk < n_tiles) head = area_begin[chunk];
+        unsigned first, rest;
+        draw_chunks(n_tiles, true, ctx->direct_out && host_out && pinned_device_alias(host_out), first, rest);
+        if (first < n_tiles) {
+            head = area_begin[first];
+            ctx->first_chunk = first;
+        }
     }
     if (head) CK(cudaMemcpyAsync(ctx->areas.p, areas, head * sizeof(osmr_styled_area), cudaMemcpyHostToDevice, ctx->stream));
     if (head < n_areas) {
@@ -480,6 +524,7 @@ static int batch_upload_impl(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_t
     CK(ctx->vis_bbox.reserve(3ull * n_areas + 1));
     CK(ctx->work.reserve(3ull * n_areas + 1));
     CK(ctx->fill_work.reserve((size_t)n_areas + 1));
+    CK(ctx->line_work.reserve(2ull * n_areas + 1));
     CK(ctx->vis_count.reserve(n_tiles));
     CK(ctx->counters.reserve(CNT_COUNT));
     // the caller's arrays may be reused as soon as we return
@@ -490,7 +535,7 @@ static int batch_upload_impl(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_t
 
 int osmr_batch_upload(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, const uint32_t* area_begin,
                       const osmr_styled_area* areas) {
-    return batch_upload_impl(ctx, tiles, n_tiles, area_begin, areas, false);
+    return batch_upload_impl(ctx, tiles, n_tiles, area_begin, areas, false, nullptr);
 }
 
 // Draws tiles [tb, tb+tc) of the uploaded batch into dev_out (which points at tile tb's image).  Synchronises the
@@ -509,6 +554,14 @@ static int run_pipeline(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t fla
             size_t words = (size_t)ctx->n_tiles * (size_t)D * (D / 32) * 4 + (1u << 20);
             CK(ctx->mask.reserve(words));
             ctx->mask_cap_words = ctx->mask.cap;
+        }
+        if (ctx->walk_alpha_cap == 0) {  // first guess: ~1.5 MB of walk cache per tile; grown on overflow
+            CK(ctx->walk_alpha.reserve((size_t)ctx->n_tiles * (192u << 10) + (1u << 20)));
+            ctx->walk_alpha_cap = ctx->walk_alpha.cap;
+        }
+        if (ctx->walk_len_cap == 0) {
+            CK(ctx->walk_len.reserve((size_t)ctx->n_tiles * (40u << 10) + (1u << 20)));
+            ctx->walk_len_cap = ctx->walk_len.cap;
         }
         Scene s{};
         s.merc = ctx->merc.p;
@@ -544,6 +597,11 @@ static int run_pipeline(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t fla
         s.vis_count = ctx->vis_count.p;
         s.work = ctx->work.p;
         s.fill_work = ctx->fill_work.p;
+        s.line_work = ctx->line_work.p;
+        s.walk_alpha = ctx->walk_alpha.p;
+        s.walk_len = ctx->walk_len.p;
+        s.walk_alpha_cap = ctx->walk_alpha_cap;
+        s.walk_len_cap = ctx->walk_len_cap;
         CK(ctx->calc_table.reserve((size_t)2 * ctx->n_styles * kCalcEntryUnits + 1));
         s.calc_table = ctx->calc_table.p;
         s.geom = ctx->geom.p;
@@ -571,7 +629,9 @@ static int run_pipeline(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t fla
         plan_ops_kernel<<<tc, kPlanThreads, 0, st>>>(s);
         build_geometry_kernel<<<ctx->num_sms * 8, kGeomThreads, 0, st>>>(s);
         fill_rows_kernel<<<ctx->num_sms * 16, kFillThreads, 0, st>>>(s);
-        launches += 3;
+        CK(cudaEventRecord(ctx->ev[3], st));
+        line_cover_kernel<<<ctx->num_sms * 8, kCoverThreads, 0, st>>>(s);
+        launches += 4;
         CK(cudaEventRecord(ctx->ev[1], st));
         const unsigned blocks = (unsigned)((D / kBW) * (D / kBH));
         raster_kernel<<<tc * blocks, kRasterThreads, 0, st>>>(s);
@@ -581,7 +641,9 @@ static int run_pipeline(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t fla
         unsigned h_cnt[CNT_COUNT];
         CK(cudaMemcpyAsync(h_cnt, ctx->counters.p, sizeof h_cnt, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
-        if (h_cnt[CNT_BAD_INPUT]) return ctx->fail(OSMR_E_INVALID, "styled area references an entity or style that does not exist");
+        if (h_cnt[CNT_BAD_INPUT] & 1u) return ctx->fail(OSMR_E_INVALID, "styled area references an entity or style that does not exist");
+        if (h_cnt[CNT_BAD_INPUT] & 2u) return ctx->fail(OSMR_E_INVALID, "line wider than 500 pixels (width * scale): not supported");
+        if (h_cnt[CNT_WALK_TRUNC]) return ctx->fail(OSMR_E_CUDA, "internal error: a perpendicular walk exceeded its proven bound");
         if (h_cnt[CNT_OVERFLOW]) {  // grow the scratch that ran out and redo the batch
             if (h_cnt[CNT_OVERFLOW] & 1u) {
                 size_t need = (size_t)h_cnt[CNT_GEOM_USED] + (size_t)h_cnt[CNT_GEOM_USED] / 2 + 1024;
@@ -589,6 +651,21 @@ static int run_pipeline(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t fla
                 if (need >= 0xffffffffull) return ctx->fail(OSMR_E_NOMEM, "geometry scratch exceeds 64 GiB; split the batch");
                 CK(ctx->geom.reserve(need));
                 ctx->geom_cap_units = ctx->geom.cap;
+            }
+            if (h_cnt[CNT_OVERFLOW] & 4u) {
+                unsigned long long used_alpha, used_len;
+                memcpy(&used_alpha, &h_cnt[CNT_WALK_ALPHA], 8);
+                memcpy(&used_len, &h_cnt[CNT_WALK_LEN], 8);
+                if (used_len >= 0xffffffffull) return ctx->fail(OSMR_E_NOMEM, "walk cache exceeds 2^32 walks; split the batch");
+                size_t need_a = (size_t)used_alpha + (size_t)used_alpha / 4 + 1024, need_l = (size_t)used_len + (size_t)used_len / 4 + 1024;
+                if (need_a > ctx->walk_alpha_cap) {
+                    if (ctx->walk_alpha.reserve(need_a) != cudaSuccess) return ctx->fail(OSMR_E_NOMEM, "walk cache does not fit in device memory; split the batch");
+                    ctx->walk_alpha_cap = ctx->walk_alpha.cap;
+                }
+                if (need_l > ctx->walk_len_cap) {
+                    CK(ctx->walk_len.reserve(need_l));
+                    ctx->walk_len_cap = ctx->walk_len.cap;
+                }
             }
             if (h_cnt[CNT_OVERFLOW] & 2u) {
                 size_t need = (size_t)h_cnt[CNT_MASK_USED] + (size_t)h_cnt[CNT_MASK_USED] / 2 + 1024;
@@ -599,9 +676,18 @@ static int run_pipeline(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t fla
             }
             continue;
         }
-        float ms_plan = 0, ms_raster = 0;
-        cudaEventElapsedTime(&ms_plan, ctx->ev[0], ctx->ev[1]);
+        float ms_plan = 0, ms_cover = 0, ms_raster = 0;
+        cudaEventElapsedTime(&ms_plan, ctx->ev[0], ctx->ev[3]);
+        cudaEventElapsedTime(&ms_cover, ctx->ev[3], ctx->ev[1]);
         cudaEventElapsedTime(&ms_raster, ctx->ev[1], ctx->ev[2]);
+        {
+            unsigned long long used_alpha;
+            memcpy(&used_alpha, &h_cnt[CNT_WALK_ALPHA], 8);
+            ctx->stats.walk_bytes += used_alpha * 8ull;
+            unsigned long long steps;
+            memcpy(&steps, &h_cnt[CNT_WALK_STEPS], 8);
+            ctx->stats.walk_steps += steps;
+        }
         ctx->stats.n_tiles += tc;
         ctx->stats.n_areas += n_areas;
         ctx->stats.n_visible_ops += h_cnt[CNT_VISIBLE];
@@ -611,7 +697,8 @@ static int run_pipeline(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t fla
         ctx->stats.mask_bytes += (uint64_t)h_cnt[CNT_MASK_USED] * 4ull;
         ctx->stats.ms_plan += ms_plan;
         ctx->stats.ms_raster += ms_raster;
-        ctx->stats.ms_total += ms_plan + ms_raster;
+        ctx->stats.ms_cover += ms_cover;
+        ctx->stats.ms_total += ms_plan + ms_cover + ms_raster;
         return OSMR_OK;
     }
     return ctx->fail(OSMR_E_NOMEM, "scratch kept overflowing");
@@ -624,22 +711,26 @@ int osmr_batch_draw(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t flags, 
     cudaSetDevice(ctx->device);
     const size_t D = 256 * (size_t)ctx->scale;
     const size_t bytes = (size_t)ctx->n_tiles * D * D * ((flags & OSMR_DRAW_OUT_RGBA) ? 4 : 3);
+    const bool to_host = out && !(flags & OSMR_DRAW_OUT_DEVICE);
+    unsigned char* alias = (to_host && ctx->direct_out) ? pinned_device_alias(out) : nullptr;
     unsigned char* dev_out;
     if (out && (flags & OSMR_DRAW_OUT_DEVICE)) {
         dev_out = out;
+    } else if (alias) {
+        dev_out = alias;  // raster_kernel writes into the caller's page-locked buffer
     } else {
         CK(ctx->out.reserve(bytes));
         dev_out = ctx->out.p;
+        ctx->out_bytes = bytes;
     }
-    ctx->out_bytes = bytes;
     ctx->stats = osmr_stats{};
     const size_t tile_bytes = D * D * ((flags & OSMR_DRAW_OUT_RGBA) ? 4 : 3);
-    const bool to_host = out && !(flags & OSMR_DRAW_OUT_DEVICE);
-    // Host output: draw in chunks and copy chunk i back on a second stream while chunk i+1 is being drawn
-    // (the copy really overlaps only when `out` is page-locked, e.g. from osmr_alloc_pinned).
-    const unsigned chunk = draw_chunk_tiles(ctx, ctx->n_tiles, to_host);
-    for (unsigned tb = 0; tb < ctx->n_tiles; tb += chunk) {
-        const unsigned tc = std::min(chunk, ctx->n_tiles - tb);
+    const bool staged = to_host && !alias;
+    unsigned first, rest;
+    draw_chunks(ctx->n_tiles, to_host, alias != nullptr, first, rest);
+    if (ctx->areas_deferred && ctx->first_chunk) first = ctx->first_chunk;  // the split the upload was made for
+    for (unsigned tb = 0; tb < ctx->n_tiles;) {
+        const unsigned tc = std::min(tb == 0 ? first : rest, ctx->n_tiles - tb);
         if (tb > 0 && ctx->areas_deferred) {  // the tail of the styled-area list was uploaded on the copy stream
             CK(cudaStreamWaitEvent(ctx->stream, ctx->areas_ready, 0));
             ctx->areas_deferred = false;
@@ -649,11 +740,12 @@ int osmr_batch_draw(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t flags, 
             cudaStreamSynchronize(ctx->copy_stream);
             return rc;
         }
-        if (to_host)  // the compute stream is idle here (run_pipeline synchronised it), so the slice is complete
+        if (staged)  // the compute stream is idle here (run_pipeline synchronised it), so the slice is complete
             CK(cudaMemcpyAsync(out + (size_t)tb * tile_bytes, dev_out + (size_t)tb * tile_bytes, (size_t)tc * tile_bytes,
                                cudaMemcpyDeviceToHost, ctx->copy_stream));
+        tb += tc;
     }
-    if (to_host) CK(cudaStreamSynchronize(ctx->copy_stream));
+    if (staged) CK(cudaStreamSynchronize(ctx->copy_stream));
     if (gpu_ms) *gpu_ms = ctx->stats.ms_total;
     return OSMR_OK;
 }
@@ -669,7 +761,7 @@ int osmr_draw_tiles(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, con
                     const osmr_styled_area* areas, const uint8_t canvas_rgb[3], uint32_t flags, uint8_t* out) {
     if (!ctx) return OSMR_E_INVALID;
     if (!out) return ctx->fail(OSMR_E_INVALID, "null output buffer");
-    int rc = batch_upload_impl(ctx, tiles, n_tiles, area_begin, areas, !(flags & OSMR_DRAW_OUT_DEVICE));
+    int rc = batch_upload_impl(ctx, tiles, n_tiles, area_begin, areas, !(flags & OSMR_DRAW_OUT_DEVICE), out);
     if (rc) return rc;
     rc = osmr_batch_draw(ctx, canvas_rgb, flags, out, nullptr);
     if (ctx->areas_deferred) {  // error path before the tail was consumed: do not leave a copy of the caller's memory in flight
@@ -773,7 +865,7 @@ int osmr_draw_tiles_labeled(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_ti
     if (!out) return ctx->fail(OSMR_E_INVALID, "null output buffer");
     if (!label_begin) return ctx->fail(OSMR_E_INVALID, "null label_begin");
     if (!ctx->font.loaded()) return ctx->fail(OSMR_E_STATE, "osmr_set_font has not been called");
-    int rc = batch_upload_impl(ctx, tiles, n_tiles, area_begin, areas, false);
+    int rc = batch_upload_impl(ctx, tiles, n_tiles, area_begin, areas, false, nullptr);
     if (rc) return rc;
     const int D = 256 * ctx->scale, E = 3 * D;
     // ---- host half: layout (string / font / heap work, as the reference does it on the CPU), tiles in parallel ----

@@ -10,6 +10,10 @@
 
 #include "osmr.h"
 
+#ifndef OSMR_COUNT
+#define OSMR_COUNT(name, n) ((void)0)  // event counters exist only in the host emulator build (tests/emu/)
+#endif
+
 namespace osmr {
 
 constexpr double kPi = 3.14159265358979323846264338327950288;

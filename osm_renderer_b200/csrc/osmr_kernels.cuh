@@ -38,14 +38,18 @@ struct VisOp {
 };
 enum { OP_FILL_COLOR = 0, OP_FILL_IMAGE = 1, OP_LINE = 2 };
 
-struct SegRec {  // 48 bytes: one line segment (or outer cap line) that can touch the tile
+struct SegRec {  // 64 bytes: one line segment (or outer cap line) that can touch the tile
     int x1, y1, x2, y2;
     double traveled;           // OpacityCalculator.traveled_distance when this segment is drawn (line.rs:31)
     double denom;              // center_dist_denom (line.rs:106)
     unsigned long long magic;  // floor(2^64 / (2*mx_d)) + 1: exact quotients for numerators < 2^32 (flags bit1)
-    unsigned flags;            // bit0: outer cap calculator (line.rs:22,33-57); bit1: 32-bit fast path valid
-    unsigned pad;
+    unsigned flags;            // bit0: outer cap calculator (line.rs:22,33-57); bit1: 32-bit fast path valid; bit2: coords < 2^24
+    int k0;                    // first main step whose perpendiculars can reach the tile; the walk cache covers k0 .. k0+n_k-1
+    unsigned n_k;
+    unsigned len_off;              // walk_len index of walk (k0, +, v0); walks are ordered ((k - k0) * 2 + dir) * 2 + v
+    unsigned long long alpha_off;  // walk_alpha index of that walk's step 0; every walk of the op owns S = line_reach(hw) doubles
 };
+static_assert(sizeof(SegRec) == 64, "SegRec layout");
 // Opacity calculators depend only on (style, pass, scale, use_caps_for_dashes): style_calc_kernel builds them once per
 // draw into a table; entry (style, pass) = one full OpacityCalc (dashes of the op) + header and first segment of the
 // outer-cap calculator.
@@ -58,7 +62,7 @@ enum {
     CNT_MASK_USED = 1,   // words
     CNT_N_WORK = 2,      // visible ops (all kinds)
     CNT_N_FILL_WORK = 3,
-    CNT_OVERFLOW = 4,    // bit0 geometry scratch, bit1 mask scratch
+    CNT_OVERFLOW = 4,    // bit0 geometry scratch, bit1 mask scratch, bit2 walk cache
     CNT_BAD_INPUT = 5,   // entity / style index out of range
     CNT_WORK_CURSOR = 6,
     CNT_FILL_CURSOR = 7,
@@ -66,7 +70,13 @@ enum {
     CNT_NODE_REFS_HI = 9,
     CNT_VISIBLE = 10,
     CNT_BIG_COORDS = 11,  // some visible segment has a coordinate >= 2^24 (raster uses exact i64 cross products)
-    CNT_COUNT = 16
+    CNT_WALK_ALPHA = 12,  // 64-bit (12,13): doubles of the walk cache handed out by build_geometry_kernel
+    CNT_WALK_LEN = 14,    // 64-bit (14,15): walks handed out
+    CNT_N_LINE_WORK = 16,
+    CNT_LINE_CURSOR = 17,
+    CNT_WALK_STEPS = 20,  // 64-bit (20,21): in-line steps stored in the walk cache (statistics)
+    CNT_WALK_TRUNC = 18,  // a perpendicular walk outlived its proven bound (never observed; the draw fails loudly)
+    CNT_COUNT = 24
 };
 
 // what the label pass leaves for a pixel of the centre tile: the pending pixel of the last successful label that
@@ -109,6 +119,10 @@ struct Scene {
     unsigned* vis_count;   // per tile
     unsigned* work;        // global indices into vis (all visible ops)
     unsigned* fill_work;   // global indices into vis (fills)
+    unsigned* line_work;   // global indices into vis (lines)
+    double* walk_alpha;    // walk cache (line_cover_kernel -> raster_kernel): alpha of every in-line step of every walk
+    unsigned char* walk_len;  // number of in-line steps per walk
+    unsigned long long walk_alpha_cap, walk_len_cap;
     const uint4* calc_table;  // kCalcEntryUnits per (style, pass-1), built by style_calc_kernel
     uint4* geom;           // geometry scratch, 16-byte units
     unsigned geom_cap;
@@ -359,6 +373,7 @@ __global__ void __launch_bounds__(kPlanThreads) plan_ops_kernel(Scene s) {
                         op.kind = OP_LINE;
                         double hw = lp.width / 2.0;
                         int reach = line_reach(hw);
+                        if (reach > 255) atomicOr(&s.counters[CNT_BAD_INPUT], 2u);  // walk lengths are cached as bytes
                         if (is_non_trivial_cap(lp.cap)) reach = 2 * reach;  // outer cap lines start hw away
                         long long lx0 = (long long)x0 - reach, ly0 = (long long)y0 - reach;
                         long long lx1 = (long long)x1 + reach, ly1 = (long long)y1 + reach;
@@ -366,7 +381,7 @@ __global__ void __launch_bounds__(kPlanThreads) plan_ops_kernel(Scene s) {
                         y0 = (int)max(ly0, -2147483647LL);
                         x1 = (int)min(lx1, 2147483647LL);
                         y1 = (int)min(ly1, 2147483647LL);
-                        geom_units = 3u * (info.npts + 1u);  // <= npts-1 segments + 2 caps of 48 bytes
+                        geom_units = 4u * (info.npts + 1u);  // <= npts-1 segments + 2 caps of 64 bytes
                     }
                 }
                 if (active && x0 <= D - 1 && x1 >= 0 && y0 <= D - 1 && y1 >= 0) {
@@ -416,7 +431,10 @@ __global__ void __launch_bounds__(kPlanThreads) plan_ops_kernel(Scene s) {
             s.vis_bbox[3ull * base + pos] = make_short4(op.x0, op.y0, op.x1, op.y1);
             unsigned gi = (unsigned)(3ull * base + pos);
             s.work[atomicAdd(&s.counters[CNT_N_WORK], 1u)] = gi;
-            if (op.kind != OP_LINE) s.fill_work[atomicAdd(&s.counters[CNT_N_FILL_WORK], 1u)] = gi;
+            if (op.kind != OP_LINE)
+                s.fill_work[atomicAdd(&s.counters[CNT_N_FILL_WORK], 1u)] = gi;
+            else
+                s.line_work[atomicAdd(&s.counters[CNT_N_LINE_WORK], 1u)] = gi;
         }
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -521,10 +539,27 @@ __global__ void __launch_bounds__(kGeomThreads) build_geometry_kernel(Scene s) {
                 bool fast = mxd < 32768 && mxd > 0;  // numerators 2*mn_d*n stay below 2^31
                 rec.magic = fast ? (0xffffffffffffffffull / (unsigned long long)(2 * mxd)) + 1ull : 0ull;
                 rec.flags = (is_cap ? 1u : 0u) | (fast ? 2u : 0u) | (small ? 4u : 0u);
-                rec.pad = 0;
                 if (!small) atomicOr(&s.counters[CNT_BIG_COORDS], 1u);
+                // main steps k (line.rs:133-158) whose major coordinate lies within `reach` of the tile: the only ones
+                // whose perpendiculars can put a pixel into it
+                const bool swp = dx > dy;
+                const int mx0 = swp ? ax : ay;
+                const int mx_inc = swp ? (ax <= bx ? 1 : -1) : (ay <= by ? 1 : -1);
+                const long long lo = -(long long)reach, hi = (long long)D - 1 + reach;
+                long long ka = mx_inc > 0 ? lo - mx0 : (long long)mx0 - hi;
+                long long kb = mx_inc > 0 ? hi - mx0 : (long long)mx0 - lo;
+                if (ka < 0) ka = 0;
+                if (kb > mxd) kb = mxd;
+                rec.k0 = (int)ka;
+                rec.n_k = kb >= ka ? (unsigned)(kb - ka + 1) : 0u;
+                rec.len_off = 0;
+                rec.alpha_off = 0;
                 return rec;
             };
+            // walk cache: 4 walks (2 directions x {regular, extra}) of S steps per main step, handed out per 32 segments
+            const unsigned long long S = (unsigned long long)reach;
+            unsigned long long* walk_alpha_used = reinterpret_cast<unsigned long long*>(&s.counters[CNT_WALK_ALPHA]);
+            unsigned long long* walk_len_used = reinterpret_cast<unsigned long long*>(&s.counters[CNT_WALK_LEN]);
             for (unsigned b = 0; b < n_pairs; b += 32) {
                 unsigned e = b + lane;
                 bool valid = e < n_pairs;
@@ -550,9 +585,6 @@ __global__ void __launch_bounds__(kGeomThreads) build_geometry_kernel(Scene s) {
                     return mnx <= D - 1 && mxx >= 0 && mny <= D - 1 && mxy >= 0;
                 };
                 bool keep = nondeg && touches(p1.x, p1.y, p2.x, p2.y);
-                unsigned bal = __ballot_sync(0xffffffffu, keep);
-                if (keep) out[count + __popc(bal & ((1u << lane) - 1u))] = make_rec(p1.x, p1.y, p2.x, p2.y, trav, 0u);
-                count += __popc(bal);
                 // outer caps: only for a non-degenerate first / last pair (line.rs:33-57)
                 bool first_cap = caps && nondeg && e == 0;
                 bool last_cap = caps && nondeg && e + 1 == n_pairs;
@@ -566,11 +598,57 @@ __global__ void __launch_bounds__(kGeomThreads) build_geometry_kernel(Scene s) {
                     c2 = push_away_from(p2.x, p2.y, p1.x, p1.y, hw);
                     k2 = (c2.x != p2.x || c2.y != p2.y) && touches(p2.x, p2.y, c2.x, c2.y);
                 }
+                SegRec r0, r1, r2;
+                unsigned nk = 0;  // main steps of this lane's records
+                if (keep) {
+                    r0 = make_rec(p1.x, p1.y, p2.x, p2.y, trav, 0u);
+                    nk += r0.n_k;
+                }
+                if (k1) {
+                    r1 = make_rec(p1.x, p1.y, c1.x, c1.y, 0.0, 1u);
+                    nk += r1.n_k;
+                }
+                if (k2) {
+                    r2 = make_rec(p2.x, p2.y, c2.x, c2.y, 0.0, 1u);
+                    nk += r2.n_k;
+                }
+                unsigned incl = nk;
+                for (int o = 1; o < 32; o <<= 1) {
+                    unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+                    if ((int)lane >= o) incl += v;
+                }
+                const unsigned total_k = __shfl_sync(0xffffffffu, incl, 31);
+                unsigned long long base_len = 0, base_alpha = 0;
+                if (lane == 0 && total_k) {
+                    base_len = atomicAdd(walk_len_used, 4ull * total_k);
+                    base_alpha = atomicAdd(walk_alpha_used, 4ull * S * total_k);
+                }
+                base_len = __shfl_sync(0xffffffffu, base_len, 0);
+                base_alpha = __shfl_sync(0xffffffffu, base_alpha, 0);
+                const bool fits = base_len + 4ull * total_k <= s.walk_len_cap && base_alpha + 4ull * S * total_k <= s.walk_alpha_cap &&
+                                  base_len + 4ull * total_k <= 0xffffffffull;
+                if (!fits && lane == 0 && total_k) atomicOr(&s.counters[CNT_OVERFLOW], 4u);
+                unsigned long long kpos = (unsigned long long)(incl - nk);  // main steps of the lanes before me
+                auto place = [&](SegRec& rec) {
+                    if (!fits) {
+                        rec.n_k = 0;  // nothing of this record is covered; the host grows the cache and redoes the batch
+                    } else {
+                        rec.len_off = (unsigned)(base_len + 4ull * kpos);
+                        rec.alpha_off = base_alpha + 4ull * S * kpos;
+                        kpos += rec.n_k;
+                    }
+                };
+                if (keep) place(r0);
+                if (k1) place(r1);
+                if (k2) place(r2);
+                unsigned bal = __ballot_sync(0xffffffffu, keep);
+                if (keep) out[count + __popc(bal & ((1u << lane) - 1u))] = r0;
+                count += __popc(bal);
                 unsigned b1 = __ballot_sync(0xffffffffu, k1);
                 unsigned b2 = __ballot_sync(0xffffffffu, k2);
-                if (k1) out[count] = make_rec(p1.x, p1.y, c1.x, c1.y, 0.0, 1u);
+                if (k1) out[count] = r1;
                 count += b1 ? 1u : 0u;
-                if (k2) out[count] = make_rec(p2.x, p2.y, c2.x, c2.y, 0.0, 1u);
+                if (k2) out[count] = r2;
                 count += b2 ? 1u : 0u;
             }
         }
@@ -778,53 +856,80 @@ constexpr int kBH = OSMR_BH;
 constexpr int kBP = kBW * kBH;
 static_assert((kBW == 16 || kBW == 32) && kBP % 32 == 0 && 256 % kBW == 0 && 256 % kBH == 0, "block shape");
 constexpr int kRasterThreads = 32;
+#ifndef OSMR_RASTER_MIN_BLOCKS
+#define OSMR_RASTER_MIN_BLOCKS 20  // resident one-warp CTAs per SM the register allocation must allow
+#endif
 
-struct SegHit {
-    int x1, y1, x2, y2;
-    double traveled;
-    int k0;
-    unsigned flags;            // SegRec.flags: bit0 outer cap, bit1 32-bit fast path valid, bit2 all coordinates < 2^24
-    unsigned long long magic;  // floor(2^64 / (2*mx_d)) + 1 (exact quotients for numerators < 2^32)
-    double denom;              // center_dist_denom (line.rs:106)
+// ------------------------------------------------------------------------------------------------------
+// Perpendicular walks (a4/a5).  The reference draws a thick line by walking, from every pixel k of the segment's
+// Bresenham main line, one perpendicular Bresenham line to each side until the opacity calculator says "not in line"
+// (line.rs:65-158).  Here the f64 work of a walk is done ONCE per tile by line_cover_kernel, which stores the alpha
+// of every in-line step in the walk cache; raster_kernel's 16x16 blocks then replay the integer stepping of the
+// walks that can reach them and take the alphas from the cache.  (Before the cache every block re-evaluated the
+// walks from their start: two thirds of all opacity evaluations fell outside the evaluating block.)
+// ------------------------------------------------------------------------------------------------------
+struct WalkItem {  // line.rs:65-118,133-158: the state of the main line at step k
+    bool swap;
+    int mn_inc, mx_inc, mn_d, mx_d;
+    int mn, mx;    // main-line pixel at step k (minor / major coordinate)
+    int p_error;   // i32 (wrapping) like the reference's `p_error`
+    bool extra;    // step k also starts the extra perpendicular of a double correction (line.rs:150-155)
 };
 
-struct RasterSmem {
-    double canvas[3][kBP];
-    unsigned long long plane[kBP];
-    OpacityCalc calc[2];  // [0] dashes of the op, [1] outer caps
-    SegHit hits[32];
-    unsigned pre[32];
-};
+__device__ __forceinline__ void walk_item_setup(int x1, int y1, int x2, int y2, unsigned flags, unsigned long long magic, int k,
+                                                WalkItem& w) {
+    const int dx = abs(wsub(x2, x1)), dy = abs(wsub(y2, y1));
+    w.swap = dx > dy;
+    const int mn0 = w.swap ? y1 : x1, mx0 = w.swap ? x1 : y1;
+    w.mn_d = w.swap ? dy : dx;
+    w.mx_d = w.swap ? dx : dy;
+    const int inc_x = (x1 <= x2) ? 1 : -1, inc_y = (y1 <= y2) ? 1 : -1;
+    w.mn_inc = w.swap ? inc_y : inc_x;
+    w.mx_inc = w.swap ? inc_x : inc_y;
+    // Bresenham state at main step k (closed form; exact quotients via the per-segment magic)
+    long long c, pc;
+    if (flags & 2u) {
+        int num = 2 * w.mn_d * k - w.mx_d;
+        c = num <= 0 ? 0 : (long long)__umul64hi((unsigned long long)(unsigned)(num + 2 * w.mx_d - 1), magic);
+        int num2 = 2 * w.mn_d * (int)c - w.mx_d;
+        pc = num2 <= 0 ? 0 : (long long)__umul64hi((unsigned long long)(unsigned)(num2 + 2 * w.mx_d - 1), magic);
+    } else {
+        c = ncorr(0, k, w.mn_d, w.mx_d);
+        pc = ncorr(0, c, w.mn_d, w.mx_d);
+    }
+    w.mx = mx0 + w.mx_inc * k;
+    w.mn = mn0 + w.mn_inc * (int)c;
+    w.p_error = (int)(2ll * w.mn_d * c - 2ll * w.mx_d * pc);
+    const int e_main = (int)(2ll * w.mn_d * k - 2ll * w.mx_d * c);  // main error before step k
+    w.extra = k < w.mx_d && wadd(e_main, 2 * w.mn_d) > w.mx_d && wadd(w.p_error, 2 * w.mn_d) > w.mx_d;
+}
 
-// per-segment constants of line.rs:65-118
+// per-segment f64 constants of line.rs:98-118
 struct SegConst {
     int x1, y1;
-    bool swap;
-    int mn_inc, mx_inc;
-    int mn_d, mx_d;
     long long numer_const, sdx, sdy;
     double denom;
     double traveled;
     bool small;  // all coordinates < 2^24: `raw as f64` can be carried exactly in f64
 };
 
-// draw_one_perpendicular (line.rs:89-131) restricted to one 16x16 block.
-__device__ __forceinline__ void walk_perpendicular(unsigned long long* plane, const SegConst& sc, const OpacityCalc& calc,
-                                                   int mn, int mx, int p_error, int mul, double opacity0, int bx0, int by0) {
-    int p_mn = mx;
+// draw_one_perpendicular (line.rs:89-131): evaluates the walk from its start until the first pixel that is not in the
+// line (or until it has left the tile for good on its monotone axis) and stores the alpha of every in-line step.
+// Returns the number of steps stored (<= S).
+__device__ __forceinline__ unsigned cover_walk(double* alpha_out, unsigned S, const WalkItem& w, const SegConst& sc, const OpacityCalc& calc,
+                                               int mn, int p_error, int mul, double opacity0, int D, unsigned* trunc_flag) {
+    int p_mn = w.mx;
     int p_mx = mn;
     int err = mul * p_error;  // i32 like the reference (line.rs:80-91)
-    // p_mx moves by mul*mn_inc every step: once it leaves the block on that side it never comes back
-    const int step = mul * sc.mn_inc;
-    const int corr = -mul * sc.mx_inc;
-    const int lo = sc.swap ? by0 : bx0;
-    const int hi = lo + (sc.swap ? kBH : kBW) - 1;
+    // p_mx moves by mul*mn_inc every step: once it leaves the tile on that side it never comes back
+    const int step = mul * w.mn_inc;
+    const int corr = -mul * w.mx_inc;
     // raw = numer_const + sdy*px - sdx*py (i64, line.rs:102-103); its per-step increments are integers
-    const long long d_step = sc.swap ? -sc.sdx * step : sc.sdy * step;
-    const long long d_corr = sc.swap ? sc.sdy * corr : -sc.sdx * corr;
+    const long long d_step = w.swap ? -sc.sdx * step : sc.sdy * step;
+    const long long d_corr = w.swap ? sc.sdy * corr : -sc.sdx * corr;
     long long raw;
     {
-        int px = sc.swap ? p_mn : p_mx, py = sc.swap ? p_mx : p_mn;
+        int px = w.swap ? p_mn : p_mx, py = w.swap ? p_mx : p_mn;
         raw = sc.numer_const + (sc.sdy * (long long)px - sc.sdx * (long long)py);
     }
     // `raw as f64` (line.rs:104): when every coordinate is below 2^24 the value is an integer below 2^53 and is
@@ -837,8 +942,9 @@ __device__ __forceinline__ void walk_perpendicular(unsigned long long* plane, co
     const bool quick = !(dashed && calc.round_caps);
     const double t_in = calc.feather_from * sc.denom * (1.0 - 9.0e-13);
     const double t_out = calc.feather_to * sc.denom * (1.0 + 9.0e-13);
+    unsigned t = 0;
     for (;;) {
-        if (step > 0 ? (p_mx > hi) : (p_mx < lo)) break;
+        if (step > 0 ? (p_mx > D - 1) : (p_mx < 0)) break;
         const double araw = fabs(sc.small ? fraw : (double)raw);
         double opacity;
         bool in_line;
@@ -852,33 +958,202 @@ __device__ __forceinline__ void walk_perpendicular(unsigned long long* plane, co
             double center_dist = div_pos_peeled(araw, sc.denom);
             double short_start = 0.0;
             if (dashed) {
-                int px = sc.swap ? p_mn : p_mx, py = sc.swap ? p_mx : p_mn;
+                int px = w.swap ? p_mn : p_mx, py = w.swap ? p_mx : p_mn;
                 double long_start = point_dist(px, py, sc.x1, sc.y1);
                 short_start = sqrt_peeled(fmax(long_start * long_start - center_dist * center_dist, 0.0));
             }
             calc_opacity(calc, sc.traveled, center_dist, short_start, opacity, in_line);
         }
+        OSMR_COUNT("cover.steps_evaluated", 1);
         if (!in_line) break;
-        const int lx = (sc.swap ? p_mn : p_mx) - bx0, ly = (sc.swap ? p_mx : p_mn) - by0;
-        if ((unsigned)lx < (unsigned)kBW && (unsigned)ly < (unsigned)kBH) {
-            double a = opacity0 * opacity;  // RgbaColor::from_color(color, initial_opacity * opacity).a
-            unsigned long long bits = (unsigned long long)__double_as_longlong(a);
-            unsigned long long* cell = &plane[ly * kBW + lx];
-            if (a > 0.0 && bits > *cell) atomicMax(cell, bits);
+        if (t >= S) {  // cannot happen (line_reach is a proven bound on the in-line steps); never continue silently
+            atomicOr(trunc_flag, 1u);
+            break;
         }
+        alpha_out[t] = opacity0 * opacity;  // RgbaColor::from_color(color, initial_opacity * opacity).a
+        ++t;
         // update_error (line.rs:82-91), wrapping i32 arithmetic
-        if (wadd(err, 2 * sc.mn_d) > sc.mx_d) {
-            err = wsub(err, 2 * sc.mx_d);
+        if (wadd(err, 2 * w.mn_d) > w.mx_d) {
+            err = wsub(err, 2 * w.mx_d);
             p_mn += corr;
             if (sc.small) fraw += f_corr; else raw += d_corr;
         }
-        err = wadd(err, 2 * sc.mn_d);
+        err = wadd(err, 2 * w.mn_d);
         p_mx += step;
         if (sc.small) fraw += f_step; else raw += d_step;
     }
+    return t;
 }
 
-__global__ void __launch_bounds__(kRasterThreads, 16) raster_kernel(Scene s) {
+// ------------------------------------------------------------------------------------------------------
+// line_cover_kernel: one warp per visible line op (dynamic fetch).  32 segment records at a time; their
+// (main step, direction) pairs are spread over the lanes, every lane evaluates its walk(s) to the end.
+// ------------------------------------------------------------------------------------------------------
+constexpr int kCoverThreads = 128;
+constexpr int kCoverWarps = kCoverThreads / 32;
+
+struct CoverSmem {
+    OpacityCalc calc[2];  // [0] dashes of the op, [1] outer caps
+    SegRec recs[32];
+    unsigned pre[32];
+};
+
+__global__ void __launch_bounds__(kCoverThreads) line_cover_kernel(Scene s) {
+    __shared__ CoverSmem smem[kCoverWarps];
+    CoverSmem& sm = smem[threadIdx.x >> 5];
+    const unsigned lane = lane_id();
+    const int D = s.D;
+    for (;;) {
+        unsigned wi = 0;
+        if (lane == 0) wi = atomicAdd(&s.counters[CNT_LINE_CURSOR], 1u);
+        wi = __shfl_sync(0xffffffffu, wi, 0);
+        if (wi >= s.counters[CNT_N_LINE_WORK]) break;
+        const unsigned gi = s.line_work[wi];
+        unsigned tile, pass;
+        osmr_styled_area ar;
+        decode_op(s, gi, tile, pass, ar);
+        const VisOp op = s.vis[gi];
+        const osmr_style& st = s.styles[ar.style];
+        LineParams lp;
+        line_params(s, st, (int)pass, lp);
+        const double hw = lp.width / 2.0;
+        const int reach = line_reach(hw);
+        const unsigned S = (unsigned)reach;
+        const SegRec* segs = reinterpret_cast<const SegRec*>(s.geom + op.geom_off);
+        const unsigned n_seg = op.geom_cnt;
+        unsigned steps_stored = 0;
+        __syncwarp();  // the previous op's walks are done with sm.calc
+        {  // the op's opacity calculators (built by style_calc_kernel), 16 bytes per lane and step
+            const uint4* src = s.calc_table + (size_t)(2u * ar.style + (pass - 1u)) * kCalcEntryUnits;
+            uint4* dst0 = reinterpret_cast<uint4*>(&sm.calc[0]);
+            uint4* dst1 = reinterpret_cast<uint4*>(&sm.calc[1]);
+            const unsigned n_main = 4u + 4u * (unsigned)reinterpret_cast<const OpacityCalc*>(src)->n_segs;
+            for (unsigned u = lane; u < n_main; u += 32) dst0[u] = src[u];
+            if (lane < kCapCalcUnits) dst1[lane] = src[kMainCalcUnits + lane];
+        }
+        for (unsigned sb = 0; sb < n_seg; sb += 32) {
+            const unsigned si = sb + lane;
+            unsigned items = 0;
+            __syncwarp();  // the previous batch's items are done with sm.recs / sm.pre
+            if (si < n_seg) {
+                const uint4* src = reinterpret_cast<const uint4*>(&segs[si]);
+                uint4* dst = reinterpret_cast<uint4*>(&sm.recs[lane]);
+                for (int u = 0; u < 4; ++u) dst[u] = src[u];
+                items = 2u * sm.recs[lane].n_k;
+            }
+            unsigned incl = items;
+            for (int o = 1; o < 32; o <<= 1) {
+                unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+                if ((int)lane >= o) incl += v;
+            }
+            const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+            sm.pre[lane] = incl - items;
+            __syncwarp();
+            for (unsigned item = lane; item < total; item += 32) {
+                int lo = 0, hi = 32;  // largest slot with pre <= item
+                while (hi - lo > 1) {
+                    int mid = (lo + hi) >> 1;
+                    if (sm.pre[mid] <= item)
+                        lo = mid;
+                    else
+                        hi = mid;
+                }
+                const SegRec& h = sm.recs[lo];
+                const unsigned local = item - sm.pre[lo];
+                const int k = h.k0 + (int)(local >> 1);
+                const int mul = (local & 1u) ? -1 : 1;
+                const OpacityCalc& calc = sm.calc[h.flags & 1u];
+                WalkItem w;
+                walk_item_setup(h.x1, h.y1, h.x2, h.y2, h.flags, h.magic, k, w);
+                SegConst sc;
+                sc.x1 = h.x1;
+                sc.y1 = h.y1;
+                sc.numer_const = (long long)h.x2 * (long long)h.y1 - (long long)h.y2 * (long long)h.x1;
+                sc.sdx = (long long)h.x2 - (long long)h.x1;
+                sc.sdy = (long long)h.y2 - (long long)h.y1;
+                sc.denom = h.denom;
+                sc.traveled = h.traveled;
+                sc.small = (h.flags & 4u) != 0;
+                const unsigned long long widx = 2ull * local;  // ((k - k0) * 2 + dir) * 2
+                unsigned char* len_out = s.walk_len + h.len_off + widx;
+                double* alpha_out = s.walk_alpha + h.alpha_off + widx * S;
+                // the walk of step k, then the extra one of a double correction (line.rs:150-155); a walk whose start is
+                // more than `reach` outside the tile on its own axis cannot put a pixel into it
+                int mn = w.mn, p_error = w.p_error;
+                for (int v = 0; v < 2; ++v) {
+                    unsigned len = 0;
+                    if (v == 0 || w.extra) {
+                        if (v == 1) {
+                            p_error = wadd(wsub(p_error, 2 * w.mx_d), 2 * w.mn_d);
+                            mn += w.mn_inc;
+                        }
+                        if (mn >= -reach && mn <= D - 1 + reach)
+                            len = cover_walk(alpha_out + (size_t)v * S, S, w, sc, calc, mn, p_error, mul, lp.opacity, D, &s.counters[CNT_WALK_TRUNC]);
+                    }
+                    len_out[v] = (unsigned char)len;
+                    steps_stored += len;
+                    OSMR_COUNT("cover.walks", len != 0);
+                }
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) steps_stored += __shfl_xor_sync(0xffffffffu, steps_stored, o);
+        if (lane == 0 && steps_stored)
+            atomicAdd(reinterpret_cast<unsigned long long*>(&s.counters[CNT_WALK_STEPS]), (unsigned long long)steps_stored);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// raster_kernel's half of the walks
+// ------------------------------------------------------------------------------------------------------
+struct SegHit {  // 48 bytes: what a block needs of a segment record that can reach it
+    int x1, y1, x2, y2;
+    int ka;                    // first main step within reach of the block
+    unsigned flags;            // SegRec.flags
+    unsigned long long magic;  // floor(2^64 / (2*mx_d)) + 1 (exact quotients for numerators < 2^32)
+    int k0;                    // SegRec.k0: first main step in the walk cache
+    unsigned len_off;
+    unsigned long long alpha_off;
+};
+
+struct RasterSmem {
+    double canvas[3][kBP];
+    unsigned long long plane[kBP];
+    SegHit hits[32];
+    unsigned pre[32];
+};
+
+// Replays the integer stepping of one cached walk (line.rs:82-96,120-130) and max-combines the alphas of the steps
+// that fall into the block.
+__device__ __forceinline__ void gather_walk(unsigned long long* plane, const double* __restrict__ alpha, unsigned len, const WalkItem& w,
+                                            int mn, int p_error, int mul, int bx0, int by0) {
+    int p_mn = w.mx;
+    int p_mx = mn;
+    int err = mul * p_error;
+    const int step = mul * w.mn_inc;
+    const int corr = -mul * w.mx_inc;
+    const int lo = w.swap ? by0 : bx0;
+    const int hi = lo + (w.swap ? kBH : kBW) - 1;
+    for (unsigned t = 0; t < len; ++t) {
+        if (step > 0 ? (p_mx > hi) : (p_mx < lo)) break;  // left the block on the monotone axis: never comes back
+        const int lx = (w.swap ? p_mn : p_mx) - bx0, ly = (w.swap ? p_mx : p_mn) - by0;
+        if ((unsigned)lx < (unsigned)kBW && (unsigned)ly < (unsigned)kBH) {
+            OSMR_COUNT("raster.steps_in_block", 1);
+            const double a = alpha[t];
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(a);
+            unsigned long long* cell = &plane[ly * kBW + lx];
+            if (a > 0.0 && bits > *cell) atomicMax(cell, bits);
+        }
+        OSMR_COUNT("raster.steps_replayed", 1);
+        if (wadd(err, 2 * w.mn_d) > w.mx_d) {
+            err = wsub(err, 2 * w.mx_d);
+            p_mn += corr;
+        }
+        err = wadd(err, 2 * w.mn_d);
+        p_mx += step;
+    }
+}
+
+__global__ void __launch_bounds__(kRasterThreads, OSMR_RASTER_MIN_BLOCKS) raster_kernel(Scene s) {
     __shared__ RasterSmem sm;
     const int D = s.D;
     const int bpr = D / kBW, bpc = D / kBH;  // blocks per tile row / column
@@ -971,11 +1246,12 @@ __global__ void __launch_bounds__(kRasterThreads, 16) raster_kernel(Scene s) {
                 continue;
             }
 
-            // ---------------- line: coverage into the alpha plane, then blend ----------------
+            // ---------------- line: gather the cached walk alphas into the alpha plane, then blend ----------------
             LineParams lp;
             line_params(s, st, (int)pass, lp);
             const double hw = lp.width / 2.0;
             const int reach = line_reach(hw);
+            const unsigned S = (unsigned)reach;  // doubles per cached walk
             const SegRec* segs = reinterpret_cast<const SegRec*>(s.geom + op.geom_off);
             const unsigned n_seg = op.geom_cnt;
             bool any = false;
@@ -1007,32 +1283,30 @@ __global__ void __launch_bounds__(kRasterThreads, 16) raster_kernel(Scene s) {
                         }
                         if (ka < 0) ka = 0;
                         if (kb > mxd) kb = mxd;
+                        const SegRec& full = segs[si];
+                        // the cache holds the steps within reach of the TILE (a superset); a record that lost its cache
+                        // slice to an overflow has n_k == 0 and the batch is redone
+                        const long long c0 = full.k0, c1 = (long long)full.k0 + (long long)full.n_k - 1;
+                        if (ka < c0) ka = c0;
+                        if (kb > c1) kb = c1;
                         if (kb >= ka) {
                             items = 2u * (unsigned)(kb - ka + 1);
-                            const SegRec& full = segs[si];
                             hrec.x1 = sr.x;
                             hrec.y1 = sr.y;
                             hrec.x2 = sr.z;
                             hrec.y2 = sr.w;
-                            hrec.traveled = full.traveled;
-                            hrec.k0 = (int)ka;
+                            hrec.ka = (int)ka;
                             hrec.flags = full.flags;
                             hrec.magic = full.magic;
-                            hrec.denom = full.denom;
+                            hrec.k0 = full.k0;
+                            hrec.len_off = full.len_off;
+                            hrec.alpha_off = full.alpha_off;
                         }
                     }
                 }
                 unsigned hb = __ballot_sync(0xffffffffu, items != 0);
+                OSMR_COUNT("raster.seg_batches", lane == 0);
                 if (!hb) continue;
-                if (!any) {  // first segment that reaches my block: fetch the op's opacity calculators (built by
-                             // style_calc_kernel) into shared memory, 16 bytes per lane and step
-                    const uint4* src = s.calc_table + (size_t)(2u * ar.style + (pass - 1u)) * kCalcEntryUnits;
-                    uint4* dst0 = reinterpret_cast<uint4*>(&sm.calc[0]);
-                    uint4* dst1 = reinterpret_cast<uint4*>(&sm.calc[1]);
-                    const unsigned n_main = 4u + 4u * (unsigned)reinterpret_cast<const OpacityCalc*>(src)->n_segs;
-                    for (unsigned u = lane; u < n_main; u += 32) dst0[u] = src[u];
-                    if (lane < kCapCalcUnits) dst1[lane] = src[kMainCalcUnits + lane];
-                }
                 any = true;
                 // exclusive scan of the item counts
                 unsigned incl = items;
@@ -1045,6 +1319,7 @@ __global__ void __launch_bounds__(kRasterThreads, 16) raster_kernel(Scene s) {
                 sm.pre[lane] = incl - items;
                 if (items) sm.hits[lane] = hrec;
                 __syncwarp();
+                const int rlo = -reach, rhi = reach;  // minor-axis cull relative to the block (see below)
                 for (unsigned item = lane; item < total; item += 32) {
                     int lo = 0, hi = 32;  // largest slot with pre <= item
                     while (hi - lo > 1) {
@@ -1056,55 +1331,26 @@ __global__ void __launch_bounds__(kRasterThreads, 16) raster_kernel(Scene s) {
                     }
                     const SegHit& h = sm.hits[lo];
                     const unsigned local = item - sm.pre[lo];
-                    const int k = h.k0 + (int)(local >> 1);
+                    const int k = h.ka + (int)(local >> 1);
                     const int mul = (local & 1u) ? -1 : 1;
-                    const OpacityCalc& calc = sm.calc[h.flags & 1u];
-
-                    // line.rs:65-118 set-up
-                    SegConst sc;
-                    const int dx = abs(wsub(h.x2, h.x1)), dy = abs(wsub(h.y2, h.y1));
-                    sc.x1 = h.x1;
-                    sc.y1 = h.y1;
-                    sc.swap = dx > dy;
-                    const int mn0 = sc.swap ? h.y1 : h.x1, mx0 = sc.swap ? h.x1 : h.y1;
-                    sc.mn_d = sc.swap ? dy : dx;
-                    sc.mx_d = sc.swap ? dx : dy;
-                    const int inc_x = (h.x1 <= h.x2) ? 1 : -1, inc_y = (h.y1 <= h.y2) ? 1 : -1;
-                    sc.mn_inc = sc.swap ? inc_y : inc_x;
-                    sc.mx_inc = sc.swap ? inc_x : inc_y;
-                    sc.numer_const = (long long)h.x2 * (long long)h.y1 - (long long)h.y2 * (long long)h.x1;
-                    sc.sdx = (long long)h.x2 - (long long)h.x1;
-                    sc.sdy = (long long)h.y2 - (long long)h.y1;
-                    sc.denom = h.denom;
-                    sc.traveled = h.traveled;
-                    sc.small = (h.flags & 4u) != 0;
-
-                    // Bresenham state at main step k (closed form; exact quotients via the per-segment magic)
-                    long long c, pc;
-                    if (h.flags & 2u) {
-                        int num = 2 * sc.mn_d * k - sc.mx_d;
-                        c = num <= 0 ? 0 : (long long)__umul64hi((unsigned long long)(unsigned)(num + 2 * sc.mx_d - 1), h.magic);
-                        int num2 = 2 * sc.mn_d * (int)c - sc.mx_d;
-                        pc = num2 <= 0 ? 0 : (long long)__umul64hi((unsigned long long)(unsigned)(num2 + 2 * sc.mx_d - 1), h.magic);
-                    } else {
-                        c = ncorr(0, k, sc.mn_d, sc.mx_d);
-                        pc = ncorr(0, c, sc.mn_d, sc.mx_d);
-                    }
-                    const int mx = mx0 + sc.mx_inc * k;
-                    int mn = mn0 + sc.mn_inc * (int)c;
-                    // i32 (wrapping) like the reference's `error` / `p_error`
-                    int p_error = (int)(2ll * sc.mn_d * c - 2ll * sc.mx_d * pc);
-                    const int e_main = (int)(2ll * sc.mn_d * k - 2ll * sc.mx_d * c);  // main error before step k
-                    // the walk of step k, then the extra one of a double correction (line.rs:150-155)
-                    const bool extra = k < sc.mx_d && wadd(e_main, 2 * sc.mn_d) > sc.mx_d && wadd(p_error, 2 * sc.mn_d) > sc.mx_d;
-                    const int rlo = (sc.swap ? by0 : bx0) - reach, rhi = (sc.swap ? by0 + kBH : bx0 + kBW) - 1 + reach;
-                    for (int v = 0; v < (extra ? 2 : 1); ++v) {
+                    OSMR_COUNT("raster.items", 1);
+                    const unsigned long long widx = 2ull * (2ull * (unsigned long long)(k - h.k0) + (local & 1u));
+                    const unsigned lens = *reinterpret_cast<const unsigned short*>(s.walk_len + h.len_off + widx);  // v0 | v1 << 8
+                    if (!lens) continue;
+                    WalkItem w;
+                    walk_item_setup(h.x1, h.y1, h.x2, h.y2, h.flags, h.magic, k, w);
+                    const double* alpha = s.walk_alpha + h.alpha_off + widx * S;
+                    const int blo = (w.swap ? by0 : bx0) + rlo, bhi = (w.swap ? by0 + kBH : bx0 + kBW) - 1 + rhi;
+                    int mn = w.mn, p_error = w.p_error;
+                    for (int v = 0; v < 2; ++v) {
+                        const unsigned len = v ? (lens >> 8) : (lens & 0xffu);
                         if (v == 1) {
-                            p_error = wadd(wsub(p_error, 2 * sc.mx_d), 2 * sc.mn_d);
-                            mn += sc.mn_inc;
+                            if (!len) break;
+                            p_error = wadd(wsub(p_error, 2 * w.mx_d), 2 * w.mn_d);
+                            mn += w.mn_inc;
                         }
-                        // minor-axis cull: a walk starts at mn and moves away from it
-                        if (mn >= rlo && mn <= rhi) walk_perpendicular(sm.plane, sc, calc, mn, mx, p_error, mul, lp.opacity, bx0, by0);
+                        // minor-axis cull: a walk starts at mn and moves away from it, at most `reach` pixels
+                        if (len && mn >= blo && mn <= bhi) gather_walk(sm.plane, alpha + (size_t)v * S, len, w, mn, p_error, mul, bx0, by0);
                     }
                 }
             }

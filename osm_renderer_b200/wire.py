@@ -85,12 +85,14 @@ class StatsStruct(C.Structure):
         ("kernel_launches", C.c_uint64),
         ("geom_bytes", C.c_uint64),
         ("mask_bytes", C.c_uint64),
+        ("walk_bytes", C.c_uint64),
+        ("walk_steps", C.c_uint64),
         ("ms_plan", C.c_float),
         ("ms_raster", C.c_float),
         ("ms_total", C.c_float),
         ("ms_label_layout", C.c_float),
         ("ms_label_device", C.c_float),
-        ("reserved", C.c_float),
+        ("ms_cover", C.c_float),
     ]
 
 

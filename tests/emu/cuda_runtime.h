@@ -404,6 +404,29 @@ static inline int atomicOr(volatile int* p, int v) {
     return old;
 }
 
+// named event counters for divergence / work statistics (printed at exit when OSMR_EMU_STATS is set); the kernels use
+// them through OSMR_COUNT(name, n), which is a no-op in the CUDA build
+namespace emu {
+struct Counters {
+    std::vector<std::pair<std::string, unsigned long long>> c;
+    ~Counters() {
+        if (getenv("OSMR_EMU_STATS"))
+            for (auto& kv : c) fprintf(stderr, "[emu-stat] %-40s %llu\n", kv.first.c_str(), kv.second);
+    }
+    unsigned long long& at(const char* name) {
+        for (auto& kv : c)
+            if (kv.first == name) return kv.second;
+        c.emplace_back(name, 0ull);
+        return c.back().second;
+    }
+};
+inline Counters& counters() {
+    static Counters k;
+    return k;
+}
+}  // namespace emu
+#define OSMR_COUNT(name, n) (emu::counters().at(name) += (unsigned long long)(n))
+
 #define EMU_LAUNCH(kernel, grid, block, ...) emu::launch(#kernel, dim3(grid), dim3(block), [=]() { kernel(__VA_ARGS__); })
 
 // ---------------------------------------------------------------------------------------------------------
@@ -480,6 +503,22 @@ static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcp
 }
 static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) {
     memset(d, v, n);
+    return cudaSuccess;
+}
+enum cudaMemoryType { cudaMemoryTypeUnregistered = 0, cudaMemoryTypeHost = 1, cudaMemoryTypeDevice = 2, cudaMemoryTypeManaged = 3 };
+struct cudaPointerAttributes {
+    cudaMemoryType type;
+    int device;
+    void* devicePointer;
+    void* hostPointer;
+};
+static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void* p) {
+    // OSMR_EMU_PINNED=1: treat every host pointer as page-locked and mapped (exercises the direct-output path)
+    const bool pinned = getenv("OSMR_EMU_PINNED") != nullptr;
+    a->type = pinned ? cudaMemoryTypeHost : cudaMemoryTypeUnregistered;
+    a->device = 0;
+    a->devicePointer = pinned ? const_cast<void*>(p) : nullptr;
+    a->hostPointer = const_cast<void*>(p);
     return cudaSuccess;
 }
 template <typename T>
