@@ -65,6 +65,7 @@ def build_workload(name: str, cache_dir: str | None = None):
     return {
         "bin": data,
         "reader": rd,
+        "builder": fb,
         "table": table,
         "tiles": np.array(tiles, dtype=TILE_DTYPE),
         "area_begin": begins,
@@ -191,6 +192,7 @@ def main():
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-sample", type=int, default=0, help="tiles in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--lib", default=None, help="experiments only: load this build of libosmr_b200.so (e.g. other -D flags)")
     ap.add_argument("--e2e-direct", type=int, default=1, choices=[0, 1],
                     help="e2e leg: 1 = raster_kernel stores the tiles straight into the page-locked host buffer (default), "
                          "0 = stage them in HBM and copy back on a second stream")
@@ -263,9 +265,11 @@ def main():
     else:
         torch.cuda.set_device(local_rank)
 
+    from osm_renderer_b200 import _lib, sharding
     from osm_renderer_b200.drawer import GpuContext
 
-    from osm_renderer_b200 import sharding
+    if args.lib:
+        _lib.LIB_PATH = os.path.abspath(args.lib)
 
     w = build_workload(args.workload)
     # weak scaling: the global request list is `world` interleaved copies of the batch; rank r renders the requests

@@ -160,6 +160,8 @@ typedef struct osmr_stats {
     float ms_label_layout;   /* osmr_draw_tiles_labeled: host layout (wall clock) and label kernels (CUDA events) */
     float ms_label_device;
     float ms_cover;          /* line_cover_kernel */
+    float ms_auto;           /* osmr_draw_tiles_auto: candidate lookup + ordering on the device */
+    float reserved;
 } osmr_stats;
 int osmr_get_stats(osmr_ctx* ctx, osmr_stats* out);
 
@@ -214,6 +216,31 @@ int osmr_set_label_styles(osmr_ctx* ctx, const osmr_label_style* styles, uint32_
 int osmr_draw_tiles_labeled(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, const uint32_t* area_begin,
                             const osmr_styled_area* areas, const uint32_t* label_begin, const osmr_label* labels,
                             const uint8_t canvas_rgb[3], uint32_t flags, uint8_t* out);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * the step BEFORE the draw path on the device -- tile -> candidate entities -> ordered styled areas.
+ * Replaces GeodataReader::get_entities_in_tile_with_neighbors (src/geodata/reader.rs:60-180), Styler::style_areas
+ * (src/mapcss/styler.rs:115-203) and the painter's order of compare_styled_entities (styler.rs:246-272) for the area
+ * passes.  MapCSS selector matching (strings) stays on the host, exactly as cached by the reference's StyleCache
+ * (src/mapcss/style_cache.rs:68-87, key = entity + zoom): per zoom the host provides, for every way and multipolygon of
+ * the `.bin`, the id of its style list ("class", 0xffffffff = no styles) and per class the ordered list of its styles.
+ * osmr_class_style.order is the dense rank (equal keys -> equal rank) of the style's sort key
+ * (layer.unwrap_or(0), is_foreground_fill, z_index) among all class styles of the zoom; the library appends the rest of
+ * the reference's comparison (global id, multipolygon before way, local id, position in the style list) itself.
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct osmr_class_style {
+    uint32_t style; /* index into the table of osmr_set_styles */
+    uint32_t order; /* < 2^20 */
+} osmr_class_style;
+int osmr_set_zoom_styles(osmr_ctx* ctx, uint32_t zoom, const uint32_t* way_class /* n_ways */, const uint32_t* mp_class /* n_multipolygons */,
+                         const uint32_t* class_begin /* n_classes + 1 */, const osmr_class_style* class_styles, uint32_t n_classes);
+/* osmr_draw_tiles with the styled-area lists built on the device: only the tile list crosses the bus.  All tiles of a call
+ * share one zoom (<= 18, tile.rs:5) and one scale.  Areas whose bounding box (plus the widest line reach of their styles)
+ * cannot touch the tile are dropped before ordering; the image is the one osmr_draw_tiles produces from the reference's
+ * full list. */
+int osmr_draw_tiles_auto(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, const uint8_t canvas_rgb[3], uint32_t flags, uint8_t* out);
+/* the styled-area lists of the last osmr_draw_tiles_auto call (tests): area_begin[n_tiles + 1], areas[area_begin[n_tiles]] */
+int osmr_auto_readback(osmr_ctx* ctx, uint32_t* area_begin, osmr_styled_area* areas, uint32_t areas_cap);
 
 /* Optional page-locked host memory for callers that want full-speed host<->device copies of `out` / batch
  * arrays (plain malloc'ed buffers work too, at pageable-copy speed). */

@@ -34,6 +34,9 @@ EXPORTS = [
     "osmr_set_label_icons",
     "osmr_set_label_styles",
     "osmr_draw_tiles_labeled",
+    "osmr_set_zoom_styles",
+    "osmr_draw_tiles_auto",
+    "osmr_auto_readback",
 ]
 
 _lib = None
@@ -95,5 +98,11 @@ def load():
     L.osmr_set_label_styles.argtypes = [vp, vp, u32, C.c_char_p, sz]
     L.osmr_draw_tiles_labeled.restype = C.c_int
     L.osmr_draw_tiles_labeled.argtypes = [vp, vp, u32, vp, vp, vp, vp, vp, u32, vp]
+    L.osmr_set_zoom_styles.restype = C.c_int
+    L.osmr_set_zoom_styles.argtypes = [vp, u32, vp, vp, vp, vp, u32]
+    L.osmr_draw_tiles_auto.restype = C.c_int
+    L.osmr_draw_tiles_auto.argtypes = [vp, vp, u32, vp, u32, vp]
+    L.osmr_auto_readback.restype = C.c_int
+    L.osmr_auto_readback.argtypes = [vp, vp, vp, u32]
     _lib = L
     return L

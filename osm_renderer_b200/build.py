@@ -16,6 +16,8 @@ SOURCES = [os.path.join(HERE, "csrc", "osmr_capi.cu")]
 HEADERS = [
     os.path.join(HERE, "csrc", "osmr_kernels.cuh"),
     os.path.join(HERE, "csrc", "osmr_device.cuh"),
+    os.path.join(HERE, "csrc", "osmr_auto.cuh"),
+    os.path.join(HERE, "csrc", "osmr_labels_host.hpp"),
     os.path.join(ROOT, "include", "osmr.h"),
 ]
 

@@ -16,6 +16,7 @@
 
 #include "osmr.h"
 #include "osmr_kernels.cuh"
+#include "osmr_auto.cuh"
 #include "osmr_labels_host.hpp"
 
 using namespace osmr;
@@ -64,6 +65,8 @@ struct PinnedBuf {  // page-locked host staging, grown on demand and kept
     }
 };
 
+constexpr unsigned kMaxChunks = 16;  // draw chunks of one call (host output is pipelined chunk by chunk)
+
 struct LabelWorkItem {  // a run of consecutive labels of one tile, laid out by one host thread
     uint32_t tile, first, count;
     std::vector<osmr_host::LabelRec> recs;
@@ -77,7 +80,11 @@ struct osmr_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;
-    cudaEvent_t chunk_done[2] = {nullptr, nullptr};
+    cudaStream_t d2h_stream = nullptr;
+    cudaEvent_t chunk_done[kMaxChunks] = {};
+    cudaEvent_t cev[kMaxChunks][4] = {};   // per draw chunk: start, after cover, after raster, before cover
+    unsigned chunk_launches[kMaxChunks] = {};
+    PinnedBuf<unsigned> h_cnt;             // per draw chunk: its counters, copied back asynchronously
     cudaEvent_t areas_ready = nullptr;
     bool areas_deferred = false;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -131,6 +138,7 @@ struct osmr_ctx {
     // scratch
     DevBuf<AreaInfo> area_info;
     DevBuf<VisOp> vis;
+    DevBuf<RasterOp> rop;
     DevBuf<short4> vis_bbox;
     DevBuf<unsigned> vis_count, work, fill_work, line_work, counters, mask;
     DevBuf<uint4> geom, calc_table;
@@ -139,8 +147,24 @@ struct osmr_ctx {
     size_t geom_cap_units = 0, mask_cap_words = 0, walk_alpha_cap = 0, walk_len_cap = 0;
     DevBuf<unsigned char> out;
     size_t out_bytes = 0;
+    // f3: device-side candidate lookup + painter's order (osmr_auto.cuh)
+    struct ZoomTable {
+        DevBuf<unsigned> way_class, mp_class, class_begin;
+        DevBuf<osmr_class_style> class_styles;
+        DevBuf<int> class_reach;
+        unsigned n_classes = 0, n_class_styles = 0;
+        bool set = false;
+    };
+    ZoomTable zoom_tables[19];
+    std::string auto_unavailable;  // why the tile index of the image cannot drive the device-side lookup ("" = it can)
+    unsigned n_idx = 0;
+    DevBuf<uint2> idx_xy, idx_w, idx_m, way_min_tile, mp_min_tile;
+    DevBuf<unsigned> way_rank, mp_rank, rank_entity;
+    DevBuf<unsigned> auto_bound, auto_cand, auto_cand_cnt, auto_inst;
+    DevBuf<unsigned long long> auto_big_keys;
     int fill_cap = kFillCap;
-    bool direct_out = true;  // page-locked `out`: raster_kernel stores the tiles straight into host memory (no D2H stage)
+    bool direct_out = false;  // debug key "direct_out": raster_kernel stores the tiles straight into a page-locked `out`
+                              // (no D2H stage; measured slower than the staged pipeline: PCIe-bound stores, 26 GB/s)
     unsigned first_chunk = 0;  // tiles in the first draw chunk of the current upload (0: one chunk)
     osmr_stats stats{};
 
@@ -182,7 +206,10 @@ int osmr_ctx_create(int device, osmr_ctx** out_ctx) {
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
-    for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->chunk_done[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking);
+    for (unsigned i = 0; i < kMaxChunks && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->chunk_done[i], cudaEventDisableTiming);
+    for (unsigned i = 0; i < kMaxChunks; ++i)
+        for (int j = 0; j < 4 && e == cudaSuccess; ++j) e = cudaEventCreate(&ctx->cev[i][j]);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->areas_ready, cudaEventDisableTiming);
     for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_label0);
@@ -222,10 +249,31 @@ void osmr_ctx_destroy(osmr_ctx* ctx) {
     ctx->areas.release();
     ctx->area_info.release();
     ctx->vis.release();
+    ctx->rop.release();
     ctx->vis_bbox.release();
     ctx->vis_count.release();
     ctx->work.release();
     ctx->fill_work.release();
+    for (auto& z : ctx->zoom_tables) {
+        z.way_class.release();
+        z.mp_class.release();
+        z.class_begin.release();
+        z.class_styles.release();
+        z.class_reach.release();
+    }
+    ctx->idx_xy.release();
+    ctx->idx_w.release();
+    ctx->idx_m.release();
+    ctx->way_min_tile.release();
+    ctx->mp_min_tile.release();
+    ctx->way_rank.release();
+    ctx->mp_rank.release();
+    ctx->rank_entity.release();
+    ctx->auto_bound.release();
+    ctx->auto_cand.release();
+    ctx->auto_cand_cnt.release();
+    ctx->auto_inst.release();
+    ctx->auto_big_keys.release();
     ctx->line_work.release();
     ctx->walk_alpha.release();
     ctx->walk_len.release();
@@ -251,6 +299,11 @@ void osmr_ctx_destroy(osmr_ctx* ctx) {
         if (e) cudaEventDestroy(e);
     for (auto& e : ctx->chunk_done)
         if (e) cudaEventDestroy(e);
+    for (auto& row : ctx->cev)
+        for (auto& e : row)
+            if (e) cudaEventDestroy(e);
+    ctx->h_cnt.release();
+    if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
     if (ctx->areas_ready) cudaEventDestroy(ctx->areas_ready);
     if (ctx->ev_label0) cudaEventDestroy(ctx->ev_label0);
     if (ctx->ev_label1) cudaEventDestroy(ctx->ev_label1);
@@ -372,6 +425,108 @@ int osmr_set_geodata(osmr_ctx* ctx, const void* bin, size_t len) {
     ctx->n_ints = n_ints;
     ctx->has_geo = true;
     ctx->has_batch = false;
+    for (auto& z : ctx->zoom_tables) z.set = false;  // classes are per dataset
+
+    // ---- f3: the tile index (reader.rs:135-180) + what the device-side lookup derives from it ----
+    {
+        const uint32_t n_idx = cnt[4];
+        ctx->n_idx = n_idx;
+        ctx->auto_unavailable.clear();
+        std::vector<uint2> ixy(n_idx), iw(n_idx), im(n_idx);
+        struct Ext {
+            uint32_t x0 = 0xffffffffu, y0 = 0xffffffffu, x1 = 0, y1 = 0, n = 0;
+        };
+        std::vector<Ext> wext(n_ways), mext(n_mps);
+        for (uint32_t i = 0; i < n_idx && ctx->auto_unavailable.empty(); ++i) {
+            const uint8_t* r = base[4] + (size_t)i * 32;
+            ixy[i] = make_uint2(rd_u32(r), rd_u32(r + 4));
+            iw[i] = make_uint2(rd_u32(r + 16), rd_u32(r + 20));
+            im[i] = make_uint2(rd_u32(r + 24), rd_u32(r + 28));
+            if (i && !(ixy[i - 1].x < ixy[i].x || (ixy[i - 1].x == ixy[i].x && ixy[i - 1].y < ixy[i].y)))
+                ctx->auto_unavailable = "tile index is not sorted by (x, y)";
+            if (!range_ok(iw[i].x, iw[i].y) || !range_ok(im[i].x, im[i].y)) ctx->auto_unavailable = "tile index id list out of range";
+            if (!ctx->auto_unavailable.empty()) break;
+            auto note = [&](std::vector<Ext>& ext, uint32_t e) {
+                if (e >= ext.size()) {
+                    ctx->auto_unavailable = "tile index references a missing entity";
+                    return;
+                }
+                Ext& x = ext[e];
+                x.x0 = std::min(x.x0, ixy[i].x);
+                x.y0 = std::min(x.y0, ixy[i].y);
+                x.x1 = std::max(x.x1, ixy[i].x);
+                x.y1 = std::max(x.y1, ixy[i].y);
+                ++x.n;
+            };
+            for (uint32_t k = 0; k < iw[i].y; ++k) note(wext, ints[iw[i].x + k]);
+            for (uint32_t k = 0; k < im[i].y; ++k) note(mext, ints[im[i].x + k]);
+        }
+        // every entity must be listed in the full rectangle of index tiles between its extreme tiles (saver.rs:194-226):
+        // the device-side dedup relies on it
+        auto rectangular = [](const std::vector<Ext>& ext) {
+            for (const Ext& x : ext)
+                if (x.n && (uint64_t)(x.x1 - x.x0 + 1) * (uint64_t)(x.y1 - x.y0 + 1) != x.n) return false;
+            return true;
+        };
+        if (ctx->auto_unavailable.empty() && !(rectangular(wext) && rectangular(mext)))
+            ctx->auto_unavailable = "tile index does not list every entity in the full rectangle of its z18 tiles";
+        if (ctx->auto_unavailable.empty()) {
+            std::vector<uint2> wmin(n_ways), mmin(n_mps);
+            for (uint32_t i = 0; i < n_ways; ++i) wmin[i] = make_uint2(wext[i].x0, wext[i].y0);
+            for (uint32_t i = 0; i < n_mps; ++i) mmin[i] = make_uint2(mext[i].x0, mext[i].y0);
+            // rank of (global id, multipolygon before way, local id): the tail of the painter's order (styler.rs:172-203,268-271)
+            struct Key {
+                uint64_t gid;
+                uint32_t is_way, loc;
+            };
+            std::vector<Key> keys(n_ways + (size_t)n_mps);
+            for (uint32_t i = 0; i < n_mps; ++i) {
+                uint64_t g;
+                memcpy(&g, base[3] + (size_t)i * 24, 8);
+                keys[i] = Key{g, 0u, i};
+            }
+            for (uint32_t i = 0; i < n_ways; ++i) {
+                uint64_t g;
+                memcpy(&g, base[1] + (size_t)i * 24, 8);
+                keys[n_mps + i] = Key{g, 1u, i};
+            }
+            std::sort(keys.begin(), keys.end(), [](const Key& a, const Key& b) {
+                if (a.gid != b.gid) return a.gid < b.gid;
+                if (a.is_way != b.is_way) return a.is_way < b.is_way;
+                return a.loc < b.loc;
+            });
+            std::vector<unsigned> wrank(n_ways), mrank(n_mps), rank_entity(keys.size());
+            for (size_t r = 0; r < keys.size(); ++r) {
+                if (keys[r].is_way) {
+                    wrank[keys[r].loc] = (unsigned)r;
+                    rank_entity[r] = keys[r].loc;
+                } else {
+                    mrank[keys[r].loc] = (unsigned)r;
+                    rank_entity[r] = keys[r].loc | OSMR_AREA_MULTIPOLYGON;
+                }
+            }
+            CK(ctx->idx_xy.reserve(n_idx + 1));
+            CK(ctx->idx_w.reserve(n_idx + 1));
+            CK(ctx->idx_m.reserve(n_idx + 1));
+            CK(ctx->way_min_tile.reserve(n_ways + 1));
+            CK(ctx->mp_min_tile.reserve(n_mps + 1));
+            CK(ctx->way_rank.reserve(n_ways + 1));
+            CK(ctx->mp_rank.reserve(n_mps + 1));
+            CK(ctx->rank_entity.reserve(keys.size() + 1));
+            auto up = [&](void* d, const void* h, size_t bytes) {
+                return bytes ? cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->stream) : cudaSuccess;
+            };
+            CK(up(ctx->idx_xy.p, ixy.data(), (size_t)n_idx * 8));
+            CK(up(ctx->idx_w.p, iw.data(), (size_t)n_idx * 8));
+            CK(up(ctx->idx_m.p, im.data(), (size_t)n_idx * 8));
+            CK(up(ctx->way_min_tile.p, wmin.data(), (size_t)n_ways * 8));
+            CK(up(ctx->mp_min_tile.p, mmin.data(), (size_t)n_mps * 8));
+            CK(up(ctx->way_rank.p, wrank.data(), (size_t)n_ways * 4));
+            CK(up(ctx->mp_rank.p, mrank.data(), (size_t)n_mps * 4));
+            CK(up(ctx->rank_entity.p, rank_entity.data(), keys.size() * 4));
+            CK(cudaStreamSynchronize(ctx->stream));
+        }
+    }
     return OSMR_OK;
 }
 
@@ -468,7 +623,8 @@ static unsigned char* pinned_device_alias(const void* p) {
 }
 
 // Host output is drawn in chunks so that transfers overlap the drawing:
-//   staged (pageable `out`, or direct_out off): 4 equal chunks, the D2H copy of chunk i runs while chunk i+1 is drawn;
+//   staged (the default): 8 equal chunks, all enqueued back to back; the D2H copy of chunk i runs on its own stream while
+//   the later chunks are drawn (it really overlaps only when `out` is page-locked, e.g. from osmr_alloc_pinned);
 //   direct (page-locked `out`): a small first chunk hides the upload of the remaining styled areas, the tiles themselves
 //   are written to host memory by raster_kernel as they are finished.
 static void draw_chunks(unsigned n_tiles, bool to_host, bool direct, unsigned& first, unsigned& rest) {
@@ -478,7 +634,7 @@ static void draw_chunks(unsigned n_tiles, bool to_host, bool direct, unsigned& f
         first = std::max(32u, n_tiles / 8);
         rest = n_tiles - first;
     } else {
-        first = rest = std::max(64u, (n_tiles + 3) / 4);
+        first = rest = std::max(64u, (n_tiles + 7) / 8);
     }
 }
 
@@ -521,6 +677,7 @@ static int batch_upload_impl(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_t
     // scratch that scales with the batch
     CK(ctx->area_info.reserve(n_areas + 1));
     CK(ctx->vis.reserve(3ull * n_areas + 1));
+    CK(ctx->rop.reserve(3ull * n_areas + 1));
     CK(ctx->vis_bbox.reserve(3ull * n_areas + 1));
     CK(ctx->work.reserve(3ull * n_areas + 1));
     CK(ctx->fill_work.reserve((size_t)n_areas + 1));
@@ -538,170 +695,159 @@ int osmr_batch_upload(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, c
     return batch_upload_impl(ctx, tiles, n_tiles, area_begin, areas, false, nullptr);
 }
 
-// Draws tiles [tb, tb+tc) of the uploaded batch into dev_out (which points at tile tb's image).  Synchronises the
-// compute stream (the scratch-overflow check needs the counters) and adds to ctx->stats.
-static int run_pipeline(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t flags, unsigned char* dev_out, unsigned tb, unsigned tc) {
+// Enqueues the whole pipeline for tiles [tb, tb+tc) of the uploaded batch on the compute stream (nothing here waits for
+// the device): the chunk's counters land in page-locked slot `slot` and are judged by collect_chunk after the stream
+// has been synchronised.  dev_out points at tile tb's image.
+static int launch_chunk(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t flags, unsigned char* dev_out, unsigned tb, unsigned tc,
+                        unsigned slot) {
     const int D = 256 * ctx->scale;
     const unsigned area_base = ctx->h_area_begin[tb];
     const unsigned n_areas = ctx->h_area_begin[tb + tc] - area_base;
-    for (int attempt = 0; attempt < 6; ++attempt) {
-        if (ctx->geom_cap_units == 0) {
-            size_t units = (size_t)ctx->n_areas * 8 + (1u << 20);  // first guess; grown on overflow
-            CK(ctx->geom.reserve(units));
+    Scene s{};
+    s.merc = ctx->merc.p;
+    s.ways = ctx->ways.p;
+    s.polys = ctx->polys.p;
+    s.mps = ctx->mps.p;
+    s.ints = ctx->ints.p;
+    s.n_nodes = ctx->n_nodes;
+    s.n_ways = ctx->n_ways;
+    s.n_polys = ctx->n_polys;
+    s.n_mps = ctx->n_mps;
+    s.n_ints = ctx->n_ints;
+    s.styles = ctx->styles.p;
+    s.dashes = ctx->dashes.p;
+    s.n_styles = ctx->n_styles;
+    s.n_dashes = ctx->n_dashes;
+    s.icons = ctx->icons.p;
+    s.icon_px = ctx->icon_px.p;
+    s.n_icons = ctx->n_icons;
+    s.tiles = ctx->tiles.p + tb;
+    s.area_begin = ctx->area_begin.p + tb;
+    s.areas = ctx->areas.p;
+    s.n_tiles = tc;
+    s.n_areas = n_areas;
+    s.area_base = area_base;
+    s.D = D;
+    s.scale = ctx->scale;
+    s.flags = flags;
+    if (flags & OSMR_DRAW_HAS_CANVAS_COLOR) memcpy(s.canvas, canvas_rgb, 3);
+    s.area_info = ctx->area_info.p;
+    s.vis = ctx->vis.p;
+    s.rop = ctx->rop.p;
+    s.vis_bbox = ctx->vis_bbox.p;
+    s.vis_count = ctx->vis_count.p;
+    s.work = ctx->work.p;
+    s.fill_work = ctx->fill_work.p;
+    s.line_work = ctx->line_work.p;
+    s.walk_alpha = ctx->walk_alpha.p;
+    s.walk_len = ctx->walk_len.p;
+    s.walk_alpha_cap = ctx->walk_alpha_cap;
+    s.walk_len_cap = ctx->walk_len_cap;
+    s.calc_table = ctx->calc_table.p;
+    s.geom = ctx->geom.p;
+    s.geom_cap = (unsigned)std::min<size_t>(ctx->geom_cap_units, 0xffffffffu);
+    s.mask = ctx->mask.p;
+    s.mask_cap = (unsigned)std::min<size_t>(ctx->mask_cap_words, 0xffffffffu);
+    s.counters = ctx->counters.p + (size_t)slot * CNT_COUNT;
+    s.fill_cap = ctx->fill_cap;
+    s.label_plane = ctx->label_plane_active ? ctx->label_plane.p + (size_t)tb * D * D : nullptr;
+    s.label_icon_px = ctx->label_icon_px.p;
+    s.out = dev_out;
+
+    cudaStream_t st = ctx->stream;
+    cudaEvent_t* ev = ctx->cev[slot];
+    CK(cudaEventRecord(ev[0], st));
+    CK(cudaMemsetAsync(s.counters, 0, CNT_COUNT * sizeof(unsigned), st));
+    unsigned launches = 0;
+    if (ctx->n_styles && slot == 0) {  // the calculators depend on (styles, scale, flags) only: once per draw
+        style_calc_kernel<<<(2 * ctx->n_styles + 127) / 128, 128, 0, st>>>(s, ctx->calc_table.p);
+        ++launches;
+    }
+    if (n_areas) {
+        area_bbox_kernel<<<(n_areas + 255) / 256, 256, 0, st>>>(s);
+        ++launches;
+    }
+    plan_ops_kernel<<<tc, kPlanThreads, 0, st>>>(s);
+    build_geometry_kernel<<<ctx->num_sms * 8, kGeomThreads, 0, st>>>(s);
+    fill_rows_kernel<<<ctx->num_sms * 16, kFillThreads, 0, st>>>(s);
+    CK(cudaEventRecord(ev[3], st));
+    line_cover_kernel<<<ctx->num_sms * 8, kCoverThreads, 0, st>>>(s);
+    launches += 4;
+    CK(cudaEventRecord(ev[1], st));
+    const unsigned blocks = (unsigned)((D / kBW) * (D / kBH));
+    raster_kernel<<<tc * blocks, kRasterThreads, 0, st>>>(s);
+    ++launches;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ev[2], st));
+    CK(cudaMemcpyAsync(ctx->h_cnt.p + (size_t)slot * CNT_COUNT, s.counters, CNT_COUNT * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    ctx->chunk_launches[slot] = launches;
+    return OSMR_OK;
+}
+
+// After the compute stream has been synchronised: errors of chunk `slot`, scratch growth on overflow (*redo = true), else
+// its statistics.
+static int collect_chunk(osmr_ctx* ctx, unsigned slot, unsigned tb, unsigned tc, bool* redo) {
+    const unsigned* h_cnt = ctx->h_cnt.p + (size_t)slot * CNT_COUNT;
+    const unsigned n_areas = ctx->h_area_begin[tb + tc] - ctx->h_area_begin[tb];
+    if (h_cnt[CNT_BAD_INPUT] & 1u) return ctx->fail(OSMR_E_INVALID, "styled area references an entity or style that does not exist");
+    if (h_cnt[CNT_BAD_INPUT] & 2u) return ctx->fail(OSMR_E_INVALID, "line wider than 240 pixels (width * scale): not supported");
+    if (h_cnt[CNT_WALK_TRUNC]) return ctx->fail(OSMR_E_CUDA, "internal error: a perpendicular walk exceeded its proven bound");
+    if (h_cnt[CNT_OVERFLOW]) {  // grow the scratch that ran out; the caller redoes the draw
+        *redo = true;
+        if (h_cnt[CNT_OVERFLOW] & 1u) {
+            size_t need = (size_t)h_cnt[CNT_GEOM_USED] + (size_t)h_cnt[CNT_GEOM_USED] / 2 + 1024;
+            if (need <= ctx->geom_cap_units) need = ctx->geom_cap_units * 2;
+            if (need >= 0xffffffffull) return ctx->fail(OSMR_E_NOMEM, "geometry scratch exceeds 64 GiB; split the batch");
+            CK(ctx->geom.reserve(need));
             ctx->geom_cap_units = ctx->geom.cap;
         }
-        if (ctx->mask_cap_words == 0) {
-            size_t words = (size_t)ctx->n_tiles * (size_t)D * (D / 32) * 4 + (1u << 20);
-            CK(ctx->mask.reserve(words));
+        if (h_cnt[CNT_OVERFLOW] & 4u) {
+            unsigned long long used_alpha, used_len;
+            memcpy(&used_alpha, &h_cnt[CNT_WALK_ALPHA], 8);
+            memcpy(&used_len, &h_cnt[CNT_WALK_LEN], 8);
+            if (used_len >= 0xffffffffull) return ctx->fail(OSMR_E_NOMEM, "walk cache exceeds 2^32 walks; split the batch");
+            size_t need_a = (size_t)used_alpha + (size_t)used_alpha / 4 + 1024, need_l = (size_t)used_len + (size_t)used_len / 4 + 1024;
+            if (need_a > ctx->walk_alpha_cap) {
+                if (ctx->walk_alpha.reserve(need_a) != cudaSuccess)
+                    return ctx->fail(OSMR_E_NOMEM, "walk cache does not fit in device memory; split the batch");
+                ctx->walk_alpha_cap = ctx->walk_alpha.cap;
+            }
+            if (need_l > ctx->walk_len_cap) {
+                CK(ctx->walk_len.reserve(need_l));
+                ctx->walk_len_cap = ctx->walk_len.cap;
+            }
+        }
+        if (h_cnt[CNT_OVERFLOW] & 2u) {
+            size_t need = (size_t)h_cnt[CNT_MASK_USED] + (size_t)h_cnt[CNT_MASK_USED] / 2 + 1024;
+            if (need <= ctx->mask_cap_words) need = ctx->mask_cap_words * 2;
+            if (need >= 0xffffffffull) return ctx->fail(OSMR_E_NOMEM, "mask scratch exceeds 16 GiB; split the batch");
+            CK(ctx->mask.reserve(need));
             ctx->mask_cap_words = ctx->mask.cap;
         }
-        if (ctx->walk_alpha_cap == 0) {  // first guess: ~1.5 MB of walk cache per tile; grown on overflow
-            CK(ctx->walk_alpha.reserve((size_t)ctx->n_tiles * (192u << 10) + (1u << 20)));
-            ctx->walk_alpha_cap = ctx->walk_alpha.cap;
-        }
-        if (ctx->walk_len_cap == 0) {
-            CK(ctx->walk_len.reserve((size_t)ctx->n_tiles * (40u << 10) + (1u << 20)));
-            ctx->walk_len_cap = ctx->walk_len.cap;
-        }
-        Scene s{};
-        s.merc = ctx->merc.p;
-        s.ways = ctx->ways.p;
-        s.polys = ctx->polys.p;
-        s.mps = ctx->mps.p;
-        s.ints = ctx->ints.p;
-        s.n_nodes = ctx->n_nodes;
-        s.n_ways = ctx->n_ways;
-        s.n_polys = ctx->n_polys;
-        s.n_mps = ctx->n_mps;
-        s.n_ints = ctx->n_ints;
-        s.styles = ctx->styles.p;
-        s.dashes = ctx->dashes.p;
-        s.n_styles = ctx->n_styles;
-        s.n_dashes = ctx->n_dashes;
-        s.icons = ctx->icons.p;
-        s.icon_px = ctx->icon_px.p;
-        s.n_icons = ctx->n_icons;
-        s.tiles = ctx->tiles.p + tb;
-        s.area_begin = ctx->area_begin.p + tb;
-        s.areas = ctx->areas.p;
-        s.n_tiles = tc;
-        s.n_areas = n_areas;
-        s.area_base = area_base;
-        s.D = D;
-        s.scale = ctx->scale;
-        s.flags = flags;
-        if (flags & OSMR_DRAW_HAS_CANVAS_COLOR) memcpy(s.canvas, canvas_rgb, 3);
-        s.area_info = ctx->area_info.p;
-        s.vis = ctx->vis.p;
-        s.vis_bbox = ctx->vis_bbox.p;
-        s.vis_count = ctx->vis_count.p;
-        s.work = ctx->work.p;
-        s.fill_work = ctx->fill_work.p;
-        s.line_work = ctx->line_work.p;
-        s.walk_alpha = ctx->walk_alpha.p;
-        s.walk_len = ctx->walk_len.p;
-        s.walk_alpha_cap = ctx->walk_alpha_cap;
-        s.walk_len_cap = ctx->walk_len_cap;
-        CK(ctx->calc_table.reserve((size_t)2 * ctx->n_styles * kCalcEntryUnits + 1));
-        s.calc_table = ctx->calc_table.p;
-        s.geom = ctx->geom.p;
-        s.geom_cap = (unsigned)std::min<size_t>(ctx->geom_cap_units, 0xffffffffu);
-        s.mask = ctx->mask.p;
-        s.mask_cap = (unsigned)std::min<size_t>(ctx->mask_cap_words, 0xffffffffu);
-        s.counters = ctx->counters.p;
-        s.fill_cap = ctx->fill_cap;
-        s.label_plane = ctx->label_plane_active ? ctx->label_plane.p + (size_t)tb * D * D : nullptr;
-        s.label_icon_px = ctx->label_icon_px.p;
-        s.out = dev_out;
-
-        cudaStream_t st = ctx->stream;
-        CK(cudaEventRecord(ctx->ev[0], st));
-        CK(cudaMemsetAsync(ctx->counters.p, 0, CNT_COUNT * sizeof(unsigned), st));
-        unsigned launches = 0;
-        if (ctx->n_styles) {
-            style_calc_kernel<<<(2 * ctx->n_styles + 127) / 128, 128, 0, st>>>(s, ctx->calc_table.p);
-            ++launches;
-        }
-        if (n_areas) {
-            area_bbox_kernel<<<(n_areas + 255) / 256, 256, 0, st>>>(s);
-            ++launches;
-        }
-        plan_ops_kernel<<<tc, kPlanThreads, 0, st>>>(s);
-        build_geometry_kernel<<<ctx->num_sms * 8, kGeomThreads, 0, st>>>(s);
-        fill_rows_kernel<<<ctx->num_sms * 16, kFillThreads, 0, st>>>(s);
-        CK(cudaEventRecord(ctx->ev[3], st));
-        line_cover_kernel<<<ctx->num_sms * 8, kCoverThreads, 0, st>>>(s);
-        launches += 4;
-        CK(cudaEventRecord(ctx->ev[1], st));
-        const unsigned blocks = (unsigned)((D / kBW) * (D / kBH));
-        raster_kernel<<<tc * blocks, kRasterThreads, 0, st>>>(s);
-        ++launches;
-        CK(cudaGetLastError());
-        CK(cudaEventRecord(ctx->ev[2], st));
-        unsigned h_cnt[CNT_COUNT];
-        CK(cudaMemcpyAsync(h_cnt, ctx->counters.p, sizeof h_cnt, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        if (h_cnt[CNT_BAD_INPUT] & 1u) return ctx->fail(OSMR_E_INVALID, "styled area references an entity or style that does not exist");
-        if (h_cnt[CNT_BAD_INPUT] & 2u) return ctx->fail(OSMR_E_INVALID, "line wider than 500 pixels (width * scale): not supported");
-        if (h_cnt[CNT_WALK_TRUNC]) return ctx->fail(OSMR_E_CUDA, "internal error: a perpendicular walk exceeded its proven bound");
-        if (h_cnt[CNT_OVERFLOW]) {  // grow the scratch that ran out and redo the batch
-            if (h_cnt[CNT_OVERFLOW] & 1u) {
-                size_t need = (size_t)h_cnt[CNT_GEOM_USED] + (size_t)h_cnt[CNT_GEOM_USED] / 2 + 1024;
-                if (need <= ctx->geom_cap_units) need = ctx->geom_cap_units * 2;
-                if (need >= 0xffffffffull) return ctx->fail(OSMR_E_NOMEM, "geometry scratch exceeds 64 GiB; split the batch");
-                CK(ctx->geom.reserve(need));
-                ctx->geom_cap_units = ctx->geom.cap;
-            }
-            if (h_cnt[CNT_OVERFLOW] & 4u) {
-                unsigned long long used_alpha, used_len;
-                memcpy(&used_alpha, &h_cnt[CNT_WALK_ALPHA], 8);
-                memcpy(&used_len, &h_cnt[CNT_WALK_LEN], 8);
-                if (used_len >= 0xffffffffull) return ctx->fail(OSMR_E_NOMEM, "walk cache exceeds 2^32 walks; split the batch");
-                size_t need_a = (size_t)used_alpha + (size_t)used_alpha / 4 + 1024, need_l = (size_t)used_len + (size_t)used_len / 4 + 1024;
-                if (need_a > ctx->walk_alpha_cap) {
-                    if (ctx->walk_alpha.reserve(need_a) != cudaSuccess) return ctx->fail(OSMR_E_NOMEM, "walk cache does not fit in device memory; split the batch");
-                    ctx->walk_alpha_cap = ctx->walk_alpha.cap;
-                }
-                if (need_l > ctx->walk_len_cap) {
-                    CK(ctx->walk_len.reserve(need_l));
-                    ctx->walk_len_cap = ctx->walk_len.cap;
-                }
-            }
-            if (h_cnt[CNT_OVERFLOW] & 2u) {
-                size_t need = (size_t)h_cnt[CNT_MASK_USED] + (size_t)h_cnt[CNT_MASK_USED] / 2 + 1024;
-                if (need <= ctx->mask_cap_words) need = ctx->mask_cap_words * 2;
-                if (need >= 0xffffffffull) return ctx->fail(OSMR_E_NOMEM, "mask scratch exceeds 16 GiB; split the batch");
-                CK(ctx->mask.reserve(need));
-                ctx->mask_cap_words = ctx->mask.cap;
-            }
-            continue;
-        }
-        float ms_plan = 0, ms_cover = 0, ms_raster = 0;
-        cudaEventElapsedTime(&ms_plan, ctx->ev[0], ctx->ev[3]);
-        cudaEventElapsedTime(&ms_cover, ctx->ev[3], ctx->ev[1]);
-        cudaEventElapsedTime(&ms_raster, ctx->ev[1], ctx->ev[2]);
-        {
-            unsigned long long used_alpha;
-            memcpy(&used_alpha, &h_cnt[CNT_WALK_ALPHA], 8);
-            ctx->stats.walk_bytes += used_alpha * 8ull;
-            unsigned long long steps;
-            memcpy(&steps, &h_cnt[CNT_WALK_STEPS], 8);
-            ctx->stats.walk_steps += steps;
-        }
-        ctx->stats.n_tiles += tc;
-        ctx->stats.n_areas += n_areas;
-        ctx->stats.n_visible_ops += h_cnt[CNT_VISIBLE];
-        ctx->stats.n_node_refs += ((uint64_t)h_cnt[CNT_NODE_REFS_HI] << 32) | h_cnt[CNT_NODE_REFS_LO];
-        ctx->stats.kernel_launches += launches;
-        ctx->stats.geom_bytes += (uint64_t)h_cnt[CNT_GEOM_USED] * 16ull;
-        ctx->stats.mask_bytes += (uint64_t)h_cnt[CNT_MASK_USED] * 4ull;
-        ctx->stats.ms_plan += ms_plan;
-        ctx->stats.ms_raster += ms_raster;
-        ctx->stats.ms_cover += ms_cover;
-        ctx->stats.ms_total += ms_plan + ms_cover + ms_raster;
         return OSMR_OK;
     }
-    return ctx->fail(OSMR_E_NOMEM, "scratch kept overflowing");
+    cudaEvent_t* ev = ctx->cev[slot];
+    float ms_plan = 0, ms_cover = 0, ms_raster = 0;
+    cudaEventElapsedTime(&ms_plan, ev[0], ev[3]);
+    cudaEventElapsedTime(&ms_cover, ev[3], ev[1]);
+    cudaEventElapsedTime(&ms_raster, ev[1], ev[2]);
+    unsigned long long used_alpha, steps;
+    memcpy(&used_alpha, &h_cnt[CNT_WALK_ALPHA], 8);
+    memcpy(&steps, &h_cnt[CNT_WALK_STEPS], 8);
+    ctx->stats.walk_bytes += used_alpha * 8ull;
+    ctx->stats.walk_steps += steps;
+    ctx->stats.n_tiles += tc;
+    ctx->stats.n_areas += n_areas;
+    ctx->stats.n_visible_ops += h_cnt[CNT_VISIBLE];
+    ctx->stats.n_node_refs += ((uint64_t)h_cnt[CNT_NODE_REFS_HI] << 32) | h_cnt[CNT_NODE_REFS_LO];
+    ctx->stats.kernel_launches += ctx->chunk_launches[slot];
+    ctx->stats.geom_bytes += (uint64_t)h_cnt[CNT_GEOM_USED] * 16ull;
+    ctx->stats.mask_bytes += (uint64_t)h_cnt[CNT_MASK_USED] * 4ull;
+    ctx->stats.ms_plan += ms_plan;
+    ctx->stats.ms_raster += ms_raster;
+    ctx->stats.ms_cover += ms_cover;
+    ctx->stats.ms_total += ms_plan + ms_cover + ms_raster;
+    return OSMR_OK;
 }
 
 int osmr_batch_draw(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t flags, uint8_t* out, float* gpu_ms) {
@@ -709,7 +855,8 @@ int osmr_batch_draw(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t flags, 
     if (!ctx->has_batch) return ctx->fail(OSMR_E_STATE, "no batch uploaded");
     if ((flags & OSMR_DRAW_HAS_CANVAS_COLOR) && !canvas_rgb) return ctx->fail(OSMR_E_INVALID, "null canvas colour");
     cudaSetDevice(ctx->device);
-    const size_t D = 256 * (size_t)ctx->scale;
+    const int Di = 256 * ctx->scale;
+    const size_t D = (size_t)Di;
     const size_t bytes = (size_t)ctx->n_tiles * D * D * ((flags & OSMR_DRAW_OUT_RGBA) ? 4 : 3);
     const bool to_host = out && !(flags & OSMR_DRAW_OUT_DEVICE);
     unsigned char* alias = (to_host && ctx->direct_out) ? pinned_device_alias(out) : nullptr;
@@ -723,31 +870,77 @@ int osmr_batch_draw(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t flags, 
         dev_out = ctx->out.p;
         ctx->out_bytes = bytes;
     }
-    ctx->stats = osmr_stats{};
     const size_t tile_bytes = D * D * ((flags & OSMR_DRAW_OUT_RGBA) ? 4 : 3);
     const bool staged = to_host && !alias;
     unsigned first, rest;
     draw_chunks(ctx->n_tiles, to_host, alias != nullptr, first, rest);
     if (ctx->areas_deferred && ctx->first_chunk) first = ctx->first_chunk;  // the split the upload was made for
-    for (unsigned tb = 0; tb < ctx->n_tiles;) {
-        const unsigned tc = std::min(tb == 0 ? first : rest, ctx->n_tiles - tb);
-        if (tb > 0 && ctx->areas_deferred) {  // the tail of the styled-area list was uploaded on the copy stream
-            CK(cudaStreamWaitEvent(ctx->stream, ctx->areas_ready, 0));
-            ctx->areas_deferred = false;
+    CK(ctx->counters.reserve((size_t)kMaxChunks * CNT_COUNT));
+    CK(ctx->h_cnt.reserve((size_t)kMaxChunks * CNT_COUNT));
+    CK(ctx->calc_table.reserve((size_t)2 * ctx->n_styles * kCalcEntryUnits + 1));
+    for (int attempt = 0; attempt < 8; ++attempt) {
+        // scratch: first guesses, grown by collect_chunk when a bump allocator overflowed
+        if (ctx->geom_cap_units == 0) {
+            CK(ctx->geom.reserve((size_t)ctx->n_areas * 8 + (1u << 20)));
+            ctx->geom_cap_units = ctx->geom.cap;
         }
-        int rc = run_pipeline(ctx, canvas_rgb, flags, dev_out + (size_t)tb * tile_bytes, tb, tc);
-        if (rc) {
-            cudaStreamSynchronize(ctx->copy_stream);
-            return rc;
+        if (ctx->mask_cap_words == 0) {
+            CK(ctx->mask.reserve((size_t)ctx->n_tiles * D * (D / 32) * 4 + (1u << 20)));
+            ctx->mask_cap_words = ctx->mask.cap;
         }
-        if (staged)  // the compute stream is idle here (run_pipeline synchronised it), so the slice is complete
-            CK(cudaMemcpyAsync(out + (size_t)tb * tile_bytes, dev_out + (size_t)tb * tile_bytes, (size_t)tc * tile_bytes,
-                               cudaMemcpyDeviceToHost, ctx->copy_stream));
-        tb += tc;
+        if (ctx->walk_alpha_cap == 0) {  // 2.5 MB of walk cache per tile
+            CK(ctx->walk_alpha.reserve((size_t)ctx->n_tiles * (320u << 10) + (1u << 20)));
+            ctx->walk_alpha_cap = ctx->walk_alpha.cap;
+        }
+        if (ctx->walk_len_cap == 0) {
+            CK(ctx->walk_len.reserve((size_t)ctx->n_tiles * (80u << 10) + (1u << 20)));
+            ctx->walk_len_cap = ctx->walk_len.cap;
+        }
+        ctx->stats = osmr_stats{};
+        // every chunk is enqueued without waiting for the previous one; with staged host output the D2H copy of chunk i
+        // (third stream) runs while the later chunks are drawn
+        unsigned n_chunks = 0;
+        unsigned cb[kMaxChunks], cc[kMaxChunks];
+        for (unsigned tb = 0; tb < ctx->n_tiles;) {
+            unsigned tc = std::min(tb == 0 ? first : rest, ctx->n_tiles - tb);
+            if (n_chunks + 1 == kMaxChunks) tc = ctx->n_tiles - tb;
+            if (tb > 0 && ctx->areas_deferred) {  // the tail of the styled-area list was uploaded on the copy stream
+                CK(cudaStreamWaitEvent(ctx->stream, ctx->areas_ready, 0));
+                ctx->areas_deferred = false;
+            }
+            int rc = launch_chunk(ctx, canvas_rgb, flags, dev_out + (size_t)tb * tile_bytes, tb, tc, n_chunks);
+            if (rc) {
+                cudaStreamSynchronize(ctx->stream);
+                cudaStreamSynchronize(ctx->d2h_stream);
+                return rc;
+            }
+            if (staged) {
+                CK(cudaEventRecord(ctx->chunk_done[n_chunks], ctx->stream));
+                CK(cudaStreamWaitEvent(ctx->d2h_stream, ctx->chunk_done[n_chunks], 0));
+                CK(cudaMemcpyAsync(out + (size_t)tb * tile_bytes, dev_out + (size_t)tb * tile_bytes, (size_t)tc * tile_bytes,
+                                   cudaMemcpyDeviceToHost, ctx->d2h_stream));
+            }
+            cb[n_chunks] = tb;
+            cc[n_chunks] = tc;
+            ++n_chunks;
+            tb += tc;
+        }
+        CK(cudaStreamSynchronize(ctx->stream));
+        bool redo = false;
+        for (unsigned c = 0; c < n_chunks; ++c) {
+            int rc = collect_chunk(ctx, c, cb[c], cc[c], &redo);
+            if (rc) {
+                cudaStreamSynchronize(ctx->d2h_stream);
+                return rc;
+            }
+        }
+        if (redo) continue;  // (copies of the incomplete images are simply overwritten by the second round, in stream order)
+        if (staged) CK(cudaStreamSynchronize(ctx->d2h_stream));
+        if (gpu_ms) *gpu_ms = ctx->stats.ms_total;
+        return OSMR_OK;
     }
-    if (staged) CK(cudaStreamSynchronize(ctx->copy_stream));
-    if (gpu_ms) *gpu_ms = ctx->stats.ms_total;
-    return OSMR_OK;
+    cudaStreamSynchronize(ctx->d2h_stream);
+    return ctx->fail(OSMR_E_NOMEM, "scratch kept overflowing");
 }
 
 int osmr_batch_output(osmr_ctx* ctx, const uint8_t** dev_ptr, size_t* n_bytes) {
@@ -769,6 +962,195 @@ int osmr_draw_tiles(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, con
         ctx->areas_deferred = false;
     }
     return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// f3: styles per zoom + device-side candidate lookup and ordering (osmr_auto.cuh)
+// ---------------------------------------------------------------------------------------------------------
+int osmr_set_zoom_styles(osmr_ctx* ctx, uint32_t zoom, const uint32_t* way_class, const uint32_t* mp_class, const uint32_t* class_begin,
+                         const osmr_class_style* class_styles, uint32_t n_classes) {
+    if (!ctx) return OSMR_E_INVALID;
+    if (!ctx->has_geo) return ctx->fail(OSMR_E_STATE, "osmr_set_geodata has not been called");
+    if (zoom > 18) return ctx->fail(OSMR_E_INVALID, "zoom must be <= 18 (tile.rs:5 MAX_ZOOM)");
+    if ((ctx->n_ways && !way_class) || (ctx->n_mps && !mp_class) || !class_begin) return ctx->fail(OSMR_E_INVALID, "null class table");
+    if (class_begin[0] != 0) return ctx->fail(OSMR_E_INVALID, "class_begin[0] must be 0");
+    for (uint32_t c = 0; c < n_classes; ++c) {
+        if (class_begin[c + 1] < class_begin[c]) return ctx->fail(OSMR_E_INVALID, "class_begin must be non-decreasing");
+        if (class_begin[c + 1] - class_begin[c] >= (1u << kAutoWithinBits)) return ctx->fail(OSMR_E_INVALID, "more than 4095 styles in one class");
+    }
+    const uint32_t n_cs = class_begin[n_classes];
+    if (n_cs && !class_styles) return ctx->fail(OSMR_E_INVALID, "null class style list");
+    for (uint32_t i = 0; i < n_cs; ++i)
+        if (class_styles[i].order >= (1u << kAutoOrderBits)) return ctx->fail(OSMR_E_INVALID, "style order rank must be below 2^20");
+    cudaSetDevice(ctx->device);
+    osmr_ctx::ZoomTable& z = ctx->zoom_tables[zoom];
+    z.set = false;
+    CK(z.way_class.reserve(ctx->n_ways + 1));
+    CK(z.mp_class.reserve(ctx->n_mps + 1));
+    CK(z.class_begin.reserve(n_classes + 1));
+    CK(z.class_styles.reserve(n_cs + 1));
+    CK(z.class_reach.reserve(n_classes + 1));
+    if (ctx->n_ways) CK(cudaMemcpyAsync(z.way_class.p, way_class, (size_t)ctx->n_ways * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->n_mps) CK(cudaMemcpyAsync(z.mp_class.p, mp_class, (size_t)ctx->n_mps * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(z.class_begin.p, class_begin, (size_t)(n_classes + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (n_cs) CK(cudaMemcpyAsync(z.class_styles.p, class_styles, (size_t)n_cs * sizeof(osmr_class_style), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    z.n_classes = n_classes;
+    z.n_class_styles = n_cs;
+    z.set = true;
+    return OSMR_OK;
+}
+
+int osmr_draw_tiles_auto(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, const uint8_t canvas_rgb[3], uint32_t flags, uint8_t* out) {
+    if (!ctx) return OSMR_E_INVALID;
+    if (!ctx->has_geo) return ctx->fail(OSMR_E_STATE, "osmr_set_geodata has not been called");
+    if (!ctx->auto_unavailable.empty()) return ctx->fail(OSMR_E_STATE, ctx->auto_unavailable.c_str());
+    if (n_tiles == 0 || !tiles) return ctx->fail(OSMR_E_INVALID, "empty batch");
+    const uint32_t zoom = tiles[0].zoom, scale = tiles[0].scale;
+    if (scale < 1 || scale > 8) return ctx->fail(OSMR_E_INVALID, "scale must be 1..8");
+    if (zoom > 18) return ctx->fail(OSMR_E_INVALID, "zoom must be <= 18 (tile.rs:5 MAX_ZOOM)");
+    for (uint32_t t = 0; t < n_tiles; ++t) {
+        if (tiles[t].zoom != zoom || tiles[t].scale != scale) return ctx->fail(OSMR_E_INVALID, "all tiles of a batch must share one zoom and one scale");
+        if (((uint64_t)tiles[t].x + 2) << (18 - zoom) > 0xffffffffull || ((uint64_t)tiles[t].y + 2) << (18 - zoom) > 0xffffffffull)
+            return ctx->fail(OSMR_E_INVALID, "tile coordinates out of range for the zoom");
+    }
+    osmr_ctx::ZoomTable& z = ctx->zoom_tables[zoom];
+    if (!z.set) return ctx->fail(OSMR_E_STATE, "osmr_set_zoom_styles has not been called for this zoom");
+    if ((flags & OSMR_DRAW_HAS_CANVAS_COLOR) && !canvas_rgb) return ctx->fail(OSMR_E_INVALID, "null canvas colour");
+    cudaSetDevice(ctx->device);
+    ctx->has_batch = false;
+    ctx->areas_deferred = false;
+    ctx->first_chunk = 0;
+    cudaStream_t st = ctx->stream;
+    CK(ctx->tiles.reserve(n_tiles));
+    CK(ctx->area_begin.reserve(n_tiles + 1));
+    CK(ctx->counters.reserve((size_t)(kMaxChunks + 1) * CNT_COUNT));
+    CK(ctx->h_cnt.reserve((size_t)(kMaxChunks + 1) * CNT_COUNT));
+    CK(ctx->auto_bound.reserve(n_tiles + 2));
+    CK(ctx->auto_cand_cnt.reserve(n_tiles + 1));
+    CK(ctx->auto_inst.reserve(n_tiles + 2));
+    CK(cudaMemcpyAsync(ctx->tiles.p, tiles, (size_t)n_tiles * sizeof(osmr_tile), cudaMemcpyHostToDevice, st));
+
+    Scene s{};
+    s.merc = ctx->merc.p;
+    s.ways = ctx->ways.p;
+    s.polys = ctx->polys.p;
+    s.mps = ctx->mps.p;
+    s.ints = ctx->ints.p;
+    s.n_nodes = ctx->n_nodes;
+    s.n_ways = ctx->n_ways;
+    s.n_polys = ctx->n_polys;
+    s.n_mps = ctx->n_mps;
+    s.n_ints = ctx->n_ints;
+    s.styles = ctx->styles.p;
+    s.dashes = ctx->dashes.p;
+    s.n_styles = ctx->n_styles;
+    s.n_dashes = ctx->n_dashes;
+    s.n_icons = ctx->n_icons;
+    s.tiles = ctx->tiles.p;
+    s.n_tiles = n_tiles;
+    s.D = 256 * (int)scale;
+    s.scale = (int)scale;
+    s.flags = flags;
+    unsigned* auto_counters = ctx->counters.p + (size_t)kMaxChunks * CNT_COUNT;
+    unsigned* h_auto = ctx->h_cnt.p + (size_t)kMaxChunks * CNT_COUNT;
+    s.counters = auto_counters;
+    AutoScene a{};
+    a.idx_xy = ctx->idx_xy.p;
+    a.idx_w = ctx->idx_w.p;
+    a.idx_m = ctx->idx_m.p;
+    a.n_idx = ctx->n_idx;
+    a.way_min_tile = ctx->way_min_tile.p;
+    a.mp_min_tile = ctx->mp_min_tile.p;
+    a.way_rank = ctx->way_rank.p;
+    a.mp_rank = ctx->mp_rank.p;
+    a.rank_entity = ctx->rank_entity.p;
+    a.way_class = z.way_class.p;
+    a.mp_class = z.mp_class.p;
+    a.class_begin = z.class_begin.p;
+    a.class_styles = z.class_styles.p;
+    a.n_classes = z.n_classes;
+    a.n_class_styles = z.n_class_styles;
+    a.class_reach = z.class_reach.p;
+    a.bound = ctx->auto_bound.p;
+    a.cand_cnt = ctx->auto_cand_cnt.p;
+    a.inst_cnt = ctx->auto_inst.p;
+
+    CK(cudaEventRecord(ctx->ev[0], st));
+    CK(cudaMemsetAsync(auto_counters, 0, CNT_COUNT * sizeof(unsigned), st));
+    if (z.n_classes) class_reach_kernel<<<(z.n_classes + 127) / 128, 128, 0, st>>>(s, a);
+    // candidates per tile: upper bound -> offsets -> compact list
+    auto_bound_kernel<<<n_tiles, kAutoThreads, 0, st>>>(s, a);
+    auto_scan_kernel<<<1, 1024, 0, st>>>(ctx->auto_bound.p, n_tiles, &auto_counters[CNT_OVERFLOW]);
+    unsigned total_bound = 0;
+    CK(cudaMemcpyAsync(&total_bound, ctx->auto_bound.p + n_tiles, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_auto, auto_counters, CNT_COUNT * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (h_auto[CNT_OVERFLOW]) return ctx->fail(OSMR_E_NOMEM, "more than 2^32 candidate references; split the batch");
+    if (h_auto[CNT_BAD_INPUT]) return ctx->fail(OSMR_E_INVALID, "class style list references a style that does not exist");
+    CK(ctx->auto_cand.reserve((size_t)total_bound + 1));
+    a.cand = ctx->auto_cand.p;
+    auto_gather_kernel<<<n_tiles, kAutoThreads, 0, st>>>(s, a);
+    auto_scan_kernel<<<1, 1024, 0, st>>>(ctx->auto_inst.p, n_tiles, &auto_counters[CNT_OVERFLOW]);
+    // area_begin = the scanned styled-area counts (device + host copy)
+    CK(cudaMemcpyAsync(ctx->area_begin.p, ctx->auto_inst.p, (size_t)(n_tiles + 1) * 4, cudaMemcpyDeviceToDevice, st));
+    ctx->h_area_begin.resize(n_tiles + 1);
+    CK(cudaMemcpyAsync(ctx->h_area_begin.data(), ctx->auto_inst.p, (size_t)(n_tiles + 1) * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_auto, auto_counters, CNT_COUNT * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (h_auto[CNT_OVERFLOW]) return ctx->fail(OSMR_E_NOMEM, "more than 2^32 styled areas; split the batch");
+    if (h_auto[CNT_BAD_INPUT]) return ctx->fail(OSMR_E_INVALID, "tile index references an entity that does not exist");
+    const uint32_t n_areas = ctx->h_area_begin[n_tiles];
+    if ((uint64_t)n_areas * 3ull >= 0xffffffffull) return ctx->fail(OSMR_E_INVALID, "batch too large");
+    CK(ctx->areas.reserve((size_t)n_areas + 1));
+    a.areas_out = ctx->areas.p;
+    for (int attempt = 0;; ++attempt) {
+        a.big_keys = ctx->auto_big_keys.p;
+        a.big_cap = ctx->auto_big_keys.cap;
+        CK(cudaMemsetAsync(auto_counters, 0, CNT_COUNT * sizeof(unsigned), st));
+        auto_sort_kernel<<<n_tiles, kAutoThreads, 0, st>>>(s, a);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(h_auto, auto_counters, CNT_COUNT * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (!(h_auto[CNT_OVERFLOW] & 8u)) break;
+        if (attempt >= 2) return ctx->fail(OSMR_E_NOMEM, "sort scratch kept overflowing");
+        unsigned long long need;
+        memcpy(&need, &h_auto[CNT_WALK_ALPHA], 8);
+        CK(ctx->auto_big_keys.reserve((size_t)need + 1024));
+    }
+    CK(cudaEventRecord(ctx->ev[1], st));
+    // from here on this is an ordinary resident batch
+    ctx->n_tiles = n_tiles;
+    ctx->n_areas = n_areas;
+    ctx->scale = (int)scale;
+    CK(ctx->area_info.reserve((size_t)n_areas + 1));
+    CK(ctx->vis.reserve(3ull * n_areas + 1));
+    CK(ctx->rop.reserve(3ull * n_areas + 1));
+    CK(ctx->vis_bbox.reserve(3ull * n_areas + 1));
+    CK(ctx->work.reserve(3ull * n_areas + 1));
+    CK(ctx->fill_work.reserve((size_t)n_areas + 1));
+    CK(ctx->line_work.reserve(2ull * n_areas + 1));
+    CK(ctx->vis_count.reserve(n_tiles));
+    ctx->has_batch = true;
+    int rc = osmr_batch_draw(ctx, canvas_rgb, flags, out, nullptr);
+    float ms_auto = 0.f;
+    cudaEventElapsedTime(&ms_auto, ctx->ev[0], ctx->ev[1]);
+    ctx->stats.ms_auto = ms_auto;
+    ctx->stats.ms_total += ms_auto;
+    return rc;
+}
+
+int osmr_auto_readback(osmr_ctx* ctx, uint32_t* area_begin, osmr_styled_area* areas, uint32_t areas_cap) {
+    if (!ctx || !area_begin) return OSMR_E_INVALID;
+    if (!ctx->has_batch) return ctx->fail(OSMR_E_STATE, "no batch");
+    cudaSetDevice(ctx->device);
+    memcpy(area_begin, ctx->h_area_begin.data(), (size_t)(ctx->n_tiles + 1) * 4);
+    if (areas) {
+        if (areas_cap < ctx->n_areas) return ctx->fail(OSMR_E_INVALID, "areas_cap too small");
+        if (ctx->n_areas) CK(cudaMemcpyAsync(areas, ctx->areas.p, (size_t)ctx->n_areas * sizeof(osmr_styled_area), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return OSMR_OK;
 }
 
 int osmr_get_stats(osmr_ctx* ctx, osmr_stats* out) {

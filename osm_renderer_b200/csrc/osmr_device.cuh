@@ -43,15 +43,27 @@ __device__ __forceinline__ unsigned f64_as_u8(double v) {
 // results are identical: sqrt(+-0) = +-0, sqrt(x<0) = NaN, +-0 / positive = +-0.
 // (The special operand is replaced by 1.0 *before* the operation and the result selected afterwards: a plain
 // `if (x == 0) return x;` is if-converted by the compiler, which then still sends those lanes down the slow path.)
+// OSMR_OPAQUE_F64 hides the substituted operand from the optimiser, which otherwise proves that the substitution never
+// changes the result, folds it away again and sends the special operands back down the slow path (seen in the SASS of
+// line_cover_kernel: MUFU.RSQ64H on the raw operand + CALL ..dsqrt_rn_f64_mediumpath for every zero).
+#ifdef OSMR_EMULATED
+#define OSMR_OPAQUE_F64(v) ((void)0)
+#else
+#define OSMR_OPAQUE_F64(v) asm volatile("" : "+d"(v))
+#endif
 __device__ __forceinline__ double sqrt_peeled(double x) {
     const bool special = !(x > 0.0);  // zero, negative or NaN
-    const double r = sqrt(special ? 1.0 : x);
+    double arg = special ? 1.0 : x;
+    OSMR_OPAQUE_F64(arg);
+    const double r = sqrt(arg);
     if (!special) return r;
     return (x == 0.0) ? x : __longlong_as_double(0x7ff8000000000000LL);
 }
 __device__ __forceinline__ double div_pos_peeled(double a, double b) {  // b > 0 and finite
     const bool zero = (a == 0.0);
-    const double q = (zero ? 1.0 : a) / b;
+    double num = zero ? 1.0 : a;
+    OSMR_OPAQUE_F64(num);
+    const double q = num / b;
     return zero ? a : q;
 }
 
@@ -272,9 +284,13 @@ __device__ inline void build_calc(OpacityCalc& c, double hw, const double* dashe
 // f64 `%` for x >= 0, y > 0.  fmod's result x - n*y (n = floor(x/y)) is always representable, so one FMA with the
 // right integer n yields it exactly; a quotient that rounded across an integer is repaired by the sign test.
 // Much smaller than libdevice's general fmod, which matters for the instruction cache of raster_kernel.
-__device__ __noinline__ double fmod_general(double x, double y) { return fmod(x, y); }
+__device__ __noinline__ double fmod_general(double x, double y) {
+    OSMR_COUNT("fmod_general", 1);
+    return fmod(x, y);
+}
 __device__ __noinline__ double div_general(double a, double b) { return a / b; }
 __device__ __forceinline__ double fmod_exact(double x, double y, double inv_y) {
+    OSMR_COUNT("fmod_exact", 1);
     if (x >= 0.0 && x < y) return x;
     double qf = x * inv_y;  // estimate of x / y, off by far less than one for quotients below 2^50
     if (!(x >= 0.0) || !(qf < 1.0e15)) return fmod_general(x, y);

@@ -26,7 +26,7 @@ struct AreaInfo {  // per (tile, styled area)
 };
 
 // One visible generation.  g = pass * n_areas_of_tile + index (drawer.rs:94-100: Fill, Casing, Stroke).
-struct VisOp {
+struct VisOp {  // 48 bytes: what the geometry / fill / cover kernels need of an op (no look-up chain through the batch arrays)
     unsigned g;
     short x0, y0, x1, y1;  // reach bbox clamped to [-1, D]
     unsigned geom_off;     // first 16-byte unit of its records in the geometry scratch
@@ -35,8 +35,24 @@ struct VisOp {
     unsigned kind;         // OP_*
     unsigned area;         // index of the styled area inside its tile (g = pass * n + area)
     unsigned pass;         // 0 Fill, 1 Casing, 2 Stroke
+    unsigned tile;         // tile index inside the range being drawn
+    unsigned entity;       // osmr_styled_area of the op
+    unsigned style;
 };
 enum { OP_FILL_COLOR = 0, OP_FILL_IMAGE = 1, OP_LINE = 2 };
+
+// The 32 bytes raster_kernel reads per op that hits a block (one aligned record instead of the chain
+// vis -> areas -> styles and the style mapping of drawer.rs:156-219).
+struct alignas(16) RasterOp {
+    unsigned a;       // lines: geom_off; fills: mask_off
+    unsigned b;       // lines: geom_cnt (written by build_geometry_kernel); image fills: icon index
+    short y0, y1;     // VisOp.y0 / y1
+    unsigned char kind, reach;  // OP_*; lines: line_reach(half width) = doubles per cached walk
+    unsigned char rgb[3];       // colour of the pass
+    unsigned char pad[3];
+    double opacity;   // colour fills: fill-opacity (lines carry theirs in the cached alphas)
+};
+static_assert(sizeof(RasterOp) == 32, "RasterOp layout");
 
 struct SegRec {  // 64 bytes: one line segment (or outer cap line) that can touch the tile
     int x1, y1, x2, y2;
@@ -46,7 +62,8 @@ struct SegRec {  // 64 bytes: one line segment (or outer cap line) that can touc
     unsigned flags;            // bit0: outer cap calculator (line.rs:22,33-57); bit1: 32-bit fast path valid; bit2: coords < 2^24
     int k0;                    // first main step whose perpendiculars can reach the tile; the walk cache covers k0 .. k0+n_k-1
     unsigned n_k;
-    unsigned len_off;              // walk_len index of walk (k0, +, v0); walks are ordered ((k - k0) * 2 + dir) * 2 + v
+    unsigned len_off;              // walk_len index of walk (k0, +); regular walks are ordered (k - k0) * 2 + dir, the (rare) extra
+                                   // perpendiculars of double corrections follow at 2 * n_k + the same index
     unsigned long long alpha_off;  // walk_alpha index of that walk's step 0; every walk of the op owns S = line_reach(hw) doubles
 };
 static_assert(sizeof(SegRec) == 64, "SegRec layout");
@@ -115,6 +132,7 @@ struct Scene {
     // scratch
     AreaInfo* area_info;
     VisOp* vis;            // tile t owns vis[3*area_begin[t] ...)
+    RasterOp* rop;         // same indexing as vis
     short4* vis_bbox;      // reach bbox of vis[i] (8 bytes; what the raster warps scan)
     unsigned* vis_count;   // per tile
     unsigned* work;        // global indices into vis (all visible ops)
@@ -342,6 +360,13 @@ __global__ void __launch_bounds__(kPlanThreads) plan_ops_kernel(Scene s) {
         unsigned g = start + threadIdx.x;
         bool visible = false;
         VisOp op;
+        RasterOp rop;
+        rop.a = rop.b = 0;
+        rop.y0 = rop.y1 = 0;
+        rop.kind = rop.reach = 0;
+        rop.rgb[0] = rop.rgb[1] = rop.rgb[2] = 0;
+        rop.pad[0] = rop.pad[1] = rop.pad[2] = 0;
+        rop.opacity = 1.0;
         unsigned geom_units = 0, mask_words = 0;
         if (g < total) {
             unsigned pass = g / n;
@@ -357,9 +382,14 @@ __global__ void __launch_bounds__(kPlanThreads) plan_ops_kernel(Scene s) {
                     if (st.flags & OSMR_STYLE_FILL_COLOR) {
                         active = true;
                         op.kind = OP_FILL_COLOR;
+                        rop.opacity = (st.flags & OSMR_STYLE_FILL_OPACITY) ? st.fill_opacity : 1.0;
+                        rop.rgb[0] = st.fill_color[0];
+                        rop.rgb[1] = st.fill_color[1];
+                        rop.rgb[2] = st.fill_color[2];
                     } else if ((st.flags & OSMR_STYLE_FILL_IMAGE) && st.fill_image >= 0 && (unsigned)st.fill_image < s.n_icons) {
                         active = true;
                         op.kind = OP_FILL_IMAGE;
+                        rop.b = (unsigned)st.fill_image;
                     }
                     if (active) {
                         geom_units = info.npts;  // <= npts-1 edge records of 16 bytes
@@ -373,7 +403,11 @@ __global__ void __launch_bounds__(kPlanThreads) plan_ops_kernel(Scene s) {
                         op.kind = OP_LINE;
                         double hw = lp.width / 2.0;
                         int reach = line_reach(hw);
-                        if (reach > 255) atomicOr(&s.counters[CNT_BAD_INPUT], 2u);  // walk lengths are cached as bytes
+                        if (reach > 127) atomicOr(&s.counters[CNT_BAD_INPUT], 2u);  // walk lengths are cached in 7 bits
+                        rop.reach = (unsigned char)reach;
+                        rop.rgb[0] = lp.rgb[0];
+                        rop.rgb[1] = lp.rgb[1];
+                        rop.rgb[2] = lp.rgb[2];
                         if (is_non_trivial_cap(lp.cap)) reach = 2 * reach;  // outer cap lines start hw away
                         long long lx0 = (long long)x0 - reach, ly0 = (long long)y0 - reach;
                         long long lx1 = (long long)x1 + reach, ly1 = (long long)y1 + reach;
@@ -396,6 +430,9 @@ __global__ void __launch_bounds__(kPlanThreads) plan_ops_kernel(Scene s) {
                     op.mask_off = 0;
                     op.area = i;
                     op.pass = pass;
+                    op.tile = t;
+                    op.entity = ar.entity;
+                    op.style = ar.style;
                 }
             }
         }
@@ -428,6 +465,11 @@ __global__ void __launch_bounds__(kPlanThreads) plan_ops_kernel(Scene s) {
         pos += __popc(bal & ((1u << lane_id()) - 1u));
         if (visible) {
             vis[pos] = op;
+            rop.a = (op.kind == OP_LINE) ? op.geom_off : op.mask_off;
+            rop.y0 = op.y0;
+            rop.y1 = op.y1;
+            rop.kind = (unsigned char)op.kind;
+            s.rop[3ull * base + pos] = rop;
             s.vis_bbox[3ull * base + pos] = make_short4(op.x0, op.y0, op.x1, op.y1);
             unsigned gi = (unsigned)(3ull * base + pos);
             s.work[atomicAdd(&s.counters[CNT_N_WORK], 1u)] = gi;
@@ -455,24 +497,6 @@ __global__ void __launch_bounds__(kPlanThreads) plan_ops_kernel(Scene s) {
 // ------------------------------------------------------------------------------------------------------
 constexpr int kGeomThreads = 128;
 
-__device__ __forceinline__ void decode_op(const Scene& s, unsigned gi, unsigned& tile, unsigned& pass, osmr_styled_area& ar) {
-    // gi indexes s.vis; tile t owns [3*area_begin[t], 3*area_begin[t+1])
-    unsigned lo = 0, hi = s.n_tiles;
-    while (hi - lo > 1) {
-        unsigned mid = (lo + hi) >> 1;
-        if (3ull * s.area_begin[mid] <= gi)
-            lo = mid;
-        else
-            hi = mid;
-    }
-    tile = lo;
-    unsigned base = s.area_begin[tile];
-    unsigned n = s.area_begin[tile + 1] - base;
-    unsigned g = s.vis[gi].g;
-    pass = g / n;
-    ar = s.areas[base + (g - pass * n)];
-}
-
 __global__ void __launch_bounds__(kGeomThreads) build_geometry_kernel(Scene s) {
     const unsigned lane = lane_id();
     const int D = s.D;
@@ -482,11 +506,12 @@ __global__ void __launch_bounds__(kGeomThreads) build_geometry_kernel(Scene s) {
         wi = __shfl_sync(0xffffffffu, wi, 0);
         if (wi >= s.counters[CNT_N_WORK]) break;
         unsigned gi = s.work[wi];
-        unsigned tile, pass;
-        osmr_styled_area ar;
-        decode_op(s, gi, tile, pass, ar);
         VisOp& op = s.vis[gi];
-        TileXform xf = make_xform(s.tiles[tile]);
+        const unsigned pass = op.pass;
+        osmr_styled_area ar;
+        ar.entity = op.entity;
+        ar.style = op.style;
+        TileXform xf = make_xform(s.tiles[op.tile]);
         RingIter it(s, ar.entity);
         unsigned count = 0;
         if (op.kind != OP_LINE) {
@@ -572,10 +597,11 @@ __global__ void __launch_bounds__(kGeomThreads) build_geometry_kernel(Scene s) {
                 }
                 double trav = 0.0;
                 if (dashed) {  // sequential f64 summation, same order as add_traveled_distance (line.rs:31)
-                    for (int j = 0; j < 32; ++j) {
+                    const int nj = (int)min(32u, n_pairs - b);
+                    for (int j = 0; j < nj; ++j) {
                         double dj = __shfl_sync(0xffffffffu, d, j);
                         if ((int)lane == j) trav = acc;
-                        if (b + j < n_pairs) acc = acc + dj;
+                        acc = acc + dj;
                     }
                 }
                 bool nondeg = valid && (p1.x != p2.x || p1.y != p2.y);
@@ -652,7 +678,10 @@ __global__ void __launch_bounds__(kGeomThreads) build_geometry_kernel(Scene s) {
                 count += b2 ? 1u : 0u;
             }
         }
-        if (lane == 0) op.geom_cnt = count;
+        if (lane == 0) {
+            op.geom_cnt = count;
+            if (op.kind == OP_LINE) s.rop[gi].b = count;
+        }
     }
 }
 
@@ -1009,10 +1038,11 @@ __global__ void __launch_bounds__(kCoverThreads) line_cover_kernel(Scene s) {
         wi = __shfl_sync(0xffffffffu, wi, 0);
         if (wi >= s.counters[CNT_N_LINE_WORK]) break;
         const unsigned gi = s.line_work[wi];
-        unsigned tile, pass;
-        osmr_styled_area ar;
-        decode_op(s, gi, tile, pass, ar);
         const VisOp op = s.vis[gi];
+        const unsigned pass = op.pass;
+        osmr_styled_area ar;
+        ar.entity = op.entity;
+        ar.style = op.style;
         const osmr_style& st = s.styles[ar.style];
         LineParams lp;
         line_params(s, st, (int)pass, lp);
@@ -1074,26 +1104,26 @@ __global__ void __launch_bounds__(kCoverThreads) line_cover_kernel(Scene s) {
                 sc.denom = h.denom;
                 sc.traveled = h.traveled;
                 sc.small = (h.flags & 4u) != 0;
-                const unsigned long long widx = 2ull * local;  // ((k - k0) * 2 + dir) * 2
-                unsigned char* len_out = s.walk_len + h.len_off + widx;
-                double* alpha_out = s.walk_alpha + h.alpha_off + widx * S;
+                // walk (k, dir) lives at index `local`, its extra perpendicular at 2 * n_k + local
+                unsigned char* len_out = s.walk_len + h.len_off + local;
+                double* alpha_out = s.walk_alpha + h.alpha_off + (unsigned long long)local * S;
+                const unsigned long long extra_at = 2ull * h.n_k;
                 // the walk of step k, then the extra one of a double correction (line.rs:150-155); a walk whose start is
                 // more than `reach` outside the tile on its own axis cannot put a pixel into it
                 int mn = w.mn, p_error = w.p_error;
-                for (int v = 0; v < 2; ++v) {
-                    unsigned len = 0;
-                    if (v == 0 || w.extra) {
-                        if (v == 1) {
-                            p_error = wadd(wsub(p_error, 2 * w.mx_d), 2 * w.mn_d);
-                            mn += w.mn_inc;
-                        }
-                        if (mn >= -reach && mn <= D - 1 + reach)
-                            len = cover_walk(alpha_out + (size_t)v * S, S, w, sc, calc, mn, p_error, mul, lp.opacity, D, &s.counters[CNT_WALK_TRUNC]);
-                    }
-                    len_out[v] = (unsigned char)len;
-                    steps_stored += len;
-                    OSMR_COUNT("cover.walks", len != 0);
+                unsigned len0 = 0, len1 = 0;
+                if (mn >= -reach && mn <= D - 1 + reach)
+                    len0 = cover_walk(alpha_out, S, w, sc, calc, mn, p_error, mul, lp.opacity, D, &s.counters[CNT_WALK_TRUNC]);
+                if (w.extra) {
+                    p_error = wadd(wsub(p_error, 2 * w.mx_d), 2 * w.mn_d);
+                    mn += w.mn_inc;
+                    if (mn >= -reach && mn <= D - 1 + reach)
+                        len1 = cover_walk(alpha_out + extra_at * S, S, w, sc, calc, mn, p_error, mul, lp.opacity, D, &s.counters[CNT_WALK_TRUNC]);
+                    if (len1) len_out[extra_at] = (unsigned char)len1;
                 }
+                len_out[0] = (unsigned char)(len0 | (len1 ? 0x80u : 0u));  // bit 7: the extra walk has steps
+                steps_stored += len0 + len1;
+                OSMR_COUNT("cover.walks", (len0 != 0) + (len1 != 0));
             }
         }
         for (int o = 16; o > 0; o >>= 1) steps_stored += __shfl_xor_sync(0xffffffffu, steps_stored, o);
@@ -1108,7 +1138,7 @@ __global__ void __launch_bounds__(kCoverThreads) line_cover_kernel(Scene s) {
 struct SegHit {  // 48 bytes: what a block needs of a segment record that can reach it
     int x1, y1, x2, y2;
     int ka;                    // first main step within reach of the block
-    unsigned flags;            // SegRec.flags
+    unsigned flags;            // SegRec.flags | SegRec.n_k << 8
     unsigned long long magic;  // floor(2^64 / (2*mx_d)) + 1 (exact quotients for numerators < 2^32)
     int k0;                    // SegRec.k0: first main step in the walk cache
     unsigned len_off;
@@ -1166,7 +1196,7 @@ __global__ void __launch_bounds__(kRasterThreads, OSMR_RASTER_MIN_BLOCKS) raster
     const int by0 = (int)((grp / grp_per_row) * 2u + (in_grp / 2u)) * kBH;
     const unsigned lane = threadIdx.x;
     const unsigned base = s.area_begin[tile];
-    const VisOp* vis = s.vis + 3ull * base;
+    const RasterOp* rops = s.rop + 3ull * base;
     const short4* vbb = s.vis_bbox + 3ull * base;
     const unsigned n_vis = s.vis_count[tile];
 
@@ -1196,10 +1226,13 @@ __global__ void __launch_bounds__(kRasterThreads, OSMR_RASTER_MIN_BLOCKS) raster
         while (todo) {
             const unsigned qi = chunk + (unsigned)(__ffs(todo) - 1);
             todo &= todo - 1;
-            const VisOp op = vis[qi];
-            const unsigned pass = op.pass;
-            const osmr_styled_area ar = s.areas[base + op.area];
-            const osmr_style& st = s.styles[ar.style];
+            RasterOp op;
+            {
+                const uint4* src = reinterpret_cast<const uint4*>(&rops[qi]);
+                uint4* dst = reinterpret_cast<uint4*>(&op);
+                dst[0] = src[0];
+                dst[1] = src[1];
+            }
 
             if (op.kind != OP_LINE) {
                 // ---------------- fill: blend straight from the row masks ----------------
@@ -1208,11 +1241,11 @@ __global__ void __launch_bounds__(kRasterThreads, OSMR_RASTER_MIN_BLOCKS) raster
                 double src[4];
                 const DevIcon* icon = nullptr;
                 if (op.kind == OP_FILL_COLOR) {
-                    double opacity = (st.flags & OSMR_STYLE_FILL_OPACITY) ? st.fill_opacity : 1.0;
-                    for (int k = 0; k < 3; ++k) src[k] = opacity * unit_of_u8(st.fill_color[k]);
+                    const double opacity = op.opacity;  // fill-opacity or 1.0 (drawer.rs:172-178)
+                    for (int k = 0; k < 3; ++k) src[k] = opacity * unit_of_u8(op.rgb[k]);
                     src[3] = opacity;
                 } else {
-                    icon = &s.icons[st.fill_image];
+                    icon = &s.icons[op.b];
                 }
                 const int col = (int)(lane % (unsigned)kBW);
 #pragma unroll 1
@@ -1220,7 +1253,7 @@ __global__ void __launch_bounds__(kRasterThreads, OSMR_RASTER_MIN_BLOCKS) raster
                     const int r = (j * 32 + (int)lane) / kBW;
                     const int y = by0 + r;
                     if (y < (int)op.y0 || y > (int)op.y1) continue;
-                    const unsigned mword = s.mask[op.mask_off + (size_t)(y - ya) * wpr + (bx0 >> 5)];
+                    const unsigned mword = s.mask[op.a + (size_t)(y - ya) * wpr + (bx0 >> 5)];
                     if (!((mword >> ((bx0 & 31) + col)) & 1u)) continue;
                     const int idx = r * kBW + col;
                     double c0, c1, c2, a;
@@ -1247,13 +1280,10 @@ __global__ void __launch_bounds__(kRasterThreads, OSMR_RASTER_MIN_BLOCKS) raster
             }
 
             // ---------------- line: gather the cached walk alphas into the alpha plane, then blend ----------------
-            LineParams lp;
-            line_params(s, st, (int)pass, lp);
-            const double hw = lp.width / 2.0;
-            const int reach = line_reach(hw);
+            const int reach = (int)op.reach;     // line_reach(half width)
             const unsigned S = (unsigned)reach;  // doubles per cached walk
-            const SegRec* segs = reinterpret_cast<const SegRec*>(s.geom + op.geom_off);
-            const unsigned n_seg = op.geom_cnt;
+            const SegRec* segs = reinterpret_cast<const SegRec*>(s.geom + op.a);
+            const unsigned n_seg = op.b;
             bool any = false;
             for (unsigned sb = 0; sb < n_seg; sb += 32) {
                 // one segment per lane: can any of its perpendiculars reach my block?
@@ -1296,7 +1326,7 @@ __global__ void __launch_bounds__(kRasterThreads, OSMR_RASTER_MIN_BLOCKS) raster
                             hrec.x2 = sr.z;
                             hrec.y2 = sr.w;
                             hrec.ka = (int)ka;
-                            hrec.flags = full.flags;
+                            hrec.flags = full.flags | (full.n_k << 8);
                             hrec.magic = full.magic;
                             hrec.k0 = full.k0;
                             hrec.len_off = full.len_off;
@@ -1334,23 +1364,22 @@ __global__ void __launch_bounds__(kRasterThreads, OSMR_RASTER_MIN_BLOCKS) raster
                     const int k = h.ka + (int)(local >> 1);
                     const int mul = (local & 1u) ? -1 : 1;
                     OSMR_COUNT("raster.items", 1);
-                    const unsigned long long widx = 2ull * (2ull * (unsigned long long)(k - h.k0) + (local & 1u));
-                    const unsigned lens = *reinterpret_cast<const unsigned short*>(s.walk_len + h.len_off + widx);  // v0 | v1 << 8
+                    const unsigned long long widx = 2ull * (unsigned long long)(k - h.k0) + (local & 1u);
+                    const unsigned lens = s.walk_len[h.len_off + widx];  // steps of the regular walk | 0x80: the extra one has steps
                     if (!lens) continue;
                     WalkItem w;
                     walk_item_setup(h.x1, h.y1, h.x2, h.y2, h.flags, h.magic, k, w);
                     const double* alpha = s.walk_alpha + h.alpha_off + widx * S;
                     const int blo = (w.swap ? by0 : bx0) + rlo, bhi = (w.swap ? by0 + kBH : bx0 + kBW) - 1 + rhi;
                     int mn = w.mn, p_error = w.p_error;
-                    for (int v = 0; v < 2; ++v) {
-                        const unsigned len = v ? (lens >> 8) : (lens & 0xffu);
-                        if (v == 1) {
-                            if (!len) break;
-                            p_error = wadd(wsub(p_error, 2 * w.mx_d), 2 * w.mn_d);
-                            mn += w.mn_inc;
-                        }
-                        // minor-axis cull: a walk starts at mn and moves away from it, at most `reach` pixels
-                        if (len && mn >= blo && mn <= bhi) gather_walk(sm.plane, alpha + (size_t)v * S, len, w, mn, p_error, mul, bx0, by0);
+                    // minor-axis cull: a walk starts at mn and moves away from it, at most `reach` pixels
+                    if ((lens & 0x7fu) && mn >= blo && mn <= bhi) gather_walk(sm.plane, alpha, lens & 0x7fu, w, mn, p_error, mul, bx0, by0);
+                    if (lens & 0x80u) {  // the extra perpendicular of a double correction (line.rs:150-155)
+                        const unsigned long long extra_at = 2ull * (h.flags >> 8);
+                        const unsigned len1 = s.walk_len[h.len_off + extra_at + widx];
+                        p_error = wadd(wsub(p_error, 2 * w.mx_d), 2 * w.mn_d);
+                        mn += w.mn_inc;
+                        if (mn >= blo && mn <= bhi) gather_walk(sm.plane, alpha + extra_at * S, len1, w, mn, p_error, mul, bx0, by0);
                     }
                 }
             }
@@ -1358,7 +1387,7 @@ __global__ void __launch_bounds__(kRasterThreads, OSMR_RASTER_MIN_BLOCKS) raster
             if (any) {
                 // blend: pending pixel = from_color(color, alpha_max) (tile_pixels.rs:13-22), then over
                 double cn[3];
-                for (int k = 0; k < 3; ++k) cn[k] = unit_of_u8(lp.rgb[k]);
+                for (int k = 0; k < 3; ++k) cn[k] = unit_of_u8(op.rgb[k]);
 #pragma unroll 2
                 for (int j = 0; j < kBP / 32; ++j) {
                     const int idx = j * 32 + (int)lane;

@@ -199,6 +199,41 @@ class GpuContext:
         )
         return out
 
+    # ---- f3: styled-area lists built on the device ---------------------------------------------------------------
+    def set_zoom_styles(self, zoom: int, way_class, mp_class, class_begin, class_styles):
+        """osmr_set_zoom_styles: per-zoom style classes of every way / multipolygon (the host styler's cache)."""
+        from .wire import CLASS_STYLE_DTYPE
+
+        way_class = np.ascontiguousarray(way_class, dtype=np.uint32)
+        mp_class = np.ascontiguousarray(mp_class, dtype=np.uint32)
+        class_begin = np.ascontiguousarray(class_begin, dtype=np.uint32)
+        class_styles = np.ascontiguousarray(class_styles, dtype=CLASS_STYLE_DTYPE)
+        self._check(
+            self.L.osmr_set_zoom_styles(self.h, zoom, way_class.ctypes.data, mp_class.ctypes.data, class_begin.ctypes.data,
+                                        class_styles.ctypes.data, len(class_begin) - 1),
+            "osmr_set_zoom_styles",
+        )
+
+    def draw_tiles_auto(self, tiles, canvas_rgb, use_caps_for_dashes=True, rgba=False, out=None):
+        """osmr_draw_tiles_auto: only the tile list is sent; candidates, styling order and drawing happen on the device."""
+        tiles = np.ascontiguousarray(tiles, dtype=TILE_DTYPE)
+        n = len(tiles)
+        d = 256 * int(tiles["scale"][0]) if n else 256
+        if out is None:
+            out = np.empty((n, d, d, 4 if rgba else 3), dtype=np.uint8)
+        flags, canvas = self._flags(canvas_rgb, use_caps_for_dashes, rgba)
+        self._check(self.L.osmr_draw_tiles_auto(self.h, tiles.ctypes.data, n, canvas.ctypes.data, flags, out.ctypes.data), "osmr_draw_tiles_auto")
+        self._auto_tiles = n
+        return out
+
+    def auto_readback(self):
+        """(area_begin, areas) of the last draw_tiles_auto call."""
+        begins = np.zeros(self._auto_tiles + 1, dtype=np.uint32)
+        self._check(self.L.osmr_auto_readback(self.h, begins.ctypes.data, None, 0), "osmr_auto_readback")
+        areas = np.zeros(int(begins[-1]), dtype=AREA_DTYPE)
+        self._check(self.L.osmr_auto_readback(self.h, begins.ctypes.data, areas.ctypes.data, len(areas)), "osmr_auto_readback")
+        return begins, areas
+
     def debug_set(self, key: str, value: int):
         self._check(self.L.osmr_debug_set(self.h, key.encode(), value), "osmr_debug_set")
 

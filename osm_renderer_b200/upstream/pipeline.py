@@ -197,6 +197,45 @@ class FastBatchBuilder:
         return out
 
 
+def zoom_class_tables(fb: "FastBatchBuilder", zoom: int):
+    """The per-zoom style classes osmr_set_zoom_styles takes: what the reference's StyleCache
+    (style_cache.rs:68-87) would hold after every way and multipolygon has been styled once at `zoom`.
+
+    Returns (way_class u32[n_ways], mp_class u32[n_mps], class_begin u32[n_classes+1], class_styles CLASS_STYLE_DTYPE).
+    A class is a distinct (closedness, tag list); `order` is the dense rank of (layer, is_foreground_fill, z_index).
+    """
+    from ..wire import CLASS_STYLE_DTYPE, NO_CLASS
+
+    lists = []  # per class: (style ids, layer, fg, z)
+    def classes_of(kinds, tagkeys):
+        out = np.full(len(kinds), NO_CLASS, dtype=np.uint32)
+        for kind in np.unique(kinds):
+            m = np.nonzero(kinds == kind)[0]
+            inv, ls = fb._styles_csr(zoom, int(kind), tagkeys[m])
+            base = len(lists)
+            lists.extend(ls)
+            out[m] = (base + inv).astype(np.uint32)
+        return out
+
+    way_class = classes_of(fb.way_kind, fb.way_tagkey)
+    mp_class = classes_of(np.full(len(fb.mp_gid), KIND_MULTIPOLYGON, dtype=np.int64), fb.mp_tagkey)
+    counts = np.array([len(l[0]) for l in lists], dtype=np.int64)
+    class_begin = np.zeros(len(lists) + 1, dtype=np.uint32)
+    class_begin[1:] = np.cumsum(counts)
+    n = int(class_begin[-1])
+    cs = np.zeros(n, dtype=CLASS_STYLE_DTYPE)
+    if n:
+        sid = np.concatenate([l[0] for l in lists])
+        lay = np.concatenate([l[1] for l in lists])
+        fg = np.concatenate([l[2] for l in lists])
+        zi = np.concatenate([l[3] for l in lists])
+        trip = np.stack([lay.astype(np.float64), fg.astype(np.float64), zi], axis=1)
+        _, order = np.unique(trip, axis=0, return_inverse=True)  # rows sort lexicographically: layer, fg, z_index
+        cs["style"] = sid
+        cs["order"] = np.asarray(order).reshape(-1)
+    return way_class, mp_class, class_begin, cs
+
+
 class LabelListBuilder:
     """The label generations of a tile in the order the reference draws them (drawer.rs:106-119, 221-262):
     styled areas with for_labels=true (ways: text on the line, multipolygons: centred), then styled nodes.

@@ -76,6 +76,10 @@ class IconStruct(C.Structure):
     _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("rgba", C.c_void_p)]
 
 
+CLASS_STYLE_DTYPE = np.dtype([("style", "<u4"), ("order", "<u4")])  # osmr_class_style
+NO_CLASS = 0xFFFFFFFF
+
+
 class StatsStruct(C.Structure):
     _fields_ = [
         ("n_tiles", C.c_uint64),
@@ -93,6 +97,8 @@ class StatsStruct(C.Structure):
         ("ms_label_layout", C.c_float),
         ("ms_label_device", C.c_float),
         ("ms_cover", C.c_float),
+        ("ms_auto", C.c_float),
+        ("reserved", C.c_float),
     ]
 
 

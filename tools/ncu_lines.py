@@ -6,6 +6,20 @@ usage: tools/ncu_lines.py <report.ncu-rep> <lib.so> <mangled kernel name substri
 import csv, io, os, re, subprocess, sys, tempfile
 from collections import defaultdict
 
+
+def select_kernel(rows):
+    """multi-kernel reports: keep the first source-page section of the kernel named by NCU_KERNEL"""
+    k = os.environ.get("NCU_KERNEL")
+    if not k:
+        return rows
+    starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+    for n, i in enumerate(starts):
+        if k in rows[i][1]:
+            end = starts[n + 1] if n + 1 < len(starts) else len(rows)
+            return rows[i:end]
+    raise SystemExit(f"kernel {k} not in report")
+
+
 rep, lib, kname = sys.argv[1], sys.argv[2], sys.argv[3]
 topn = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 tmp = tempfile.mkdtemp()
@@ -27,7 +41,7 @@ for ln in dis.splitlines():
     if m and infunc:
         line_of[int(m.group(1), 16)] = cur
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
-rows = list(csv.reader(io.StringIO(src)))
+rows = select_kernel(list(csv.reader(io.StringIO(src))))
 hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 cols = {n: i for i, n in enumerate(rows[hi])}
 data = [r for r in rows[hi + 1 :] if len(r) > cols["Instructions Executed"]]

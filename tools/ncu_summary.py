@@ -4,10 +4,25 @@
 usage: tools/ncu_summary.py gpurun_out/prof_raster.ncu-rep > profiles/<name>.txt
 """
 import csv
+import os
 import io
 import subprocess
 import sys
 from collections import defaultdict
+
+
+def select_kernel(rows):
+    """multi-kernel reports: keep the first source-page section of the kernel named by NCU_KERNEL"""
+    k = os.environ.get("NCU_KERNEL")
+    if not k:
+        return rows
+    starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+    for n, i in enumerate(starts):
+        if k in rows[i][1]:
+            end = starts[n + 1] if n + 1 < len(starts) else len(rows)
+            return rows[i:end]
+    raise SystemExit(f"kernel {k} not in report")
+
 
 rep = sys.argv[1]
 
@@ -17,7 +32,9 @@ def ncu(page):
 
 
 raw = list(csv.reader(io.StringIO(ncu("raw"))))
-hdr, units, vals = raw[0], raw[1], raw[2]
+hdr, units = raw[0], raw[1]
+ki = hdr.index("Kernel Name")
+vals = next((r for r in raw[2:] if os.environ.get("NCU_KERNEL", "") in r[ki]), raw[2])
 want = [
     "Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "launch__registers_per_thread", "launch__occupancy_limit_registers",
     "launch__occupancy_limit_shared_mem", "launch__shared_mem_per_block_dynamic", "sm__warps_active.avg.pct_of_peak_sustained_active",
@@ -43,7 +60,7 @@ for h, u, v in zip(hdr, units, vals):
         except ValueError:
             pass
 
-src = list(csv.reader(io.StringIO(ncu("source"))))
+src = select_kernel(list(csv.reader(io.StringIO(ncu("source")))))
 # find header row
 hi = next(i for i, r in enumerate(src) if r and r[0] == "Address")
 cols = {n: i for i, n in enumerate(src[hi])}
