@@ -193,9 +193,11 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0, help="tiles in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--lib", default=None, help="experiments only: load this build of libosmr_b200.so (e.g. other -D flags)")
-    ap.add_argument("--e2e-direct", type=int, default=1, choices=[0, 1],
-                    help="e2e leg: 1 = raster_kernel stores the tiles straight into the page-locked host buffer (default), "
-                         "0 = stage them in HBM and copy back on a second stream")
+    ap.add_argument("--e2e-direct", type=int, default=0, choices=[0, 1],
+                    help="e2e leg: 0 = tiles staged in HBM, chunk-wise D2H on its own stream while later chunks are drawn (default), "
+                         "1 = raster_kernel stores the tiles straight into the page-locked host buffer")
+    ap.add_argument("--e2e-chunks", type=int, default=0, help="experiments: draw chunks of the staged e2e call (0 = library default)")
+    ap.add_argument("--skip-auto", action="store_true", help="skip the osmr_draw_tiles_auto leg (f3)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -324,6 +326,8 @@ def main():
     h2d = int(sum(a.nbytes for a in in_arrays))
     flags, canvas = ctx._flags(w["canvas"], w["caps"], False)
     ctx.debug_set("direct_out", args.e2e_direct)
+    if args.e2e_chunks:
+        ctx.debug_set("host_chunks", args.e2e_chunks)
 
     def e2e_step():
         rc = L.osmr_draw_tiles(ctx.h, pins[0], n_tiles, pins[1], pins[2], canvas.ctypes.data, flags, pin_out)
@@ -339,6 +343,40 @@ def main():
     barrier()
     e2e_wall = time.perf_counter() - t1
     checksum = int(np.frombuffer((C.c_uint8 * 4096).from_address(pin_out), dtype=np.uint8).sum())
+
+    # ---- e2e_auto (f3): only the tile list crosses the bus; candidate lookup + painter's order on the device ----
+    auto = None
+    if not args.skip_auto:
+        from osm_renderer_b200.upstream import pipeline
+
+        t_cls = time.perf_counter()
+        wc, mc, cb, cs = pipeline.zoom_class_tables(w["builder"], zoom)
+        ctx.set_table(w["table"])
+        ctx.set_zoom_styles(zoom, wc, mc, cb, cs)
+        t_cls = time.perf_counter() - t_cls
+        pin_auto = L.osmr_alloc_pinned(out_bytes)
+
+        def auto_step():
+            rc = L.osmr_draw_tiles_auto(ctx.h, pins[0], n_tiles, canvas.ctypes.data, flags, pin_auto)
+            if rc != 0:
+                raise RuntimeError(L.osmr_last_error(ctx.h))
+
+        for _ in range(max(1, min(args.warmup, 2))):
+            auto_step()
+        barrier()
+        t2 = time.perf_counter()
+        for _ in range(args.steps):
+            auto_step()
+        barrier()
+        auto_wall = time.perf_counter() - t2
+        ast = ctx.stats()
+        same = bool((np.frombuffer((C.c_uint8 * out_bytes).from_address(pin_auto), dtype=np.uint8)
+                     == np.frombuffer((C.c_uint8 * out_bytes).from_address(pin_out), dtype=np.uint8)).all())
+        auto = {"value": n_tiles * args.steps / auto_wall, "unit": "tiles/s", "ms_per_step": 1000.0 * auto_wall / args.steps,
+                "h2d_bytes_per_step": int(in_arrays[0].nbytes), "d2h_bytes_per_step": out_bytes,
+                "api": "osmr_draw_tiles_auto (tile list only; styled-area lists built on the device)",
+                "ms_auto_stage": float(ast["ms_auto"]), "styled_areas_after_culling": int(ast["n_areas"]),
+                "identical_to_e2e_output": same, "class_tables_host_s": t_cls}
 
     # ---- max over ranks (time), sum over ranks (tiles): the only collectives of the whole job ----
     job_tiles = n_tiles * args.steps
@@ -439,6 +477,7 @@ def main():
                 "ms_per_step": 1000.0 * e2e_wall / args.steps, "api": "osmr_draw_tiles (pinned host buffers; " + ("tiles stored straight into the host buffer by raster_kernel" if args.e2e_direct
                                                                       else "tiles staged in HBM, chunked D2H on a copy stream") + ")",
                 "checksum": checksum},
+        "e2e_auto": auto,
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": cpu,

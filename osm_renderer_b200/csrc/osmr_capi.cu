@@ -165,6 +165,7 @@ struct osmr_ctx {
     int fill_cap = kFillCap;
     bool direct_out = false;  // debug key "direct_out": raster_kernel stores the tiles straight into a page-locked `out`
                               // (no D2H stage; measured slower than the staged pipeline: PCIe-bound stores, 26 GB/s)
+    unsigned host_chunks = 0;  // 0: tapered default schedule (plan_chunks)
     unsigned first_chunk = 0;  // tiles in the first draw chunk of the current upload (0: one chunk)
     osmr_stats stats{};
 
@@ -323,6 +324,11 @@ int osmr_debug_set(osmr_ctx* ctx, const char* key, int value) {
     }
     if (strcmp(key, "direct_out") == 0) {  // 0: always stage the tiles in HBM and copy them back (A/B measurements)
         ctx->direct_out = value != 0;
+        return OSMR_OK;
+    }
+    if (strcmp(key, "host_chunks") == 0) {  // equal draw chunks of a staged host-output call (0: tapered default)
+        if (value < 0 || value > (int)kMaxChunks) return ctx->fail(OSMR_E_INVALID, "host_chunks must be 0..16");
+        ctx->host_chunks = (unsigned)value;
         return OSMR_OK;
     }
     if (strcmp(key, "fill_cap") == 0) {
@@ -622,20 +628,38 @@ static unsigned char* pinned_device_alias(const void* p) {
     return static_cast<unsigned char*>(a.devicePointer);
 }
 
-// Host output is drawn in chunks so that transfers overlap the drawing:
-//   staged (the default): 8 equal chunks, all enqueued back to back; the D2H copy of chunk i runs on its own stream while
-//   the later chunks are drawn (it really overlaps only when `out` is page-locked, e.g. from osmr_alloc_pinned);
-//   direct (page-locked `out`): a small first chunk hides the upload of the remaining styled areas, the tiles themselves
-//   are written to host memory by raster_kernel as they are finished.
-static void draw_chunks(unsigned n_tiles, bool to_host, bool direct, unsigned& first, unsigned& rest) {
-    first = rest = n_tiles;
-    if (!to_host || n_tiles < 128) return;
-    if (direct) {
-        first = std::max(32u, n_tiles / 8);
-        rest = n_tiles - first;
+// Host output is drawn in chunks so that transfers overlap the drawing (all chunks are enqueued back to back):
+//   staged (the default): the D2H copy of chunk i runs on its own stream while the later chunks are drawn (it really
+//   overlaps only when `out` is page-locked, e.g. from osmr_alloc_pinned).  What stays exposed is the upload of the first
+//   chunk's styled areas and the copy of the last chunk's tiles, so the schedule tapers: 1/4, 5/16, 1/4, 1/8, 1/16 of the
+//   batch (measured on the C2 batch, B200: 4 equal chunks 11.8 ms, 8: 12.5, 16: 14.7 -- every chunk costs ~0.15 ms of
+//   launch tails).  Debug key "host_chunks" = n > 0 forces n equal chunks.
+//   direct (debug key "direct_out", page-locked `out`): a small first chunk hides the upload of the remaining styled
+//   areas, raster_kernel stores the tiles straight into host memory (PCIe-bound stores, 26 GB/s: slower than staging).
+static unsigned plan_chunks(unsigned n_tiles, bool to_host, bool direct, unsigned host_chunks, unsigned sizes[kMaxChunks]) {
+    unsigned n = 0;
+    if (!to_host || n_tiles < 128) {
+        sizes[n++] = n_tiles;
+    } else if (direct) {
+        sizes[n++] = std::max(32u, n_tiles / 8);
+        sizes[n++] = n_tiles - sizes[0];
+    } else if (host_chunks) {
+        const unsigned c = std::max(64u, (n_tiles + host_chunks - 1) / host_chunks);
+        for (unsigned done = 0; done < n_tiles && n < kMaxChunks; done += c) sizes[n++] = std::min(c, n_tiles - done);
+        unsigned sum = 0;
+        for (unsigned i = 0; i < n; ++i) sum += sizes[i];
+        sizes[n - 1] += n_tiles - sum;
     } else {
-        first = rest = std::max(64u, (n_tiles + 7) / 8);
+        static const unsigned sixteenths[5] = {4, 5, 4, 2, 1};
+        unsigned done = 0;
+        for (unsigned i = 0; i < 5 && done < n_tiles; ++i) {
+            unsigned c = (i == 4) ? n_tiles - done : std::min(n_tiles - done, std::max(32u, n_tiles * sixteenths[i] / 16));
+            sizes[n++] = c;
+            done += c;
+        }
+        if (done < n_tiles) sizes[n - 1] += n_tiles - done;
     }
+    return n;
 }
 
 static int batch_upload_impl(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, const uint32_t* area_begin,
@@ -656,11 +680,11 @@ static int batch_upload_impl(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_t
     size_t head = n_areas;
     ctx->first_chunk = 0;
     if (defer_tail) {
-        unsigned first, rest;
-        draw_chunks(n_tiles, true, ctx->direct_out && host_out && pinned_device_alias(host_out), first, rest);
-        if (first < n_tiles) {
-            head = area_begin[first];
-            ctx->first_chunk = first;
+        unsigned sizes[kMaxChunks];
+        plan_chunks(n_tiles, true, ctx->direct_out && host_out && pinned_device_alias(host_out), ctx->host_chunks, sizes);
+        if (sizes[0] < n_tiles) {
+            head = area_begin[sizes[0]];
+            ctx->first_chunk = sizes[0];
         }
     }
     if (head) CK(cudaMemcpyAsync(ctx->areas.p, areas, head * sizeof(osmr_styled_area), cudaMemcpyHostToDevice, ctx->stream));
@@ -872,9 +896,10 @@ int osmr_batch_draw(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t flags, 
     }
     const size_t tile_bytes = D * D * ((flags & OSMR_DRAW_OUT_RGBA) ? 4 : 3);
     const bool staged = to_host && !alias;
-    unsigned first, rest;
-    draw_chunks(ctx->n_tiles, to_host, alias != nullptr, first, rest);
-    if (ctx->areas_deferred && ctx->first_chunk) first = ctx->first_chunk;  // the split the upload was made for
+    unsigned sizes[kMaxChunks];
+    const unsigned n_planned = plan_chunks(ctx->n_tiles, to_host, alias != nullptr, ctx->host_chunks, sizes);
+    if (ctx->areas_deferred && ctx->first_chunk && sizes[0] != ctx->first_chunk)
+        return ctx->fail(OSMR_E_STATE, "internal error: draw chunks differ from the upload split");
     CK(ctx->counters.reserve((size_t)kMaxChunks * CNT_COUNT));
     CK(ctx->h_cnt.reserve((size_t)kMaxChunks * CNT_COUNT));
     CK(ctx->calc_table.reserve((size_t)2 * ctx->n_styles * kCalcEntryUnits + 1));
@@ -902,8 +927,8 @@ int osmr_batch_draw(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t flags, 
         unsigned n_chunks = 0;
         unsigned cb[kMaxChunks], cc[kMaxChunks];
         for (unsigned tb = 0; tb < ctx->n_tiles;) {
-            unsigned tc = std::min(tb == 0 ? first : rest, ctx->n_tiles - tb);
-            if (n_chunks + 1 == kMaxChunks) tc = ctx->n_tiles - tb;
+            const unsigned tc = sizes[n_chunks];
+            if (n_chunks >= n_planned || tc == 0 || tb + tc > ctx->n_tiles) return ctx->fail(OSMR_E_STATE, "internal error: bad draw chunk plan");
             if (tb > 0 && ctx->areas_deferred) {  // the tail of the styled-area list was uploaded on the copy stream
                 CK(cudaStreamWaitEvent(ctx->stream, ctx->areas_ready, 0));
                 ctx->areas_deferred = false;

@@ -157,6 +157,24 @@ constexpr int kFillCap = 128;
 
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
 
+// Bump allocation with ONE atomic per warp: every lane asks for n units (0: none) and gets its own offset.  Must be called by
+// all 32 lanes.  (650 k single-address atomics per counter and batch were a third of plan_ops / build_geometry.)
+__device__ __forceinline__ unsigned warp_alloc(unsigned* counter, unsigned n) {
+    unsigned incl = n;
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)lane_id() >= o) incl += v;
+    }
+    const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+    unsigned base = 0;
+    if (lane_id() == 0 && total) base = atomicAdd(counter, total);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    return base + incl - n;
+}
+
+// Dynamic work distribution of the persistent kernels: a warp takes kWorkBatch consecutive items per atomic.
+constexpr unsigned kWorkBatch = 4;
+
 // ------------------------------------------------------------------------------------------------------
 // a1 (transcendental half): reference src/tile.rs:88-101 up to `factor`.
 // ------------------------------------------------------------------------------------------------------
@@ -437,16 +455,18 @@ __global__ void __launch_bounds__(kPlanThreads) plan_ops_kernel(Scene s) {
             }
         }
         // scratch allocation (order irrelevant); failure marks the op invisible and raises the overflow flag
-        if (visible) {
-            unsigned off = atomicAdd(&s.counters[CNT_GEOM_USED], geom_units);
-            if (off + geom_units > s.geom_cap || off + geom_units < off) {
-                atomicOr(&s.counters[CNT_OVERFLOW], 1u);
-                visible = false;
-            } else {
-                op.geom_off = off;
+        {
+            const unsigned off = warp_alloc(&s.counters[CNT_GEOM_USED], visible ? geom_units : 0u);
+            if (visible) {
+                if (off + geom_units > s.geom_cap || off + geom_units < off) {
+                    atomicOr(&s.counters[CNT_OVERFLOW], 1u);
+                    visible = false;
+                } else {
+                    op.geom_off = off;
+                }
             }
+            const unsigned moff = warp_alloc(&s.counters[CNT_MASK_USED], visible ? mask_words : 0u);
             if (visible && mask_words) {
-                unsigned moff = atomicAdd(&s.counters[CNT_MASK_USED], mask_words);
                 if (moff + mask_words > s.mask_cap || moff + mask_words < moff) {
                     atomicOr(&s.counters[CNT_OVERFLOW], 2u);
                     visible = false;
@@ -471,12 +491,16 @@ __global__ void __launch_bounds__(kPlanThreads) plan_ops_kernel(Scene s) {
             rop.kind = (unsigned char)op.kind;
             s.rop[3ull * base + pos] = rop;
             s.vis_bbox[3ull * base + pos] = make_short4(op.x0, op.y0, op.x1, op.y1);
-            unsigned gi = (unsigned)(3ull * base + pos);
-            s.work[atomicAdd(&s.counters[CNT_N_WORK], 1u)] = gi;
-            if (op.kind != OP_LINE)
-                s.fill_work[atomicAdd(&s.counters[CNT_N_FILL_WORK], 1u)] = gi;
-            else
-                s.line_work[atomicAdd(&s.counters[CNT_N_LINE_WORK], 1u)] = gi;
+        }
+        {  // work lists of the per-op kernels (their order is irrelevant)
+            const unsigned gi = (unsigned)(3ull * base + pos);
+            const bool is_line = visible && op.kind == OP_LINE, is_fill = visible && op.kind != OP_LINE;
+            const unsigned wa = warp_alloc(&s.counters[CNT_N_WORK], visible ? 1u : 0u);
+            const unsigned wf = warp_alloc(&s.counters[CNT_N_FILL_WORK], is_fill ? 1u : 0u);
+            const unsigned wl = warp_alloc(&s.counters[CNT_N_LINE_WORK], is_line ? 1u : 0u);
+            if (visible) s.work[wa] = gi;
+            if (is_fill) s.fill_work[wf] = gi;
+            if (is_line) s.line_work[wl] = gi;
         }
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -496,15 +520,25 @@ __global__ void __launch_bounds__(kPlanThreads) plan_ops_kernel(Scene s) {
 // build_geometry_kernel: one warp per visible op (dynamic work fetch)
 // ------------------------------------------------------------------------------------------------------
 constexpr int kGeomThreads = 128;
+constexpr unsigned long long kSlabLen = 2048, kSlabAlpha = 16384;  // walk cache units a warp reserves per atomic (2 KB / 128 KB)
 
-__global__ void __launch_bounds__(kGeomThreads) build_geometry_kernel(Scene s) {
+#ifndef OSMR_GEOM_MIN_BLOCKS
+#define OSMR_GEOM_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(kGeomThreads, OSMR_GEOM_MIN_BLOCKS) build_geometry_kernel(Scene s) {
     const unsigned lane = lane_id();
     const int D = s.D;
-    for (;;) {
-        unsigned wi = 0;
-        if (lane == 0) wi = atomicAdd(&s.counters[CNT_WORK_CURSOR], 1u);
-        wi = __shfl_sync(0xffffffffu, wi, 0);
-        if (wi >= s.counters[CNT_N_WORK]) break;
+    const unsigned n_work = s.counters[CNT_N_WORK];
+    // walk cache slabs: the warp takes kSlab units per atomic and hands them out to its ops itself
+    unsigned long long slab_len = 0, slab_len_end = 0, slab_alpha = 0, slab_alpha_end = 0;
+    unsigned wi = 0, wi_end = 0;
+    for (;; ++wi) {
+        if (wi >= wi_end) {
+            if (lane == 0) wi = atomicAdd(&s.counters[CNT_WORK_CURSOR], kWorkBatch);
+            wi = __shfl_sync(0xffffffffu, wi, 0);
+            wi_end = wi + kWorkBatch;
+        }
+        if (wi >= n_work) break;
         unsigned gi = s.work[wi];
         VisOp& op = s.vis[gi];
         const unsigned pass = op.pass;
@@ -646,8 +680,21 @@ __global__ void __launch_bounds__(kGeomThreads) build_geometry_kernel(Scene s) {
                 const unsigned total_k = __shfl_sync(0xffffffffu, incl, 31);
                 unsigned long long base_len = 0, base_alpha = 0;
                 if (lane == 0 && total_k) {
-                    base_len = atomicAdd(walk_len_used, 4ull * total_k);
-                    base_alpha = atomicAdd(walk_alpha_used, 4ull * S * total_k);
+                    const unsigned long long need_len = 4ull * total_k, need_alpha = 4ull * S * total_k;
+                    if (slab_len + need_len > slab_len_end) {
+                        const unsigned long long take = need_len > kSlabLen ? need_len : kSlabLen;
+                        slab_len = atomicAdd(walk_len_used, take);
+                        slab_len_end = slab_len + take;
+                    }
+                    if (slab_alpha + need_alpha > slab_alpha_end) {
+                        const unsigned long long take = need_alpha > kSlabAlpha ? need_alpha : kSlabAlpha;
+                        slab_alpha = atomicAdd(walk_alpha_used, take);
+                        slab_alpha_end = slab_alpha + take;
+                    }
+                    base_len = slab_len;
+                    base_alpha = slab_alpha;
+                    slab_len += need_len;
+                    slab_alpha += need_alpha;
                 }
                 base_len = __shfl_sync(0xffffffffu, base_len, 0);
                 base_alpha = __shfl_sync(0xffffffffu, base_alpha, 0);
@@ -717,12 +764,16 @@ __global__ void __launch_bounds__(kFillThreads) fill_rows_kernel(Scene s) {
     const int D = s.D;
     const int wpr = D / 32;
     const int cap = s.fill_cap;
-    // every warp is an independent worker: fetch one fill op, produce all its rows, repeat (no CTA barrier)
-    for (;;) {
-        unsigned wi = 0;
-        if (lane == 0) wi = atomicAdd(&s.counters[CNT_FILL_CURSOR], 1u);
-        wi = __shfl_sync(0xffffffffu, wi, 0);
-        if (wi >= s.counters[CNT_N_FILL_WORK]) break;
+    const unsigned n_work = s.counters[CNT_N_FILL_WORK];
+    // every warp is an independent worker: fetch fill ops, produce all their rows, repeat (no CTA barrier)
+    unsigned wi = 0, wi_end = 0;
+    for (;; ++wi) {
+        if (wi >= wi_end) {
+            if (lane == 0) wi = atomicAdd(&s.counters[CNT_FILL_CURSOR], kWorkBatch);
+            wi = __shfl_sync(0xffffffffu, wi, 0);
+            wi_end = wi + kWorkBatch;
+        }
+        if (wi >= n_work) break;
         const VisOp op = s.vis[s.fill_work[wi]];
         const int4* edges = reinterpret_cast<const int4*>(s.geom + op.geom_off);
         const int ne = (int)op.geom_cnt;
@@ -886,7 +937,7 @@ constexpr int kBP = kBW * kBH;
 static_assert((kBW == 16 || kBW == 32) && kBP % 32 == 0 && 256 % kBW == 0 && 256 % kBH == 0, "block shape");
 constexpr int kRasterThreads = 32;
 #ifndef OSMR_RASTER_MIN_BLOCKS
-#define OSMR_RASTER_MIN_BLOCKS 20  // resident one-warp CTAs per SM the register allocation must allow
+#define OSMR_RASTER_MIN_BLOCKS 24  // resident one-warp CTAs per SM the register allocation must allow (16: 4.5 ms, 20: 4.06, 24: 3.66)
 #endif
 
 // ------------------------------------------------------------------------------------------------------
@@ -1027,16 +1078,23 @@ struct CoverSmem {
     unsigned pre[32];
 };
 
-__global__ void __launch_bounds__(kCoverThreads) line_cover_kernel(Scene s) {
+#ifndef OSMR_COVER_MIN_BLOCKS
+#define OSMR_COVER_MIN_BLOCKS 6  // 4: 2.03 ms, 6: 1.77, 8: 1.83 (C2 batch)
+#endif
+__global__ void __launch_bounds__(kCoverThreads, OSMR_COVER_MIN_BLOCKS) line_cover_kernel(Scene s) {
     __shared__ CoverSmem smem[kCoverWarps];
     CoverSmem& sm = smem[threadIdx.x >> 5];
     const unsigned lane = lane_id();
     const int D = s.D;
-    for (;;) {
-        unsigned wi = 0;
-        if (lane == 0) wi = atomicAdd(&s.counters[CNT_LINE_CURSOR], 1u);
-        wi = __shfl_sync(0xffffffffu, wi, 0);
-        if (wi >= s.counters[CNT_N_LINE_WORK]) break;
+    const unsigned n_work = s.counters[CNT_N_LINE_WORK];
+    unsigned wi = 0, wi_end = 0;
+    for (;; ++wi) {
+        if (wi >= wi_end) {
+            if (lane == 0) wi = atomicAdd(&s.counters[CNT_LINE_CURSOR], kWorkBatch);
+            wi = __shfl_sync(0xffffffffu, wi, 0);
+            wi_end = wi + kWorkBatch;
+        }
+        if (wi >= n_work) break;
         const unsigned gi = s.line_work[wi];
         const VisOp op = s.vis[gi];
         const unsigned pass = op.pass;
@@ -1153,9 +1211,14 @@ struct RasterSmem {
 };
 
 // Replays the integer stepping of one cached walk (line.rs:82-96,120-130) and max-combines the alphas of the steps
-// that fall into the block.
+// that fall into the block.  The first alphas of the walk are fetched together before the stepping starts: independent
+// loads instead of one exposed memory latency per step (walks are 2-4 steps long for ordinary street widths).
 __device__ __forceinline__ void gather_walk(unsigned long long* plane, const double* __restrict__ alpha, unsigned len, const WalkItem& w,
                                             int mn, int p_error, int mul, int bx0, int by0) {
+    constexpr int kPre = 4;
+    double a_pre[kPre];
+#pragma unroll
+    for (int i = 0; i < kPre; ++i) a_pre[i] = (unsigned)i < len ? alpha[i] : 0.0;
     int p_mn = w.mx;
     int p_mx = mn;
     int err = mul * p_error;
@@ -1163,12 +1226,11 @@ __device__ __forceinline__ void gather_walk(unsigned long long* plane, const dou
     const int corr = -mul * w.mx_inc;
     const int lo = w.swap ? by0 : bx0;
     const int hi = lo + (w.swap ? kBH : kBW) - 1;
-    for (unsigned t = 0; t < len; ++t) {
-        if (step > 0 ? (p_mx > hi) : (p_mx < lo)) break;  // left the block on the monotone axis: never comes back
+    auto visit = [&](double a) -> bool {  // false: the walk has left the block on its monotone axis and never comes back
+        if (step > 0 ? (p_mx > hi) : (p_mx < lo)) return false;
         const int lx = (w.swap ? p_mn : p_mx) - bx0, ly = (w.swap ? p_mx : p_mn) - by0;
         if ((unsigned)lx < (unsigned)kBW && (unsigned)ly < (unsigned)kBH) {
             OSMR_COUNT("raster.steps_in_block", 1);
-            const double a = alpha[t];
             const unsigned long long bits = (unsigned long long)__double_as_longlong(a);
             unsigned long long* cell = &plane[ly * kBW + lx];
             if (a > 0.0 && bits > *cell) atomicMax(cell, bits);
@@ -1180,7 +1242,15 @@ __device__ __forceinline__ void gather_walk(unsigned long long* plane, const dou
         }
         err = wadd(err, 2 * w.mn_d);
         p_mx += step;
+        return true;
+    };
+#pragma unroll
+    for (int i = 0; i < kPre; ++i) {
+        if ((unsigned)i >= len) return;
+        if (!visit(a_pre[i])) return;
     }
+    for (unsigned t = kPre; t < len; ++t)
+        if (!visit(alpha[t])) return;
 }
 
 __global__ void __launch_bounds__(kRasterThreads, OSMR_RASTER_MIN_BLOCKS) raster_kernel(Scene s) {
@@ -1214,13 +1284,20 @@ __global__ void __launch_bounds__(kRasterThreads, OSMR_RASTER_MIN_BLOCKS) raster
     }
     __syncwarp();
 
+    short4 o_next = make_short4(0, 0, -1, -1);  // the next chunk's bboxes are in flight while this chunk is drawn
+    if (lane < n_vis) o_next = vbb[lane];
     for (unsigned chunk = 0; chunk < n_vis; chunk += 32) {
         // ---- the ops of this chunk whose reach bbox meets my block, in order ----
         unsigned vi = chunk + lane;
-        bool hit = false;
-        if (vi < n_vis) {
-            const short4 o = vbb[vi];
-            hit = o.x <= bx0 + kBW - 1 && o.z >= bx0 && o.y <= by0 + kBH - 1 && o.w >= by0;
+        const short4 o = o_next;
+        if (vi + 32 < n_vis) o_next = vbb[vi + 32];
+        const bool hit = vi < n_vis && o.x <= bx0 + kBW - 1 && o.z >= bx0 && o.y <= by0 + kBH - 1 && o.w >= by0;
+        // every lane fetches the record of ITS op now (independent loads); the records are handed round by shuffles
+        uint4 my_rop0 = make_uint4(0, 0, 0, 0), my_rop1 = make_uint4(0, 0, 0, 0);
+        if (hit) {
+            const uint4* src = reinterpret_cast<const uint4*>(&rops[vi]);
+            my_rop0 = src[0];
+            my_rop1 = src[1];
         }
         unsigned todo = __ballot_sync(0xffffffffu, hit);
         while (todo) {
@@ -1228,10 +1305,19 @@ __global__ void __launch_bounds__(kRasterThreads, OSMR_RASTER_MIN_BLOCKS) raster
             todo &= todo - 1;
             RasterOp op;
             {
-                const uint4* src = reinterpret_cast<const uint4*>(&rops[qi]);
+                const int from = (int)(qi - chunk);
+                uint4 r0, r1;
+                r0.x = __shfl_sync(0xffffffffu, my_rop0.x, from);
+                r0.y = __shfl_sync(0xffffffffu, my_rop0.y, from);
+                r0.z = __shfl_sync(0xffffffffu, my_rop0.z, from);
+                r0.w = __shfl_sync(0xffffffffu, my_rop0.w, from);
+                r1.x = __shfl_sync(0xffffffffu, my_rop1.x, from);
+                r1.y = __shfl_sync(0xffffffffu, my_rop1.y, from);
+                r1.z = __shfl_sync(0xffffffffu, my_rop1.z, from);
+                r1.w = __shfl_sync(0xffffffffu, my_rop1.w, from);
                 uint4* dst = reinterpret_cast<uint4*>(&op);
-                dst[0] = src[0];
-                dst[1] = src[1];
+                dst[0] = r0;
+                dst[1] = r1;
             }
 
             if (op.kind != OP_LINE) {
