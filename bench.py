@@ -197,7 +197,7 @@ def main():
                     help="e2e leg: 0 = tiles staged in HBM, chunk-wise D2H on its own stream while later chunks are drawn (default), "
                          "1 = raster_kernel stores the tiles straight into the page-locked host buffer")
     ap.add_argument("--e2e-chunks", type=int, default=0, help="experiments: draw chunks of the staged e2e call (0 = library default)")
-    ap.add_argument("--skip-auto", action="store_true", help="skip the osmr_draw_tiles_auto leg (f3)")
+    ap.add_argument("--skip-auto", action="store_true", help="skip the osmr_draw_tiles_auto (f3) and osmr_draw_tiles_png (f4) legs")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -378,6 +378,31 @@ def main():
                 "ms_auto_stage": float(ast["ms_auto"]), "styled_areas_after_culling": int(ast["n_areas"]),
                 "identical_to_e2e_output": same, "class_tables_host_s": t_cls}
 
+    # ---- e2e_png (f4): PNG files instead of RGB triples; the files of the batch come back packed ----
+    png = None
+    if not args.skip_auto:
+        cap = n_tiles * int(L.osmr_png_bound(scale))
+        pin_png = L.osmr_alloc_pinned(cap)
+        offs = np.zeros(n_tiles + 1, dtype=np.uint64)
+
+        def png_step():
+            rc = L.osmr_draw_tiles_png(ctx.h, pins[0], n_tiles, pins[1], pins[2], canvas.ctypes.data, flags, pin_png, cap, offs.ctypes.data)
+            if rc != 0:
+                raise RuntimeError(L.osmr_last_error(ctx.h))
+
+        for _ in range(max(1, min(args.warmup, 2))):
+            png_step()
+        barrier()
+        t3 = time.perf_counter()
+        for _ in range(args.steps):
+            png_step()
+        barrier()
+        png_wall = time.perf_counter() - t3
+        pst = ctx.stats()
+        png = {"value": n_tiles * args.steps / png_wall, "unit": "tiles/s", "ms_per_step": 1000.0 * png_wall / args.steps,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(offs[-1]), "mean_png_bytes": float(offs[-1]) / n_tiles,
+               "ms_png_stage": float(pst["ms_png"]), "api": "osmr_draw_tiles_png (filter + deflate + checksums on the device)"}
+
     # ---- max over ranks (time), sum over ranks (tiles): the only collectives of the whole job ----
     job_tiles = n_tiles * args.steps
     dev_s, total_tiles = sharding.reduce_job(dist, dev_s, job_tiles, device="cuda")
@@ -478,6 +503,7 @@ def main():
                                                                       else "tiles staged in HBM, chunked D2H on a copy stream") + ")",
                 "checksum": checksum},
         "e2e_auto": auto,
+        "e2e_png": png,
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": cpu,

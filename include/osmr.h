@@ -161,7 +161,7 @@ typedef struct osmr_stats {
     float ms_label_device;
     float ms_cover;          /* line_cover_kernel */
     float ms_auto;           /* osmr_draw_tiles_auto: candidate lookup + ordering on the device */
-    float reserved;
+    float ms_png;            /* osmr_draw_tiles_png: filter + deflate + checksums on the device */
 } osmr_stats;
 int osmr_get_stats(osmr_ctx* ctx, osmr_stats* out);
 
@@ -241,6 +241,20 @@ int osmr_set_zoom_styles(osmr_ctx* ctx, uint32_t zoom, const uint32_t* way_class
 int osmr_draw_tiles_auto(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, const uint8_t canvas_rgb[3], uint32_t flags, uint8_t* out);
 /* the styled-area lists of the last osmr_draw_tiles_auto call (tests): area_begin[n_tiles + 1], areas[area_begin[n_tiles]] */
 int osmr_auto_readback(osmr_ctx* ctx, uint32_t* area_begin, osmr_styled_area* areas, uint32_t areas_cap);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * the step AFTER the draw path -- PNG files instead of RGB triples.
+ * Replaces Drawer::draw_tile = draw_to_pixels + rgb_triples_to_png (src/draw/drawer.rs:40-58, src/draw/png_writer.rs:4-21:
+ * 8-bit RGB, one IDAT chunk).  Filter choice and deflate stream are the encoder's (per-row None/Sub/Up/Paeth by smallest
+ * absolute residual sum, fixed Huffman code, run-length matches), the decoded image is exactly the RGB tile.
+ * The files of the batch are packed back to back into png_out: tile t occupies [png_offset[t], png_offset[t+1]).
+ * png_cap >= n_tiles * osmr_png_bound(scale) always suffices (the call fails with OSMR_E_NOMEM otherwise, png_offset
+ * then still holds the sizes).
+ * ------------------------------------------------------------------------------------------------------------ */
+size_t osmr_png_bound(uint32_t scale);
+int osmr_draw_tiles_png(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, const uint32_t* area_begin,
+                        const osmr_styled_area* areas, const uint8_t canvas_rgb[3], uint32_t flags, uint8_t* png_out, size_t png_cap,
+                        uint64_t* png_offset /* n_tiles + 1 */);
 
 /* Optional page-locked host memory for callers that want full-speed host<->device copies of `out` / batch
  * arrays (plain malloc'ed buffers work too, at pageable-copy speed). */

@@ -37,6 +37,8 @@ EXPORTS = [
     "osmr_set_zoom_styles",
     "osmr_draw_tiles_auto",
     "osmr_auto_readback",
+    "osmr_png_bound",
+    "osmr_draw_tiles_png",
 ]
 
 _lib = None
@@ -104,5 +106,9 @@ def load():
     L.osmr_draw_tiles_auto.argtypes = [vp, vp, u32, vp, u32, vp]
     L.osmr_auto_readback.restype = C.c_int
     L.osmr_auto_readback.argtypes = [vp, vp, vp, u32]
+    L.osmr_png_bound.restype = sz
+    L.osmr_png_bound.argtypes = [u32]
+    L.osmr_draw_tiles_png.restype = C.c_int
+    L.osmr_draw_tiles_png.argtypes = [vp, vp, u32, vp, vp, vp, u32, vp, sz, vp]
     _lib = L
     return L

@@ -17,6 +17,7 @@ HEADERS = [
     os.path.join(HERE, "csrc", "osmr_kernels.cuh"),
     os.path.join(HERE, "csrc", "osmr_device.cuh"),
     os.path.join(HERE, "csrc", "osmr_auto.cuh"),
+    os.path.join(HERE, "csrc", "osmr_png.cuh"),
     os.path.join(HERE, "csrc", "osmr_labels_host.hpp"),
     os.path.join(ROOT, "include", "osmr.h"),
 ]

@@ -17,6 +17,7 @@
 #include "osmr.h"
 #include "osmr_kernels.cuh"
 #include "osmr_auto.cuh"
+#include "osmr_png.cuh"
 #include "osmr_labels_host.hpp"
 
 using namespace osmr;
@@ -162,6 +163,10 @@ struct osmr_ctx {
     DevBuf<unsigned> way_rank, mp_rank, rank_entity;
     DevBuf<unsigned> auto_bound, auto_cand, auto_cand_cnt, auto_inst;
     DevBuf<unsigned long long> auto_big_keys;
+    // f4: PNG encode on the device (osmr_png.cuh)
+    DevBuf<unsigned> png_band_words, png_band_bytes, png_band_len, png_tile_off;
+    DevBuf<uint2> png_band_adler;
+    DevBuf<unsigned char> png_out;
     int fill_cap = kFillCap;
     bool direct_out = false;  // debug key "direct_out": raster_kernel stores the tiles straight into a page-locked `out`
                               // (no D2H stage; measured slower than the staged pipeline: PCIe-bound stores, 26 GB/s)
@@ -275,6 +280,12 @@ void osmr_ctx_destroy(osmr_ctx* ctx) {
     ctx->auto_cand_cnt.release();
     ctx->auto_inst.release();
     ctx->auto_big_keys.release();
+    ctx->png_band_words.release();
+    ctx->png_band_bytes.release();
+    ctx->png_band_len.release();
+    ctx->png_tile_off.release();
+    ctx->png_band_adler.release();
+    ctx->png_out.release();
     ctx->line_work.release();
     ctx->walk_alpha.release();
     ctx->walk_len.release();
@@ -814,7 +825,7 @@ static int collect_chunk(osmr_ctx* ctx, unsigned slot, unsigned tb, unsigned tc,
     const unsigned* h_cnt = ctx->h_cnt.p + (size_t)slot * CNT_COUNT;
     const unsigned n_areas = ctx->h_area_begin[tb + tc] - ctx->h_area_begin[tb];
     if (h_cnt[CNT_BAD_INPUT] & 1u) return ctx->fail(OSMR_E_INVALID, "styled area references an entity or style that does not exist");
-    if (h_cnt[CNT_BAD_INPUT] & 2u) return ctx->fail(OSMR_E_INVALID, "line wider than 240 pixels (width * scale): not supported");
+    if (h_cnt[CNT_BAD_INPUT] & 2u) return ctx->fail(OSMR_E_INVALID, "line wider than 248 pixels (width * scale): not supported");
     if (h_cnt[CNT_WALK_TRUNC]) return ctx->fail(OSMR_E_CUDA, "internal error: a perpendicular walk exceeded its proven bound");
     if (h_cnt[CNT_OVERFLOW]) {  // grow the scratch that ran out; the caller redoes the draw
         *redo = true;
@@ -1175,6 +1186,77 @@ int osmr_auto_readback(osmr_ctx* ctx, uint32_t* area_begin, osmr_styled_area* ar
         if (ctx->n_areas) CK(cudaMemcpyAsync(areas, ctx->areas.p, (size_t)ctx->n_areas * sizeof(osmr_styled_area), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
     }
+    return OSMR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// f4: PNG files instead of RGB triples (osmr_png.cuh)
+// ---------------------------------------------------------------------------------------------------------
+static unsigned png_band_cap_words(unsigned scale) {
+    const unsigned long long D = 256ull * scale, rows = D / kPngBands, np = 3 * D + 1;
+    return (unsigned)((rows * np * 9ull + 128ull) / 32ull + 8ull);  // every byte a 9-bit literal + block framing
+}
+
+size_t osmr_png_bound(uint32_t scale) {
+    if (scale < 1 || scale > 8) return 0;
+    return (size_t)kPngFixed + (size_t)kPngBands * png_band_cap_words(scale) * 4u;
+}
+
+int osmr_draw_tiles_png(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, const uint32_t* area_begin, const osmr_styled_area* areas,
+                        const uint8_t canvas_rgb[3], uint32_t flags, uint8_t* png_out, size_t png_cap, uint64_t* png_offset) {
+    if (!ctx) return OSMR_E_INVALID;
+    if (!png_out || !png_offset) return ctx->fail(OSMR_E_INVALID, "null output buffer");
+    if (flags & (OSMR_DRAW_OUT_RGBA | OSMR_DRAW_OUT_DEVICE)) return ctx->fail(OSMR_E_INVALID, "osmr_draw_tiles_png encodes RGB into host memory");
+    int rc = batch_upload_impl(ctx, tiles, n_tiles, area_begin, areas, false, nullptr);
+    if (rc) return rc;
+    rc = osmr_batch_draw(ctx, canvas_rgb, flags, nullptr, nullptr);  // the RGB tiles stay in HBM (ctx->out)
+    if (rc) return rc;
+    cudaStream_t st = ctx->stream;
+    const unsigned scale = (unsigned)ctx->scale;
+    PngScene ps{};
+    ps.rgb = ctx->out.p;
+    ps.D = 256 * (int)scale;
+    ps.n_tiles = n_tiles;
+    ps.band_cap_words = png_band_cap_words(scale);
+    const size_t n_bands = (size_t)n_tiles * kPngBands;
+    CK(ctx->png_band_words.reserve(n_bands * ps.band_cap_words));
+    CK(ctx->png_band_bytes.reserve(n_bands));
+    CK(ctx->png_band_len.reserve(n_bands));
+    CK(ctx->png_band_adler.reserve(n_bands));
+    CK(ctx->png_tile_off.reserve(n_tiles + 2));
+    CK(ctx->counters.reserve((size_t)(kMaxChunks + 1) * CNT_COUNT));
+    ps.band_words = ctx->png_band_words.p;
+    ps.band_bytes = ctx->png_band_bytes.p;
+    ps.band_len = ctx->png_band_len.p;
+    ps.band_adler = ctx->png_band_adler.p;
+    ps.tile_off = ctx->png_tile_off.p;
+    unsigned* flag = ctx->counters.p + (size_t)kMaxChunks * CNT_COUNT + CNT_OVERFLOW;
+    CK(cudaEventRecord(ctx->ev[0], st));
+    CK(cudaMemsetAsync(flag, 0, sizeof(unsigned), st));
+    png_encode_kernel<<<n_tiles, kPngThreads, 0, st>>>(ps);
+    png_size_kernel<<<(n_tiles + 127) / 128, 128, 0, st>>>(ps);
+    auto_scan_kernel<<<1, 1024, 0, st>>>(ps.tile_off, n_tiles, flag);
+    std::vector<unsigned> off(n_tiles + 1);
+    unsigned h_flag = 0;
+    CK(cudaMemcpyAsync(off.data(), ps.tile_off, (size_t)(n_tiles + 1) * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&h_flag, flag, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (h_flag) return ctx->fail(OSMR_E_NOMEM, "more than 4 GiB of PNG data; split the batch");
+    const size_t total = off[n_tiles];
+    for (uint32_t t = 0; t <= n_tiles; ++t) png_offset[t] = off[t];
+    if (total > png_cap) return ctx->fail(OSMR_E_NOMEM, "png_out is too small (n_tiles * osmr_png_bound(scale) always suffices)");
+    CK(ctx->png_out.reserve(total + 16));
+    ps.out = ctx->png_out.p;
+    png_finish_kernel<<<n_tiles, kPngThreads, 0, st>>>(ps);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev[1], st));
+    CK(cudaMemcpyAsync(png_out, ps.out, total, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+    ctx->stats.ms_png = ms;
+    ctx->stats.ms_total += ms;
+    ctx->stats.kernel_launches += 4;
     return OSMR_OK;
 }
 

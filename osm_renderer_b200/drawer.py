@@ -234,6 +234,24 @@ class GpuContext:
         self._check(self.L.osmr_auto_readback(self.h, begins.ctypes.data, areas.ctypes.data, len(areas)), "osmr_auto_readback")
         return begins, areas
 
+    # ---- f4: PNG files ------------------------------------------------------------------------------------------------
+    def draw_tiles_png(self, tiles, area_begin, areas, canvas_rgb, use_caps_for_dashes=True):
+        """osmr_draw_tiles_png: list of `bytes`, one PNG file per tile (Drawer::draw_tile, drawer.rs:40-58)."""
+        tiles = np.ascontiguousarray(tiles, dtype=TILE_DTYPE)
+        area_begin = np.ascontiguousarray(area_begin, dtype=np.uint32)
+        areas = np.ascontiguousarray(areas, dtype=AREA_DTYPE)
+        n = len(tiles)
+        cap = n * int(self.L.osmr_png_bound(int(tiles["scale"][0]))) if n else 0
+        buf = np.empty(cap, dtype=np.uint8)
+        offs = np.zeros(n + 1, dtype=np.uint64)
+        flags, canvas = self._flags(canvas_rgb, use_caps_for_dashes, False)
+        self._check(
+            self.L.osmr_draw_tiles_png(self.h, tiles.ctypes.data, n, area_begin.ctypes.data, areas.ctypes.data, canvas.ctypes.data, flags,
+                                       buf.ctypes.data, cap, offs.ctypes.data),
+            "osmr_draw_tiles_png",
+        )
+        return [buf[int(offs[i]) : int(offs[i + 1])].tobytes() for i in range(n)]
+
     def debug_set(self, key: str, value: int):
         self._check(self.L.osmr_debug_set(self.h, key.encode(), value), "osmr_debug_set")
 

@@ -98,7 +98,7 @@ class StatsStruct(C.Structure):
         ("ms_label_device", C.c_float),
         ("ms_cover", C.c_float),
         ("ms_auto", C.c_float),
-        ("reserved", C.c_float),
+        ("ms_png", C.c_float),
     ]
 
 

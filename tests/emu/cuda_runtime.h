@@ -116,6 +116,12 @@ static inline int __double2int_rz(double v) {  // cvt.rzi.s32.f64: saturating, N
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 static inline int __clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
+static inline unsigned __brev(unsigned v) {
+    v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1);
+    v = ((v >> 2) & 0x33333333u) | ((v & 0x33333333u) << 2);
+    v = ((v >> 4) & 0x0f0f0f0fu) | ((v & 0x0f0f0f0fu) << 4);
+    return __builtin_bswap32(v);
+}
 static inline unsigned long long __umul64hi(unsigned long long a, unsigned long long b) {
     return (unsigned long long)(((unsigned __int128)a * (unsigned __int128)b) >> 64);
 }
