@@ -719,8 +719,9 @@ static int batch_upload_impl(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_t
     CK(ctx->line_work.reserve(2ull * n_areas + 1));
     CK(ctx->vis_count.reserve(n_tiles));
     CK(ctx->counters.reserve(CNT_COUNT));
-    // the caller's arrays may be reused as soon as we return
-    CK(cudaStreamSynchronize(ctx->stream));
+    // osmr_batch_upload: the caller's arrays may be reused as soon as we return.  osmr_draw_tiles (defer_tail) keeps them
+    // alive until the draw has finished, so the kernels are enqueued right behind the copies without a host round trip.
+    if (!defer_tail) CK(cudaStreamSynchronize(ctx->stream));
     ctx->has_batch = true;
     return OSMR_OK;
 }

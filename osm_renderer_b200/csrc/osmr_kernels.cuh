@@ -768,10 +768,10 @@ __global__ void __launch_bounds__(kFillThreads) fill_rows_kernel(Scene s) {
     // every warp is an independent worker: fetch fill ops, produce all their rows, repeat (no CTA barrier)
     unsigned wi = 0, wi_end = 0;
     for (;; ++wi) {
-        if (wi >= wi_end) {
-            if (lane == 0) wi = atomicAdd(&s.counters[CNT_FILL_CURSOR], kWorkBatch);
+        if (wi >= wi_end) {  // one op per fetch: the rows of a fill op are too uneven a load for batches (0.78 -> 0.85 ms with 4)
+            if (lane == 0) wi = atomicAdd(&s.counters[CNT_FILL_CURSOR], 1u);
             wi = __shfl_sync(0xffffffffu, wi, 0);
-            wi_end = wi + kWorkBatch;
+            wi_end = wi + 1u;
         }
         if (wi >= n_work) break;
         const VisOp op = s.vis[s.fill_work[wi]];
@@ -936,6 +936,13 @@ constexpr int kBH = OSMR_BH;
 constexpr int kBP = kBW * kBH;
 static_assert((kBW == 16 || kBW == 32) && kBP % 32 == 0 && 256 % kBW == 0 && 256 % kBH == 0, "block shape");
 constexpr int kRasterThreads = 32;
+// prefetching in raster_kernel (bit mask; A/B measured on the C2 batch):
+//   1: the next chunk's op bboxes are loaded while the current chunk is drawn
+//   2: every lane loads the RasterOp of its own hit op, records are handed round by shuffles (instead of one dependent load per op)
+//   4: the first four alphas of a cached walk are loaded together before the stepping starts
+#ifndef OSMR_RASTER_PREFETCH
+#define OSMR_RASTER_PREFETCH 7
+#endif
 #ifndef OSMR_RASTER_MIN_BLOCKS
 #define OSMR_RASTER_MIN_BLOCKS 24  // resident one-warp CTAs per SM the register allocation must allow (16: 4.5 ms, 20: 4.06, 24: 3.66)
 #endif
@@ -1215,8 +1222,8 @@ struct RasterSmem {
 // loads instead of one exposed memory latency per step (walks are 2-4 steps long for ordinary street widths).
 __device__ __forceinline__ void gather_walk(unsigned long long* plane, const double* __restrict__ alpha, unsigned len, const WalkItem& w,
                                             int mn, int p_error, int mul, int bx0, int by0) {
-    constexpr int kPre = 4;
-    double a_pre[kPre];
+    constexpr int kPre = (OSMR_RASTER_PREFETCH & 4) ? 4 : 0;
+    double a_pre[kPre + 1];
 #pragma unroll
     for (int i = 0; i < kPre; ++i) a_pre[i] = (unsigned)i < len ? alpha[i] : 0.0;
     int p_mn = w.mx;
@@ -1289,21 +1296,37 @@ __global__ void __launch_bounds__(kRasterThreads, OSMR_RASTER_MIN_BLOCKS) raster
     for (unsigned chunk = 0; chunk < n_vis; chunk += 32) {
         // ---- the ops of this chunk whose reach bbox meets my block, in order ----
         unsigned vi = chunk + lane;
+#if OSMR_RASTER_PREFETCH & 1
         const short4 o = o_next;
         if (vi + 32 < n_vis) o_next = vbb[vi + 32];
+#else
+        const short4 o = vi < n_vis ? vbb[vi] : o_next;
+#endif
         const bool hit = vi < n_vis && o.x <= bx0 + kBW - 1 && o.z >= bx0 && o.y <= by0 + kBH - 1 && o.w >= by0;
         // every lane fetches the record of ITS op now (independent loads); the records are handed round by shuffles
         uint4 my_rop0 = make_uint4(0, 0, 0, 0), my_rop1 = make_uint4(0, 0, 0, 0);
+#if OSMR_RASTER_PREFETCH & 2
         if (hit) {
             const uint4* src = reinterpret_cast<const uint4*>(&rops[vi]);
             my_rop0 = src[0];
             my_rop1 = src[1];
         }
+#endif
         unsigned todo = __ballot_sync(0xffffffffu, hit);
         while (todo) {
             const unsigned qi = chunk + (unsigned)(__ffs(todo) - 1);
             todo &= todo - 1;
             RasterOp op;
+#if !(OSMR_RASTER_PREFETCH & 2)
+            {
+                const uint4* src = reinterpret_cast<const uint4*>(&rops[qi]);
+                uint4* dst = reinterpret_cast<uint4*>(&op);
+                dst[0] = src[0];
+                dst[1] = src[1];
+                (void)my_rop0;
+                (void)my_rop1;
+            }
+#else
             {
                 const int from = (int)(qi - chunk);
                 uint4 r0, r1;
@@ -1319,6 +1342,7 @@ __global__ void __launch_bounds__(kRasterThreads, OSMR_RASTER_MIN_BLOCKS) raster
                 dst[0] = r0;
                 dst[1] = r1;
             }
+#endif
 
             if (op.kind != OP_LINE) {
                 // ---------------- fill: blend straight from the row masks ----------------

@@ -99,7 +99,13 @@ __device__ __forceinline__ void png_match_dist1(unsigned len, unsigned& bits, un
     nb += 5;  // distance code 0 (distance 1): five zero bits, no extra bits
 }
 
+#ifndef OSMR_PNG_ROW_CACHE
+#define OSMR_PNG_ROW_CACHE 3080
+#endif
+constexpr int kPngRowCache = OSMR_PNG_ROW_CACHE;  // filtered bytes of a row kept in shared memory (scale <= 4; larger rows are recomputed)
+
 struct PngWarpSmem {
+    unsigned char frow[kPngRowCache];
     unsigned stage[64];   // bit staging: stage[0] holds the stream's partial word
     unsigned emask[200];  // e[i] = filtered[i] == filtered[i-1], one bit per position of the row (<= 6145 positions)
     int lastz[200];       // last position with e == 0 at or before the end of word g
@@ -187,14 +193,28 @@ __global__ void __launch_bounds__(kPngThreads) png_encode_kernel(PngScene ps) {
         }
         // ---- equality mask of the filtered row + Adler-32 sums ----
         unsigned long long r1 = 0, r2 = 0;
+        const bool cached = NP <= kPngRowCache;
+        if (cached) {
+            for (int i = (int)lane; i < NP; i += 32) {
+                const unsigned f = png_filtered(cur, up, filter, i);
+                sm.frow[i] = (unsigned char)f;
+                r1 += f;
+                r2 += (unsigned long long)(NP - i) * f;
+            }
+            __syncwarp();
+        }
         for (int g = 0; g < n_words; ++g) {
             const int i = 32 * g + (int)lane;
             bool e = false;
             if (i < NP) {
-                const unsigned f = png_filtered(cur, up, filter, i);
-                r1 += f;
-                r2 += (unsigned long long)(NP - i) * f;
-                e = i >= 1 && f == png_filtered(cur, up, filter, i - 1);
+                if (cached) {
+                    e = i >= 1 && sm.frow[i] == sm.frow[i - 1];
+                } else {
+                    const unsigned f = png_filtered(cur, up, filter, i);
+                    r1 += f;
+                    r2 += (unsigned long long)(NP - i) * f;
+                    e = i >= 1 && f == png_filtered(cur, up, filter, i - 1);
+                }
             }
             const unsigned m = __ballot_sync(0xffffffffu, e);
             if (lane == 0) sm.emask[g] = m;
@@ -209,19 +229,34 @@ __global__ void __launch_bounds__(kPngThreads) png_encode_kernel(PngScene ps) {
         n_done += (unsigned long long)NP;
         __syncwarp();
         // ---- last / first zero of the mask per word (positions beyond the row count as zeros) ----
-        if (lane == 0) {
-            int last = 0;  // e[0] == 0 always
-            for (int g = 0; g < n_words; ++g) {
-                const unsigned z = ~sm.emask[g];
-                if (z) last = 32 * g + 31 - __clz(z);
-                sm.lastz[g] = last;  // only lastz[g - 1] of a word g inside the row is ever read: always a valid position
+        // (one mask word per lane: inclusive max-scan from the left / min-scan from the right, 32 words at a time)
+        {
+            int carry = 0;  // e[0] == 0 always
+            for (int g0 = 0; g0 < n_words; g0 += 32) {
+                const int g = g0 + (int)lane;
+                const unsigned z = g < n_words ? ~sm.emask[g] : 0u;
+                int v = z ? 32 * g + 31 - __clz(z) : -1;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int u = __shfl_up_sync(0xffffffffu, v, o);
+                    if ((int)lane >= o) v = max(v, u);
+                }
+                v = max(v, carry);
+                if (g < n_words) sm.lastz[g] = v;  // only lastz[g - 1] of a word g inside the row is ever read: a valid position
+                carry = __shfl_sync(0xffffffffu, v, 31);
             }
-            int first = NP;
-            sm.firstz[n_words] = NP;
-            for (int g = n_words - 1; g >= 0; --g) {
-                const unsigned z = ~sm.emask[g];
-                if (z) first = min(32 * g + __ffs(z) - 1, NP);
-                sm.firstz[g] = first;
+            carry = NP;
+            if (lane == 0) sm.firstz[n_words] = NP;
+            for (int g0 = ((n_words - 1) / 32) * 32; g0 >= 0; g0 -= 32) {
+                const int g = g0 + (int)lane;
+                const unsigned z = g < n_words ? ~sm.emask[g] : 0u;
+                int v = z ? min(32 * g + __ffs(z) - 1, NP) : NP;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int u = __shfl_down_sync(0xffffffffu, v, o);
+                    if ((int)lane + o < 32) v = min(v, u);
+                }
+                v = min(v, carry);
+                if (g < n_words) sm.firstz[g] = v;
+                carry = __shfl_sync(0xffffffffu, v, 0);
             }
         }
         __syncwarp();
@@ -245,8 +280,9 @@ __global__ void __launch_bounds__(kPngThreads) png_encode_kernel(PngScene ps) {
                         if (off - 258 * chunk == 0) png_match_dist1((unsigned)Lc, bits, nb);
                     }
                 }
-                if (literal) png_literal(png_filtered(cur, up, filter, i), bits, nb);
+                if (literal) png_literal(cached ? (unsigned)sm.frow[i] : png_filtered(cur, up, filter, i), bits, nb);
             }
+            if (!__any_sync(0xffffffffu, nb != 0)) continue;  // 32 positions inside one long run: nothing to emit
             emit(bits, nb);
         }
     }
