@@ -141,7 +141,8 @@ struct osmr_ctx {
     DevBuf<VisOp> vis;
     DevBuf<RasterOp> rop;
     DevBuf<short4> vis_bbox;
-    DevBuf<unsigned> vis_count, work, fill_work, line_work, counters, mask;
+    DevBuf<unsigned> vis_count, work, counters, mask;
+    DevBuf<uint2> fill_work, line_work;
     DevBuf<uint4> geom, calc_table;
     DevBuf<double> walk_alpha;        // walk cache (line_cover_kernel -> raster_kernel)
     DevBuf<unsigned char> walk_len;
@@ -170,6 +171,7 @@ struct osmr_ctx {
     int fill_cap = kFillCap;
     bool direct_out = false;  // debug key "direct_out": raster_kernel stores the tiles straight into a page-locked `out`
                               // (no D2H stage; measured slower than the staged pipeline: PCIe-bound stores, 26 GB/s)
+    unsigned work_items_limit = 0;  // debug key "work_items": pretend the work lists are this short once (exercises their growth)
     unsigned host_chunks = 0;  // 0: tapered default schedule (plan_chunks)
     unsigned first_chunk = 0;  // tiles in the first draw chunk of the current upload (0: one chunk)
     osmr_stats stats{};
@@ -340,6 +342,11 @@ int osmr_debug_set(osmr_ctx* ctx, const char* key, int value) {
     if (strcmp(key, "host_chunks") == 0) {  // equal draw chunks of a staged host-output call (0: tapered default)
         if (value < 0 || value > (int)kMaxChunks) return ctx->fail(OSMR_E_INVALID, "host_chunks must be 0..16");
         ctx->host_chunks = (unsigned)value;
+        return OSMR_OK;
+    }
+    if (strcmp(key, "work_items") == 0) {
+        if (value < 1) return ctx->fail(OSMR_E_INVALID, "work_items must be positive");
+        ctx->work_items_limit = (unsigned)value;
         return OSMR_OK;
     }
     if (strcmp(key, "fill_cap") == 0) {
@@ -715,9 +722,9 @@ static int batch_upload_impl(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_t
     CK(ctx->rop.reserve(3ull * n_areas + 1));
     CK(ctx->vis_bbox.reserve(3ull * n_areas + 1));
     CK(ctx->work.reserve(3ull * n_areas + 1));
-    CK(ctx->fill_work.reserve((size_t)n_areas + 1));
-    CK(ctx->line_work.reserve(2ull * n_areas + 1));
-    CK(ctx->vis_count.reserve(n_tiles));
+    CK(ctx->fill_work.reserve((size_t)n_areas + n_areas / 2 + 4096));  // work items; grown when a batch has more
+    CK(ctx->line_work.reserve(2ull * n_areas + n_areas / 2 + 4096));
+    CK(ctx->vis_count.reserve(3ull * n_tiles));
     CK(ctx->counters.reserve(CNT_COUNT));
     // osmr_batch_upload: the caller's arrays may be reused as soon as we return.  osmr_draw_tiles (defer_tail) keeps them
     // alive until the draw has finished, so the kernels are enqueued right behind the copies without a host round trip.
@@ -775,6 +782,12 @@ static int launch_chunk(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t fla
     s.work = ctx->work.p;
     s.fill_work = ctx->fill_work.p;
     s.line_work = ctx->line_work.p;
+    s.fill_work_cap = (unsigned)std::min<size_t>(ctx->fill_work.cap, 0xffffffffu);
+    s.line_work_cap = (unsigned)std::min<size_t>(ctx->line_work.cap, 0xffffffffu);
+    if (ctx->work_items_limit) {
+        s.fill_work_cap = std::min(s.fill_work_cap, ctx->work_items_limit);
+        s.line_work_cap = std::min(s.line_work_cap, ctx->work_items_limit);
+    }
     s.walk_alpha = ctx->walk_alpha.p;
     s.walk_len = ctx->walk_len.p;
     s.walk_alpha_cap = ctx->walk_alpha_cap;
@@ -803,7 +816,7 @@ static int launch_chunk(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t fla
         area_bbox_kernel<<<(n_areas + 255) / 256, 256, 0, st>>>(s);
         ++launches;
     }
-    plan_ops_kernel<<<tc, kPlanThreads, 0, st>>>(s);
+    plan_ops_kernel<<<3 * tc, kPlanThreads, 0, st>>>(s);
     build_geometry_kernel<<<ctx->num_sms * 8, kGeomThreads, 0, st>>>(s);
     fill_rows_kernel<<<ctx->num_sms * 16, kFillThreads, 0, st>>>(s);
     CK(cudaEventRecord(ev[3], st));
@@ -853,6 +866,9 @@ static int collect_chunk(osmr_ctx* ctx, unsigned slot, unsigned tb, unsigned tc,
                 ctx->walk_len_cap = ctx->walk_len.cap;
             }
         }
+        if (h_cnt[CNT_OVERFLOW] & 16u) CK(ctx->fill_work.reserve((size_t)h_cnt[CNT_N_FILL_WORK] + 1024));
+        if (h_cnt[CNT_OVERFLOW] & 32u) CK(ctx->line_work.reserve((size_t)h_cnt[CNT_N_LINE_WORK] + 1024));
+        if (h_cnt[CNT_OVERFLOW] & 48u) ctx->work_items_limit = 0;
         if (h_cnt[CNT_OVERFLOW] & 2u) {
             size_t need = (size_t)h_cnt[CNT_MASK_USED] + (size_t)h_cnt[CNT_MASK_USED] / 2 + 1024;
             if (need <= ctx->mask_cap_words) need = ctx->mask_cap_words * 2;
@@ -1165,9 +1181,9 @@ int osmr_draw_tiles_auto(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles
     CK(ctx->rop.reserve(3ull * n_areas + 1));
     CK(ctx->vis_bbox.reserve(3ull * n_areas + 1));
     CK(ctx->work.reserve(3ull * n_areas + 1));
-    CK(ctx->fill_work.reserve((size_t)n_areas + 1));
-    CK(ctx->line_work.reserve(2ull * n_areas + 1));
-    CK(ctx->vis_count.reserve(n_tiles));
+    CK(ctx->fill_work.reserve((size_t)n_areas + n_areas / 2 + 4096));  // work items; grown when a batch has more
+    CK(ctx->line_work.reserve(2ull * n_areas + n_areas / 2 + 4096));
+    CK(ctx->vis_count.reserve(3ull * n_tiles));
     ctx->has_batch = true;
     int rc = osmr_batch_draw(ctx, canvas_rgb, flags, out, nullptr);
     float ms_auto = 0.f;

@@ -79,7 +79,7 @@ enum {
     CNT_MASK_USED = 1,   // words
     CNT_N_WORK = 2,      // visible ops (all kinds)
     CNT_N_FILL_WORK = 3,
-    CNT_OVERFLOW = 4,    // bit0 geometry scratch, bit1 mask scratch, bit2 walk cache
+    CNT_OVERFLOW = 4,    // bit0 geometry scratch, bit1 mask scratch, bit2 walk cache, bit3 sort scratch (f3), bit4 fill / bit5 line work list
     CNT_BAD_INPUT = 5,   // entity / style index out of range
     CNT_WORK_CURSOR = 6,
     CNT_FILL_CURSOR = 7,
@@ -136,8 +136,9 @@ struct Scene {
     short4* vis_bbox;      // reach bbox of vis[i] (8 bytes; what the raster warps scan)
     unsigned* vis_count;   // per tile
     unsigned* work;        // global indices into vis (all visible ops)
-    unsigned* fill_work;   // global indices into vis (fills)
-    unsigned* line_work;   // global indices into vis (lines)
+    uint2* fill_work;      // (global index into vis, chunk of 32 mask rows): work items of fill_rows_kernel
+    uint2* line_work;      // (global index into vis, batch of 32 segment records): work items of line_cover_kernel
+    unsigned fill_work_cap, line_work_cap;
     double* walk_alpha;    // walk cache (line_cover_kernel -> raster_kernel): alpha of every in-line step of every walk
     unsigned char* walk_len;  // number of in-line steps per walk
     unsigned long long walk_alpha_cap, walk_len_cap;
@@ -359,22 +360,26 @@ __global__ void style_calc_kernel(Scene s, uint4* table) {
 }
 
 // ------------------------------------------------------------------------------------------------------
-// plan_ops_kernel: one CTA per tile; ordered compaction of the visible generations (a8)
+// plan_ops_kernel: one CTA per (tile, pass); ordered compaction of the visible generations of that pass (a8).
+// The passes of a tile fill three separate sub-lists (pass p of a tile with n styled areas owns vis[3*base + p*n ..]), which
+// raster_kernel walks one after the other: three times the CTAs of a per-tile kernel (a chunk of 256 tiles no longer
+// leaves half of the SMs without a plan CTA) and no dependency between the passes.
 // ------------------------------------------------------------------------------------------------------
 constexpr int kPlanThreads = 256;
 
 __global__ void __launch_bounds__(kPlanThreads) plan_ops_kernel(Scene s) {
     __shared__ unsigned warp_cnt[kPlanThreads / 32];
     __shared__ unsigned running;
-    unsigned t = blockIdx.x;
+    const unsigned t = blockIdx.x / 3u, the_pass = blockIdx.x % 3u;
     unsigned base = s.area_begin[t];
     unsigned n = s.area_begin[t + 1] - base;
-    unsigned total = 3u * n;
-    VisOp* vis = s.vis + 3ull * base;
+    const unsigned g_begin = the_pass * n, total = g_begin + n;
+    const unsigned long long list0 = 3ull * base + (unsigned long long)the_pass * n;  // first slot of this pass's sub-list
+    VisOp* vis = s.vis + list0;
     const int D = s.D;
     if (threadIdx.x == 0) running = 0;
     __syncthreads();
-    for (unsigned start = 0; start < total; start += kPlanThreads) {
+    for (unsigned start = g_begin; start < total; start += kPlanThreads) {
         unsigned g = start + threadIdx.x;
         bool visible = false;
         VisOp op;
@@ -489,18 +494,32 @@ __global__ void __launch_bounds__(kPlanThreads) plan_ops_kernel(Scene s) {
             rop.y0 = op.y0;
             rop.y1 = op.y1;
             rop.kind = (unsigned char)op.kind;
-            s.rop[3ull * base + pos] = rop;
-            s.vis_bbox[3ull * base + pos] = make_short4(op.x0, op.y0, op.x1, op.y1);
+            s.rop[list0 + pos] = rop;
+            s.vis_bbox[list0 + pos] = make_short4(op.x0, op.y0, op.x1, op.y1);
         }
         {  // work lists of the per-op kernels (their order is irrelevant)
-            const unsigned gi = (unsigned)(3ull * base + pos);
+            const unsigned gi = (unsigned)(list0 + pos);
             const bool is_line = visible && op.kind == OP_LINE, is_fill = visible && op.kind != OP_LINE;
+            // big ops are split so that no single warp becomes the tail of its kernel: a fill op into chunks of 32 mask rows,
+            // a line op into batches of 32 segment records (at most npts - 1 segments + 2 cap lines)
+            const unsigned n_fill = is_fill ? (unsigned)((min((int)op.y1, D - 1) - max((int)op.y0, 0)) / 32 + 1) : 0u;
+            const unsigned n_line = is_line ? (geom_units / 4u + 31u) / 32u : 0u;
             const unsigned wa = warp_alloc(&s.counters[CNT_N_WORK], visible ? 1u : 0u);
-            const unsigned wf = warp_alloc(&s.counters[CNT_N_FILL_WORK], is_fill ? 1u : 0u);
-            const unsigned wl = warp_alloc(&s.counters[CNT_N_LINE_WORK], is_line ? 1u : 0u);
+            const unsigned wf = warp_alloc(&s.counters[CNT_N_FILL_WORK], n_fill);
+            const unsigned wl = warp_alloc(&s.counters[CNT_N_LINE_WORK], n_line);
             if (visible) s.work[wa] = gi;
-            if (is_fill) s.fill_work[wf] = gi;
-            if (is_line) s.line_work[wl] = gi;
+            if (n_fill) {
+                if (wf + n_fill > s.fill_work_cap || wf + n_fill < wf)
+                    atomicOr(&s.counters[CNT_OVERFLOW], 16u);
+                else
+                    for (unsigned j = 0; j < n_fill; ++j) s.fill_work[wf + j] = make_uint2(gi, j);
+            }
+            if (n_line) {
+                if (wl + n_line > s.line_work_cap || wl + n_line < wl)
+                    atomicOr(&s.counters[CNT_OVERFLOW], 32u);
+                else
+                    for (unsigned j = 0; j < n_line; ++j) s.line_work[wl + j] = make_uint2(gi, j);
+            }
         }
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -511,7 +530,7 @@ __global__ void __launch_bounds__(kPlanThreads) plan_ops_kernel(Scene s) {
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        s.vis_count[t] = running;
+        s.vis_count[blockIdx.x] = running;  // [3 * tile + pass]
         atomicAdd(&s.counters[CNT_VISIBLE], running);
     }
 }
@@ -774,11 +793,13 @@ __global__ void __launch_bounds__(kFillThreads) fill_rows_kernel(Scene s) {
             wi_end = wi + 1u;
         }
         if (wi >= n_work) break;
-        const VisOp op = s.vis[s.fill_work[wi]];
+        const uint2 item = s.fill_work[wi];  // (op, chunk of 32 rows)
+        const VisOp op = s.vis[item.x];
         const int4* edges = reinterpret_cast<const int4*>(s.geom + op.geom_off);
         const int ne = (int)op.geom_cnt;
         const int ya = max((int)op.y0, 0), yb = min((int)op.y1, D - 1);
-        for (int y = ya; y <= yb; ++y) {
+        const int y_first = ya + 32 * (int)item.y, y_last = min(yb, y_first + 31);
+        for (int y = y_first; y <= y_last; ++y) {
             unsigned* mrow = s.mask + op.mask_off + (size_t)(y - ya) * wpr;
             // ---- gather the non-poisoned spans of this row, in edge order ----
             int m = 0;
@@ -940,8 +961,10 @@ constexpr int kRasterThreads = 32;
 //   1: the next chunk's op bboxes are loaded while the current chunk is drawn
 //   2: every lane loads the RasterOp of its own hit op, records are handed round by shuffles (instead of one dependent load per op)
 //   4: the first four alphas of a cached walk are loaded together before the stepping starts
+// raster_kernel on the C2 batch: 0: 3.64 ms, 1: 3.60, 2: 3.57, 4: 3.82, 5: 3.94, 7: 3.92 -- the alpha preload costs more
+// instructions (predicated loads + the unrolled replay) than the latency it hides
 #ifndef OSMR_RASTER_PREFETCH
-#define OSMR_RASTER_PREFETCH 7
+#define OSMR_RASTER_PREFETCH 3
 #endif
 #ifndef OSMR_RASTER_MIN_BLOCKS
 #define OSMR_RASTER_MIN_BLOCKS 24  // resident one-warp CTAs per SM the register allocation must allow (16: 4.5 ms, 20: 4.06, 24: 3.66)
@@ -1102,8 +1125,10 @@ __global__ void __launch_bounds__(kCoverThreads, OSMR_COVER_MIN_BLOCKS) line_cov
             wi_end = wi + kWorkBatch;
         }
         if (wi >= n_work) break;
-        const unsigned gi = s.line_work[wi];
+        const uint2 item = s.line_work[wi];  // (op, batch of 32 segment records)
+        const unsigned gi = item.x;
         const VisOp op = s.vis[gi];
+        if (32u * item.y >= op.geom_cnt) continue;  // the batches were counted from an upper bound of the record count
         const unsigned pass = op.pass;
         osmr_styled_area ar;
         ar.entity = op.entity;
@@ -1126,7 +1151,8 @@ __global__ void __launch_bounds__(kCoverThreads, OSMR_COVER_MIN_BLOCKS) line_cov
             for (unsigned u = lane; u < n_main; u += 32) dst0[u] = src[u];
             if (lane < kCapCalcUnits) dst1[lane] = src[kMainCalcUnits + lane];
         }
-        for (unsigned sb = 0; sb < n_seg; sb += 32) {
+        {
+            const unsigned sb = 32u * item.y;
             const unsigned si = sb + lane;
             unsigned items = 0;
             __syncwarp();  // the previous batch's items are done with sm.recs / sm.pre
@@ -1273,9 +1299,7 @@ __global__ void __launch_bounds__(kRasterThreads, OSMR_RASTER_MIN_BLOCKS) raster
     const int by0 = (int)((grp / grp_per_row) * 2u + (in_grp / 2u)) * kBH;
     const unsigned lane = threadIdx.x;
     const unsigned base = s.area_begin[tile];
-    const RasterOp* rops = s.rop + 3ull * base;
-    const short4* vbb = s.vis_bbox + 3ull * base;
-    const unsigned n_vis = s.vis_count[tile];
+    const unsigned n_areas_tile = s.area_begin[tile + 1] - base;
 
     // TilePixels::reset (tile_pixels.rs:89-105): canvas colour premultiplied with opacity 1.0, or (0,0,0,1)
     {
@@ -1291,6 +1315,11 @@ __global__ void __launch_bounds__(kRasterThreads, OSMR_RASTER_MIN_BLOCKS) raster
     }
     __syncwarp();
 
+    for (unsigned the_pass = 0; the_pass < 3u; ++the_pass) {  // Fill, Casing, Stroke (drawer.rs:94-100): the tile's three op lists
+    const unsigned long long list0 = 3ull * base + (unsigned long long)the_pass * n_areas_tile;
+    const RasterOp* rops = s.rop + list0;
+    const short4* vbb = s.vis_bbox + list0;
+    const unsigned n_vis = s.vis_count[3u * tile + the_pass];
     short4 o_next = make_short4(0, 0, -1, -1);  // the next chunk's bboxes are in flight while this chunk is drawn
     if (lane < n_vis) o_next = vbb[lane];
     for (unsigned chunk = 0; chunk < n_vis; chunk += 32) {
@@ -1514,6 +1543,7 @@ __global__ void __launch_bounds__(kRasterThreads, OSMR_RASTER_MIN_BLOCKS) raster
             }
             __syncwarp();
         }
+    }
     }
 
     // ---- export (tile_pixels.rs:164-181): alpha == 1.0, so postdivide is the identity ----

@@ -28,7 +28,8 @@ def test_scratch_overflow_grows_and_redoes_the_batch(fx):
     try:
         ctx.set_geodata(fx.bin)
         ctx.set_table(fx.table)
-        ctx.debug_set("scratch_units", 64)  # far too small: both allocators overflow, the library must grow and redo
+        ctx.debug_set("scratch_units", 64)  # far too small: every bump allocator overflows, the library must grow and redo
+        ctx.debug_set("work_items", 16)  # ... and so do the work lists of the per-op kernels
         got = ctx.draw_tiles(tiles, begins, areas, fx.canvas_rgb, True)
     finally:
         ctx.close()
@@ -108,3 +109,62 @@ def test_argument_validation(fx, gpu_ctx):
         gpu_ctx.draw_tiles(tiles, badb, areas, fx.canvas_rgb, True)
     with pytest.raises(OsmrError):
         gpu_ctx.debug_set("fill_cap", 9999)
+
+
+def _two_line_scene(width):
+    from osm_renderer_b200.upstream import synth
+    from osm_renderer_b200.wire import AREA_DTYPE, OSMR_STYLE_COLOR, OSMR_STYLE_DASHES, OSMR_STYLE_WIDTH, STYLE_DTYPE, TILE_DTYPE, StyleTable
+    from synthgeom import TX, TY
+
+    b = synth._Builder()
+    ts = b.tagset({"k": "v"})
+    ox, oy = TX * 256, TY * 256
+    for (x0, y0, x1, y1) in [(-300, 40, 500, 200), (128, -200, 100, 400)]:
+        ids = b.add_nodes([x0 + ox, x1 + ox], [y0 + oy, y1 + oy])
+        b.way_nodes.append(ids)
+        b.way_tags.append(ts)
+    image = synth._serialise(b, with_index=False)
+    table = StyleTable(None)
+    rows = np.zeros(2, dtype=STYLE_DTYPE)
+    rows[0]["flags"] = OSMR_STYLE_COLOR | OSMR_STYLE_WIDTH
+    rows[0]["color"] = (200, 30, 30)
+    rows[0]["width"] = width
+    rows[0]["line_cap"] = 2
+    rows[1]["flags"] = OSMR_STYLE_COLOR | OSMR_STYLE_WIDTH | OSMR_STYLE_DASHES
+    rows[1]["color"] = (20, 60, 220)
+    rows[1]["width"] = width / 2
+    rows[1]["opacity"] = 1.0
+    rows[1]["dashes_off"], rows[1]["dashes_len"] = 0, 2
+    rows[1]["line_cap"] = 2
+    table.rows = list(rows)
+    table.dashes = [40.0, 25.0]
+    areas = np.array([(0, 0), (1, 1)], dtype=AREA_DTYPE)
+    tiles = np.array([(18, TX, TY, 1)], dtype=TILE_DTYPE)
+    return image, table, tiles, np.array([0, 2], dtype=np.uint32), areas
+
+
+def test_widest_supported_line_and_the_loud_refusal_beyond_it():
+    """Walk lengths are cached in 7 bits: half widths up to 124 px are drawn (bit-exact), anything wider is an error, never
+    a wrong image."""
+    from osm_renderer_b200._lib import OsmrError
+    from osm_renderer_b200.drawer import GpuContext
+
+    image, table, tiles, begins, areas = _two_line_scene(240.0)
+    ctx = GpuContext(0)
+    try:
+        ctx.set_geodata(image)
+        ctx.set_table(table)
+        got = ctx.draw_tiles(tiles, begins, areas, (255, 255, 255), True)
+    finally:
+        ctx.close()
+    want = np.stack(oracle.draw_tiles(image, table, tiles, begins, areas, (255, 255, 255), True))
+    assert (got == want).all()
+    image, table, tiles, begins, areas = _two_line_scene(260.0)
+    ctx = GpuContext(0)
+    try:
+        ctx.set_geodata(image)
+        ctx.set_table(table)
+        with pytest.raises(OsmrError, match="wider than 248"):
+            ctx.draw_tiles(tiles, begins, areas, (255, 255, 255), True)
+    finally:
+        ctx.close()
