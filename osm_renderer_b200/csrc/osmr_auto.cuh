@@ -157,21 +157,11 @@ __device__ __forceinline__ void auto_visit_tile(const Scene& s, const AutoScene&
                 const unsigned n_inst = a.class_begin[c + 1] - a.class_begin[c];
                 const int reach = a.class_reach[c];
                 if (n_inst == 0 || reach < 0) continue;
-                // bbox of all its points, exactly like area_bbox_kernel / plan_ops_kernel
-                int x0 = 0x7fffffff, y0 = 0x7fffffff, x1 = (int)0x80000000, y1 = (int)0x80000000;
-                unsigned npts = 0;
-                RingIter it(s, is_mp ? (e | OSMR_AREA_MULTIPOLYGON) : e);
-                for (unsigned k = 0; k < it.n_rings; ++k) {
-                    const uint2 r = it.ring(k);
-                    for (unsigned q = 0; q < r.y; ++q) {
-                        const int2 p = project_point(s.merc[s.ints[r.x + q]], xf);
-                        x0 = min(x0, p.x);
-                        y0 = min(y0, p.y);
-                        x1 = max(x1, p.x);
-                        y1 = max(y1, p.y);
-                    }
-                    npts += r.y;
-                }
+                // pixel bbox of all its points, exactly like area_bbox_kernel
+                const EntBox eb = (is_mp ? s.mp_box : s.way_box)[e];
+                int x0, y0, x1, y1;
+                entity_pixel_bbox(eb, xf, x0, y0, x1, y1);
+                const unsigned npts = eb.npts;
                 if (npts < 2) continue;
                 if ((long long)x0 - reach > D - 1 || (long long)x1 + reach < 0 || (long long)y0 - reach > D - 1 || (long long)y1 + reach < 0) continue;
                 const unsigned pos = atomicAdd(&sh_counts[0], 1u);

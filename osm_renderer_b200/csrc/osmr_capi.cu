@@ -96,6 +96,7 @@ struct osmr_ctx {
     bool has_geo = false;
     unsigned n_nodes = 0, n_ways = 0, n_polys = 0, n_mps = 0, n_ints = 0;
     DevBuf<double2> merc;
+    DevBuf<EntBox> way_box, mp_box;
     DevBuf<uint2> ways, polys, mps;
     DevBuf<unsigned> ints;
     std::vector<unsigned> h_way_len, h_mp_pts;  // node counts per entity (host copy, for scratch sizing)
@@ -244,6 +245,8 @@ void osmr_ctx_destroy(osmr_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     ctx->merc.release();
+    ctx->way_box.release();
+    ctx->mp_box.release();
     ctx->ways.release();
     ctx->polys.release();
     ctx->mps.release();
@@ -436,6 +439,20 @@ int osmr_set_geodata(osmr_ctx* ctx, const void* bin, size_t len) {
     if (n_ints) CK(cudaMemcpyAsync(ctx->ints.p, ints.data(), (size_t)n_ints * 4, cudaMemcpyHostToDevice, ctx->stream));
     if (n_nodes) {
         project_nodes_kernel<<<(n_nodes + 255) / 256, 256, 0, ctx->stream>>>(raw_nodes.p, n_nodes, ctx->merc.p);
+        CK(cudaGetLastError());
+    }
+    CK(ctx->way_box.reserve(n_ways + 1));
+    CK(ctx->mp_box.reserve(n_mps + 1));
+    if (n_ways + n_mps) {
+        Scene gs{};
+        gs.merc = ctx->merc.p;
+        gs.ways = ctx->ways.p;
+        gs.polys = ctx->polys.p;
+        gs.mps = ctx->mps.p;
+        gs.ints = ctx->ints.p;
+        gs.n_ways = n_ways;
+        gs.n_mps = n_mps;
+        entity_box_kernel<<<(n_ways + n_mps + 127) / 128, 128, 0, ctx->stream>>>(gs, ctx->way_box.p, ctx->mp_box.p);
         CK(cudaGetLastError());
     }
     CK(cudaStreamSynchronize(ctx->stream));
@@ -748,6 +765,8 @@ static int launch_chunk(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t fla
     const unsigned n_areas = ctx->h_area_begin[tb + tc] - area_base;
     Scene s{};
     s.merc = ctx->merc.p;
+    s.way_box = ctx->way_box.p;
+    s.mp_box = ctx->mp_box.p;
     s.ways = ctx->ways.p;
     s.polys = ctx->polys.p;
     s.mps = ctx->mps.p;
@@ -1086,6 +1105,8 @@ int osmr_draw_tiles_auto(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles
 
     Scene s{};
     s.merc = ctx->merc.p;
+    s.way_box = ctx->way_box.p;
+    s.mp_box = ctx->mp_box.p;
     s.ways = ctx->ways.p;
     s.polys = ctx->polys.p;
     s.mps = ctx->mps.p;

@@ -104,9 +104,23 @@ struct LabelPix {
     unsigned pad;
 };
 
+// Bounding box of an entity (way: its nodes; multipolygon: the nodes of all its rings) in Mercator factor units, computed once
+// per dataset.  project_point is monotone in each coordinate (multiplication by a positive power of two, subtraction of a
+// constant, multiplication by the positive scale, round, saturating cast), so the pixel bbox of the entity in ANY tile is
+// the projection of these two corners: no per-tile pass over the nodes.  NaN coordinates (which project to pixel 0 in every
+// tile) are carried as flags.
+struct alignas(16) EntBox {
+    double x0, y0, x1, y1;
+    unsigned npts;
+    unsigned nan_flags;  // bit0: some x is NaN, bit1: some y is NaN
+    unsigned pad[2];
+};
+
 struct Scene {
     // dataset
     const double2* merc;
+    const EntBox* way_box;
+    const EntBox* mp_box;
     const uint2* ways;
     const uint2* polys;
     const uint2* mps;
@@ -245,6 +259,61 @@ __device__ __forceinline__ bool entity_valid(const Scene& s, unsigned entity) {
 }
 
 // ------------------------------------------------------------------------------------------------------
+// entity_box_kernel: once per dataset, one thread per way / multipolygon
+// ------------------------------------------------------------------------------------------------------
+__global__ void entity_box_kernel(Scene s, EntBox* way_box, EntBox* mp_box) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= s.n_ways + s.n_mps) return;
+    const bool is_mp = i >= s.n_ways;
+    const unsigned e = is_mp ? i - s.n_ways : i;
+    EntBox b;
+    b.x0 = b.y0 = __longlong_as_double(0x7ff0000000000000LL);   // +inf
+    b.x1 = b.y1 = __longlong_as_double((long long)0xfff0000000000000ULL);  // -inf
+    b.npts = 0;
+    b.nan_flags = 0;
+    b.pad[0] = b.pad[1] = 0;
+    RingIter it(s, is_mp ? (e | OSMR_AREA_MULTIPOLYGON) : e);
+    for (unsigned k = 0; k < it.n_rings; ++k) {
+        const uint2 r = it.ring(k);
+        for (unsigned q = 0; q < r.y; ++q) {
+            const double2 m = s.merc[s.ints[r.x + q]];
+            if (m.x != m.x) b.nan_flags |= 1u;
+            if (m.y != m.y) b.nan_flags |= 2u;
+            b.x0 = fmin(b.x0, m.x);  // fmin / fmax ignore NaN
+            b.y0 = fmin(b.y0, m.y);
+            b.x1 = fmax(b.x1, m.x);
+            b.y1 = fmax(b.y1, m.y);
+        }
+        b.npts += r.y;
+    }
+    (is_mp ? mp_box : way_box)[e] = b;
+}
+
+// pixel bbox of an entity in a tile from its EntBox (see there); x0 > x1 when it has no points
+__device__ __forceinline__ void entity_pixel_bbox(const EntBox& b, const TileXform& xf, int& x0, int& y0, int& x1, int& y1) {
+    x0 = y0 = 0x7fffffff;
+    x1 = y1 = (int)0x80000000;
+    if (b.x0 <= b.x1) {
+        const int2 lo = project_point(make_double2(b.x0, b.y0), xf), hi = project_point(make_double2(b.x1, b.y1), xf);
+        x0 = lo.x;
+        x1 = hi.x;
+    }
+    if (b.y0 <= b.y1) {
+        const int2 lo = project_point(make_double2(b.x0, b.y0), xf), hi = project_point(make_double2(b.x1, b.y1), xf);
+        y0 = lo.y;
+        y1 = hi.y;
+    }
+    if (b.nan_flags & 1u) {  // `as i32` of NaN is 0
+        x0 = min(x0, 0);
+        x1 = max(x1, 0);
+    }
+    if (b.nan_flags & 2u) {
+        y0 = min(y0, 0);
+        y1 = max(y1, 0);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
 // area_bbox_kernel: one thread per (tile, styled area)
 // ------------------------------------------------------------------------------------------------------
 __global__ void area_bbox_kernel(Scene s) {
@@ -263,18 +332,10 @@ __global__ void area_bbox_kernel(Scene s) {
         } else {
             unsigned t = tile_of_area(s.area_begin, s.n_tiles, a);
             TileXform xf = make_xform(s.tiles[t]);
-            RingIter it(s, ar.entity);
-            for (unsigned k = 0; k < it.n_rings; ++k) {
-                uint2 r = it.ring(k);
-                for (unsigned i = 0; i < r.y; ++i) {
-                    int2 p = project_point(s.merc[s.ints[r.x + i]], xf);
-                    info.x0 = min(info.x0, p.x);
-                    info.y0 = min(info.y0, p.y);
-                    info.x1 = max(info.x1, p.x);
-                    info.y1 = max(info.y1, p.y);
-                }
-                info.npts += r.y;
-            }
+            const bool is_mp = (ar.entity & OSMR_AREA_MULTIPOLYGON) != 0;
+            const EntBox b = (is_mp ? s.mp_box : s.way_box)[ar.entity & ~OSMR_AREA_MULTIPOLYGON];
+            entity_pixel_bbox(b, xf, info.x0, info.y0, info.x1, info.y1);
+            info.npts = b.npts;
             refs = info.npts;
         }
         s.area_info[a] = info;
@@ -783,6 +844,9 @@ __global__ void __launch_bounds__(kFillThreads) fill_rows_kernel(Scene s) {
     const int D = s.D;
     const int wpr = D / 32;
     const int cap = s.fill_cap;
+    // A scratch or work-list overflow means the host grows the buffer and redoes the draw: the work lists may have holes and
+    // the scratch of some ops does not exist, so the rest of this attempt is skipped instead of reading garbage.
+    if (s.counters[CNT_OVERFLOW]) return;
     const unsigned n_work = s.counters[CNT_N_FILL_WORK];
     // every warp is an independent worker: fetch fill ops, produce all their rows, repeat (no CTA barrier)
     unsigned wi = 0, wi_end = 0;
@@ -1116,6 +1180,7 @@ __global__ void __launch_bounds__(kCoverThreads, OSMR_COVER_MIN_BLOCKS) line_cov
     CoverSmem& sm = smem[threadIdx.x >> 5];
     const unsigned lane = lane_id();
     const int D = s.D;
+    if (s.counters[CNT_OVERFLOW]) return;  // the draw is redone with larger buffers (see fill_rows_kernel)
     const unsigned n_work = s.counters[CNT_N_LINE_WORK];
     unsigned wi = 0, wi_end = 0;
     for (;; ++wi) {
@@ -1298,6 +1363,7 @@ __global__ void __launch_bounds__(kRasterThreads, OSMR_RASTER_MIN_BLOCKS) raster
     const int bx0 = (int)((grp % grp_per_row) * 2u + (in_grp % 2u)) * kBW;
     const int by0 = (int)((grp / grp_per_row) * 2u + (in_grp / 2u)) * kBH;
     const unsigned lane = threadIdx.x;
+    if (s.counters[CNT_OVERFLOW]) return;  // the draw is redone with larger buffers (see fill_rows_kernel)
     const unsigned base = s.area_begin[tile];
     const unsigned n_areas_tile = s.area_begin[tile + 1] - base;
 

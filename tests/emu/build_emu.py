@@ -2,7 +2,12 @@
 tests/emu/cuda_runtime.h.  TEST INFRASTRUCTURE ONLY (kernel-logic checks in the GPU-less container); the product
 library is osm_renderer_b200/libosmr_b200.so and nothing in the package ever loads this one.
 
-    python tests/emu/build_emu.py [-DNAME=VALUE ...]
+    python tests/emu/build_emu.py [-DNAME=VALUE ...] [--asan]
+
+--asan builds tests/emu/_build/libosmr_emu_asan.so with AddressSanitizer (heap checks work across the fibers); run with
+    LD_PRELOAD=$(g++ -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0:detect_stack_use_after_return=0 \
+        OSMR_EMU_LIB=tests/emu/_build/libosmr_emu_asan.so python tests/emu/run_emu.py 17 0 7 12
+(this is how the read of an unwritten work-list slot after a forced overflow was found).
 """
 from __future__ import annotations
 
@@ -44,7 +49,7 @@ def rewrite(src: str) -> str:
     return LAUNCH.sub(repl, src)
 
 
-def build(defines: list[str] | None = None, lib: str = LIB) -> str:
+def build(defines: list[str] | None = None, lib: str = LIB, asan: bool = False) -> str:
     os.makedirs(OUT_DIR, exist_ok=True)
     cu = os.path.join(CSRC, "osmr_capi.cu")
     cpp = os.path.join(OUT_DIR, "osmr_capi_emu.cpp")
@@ -53,8 +58,12 @@ def build(defines: list[str] | None = None, lib: str = LIB) -> str:
     assert "<<<" not in text
     with open(cpp, "w") as f:
         f.write(f'#line 1 "{cu}"\n' + text)
-    cmd = ["g++", "-O1", "-g", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-fno-strict-aliasing",
+    if asan:
+        lib = lib.replace(".so", "_asan.so")
+    cmd = ["g++", "-O1", "-g", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-fno-strict-aliasing", "-w",
            "-I", HERE, "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", lib, cpp] + (defines or [])
+    if asan:
+        cmd[1:1] = ["-fsanitize=address", "-fno-omit-frame-pointer"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("g++ failed:\n" + res.stderr[-6000:])
@@ -62,4 +71,4 @@ def build(defines: list[str] | None = None, lib: str = LIB) -> str:
 
 
 if __name__ == "__main__":
-    print(build([a for a in sys.argv[1:] if a.startswith("-D")]))
+    print(build([a for a in sys.argv[1:] if a.startswith("-D")], asan="--asan" in sys.argv))
