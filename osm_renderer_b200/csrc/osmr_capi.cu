@@ -138,7 +138,6 @@ struct osmr_ctx {
     DevBuf<osmr_styled_area> areas;
     std::vector<uint32_t> h_area_begin;
     // scratch
-    DevBuf<AreaInfo> area_info;
     DevBuf<VisOp> vis;
     DevBuf<RasterOp> rop;
     DevBuf<short4> vis_bbox;
@@ -258,7 +257,6 @@ void osmr_ctx_destroy(osmr_ctx* ctx) {
     ctx->tiles.release();
     ctx->area_begin.release();
     ctx->areas.release();
-    ctx->area_info.release();
     ctx->vis.release();
     ctx->rop.release();
     ctx->vis_bbox.release();
@@ -734,7 +732,6 @@ static int batch_upload_impl(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_t
     ctx->scale = (int)tiles[0].scale;
     ctx->h_area_begin.assign(area_begin, area_begin + n_tiles + 1);
     // scratch that scales with the batch
-    CK(ctx->area_info.reserve(n_areas + 1));
     CK(ctx->vis.reserve(3ull * n_areas + 1));
     CK(ctx->rop.reserve(3ull * n_areas + 1));
     CK(ctx->vis_bbox.reserve(3ull * n_areas + 1));
@@ -793,7 +790,6 @@ static int launch_chunk(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t fla
     s.scale = ctx->scale;
     s.flags = flags;
     if (flags & OSMR_DRAW_HAS_CANVAS_COLOR) memcpy(s.canvas, canvas_rgb, 3);
-    s.area_info = ctx->area_info.p;
     s.vis = ctx->vis.p;
     s.rop = ctx->rop.p;
     s.vis_bbox = ctx->vis_bbox.p;
@@ -829,10 +825,6 @@ static int launch_chunk(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t fla
     unsigned launches = 0;
     if (ctx->n_styles && slot == 0) {  // the calculators depend on (styles, scale, flags) only: once per draw
         style_calc_kernel<<<(2 * ctx->n_styles + 127) / 128, 128, 0, st>>>(s, ctx->calc_table.p);
-        ++launches;
-    }
-    if (n_areas) {
-        area_bbox_kernel<<<(n_areas + 255) / 256, 256, 0, st>>>(s);
         ++launches;
     }
     plan_ops_kernel<<<3 * tc, kPlanThreads, 0, st>>>(s);
@@ -1197,7 +1189,6 @@ int osmr_draw_tiles_auto(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles
     ctx->n_tiles = n_tiles;
     ctx->n_areas = n_areas;
     ctx->scale = (int)scale;
-    CK(ctx->area_info.reserve((size_t)n_areas + 1));
     CK(ctx->vis.reserve(3ull * n_areas + 1));
     CK(ctx->rop.reserve(3ull * n_areas + 1));
     CK(ctx->vis_bbox.reserve(3ull * n_areas + 1));

@@ -19,10 +19,9 @@ struct DevIcon {
     unsigned w, h, off, pad;  // off: first texel in icon_px
 };
 
-struct AreaInfo {  // per (tile, styled area)
+struct AreaInfo {  // a styled area in a tile
     int x0, y0, x1, y1;  // integer pixel bbox of all its points (x0 > x1: no points)
     unsigned npts;
-    unsigned pad[3];
 };
 
 // One visible generation.  g = pass * n_areas_of_tile + index (drawer.rs:94-100: Fill, Casing, Stroke).
@@ -144,7 +143,6 @@ struct Scene {
     unsigned flags;
     unsigned char canvas[3];
     // scratch
-    AreaInfo* area_info;
     VisOp* vis;            // tile t owns vis[3*area_begin[t] ...)
     RasterOp* rop;         // same indexing as vis
     short4* vis_bbox;      // reach bbox of vis[i] (8 bytes; what the raster warps scan)
@@ -220,18 +218,6 @@ __global__ void project_all_kernel(const double2* __restrict__ merc, unsigned n,
 // ------------------------------------------------------------------------------------------------------
 // helpers over the entity tables
 // ------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned tile_of_area(const unsigned* area_begin, unsigned n_tiles, unsigned a) {
-    unsigned lo = 0, hi = n_tiles;  // largest t with area_begin[t] <= a
-    while (hi - lo > 1) {
-        unsigned mid = (lo + hi) >> 1;
-        if (area_begin[mid] <= a)
-            lo = mid;
-        else
-            hi = mid;
-    }
-    return lo;
-}
-
 struct RingIter {  // iterates the rings of a way (1 ring) or multipolygon (polygon_count rings)
     const Scene& s;
     bool is_mp;
@@ -310,43 +296,6 @@ __device__ __forceinline__ void entity_pixel_bbox(const EntBox& b, const TileXfo
     if (b.nan_flags & 2u) {
         y0 = min(y0, 0);
         y1 = max(y1, 0);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------------
-// area_bbox_kernel: one thread per (tile, styled area)
-// ------------------------------------------------------------------------------------------------------
-__global__ void area_bbox_kernel(Scene s) {
-    const unsigned rel = blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned a = s.area_base + rel;
-    unsigned long long refs = 0;
-    if (rel < s.n_areas) {
-        AreaInfo info;
-        info.x0 = info.y0 = 0x7fffffff;
-        info.x1 = info.y1 = (int)0x80000000;
-        info.npts = 0;
-        info.pad[0] = info.pad[1] = info.pad[2] = 0;
-        osmr_styled_area ar = s.areas[a];
-        if (!entity_valid(s, ar.entity) || ar.style >= s.n_styles) {
-            atomicOr(&s.counters[CNT_BAD_INPUT], 1u);
-        } else {
-            unsigned t = tile_of_area(s.area_begin, s.n_tiles, a);
-            TileXform xf = make_xform(s.tiles[t]);
-            const bool is_mp = (ar.entity & OSMR_AREA_MULTIPOLYGON) != 0;
-            const EntBox b = (is_mp ? s.mp_box : s.way_box)[ar.entity & ~OSMR_AREA_MULTIPOLYGON];
-            entity_pixel_bbox(b, xf, info.x0, info.y0, info.x1, info.y1);
-            info.npts = b.npts;
-            refs = info.npts;
-        }
-        s.area_info[a] = info;
-    }
-    // statistics: R = node references of the batch
-    for (int o = 16; o > 0; o >>= 1) refs += __shfl_down_sync(0xffffffffu, refs, o);
-    if (lane_id() == 0 && refs) {
-        unsigned lo = (unsigned)refs;
-        unsigned old = atomicAdd(&s.counters[CNT_NODE_REFS_LO], lo);
-        if (old + lo < old) atomicAdd(&s.counters[CNT_NODE_REFS_HI], 1u);
-        atomicAdd(&s.counters[CNT_NODE_REFS_HI], (unsigned)(refs >> 32));
     }
 }
 
@@ -438,11 +387,14 @@ __global__ void __launch_bounds__(kPlanThreads) plan_ops_kernel(Scene s) {
     const unsigned long long list0 = 3ull * base + (unsigned long long)the_pass * n;  // first slot of this pass's sub-list
     VisOp* vis = s.vis + list0;
     const int D = s.D;
+    const TileXform xf = make_xform(s.tiles[t]);
+    unsigned long long refs_total = 0;
     if (threadIdx.x == 0) running = 0;
     __syncthreads();
     for (unsigned start = g_begin; start < total; start += kPlanThreads) {
         unsigned g = start + threadIdx.x;
         bool visible = false;
+        unsigned long long refs = 0;
         VisOp op;
         RasterOp rop;
         rop.a = rop.b = 0;
@@ -456,8 +408,20 @@ __global__ void __launch_bounds__(kPlanThreads) plan_ops_kernel(Scene s) {
             unsigned pass = g / n;
             unsigned i = g - pass * n;
             osmr_styled_area ar = s.areas[base + i];
-            AreaInfo info = s.area_info[base + i];
             bool is_mp = (ar.entity & OSMR_AREA_MULTIPOLYGON) != 0;
+            // pixel bbox + point count of the area in this tile: two projected corners of the entity's resident box
+            AreaInfo info;
+            info.x0 = info.y0 = 0x7fffffff;
+            info.x1 = info.y1 = (int)0x80000000;
+            info.npts = 0;
+            if (!entity_valid(s, ar.entity) || ar.style >= s.n_styles) {
+                atomicOr(&s.counters[CNT_BAD_INPUT], 1u);
+            } else {
+                const EntBox eb = (is_mp ? s.mp_box : s.way_box)[ar.entity & ~OSMR_AREA_MULTIPOLYGON];
+                entity_pixel_bbox(eb, xf, info.x0, info.y0, info.x1, info.y1);
+                info.npts = eb.npts;
+                if (the_pass == 0) refs = eb.npts;  // statistics: R = node references of the batch
+            }
             if (info.npts >= 2 && ar.style < s.n_styles) {
                 const osmr_style& st = s.styles[ar.style];
                 int x0 = info.x0, y0 = info.y0, x1 = info.x1, y1 = info.y1;
@@ -541,6 +505,7 @@ __global__ void __launch_bounds__(kPlanThreads) plan_ops_kernel(Scene s) {
                 }
             }
         }
+        refs_total += refs;
         // ordered compaction
         unsigned bal = __ballot_sync(0xffffffffu, visible);
         unsigned w = threadIdx.x >> 5;
@@ -589,6 +554,15 @@ __global__ void __launch_bounds__(kPlanThreads) plan_ops_kernel(Scene s) {
             running += add;
         }
         __syncthreads();
+    }
+    if (the_pass == 0) {
+        for (int o = 16; o > 0; o >>= 1) refs_total += __shfl_down_sync(0xffffffffu, refs_total, o);
+        if (lane_id() == 0 && refs_total) {
+            unsigned lo = (unsigned)refs_total;
+            unsigned old = atomicAdd(&s.counters[CNT_NODE_REFS_LO], lo);
+            if (old + lo < old) atomicAdd(&s.counters[CNT_NODE_REFS_HI], 1u);
+            atomicAdd(&s.counters[CNT_NODE_REFS_HI], (unsigned)(refs_total >> 32));
+        }
     }
     if (threadIdx.x == 0) {
         s.vis_count[blockIdx.x] = running;  // [3 * tile + pass]

@@ -26,5 +26,9 @@ echo "== ncu full (raster_kernel, line_cover_kernel, build_geometry_kernel)"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"raster_kernel|line_cover_kernel|build_geometry_kernel" -s 3 -c 3 -f -o gpurun_out/prof_r01 \
     python bench.py --steps 2 --warmup 1 --skip-cpu-baseline --skip-auto > gpurun_out/ncu_full.log 2>&1
 tail -2 gpurun_out/ncu_full.log | cut -c1-300
+echo "== ncu launch list of the f3 / f4 kernels"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"auto_|png_|class_reach|entity_box" -c 60 --csv --log-file gpurun_out/launches_f3f4.csv \
+    python bench.py --steps 2 --warmup 1 --skip-cpu-baseline > gpurun_out/ncu_f3f4.log 2>&1
+tail -1 gpurun_out/ncu_f3f4.log | cut -c1-200
 ls -la gpurun_out
 fi
