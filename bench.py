@@ -408,6 +408,12 @@ def main():
     dev_s, total_tiles = sharding.reduce_job(dist, dev_s, job_tiles, device="cuda")
     wall, _ = sharding.reduce_job(dist, wall, job_tiles, device="cuda")
     e2e_wall, _ = sharding.reduce_job(dist, e2e_wall, job_tiles, device="cuda")
+    if auto is not None:  # whole-job numbers for the extra legs too: max wall over ranks, tiles of all ranks
+        aw, at = sharding.reduce_job(dist, auto_wall, job_tiles, device="cuda")
+        auto["value"], auto["ms_per_step"] = at / aw, 1000.0 * aw / args.steps
+    if png is not None:
+        pw, pt = sharding.reduce_job(dist, png_wall, job_tiles, device="cuda")
+        png["value"], png["ms_per_step"] = pt / pw, 1000.0 * pw / args.steps
     raster_mean_ms, _ = sharding.reduce_job(dist, float(np.mean(raster_ms)), job_tiles, device="cuda")
     cover_mean_ms, _ = sharding.reduce_job(dist, float(np.mean(cover_ms)), job_tiles, device="cuda")
 

@@ -1280,13 +1280,14 @@ struct RasterSmem {
     unsigned long long plane[kBP];
     SegHit hits[32];
     unsigned pre[32];
+    unsigned dirty;  // rows of the alpha plane the current line op has written (bit = row): the blend sweeps only those
 };
 
 // Replays the integer stepping of one cached walk (line.rs:82-96,120-130) and max-combines the alphas of the steps
 // that fall into the block.  The first alphas of the walk are fetched together before the stepping starts: independent
 // loads instead of one exposed memory latency per step (walks are 2-4 steps long for ordinary street widths).
-__device__ __forceinline__ void gather_walk(unsigned long long* plane, const double* __restrict__ alpha, unsigned len, const WalkItem& w,
-                                            int mn, int p_error, int mul, int bx0, int by0) {
+__device__ __forceinline__ void gather_walk(unsigned long long* plane, unsigned* dirty, const double* __restrict__ alpha, unsigned len,
+                                            const WalkItem& w, int mn, int p_error, int mul, int bx0, int by0) {
     constexpr int kPre = (OSMR_RASTER_PREFETCH & 4) ? 4 : 0;
     double a_pre[kPre + 1];
 #pragma unroll
@@ -1305,7 +1306,10 @@ __device__ __forceinline__ void gather_walk(unsigned long long* plane, const dou
             OSMR_COUNT("raster.steps_in_block", 1);
             const unsigned long long bits = (unsigned long long)__double_as_longlong(a);
             unsigned long long* cell = &plane[ly * kBW + lx];
-            if (a > 0.0 && bits > *cell) atomicMax(cell, bits);
+            if (a > 0.0 && bits > *cell) {
+                atomicMax(cell, bits);
+                if (!((*dirty >> ly) & 1u)) atomicOr(dirty, 1u << ly);
+            }
         }
         OSMR_COUNT("raster.steps_replayed", 1);
         if (wadd(err, 2 * w.mn_d) > w.mx_d) {
@@ -1464,6 +1468,8 @@ __global__ void __launch_bounds__(kRasterThreads, OSMR_RASTER_MIN_BLOCKS) raster
             const SegRec* segs = reinterpret_cast<const SegRec*>(s.geom + op.a);
             const unsigned n_seg = op.b;
             bool any = false;
+            if (lane == 0) sm.dirty = 0u;
+            __syncwarp();
             for (unsigned sb = 0; sb < n_seg; sb += 32) {
                 // one segment per lane: can any of its perpendiculars reach my block?
                 unsigned si = sb + lane;
@@ -1499,7 +1505,7 @@ __global__ void __launch_bounds__(kRasterThreads, OSMR_RASTER_MIN_BLOCKS) raster
                         if (ka < c0) ka = c0;
                         if (kb > c1) kb = c1;
                         if (kb >= ka) {
-                            items = 2u * (unsigned)(kb - ka + 1);
+                            items = (unsigned)(kb - ka + 1);  // one item per main step: both perpendiculars share its set-up
                             hrec.x1 = sr.x;
                             hrec.y1 = sr.y;
                             hrec.x2 = sr.z;
@@ -1540,25 +1546,32 @@ __global__ void __launch_bounds__(kRasterThreads, OSMR_RASTER_MIN_BLOCKS) raster
                     }
                     const SegHit& h = sm.hits[lo];
                     const unsigned local = item - sm.pre[lo];
-                    const int k = h.ka + (int)(local >> 1);
-                    const int mul = (local & 1u) ? -1 : 1;
+                    const int k = h.ka + (int)local;
                     OSMR_COUNT("raster.items", 1);
-                    const unsigned long long widx = 2ull * (unsigned long long)(k - h.k0) + (local & 1u);
-                    const unsigned lens = s.walk_len[h.len_off + widx];  // steps of the regular walk | 0x80: the extra one has steps
-                    if (!lens) continue;
+                    const unsigned long long widx0 = 2ull * (unsigned long long)(k - h.k0);  // walk (k, +); (k, -) follows
+                    // steps of the two regular walks (| 0x80: the extra one has steps): two adjacent bytes, 2-byte aligned
+                    const unsigned lens2 = *reinterpret_cast<const unsigned short*>(s.walk_len + h.len_off + widx0);
+                    if (!lens2) continue;
                     WalkItem w;
                     walk_item_setup(h.x1, h.y1, h.x2, h.y2, h.flags, h.magic, k, w);
-                    const double* alpha = s.walk_alpha + h.alpha_off + widx * S;
                     const int blo = (w.swap ? by0 : bx0) + rlo, bhi = (w.swap ? by0 + kBH : bx0 + kBW) - 1 + rhi;
-                    int mn = w.mn, p_error = w.p_error;
-                    // minor-axis cull: a walk starts at mn and moves away from it, at most `reach` pixels
-                    if ((lens & 0x7fu) && mn >= blo && mn <= bhi) gather_walk(sm.plane, alpha, lens & 0x7fu, w, mn, p_error, mul, bx0, by0);
-                    if (lens & 0x80u) {  // the extra perpendicular of a double correction (line.rs:150-155)
-                        const unsigned long long extra_at = 2ull * (h.flags >> 8);
-                        const unsigned len1 = s.walk_len[h.len_off + extra_at + widx];
-                        p_error = wadd(wsub(p_error, 2 * w.mx_d), 2 * w.mn_d);
-                        mn += w.mn_inc;
-                        if (mn >= blo && mn <= bhi) gather_walk(sm.plane, alpha + extra_at * S, len1, w, mn, p_error, mul, bx0, by0);
+#pragma unroll 1
+                    for (unsigned side = 0; side < 2u; ++side) {
+                        const unsigned lens = (lens2 >> (8u * side)) & 0xffu;
+                        if (!lens) continue;
+                        const int mul = side ? -1 : 1;
+                        const unsigned long long widx = widx0 + side;
+                        const double* alpha = s.walk_alpha + h.alpha_off + widx * S;
+                        int mn = w.mn, p_error = w.p_error;
+                        // minor-axis cull: a walk starts at mn and moves away from it, at most `reach` pixels
+                        if ((lens & 0x7fu) && mn >= blo && mn <= bhi) gather_walk(sm.plane, &sm.dirty, alpha, lens & 0x7fu, w, mn, p_error, mul, bx0, by0);
+                        if (lens & 0x80u) {  // the extra perpendicular of a double correction (line.rs:150-155)
+                            const unsigned long long extra_at = 2ull * (h.flags >> 8);
+                            const unsigned len1 = s.walk_len[h.len_off + extra_at + widx];
+                            p_error = wadd(wsub(p_error, 2 * w.mx_d), 2 * w.mn_d);
+                            mn += w.mn_inc;
+                            if (mn >= blo && mn <= bhi) gather_walk(sm.plane, &sm.dirty, alpha + extra_at * S, len1, w, mn, p_error, mul, bx0, by0);
+                        }
                     }
                 }
             }
@@ -1567,8 +1580,11 @@ __global__ void __launch_bounds__(kRasterThreads, OSMR_RASTER_MIN_BLOCKS) raster
                 // blend: pending pixel = from_color(color, alpha_max) (tile_pixels.rs:13-22), then over
                 double cn[3];
                 for (int k = 0; k < 3; ++k) cn[k] = unit_of_u8(op.rgb[k]);
+                const unsigned dirty = sm.dirty;
+                constexpr int kRowsPerIter = 32 / kBW;  // plane rows one sweep iteration covers
 #pragma unroll 2
                 for (int j = 0; j < kBP / 32; ++j) {
+                    if (!((dirty >> (j * kRowsPerIter)) & ((1u << kRowsPerIter) - 1u))) continue;  // untouched rows
                     const int idx = j * 32 + (int)lane;
                     unsigned long long bits = sm.plane[idx];
                     if (bits) {
