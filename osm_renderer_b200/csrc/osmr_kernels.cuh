@@ -1001,6 +1001,17 @@ constexpr int kRasterThreads = 32;
 //   4: the first four alphas of a cached walk are loaded together before the stepping starts
 // raster_kernel on the C2 batch: 0: 3.64 ms, 1: 3.60, 2: 3.57, 4: 3.82, 5: 3.94, 7: 3.92 -- the alpha preload costs more
 // instructions (predicated loads + the unrolled replay) than the latency it hides
+// OSMR_ITEM_PER_SIDE 1: a raster work item is one (main step, side) pair, 0: one main step whose two perpendiculars share the
+// set-up (half the set-ups, but half the lanes busy when an op reaches the block with few steps)
+// (C2 batch, same box: 1: 3.84 ms, 0: 3.79 ms)
+#ifndef OSMR_ITEM_PER_SIDE
+#define OSMR_ITEM_PER_SIDE 0
+#endif
+// OSMR_DIRTY_ROWS 1: the blend of a line op sweeps only the plane rows the op wrote (measured: the extra shared-memory
+// atomic per written pixel costs more than the skipped rows save: 3.84 ms with, 3.62 ms without)
+#ifndef OSMR_DIRTY_ROWS
+#define OSMR_DIRTY_ROWS 0
+#endif
 #ifndef OSMR_RASTER_PREFETCH
 #define OSMR_RASTER_PREFETCH 3
 #endif
@@ -1308,7 +1319,7 @@ __device__ __forceinline__ void gather_walk(unsigned long long* plane, unsigned*
             unsigned long long* cell = &plane[ly * kBW + lx];
             if (a > 0.0 && bits > *cell) {
                 atomicMax(cell, bits);
-                if (!((*dirty >> ly) & 1u)) atomicOr(dirty, 1u << ly);
+                if (OSMR_DIRTY_ROWS && !((*dirty >> ly) & 1u)) atomicOr(dirty, 1u << ly);
             }
         }
         OSMR_COUNT("raster.steps_replayed", 1);
@@ -1505,7 +1516,7 @@ __global__ void __launch_bounds__(kRasterThreads, OSMR_RASTER_MIN_BLOCKS) raster
                         if (ka < c0) ka = c0;
                         if (kb > c1) kb = c1;
                         if (kb >= ka) {
-                            items = (unsigned)(kb - ka + 1);  // one item per main step: both perpendiculars share its set-up
+                            items = (OSMR_ITEM_PER_SIDE ? 2u : 1u) * (unsigned)(kb - ka + 1);
                             hrec.x1 = sr.x;
                             hrec.y1 = sr.y;
                             hrec.x2 = sr.z;
@@ -1546,17 +1557,26 @@ __global__ void __launch_bounds__(kRasterThreads, OSMR_RASTER_MIN_BLOCKS) raster
                     }
                     const SegHit& h = sm.hits[lo];
                     const unsigned local = item - sm.pre[lo];
-                    const int k = h.ka + (int)local;
-                    OSMR_COUNT("raster.items", 1);
+#if OSMR_ITEM_PER_SIDE
+                    const int k = h.ka + (int)(local >> 1);
+                    const unsigned side0 = local & 1u, side1 = side0 + 1u;
                     const unsigned long long widx0 = 2ull * (unsigned long long)(k - h.k0);  // walk (k, +); (k, -) follows
-                    // steps of the two regular walks (| 0x80: the extra one has steps): two adjacent bytes, 2-byte aligned
+                    // steps of the regular walk | 0x80: the extra one has steps
+                    const unsigned lens2 = (unsigned)s.walk_len[h.len_off + widx0 + side0] << (8u * side0);
+#else
+                    const int k = h.ka + (int)local;
+                    const unsigned side0 = 0u, side1 = 2u;
+                    const unsigned long long widx0 = 2ull * (unsigned long long)(k - h.k0);
+                    // the two regular walks of the step: two adjacent bytes, 2-byte aligned
                     const unsigned lens2 = *reinterpret_cast<const unsigned short*>(s.walk_len + h.len_off + widx0);
+#endif
+                    OSMR_COUNT("raster.items", 1);
                     if (!lens2) continue;
                     WalkItem w;
                     walk_item_setup(h.x1, h.y1, h.x2, h.y2, h.flags, h.magic, k, w);
                     const int blo = (w.swap ? by0 : bx0) + rlo, bhi = (w.swap ? by0 + kBH : bx0 + kBW) - 1 + rhi;
 #pragma unroll 1
-                    for (unsigned side = 0; side < 2u; ++side) {
+                    for (unsigned side = side0; side < side1; ++side) {
                         const unsigned lens = (lens2 >> (8u * side)) & 0xffu;
                         if (!lens) continue;
                         const int mul = side ? -1 : 1;
@@ -1580,7 +1600,7 @@ __global__ void __launch_bounds__(kRasterThreads, OSMR_RASTER_MIN_BLOCKS) raster
                 // blend: pending pixel = from_color(color, alpha_max) (tile_pixels.rs:13-22), then over
                 double cn[3];
                 for (int k = 0; k < 3; ++k) cn[k] = unit_of_u8(op.rgb[k]);
-                const unsigned dirty = sm.dirty;
+                const unsigned dirty = OSMR_DIRTY_ROWS ? sm.dirty : 0xffffffffu;
                 constexpr int kRowsPerIter = 32 / kBW;  // plane rows one sweep iteration covers
 #pragma unroll 2
                 for (int j = 0; j < kBP / 32; ++j) {

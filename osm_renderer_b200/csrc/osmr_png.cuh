@@ -162,16 +162,24 @@ __global__ void __launch_bounds__(kPngThreads) png_encode_kernel(PngScene ps) {
         const unsigned char* up = y > 0 ? cur - W : nullptr;
         // ---- filter choice: smallest sum of |residual as signed byte| (ties: the lowest filter number) ----
         unsigned sum[4] = {0, 0, 0, 0};
-        for (int j = (int)lane; j < W; j += 32) {
-            const int x = cur[j];
-            const int a = j >= 3 ? cur[j - 3] : 0;
-            const int b = up ? up[j] : 0;
-            const int c = (up && j >= 3) ? up[j - 3] : 0;
-            const int res[4] = {x, x - a, x - b, x - png_paeth(a, b, c)};
+        // four bytes per lane and iteration: the row and the one above as 32-bit words (rows are 4-byte aligned: 3 * D bytes)
+        const unsigned* cw = reinterpret_cast<const unsigned*>(cur);
+        const unsigned* uw = reinterpret_cast<const unsigned*>(up);
+        for (int wd = (int)lane; wd < W / 4; wd += 32) {
+            const unsigned x4 = cw[wd], xp4 = wd ? cw[wd - 1] : 0u;
+            const unsigned u4 = up ? uw[wd] : 0u, up4 = (up && wd) ? uw[wd - 1] : 0u;
+            const unsigned a4 = (xp4 >> 8) | (x4 << 24);  // the bytes three positions to the left (zeros before the row)
+            const unsigned c4 = (up4 >> 8) | (u4 << 24);
 #pragma unroll
-            for (int f = 0; f < 4; ++f) {
-                const int v = res[f] & 0xff;
-                sum[f] += (unsigned)(v < 128 ? v : 256 - v);
+            for (int q = 0; q < 4; ++q) {
+                const int x = (int)((x4 >> (8 * q)) & 0xffu), a = (int)((a4 >> (8 * q)) & 0xffu);
+                const int b = (int)((u4 >> (8 * q)) & 0xffu), c = (int)((c4 >> (8 * q)) & 0xffu);
+                const int res[4] = {x, x - a, x - b, x - png_paeth(a, b, c)};
+#pragma unroll
+                for (int f = 0; f < 4; ++f) {
+                    const int v = res[f] & 0xff;
+                    sum[f] += (unsigned)(v < 128 ? v : 256 - v);
+                }
             }
         }
 #pragma unroll
@@ -195,11 +203,27 @@ __global__ void __launch_bounds__(kPngThreads) png_encode_kernel(PngScene ps) {
         unsigned long long r1 = 0, r2 = 0;
         const bool cached = NP <= kPngRowCache;
         if (cached) {
-            for (int i = (int)lane; i < NP; i += 32) {
-                const unsigned f = png_filtered(cur, up, filter, i);
-                sm.frow[i] = (unsigned char)f;
-                r1 += f;
-                r2 += (unsigned long long)(NP - i) * f;
+            if (lane == 0) {
+                sm.frow[0] = (unsigned char)filter;
+                r1 += (unsigned)filter;
+                r2 += (unsigned long long)NP * (unsigned)filter;
+            }
+            for (int wd = (int)lane; wd < W / 4; wd += 32) {
+                const unsigned x4 = cw[wd], xp4 = wd ? cw[wd - 1] : 0u;
+                const unsigned u4 = up ? uw[wd] : 0u, up4 = (up && wd) ? uw[wd - 1] : 0u;
+                const unsigned a4 = (xp4 >> 8) | (x4 << 24);
+                const unsigned c4 = (up4 >> 8) | (u4 << 24);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int x = (int)((x4 >> (8 * q)) & 0xffu), a = (int)((a4 >> (8 * q)) & 0xffu);
+                    const int b = (int)((u4 >> (8 * q)) & 0xffu), c = (int)((c4 >> (8 * q)) & 0xffu);
+                    const int pred = filter == 1 ? a : (filter == 2 ? b : (filter == 4 ? png_paeth(a, b, c) : 0));
+                    const unsigned f = (unsigned)(x - pred) & 0xffu;
+                    const int i = 4 * wd + q + 1;
+                    sm.frow[i] = (unsigned char)f;
+                    r1 += f;
+                    r2 += (unsigned long long)(NP - i) * f;
+                }
             }
             __syncwarp();
         }
