@@ -1072,11 +1072,31 @@ struct SegConst {
     bool small;  // all coordinates < 2^24: `raw as f64` can be carried exactly in f64
 };
 
+// Interior classification under round dash caps (OSMR_DASH_INTERIOR).  With LineCap::Round the half width of a dashed line
+// depends on the distance to the nearest dash (opacity_calculator.rs:62-96), so every pixel needs the dash phase: two square
+// roots, a division and an exact `%` (line.rs:108-114) before the dash loop.  For a pixel well inside the line the result is
+// nevertheless a per-op constant, and a conservative test on APPROXIMATE quantities proves it:
+//   d~  = (traveled + |dot(p - p1, dir)| / denom) mod total      (= dist_rem up to eps, Pythagoras: long^2 - centre^2 = along^2)
+//   eps = |p - p1|^2 * 2^-49 / along + 4e-8                        (bound of the reference's own rounding in sqrt(long^2 - centre^2))
+//   if d~ lies in the flat part (start_to, end_from) of a dash segment by more than eps, that segment matches with base = 1;
+//   its cap distance (+ eps) bounds the minimum `cap` from above, hence sqrt(hw^2 - cap^2) from below; if that lower bound
+//   is >= 0.5 and centre distance + 0.5 is below it (relative margins 1e-9), the reference takes
+//   sd_opacity = opacity_mul (all segments share it, checked per op), centre opacity = 1.0 * 1.0, so
+//   opacity = min(opacity_mul, 1.0) and is_in_line = true -- exactly, because every comparison it makes has that margin.
+// Anything else (feather zone, ramps, phase near a wrap, long segments where eps is not small) takes the reference's path.
+// MEASURED AND SWITCHED OFF: bit-exact on the whole suite and 41 % of the dashed evaluations of the C2 batch qualify, but the
+// lanes of a warp rarely qualify together, so the warp pays the test AND the reference path: line_cover_kernel 1.60 ms
+// without, 2.52 ms with (B200, same box).  Kept as a record of the bound derivation.
+#ifndef OSMR_DASH_INTERIOR
+#define OSMR_DASH_INTERIOR 0
+#endif
+
 // draw_one_perpendicular (line.rs:89-131): evaluates the walk from its start until the first pixel that is not in the
 // line (or until it has left the tile for good on its monotone axis) and stores the alpha of every in-line step.
 // Returns the number of steps stored (<= S).
 __device__ __forceinline__ unsigned cover_walk(double* alpha_out, unsigned S, const WalkItem& w, const SegConst& sc, const OpacityCalc& calc,
-                                               int mn, int p_error, int mul, double opacity0, int D, unsigned* trunc_flag) {
+                                               int mn, int p_error, int mul, double opacity0, int D, unsigned* trunc_flag,
+                                               double uniform_mul) {
     int p_mn = w.mx;
     int p_mx = mn;
     int err = mul * p_error;  // i32 like the reference (line.rs:80-91)
@@ -1101,6 +1121,12 @@ __device__ __forceinline__ unsigned cover_walk(double* alpha_out, unsigned S, co
     const bool quick = !(dashed && calc.round_caps);
     const double t_in = calc.feather_from * sc.denom * (1.0 - 9.0e-13);
     const double t_out = calc.feather_to * sc.denom * (1.0 + 9.0e-13);
+    // interior classification under round dash caps: only when every dash segment has the same opacity_mul (uniform_mul is
+    // NaN otherwise), the phase cannot lose precision (traveled < 2^24) and the segment is short enough for eps to be small
+    const bool interior_ok = OSMR_DASH_INTERIOR && !quick && uniform_mul == uniform_mul && sc.small && sc.traveled < 16777216.0 &&
+                             sc.denom < 60000.0 && calc.total_dash_len > 0.0;
+    const double inv_denom = interior_ok ? 1.0 / sc.denom : 0.0;
+    const double hw_sq = calc.half_line_width * calc.half_line_width;
     unsigned t = 0;
     for (;;) {
         if (step > 0 ? (p_mx > D - 1) : (p_mx < 0)) break;
@@ -1110,18 +1136,53 @@ __device__ __forceinline__ unsigned cover_walk(double* alpha_out, unsigned S, co
         if (quick && !dashed && araw < t_in) {
             opacity = fmin(1.0, calc.opacity_mul * 1.0);  // sd = 1.0, cd = mul * 1.0
             in_line = calc.opacity_mul * 1.0 > 0.0;
-        } else if (quick && araw > t_out) {
-            in_line = false;  // cd = mul * 0.0
+        } else if (araw > t_out) {
+            // cd = mul * 0.0.  Also true under round dash caps: they can only shrink the half width (sqrt(hw^2 - cap^2) <= hw,
+            // NaN -> feather_to 1.0 <= the op's), so a pixel beyond the op's feather_to is beyond every per-pixel one: the
+            // evaluation that ends a walk -- a quarter of all evaluations -- needs neither the dash phase nor a square root
+            in_line = false;
             opacity = 0.0;
         } else {
-            double center_dist = div_pos_peeled(araw, sc.denom);
-            double short_start = 0.0;
-            if (dashed) {
-                int px = w.swap ? p_mn : p_mx, py = w.swap ? p_mx : p_mn;
-                double long_start = point_dist(px, py, sc.x1, sc.y1);
-                short_start = sqrt_peeled(fmax(long_start * long_start - center_dist * center_dist, 0.0));
+            bool decided = false;
+            if (interior_ok) {
+                const int px = w.swap ? p_mn : p_mx, py = w.swap ? p_mx : p_mn;
+                const double ex = (double)(px - sc.x1), ey = (double)(py - sc.y1);  // exact: coordinates below 2^24
+                const double along = fabs(ex * (double)sc.sdx + ey * (double)sc.sdy) * inv_denom;
+                if (along >= 0.0625) {
+                    const double eps = (ex * ex + ey * ey) * 1.7763568394002505e-15 / along + 4.0e-8;  // 2^-49
+                    const double dist = sc.traveled + along;
+                    const double q = floor(dist * calc.inv_total);
+                    const double d = __fma_rn(-q, calc.total_dash_len, dist);
+                    if (eps < 1.0e-3 && d > eps && d < calc.total_dash_len - eps) {
+                        const double cd_hi = araw * inv_denom * (1.0 + 1.0e-9) + 0.5 + 1.0e-9;
+                        for (int i = 0; i < calc.n_segs; ++i) {
+                            const DashSeg& sg = calc.segs[i];
+                            if (d > sg.start_to + eps && d < sg.end_from - eps) {
+                                const double cap_hi = fmax(fmax(sg.orig_a - d, d - sg.orig_b), 0.0) + eps;
+                                const double hw2_lo = (hw_sq - cap_hi * cap_hi) * (1.0 - 1.0e-9);
+                                if (hw2_lo >= 0.26 && cd_hi * cd_hi < hw2_lo) {
+                                    opacity = fmin(uniform_mul, 1.0);
+                                    in_line = true;
+                                    decided = true;
+                                    OSMR_COUNT("cover.dash_interior", 1);
+                                }
+                                break;
+                            }
+                        }
+                    }
+                }
             }
-            calc_opacity(calc, sc.traveled, center_dist, short_start, opacity, in_line);
+            if (!decided) {
+                double center_dist = div_pos_peeled(araw, sc.denom);
+                double short_start = 0.0;
+                if (dashed) {
+                    int px = w.swap ? p_mn : p_mx, py = w.swap ? p_mx : p_mn;
+                    double long_start = point_dist(px, py, sc.x1, sc.y1);
+                    short_start = sqrt_peeled(fmax(long_start * long_start - center_dist * center_dist, 0.0));
+                }
+                calc_opacity(calc, sc.traveled, center_dist, short_start, opacity, in_line);
+                OSMR_COUNT("cover.slow_path", 1);
+            }
         }
         OSMR_COUNT("cover.steps_evaluated", 1);
         if (!in_line) break;
@@ -1201,6 +1262,15 @@ __global__ void __launch_bounds__(kCoverThreads, OSMR_COVER_MIN_BLOCKS) line_cov
             for (unsigned u = lane; u < n_main; u += 32) dst0[u] = src[u];
             if (lane < kCapCalcUnits) dst1[lane] = src[kMainCalcUnits + lane];
         }
+        __syncwarp();
+        // common opacity_mul of the op's dash segments (NaN: they differ, or there are none)
+        double uniform_mul = __longlong_as_double(0x7ff8000000000000LL);
+        if (sm.calc[0].n_segs > 0 && sm.calc[0].round_caps) {
+            uniform_mul = sm.calc[0].segs[0].opacity_mul;
+            for (int i = 1; i < sm.calc[0].n_segs; ++i)
+                if (sm.calc[0].segs[i].opacity_mul != uniform_mul) uniform_mul = __longlong_as_double(0x7ff8000000000000LL);
+            if (!(uniform_mul >= 0.0)) uniform_mul = __longlong_as_double(0x7ff8000000000000LL);
+        }
         {
             const unsigned sb = 32u * item.y;
             const unsigned si = sb + lane;
@@ -1254,12 +1324,14 @@ __global__ void __launch_bounds__(kCoverThreads, OSMR_COVER_MIN_BLOCKS) line_cov
                 int mn = w.mn, p_error = w.p_error;
                 unsigned len0 = 0, len1 = 0;
                 if (mn >= -reach && mn <= D - 1 + reach)
-                    len0 = cover_walk(alpha_out, S, w, sc, calc, mn, p_error, mul, lp.opacity, D, &s.counters[CNT_WALK_TRUNC]);
+                    len0 = cover_walk(alpha_out, S, w, sc, calc, mn, p_error, mul, lp.opacity, D, &s.counters[CNT_WALK_TRUNC],
+                                      (h.flags & 1u) ? __longlong_as_double(0x7ff8000000000000LL) : uniform_mul);
                 if (w.extra) {
                     p_error = wadd(wsub(p_error, 2 * w.mx_d), 2 * w.mn_d);
                     mn += w.mn_inc;
                     if (mn >= -reach && mn <= D - 1 + reach)
-                        len1 = cover_walk(alpha_out + extra_at * S, S, w, sc, calc, mn, p_error, mul, lp.opacity, D, &s.counters[CNT_WALK_TRUNC]);
+                        len1 = cover_walk(alpha_out + extra_at * S, S, w, sc, calc, mn, p_error, mul, lp.opacity, D, &s.counters[CNT_WALK_TRUNC],
+                                          (h.flags & 1u) ? __longlong_as_double(0x7ff8000000000000LL) : uniform_mul);
                     if (len1) len_out[extra_at] = (unsigned char)len1;
                 }
                 len_out[0] = (unsigned char)(len0 | (len1 ? 0x80u : 0u));  // bit 7: the extra walk has steps
