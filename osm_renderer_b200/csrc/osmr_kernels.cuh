@@ -799,6 +799,15 @@ __global__ void __launch_bounds__(kGeomThreads, OSMR_GEOM_MIN_BLOCKS) build_geom
 constexpr int kFillThreads = 128;
 constexpr int kFillWarps = kFillThreads / 32;
 constexpr int kMaxD = 2048;  // scale <= 8
+// Row-parallel path of fill_rows_kernel: a lane owns a ROW of the work item's 32 and walks the op's edges itself (the edge
+// record is a broadcast load), keeping up to kRowLocal spans.  An ordinary polygon (a building: 5-13 edges, 2-4 spans per row)
+// keeps all 32 lanes busy this way; with a lane per edge and a loop over the rows only ne of 32 lanes worked.  Rows with more
+// spans, tiles wider than 32 * kRowWords pixels and the fill_cap test hook take the row-serial path below.
+constexpr int kRowLocal = 8;
+constexpr int kRowWords = 16;
+#ifndef OSMR_FILL_ROW_PARALLEL
+#define OSMR_FILL_ROW_PARALLEL 1
+#endif
 
 __device__ __forceinline__ unsigned bits_in_word(int from, int to, int w) {
     // bits of [from, to] that fall into word w (pixels 32w .. 32w+31); from <= to
@@ -813,6 +822,8 @@ __global__ void __launch_bounds__(kFillThreads) fill_rows_kernel(Scene s) {
     __shared__ int2 act[kFillWarps][kFillCap];
     __shared__ int2 sorted[kFillWarps][kFillCap];
     __shared__ unsigned hist[kFillWarps][kMaxD / 8 + 1];  // slow path: x_min histogram in 8 passes of D/8 columns
+    __shared__ int2 rspan[kFillWarps][kRowLocal][32];      // row-parallel path: the spans of row `lane`, in edge order
+    __shared__ unsigned rmask[kFillWarps][kRowWords][32];  // ... and its mask words
     const unsigned lane = lane_id();
     const unsigned w = threadIdx.x >> 5;
     const int D = s.D;
@@ -837,6 +848,44 @@ __global__ void __launch_bounds__(kFillThreads) fill_rows_kernel(Scene s) {
         const int ne = (int)op.geom_cnt;
         const int ya = max((int)op.y0, 0), yb = min((int)op.y1, D - 1);
         const int y_first = ya + 32 * (int)item.y, y_last = min(yb, y_first + 31);
+        if (OSMR_FILL_ROW_PARALLEL && wpr <= kRowWords && cap == kFillCap) {
+            const int y = y_first + (int)lane;
+            const bool live = y <= y_last;
+            int m = 0;
+            for (int e = 0; e < ne; ++e) {
+                const int4 ed = edges[e];
+                int xmin, xmax;
+                bool poisoned;
+                if (live && fill_edge_row_span(ed.x, ed.y, ed.z, ed.w, y, xmin, xmax, poisoned) && !poisoned) {
+                    if (m < kRowLocal) rspan[w][m][lane] = make_int2(xmin, xmax);
+                    ++m;
+                }
+            }
+            if (!__any_sync(0xffffffffu, m > kRowLocal)) {
+                // stable insertion sort by x_min (fill.rs:25), then pair (0,1), (2,3), ... (fill.rs:27-45)
+                for (int i = 1; i < m; ++i) {
+                    const int2 v = rspan[w][i][lane];
+                    int j = i - 1;
+                    while (j >= 0 && rspan[w][j][lane].x > v.x) {
+                        rspan[w][j + 1][lane] = rspan[w][j][lane];
+                        --j;
+                    }
+                    rspan[w][j + 1][lane] = v;
+                }
+                for (int k = 0; k < wpr; ++k) rmask[w][k][lane] = 0u;
+                for (int q = 0; 2 * q + 1 < m; ++q) {
+                    const int from = max(rspan[w][2 * q][lane].x, 0);
+                    const int to = min(rspan[w][2 * q + 1][lane].y, D - 1);
+                    if (from <= to)
+                        for (int wd = from >> 5; wd <= (to >> 5); ++wd) rmask[w][wd][lane] |= bits_in_word(from, to, wd);
+                }
+                if (live) {
+                    unsigned* mrow = s.mask + op.mask_off + (size_t)(y - ya) * wpr;
+                    for (int k = 0; k < wpr; ++k) mrow[k] = rmask[w][k][lane];
+                }
+                continue;
+            }
+        }
         for (int y = y_first; y <= y_last; ++y) {
             unsigned* mrow = s.mask + op.mask_off + (size_t)(y - ya) * wpr;
             // ---- gather the non-poisoned spans of this row, in edge order ----
