@@ -575,6 +575,10 @@ __global__ void __launch_bounds__(kPlanThreads) plan_ops_kernel(Scene s) {
 // ------------------------------------------------------------------------------------------------------
 constexpr int kGeomThreads = 128;
 constexpr unsigned long long kSlabLen = 2048, kSlabAlpha = 16384;  // walk cache units a warp reserves per atomic (2 KB / 128 KB)
+constexpr unsigned kLaneFillMax = 48;  // nodes of a way whose fill edges are produced by a single lane
+#ifndef OSMR_GEOM_LANE_FILLS
+#define OSMR_GEOM_LANE_FILLS 1
+#endif
 
 #ifndef OSMR_GEOM_MIN_BLOCKS
 #define OSMR_GEOM_MIN_BLOCKS 4
@@ -585,15 +589,45 @@ __global__ void __launch_bounds__(kGeomThreads, OSMR_GEOM_MIN_BLOCKS) build_geom
     const unsigned n_work = s.counters[CNT_N_WORK];
     // walk cache slabs: the warp takes kSlab units per atomic and hands them out to its ops itself
     unsigned long long slab_len = 0, slab_len_end = 0, slab_alpha = 0, slab_alpha_end = 0;
-    unsigned wi = 0, wi_end = 0;
-    for (;; ++wi) {
-        if (wi >= wi_end) {
-            if (lane == 0) wi = atomicAdd(&s.counters[CNT_WORK_CURSOR], kWorkBatch);
-            wi = __shfl_sync(0xffffffffu, wi, 0);
-            wi_end = wi + kWorkBatch;
+    for (;;) {
+        // 32 ops per fetch, one per lane.  A fill of a short way (a building: the majority of all ops) is done by its lane
+        // alone -- 32 such ops side by side instead of one op on a quarter of the lanes; everything else (lines,
+        // multipolygons, long rings) is then taken in turn by the whole warp.
+        unsigned wi0 = 0;
+        if (lane == 0) wi0 = atomicAdd(&s.counters[CNT_WORK_CURSOR], 32u);
+        wi0 = __shfl_sync(0xffffffffu, wi0, 0);
+        if (wi0 >= n_work) break;
+        const bool have = wi0 + lane < n_work;
+        const unsigned my_gi = have ? s.work[wi0 + lane] : 0u;
+        bool lane_done = !have;
+#if OSMR_GEOM_LANE_FILLS
+        if (have) {
+            VisOp& o = s.vis[my_gi];
+            if (o.kind != OP_LINE && !(o.entity & OSMR_AREA_MULTIPOLYGON)) {
+                const uint2 r = s.ways[o.entity];
+                if (r.y <= kLaneFillMax) {
+                    const TileXform xf1 = make_xform(s.tiles[o.tile]);
+                    int4* out1 = reinterpret_cast<int4*>(s.geom + o.geom_off);
+                    unsigned n1 = 0;
+                    int2 prev = make_int2(0, 0);
+                    for (unsigned q = 0; q < r.y; ++q) {
+                        const int2 cur = project_point(s.merc[s.ints[r.x + q]], xf1);
+                        if (q && prev.y != cur.y && max(prev.y, cur.y) >= 0 && min(prev.y, cur.y) <= D - 1)
+                            out1[n1++] = make_int4(prev.x, prev.y, cur.x, cur.y);
+                        prev = cur;
+                    }
+                    o.geom_cnt = n1;
+                    lane_done = true;
+                    OSMR_COUNT("geom.lane_fills", 1);
+                }
+            }
         }
-        if (wi >= n_work) break;
-        unsigned gi = s.work[wi];
+#endif
+        unsigned rest = __ballot_sync(0xffffffffu, !lane_done);
+        while (rest) {
+        const int src_lane = __ffs(rest) - 1;
+        rest &= rest - 1;
+        unsigned gi = __shfl_sync(0xffffffffu, my_gi, src_lane);
         VisOp& op = s.vis[gi];
         const unsigned pass = op.pass;
         osmr_styled_area ar;
@@ -782,6 +816,7 @@ __global__ void __launch_bounds__(kGeomThreads, OSMR_GEOM_MIN_BLOCKS) build_geom
         if (lane == 0) {
             op.geom_cnt = count;
             if (op.kind == OP_LINE) s.rop[gi].b = count;
+        }
         }
     }
 }
