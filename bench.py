@@ -197,6 +197,7 @@ def main():
                     help="e2e leg: 0 = tiles staged in HBM, chunk-wise D2H on its own stream while later chunks are drawn (default), "
                          "1 = raster_kernel stores the tiles straight into the page-locked host buffer")
     ap.add_argument("--e2e-chunks", type=int, default=0, help="experiments: draw chunks of the staged e2e call (0 = library default)")
+    ap.add_argument("--two-streams", type=int, default=1, choices=[0, 1], help="experiments: draw chunks of the e2e call on two streams")
     ap.add_argument("--skip-auto", action="store_true", help="skip the osmr_draw_tiles_auto (f3) and osmr_draw_tiles_png (f4) legs")
     args = ap.parse_args()
 
@@ -326,6 +327,7 @@ def main():
     h2d = int(sum(a.nbytes for a in in_arrays))
     flags, canvas = ctx._flags(w["canvas"], w["caps"], False)
     ctx.debug_set("direct_out", args.e2e_direct)
+    ctx.debug_set("two_streams", args.two_streams)
     if args.e2e_chunks:
         ctx.debug_set("host_chunks", args.e2e_chunks)
 
@@ -343,6 +345,26 @@ def main():
     barrier()
     e2e_wall = time.perf_counter() - t1
     checksum = int(np.frombuffer((C.c_uint8 * 4096).from_address(pin_out), dtype=np.uint8).sum())
+
+    # ---- context for e2e: what the bus of this box gives a plain pinned copy of the step's output / input ----
+    pcie = None
+    try:
+        dev_buf = torch.empty(out_bytes, dtype=torch.uint8, device="cuda")
+        host_buf = torch.empty(out_bytes, dtype=torch.uint8, pin_memory=True)
+        ev0, ev1, ev2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        host_buf.copy_(dev_buf, non_blocking=True)
+        torch.cuda.synchronize()
+        ev0.record()
+        host_buf.copy_(dev_buf, non_blocking=True)
+        ev1.record()
+        dev_buf[:h2d].copy_(host_buf[:h2d], non_blocking=True)
+        ev2.record()
+        torch.cuda.synchronize()
+        pcie = {"d2h_gbs": out_bytes / ev0.elapsed_time(ev1) / 1e6, "h2d_gbs": h2d / ev1.elapsed_time(ev2) / 1e6,
+                "d2h_ms_for_step_output": ev0.elapsed_time(ev1)}
+        del dev_buf, host_buf
+    except Exception as exc:  # the probe is context, never a reason to fail the bench
+        pcie = {"error": str(exc)}
 
     # ---- e2e_auto (f3): only the tile list crosses the bus; candidate lookup + painter's order on the device ----
     auto = None
@@ -508,6 +530,7 @@ def main():
                 "ms_per_step": 1000.0 * e2e_wall / args.steps, "api": "osmr_draw_tiles (pinned host buffers; " + ("tiles stored straight into the host buffer by raster_kernel" if args.e2e_direct
                                                                       else "tiles staged in HBM, chunked D2H on a copy stream") + ")",
                 "checksum": checksum},
+        "pcie_probe": pcie,
         "e2e_auto": auto,
         "e2e_png": png,
         "gpu_launches": int(launches),

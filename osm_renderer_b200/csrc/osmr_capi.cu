@@ -146,6 +146,26 @@ struct osmr_ctx {
     DevBuf<uint4> geom, calc_table;
     DevBuf<double> walk_alpha;        // walk cache (line_cover_kernel -> raster_kernel)
     DevBuf<unsigned char> walk_len;
+    // Second set of the bump-allocated scratch: the draw chunks of a host-output call alternate between two streams
+    // (chunk i+1 is planned while chunk i is still being rastered), so consecutive chunks must not share scratch.
+    struct ScratchB {
+        DevBuf<uint4> geom;
+        DevBuf<unsigned> mask;
+        DevBuf<uint2> fill_work, line_work;
+        DevBuf<double> walk_alpha;
+        DevBuf<unsigned char> walk_len;
+        void release() {
+            geom.release();
+            mask.release();
+            fill_work.release();
+            line_work.release();
+            walk_alpha.release();
+            walk_len.release();
+        }
+    } scrB;
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t prep_done = nullptr;  // upload + style calculators on `stream`: what stream2's first chunk waits for
+    bool two_streams = true;          // debug key "two_streams"
     size_t geom_cap_units = 0, mask_cap_words = 0, walk_alpha_cap = 0, walk_len_cap = 0;
     DevBuf<unsigned char> out;
     size_t out_bytes = 0;
@@ -215,6 +235,8 @@ int osmr_ctx_create(int device, osmr_ctx** out_ctx) {
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->prep_done, cudaEventDisableTiming);
     for (unsigned i = 0; i < kMaxChunks && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->chunk_done[i], cudaEventDisableTiming);
     for (unsigned i = 0; i < kMaxChunks; ++i)
         for (int j = 0; j < 4 && e == cudaSuccess; ++j) e = cudaEventCreate(&ctx->cev[i][j]);
@@ -308,6 +330,9 @@ void osmr_ctx_destroy(osmr_ctx* ctx) {
     ctx->h_label_segs.release();
     ctx->label_plane.release();
     ctx->geom.release();
+    ctx->scrB.release();
+    if (ctx->prep_done) cudaEventDestroy(ctx->prep_done);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     ctx->calc_table.release();
     ctx->out.release();
     for (auto& e : ctx->ev)
@@ -345,6 +370,10 @@ int osmr_debug_set(osmr_ctx* ctx, const char* key, int value) {
         ctx->host_chunks = (unsigned)value;
         return OSMR_OK;
     }
+    if (strcmp(key, "two_streams") == 0) {  // 0: all draw chunks of a host-output call on one stream (A/B measurements)
+        ctx->two_streams = value != 0;
+        return OSMR_OK;
+    }
     if (strcmp(key, "work_items") == 0) {
         if (value < 1) return ctx->fail(OSMR_E_INVALID, "work_items must be positive");
         ctx->work_items_limit = (unsigned)value;
@@ -361,6 +390,7 @@ int osmr_debug_set(osmr_ctx* ctx, const char* key, int value) {
         ctx->mask.release();
         ctx->walk_alpha.release();
         ctx->walk_len.release();
+        ctx->scrB.release();
         cudaError_t e1 = ctx->geom.reserve((size_t)value);
         cudaError_t e2 = ctx->mask.reserve((size_t)value);
         if (e1 == cudaSuccess) e1 = ctx->walk_alpha.reserve((size_t)value);
@@ -756,7 +786,7 @@ int osmr_batch_upload(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, c
 // the device): the chunk's counters land in page-locked slot `slot` and are judged by collect_chunk after the stream
 // has been synchronised.  dev_out points at tile tb's image.
 static int launch_chunk(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t flags, unsigned char* dev_out, unsigned tb, unsigned tc,
-                        unsigned slot) {
+                        unsigned slot, unsigned set) {
     const int D = 256 * ctx->scale;
     const unsigned area_base = ctx->h_area_begin[tb];
     const unsigned n_areas = ctx->h_area_begin[tb + tc] - area_base;
@@ -793,32 +823,38 @@ static int launch_chunk(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t fla
     s.vis = ctx->vis.p;
     s.rop = ctx->rop.p;
     s.vis_bbox = ctx->vis_bbox.p;
-    s.vis_count = ctx->vis_count.p;
-    s.work = ctx->work.p;
-    s.fill_work = ctx->fill_work.p;
-    s.line_work = ctx->line_work.p;
-    s.fill_work_cap = (unsigned)std::min<size_t>(ctx->fill_work.cap, 0xffffffffu);
-    s.line_work_cap = (unsigned)std::min<size_t>(ctx->line_work.cap, 0xffffffffu);
+    s.vis_count = ctx->vis_count.p + 3ull * tb;  // per chunk: concurrent chunks must not share the per-tile counts
+    s.work = ctx->work.p + 3ull * area_base;  // a chunk's ops fit into the slice of its own styled areas
+    auto& fill_work = set ? ctx->scrB.fill_work : ctx->fill_work;
+    auto& line_work = set ? ctx->scrB.line_work : ctx->line_work;
+    auto& walk_alpha = set ? ctx->scrB.walk_alpha : ctx->walk_alpha;
+    auto& walk_len = set ? ctx->scrB.walk_len : ctx->walk_len;
+    auto& geom = set ? ctx->scrB.geom : ctx->geom;
+    auto& mask = set ? ctx->scrB.mask : ctx->mask;
+    s.fill_work = fill_work.p;
+    s.line_work = line_work.p;
+    s.fill_work_cap = (unsigned)std::min<size_t>(fill_work.cap, 0xffffffffu);
+    s.line_work_cap = (unsigned)std::min<size_t>(line_work.cap, 0xffffffffu);
     if (ctx->work_items_limit) {
         s.fill_work_cap = std::min(s.fill_work_cap, ctx->work_items_limit);
         s.line_work_cap = std::min(s.line_work_cap, ctx->work_items_limit);
     }
-    s.walk_alpha = ctx->walk_alpha.p;
-    s.walk_len = ctx->walk_len.p;
-    s.walk_alpha_cap = ctx->walk_alpha_cap;
-    s.walk_len_cap = ctx->walk_len_cap;
+    s.walk_alpha = walk_alpha.p;
+    s.walk_len = walk_len.p;
+    s.walk_alpha_cap = std::min<size_t>(ctx->walk_alpha_cap, walk_alpha.cap);
+    s.walk_len_cap = std::min<size_t>(ctx->walk_len_cap, walk_len.cap);
     s.calc_table = ctx->calc_table.p;
-    s.geom = ctx->geom.p;
-    s.geom_cap = (unsigned)std::min<size_t>(ctx->geom_cap_units, 0xffffffffu);
-    s.mask = ctx->mask.p;
-    s.mask_cap = (unsigned)std::min<size_t>(ctx->mask_cap_words, 0xffffffffu);
+    s.geom = geom.p;
+    s.geom_cap = (unsigned)std::min<size_t>(std::min<size_t>(ctx->geom_cap_units, geom.cap), 0xffffffffu);
+    s.mask = mask.p;
+    s.mask_cap = (unsigned)std::min<size_t>(std::min<size_t>(ctx->mask_cap_words, mask.cap), 0xffffffffu);
     s.counters = ctx->counters.p + (size_t)slot * CNT_COUNT;
     s.fill_cap = ctx->fill_cap;
     s.label_plane = ctx->label_plane_active ? ctx->label_plane.p + (size_t)tb * D * D : nullptr;
     s.label_icon_px = ctx->label_icon_px.p;
     s.out = dev_out;
 
-    cudaStream_t st = ctx->stream;
+    cudaStream_t st = set ? ctx->stream2 : ctx->stream;
     cudaEvent_t* ev = ctx->cev[slot];
     CK(cudaEventRecord(ev[0], st));
     CK(cudaMemsetAsync(s.counters, 0, CNT_COUNT * sizeof(unsigned), st));
@@ -827,6 +863,7 @@ static int launch_chunk(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t fla
         style_calc_kernel<<<(2 * ctx->n_styles + 127) / 128, 128, 0, st>>>(s, ctx->calc_table.p);
         ++launches;
     }
+    if (slot == 0) CK(cudaEventRecord(ctx->prep_done, st));  // batch description + calculators are in place
     plan_ops_kernel<<<3 * tc, kPlanThreads, 0, st>>>(s);
     build_geometry_kernel<<<ctx->num_sms * 8, kGeomThreads, 0, st>>>(s);
     fill_rows_kernel<<<ctx->num_sms * 16, kFillThreads, 0, st>>>(s);
@@ -841,6 +878,17 @@ static int launch_chunk(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t fla
     CK(cudaEventRecord(ev[2], st));
     CK(cudaMemcpyAsync(ctx->h_cnt.p + (size_t)slot * CNT_COUNT, s.counters, CNT_COUNT * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
     ctx->chunk_launches[slot] = launches;
+    return OSMR_OK;
+}
+
+// the second scratch set mirrors the first one's sizes
+static int ensure_scrB(osmr_ctx* ctx) {
+    CK(ctx->scrB.geom.reserve(ctx->geom.cap));
+    CK(ctx->scrB.mask.reserve(ctx->mask.cap));
+    CK(ctx->scrB.fill_work.reserve(ctx->fill_work.cap));
+    CK(ctx->scrB.line_work.reserve(ctx->line_work.cap));
+    CK(ctx->scrB.walk_alpha.reserve(ctx->walk_alpha.cap));
+    CK(ctx->scrB.walk_len.reserve(ctx->walk_len.cap));
     return OSMR_OK;
 }
 
@@ -962,24 +1010,35 @@ int osmr_batch_draw(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t flags, 
         }
         ctx->stats = osmr_stats{};
         // every chunk is enqueued without waiting for the previous one; with staged host output the D2H copy of chunk i
-        // (third stream) runs while the later chunks are drawn
+        // (third stream) runs while the later chunks are drawn.  The chunks alternate between two compute streams with
+        // their own scratch, so the plan / geometry / cover kernels of chunk i+1 fill the SMs that the tail of chunk i's
+        // kernels leaves idle (a chunk of a few hundred tiles cannot keep 148 SMs busy through its launch tails).
+        const bool use2 = ctx->two_streams && n_planned > 1;
+        if (use2) {
+            int rcb = ensure_scrB(ctx);
+            if (rcb) return rcb;
+        }
         unsigned n_chunks = 0;
         unsigned cb[kMaxChunks], cc[kMaxChunks];
         for (unsigned tb = 0; tb < ctx->n_tiles;) {
             const unsigned tc = sizes[n_chunks];
             if (n_chunks >= n_planned || tc == 0 || tb + tc > ctx->n_tiles) return ctx->fail(OSMR_E_STATE, "internal error: bad draw chunk plan");
+            const unsigned set = use2 ? (n_chunks & 1u) : 0u;
+            cudaStream_t cst = set ? ctx->stream2 : ctx->stream;
+            if (n_chunks == 1 && set) CK(cudaStreamWaitEvent(cst, ctx->prep_done, 0));
             if (tb > 0 && ctx->areas_deferred) {  // the tail of the styled-area list was uploaded on the copy stream
-                CK(cudaStreamWaitEvent(ctx->stream, ctx->areas_ready, 0));
-                ctx->areas_deferred = false;
+                CK(cudaStreamWaitEvent(cst, ctx->areas_ready, 0));
+                if (!use2 || n_chunks >= 2) ctx->areas_deferred = false;  // both compute streams have waited
             }
-            int rc = launch_chunk(ctx, canvas_rgb, flags, dev_out + (size_t)tb * tile_bytes, tb, tc, n_chunks);
+            int rc = launch_chunk(ctx, canvas_rgb, flags, dev_out + (size_t)tb * tile_bytes, tb, tc, n_chunks, set);
             if (rc) {
                 cudaStreamSynchronize(ctx->stream);
+                cudaStreamSynchronize(ctx->stream2);
                 cudaStreamSynchronize(ctx->d2h_stream);
                 return rc;
             }
             if (staged) {
-                CK(cudaEventRecord(ctx->chunk_done[n_chunks], ctx->stream));
+                CK(cudaEventRecord(ctx->chunk_done[n_chunks], cst));
                 CK(cudaStreamWaitEvent(ctx->d2h_stream, ctx->chunk_done[n_chunks], 0));
                 CK(cudaMemcpyAsync(out + (size_t)tb * tile_bytes, dev_out + (size_t)tb * tile_bytes, (size_t)tc * tile_bytes,
                                    cudaMemcpyDeviceToHost, ctx->d2h_stream));
@@ -990,6 +1049,8 @@ int osmr_batch_draw(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t flags, 
             tb += tc;
         }
         CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream2));
+        ctx->areas_deferred = false;
         bool redo = false;
         for (unsigned c = 0; c < n_chunks; ++c) {
             int rc = collect_chunk(ctx, c, cb[c], cc[c], &redo);

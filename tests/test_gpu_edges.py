@@ -168,3 +168,23 @@ def test_widest_supported_line_and_the_loud_refusal_beyond_it():
             ctx.draw_tiles(tiles, begins, areas, (255, 255, 255), True)
     finally:
         ctx.close()
+
+
+def test_chunked_host_output_pipeline(fx, gpu_ctx):
+    """148 tiles in one call: the library draws them in chunks on two compute streams with separate scratch while a third
+    stream copies finished chunks back; every tile must still be the oracle's."""
+    tiles, begins, areas = fx.batches["18"]
+    sel = list(range(64)) + list(range(64)) + list(range(20))
+    parts = [areas[begins[i] : begins[i + 1]] for i in sel]
+    b = np.concatenate([[0], np.cumsum([len(p) for p in parts])]).astype(np.uint32)
+    a = np.concatenate(parts)
+    uniq = np.stack(oracle.draw_tiles(fx.bin, fx.table, tiles[:64], begins[:65], areas[: begins[64]], fx.canvas_rgb, True, n_threads=8))
+    for two in (1, 0):
+        gpu_ctx.debug_set("two_streams", two)
+        got = gpu_ctx.draw_tiles(tiles[sel], b, a, fx.canvas_rgb, True)
+        assert (got == uniq[sel]).all(), two
+    gpu_ctx.debug_set("two_streams", 1)
+    gpu_ctx.debug_set("host_chunks", 2)
+    got = gpu_ctx.draw_tiles(tiles[sel], b, a, fx.canvas_rgb, True)
+    gpu_ctx.debug_set("host_chunks", 0)
+    assert (got == uniq[sel]).all()
