@@ -198,6 +198,7 @@ def main():
                          "1 = raster_kernel stores the tiles straight into the page-locked host buffer")
     ap.add_argument("--e2e-chunks", type=int, default=0, help="experiments: draw chunks of the staged e2e call (0 = library default)")
     ap.add_argument("--two-streams", type=int, default=1, choices=[0, 1], help="experiments: draw chunks of the e2e call on two streams")
+    ap.add_argument("--resident-chunks", type=int, default=0, help="experiments: draw chunks of the resident (value) leg (0 = library default)")
     ap.add_argument("--skip-auto", action="store_true", help="skip the osmr_draw_tiles_auto (f3) and osmr_draw_tiles_png (f4) legs")
     args = ap.parse_args()
 
@@ -292,6 +293,8 @@ def main():
             torch.cuda.synchronize()
 
     # ---- value: batch resident in HBM, output stays in HBM ----
+    if args.resident_chunks:
+        ctx.debug_set("resident_chunks", args.resident_chunks)
     ctx.batch_upload(w["tiles"], w["area_begin"], w["areas"])
     for _ in range(args.warmup):
         ctx.batch_draw(w["canvas"], w["caps"])

@@ -164,6 +164,7 @@ struct osmr_ctx {
         }
     } scrB;
     cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_wall0 = nullptr, ev_wall1 = nullptr, join2 = nullptr;  // device wall time of a draw across both streams
     cudaEvent_t prep_done = nullptr;  // upload + style calculators on `stream`: what stream2's first chunk waits for
     bool two_streams = true;          // debug key "two_streams"
     size_t geom_cap_units = 0, mask_cap_words = 0, walk_alpha_cap = 0, walk_len_cap = 0;
@@ -193,6 +194,7 @@ struct osmr_ctx {
                               // (no D2H stage; measured slower than the staged pipeline: PCIe-bound stores, 26 GB/s)
     unsigned work_items_limit = 0;  // debug key "work_items": pretend the work lists are this short once (exercises their growth)
     unsigned host_chunks = 0;  // 0: tapered default schedule (plan_chunks)
+    unsigned resident_chunks = 1;  // debug key "resident_chunks": draw chunks when the output stays in HBM
     unsigned first_chunk = 0;  // tiles in the first draw chunk of the current upload (0: one chunk)
     osmr_stats stats{};
 
@@ -237,6 +239,9 @@ int osmr_ctx_create(int device, osmr_ctx** out_ctx) {
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->prep_done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->join2, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_wall0);
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_wall1);
     for (unsigned i = 0; i < kMaxChunks && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->chunk_done[i], cudaEventDisableTiming);
     for (unsigned i = 0; i < kMaxChunks; ++i)
         for (int j = 0; j < 4 && e == cudaSuccess; ++j) e = cudaEventCreate(&ctx->cev[i][j]);
@@ -332,6 +337,9 @@ void osmr_ctx_destroy(osmr_ctx* ctx) {
     ctx->geom.release();
     ctx->scrB.release();
     if (ctx->prep_done) cudaEventDestroy(ctx->prep_done);
+    if (ctx->join2) cudaEventDestroy(ctx->join2);
+    if (ctx->ev_wall0) cudaEventDestroy(ctx->ev_wall0);
+    if (ctx->ev_wall1) cudaEventDestroy(ctx->ev_wall1);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     ctx->calc_table.release();
     ctx->out.release();
@@ -368,6 +376,11 @@ int osmr_debug_set(osmr_ctx* ctx, const char* key, int value) {
     if (strcmp(key, "host_chunks") == 0) {  // equal draw chunks of a staged host-output call (0: tapered default)
         if (value < 0 || value > (int)kMaxChunks) return ctx->fail(OSMR_E_INVALID, "host_chunks must be 0..16");
         ctx->host_chunks = (unsigned)value;
+        return OSMR_OK;
+    }
+    if (strcmp(key, "resident_chunks") == 0) {
+        if (value < 1 || value > (int)kMaxChunks) return ctx->fail(OSMR_E_INVALID, "resident_chunks must be 1..16");
+        ctx->resident_chunks = (unsigned)value;
         return OSMR_OK;
     }
     if (strcmp(key, "two_streams") == 0) {  // 0: all draw chunks of a host-output call on one stream (A/B measurements)
@@ -699,9 +712,15 @@ static unsigned char* pinned_device_alias(const void* p) {
 //   launch tails).  Debug key "host_chunks" = n > 0 forces n equal chunks.
 //   direct (debug key "direct_out", page-locked `out`): a small first chunk hides the upload of the remaining styled
 //   areas, raster_kernel stores the tiles straight into host memory (PCIe-bound stores, 26 GB/s: slower than staging).
-static unsigned plan_chunks(unsigned n_tiles, bool to_host, bool direct, unsigned host_chunks, unsigned sizes[kMaxChunks]) {
+static unsigned plan_chunks(unsigned n_tiles, bool to_host, bool direct, unsigned host_chunks, unsigned resident_chunks,
+                            unsigned sizes[kMaxChunks]) {
     unsigned n = 0;
-    if (!to_host || n_tiles < 128) {
+    if (!to_host && resident_chunks > 1 && n_tiles >= 128 * resident_chunks) {
+        // output stays in HBM: equal chunks alternating between the two compute streams (no transfers to hide, but the
+        // launch tails of one chunk's kernels overlap the other chunk's work)
+        const unsigned c = (n_tiles + resident_chunks - 1) / resident_chunks;
+        for (unsigned done = 0; done < n_tiles; done += c) sizes[n++] = std::min(c, n_tiles - done);
+    } else if (!to_host || n_tiles < 128) {
         sizes[n++] = n_tiles;
     } else if (direct) {
         sizes[n++] = std::max(32u, n_tiles / 8);
@@ -744,7 +763,7 @@ static int batch_upload_impl(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_t
     ctx->first_chunk = 0;
     if (defer_tail) {
         unsigned sizes[kMaxChunks];
-        plan_chunks(n_tiles, true, ctx->direct_out && host_out && pinned_device_alias(host_out), ctx->host_chunks, sizes);
+        plan_chunks(n_tiles, true, ctx->direct_out && host_out && pinned_device_alias(host_out), ctx->host_chunks, 1, sizes);
         if (sizes[0] < n_tiles) {
             head = area_begin[sizes[0]];
             ctx->first_chunk = sizes[0];
@@ -984,7 +1003,7 @@ int osmr_batch_draw(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t flags, 
     const size_t tile_bytes = D * D * ((flags & OSMR_DRAW_OUT_RGBA) ? 4 : 3);
     const bool staged = to_host && !alias;
     unsigned sizes[kMaxChunks];
-    const unsigned n_planned = plan_chunks(ctx->n_tiles, to_host, alias != nullptr, ctx->host_chunks, sizes);
+    const unsigned n_planned = plan_chunks(ctx->n_tiles, to_host, alias != nullptr, ctx->host_chunks, ctx->resident_chunks, sizes);
     if (ctx->areas_deferred && ctx->first_chunk && sizes[0] != ctx->first_chunk)
         return ctx->fail(OSMR_E_STATE, "internal error: draw chunks differ from the upload split");
     CK(ctx->counters.reserve((size_t)kMaxChunks * CNT_COUNT));
@@ -1020,6 +1039,7 @@ int osmr_batch_draw(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t flags, 
         }
         unsigned n_chunks = 0;
         unsigned cb[kMaxChunks], cc[kMaxChunks];
+        CK(cudaEventRecord(ctx->ev_wall0, ctx->stream));
         for (unsigned tb = 0; tb < ctx->n_tiles;) {
             const unsigned tc = sizes[n_chunks];
             if (n_chunks >= n_planned || tc == 0 || tb + tc > ctx->n_tiles) return ctx->fail(OSMR_E_STATE, "internal error: bad draw chunk plan");
@@ -1048,6 +1068,11 @@ int osmr_batch_draw(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t flags, 
             ++n_chunks;
             tb += tc;
         }
+        if (use2) {  // the end of the draw on the device: both streams
+            CK(cudaEventRecord(ctx->join2, ctx->stream2));
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->join2, 0));
+        }
+        CK(cudaEventRecord(ctx->ev_wall1, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream2));
         ctx->areas_deferred = false;
@@ -1061,7 +1086,11 @@ int osmr_batch_draw(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t flags, 
         }
         if (redo) continue;  // (copies of the incomplete images are simply overwritten by the second round, in stream order)
         if (staged) CK(cudaStreamSynchronize(ctx->d2h_stream));
-        if (gpu_ms) *gpu_ms = ctx->stats.ms_total;
+        if (gpu_ms) {  // device wall time of the draw (with several chunks on two streams the stage times overlap)
+            float wall = 0.f;
+            cudaEventElapsedTime(&wall, ctx->ev_wall0, ctx->ev_wall1);
+            *gpu_ms = wall;
+        }
         return OSMR_OK;
     }
     cudaStreamSynchronize(ctx->d2h_stream);
