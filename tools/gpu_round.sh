@@ -30,5 +30,8 @@ echo "== ncu launch list of the f3 / f4 kernels"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"auto_|png_|class_reach|entity_box" -c 60 --csv --log-file gpurun_out/launches_f3f4.csv \
     python bench.py --steps 2 --warmup 1 --skip-cpu-baseline > gpurun_out/ncu_f3f4.log 2>&1
 tail -1 gpurun_out/ncu_f3f4.log | cut -c1-200
+echo "== bench C3 (@2x)"
+timeout 600 python bench.py --workload C3 --steps 5 --warmup 3 --skip-auto > gpurun_out/bench_c3.json 2> gpurun_out/bench_c3.err; tail -1 gpurun_out/bench_c3.err
+python -c "import json;d=json.load(open('gpurun_out/bench_c3.json'));print('C3 value',round(d['value']),'e2e',round(d['e2e']['value']),'cpu',d['cpu_baseline'],'diff',d['max_abs_diff_rgb_vs_cpu'])"
 ls -la gpurun_out
 fi
