@@ -1083,6 +1083,9 @@ constexpr int kRasterThreads = 32;
 //   1: the next chunk's op bboxes are loaded while the current chunk is drawn
 //   2: every lane loads the RasterOp of its own hit op, records are handed round by shuffles (instead of one dependent load per op)
 //   4: the first four alphas of a cached walk are loaded together before the stepping starts
+//   8: one-deep software pipeline over a walk's alphas (the next one is loaded while the current step is replayed)
+//  16: the op bboxes are prefetched two chunks ahead instead of one (needs 1)
+// (second A/B, same box, default 3 = 3.56 ms: 11 -> 3.66, 19 -> 3.61, 27 -> 3.67)
 // raster_kernel on the C2 batch: 0: 3.64 ms, 1: 3.60, 2: 3.57, 4: 3.82, 5: 3.94, 7: 3.92 -- the alpha preload costs more
 // instructions (predicated loads + the unrolled replay) than the latency it hides
 // OSMR_ITEM_PER_SIDE 1: a raster work item is one (main step, side) pair, 0: one main step whose two perpendiculars share the
@@ -1293,6 +1296,10 @@ __device__ __forceinline__ unsigned cover_walk(double* alpha_out, unsigned S, co
 // line_cover_kernel: one warp per visible line op (dynamic fetch).  32 segment records at a time; their
 // (main step, direction) pairs are spread over the lanes, every lane evaluates its walk(s) to the end.
 // ------------------------------------------------------------------------------------------------------
+#ifndef OSMR_COVER_BATCH
+#define OSMR_COVER_BATCH 2  // 4: 1.594 ms, 2: 1.569, 1: 1.571 (C2 batch, same box)
+#endif
+constexpr unsigned kCoverBatch = OSMR_COVER_BATCH;  // work items a warp takes per cursor atomic
 constexpr int kCoverThreads = 128;
 constexpr int kCoverWarps = kCoverThreads / 32;
 
@@ -1315,9 +1322,9 @@ __global__ void __launch_bounds__(kCoverThreads, OSMR_COVER_MIN_BLOCKS) line_cov
     unsigned wi = 0, wi_end = 0;
     for (;; ++wi) {
         if (wi >= wi_end) {
-            if (lane == 0) wi = atomicAdd(&s.counters[CNT_LINE_CURSOR], kWorkBatch);
+            if (lane == 0) wi = atomicAdd(&s.counters[CNT_LINE_CURSOR], kCoverBatch);
             wi = __shfl_sync(0xffffffffu, wi, 0);
-            wi_end = wi + kWorkBatch;
+            wi_end = wi + kCoverBatch;
         }
         if (wi >= n_work) break;
         const uint2 item = s.line_work[wi];  // (op, batch of 32 segment records)
@@ -1492,8 +1499,18 @@ __device__ __forceinline__ void gather_walk(unsigned long long* plane, unsigned*
         if ((unsigned)i >= len) return;
         if (!visit(a_pre[i])) return;
     }
+#if OSMR_RASTER_PREFETCH & 8
+    if ((unsigned)kPre >= len) return;
+    double a_cur = alpha[kPre];  // software pipeline: the next step's alpha is in flight while this step is replayed
+    for (unsigned t = kPre; t < len; ++t) {
+        const double a_nxt = t + 1 < len ? alpha[t + 1] : 0.0;
+        if (!visit(a_cur)) return;
+        a_cur = a_nxt;
+    }
+#else
     for (unsigned t = kPre; t < len; ++t)
         if (!visit(alpha[t])) return;
+#endif
 }
 
 __global__ void __launch_bounds__(kRasterThreads, OSMR_RASTER_MIN_BLOCKS) raster_kernel(Scene s) {
@@ -1533,10 +1550,18 @@ __global__ void __launch_bounds__(kRasterThreads, OSMR_RASTER_MIN_BLOCKS) raster
     const unsigned n_vis = s.vis_count[3u * tile + the_pass];
     short4 o_next = make_short4(0, 0, -1, -1);  // the next chunk's bboxes are in flight while this chunk is drawn
     if (lane < n_vis) o_next = vbb[lane];
+#if OSMR_RASTER_PREFETCH & 16
+    short4 o_next2 = make_short4(0, 0, -1, -1);
+    if (lane + 32 < n_vis) o_next2 = vbb[lane + 32];
+#endif
     for (unsigned chunk = 0; chunk < n_vis; chunk += 32) {
         // ---- the ops of this chunk whose reach bbox meets my block, in order ----
         unsigned vi = chunk + lane;
-#if OSMR_RASTER_PREFETCH & 1
+#if (OSMR_RASTER_PREFETCH & 17) == 17
+        const short4 o = o_next;
+        o_next = o_next2;
+        if (vi + 64 < n_vis) o_next2 = vbb[vi + 64];
+#elif OSMR_RASTER_PREFETCH & 1
         const short4 o = o_next;
         if (vi + 32 < n_vis) o_next = vbb[vi + 32];
 #else
