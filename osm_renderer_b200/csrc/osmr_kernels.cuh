@@ -1079,29 +1079,12 @@ constexpr int kBH = OSMR_BH;
 constexpr int kBP = kBW * kBH;
 static_assert((kBW == 16 || kBW == 32) && kBP % 32 == 0 && 256 % kBW == 0 && 256 % kBH == 0, "block shape");
 constexpr int kRasterThreads = 32;
-// prefetching in raster_kernel (bit mask; A/B measured on the C2 batch):
-//   1: the next chunk's op bboxes are loaded while the current chunk is drawn
-//   2: every lane loads the RasterOp of its own hit op, records are handed round by shuffles (instead of one dependent load per op)
-//   4: the first four alphas of a cached walk are loaded together before the stepping starts
-//   8: one-deep software pipeline over a walk's alphas (the next one is loaded while the current step is replayed)
-//  16: the op bboxes are prefetched two chunks ahead instead of one (needs 1)
-// (second A/B, same box, default 3 = 3.56 ms: 11 -> 3.66, 19 -> 3.61, 27 -> 3.67)
-// raster_kernel on the C2 batch: 0: 3.64 ms, 1: 3.60, 2: 3.57, 4: 3.82, 5: 3.94, 7: 3.92 -- the alpha preload costs more
-// instructions (predicated loads + the unrolled replay) than the latency it hides
-// OSMR_ITEM_PER_SIDE 1: a raster work item is one (main step, side) pair, 0: one main step whose two perpendiculars share the
-// set-up (half the set-ups, but half the lanes busy when an op reaches the block with few steps)
-// (C2 batch, same box: 1: 3.84 ms, 0: 3.79 ms)
-#ifndef OSMR_ITEM_PER_SIDE
-#define OSMR_ITEM_PER_SIDE 0
-#endif
-// OSMR_DIRTY_ROWS 1: the blend of a line op sweeps only the plane rows the op wrote (measured: the extra shared-memory
-// atomic per written pixel costs more than the skipped rows save: 3.84 ms with, 3.62 ms without)
-#ifndef OSMR_DIRTY_ROWS
-#define OSMR_DIRTY_ROWS 0
-#endif
-#ifndef OSMR_RASTER_PREFETCH
-#define OSMR_RASTER_PREFETCH 3
-#endif
+// Measured variants of raster_kernel (same-box A/B on the C2 batch, default 3.56 ms) that are NOT in the code any
+// more: preloading a walk's first four alphas (3.82 ms) or pipelining them one deep (3.66), prefetching the op bboxes two
+// chunks ahead (3.61), tracking the plane rows a line op wrote for the blend (+0.22 ms), one work item per (step, side)
+// instead of per step (+0.05 ms), 16x8 / 32x8 / 32x16 blocks (3.97 / 3.95 / 4.80).  What stayed: the next chunk's bboxes
+// are loaded while the current chunk is drawn (3.64 -> 3.60) and every lane loads the RasterOp of its own hit op, the
+// records being handed round by shuffles (-> 3.57).
 #ifndef OSMR_RASTER_MIN_BLOCKS
 #define OSMR_RASTER_MIN_BLOCKS 24  // resident one-warp CTAs per SM the register allocation must allow (16: 4.5 ms, 20: 4.06, 24: 3.66)
 #endif
@@ -1159,31 +1142,16 @@ struct SegConst {
     bool small;  // all coordinates < 2^24: `raw as f64` can be carried exactly in f64
 };
 
-// Interior classification under round dash caps (OSMR_DASH_INTERIOR).  With LineCap::Round the half width of a dashed line
-// depends on the distance to the nearest dash (opacity_calculator.rs:62-96), so every pixel needs the dash phase: two square
-// roots, a division and an exact `%` (line.rs:108-114) before the dash loop.  For a pixel well inside the line the result is
-// nevertheless a per-op constant, and a conservative test on APPROXIMATE quantities proves it:
-//   d~  = (traveled + |dot(p - p1, dir)| / denom) mod total      (= dist_rem up to eps, Pythagoras: long^2 - centre^2 = along^2)
-//   eps = |p - p1|^2 * 2^-49 / along + 4e-8                        (bound of the reference's own rounding in sqrt(long^2 - centre^2))
-//   if d~ lies in the flat part (start_to, end_from) of a dash segment by more than eps, that segment matches with base = 1;
-//   its cap distance (+ eps) bounds the minimum `cap` from above, hence sqrt(hw^2 - cap^2) from below; if that lower bound
-//   is >= 0.5 and centre distance + 0.5 is below it (relative margins 1e-9), the reference takes
-//   sd_opacity = opacity_mul (all segments share it, checked per op), centre opacity = 1.0 * 1.0, so
-//   opacity = min(opacity_mul, 1.0) and is_in_line = true -- exactly, because every comparison it makes has that margin.
-// Anything else (feather zone, ramps, phase near a wrap, long segments where eps is not small) takes the reference's path.
-// MEASURED AND SWITCHED OFF: bit-exact on the whole suite and 41 % of the dashed evaluations of the C2 batch qualify, but the
-// lanes of a warp rarely qualify together, so the warp pays the test AND the reference path: line_cover_kernel 1.60 ms
-// without, 2.52 ms with (B200, same box).  Kept as a record of the bound derivation.
-#ifndef OSMR_DASH_INTERIOR
-#define OSMR_DASH_INTERIOR 0
-#endif
+// (An interior classification under round dash caps -- approximate dash phase with an error bound, proving that a pixel well
+// inside the line gets opacity_mul without the two square roots, the division and the exact `%` -- was derived, verified
+// bit-exact on the whole suite and removed again: 41 % of the dashed evaluations qualify, but the lanes of a warp rarely
+// qualify together, so the warp paid the test and the reference path: line_cover_kernel 1.60 -> 2.52 ms.  DESIGN.md 4.)
 
 // draw_one_perpendicular (line.rs:89-131): evaluates the walk from its start until the first pixel that is not in the
 // line (or until it has left the tile for good on its monotone axis) and stores the alpha of every in-line step.
 // Returns the number of steps stored (<= S).
 __device__ __forceinline__ unsigned cover_walk(double* alpha_out, unsigned S, const WalkItem& w, const SegConst& sc, const OpacityCalc& calc,
-                                               int mn, int p_error, int mul, double opacity0, int D, unsigned* trunc_flag,
-                                               double uniform_mul) {
+                                               int mn, int p_error, int mul, double opacity0, int D, unsigned* trunc_flag) {
     int p_mn = w.mx;
     int p_mx = mn;
     int err = mul * p_error;  // i32 like the reference (line.rs:80-91)
@@ -1208,12 +1176,6 @@ __device__ __forceinline__ unsigned cover_walk(double* alpha_out, unsigned S, co
     const bool quick = !(dashed && calc.round_caps);
     const double t_in = calc.feather_from * sc.denom * (1.0 - 9.0e-13);
     const double t_out = calc.feather_to * sc.denom * (1.0 + 9.0e-13);
-    // interior classification under round dash caps: only when every dash segment has the same opacity_mul (uniform_mul is
-    // NaN otherwise), the phase cannot lose precision (traveled < 2^24) and the segment is short enough for eps to be small
-    const bool interior_ok = OSMR_DASH_INTERIOR && !quick && uniform_mul == uniform_mul && sc.small && sc.traveled < 16777216.0 &&
-                             sc.denom < 60000.0 && calc.total_dash_len > 0.0;
-    const double inv_denom = interior_ok ? 1.0 / sc.denom : 0.0;
-    const double hw_sq = calc.half_line_width * calc.half_line_width;
     unsigned t = 0;
     for (;;) {
         if (step > 0 ? (p_mx > D - 1) : (p_mx < 0)) break;
@@ -1230,46 +1192,14 @@ __device__ __forceinline__ unsigned cover_walk(double* alpha_out, unsigned S, co
             in_line = false;
             opacity = 0.0;
         } else {
-            bool decided = false;
-            if (interior_ok) {
-                const int px = w.swap ? p_mn : p_mx, py = w.swap ? p_mx : p_mn;
-                const double ex = (double)(px - sc.x1), ey = (double)(py - sc.y1);  // exact: coordinates below 2^24
-                const double along = fabs(ex * (double)sc.sdx + ey * (double)sc.sdy) * inv_denom;
-                if (along >= 0.0625) {
-                    const double eps = (ex * ex + ey * ey) * 1.7763568394002505e-15 / along + 4.0e-8;  // 2^-49
-                    const double dist = sc.traveled + along;
-                    const double q = floor(dist * calc.inv_total);
-                    const double d = __fma_rn(-q, calc.total_dash_len, dist);
-                    if (eps < 1.0e-3 && d > eps && d < calc.total_dash_len - eps) {
-                        const double cd_hi = araw * inv_denom * (1.0 + 1.0e-9) + 0.5 + 1.0e-9;
-                        for (int i = 0; i < calc.n_segs; ++i) {
-                            const DashSeg& sg = calc.segs[i];
-                            if (d > sg.start_to + eps && d < sg.end_from - eps) {
-                                const double cap_hi = fmax(fmax(sg.orig_a - d, d - sg.orig_b), 0.0) + eps;
-                                const double hw2_lo = (hw_sq - cap_hi * cap_hi) * (1.0 - 1.0e-9);
-                                if (hw2_lo >= 0.26 && cd_hi * cd_hi < hw2_lo) {
-                                    opacity = fmin(uniform_mul, 1.0);
-                                    in_line = true;
-                                    decided = true;
-                                    OSMR_COUNT("cover.dash_interior", 1);
-                                }
-                                break;
-                            }
-                        }
-                    }
-                }
+            double center_dist = div_pos_peeled(araw, sc.denom);
+            double short_start = 0.0;
+            if (dashed) {
+                int px = w.swap ? p_mn : p_mx, py = w.swap ? p_mx : p_mn;
+                double long_start = point_dist(px, py, sc.x1, sc.y1);
+                short_start = sqrt_peeled(fmax(long_start * long_start - center_dist * center_dist, 0.0));
             }
-            if (!decided) {
-                double center_dist = div_pos_peeled(araw, sc.denom);
-                double short_start = 0.0;
-                if (dashed) {
-                    int px = w.swap ? p_mn : p_mx, py = w.swap ? p_mx : p_mn;
-                    double long_start = point_dist(px, py, sc.x1, sc.y1);
-                    short_start = sqrt_peeled(fmax(long_start * long_start - center_dist * center_dist, 0.0));
-                }
-                calc_opacity(calc, sc.traveled, center_dist, short_start, opacity, in_line);
-                OSMR_COUNT("cover.slow_path", 1);
-            }
+            calc_opacity(calc, sc.traveled, center_dist, short_start, opacity, in_line);
         }
         OSMR_COUNT("cover.steps_evaluated", 1);
         if (!in_line) break;
@@ -1353,15 +1283,6 @@ __global__ void __launch_bounds__(kCoverThreads, OSMR_COVER_MIN_BLOCKS) line_cov
             for (unsigned u = lane; u < n_main; u += 32) dst0[u] = src[u];
             if (lane < kCapCalcUnits) dst1[lane] = src[kMainCalcUnits + lane];
         }
-        __syncwarp();
-        // common opacity_mul of the op's dash segments (NaN: they differ, or there are none)
-        double uniform_mul = __longlong_as_double(0x7ff8000000000000LL);
-        if (sm.calc[0].n_segs > 0 && sm.calc[0].round_caps) {
-            uniform_mul = sm.calc[0].segs[0].opacity_mul;
-            for (int i = 1; i < sm.calc[0].n_segs; ++i)
-                if (sm.calc[0].segs[i].opacity_mul != uniform_mul) uniform_mul = __longlong_as_double(0x7ff8000000000000LL);
-            if (!(uniform_mul >= 0.0)) uniform_mul = __longlong_as_double(0x7ff8000000000000LL);
-        }
         {
             const unsigned sb = 32u * item.y;
             const unsigned si = sb + lane;
@@ -1415,14 +1336,12 @@ __global__ void __launch_bounds__(kCoverThreads, OSMR_COVER_MIN_BLOCKS) line_cov
                 int mn = w.mn, p_error = w.p_error;
                 unsigned len0 = 0, len1 = 0;
                 if (mn >= -reach && mn <= D - 1 + reach)
-                    len0 = cover_walk(alpha_out, S, w, sc, calc, mn, p_error, mul, lp.opacity, D, &s.counters[CNT_WALK_TRUNC],
-                                      (h.flags & 1u) ? __longlong_as_double(0x7ff8000000000000LL) : uniform_mul);
+                    len0 = cover_walk(alpha_out, S, w, sc, calc, mn, p_error, mul, lp.opacity, D, &s.counters[CNT_WALK_TRUNC]);
                 if (w.extra) {
                     p_error = wadd(wsub(p_error, 2 * w.mx_d), 2 * w.mn_d);
                     mn += w.mn_inc;
                     if (mn >= -reach && mn <= D - 1 + reach)
-                        len1 = cover_walk(alpha_out + extra_at * S, S, w, sc, calc, mn, p_error, mul, lp.opacity, D, &s.counters[CNT_WALK_TRUNC],
-                                          (h.flags & 1u) ? __longlong_as_double(0x7ff8000000000000LL) : uniform_mul);
+                        len1 = cover_walk(alpha_out + extra_at * S, S, w, sc, calc, mn, p_error, mul, lp.opacity, D, &s.counters[CNT_WALK_TRUNC]);
                     if (len1) len_out[extra_at] = (unsigned char)len1;
                 }
                 len_out[0] = (unsigned char)(len0 | (len1 ? 0x80u : 0u));  // bit 7: the extra walk has steps
@@ -1454,18 +1373,12 @@ struct RasterSmem {
     unsigned long long plane[kBP];
     SegHit hits[32];
     unsigned pre[32];
-    unsigned dirty;  // rows of the alpha plane the current line op has written (bit = row): the blend sweeps only those
 };
 
 // Replays the integer stepping of one cached walk (line.rs:82-96,120-130) and max-combines the alphas of the steps
-// that fall into the block.  The first alphas of the walk are fetched together before the stepping starts: independent
-// loads instead of one exposed memory latency per step (walks are 2-4 steps long for ordinary street widths).
-__device__ __forceinline__ void gather_walk(unsigned long long* plane, unsigned* dirty, const double* __restrict__ alpha, unsigned len,
-                                            const WalkItem& w, int mn, int p_error, int mul, int bx0, int by0) {
-    constexpr int kPre = (OSMR_RASTER_PREFETCH & 4) ? 4 : 0;
-    double a_pre[kPre + 1];
-#pragma unroll
-    for (int i = 0; i < kPre; ++i) a_pre[i] = (unsigned)i < len ? alpha[i] : 0.0;
+// that fall into the block.
+__device__ __forceinline__ void gather_walk(unsigned long long* plane, const double* __restrict__ alpha, unsigned len, const WalkItem& w,
+                                            int mn, int p_error, int mul, int bx0, int by0) {
     int p_mn = w.mx;
     int p_mx = mn;
     int err = mul * p_error;
@@ -1473,17 +1386,15 @@ __device__ __forceinline__ void gather_walk(unsigned long long* plane, unsigned*
     const int corr = -mul * w.mx_inc;
     const int lo = w.swap ? by0 : bx0;
     const int hi = lo + (w.swap ? kBH : kBW) - 1;
-    auto visit = [&](double a) -> bool {  // false: the walk has left the block on its monotone axis and never comes back
-        if (step > 0 ? (p_mx > hi) : (p_mx < lo)) return false;
+    for (unsigned t = 0; t < len; ++t) {
+        if (step > 0 ? (p_mx > hi) : (p_mx < lo)) return;  // left the block on the monotone axis: never comes back
         const int lx = (w.swap ? p_mn : p_mx) - bx0, ly = (w.swap ? p_mx : p_mn) - by0;
         if ((unsigned)lx < (unsigned)kBW && (unsigned)ly < (unsigned)kBH) {
             OSMR_COUNT("raster.steps_in_block", 1);
+            const double a = alpha[t];
             const unsigned long long bits = (unsigned long long)__double_as_longlong(a);
             unsigned long long* cell = &plane[ly * kBW + lx];
-            if (a > 0.0 && bits > *cell) {
-                atomicMax(cell, bits);
-                if (OSMR_DIRTY_ROWS && !((*dirty >> ly) & 1u)) atomicOr(dirty, 1u << ly);
-            }
+            if (a > 0.0 && bits > *cell) atomicMax(cell, bits);
         }
         OSMR_COUNT("raster.steps_replayed", 1);
         if (wadd(err, 2 * w.mn_d) > w.mx_d) {
@@ -1492,25 +1403,7 @@ __device__ __forceinline__ void gather_walk(unsigned long long* plane, unsigned*
         }
         err = wadd(err, 2 * w.mn_d);
         p_mx += step;
-        return true;
-    };
-#pragma unroll
-    for (int i = 0; i < kPre; ++i) {
-        if ((unsigned)i >= len) return;
-        if (!visit(a_pre[i])) return;
     }
-#if OSMR_RASTER_PREFETCH & 8
-    if ((unsigned)kPre >= len) return;
-    double a_cur = alpha[kPre];  // software pipeline: the next step's alpha is in flight while this step is replayed
-    for (unsigned t = kPre; t < len; ++t) {
-        const double a_nxt = t + 1 < len ? alpha[t + 1] : 0.0;
-        if (!visit(a_cur)) return;
-        a_cur = a_nxt;
-    }
-#else
-    for (unsigned t = kPre; t < len; ++t)
-        if (!visit(alpha[t])) return;
-#endif
 }
 
 __global__ void __launch_bounds__(kRasterThreads, OSMR_RASTER_MIN_BLOCKS) raster_kernel(Scene s) {
@@ -1550,48 +1443,24 @@ __global__ void __launch_bounds__(kRasterThreads, OSMR_RASTER_MIN_BLOCKS) raster
     const unsigned n_vis = s.vis_count[3u * tile + the_pass];
     short4 o_next = make_short4(0, 0, -1, -1);  // the next chunk's bboxes are in flight while this chunk is drawn
     if (lane < n_vis) o_next = vbb[lane];
-#if OSMR_RASTER_PREFETCH & 16
-    short4 o_next2 = make_short4(0, 0, -1, -1);
-    if (lane + 32 < n_vis) o_next2 = vbb[lane + 32];
-#endif
     for (unsigned chunk = 0; chunk < n_vis; chunk += 32) {
         // ---- the ops of this chunk whose reach bbox meets my block, in order ----
         unsigned vi = chunk + lane;
-#if (OSMR_RASTER_PREFETCH & 17) == 17
-        const short4 o = o_next;
-        o_next = o_next2;
-        if (vi + 64 < n_vis) o_next2 = vbb[vi + 64];
-#elif OSMR_RASTER_PREFETCH & 1
         const short4 o = o_next;
         if (vi + 32 < n_vis) o_next = vbb[vi + 32];
-#else
-        const short4 o = vi < n_vis ? vbb[vi] : o_next;
-#endif
         const bool hit = vi < n_vis && o.x <= bx0 + kBW - 1 && o.z >= bx0 && o.y <= by0 + kBH - 1 && o.w >= by0;
         // every lane fetches the record of ITS op now (independent loads); the records are handed round by shuffles
         uint4 my_rop0 = make_uint4(0, 0, 0, 0), my_rop1 = make_uint4(0, 0, 0, 0);
-#if OSMR_RASTER_PREFETCH & 2
         if (hit) {
             const uint4* src = reinterpret_cast<const uint4*>(&rops[vi]);
             my_rop0 = src[0];
             my_rop1 = src[1];
         }
-#endif
         unsigned todo = __ballot_sync(0xffffffffu, hit);
         while (todo) {
             const unsigned qi = chunk + (unsigned)(__ffs(todo) - 1);
             todo &= todo - 1;
             RasterOp op;
-#if !(OSMR_RASTER_PREFETCH & 2)
-            {
-                const uint4* src = reinterpret_cast<const uint4*>(&rops[qi]);
-                uint4* dst = reinterpret_cast<uint4*>(&op);
-                dst[0] = src[0];
-                dst[1] = src[1];
-                (void)my_rop0;
-                (void)my_rop1;
-            }
-#else
             {
                 const int from = (int)(qi - chunk);
                 uint4 r0, r1;
@@ -1607,7 +1476,6 @@ __global__ void __launch_bounds__(kRasterThreads, OSMR_RASTER_MIN_BLOCKS) raster
                 dst[0] = r0;
                 dst[1] = r1;
             }
-#endif
 
             if (op.kind != OP_LINE) {
                 // ---------------- fill: blend straight from the row masks ----------------
@@ -1660,8 +1528,6 @@ __global__ void __launch_bounds__(kRasterThreads, OSMR_RASTER_MIN_BLOCKS) raster
             const SegRec* segs = reinterpret_cast<const SegRec*>(s.geom + op.a);
             const unsigned n_seg = op.b;
             bool any = false;
-            if (lane == 0) sm.dirty = 0u;
-            __syncwarp();
             for (unsigned sb = 0; sb < n_seg; sb += 32) {
                 // one segment per lane: can any of its perpendiculars reach my block?
                 unsigned si = sb + lane;
@@ -1697,7 +1563,7 @@ __global__ void __launch_bounds__(kRasterThreads, OSMR_RASTER_MIN_BLOCKS) raster
                         if (ka < c0) ka = c0;
                         if (kb > c1) kb = c1;
                         if (kb >= ka) {
-                            items = (OSMR_ITEM_PER_SIDE ? 2u : 1u) * (unsigned)(kb - ka + 1);
+                            items = (unsigned)(kb - ka + 1);  // one work item per main step: its two perpendiculars share the set-up
                             hrec.x1 = sr.x;
                             hrec.y1 = sr.y;
                             hrec.x2 = sr.z;
@@ -1738,26 +1604,17 @@ __global__ void __launch_bounds__(kRasterThreads, OSMR_RASTER_MIN_BLOCKS) raster
                     }
                     const SegHit& h = sm.hits[lo];
                     const unsigned local = item - sm.pre[lo];
-#if OSMR_ITEM_PER_SIDE
-                    const int k = h.ka + (int)(local >> 1);
-                    const unsigned side0 = local & 1u, side1 = side0 + 1u;
-                    const unsigned long long widx0 = 2ull * (unsigned long long)(k - h.k0);  // walk (k, +); (k, -) follows
-                    // steps of the regular walk | 0x80: the extra one has steps
-                    const unsigned lens2 = (unsigned)s.walk_len[h.len_off + widx0 + side0] << (8u * side0);
-#else
                     const int k = h.ka + (int)local;
-                    const unsigned side0 = 0u, side1 = 2u;
                     const unsigned long long widx0 = 2ull * (unsigned long long)(k - h.k0);
                     // the two regular walks of the step: two adjacent bytes, 2-byte aligned
                     const unsigned lens2 = *reinterpret_cast<const unsigned short*>(s.walk_len + h.len_off + widx0);
-#endif
                     OSMR_COUNT("raster.items", 1);
                     if (!lens2) continue;
                     WalkItem w;
                     walk_item_setup(h.x1, h.y1, h.x2, h.y2, h.flags, h.magic, k, w);
                     const int blo = (w.swap ? by0 : bx0) + rlo, bhi = (w.swap ? by0 + kBH : bx0 + kBW) - 1 + rhi;
 #pragma unroll 1
-                    for (unsigned side = side0; side < side1; ++side) {
+                    for (unsigned side = 0; side < 2u; ++side) {
                         const unsigned lens = (lens2 >> (8u * side)) & 0xffu;
                         if (!lens) continue;
                         const int mul = side ? -1 : 1;
@@ -1765,13 +1622,13 @@ __global__ void __launch_bounds__(kRasterThreads, OSMR_RASTER_MIN_BLOCKS) raster
                         const double* alpha = s.walk_alpha + h.alpha_off + widx * S;
                         int mn = w.mn, p_error = w.p_error;
                         // minor-axis cull: a walk starts at mn and moves away from it, at most `reach` pixels
-                        if ((lens & 0x7fu) && mn >= blo && mn <= bhi) gather_walk(sm.plane, &sm.dirty, alpha, lens & 0x7fu, w, mn, p_error, mul, bx0, by0);
+                        if ((lens & 0x7fu) && mn >= blo && mn <= bhi) gather_walk(sm.plane, alpha, lens & 0x7fu, w, mn, p_error, mul, bx0, by0);
                         if (lens & 0x80u) {  // the extra perpendicular of a double correction (line.rs:150-155)
                             const unsigned long long extra_at = 2ull * (h.flags >> 8);
                             const unsigned len1 = s.walk_len[h.len_off + extra_at + widx];
                             p_error = wadd(wsub(p_error, 2 * w.mx_d), 2 * w.mn_d);
                             mn += w.mn_inc;
-                            if (mn >= blo && mn <= bhi) gather_walk(sm.plane, &sm.dirty, alpha + extra_at * S, len1, w, mn, p_error, mul, bx0, by0);
+                            if (mn >= blo && mn <= bhi) gather_walk(sm.plane, alpha + extra_at * S, len1, w, mn, p_error, mul, bx0, by0);
                         }
                     }
                 }
@@ -1781,11 +1638,8 @@ __global__ void __launch_bounds__(kRasterThreads, OSMR_RASTER_MIN_BLOCKS) raster
                 // blend: pending pixel = from_color(color, alpha_max) (tile_pixels.rs:13-22), then over
                 double cn[3];
                 for (int k = 0; k < 3; ++k) cn[k] = unit_of_u8(op.rgb[k]);
-                const unsigned dirty = OSMR_DIRTY_ROWS ? sm.dirty : 0xffffffffu;
-                constexpr int kRowsPerIter = 32 / kBW;  // plane rows one sweep iteration covers
 #pragma unroll 2
                 for (int j = 0; j < kBP / 32; ++j) {
-                    if (!((dirty >> (j * kRowsPerIter)) & ((1u << kRowsPerIter) - 1u))) continue;  // untouched rows
                     const int idx = j * 32 + (int)lane;
                     unsigned long long bits = sm.plane[idx];
                     if (bits) {

@@ -24,3 +24,40 @@ def test_emulated_kernels_equal_oracle(args):
     assert res.returncode == 0, res.stdout + res.stderr
     assert "differing pixels vs oracle: 0" in res.stdout
     assert "[emu]" not in res.stderr, res.stderr  # divergent collective / deadlock reports
+
+
+def _run(script_args, timeout=900):
+    sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+    import build_emu
+
+    build_emu.build()
+    return subprocess.run([sys.executable] + script_args, capture_output=True, text=True, timeout=timeout)
+
+
+def test_emulated_device_side_lists_equal_host_lists():
+    """f3 (osmr_draw_tiles_auto) on the emulator: same pixels and the same relative order as the host-built lists."""
+    res = _run([os.path.join(ROOT, "tests", "emu", "run_auto.py"), "17", "4"])
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "order violations 0, differing pixels auto vs host lists: 0" in res.stdout
+    assert "[emu]" not in res.stderr, res.stderr
+
+
+def test_emulated_png_encoder_round_trips():
+    """f4 (osmr_draw_tiles_png) on the emulator: the files pass a strict decoder and decode to the RGB tiles."""
+    code = (
+        "import sys, os, numpy as np\n"
+        f"sys.path[:0] = [{ROOT!r}, {os.path.join(ROOT, 'tests')!r}, {os.path.join(ROOT, 'tests', 'emu')!r}]\n"
+        "from run_emu import emu_context\n"
+        "from conftest import FixtureInputs\n"
+        "from test_gpu_png import decode_png\n"
+        "fx = FixtureInputs(); ctx = emu_context(); ctx.set_geodata(fx.bin); ctx.set_table(fx.table)\n"
+        "tiles, begins, areas = fx.batches['17']\n"
+        "n = 2\n"
+        "want = ctx.draw_tiles(tiles[:n], begins[:n + 1], areas[:begins[n]], fx.canvas_rgb, True)\n"
+        "files = ctx.draw_tiles_png(tiles[:n], begins[:n + 1], areas[:begins[n]], fx.canvas_rgb, True)\n"
+        "assert all((decode_png(f) == w).all() for f, w in zip(files, want))\n"
+        "print('png ok', [len(f) for f in files])\n"
+    )
+    res = _run(["-c", code])
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "png ok" in res.stdout
