@@ -224,7 +224,7 @@ def main():
             return
         w = build_workload(args.workload)
         threads = host_threads()
-        sample = args.cpu_sample or max(threads, 16)
+        sample = args.cpu_sample or min(n * n, max(16 * threads, 256))  # several tiles per thread: the threads stay busy
         for _ in range(max(0, min(args.warmup, 1))):
             cpu_port_throughput(w, min(sample, threads), threads)
         t_tot, n_tot = 0.0, 0
