@@ -261,6 +261,9 @@ def main():
 
     dist = None
     if world > 1:
+        # NCCL prints its version banner to STDOUT at NCCL_DEBUG >= VERSION; stdout carries exactly one JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+            os.environ["NCCL_DEBUG"] = "NONE"
         import torch.distributed as dist_mod
 
         dist = dist_mod
