@@ -261,12 +261,19 @@ int osmr_draw_tiles_png(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles,
 void* osmr_alloc_pinned(size_t bytes);
 void osmr_free_pinned(void* p);
 
-/* Test hook: "fill_cap" (0..128) lowers the number of row spans ranked in shared memory so that the
- * order-free streaming form of the even-odd rule is exercised on ordinary data; "scratch_units" restarts the
- * bump-allocated geometry / mask scratch at that many units so the grow-and-redo path runs. */
+/* Test / measurement hooks (never needed for correct results):
+ *   "fill_cap" (0..128)     lowers the number of row spans ranked in shared memory so that the order-free streaming form
+ *                           of the even-odd rule is exercised on ordinary data (also switches the row-parallel path off);
+ *   "scratch_units" (n)     restarts the bump-allocated geometry / mask / walk-cache scratch at n units and "work_items" (n)
+ *                           pretends the per-op work lists hold n items, so the grow-and-redo paths run;
+ *   "label_threads" (1..256) host threads of the label layout;
+ *   "host_chunks" (0..16)   equal draw chunks of a host-output call (0: the tapered default schedule);
+ *   "two_streams" (0/1)     draw chunks alternate between two compute streams (default 1);
+ *   "resident_chunks" (1..16) draw chunks when the output stays in HBM (default 1);
+ *   "direct_out" (0/1)      raster_kernel stores the tiles straight into a page-locked `out` (default 0: staged D2H). */
 int osmr_debug_set(osmr_ctx* ctx, const char* key, int value);
 
-uint32_t osmr_abi_version(void); /* 2: osmr_stats gained walk_bytes / ms_cover */
+uint32_t osmr_abi_version(void); /* 2: osmr_stats gained walk_bytes / walk_steps / ms_cover / ms_auto / ms_png; f3 and f4 entry points */
 
 #ifdef __cplusplus
 }
