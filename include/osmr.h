@@ -256,6 +256,11 @@ int osmr_draw_tiles_png(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles,
                         const osmr_styled_area* areas, const uint8_t canvas_rgb[3], uint32_t flags, uint8_t* png_out, size_t png_cap,
                         uint64_t* png_offset /* n_tiles + 1 */);
 
+/* rgb_triples_to_png itself (png_writer.rs:4-21) for images the caller already holds: n_images RGB images of
+ * (256 * scale)^2 pixels, tightly packed in host memory -> packed PNG files as in osmr_draw_tiles_png. */
+int osmr_rgb_to_png(osmr_ctx* ctx, const uint8_t* rgb, uint32_t n_images, uint32_t scale, uint8_t* png_out, size_t png_cap,
+                    uint64_t* png_offset /* n_images + 1 */);
+
 /* Optional page-locked host memory for callers that want full-speed host<->device copies of `out` / batch
  * arrays (plain malloc'ed buffers work too, at pageable-copy speed). */
 void* osmr_alloc_pinned(size_t bytes);

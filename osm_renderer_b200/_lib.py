@@ -39,6 +39,7 @@ EXPORTS = [
     "osmr_auto_readback",
     "osmr_png_bound",
     "osmr_draw_tiles_png",
+    "osmr_rgb_to_png",
 ]
 
 _lib = None
@@ -110,5 +111,7 @@ def load():
     L.osmr_png_bound.argtypes = [u32]
     L.osmr_draw_tiles_png.restype = C.c_int
     L.osmr_draw_tiles_png.argtypes = [vp, vp, u32, vp, vp, vp, u32, vp, sz, vp]
+    L.osmr_rgb_to_png.restype = C.c_int
+    L.osmr_rgb_to_png.argtypes = [vp, vp, u32, u32, vp, sz, vp]
     _lib = L
     return L

@@ -1321,19 +1321,12 @@ size_t osmr_png_bound(uint32_t scale) {
     return (size_t)kPngFixed + (size_t)kPngBands * png_band_cap_words(scale) * 4u;
 }
 
-int osmr_draw_tiles_png(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, const uint32_t* area_begin, const osmr_styled_area* areas,
-                        const uint8_t canvas_rgb[3], uint32_t flags, uint8_t* png_out, size_t png_cap, uint64_t* png_offset) {
-    if (!ctx) return OSMR_E_INVALID;
-    if (!png_out || !png_offset) return ctx->fail(OSMR_E_INVALID, "null output buffer");
-    if (flags & (OSMR_DRAW_OUT_RGBA | OSMR_DRAW_OUT_DEVICE)) return ctx->fail(OSMR_E_INVALID, "osmr_draw_tiles_png encodes RGB into host memory");
-    int rc = batch_upload_impl(ctx, tiles, n_tiles, area_begin, areas, false, nullptr);
-    if (rc) return rc;
-    rc = osmr_batch_draw(ctx, canvas_rgb, flags, nullptr, nullptr);  // the RGB tiles stay in HBM (ctx->out)
-    if (rc) return rc;
+// n_tiles RGB images of (256 * scale)^2 pixels in HBM -> packed PNG files in host memory
+static int encode_png_from_device(osmr_ctx* ctx, const unsigned char* rgb_dev, uint32_t n_tiles, unsigned scale, uint8_t* png_out,
+                                  size_t png_cap, uint64_t* png_offset) {
     cudaStream_t st = ctx->stream;
-    const unsigned scale = (unsigned)ctx->scale;
     PngScene ps{};
-    ps.rgb = ctx->out.p;
+    ps.rgb = rgb_dev;
     ps.D = 256 * (int)scale;
     ps.n_tiles = n_tiles;
     ps.band_cap_words = png_band_cap_words(scale);
@@ -1377,6 +1370,33 @@ int osmr_draw_tiles_png(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles,
     ctx->stats.ms_total += ms;
     ctx->stats.kernel_launches += 4;
     return OSMR_OK;
+}
+
+int osmr_draw_tiles_png(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, const uint32_t* area_begin, const osmr_styled_area* areas,
+                        const uint8_t canvas_rgb[3], uint32_t flags, uint8_t* png_out, size_t png_cap, uint64_t* png_offset) {
+    if (!ctx) return OSMR_E_INVALID;
+    if (!png_out || !png_offset) return ctx->fail(OSMR_E_INVALID, "null output buffer");
+    if (flags & (OSMR_DRAW_OUT_RGBA | OSMR_DRAW_OUT_DEVICE)) return ctx->fail(OSMR_E_INVALID, "osmr_draw_tiles_png encodes RGB into host memory");
+    int rc = batch_upload_impl(ctx, tiles, n_tiles, area_begin, areas, false, nullptr);
+    if (rc) return rc;
+    rc = osmr_batch_draw(ctx, canvas_rgb, flags, nullptr, nullptr);  // the RGB tiles stay in HBM (ctx->out)
+    if (rc) return rc;
+    return encode_png_from_device(ctx, ctx->out.p, n_tiles, (unsigned)ctx->scale, png_out, png_cap, png_offset);
+}
+
+int osmr_rgb_to_png(osmr_ctx* ctx, const uint8_t* rgb, uint32_t n_images, uint32_t scale, uint8_t* png_out, size_t png_cap,
+                    uint64_t* png_offset) {
+    if (!ctx) return OSMR_E_INVALID;
+    if (!rgb || !png_out || !png_offset) return ctx->fail(OSMR_E_INVALID, "null argument");
+    if (n_images == 0) return ctx->fail(OSMR_E_INVALID, "no images");
+    if (scale < 1 || scale > 8) return ctx->fail(OSMR_E_INVALID, "scale must be 1..8");
+    cudaSetDevice(ctx->device);
+    const size_t D = 256 * (size_t)scale, bytes = (size_t)n_images * D * D * 3;
+    CK(ctx->out.reserve(bytes));
+    ctx->out_bytes = bytes;
+    ctx->stats = osmr_stats{};
+    CK(cudaMemcpyAsync(ctx->out.p, rgb, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return encode_png_from_device(ctx, ctx->out.p, n_images, scale, png_out, png_cap, png_offset);
 }
 
 int osmr_get_stats(osmr_ctx* ctx, osmr_stats* out) {

@@ -252,6 +252,18 @@ class GpuContext:
         )
         return [buf[int(offs[i]) : int(offs[i + 1])].tobytes() for i in range(n)]
 
+    def rgb_to_png(self, images):
+        """osmr_rgb_to_png: uint8 [n, D, D, 3] (D = 256 * scale) -> list of PNG files (png_writer.rs:4-21)."""
+        images = np.ascontiguousarray(images, dtype=np.uint8)
+        n, d = images.shape[0], images.shape[1]
+        assert images.shape == (n, d, d, 3) and d % 256 == 0
+        scale = d // 256
+        cap = n * int(self.L.osmr_png_bound(scale))
+        buf = np.empty(cap, dtype=np.uint8)
+        offs = np.zeros(n + 1, dtype=np.uint64)
+        self._check(self.L.osmr_rgb_to_png(self.h, images.ctypes.data, n, scale, buf.ctypes.data, cap, offs.ctypes.data), "osmr_rgb_to_png")
+        return [buf[int(offs[i]) : int(offs[i + 1])].tobytes() for i in range(n)]
+
     def debug_set(self, key: str, value: int):
         self._check(self.L.osmr_debug_set(self.h, key.encode(), value), "osmr_debug_set")
 

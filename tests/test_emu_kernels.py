@@ -56,6 +56,9 @@ def test_emulated_png_encoder_round_trips():
         "want = ctx.draw_tiles(tiles[:n], begins[:n + 1], areas[:begins[n]], fx.canvas_rgb, True)\n"
         "files = ctx.draw_tiles_png(tiles[:n], begins[:n + 1], areas[:begins[n]], fx.canvas_rgb, True)\n"
         "assert all((decode_png(f) == w).all() for f, w in zip(files, want))\n"
+        "from test_gpu_png import _edge_case_images\n"
+        "imgs = _edge_case_images()\n"
+        "assert all((decode_png(f) == im).all() for f, im in zip(ctx.rgb_to_png(imgs), imgs))\n"
         "print('png ok', [len(f) for f in files])\n"
     )
     res = _run(["-c", code])

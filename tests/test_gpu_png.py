@@ -89,3 +89,42 @@ def test_png_of_noise_fits_the_bound(gpu_ctx, fx):
     for f in files:
         assert len(f) <= n
         decode_png(f)
+
+
+def _edge_case_images():
+    """256x256 images that hit the encoder's corner cases: runs of every length around the 258 limit (the tail of a run
+    shorter than 3 must become literals), runs crossing row ends, incompressible noise, a flat image, gradients that make
+    each of the four filters win somewhere."""
+    rng = np.random.default_rng(7)
+    imgs = []
+    a = np.zeros((256, 256, 3), dtype=np.uint8)  # row y: y+1 zero bytes at the start ... then a non-repeating ramp
+    ramp = (np.arange(768) * 7 % 251 + 1).astype(np.uint8)
+    for y in range(256):
+        row = ramp.copy()
+        n = 250 + y  # zero runs of 250 .. 505 bytes (after the None/Sub filter these stay runs)
+        row[: min(n, 768)] = 0
+        a[y] = row.reshape(256, 3)
+    imgs.append(a)
+    imgs.append(rng.integers(0, 256, size=(256, 256, 3), dtype=np.uint8))  # noise: every byte a literal
+    imgs.append(np.full((256, 256, 3), 200, dtype=np.uint8))  # flat
+    g = np.zeros((256, 256, 3), dtype=np.uint8)  # horizontal + vertical gradients, a checker in one band
+    g[..., 0] = np.arange(256, dtype=np.uint8)[None, :]
+    g[..., 1] = np.arange(256, dtype=np.uint8)[:, None]
+    g[64:96, :, 2] = ((np.arange(256)[None, :] // 3 + np.arange(32)[:, None]) % 2 * 255).astype(np.uint8)
+    imgs.append(g)
+    b = rng.integers(0, 256, size=(256, 256, 3), dtype=np.uint8)  # noise rows alternating with copies of the row above (Up wins)
+    b[1::2] = b[0::2]
+    imgs.append(b)
+    return np.stack(imgs)
+
+
+def test_rgb_to_png_corner_cases(gpu_ctx):
+    imgs = _edge_case_images()
+    files = gpu_ctx.rgb_to_png(imgs)
+    assert len(files) == len(imgs)
+    bound = gpu_ctx.L.osmr_png_bound(1)
+    for f, im in zip(files, imgs):
+        assert len(f) <= bound
+        assert (decode_png(f) == im).all()
+    assert len(files[2]) < 2500  # a flat image is a handful of maximal runs per row
+    assert len(files[4]) < len(files[1]) * 0.6  # the copied rows cost nothing with the Up filter
