@@ -115,8 +115,9 @@ void osmr_ctx_destroy(osmr_ctx* ctx);
 const char* osmr_last_error(const osmr_ctx* ctx);
 
 /* replaces GeodataReader::load (src/geodata/reader.rs:44-58): `bin` is the geodata file image in the
- * reference's on-disk format (saver.rs:21-165).  Node coordinates are projected on the device once
- * (a1, transcendental part) and kept resident together with the way/polygon/multipolygon tables. */
+ * reference's on-disk format (saver.rs:21-165).  The zoom-independent Mercator factor of every node (a1, transcendental
+ * part) is computed once -- with the platform libm, like the reference -- and kept resident together with the way / polygon /
+ * multipolygon tables, the entities' bounding boxes and the tile index. */
 int osmr_set_geodata(osmr_ctx* ctx, const void* bin, size_t bin_len);
 
 /* replaces IconCache for `fill-image` patterns (src/draw/icon_cache.rs:21-45, icon.rs:14-58) */
@@ -275,7 +276,9 @@ void osmr_free_pinned(void* p);
  *   "host_chunks" (0..16)   equal draw chunks of a host-output call (0: the tapered default schedule);
  *   "two_streams" (0/1)     draw chunks alternate between two compute streams (default 1);
  *   "resident_chunks" (1..16) draw chunks when the output stays in HBM (default 1);
- *   "direct_out" (0/1)      raster_kernel stores the tiles straight into a page-locked `out` (default 0: staged D2H). */
+ *   "direct_out" (0/1)      raster_kernel stores the tiles straight into a page-locked `out` (default 0: staged D2H);
+ *   "device_merc" (0/1)     per-node Mercator factors by the device's tan / log at the next osmr_set_geodata (default 0: the
+ *                           host libm, i.e. the reference's own values to the last bit). */
 int osmr_debug_set(osmr_ctx* ctx, const char* key, int value);
 
 uint32_t osmr_abi_version(void); /* 2: osmr_stats gained walk_bytes / walk_steps / ms_cover / ms_auto / ms_png; f3 and f4 entry points */

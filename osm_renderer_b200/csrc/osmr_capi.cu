@@ -192,6 +192,7 @@ struct osmr_ctx {
     int fill_cap = kFillCap;
     bool direct_out = false;  // debug key "direct_out": raster_kernel stores the tiles straight into a page-locked `out`
                               // (no D2H stage; measured slower than the staged pipeline: PCIe-bound stores, 26 GB/s)
+    bool device_merc = false;  // debug key "device_merc": Mercator factors by project_nodes_kernel instead of the host libm
     unsigned work_items_limit = 0;  // debug key "work_items": pretend the work lists are this short once (exercises their growth)
     unsigned host_chunks = 0;  // 0: tapered default schedule (plan_chunks)
     unsigned resident_chunks = 1;  // debug key "resident_chunks": draw chunks when the output stays in HBM
@@ -378,6 +379,10 @@ int osmr_debug_set(osmr_ctx* ctx, const char* key, int value) {
         ctx->host_chunks = (unsigned)value;
         return OSMR_OK;
     }
+    if (strcmp(key, "device_merc") == 0) {  // takes effect at the next osmr_set_geodata
+        ctx->device_merc = value != 0;
+        return OSMR_OK;
+    }
     if (strcmp(key, "resident_chunks") == 0) {
         if (value < 1 || value > (int)kMaxChunks) return ctx->fail(OSMR_E_INVALID, "resident_chunks must be 1..16");
         ctx->resident_chunks = (unsigned)value;
@@ -478,7 +483,34 @@ int osmr_set_geodata(osmr_ctx* ctx, const void* bin, size_t len) {
     if (n_polys) CK(cudaMemcpyAsync(ctx->polys.p, polys.data(), (size_t)n_polys * 8, cudaMemcpyHostToDevice, ctx->stream));
     if (n_mps) CK(cudaMemcpyAsync(ctx->mps.p, mps.data(), (size_t)n_mps * 8, cudaMemcpyHostToDevice, ctx->stream));
     if (n_ints) CK(cudaMemcpyAsync(ctx->ints.p, ints.data(), (size_t)n_ints * 4, cudaMemcpyHostToDevice, ctx->stream));
-    if (n_nodes) {
+    // a1, transcendental half (tile.rs:88-101 up to the zoom-independent factor), once per dataset.  By default on the HOST with
+    // the platform libm -- glibc's tan / log are what the reference (Rust f64::tan / ln on Linux) calls, so the factors are the
+    // reference's to the last bit; the device's tan / log differ from glibc's in the last place for a few arguments, which
+    // could flip the integer pixel of a node that sits within ~1e-9 px of an exact .5 tie.  Debug key "device_merc" selects
+    // project_nodes_kernel instead (0.02 ms for 1.9 M nodes; the host loop takes ~20 ms on 16 threads).
+    std::vector<double2> h_merc;
+    if (n_nodes && !ctx->device_merc) {
+        h_merc.resize(n_nodes);
+        const unsigned n_thr = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+        auto work = [&](unsigned t) {
+            const double rads_per_deg = kPi / 180.0;  // f64::to_radians
+            for (size_t i = t; i < n_nodes; i += n_thr) {
+                double lat, lon;
+                memcpy(&lat, base[0] + i * 32 + 8, 8);
+                memcpy(&lon, base[0] + i * 32 + 16, 8);
+                const double lat_rad = lat * rads_per_deg;
+                const double lon_rad = lon * rads_per_deg;
+                const double x = lon_rad + kPi;
+                const double y = kPi - std::log(std::tan((kPi / 4.0) + (lat_rad / 2.0)));
+                h_merc[i] = make_double2(x / (2.0 * kPi), y / (2.0 * kPi));
+            }
+        };
+        std::vector<std::thread> pool;
+        for (unsigned t = 1; t < n_thr; ++t) pool.emplace_back(work, t);
+        work(0);
+        for (auto& th : pool) th.join();
+        CK(cudaMemcpyAsync(ctx->merc.p, h_merc.data(), (size_t)n_nodes * sizeof(double2), cudaMemcpyHostToDevice, ctx->stream));
+    } else if (n_nodes) {
         project_nodes_kernel<<<(n_nodes + 255) / 256, 256, 0, ctx->stream>>>(raw_nodes.p, n_nodes, ctx->merc.p);
         CK(cudaGetLastError());
     }
