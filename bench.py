@@ -493,6 +493,8 @@ def main():
         "algorithmic_bytes_per_launch": int(algo_bytes),
         "kernel_ms": dom_ms,
         "kernel_share_of_step": dom_ms / (1000.0 * dev_s / args.steps),
+        # the write-only variant north_star quotes: whole-path tiles/s x 4*D^2 output bytes against the HBM peak
+        "north_star_write_frac": (value / world) * (4.0 * D * D) / (peak * 1e9),
         "note": "the path is FP64/integer-issue and shared-memory bound, not HBM bound (SURVEY.md F6); see profiles/",
     }
 
