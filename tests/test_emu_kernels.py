@@ -64,3 +64,11 @@ def test_emulated_png_encoder_round_trips():
     res = _run(["-c", code])
     assert res.returncode == 0, res.stdout + res.stderr
     assert "png ok" in res.stdout
+
+
+def test_bench_script_assembles_its_json_line():
+    """bench.py's whole flow (value, e2e, auto, png, pcie probe, roofline, cpu baseline) on the emulator with a 16-tile cut
+    of the workload and torch.cuda stubbed: the driver-facing keys are all there, the outputs agree with the CPU."""
+    res = _run([os.path.join(ROOT, "tests", "emu", "bench_dry_run.py")], timeout=1500)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert "bench dry run ok" in res.stdout
