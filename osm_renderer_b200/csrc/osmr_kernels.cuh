@@ -1449,6 +1449,10 @@ __global__ void __launch_bounds__(kRasterThreads, OSMR_RASTER_MIN_BLOCKS) raster
         const short4 o = o_next;
         if (vi + 32 < n_vis) o_next = vbb[vi + 32];
         const bool hit = vi < n_vis && o.x <= bx0 + kBW - 1 && o.z >= bx0 && o.y <= by0 + kBH - 1 && o.w >= by0;
+        // (emulator statistics for a coarse binning of the op list: ops scanned / ops whose bbox meets the block's 64x64 cell)
+        OSMR_COUNT("raster.ops_scanned", vi < n_vis);
+        OSMR_COUNT("raster.ops_in_cell64", vi < n_vis && o.x <= (bx0 | 63) && o.z >= (bx0 & ~63) && o.y <= (by0 | 63) && o.w >= (by0 & ~63));
+        OSMR_COUNT("raster.ops_hit", hit);
         // every lane fetches the record of ITS op now (independent loads); the records are handed round by shuffles
         uint4 my_rop0 = make_uint4(0, 0, 0, 0), my_rop1 = make_uint4(0, 0, 0, 0);
         if (hit) {
