@@ -72,3 +72,12 @@ def test_bench_script_assembles_its_json_line():
     res = _run([os.path.join(ROOT, "tests", "emu", "bench_dry_run.py")], timeout=1500)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert "bench dry run ok" in res.stdout
+
+
+def test_emulated_chunked_host_pipeline():
+    """148 tiles in one call: the draw is split into chunks that alternate between the two scratch sets (the emulator runs them
+    in order, so this checks the chunk plan, the per-chunk slices and offsets -- not the concurrency, which the GPU test does)."""
+    idx = [str(i) for i in list(range(64)) + list(range(64)) + list(range(20))]
+    res = _run([os.path.join(ROOT, "tests", "emu", "run_emu.py"), "18"] + idx, timeout=1500)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert "differing pixels vs oracle: 0" in res.stdout
