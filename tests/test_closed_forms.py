@@ -184,3 +184,120 @@ def test_thick_line_random_access_equals_sequential_traversal():
         if p1 == p2:
             continue
         assert _line_walks_reference(p1, p2, 7) == _line_walks_closed(p1, p2, 7), (p1, p2)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Properties behind the per-dataset entity boxes, the device-side dedup and the parallel CRC (round 1 additions)
+# ------------------------------------------------------------------------------------------------------------------
+def _project(m, dim, t256, scale):
+    """project_point of osmr_device.cuh for one coordinate (numpy float64 = the device's IEEE operations)."""
+    x = m * dim - t256
+    r = np.round(np.abs(x * scale)) * np.sign(x * scale)  # f64::round: half away from zero (np.round is half to even)
+    frac = np.abs(x * scale) - np.floor(np.abs(x * scale))
+    r = np.where(frac == 0.5, (np.floor(np.abs(x * scale)) + 1.0) * np.sign(x * scale), r)
+    r = np.where(np.isnan(r), 0.0, r)
+    return np.clip(r, -2147483648.0, 2147483647.0).astype(np.int64)
+
+
+def test_pixel_bbox_of_an_entity_is_the_projection_of_its_mercator_box():
+    """entity_pixel_bbox: project_point is monotone per coordinate, so min / max commute with it -- for every zoom, tile
+    and scale, including coordinates that land exactly on .5 ties and far outside the tile."""
+    rng = np.random.default_rng(11)
+    for _ in range(300):
+        zoom = int(rng.integers(0, 19))
+        scale = float(rng.integers(1, 9))
+        dim = float(256 * (1 << zoom))
+        tx = int(rng.integers(0, 1 << zoom))
+        t256 = float((tx * 256) & 0xFFFFFFFF)
+        k = int(rng.integers(1, 40))
+        centre = (tx + rng.random()) / (1 << zoom)
+        m = centre + rng.normal(0.0, 2.0 ** -rng.integers(8, 30), size=k)
+        # put some coordinates exactly on half pixels
+        ties = (np.floor(m[: k // 3] * dim * scale) + 0.5) / (dim * scale)
+        m[: k // 3] = ties
+        px = _project(m, dim, t256, scale)
+        lo = _project(np.array([m.min()]), dim, t256, scale)[0]
+        hi = _project(np.array([m.max()]), dim, t256, scale)[0]
+        assert px.min() == lo and px.max() == hi
+
+
+def test_ownership_rule_emits_every_listed_entity_exactly_once():
+    """osmr_auto.cuh: an entity listed in every index tile of its rectangle is emitted by exactly one record of a query
+    rectangle -- the one at (max(ent.min_x, rect.min_x), max(ent.min_y, rect.min_y)) -- iff the rectangles intersect."""
+    rng = random.Random(5)
+    for _ in range(2000):
+        ex0, ey0 = rng.randrange(0, 40), rng.randrange(0, 40)
+        ex1, ey1 = ex0 + rng.randrange(0, 6), ey0 + rng.randrange(0, 6)
+        xa, ya = rng.randrange(0, 40), rng.randrange(0, 40)
+        xb, yb = xa + rng.randrange(0, 12), ya + rng.randrange(0, 12)
+        owners = 0
+        for x in range(max(ex0, xa), min(ex1, xb) + 1):  # the index records inside the query that list the entity
+            for y in range(max(ey0, ya), min(ey1, yb) + 1):
+                if x == max(ex0, xa) and y == max(ey0, ya):
+                    owners += 1
+        intersects = ex0 <= xb and ex1 >= xa and ey0 <= yb and ey1 >= ya
+        assert owners == (1 if intersects else 0)
+
+
+def test_crc32_slices_combine_like_png_finish_kernel():
+    """png_finish_kernel: a raw CRC (zero start, no final inversion) ignores leading zeros and combines by multiplication
+    with x^(8n) mod P; the standard CRC-32 is raw ^ (all-ones pushed through n bytes) ^ all-ones (zlib's crc32_combine
+    arithmetic in the reflected domain)."""
+    import zlib
+
+    POLY = 0xEDB88320
+
+    def multmodp(a, b):
+        m, p = 1 << 31, 0
+        while True:
+            if a & m:
+                p ^= b
+                if (a & (m - 1)) == 0:
+                    break
+            m >>= 1
+            b = (b >> 1) ^ POLY if b & 1 else b >> 1
+        return p
+
+    x2n = [1 << 30]
+    for _ in range(31):
+        x2n.append(multmodp(x2n[-1], x2n[-1]))
+
+    def x2nmodp(n, k):
+        p = 1 << 31
+        while n:
+            if n & 1:
+                p = multmodp(x2n[k & 31], p)
+            n >>= 1
+            k += 1
+        return p
+
+    table = []
+    for i in range(256):
+        c = i
+        for _ in range(8):
+            c = (c >> 1) ^ POLY if c & 1 else c >> 1
+        table.append(c)
+
+    def raw(data):
+        c = 0
+        for byte in data:
+            c = table[(c ^ byte) & 0xFF] ^ (c >> 8)
+        return c
+
+    rng = random.Random(3)
+    for n in (1, 5, 255, 256, 257, 1000, 4099):
+        msg = bytes(rng.randrange(256) for _ in range(n))
+        threads = 16
+        lc = (n + threads - 1) // threads
+        pad = lc * threads - n
+        framed = b"\0" * pad + msg  # right-aligned frame: the leading zeros do not change a raw CRC
+        part = [raw(framed[t * lc : (t + 1) * lc]) for t in range(threads)]
+        mul = x2nmodp(lc, 3)
+        stride = 1
+        while stride < threads:  # the combine tree of the kernel
+            for t in range(0, threads, 2 * stride):
+                part[t] = multmodp(mul, part[t]) ^ part[t + stride]
+            mul = multmodp(mul, mul)
+            stride *= 2
+        crc = part[0] ^ multmodp(x2nmodp(n, 3), 0xFFFFFFFF) ^ 0xFFFFFFFF
+        assert crc == zlib.crc32(msg)
