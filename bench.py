@@ -501,7 +501,7 @@ def main():
     # ---- CPU baseline beside it (bounded sample, rank 0 only) ----
     cpu = None
     max_abs_diff = None
-    if not args.skip_cpu_baseline:
+    if not args.skip_cpu_baseline and world == 1:  # the CPU baseline belongs to the N=1 line only
         threads = host_threads()
         probe_tps, _ = cpu_port_throughput(w, threads, threads)
         sample = args.cpu_sample or int(min(n_tiles, max(threads, probe_tps * 15.0)))
