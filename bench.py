@@ -113,7 +113,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                ["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -316,7 +316,6 @@ def main():
         launches += st["kernel_launches"]
     barrier()
     wall = time.perf_counter() - t0
-    clocks = sampler.stop()
     stats = ctx.stats()
     dev_s = sum(ev_ms) / 1000.0
 
@@ -350,6 +349,7 @@ def main():
         e2e_step()
     barrier()
     e2e_wall = time.perf_counter() - t1
+    clocks = sampler.stop()  # sampled every 50 ms across both timed regions (resident steps + end-to-end steps)
     checksum = int(np.frombuffer((C.c_uint8 * 4096).from_address(pin_out), dtype=np.uint8).sum())
 
     # ---- context for e2e: what the bus of this box gives a plain pinned copy of the step's output / input ----
