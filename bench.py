@@ -316,6 +316,7 @@ def main():
         launches += st["kernel_launches"]
     barrier()
     wall = time.perf_counter() - t0
+    clocks = sampler.stop()  # sampled every 50 ms, only while the timed resident steps run (idle gaps would drag the median down)
     stats = ctx.stats()
     dev_s = sum(ev_ms) / 1000.0
 
@@ -349,7 +350,6 @@ def main():
         e2e_step()
     barrier()
     e2e_wall = time.perf_counter() - t1
-    clocks = sampler.stop()  # sampled every 50 ms across both timed regions (resident steps + end-to-end steps)
     checksum = int(np.frombuffer((C.c_uint8 * 4096).from_address(pin_out), dtype=np.uint8).sum())
 
     # ---- context for e2e: what the bus of this box gives a plain pinned copy of the step's output / input ----
