@@ -11,6 +11,8 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <stdexcept>
+#include <system_error>
 #include <string>
 #include <vector>
 
@@ -25,9 +27,13 @@ using namespace osmr;
 namespace {
 
 template <typename T>
-struct DevBuf {
+struct DevBuf {  // owns its allocation: error paths that return early (CK) do not leak device memory
     T* p = nullptr;
     size_t cap = 0;  // elements
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
     cudaError_t reserve(size_t n) {
         if (n <= cap) return cudaSuccess;
         if (p) cudaFree(p);
@@ -49,6 +55,10 @@ template <typename T>
 struct PinnedBuf {  // page-locked host staging, grown on demand and kept
     T* p = nullptr;
     size_t cap = 0;
+    PinnedBuf() = default;
+    PinnedBuf(const PinnedBuf&) = delete;
+    PinnedBuf& operator=(const PinnedBuf&) = delete;
+    ~PinnedBuf() { release(); }
     cudaError_t reserve(size_t n) {
         if (n <= cap) return cudaSuccess;
         if (p) cudaFreeHost(p);
@@ -199,16 +209,34 @@ struct osmr_ctx {
     unsigned first_chunk = 0;  // tiles in the first draw chunk of the current upload (0: one chunk)
     osmr_stats stats{};
 
-    int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
+    int fail(int code, const char* what, cudaError_t e = cudaSuccess) noexcept {
         char buf[512];
         if (e != cudaSuccess)
             snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
         else
             snprintf(buf, sizeof buf, "%s", what);
-        err = buf;
+        try {
+            err = buf;
+        } catch (...) {  // the message itself could not be allocated: keep whatever fits without allocating
+            err.clear();
+        }
         return code;
     }
 };
+
+// No exception may cross the C boundary (include/osmr.h): every exported function is a function-try-block ending in one of
+// these handlers.  std::bad_alloc (host vectors / strings / thread stacks) -> OSMR_E_NOMEM, std::system_error (thread creation)
+// and anything else -> OSMR_E_INVALID with the exception's message as osmr_last_error.
+static int osmr_exception_to_code(osmr_ctx* ctx, int code, const char* what) noexcept {
+    if (ctx) return ctx->fail(code, what);
+    return code;
+}
+#define OSMR_CATCH_INT(ctxp)                                                                                         \
+    catch (const std::bad_alloc&) { return osmr_exception_to_code((ctxp), OSMR_E_NOMEM, "out of host memory"); }       \
+    catch (const std::exception& ex_) { return osmr_exception_to_code((ctxp), OSMR_E_INVALID, ex_.what()); }           \
+    catch (...) { return osmr_exception_to_code((ctxp), OSMR_E_INVALID, "unknown C++ exception"); }
+#define OSMR_CATCH_VAL(v) \
+    catch (...) { return (v); }
 
 #define CK(call)                                                       \
     do {                                                               \
@@ -226,7 +254,7 @@ extern "C" {
 
 uint32_t osmr_abi_version(void) { return 2; }
 
-int osmr_ctx_create(int device, osmr_ctx** out_ctx) {
+int osmr_ctx_create(int device, osmr_ctx** out_ctx) try {
     if (!out_ctx) return OSMR_E_INVALID;
     *out_ctx = nullptr;
     int n_dev = 0;
@@ -265,7 +293,7 @@ int osmr_ctx_create(int device, osmr_ctx** out_ctx) {
     }
     *out_ctx = ctx;
     return OSMR_OK;
-}
+} OSMR_CATCH_INT(nullptr)
 
 void osmr_ctx_destroy(osmr_ctx* ctx) {
     if (!ctx) return;
@@ -363,7 +391,7 @@ void osmr_ctx_destroy(osmr_ctx* ctx) {
 
 const char* osmr_last_error(const osmr_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
-int osmr_debug_set(osmr_ctx* ctx, const char* key, int value) {
+int osmr_debug_set(osmr_ctx* ctx, const char* key, int value) try {
     if (!ctx || !key) return OSMR_E_INVALID;
     if (strcmp(key, "label_threads") == 0) {  // host threads of the label layout (1: serial)
         if (value < 1 || value > 256) return ctx->fail(OSMR_E_INVALID, "label_threads must be 1..256");
@@ -421,10 +449,10 @@ int osmr_debug_set(osmr_ctx* ctx, const char* key, int value) {
         return OSMR_OK;
     }
     return ctx->fail(OSMR_E_INVALID, "unknown debug key");
-}
+} OSMR_CATCH_INT(ctx)
 
 // ---------------------------------------------------------------------------------------------------------
-int osmr_set_geodata(osmr_ctx* ctx, const void* bin, size_t len) {
+int osmr_set_geodata(osmr_ctx* ctx, const void* bin, size_t len) try {
     if (!ctx) return OSMR_E_INVALID;
     if (!bin) return ctx->fail(OSMR_E_INVALID, "null geodata image");
     cudaSetDevice(ctx->device);
@@ -642,9 +670,9 @@ int osmr_set_geodata(osmr_ctx* ctx, const void* bin, size_t len) {
         }
     }
     return OSMR_OK;
-}
+} OSMR_CATCH_INT(ctx)
 
-int osmr_set_icons(osmr_ctx* ctx, const osmr_icon* icons, uint32_t n_icons) {
+int osmr_set_icons(osmr_ctx* ctx, const osmr_icon* icons, uint32_t n_icons) try {
     if (!ctx) return OSMR_E_INVALID;
     if (n_icons && !icons) return ctx->fail(OSMR_E_INVALID, "null icon table");
     cudaSetDevice(ctx->device);
@@ -679,9 +707,9 @@ int osmr_set_icons(osmr_ctx* ctx, const osmr_icon* icons, uint32_t n_icons) {
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->n_icons = n_icons;
     return OSMR_OK;
-}
+} OSMR_CATCH_INT(ctx)
 
-int osmr_set_styles(osmr_ctx* ctx, const osmr_style* styles, uint32_t n_styles, const double* dashes, uint32_t n_dashes) {
+int osmr_set_styles(osmr_ctx* ctx, const osmr_style* styles, uint32_t n_styles, const double* dashes, uint32_t n_dashes) try {
     if (!ctx) return OSMR_E_INVALID;
     if ((n_styles && !styles) || (n_dashes && !dashes)) return ctx->fail(OSMR_E_INVALID, "null style table");
     cudaSetDevice(ctx->device);
@@ -702,7 +730,7 @@ int osmr_set_styles(osmr_ctx* ctx, const osmr_style* styles, uint32_t n_styles, 
     ctx->n_styles = n_styles;
     ctx->n_dashes = n_dashes;
     return OSMR_OK;
-}
+} OSMR_CATCH_INT(ctx)
 
 // ---------------------------------------------------------------------------------------------------------
 static int validate_batch(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, const uint32_t* area_begin) {
@@ -829,9 +857,9 @@ static int batch_upload_impl(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_t
 }
 
 int osmr_batch_upload(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, const uint32_t* area_begin,
-                      const osmr_styled_area* areas) {
+                      const osmr_styled_area* areas) try {
     return batch_upload_impl(ctx, tiles, n_tiles, area_begin, areas, false, nullptr);
-}
+} OSMR_CATCH_INT(ctx)
 
 // Enqueues the whole pipeline for tiles [tb, tb+tc) of the uploaded batch on the compute stream (nothing here waits for
 // the device): the chunk's counters land in page-locked slot `slot` and are judged by collect_chunk after the stream
@@ -1012,7 +1040,7 @@ static int collect_chunk(osmr_ctx* ctx, unsigned slot, unsigned tb, unsigned tc,
     return OSMR_OK;
 }
 
-int osmr_batch_draw(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t flags, uint8_t* out, float* gpu_ms) {
+int osmr_batch_draw(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t flags, uint8_t* out, float* gpu_ms) try {
     if (!ctx) return OSMR_E_INVALID;
     if (!ctx->has_batch) return ctx->fail(OSMR_E_STATE, "no batch uploaded");
     if ((flags & OSMR_DRAW_HAS_CANVAS_COLOR) && !canvas_rgb) return ctx->fail(OSMR_E_INVALID, "null canvas colour");
@@ -1127,17 +1155,17 @@ int osmr_batch_draw(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t flags, 
     }
     cudaStreamSynchronize(ctx->d2h_stream);
     return ctx->fail(OSMR_E_NOMEM, "scratch kept overflowing");
-}
+} OSMR_CATCH_INT(ctx)
 
-int osmr_batch_output(osmr_ctx* ctx, const uint8_t** dev_ptr, size_t* n_bytes) {
+int osmr_batch_output(osmr_ctx* ctx, const uint8_t** dev_ptr, size_t* n_bytes) try {
     if (!ctx || !dev_ptr || !n_bytes) return OSMR_E_INVALID;
     *dev_ptr = ctx->out.p;
     *n_bytes = ctx->out_bytes;
     return OSMR_OK;
-}
+} OSMR_CATCH_INT(ctx)
 
 int osmr_draw_tiles(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, const uint32_t* area_begin,
-                    const osmr_styled_area* areas, const uint8_t canvas_rgb[3], uint32_t flags, uint8_t* out) {
+                    const osmr_styled_area* areas, const uint8_t canvas_rgb[3], uint32_t flags, uint8_t* out) try {
     if (!ctx) return OSMR_E_INVALID;
     if (!out) return ctx->fail(OSMR_E_INVALID, "null output buffer");
     int rc = batch_upload_impl(ctx, tiles, n_tiles, area_begin, areas, !(flags & OSMR_DRAW_OUT_DEVICE), out);
@@ -1148,13 +1176,13 @@ int osmr_draw_tiles(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, con
         ctx->areas_deferred = false;
     }
     return rc;
-}
+} OSMR_CATCH_INT(ctx)
 
 // ---------------------------------------------------------------------------------------------------------
 // f3: styles per zoom + device-side candidate lookup and ordering (osmr_auto.cuh)
 // ---------------------------------------------------------------------------------------------------------
 int osmr_set_zoom_styles(osmr_ctx* ctx, uint32_t zoom, const uint32_t* way_class, const uint32_t* mp_class, const uint32_t* class_begin,
-                         const osmr_class_style* class_styles, uint32_t n_classes) {
+                         const osmr_class_style* class_styles, uint32_t n_classes) try {
     if (!ctx) return OSMR_E_INVALID;
     if (!ctx->has_geo) return ctx->fail(OSMR_E_STATE, "osmr_set_geodata has not been called");
     if (zoom > 18) return ctx->fail(OSMR_E_INVALID, "zoom must be <= 18 (tile.rs:5 MAX_ZOOM)");
@@ -1185,9 +1213,9 @@ int osmr_set_zoom_styles(osmr_ctx* ctx, uint32_t zoom, const uint32_t* way_class
     z.n_class_styles = n_cs;
     z.set = true;
     return OSMR_OK;
-}
+} OSMR_CATCH_INT(ctx)
 
-int osmr_draw_tiles_auto(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, const uint8_t canvas_rgb[3], uint32_t flags, uint8_t* out) {
+int osmr_draw_tiles_auto(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, const uint8_t canvas_rgb[3], uint32_t flags, uint8_t* out) try {
     if (!ctx) return OSMR_E_INVALID;
     if (!ctx->has_geo) return ctx->fail(OSMR_E_STATE, "osmr_set_geodata has not been called");
     if (!ctx->auto_unavailable.empty()) return ctx->fail(OSMR_E_STATE, ctx->auto_unavailable.c_str());
@@ -1325,9 +1353,9 @@ int osmr_draw_tiles_auto(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles
     ctx->stats.ms_auto = ms_auto;
     ctx->stats.ms_total += ms_auto;
     return rc;
-}
+} OSMR_CATCH_INT(ctx)
 
-int osmr_auto_readback(osmr_ctx* ctx, uint32_t* area_begin, osmr_styled_area* areas, uint32_t areas_cap) {
+int osmr_auto_readback(osmr_ctx* ctx, uint32_t* area_begin, osmr_styled_area* areas, uint32_t areas_cap) try {
     if (!ctx || !area_begin) return OSMR_E_INVALID;
     if (!ctx->has_batch) return ctx->fail(OSMR_E_STATE, "no batch");
     cudaSetDevice(ctx->device);
@@ -1338,7 +1366,7 @@ int osmr_auto_readback(osmr_ctx* ctx, uint32_t* area_begin, osmr_styled_area* ar
         CK(cudaStreamSynchronize(ctx->stream));
     }
     return OSMR_OK;
-}
+} OSMR_CATCH_INT(ctx)
 
 // ---------------------------------------------------------------------------------------------------------
 // f4: PNG files instead of RGB triples (osmr_png.cuh)
@@ -1348,10 +1376,10 @@ static unsigned png_band_cap_words(unsigned scale) {
     return (unsigned)((rows * np * 9ull + 128ull) / 32ull + 8ull);  // every byte a 9-bit literal + block framing
 }
 
-size_t osmr_png_bound(uint32_t scale) {
+size_t osmr_png_bound(uint32_t scale) try {
     if (scale < 1 || scale > 8) return 0;
     return (size_t)kPngFixed + (size_t)kPngBands * png_band_cap_words(scale) * 4u;
-}
+} OSMR_CATCH_VAL(0)
 
 // n_tiles RGB images of (256 * scale)^2 pixels in HBM -> packed PNG files in host memory
 static int encode_png_from_device(osmr_ctx* ctx, const unsigned char* rgb_dev, uint32_t n_tiles, unsigned scale, uint8_t* png_out,
@@ -1405,7 +1433,7 @@ static int encode_png_from_device(osmr_ctx* ctx, const unsigned char* rgb_dev, u
 }
 
 int osmr_draw_tiles_png(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, const uint32_t* area_begin, const osmr_styled_area* areas,
-                        const uint8_t canvas_rgb[3], uint32_t flags, uint8_t* png_out, size_t png_cap, uint64_t* png_offset) {
+                        const uint8_t canvas_rgb[3], uint32_t flags, uint8_t* png_out, size_t png_cap, uint64_t* png_offset) try {
     if (!ctx) return OSMR_E_INVALID;
     if (!png_out || !png_offset) return ctx->fail(OSMR_E_INVALID, "null output buffer");
     if (flags & (OSMR_DRAW_OUT_RGBA | OSMR_DRAW_OUT_DEVICE)) return ctx->fail(OSMR_E_INVALID, "osmr_draw_tiles_png encodes RGB into host memory");
@@ -1414,10 +1442,10 @@ int osmr_draw_tiles_png(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles,
     rc = osmr_batch_draw(ctx, canvas_rgb, flags, nullptr, nullptr);  // the RGB tiles stay in HBM (ctx->out)
     if (rc) return rc;
     return encode_png_from_device(ctx, ctx->out.p, n_tiles, (unsigned)ctx->scale, png_out, png_cap, png_offset);
-}
+} OSMR_CATCH_INT(ctx)
 
 int osmr_rgb_to_png(osmr_ctx* ctx, const uint8_t* rgb, uint32_t n_images, uint32_t scale, uint8_t* png_out, size_t png_cap,
-                    uint64_t* png_offset) {
+                    uint64_t* png_offset) try {
     if (!ctx) return OSMR_E_INVALID;
     if (!rgb || !png_out || !png_offset) return ctx->fail(OSMR_E_INVALID, "null argument");
     if (n_images == 0) return ctx->fail(OSMR_E_INVALID, "no images");
@@ -1429,15 +1457,15 @@ int osmr_rgb_to_png(osmr_ctx* ctx, const uint8_t* rgb, uint32_t n_images, uint32
     ctx->stats = osmr_stats{};
     CK(cudaMemcpyAsync(ctx->out.p, rgb, bytes, cudaMemcpyHostToDevice, ctx->stream));
     return encode_png_from_device(ctx, ctx->out.p, n_images, scale, png_out, png_cap, png_offset);
-}
+} OSMR_CATCH_INT(ctx)
 
-int osmr_get_stats(osmr_ctx* ctx, osmr_stats* out) {
+int osmr_get_stats(osmr_ctx* ctx, osmr_stats* out) try {
     if (!ctx || !out) return OSMR_E_INVALID;
     *out = ctx->stats;
     return OSMR_OK;
-}
+} OSMR_CATCH_INT(ctx)
 
-int osmr_project_nodes(osmr_ctx* ctx, const osmr_tile* tile, int32_t* out_xy) {
+int osmr_project_nodes(osmr_ctx* ctx, const osmr_tile* tile, int32_t* out_xy) try {
     if (!ctx) return OSMR_E_INVALID;
     if (!ctx->has_geo) return ctx->fail(OSMR_E_STATE, "osmr_set_geodata has not been called");
     if (!tile || !out_xy) return ctx->fail(OSMR_E_INVALID, "null argument");
@@ -1452,19 +1480,19 @@ int osmr_project_nodes(osmr_ctx* ctx, const osmr_tile* tile, int32_t* out_xy) {
     CK(cudaStreamSynchronize(ctx->stream));
     tmp.release();
     return OSMR_OK;
-}
+} OSMR_CATCH_INT(ctx)
 
 // ---------------------------------------------------------------------------------------------------------
 // label pass
 // ---------------------------------------------------------------------------------------------------------
-int osmr_set_font(osmr_ctx* ctx, const void* ttf, size_t len) {
+int osmr_set_font(osmr_ctx* ctx, const void* ttf, size_t len) try {
     if (!ctx) return OSMR_E_INVALID;
     if (!ttf || len < 64) return ctx->fail(OSMR_E_INVALID, "null or truncated font");
     if (!ctx->font.load((const uint8_t*)ttf, len)) return ctx->fail(OSMR_E_INVALID, "not a TrueType font with a Unicode cmap and glyf outlines");
     return OSMR_OK;
-}
+} OSMR_CATCH_INT(ctx)
 
-int osmr_set_label_icons(osmr_ctx* ctx, const osmr_icon* icons, uint32_t n_icons) {
+int osmr_set_label_icons(osmr_ctx* ctx, const osmr_icon* icons, uint32_t n_icons) try {
     if (!ctx) return OSMR_E_INVALID;
     if (n_icons && !icons) return ctx->fail(OSMR_E_INVALID, "null icon table");
     cudaSetDevice(ctx->device);
@@ -1499,9 +1527,9 @@ int osmr_set_label_icons(osmr_ctx* ctx, const osmr_icon* icons, uint32_t n_icons
     if (!px.empty()) CK(cudaMemcpyAsync(ctx->label_icon_px.p, px.data(), px.size() * sizeof(double4), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return OSMR_OK;
-}
+} OSMR_CATCH_INT(ctx)
 
-int osmr_set_label_styles(osmr_ctx* ctx, const osmr_label_style* styles, uint32_t n_styles, const char* strings, size_t strings_len) {
+int osmr_set_label_styles(osmr_ctx* ctx, const osmr_label_style* styles, uint32_t n_styles, const char* strings, size_t strings_len) try {
     if (!ctx) return OSMR_E_INVALID;
     if (n_styles && !styles) return ctx->fail(OSMR_E_INVALID, "null label style table");
     std::vector<osmr_host::LabelStyleHost> tmp(n_styles);
@@ -1516,11 +1544,11 @@ int osmr_set_label_styles(osmr_ctx* ctx, const osmr_label_style* styles, uint32_
     }
     ctx->label_styles.swap(tmp);
     return OSMR_OK;
-}
+} OSMR_CATCH_INT(ctx)
 
 int osmr_draw_tiles_labeled(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, const uint32_t* area_begin,
                             const osmr_styled_area* areas, const uint32_t* label_begin, const osmr_label* labels,
-                            const uint8_t canvas_rgb[3], uint32_t flags, uint8_t* out) {
+                            const uint8_t canvas_rgb[3], uint32_t flags, uint8_t* out) try {
     if (!ctx) return OSMR_E_INVALID;
     if (!out) return ctx->fail(OSMR_E_INVALID, "null output buffer");
     if (!label_begin) return ctx->fail(OSMR_E_INVALID, "null label_begin");
@@ -1678,14 +1706,14 @@ int osmr_draw_tiles_labeled(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_ti
     ctx->stats.ms_label_layout = ctx->stats_label_layout_ms;
     ctx->stats.ms_label_device = ctx->stats_label_device_ms;
     return rc;
-}
+} OSMR_CATCH_INT(ctx)
 
 // pinned host memory for callers that want full-speed transfers (optional)
-void* osmr_alloc_pinned(size_t bytes) {
+void* osmr_alloc_pinned(size_t bytes) try {
     void* p = nullptr;
     if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
     return p;
-}
+} OSMR_CATCH_VAL(nullptr)
 void osmr_free_pinned(void* p) {
     if (p) cudaFreeHost(p);
 }

@@ -66,8 +66,13 @@ class GpuContext:
             raise _lib.OsmrError(f"osmr_ctx_create(device={device}) failed with {rc}: no usable CUDA device (no CPU fallback)")
         self.h = h
         self._geodata_id = None
-        self._n_styles = -1
-        self._n_icons = -1
+        # what this context holds on the device: (identity of the table, rows, icons).  A context is one worker's scratch
+        # (TilePixels); several of them may serve one shared Drawer, and a Drawer may be replaced by another with equally
+        # long tables -- so the key is the table object and its length, tracked PER CONTEXT.
+        self._style_key = None
+        self._icon_key = None
+        self._label_key = None
+        self._font_key = None
         self._keep = []
 
     def close(self):
@@ -94,18 +99,22 @@ class GpuContext:
         self.n_nodes = int(np.frombuffer(image, dtype="<u4", count=1)[0])
 
     def set_table(self, table: StyleTable):
-        if len(table.icons) != self._n_icons:
+        icon_key = (id(table), len(table.icons))
+        if icon_key != self._icon_key:
             icons, keep = table.icon_structs()
             self._check(self.L.osmr_set_icons(self.h, C.addressof(icons), len(table.icons)), "osmr_set_icons")
-            self._n_icons = len(table.icons)
-        if len(table.rows) != self._n_styles:
+            self._icon_key = icon_key
+            self._keep_table = table  # keeps id(table) from being reused while it is the key
+        style_key = (id(table), len(table.rows), len(table.dashes))
+        if style_key != self._style_key:
             styles = table.styles_array()
             dashes = table.dashes_array()
             self._check(
                 self.L.osmr_set_styles(self.h, styles.ctypes.data, len(styles), dashes.ctypes.data, len(dashes)),
                 "osmr_set_styles",
             )
-            self._n_styles = len(table.rows)
+            self._style_key = style_key
+            self._keep_table = table
 
     # ---- drawing ------------------------------------------------------------------------------------------------
     @staticmethod
@@ -169,15 +178,25 @@ class GpuContext:
 
     # ---- label pass ---------------------------------------------------------------------------------------------
     def set_font(self, ttf: bytes):
+        key = (id(ttf), len(ttf))
+        if key == self._font_key:
+            return
         buf = np.frombuffer(ttf, dtype=np.uint8)
         self._check(self.L.osmr_set_font(self.h, buf.ctypes.data, len(ttf)), "osmr_set_font")
+        self._font_key = key
+        self._keep_font = ttf
 
     def set_label_table(self, ltable):
+        key = (id(ltable), len(ltable.rows), len(ltable.icons), len(ltable.strings))
+        if key == self._label_key:
+            return
         icons, keep = ltable.icon_structs()
         self._check(self.L.osmr_set_label_icons(self.h, C.addressof(icons), len(ltable.icons)), "osmr_set_label_icons")
         styles = ltable.styles_array()
         blob = bytes(ltable.strings)
         self._check(self.L.osmr_set_label_styles(self.h, styles.ctypes.data, len(styles), blob, len(blob)), "osmr_set_label_styles")
+        self._label_key = key
+        self._keep_ltable = ltable
 
     def draw_tiles_labeled(self, tiles, area_begin, areas, label_begin, labels, canvas_rgb, use_caps_for_dashes=True, rgba=False):
         """osmr_draw_tiles_labeled: area passes + label pass, host buffers."""
@@ -287,7 +306,6 @@ class Drawer:
         self.table = StyleTable(base_path, icon_loader)  # icon cache (fill patterns) + interned styles
         self.ltable = LabelStyleTable(base_path, icon_loader)  # icon cache (label icons) + interned label styles
         self.font = font
-        self._n_lstyles = -1
 
     def _builders(self, reader, styler):
         from .upstream.pipeline import LabelListBuilder, TileStyler
@@ -347,12 +365,8 @@ class Drawer:
             lbegins = np.zeros(len(lparts) + 1, dtype=np.uint32)
             lbegins[1:] = np.cumsum([len(p) for p in lparts])
             labels = np.concatenate(lparts)
-            if not getattr(ctx, "_font_set", False):
-                ctx.set_font(self.font)
-                ctx._font_set = True
-            if len(self.ltable.rows) != self._n_lstyles:
-                ctx.set_label_table(self.ltable)
-                self._n_lstyles = len(self.ltable.rows)
+            ctx.set_font(self.font)  # both are no-ops when THIS context already holds them (tracked per context:
+            ctx.set_label_table(self.ltable)  # one Drawer is shared by many TilePixels, http_server.rs:42-48,69-72)
             img = ctx.draw_tiles_labeled(tarr, begins, areas, lbegins, labels, styler.canvas_fill_color, styler.use_caps_for_dashes)
         d = 256 * scale
         return [TileRenderedPixels(img[i], d) for i in range(len(tiles))]

@@ -52,6 +52,30 @@ def test_wire_struct_layouts_match_header():
     assert (off["width"], off["opacity"], off["fill_opacity"], off["casing_width"], off["dashes_off"], off["casing_dashes_len"]) == (24, 32, 40, 48, 56, 68)
 
 
+def test_c99_client_compiles_against_the_header_and_runs(tmp_path):
+    """tests/abi_client.c: gcc -std=c99 against include/osmr.h (static assertions on every sizeof / offsetof that crosses the
+    boundary), linked to libosmr_b200.so, one real call sequence (context creation fails loudly without a device)."""
+    import shutil
+    import subprocess
+
+    from osm_renderer_b200 import _lib, build
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    if not os.path.exists(_lib.LIB_PATH):
+        build.build_lib()
+    exe = str(tmp_path / "abi_client")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    cmd = [gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "abi_client.c"), "-o", exe, "-L", libdir, "-losmr_b200", f"-Wl,-rpath,{libdir}"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout + res.stderr
+    run = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0, run.stdout + run.stderr
+    assert "abi_version" in run.stdout
+
+
 def test_product_package_does_not_reference_the_oracle():
     pkg = os.path.join(ROOT, "osm_renderer_b200")
     for dirpath, _, files in os.walk(pkg):
