@@ -257,6 +257,12 @@ int osmr_draw_tiles_png(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles,
                         const osmr_styled_area* areas, const uint8_t canvas_rgb[3], uint32_t flags, uint8_t* png_out, size_t png_cap,
                         uint64_t* png_offset /* n_tiles + 1 */);
 
+/* f3 + f4 around the draw path = Drawer::draw_tile as the server calls it (src/http_server.rs:150-177: entities of the tile,
+ * draw_tile, PNG bytes to the client): only the tile list goes to the device, only PNG files come back.  Same conditions as
+ * osmr_draw_tiles_auto (one zoom and one scale per call, osmr_set_zoom_styles first), output as osmr_draw_tiles_png. */
+int osmr_draw_tiles_auto_png(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, const uint8_t canvas_rgb[3], uint32_t flags,
+                             uint8_t* png_out, size_t png_cap, uint64_t* png_offset /* n_tiles + 1 */);
+
 /* rgb_triples_to_png itself (png_writer.rs:4-21) for images the caller already holds: n_images RGB images of
  * (256 * scale)^2 pixels, tightly packed in host memory -> packed PNG files as in osmr_draw_tiles_png. */
 int osmr_rgb_to_png(osmr_ctx* ctx, const uint8_t* rgb, uint32_t n_images, uint32_t scale, uint8_t* png_out, size_t png_cap,

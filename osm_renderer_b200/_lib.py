@@ -40,6 +40,7 @@ EXPORTS = [
     "osmr_png_bound",
     "osmr_draw_tiles_png",
     "osmr_rgb_to_png",
+    "osmr_draw_tiles_auto_png",
 ]
 
 _lib = None
@@ -113,5 +114,7 @@ def load():
     L.osmr_draw_tiles_png.argtypes = [vp, vp, u32, vp, vp, vp, u32, vp, sz, vp]
     L.osmr_rgb_to_png.restype = C.c_int
     L.osmr_rgb_to_png.argtypes = [vp, vp, u32, u32, vp, sz, vp]
+    L.osmr_draw_tiles_auto_png.restype = C.c_int
+    L.osmr_draw_tiles_auto_png.argtypes = [vp, vp, u32, vp, u32, vp, sz, vp]
     _lib = L
     return L

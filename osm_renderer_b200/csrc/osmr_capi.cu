@@ -539,7 +539,8 @@ int osmr_set_geodata(osmr_ctx* ctx, const void* bin, size_t len) try {
         for (auto& th : pool) th.join();
         CK(cudaMemcpyAsync(ctx->merc.p, h_merc.data(), (size_t)n_nodes * sizeof(double2), cudaMemcpyHostToDevice, ctx->stream));
     } else if (n_nodes) {
-        project_nodes_kernel<<<(n_nodes + 255) / 256, 256, 0, ctx->stream>>>(raw_nodes.p, n_nodes, ctx->merc.p);
+        const unsigned char* raw_p = raw_nodes.p;
+        project_nodes_kernel<<<(n_nodes + 255) / 256, 256, 0, ctx->stream>>>(raw_p, n_nodes, ctx->merc.p);
         CK(cudaGetLastError());
     }
     CK(ctx->way_box.reserve(n_ways + 1));
@@ -1181,6 +1182,8 @@ int osmr_draw_tiles(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, con
 // ---------------------------------------------------------------------------------------------------------
 // f3: styles per zoom + device-side candidate lookup and ordering (osmr_auto.cuh)
 // ---------------------------------------------------------------------------------------------------------
+static int encode_png_from_device(osmr_ctx* ctx, const unsigned char* rgb_dev, uint32_t n_tiles, unsigned scale, uint8_t* png_out,
+                                  size_t png_cap, uint64_t* png_offset);
 int osmr_set_zoom_styles(osmr_ctx* ctx, uint32_t zoom, const uint32_t* way_class, const uint32_t* mp_class, const uint32_t* class_begin,
                          const osmr_class_style* class_styles, uint32_t n_classes) try {
     if (!ctx) return OSMR_E_INVALID;
@@ -1215,8 +1218,10 @@ int osmr_set_zoom_styles(osmr_ctx* ctx, uint32_t zoom, const uint32_t* way_class
     return OSMR_OK;
 } OSMR_CATCH_INT(ctx)
 
-int osmr_draw_tiles_auto(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, const uint8_t canvas_rgb[3], uint32_t flags, uint8_t* out) try {
-    if (!ctx) return OSMR_E_INVALID;
+// f3 up to "an ordinary resident batch": candidate lookup, ownership dedup, culling and the painter's order on the device.
+// On success ctx holds the batch (tiles, area_begin, areas) exactly as osmr_batch_upload would have left it and the events
+// ctx->ev[0] / ev[1] bracket the stage.
+static int auto_prepare(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, const uint8_t canvas_rgb[3], uint32_t flags) {
     if (!ctx->has_geo) return ctx->fail(OSMR_E_STATE, "osmr_set_geodata has not been called");
     if (!ctx->auto_unavailable.empty()) return ctx->fail(OSMR_E_STATE, ctx->auto_unavailable.c_str());
     if (n_tiles == 0 || !tiles) return ctx->fail(OSMR_E_INVALID, "empty batch");
@@ -1347,12 +1352,39 @@ int osmr_draw_tiles_auto(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles
     CK(ctx->line_work.reserve(2ull * n_areas + n_areas / 2 + 4096));
     CK(ctx->vis_count.reserve(3ull * n_tiles));
     ctx->has_batch = true;
-    int rc = osmr_batch_draw(ctx, canvas_rgb, flags, out, nullptr);
-    float ms_auto = 0.f;
+    return OSMR_OK;
+}
+
+int osmr_draw_tiles_auto(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, const uint8_t canvas_rgb[3], uint32_t flags, uint8_t* out) try {
+    if (!ctx) return OSMR_E_INVALID;
+    int rc = auto_prepare(ctx, tiles, n_tiles, canvas_rgb, flags);
+    if (rc) return rc;
+    float ms_auto = 0.f;  // the stage's events are reused by later stages: read them before the draw
+    cudaEventSynchronize(ctx->ev[1]);
     cudaEventElapsedTime(&ms_auto, ctx->ev[0], ctx->ev[1]);
+    rc = osmr_batch_draw(ctx, canvas_rgb, flags, out, nullptr);
     ctx->stats.ms_auto = ms_auto;
     ctx->stats.ms_total += ms_auto;
     return rc;
+} OSMR_CATCH_INT(ctx)
+
+// Drawer::draw_tile for a tile list (drawer.rs:40-58 as the server calls it, http_server.rs:150-177): f3 in front of the draw
+// path, f4 behind it -- only the tile list goes to the device and only PNG files come back.
+int osmr_draw_tiles_auto_png(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, const uint8_t canvas_rgb[3], uint32_t flags,
+                             uint8_t* png_out, size_t png_cap, uint64_t* png_offset) try {
+    if (!ctx) return OSMR_E_INVALID;
+    if (!png_out || !png_offset) return ctx->fail(OSMR_E_INVALID, "null output buffer");
+    if (flags & (OSMR_DRAW_OUT_RGBA | OSMR_DRAW_OUT_DEVICE)) return ctx->fail(OSMR_E_INVALID, "osmr_draw_tiles_auto_png encodes RGB into host memory");
+    int rc = auto_prepare(ctx, tiles, n_tiles, canvas_rgb, flags);
+    if (rc) return rc;
+    float ms_auto = 0.f;
+    cudaEventSynchronize(ctx->ev[1]);
+    cudaEventElapsedTime(&ms_auto, ctx->ev[0], ctx->ev[1]);
+    rc = osmr_batch_draw(ctx, canvas_rgb, flags, nullptr, nullptr);  // the RGB tiles stay in HBM (ctx->out)
+    if (rc) return rc;
+    ctx->stats.ms_auto = ms_auto;
+    ctx->stats.ms_total += ms_auto;
+    return encode_png_from_device(ctx, ctx->out.p, n_tiles, (unsigned)ctx->scale, png_out, png_cap, png_offset);
 } OSMR_CATCH_INT(ctx)
 
 int osmr_auto_readback(osmr_ctx* ctx, uint32_t* area_begin, osmr_styled_area* areas, uint32_t areas_cap) try {
@@ -1474,7 +1506,8 @@ int osmr_project_nodes(osmr_ctx* ctx, const osmr_tile* tile, int32_t* out_xy) tr
     if (ctx->n_nodes == 0) return OSMR_OK;
     DevBuf<int2> tmp;
     CK(tmp.reserve(ctx->n_nodes));
-    project_all_kernel<<<(ctx->n_nodes + 255) / 256, 256, 0, ctx->stream>>>(ctx->merc.p, ctx->n_nodes, *tile, tmp.p);
+    int2* tmp_p = tmp.p;
+    project_all_kernel<<<(ctx->n_nodes + 255) / 256, 256, 0, ctx->stream>>>(ctx->merc.p, ctx->n_nodes, *tile, tmp_p);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out_xy, tmp.p, (size_t)ctx->n_nodes * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));

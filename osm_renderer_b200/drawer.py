@@ -271,6 +271,21 @@ class GpuContext:
         )
         return [buf[int(offs[i]) : int(offs[i + 1])].tobytes() for i in range(n)]
 
+    def draw_tiles_auto_png(self, tiles, canvas_rgb, use_caps_for_dashes=True):
+        """osmr_draw_tiles_auto_png: tile list in, one PNG file per tile out (Drawer::draw_tile behind the server's lookup)."""
+        tiles = np.ascontiguousarray(tiles, dtype=TILE_DTYPE)
+        n = len(tiles)
+        cap = n * int(self.L.osmr_png_bound(int(tiles["scale"][0]))) if n else 0
+        buf = np.empty(cap, dtype=np.uint8)
+        offs = np.zeros(n + 1, dtype=np.uint64)
+        flags, canvas = self._flags(canvas_rgb, use_caps_for_dashes, False)
+        self._check(
+            self.L.osmr_draw_tiles_auto_png(self.h, tiles.ctypes.data, n, canvas.ctypes.data, flags, buf.ctypes.data, cap, offs.ctypes.data),
+            "osmr_draw_tiles_auto_png",
+        )
+        self._auto_tiles = n
+        return [buf[int(offs[i]) : int(offs[i + 1])].tobytes() for i in range(n)]
+
     def rgb_to_png(self, images):
         """osmr_rgb_to_png: uint8 [n, D, D, 3] (D = 256 * scale) -> list of PNG files (png_writer.rs:4-21)."""
         images = np.ascontiguousarray(images, dtype=np.uint8)

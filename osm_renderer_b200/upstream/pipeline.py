@@ -197,6 +197,110 @@ class FastBatchBuilder:
         return out
 
 
+def _label_methods():
+    """labels_array for FastBatchBuilder (kept next to it; bound below)."""
+    from ..wire import LABEL_DTYPE, OSMR_AREA_MULTIPOLYGON, OSMR_LABEL_NODE
+    from .styler import KIND_NODE
+
+    def _label_lists(self, zoom, kind, tagkeys, ltable):
+        """per distinct tag list: (label style ids, layer, z_index) through a memo -- the reference's StyleCache entry"""
+        uniq, inv = np.unique(tagkeys, return_inverse=True)
+        lists = []
+        for k in uniq:
+            ck = ("L", zoom, kind, int(k), id(ltable))
+            ent = self._cache.get(ck)
+            if ent is None:
+                tags = self.rd.tags_of(int(k) >> 32, int(k) & 0xFFFFFFFF)
+                styles = self.styler.styles_for(tags, zoom, kind)
+                ent = (
+                    np.array([ltable.style_id(s) for s in styles], dtype=np.int64),
+                    np.array([s.layer or 0 for s in styles], dtype=np.int64),
+                    np.array([s.z_index for s in styles], dtype=np.float64),
+                )
+                self._cache[ck] = ent
+            lists.append(ent)
+        return inv, lists
+
+    def _expand_labels(self, zoom, ids, kinds, gids, tagkeys, ltable):
+        out = []
+        for kind in np.unique(kinds):
+            m = kinds == kind
+            inv, lists = _label_lists(self, zoom, int(kind), tagkeys[m], ltable)
+            cnt = np.array([len(l[0]) for l in lists], dtype=np.int64)[inv]
+            tot = int(cnt.sum())
+            if tot == 0:
+                continue
+            rep = np.repeat(np.arange(len(inv)), cnt)
+            start = np.concatenate([[0], np.cumsum(cnt)[:-1]])
+            within = np.arange(tot) - start[rep]
+            width = max(len(l[0]) for l in lists)
+            pad = lambda j, dt: np.array([np.pad(l[j], (0, width - len(l[j]))) for l in lists], dtype=dt)
+            sid, lay, zi = pad(0, np.int64), pad(1, np.int64), pad(2, np.float64)
+            u = inv[rep]
+            out.append((ids[m][rep], sid[u, within], lay[u, within], zi[u, within], gids[m][rep], within))
+        if not out:
+            z = np.zeros(0, dtype=np.int64)
+            return z, z, z, np.zeros(0), z, z
+        return tuple(np.concatenate([o[i] for o in out]) for i in range(6))
+
+    def labels_array(self, zoom, x, y, ltable) -> np.ndarray:
+        """The label generations of a tile as osmr_label records, in the reference's order (drawer.rs:106-119): the areas
+        styled with for_labels = true (styler.rs:168-203: sorted by (layer, z_index, global id) -- is_foreground_fill is
+        ignored, styler.rs:263 --, multipolygons first on ties), then the styled nodes (styler.rs:115-166)."""
+        rd = self.rd
+        ways, mps = self._candidates(zoom, x, y)
+        we = _expand_labels(self, zoom, ways, self.way_kind[ways], self.way_gid[ways], self.way_tagkey[ways], ltable)
+        me = _expand_labels(self, zoom, mps, np.full(len(mps), KIND_MULTIPOLYGON), self.mp_gid[mps], self.mp_tagkey[mps], ltable)
+        ent = np.concatenate([me[0] | OSMR_AREA_MULTIPOLYGON, we[0]])
+        sid = np.concatenate([me[1], we[1]])
+        lay = np.concatenate([me[2], we[2]])
+        zi = np.concatenate([me[3], we[3]])
+        gid = np.concatenate([me[4], we[4]])
+        is_way = np.concatenate([np.zeros(len(me[0]), dtype=np.int64), np.ones(len(we[0]), dtype=np.int64)])
+        loc = np.concatenate([me[0], we[0]])
+        within = np.concatenate([me[5], we[5]])
+        order = np.lexsort((within, loc, is_way, gid, zi, lay))
+        parts_e, parts_s = [ent[order]], [sid[order]]
+        # nodes of the 3x3 neighbourhood that carry tags (an untagged node matches no `node` selector with a condition;
+        # unconditional node rules would style it, so keep every node when the stylesheet has such a rule)
+        nodes = self._candidate_nodes(zoom, x, y)
+        if len(nodes):
+            ntl = rd.nodes["tags_len"][nodes].astype(np.int64)
+            ntk = np.where(ntl > 0, (rd.nodes["tags_off"][nodes].astype(np.int64) << 32) | ntl, 0)  # untagged nodes: one class
+            ne = _expand_labels(self, zoom, nodes, np.full(len(nodes), KIND_NODE), rd.nodes["id"][nodes].astype(np.int64), ntk, ltable)
+            order_n = np.lexsort((ne[5], ne[0], ne[4], ne[3], ne[2]))
+            parts_e.append(ne[0][order_n] | OSMR_LABEL_NODE)
+            parts_s.append(ne[1][order_n])
+        out = np.empty(sum(len(p) for p in parts_e), dtype=LABEL_DTYPE)
+        out["entity"] = np.concatenate(parts_e)
+        out["style"] = np.concatenate(parts_s)
+        return out
+
+    def _candidate_nodes(self, zoom, x, y):
+        rd = self.rd
+        mul = 1 << (18 - zoom)
+        xa, xb = (x - 1) * mul, (x + 2) * mul - 1
+        ya, yb = (y - 1) * mul, (y + 2) * mul - 1
+        lo = np.searchsorted(self._tx, max(xa, 0), side="left")
+        hi = np.searchsorted(self._tx, xb, side="right")
+        sel = np.nonzero((self._ty[lo:hi] >= ya) & (self._ty[lo:hi] <= yb))[0] + lo
+        recs = rd.tiles[sel]
+        offs = recs["n_off"].astype(np.int64)
+        lens = recs["n_len"].astype(np.int64)
+        tot = int(lens.sum())
+        if tot == 0:
+            return np.zeros(0, dtype=np.int64)
+        rep = np.repeat(np.arange(len(offs)), lens)
+        start = np.concatenate([[0], np.cumsum(lens)[:-1]])
+        idx = offs[rep] + (np.arange(tot) - start[rep])
+        return np.unique(rd.ints[idx]).astype(np.int64)
+
+    return labels_array, _candidate_nodes
+
+
+FastBatchBuilder.labels_array, FastBatchBuilder._candidate_nodes = _label_methods()
+
+
 def zoom_class_tables(fb: "FastBatchBuilder", zoom: int):
     """The per-zoom style classes osmr_set_zoom_styles takes: what the reference's StyleCache
     (style_cache.rs:68-87) would hold after every way and multipolygon has been styled once at `zoom`.

@@ -5,10 +5,13 @@ Not part of the accelerated path: this only manufactures a `.bin` image in the r
 network access.  Everything is drawn from numpy's PCG64 seeded with 0xB20005A1, so every run (here and on the
 GPU box) produces the same bytes.
 
-Content of the default metro (z14 block x in [9888,9919], y in [5104,5135] around the reference's fixture tile):
-  * jittered street grid, one way per block side, 2-6 nodes, highway=residential/tertiary/secondary/primary
-    (p = .70/.15/.10/.05), 30 % with one of 64 names
-  * 3-8 rotated rectangular building footprints per block (building=yes, closed 5-node ways)
+Content of the default metro (z14 block x in [9888,9919], y in [5104,5135] around the reference's fixture tile; SURVEY.md 8d C2):
+  * jittered street grid every 120-250 m, a way runs along 1-4 blocks of its grid line with 2-10 nodes,
+    highway=residential/tertiary/secondary/primary (p = .70/.15/.10/.05), 30 % of the streets carry one of 64 names
+    (5-18 characters, like real street names)
+  * 4-20 rotated building footprints per block (building=yes, closed ways of 5-13 nodes: rectangles, L-, U- and
+    cross-shaped outlines, sides 8-40 m)
+    [round 1 used `profile="r1"`: one way per block side, 3-8 rectangular footprints, "Synthetic Street N" names]
   * 6 % of the blocks carry a park / residential-landuse / water polygon of 16-48 nodes
   * 1 % of the blocks carry a multipolygon (natural=water outer ring, 1-3 inner rings)
   * one meandering river (waterway=river, 400 nodes) and one railway (railway=rail, 300 nodes, dashed in both
@@ -87,9 +90,35 @@ class _Builder:
             self.way_tags.append(int(ts))
 
 
-def make_metro(seed: int = SEED, zoom: int = 14, x0: int = 9888, y0: int = 5104, n: int = 32, buildings=(3, 8),
-               extra_footprints: int = 0, coastline_nodes: int = 0) -> bytes:
-    """Returns the `.bin` image.  extra_footprints / coastline_nodes add the C5 stress content."""
+_STREET_WORDS = ["Oak", "Elm", "Main", "Mill", "Park", "Lake", "Hill", "High", "Church", "Station", "Market", "Bridge", "Garden",
+                 "Linden", "Maple", "Cedar", "Victoria", "Harbour", "Orchard", "Meadow", "Castle", "Abbey"]
+_STREET_KINDS = ["St", "Ave", "Rd", "Lane", "Street", "Way", "Close", "Drive"]
+
+
+def street_names() -> list:
+    """64 deterministic names of 5-18 characters (no RNG: the same list everywhere)."""
+    out = []
+    for i in range(64):
+        out.append(f"{_STREET_WORDS[(i * 7) % len(_STREET_WORDS)]} {_STREET_KINDS[(i * 3 + i // 8) % len(_STREET_KINDS)]}")
+    return out
+
+
+# building outlines on the unit square [-1, 1]^2, counter-clockwise, closing node added by the generator (SURVEY.md 8d: 5-13 nodes)
+_OUTLINES = [
+    np.array([[-1, -1], [1, -1], [1, 1], [-1, 1]], dtype=np.float64),  # rectangle: 5 nodes
+    np.array([[-1, -1], [1, -1], [1, 0], [0, 0], [0, 1], [-1, 1]], dtype=np.float64),  # L: 7 nodes
+    np.array([[-1, -1], [1, -1], [1, 1], [0.4, 1], [0.4, -0.2], [-0.4, -0.2], [-0.4, 1], [-1, 1]], dtype=np.float64),  # U: 9 nodes
+    np.array([[-0.4, -1], [0.4, -1], [0.4, -0.4], [1, -0.4], [1, 0.4], [0.4, 0.4], [0.4, 1], [-0.4, 1], [-0.4, 0.4], [-1, 0.4],
+              [-1, -0.4], [-0.4, -0.4]], dtype=np.float64),  # cross: 13 nodes
+]
+
+
+def make_metro(seed: int = SEED, zoom: int = 14, x0: int = 9888, y0: int = 5104, n: int = 32, buildings=None,
+               extra_footprints: int = 0, coastline_nodes: int = 0, profile: str = "r2") -> bytes:
+    """Returns the `.bin` image.  extra_footprints / coastline_nodes add the C5 stress content.
+    profile "r2" is SURVEY.md 8(d)'s C2 as written; "r1" reproduces the round-1 dataset (sparser, see the module docstring)."""
+    if buildings is None:
+        buildings = (4, 20) if profile == "r2" else (3, 8)
     rng = np.random.default_rng(seed)
     mul = 256 << (MAX_ZOOM - zoom)  # z18 pixels per tile of `zoom`
     X0, Y0 = x0 * mul, y0 * mul
@@ -107,7 +136,7 @@ def make_metro(seed: int = SEED, zoom: int = 14, x0: int = 9888, y0: int = 5104,
     gx = grid_lines()
     gy = grid_lines()
     nx, ny = len(gx), len(gy)
-    names = [f"Synthetic Street {i}" for i in range(64)]
+    names = street_names() if profile == "r2" else [f"Synthetic Street {i}" for i in range(64)]
     classes = ["residential", "tertiary", "secondary", "primary"]
 
     def street_tags(cls_i, name_i):
@@ -124,6 +153,23 @@ def make_metro(seed: int = SEED, zoom: int = 14, x0: int = 9888, y0: int = 5104,
             cls_i = int(rng.choice(4, p=[0.70, 0.15, 0.10, 0.05]))
             name_i = int(rng.integers(0, 64)) if rng.random() < 0.30 else -1
             ts = b.tagset(street_tags(cls_i, name_i))
+            if profile == "r2":  # a way runs along 1-4 blocks, every block adds 1-3 nodes: 2-10 nodes per way
+                j = 0
+                while j < len(cross) - 1:
+                    span = int(min(rng.integers(1, 5), len(cross) - 1 - j))
+                    per_block = int(rng.integers(0, 3 if span <= 3 else 2))  # interior nodes per block
+                    parts = [np.linspace(cross[j + q], cross[j + q + 1], per_block + 2)[:-1] for q in range(span)]
+                    t = np.concatenate(parts + [np.array([cross[j + span]])])
+                    off = rng.normal(0.0, 4.0, size=len(t))
+                    off[0] = off[-1] = 0.0
+                    if horizontal:
+                        ids = b.add_nodes(X0 + t, Y0 + c + off)
+                    else:
+                        ids = b.add_nodes(X0 + c + off, Y0 + t)
+                    b.way_nodes.append(ids)
+                    b.way_tags.append(ts)
+                    j += span
+                continue
             k = rng.integers(2, 7, size=len(cross) - 1)  # nodes per way
             for j in range(len(cross) - 1):
                 t = np.linspace(cross[j], cross[j + 1], int(k[j]))
@@ -158,11 +204,16 @@ def make_metro(seed: int = SEED, zoom: int = 14, x0: int = 9888, y0: int = 5104,
     ang = rng.uniform(-15.0, 15.0, nbt) * math.pi / 180.0
     ca, sa = np.cos(ang), np.sin(ang)
     corners = np.array([[-1, -1], [1, -1], [1, 1], [-1, 1]], dtype=np.float64)
-    rx = cx[:, None] + (corners[None, :, 0] * hw[:, None]) * ca[:, None] - (corners[None, :, 1] * hh[:, None]) * sa[:, None]
-    ry = cy[:, None] + (corners[None, :, 0] * hw[:, None]) * sa[:, None] + (corners[None, :, 1] * hh[:, None]) * ca[:, None]
-    ids = b.add_nodes(X0 + rx, Y0 + ry).reshape(nbt, 4)
-    ids5 = np.concatenate([ids, ids[:, :1]], axis=1)
-    b.add_ways_fixed(ids5, np.full(nbt, ts_building))
+    shape = rng.choice(4, size=nbt, p=[0.60, 0.22, 0.12, 0.06]) if profile == "r2" else np.zeros(nbt, dtype=np.int64)
+    for si, outline in enumerate(_OUTLINES):
+        m = np.nonzero(shape == si)[0]
+        if len(m) == 0:
+            continue
+        ux, uy = outline[None, :, 0] * hw[m, None], outline[None, :, 1] * hh[m, None]
+        rx = cx[m, None] + ux * ca[m, None] - uy * sa[m, None]
+        ry = cy[m, None] + ux * sa[m, None] + uy * ca[m, None]
+        ids = b.add_nodes(X0 + rx, Y0 + ry).reshape(len(m), len(outline))
+        b.add_ways_fixed(np.concatenate([ids, ids[:, :1]], axis=1), np.full(len(m), ts_building))
 
     def ring(cxv, cyv, rad, k):
         th = np.sort(rng.random(k)) * 2.0 * math.pi

@@ -46,8 +46,8 @@ def main():
     torch.empty = empty
     import bench
 
-    bench.WORKLOADS["C2"] = (14, 9900, 5118, 4, 1)  # 16 tiles around the fixture tile
-    sys.argv = ["bench.py", "--steps", "1", "--warmup", "1", "--lib", lib, "--cpu-sample", "4"]
+    bench.WORKLOADS["C2"] = dict(zoom=14, x0=9900, y0=5118, n=4, scale=1, metro={})  # 16 tiles around the fixture tile
+    sys.argv = ["bench.py", "--steps", "1", "--warmup", "1", "--lib", lib, "--cpu-sample", "4", "--min-seconds", "0.01", "--no-affinity"]
     buf = io.StringIO()
     with redirect_stdout(buf):
         bench.main()
@@ -64,6 +64,8 @@ def main():
     for k in ("value", "unit", "cores", "kind", "sample"):
         assert k in d["cpu_baseline"], k
     assert d["max_abs_diff_rgb_vs_cpu"] == 0 and d["e2e_auto"]["identical_to_e2e_output"] and d["e2e_png"]["mean_png_bytes"] > 0
+    assert d["max_abs_diff_rgb_vs_cpu_labeled"] == 0 and d["e2e_labeled"]["value"] > 0 and d["e2e_auto_png"]["value"] > 0
+    assert d["sustained"]["steps"] >= 5 and d["latency_ms"] and d["roofline"]["B_tile_terms"]["sum_U"] > 0
     print("bench dry run ok:", {k: d[k] for k in ("metric", "n_gpus", "gpu_launches", "max_abs_diff_rgb_vs_cpu")})
 
 
