@@ -163,6 +163,10 @@ typedef struct osmr_stats {
     float ms_cover;          /* line_cover_kernel */
     float ms_auto;           /* osmr_draw_tiles_auto: candidate lookup + ordering on the device */
     float ms_png;            /* osmr_draw_tiles_png: filter + deflate + checksums on the device */
+    uint32_t label_path;     /* osmr_draw_tiles_labeled: 0 no label pass, 1 layout on the device, 2 layout on the host (fallback / debug key) */
+    uint32_t n_labels_active;    /* device layout: label generations with an icon or an existing text */
+    uint32_t n_labels_polylabel; /* device layout: of those, areas whose anchor is the pole of inaccessibility (labelable.rs:125-189) */
+    uint32_t label_attempts;     /* device layout: attempts of this call (> 1: scratch was grown and the call redone) */
 } osmr_stats;
 int osmr_get_stats(osmr_ctx* ctx, osmr_stats* out);
 
@@ -173,10 +177,14 @@ int osmr_project_nodes(osmr_ctx* ctx, const osmr_tile* tile, int32_t* out_xy);
 /* ------------------------------------------------------------------------------------------------------------
  * Label pass (reference src/draw/drawer.rs:106-126,221-262; src/draw/labeler.rs:16-106; src/draw/labelable.rs;
  * src/draw/font/{text_placer,rasterizer}.rs; src/draw/tile_pixels.rs:131-162,205-209).
- * Host C++ inside the library does the string / font work exactly as the reference does it on the CPU (tag lookup,
- * stb_truetype glyph outlines, glyph placement with the platform libm, polylabel); the device rasterises glyph
- * coverage (exact-area accumulation in segment order), resolves the greedy label collisions over the 3x3 canvas and
- * blends the surviving labels over the f64 tile canvas before the RGB export.
+ * String / font-table / libm work is done by host C++ inside the library ONCE, as resident tables: per (dataset, font, label
+ * style table) the text run of every entity (tag lookup, cmap, hmtx, kern) and the stb_truetype glyph outlines; per zoom the
+ * sin / cos of every named way's segment directions (glibc, like the reference).  Everything per tile and per call runs on
+ * the device: which generations can draw, polylabel anchors, glyph placement along ways / in wrapped rows, outline flattening,
+ * exact-area glyph coverage in segment order, the greedy label collisions over the 3x3 canvas, and the blend of the surviving
+ * labels over the f64 tile canvas before the RGB export.  Inputs the device path does not take (a scale that is not a power of
+ * two, zoom > 18, a flatness near-tie that only libm's hypot can decide, ...) are laid out by the host code of round 1 --
+ * same pixels either way; osmr_stats.label_path says which ran.
  * ------------------------------------------------------------------------------------------------------------ */
 #define OSMR_LABEL_NODE 0x40000000u /* osmr_label.entity: node index | OSMR_LABEL_NODE (ways / multipolygons as in
                                        osmr_styled_area) */
@@ -287,7 +295,7 @@ void osmr_free_pinned(void* p);
  *                           host libm, i.e. the reference's own values to the last bit). */
 int osmr_debug_set(osmr_ctx* ctx, const char* key, int value);
 
-uint32_t osmr_abi_version(void); /* 2: osmr_stats gained walk_bytes / walk_steps / ms_cover / ms_auto / ms_png; f3 and f4 entry points */
+uint32_t osmr_abi_version(void); /* 3: osmr_stats gained the label_* fields; osmr_draw_tiles_auto_png; label layout on the device */
 
 #ifdef __cplusplus
 }

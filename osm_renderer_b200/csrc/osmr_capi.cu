@@ -21,6 +21,9 @@
 #include "osmr_auto.cuh"
 #include "osmr_png.cuh"
 #include "osmr_labels_host.hpp"
+#include "osmr_labels_dev.cuh"
+#include <map>
+#include <unordered_map>
 
 using namespace osmr;
 
@@ -133,6 +136,36 @@ struct osmr_ctx {
     unsigned label_threads = 32;
     DevBuf<LabelPix> label_plane;
     bool label_plane_active = false;
+    // label layout on the device (osmr_labels_dev.cuh): resident tables + per-call scratch
+    struct LabelResident {
+        bool valid = false;
+        std::vector<std::string> keys;
+        DevBuf<DevLabelStyle> styles;
+        DevBuf<unsigned> text_id, text_begin, glyph_vbegin;
+        DevBuf<DevGlyphRec> glyphs;
+        DevBuf<DevVertex> verts;
+        unsigned n_keys = 0, ent_total = 0, way_base = 0, mp_base = 0, n_texts = 0;
+        std::vector<uint8_t> way_has_text;  // ways whose text may run along the line: they get direction tables
+        struct Angle {
+            bool set = false;
+            int scale = 0;
+            DevBuf<unsigned> off;
+            DevBuf<double2> sc;
+        } angle[19];
+    } lres;
+    std::vector<double2> h_merc;  // host copy of the Mercator factors (direction tables of the label layout)
+    DevBuf<osmr_label> d_label_list;
+    DevBuf<ActLabel> l_act;
+    DevBuf<unsigned> l_act_cnt, l_counters;
+    DevBuf<LabelPlace> l_place;
+    DevBuf<GlyphPlace> l_gplace;
+    DevBuf<GlyphOut> l_gout;
+    DevBuf<double2> l_ring_pts;
+    DevBuf<unsigned char> l_heap;
+    PinnedBuf<unsigned> h_lcnt;
+    size_t l_places_cap = 0, l_segs_cap = 0, l_rowrecs_cap = 0, l_cells_cap = 0, l_ring_cap = 0, l_heap_slots = 0;
+    bool label_host_only = false;  // debug key "label_host": always lay labels out on the host (round-1 path)
+    unsigned stats_label_active = 0, stats_label_poly = 0;
     // styles / icons
     unsigned n_styles = 0, n_dashes = 0, n_icons = 0;
     DevBuf<osmr_style> styles;
@@ -252,7 +285,7 @@ static inline uint32_t rd_u32(const uint8_t* p) {
 
 extern "C" {
 
-uint32_t osmr_abi_version(void) { return 2; }
+uint32_t osmr_abi_version(void) { return 3; }
 
 int osmr_ctx_create(int device, osmr_ctx** out_ctx) try {
     if (!out_ctx) return OSMR_E_INVALID;
@@ -398,6 +431,10 @@ int osmr_debug_set(osmr_ctx* ctx, const char* key, int value) try {
         ctx->label_threads = (unsigned)value;
         return OSMR_OK;
     }
+    if (strcmp(key, "label_host") == 0) {  // 1: label layout on the host for every call (the round-1 path; A/B and tests)
+        ctx->label_host_only = value != 0;
+        return OSMR_OK;
+    }
     if (strcmp(key, "direct_out") == 0) {  // 0: always stage the tiles in HBM and copy them back (A/B measurements)
         ctx->direct_out = value != 0;
         return OSMR_OK;
@@ -517,6 +554,7 @@ int osmr_set_geodata(osmr_ctx* ctx, const void* bin, size_t len) try {
     // could flip the integer pixel of a node that sits within ~1e-9 px of an exact .5 tie.  Debug key "device_merc" selects
     // project_nodes_kernel instead (0.02 ms for 1.9 M nodes; the host loop takes ~20 ms on 16 threads).
     std::vector<double2> h_merc;
+    ctx->h_merc.clear();
     if (n_nodes && !ctx->device_merc) {
         h_merc.resize(n_nodes);
         const unsigned n_thr = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
@@ -538,6 +576,8 @@ int osmr_set_geodata(osmr_ctx* ctx, const void* bin, size_t len) try {
         work(0);
         for (auto& th : pool) th.join();
         CK(cudaMemcpyAsync(ctx->merc.p, h_merc.data(), (size_t)n_nodes * sizeof(double2), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->h_merc.swap(h_merc);
     } else if (n_nodes) {
         const unsigned char* raw_p = raw_nodes.p;
         project_nodes_kernel<<<(n_nodes + 255) / 256, 256, 0, ctx->stream>>>(raw_p, n_nodes, ctx->merc.p);
@@ -568,6 +608,8 @@ int osmr_set_geodata(osmr_ctx* ctx, const void* bin, size_t len) try {
     ctx->n_ints = n_ints;
     ctx->has_geo = true;
     ctx->has_batch = false;
+    ctx->lres.valid = false;
+    for (auto& a : ctx->lres.angle) a.set = false;
     for (auto& z : ctx->zoom_tables) z.set = false;  // classes are per dataset
 
     // ---- f3: the tile index (reader.rs:135-180) + what the device-side lookup derives from it ----
@@ -1521,6 +1563,7 @@ int osmr_project_nodes(osmr_ctx* ctx, const osmr_tile* tile, int32_t* out_xy) tr
 int osmr_set_font(osmr_ctx* ctx, const void* ttf, size_t len) try {
     if (!ctx) return OSMR_E_INVALID;
     if (!ttf || len < 64) return ctx->fail(OSMR_E_INVALID, "null or truncated font");
+    ctx->lres.valid = false;
     if (!ctx->font.load((const uint8_t*)ttf, len)) return ctx->fail(OSMR_E_INVALID, "not a TrueType font with a Unicode cmap and glyf outlines");
     return OSMR_OK;
 } OSMR_CATCH_INT(ctx)
@@ -1532,6 +1575,7 @@ int osmr_set_label_icons(osmr_ctx* ctx, const osmr_icon* icons, uint32_t n_icons
     std::vector<DevIcon> meta(n_icons);
     std::vector<double4> px;
     ctx->label_icon_dims.assign(n_icons, osmr_host::IconDim{0, 0});
+    ctx->lres.valid = false;
     for (uint32_t i = 0; i < n_icons; ++i) {
         if (!icons[i].rgba || icons[i].width == 0 || icons[i].height == 0) return ctx->fail(OSMR_E_INVALID, "empty icon");
         meta[i].w = icons[i].width;
@@ -1576,18 +1620,14 @@ int osmr_set_label_styles(osmr_ctx* ctx, const osmr_label_style* styles, uint32_
         if (styles[i].text_position > OSMR_TEXT_POS_LINE) return ctx->fail(OSMR_E_INVALID, "bad text position");
     }
     ctx->label_styles.swap(tmp);
+    ctx->lres.valid = false;
     return OSMR_OK;
 } OSMR_CATCH_INT(ctx)
 
-int osmr_draw_tiles_labeled(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, const uint32_t* area_begin,
-                            const osmr_styled_area* areas, const uint32_t* label_begin, const osmr_label* labels,
-                            const uint8_t canvas_rgb[3], uint32_t flags, uint8_t* out) try {
-    if (!ctx) return OSMR_E_INVALID;
-    if (!out) return ctx->fail(OSMR_E_INVALID, "null output buffer");
-    if (!label_begin) return ctx->fail(OSMR_E_INVALID, "null label_begin");
-    if (!ctx->font.loaded()) return ctx->fail(OSMR_E_STATE, "osmr_set_font has not been called");
-    int rc = batch_upload_impl(ctx, tiles, n_tiles, area_begin, areas, false, nullptr);
-    if (rc) return rc;
+// ---- host layout (round-1 path; still the fallback of the device layout and what debug key "label_host" selects) ----
+static int labels_via_host(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, const uint32_t* label_begin, const osmr_label* labels) {
+    int rc = OSMR_OK;
+    (void)rc;
     const int D = 256 * ctx->scale, E = 3 * D;
     // ---- host half: layout (string / font / heap work, as the reference does it on the CPU), tiles in parallel ----
     const auto t_host0 = std::chrono::steady_clock::now();
@@ -1733,11 +1773,406 @@ int osmr_draw_tiles_labeled(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_ti
     CK(cudaEventRecord(ctx->ev_label1, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));  // recs / segs live on this stack frame
     CK(cudaEventElapsedTime(&ctx->stats_label_device_ms, ctx->ev_label0, ctx->ev_label1));
+    return OSMR_OK;
+}
+
+// ---- device layout (osmr_labels_dev.cuh) ----
+// Resident tables, built once per (dataset, font, label style table): the text run of every entity under every text key the
+// styles use (tag lookup + cmap + hmtx + kern = the string / font-table work of text_placer.rs:24-58,170-209), the glyph
+// outlines, the interned label styles.
+static int build_label_tables(osmr_ctx* ctx) {
+    auto& R = ctx->lres;
+    R.valid = false;
+    const osmr_host::BinView& g = ctx->h_view;
+    const osmr_host::TrueType& font = ctx->font;
+    // distinct text keys
+    R.keys.clear();
+    std::vector<DevLabelStyle> dstyles(ctx->label_styles.size());
+    for (size_t i = 0; i < ctx->label_styles.size(); ++i) {
+        const osmr_host::LabelStyleHost& st = ctx->label_styles[i];
+        DevLabelStyle d{};
+        d.icon = st.s.icon;
+        d.flags = st.s.flags;
+        d.key = -1;
+        if (st.s.flags & OSMR_LSTYLE_TEXT) {
+            size_t k = 0;
+            while (k < R.keys.size() && R.keys[k] != st.key) ++k;
+            if (k == R.keys.size()) R.keys.push_back(st.key);
+            d.key = (int)k;
+        }
+        const uint8_t* c = st.s.text_color;
+        d.rgb = (st.s.flags & OSMR_LSTYLE_TEXT_COLOR) ? ((unsigned)c[0] | ((unsigned)c[1] << 8) | ((unsigned)c[2] << 16)) : 0u;
+        d.text_position = st.s.text_position;
+        d.font_size = st.s.font_size;
+        dstyles[i] = d;
+    }
+    const uint32_t n_nodes = g.n_nodes, n_ways = g.n_ways, n_mps = g.n_mps;
+    R.n_keys = (unsigned)R.keys.size();
+    R.way_base = n_nodes;
+    R.mp_base = n_nodes + n_ways;
+    R.ent_total = n_nodes + n_ways + n_mps;
+    if ((uint64_t)R.n_keys * R.ent_total >= 0xffffffffull) return ctx->fail(OSMR_E_NOMEM, "label text table too large");
+    std::vector<unsigned> text_id((size_t)R.n_keys * R.ent_total, 0xffffffffu);
+    std::vector<unsigned> text_begin(1, 0u);
+    std::vector<DevGlyphRec> glyphs;
+    std::vector<unsigned> glyph_vbegin(1, 0u);
+    std::vector<DevVertex> verts;
+    std::unordered_map<int, int> slot_of_glyph;
+    std::unordered_map<std::string, unsigned> text_of_string;
+    std::vector<uint32_t> chars;
+    R.way_has_text.assign(n_ways, 0);
+    auto intern_text = [&](const char* val, size_t len) -> unsigned {
+        std::string key(val, len);
+        auto it = text_of_string.find(key);
+        if (it != text_of_string.end()) return it->second;
+        osmr_host::decode_utf8(val, len, chars);
+        int prev = -1;
+        for (uint32_t cp : chars) {
+            const int gi = font.glyph_index(cp);
+            DevGlyphRec r;
+            auto sit = slot_of_glyph.find(gi);
+            if (sit == slot_of_glyph.end()) {
+                int slot = -1;
+                const std::vector<osmr_host::GlyphVertex>* shape = font.shape(gi);
+                if (shape) {
+                    slot = (int)glyph_vbegin.size() - 1;
+                    for (const osmr_host::GlyphVertex& v : *shape) verts.push_back(DevVertex{v.x, v.y, v.cx, v.cy, (int)v.type});
+                    glyph_vbegin.push_back((unsigned)verts.size());
+                }
+                sit = slot_of_glyph.emplace(gi, slot).first;
+            }
+            r.slot = sit->second;
+            r.advance = font.advance(gi);
+            r.kern = prev >= 0 ? font.kerning(prev, gi) : 0;
+            r.ws = osmr_host::is_ws(cp) ? 1u : 0u;
+            glyphs.push_back(r);
+            prev = gi;
+        }
+        text_begin.push_back((unsigned)glyphs.size());
+        const unsigned id = (unsigned)text_begin.size() - 2;
+        text_of_string.emplace(std::move(key), id);
+        return id;
+    };
+    for (unsigned k = 0; k < R.n_keys; ++k) {
+        const std::string& key = R.keys[k];
+        unsigned* row = text_id.data() + (size_t)k * R.ent_total;
+        const char* val;
+        size_t vlen;
+        for (uint32_t i = 0; i < n_nodes; ++i) {
+            const uint32_t tl = osmr_host::BinView::u32(g.nodes + (size_t)i * 32 + 28);
+            if (!tl) continue;
+            if (g.tag(osmr_host::BinView::u32(g.nodes + (size_t)i * 32 + 24), tl, key.data(), key.size(), val, vlen)) row[i] = intern_text(val, vlen);
+        }
+        for (uint32_t i = 0; i < n_ways; ++i) {
+            const uint32_t tl = osmr_host::BinView::u32(g.ways + (size_t)i * 24 + 20);
+            if (!tl) continue;
+            if (g.tag(osmr_host::BinView::u32(g.ways + (size_t)i * 24 + 16), tl, key.data(), key.size(), val, vlen)) {
+                row[R.way_base + i] = intern_text(val, vlen);
+                R.way_has_text[i] = 1;
+            }
+        }
+        for (uint32_t i = 0; i < n_mps; ++i) {
+            const uint32_t tl = osmr_host::BinView::u32(g.mps + (size_t)i * 24 + 20);
+            if (!tl) continue;
+            if (g.tag(osmr_host::BinView::u32(g.mps + (size_t)i * 24 + 16), tl, key.data(), key.size(), val, vlen)) row[R.mp_base + i] = intern_text(val, vlen);
+        }
+    }
+    R.n_texts = (unsigned)text_begin.size() - 1;
+    cudaStream_t st = ctx->stream;
+    CK(R.styles.reserve(dstyles.size() + 1));
+    CK(R.text_id.reserve(text_id.size() + 1));
+    CK(R.text_begin.reserve(text_begin.size() + 1));
+    CK(R.glyphs.reserve(glyphs.size() + 1));
+    CK(R.glyph_vbegin.reserve(glyph_vbegin.size() + 1));
+    CK(R.verts.reserve(verts.size() + 1));
+    auto up = [&](void* d, const void* h, size_t bytes) { return bytes ? cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, st) : cudaSuccess; };
+    CK(up(R.styles.p, dstyles.data(), dstyles.size() * sizeof(DevLabelStyle)));
+    CK(up(R.text_id.p, text_id.data(), text_id.size() * 4));
+    CK(up(R.text_begin.p, text_begin.data(), text_begin.size() * 4));
+    CK(up(R.glyphs.p, glyphs.data(), glyphs.size() * sizeof(DevGlyphRec)));
+    CK(up(R.glyph_vbegin.p, glyph_vbegin.data(), glyph_vbegin.size() * 4));
+    CK(up(R.verts.p, verts.data(), verts.size() * sizeof(DevVertex)));
+    CK(cudaStreamSynchronize(st));
+    for (auto& a : R.angle) a.set = false;
+    R.valid = true;
+    return OSMR_OK;
+}
+
+// Per zoom: sin(-angle) / cos(-angle) of every segment of every way that has a text, angle = atan2(dy, dx) of the way's INTEGER
+// pixel differences in its drawing orientation (text_placer.rs:60-99,265-296) -- the platform-libm half of text along a way, from
+// glibc like the reference's.  The differences are the same in every tile of the zoom (see osmr_labels_dev.cuh), so tile (0, 0)
+// stands for all of them.
+static int build_angle_table(osmr_ctx* ctx, unsigned zoom, int scale) {
+    auto& R = ctx->lres;
+    auto& A = R.angle[zoom];
+    A.set = false;
+    const uint32_t n_ways = ctx->h_view.n_ways;
+    if (ctx->h_merc.size() != ctx->n_nodes) return ctx->fail(OSMR_E_STATE, "no host copy of the Mercator factors (debug key device_merc)");
+    std::vector<unsigned> off(n_ways, 0xffffffffu);
+    std::vector<double2> sc;
+    const double dim = (double)(unsigned)(256u * (1u << zoom)), fscale = (double)scale;
+    std::vector<osmr_host::IPoint> pts;
+    for (uint32_t w = 0; w < n_ways; ++w) {
+        if (!R.way_has_text[w]) continue;
+        const uint32_t o = osmr_host::BinView::u32(ctx->h_view.ways + (size_t)w * 24 + 8), len = osmr_host::BinView::u32(ctx->h_view.ways + (size_t)w * 24 + 12);
+        if (len < 2) continue;
+        pts.clear();
+        for (uint32_t i = 0; i < len; ++i) {
+            const double2 m = ctx->h_merc[ctx->h_view.int_at(o + i)];
+            volatile double x = m.x * dim, y = m.y * dim;  // project_point with the tile origin at 0 (exact IEEE steps)
+            volatile double xs = x * fscale, ys = y * fscale;
+            pts.push_back(osmr_host::IPoint{osmr_host::f64_as_i32(std::round(xs)), osmr_host::f64_as_i32(std::round(ys))});
+        }
+        if (pts.front().x > pts.back().x) std::reverse(pts.begin(), pts.end());
+        off[w] = (unsigned)sc.size();
+        for (uint32_t i = 0; i + 1 < len; ++i) {
+            const double angle = std::atan2((double)osmr_host::wsub(pts[i + 1].y, pts[i].y), (double)osmr_host::wsub(pts[i + 1].x, pts[i].x));
+            sc.push_back(make_double2(std::sin(-angle), std::cos(-angle)));
+        }
+    }
+    CK(A.off.reserve(off.size() + 1));
+    CK(A.sc.reserve(sc.size() + 1));
+    if (!off.empty()) CK(cudaMemcpyAsync(A.off.p, off.data(), off.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (!sc.empty()) CK(cudaMemcpyAsync(A.sc.p, sc.data(), sc.size() * sizeof(double2), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    A.scale = scale;
+    A.set = true;
+    return OSMR_OK;
+}
+
+static bool label_device_path_allowed(const osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles) {
+    if (ctx->label_host_only || ctx->h_merc.size() != ctx->n_nodes) return false;
+    const uint32_t scale = tiles[0].scale;
+    if (scale != 1 && scale != 2 && scale != 4 && scale != 8) return false;  // `* scale` must be exact (osmr_labels_dev.cuh)
+    for (uint32_t t = 0; t < n_tiles; ++t)
+        if (tiles[t].zoom > 18) return false;
+    return true;
+}
+
+// Enqueues the whole label pass on the compute stream (nothing here waits for the device): layout kernels, glyph coverage,
+// greedy collisions -> ctx->label_plane.  The counters land in page-locked memory; label_device_judge reads them after the
+// draw has synchronised the stream.
+static int label_device_enqueue(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, const uint32_t* label_begin, const osmr_label* labels) {
+    auto& R = ctx->lres;
+    const int D = 256 * ctx->scale, E = 3 * D;
+    if (!R.valid) {
+        int rc = build_label_tables(ctx);
+        if (rc) return rc;
+    }
+    for (uint32_t t = 0; t < n_tiles; ++t) {
+        auto& A = R.angle[tiles[t].zoom];
+        if (!A.set || A.scale != ctx->scale) {
+            int rc = build_angle_table(ctx, tiles[t].zoom, ctx->scale);
+            if (rc) return rc;
+        }
+    }
+    const uint32_t n_labels = label_begin[n_tiles];
+    cudaStream_t st = ctx->stream;
+    // first guesses of the bump-allocated scratch (grown by label_device_judge)
+    if (!ctx->l_places_cap) ctx->l_places_cap = 1u << 18;
+    if (!ctx->l_segs_cap) ctx->l_segs_cap = 1u << 21;
+    if (!ctx->l_rowrecs_cap) ctx->l_rowrecs_cap = 1u << 19;
+    if (!ctx->l_cells_cap) ctx->l_cells_cap = 1u << 23;
+    if (!ctx->l_ring_cap) ctx->l_ring_cap = 1u << 16;
+    if (!ctx->l_heap_slots) ctx->l_heap_slots = 256;
+    CK(ctx->d_label_list.reserve((size_t)n_labels + 1));
+    CK(ctx->d_label_begin.reserve(n_tiles + 1));
+    CK(ctx->l_act.reserve((size_t)n_labels + 1));
+    CK(ctx->l_place.reserve((size_t)n_labels + 1));
+    CK(ctx->d_labels.reserve((size_t)n_labels + 1));
+    CK(ctx->l_act_cnt.reserve(n_tiles + 1));
+    CK(ctx->l_counters.reserve(LCNT_COUNT));
+    CK(ctx->h_lcnt.reserve(LCNT_COUNT));
+    CK(ctx->l_gplace.reserve(ctx->l_places_cap));
+    CK(ctx->l_gout.reserve(ctx->l_places_cap));
+    CK(ctx->d_label_segs.reserve(ctx->l_segs_cap));
+    CK(ctx->d_seg_slope.reserve(ctx->l_segs_cap));
+    CK(ctx->d_seg_rows.reserve(ctx->l_segs_cap));
+    CK(ctx->d_label_rows.reserve(ctx->l_rowrecs_cap));
+    CK(ctx->label_row_keys.reserve(2 * ctx->l_rowrecs_cap + 2));
+    CK(ctx->label_acc.reserve(2 * ctx->l_cells_cap + 2));
+    CK(ctx->l_ring_pts.reserve(ctx->l_ring_cap));
+    CK(ctx->l_heap.reserve(ctx->l_heap_slots * (size_t)kPolyHeapCap * sizeof(PolyCell)));
+    CK(ctx->label_occ.reserve((size_t)n_tiles * ((size_t)E * E / 32)));
+    CK(ctx->label_plane.reserve((size_t)n_tiles * D * D));
+    CK(cudaEventRecord(ctx->ev_label0, st));
+    if (n_labels) CK(cudaMemcpyAsync(ctx->d_label_list.p, labels, (size_t)n_labels * sizeof(osmr_label), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_label_begin.p, label_begin, (size_t)(n_tiles + 1) * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(ctx->l_counters.p, 0, LCNT_COUNT * sizeof(unsigned), st));
+    Scene s{};
+    s.merc = ctx->merc.p;
+    s.ways = ctx->ways.p;
+    s.polys = ctx->polys.p;
+    s.mps = ctx->mps.p;
+    s.ints = ctx->ints.p;
+    s.n_nodes = ctx->n_nodes;
+    s.n_ways = ctx->n_ways;
+    s.n_polys = ctx->n_polys;
+    s.n_mps = ctx->n_mps;
+    s.n_ints = ctx->n_ints;
+    s.tiles = ctx->tiles.p;
+    s.n_tiles = n_tiles;
+    s.D = D;
+    s.scale = ctx->scale;
+    LabelDev ld{};
+    ld.styles = R.styles.p;
+    ld.n_styles = (unsigned)ctx->label_styles.size();
+    ld.text_id = R.text_id.p;
+    ld.n_keys = R.n_keys;
+    ld.ent_total = R.ent_total;
+    ld.way_base = R.way_base;
+    ld.mp_base = R.mp_base;
+    ld.text_begin = R.text_begin.p;
+    ld.n_texts = R.n_texts;
+    ld.glyphs = R.glyphs.p;
+    ld.glyph_vbegin = R.glyph_vbegin.p;
+    ld.verts = R.verts.p;
+    ld.ascent = ctx->font.ascent();
+    ld.descent = ctx->font.descent();
+    ld.line_gap = ctx->font.line_gap();
+    for (int z = 0; z < 19; ++z) {
+        ld.way_angle_off[z] = (R.angle[z].set && R.angle[z].scale == ctx->scale) ? R.angle[z].off.p : nullptr;
+        ld.sincos[z] = R.angle[z].sc.p;
+    }
+    ld.icons = ctx->label_icons.p;
+    ld.n_icons = (unsigned)ctx->label_icon_dims.size();
+    ld.label_begin = ctx->d_label_begin.p;
+    ld.labels = ctx->d_label_list.p;
+    ld.n_tiles = n_tiles;
+    ld.act = ctx->l_act.p;
+    ld.act_cnt = ctx->l_act_cnt.p;
+    ld.place = ctx->l_place.p;
+    ld.gplace = ctx->l_gplace.p;
+    ld.gout = ctx->l_gout.p;
+    ld.gplace_cap = (unsigned)std::min<size_t>(ctx->l_places_cap, 0xfffffff0u);
+    ld.segs = ctx->d_label_segs.p;
+    ld.segs_cap = (unsigned)std::min<size_t>(ctx->l_segs_cap, 0xfffffff0u);
+    ld.out_labels = ctx->d_labels.p;
+    ld.rowrecs = ctx->d_label_rows.p;
+    ld.rowrecs_cap = (unsigned)std::min<size_t>(ctx->l_rowrecs_cap, 0x7ffffff0u);
+    ld.cells_cap = ctx->l_cells_cap;
+    ld.ring_pts = ctx->l_ring_pts.p;
+    ld.ring_cap = (unsigned)std::min<size_t>(ctx->l_ring_cap, 0xfffffff0u);
+    ld.heap = ctx->l_heap.p;
+    ld.heap_slots = (unsigned)ctx->l_heap_slots;
+    ld.counters = ctx->l_counters.p;
+    const unsigned wide = (unsigned)ctx->num_sms * 8u;
+    label_select_kernel<<<n_tiles, kLabelSelThreads, 0, st>>>(s, ld);
+    label_layout_kernel<<<n_tiles, kLayoutThreads, 0, st>>>(s, ld);
+    label_emit_count_kernel<<<wide, 128, 0, st>>>(ld);
+    label_finish_kernel<<<n_tiles, 128, 0, st>>>(s, ld);
+    label_emit_write_kernel<<<wide, 128, 0, st>>>(ld);
+    CK(cudaGetLastError());
+    LabelScene ls{};
+    ls.labels = ctx->d_labels.p;
+    ls.label_begin = ctx->d_label_begin.p;
+    ls.segs = ctx->d_label_segs.p;
+    ls.rowrecs = ctx->d_label_rows.p;
+    ls.seg_slope = ctx->d_seg_slope.p;
+    ls.seg_rows = ctx->d_seg_rows.p;
+    ls.icons = ctx->label_icons.p;
+    ls.occ = ctx->label_occ.p;
+    ls.acc_a = ctx->label_acc.p;
+    ls.acc_s = ctx->label_acc.p + ctx->l_cells_cap;
+    ls.kmin = ctx->label_row_keys.p;
+    ls.kmax = ctx->label_row_keys.p + ctx->l_rowrecs_cap;
+    ls.plane = ctx->label_plane.p;
+    ls.D = D;
+    ls.n_segs_dev = ctx->l_counters.p + LCNT_SEGS;
+    ls.n_rowrecs_dev = ctx->l_counters.p + LCNT_ROWRECS;
+    ls.label_cnt = ctx->l_act_cnt.p;
+    ls.skip_flags = ctx->l_counters.p + LCNT_OVERFLOW;
+    label_seg_kernel<<<wide, 256, 0, st>>>(ls);
+    label_cover_kernel<<<(unsigned)ctx->num_sms * 32u, 32, 0, st>>>(ls);
+    label_commit_kernel<<<n_tiles, kLabelThreads, 0, st>>>(ls);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev_label1, st));
+    CK(cudaMemcpyAsync(ctx->h_lcnt.p, ctx->l_counters.p, LCNT_COUNT * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    return OSMR_OK;
+}
+
+// After the stream has been synchronised: 0 = the label plane of this attempt is good, 1 = scratch grown, redo the call,
+// 2 = this call needs the host layout, < 0 = error.
+static int label_device_judge(osmr_ctx* ctx) {
+    const unsigned* c = ctx->h_lcnt.p;
+    if (c[LCNT_BAD]) return ctx->fail(OSMR_E_INVALID, "label references an entity, style or icon that does not exist");
+    if (c[LCNT_FALLBACK]) return 2;
+    if (c[LCNT_OVERFLOW]) {
+        unsigned long long cells;
+        memcpy(&cells, &c[LCNT_CELLS_LO], 8);
+        auto grow = [](size_t used) { return used + used / 4 + 1024; };
+        // (a counter is an upper bound of what the attempt wanted only up to the first overflow: later stages were skipped)
+        if (c[LCNT_OVERFLOW] & 1u) ctx->l_places_cap = std::max(grow(c[LCNT_PLACES]), ctx->l_places_cap * 2);
+        if (c[LCNT_OVERFLOW] & 2u) ctx->l_segs_cap = std::max(grow(c[LCNT_SEGS]), ctx->l_segs_cap * 2);
+        if (c[LCNT_OVERFLOW] & 4u) ctx->l_rowrecs_cap = std::max(grow(c[LCNT_ROWRECS]), ctx->l_rowrecs_cap * 2);
+        if (c[LCNT_OVERFLOW] & 8u) ctx->l_cells_cap = std::max(grow((size_t)cells), ctx->l_cells_cap * 2);
+        if (c[LCNT_OVERFLOW] & 16u) ctx->l_ring_cap = std::max(grow(c[LCNT_RING_PTS]), ctx->l_ring_cap * 2);
+        if (c[LCNT_OVERFLOW] & 32u) ctx->l_heap_slots = std::max(grow(c[LCNT_POLY]), ctx->l_heap_slots * 2);
+        if (ctx->l_places_cap >= 0xfffffff0ull || ctx->l_segs_cap >= 0xfffffff0ull || ctx->l_rowrecs_cap >= 0x7ffffff0ull ||
+            ctx->l_cells_cap > (1ull << 33) || ctx->l_ring_cap >= 0xfffffff0ull)
+            return ctx->fail(OSMR_E_NOMEM, "label scratch too large; split the batch");
+        return 1;
+    }
+    ctx->stats_label_active = c[LCNT_ACTIVE];
+    ctx->stats_label_poly = c[LCNT_POLY];
+    return 0;
+}
+
+int osmr_draw_tiles_labeled(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, const uint32_t* area_begin,
+                            const osmr_styled_area* areas, const uint32_t* label_begin, const osmr_label* labels,
+                            const uint8_t canvas_rgb[3], uint32_t flags, uint8_t* out) try {
+    if (!ctx) return OSMR_E_INVALID;
+    if (!out) return ctx->fail(OSMR_E_INVALID, "null output buffer");
+    if (!label_begin) return ctx->fail(OSMR_E_INVALID, "null label_begin");
+    if (!ctx->font.loaded()) return ctx->fail(OSMR_E_STATE, "osmr_set_font has not been called");
+    int rc = batch_upload_impl(ctx, tiles, n_tiles, area_begin, areas, false, nullptr);
+    if (rc) return rc;
+    for (uint32_t t = 0; t < n_tiles; ++t) {
+        if (label_begin[t + 1] < label_begin[t]) return ctx->fail(OSMR_E_INVALID, "label_begin must be non-decreasing");
+        if (label_begin[t + 1] > label_begin[t] && !labels) return ctx->fail(OSMR_E_INVALID, "null label list");
+    }
+    if (label_begin[0] != 0) return ctx->fail(OSMR_E_INVALID, "label_begin[0] must be 0");
+    cudaSetDevice(ctx->device);
+    // ---- label layout on the device: everything is enqueued behind the upload, the draw follows without a host round trip ----
+    bool on_device = label_device_path_allowed(ctx, tiles, n_tiles);
+    for (int attempt = 0; on_device && attempt < 12; ++attempt) {
+        const auto t_host0 = std::chrono::steady_clock::now();
+        rc = label_device_enqueue(ctx, tiles, n_tiles, label_begin, labels);
+        if (rc) {
+            cudaStreamSynchronize(ctx->stream);
+            return rc;
+        }
+        const float enqueue_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_host0).count();
+        ctx->label_plane_active = true;
+        rc = osmr_batch_draw(ctx, canvas_rgb, flags, out, nullptr);  // synchronises the stream
+        ctx->label_plane_active = false;
+        if (rc) return rc;
+        const int verdict = label_device_judge(ctx);
+        if (verdict < 0) return verdict;
+        if (verdict == 0) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ctx->ev_label0, ctx->ev_label1);
+            ctx->stats.ms_label_layout = enqueue_ms;  // host time spent on labels: table look-ups and launches only
+            ctx->stats.ms_label_device = ms;
+            ctx->stats.ms_total += ms;
+            ctx->stats.kernel_launches += 8;
+            ctx->stats.label_path = 1;
+            ctx->stats.n_labels_active = ctx->stats_label_active;
+            ctx->stats.n_labels_polylabel = ctx->stats_label_poly;
+            ctx->stats.label_attempts = (uint32_t)attempt + 1;
+            return OSMR_OK;
+        }
+        if (verdict == 2) on_device = false;
+    }
+    // ---- host layout ----
+    rc = labels_via_host(ctx, tiles, n_tiles, label_begin, labels);
+    if (rc) return rc;
     ctx->label_plane_active = true;
     rc = osmr_batch_draw(ctx, canvas_rgb, flags, out, nullptr);
     ctx->label_plane_active = false;
     ctx->stats.ms_label_layout = ctx->stats_label_layout_ms;
     ctx->stats.ms_label_device = ctx->stats_label_device_ms;
+    ctx->stats.label_path = 2;
     return rc;
 } OSMR_CATCH_INT(ctx)
 

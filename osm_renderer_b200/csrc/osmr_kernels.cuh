@@ -1761,17 +1761,25 @@ struct LabelScene {
     int* kmax;
     LabelPix* plane;  // per tile D*D
     int D;
+    // device-side layout (osmr_labels_dev.cuh): the counts live in device memory and the labels of a tile are label_cnt[tile]
+    // records starting at label_begin[tile]; nullptr: host-side layout (counts in n_segs / n_rowrecs, label_begin is a prefix sum)
+    const unsigned* n_segs_dev;
+    const unsigned* n_rowrecs_dev;
+    const unsigned* label_cnt;
+    const unsigned* skip_flags;  // device layout: [0] overflow, [1] fallback -- nonzero: this attempt is abandoned
 };
 
 // Per-segment constants of Rasterizer::draw_line (rasterizer.rs:27-50), one thread per segment: the two divisions and
 // the stripe range are the same for every pixel row the segment crosses.
 __global__ void label_seg_kernel(LabelScene ls) {
-    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= ls.n_segs) return;
-    const DevSeg sg = ls.segs[i];
-    const double slope = (sg.x1 - sg.x0) / (sg.y1 - sg.y0);
-    ls.seg_slope[i] = make_double2(slope, 1.0 / slope);
-    ls.seg_rows[i] = make_int2(f64_as_i32(floor(fmin(sg.y0, sg.y1))), f64_as_i32(floor(fmax(sg.y0, sg.y1))));
+    if (ls.skip_flags && (ls.skip_flags[0] | ls.skip_flags[1])) return;
+    const unsigned n = ls.n_segs_dev ? *ls.n_segs_dev : ls.n_segs;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const DevSeg sg = ls.segs[i];
+        const double slope = (sg.x1 - sg.x0) / (sg.y1 - sg.y0);
+        ls.seg_slope[i] = make_double2(slope, 1.0 / slope);
+        ls.seg_rows[i] = make_int2(f64_as_i32(floor(fmin(sg.y0, sg.y1))), f64_as_i32(floor(fmax(sg.y0, sg.y1))));
+    }
 }
 
 // Glyph coverage of one pixel row of one label: Rasterizer::draw_line for this stripe over the label's segments in
@@ -1782,8 +1790,11 @@ __global__ void label_seg_kernel(LabelScene ls) {
 // additions happen in segment order, as on the CPU.
 __global__ void __launch_bounds__(32) label_cover_kernel(LabelScene ls) {
     constexpr unsigned kFull = 0xffffffffu;
-    const unsigned i = blockIdx.x * 32u + threadIdx.x;
+    if (ls.skip_flags && (ls.skip_flags[0] | ls.skip_flags[1])) return;
+    const unsigned n_warps = (ls.n_rowrecs_dev ? *ls.n_rowrecs_dev : ls.n_rowrecs) / 32u;
     const unsigned lane = threadIdx.x;
+    for (unsigned wi = blockIdx.x; wi < n_warps; wi += gridDim.x) {
+    const unsigned i = wi * 32u + lane;
     const DevRowRec rr = ls.rowrecs[i];
     const DevLabel L = ls.labels[rr.label];
     const bool live = rr.row != 0xffffffffu;
@@ -1793,7 +1804,18 @@ __global__ void __launch_bounds__(32) label_cover_kernel(LabelScene ls) {
     double* sacc = ls.acc_s + L.cell_off + (size_t)(live ? rr.row : 0u) * W;
     const int2* rows = ls.seg_rows + L.seg_begin;
     const int y_lo = __shfl_sync(kFull, y, 0);  // lane 0 is always live, live lanes are a prefix with increasing y
-    const int y_hi = y_lo + __popc(__ballot_sync(kFull, live)) - 1;
+    const int n_live = __popc(__ballot_sync(kFull, live));
+    const int y_hi = y_lo + n_live - 1;
+    if (ls.n_rowrecs_dev) {  // device layout: nobody cleared the coverage cells of this attempt; the warp's rows are contiguous
+        const size_t n_cells = (size_t)n_live * (size_t)W;
+        double* za = ls.acc_a + L.cell_off + (size_t)__shfl_sync(kFull, live ? rr.row : 0u, 0) * W;
+        double* zs = ls.acc_s + L.cell_off + (size_t)__shfl_sync(kFull, live ? rr.row : 0u, 0) * W;
+        for (size_t c = lane; c < n_cells; c += 32) {
+            za[c] = 0.0;
+            zs[c] = 0.0;
+        }
+        __syncwarp();
+    }
     int lo = 0x7fffffff, hi = (int)0x80000000;
     for (unsigned base = 0; base < L.seg_count; base += 32) {
         const unsigned j = base + lane;
@@ -1848,18 +1870,21 @@ __global__ void __launch_bounds__(32) label_cover_kernel(LabelScene ls) {
             }
         }
     }
-    if (!live) return;
-    ls.kmin[L.row_first + rr.row] = lo;
-    ls.kmax[L.row_first + rr.row] = hi;
-    if (lo <= hi) {
-        double run = 0.0;
-        for (int x = lo; x <= hi; ++x) {
-            const int c = x - L.bx0;
-            const bool inside = c >= 0 && c < W;  // the host bbox covers every key; defensive
-            run += inside ? sacc[c] : 0.0;
-            const double total = fmin((inside ? a[c] : 0.0) + run, 1.0);
-            if (inside) a[c] = total;
+    if (live) {
+        ls.kmin[L.row_first + rr.row] = lo;
+        ls.kmax[L.row_first + rr.row] = hi;
+        if (lo <= hi) {
+            double run = 0.0;
+            for (int x = lo; x <= hi; ++x) {
+                const int c = x - L.bx0;
+                const bool inside = c >= 0 && c < W;  // the host bbox covers every key; defensive
+                run += inside ? sacc[c] : 0.0;
+                const double total = fmin((inside ? a[c] : 0.0) + run, 1.0);
+                if (inside) a[c] = total;
+            }
         }
+    }
+    __syncwarp();
     }
 }
 
@@ -1884,7 +1909,10 @@ __global__ void __launch_bounds__(kLabelThreads) label_commit_kernel(LabelScene 
     auto in_canvas = [&](int x, int y) { return x >= -D && x <= 2 * D - 1 && y >= -D && y <= 2 * D - 1; };  // labels_bb
     auto occ_index = [&](int x, int y) { return (size_t)(y + D) * E + (size_t)(x + D); };
 
-    for (unsigned li = ls.label_begin[tile]; li < ls.label_begin[tile + 1]; ++li) {
+    const bool abandoned = ls.skip_flags && (ls.skip_flags[0] | ls.skip_flags[1]);  // (the planes above are still cleared)
+    const unsigned li_begin = ls.label_begin[tile];
+    const unsigned li_end = abandoned ? li_begin : (ls.label_cnt ? li_begin + ls.label_cnt[tile] : ls.label_begin[tile + 1]);
+    for (unsigned li = li_begin; li < li_end; ++li) {
         const DevLabel L = ls.labels[li];
         if (threadIdx.x == 0) fail = 0;
         __syncthreads();

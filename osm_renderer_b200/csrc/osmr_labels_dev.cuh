@@ -1,0 +1,942 @@
+// osmr_labels_dev.cuh -- label LAYOUT on the device (the tile-dependent half of labeler.rs / labelable.rs / font/text_placer.rs).
+//
+// Round 1 laid every label out on the host, per tile and per call (osmr_labels_host.hpp).  What the reference computes for a
+// label splits into a part that depends only on (entity, style, zoom, scale) and a part that depends on the tile:
+//   * tile-INdependent: the text of the entity (tag lookup), its glyph ids, advances and kerning (font tables), the glyph
+//     outlines, and -- for text along a way -- everything that is a function of the way's INTEGER pixel differences: segment
+//     lengths, the fit test, the segment a glyph lands on, the ratio along it and the glyph's rotation (atan2 / sin / cos of
+//     integer differences).  The integer pixels of a node in two tiles of one zoom differ by an exact multiple of 256 * scale
+//     (tile.rs:88-106: factor * 2^(8+z) is exact, the subtraction of the tile origin is exact because both operands are
+//     multiples of the minuend's ulp, `* scale` is exact for scale in {1, 2, 4, 8}), so the differences are tile-invariant.
+//   * tile-DEPENDENT (in the last bits): every f64 that has the tile-relative position added to it -- the glyph origin
+//     wx = x_i + dx * ratio, every transformed outline point wx + (...), the flatness test of the quadratic curves, the
+//     polylabel anchor of an area (labelable.rs:125-204 runs on tile-relative f64 coordinates).  These are IEEE basic
+//     operations (+, -, *, /, sqrt, comparisons), which the device reproduces bit for bit (-fmad=false).
+// So the host keeps only what needs strings, font tables or the platform libm -- as RESIDENT tables built once per dataset /
+// font / style table (text runs, glyph outlines) and once per zoom (sin / cos of every named way's segment directions, from
+// glibc like the reference's) -- and the per-call, per-tile work below runs on the device:
+//   label_select_kernel   which label generations of a tile can draw or collide at all (icon, or text that exists)
+//   label_layout_kernel   anchor (node position or polylabel), icon rectangle, glyph placement along the way / in wrapped rows
+//   label_emit_kernel     glyph outlines -> the reference's Rasterizer::draw_line call stream (quadratic curves flattened by
+//                         rasterizer.rs:86-107's recursive midpoint rule), counted first, then written
+//   label_finish_kernel   per label: segment range, pixel bbox, coverage storage, the (label, row) work items
+// The flatness rule compares platform-libm hypot values; the device decides it with sqrt whenever the two sides differ by more
+// than 1e-12 relative (the host does the same, osmr_labels_host.hpp flat_enough) and raises LCNT_FALLBACK on a near tie: the
+// call is then laid out by the host path, which asks glibc.  Scales that are not a power of two also take the host path.
+#pragma once
+#include "osmr_kernels.cuh"
+
+namespace osmr {
+
+struct DevLabelStyle {  // osmr_label_style with the text key interned
+    int icon;           // -2 none, -1 failed to load, >= 0 label icon index
+    unsigned flags;     // OSMR_LSTYLE_*
+    int key;            // index of the distinct text key, -1 none
+    unsigned rgb;       // 0x00BBGGRR (0 when TextStyle.text_color is None: black, text_placer.rs:52-55)
+    unsigned text_position;
+    unsigned pad;
+    double font_size;
+};
+struct DevGlyphRec {  // one character of a text run
+    int slot;         // index into glyph_vbegin (-1: the glyph has no outline)
+    int advance;      // hmtx advance width, font units
+    int kern;         // kern(previous glyph, this glyph), font units; 0 for the first
+    unsigned ws;      // char::is_whitespace
+};
+struct DevVertex {  // stb_truetype vertex
+    short x, y, cx, cy;
+    int type;  // 1 move, 2 line, 3 curve
+};
+
+enum {
+    LCNT_PLACES = 0,    // GlyphPlace entries handed out
+    LCNT_SEGS = 1,      // segments handed out
+    LCNT_ROWRECS = 2,   // (label, row) work items handed out (multiple of 32)
+    LCNT_CELLS_LO = 4,  // 64-bit (4,5): coverage cells handed out
+    LCNT_OVERFLOW = 6,  // bit0 places, bit1 segments, bit2 row records, bit3 cells, bit4 polylabel rings, bit5 polylabel heap
+    LCNT_FALLBACK = 7,  // bit0: flatness near-tie (needs libm hypot); bit1: input the device path does not take
+    LCNT_BAD = 8,       // label references an entity / style / icon that does not exist
+    LCNT_RING_PTS = 9,  // polylabel ring points handed out
+    LCNT_ACTIVE = 10,   // statistics: active labels
+    LCNT_POLY = 11,     // labels that ran polylabel (= heaps handed out)
+    LCNT_COUNT = 16
+};
+
+struct ActLabel {  // a label generation that can draw or collide
+    unsigned entity, style;
+    unsigned text;      // text run id, 0xffffffff: no text
+    unsigned n_glyphs;
+};
+struct GlyphPlace {  // 48 bytes: where one glyph goes
+    double a, b, c, d, e;  // text on a line: wx, wy, sin(-angle), cos(-angle), gcx; centred: x origin, baseline
+    int slot;              // glyph outline, -1 none
+    unsigned label;        // slot of the label in the per-tile regions
+};
+struct LabelPlace {  // layout result of an active label
+    int icon, ix, iy;
+    unsigned mode;       // 0: no text geometry, 1: along the way, 2: centred rows
+    unsigned place_off;  // first GlyphPlace
+    unsigned n_places;
+    unsigned rgb;
+    unsigned pad;
+    double scale;  // font units -> pixels
+    double gcy;    // (descent + ascent) / 2 (text on a line)
+};
+struct GlyphOut {  // per GlyphPlace: what the count pass found
+    unsigned n_segs;
+    unsigned seg_off;  // filled by label_finish_kernel
+    double min_x, max_x, min_y, max_y;
+};
+
+struct LabelDev {
+    // resident tables
+    const DevLabelStyle* styles;
+    unsigned n_styles;
+    const unsigned* text_id;  // [key][ent_total]; entity slot = node | way_base + way | mp_base + mp
+    unsigned n_keys, ent_total, way_base, mp_base;
+    const unsigned* text_begin;
+    unsigned n_texts;
+    const DevGlyphRec* glyphs;
+    const unsigned* glyph_vbegin;
+    const DevVertex* verts;
+    int ascent, descent, line_gap;
+    const unsigned* way_angle_off[19];  // per zoom: first (sin, cos) pair of the way's oriented segments, 0xffffffff none
+    const double2* sincos[19];
+    const DevIcon* icons;
+    unsigned n_icons;
+    // batch
+    const unsigned* label_begin;  // per tile (absolute)
+    const osmr_label* labels;
+    unsigned n_tiles;
+    // scratch
+    ActLabel* act;        // per-tile regions: act[label_begin[t] .. + act_cnt[t])
+    unsigned* act_cnt;    // per tile
+    LabelPlace* place;    // same indexing as act
+    GlyphPlace* gplace;
+    GlyphOut* gout;
+    unsigned gplace_cap;
+    DevSeg* segs;
+    unsigned segs_cap;
+    DevLabel* out_labels;  // same indexing as act
+    DevRowRec* rowrecs;
+    unsigned rowrecs_cap;
+    unsigned long long cells_cap;
+    double2* ring_pts;  // polylabel scratch
+    unsigned ring_cap;
+    unsigned char* heap;  // polylabel heaps: kPolyHeapCap cells per label that needs one
+    unsigned heap_slots;
+    unsigned* counters;  // LCNT_*
+};
+
+// ------------------------------------------------------------------------------------------------------
+// label_select_kernel: one CTA per tile, ordered compaction of the label generations that matter.
+// A generation without an icon and without text geometry is an empty successful generation: no pixel, no collision
+// (SURVEY.md A.6), so dropping it cannot change the image -- the host layout drops the same ones.
+// ------------------------------------------------------------------------------------------------------
+constexpr int kLabelSelThreads = 256;
+
+__device__ __forceinline__ bool label_entity_slot(const Scene& s, const LabelDev& ld, unsigned entity, unsigned& slot, unsigned& kind) {
+    const bool is_mp = (entity & OSMR_AREA_MULTIPOLYGON) != 0;
+    const bool is_node = !is_mp && (entity & OSMR_LABEL_NODE) != 0;
+    const unsigned idx = entity & ~(OSMR_AREA_MULTIPOLYGON | OSMR_LABEL_NODE);
+    kind = is_node ? 0u : (is_mp ? 2u : 1u);
+    if (is_node) {
+        if (idx >= s.n_nodes) return false;
+        slot = idx;
+    } else if (is_mp) {
+        if (idx >= s.n_mps) return false;
+        slot = ld.mp_base + idx;
+    } else {
+        if (idx >= s.n_ways) return false;
+        slot = ld.way_base + idx;
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(kLabelSelThreads) label_select_kernel(Scene s, LabelDev ld) {
+    __shared__ unsigned warp_cnt[kLabelSelThreads / 32];
+    __shared__ unsigned running;
+    const unsigned t = blockIdx.x;
+    const unsigned first = ld.label_begin[t], last = ld.label_begin[t + 1];
+    if (threadIdx.x == 0) running = 0;
+    __syncthreads();
+    for (unsigned start = first; start < last; start += kLabelSelThreads) {
+        const unsigned li = start + threadIdx.x;
+        bool active = false;
+        ActLabel a;
+        a.entity = a.style = 0;
+        a.text = 0xffffffffu;
+        a.n_glyphs = 0;
+        if (li < last) {
+            const osmr_label L = ld.labels[li];
+            unsigned slot = 0, kind = 0;
+            if (L.style >= ld.n_styles || !label_entity_slot(s, ld, L.entity, slot, kind)) {
+                atomicOr(&ld.counters[LCNT_BAD], 1u);
+            } else {
+                const DevLabelStyle st = ld.styles[L.style];
+                if (st.icon >= 0 && (unsigned)st.icon >= ld.n_icons) atomicOr(&ld.counters[LCNT_BAD], 1u);
+                a.entity = L.entity;
+                a.style = L.style;
+                if ((st.flags & OSMR_LSTYLE_TEXT) && (st.flags & OSMR_LSTYLE_FONT_SIZE) && st.key >= 0) {
+                    const unsigned tid = ld.text_id[(size_t)st.key * ld.ent_total + slot];
+                    if (tid != 0xffffffffu) {
+                        a.text = tid;
+                        a.n_glyphs = ld.text_begin[tid + 1] - ld.text_begin[tid];
+                    }
+                }
+                active = (st.icon >= 0 && (unsigned)st.icon < ld.n_icons) || a.text != 0xffffffffu;
+            }
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, active);
+        const unsigned w = threadIdx.x >> 5;
+        if (lane_id() == 0) warp_cnt[w] = __popc(bal);
+        __syncthreads();
+        unsigned pos = running;
+        for (unsigned k = 0; k < w; ++k) pos += warp_cnt[k];
+        pos += __popc(bal & ((1u << lane_id()) - 1u));
+        if (active) ld.act[first + pos] = a;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned add = 0;
+            for (unsigned k = 0; k < kLabelSelThreads / 32; ++k) add += warp_cnt[k];
+            running += add;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        ld.act_cnt[t] = running;
+        atomicAdd(&ld.counters[LCNT_ACTIVE], running);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// polylabel (labelable.rs:125-232) on tile-relative f64 coordinates, one thread per label.
+// std::collections::BinaryHeap's sift order is reproduced (push: sift up; pop: move the last element to the root, sift it to
+// the bottom along the larger children, sift it back up), because equal max_fitness values are common on regular shapes.
+// ------------------------------------------------------------------------------------------------------
+constexpr unsigned kPolyHeapCap = 1024;  // cells per heap (40 KB); a larger heap sends the call to the host path
+constexpr unsigned kMaxPolyRings = 64;
+
+struct PolyCell {
+    double cx, cy, half, fit, max_fit;
+};
+
+__device__ __forceinline__ double poly_seg_dist_sq(double px, double py, double2 a, double2 b) {  // labelable.rs:313-349
+    double x = a.x, y = a.y, dx = b.x - x, dy = b.y - y;
+    if (dx != 0.0 || dy != 0.0) {
+        const double t = ((px - x) * dx + (py - y) * dy) / (dx * dx + dy * dy);
+        if (t > 1.0) {
+            x = b.x;
+            y = b.y;
+        } else if (t > 0.0) {
+            x += dx * t;
+            y += dy * t;
+        }
+    }
+    dx = px - x;
+    dy = py - y;
+    return dx * dx + dy * dy;
+}
+
+struct PolyHeap {
+    PolyCell* d;
+    unsigned n;
+    bool overflow;
+    __device__ static bool le(const PolyCell& a, const PolyCell& b) { return !(a.max_fit > b.max_fit); }
+    __device__ void up(unsigned pos) {
+        const PolyCell e = d[pos];
+        while (pos > 0) {
+            const unsigned parent = (pos - 1) / 2;
+            if (le(e, d[parent])) break;
+            d[pos] = d[parent];
+            pos = parent;
+        }
+        d[pos] = e;
+    }
+    __device__ void push(const PolyCell& v) {
+        if (n >= kPolyHeapCap) {
+            overflow = true;
+            return;
+        }
+        d[n] = v;
+        up(n);
+        ++n;
+    }
+    __device__ bool pop(PolyCell& out) {
+        if (n == 0) return false;
+        const PolyCell last = d[n - 1];
+        --n;
+        if (n == 0) {
+            out = last;
+            return true;
+        }
+        out = d[0];
+        const unsigned end = n;
+        unsigned pos = 0, child = 1;
+        while (end >= 2 && child <= end - 2) {
+            if (le(d[child], d[child + 1])) ++child;
+            d[pos] = d[child];
+            pos = child;
+            child = 2 * pos + 1;
+        }
+        if (child == end - 1) {
+            d[pos] = d[child];
+            pos = child;
+        }
+        d[pos] = last;
+        up(pos);
+        return true;
+    }
+};
+
+// get_label_position (labelable.rs:191-204) for an area.  `pts` is this label's private copy of the rings (it is permuted).
+// Returns false when the entity has no points.  *overflow: the heap did not fit.
+__device__ bool poly_label_anchor(double2* pts, unsigned* off, unsigned n_rings, double scale, PolyCell* heap_mem, double& ax, double& ay,
+                                  bool& overflow) {
+    overflow = false;
+    if (n_rings == 0 || off[1] - off[0] == 0) return false;
+    // filter_polygons (labelable.rs:206-232): the ring of the largest area first, then the rings that lie inside it.  Rings are
+    // permuted as whole (offset, length) records: ring order among the kept ones follows the reference's swaps.
+    unsigned ro[kMaxPolyRings], rl[kMaxPolyRings];
+    for (unsigned k = 0; k < n_rings; ++k) {
+        ro[k] = off[k];
+        rl[k] = off[k + 1] - off[k];
+    }
+    auto ring_area = [&](unsigned k) {
+        double sacc = 0.0;
+        for (unsigned i = 1; i < rl[k]; ++i) {
+            const double2 a = pts[ro[k] + i], b = pts[ro[k] + i - 1];
+            sacc += a.x * b.y - b.x * a.y;
+        }
+        return fabs(sacc);
+    };
+    unsigned big = 0;
+    double big_area = ring_area(0);
+    for (unsigned k = 1; k < n_rings; ++k) {
+        const double a = ring_area(k);
+        if (a > big_area) {
+            big = k;
+            big_area = a;
+        }
+    }
+    {
+        unsigned t0 = ro[0], t1 = rl[0];
+        ro[0] = ro[big];
+        rl[0] = rl[big];
+        ro[big] = t0;
+        rl[big] = t1;
+    }
+    // the distance functions below take PolyRings with prefix offsets: build it over an index table instead of moving points
+    struct View {
+        const double2* pts;
+        const unsigned *ro, *rl;
+    } v{pts, ro, rl};
+    auto signed_dist = [&](double px, double py, unsigned n_use) {
+        bool inside = false;
+        double best = __longlong_as_double(0x7ff0000000000000LL);
+        for (unsigned k = 0; k < n_use; ++k) {
+            const unsigned o = v.ro[k], n = v.rl[k];
+            for (unsigned i = 1; i < n; ++i) {
+                const double2 a = v.pts[o + i], b = v.pts[o + i - 1];
+                if ((a.y > py) != (b.y > py) && px < (b.x - a.x) * (py - a.y) / (b.y - a.y) + a.x) inside = !inside;
+                best = fmin(best, poly_seg_dist_sq(px, py, a, b));
+            }
+        }
+        return (inside ? 1.0 : -1.0) * sqrt(best);
+    };
+    unsigned keep = 1;
+    for (unsigned k = 1; k < n_rings; ++k) {
+        bool all_inside = true;
+        for (unsigned i = 0; i < rl[k]; ++i) {
+            const double2 p = pts[ro[k] + i];
+            if (!(signed_dist(p.x, p.y, 1) >= 0.0)) {
+                all_inside = false;
+                break;
+            }
+        }
+        if (all_inside) {
+            unsigned t0 = ro[k], t1 = rl[k];
+            ro[k] = ro[keep];
+            rl[k] = rl[keep];
+            ro[keep] = t0;
+            rl[keep] = t1;
+            ++keep;
+        }
+    }
+    const unsigned n_use = keep;
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    double min_x = inf, max_x = -inf, min_y = inf, max_y = -inf;
+    for (unsigned i = 0; i < rl[0]; ++i) {
+        const double2 p = pts[ro[0] + i];
+        min_x = fmin(min_x, p.x);
+        max_x = fmax(max_x, p.x);
+        min_y = fmin(min_y, p.y);
+        max_y = fmax(max_y, p.y);
+    }
+    const double w = max_x - min_x, h = max_y - min_y;
+    const double precision = fmax(w, h) / 100.0 * scale;
+    const double cell = fmin(w, h), max_size = fmax(w, h);
+    if (cell == 0.0) {
+        ax = min_x;
+        ay = min_y;
+        return true;
+    }
+    double cen_x, cen_y;
+    {
+        double area = 0.0, cx = 0.0, cy = 0.0;
+        for (unsigned i = 1; i < rl[0]; ++i) {
+            const double2 a = pts[ro[0] + i], b = pts[ro[0] + i - 1];
+            const double c = a.x * b.y - b.x * a.y;
+            cx += (a.x + b.x) * c;
+            cy += (a.y + b.y) * c;
+            area += c * 3.0;
+        }
+        if (area == 0.0) {
+            cen_x = pts[ro[0]].x;
+            cen_y = pts[ro[0]].y;
+        } else {
+            cen_x = cx / area;
+            cen_y = cy / area;
+        }
+    }
+    auto fitness = [&](double cx, double cy, double d) {
+        if (d <= 0.0) return d;
+        const double dx = cx - cen_x, dy = cy - cen_y;
+        return d * (1.0 - sqrt(dx * dx + dy * dy) / max_size);
+    };
+    auto cell_at = [&](double cx, double cy, double half) {
+        const double d = signed_dist(cx, cy, n_use);
+        PolyCell c;
+        c.cx = cx;
+        c.cy = cy;
+        c.half = half;
+        c.fit = fitness(cx, cy, d);
+        c.max_fit = fitness(cx, cy, d + half * 1.41421356237309504880168872420969808);
+        return c;
+    };
+    PolyHeap heap{heap_mem, 0u, false};
+    double half = cell / 2.0;
+    for (double x = min_x; x < max_x; x += cell)
+        for (double y = min_y; y < max_y; y += cell) {
+            heap.push(cell_at(x + half, y + half, half));
+            if (heap.overflow) {
+                overflow = true;
+                return true;
+            }
+        }
+    PolyCell best = cell_at(cen_x, cen_y, 0.0), cur;
+    while (heap.pop(cur)) {
+        if (cur.fit > best.fit) best = cur;
+        if (cur.max_fit - best.fit <= precision) continue;
+        half = cur.half / 2.0;
+        for (int ix = 0; ix < 2; ++ix)
+            for (int iy = 0; iy < 2; ++iy) {
+                const double dx = ix ? 1.0 : -1.0, dy = iy ? 1.0 : -1.0;
+                heap.push(cell_at(cur.cx + dx * half, cur.cy + dy * half, half));
+            }
+        if (heap.overflow) {
+            overflow = true;
+            return true;
+        }
+    }
+    ax = best.cx;
+    ay = best.cy;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// label_layout_kernel: one thread per active label (persistent grid over (tile, label) pairs)
+// ------------------------------------------------------------------------------------------------------
+constexpr int kLayoutThreads = 64;
+
+__device__ __forceinline__ double2 tile_rel(const double2 m, const TileXform& t) {  // coords_to_xy_tile_relative * scale
+    double2 r;
+    r.x = (m.x * t.dim - t.tx256) * t.scale;
+    r.y = (m.y * t.dim - t.ty256) * t.scale;
+    return r;
+}
+
+__global__ void __launch_bounds__(kLayoutThreads) label_layout_kernel(Scene s, LabelDev ld) {
+    const unsigned t = blockIdx.x;
+    const unsigned first = ld.label_begin[t];
+    const unsigned n_act = ld.act_cnt[t];
+    const osmr_tile tile = s.tiles[t];
+    const TileXform xf = make_xform(tile);
+    const double gscale = (double)tile.scale;
+    for (unsigned ai = threadIdx.x; ai < n_act; ai += kLayoutThreads) {
+        const ActLabel a = ld.act[first + ai];
+        const DevLabelStyle st = ld.styles[a.style];
+        const bool is_mp = (a.entity & OSMR_AREA_MULTIPOLYGON) != 0;
+        const bool is_node = !is_mp && (a.entity & OSMR_LABEL_NODE) != 0;
+        const unsigned idx = a.entity & ~(OSMR_AREA_MULTIPOLYGON | OSMR_LABEL_NODE);
+        LabelPlace lp;
+        lp.icon = -1;
+        lp.ix = lp.iy = 0;
+        lp.mode = 0;
+        lp.place_off = 0;
+        lp.n_places = 0;
+        lp.rgb = st.rgb;
+        lp.pad = 0;
+        lp.scale = 0.0;
+        lp.gcy = 0.0;
+        // label anchor (labelable.rs), lazily: polylabel is expensive
+        bool anchor_done = false, anchor_ok = false;
+        double anx = 0.0, any = 0.0;
+        auto get_anchor = [&]() {
+            if (anchor_done) return anchor_ok;
+            anchor_done = true;
+            if (is_node) {
+                const int2 p = project_point(s.merc[idx], xf);
+                anx = (double)p.x;
+                any = (double)p.y;
+                anchor_ok = true;
+                return true;
+            }
+            // rings of the area as tile-relative f64 pixels, in this label's private scratch
+            RingIter it(s, is_mp ? (idx | OSMR_AREA_MULTIPOLYGON) : idx);
+            if (it.n_rings > kMaxPolyRings) {
+                atomicOr(&ld.counters[LCNT_FALLBACK], 2u);
+                return false;
+            }
+            unsigned total = 0;
+            for (unsigned k = 0; k < it.n_rings; ++k) total += it.ring(k).y;
+            const unsigned base = atomicAdd(&ld.counters[LCNT_RING_PTS], total);
+            if (base + total > ld.ring_cap || base + total < base) {
+                atomicOr(&ld.counters[LCNT_OVERFLOW], 16u);
+                return false;
+            }
+            const unsigned hslot = atomicAdd(&ld.counters[LCNT_POLY], 1u);  // a heap of its own for this label
+            if (hslot >= ld.heap_slots) {
+                atomicOr(&ld.counters[LCNT_OVERFLOW], 32u);
+                return false;
+            }
+            double2* pts = ld.ring_pts + base;
+            unsigned off[kMaxPolyRings + 1];
+            unsigned w = 0;
+            for (unsigned k = 0; k < it.n_rings; ++k) {
+                const uint2 r = it.ring(k);
+                off[k] = w;
+                for (unsigned q = 0; q < r.y; ++q) pts[w++] = tile_rel(s.merc[s.ints[r.x + q]], xf);
+            }
+            off[it.n_rings] = w;
+            bool ovf = false;
+            PolyCell* heap = reinterpret_cast<PolyCell*>(ld.heap) + (size_t)hslot * kPolyHeapCap;
+            anchor_ok = poly_label_anchor(pts, off, it.n_rings, gscale, heap, anx, any, ovf);
+            if (ovf) {
+                atomicOr(&ld.counters[LCNT_FALLBACK], 2u);  // an unusually large heap: let the host lay this call out
+                anchor_ok = false;
+            }
+            return anchor_ok;
+        };
+        unsigned y_offset = 0;
+        // label_with_icon (labeler.rs:39-68)
+        if (st.icon >= 0 && (unsigned)st.icon < ld.n_icons) {
+            if (get_anchor()) {
+                const DevIcon ic = ld.icons[st.icon];
+                lp.icon = st.icon;
+                lp.ix = f64_as_i32(anx - ((double)ic.w / 2.0));
+                lp.iy = f64_as_i32(any - ((double)ic.h / 2.0));
+                y_offset = ic.h / 2u;
+            }
+        }
+        // label_with_text -> TextPlacer::place (text_placer.rs:24-168)
+        if (a.text != 0xffffffffu) {
+            const double font_size = st.font_size * gscale;
+            const float fs = (float)font_size;
+            const float fscale = fs / (float)(ld.ascent - ld.descent);  // scale_for_pixel_height: an f32 division
+            const double scale = (double)fscale;
+            const DevGlyphRec* gl = ld.glyphs + ld.text_begin[a.text];
+            const unsigned ng = a.n_glyphs;
+            auto width_of = [&](unsigned k) {
+                double w = (double)gl[k].advance * scale;
+                if (k > 0) w += (double)gl[k].kern * scale;
+                return w;
+            };
+            double total_width = 0.0;
+            for (unsigned k = 0; k < ng; ++k) total_width += width_of(k);
+            const double ascent = (double)ld.ascent * scale, descent = (double)ld.descent * scale, line_gap = (double)ld.line_gap * scale;
+            lp.scale = scale;
+            const unsigned pos = st.text_position ? st.text_position : ((is_node || is_mp) ? (unsigned)OSMR_TEXT_POS_CENTER : (unsigned)OSMR_TEXT_POS_LINE);
+            // the label's GlyphPlace block (one entry per character)
+            unsigned poff = 0;
+            bool have_block = false;
+            auto take_block = [&]() {
+                poff = atomicAdd(&ld.counters[LCNT_PLACES], ng);
+                if (poff + ng > ld.gplace_cap || poff + ng < poff) {
+                    atomicOr(&ld.counters[LCNT_OVERFLOW], 1u);
+                    return false;
+                }
+                have_block = true;
+                return true;
+            };
+            if (pos == OSMR_TEXT_POS_LINE) {
+                if (!is_node && !is_mp) {  // only ways have waypoints (labelable.rs:33-39)
+                    const uint2 wr = s.ways[idx];
+                    const unsigned len = wr.y;
+                    const unsigned aoff = (tile.zoom <= 18u && ld.way_angle_off[tile.zoom]) ? ld.way_angle_off[tile.zoom][idx] : 0xffffffffu;
+                    if (len >= 2) {
+                        if (aoff == 0xffffffffu) {
+                            atomicOr(&ld.counters[LCNT_FALLBACK], 2u);  // no direction table for this way: host path
+                        } else {
+                            const double2* sc = ld.sincos[tile.zoom] + aoff;
+                            const int2 pf = project_point(s.merc[s.ints[wr.x]], xf), pb = project_point(s.merc[s.ints[wr.x + len - 1]], xf);
+                            const bool rev = pf.x > pb.x;
+                            auto pt = [&](unsigned i) { return project_point(s.merc[s.ints[wr.x + (rev ? len - 1 - i : i)]], xf); };
+                            double way_len = 0.0;
+                            {
+                                int2 prev = pt(0);
+                                for (unsigned i = 1; i < len; ++i) {
+                                    const int2 cur = pt(i);
+                                    way_len += point_dist(prev.x, prev.y, cur.x, cur.y);
+                                    prev = cur;
+                                }
+                            }
+                            // The direction table holds sin / cos of the INTEGER pixel differences as seen from tile (0, 0).  They
+                            // are the same in every tile except when a coordinate sits on an exact half pixel left of / above the
+                            // tile origin (round-half-away-from-zero mirrors there): such a way is laid out by the host.
+                            for (unsigned i = 0; i < len; ++i) {
+                                const double2 r = tile_rel(s.merc[s.ints[wr.x + i]], xf);
+                                if ((r.x < 0.0 && r.x - floor(r.x) == 0.5) || (r.y < 0.0 && r.y - floor(r.y) == 0.5))
+                                    atomicOr(&ld.counters[LCNT_FALLBACK], 2u);
+                            }
+                            if (!(total_width > way_len) && take_block()) {
+                                double cur = (way_len - total_width) / 2.0;
+                                lp.gcy = (descent + ascent) / 2.0;
+                                lp.mode = 1;
+                                lp.place_off = poff;
+                                lp.n_places = ng;
+                                for (unsigned k = 0; k < ng; ++k) {
+                                    const double wk = width_of(k);
+                                    const double gcx = wk / 2.0;
+                                    double wx = 0.0, wy = 0.0;
+                                    unsigned seg = 0;
+                                    // compute_way_position (text_placer.rs:265-296)
+                                    {
+                                        unsigned i = 0;
+                                        double left = cur + gcx;
+                                        bool found = false;
+                                        int2 p0 = pt(0);
+                                        while (left > 0.0 && i + 1 < len) {
+                                            const int2 p1 = pt(i + 1);
+                                            const double sd = point_dist(p0.x, p0.y, p1.x, p1.y);
+                                            if (sd >= left) {
+                                                const double ratio = left / sd;
+                                                wx = (double)p0.x + (double)wsub(p1.x, p0.x) * ratio;
+                                                wy = (double)p0.y + (double)wsub(p1.y, p0.y) * ratio;
+                                                seg = i;
+                                                found = true;
+                                                break;
+                                            }
+                                            left -= sd;
+                                            ++i;
+                                            p0 = p1;
+                                        }
+                                        if (!found) {
+                                            const int2 pl = pt(len - 1);
+                                            wx = (double)pl.x;
+                                            wy = (double)pl.y;
+                                            seg = len - 2;
+                                        }
+                                    }
+                                    GlyphPlace gp;
+                                    gp.a = wx;
+                                    gp.b = wy;
+                                    gp.c = sc[seg].x;
+                                    gp.d = sc[seg].y;
+                                    gp.e = gcx;
+                                    gp.slot = gl[k].slot;
+                                    gp.label = first + ai;
+                                    ld.gplace[poff + k] = gp;
+                                    cur += wk;
+                                }
+                            }
+                        }
+                    }
+                }
+            } else if (get_anchor() && take_block()) {
+                // centred rows with wrapping (text_placer.rs:101-168)
+                const double max_text_width = 256.0 / 8.0;  // TILE_SIZE / 8, not scaled (text_placer.rs:298)
+                unsigned n_rows = 0;
+                {
+                    double rw = 0.0;
+                    for (unsigned k = 0; k < ng; ++k) {
+                        const double wk = width_of(k);
+                        rw += wk;
+                        const bool last = k + 1 == ng;
+                        const bool brk = gl[k].ws && (rw + wk > max_text_width);
+                        if (brk || last) {
+                            ++n_rows;
+                            rw = 0.0;
+                        }
+                    }
+                }
+                const double row_h = ascent - descent + line_gap;
+                double cur_y = any;
+                if (y_offset > 0)
+                    cur_y += (double)y_offset;
+                else
+                    cur_y -= (row_h * (double)n_rows) / 2.0;
+                lp.mode = 2;
+                lp.place_off = poff;
+                lp.n_places = ng;
+                unsigned row_first = 0;
+                double rw = 0.0;
+                for (unsigned k = 0; k < ng; ++k) {
+                    const double wk = width_of(k);
+                    rw += wk;
+                    const bool last = k + 1 == ng;
+                    const bool brk = gl[k].ws && (rw + wk > max_text_width);
+                    if (brk || last) {
+                        double cur_x = anx - rw / 2.0;
+                        const double baseline = cur_y + ascent;
+                        for (unsigned q = row_first; q <= k; ++q) {
+                            GlyphPlace gp;
+                            gp.a = cur_x;
+                            gp.b = baseline;
+                            gp.c = gp.d = gp.e = 0.0;
+                            gp.slot = gl[q].slot;
+                            gp.label = first + ai;
+                            ld.gplace[poff + q] = gp;
+                            cur_x += width_of(q);
+                        }
+                        cur_y += row_h;
+                        row_first = k + 1;
+                        rw = 0.0;
+                    }
+                }
+            }
+            (void)have_block;
+        }
+        ld.place[first + ai] = lp;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// label_emit_kernel: one thread per GlyphPlace.  Glyph::rasterize (text_placer.rs:211-231): every outline vertex is scaled,
+// transformed and handed to Rasterizer::draw_line / draw_quad (rasterizer.rs:27-107).  WRITE = false counts the segments and
+// their bounds, WRITE = true stores them at the offsets label_finish_kernel assigned.
+// ------------------------------------------------------------------------------------------------------
+struct EmitSink {
+    DevSeg* out;  // nullptr: count only
+    unsigned n;
+    double min_x, max_x, min_y, max_y;
+    bool near_tie;
+    __device__ void line(double x0, double y0, double x1, double y1) {
+        if (y1 - y0 == 0.0) return;  // draw_line returns before touching anything (rasterizer.rs:30-32)
+        if (out) {
+            DevSeg sg;
+            sg.x0 = x0;
+            sg.y0 = y0;
+            sg.x1 = x1;
+            sg.y1 = y1;
+            out[n] = sg;
+        }
+        ++n;
+        // NaN-ignoring min / max (f64::min / max)
+        min_x = fmin(min_x, fmin(x0, x1));
+        max_x = fmax(max_x, fmax(x0, x1));
+        min_y = fmin(min_y, fmin(y0, y1));
+        max_y = fmax(max_y, fmax(y0, y1));
+    }
+    // draw_quad's flatness test (rasterizer.rs:86-107): hypot(p0-p1) + hypot(p1-p2) <= 1.0001 * hypot(p0-p2)
+    __device__ bool flat_enough(double x0, double y0, double x1, double y1, double x2, double y2) {
+        const double ax = fabs(x0 - x1), ay = fabs(y0 - y1), bx = fabs(x1 - x2), by = fabs(y1 - y2);
+        const double cx = fabs(x0 - x2), cy = fabs(y0 - y2);
+        const double lhs = sqrt(ax * ax + ay * ay) + sqrt(bx * bx + by * by);
+        const double rhs = 1.0001 * sqrt(cx * cx + cy * cy);
+        const double big = 1e150, tiny = 1e-150;
+        const bool safe = lhs < big && rhs < big && lhs > tiny && rhs > tiny;  // also false for NaN
+        if (safe && lhs < rhs * (1.0 - 1e-12)) return true;
+        if (safe && lhs > rhs * (1.0 + 1e-12)) return false;
+        near_tie = true;  // only libm's hypot can decide: the call goes to the host path
+        return true;
+    }
+    // the reference recurses (first half, then second half); an explicit stack keeps the same emission order
+    __device__ void quad(double x0, double y0, double x1, double y1, double x2, double y2) {
+        constexpr int kStack = 48;
+        double st[kStack][6];
+        int sp = 0;
+        st[sp][0] = x0; st[sp][1] = y0; st[sp][2] = x1; st[sp][3] = y1; st[sp][4] = x2; st[sp][5] = y2;
+        ++sp;
+        while (sp > 0) {
+            --sp;
+            const double a0 = st[sp][0], b0 = st[sp][1], a1 = st[sp][2], b1 = st[sp][3], a2 = st[sp][4], b2 = st[sp][5];
+            if (flat_enough(a0, b0, a1, b1, a2, b2) || sp + 2 > kStack) {
+                if (sp + 2 > kStack) near_tie = true;  // absurd depth: not something the device decides
+                line(a0, b0, a2, b2);
+                continue;
+            }
+            const double ax = (a0 + a1) / 2.0, ay = (b0 + b1) / 2.0, bx = (a1 + a2) / 2.0, by = (b1 + b2) / 2.0;
+            const double mx = (ax + bx) / 2.0, my = (ay + by) / 2.0;
+            // push the second half first so that the first half is processed next
+            st[sp][0] = mx; st[sp][1] = my; st[sp][2] = bx; st[sp][3] = by; st[sp][4] = a2; st[sp][5] = b2;
+            ++sp;
+            st[sp][0] = a0; st[sp][1] = b0; st[sp][2] = ax; st[sp][3] = ay; st[sp][4] = mx; st[sp][5] = my;
+            ++sp;
+        }
+    }
+};
+
+template <bool WRITE>
+__device__ __forceinline__ void label_emit_body(const LabelDev& ld) {
+    const unsigned n_places = min(ld.counters[LCNT_PLACES], ld.gplace_cap);
+    if (ld.counters[LCNT_OVERFLOW] & 1u) return;
+    if (WRITE && (ld.counters[LCNT_OVERFLOW] || ld.counters[LCNT_FALLBACK])) return;
+    for (unsigned gi = blockIdx.x * blockDim.x + threadIdx.x; gi < n_places; gi += gridDim.x * blockDim.x) {
+        const GlyphPlace gp = ld.gplace[gi];
+        GlyphOut go;
+        if (WRITE) go = ld.gout[gi];
+        EmitSink sink;
+        sink.out = WRITE ? ld.segs + go.seg_off : nullptr;
+        sink.n = 0;
+        sink.min_x = sink.min_y = __longlong_as_double(0x7ff0000000000000LL);
+        sink.max_x = sink.max_y = __longlong_as_double((long long)0xfff0000000000000ULL);
+        sink.near_tie = false;
+        if (gp.slot >= 0) {
+            const LabelPlace lp = ld.place[gp.label];
+            const double scale = lp.scale;
+            const bool on_line = lp.mode == 1;
+            const double wx = gp.a, wy = gp.b, sn = gp.c, cs = gp.d, gcx = gp.e, gcy = lp.gcy;
+            auto tr = [&](double px, double py, double& ox, double& oy) {
+                if (on_line) {  // text_placer.rs:76-93
+                    const double tx = px - gcx, ty = py - gcy;
+                    ox = wx + (tx * cs - ty * sn);
+                    oy = wy - (ty * cs + tx * sn);
+                } else {  // text_placer.rs:150-160
+                    ox = wx + px;
+                    oy = wy - py;
+                }
+            };
+            const unsigned v0 = ld.glyph_vbegin[gp.slot], v1 = ld.glyph_vbegin[gp.slot + 1];
+            double fx = 0.0, fy = 0.0;
+            for (unsigned vi = v0; vi < v1; ++vi) {
+                const DevVertex v = ld.verts[vi];
+                const double tx = (double)v.x * scale, ty = (double)v.y * scale;
+                if (v.type == 2) {
+                    double p1x, p1y, p0x, p0y;
+                    tr(fx, fy, p1x, p1y);
+                    tr(tx, ty, p0x, p0y);
+                    sink.line(p0x, p0y, p1x, p1y);
+                } else if (v.type == 3) {
+                    double p2x, p2y, p1x, p1y, p0x, p0y;
+                    tr(fx, fy, p2x, p2y);
+                    tr((double)v.cx * scale, (double)v.cy * scale, p1x, p1y);
+                    tr(tx, ty, p0x, p0y);
+                    sink.quad(p0x, p0y, p1x, p1y, p2x, p2y);
+                }
+                fx = tx;
+                fy = ty;
+            }
+        }
+        if (sink.near_tie) atomicOr(&ld.counters[LCNT_FALLBACK], 1u);
+        if (!WRITE) {
+            go.n_segs = sink.n;
+            go.seg_off = 0;
+            go.min_x = sink.min_x;
+            go.max_x = sink.max_x;
+            go.min_y = sink.min_y;
+            go.max_y = sink.max_y;
+            ld.gout[gi] = go;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) label_emit_count_kernel(LabelDev ld) { label_emit_body<false>(ld); }
+__global__ void __launch_bounds__(128) label_emit_write_kernel(LabelDev ld) { label_emit_body<true>(ld); }
+
+// ------------------------------------------------------------------------------------------------------
+// label_finish_kernel: one thread per active label -- the batch assembly the host did in osmr_draw_tiles_labeled: segment
+// range, pixel bbox of the text, rows inside the label canvas, coverage cells, (label, row) work items padded to whole warps.
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) label_finish_kernel(Scene s, LabelDev ld) {
+    const unsigned t = blockIdx.x;
+    const unsigned first = ld.label_begin[t];
+    const unsigned n_act = ld.act_cnt[t];
+    const int D = s.D;
+    if (ld.counters[LCNT_OVERFLOW] & 1u) return;
+    for (unsigned ai = threadIdx.x; ai < n_act; ai += blockDim.x) {
+        const LabelPlace lp = ld.place[first + ai];
+        DevLabel L;
+        L.icon = lp.icon;
+        L.ix = lp.ix;
+        L.iy = lp.iy;
+        L.seg_begin = 0;
+        L.seg_count = 0;
+        L.bx0 = 1;
+        L.bx1 = 0;
+        L.by0 = 1;
+        L.by1 = 0;
+        L.rgb = lp.rgb;
+        L.ry0 = 0;
+        L.rows = 0;
+        L.width = 0;
+        L.row_first = 0;
+        L.pad = 0;
+        L.cell_off = 0;
+        if (lp.mode != 0 && lp.n_places) {
+            unsigned n_segs = 0;
+            double min_x = __longlong_as_double(0x7ff0000000000000LL), min_y = min_x;
+            double max_x = __longlong_as_double((long long)0xfff0000000000000ULL), max_y = max_x;
+            for (unsigned k = 0; k < lp.n_places; ++k) {
+                const GlyphOut go = ld.gout[lp.place_off + k];
+                n_segs += go.n_segs;
+                min_x = fmin(min_x, go.min_x);
+                max_x = fmax(max_x, go.max_x);
+                min_y = fmin(min_y, go.min_y);
+                max_y = fmax(max_y, go.max_y);
+            }
+            if (n_segs) {
+                const unsigned sb = atomicAdd(&ld.counters[LCNT_SEGS], n_segs);
+                if (sb + n_segs > ld.segs_cap || sb + n_segs < sb) {
+                    atomicOr(&ld.counters[LCNT_OVERFLOW], 2u);
+                } else {
+                    unsigned o = sb;
+                    for (unsigned k = 0; k < lp.n_places; ++k) {
+                        ld.gout[lp.place_off + k].seg_off = o;
+                        o += ld.gout[lp.place_off + k].n_segs;
+                    }
+                    L.seg_begin = sb;
+                    L.seg_count = n_segs;
+                    L.bx0 = f64_as_i32(floor(min_x));
+                    L.bx1 = f64_as_i32(floor(max_x)) + 1;  // the `s` column is one past the last `a` column
+                    L.by0 = f64_as_i32(floor(min_y));
+                    L.by1 = f64_as_i32(floor(max_y));
+                    // rows outside the label canvas cannot collide or draw; columns stay complete (the sweep is a prefix sum)
+                    L.ry0 = max(L.by0, -D);
+                    const long long rows = (long long)min(L.by1, 2 * D - 1) - L.ry0 + 1;
+                    const long long cols = (long long)L.bx1 - L.bx0 + 1;
+                    const bool touches = rows > 0 && cols > 0 && L.bx1 >= -D && L.bx0 <= 2 * D - 1;
+                    if (touches) {
+                        if (cols > (1 << 20)) {
+                            atomicOr(&ld.counters[LCNT_FALLBACK], 2u);
+                        } else {
+                            const unsigned pad_rows = ((unsigned)rows + 31u) & ~31u;
+                            const unsigned rb = atomicAdd(&ld.counters[LCNT_ROWRECS], pad_rows);
+                            const unsigned long long need = (unsigned long long)rows * (unsigned long long)cols;
+                            const unsigned long long cb = atomicAdd(reinterpret_cast<unsigned long long*>(&ld.counters[LCNT_CELLS_LO]), need);
+                            if (rb + pad_rows > ld.rowrecs_cap || rb + pad_rows < rb) {
+                                atomicOr(&ld.counters[LCNT_OVERFLOW], 4u);
+                            } else if (cb + need > ld.cells_cap) {
+                                atomicOr(&ld.counters[LCNT_OVERFLOW], 8u);
+                            } else {
+                                L.rows = (int)rows;
+                                L.width = (int)cols;
+                                L.row_first = rb;
+                                L.cell_off = cb;
+                                for (unsigned y = 0; y < pad_rows; ++y) {
+                                    DevRowRec rr;
+                                    rr.label = first + ai;
+                                    rr.row = y < (unsigned)rows ? y : 0xffffffffu;
+                                    ld.rowrecs[rb + y] = rr;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        ld.out_labels[first + ai] = L;
+    }
+}
+
+}  // namespace osmr

@@ -99,6 +99,10 @@ class StatsStruct(C.Structure):
         ("ms_cover", C.c_float),
         ("ms_auto", C.c_float),
         ("ms_png", C.c_float),
+        ("label_path", C.c_uint32),
+        ("n_labels_active", C.c_uint32),
+        ("n_labels_polylabel", C.c_uint32),
+        ("label_attempts", C.c_uint32),
     ]
 
 
