@@ -10,6 +10,7 @@
 #include <thread>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <new>
 #include <stdexcept>
 #include <system_error>
@@ -126,9 +127,7 @@ struct osmr_ctx {
     DevBuf<unsigned> d_label_begin, label_occ;
     DevBuf<double> label_acc;
     DevBuf<int> label_row_keys;
-    DevBuf<DevRowRec> d_label_rows;
-    DevBuf<double2> d_seg_slope;
-    DevBuf<int2> d_seg_rows;
+    DevBuf<unsigned> d_cover_list, d_cover_cursor;
     std::vector<LabelWorkItem> label_items;  // kept between calls: their vectors' capacity is the layout arena
     PinnedBuf<osmr_host::Seg> h_label_segs;
     cudaEvent_t ev_label0 = nullptr, ev_label1 = nullptr;
@@ -187,8 +186,11 @@ struct osmr_ctx {
     DevBuf<unsigned> vis_count, work, counters, mask;
     DevBuf<uint2> fill_work, line_work;
     DevBuf<uint4> geom, calc_table;
-    DevBuf<double> walk_alpha;        // walk cache (line_cover_kernel -> raster_kernel)
-    DevBuf<unsigned char> walk_len;
+    DevBuf<double> walk_alpha;        // fragment alphas (line_cover_kernel -> raster_kernel)
+    DevBuf<unsigned char> walk_len;   // fragment pixel indices
+    DevBuf<BinEntry> bin_entries;     // (block, op) pairs in block order (bin_ops_kernel)
+    DevBuf<unsigned> frag_cnt, pair_table;
+    DevBuf<uint2> blk_range;          // per (tile, block) of the whole batch
     // Second set of the bump-allocated scratch: the draw chunks of a host-output call alternate between two streams
     // (chunk i+1 is planned while chunk i is still being rastered), so consecutive chunks must not share scratch.
     struct ScratchB {
@@ -197,7 +199,12 @@ struct osmr_ctx {
         DevBuf<uint2> fill_work, line_work;
         DevBuf<double> walk_alpha;
         DevBuf<unsigned char> walk_len;
+        DevBuf<BinEntry> bin_entries;
+        DevBuf<unsigned> frag_cnt, pair_table;
         void release() {
+            bin_entries.release();
+            frag_cnt.release();
+            pair_table.release();
             geom.release();
             mask.release();
             fill_work.release();
@@ -210,7 +217,7 @@ struct osmr_ctx {
     cudaEvent_t ev_wall0 = nullptr, ev_wall1 = nullptr, join2 = nullptr;  // device wall time of a draw across both streams
     cudaEvent_t prep_done = nullptr;  // upload + style calculators on `stream`: what stream2's first chunk waits for
     bool two_streams = true;          // debug key "two_streams"
-    size_t geom_cap_units = 0, mask_cap_words = 0, walk_alpha_cap = 0, walk_len_cap = 0;
+    size_t geom_cap_units = 0, mask_cap_words = 0, walk_alpha_cap = 0, walk_len_cap = 0, entries_cap = 0, pair_cap = 0;
     DevBuf<unsigned char> out;
     size_t out_bytes = 0;
     // f3: device-side candidate lookup + painter's order (osmr_auto.cuh)
@@ -391,9 +398,6 @@ void osmr_ctx_destroy(osmr_ctx* ctx) {
     ctx->label_occ.release();
     ctx->label_acc.release();
     ctx->label_row_keys.release();
-    ctx->d_label_rows.release();
-    ctx->d_seg_slope.release();
-    ctx->d_seg_rows.release();
     ctx->h_label_segs.release();
     ctx->label_plane.release();
     ctx->geom.release();
@@ -483,6 +487,14 @@ int osmr_debug_set(osmr_ctx* ctx, const char* key, int value) try {
         ctx->mask_cap_words = (size_t)value;
         ctx->walk_alpha_cap = (size_t)value;
         ctx->walk_len_cap = (size_t)value;
+        ctx->bin_entries.release();
+        ctx->frag_cnt.release();
+        ctx->pair_table.release();
+        if (ctx->bin_entries.reserve((size_t)value) != cudaSuccess || ctx->frag_cnt.reserve((size_t)value) != cudaSuccess ||
+            ctx->pair_table.reserve((size_t)value) != cudaSuccess)
+            return ctx->fail(OSMR_E_CUDA, "scratch_units");
+        ctx->entries_cap = (size_t)value;
+        ctx->pair_cap = (size_t)value;
         return OSMR_OK;
     }
     return ctx->fail(OSMR_E_INVALID, "unknown debug key");
@@ -764,6 +776,14 @@ int osmr_set_styles(osmr_ctx* ctx, const osmr_style* styles, uint32_t n_styles, 
             ((uint64_t)s.casing_dashes_off + s.casing_dashes_len > n_dashes || s.casing_dashes_len > 32))
             return ctx->fail(OSMR_E_INVALID, "style casing dashes out of range (at most 32 numbers)");
         if (s.line_cap > OSMR_CAP_SQUARE || s.casing_line_cap > OSMR_CAP_SQUARE) return ctx->fail(OSMR_E_INVALID, "bad line cap");
+        // The compositor keeps RGB only: the canvas alpha stays exactly 1.0 as long as every source alpha a satisfies
+        // a + fl(1 - a) == 1, which holds for a in [0, 2] (tile_pixels.rs:211-216).  The reference does not clamp `opacity` /
+        // `fill-opacity`; a stylesheet with values outside that range would make its canvas alpha drift and its export divide
+        // by it -- refuse such a table loudly instead of drawing different pixels.
+        if ((s.flags & OSMR_STYLE_OPACITY) && !(s.opacity >= 0.0 && s.opacity <= 2.0))
+            return ctx->fail(OSMR_E_INVALID, "style opacity outside [0, 2] is not supported");
+        if ((s.flags & OSMR_STYLE_FILL_OPACITY) && !(s.fill_opacity >= 0.0 && s.fill_opacity <= 2.0))
+            return ctx->fail(OSMR_E_INVALID, "style fill-opacity outside [0, 2] is not supported");
     }
     CK(ctx->styles.reserve(n_styles + 1));
     CK(ctx->dashes.reserve(n_dashes + 1));
@@ -961,10 +981,22 @@ static int launch_chunk(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t fla
         s.fill_work_cap = std::min(s.fill_work_cap, ctx->work_items_limit);
         s.line_work_cap = std::min(s.line_work_cap, ctx->work_items_limit);
     }
-    s.walk_alpha = walk_alpha.p;
-    s.walk_len = walk_len.p;
-    s.walk_alpha_cap = std::min<size_t>(ctx->walk_alpha_cap, walk_alpha.cap);
-    s.walk_len_cap = std::min<size_t>(ctx->walk_len_cap, walk_len.cap);
+    auto& bin_entries = set ? ctx->scrB.bin_entries : ctx->bin_entries;
+    auto& frag_cnt = set ? ctx->scrB.frag_cnt : ctx->frag_cnt;
+    auto& pair_table = set ? ctx->scrB.pair_table : ctx->pair_table;
+    s.frag_alpha = walk_alpha.p;
+    s.frag_pix = walk_len.p;
+    // (16 elements of slack behind the last fragment: the bulk copies of raster_kernel fetch whole 16-byte units)
+    {
+        const size_t fc = std::min<size_t>(std::min<size_t>(ctx->walk_alpha_cap, walk_alpha.cap), std::min<size_t>(ctx->walk_len_cap, walk_len.cap));
+        s.frag_cap = fc > 32 ? fc - 32 : 0;
+    }
+    s.entries = bin_entries.p;
+    s.frag_cnt = frag_cnt.p;
+    s.entries_cap = (unsigned)std::min<size_t>(std::min<size_t>(ctx->entries_cap, std::min(bin_entries.cap, frag_cnt.cap)), 0xfffffff0u);
+    s.pair = pair_table.p;
+    s.pair_cap = (unsigned)std::min<size_t>(std::min<size_t>(ctx->pair_cap, pair_table.cap), 0xfffffff0u);
+    s.blk_range = ctx->blk_range.p + (size_t)tb * (size_t)((D / kBW) * (D / kBH));
     s.calc_table = ctx->calc_table.p;
     s.geom = geom.p;
     s.geom_cap = (unsigned)std::min<size_t>(std::min<size_t>(ctx->geom_cap_units, geom.cap), 0xffffffffu);
@@ -989,9 +1021,13 @@ static int launch_chunk(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t fla
     plan_ops_kernel<<<3 * tc, kPlanThreads, 0, st>>>(s);
     build_geometry_kernel<<<ctx->num_sms * 8, kGeomThreads, 0, st>>>(s);
     fill_rows_kernel<<<ctx->num_sms * 16, kFillThreads, 0, st>>>(s);
+    {
+        const unsigned nblk = (unsigned)((D / kBW) * (D / kBH));
+        bin_ops_kernel<<<tc * ((nblk + kBinThreads - 1) / kBinThreads), kBinThreads, 0, st>>>(s);
+    }
     CK(cudaEventRecord(ev[3], st));
     line_cover_kernel<<<ctx->num_sms * 8, kCoverThreads, 0, st>>>(s);
-    launches += 4;
+    launches += 5;
     CK(cudaEventRecord(ev[1], st));
     const unsigned blocks = (unsigned)((D / kBW) * (D / kBH));
     raster_kernel<<<tc * blocks, kRasterThreads, 0, st>>>(s);
@@ -1011,6 +1047,9 @@ static int ensure_scrB(osmr_ctx* ctx) {
     CK(ctx->scrB.line_work.reserve(ctx->line_work.cap));
     CK(ctx->scrB.walk_alpha.reserve(ctx->walk_alpha.cap));
     CK(ctx->scrB.walk_len.reserve(ctx->walk_len.cap));
+    CK(ctx->scrB.bin_entries.reserve(ctx->bin_entries.cap));
+    CK(ctx->scrB.frag_cnt.reserve(ctx->frag_cnt.cap));
+    CK(ctx->scrB.pair_table.reserve(ctx->pair_table.cap));
     return OSMR_OK;
 }
 
@@ -1020,8 +1059,10 @@ static int collect_chunk(osmr_ctx* ctx, unsigned slot, unsigned tb, unsigned tc,
     const unsigned* h_cnt = ctx->h_cnt.p + (size_t)slot * CNT_COUNT;
     const unsigned n_areas = ctx->h_area_begin[tb + tc] - ctx->h_area_begin[tb];
     if (h_cnt[CNT_BAD_INPUT] & 1u) return ctx->fail(OSMR_E_INVALID, "styled area references an entity or style that does not exist");
-    if (h_cnt[CNT_BAD_INPUT] & 2u) return ctx->fail(OSMR_E_INVALID, "line wider than 248 pixels (width * scale): not supported");
-    if (h_cnt[CNT_WALK_TRUNC]) return ctx->fail(OSMR_E_CUDA, "internal error: a perpendicular walk exceeded its proven bound");
+    if (h_cnt[CNT_BAD_INPUT] & 2u) return ctx->fail(OSMR_E_INVALID, "line wider than 65000 pixels (width * scale): not supported");
+    if (h_cnt[CNT_WALK_TRUNC] & 1u) return ctx->fail(OSMR_E_CUDA, "internal error: a perpendicular walk exceeded its proven bound");
+    if (h_cnt[CNT_WALK_TRUNC] & 2u) return ctx->fail(OSMR_E_CUDA, "internal error: a line fragment fell into a block the binning had ruled out");
+    if (h_cnt[CNT_OVERFLOW] & 256u) return ctx->fail(OSMR_E_CUDA, "internal error: a fragment list outgrew its proven capacity");
     if (h_cnt[CNT_OVERFLOW]) {  // grow the scratch that ran out; the caller redoes the draw
         *redo = true;
         if (h_cnt[CNT_OVERFLOW] & 1u) {
@@ -1031,21 +1072,30 @@ static int collect_chunk(osmr_ctx* ctx, unsigned slot, unsigned tb, unsigned tc,
             CK(ctx->geom.reserve(need));
             ctx->geom_cap_units = ctx->geom.cap;
         }
-        if (h_cnt[CNT_OVERFLOW] & 4u) {
-            unsigned long long used_alpha, used_len;
-            memcpy(&used_alpha, &h_cnt[CNT_WALK_ALPHA], 8);
-            memcpy(&used_len, &h_cnt[CNT_WALK_LEN], 8);
-            if (used_len >= 0xffffffffull) return ctx->fail(OSMR_E_NOMEM, "walk cache exceeds 2^32 walks; split the batch");
-            size_t need_a = (size_t)used_alpha + (size_t)used_alpha / 4 + 1024, need_l = (size_t)used_len + (size_t)used_len / 4 + 1024;
-            if (need_a > ctx->walk_alpha_cap) {
-                if (ctx->walk_alpha.reserve(need_a) != cudaSuccess)
-                    return ctx->fail(OSMR_E_NOMEM, "walk cache does not fit in device memory; split the batch");
-                ctx->walk_alpha_cap = ctx->walk_alpha.cap;
-            }
-            if (need_l > ctx->walk_len_cap) {
-                CK(ctx->walk_len.reserve(need_l));
-                ctx->walk_len_cap = ctx->walk_len.cap;
-            }
+        if (h_cnt[CNT_OVERFLOW] & 4u) {  // fragment storage: the counter holds what the batch asked for (all CTAs add before they check)
+            unsigned long long want;
+            memcpy(&want, &h_cnt[CNT_WALK_ALPHA], 8);
+            if (want >= 0xfffffff0ull) return ctx->fail(OSMR_E_NOMEM, "more than 2^32 line fragment slots; split the batch");
+            size_t need = (size_t)want + (size_t)want / 8 + 4096;
+            if (need <= ctx->walk_alpha_cap) need = ctx->walk_alpha_cap * 2;
+            if (ctx->walk_alpha.reserve(need) != cudaSuccess || ctx->walk_len.reserve(need) != cudaSuccess)
+                return ctx->fail(OSMR_E_NOMEM, "line fragment storage does not fit in device memory; split the batch");
+            ctx->walk_alpha_cap = ctx->walk_alpha.cap;
+            ctx->walk_len_cap = ctx->walk_len.cap;
+        }
+        if (h_cnt[CNT_OVERFLOW] & 64u) {
+            size_t need = (size_t)h_cnt[CNT_BIN_ENTRIES] + (size_t)h_cnt[CNT_BIN_ENTRIES] / 8 + 4096;
+            if (need <= ctx->entries_cap) need = ctx->entries_cap * 2;
+            CK(ctx->bin_entries.reserve(need));
+            CK(ctx->frag_cnt.reserve(need));
+            ctx->entries_cap = std::min(ctx->bin_entries.cap, ctx->frag_cnt.cap);
+        }
+        if (h_cnt[CNT_OVERFLOW] & 128u) {
+            size_t need = (size_t)h_cnt[CNT_PAIR_USED] + (size_t)h_cnt[CNT_PAIR_USED] / 8 + 4096;
+            if (need <= ctx->pair_cap) need = ctx->pair_cap * 2;
+            if (need >= 0xfffffff0ull) return ctx->fail(OSMR_E_NOMEM, "pair tables exceed 2^32 cells; split the batch");
+            CK(ctx->pair_table.reserve(need));
+            ctx->pair_cap = ctx->pair_table.cap;
         }
         if (h_cnt[CNT_OVERFLOW] & 16u) CK(ctx->fill_work.reserve((size_t)h_cnt[CNT_N_FILL_WORK] + 1024));
         if (h_cnt[CNT_OVERFLOW] & 32u) CK(ctx->line_work.reserve((size_t)h_cnt[CNT_N_LINE_WORK] + 1024));
@@ -1067,8 +1117,8 @@ static int collect_chunk(osmr_ctx* ctx, unsigned slot, unsigned tb, unsigned tc,
     unsigned long long used_alpha, steps;
     memcpy(&used_alpha, &h_cnt[CNT_WALK_ALPHA], 8);
     memcpy(&steps, &h_cnt[CNT_WALK_STEPS], 8);
-    ctx->stats.walk_bytes += used_alpha * 8ull;
-    ctx->stats.walk_steps += steps;
+    ctx->stats.walk_bytes += used_alpha * 9ull;  // fragment slots handed out (8-byte alpha + pixel byte each)
+    ctx->stats.walk_steps += steps;              // fragments stored
     ctx->stats.n_tiles += tc;
     ctx->stats.n_areas += n_areas;
     ctx->stats.n_visible_ops += h_cnt[CNT_VISIBLE];
@@ -1112,7 +1162,7 @@ int osmr_batch_draw(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t flags, 
     CK(ctx->counters.reserve((size_t)kMaxChunks * CNT_COUNT));
     CK(ctx->h_cnt.reserve((size_t)kMaxChunks * CNT_COUNT));
     CK(ctx->calc_table.reserve((size_t)2 * ctx->n_styles * kCalcEntryUnits + 1));
-    for (int attempt = 0; attempt < 8; ++attempt) {
+    for (int attempt = 0; attempt < 12; ++attempt) {
         // scratch: first guesses, grown by collect_chunk when a bump allocator overflowed
         if (ctx->geom_cap_units == 0) {
             CK(ctx->geom.reserve((size_t)ctx->n_areas * 8 + (1u << 20)));
@@ -1122,14 +1172,22 @@ int osmr_batch_draw(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t flags, 
             CK(ctx->mask.reserve((size_t)ctx->n_tiles * D * (D / 32) * 4 + (1u << 20)));
             ctx->mask_cap_words = ctx->mask.cap;
         }
-        if (ctx->walk_alpha_cap == 0) {  // 2.5 MB of walk cache per tile
-            CK(ctx->walk_alpha.reserve((size_t)ctx->n_tiles * (320u << 10) + (1u << 20)));
+        if (ctx->walk_alpha_cap == 0 || ctx->walk_len_cap == 0) {  // fragment slots: 1.5 M per tile to start with
+            CK(ctx->walk_alpha.reserve((size_t)ctx->n_tiles * (1536u << 10) / 4 + (1u << 20)));
+            CK(ctx->walk_len.reserve(ctx->walk_alpha.cap));
             ctx->walk_alpha_cap = ctx->walk_alpha.cap;
-        }
-        if (ctx->walk_len_cap == 0) {
-            CK(ctx->walk_len.reserve((size_t)ctx->n_tiles * (80u << 10) + (1u << 20)));
             ctx->walk_len_cap = ctx->walk_len.cap;
         }
+        if (ctx->entries_cap == 0) {
+            CK(ctx->bin_entries.reserve((size_t)ctx->n_areas * 4 + (1u << 20)));
+            CK(ctx->frag_cnt.reserve(ctx->bin_entries.cap));
+            ctx->entries_cap = std::min(ctx->bin_entries.cap, ctx->frag_cnt.cap);
+        }
+        if (ctx->pair_cap == 0) {
+            CK(ctx->pair_table.reserve((size_t)ctx->n_areas * 4 + (1u << 20)));
+            ctx->pair_cap = ctx->pair_table.cap;
+        }
+        CK(ctx->blk_range.reserve((size_t)ctx->n_tiles * (size_t)((Di / kBW) * (Di / kBH)) + 1));
         ctx->stats = osmr_stats{};
         // every chunk is enqueued without waiting for the previous one; with staged host output the D2H copy of chunk i
         // (third stream) runs while the later chunks are drawn.  The chunks alternate between two compute streams with
@@ -1674,11 +1732,11 @@ static int labels_via_host(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_til
         if (!osmr_host::layout_tile(env, tiles[it.tile], labels + it.first, it.count, it.recs, it.segs)) bad.store(true);
     });
     if (bad.load()) return ctx->fail(OSMR_E_INVALID, "label references an entity, style or icon that does not exist");
-    // batch assembly: global segment indices, coverage storage and the (label, row) work list of label_cover_kernel
+    // batch assembly: global segment indices, coverage storage and the work list of label_cover_kernel
     std::vector<osmr_host::LabelRec> recs;
-    std::vector<osmr_host::RowRec> rowrecs;
+    std::vector<unsigned> cover_list;
     std::vector<unsigned> lbegin(n_tiles + 1, 0);
-    unsigned long long cells = 0;
+    unsigned long long cells = 0, n_rows = 0;
     size_t n_segs = 0;
     {
         size_t nr = 0;
@@ -1708,13 +1766,15 @@ static int labels_via_host(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_til
             const bool touches = r.seg_count && rows > 0 && cols > 0 && r.bx1 >= -D && r.bx0 <= 2 * D - 1;
             r.rows = touches ? (int)rows : 0;
             r.width = touches ? (int)cols : 0;
-            r.row_first = (unsigned)rowrecs.size();
+            r.row_first = (unsigned)n_rows;
+            r.n_ranges = 0;
+            r.range_off = 0;
             r.cell_off = cells;
             if (r.icon < 0 && !touches) continue;  // cannot draw, claim or collide
             if (touches) {
                 if (cols > (1 << 20)) return ctx->fail(OSMR_E_NOMEM, "label text wider than 2^20 pixels");
-                for (int y = 0; y < r.rows; ++y) rowrecs.push_back({(unsigned)recs.size(), (unsigned)y});
-                while (rowrecs.size() % 32) rowrecs.push_back({(unsigned)recs.size(), 0xffffffffu});  // a warp never mixes labels
+                cover_list.push_back((unsigned)recs.size());
+                n_rows += (unsigned long long)rows;
                 cells += (unsigned long long)rows * cols;
             }
             recs.push_back(r);
@@ -1722,50 +1782,43 @@ static int labels_via_host(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_til
         lbegin[it.tile + 1] = (unsigned)recs.size();
     }
     for (uint32_t t = 0; t < n_tiles; ++t) lbegin[t + 1] = std::max(lbegin[t + 1], lbegin[t]);  // tiles without labels
-    if (cells > (1ull << 31) || rowrecs.size() >= 0x7fffffffull) return ctx->fail(OSMR_E_NOMEM, "label scratch too large; split the batch");
+    if (cells > (1ull << 31) || n_rows >= 0x7fffffffull) return ctx->fail(OSMR_E_NOMEM, "label scratch too large; split the batch");
     ctx->stats_label_layout_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_host0).count();
-    static_assert(sizeof(osmr_host::LabelRec) == sizeof(DevLabel) && sizeof(osmr_host::Seg) == sizeof(DevSeg) &&
-                      sizeof(osmr_host::RowRec) == sizeof(DevRowRec),
-                  "label wire layout");
+    static_assert(sizeof(osmr_host::LabelRec) == sizeof(DevLabel) && sizeof(osmr_host::Seg) == sizeof(DevSeg), "label wire layout");
     // ---- device half ----
     CK(ctx->d_labels.reserve(recs.size() + 1));
     CK(ctx->d_label_segs.reserve(n_segs + 1));
-    CK(ctx->d_seg_slope.reserve(n_segs + 1));
-    CK(ctx->d_seg_rows.reserve(n_segs + 1));
-    CK(ctx->d_label_rows.reserve(rowrecs.size() + 1));
+    CK(ctx->d_cover_list.reserve(cover_list.size() + 1));
+    CK(ctx->d_cover_cursor.reserve(4));
     CK(ctx->d_label_begin.reserve(n_tiles + 1));
     CK(ctx->label_occ.reserve((size_t)n_tiles * ((size_t)E * E / 32)));
     CK(ctx->label_acc.reserve(2 * (size_t)cells + 2));
-    CK(ctx->label_row_keys.reserve(2 * rowrecs.size() + 2));
+    CK(ctx->label_row_keys.reserve(2 * (size_t)n_rows + 2));
     CK(ctx->label_plane.reserve((size_t)n_tiles * D * D));
     CK(cudaEventRecord(ctx->ev_label0, ctx->stream));
     if (!recs.empty()) CK(cudaMemcpyAsync(ctx->d_labels.p, recs.data(), recs.size() * sizeof(DevLabel), cudaMemcpyHostToDevice, ctx->stream));
     if (n_segs) CK(cudaMemcpyAsync(ctx->d_label_segs.p, seg_stage, n_segs * sizeof(DevSeg), cudaMemcpyHostToDevice, ctx->stream));
-    if (!rowrecs.empty())
-        CK(cudaMemcpyAsync(ctx->d_label_rows.p, rowrecs.data(), rowrecs.size() * sizeof(DevRowRec), cudaMemcpyHostToDevice, ctx->stream));
+    if (!cover_list.empty())
+        CK(cudaMemcpyAsync(ctx->d_cover_list.p, cover_list.data(), cover_list.size() * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_label_begin.p, lbegin.data(), (n_tiles + 1) * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
-    if (cells) CK(cudaMemsetAsync(ctx->label_acc.p, 0, 2 * (size_t)cells * sizeof(double), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_cover_cursor.p, 0, sizeof(unsigned), ctx->stream));
     LabelScene ls{};
     ls.labels = ctx->d_labels.p;
     ls.label_begin = ctx->d_label_begin.p;
     ls.segs = ctx->d_label_segs.p;
-    ls.rowrecs = ctx->d_label_rows.p;
-    ls.n_rowrecs = (unsigned)rowrecs.size();
-    ls.n_segs = (unsigned)n_segs;
-    ls.seg_slope = ctx->d_seg_slope.p;
-    ls.seg_rows = ctx->d_seg_rows.p;
+    ls.cover_list = ctx->d_cover_list.p;
+    ls.n_cover = (unsigned)cover_list.size();
     ls.icons = ctx->label_icons.p;
     ls.occ = ctx->label_occ.p;
     ls.acc_a = ctx->label_acc.p;
     ls.acc_s = ctx->label_acc.p + cells;
     ls.kmin = ctx->label_row_keys.p;
-    ls.kmax = ctx->label_row_keys.p + rowrecs.size();
+    ls.kmax = ctx->label_row_keys.p + n_rows;
     ls.plane = ctx->label_plane.p;
     ls.D = D;
-    if (ls.n_rowrecs) {
-        label_seg_kernel<<<(ls.n_segs + 255) / 256, 256, 0, ctx->stream>>>(ls);
-        CK(cudaGetLastError());
-        label_cover_kernel<<<ls.n_rowrecs / 32, 32, 0, ctx->stream>>>(ls);  // rowrecs are padded per label to whole warps
+    ls.cover_cursor = ctx->d_cover_cursor.p;
+    if (ls.n_cover) {
+        label_cover_kernel<<<std::min<unsigned>(ls.n_cover, (unsigned)ctx->num_sms * 16u), 32, 0, ctx->stream>>>(ls);
         CK(cudaGetLastError());
     }
     label_commit_kernel<<<n_tiles, kLabelThreads, 0, ctx->stream>>>(ls);
@@ -1986,9 +2039,8 @@ static int label_device_enqueue(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t 
     CK(ctx->l_gplace.reserve(ctx->l_places_cap));
     CK(ctx->l_gout.reserve(ctx->l_places_cap));
     CK(ctx->d_label_segs.reserve(ctx->l_segs_cap));
-    CK(ctx->d_seg_slope.reserve(ctx->l_segs_cap));
-    CK(ctx->d_seg_rows.reserve(ctx->l_segs_cap));
-    CK(ctx->d_label_rows.reserve(ctx->l_rowrecs_cap));
+    CK(ctx->d_cover_list.reserve((size_t)n_labels + 1));
+    CK(ctx->d_cover_cursor.reserve(4));
     CK(ctx->label_row_keys.reserve(2 * ctx->l_rowrecs_cap + 2));
     CK(ctx->label_acc.reserve(2 * ctx->l_cells_cap + 2));
     CK(ctx->l_ring_pts.reserve(ctx->l_ring_cap));
@@ -2048,7 +2100,7 @@ static int label_device_enqueue(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t 
     ld.segs = ctx->d_label_segs.p;
     ld.segs_cap = (unsigned)std::min<size_t>(ctx->l_segs_cap, 0xfffffff0u);
     ld.out_labels = ctx->d_labels.p;
-    ld.rowrecs = ctx->d_label_rows.p;
+    ld.cover_list = ctx->d_cover_list.p;
     ld.rowrecs_cap = (unsigned)std::min<size_t>(ctx->l_rowrecs_cap, 0x7ffffff0u);
     ld.cells_cap = ctx->l_cells_cap;
     ld.ring_pts = ctx->l_ring_pts.p;
@@ -2059,17 +2111,17 @@ static int label_device_enqueue(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t 
     const unsigned wide = (unsigned)ctx->num_sms * 8u;
     label_select_kernel<<<n_tiles, kLabelSelThreads, 0, st>>>(s, ld);
     label_layout_kernel<<<n_tiles, kLayoutThreads, 0, st>>>(s, ld);
-    label_emit_count_kernel<<<wide, 128, 0, st>>>(ld);
+    label_emit_kernel<<<wide, kEmitThreads, 0, st>>>(ld);
     label_finish_kernel<<<n_tiles, 128, 0, st>>>(s, ld);
-    label_emit_write_kernel<<<wide, 128, 0, st>>>(ld);
     CK(cudaGetLastError());
+    CK(cudaMemsetAsync(ctx->d_cover_cursor.p, 0, sizeof(unsigned), st));
     LabelScene ls{};
     ls.labels = ctx->d_labels.p;
     ls.label_begin = ctx->d_label_begin.p;
     ls.segs = ctx->d_label_segs.p;
-    ls.rowrecs = ctx->d_label_rows.p;
-    ls.seg_slope = ctx->d_seg_slope.p;
-    ls.seg_rows = ctx->d_seg_rows.p;
+    ls.gout = ctx->l_gout.p;
+    ls.cover_list = ctx->d_cover_list.p;
+    ls.cover_cursor = ctx->d_cover_cursor.p;
     ls.icons = ctx->label_icons.p;
     ls.occ = ctx->label_occ.p;
     ls.acc_a = ctx->label_acc.p;
@@ -2078,12 +2130,10 @@ static int label_device_enqueue(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t 
     ls.kmax = ctx->label_row_keys.p + ctx->l_rowrecs_cap;
     ls.plane = ctx->label_plane.p;
     ls.D = D;
-    ls.n_segs_dev = ctx->l_counters.p + LCNT_SEGS;
-    ls.n_rowrecs_dev = ctx->l_counters.p + LCNT_ROWRECS;
+    ls.n_cover_dev = ctx->l_counters.p + LCNT_COVER;
     ls.label_cnt = ctx->l_act_cnt.p;
     ls.skip_flags = ctx->l_counters.p + LCNT_OVERFLOW;
-    label_seg_kernel<<<wide, 256, 0, st>>>(ls);
-    label_cover_kernel<<<(unsigned)ctx->num_sms * 32u, 32, 0, st>>>(ls);
+    label_cover_kernel<<<(unsigned)ctx->num_sms * 16u, 32, 0, st>>>(ls);
     label_commit_kernel<<<n_tiles, kLabelThreads, 0, st>>>(ls);
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev_label1, st));
@@ -2115,6 +2165,12 @@ static int label_device_judge(osmr_ctx* ctx) {
     }
     ctx->stats_label_active = c[LCNT_ACTIVE];
     ctx->stats_label_poly = c[LCNT_POLY];
+    if (getenv("OSMR_LABEL_DEBUG")) {
+        unsigned long long cells;
+        memcpy(&cells, &c[LCNT_CELLS_LO], 8);
+        fprintf(stderr, "[osmr labels] active %u places %u segs %u rows %u cells %llu ring_pts %u polylabel %u covered %u\n", c[LCNT_ACTIVE], c[LCNT_PLACES],
+                c[LCNT_SEGS], c[LCNT_ROWRECS], cells, c[LCNT_RING_PTS], c[LCNT_POLY], c[LCNT_COVER]);
+    }
     return 0;
 }
 
@@ -2155,7 +2211,7 @@ int osmr_draw_tiles_labeled(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_ti
             ctx->stats.ms_label_layout = enqueue_ms;  // host time spent on labels: table look-ups and launches only
             ctx->stats.ms_label_device = ms;
             ctx->stats.ms_total += ms;
-            ctx->stats.kernel_launches += 8;
+            ctx->stats.kernel_launches += 6;
             ctx->stats.label_path = 1;
             ctx->stats.n_labels_active = ctx->stats_label_active;
             ctx->stats.n_labels_polylabel = ctx->stats_label_poly;

@@ -30,7 +30,7 @@ struct VisOp {  // 48 bytes: what the geometry / fill / cover kernels need of an
     short x0, y0, x1, y1;  // reach bbox clamped to [-1, D]
     unsigned geom_off;     // first 16-byte unit of its records in the geometry scratch
     unsigned geom_cnt;     // records written by build_geometry_kernel
-    unsigned mask_off;     // fills: first word of its row masks
+    unsigned mask_off;     // fills: first word of its row masks; lines: first cell of its (block -> bin entry) pair table
     unsigned kind;         // OP_*
     unsigned area;         // index of the styled area inside its tile (g = pass * n + area)
     unsigned pass;         // 0 Fill, 1 Casing, 2 Stroke
@@ -46,10 +46,11 @@ struct alignas(16) RasterOp {
     unsigned a;       // lines: geom_off; fills: mask_off
     unsigned b;       // lines: geom_cnt (written by build_geometry_kernel); image fills: icon index
     short y0, y1;     // VisOp.y0 / y1
-    unsigned char kind, reach;  // OP_*; lines: line_reach(half width) = doubles per cached walk
-    unsigned char rgb[3];       // colour of the pass
-    unsigned char pad[3];
-    double opacity;   // colour fills: fill-opacity (lines carry theirs in the cached alphas)
+    unsigned char kind;    // OP_*
+    unsigned char rgb[3];  // colour of the pass
+    unsigned short reach;  // lines: line_reach(half width), the culling margin around a segment
+    unsigned short pad;
+    double opacity;   // colour fills: fill-opacity (lines carry theirs in the fragment alphas)
 };
 static_assert(sizeof(RasterOp) == 32, "RasterOp layout");
 
@@ -59,11 +60,10 @@ struct SegRec {  // 64 bytes: one line segment (or outer cap line) that can touc
     double denom;              // center_dist_denom (line.rs:106)
     unsigned long long magic;  // floor(2^64 / (2*mx_d)) + 1: exact quotients for numerators < 2^32 (flags bit1)
     unsigned flags;            // bit0: outer cap calculator (line.rs:22,33-57); bit1: 32-bit fast path valid; bit2: coords < 2^24
-    int k0;                    // first main step whose perpendiculars can reach the tile; the walk cache covers k0 .. k0+n_k-1
+    int k0;                    // first main step whose perpendiculars can reach the tile; line_cover_kernel walks k0 .. k0+n_k-1
     unsigned n_k;
-    unsigned len_off;              // walk_len index of walk (k0, +); regular walks are ordered (k - k0) * 2 + dir, the (rare) extra
-                                   // perpendiculars of double corrections follow at 2 * n_k + the same index
-    unsigned long long alpha_off;  // walk_alpha index of that walk's step 0; every walk of the op owns S = line_reach(hw) doubles
+    unsigned pad0;
+    unsigned long long pad1;
 };
 static_assert(sizeof(SegRec) == 64, "SegRec layout");
 // Opacity calculators depend only on (style, pass, scale, use_caps_for_dashes): style_calc_kernel builds them once per
@@ -78,7 +78,8 @@ enum {
     CNT_MASK_USED = 1,   // words
     CNT_N_WORK = 2,      // visible ops (all kinds)
     CNT_N_FILL_WORK = 3,
-    CNT_OVERFLOW = 4,    // bit0 geometry scratch, bit1 mask scratch, bit2 walk cache, bit3 sort scratch (f3), bit4 fill / bit5 line work list
+    CNT_OVERFLOW = 4,    // bit0 geometry scratch, bit1 mask scratch, bit2 fragment storage, bit3 sort scratch (f3), bit4 fill / bit5 line
+                         // work list, bit6 bin entries, bit7 pair tables, bit8 a (block, op) fragment list outgrew its proven capacity
     CNT_BAD_INPUT = 5,   // entity / style index out of range
     CNT_WORK_CURSOR = 6,
     CNT_FILL_CURSOR = 7,
@@ -86,12 +87,15 @@ enum {
     CNT_NODE_REFS_HI = 9,
     CNT_VISIBLE = 10,
     CNT_BIG_COORDS = 11,  // some visible segment has a coordinate >= 2^24 (raster uses exact i64 cross products)
-    CNT_WALK_ALPHA = 12,  // 64-bit (12,13): doubles of the walk cache handed out by build_geometry_kernel
-    CNT_WALK_LEN = 14,    // 64-bit (14,15): walks handed out
+    CNT_WALK_ALPHA = 12,  // 64-bit (12,13): fragment slots handed out by bin_ops_kernel (sum of the pair capacities)
+    CNT_WALK_LEN = 14,    // 64-bit (14,15): (f3 reuses 12,13 for its sort scratch; unused by the draw path)
     CNT_N_LINE_WORK = 16,
     CNT_LINE_CURSOR = 17,
-    CNT_WALK_STEPS = 20,  // 64-bit (20,21): in-line steps stored in the walk cache (statistics)
-    CNT_WALK_TRUNC = 18,  // a perpendicular walk outlived its proven bound (never observed; the draw fails loudly)
+    CNT_WALK_STEPS = 20,  // 64-bit (20,21): fragments stored by line_cover_kernel (statistics)
+    CNT_WALK_TRUNC = 18,  // bit0: a perpendicular walk outlived its proven bound; bit1: a fragment fell into a block the binning had
+                          // ruled out (never observed; the draw fails loudly)
+    CNT_BIN_ENTRIES = 19, // (block, op) entries handed out by bin_ops_kernel
+    CNT_PAIR_USED = 22,   // pair table cells handed out by plan_ops_kernel
     CNT_COUNT = 24
 };
 
@@ -151,9 +155,17 @@ struct Scene {
     uint2* fill_work;      // (global index into vis, chunk of 32 mask rows): work items of fill_rows_kernel
     uint2* line_work;      // (global index into vis, batch of 32 segment records): work items of line_cover_kernel
     unsigned fill_work_cap, line_work_cap;
-    double* walk_alpha;    // walk cache (line_cover_kernel -> raster_kernel): alpha of every in-line step of every walk
-    unsigned char* walk_len;  // number of in-line steps per walk
-    unsigned long long walk_alpha_cap, walk_len_cap;
+    // Fragments (line_cover_kernel -> raster_kernel): every in-line, in-tile step of every perpendicular walk as (pixel inside its
+    // 16x16 block, alpha), appended to the list of its (block, op) pair.  bin_ops_kernel sizes the lists and orders the pairs.
+    double* frag_alpha;
+    unsigned char* frag_pix;
+    unsigned long long frag_cap;
+    struct BinEntry* entries;  // per (block, op) pair, grouped by block in generation order
+    unsigned* frag_cnt;        // fragments stored per entry
+    unsigned entries_cap;
+    uint2* blk_range;          // per (tile, block): first entry, number of entries
+    unsigned* pair;            // per line op: entry index of every block of its bbox rectangle (0xffffffff: no segment reaches it)
+    unsigned pair_cap;
     const uint4* calc_table;  // kCalcEntryUnits per (style, pass-1), built by style_calc_kernel
     uint4* geom;           // geometry scratch, 16-byte units
     unsigned geom_cap;
@@ -164,6 +176,32 @@ struct Scene {
     const struct LabelPix* label_plane;  // per tile D*D entries written by label_kernel, or nullptr (no label pass)
     const double4* label_icon_px;        // premultiplied texels of the label icons
     unsigned char* out;
+};
+
+#ifndef OSMR_BW
+#define OSMR_BW 16
+#endif
+#ifndef OSMR_BH
+#define OSMR_BH 16
+#endif
+constexpr int kBW = OSMR_BW;  // block owned by one raster warp: kBW x kBH pixels
+constexpr int kBH = OSMR_BH;
+constexpr int kBP = kBW * kBH;
+static_assert((kBW == 16 || kBW == 32) && kBP % 32 == 0 && 256 % kBW == 0 && 256 % kBH == 0 && kBP <= 256, "block shape (a pixel index is one byte)");
+
+// blocks of the tile covered by an op's reach bbox (VisOp.x0..y1, clamped to [-1, D]): first block column / row, columns, rows
+__device__ __forceinline__ void op_block_rect(int x0, int y0, int x1, int y1, int D, int& bx0, int& by0, int& nbx, int& nby) {
+    bx0 = max(x0, 0) / kBW;
+    by0 = max(y0, 0) / kBH;
+    nbx = min(x1, D - 1) / kBW - bx0 + 1;
+    nby = min(y1, D - 1) / kBH - by0 + 1;
+}
+
+struct alignas(16) BinEntry {
+    unsigned op;        // global index into Scene.rop / vis
+    unsigned frag_off;  // lines: first fragment slot
+    unsigned frag_cap;  // lines: slots (a proven upper bound of what line_cover_kernel can store)
+    unsigned pad;
 };
 
 constexpr int kFillCap = 128;
@@ -399,11 +437,12 @@ __global__ void __launch_bounds__(kPlanThreads) plan_ops_kernel(Scene s) {
         RasterOp rop;
         rop.a = rop.b = 0;
         rop.y0 = rop.y1 = 0;
-        rop.kind = rop.reach = 0;
+        rop.kind = 0;
+        rop.reach = 0;
         rop.rgb[0] = rop.rgb[1] = rop.rgb[2] = 0;
-        rop.pad[0] = rop.pad[1] = rop.pad[2] = 0;
+        rop.pad = 0;
         rop.opacity = 1.0;
-        unsigned geom_units = 0, mask_words = 0;
+        unsigned geom_units = 0, mask_words = 0, pair_cells = 0;
         if (g < total) {
             unsigned pass = g / n;
             unsigned i = g - pass * n;
@@ -451,8 +490,8 @@ __global__ void __launch_bounds__(kPlanThreads) plan_ops_kernel(Scene s) {
                         op.kind = OP_LINE;
                         double hw = lp.width / 2.0;
                         int reach = line_reach(hw);
-                        if (reach > 127) atomicOr(&s.counters[CNT_BAD_INPUT], 2u);  // walk lengths are cached in 7 bits
-                        rop.reach = (unsigned char)reach;
+                        if (reach > 32767) atomicOr(&s.counters[CNT_BAD_INPUT], 2u);  // half width beyond 2^15 pixels
+                        rop.reach = (unsigned short)reach;
                         rop.rgb[0] = lp.rgb[0];
                         rop.rgb[1] = lp.rgb[1];
                         rop.rgb[2] = lp.rgb[2];
@@ -481,27 +520,41 @@ __global__ void __launch_bounds__(kPlanThreads) plan_ops_kernel(Scene s) {
                     op.tile = t;
                     op.entity = ar.entity;
                     op.style = ar.style;
+                    if (op.kind == OP_LINE)  // one pair-table cell per block of the reach bbox inside the tile
+                        pair_cells = (unsigned)((min(x1, D - 1) / kBW - max(x0, 0) / kBW + 1) * (min(y1, D - 1) / kBH - max(y0, 0) / kBH + 1));
                 }
             }
         }
-        // scratch allocation (order irrelevant); failure marks the op invisible and raises the overflow flag
+        // scratch allocation (order irrelevant); failure marks the op invisible and raises the overflow flag.  Every allocator sees
+        // the requests of ALL visible ops even when an earlier one has already failed: one attempt then reports the full need
+        // of each, and the host grows them all before the redo.
         {
-            const unsigned off = warp_alloc(&s.counters[CNT_GEOM_USED], visible ? geom_units : 0u);
-            if (visible) {
+            const bool want = visible;
+            const unsigned off = warp_alloc(&s.counters[CNT_GEOM_USED], want ? geom_units : 0u);
+            const unsigned moff = warp_alloc(&s.counters[CNT_MASK_USED], want ? mask_words : 0u);
+            const unsigned poff = warp_alloc(&s.counters[CNT_PAIR_USED], want ? pair_cells : 0u);
+            if (want) {
                 if (off + geom_units > s.geom_cap || off + geom_units < off) {
                     atomicOr(&s.counters[CNT_OVERFLOW], 1u);
                     visible = false;
                 } else {
                     op.geom_off = off;
                 }
-            }
-            const unsigned moff = warp_alloc(&s.counters[CNT_MASK_USED], visible ? mask_words : 0u);
-            if (visible && mask_words) {
-                if (moff + mask_words > s.mask_cap || moff + mask_words < moff) {
-                    atomicOr(&s.counters[CNT_OVERFLOW], 2u);
-                    visible = false;
-                } else {
-                    op.mask_off = moff;
+                if (mask_words) {
+                    if (moff + mask_words > s.mask_cap || moff + mask_words < moff) {
+                        atomicOr(&s.counters[CNT_OVERFLOW], 2u);
+                        visible = false;
+                    } else {
+                        op.mask_off = moff;
+                    }
+                }
+                if (pair_cells) {
+                    if (poff + pair_cells > s.pair_cap || poff + pair_cells < poff) {
+                        atomicOr(&s.counters[CNT_OVERFLOW], 128u);
+                        visible = false;
+                    } else {
+                        op.mask_off = poff;
+                    }
                 }
             }
         }
@@ -574,7 +627,6 @@ __global__ void __launch_bounds__(kPlanThreads) plan_ops_kernel(Scene s) {
 // build_geometry_kernel: one warp per visible op (dynamic work fetch)
 // ------------------------------------------------------------------------------------------------------
 constexpr int kGeomThreads = 128;
-constexpr unsigned long long kSlabLen = 2048, kSlabAlpha = 16384;  // walk cache units a warp reserves per atomic (2 KB / 128 KB)
 constexpr unsigned kLaneFillMax = 48;  // nodes of a way whose fill edges are produced by a single lane
 #ifndef OSMR_GEOM_LANE_FILLS
 #define OSMR_GEOM_LANE_FILLS 1
@@ -587,8 +639,6 @@ __global__ void __launch_bounds__(kGeomThreads, OSMR_GEOM_MIN_BLOCKS) build_geom
     const unsigned lane = lane_id();
     const int D = s.D;
     const unsigned n_work = s.counters[CNT_N_WORK];
-    // walk cache slabs: the warp takes kSlab units per atomic and hands them out to its ops itself
-    unsigned long long slab_len = 0, slab_len_end = 0, slab_alpha = 0, slab_alpha_end = 0;
     for (;;) {
         // 32 ops per fetch, one per lane.  A fill of a short way (a building: the majority of all ops) is done by its lane
         // alone -- 32 such ops side by side instead of one op on a quarter of the lanes; everything else (lines,
@@ -699,14 +749,10 @@ __global__ void __launch_bounds__(kGeomThreads, OSMR_GEOM_MIN_BLOCKS) build_geom
                 if (kb > mxd) kb = mxd;
                 rec.k0 = (int)ka;
                 rec.n_k = kb >= ka ? (unsigned)(kb - ka + 1) : 0u;
-                rec.len_off = 0;
-                rec.alpha_off = 0;
+                rec.pad0 = 0;
+                rec.pad1 = 0;
                 return rec;
             };
-            // walk cache: 4 walks (2 directions x {regular, extra}) of S steps per main step, handed out per 32 segments
-            const unsigned long long S = (unsigned long long)reach;
-            unsigned long long* walk_alpha_used = reinterpret_cast<unsigned long long*>(&s.counters[CNT_WALK_ALPHA]);
-            unsigned long long* walk_len_used = reinterpret_cast<unsigned long long*>(&s.counters[CNT_WALK_LEN]);
             for (unsigned b = 0; b < n_pairs; b += 32) {
                 unsigned e = b + lane;
                 bool valid = e < n_pairs;
@@ -747,61 +793,9 @@ __global__ void __launch_bounds__(kGeomThreads, OSMR_GEOM_MIN_BLOCKS) build_geom
                     k2 = (c2.x != p2.x || c2.y != p2.y) && touches(p2.x, p2.y, c2.x, c2.y);
                 }
                 SegRec r0, r1, r2;
-                unsigned nk = 0;  // main steps of this lane's records
-                if (keep) {
-                    r0 = make_rec(p1.x, p1.y, p2.x, p2.y, trav, 0u);
-                    nk += r0.n_k;
-                }
-                if (k1) {
-                    r1 = make_rec(p1.x, p1.y, c1.x, c1.y, 0.0, 1u);
-                    nk += r1.n_k;
-                }
-                if (k2) {
-                    r2 = make_rec(p2.x, p2.y, c2.x, c2.y, 0.0, 1u);
-                    nk += r2.n_k;
-                }
-                unsigned incl = nk;
-                for (int o = 1; o < 32; o <<= 1) {
-                    unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
-                    if ((int)lane >= o) incl += v;
-                }
-                const unsigned total_k = __shfl_sync(0xffffffffu, incl, 31);
-                unsigned long long base_len = 0, base_alpha = 0;
-                if (lane == 0 && total_k) {
-                    const unsigned long long need_len = 4ull * total_k, need_alpha = 4ull * S * total_k;
-                    if (slab_len + need_len > slab_len_end) {
-                        const unsigned long long take = need_len > kSlabLen ? need_len : kSlabLen;
-                        slab_len = atomicAdd(walk_len_used, take);
-                        slab_len_end = slab_len + take;
-                    }
-                    if (slab_alpha + need_alpha > slab_alpha_end) {
-                        const unsigned long long take = need_alpha > kSlabAlpha ? need_alpha : kSlabAlpha;
-                        slab_alpha = atomicAdd(walk_alpha_used, take);
-                        slab_alpha_end = slab_alpha + take;
-                    }
-                    base_len = slab_len;
-                    base_alpha = slab_alpha;
-                    slab_len += need_len;
-                    slab_alpha += need_alpha;
-                }
-                base_len = __shfl_sync(0xffffffffu, base_len, 0);
-                base_alpha = __shfl_sync(0xffffffffu, base_alpha, 0);
-                const bool fits = base_len + 4ull * total_k <= s.walk_len_cap && base_alpha + 4ull * S * total_k <= s.walk_alpha_cap &&
-                                  base_len + 4ull * total_k <= 0xffffffffull;
-                if (!fits && lane == 0 && total_k) atomicOr(&s.counters[CNT_OVERFLOW], 4u);
-                unsigned long long kpos = (unsigned long long)(incl - nk);  // main steps of the lanes before me
-                auto place = [&](SegRec& rec) {
-                    if (!fits) {
-                        rec.n_k = 0;  // nothing of this record is covered; the host grows the cache and redoes the batch
-                    } else {
-                        rec.len_off = (unsigned)(base_len + 4ull * kpos);
-                        rec.alpha_off = base_alpha + 4ull * S * kpos;
-                        kpos += rec.n_k;
-                    }
-                };
-                if (keep) place(r0);
-                if (k1) place(r1);
-                if (k2) place(r2);
+                if (keep) r0 = make_rec(p1.x, p1.y, p2.x, p2.y, trav, 0u);
+                if (k1) r1 = make_rec(p1.x, p1.y, c1.x, c1.y, 0.0, 1u);
+                if (k2) r2 = make_rec(p2.x, p2.y, c2.x, c2.y, 0.0, 1u);
                 unsigned bal = __ballot_sync(0xffffffffu, keep);
                 if (keep) out[count + __popc(bal & ((1u << lane) - 1u))] = r0;
                 count += __popc(bal);
@@ -1056,46 +1050,12 @@ __global__ void __launch_bounds__(kFillThreads) fill_rows_kernel(Scene s) {
 }
 
 // ------------------------------------------------------------------------------------------------------
-// raster_kernel (a3 blend, a4/a5, a6, a7): ONE WARP (= one 32-thread CTA) per 16x16-pixel block of a tile.
-//
-// Compositor invariants used (tile_pixels.rs:107-129,205-223): inside one generation the
-// surviving source of a pixel is the contribution with the largest alpha; generations blend in order with
-// premultiplied over; canvas alpha stays exactly 1.0, so only RGB is kept and export is trunc(255*c).
-//
-// The warp owns its block for the whole ordered op list of the tile: f64 canvas + f64 alpha plane in shared
-// memory, it culls ops and segments against its own block and walks every perpendicular that can reach it.
-// There is no CTA barrier anywhere (v1 shared a 64x32 region between 8 warps and was barrier-bound, v2 kept a
-// per-chunk barrier and lost to load imbalance: profiles/r01_raster_v{1,2}_ncu_summary.txt); the hardware block
-// scheduler balances the 16x16 blocks.
-// ------------------------------------------------------------------------------------------------------
-#ifndef OSMR_BW
-#define OSMR_BW 16
-#endif
-#ifndef OSMR_BH
-#define OSMR_BH 16
-#endif
-constexpr int kBW = OSMR_BW;  // block owned by one warp: kBW x kBH pixels (kBW 16 or 32)
-constexpr int kBH = OSMR_BH;
-constexpr int kBP = kBW * kBH;
-static_assert((kBW == 16 || kBW == 32) && kBP % 32 == 0 && 256 % kBW == 0 && 256 % kBH == 0, "block shape");
-constexpr int kRasterThreads = 32;
-// Measured variants of raster_kernel (same-box A/B on the C2 batch, default 3.56 ms) that are NOT in the code any
-// more: preloading a walk's first four alphas (3.82 ms) or pipelining them one deep (3.66), prefetching the op bboxes two
-// chunks ahead (3.61), tracking the plane rows a line op wrote for the blend (+0.22 ms), one work item per (step, side)
-// instead of per step (+0.05 ms), 16x8 / 32x8 / 32x16 blocks (3.97 / 3.95 / 4.80).  What stayed: the next chunk's bboxes
-// are loaded while the current chunk is drawn (3.64 -> 3.60) and every lane loads the RasterOp of its own hit op, the
-// records being handed round by shuffles (-> 3.57).
-#ifndef OSMR_RASTER_MIN_BLOCKS
-#define OSMR_RASTER_MIN_BLOCKS 24  // resident one-warp CTAs per SM the register allocation must allow (16: 4.5 ms, 20: 4.06, 24: 3.66)
-#endif
-
-// ------------------------------------------------------------------------------------------------------
 // Perpendicular walks (a4/a5).  The reference draws a thick line by walking, from every pixel k of the segment's
 // Bresenham main line, one perpendicular Bresenham line to each side until the opacity calculator says "not in line"
-// (line.rs:65-158).  Here the f64 work of a walk is done ONCE per tile by line_cover_kernel, which stores the alpha
-// of every in-line step in the walk cache; raster_kernel's 16x16 blocks then replay the integer stepping of the
-// walks that can reach them and take the alphas from the cache.  (Before the cache every block re-evaluated the
-// walks from their start: two thirds of all opacity evaluations fell outside the evaluating block.)
+// (line.rs:65-158).  Here every walk is evaluated ONCE per tile by line_cover_kernel, which appends each covered pixel
+// as a fragment (pixel, alpha) to the list of the 16x16 block it falls into; raster_kernel's blocks only stream their
+// lists.  (History: up to round 1's v6 every block evaluated the walks itself -- two thirds of all opacity evaluations
+// fell outside the evaluating block; v7-v11 cached the alphas per walk and the blocks replayed the integer stepping.)
 // ------------------------------------------------------------------------------------------------------
 struct WalkItem {  // line.rs:65-118,133-158: the state of the main line at step k
     bool swap;
@@ -1148,9 +1108,49 @@ struct SegConst {
 // qualify together, so the warp paid the test and the reference path: line_cover_kernel 1.60 -> 2.52 ms.  DESIGN.md 4.)
 
 // draw_one_perpendicular (line.rs:89-131): evaluates the walk from its start until the first pixel that is not in the
-// line (or until it has left the tile for good on its monotone axis) and stores the alpha of every in-line step.
-// Returns the number of steps stored (<= S).
-__device__ __forceinline__ unsigned cover_walk(double* alpha_out, unsigned S, const WalkItem& w, const SegConst& sc, const OpacityCalc& calc,
+// line (or until it has left the tile for good on its monotone axis) and appends every in-line, in-tile step with a positive
+// alpha as a fragment (pixel, alpha) to the list of its 16x16 block.  Returns the number of fragments stored.
+struct FragSink {  // where the fragments of one line op go: its (block -> bin entry) pair table, the last entry looked up
+    const unsigned* pair;   // the op's pair table (Scene.pair + VisOp.mask_off)
+    const BinEntry* entries;
+    unsigned* frag_cnt;
+    double* frag_alpha;
+    unsigned char* frag_pix;
+    unsigned* counters;
+    int bx0, by0, nbx, nby; // block rectangle of the op's reach bbox
+    int last_block;         // block (by * 4096 + bx) of last_entry, -1: none yet
+    unsigned last_entry, last_off, last_cap;
+};
+
+__device__ __forceinline__ void frag_put(FragSink& fs, int px, int py, double alpha) {
+    const int bx = px / kBW, by = py / kBH;  // px, py are inside the tile
+    const int key = by * 4096 + bx;
+    if (key != fs.last_block) {
+        const int cx = bx - fs.bx0, cy = by - fs.by0;
+        unsigned e = 0xffffffffu;
+        if (cx >= 0 && cx < fs.nbx && cy >= 0 && cy < fs.nby) e = fs.pair[cy * fs.nbx + cx];
+        fs.last_block = key;
+        fs.last_entry = e;
+        if (e != 0xffffffffu) {
+            const BinEntry be = fs.entries[e];
+            fs.last_off = be.frag_off;
+            fs.last_cap = be.frag_cap;
+        }
+    }
+    if (fs.last_entry == 0xffffffffu) {  // the binning proved that no segment of this op reaches this block: a logic error, never silent
+        atomicOr(&fs.counters[CNT_WALK_TRUNC], 2u);
+        return;
+    }
+    const unsigned pos = atomicAdd(&fs.frag_cnt[fs.last_entry], 1u);
+    if (pos >= fs.last_cap) {  // the capacity is a proven bound; if it ever fails the draw is refused, not clipped
+        atomicOr(&fs.counters[CNT_OVERFLOW], 256u);
+        return;
+    }
+    fs.frag_alpha[(size_t)fs.last_off + pos] = alpha;
+    fs.frag_pix[(size_t)fs.last_off + pos] = (unsigned char)((py % kBH) * kBW + (px % kBW));
+}
+
+__device__ __forceinline__ unsigned cover_walk(FragSink& fs, unsigned S, const WalkItem& w, const SegConst& sc, const OpacityCalc& calc,
                                                int mn, int p_error, int mul, double opacity0, int D, unsigned* trunc_flag) {
     int p_mn = w.mx;
     int p_mx = mn;
@@ -1176,7 +1176,7 @@ __device__ __forceinline__ unsigned cover_walk(double* alpha_out, unsigned S, co
     const bool quick = !(dashed && calc.round_caps);
     const double t_in = calc.feather_from * sc.denom * (1.0 - 9.0e-13);
     const double t_out = calc.feather_to * sc.denom * (1.0 + 9.0e-13);
-    unsigned t = 0;
+    unsigned t = 0, n_put = 0;
     for (;;) {
         if (step > 0 ? (p_mx > D - 1) : (p_mx < 0)) break;
         const double araw = fabs(sc.small ? fraw : (double)raw);
@@ -1207,7 +1207,14 @@ __device__ __forceinline__ unsigned cover_walk(double* alpha_out, unsigned S, co
             atomicOr(trunc_flag, 1u);
             break;
         }
-        alpha_out[t] = opacity0 * opacity;  // RgbaColor::from_color(color, initial_opacity * opacity).a
+        {
+            const double a = opacity0 * opacity;  // RgbaColor::from_color(color, initial_opacity * opacity).a
+            const int px = w.swap ? p_mn : p_mx, py = w.swap ? p_mx : p_mn;
+            if (a > 0.0 && (unsigned)px < (unsigned)D && (unsigned)py < (unsigned)D) {  // set_pixel ignores everything outside the tile
+                frag_put(fs, px, py, a);
+                ++n_put;
+            }
+        }
         ++t;
         // update_error (line.rs:82-91), wrapping i32 arithmetic
         if (wadd(err, 2 * w.mn_d) > w.mx_d) {
@@ -1219,7 +1226,7 @@ __device__ __forceinline__ unsigned cover_walk(double* alpha_out, unsigned S, co
         p_mx += step;
         if (sc.small) fraw += f_step; else raw += d_step;
     }
-    return t;
+    return n_put;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -1274,6 +1281,17 @@ __global__ void __launch_bounds__(kCoverThreads, OSMR_COVER_MIN_BLOCKS) line_cov
         const SegRec* segs = reinterpret_cast<const SegRec*>(s.geom + op.geom_off);
         const unsigned n_seg = op.geom_cnt;
         unsigned steps_stored = 0;
+        FragSink fs;
+        fs.pair = s.pair + op.mask_off;
+        fs.entries = s.entries;
+        fs.frag_cnt = s.frag_cnt;
+        fs.frag_alpha = s.frag_alpha;
+        fs.frag_pix = s.frag_pix;
+        fs.counters = s.counters;
+        op_block_rect(op.x0, op.y0, op.x1, op.y1, D, fs.bx0, fs.by0, fs.nbx, fs.nby);
+        fs.last_block = -1;
+        fs.last_entry = 0xffffffffu;
+        fs.last_off = fs.last_cap = 0;
         __syncwarp();  // the previous op's walks are done with sm.calc
         {  // the op's opacity calculators (built by style_calc_kernel), 16 bytes per lane and step
             const uint4* src = s.calc_table + (size_t)(2u * ar.style + (pass - 1u)) * kCalcEntryUnits;
@@ -1327,24 +1345,18 @@ __global__ void __launch_bounds__(kCoverThreads, OSMR_COVER_MIN_BLOCKS) line_cov
                 sc.denom = h.denom;
                 sc.traveled = h.traveled;
                 sc.small = (h.flags & 4u) != 0;
-                // walk (k, dir) lives at index `local`, its extra perpendicular at 2 * n_k + local
-                unsigned char* len_out = s.walk_len + h.len_off + local;
-                double* alpha_out = s.walk_alpha + h.alpha_off + (unsigned long long)local * S;
-                const unsigned long long extra_at = 2ull * h.n_k;
                 // the walk of step k, then the extra one of a double correction (line.rs:150-155); a walk whose start is
                 // more than `reach` outside the tile on its own axis cannot put a pixel into it
                 int mn = w.mn, p_error = w.p_error;
                 unsigned len0 = 0, len1 = 0;
                 if (mn >= -reach && mn <= D - 1 + reach)
-                    len0 = cover_walk(alpha_out, S, w, sc, calc, mn, p_error, mul, lp.opacity, D, &s.counters[CNT_WALK_TRUNC]);
+                    len0 = cover_walk(fs, S, w, sc, calc, mn, p_error, mul, lp.opacity, D, &s.counters[CNT_WALK_TRUNC]);
                 if (w.extra) {
                     p_error = wadd(wsub(p_error, 2 * w.mx_d), 2 * w.mn_d);
                     mn += w.mn_inc;
                     if (mn >= -reach && mn <= D - 1 + reach)
-                        len1 = cover_walk(alpha_out + extra_at * S, S, w, sc, calc, mn, p_error, mul, lp.opacity, D, &s.counters[CNT_WALK_TRUNC]);
-                    if (len1) len_out[extra_at] = (unsigned char)len1;
+                        len1 = cover_walk(fs, S, w, sc, calc, mn, p_error, mul, lp.opacity, D, &s.counters[CNT_WALK_TRUNC]);
                 }
-                len_out[0] = (unsigned char)(len0 | (len1 ? 0x80u : 0u));  // bit 7: the extra walk has steps
                 steps_stored += len0 + len1;
                 OSMR_COUNT("cover.walks", (len0 != 0) + (len1 != 0));
             }
@@ -1356,55 +1368,262 @@ __global__ void __launch_bounds__(kCoverThreads, OSMR_COVER_MIN_BLOCKS) line_cov
 }
 
 // ------------------------------------------------------------------------------------------------------
-// raster_kernel's half of the walks
+// bin_ops_kernel: per 16x16 block of every tile the ORDERED list of the generations that can touch it, and per
+// (block, line op) pair the storage of its fragments.
+//
+// Until round 1's v11 every raster warp scanned the bboxes of all visible ops of its tile, then the segments of every hit
+// line op, then replayed the integer stepping of every cached walk that could reach its block (8 of 32 lanes busy).  Now
+// the scan happens once, here, a thread per block; line_cover_kernel appends every covered pixel to the list of its
+// (block, op) pair; and raster_kernel only streams its block's lists.
+//
+// A thread owns one block and runs twice over the tile's three op lists (Fill, Casing, Stroke, in order): the first
+// sweep counts its entries and their fragment capacity, a CTA scan + one atomic per CTA turn the counts into offsets,
+// the second sweep writes the entries, zeroes their fragment counters and fills the line ops' pair tables.
+// Fragment capacity of a (block, segment): main steps within reach of the block x 4 walks (two sides, each possibly with the
+// extra perpendicular of a double correction) x the longest stretch of a walk inside the block -- a walk moves one pixel per
+// step along one axis, so at most 16 of its steps lie in a 16-pixel block, and it has at most `reach` in-line steps.
 // ------------------------------------------------------------------------------------------------------
-struct SegHit {  // 48 bytes: what a block needs of a segment record that can reach it
-    int x1, y1, x2, y2;
-    int ka;                    // first main step within reach of the block
-    unsigned flags;            // SegRec.flags | SegRec.n_k << 8
-    unsigned long long magic;  // floor(2^64 / (2*mx_d)) + 1 (exact quotients for numerators < 2^32)
-    int k0;                    // SegRec.k0: first main step in the walk cache
-    unsigned len_off;
-    unsigned long long alpha_off;
+constexpr int kBinThreads = 256;
+
+// main steps k (line.rs:133-158) of a segment whose major coordinate lies within `reach` of the block at (bx0, by0), cut to the
+// steps [k0, k0 + n_k) that line_cover_kernel walks; returns the number of steps (0: the segment cannot reach the block)
+__device__ __forceinline__ unsigned seg_block_steps(const int4 sr, int reach, int bx0, int by0, int k0, unsigned n_k) {
+    const int mnx = min(sr.x, sr.z), mxx = max(sr.x, sr.z), mny = min(sr.y, sr.w), mxy = max(sr.y, sr.w);
+    if (!((long long)mnx - reach <= bx0 + kBW - 1 && (long long)mxx + reach >= bx0 && (long long)mny - reach <= by0 + kBH - 1 &&
+          (long long)mxy + reach >= by0))
+        return 0u;
+    const int dx = abs(wsub(sr.z, sr.x)), dy = abs(wsub(sr.w, sr.y));
+    const bool swap = dx > dy;
+    const int mx0 = swap ? sr.x : sr.y;
+    const int mxd = swap ? dx : dy;
+    const int mx_inc = swap ? (sr.x <= sr.z ? 1 : -1) : (sr.y <= sr.w ? 1 : -1);
+    const long long lo = (long long)(swap ? bx0 : by0) - reach;
+    const long long hi = (long long)(swap ? bx0 + kBW : by0 + kBH) - 1 + reach;
+    long long ka, kb;
+    if (mx_inc > 0) {
+        ka = lo - mx0;
+        kb = hi - mx0;
+    } else {
+        ka = (long long)mx0 - hi;
+        kb = (long long)mx0 - lo;
+    }
+    if (ka < 0) ka = 0;
+    if (kb > mxd) kb = mxd;
+    const long long c0 = k0, c1 = (long long)k0 + (long long)n_k - 1;
+    if (ka < c0) ka = c0;
+    if (kb > c1) kb = c1;
+    return kb >= ka ? (unsigned)(kb - ka + 1) : 0u;
+}
+
+__global__ void __launch_bounds__(kBinThreads) bin_ops_kernel(Scene s) {
+    __shared__ short4 s_bb[kBinThreads];
+    __shared__ uint4 s_rop[kBinThreads];  // first half of the RasterOp: a, b, (y0, y1), (kind, rgb)
+    __shared__ unsigned s_reach[kBinThreads];
+    __shared__ unsigned s_pair[kBinThreads];
+    __shared__ unsigned w_ent[kBinThreads / 32];
+    __shared__ unsigned long long w_cap[kBinThreads / 32];
+    __shared__ unsigned base_ent;
+    __shared__ unsigned long long base_cap;
+    __shared__ int s_go;
+    const int D = s.D;
+    const int bpr = D / kBW, bpc = D / kBH, nblk = bpr * bpc;
+    const unsigned groups = (unsigned)((nblk + kBinThreads - 1) / kBinThreads);
+    const unsigned tile = blockIdx.x / groups, grp = blockIdx.x % groups;
+    const unsigned b = grp * kBinThreads + threadIdx.x;  // my block, row-major
+    const bool live = b < (unsigned)nblk;
+    const int bx0 = (int)(b % (unsigned)bpr) * kBW, by0 = (int)(b / (unsigned)bpr) * kBH;
+    if (threadIdx.x == 0) s_go = s.counters[CNT_OVERFLOW] == 0u;  // (one read per CTA: other CTAs may raise the flag meanwhile)
+    __syncthreads();
+    if (!s_go) return;  // the draw is redone with larger buffers
+    const unsigned base = s.area_begin[tile];
+    const unsigned n_areas_tile = s.area_begin[tile + 1] - base;
+    // the y range of this warp's blocks (32 consecutive blocks = whole block rows or a part of one)
+    const unsigned wb0 = grp * kBinThreads + (threadIdx.x & ~31u);
+    const int wy0 = (int)(wb0 / (unsigned)bpr) * kBH, wy1 = (int)(min(wb0 + 31u, (unsigned)nblk - 1u) / (unsigned)bpr) * kBH + kBH - 1;
+    unsigned out_ent = 0;
+    unsigned long long out_cap = 0;
+    for (int sweep = 0; sweep < 2; ++sweep) {
+        unsigned n_ent = 0;
+        unsigned long long cap_sum = 0;
+        for (unsigned the_pass = 0; the_pass < 3u; ++the_pass) {
+            const unsigned long long list0 = 3ull * base + (unsigned long long)the_pass * n_areas_tile;
+            const unsigned n_vis = s.vis_count[3u * tile + the_pass];
+            for (unsigned chunk = 0; chunk < n_vis; chunk += kBinThreads) {
+                __syncthreads();
+                const unsigned vi = chunk + threadIdx.x;
+                if (vi < n_vis) {
+                    s_bb[threadIdx.x] = s.vis_bbox[list0 + vi];
+                    const uint4 r0 = *reinterpret_cast<const uint4*>(&s.rop[list0 + vi]);
+                    s_rop[threadIdx.x] = r0;
+                    const RasterOp& full = s.rop[list0 + vi];
+                    s_reach[threadIdx.x] = full.reach;
+                    s_pair[threadIdx.x] = s.vis[list0 + vi].mask_off;
+                }
+                __syncthreads();
+                const unsigned n_here = min((unsigned)kBinThreads, n_vis - chunk);
+                for (unsigned q = 0; q < n_here; ++q) {
+                    const short4 o = s_bb[q];
+                    if (o.w < wy0 || o.y > wy1) continue;  // warp-uniform: the op misses all of this warp's blocks
+                    const bool box_hit = live && o.x <= bx0 + kBW - 1 && o.z >= bx0 && o.y <= by0 + kBH - 1 && o.w >= by0;
+                    if (!box_hit) continue;
+                    const uint4 r0 = s_rop[q];
+                    const unsigned kind = r0.w & 0xffu;
+                    unsigned cap = 0;
+                    bool hit = true;
+                    if (kind == OP_LINE) {
+                        const int reach = (int)s_reach[q];
+                        const SegRec* segs = reinterpret_cast<const SegRec*>(s.geom + r0.x);
+                        const unsigned n_seg = r0.y;
+                        const unsigned per_step = 4u * (unsigned)min(reach, max(kBW, kBH));
+                        unsigned long long c = 0;
+                        for (unsigned si = 0; si < n_seg; ++si) {
+                            const int4 sr = *reinterpret_cast<const int4*>(&segs[si]);
+                            const uint4 tail = *reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(&segs[si]) + 40);  // flags, k0, n_k
+                            c += (unsigned long long)seg_block_steps(sr, reach, bx0, by0, (int)tail.y, tail.z) * per_step;
+                        }
+                        hit = c != 0;
+                        cap = (unsigned)min(c, 0xffffffffull);
+                        // pair table cell of this block (written whether or not a segment reaches it)
+                        if (sweep == 1) {
+                            int rbx0, rby0, nbx, nby;
+                            op_block_rect(o.x, o.y, o.z, o.w, D, rbx0, rby0, nbx, nby);
+                            const int cx = bx0 / kBW - rbx0, cy = by0 / kBH - rby0;
+                            s.pair[s_pair[q] + (unsigned)(cy * nbx + cx)] = hit ? (out_ent + n_ent) : 0xffffffffu;
+                        }
+                    }
+                    if (!hit) continue;
+                    if (sweep == 1) {
+                        const unsigned e = out_ent + n_ent;
+                        BinEntry be;
+                        be.op = (unsigned)(list0 + chunk + q);
+                        be.frag_off = (unsigned)(out_cap + cap_sum);
+                        be.frag_cap = cap;
+                        be.pad = 0;
+                        s.entries[e] = be;
+                        s.frag_cnt[e] = 0u;
+                    }
+                    ++n_ent;
+                    cap_sum += cap;
+                }
+            }
+        }
+        if (sweep == 0) {
+            // exclusive scan over the CTA's threads, one global bump allocation per CTA
+            unsigned incl_e = n_ent;
+            unsigned long long incl_c = cap_sum;
+            for (int off = 1; off < 32; off <<= 1) {
+                const unsigned ye = __shfl_up_sync(0xffffffffu, incl_e, off);
+                const unsigned long long yc = __shfl_up_sync(0xffffffffu, incl_c, off);
+                if ((int)lane_id() >= off) {
+                    incl_e += ye;
+                    incl_c += yc;
+                }
+            }
+            const unsigned w = threadIdx.x >> 5;
+            if (lane_id() == 31) {
+                w_ent[w] = incl_e;
+                w_cap[w] = incl_c;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                unsigned te = 0;
+                unsigned long long tc = 0;
+                for (unsigned k = 0; k < kBinThreads / 32; ++k) {
+                    te += w_ent[k];
+                    tc += w_cap[k];
+                }
+                base_ent = te ? atomicAdd(&s.counters[CNT_BIN_ENTRIES], te) : 0u;
+                base_cap = tc ? atomicAdd(reinterpret_cast<unsigned long long*>(&s.counters[CNT_WALK_ALPHA]), tc) : 0ull;
+                const bool ent_fits = (unsigned long long)base_ent + te <= s.entries_cap;
+                const bool cap_fits = base_cap + tc <= s.frag_cap && base_cap + tc <= 0xfffffff0ull;
+                if (!ent_fits) atomicOr(&s.counters[CNT_OVERFLOW], 64u);
+                if (!cap_fits) atomicOr(&s.counters[CNT_OVERFLOW], 4u);
+                s_go = ent_fits && cap_fits;  // a CTA whose own allocation is out of range skips its second sweep
+            }
+            __syncthreads();
+            unsigned before_e = base_ent;
+            unsigned long long before_c = base_cap;
+            for (unsigned k = 0; k < w; ++k) {
+                before_e += w_ent[k];
+                before_c += w_cap[k];
+            }
+            out_ent = before_e + incl_e - n_ent;
+            out_cap = before_c + incl_c - cap_sum;
+            if (!s_go) return;
+            if (live) s.blk_range[(size_t)tile * nblk + b] = make_uint2(out_ent, n_ent);
+        }
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------------
+// raster_kernel (a3 blend, a4 / a5 combine, a6, a7): ONE WARP (= one 32-thread CTA) per 16x16-pixel block of a tile.
+//
+// Compositor invariants used (tile_pixels.rs:107-129,205-223): inside one generation the surviving source of a
+// pixel is the contribution with the largest alpha; generations blend in order with premultiplied over; canvas alpha stays
+// exactly 1.0, so only RGB is kept and export is trunc(255*c).
+//
+// The warp owns its block for the whole ordered entry list bin_ops_kernel made for it: f64 canvas + f64 alpha plane in shared
+// memory.  A fill entry blends straight from the op's row masks; a line entry max-combines the fragments line_cover_kernel
+// appended to this (block, op) pair into the alpha plane and blends the plane.  No CTA barrier anywhere (v1 shared a 64x32
+// region between 8 warps and was barrier-bound, profiles/r01_raster_v1_ncu_summary.txt); the hardware block scheduler balances
+// the blocks.  The next entry's fragment list is fetched into shared memory by the bulk-copy engine (cp.async.bulk + mbarrier)
+// while the current entry is combined and blended.
+// ------------------------------------------------------------------------------------------------------
+constexpr int kRasterThreads = 32;
+#ifndef OSMR_RASTER_MIN_BLOCKS
+#define OSMR_RASTER_MIN_BLOCKS 24  // resident one-warp CTAs per SM the register allocation must allow
+#endif
+#ifndef OSMR_RASTER_TMA
+#define OSMR_RASTER_TMA 1  // 1: fragment lists are staged in shared memory by cp.async.bulk, double buffered
+#endif
+constexpr unsigned kStageFrags = 192;  // fragments per staging buffer (alphas 1536 B + pixel bytes 192 B)
+
+struct alignas(16) FragStage {
+    double alpha[kStageFrags];
+    unsigned char pix[kStageFrags];
 };
 
 struct RasterSmem {
     double canvas[3][kBP];
     unsigned long long plane[kBP];
-    SegHit hits[32];
-    unsigned pre[32];
+#if OSMR_RASTER_TMA
+    FragStage stage[2];
+    unsigned long long bar[2];  // mbarriers of the two staging buffers
+#endif
 };
 
-// Replays the integer stepping of one cached walk (line.rs:82-96,120-130) and max-combines the alphas of the steps
-// that fall into the block.
-__device__ __forceinline__ void gather_walk(unsigned long long* plane, const double* __restrict__ alpha, unsigned len, const WalkItem& w,
-                                            int mn, int p_error, int mul, int bx0, int by0) {
-    int p_mn = w.mx;
-    int p_mx = mn;
-    int err = mul * p_error;
-    const int step = mul * w.mn_inc;
-    const int corr = -mul * w.mx_inc;
-    const int lo = w.swap ? by0 : bx0;
-    const int hi = lo + (w.swap ? kBH : kBW) - 1;
-    for (unsigned t = 0; t < len; ++t) {
-        if (step > 0 ? (p_mx > hi) : (p_mx < lo)) return;  // left the block on the monotone axis: never comes back
-        const int lx = (w.swap ? p_mn : p_mx) - bx0, ly = (w.swap ? p_mx : p_mn) - by0;
-        if ((unsigned)lx < (unsigned)kBW && (unsigned)ly < (unsigned)kBH) {
-            OSMR_COUNT("raster.steps_in_block", 1);
-            const double a = alpha[t];
-            const unsigned long long bits = (unsigned long long)__double_as_longlong(a);
-            unsigned long long* cell = &plane[ly * kBW + lx];
-            if (a > 0.0 && bits > *cell) atomicMax(cell, bits);
-        }
-        OSMR_COUNT("raster.steps_replayed", 1);
-        if (wadd(err, 2 * w.mn_d) > w.mx_d) {
-            err = wsub(err, 2 * w.mx_d);
-            p_mn += corr;
-        }
-        err = wadd(err, 2 * w.mn_d);
-        p_mx += step;
-    }
+#if OSMR_RASTER_TMA && !defined(OSMR_EMULATED)
+// 1-D bulk copies global -> shared with mbarrier completion (sm_90+ / sm_100a): the copy engine moves the bytes, the warp
+// only waits on the barrier's phase.  Sizes and both addresses must be multiples of 16 bytes.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra.uni WAIT_DONE;\n"
+        "bra.uni WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(phase)
+        : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+#endif
 
 __global__ void __launch_bounds__(kRasterThreads, OSMR_RASTER_MIN_BLOCKS) raster_kernel(Scene s) {
     __shared__ RasterSmem sm;
@@ -1412,15 +1631,13 @@ __global__ void __launch_bounds__(kRasterThreads, OSMR_RASTER_MIN_BLOCKS) raster
     const int bpr = D / kBW, bpc = D / kBH;  // blocks per tile row / column
     const unsigned tile = blockIdx.x / (unsigned)(bpr * bpc);
     const unsigned blk = blockIdx.x % (unsigned)(bpr * bpc);
-    // consecutive CTAs cover a 2x2 group of blocks before moving on, so neighbours share op lists in L1/L2
+    // consecutive CTAs cover a 2x2 group of blocks before moving on, so neighbours share masks and op records in L1/L2
     const unsigned grp = blk / 4u, in_grp = blk % 4u;
     const unsigned grp_per_row = (unsigned)bpr / 2u;
-    const int bx0 = (int)((grp % grp_per_row) * 2u + (in_grp % 2u)) * kBW;
-    const int by0 = (int)((grp / grp_per_row) * 2u + (in_grp / 2u)) * kBH;
+    const int bxi = (int)((grp % grp_per_row) * 2u + (in_grp % 2u)), byi = (int)((grp / grp_per_row) * 2u + (in_grp / 2u));
+    const int bx0 = bxi * kBW, by0 = byi * kBH;
     const unsigned lane = threadIdx.x;
     if (s.counters[CNT_OVERFLOW]) return;  // the draw is redone with larger buffers (see fill_rows_kernel)
-    const unsigned base = s.area_begin[tile];
-    const unsigned n_areas_tile = s.area_begin[tile + 1] - base;
 
     // TilePixels::reset (tile_pixels.rs:89-105): canvas colour premultiplied with opacity 1.0, or (0,0,0,1)
     {
@@ -1434,53 +1651,72 @@ __global__ void __launch_bounds__(kRasterThreads, OSMR_RASTER_MIN_BLOCKS) raster
             sm.plane[i] = 0ull;
         }
     }
+#if OSMR_RASTER_TMA && !defined(OSMR_EMULATED)
+    if (lane == 0) {
+        mbar_init(&sm.bar[0], 1);
+        mbar_init(&sm.bar[1], 1);
+        fence_barrier_init();
+    }
+    unsigned phases = 0u;  // bit b: parity the next wait on staging buffer b expects
+#endif
     __syncwarp();
 
-    for (unsigned the_pass = 0; the_pass < 3u; ++the_pass) {  // Fill, Casing, Stroke (drawer.rs:94-100): the tile's three op lists
-    const unsigned long long list0 = 3ull * base + (unsigned long long)the_pass * n_areas_tile;
-    const RasterOp* rops = s.rop + list0;
-    const short4* vbb = s.vis_bbox + list0;
-    const unsigned n_vis = s.vis_count[3u * tile + the_pass];
-    short4 o_next = make_short4(0, 0, -1, -1);  // the next chunk's bboxes are in flight while this chunk is drawn
-    if (lane < n_vis) o_next = vbb[lane];
-    for (unsigned chunk = 0; chunk < n_vis; chunk += 32) {
-        // ---- the ops of this chunk whose reach bbox meets my block, in order ----
-        unsigned vi = chunk + lane;
-        const short4 o = o_next;
-        if (vi + 32 < n_vis) o_next = vbb[vi + 32];
-        const bool hit = vi < n_vis && o.x <= bx0 + kBW - 1 && o.z >= bx0 && o.y <= by0 + kBH - 1 && o.w >= by0;
-        // (emulator statistics for a coarse binning of the op list: ops scanned / ops whose bbox meets the block's 64x64 cell)
-        OSMR_COUNT("raster.ops_scanned", vi < n_vis);
-        OSMR_COUNT("raster.ops_in_cell64", vi < n_vis && o.x <= (bx0 | 63) && o.z >= (bx0 & ~63) && o.y <= (by0 | 63) && o.w >= (by0 & ~63));
-        OSMR_COUNT("raster.ops_hit", hit);
-        // every lane fetches the record of ITS op now (independent loads); the records are handed round by shuffles
+    const uint2 range = s.blk_range[(size_t)tile * (bpr * bpc) + (unsigned)(byi * bpr + bxi)];
+    const BinEntry* ents = s.entries + range.x;
+    const unsigned n_ent = range.y;
+    for (unsigned chunk = 0; chunk < n_ent; chunk += 32) {
+        // ---- 32 entries of my block: every lane fetches the records of ITS entry now (independent loads) ----
+        const unsigned ei = chunk + lane;
+        BinEntry my_ent;
+        my_ent.op = my_ent.frag_off = my_ent.frag_cap = my_ent.pad = 0;
         uint4 my_rop0 = make_uint4(0, 0, 0, 0), my_rop1 = make_uint4(0, 0, 0, 0);
-        if (hit) {
-            const uint4* src = reinterpret_cast<const uint4*>(&rops[vi]);
+        unsigned my_cnt = 0;
+        if (ei < n_ent) {
+            my_ent = ents[ei];
+            const uint4* src = reinterpret_cast<const uint4*>(&s.rop[my_ent.op]);
             my_rop0 = src[0];
             my_rop1 = src[1];
+            if ((my_rop0.w & 0xffu) == OP_LINE) my_cnt = min(s.frag_cnt[range.x + ei], my_ent.frag_cap);
         }
-        unsigned todo = __ballot_sync(0xffffffffu, hit);
-        while (todo) {
-            const unsigned qi = chunk + (unsigned)(__ffs(todo) - 1);
-            todo &= todo - 1;
+        const unsigned n_here = min(32u, n_ent - chunk);
+#if OSMR_RASTER_TMA && !defined(OSMR_EMULATED)
+        // Software pipeline over the fragment lists of this chunk: they are cut into pieces of <= kPiece fragments; while a
+        // piece is combined, the next piece (of this entry or of the next line entry) is already on its way into the other
+        // staging buffer -- and stays in flight across the fill entries in between.
+        constexpr unsigned kPiece = kStageFrags - 16u;  // room for the alignment skew of both arrays
+        const unsigned line_mask = __ballot_sync(0xffffffffu, my_cnt > 0u);
+        auto piece_issue = [&](unsigned q, unsigned done, int buf) {
+            const unsigned nq = __shfl_sync(0xffffffffu, my_cnt, q);
+            const unsigned off = __shfl_sync(0xffffffffu, my_ent.frag_off, q) + done;
+            const unsigned n = min(kPiece, nq - done);
+            if (lane == 0) {
+                // both arrays are copied from the 16-byte aligned address at or below their first element
+                const unsigned a_skew = off & 1u, p_skew = off & 15u;
+                const unsigned a_bytes = ((n + a_skew) * 8u + 15u) & ~15u, p_bytes = (n + p_skew + 15u) & ~15u;
+                mbar_expect_tx(&sm.bar[buf], a_bytes + p_bytes);
+                bulk_g2s(sm.stage[buf].alpha, s.frag_alpha + (off - a_skew), a_bytes, &sm.bar[buf]);
+                bulk_g2s(sm.stage[buf].pix, s.frag_pix + (off - p_skew), p_bytes, &sm.bar[buf]);
+            }
+        };
+        int cur_buf = 0;
+        if (line_mask) piece_issue((unsigned)(__ffs(line_mask) - 1), 0u, cur_buf);
+#endif
+        for (unsigned q = 0; q < n_here; ++q) {
             RasterOp op;
             {
-                const int from = (int)(qi - chunk);
                 uint4 r0, r1;
-                r0.x = __shfl_sync(0xffffffffu, my_rop0.x, from);
-                r0.y = __shfl_sync(0xffffffffu, my_rop0.y, from);
-                r0.z = __shfl_sync(0xffffffffu, my_rop0.z, from);
-                r0.w = __shfl_sync(0xffffffffu, my_rop0.w, from);
-                r1.x = __shfl_sync(0xffffffffu, my_rop1.x, from);
-                r1.y = __shfl_sync(0xffffffffu, my_rop1.y, from);
-                r1.z = __shfl_sync(0xffffffffu, my_rop1.z, from);
-                r1.w = __shfl_sync(0xffffffffu, my_rop1.w, from);
+                r0.x = __shfl_sync(0xffffffffu, my_rop0.x, q);
+                r0.y = __shfl_sync(0xffffffffu, my_rop0.y, q);
+                r0.z = __shfl_sync(0xffffffffu, my_rop0.z, q);
+                r0.w = __shfl_sync(0xffffffffu, my_rop0.w, q);
+                r1.x = __shfl_sync(0xffffffffu, my_rop1.x, q);
+                r1.y = __shfl_sync(0xffffffffu, my_rop1.y, q);
+                r1.z = __shfl_sync(0xffffffffu, my_rop1.z, q);
+                r1.w = __shfl_sync(0xffffffffu, my_rop1.w, q);
                 uint4* dst = reinterpret_cast<uint4*>(&op);
                 dst[0] = r0;
                 dst[1] = r1;
             }
-
             if (op.kind != OP_LINE) {
                 // ---------------- fill: blend straight from the row masks ----------------
                 const int ya = max((int)op.y0, 0);
@@ -1525,120 +1761,45 @@ __global__ void __launch_bounds__(kRasterThreads, OSMR_RASTER_MIN_BLOCKS) raster
                 __syncwarp();
                 continue;
             }
-
-            // ---------------- line: gather the cached walk alphas into the alpha plane, then blend ----------------
-            const int reach = (int)op.reach;     // line_reach(half width)
-            const unsigned S = (unsigned)reach;  // doubles per cached walk
-            const SegRec* segs = reinterpret_cast<const SegRec*>(s.geom + op.a);
-            const unsigned n_seg = op.b;
-            bool any = false;
-            for (unsigned sb = 0; sb < n_seg; sb += 32) {
-                // one segment per lane: can any of its perpendiculars reach my block?
-                unsigned si = sb + lane;
-                unsigned items = 0;
-                SegHit hrec;
-                if (si < n_seg) {
-                    const int4 sr = *reinterpret_cast<const int4*>(&segs[si]);  // x1, y1, x2, y2
-                    int mnx = min(sr.x, sr.z), mxx = max(sr.x, sr.z), mny = min(sr.y, sr.w), mxy = max(sr.y, sr.w);
-                    if ((long long)mnx - reach <= bx0 + kBW - 1 && (long long)mxx + reach >= bx0 &&
-                        (long long)mny - reach <= by0 + kBH - 1 && (long long)mxy + reach >= by0) {
-                        int dx = abs(wsub(sr.z, sr.x)), dy = abs(wsub(sr.w, sr.y));
-                        bool swap = dx > dy;
-                        int mx0 = swap ? sr.x : sr.y;
-                        int mxd = swap ? dx : dy;
-                        int mx_inc = swap ? (sr.x <= sr.z ? 1 : -1) : (sr.y <= sr.w ? 1 : -1);
-                        // main steps whose major coordinate lies within `reach` of the block
-                        long long lo = (long long)(swap ? bx0 : by0) - reach;
-                        long long hi = (long long)(swap ? bx0 + kBW : by0 + kBH) - 1 + reach;
-                        long long ka, kb;
-                        if (mx_inc > 0) {
-                            ka = lo - mx0;
-                            kb = hi - mx0;
-                        } else {
-                            ka = (long long)mx0 - hi;
-                            kb = (long long)mx0 - lo;
-                        }
-                        if (ka < 0) ka = 0;
-                        if (kb > mxd) kb = mxd;
-                        const SegRec& full = segs[si];
-                        // the cache holds the steps within reach of the TILE (a superset); a record that lost its cache
-                        // slice to an overflow has n_k == 0 and the batch is redone
-                        const long long c0 = full.k0, c1 = (long long)full.k0 + (long long)full.n_k - 1;
-                        if (ka < c0) ka = c0;
-                        if (kb > c1) kb = c1;
-                        if (kb >= ka) {
-                            items = (unsigned)(kb - ka + 1);  // one work item per main step: its two perpendiculars share the set-up
-                            hrec.x1 = sr.x;
-                            hrec.y1 = sr.y;
-                            hrec.x2 = sr.z;
-                            hrec.y2 = sr.w;
-                            hrec.ka = (int)ka;
-                            hrec.flags = full.flags | (full.n_k << 8);
-                            hrec.magic = full.magic;
-                            hrec.k0 = full.k0;
-                            hrec.len_off = full.len_off;
-                            hrec.alpha_off = full.alpha_off;
-                        }
-                    }
+            // ---------------- line: max-combine this pair's fragments into the alpha plane, then blend ----------------
+            const unsigned n_frag = __shfl_sync(0xffffffffu, my_cnt, q);
+            const unsigned f_off = __shfl_sync(0xffffffffu, my_ent.frag_off, q);
+            if (!n_frag) continue;
+#if OSMR_RASTER_TMA && !defined(OSMR_EMULATED)
+            for (unsigned done = 0; done < n_frag; done += kPiece) {
+                const unsigned n = min(kPiece, n_frag - done);
+                const unsigned off = f_off + done;
+                // the piece (q, done) is in flight in cur_buf; start the one after it
+                if (done + kPiece < n_frag) {
+                    piece_issue(q, done + kPiece, cur_buf ^ 1);
+                } else {
+                    const unsigned rest = q >= 31u ? 0u : (line_mask & ~((2u << q) - 1u));
+                    if (rest) piece_issue((unsigned)(__ffs(rest) - 1), 0u, cur_buf ^ 1);
                 }
-                unsigned hb = __ballot_sync(0xffffffffu, items != 0);
-                OSMR_COUNT("raster.seg_batches", lane == 0);
-                if (!hb) continue;
-                any = true;
-                // exclusive scan of the item counts
-                unsigned incl = items;
-                for (int o = 1; o < 32; o <<= 1) {
-                    unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
-                    if ((int)lane >= o) incl += v;
+                mbar_wait(&sm.bar[cur_buf], (phases >> cur_buf) & 1u);
+                phases ^= 1u << cur_buf;
+                const unsigned a_skew = off & 1u, p_skew = off & 15u;
+                for (unsigned i = lane; i < n; i += 32) {
+                    const double a = sm.stage[cur_buf].alpha[i + a_skew];
+                    const unsigned pix = sm.stage[cur_buf].pix[i + p_skew];
+                    const unsigned long long bits = (unsigned long long)__double_as_longlong(a);
+                    unsigned long long* cell = &sm.plane[pix];
+                    if (bits > *cell) atomicMax(cell, bits);
                 }
-                const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
                 __syncwarp();
-                sm.pre[lane] = incl - items;
-                if (items) sm.hits[lane] = hrec;
-                __syncwarp();
-                const int rlo = -reach, rhi = reach;  // minor-axis cull relative to the block (see below)
-                for (unsigned item = lane; item < total; item += 32) {
-                    int lo = 0, hi = 32;  // largest slot with pre <= item
-                    while (hi - lo > 1) {
-                        int mid = (lo + hi) >> 1;
-                        if (sm.pre[mid] <= item)
-                            lo = mid;
-                        else
-                            hi = mid;
-                    }
-                    const SegHit& h = sm.hits[lo];
-                    const unsigned local = item - sm.pre[lo];
-                    const int k = h.ka + (int)local;
-                    const unsigned long long widx0 = 2ull * (unsigned long long)(k - h.k0);
-                    // the two regular walks of the step: two adjacent bytes, 2-byte aligned
-                    const unsigned lens2 = *reinterpret_cast<const unsigned short*>(s.walk_len + h.len_off + widx0);
-                    OSMR_COUNT("raster.items", 1);
-                    if (!lens2) continue;
-                    WalkItem w;
-                    walk_item_setup(h.x1, h.y1, h.x2, h.y2, h.flags, h.magic, k, w);
-                    const int blo = (w.swap ? by0 : bx0) + rlo, bhi = (w.swap ? by0 + kBH : bx0 + kBW) - 1 + rhi;
-#pragma unroll 1
-                    for (unsigned side = 0; side < 2u; ++side) {
-                        const unsigned lens = (lens2 >> (8u * side)) & 0xffu;
-                        if (!lens) continue;
-                        const int mul = side ? -1 : 1;
-                        const unsigned long long widx = widx0 + side;
-                        const double* alpha = s.walk_alpha + h.alpha_off + widx * S;
-                        int mn = w.mn, p_error = w.p_error;
-                        // minor-axis cull: a walk starts at mn and moves away from it, at most `reach` pixels
-                        if ((lens & 0x7fu) && mn >= blo && mn <= bhi) gather_walk(sm.plane, alpha, lens & 0x7fu, w, mn, p_error, mul, bx0, by0);
-                        if (lens & 0x80u) {  // the extra perpendicular of a double correction (line.rs:150-155)
-                            const unsigned long long extra_at = 2ull * (h.flags >> 8);
-                            const unsigned len1 = s.walk_len[h.len_off + extra_at + widx];
-                            p_error = wadd(wsub(p_error, 2 * w.mx_d), 2 * w.mn_d);
-                            mn += w.mn_inc;
-                            if (mn >= blo && mn <= bhi) gather_walk(sm.plane, alpha + extra_at * S, len1, w, mn, p_error, mul, bx0, by0);
-                        }
-                    }
-                }
+                cur_buf ^= 1;
             }
+#else
+            for (unsigned i = lane; i < n_frag; i += 32) {
+                const double a = s.frag_alpha[(size_t)f_off + i];
+                const unsigned pix = s.frag_pix[(size_t)f_off + i];
+                const unsigned long long bits = (unsigned long long)__double_as_longlong(a);
+                unsigned long long* cell = &sm.plane[pix];
+                if (bits > *cell) atomicMax(cell, bits);
+            }
+#endif
             __syncwarp();
-            if (any) {
+            {
                 // blend: pending pixel = from_color(color, alpha_max) (tile_pixels.rs:13-22), then over
                 double cn[3];
                 for (int k = 0; k < 3; ++k) cn[k] = unit_of_u8(op.rgb[k]);
@@ -1658,7 +1819,6 @@ __global__ void __launch_bounds__(kRasterThreads, OSMR_RASTER_MIN_BLOCKS) raster
             }
             __syncwarp();
         }
-    }
     }
 
     // ---- export (tile_pixels.rs:164-181): alpha == 1.0, so postdivide is the identity ----
@@ -1702,19 +1862,24 @@ __global__ void __launch_bounds__(kRasterThreads, OSMR_RASTER_MIN_BLOCKS) raster
             out[(size_t)(by0 + r) * D + bx0 + x] = v;
         }
     } else {
-        // kBH rows of 3*kBW bytes = 3*kBW/4 aligned words each
-        constexpr int wpb = 3 * kBW / 4;
+        // kBH rows of 3*kBW bytes = 3*kBW/16 aligned 128-bit words each (kBW = 16: 48 bytes = 3 words per row)
+        constexpr int qpr = 3 * kBW / 16;
         unsigned char* tile_out = s.out + (size_t)tile * D * D * 3;
-        for (int i = (int)lane; i < kBH * wpb; i += 32) {
-            int r = i / wpb, j = i % wpb;
-            unsigned word = 0;
+        for (int i = (int)lane; i < kBH * qpr; i += 32) {
+            const int r = i / qpr, j = i % qpr;
+            unsigned w4[4];
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                int byte = 4 * j + b;
-                word |= texel(byte % 3, r * kBW + byte / 3) << (8 * b);
+            for (int wd = 0; wd < 4; ++wd) {
+                unsigned word = 0;
+#pragma unroll
+                for (int bb = 0; bb < 4; ++bb) {
+                    const int byte = 16 * j + 4 * wd + bb;
+                    word |= texel(byte % 3, r * kBW + byte / 3) << (8 * bb);
+                }
+                w4[wd] = word;
             }
-            unsigned* dst = reinterpret_cast<unsigned*>(tile_out + ((size_t)(by0 + r) * D + bx0) * 3);
-            dst[j] = word;
+            uint4* dst = reinterpret_cast<uint4*>(tile_out + ((size_t)(by0 + r) * D + bx0) * 3);
+            dst[j] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
         }
     }
 }
@@ -1731,160 +1896,256 @@ __global__ void __launch_bounds__(kRasterThreads, OSMR_RASTER_MIN_BLOCKS) raster
 // ------------------------------------------------------------------------------------------------------
 struct DevLabel {  // == osmr_host::LabelRec
     int icon, ix, iy;
-    unsigned seg_begin, seg_count;
+    unsigned seg_begin, seg_count;  // host layout: the label's segments are segs[seg_begin .. + seg_count)
     int bx0, by0, bx1, by1;
     unsigned rgb;
     int ry0, rows, width;
-    unsigned row_first, pad;
+    unsigned row_first;  // first entry of this label in kmin / kmax
+    unsigned n_ranges;   // device layout: the segments come in n_ranges glyph ranges gout[range_off ..] (0: one range, above)
+    unsigned range_off;
     unsigned long long cell_off;
 };
 struct DevSeg {
     double x0, y0, x1, y1;
 };
-struct DevRowRec {
-    unsigned label, row;
+struct GlyphOut {  // per glyph of a device-laid-out label: its segment range and their bounds
+    unsigned n_segs;
+    unsigned seg_off;
+    double min_x, max_x, min_y, max_y;
 };
 struct LabelScene {
     const DevLabel* labels;
     const unsigned* label_begin;  // per tile
     const DevSeg* segs;
-    const DevRowRec* rowrecs;
-    unsigned n_rowrecs;
-    unsigned n_segs;
-    double2* seg_slope;  // per segment: (x1 - x0) / (y1 - y0) and its reciprocal
-    int2* seg_rows;      // per segment: first / last pixel row it crosses
+    const GlyphOut* gout;
+    const unsigned* cover_list;  // slots of the labels that have text coverage to compute
+    unsigned n_cover;
     const DevIcon* icons;
     unsigned* occ;   // per tile (3D)^2 bits
     double* acc_a;   // coverage: per label rows x width cells (`a` map, then the swept totals)
-    double* acc_s;   // the `s` map
+    double* acc_s;   // the `s` map (only for labels whose cells do not fit in shared memory)
     int* kmin;       // per (label, row): smallest / largest touched key
     int* kmax;
     LabelPix* plane;  // per tile D*D
     int D;
     // device-side layout (osmr_labels_dev.cuh): the counts live in device memory and the labels of a tile are label_cnt[tile]
-    // records starting at label_begin[tile]; nullptr: host-side layout (counts in n_segs / n_rowrecs, label_begin is a prefix sum)
-    const unsigned* n_segs_dev;
-    const unsigned* n_rowrecs_dev;
+    // records starting at label_begin[tile]; nullptr: host-side layout (n_cover, label_begin is a prefix sum)
+    const unsigned* n_cover_dev;
     const unsigned* label_cnt;
     const unsigned* skip_flags;  // device layout: [0] overflow, [1] fallback -- nonzero: this attempt is abandoned
+    unsigned* cover_cursor;      // work distribution of label_cover_kernel (zeroed before the launch)
 };
 
-// Per-segment constants of Rasterizer::draw_line (rasterizer.rs:27-50), one thread per segment: the two divisions and
-// the stripe range are the same for every pixel row the segment crosses.
-__global__ void label_seg_kernel(LabelScene ls) {
-    if (ls.skip_flags && (ls.skip_flags[0] | ls.skip_flags[1])) return;
-    const unsigned n = ls.n_segs_dev ? *ls.n_segs_dev : ls.n_segs;
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const DevSeg sg = ls.segs[i];
-        const double slope = (sg.x1 - sg.x0) / (sg.y1 - sg.y0);
-        ls.seg_slope[i] = make_double2(slope, 1.0 / slope);
-        ls.seg_rows[i] = make_int2(f64_as_i32(floor(fmin(sg.y0, sg.y1))), f64_as_i32(floor(fmax(sg.y0, sg.y1))));
+// ------------------------------------------------------------------------------------------------------
+// label_cover_kernel (f2): exact-area glyph coverage of a label, Rasterizer::draw_line for every segment IN SEGMENT ORDER
+// (rasterizer.rs:27-84: the BTreeMaps `a` and `s` are dense per-row arrays here), then the left-to-right sweep of
+// save_to_figure (rasterizer.rs:109-148).
+//
+// The reference's flatness rule (1.0001) turns every curve into ~64 sub-pixel segments, so a label is thousands of segments that
+// each touch one or two cells.  f64 addition does not commute with reordering, so a cell must receive its contributions in
+// segment order -- but only the ADDITION is ordered, the area arithmetic in front of it is not.  One warp owns a label: 32
+// consecutive segments at a time, every lane does the arithmetic of its segment (phase A, parallel), then the lanes add their
+// results into the accumulators one after the other in lane order (phase B, a couple of instructions per lane).  Accumulators
+// live in shared memory when the label's cells fit (the usual case), else in the global coverage arrays.
+// (Round 1 gave a warp 32 pixel rows and made it scan all segments of the label per row group: 21 ms per C2 batch.)
+// ------------------------------------------------------------------------------------------------------
+constexpr int kCovCells = 1024;  // shared-memory accumulator cells per array (a, s): 16 KB per warp
+constexpr int kCovRows = 384;    // rows whose touched key range is tracked in shared memory
+
+struct CovEntry {  // one `+=` of draw_line
+    int idx;       // cell index in the label's arrays; bit 30: the `s` array; -1: nothing
+    double v;
+};
+
+// draw_line of one segment restricted to pixel row y (rasterizer.rs:52-83); calls add_a(x, value) for every touched cell of `a`
+// and add_s(x, value) once
+template <typename FA, typename FS>
+__device__ __forceinline__ void cover_segment_row(const DevSeg& sg, double slope, double rslope, int y, FA add_a, FS add_s) {
+    const double y_min = fmin(sg.y0, sg.y1), y_max = fmax(sg.y0, sg.y1);
+    const double sign = (sg.y0 <= sg.y1) ? 1.0 : -1.0;
+    const double y_bottom = fmax((double)y, y_min);
+    const double y_top = fmin((double)(y + 1), y_max);
+    const double y_delta = y_top - y_bottom;
+    const double x_at_bottom = sg.x0 + (y_bottom - sg.y0) * slope;
+    const double x_at_top = sg.x0 + (y_top - sg.y0) * slope;
+    const bool flip = !(x_at_bottom <= x_at_top);
+    const double x_smallest = flip ? x_at_top : x_at_bottom;
+    const double x_largest = flip ? x_at_bottom : x_at_top;
+    const int x_to = f64_as_i32(floor(x_largest));
+    for (int x = f64_as_i32(floor(x_smallest)); x <= x_to; ++x) {
+        const double x_left = fmax((double)x, x_smallest);
+        const double x_next = (double)(x + 1);
+        const double x_right = fmin(x_next, x_largest);
+        double pixel_area = (x_next - x_right) * y_delta;
+        const double tw = x_right - x_left;
+        if (tw > 0.0) {
+            const double y_at_left = sg.y0 + (x_left - sg.x0) * rslope;
+            const double y_at_right = sg.y0 + (x_right - sg.x0) * rslope;
+            const double th = flip ? (y_top - y_at_left) + (y_top - y_at_right) : (y_at_left - y_bottom) + (y_at_right - y_bottom);
+            pixel_area += tw * th / 2.0;
+        }
+        add_a(x, sign * pixel_area);
+        if (x == 0x7fffffff) break;
     }
+    add_s(x_to + 1, sign * y_delta);
 }
 
-// Glyph coverage of one pixel row of one label: Rasterizer::draw_line for this stripe over the label's segments in
-// order (rasterizer.rs:27-84), then the left-to-right sweep of save_to_figure (rasterizer.rs:109-148).
-// A warp holds up to 32 stripes of ONE label (the host pads every label's rows to a multiple of 32 with dead entries).
-// The warp reads the segments' stripe ranges 32 at a time, each lane collects the bit mask of the segments that cross
-// its stripe, and the lanes then do the area arithmetic together, lowest bit (= earliest segment) first: per stripe the
-// additions happen in segment order, as on the CPU.
 __global__ void __launch_bounds__(32) label_cover_kernel(LabelScene ls) {
     constexpr unsigned kFull = 0xffffffffu;
+    __shared__ double sa[kCovCells], ss[kCovCells];
+    __shared__ int s_kmin[kCovRows], s_kmax[kCovRows];
     if (ls.skip_flags && (ls.skip_flags[0] | ls.skip_flags[1])) return;
-    const unsigned n_warps = (ls.n_rowrecs_dev ? *ls.n_rowrecs_dev : ls.n_rowrecs) / 32u;
+    const unsigned n_cover = ls.n_cover_dev ? *ls.n_cover_dev : ls.n_cover;
     const unsigned lane = threadIdx.x;
-    for (unsigned wi = blockIdx.x; wi < n_warps; wi += gridDim.x) {
-    const unsigned i = wi * 32u + lane;
-    const DevRowRec rr = ls.rowrecs[i];
-    const DevLabel L = ls.labels[rr.label];
-    const bool live = rr.row != 0xffffffffu;
-    const int W = L.width;
-    const int y = L.ry0 + (int)(live ? rr.row : 0u);
-    double* a = ls.acc_a + L.cell_off + (size_t)(live ? rr.row : 0u) * W;
-    double* sacc = ls.acc_s + L.cell_off + (size_t)(live ? rr.row : 0u) * W;
-    const int2* rows = ls.seg_rows + L.seg_begin;
-    const int y_lo = __shfl_sync(kFull, y, 0);  // lane 0 is always live, live lanes are a prefix with increasing y
-    const int n_live = __popc(__ballot_sync(kFull, live));
-    const int y_hi = y_lo + n_live - 1;
-    if (ls.n_rowrecs_dev) {  // device layout: nobody cleared the coverage cells of this attempt; the warp's rows are contiguous
-        const size_t n_cells = (size_t)n_live * (size_t)W;
-        double* za = ls.acc_a + L.cell_off + (size_t)__shfl_sync(kFull, live ? rr.row : 0u, 0) * W;
-        double* zs = ls.acc_s + L.cell_off + (size_t)__shfl_sync(kFull, live ? rr.row : 0u, 0) * W;
+    for (;;) {
+        unsigned ci = 0;
+        if (lane == 0) ci = atomicAdd(ls.cover_cursor, 1u);
+        ci = __shfl_sync(kFull, ci, 0);
+        if (ci >= n_cover) break;
+        const unsigned slot = ls.cover_list[ci];
+        const DevLabel L = ls.labels[slot];
+        const int W = L.width, R = L.rows;
+        if (R <= 0 || W <= 0) continue;
+        const size_t n_cells = (size_t)R * (size_t)W;
+        const bool in_smem = n_cells <= (size_t)kCovCells;
+        const bool rows_smem = R <= kCovRows;
+        double* A = in_smem ? sa : ls.acc_a + L.cell_off;
+        double* S = in_smem ? ss : ls.acc_s + L.cell_off;
+        int* kmin = rows_smem ? s_kmin : ls.kmin + L.row_first;
+        int* kmax = rows_smem ? s_kmax : ls.kmax + L.row_first;
+        __syncwarp();
         for (size_t c = lane; c < n_cells; c += 32) {
-            za[c] = 0.0;
-            zs[c] = 0.0;
+            A[c] = 0.0;
+            S[c] = 0.0;
+        }
+        for (int r = (int)lane; r < R; r += 32) {
+            kmin[r] = 0x7fffffff;
+            kmax[r] = (int)0x80000000;
         }
         __syncwarp();
-    }
-    int lo = 0x7fffffff, hi = (int)0x80000000;
-    for (unsigned base = 0; base < L.seg_count; base += 32) {
-        const unsigned j = base + lane;
-        const int2 ry = j < L.seg_count ? rows[j] : make_int2(1, 0);
-        unsigned cand = __ballot_sync(kFull, ry.x <= ry.y && ry.y >= y_lo && ry.x <= y_hi);
-        unsigned mine = 0;
-        for (; cand; cand &= cand - 1) {
-            const int bsel = __ffs(cand) - 1;
-            const int r0 = __shfl_sync(kFull, ry.x, bsel), r1 = __shfl_sync(kFull, ry.y, bsel);
-            if (live && y >= r0 && y <= r1) mine |= 1u << bsel;
-        }
-        while (__any_sync(kFull, mine != 0)) {
-            if (mine) {
-                const unsigned k = base + (unsigned)(__ffs(mine) - 1);
-                mine &= mine - 1;
-                const DevSeg sg = ls.segs[L.seg_begin + k];
-                const double2 sl = ls.seg_slope[L.seg_begin + k];
-                const double slope = sl.x, rslope = sl.y;
-                const double y_min = fmin(sg.y0, sg.y1), y_max = fmax(sg.y0, sg.y1);
-                const double sign = (sg.y0 <= sg.y1) ? 1.0 : -1.0;
-                const double y_bottom = fmax((double)y, y_min);
-                const double y_top = fmin((double)(y + 1), y_max);
-                const double y_delta = y_top - y_bottom;
-                const double x_at_bottom = sg.x0 + (y_bottom - sg.y0) * slope;
-                const double x_at_top = sg.x0 + (y_top - sg.y0) * slope;
-                const bool flip = !(x_at_bottom <= x_at_top);
-                const double x_smallest = flip ? x_at_top : x_at_bottom;
-                const double x_largest = flip ? x_at_bottom : x_at_top;
-                const int x_to = f64_as_i32(floor(x_largest));
-                for (int x = f64_as_i32(floor(x_smallest)); x <= x_to; ++x) {
-                    const double x_left = fmax((double)x, x_smallest);
-                    const double x_next = (double)(x + 1);
-                    const double x_right = fmin(x_next, x_largest);
-                    double pixel_area = (x_next - x_right) * y_delta;
-                    const double tw = x_right - x_left;
-                    if (tw > 0.0) {
-                        const double y_at_left = sg.y0 + (x_left - sg.x0) * rslope;
-                        const double y_at_right = sg.y0 + (x_right - sg.x0) * rslope;
-                        const double th =
-                            flip ? (y_top - y_at_left) + (y_top - y_at_right) : (y_at_left - y_bottom) + (y_at_right - y_bottom);
-                        pixel_area += tw * th / 2.0;
-                    }
-                    const int cx = x - L.bx0;
-                    if (cx >= 0 && cx < W) a[cx] += sign * pixel_area;
-                    lo = min(lo, x);
-                    hi = max(hi, x);
+        const int row_lo = L.ry0, row_hi = L.ry0 + R - 1;
+        // the (`a` or `s`, row, x) -> accumulate step of phase B; only one lane at a time runs it
+        auto touch = [&](int r, int x) {
+            kmin[r] = min(kmin[r], x);
+            kmax[r] = max(kmax[r], x);
+        };
+        const unsigned n_ranges = L.n_ranges ? L.n_ranges : 1u;
+        for (unsigned rg = 0; rg < n_ranges; ++rg) {
+            unsigned seg0 = L.seg_begin, nseg = L.seg_count;
+            if (L.n_ranges) {
+                const GlyphOut go = ls.gout[L.range_off + rg];
+                seg0 = go.seg_off;
+                nseg = go.n_segs;
+            }
+            for (unsigned base = 0; base < nseg; base += 32) {
+                const unsigned j = base + lane;
+                // ---- phase A: the lane's segment, arithmetic only ----
+                DevSeg sg;
+                sg.x0 = sg.y0 = sg.x1 = sg.y1 = 0.0;
+                double slope = 0.0, rslope = 0.0;
+                int r0 = 1, r1 = 0;  // pixel rows of the segment inside the label's stored rows
+                if (j < nseg) {
+                    sg = ls.segs[seg0 + j];
+                    slope = (sg.x1 - sg.x0) / (sg.y1 - sg.y0);  // rasterizer.rs:34-35
+                    rslope = 1.0 / slope;
+                    r0 = max(f64_as_i32(floor(fmin(sg.y0, sg.y1))), row_lo);
+                    r1 = min(f64_as_i32(floor(fmax(sg.y0, sg.y1))), row_hi);
                 }
-                const int cs = x_to + 1 - L.bx0;
-                if (cs >= 0 && cs < W) sacc[cs] += sign * y_delta;
-                lo = min(lo, x_to + 1);
-                hi = max(hi, x_to + 1);
+                // the common case -- one row, at most two `a` cells -- is staged in registers; anything else runs whole in phase B
+                CovEntry e0, e1, e2;
+                e0.idx = e1.idx = e2.idx = -1;
+                e0.v = e1.v = e2.v = 0.0;
+                int ex0 = 0, ex2 = 0;  // keys of e0 / e2 (kmin / kmax)
+                bool big = false;
+                if (r0 <= r1) {
+                    if (r0 == r1) {
+                        int n_a = 0;
+                        cover_segment_row(
+                            sg, slope, rslope, r0,
+                            [&](int x, double v) {
+                                const int cx = x - L.bx0;
+                                const int idx = (cx >= 0 && cx < W) ? (r0 - row_lo) * W + cx : -1;
+                                if (n_a == 0) {
+                                    e0.idx = idx;
+                                    e0.v = v;
+                                    ex0 = x;
+                                } else if (n_a == 1) {
+                                    e1.idx = idx;
+                                    e1.v = v;
+                                }
+                                ++n_a;
+                            },
+                            [&](int x, double v) {
+                                const int cx = x - L.bx0;
+                                e2.idx = (cx >= 0 && cx < W) ? ((r0 - row_lo) * W + cx) | 0x40000000 : -1;
+                                e2.v = v;
+                                ex2 = x;
+                            });
+                        big = n_a > 2;
+                    } else {
+                        big = true;
+                    }
+                }
+                // ---- phase B: the lanes add in lane (= segment) order ----
+                unsigned work = __ballot_sync(kFull, r0 <= r1);
+                while (work) {
+                    const unsigned turn = (unsigned)(__ffs(work) - 1);
+                    work &= work - 1;
+                    if (lane == turn) {
+                        if (!big) {
+                            const int r = r0 - row_lo;
+                            if (e0.idx >= 0) A[e0.idx] += e0.v;
+                            if (e1.idx >= 0) A[e1.idx] += e1.v;
+                            if (e2.idx >= 0) S[e2.idx & 0x3fffffff] += e2.v;
+                            touch(r, ex0);      // keys are tracked even when they fall outside the stored columns, like the BTreeMap's
+                            touch(r, ex2);      // (x_to + 1 >= every `a` key of the segment)
+                        } else {
+                            for (int y = r0; y <= r1; ++y) {
+                                const int r = y - row_lo;
+                                cover_segment_row(
+                                    sg, slope, rslope, y,
+                                    [&](int x, double v) {
+                                        const int cx = x - L.bx0;
+                                        if (cx >= 0 && cx < W) A[r * W + cx] += v;
+                                        touch(r, x);
+                                    },
+                                    [&](int x, double v) {
+                                        const int cx = x - L.bx0;
+                                        if (cx >= 0 && cx < W) S[r * W + cx] += v;
+                                        touch(r, x);
+                                    });
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
             }
         }
-    }
-    if (live) {
-        ls.kmin[L.row_first + rr.row] = lo;
-        ls.kmax[L.row_first + rr.row] = hi;
-        if (lo <= hi) {
-            double run = 0.0;
-            for (int x = lo; x <= hi; ++x) {
-                const int c = x - L.bx0;
-                const bool inside = c >= 0 && c < W;  // the host bbox covers every key; defensive
-                run += inside ? sacc[c] : 0.0;
-                const double total = fmin((inside ? a[c] : 0.0) + run, 1.0);
-                if (inside) a[c] = total;
+        __syncwarp();
+        // ---- sweep (save_to_figure): a lane per row, left to right over the touched keys ----
+        for (int r = (int)lane; r < R; r += 32) {
+            const int lo = kmin[r], hi = kmax[r];
+            ls.kmin[L.row_first + r] = lo;
+            ls.kmax[L.row_first + r] = hi;
+            if (lo <= hi) {
+                double run = 0.0;
+                double* a = A + (size_t)r * W;
+                const double* sacc = S + (size_t)r * W;
+                for (int x = lo; x <= hi; ++x) {
+                    const int c = x - L.bx0;
+                    const bool inside = c >= 0 && c < W;  // the bbox covers every key; defensive
+                    run += inside ? sacc[c] : 0.0;
+                    const double total = fmin((inside ? a[c] : 0.0) + run, 1.0);
+                    if (inside) a[c] = total;
+                }
             }
         }
-    }
-    __syncwarp();
+        __syncwarp();
+        if (in_smem) {  // the totals go where label_commit_kernel reads them
+            double* out = ls.acc_a + L.cell_off;
+            for (size_t c = lane; c < n_cells; c += 32) out[c] = sa[c];
+        }
+        __syncwarp();
     }
 }
 

@@ -18,8 +18,8 @@
 //   label_select_kernel   which label generations of a tile can draw or collide at all (icon, or text that exists)
 //   label_layout_kernel   anchor (node position or polylabel), icon rectangle, glyph placement along the way / in wrapped rows
 //   label_emit_kernel     glyph outlines -> the reference's Rasterizer::draw_line call stream (quadratic curves flattened by
-//                         rasterizer.rs:86-107's recursive midpoint rule), counted first, then written
-//   label_finish_kernel   per label: segment range, pixel bbox, coverage storage, the (label, row) work items
+//                         rasterizer.rs:86-107's recursive midpoint rule), a warp per glyph, lanes over its vertices
+//   label_finish_kernel   per label: pixel bbox, coverage storage, the work list of label_cover_kernel
 // The flatness rule compares platform-libm hypot values; the device decides it with sqrt whenever the two sides differ by more
 // than 1e-12 relative (the host does the same, osmr_labels_host.hpp flat_enough) and raises LCNT_FALLBACK on a near tie: the
 // call is then laid out by the host path, which asks glibc.  Scales that are not a power of two also take the host path.
@@ -59,6 +59,7 @@ enum {
     LCNT_RING_PTS = 9,  // polylabel ring points handed out
     LCNT_ACTIVE = 10,   // statistics: active labels
     LCNT_POLY = 11,     // labels that ran polylabel (= heaps handed out)
+    LCNT_COVER = 12,    // labels whose text coverage label_cover_kernel computes
     LCNT_COUNT = 16
 };
 
@@ -82,11 +83,7 @@ struct LabelPlace {  // layout result of an active label
     double scale;  // font units -> pixels
     double gcy;    // (descent + ascent) / 2 (text on a line)
 };
-struct GlyphOut {  // per GlyphPlace: what the count pass found
-    unsigned n_segs;
-    unsigned seg_off;  // filled by label_finish_kernel
-    double min_x, max_x, min_y, max_y;
-};
+// (GlyphOut -- a glyph's segment range and bounds -- is declared in osmr_kernels.cuh next to its reader, label_cover_kernel)
 
 struct LabelDev {
     // resident tables
@@ -118,8 +115,8 @@ struct LabelDev {
     DevSeg* segs;
     unsigned segs_cap;
     DevLabel* out_labels;  // same indexing as act
-    DevRowRec* rowrecs;
-    unsigned rowrecs_cap;
+    unsigned* cover_list;  // slots of the labels with text coverage (as long as the label list)
+    unsigned rowrecs_cap;  // rows of kmin / kmax
     unsigned long long cells_cap;
     double2* ring_pts;  // polylabel scratch
     unsigned ring_cap;
@@ -753,7 +750,7 @@ struct EmitSink {
     }
     // the reference recurses (first half, then second half); an explicit stack keeps the same emission order
     __device__ void quad(double x0, double y0, double x1, double y1, double x2, double y2) {
-        constexpr int kStack = 48;
+        constexpr int kStack = 20;
         double st[kStack][6];
         int sp = 0;
         st[sp][0] = x0; st[sp][1] = y0; st[sp][2] = x1; st[sp][3] = y1; st[sp][4] = x2; st[sp][5] = y2;
@@ -777,83 +774,150 @@ struct EmitSink {
     }
 };
 
-template <bool WRITE>
-__device__ __forceinline__ void label_emit_body(const LabelDev& ld) {
+// One outline vertex -> its draw_line calls (count, bounds, optionally the segments themselves at out[0..)).
+__device__ __forceinline__ unsigned emit_vertex(const LabelDev& ld, const GlyphPlace& gp, const LabelPlace& lp, unsigned vi, unsigned v0, DevSeg* out,
+                                                double& min_x, double& max_x, double& min_y, double& max_y, bool& near_tie) {
+    const DevVertex v = ld.verts[vi];
+    if (v.type != 2 && v.type != 3) return 0u;  // a move draws nothing
+    const double scale = lp.scale;
+    const bool on_line = lp.mode == 1;
+    const double wx = gp.a, wy = gp.b, sn = gp.c, cs = gp.d, gcx = gp.e, gcy = lp.gcy;
+    auto tr = [&](double px, double py, double& ox, double& oy) {
+        if (on_line) {  // text_placer.rs:76-93
+            const double tx = px - gcx, ty = py - gcy;
+            ox = wx + (tx * cs - ty * sn);
+            oy = wy - (ty * cs + tx * sn);
+        } else {  // text_placer.rs:150-160
+            ox = wx + px;
+            oy = wy - py;
+        }
+    };
+    // `from` is the previous vertex's point ((0, 0) before the first one, text_placer.rs:213)
+    double fx = 0.0, fy = 0.0;
+    if (vi > v0) {
+        const DevVertex pv = ld.verts[vi - 1];
+        fx = (double)pv.x * scale;
+        fy = (double)pv.y * scale;
+    }
+    const double tx = (double)v.x * scale, ty = (double)v.y * scale;
+    EmitSink sink;
+    sink.out = out;
+    sink.n = 0;
+    sink.min_x = min_x;
+    sink.max_x = max_x;
+    sink.min_y = min_y;
+    sink.max_y = max_y;
+    sink.near_tie = false;
+    if (v.type == 2) {
+        double p1x, p1y, p0x, p0y;
+        tr(fx, fy, p1x, p1y);
+        tr(tx, ty, p0x, p0y);
+        sink.line(p0x, p0y, p1x, p1y);
+    } else {
+        double p2x, p2y, p1x, p1y, p0x, p0y;
+        tr(fx, fy, p2x, p2y);
+        tr((double)v.cx * scale, (double)v.cy * scale, p1x, p1y);
+        tr(tx, ty, p0x, p0y);
+        sink.quad(p0x, p0y, p1x, p1y, p2x, p2y);
+    }
+    min_x = sink.min_x;
+    max_x = sink.max_x;
+    min_y = sink.min_y;
+    max_y = sink.max_y;
+    near_tie = near_tie || sink.near_tie;
+    return sink.n;
+}
+
+// label_emit_kernel: one WARP per GlyphPlace, lanes over the outline's vertices (a curve flattens into ~64 tiny segments under the
+// reference's 1.0001 flatness rule, so a vertex is a decent unit of work).  First sweep: segments per vertex; then one bump
+// allocation for the glyph; second sweep: the lanes write their segments at their scanned offsets -- the glyph's segments end
+// up contiguous and in the reference's order (vertex order, subdivision order).
+constexpr int kEmitThreads = 128;
+constexpr unsigned kEmitChunks = 4;  // vertex chunks of 32 whose per-lane counts are kept in registers
+
+__global__ void __launch_bounds__(kEmitThreads) label_emit_kernel(LabelDev ld) {
+    constexpr unsigned kFull = 0xffffffffu;
     const unsigned n_places = min(ld.counters[LCNT_PLACES], ld.gplace_cap);
     if (ld.counters[LCNT_OVERFLOW] & 1u) return;
-    if (WRITE && (ld.counters[LCNT_OVERFLOW] || ld.counters[LCNT_FALLBACK])) return;
-    for (unsigned gi = blockIdx.x * blockDim.x + threadIdx.x; gi < n_places; gi += gridDim.x * blockDim.x) {
+    const unsigned lane = lane_id();
+    const unsigned warp = (blockIdx.x * kEmitThreads + threadIdx.x) >> 5, n_warps = (gridDim.x * kEmitThreads) >> 5;
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    for (unsigned gi = warp; gi < n_places; gi += n_warps) {
         const GlyphPlace gp = ld.gplace[gi];
         GlyphOut go;
-        if (WRITE) go = ld.gout[gi];
-        EmitSink sink;
-        sink.out = WRITE ? ld.segs + go.seg_off : nullptr;
-        sink.n = 0;
-        sink.min_x = sink.min_y = __longlong_as_double(0x7ff0000000000000LL);
-        sink.max_x = sink.max_y = __longlong_as_double((long long)0xfff0000000000000ULL);
-        sink.near_tie = false;
+        go.n_segs = 0;
+        go.seg_off = 0;
+        go.min_x = go.min_y = inf;
+        go.max_x = go.max_y = -inf;
         if (gp.slot >= 0) {
             const LabelPlace lp = ld.place[gp.label];
-            const double scale = lp.scale;
-            const bool on_line = lp.mode == 1;
-            const double wx = gp.a, wy = gp.b, sn = gp.c, cs = gp.d, gcx = gp.e, gcy = lp.gcy;
-            auto tr = [&](double px, double py, double& ox, double& oy) {
-                if (on_line) {  // text_placer.rs:76-93
-                    const double tx = px - gcx, ty = py - gcy;
-                    ox = wx + (tx * cs - ty * sn);
-                    oy = wy - (ty * cs + tx * sn);
-                } else {  // text_placer.rs:150-160
-                    ox = wx + px;
-                    oy = wy - py;
-                }
-            };
             const unsigned v0 = ld.glyph_vbegin[gp.slot], v1 = ld.glyph_vbegin[gp.slot + 1];
-            double fx = 0.0, fy = 0.0;
-            for (unsigned vi = v0; vi < v1; ++vi) {
-                const DevVertex v = ld.verts[vi];
-                const double tx = (double)v.x * scale, ty = (double)v.y * scale;
-                if (v.type == 2) {
-                    double p1x, p1y, p0x, p0y;
-                    tr(fx, fy, p1x, p1y);
-                    tr(tx, ty, p0x, p0y);
-                    sink.line(p0x, p0y, p1x, p1y);
-                } else if (v.type == 3) {
-                    double p2x, p2y, p1x, p1y, p0x, p0y;
-                    tr(fx, fy, p2x, p2y);
-                    tr((double)v.cx * scale, (double)v.cy * scale, p1x, p1y);
-                    tr(tx, ty, p0x, p0y);
-                    sink.quad(p0x, p0y, p1x, p1y, p2x, p2y);
+            unsigned cnt[kEmitChunks] = {0u, 0u, 0u, 0u};
+            unsigned total = 0;
+            double mnx = inf, mxx = -inf, mny = inf, mxy = -inf;
+            bool tie = false;
+            unsigned ch = 0;
+            for (unsigned base = v0; base < v1; base += 32, ++ch) {
+                const unsigned vi = base + lane;
+                const unsigned c = vi < v1 ? emit_vertex(ld, gp, lp, vi, v0, nullptr, mnx, mxx, mny, mxy, tie) : 0u;
+                if (ch < kEmitChunks) cnt[ch] = c;
+                total += c;
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                total += __shfl_xor_sync(kFull, total, o);
+                mnx = fmin(mnx, __shfl_xor_sync(kFull, mnx, o));
+                mxx = fmax(mxx, __shfl_xor_sync(kFull, mxx, o));
+                mny = fmin(mny, __shfl_xor_sync(kFull, mny, o));
+                mxy = fmax(mxy, __shfl_xor_sync(kFull, mxy, o));
+            }
+            if (__any_sync(kFull, tie) && lane == 0) atomicOr(&ld.counters[LCNT_FALLBACK], 1u);
+            unsigned off = 0;
+            if (lane == 0 && total) off = atomicAdd(&ld.counters[LCNT_SEGS], total);
+            off = __shfl_sync(kFull, off, 0);
+            const bool fits = off + total <= ld.segs_cap && off + total >= off;
+            if (!fits && lane == 0) atomicOr(&ld.counters[LCNT_OVERFLOW], 2u);
+            if (fits && total) {
+                unsigned running = off;
+                ch = 0;
+                for (unsigned base = v0; base < v1; base += 32, ++ch) {
+                    const unsigned vi = base + lane;
+                    double d0 = inf, d1 = -inf, d2 = inf, d3 = -inf;
+                    bool t2 = false;
+                    unsigned c = 0;
+                    if (ch < kEmitChunks)
+                        c = cnt[ch];
+                    else if (vi < v1)
+                        c = emit_vertex(ld, gp, lp, vi, v0, nullptr, d0, d1, d2, d3, t2);
+                    unsigned incl = c;
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const unsigned y = __shfl_up_sync(kFull, incl, o);
+                        if ((int)lane >= o) incl += y;
+                    }
+                    if (vi < v1 && c) emit_vertex(ld, gp, lp, vi, v0, ld.segs + running + incl - c, d0, d1, d2, d3, t2);
+                    running += __shfl_sync(kFull, incl, 31);
                 }
-                fx = tx;
-                fy = ty;
+                go.n_segs = total;
+                go.seg_off = off;
+                go.min_x = mnx;
+                go.max_x = mxx;
+                go.min_y = mny;
+                go.max_y = mxy;
             }
         }
-        if (sink.near_tie) atomicOr(&ld.counters[LCNT_FALLBACK], 1u);
-        if (!WRITE) {
-            go.n_segs = sink.n;
-            go.seg_off = 0;
-            go.min_x = sink.min_x;
-            go.max_x = sink.max_x;
-            go.min_y = sink.min_y;
-            go.max_y = sink.max_y;
-            ld.gout[gi] = go;
-        }
+        if (lane == 0) ld.gout[gi] = go;
     }
 }
 
-__global__ void __launch_bounds__(128) label_emit_count_kernel(LabelDev ld) { label_emit_body<false>(ld); }
-__global__ void __launch_bounds__(128) label_emit_write_kernel(LabelDev ld) { label_emit_body<true>(ld); }
-
 // ------------------------------------------------------------------------------------------------------
-// label_finish_kernel: one thread per active label -- the batch assembly the host did in osmr_draw_tiles_labeled: segment
-// range, pixel bbox of the text, rows inside the label canvas, coverage cells, (label, row) work items padded to whole warps.
+// label_finish_kernel: one thread per active label -- the batch assembly the host did in osmr_draw_tiles_labeled: pixel bbox of
+// the text, rows inside the label canvas, coverage cells, the work list of label_cover_kernel.
 // ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) label_finish_kernel(Scene s, LabelDev ld) {
     const unsigned t = blockIdx.x;
     const unsigned first = ld.label_begin[t];
     const unsigned n_act = ld.act_cnt[t];
     const int D = s.D;
-    if (ld.counters[LCNT_OVERFLOW] & 1u) return;
+    if (ld.counters[LCNT_OVERFLOW] & 3u) return;
     for (unsigned ai = threadIdx.x; ai < n_act; ai += blockDim.x) {
         const LabelPlace lp = ld.place[first + ai];
         DevLabel L;
@@ -871,7 +935,8 @@ __global__ void __launch_bounds__(128) label_finish_kernel(Scene s, LabelDev ld)
         L.rows = 0;
         L.width = 0;
         L.row_first = 0;
-        L.pad = 0;
+        L.n_ranges = 0;
+        L.range_off = 0;
         L.cell_off = 0;
         if (lp.mode != 0 && lp.n_places) {
             unsigned n_segs = 0;
@@ -886,50 +951,36 @@ __global__ void __launch_bounds__(128) label_finish_kernel(Scene s, LabelDev ld)
                 max_y = fmax(max_y, go.max_y);
             }
             if (n_segs) {
-                const unsigned sb = atomicAdd(&ld.counters[LCNT_SEGS], n_segs);
-                if (sb + n_segs > ld.segs_cap || sb + n_segs < sb) {
-                    atomicOr(&ld.counters[LCNT_OVERFLOW], 2u);
-                } else {
-                    unsigned o = sb;
-                    for (unsigned k = 0; k < lp.n_places; ++k) {
-                        ld.gout[lp.place_off + k].seg_off = o;
-                        o += ld.gout[lp.place_off + k].n_segs;
-                    }
-                    L.seg_begin = sb;
-                    L.seg_count = n_segs;
-                    L.bx0 = f64_as_i32(floor(min_x));
-                    L.bx1 = f64_as_i32(floor(max_x)) + 1;  // the `s` column is one past the last `a` column
-                    L.by0 = f64_as_i32(floor(min_y));
-                    L.by1 = f64_as_i32(floor(max_y));
-                    // rows outside the label canvas cannot collide or draw; columns stay complete (the sweep is a prefix sum)
-                    L.ry0 = max(L.by0, -D);
-                    const long long rows = (long long)min(L.by1, 2 * D - 1) - L.ry0 + 1;
-                    const long long cols = (long long)L.bx1 - L.bx0 + 1;
-                    const bool touches = rows > 0 && cols > 0 && L.bx1 >= -D && L.bx0 <= 2 * D - 1;
-                    if (touches) {
-                        if (cols > (1 << 20)) {
-                            atomicOr(&ld.counters[LCNT_FALLBACK], 2u);
+                L.seg_count = n_segs;  // in n_ranges glyph ranges (GlyphOut.seg_off / n_segs)
+                L.range_off = lp.place_off;
+                L.n_ranges = lp.n_places;
+                L.bx0 = f64_as_i32(floor(min_x));
+                L.bx1 = f64_as_i32(floor(max_x)) + 1;  // the `s` column is one past the last `a` column
+                L.by0 = f64_as_i32(floor(min_y));
+                L.by1 = f64_as_i32(floor(max_y));
+                // rows outside the label canvas cannot collide or draw; columns stay complete (the sweep is a prefix sum)
+                L.ry0 = max(L.by0, -D);
+                const long long rows = (long long)min(L.by1, 2 * D - 1) - L.ry0 + 1;
+                const long long cols = (long long)L.bx1 - L.bx0 + 1;
+                const bool touches = rows > 0 && cols > 0 && L.bx1 >= -D && L.bx0 <= 2 * D - 1;
+                if (touches) {
+                    if (cols > (1 << 20)) {
+                        atomicOr(&ld.counters[LCNT_FALLBACK], 2u);
+                    } else {
+                        const unsigned rb = atomicAdd(&ld.counters[LCNT_ROWRECS], (unsigned)rows);
+                        const unsigned long long need = (unsigned long long)rows * (unsigned long long)cols;
+                        const unsigned long long cb = atomicAdd(reinterpret_cast<unsigned long long*>(&ld.counters[LCNT_CELLS_LO]), need);
+                        const unsigned ci = atomicAdd(&ld.counters[LCNT_COVER], 1u);
+                        if (rb + (unsigned)rows > ld.rowrecs_cap || rb + (unsigned)rows < rb) {
+                            atomicOr(&ld.counters[LCNT_OVERFLOW], 4u);
+                        } else if (cb + need > ld.cells_cap) {
+                            atomicOr(&ld.counters[LCNT_OVERFLOW], 8u);
                         } else {
-                            const unsigned pad_rows = ((unsigned)rows + 31u) & ~31u;
-                            const unsigned rb = atomicAdd(&ld.counters[LCNT_ROWRECS], pad_rows);
-                            const unsigned long long need = (unsigned long long)rows * (unsigned long long)cols;
-                            const unsigned long long cb = atomicAdd(reinterpret_cast<unsigned long long*>(&ld.counters[LCNT_CELLS_LO]), need);
-                            if (rb + pad_rows > ld.rowrecs_cap || rb + pad_rows < rb) {
-                                atomicOr(&ld.counters[LCNT_OVERFLOW], 4u);
-                            } else if (cb + need > ld.cells_cap) {
-                                atomicOr(&ld.counters[LCNT_OVERFLOW], 8u);
-                            } else {
-                                L.rows = (int)rows;
-                                L.width = (int)cols;
-                                L.row_first = rb;
-                                L.cell_off = cb;
-                                for (unsigned y = 0; y < pad_rows; ++y) {
-                                    DevRowRec rr;
-                                    rr.label = first + ai;
-                                    rr.row = y < (unsigned)rows ? y : 0xffffffffu;
-                                    ld.rowrecs[rb + y] = rr;
-                                }
-                            }
+                            L.rows = (int)rows;
+                            L.width = (int)cols;
+                            L.row_first = rb;
+                            L.cell_off = cb;
+                            ld.cover_list[ci] = first + ai;  // (at most one entry per label slot: the list is as long as the label list)
                         }
                     }
                 }

@@ -42,13 +42,10 @@ struct LabelRec {
     int ry0;                  // first stored row (by0 clipped to the 3x3 canvas)
     int rows;                 // stored rows (0: the text cannot touch the canvas)
     int width;                // bx1 - bx0 + 1
-    unsigned row_first;       // index of the first (label, row) work item
-    unsigned pad;
+    unsigned row_first;       // first entry of this label in the per-row key range arrays
+    unsigned n_ranges;        // 0: the segments are one range (device layout: glyph ranges)
+    unsigned range_off;
     unsigned long long cell_off;  // first cell of this label in the coverage arrays
-};
-struct RowRec {  // one unit of work of label_cover_kernel
-    unsigned label;
-    unsigned row;  // 0 .. rows-1; 0xffffffff: padding (every label's rows are padded to a multiple of 32)
 };
 struct Seg {
     double x0, y0, x1, y1;
@@ -178,11 +175,22 @@ struct GlyphVertex {
 
 class TrueType {
    public:
+    // Every offset read from the file is checked against its length: accessors return 0 for bytes beyond the end, so a
+    // truncated or corrupt font yields missing glyphs (or a failed load), never an out-of-bounds read.
     bool load(const uint8_t* data, size_t len) {
-        bytes_.assign(data, data + len);
-        d_ = bytes_.data();
+        index_map_ = 0;  // a failed load leaves the object unloaded
+        d_ = nullptr;
         glyph_cache_.clear();
+        bytes_.assign(data, data + len);
+        // zero padding behind the file: multi-byte reads that start inside the file never leave the buffer
+        bytes_.resize(len + 16, 0);
+        len_ = len;
         if (len < 12) return false;
+        d_ = bytes_.data();
+        if (12 + 16 * (size_t)be16(4) > len) {
+            d_ = nullptr;
+            return false;
+        }
         cmap_ = table("cmap");
         loca_ = table("loca");
         head_ = table("head");
@@ -190,7 +198,11 @@ class TrueType {
         hhea_ = table("hhea");
         hmtx_ = table("hmtx");
         kern_ = table("kern");
-        if (!cmap_ || !loca_ || !head_ || !glyf_ || !hhea_ || !hmtx_) return false;
+        if (!cmap_ || !loca_ || !head_ || !glyf_ || !hhea_ || !hmtx_ || (size_t)head_ + 54 > len || (size_t)hhea_ + 36 > len ||
+            (size_t)cmap_ + 4 > len) {
+            d_ = nullptr;
+            return false;
+        }
         uint32_t maxp = table("maxp");
         num_glyphs_ = maxp ? be16(maxp + 4) : 0xffff;
         index_map_ = 0;
@@ -202,7 +214,12 @@ class TrueType {
         }
         loc_format_ = be16(head_ + 50);
         glyph_cache_.clear();
-        return index_map_ != 0;
+        if (index_map_ == 0 || index_map_ >= len) {
+            index_map_ = 0;
+            d_ = nullptr;
+            return false;
+        }
+        return true;
     }
     bool loaded() const { return d_ != nullptr && index_map_ != 0; }
     int ascent() const { return sbe16(hhea_ + 4); }
@@ -246,7 +263,7 @@ class TrueType {
             }
             return 0;
         }
-        if (fmt == 0) return (int)cp < be16(m + 2) - 6 ? d_[m + 6 + cp] : 0;
+        if (fmt == 0) return (int)cp < be16(m + 2) - 6 ? u8(m + 6 + cp) : 0;
         if (fmt == 6) {
             uint32_t first = be16(m + 6), count = be16(m + 8);
             return (cp >= first && cp < first + count) ? be16(m + 10 + (cp - first) * 2) : 0;
@@ -293,16 +310,19 @@ class TrueType {
     const uint8_t* d_ = nullptr;
     uint32_t cmap_ = 0, loca_ = 0, head_ = 0, glyf_ = 0, hhea_ = 0, hmtx_ = 0, kern_ = 0, index_map_ = 0;
     int num_glyphs_ = 0, loc_format_ = 0;
+    size_t len_ = 0;
     mutable std::unordered_map<int, std::vector<GlyphVertex>> glyph_cache_;
     mutable std::shared_mutex glyph_mu_;
 
-    int be16(uint32_t o) const { return d_[o] * 256 + d_[o + 1]; }
-    int sbe16(uint32_t o) const { return (int16_t)(d_[o] * 256 + d_[o + 1]); }
-    uint32_t be32(uint32_t o) const { return ((uint32_t)d_[o] << 24) | (d_[o + 1] << 16) | (d_[o + 2] << 8) | d_[o + 3]; }
+    // (the buffer carries 16 zero bytes behind the file, so a read that STARTS inside the file is always in bounds)
+    int u8(uint64_t o) const { return o < len_ ? d_[o] : 0; }
+    int be16(uint64_t o) const { return o < len_ ? d_[o] * 256 + d_[o + 1] : 0; }
+    int sbe16(uint64_t o) const { return o < len_ ? (int16_t)(d_[o] * 256 + d_[o + 1]) : 0; }
+    uint32_t be32(uint64_t o) const { return o < len_ ? (((uint32_t)d_[o] << 24) | (d_[o + 1] << 16) | (d_[o + 2] << 8) | d_[o + 3]) : 0u; }
     uint32_t table(const char* tag) const {
         int n = be16(4);
         for (int i = 0; i < n; ++i)
-            if (memcmp(d_ + 12 + 16 * i, tag, 4) == 0) return be32(12 + 16 * i + 8);
+            if ((size_t)12 + 16 * i + 16 <= len_ && memcmp(d_ + 12 + 16 * i, tag, 4) == 0) return be32(12 + 16 * i + 8);
         return 0;
     }
     int glyf_offset(int g) const {
@@ -349,8 +369,8 @@ class TrueType {
             uint8_t flags = 0;
             for (int i = 0; i < n; ++i) {
                 if (repeat == 0) {
-                    flags = d_[p++];
-                    if (flags & 8) repeat = d_[p++];
+                    flags = (uint8_t)u8(p++);
+                    if (flags & 8) repeat = u8(p++);
                 } else {
                     --repeat;
                 }
@@ -359,7 +379,7 @@ class TrueType {
             int x = 0;
             for (int i = 0; i < n; ++i) {
                 if (fl[i] & 2) {
-                    int dx = d_[p++];
+                    int dx = u8(p++);
                     x += (fl[i] & 16) ? dx : -dx;
                 } else if (!(fl[i] & 16)) {
                     x += sbe16(p);
@@ -370,7 +390,7 @@ class TrueType {
             int y = 0;
             for (int i = 0; i < n; ++i) {
                 if (fl[i] & 4) {
-                    int dy = d_[p++];
+                    int dy = u8(p++);
                     y += (fl[i] & 32) ? dy : -dy;
                 } else if (!(fl[i] & 32)) {
                     y += sbe16(p);
@@ -432,8 +452,8 @@ class TrueType {
                     mtx[5] = (float)sbe16(comp + 2);
                     comp += 4;
                 } else {
-                    mtx[4] = (float)(int8_t)d_[comp];
-                    mtx[5] = (float)(int8_t)d_[comp + 1];
+                    mtx[4] = (float)(int8_t)u8(comp);
+                    mtx[5] = (float)(int8_t)u8(comp + 1);
                     comp += 2;
                 }
                 if (flags & (1 << 3)) {

@@ -45,7 +45,7 @@ def test_resident_batch_api_equals_one_shot(fx, gpu_ctx):
     ms2 = gpu_ctx.batch_draw(fx.canvas_rgb, True)  # output stays in HBM
     assert (out == one).all() and ms1 > 0 and ms2 > 0
     st = gpu_ctx.stats()
-    assert st["n_tiles"] == len(tiles) and st["n_areas"] == len(areas) and st["kernel_launches"] == 6
+    assert st["n_tiles"] == len(tiles) and st["n_areas"] == len(areas) and st["kernel_launches"] == 7  # style_calc, plan, geometry, fill_rows, bin, cover, raster
 
 
 def test_huge_coordinates_take_the_exact_i64_path():
@@ -143,13 +143,13 @@ def _two_line_scene(width):
     return image, table, tiles, np.array([0, 2], dtype=np.uint32), areas
 
 
-def test_widest_supported_line_and_the_loud_refusal_beyond_it():
-    """Walk lengths are cached in 7 bits: half widths up to 124 px are drawn (bit-exact), anything wider is an error, never
-    a wrong image."""
-    from osm_renderer_b200._lib import OsmrError
+@pytest.mark.parametrize("width", [240.0, 260.0, 700.0])
+def test_very_wide_lines_are_drawn_like_the_reference(width):
+    """Round 1 cached walk lengths in 7 bits and refused lines wider than 248 px; the reference has no such limit.  Fragments
+    carry no length, so any width the reference draws is drawn (bit-exact) -- here up to lines wider than the whole tile."""
     from osm_renderer_b200.drawer import GpuContext
 
-    image, table, tiles, begins, areas = _two_line_scene(240.0)
+    image, table, tiles, begins, areas = _two_line_scene(width)
     ctx = GpuContext(0)
     try:
         ctx.set_geodata(image)
@@ -159,15 +159,6 @@ def test_widest_supported_line_and_the_loud_refusal_beyond_it():
         ctx.close()
     want = np.stack(oracle.draw_tiles(image, table, tiles, begins, areas, (255, 255, 255), True))
     assert (got == want).all()
-    image, table, tiles, begins, areas = _two_line_scene(260.0)
-    ctx = GpuContext(0)
-    try:
-        ctx.set_geodata(image)
-        ctx.set_table(table)
-        with pytest.raises(OsmrError, match="wider than 248"):
-            ctx.draw_tiles(tiles, begins, areas, (255, 255, 255), True)
-    finally:
-        ctx.close()
 
 
 def test_chunked_host_output_pipeline(fx, gpu_ctx):
@@ -188,3 +179,30 @@ def test_chunked_host_output_pipeline(fx, gpu_ctx):
     got = gpu_ctx.draw_tiles(tiles[sel], b, a, fx.canvas_rgb, True)
     gpu_ctx.debug_set("host_chunks", 0)
     assert (got == uniq[sel]).all()
+
+
+def test_opacity_outside_the_exact_range_is_refused(fx):
+    """The compositor keeps RGB only, which is exact while every source alpha a satisfies a + fl(1 - a) == 1 (a in [0, 2]);
+    the reference does not clamp opacity, so a table outside that range is refused instead of drawn differently."""
+    import copy
+
+    from osm_renderer_b200._lib import OsmrError
+    from osm_renderer_b200.drawer import GpuContext
+    from osm_renderer_b200.wire import OSMR_STYLE_FILL_OPACITY, OSMR_STYLE_OPACITY, StyleTable
+
+    ctx = GpuContext(0)
+    for field, flag, val in (("opacity", OSMR_STYLE_OPACITY, 2.5), ("fill_opacity", OSMR_STYLE_FILL_OPACITY, -0.25), ("opacity", OSMR_STYLE_OPACITY, float("nan"))):
+        t = StyleTable(None)
+        t.rows = [r.copy() for r in fx.table.rows]
+        t.dashes = list(fx.table.dashes)
+        t.rows[0][field] = val
+        t.rows[0]["flags"] |= flag
+        with pytest.raises(OsmrError, match="outside"):
+            ctx.set_table(t)
+    t = StyleTable(None)  # the boundary values are fine
+    t.rows = [r.copy() for r in fx.table.rows]
+    t.dashes = list(fx.table.dashes)
+    t.rows[0]["opacity"] = 2.0
+    t.rows[0]["flags"] |= OSMR_STYLE_OPACITY
+    ctx.set_table(t)
+    ctx.close()

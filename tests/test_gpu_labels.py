@@ -83,3 +83,63 @@ def test_label_api_rejects_bad_input(fx, label_ctx):
     # the context stays usable
     ok = ctx.draw_tiles_labeled(tiles[:2], begins[:3], areas[: int(begins[2])], lb[:3], labels[: int(lb[2])], fx.canvas_rgb, True)
     assert ok.shape[0] == 2
+
+
+def test_truncated_and_corrupt_fonts_never_crash(fx):
+    """osmr.h: no entry point aborts.  A truncated or bit-flipped TrueType file must either be refused or load with missing
+    glyphs -- every offset read from the file is bounds-checked."""
+    from osm_renderer_b200._lib import OsmrError
+    from osm_renderer_b200.drawer import GpuContext
+
+    ltable, font, per = fx.labels()
+    ctx = GpuContext(0)
+    ctx.set_geodata(fx.bin)
+    ctx.set_table(fx.table)
+    ctx.set_label_table(ltable)
+    tiles, begins, areas = fx.batches["17"]
+    lb, labels = per["17"]
+    sel = slice(0, 2)
+    rng = np.random.default_rng(5)
+    variants = [font[:64], font[:300], font[: len(font) // 3], font[: len(font) - 1000]]
+    for _ in range(6):
+        b = bytearray(font)
+        for pos in rng.integers(0, 4000, size=40):  # table directory, head, hhea, cmap headers live in the first kilobytes
+            b[int(pos)] ^= int(rng.integers(1, 256))
+        variants.append(bytes(b))
+    loaded = 0
+    for v in variants:
+        try:
+            ctx.set_font(v)
+        except OsmrError:
+            continue
+        loaded += 1
+        try:
+            ctx.draw_tiles_labeled(tiles[sel], begins[:3], areas[: begins[2]], lb[:3], labels[: lb[2]], fx.canvas_rgb, True)
+        except OsmrError:
+            pass
+    ctx.set_font(font)  # and the context is still usable afterwards
+    good = ctx.draw_tiles_labeled(tiles[sel], begins[:3], areas[: begins[2]], lb[:3], labels[: lb[2]], fx.canvas_rgb, True)
+    golden, _ = fx.golden("17")
+    diff = (good != golden[sel]).any(axis=-1)
+    diff[:, 0, :] = False
+    diff[:, :, 255] = False
+    assert diff.sum() == 0
+    ctx.close()
+
+
+@pytest.mark.parametrize("name", ["16", "18_2x"])
+def test_device_layout_equals_host_layout(fx, label_ctx, name):
+    """The label layout runs on the device (osmr_labels_dev.cuh); the host layout of round 1 is its fallback.  Same pixels."""
+    ctx, per = label_ctx
+    tiles, begins, areas = fx.batches[name]
+    lb, labels = per[name]
+    dev = ctx.draw_tiles_labeled(tiles, begins, areas, lb, labels, fx.canvas_rgb, True)
+    st = ctx.stats()
+    assert st["label_path"] == 1 and st["n_labels_active"] > 0 and st["n_labels_polylabel"] > 0
+    try:
+        ctx.debug_set("label_host", 1)
+        host = ctx.draw_tiles_labeled(tiles, begins, areas, lb, labels, fx.canvas_rgb, True)
+        assert ctx.stats()["label_path"] == 2
+    finally:
+        ctx.debug_set("label_host", 0)
+    assert (dev == host).all()
