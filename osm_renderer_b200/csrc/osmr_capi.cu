@@ -158,7 +158,9 @@ struct osmr_ctx {
     DevBuf<unsigned> l_act_cnt, l_counters;
     DevBuf<LabelPlace> l_place;
     DevBuf<GlyphPlace> l_gplace;
-    DevBuf<GlyphOut> l_gout;
+    DevBuf<unsigned> l_place_vinst, l_vinst_place, l_vcnt, l_curve_list, l_scan_blocks;
+    DevBuf<double4> l_vbox;
+    size_t l_verts_cap = 0;
     DevBuf<double2> l_ring_pts;
     DevBuf<unsigned char> l_heap;
     PinnedBuf<unsigned> h_lcnt;
@@ -2024,6 +2026,7 @@ static int label_device_enqueue(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t 
     // first guesses of the bump-allocated scratch (grown by label_device_judge)
     if (!ctx->l_places_cap) ctx->l_places_cap = 1u << 18;
     if (!ctx->l_segs_cap) ctx->l_segs_cap = 1u << 21;
+    if (!ctx->l_verts_cap) ctx->l_verts_cap = 1u << 20;
     if (!ctx->l_rowrecs_cap) ctx->l_rowrecs_cap = 1u << 19;
     if (!ctx->l_cells_cap) ctx->l_cells_cap = 1u << 23;
     if (!ctx->l_ring_cap) ctx->l_ring_cap = 1u << 16;
@@ -2037,7 +2040,13 @@ static int label_device_enqueue(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t 
     CK(ctx->l_counters.reserve(LCNT_COUNT));
     CK(ctx->h_lcnt.reserve(LCNT_COUNT));
     CK(ctx->l_gplace.reserve(ctx->l_places_cap));
-    CK(ctx->l_gout.reserve(ctx->l_places_cap));
+    CK(ctx->l_place_vinst.reserve(ctx->l_places_cap));
+    const unsigned n_scan_blocks = (unsigned)((ctx->l_verts_cap + kScanBlock) / kScanBlock) + 1u;
+    CK(ctx->l_vinst_place.reserve(ctx->l_verts_cap + 8));
+    CK(ctx->l_vcnt.reserve(ctx->l_verts_cap + 8));
+    CK(ctx->l_vbox.reserve(ctx->l_verts_cap + 8));
+    CK(ctx->l_curve_list.reserve(ctx->l_verts_cap + 8));
+    CK(ctx->l_scan_blocks.reserve(n_scan_blocks + 8));
     CK(ctx->d_label_segs.reserve(ctx->l_segs_cap));
     CK(ctx->d_cover_list.reserve((size_t)n_labels + 1));
     CK(ctx->d_cover_cursor.reserve(4));
@@ -2095,7 +2104,14 @@ static int label_device_enqueue(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t 
     ld.act_cnt = ctx->l_act_cnt.p;
     ld.place = ctx->l_place.p;
     ld.gplace = ctx->l_gplace.p;
-    ld.gout = ctx->l_gout.p;
+    ld.place_vinst = ctx->l_place_vinst.p;
+    ld.vinst_place = ctx->l_vinst_place.p;
+    ld.vcnt = ctx->l_vcnt.p;
+    ld.vbox = ctx->l_vbox.p;
+    ld.curve_list = ctx->l_curve_list.p;
+    ld.verts_cap = (unsigned)std::min<size_t>(ctx->l_verts_cap, 0xfffffff0u);
+    ld.scan_blocks = ctx->l_scan_blocks.p;
+    ld.n_scan_blocks = n_scan_blocks;
     ld.gplace_cap = (unsigned)std::min<size_t>(ctx->l_places_cap, 0xfffffff0u);
     ld.segs = ctx->d_label_segs.p;
     ld.segs_cap = (unsigned)std::min<size_t>(ctx->l_segs_cap, 0xfffffff0u);
@@ -2111,15 +2127,21 @@ static int label_device_enqueue(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t 
     const unsigned wide = (unsigned)ctx->num_sms * 8u;
     label_select_kernel<<<n_tiles, kLabelSelThreads, 0, st>>>(s, ld);
     label_layout_kernel<<<n_tiles, kLayoutThreads, 0, st>>>(s, ld);
-    label_emit_kernel<<<wide, kEmitThreads, 0, st>>>(ld);
+    label_vfill_kernel<<<wide, 128, 0, st>>>(ld);
+    label_vline_count_kernel<<<wide, 128, 0, st>>>(ld);
+    label_curve_count_kernel<<<wide, 128, 0, st>>>(ld);
+    label_scan_sums_kernel<<<n_scan_blocks, 256, 0, st>>>(ld);
+    auto_scan_kernel<<<1, 1024, 0, st>>>(ctx->l_scan_blocks.p, n_scan_blocks, ctx->l_counters.p + LCNT_SCAN_OVF);
+    label_scan_apply_kernel<<<n_scan_blocks, 256, 0, st>>>(ld);
     label_finish_kernel<<<n_tiles, 128, 0, st>>>(s, ld);
+    label_vline_write_kernel<<<wide, 128, 0, st>>>(ld);
+    label_curve_write_kernel<<<wide, 128, 0, st>>>(ld);
     CK(cudaGetLastError());
     CK(cudaMemsetAsync(ctx->d_cover_cursor.p, 0, sizeof(unsigned), st));
     LabelScene ls{};
     ls.labels = ctx->d_labels.p;
     ls.label_begin = ctx->d_label_begin.p;
     ls.segs = ctx->d_label_segs.p;
-    ls.gout = ctx->l_gout.p;
     ls.cover_list = ctx->d_cover_list.p;
     ls.cover_cursor = ctx->d_cover_cursor.p;
     ls.icons = ctx->label_icons.p;
@@ -2158,6 +2180,7 @@ static int label_device_judge(osmr_ctx* ctx) {
         if (c[LCNT_OVERFLOW] & 8u) ctx->l_cells_cap = std::max(grow((size_t)cells), ctx->l_cells_cap * 2);
         if (c[LCNT_OVERFLOW] & 16u) ctx->l_ring_cap = std::max(grow(c[LCNT_RING_PTS]), ctx->l_ring_cap * 2);
         if (c[LCNT_OVERFLOW] & 32u) ctx->l_heap_slots = std::max(grow(c[LCNT_POLY]), ctx->l_heap_slots * 2);
+        if (c[LCNT_OVERFLOW] & 64u) ctx->l_verts_cap = std::max(grow(c[LCNT_VERTS]), ctx->l_verts_cap * 2);
         if (ctx->l_places_cap >= 0xfffffff0ull || ctx->l_segs_cap >= 0xfffffff0ull || ctx->l_rowrecs_cap >= 0x7ffffff0ull ||
             ctx->l_cells_cap > (1ull << 33) || ctx->l_ring_cap >= 0xfffffff0ull)
             return ctx->fail(OSMR_E_NOMEM, "label scratch too large; split the batch");
@@ -2211,7 +2234,7 @@ int osmr_draw_tiles_labeled(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_ti
             ctx->stats.ms_label_layout = enqueue_ms;  // host time spent on labels: table look-ups and launches only
             ctx->stats.ms_label_device = ms;
             ctx->stats.ms_total += ms;
-            ctx->stats.kernel_launches += 6;
+            ctx->stats.kernel_launches += 13;
             ctx->stats.label_path = 1;
             ctx->stats.n_labels_active = ctx->stats_label_active;
             ctx->stats.n_labels_polylabel = ctx->stats_label_poly;

@@ -1901,23 +1901,17 @@ struct DevLabel {  // == osmr_host::LabelRec
     unsigned rgb;
     int ry0, rows, width;
     unsigned row_first;  // first entry of this label in kmin / kmax
-    unsigned n_ranges;   // device layout: the segments come in n_ranges glyph ranges gout[range_off ..] (0: one range, above)
+    unsigned n_ranges;   // (reserved)
     unsigned range_off;
     unsigned long long cell_off;
 };
 struct DevSeg {
     double x0, y0, x1, y1;
 };
-struct GlyphOut {  // per glyph of a device-laid-out label: its segment range and their bounds
-    unsigned n_segs;
-    unsigned seg_off;
-    double min_x, max_x, min_y, max_y;
-};
 struct LabelScene {
     const DevLabel* labels;
     const unsigned* label_begin;  // per tile
     const DevSeg* segs;
-    const GlyphOut* gout;
     const unsigned* cover_list;  // slots of the labels that have text coverage to compute
     unsigned n_cover;
     const DevIcon* icons;
@@ -1942,20 +1936,16 @@ struct LabelScene {
 // save_to_figure (rasterizer.rs:109-148).
 //
 // The reference's flatness rule (1.0001) turns every curve into ~64 sub-pixel segments, so a label is thousands of segments that
-// each touch one or two cells.  f64 addition does not commute with reordering, so a cell must receive its contributions in
-// segment order -- but only the ADDITION is ordered, the area arithmetic in front of it is not.  One warp owns a label: 32
-// consecutive segments at a time, every lane does the arithmetic of its segment (phase A, parallel), then the lanes add their
-// results into the accumulators one after the other in lane order (phase B, a couple of instructions per lane).  Accumulators
-// live in shared memory when the label's cells fit (the usual case), else in the global coverage arrays.
-// (Round 1 gave a warp 32 pixel rows and made it scan all segments of the label per row group: 21 ms per C2 batch.)
+// each touch one or two cells of one pixel row.  f64 addition does not commute with reordering: a cell must receive its
+// contributions in segment order.  Cells of different ROWS never interact, so the unit of parallelism is the row: one warp owns
+// a label, takes its segments in batches, buckets the (segment, row) crossings of a batch by row with a STABLE counting sort
+// (shared memory; a few instructions per segment), and then every lane walks the bucket of its own rows in order, doing the area
+// arithmetic and adding straight into its private row of the coverage arrays -- no conflicts, no ordering protocol.
+// (Round 1 gave a warp 32 rows and made it scan ALL segments of the label per row group: 21 ms per C2 batch; an intermediate
+// version parallelised over segments and committed the additions lane by lane: 12.7 ms.)
 // ------------------------------------------------------------------------------------------------------
-constexpr int kCovCells = 1024;  // shared-memory accumulator cells per array (a, s): 16 KB per warp
-constexpr int kCovRows = 384;    // rows whose touched key range is tracked in shared memory
-
-struct CovEntry {  // one `+=` of draw_line
-    int idx;       // cell index in the label's arrays; bit 30: the `s` array; -1: nothing
-    double v;
-};
+constexpr int kCovUnits = 2048;  // (segment, row) crossings per batch
+constexpr int kCovRows = 256;    // rows per band (a taller label is processed band by band)
 
 // draw_line of one segment restricted to pixel row y (rasterizer.rs:52-83); calls add_a(x, value) for every touched cell of `a`
 // and add_s(x, value) once
@@ -1992,8 +1982,10 @@ __device__ __forceinline__ void cover_segment_row(const DevSeg& sg, double slope
 
 __global__ void __launch_bounds__(32) label_cover_kernel(LabelScene ls) {
     constexpr unsigned kFull = 0xffffffffu;
-    __shared__ double sa[kCovCells], ss[kCovCells];
-    __shared__ int s_kmin[kCovRows], s_kmax[kCovRows];
+    __shared__ unsigned s_unit[kCovUnits];  // segment (index inside the batch) of every crossing, bucketed by row, in segment order
+    __shared__ unsigned s_rng[kCovUnits];   // per segment of the batch: first row inside the band (16 bits) | rows (16 bits)
+    __shared__ unsigned s_off[kCovRows + 1];
+    __shared__ unsigned s_cur[kCovRows];
     if (ls.skip_flags && (ls.skip_flags[0] | ls.skip_flags[1])) return;
     const unsigned n_cover = ls.n_cover_dev ? *ls.n_cover_dev : ls.n_cover;
     const unsigned lane = threadIdx.x;
@@ -2006,146 +1998,172 @@ __global__ void __launch_bounds__(32) label_cover_kernel(LabelScene ls) {
         const DevLabel L = ls.labels[slot];
         const int W = L.width, R = L.rows;
         if (R <= 0 || W <= 0) continue;
-        const size_t n_cells = (size_t)R * (size_t)W;
-        const bool in_smem = n_cells <= (size_t)kCovCells;
-        const bool rows_smem = R <= kCovRows;
-        double* A = in_smem ? sa : ls.acc_a + L.cell_off;
-        double* S = in_smem ? ss : ls.acc_s + L.cell_off;
-        int* kmin = rows_smem ? s_kmin : ls.kmin + L.row_first;
-        int* kmax = rows_smem ? s_kmax : ls.kmax + L.row_first;
-        __syncwarp();
-        for (size_t c = lane; c < n_cells; c += 32) {
-            A[c] = 0.0;
-            S[c] = 0.0;
-        }
-        for (int r = (int)lane; r < R; r += 32) {
-            kmin[r] = 0x7fffffff;
-            kmax[r] = (int)0x80000000;
-        }
-        __syncwarp();
-        const int row_lo = L.ry0, row_hi = L.ry0 + R - 1;
-        // the (`a` or `s`, row, x) -> accumulate step of phase B; only one lane at a time runs it
-        auto touch = [&](int r, int x) {
-            kmin[r] = min(kmin[r], x);
-            kmax[r] = max(kmax[r], x);
-        };
-        const unsigned n_ranges = L.n_ranges ? L.n_ranges : 1u;
-        for (unsigned rg = 0; rg < n_ranges; ++rg) {
-            unsigned seg0 = L.seg_begin, nseg = L.seg_count;
-            if (L.n_ranges) {
-                const GlyphOut go = ls.gout[L.range_off + rg];
-                seg0 = go.seg_off;
-                nseg = go.n_segs;
+        double* A = ls.acc_a + L.cell_off;
+        double* S = ls.acc_s + L.cell_off;
+        const DevSeg* segs = ls.segs + L.seg_begin;
+        const unsigned nseg = L.seg_count;
+        for (int band = 0; band < R; band += kCovRows) {
+            const int band_rows = min(kCovRows, R - band);
+            const int row_lo = L.ry0 + band;  // pixel row of the band's first row
+            // nobody cleared the coverage cells: the band's rows are contiguous
+            {
+                const size_t c0 = (size_t)band * (size_t)W, c1 = c0 + (size_t)band_rows * (size_t)W;
+                for (size_t c = c0 + lane; c < c1; c += 32) {
+                    A[c] = 0.0;
+                    S[c] = 0.0;
+                }
             }
-            for (unsigned base = 0; base < nseg; base += 32) {
-                const unsigned j = base + lane;
-                // ---- phase A: the lane's segment, arithmetic only ----
-                DevSeg sg;
-                sg.x0 = sg.y0 = sg.x1 = sg.y1 = 0.0;
-                double slope = 0.0, rslope = 0.0;
-                int r0 = 1, r1 = 0;  // pixel rows of the segment inside the label's stored rows
-                if (j < nseg) {
-                    sg = ls.segs[seg0 + j];
-                    slope = (sg.x1 - sg.x0) / (sg.y1 - sg.y0);  // rasterizer.rs:34-35
-                    rslope = 1.0 / slope;
-                    r0 = max(f64_as_i32(floor(fmin(sg.y0, sg.y1))), row_lo);
-                    r1 = min(f64_as_i32(floor(fmax(sg.y0, sg.y1))), row_hi);
-                }
-                // the common case -- one row, at most two `a` cells -- is staged in registers; anything else runs whole in phase B
-                CovEntry e0, e1, e2;
-                e0.idx = e1.idx = e2.idx = -1;
-                e0.v = e1.v = e2.v = 0.0;
-                int ex0 = 0, ex2 = 0;  // keys of e0 / e2 (kmin / kmax)
-                bool big = false;
-                if (r0 <= r1) {
-                    if (r0 == r1) {
-                        int n_a = 0;
-                        cover_segment_row(
-                            sg, slope, rslope, r0,
-                            [&](int x, double v) {
-                                const int cx = x - L.bx0;
-                                const int idx = (cx >= 0 && cx < W) ? (r0 - row_lo) * W + cx : -1;
-                                if (n_a == 0) {
-                                    e0.idx = idx;
-                                    e0.v = v;
-                                    ex0 = x;
-                                } else if (n_a == 1) {
-                                    e1.idx = idx;
-                                    e1.v = v;
-                                }
-                                ++n_a;
-                            },
-                            [&](int x, double v) {
-                                const int cx = x - L.bx0;
-                                e2.idx = (cx >= 0 && cx < W) ? ((r0 - row_lo) * W + cx) | 0x40000000 : -1;
-                                e2.v = v;
-                                ex2 = x;
-                            });
-                        big = n_a > 2;
-                    } else {
-                        big = true;
+            // touched key range of my rows (rows lane, lane + 32, ... of the band), kept in registers across the batches
+            int kmin_r[kCovRows / 32], kmax_r[kCovRows / 32];
+#pragma unroll
+            for (int q = 0; q < kCovRows / 32; ++q) {
+                kmin_r[q] = 0x7fffffff;
+                kmax_r[q] = (int)0x80000000;
+            }
+            __syncwarp();
+            unsigned sc = 0;  // first segment of the current batch
+            while (sc < nseg) {
+                // ---- pass 1: row ranges of the batch's segments, crossings per row ----
+                for (int r = (int)lane; r < band_rows; r += 32) s_cur[r] = 0u;
+                __syncwarp();
+                unsigned n_in = 0, units = 0;  // segments / crossings taken into the batch so far
+                while (sc + n_in < nseg && n_in < (unsigned)kCovUnits) {
+                    const unsigned j = sc + n_in + lane;
+                    int r0 = 1, r1 = 0;
+                    if (j < nseg && n_in + lane < (unsigned)kCovUnits) {
+                        const DevSeg sg = segs[j];
+                        r0 = max(f64_as_i32(floor(fmin(sg.y0, sg.y1))), row_lo) - row_lo;
+                        r1 = min(f64_as_i32(floor(fmax(sg.y0, sg.y1))), row_lo + band_rows - 1) - row_lo;
                     }
-                }
-                // ---- phase B: the lanes add in lane (= segment) order ----
-                unsigned work = __ballot_sync(kFull, r0 <= r1);
-                while (work) {
-                    const unsigned turn = (unsigned)(__ffs(work) - 1);
-                    work &= work - 1;
-                    if (lane == turn) {
-                        if (!big) {
-                            const int r = r0 - row_lo;
-                            if (e0.idx >= 0) A[e0.idx] += e0.v;
-                            if (e1.idx >= 0) A[e1.idx] += e1.v;
-                            if (e2.idx >= 0) S[e2.idx & 0x3fffffff] += e2.v;
-                            touch(r, ex0);      // keys are tracked even when they fall outside the stored columns, like the BTreeMap's
-                            touch(r, ex2);      // (x_to + 1 >= every `a` key of the segment)
-                        } else {
-                            for (int y = r0; y <= r1; ++y) {
-                                const int r = y - row_lo;
-                                cover_segment_row(
-                                    sg, slope, rslope, y,
-                                    [&](int x, double v) {
-                                        const int cx = x - L.bx0;
-                                        if (cx >= 0 && cx < W) A[r * W + cx] += v;
-                                        touch(r, x);
-                                    },
-                                    [&](int x, double v) {
-                                        const int cx = x - L.bx0;
-                                        if (cx >= 0 && cx < W) S[r * W + cx] += v;
-                                        touch(r, x);
-                                    });
-                            }
-                        }
+                    const unsigned nr = r1 >= r0 ? (unsigned)(r1 - r0 + 1) : 0u;
+                    unsigned incl = nr;
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const unsigned y = __shfl_up_sync(kFull, incl, o);
+                        if ((int)lane >= o) incl += y;
+                    }
+                    // the lanes whose crossings still fit into the batch (a prefix; a segment has at most kCovRows crossings)
+                    const unsigned fit = __ballot_sync(kFull, units + incl <= (unsigned)kCovUnits && j < nseg && n_in + lane < (unsigned)kCovUnits);
+                    const unsigned take = (fit == kFull) ? 32u : (unsigned)(__ffs(~fit) - 1);
+                    if (take == 0u) break;
+                    if (lane < take) s_rng[n_in + lane] = nr ? ((unsigned)r0 | (nr << 16)) : 0u;
+                    // count per row: the union of the taken lanes' row ranges is short (a glyph is a few rows tall)
+                    const bool mine = lane < take && nr;
+                    int lo = mine ? r0 : 0x7fffffff, hi = mine ? r1 : -1;
+                    for (int o = 16; o > 0; o >>= 1) {
+                        lo = min(lo, __shfl_xor_sync(kFull, lo, o));
+                        hi = max(hi, __shfl_xor_sync(kFull, hi, o));
+                    }
+                    for (int r = lo; r <= hi; ++r) {
+                        const unsigned m = __ballot_sync(kFull, mine && r0 <= r && r <= r1);
+                        if (lane == 0 && m) s_cur[r] += (unsigned)__popc(m);
                     }
                     __syncwarp();
+                    units += __shfl_sync(kFull, incl, (int)take - 1);
+                    n_in += take;
+                    if (take < 32u) break;
+                }
+                if (n_in == 0u) break;  // (cannot happen: one segment always fits)
+                // ---- exclusive scan of the per-row counts ----
+                {
+                    unsigned carry = 0;
+                    for (int base = 0; base < band_rows; base += 32) {
+                        const int r = base + (int)lane;
+                        const unsigned v = r < band_rows ? s_cur[r] : 0u;
+                        unsigned incl = v;
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const unsigned y = __shfl_up_sync(kFull, incl, o);
+                            if ((int)lane >= o) incl += y;
+                        }
+                        if (r < band_rows) {
+                            s_off[r] = carry + incl - v;
+                            s_cur[r] = carry + incl - v;
+                        }
+                        carry += __shfl_sync(kFull, incl, 31);
+                    }
+                    if (lane == 0) s_off[band_rows] = carry;
+                }
+                __syncwarp();
+                // ---- pass 2: stable scatter of the crossings into their row buckets ----
+                for (unsigned base = 0; base < n_in; base += 32) {
+                    const unsigned k = base + lane;
+                    const unsigned rg = k < n_in ? s_rng[k] : 0u;
+                    const int r0 = (int)(rg & 0xffffu), nr = (int)(rg >> 16);
+                    const bool mine = nr != 0;
+                    int lo = mine ? r0 : 0x7fffffff, hi = mine ? r0 + nr - 1 : -1;
+                    for (int o = 16; o > 0; o >>= 1) {
+                        lo = min(lo, __shfl_xor_sync(kFull, lo, o));
+                        hi = max(hi, __shfl_xor_sync(kFull, hi, o));
+                    }
+                    for (int r = lo; r <= hi; ++r) {
+                        const bool in = mine && r0 <= r && r < r0 + nr;
+                        const unsigned m = __ballot_sync(kFull, in);
+                        if (in) s_unit[s_cur[r] + (unsigned)__popc(m & ((1u << lane) - 1u))] = k;
+                        __syncwarp();
+                        if (lane == 0 && m) s_cur[r] += (unsigned)__popc(m);
+                        __syncwarp();
+                    }
+                }
+                __syncwarp();
+                // ---- pass 3: a lane per row, its crossings in segment order ----
+#pragma unroll
+                for (int q = 0; q < kCovRows / 32; ++q) {
+                    const int r = q * 32 + (int)lane;
+                    if (r < band_rows) {
+                        const int y = row_lo + r;
+                        double* a = A + (size_t)(band + r) * W;
+                        double* sacc = S + (size_t)(band + r) * W;
+                        int kmn = kmin_r[q], kmx = kmax_r[q];
+                        const unsigned u1 = s_off[r + 1];
+                        for (unsigned u = s_off[r]; u < u1; ++u) {
+                            const DevSeg sg = segs[sc + s_unit[u]];
+                            const double slope = (sg.x1 - sg.x0) / (sg.y1 - sg.y0);  // rasterizer.rs:34-35
+                            const double rslope = 1.0 / slope;
+                            cover_segment_row(
+                                sg, slope, rslope, y,
+                                [&](int x, double v) {
+                                    const int cx = x - L.bx0;
+                                    if (cx >= 0 && cx < W) a[cx] += v;
+                                    kmn = min(kmn, x);
+                                    kmx = max(kmx, x);
+                                },
+                                [&](int x, double v) {
+                                    const int cx = x - L.bx0;
+                                    if (cx >= 0 && cx < W) sacc[cx] += v;
+                                    kmn = min(kmn, x);
+                                    kmx = max(kmx, x);
+                                });
+                        }
+                        kmin_r[q] = kmn;
+                        kmax_r[q] = kmx;
+                    }
+                }
+                __syncwarp();
+                sc += n_in;
+            }
+            // ---- sweep (save_to_figure): the lane of a row, left to right over the touched keys ----
+#pragma unroll
+            for (int q = 0; q < kCovRows / 32; ++q) {
+                const int r = q * 32 + (int)lane;
+                if (r < band_rows) {
+                    const int lo = kmin_r[q], hi = kmax_r[q];
+                    ls.kmin[L.row_first + band + r] = lo;
+                    ls.kmax[L.row_first + band + r] = hi;
+                    if (lo <= hi) {
+                        double run = 0.0;
+                        double* a = A + (size_t)(band + r) * W;
+                        const double* sacc = S + (size_t)(band + r) * W;
+                        for (int x = lo; x <= hi; ++x) {
+                            const int c = x - L.bx0;
+                            const bool inside = c >= 0 && c < W;  // the bbox covers every key; defensive
+                            run += inside ? sacc[c] : 0.0;
+                            const double total = fmin((inside ? a[c] : 0.0) + run, 1.0);
+                            if (inside) a[c] = total;
+                        }
+                    }
                 }
             }
+            __syncwarp();
         }
-        __syncwarp();
-        // ---- sweep (save_to_figure): a lane per row, left to right over the touched keys ----
-        for (int r = (int)lane; r < R; r += 32) {
-            const int lo = kmin[r], hi = kmax[r];
-            ls.kmin[L.row_first + r] = lo;
-            ls.kmax[L.row_first + r] = hi;
-            if (lo <= hi) {
-                double run = 0.0;
-                double* a = A + (size_t)r * W;
-                const double* sacc = S + (size_t)r * W;
-                for (int x = lo; x <= hi; ++x) {
-                    const int c = x - L.bx0;
-                    const bool inside = c >= 0 && c < W;  // the bbox covers every key; defensive
-                    run += inside ? sacc[c] : 0.0;
-                    const double total = fmin((inside ? a[c] : 0.0) + run, 1.0);
-                    if (inside) a[c] = total;
-                }
-            }
-        }
-        __syncwarp();
-        if (in_smem) {  // the totals go where label_commit_kernel reads them
-            double* out = ls.acc_a + L.cell_off;
-            for (size_t c = lane; c < n_cells; c += 32) out[c] = sa[c];
-        }
-        __syncwarp();
     }
 }
 

@@ -17,9 +17,9 @@
 // glibc like the reference's) -- and the per-call, per-tile work below runs on the device:
 //   label_select_kernel   which label generations of a tile can draw or collide at all (icon, or text that exists)
 //   label_layout_kernel   anchor (node position or polylabel), icon rectangle, glyph placement along the way / in wrapped rows
-//   label_emit_kernel     glyph outlines -> the reference's Rasterizer::draw_line call stream (quadratic curves flattened by
-//                         rasterizer.rs:86-107's recursive midpoint rule), a warp per glyph, lanes over its vertices
-//   label_finish_kernel   per label: pixel bbox, coverage storage, the work list of label_cover_kernel
+//   label_vfill / vline / curve / scan kernels   glyph outlines -> the reference's Rasterizer::draw_line call stream (quadratic
+//                         curves flattened by rasterizer.rs:86-107's recursive midpoint rule): counted, scanned, written
+//   label_finish_kernel   per label: segment range, pixel bbox, coverage storage, the work list of label_cover_kernel
 // The flatness rule compares platform-libm hypot values; the device decides it with sqrt whenever the two sides differ by more
 // than 1e-12 relative (the host does the same, osmr_labels_host.hpp flat_enough) and raises LCNT_FALLBACK on a near tie: the
 // call is then laid out by the host path, which asks glibc.  Scales that are not a power of two also take the host path.
@@ -53,13 +53,16 @@ enum {
     LCNT_SEGS = 1,      // segments handed out
     LCNT_ROWRECS = 2,   // (label, row) work items handed out (multiple of 32)
     LCNT_CELLS_LO = 4,  // 64-bit (4,5): coverage cells handed out
-    LCNT_OVERFLOW = 6,  // bit0 places, bit1 segments, bit2 row records, bit3 cells, bit4 polylabel rings, bit5 polylabel heap
+    LCNT_OVERFLOW = 6,  // bit0 places, bit1 segments, bit2 rows, bit3 cells, bit4 polylabel rings, bit5 polylabel heap, bit6 vertex instances
     LCNT_FALLBACK = 7,  // bit0: flatness near-tie (needs libm hypot); bit1: input the device path does not take
     LCNT_BAD = 8,       // label references an entity / style / icon that does not exist
     LCNT_RING_PTS = 9,  // polylabel ring points handed out
     LCNT_ACTIVE = 10,   // statistics: active labels
     LCNT_POLY = 11,     // labels that ran polylabel (= heaps handed out)
     LCNT_COVER = 12,    // labels whose text coverage label_cover_kernel computes
+    LCNT_VERTS = 13,    // outline vertex instances handed out (one per vertex of every placed glyph)
+    LCNT_CURVES = 14,   // of those, curves (the expensive ones: they get a compact work list of their own)
+    LCNT_SCAN_OVF = 15,  // (overflow word of the block-sum scan: segment counts beyond 2^32 also trip the capacity check)
     LCNT_COUNT = 16
 };
 
@@ -82,6 +85,8 @@ struct LabelPlace {  // layout result of an active label
     unsigned pad;
     double scale;  // font units -> pixels
     double gcy;    // (descent + ascent) / 2 (text on a line)
+    unsigned vinst_off;  // first outline vertex instance of the label (its glyphs' vertices, glyph after glyph)
+    unsigned n_vinst;
 };
 // (GlyphOut -- a glyph's segment range and bounds -- is declared in osmr_kernels.cuh next to its reader, label_cover_kernel)
 
@@ -110,8 +115,15 @@ struct LabelDev {
     unsigned* act_cnt;    // per tile
     LabelPlace* place;    // same indexing as act
     GlyphPlace* gplace;
-    GlyphOut* gout;
+    unsigned* place_vinst;  // per GlyphPlace: its first vertex instance
     unsigned gplace_cap;
+    unsigned* vinst_place;  // per vertex instance: its GlyphPlace
+    unsigned* vcnt;         // per vertex instance: segments it draws; after the scan: offset of its first segment ([n]: total)
+    double4* vbox;          // per vertex instance: bounds of its segments (min x, max x, min y, max y)
+    unsigned* curve_list;   // vertex instances that are curves
+    unsigned verts_cap;
+    unsigned* scan_blocks;  // block sums of the segment-offset scan
+    unsigned n_scan_blocks;
     DevSeg* segs;
     unsigned segs_cap;
     DevLabel* out_labels;  // same indexing as act
@@ -476,6 +488,8 @@ __global__ void __launch_bounds__(kLayoutThreads) label_layout_kernel(Scene s, L
         lp.pad = 0;
         lp.scale = 0.0;
         lp.gcy = 0.0;
+        lp.vinst_off = 0;
+        lp.n_vinst = 0;
         // label anchor (labelable.rs), lazily: polylabel is expensive
         bool anchor_done = false, anchor_ok = false;
         double anx = 0.0, any = 0.0;
@@ -703,6 +717,25 @@ __global__ void __launch_bounds__(kLayoutThreads) label_layout_kernel(Scene s, L
                 }
             }
             (void)have_block;
+            if (lp.mode != 0 && lp.n_places) {  // the label's outline vertex instances, glyph after glyph
+                unsigned V = 0;
+                for (unsigned k = 0; k < ng; ++k)
+                    if (gl[k].slot >= 0) V += ld.glyph_vbegin[gl[k].slot + 1] - ld.glyph_vbegin[gl[k].slot];
+                const unsigned vb = atomicAdd(&ld.counters[LCNT_VERTS], V);
+                if (vb + V > ld.verts_cap || vb + V < vb) {
+                    atomicOr(&ld.counters[LCNT_OVERFLOW], 64u);
+                    lp.mode = 0;
+                    lp.n_places = 0;
+                } else {
+                    unsigned o = vb;
+                    for (unsigned k = 0; k < ng; ++k) {
+                        ld.place_vinst[lp.place_off + k] = o;
+                        if (gl[k].slot >= 0) o += ld.glyph_vbegin[gl[k].slot + 1] - ld.glyph_vbegin[gl[k].slot];
+                    }
+                    lp.vinst_off = vb;
+                    lp.n_vinst = V;
+                }
+            }
         }
         ld.place[first + ai] = lp;
     }
@@ -739,6 +772,17 @@ struct EmitSink {
     __device__ bool flat_enough(double x0, double y0, double x1, double y1, double x2, double y2) {
         const double ax = fabs(x0 - x1), ay = fabs(y0 - y1), bx = fabs(x1 - x2), by = fabs(y1 - y2);
         const double cx = fabs(x0 - x2), cy = fabs(y0 - y2);
+        {
+            // (|a| + |b|)^2 = A + B + 2 sqrt(A B) against 1.0001^2 C: one square root instead of three.  Both sides carry a few ulp
+            // of error, the decision is taken only with a 1e-11 relative margin -- far outside anything the rounding of the
+            // reference's own hypot sum could flip -- and everything closer goes to the three-root form below.
+            const double A = ax * ax + ay * ay, B = bx * bx + by * by, C = cx * cx + cy * cy;
+            const double X = A + B + 2.0 * sqrt(A * B), Y = 1.00020001 * C;
+            if (X < 1e290 && Y < 1e290 && X > 1e-290 && Y > 1e-290) {
+                if (X < Y * (1.0 - 1e-11)) return true;
+                if (X > Y * (1.0 + 1e-11)) return false;
+            }
+        }
         const double lhs = sqrt(ax * ax + ay * ay) + sqrt(bx * bx + by * by);
         const double rhs = 1.0001 * sqrt(cx * cx + cy * cy);
         const double big = 1e150, tiny = 1e-150;
@@ -828,96 +872,141 @@ __device__ __forceinline__ unsigned emit_vertex(const LabelDev& ld, const GlyphP
     return sink.n;
 }
 
-// label_emit_kernel: one WARP per GlyphPlace, lanes over the outline's vertices (a curve flattens into ~64 tiny segments under the
-// reference's 1.0001 flatness rule, so a vertex is a decent unit of work).  First sweep: segments per vertex; then one bump
-// allocation for the glyph; second sweep: the lanes write their segments at their scanned offsets -- the glyph's segments end
-// up contiguous and in the reference's order (vertex order, subdivision order).
-constexpr int kEmitThreads = 128;
-constexpr unsigned kEmitChunks = 4;  // vertex chunks of 32 whose per-lane counts are kept in registers
-
-__global__ void __launch_bounds__(kEmitThreads) label_emit_kernel(LabelDev ld) {
-    constexpr unsigned kFull = 0xffffffffu;
+// The outline pass.  A glyph is ~30 vertices: straight lines (one draw_line each) and quadratic curves (~64 draw_line calls each
+// under the 1.0001 flatness rule, ~20k instructions).  Lanes that hold lines would idle next to lanes that hold curves, so the
+// curves get a compact work list of their own and every lane of the curve kernels flattens a curve:
+//   label_vfill_kernel    thread per GlyphPlace: back pointers of its vertex instances, curves appended to the curve list
+//   label_vline_kernel    thread per vertex instance that is not a curve  } COUNT: segments + bounds per instance,
+//   label_curve_kernel    thread per curve                                } WRITE: the segments at their scanned offsets
+//   label_scan_*          exclusive scan of the per-instance counts -> segment offsets: a label's segments are contiguous and in
+//                         the reference's order (glyph, vertex, subdivision order)
+__global__ void __launch_bounds__(128) label_vfill_kernel(LabelDev ld) {
     const unsigned n_places = min(ld.counters[LCNT_PLACES], ld.gplace_cap);
-    if (ld.counters[LCNT_OVERFLOW] & 1u) return;
-    const unsigned lane = lane_id();
-    const unsigned warp = (blockIdx.x * kEmitThreads + threadIdx.x) >> 5, n_warps = (gridDim.x * kEmitThreads) >> 5;
-    const double inf = __longlong_as_double(0x7ff0000000000000LL);
-    for (unsigned gi = warp; gi < n_places; gi += n_warps) {
+    if (ld.counters[LCNT_OVERFLOW] & 65u) return;
+    for (unsigned gi = blockIdx.x * blockDim.x + threadIdx.x; gi < n_places; gi += gridDim.x * blockDim.x) {
         const GlyphPlace gp = ld.gplace[gi];
-        GlyphOut go;
-        go.n_segs = 0;
-        go.seg_off = 0;
-        go.min_x = go.min_y = inf;
-        go.max_x = go.max_y = -inf;
-        if (gp.slot >= 0) {
-            const LabelPlace lp = ld.place[gp.label];
-            const unsigned v0 = ld.glyph_vbegin[gp.slot], v1 = ld.glyph_vbegin[gp.slot + 1];
-            unsigned cnt[kEmitChunks] = {0u, 0u, 0u, 0u};
-            unsigned total = 0;
-            double mnx = inf, mxx = -inf, mny = inf, mxy = -inf;
-            bool tie = false;
-            unsigned ch = 0;
-            for (unsigned base = v0; base < v1; base += 32, ++ch) {
-                const unsigned vi = base + lane;
-                const unsigned c = vi < v1 ? emit_vertex(ld, gp, lp, vi, v0, nullptr, mnx, mxx, mny, mxy, tie) : 0u;
-                if (ch < kEmitChunks) cnt[ch] = c;
-                total += c;
-            }
-            for (int o = 16; o > 0; o >>= 1) {
-                total += __shfl_xor_sync(kFull, total, o);
-                mnx = fmin(mnx, __shfl_xor_sync(kFull, mnx, o));
-                mxx = fmax(mxx, __shfl_xor_sync(kFull, mxx, o));
-                mny = fmin(mny, __shfl_xor_sync(kFull, mny, o));
-                mxy = fmax(mxy, __shfl_xor_sync(kFull, mxy, o));
-            }
-            if (__any_sync(kFull, tie) && lane == 0) atomicOr(&ld.counters[LCNT_FALLBACK], 1u);
-            unsigned off = 0;
-            if (lane == 0 && total) off = atomicAdd(&ld.counters[LCNT_SEGS], total);
-            off = __shfl_sync(kFull, off, 0);
-            const bool fits = off + total <= ld.segs_cap && off + total >= off;
-            if (!fits && lane == 0) atomicOr(&ld.counters[LCNT_OVERFLOW], 2u);
-            if (fits && total) {
-                unsigned running = off;
-                ch = 0;
-                for (unsigned base = v0; base < v1; base += 32, ++ch) {
-                    const unsigned vi = base + lane;
-                    double d0 = inf, d1 = -inf, d2 = inf, d3 = -inf;
-                    bool t2 = false;
-                    unsigned c = 0;
-                    if (ch < kEmitChunks)
-                        c = cnt[ch];
-                    else if (vi < v1)
-                        c = emit_vertex(ld, gp, lp, vi, v0, nullptr, d0, d1, d2, d3, t2);
-                    unsigned incl = c;
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const unsigned y = __shfl_up_sync(kFull, incl, o);
-                        if ((int)lane >= o) incl += y;
-                    }
-                    if (vi < v1 && c) emit_vertex(ld, gp, lp, vi, v0, ld.segs + running + incl - c, d0, d1, d2, d3, t2);
-                    running += __shfl_sync(kFull, incl, 31);
-                }
-                go.n_segs = total;
-                go.seg_off = off;
-                go.min_x = mnx;
-                go.max_x = mxx;
-                go.min_y = mny;
-                go.max_y = mxy;
-            }
+        if (gp.slot < 0) continue;
+        const LabelPlace lp = ld.place[gp.label];
+        if (lp.mode == 0) continue;  // the label lost its vertex block to an overflow
+        const unsigned v0 = ld.glyph_vbegin[gp.slot], v1 = ld.glyph_vbegin[gp.slot + 1];
+        const unsigned vo = ld.place_vinst[gi];
+        for (unsigned vi = v0; vi < v1; ++vi) {
+            ld.vinst_place[vo + (vi - v0)] = gi;
+            if (ld.verts[vi].type == 3) ld.curve_list[atomicAdd(&ld.counters[LCNT_CURVES], 1u)] = vo + (vi - v0);
         }
-        if (lane == 0) ld.gout[gi] = go;
+    }
+}
+
+template <bool WRITE>
+__device__ __forceinline__ void label_vertex_instance(const LabelDev& ld, unsigned inst) {
+    const unsigned gi = ld.vinst_place[inst];
+    const GlyphPlace gp = ld.gplace[gi];
+    const LabelPlace lp = ld.place[gp.label];
+    const unsigned v0 = ld.glyph_vbegin[gp.slot];
+    const unsigned vi = v0 + (inst - ld.place_vinst[gi]);
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    double mnx = inf, mxx = -inf, mny = inf, mxy = -inf;
+    bool tie = false;
+    if (WRITE) {
+        const unsigned off = ld.vcnt[inst], n = ld.vcnt[inst + 1] - off;
+        if (n) emit_vertex(ld, gp, lp, vi, v0, ld.segs + off, mnx, mxx, mny, mxy, tie);
+    } else {
+        const unsigned n = emit_vertex(ld, gp, lp, vi, v0, nullptr, mnx, mxx, mny, mxy, tie);
+        ld.vcnt[inst] = n;
+        ld.vbox[inst] = make_double4(mnx, mxx, mny, mxy);
+        if (tie) atomicOr(&ld.counters[LCNT_FALLBACK], 1u);
+    }
+}
+
+template <bool WRITE>
+__device__ __forceinline__ void label_vline_body(const LabelDev& ld) {
+    const unsigned n_verts = min(ld.counters[LCNT_VERTS], ld.verts_cap);
+    if (ld.counters[LCNT_OVERFLOW] & 65u) return;
+    if (WRITE && (ld.counters[LCNT_OVERFLOW] || ld.counters[LCNT_FALLBACK])) return;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n_verts; i += gridDim.x * blockDim.x) {
+        const unsigned gi = ld.vinst_place[i];
+        const unsigned vi = ld.glyph_vbegin[ld.gplace[gi].slot] + (i - ld.place_vinst[gi]);
+        if (ld.verts[vi].type == 3) continue;  // curves: label_curve_kernel
+        label_vertex_instance<WRITE>(ld, i);
+    }
+}
+template <bool WRITE>
+__device__ __forceinline__ void label_curve_body(const LabelDev& ld) {
+    const unsigned n_curves = min(ld.counters[LCNT_CURVES], ld.verts_cap);
+    if (ld.counters[LCNT_OVERFLOW] & 65u) return;
+    if (WRITE && (ld.counters[LCNT_OVERFLOW] || ld.counters[LCNT_FALLBACK])) return;
+    for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < n_curves; k += gridDim.x * blockDim.x) label_vertex_instance<WRITE>(ld, ld.curve_list[k]);
+}
+__global__ void __launch_bounds__(128) label_vline_count_kernel(LabelDev ld) { label_vline_body<false>(ld); }
+__global__ void __launch_bounds__(128) label_vline_write_kernel(LabelDev ld) { label_vline_body<true>(ld); }
+__global__ void __launch_bounds__(128) label_curve_count_kernel(LabelDev ld) { label_curve_body<false>(ld); }
+__global__ void __launch_bounds__(128) label_curve_write_kernel(LabelDev ld) { label_curve_body<true>(ld); }
+
+// exclusive scan of vcnt[0 .. n) in place (n = the vertex instance counter), vcnt[n] = total = the number of segments.
+// Three launches: sums of blocks of 1024 elements, auto_scan_kernel over the block sums, local scans + block offsets.
+constexpr unsigned kScanBlock = 1024;
+__global__ void __launch_bounds__(256) label_scan_sums_kernel(LabelDev ld) {
+    __shared__ unsigned wsum[8];
+    const unsigned n = min(ld.counters[LCNT_VERTS], ld.verts_cap);
+    const unsigned base = blockIdx.x * kScanBlock;
+    unsigned v = 0;
+    for (unsigned k = 0; k < kScanBlock / 256; ++k) {
+        const unsigned i = base + k * 256 + threadIdx.x;
+        if (i < n) v += ld.vcnt[i];
+    }
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane_id() == 0) wsum[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = 0;
+        for (int k = 0; k < 8; ++k) t += wsum[k];
+        ld.scan_blocks[blockIdx.x] = t;
+    }
+}
+__global__ void __launch_bounds__(256) label_scan_apply_kernel(LabelDev ld) {
+    __shared__ unsigned wsum[8];
+    const unsigned n = min(ld.counters[LCNT_VERTS], ld.verts_cap);
+    const unsigned base = blockIdx.x * kScanBlock;
+    if (base > n) return;
+    // thread t owns 4 consecutive elements
+    const unsigned i0 = base + threadIdx.x * 4;
+    unsigned x[4];
+    unsigned mine = 0;
+    for (int k = 0; k < 4; ++k) {
+        x[k] = i0 + k < n ? ld.vcnt[i0 + k] : 0u;
+        mine += x[k];
+    }
+    unsigned incl = mine;
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned y = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)lane_id() >= o) incl += y;
+    }
+    if (lane_id() == 31) wsum[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    unsigned before = ld.scan_blocks[blockIdx.x];  // already exclusive (auto_scan_kernel)
+    for (unsigned k = 0; k < (threadIdx.x >> 5); ++k) before += wsum[k];
+    unsigned run = before + incl - mine;
+    for (int k = 0; k < 4; ++k) {
+        if (i0 + k <= n) ld.vcnt[i0 + k] = run;  // (element n receives the total)
+        run += x[k];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const unsigned total = ld.scan_blocks[ld.n_scan_blocks];
+        ld.counters[LCNT_SEGS] = total;
+        if (total > ld.segs_cap) atomicOr(&ld.counters[LCNT_OVERFLOW], 2u);
     }
 }
 
 // ------------------------------------------------------------------------------------------------------
-// label_finish_kernel: one thread per active label -- the batch assembly the host did in osmr_draw_tiles_labeled: pixel bbox of
-// the text, rows inside the label canvas, coverage cells, the work list of label_cover_kernel.
+// label_finish_kernel: one thread per active label -- the batch assembly the host did in osmr_draw_tiles_labeled: segment range,
+// pixel bbox of the text, rows inside the label canvas, coverage cells, the work list of label_cover_kernel.
 // ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) label_finish_kernel(Scene s, LabelDev ld) {
     const unsigned t = blockIdx.x;
     const unsigned first = ld.label_begin[t];
     const unsigned n_act = ld.act_cnt[t];
     const int D = s.D;
-    if (ld.counters[LCNT_OVERFLOW] & 3u) return;
+    if (ld.counters[LCNT_OVERFLOW] & 67u) return;
     for (unsigned ai = threadIdx.x; ai < n_act; ai += blockDim.x) {
         const LabelPlace lp = ld.place[first + ai];
         DevLabel L;
@@ -938,22 +1027,20 @@ __global__ void __launch_bounds__(128) label_finish_kernel(Scene s, LabelDev ld)
         L.n_ranges = 0;
         L.range_off = 0;
         L.cell_off = 0;
-        if (lp.mode != 0 && lp.n_places) {
-            unsigned n_segs = 0;
-            double min_x = __longlong_as_double(0x7ff0000000000000LL), min_y = min_x;
-            double max_x = __longlong_as_double((long long)0xfff0000000000000ULL), max_y = max_x;
-            for (unsigned k = 0; k < lp.n_places; ++k) {
-                const GlyphOut go = ld.gout[lp.place_off + k];
-                n_segs += go.n_segs;
-                min_x = fmin(min_x, go.min_x);
-                max_x = fmax(max_x, go.max_x);
-                min_y = fmin(min_y, go.min_y);
-                max_y = fmax(max_y, go.max_y);
-            }
+        if (lp.mode != 0 && lp.n_vinst) {
+            const unsigned sb = ld.vcnt[lp.vinst_off], n_segs = ld.vcnt[lp.vinst_off + lp.n_vinst] - sb;
             if (n_segs) {
-                L.seg_count = n_segs;  // in n_ranges glyph ranges (GlyphOut.seg_off / n_segs)
-                L.range_off = lp.place_off;
-                L.n_ranges = lp.n_places;
+                double min_x = __longlong_as_double(0x7ff0000000000000LL), min_y = min_x;
+                double max_x = __longlong_as_double((long long)0xfff0000000000000ULL), max_y = max_x;
+                for (unsigned k = 0; k < lp.n_vinst; ++k) {
+                    const double4 bb = ld.vbox[lp.vinst_off + k];
+                    min_x = fmin(min_x, bb.x);
+                    max_x = fmax(max_x, bb.y);
+                    min_y = fmin(min_y, bb.z);
+                    max_y = fmax(max_y, bb.w);
+                }
+                L.seg_begin = sb;
+                L.seg_count = n_segs;
                 L.bx0 = f64_as_i32(floor(min_x));
                 L.bx1 = f64_as_i32(floor(max_x)) + 1;  // the `s` column is one past the last `a` column
                 L.by0 = f64_as_i32(floor(min_y));

@@ -44,6 +44,12 @@ timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"${
     python bench.py --steps 2 --warmup 1 --skip-cpu-baseline --skip-auto --skip-labeled --min-seconds 0 > gpurun_out/ncu_full_${TAG}.log 2>&1
 tail -2 gpurun_out/ncu_full_${TAG}.log | cut -c1-300
 fi
+if has labels_ncu; then
+echo "== ncu launch list of the label kernels"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:label_ -c 40 --csv --log-file gpurun_out/launches_labels_${TAG}.csv \
+    python bench.py --steps 2 --warmup 1 --skip-cpu-baseline --skip-auto --min-seconds 0 > gpurun_out/ncu_labels_${TAG}.log 2>&1
+tail -1 gpurun_out/ncu_labels_${TAG}.log | cut -c1-200
+fi
 if has strong; then
 echo "== strong scaling (under torchrun only)"
 fi
