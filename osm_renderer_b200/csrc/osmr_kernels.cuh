@@ -187,7 +187,7 @@ struct Scene {
 constexpr int kBW = OSMR_BW;  // block owned by one raster warp: kBW x kBH pixels
 constexpr int kBH = OSMR_BH;
 constexpr int kBP = kBW * kBH;
-static_assert((kBW == 16 || kBW == 32) && kBP % 32 == 0 && 256 % kBW == 0 && 256 % kBH == 0 && kBP <= 256, "block shape (a pixel index is one byte)");
+static_assert(kBW == 16 && kBH == 16, "block shape: a pixel index is one byte, a block row of a fill mask is 16 bits");
 
 // blocks of the tile covered by an op's reach bbox (VisOp.x0..y1, clamped to [-1, D]): first block column / row, columns, rows
 __device__ __forceinline__ void op_block_rect(int x0, int y0, int x1, int y1, int D, int& bx0, int& by0, int& nbx, int& nby) {
@@ -195,6 +195,21 @@ __device__ __forceinline__ void op_block_rect(int x0, int y0, int x1, int y1, in
     by0 = max(y0, 0) / kBH;
     nbx = min(x1, D - 1) / kBW - bx0 + 1;
     nby = min(y1, D - 1) / kBH - by0 + 1;
+}
+
+// Fill masks are stored BLOCK-MAJOR: per fill op one 32-byte record for every 16x16 block of its bbox rectangle, 16 bits per
+// block row (word j of a record = rows 2j and 2j+1).  raster_kernel fetches the whole record of its block with one sector read;
+// round 1 stored full tile rows per op and every raster warp loaded 8 row words one after the other (the top stall after the
+// fragment rewrite: 22 % of its samples).
+__device__ __forceinline__ void store_mask_word(unsigned* mask_base, int rbx0, int rby0, int nbx, int y, int k, unsigned word) {
+    // word k of tile row y covers block columns 2k and 2k+1
+    unsigned short* m16 = reinterpret_cast<unsigned short*>(mask_base);
+    const int cy = y / kBH - rby0, ry = y % kBH;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int cx = 2 * k + h - rbx0;
+        if (cx >= 0 && cx < nbx) m16[(size_t)(cy * nbx + cx) * kBH + ry] = (unsigned short)((word >> (16 * h)) & 0xffffu);
+    }
 }
 
 struct alignas(16) BinEntry {
@@ -481,7 +496,12 @@ __global__ void __launch_bounds__(kPlanThreads) plan_ops_kernel(Scene s) {
                     if (active) {
                         geom_units = info.npts;  // <= npts-1 edge records of 16 bytes
                         int ya = max(y0, 0), yb = min(y1, D - 1);
-                        mask_words = (yb >= ya) ? (unsigned)(yb - ya + 1) * (unsigned)(D / 32) : 0u;
+                        if (yb >= ya && x0 <= D - 1 && x1 >= 0) {
+                            int rbx0, rby0, nbx, nby;
+                            op_block_rect(x0, y0, x1, y1, D, rbx0, rby0, nbx, nby);
+                            mask_words = (unsigned)(nbx * nby) * (unsigned)(kBH / 2);  // 16 bits per block row
+                            rop.reach = (unsigned short)(rbx0 | (nbx << 8));           // fills: first block column, block columns
+                        }
                     }
                 } else if (!is_mp) {  // draw_areas(.., use_multipolygons=false) (drawer.rs:98-99,144-150)
                     LineParams lp;
@@ -877,6 +897,8 @@ __global__ void __launch_bounds__(kFillThreads) fill_rows_kernel(Scene s) {
         const int ne = (int)op.geom_cnt;
         const int ya = max((int)op.y0, 0), yb = min((int)op.y1, D - 1);
         const int y_first = ya + 32 * (int)item.y, y_last = min(yb, y_first + 31);
+        int rbx0, rby0, nbx, nby;
+        op_block_rect(op.x0, op.y0, op.x1, op.y1, D, rbx0, rby0, nbx, nby);
         if (OSMR_FILL_ROW_PARALLEL && wpr <= kRowWords && cap == kFillCap) {
             const int y = y_first + (int)lane;
             const bool live = y <= y_last;
@@ -909,14 +931,12 @@ __global__ void __launch_bounds__(kFillThreads) fill_rows_kernel(Scene s) {
                         for (int wd = from >> 5; wd <= (to >> 5); ++wd) rmask[w][wd][lane] |= bits_in_word(from, to, wd);
                 }
                 if (live) {
-                    unsigned* mrow = s.mask + op.mask_off + (size_t)(y - ya) * wpr;
-                    for (int k = 0; k < wpr; ++k) mrow[k] = rmask[w][k][lane];
+                    for (int k = rbx0 / 2; k <= (rbx0 + nbx - 1) / 2; ++k) store_mask_word(s.mask + op.mask_off, rbx0, rby0, nbx, y, k, rmask[w][k][lane]);
                 }
                 continue;
             }
         }
         for (int y = y_first; y <= y_last; ++y) {
-            unsigned* mrow = s.mask + op.mask_off + (size_t)(y - ya) * wpr;
             // ---- gather the non-poisoned spans of this row, in edge order ----
             int m = 0;
             for (int b = 0; b < ne; b += 32) {
@@ -1042,8 +1062,8 @@ __global__ void __launch_bounds__(kFillThreads) fill_rows_kernel(Scene s) {
                     }
                 }
             }
-            if ((int)lane < wpr) mrow[lane] = word;
-            if ((int)lane + 32 < wpr) mrow[lane + 32] = word2;
+            if ((int)lane < wpr) store_mask_word(s.mask + op.mask_off, rbx0, rby0, nbx, y, (int)lane, word);
+            if ((int)lane + 32 < wpr) store_mask_word(s.mask + op.mask_off, rbx0, rby0, nbx, y, (int)lane + 32, word2);
             __syncwarp();
         }
     }
@@ -1110,7 +1130,9 @@ struct SegConst {
 // draw_one_perpendicular (line.rs:89-131): evaluates the walk from its start until the first pixel that is not in the
 // line (or until it has left the tile for good on its monotone axis) and appends every in-line, in-tile step with a positive
 // alpha as a fragment (pixel, alpha) to the list of its 16x16 block.  Returns the number of fragments stored.
-struct FragSink {  // where the fragments of one line op go: its (block -> bin entry) pair table, the last entry looked up
+constexpr int kRunCap = 16;  // fragments of one walk inside one block that are buffered before they are appended together
+
+struct FragSink {  // where the fragments of one line op go: its (block -> bin entry) pair table and the run being collected
     const unsigned* pair;   // the op's pair table (Scene.pair + VisOp.mask_off)
     const BinEntry* entries;
     unsigned* frag_cnt;
@@ -1118,36 +1140,50 @@ struct FragSink {  // where the fragments of one line op go: its (block -> bin e
     unsigned char* frag_pix;
     unsigned* counters;
     int bx0, by0, nbx, nby; // block rectangle of the op's reach bbox
-    int last_block;         // block (by * 4096 + bx) of last_entry, -1: none yet
-    unsigned last_entry, last_off, last_cap;
+    // the current run: consecutive fragments of one walk that fall into one block (a walk crosses a block once)
+    int run_block;          // by * 4096 + bx, -1: no run
+    int run_n;
+    double run_alpha[kRunCap];
+    unsigned char run_pix[kRunCap];
 };
 
-__device__ __forceinline__ void frag_put(FragSink& fs, int px, int py, double alpha) {
-    const int bx = px / kBW, by = py / kBH;  // px, py are inside the tile
-    const int key = by * 4096 + bx;
-    if (key != fs.last_block) {
-        const int cx = bx - fs.bx0, cy = by - fs.by0;
-        unsigned e = 0xffffffffu;
-        if (cx >= 0 && cx < fs.nbx && cy >= 0 && cy < fs.nby) e = fs.pair[cy * fs.nbx + cx];
-        fs.last_block = key;
-        fs.last_entry = e;
-        if (e != 0xffffffffu) {
-            const BinEntry be = fs.entries[e];
-            fs.last_off = be.frag_off;
-            fs.last_cap = be.frag_cap;
-        }
-    }
-    if (fs.last_entry == 0xffffffffu) {  // the binning proved that no segment of this op reaches this block: a logic error, never silent
+// appends the collected run to the list of its (block, op) pair: ONE atomic for the whole run (a fragment at a time made every
+// step of a walk wait for the round trip of its own atomic: 13 % of line_cover_kernel's stall samples)
+__device__ __forceinline__ void frag_flush(FragSink& fs) {
+    if (fs.run_n == 0) return;
+    const int bx = fs.run_block & 4095, by = fs.run_block >> 12;
+    const int cx = bx - fs.bx0, cy = by - fs.by0;
+    unsigned e = 0xffffffffu;
+    if (cx >= 0 && cx < fs.nbx && cy >= 0 && cy < fs.nby) e = fs.pair[cy * fs.nbx + cx];
+    const int n = fs.run_n;
+    fs.run_n = 0;
+    if (e == 0xffffffffu) {  // the binning proved that no segment of this op reaches this block: a logic error, never silent
         atomicOr(&fs.counters[CNT_WALK_TRUNC], 2u);
         return;
     }
-    const unsigned pos = atomicAdd(&fs.frag_cnt[fs.last_entry], 1u);
-    if (pos >= fs.last_cap) {  // the capacity is a proven bound; if it ever fails the draw is refused, not clipped
+    const BinEntry be = fs.entries[e];
+    const unsigned pos = atomicAdd(&fs.frag_cnt[e], (unsigned)n);
+    if (pos + (unsigned)n > be.frag_cap) {  // the capacity is a proven bound; if it ever fails the draw is refused, not clipped
         atomicOr(&fs.counters[CNT_OVERFLOW], 256u);
         return;
     }
-    fs.frag_alpha[(size_t)fs.last_off + pos] = alpha;
-    fs.frag_pix[(size_t)fs.last_off + pos] = (unsigned char)((py % kBH) * kBW + (px % kBW));
+    double* fa = fs.frag_alpha + (size_t)be.frag_off + pos;
+    unsigned char* fp = fs.frag_pix + (size_t)be.frag_off + pos;
+    for (int i = 0; i < n; ++i) {
+        fa[i] = fs.run_alpha[i];
+        fp[i] = fs.run_pix[i];
+    }
+}
+
+__device__ __forceinline__ void frag_put(FragSink& fs, int px, int py, double alpha) {
+    const int key = (py / kBH) * 4096 + px / kBW;  // px, py are inside the tile
+    if (key != fs.run_block || fs.run_n == kRunCap) {
+        frag_flush(fs);
+        fs.run_block = key;
+    }
+    fs.run_alpha[fs.run_n] = alpha;
+    fs.run_pix[fs.run_n] = (unsigned char)((py % kBH) * kBW + (px % kBW));
+    ++fs.run_n;
 }
 
 __device__ __forceinline__ unsigned cover_walk(FragSink& fs, unsigned S, const WalkItem& w, const SegConst& sc, const OpacityCalc& calc,
@@ -1226,6 +1262,7 @@ __device__ __forceinline__ unsigned cover_walk(FragSink& fs, unsigned S, const W
         p_mx += step;
         if (sc.small) fraw += f_step; else raw += d_step;
     }
+    frag_flush(fs);
     return n_put;
 }
 
@@ -1289,9 +1326,8 @@ __global__ void __launch_bounds__(kCoverThreads, OSMR_COVER_MIN_BLOCKS) line_cov
         fs.frag_pix = s.frag_pix;
         fs.counters = s.counters;
         op_block_rect(op.x0, op.y0, op.x1, op.y1, D, fs.bx0, fs.by0, fs.nbx, fs.nby);
-        fs.last_block = -1;
-        fs.last_entry = 0xffffffffu;
-        fs.last_off = fs.last_cap = 0;
+        fs.run_block = -1;
+        fs.run_n = 0;
         __syncwarp();  // the previous op's walks are done with sm.calc
         {  // the op's opacity calculators (built by style_calc_kernel), 16 bytes per lane and step
             const uint4* src = s.calc_table + (size_t)(2u * ar.style + (pass - 1u)) * kCalcEntryUnits;
@@ -1427,19 +1463,25 @@ __global__ void __launch_bounds__(kBinThreads) bin_ops_kernel(Scene s) {
     __shared__ int s_go;
     const int D = s.D;
     const int bpr = D / kBW, bpc = D / kBH, nblk = bpr * bpc;
-    const unsigned groups = (unsigned)((nblk + kBinThreads - 1) / kBinThreads);
+    // A CTA covers an area of 16 x 16 blocks (D is a multiple of 256, so the areas tile the tile); a warp covers a compact region
+    // of 8 x 4 blocks inside it, a lane one block: an op is tested against the warp's region first (one op per lane), and only
+    // the survivors -- the few ops near the region -- are tested block by block.
+    static_assert(kBinThreads == 256, "area layout");
+    const unsigned areas_x = (unsigned)bpr / 16u;
+    const unsigned groups = areas_x * ((unsigned)bpc / 16u);
     const unsigned tile = blockIdx.x / groups, grp = blockIdx.x % groups;
-    const unsigned b = grp * kBinThreads + threadIdx.x;  // my block, row-major
-    const bool live = b < (unsigned)nblk;
-    const int bx0 = (int)(b % (unsigned)bpr) * kBW, by0 = (int)(b / (unsigned)bpr) * kBH;
+    const unsigned warp_in = threadIdx.x >> 5, lane_in = threadIdx.x & 31u;
+    const int rbx = (int)((grp % areas_x) * 16u + (warp_in & 1u) * 8u), rby = (int)((grp / areas_x) * 16u + (warp_in >> 1) * 4u);
+    const int bxi = rbx + (int)(lane_in & 7u), byi = rby + (int)(lane_in >> 3);
+    const unsigned b = (unsigned)(byi * bpr + bxi);  // my block, row-major
+    const bool live = true;
+    const int bx0 = bxi * kBW, by0 = byi * kBH;
+    const int wx0 = rbx * kBW, wy0 = rby * kBH, wx1 = wx0 + 8 * kBW - 1, wy1 = wy0 + 4 * kBH - 1;  // the warp's region in pixels
     if (threadIdx.x == 0) s_go = s.counters[CNT_OVERFLOW] == 0u;  // (one read per CTA: other CTAs may raise the flag meanwhile)
     __syncthreads();
     if (!s_go) return;  // the draw is redone with larger buffers
     const unsigned base = s.area_begin[tile];
     const unsigned n_areas_tile = s.area_begin[tile + 1] - base;
-    // the y range of this warp's blocks (32 consecutive blocks = whole block rows or a part of one)
-    const unsigned wb0 = grp * kBinThreads + (threadIdx.x & ~31u);
-    const int wy0 = (int)(wb0 / (unsigned)bpr) * kBH, wy1 = (int)(min(wb0 + 31u, (unsigned)nblk - 1u) / (unsigned)bpr) * kBH + kBH - 1;
     unsigned out_ent = 0;
     unsigned long long out_cap = 0;
     for (int sweep = 0; sweep < 2; ++sweep) {
@@ -1461,9 +1503,17 @@ __global__ void __launch_bounds__(kBinThreads) bin_ops_kernel(Scene s) {
                 }
                 __syncthreads();
                 const unsigned n_here = min((unsigned)kBinThreads, n_vis - chunk);
-                for (unsigned q = 0; q < n_here; ++q) {
+                for (unsigned sub = 0; sub < n_here; sub += 32) {
+                unsigned surv;
+                {
+                    const unsigned t = sub + lane_in;
+                    const short4 ot = s_bb[min(t, n_here - 1u)];
+                    surv = __ballot_sync(0xffffffffu, t < n_here && ot.x <= wx1 && ot.z >= wx0 && ot.y <= wy1 && ot.w >= wy0);
+                }
+                while (surv) {
+                    const unsigned q = sub + (unsigned)(__ffs(surv) - 1);
+                    surv &= surv - 1;
                     const short4 o = s_bb[q];
-                    if (o.w < wy0 || o.y > wy1) continue;  // warp-uniform: the op misses all of this warp's blocks
                     const bool box_hit = live && o.x <= bx0 + kBW - 1 && o.z >= bx0 && o.y <= by0 + kBH - 1 && o.w >= by0;
                     if (!box_hit) continue;
                     const uint4 r0 = s_rop[q];
@@ -1504,6 +1554,7 @@ __global__ void __launch_bounds__(kBinThreads) bin_ops_kernel(Scene s) {
                     }
                     ++n_ent;
                     cap_sum += cap;
+                }
                 }
             }
         }
@@ -1671,12 +1722,22 @@ __global__ void __launch_bounds__(kRasterThreads, OSMR_RASTER_MIN_BLOCKS) raster
         my_ent.op = my_ent.frag_off = my_ent.frag_cap = my_ent.pad = 0;
         uint4 my_rop0 = make_uint4(0, 0, 0, 0), my_rop1 = make_uint4(0, 0, 0, 0);
         unsigned my_cnt = 0;
+        uint4 my_m0 = make_uint4(0, 0, 0, 0), my_m1 = make_uint4(0, 0, 0, 0);  // fills: the mask record of my block (16 rows x 16 bits)
         if (ei < n_ent) {
             my_ent = ents[ei];
             const uint4* src = reinterpret_cast<const uint4*>(&s.rop[my_ent.op]);
             my_rop0 = src[0];
             my_rop1 = src[1];
-            if ((my_rop0.w & 0xffu) == OP_LINE) my_cnt = min(s.frag_cnt[range.x + ei], my_ent.frag_cap);
+            if ((my_rop0.w & 0xffu) == OP_LINE) {
+                my_cnt = min(s.frag_cnt[range.x + ei], my_ent.frag_cap);
+            } else {
+                const int oy0 = (int)(short)(my_rop0.z & 0xffffu);
+                const unsigned rect = my_rop1.x & 0xffffu;  // RasterOp.reach of a fill: first block column | block columns << 8
+                const int rbx0 = (int)(rect & 0xffu), nbx = (int)(rect >> 8), rby0 = max(oy0, 0) / kBH;
+                const uint4* rec = reinterpret_cast<const uint4*>(s.mask + my_rop0.x) + (size_t)((byi - rby0) * nbx + (bxi - rbx0)) * 2;
+                my_m0 = rec[0];
+                my_m1 = rec[1];
+            }
         }
         const unsigned n_here = min(32u, n_ent - chunk);
 #if OSMR_RASTER_TMA && !defined(OSMR_EMULATED)
@@ -1731,13 +1792,23 @@ __global__ void __launch_bounds__(kRasterThreads, OSMR_RASTER_MIN_BLOCKS) raster
                     icon = &s.icons[op.b];
                 }
                 const int col = (int)(lane % (unsigned)kBW);
-#pragma unroll 1
+                // the block's mask record, handed round from the lane that fetched it: word j = rows 2j, 2j+1, and lane l is
+                // the pixel (row 2j + l / 16, column l % 16): bit l of word j
+                unsigned mw[8];
+                mw[0] = __shfl_sync(0xffffffffu, my_m0.x, q);
+                mw[1] = __shfl_sync(0xffffffffu, my_m0.y, q);
+                mw[2] = __shfl_sync(0xffffffffu, my_m0.z, q);
+                mw[3] = __shfl_sync(0xffffffffu, my_m0.w, q);
+                mw[4] = __shfl_sync(0xffffffffu, my_m1.x, q);
+                mw[5] = __shfl_sync(0xffffffffu, my_m1.y, q);
+                mw[6] = __shfl_sync(0xffffffffu, my_m1.z, q);
+                mw[7] = __shfl_sync(0xffffffffu, my_m1.w, q);
+#pragma unroll
                 for (int j = 0; j < kBP / 32; ++j) {
                     const int r = (j * 32 + (int)lane) / kBW;
                     const int y = by0 + r;
-                    if (y < (int)op.y0 || y > (int)op.y1) continue;
-                    const unsigned mword = s.mask[op.a + (size_t)(y - ya) * wpr + (bx0 >> 5)];
-                    if (!((mword >> ((bx0 & 31) + col)) & 1u)) continue;
+                    if (y < (int)op.y0 || y > (int)op.y1) continue;  // (rows of the record outside the op's rows were never written)
+                    if (!((mw[j] >> lane) & 1u)) continue;
                     const int idx = r * kBW + col;
                     double c0, c1, c2, a;
                     if (icon) {  // Filler::Image (fill.rs:36-40): texel (x mod w, y mod h), already premultiplied
@@ -1986,6 +2057,7 @@ __global__ void __launch_bounds__(32) label_cover_kernel(LabelScene ls) {
     __shared__ unsigned s_rng[kCovUnits];   // per segment of the batch: first row inside the band (16 bits) | rows (16 bits)
     __shared__ unsigned s_off[kCovRows + 1];
     __shared__ unsigned s_cur[kCovRows];
+    __shared__ int s_kmin[kCovRows], s_kmax[kCovRows];  // touched key range per row of the band
     if (ls.skip_flags && (ls.skip_flags[0] | ls.skip_flags[1])) return;
     const unsigned n_cover = ls.n_cover_dev ? *ls.n_cover_dev : ls.n_cover;
     const unsigned lane = threadIdx.x;
@@ -2013,12 +2085,9 @@ __global__ void __launch_bounds__(32) label_cover_kernel(LabelScene ls) {
                     S[c] = 0.0;
                 }
             }
-            // touched key range of my rows (rows lane, lane + 32, ... of the band), kept in registers across the batches
-            int kmin_r[kCovRows / 32], kmax_r[kCovRows / 32];
-#pragma unroll
-            for (int q = 0; q < kCovRows / 32; ++q) {
-                kmin_r[q] = 0x7fffffff;
-                kmax_r[q] = (int)0x80000000;
+            for (int r = (int)lane; r < band_rows; r += 32) {
+                s_kmin[r] = 0x7fffffff;
+                s_kmax[r] = (int)0x80000000;
             }
             __syncwarp();
             unsigned sc = 0;  // first segment of the current batch
@@ -2105,15 +2174,19 @@ __global__ void __launch_bounds__(32) label_cover_kernel(LabelScene ls) {
                 }
                 __syncwarp();
                 // ---- pass 3: a lane per row, its crossings in segment order ----
-#pragma unroll
-                for (int q = 0; q < kCovRows / 32; ++q) {
-                    const int r = q * 32 + (int)lane;
-                    if (r < band_rows) {
+#pragma unroll 1
+                for (int r = (int)lane; r < band_rows; r += 32) {
+                    {
                         const int y = row_lo + r;
                         double* a = A + (size_t)(band + r) * W;
                         double* sacc = S + (size_t)(band + r) * W;
-                        int kmn = kmin_r[q], kmx = kmax_r[q];
+                        int kmn = s_kmin[r], kmx = s_kmax[r];
                         const unsigned u1 = s_off[r + 1];
+                        // Consecutive crossings of a row mostly hit the same cell (a curve is ~64 sub-pixel segments): the cell being
+                        // added to is kept in a register and written back when the sum moves on -- the same additions in the same
+                        // order, without a load-add-store round trip through memory per segment.
+                        int ca = -1, cs = -1;   // cached cell of `a` / `s` (-1: none)
+                        double va = 0.0, vs = 0.0;
                         for (unsigned u = s_off[r]; u < u1; ++u) {
                             const DevSeg sg = segs[sc + s_unit[u]];
                             const double slope = (sg.x1 - sg.x0) / (sg.y1 - sg.y0);  // rasterizer.rs:34-35
@@ -2122,30 +2195,45 @@ __global__ void __launch_bounds__(32) label_cover_kernel(LabelScene ls) {
                                 sg, slope, rslope, y,
                                 [&](int x, double v) {
                                     const int cx = x - L.bx0;
-                                    if (cx >= 0 && cx < W) a[cx] += v;
+                                    if (cx >= 0 && cx < W) {
+                                        if (cx != ca) {
+                                            if (ca >= 0) a[ca] = va;
+                                            ca = cx;
+                                            va = a[cx];
+                                        }
+                                        va += v;
+                                    }
                                     kmn = min(kmn, x);
                                     kmx = max(kmx, x);
                                 },
                                 [&](int x, double v) {
                                     const int cx = x - L.bx0;
-                                    if (cx >= 0 && cx < W) sacc[cx] += v;
+                                    if (cx >= 0 && cx < W) {
+                                        if (cx != cs) {
+                                            if (cs >= 0) sacc[cs] = vs;
+                                            cs = cx;
+                                            vs = sacc[cx];
+                                        }
+                                        vs += v;
+                                    }
                                     kmn = min(kmn, x);
                                     kmx = max(kmx, x);
                                 });
                         }
-                        kmin_r[q] = kmn;
-                        kmax_r[q] = kmx;
+                        if (ca >= 0) a[ca] = va;
+                        if (cs >= 0) sacc[cs] = vs;
+                        s_kmin[r] = kmn;
+                        s_kmax[r] = kmx;
                     }
                 }
                 __syncwarp();
                 sc += n_in;
             }
             // ---- sweep (save_to_figure): the lane of a row, left to right over the touched keys ----
-#pragma unroll
-            for (int q = 0; q < kCovRows / 32; ++q) {
-                const int r = q * 32 + (int)lane;
-                if (r < band_rows) {
-                    const int lo = kmin_r[q], hi = kmax_r[q];
+#pragma unroll 1
+            for (int r = (int)lane; r < band_rows; r += 32) {
+                {
+                    const int lo = s_kmin[r], hi = s_kmax[r];
                     ls.kmin[L.row_first + band + r] = lo;
                     ls.kmax[L.row_first + band + r] = hi;
                     if (lo <= hi) {
