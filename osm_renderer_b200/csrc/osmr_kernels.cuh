@@ -1130,9 +1130,9 @@ struct SegConst {
 // draw_one_perpendicular (line.rs:89-131): evaluates the walk from its start until the first pixel that is not in the
 // line (or until it has left the tile for good on its monotone axis) and appends every in-line, in-tile step with a positive
 // alpha as a fragment (pixel, alpha) to the list of its 16x16 block.  Returns the number of fragments stored.
-constexpr int kRunCap = 16;  // fragments of one walk inside one block that are buffered before they are appended together
+constexpr int kRunCap = 12;  // fragments of one walk inside one block that are buffered before they are appended together
 
-struct FragSink {  // where the fragments of one line op go: its (block -> bin entry) pair table and the run being collected
+struct FragSink {  // where the fragments of one line op go: its (block -> bin entry) pair table and the runs in flight
     const unsigned* pair;   // the op's pair table (Scene.pair + VisOp.mask_off)
     const BinEntry* entries;
     unsigned* frag_cnt;
@@ -1140,50 +1140,67 @@ struct FragSink {  // where the fragments of one line op go: its (block -> bin e
     unsigned char* frag_pix;
     unsigned* counters;
     int bx0, by0, nbx, nby; // block rectangle of the op's reach bbox
-    // the current run: consecutive fragments of one walk that fall into one block (a walk crosses a block once)
-    int run_block;          // by * 4096 + bx, -1: no run
-    int run_n;
-    double run_alpha[kRunCap];
-    unsigned char run_pix[kRunCap];
+    // Two runs (consecutive fragments of one walk inside one block): `cur` is being collected; the other one has been counted
+    // in (its atomicAdd is in flight) and is written out when the next run is handed over -- by then the atomic has long
+    // returned, so no walk ever waits for the round trip of an atomic (13 % of the kernel's stall samples when every fragment
+    // took its own).
+    int cur;                // index of the run being collected
+    int run_block;          // its block (by * 4096 + bx), -1: none
+    int run_n[2];
+    unsigned pend_pos;      // position of the pending run in its list (the atomic's return value, consumed one run later)
+    unsigned pend_off, pend_cap;
+    double run_alpha[2][kRunCap];
+    unsigned char run_pix[2][kRunCap];
 };
 
-// appends the collected run to the list of its (block, op) pair: ONE atomic for the whole run (a fragment at a time made every
-// step of a walk wait for the round trip of its own atomic: 13 % of line_cover_kernel's stall samples)
+__device__ __forceinline__ void frag_write_pending(FragSink& fs) {
+    const int p = fs.cur ^ 1;
+    const int n = fs.run_n[p];
+    if (n == 0) return;
+    fs.run_n[p] = 0;
+    if (fs.pend_pos + (unsigned)n > fs.pend_cap) {  // the capacity is a proven bound; if it ever fails the draw is refused, not clipped
+        atomicOr(&fs.counters[CNT_OVERFLOW], 256u);
+        return;
+    }
+    double* fa = fs.frag_alpha + (size_t)fs.pend_off + fs.pend_pos;
+    unsigned char* fp = fs.frag_pix + (size_t)fs.pend_off + fs.pend_pos;
+    for (int i = 0; i < n; ++i) {
+        fa[i] = fs.run_alpha[p][i];
+        fp[i] = fs.run_pix[p][i];
+    }
+}
+
+// hands the collected run over: the previous pending run is written, this one is counted in (one atomic for the whole run)
 __device__ __forceinline__ void frag_flush(FragSink& fs) {
-    if (fs.run_n == 0) return;
+    const int n = fs.run_n[fs.cur];
+    if (n == 0) return;
+    frag_write_pending(fs);
     const int bx = fs.run_block & 4095, by = fs.run_block >> 12;
     const int cx = bx - fs.bx0, cy = by - fs.by0;
     unsigned e = 0xffffffffu;
     if (cx >= 0 && cx < fs.nbx && cy >= 0 && cy < fs.nby) e = fs.pair[cy * fs.nbx + cx];
-    const int n = fs.run_n;
-    fs.run_n = 0;
     if (e == 0xffffffffu) {  // the binning proved that no segment of this op reaches this block: a logic error, never silent
         atomicOr(&fs.counters[CNT_WALK_TRUNC], 2u);
+        fs.run_n[fs.cur] = 0;
         return;
     }
     const BinEntry be = fs.entries[e];
-    const unsigned pos = atomicAdd(&fs.frag_cnt[e], (unsigned)n);
-    if (pos + (unsigned)n > be.frag_cap) {  // the capacity is a proven bound; if it ever fails the draw is refused, not clipped
-        atomicOr(&fs.counters[CNT_OVERFLOW], 256u);
-        return;
-    }
-    double* fa = fs.frag_alpha + (size_t)be.frag_off + pos;
-    unsigned char* fp = fs.frag_pix + (size_t)be.frag_off + pos;
-    for (int i = 0; i < n; ++i) {
-        fa[i] = fs.run_alpha[i];
-        fp[i] = fs.run_pix[i];
-    }
+    fs.pend_off = be.frag_off;
+    fs.pend_cap = be.frag_cap;
+    fs.pend_pos = atomicAdd(&fs.frag_cnt[e], (unsigned)n);
+    fs.cur ^= 1;  // (the run that was pending is empty now)
 }
 
 __device__ __forceinline__ void frag_put(FragSink& fs, int px, int py, double alpha) {
     const int key = (py / kBH) * 4096 + px / kBW;  // px, py are inside the tile
-    if (key != fs.run_block || fs.run_n == kRunCap) {
+    if (key != fs.run_block || fs.run_n[fs.cur] == kRunCap) {
         frag_flush(fs);
         fs.run_block = key;
     }
-    fs.run_alpha[fs.run_n] = alpha;
-    fs.run_pix[fs.run_n] = (unsigned char)((py % kBH) * kBW + (px % kBW));
-    ++fs.run_n;
+    const int i = fs.run_n[fs.cur];
+    fs.run_alpha[fs.cur][i] = alpha;
+    fs.run_pix[fs.cur][i] = (unsigned char)((py % kBH) * kBW + (px % kBW));
+    fs.run_n[fs.cur] = i + 1;
 }
 
 __device__ __forceinline__ unsigned cover_walk(FragSink& fs, unsigned S, const WalkItem& w, const SegConst& sc, const OpacityCalc& calc,
@@ -1326,8 +1343,10 @@ __global__ void __launch_bounds__(kCoverThreads, OSMR_COVER_MIN_BLOCKS) line_cov
         fs.frag_pix = s.frag_pix;
         fs.counters = s.counters;
         op_block_rect(op.x0, op.y0, op.x1, op.y1, D, fs.bx0, fs.by0, fs.nbx, fs.nby);
+        fs.cur = 0;
         fs.run_block = -1;
-        fs.run_n = 0;
+        fs.run_n[0] = fs.run_n[1] = 0;
+        fs.pend_pos = fs.pend_off = fs.pend_cap = 0;
         __syncwarp();  // the previous op's walks are done with sm.calc
         {  // the op's opacity calculators (built by style_calc_kernel), 16 bytes per lane and step
             const uint4* src = s.calc_table + (size_t)(2u * ar.style + (pass - 1u)) * kCalcEntryUnits;
@@ -1397,6 +1416,8 @@ __global__ void __launch_bounds__(kCoverThreads, OSMR_COVER_MIN_BLOCKS) line_cov
                 OSMR_COUNT("cover.walks", (len0 != 0) + (len1 != 0));
             }
         }
+        frag_flush(fs);          // the run being collected (cover_walk has handed over every finished walk already) ...
+        frag_write_pending(fs);  // ... and the one whose atomic is in flight
         for (int o = 16; o > 0; o >>= 1) steps_stored += __shfl_xor_sync(0xffffffffu, steps_stored, o);
         if (lane == 0 && steps_stored)
             atomicAdd(reinterpret_cast<unsigned long long*>(&s.counters[CNT_WALK_STEPS]), (unsigned long long)steps_stored);
@@ -2016,7 +2037,7 @@ struct LabelScene {
 // version parallelised over segments and committed the additions lane by lane: 12.7 ms.)
 // ------------------------------------------------------------------------------------------------------
 constexpr int kCovUnits = 2048;  // (segment, row) crossings per batch
-constexpr int kCovRows = 256;    // rows per band (a taller label is processed band by band)
+constexpr int kCovRows = 128;    // rows per band (a taller label is processed band by band)
 
 // draw_line of one segment restricted to pixel row y (rasterizer.rs:52-83); calls add_a(x, value) for every touched cell of `a`
 // and add_s(x, value) once
@@ -2054,7 +2075,7 @@ __device__ __forceinline__ void cover_segment_row(const DevSeg& sg, double slope
 __global__ void __launch_bounds__(32) label_cover_kernel(LabelScene ls) {
     constexpr unsigned kFull = 0xffffffffu;
     __shared__ unsigned s_unit[kCovUnits];  // segment (index inside the batch) of every crossing, bucketed by row, in segment order
-    __shared__ unsigned s_rng[kCovUnits];   // per segment of the batch: first row inside the band (16 bits) | rows (16 bits)
+    __shared__ unsigned s_rng[kCovUnits];   // per segment of the batch: first row (7 bits) | rows (8) | first column bin (8) | last bin (8)
     __shared__ unsigned s_off[kCovRows + 1];
     __shared__ unsigned s_cur[kCovRows];
     __shared__ int s_kmin[kCovRows], s_kmax[kCovRows];  // touched key range per row of the band
@@ -2077,6 +2098,11 @@ __global__ void __launch_bounds__(32) label_cover_kernel(LabelScene ls) {
         for (int band = 0; band < R; band += kCovRows) {
             const int band_rows = min(kCovRows, R - band);
             const int row_lo = L.ry0 + band;  // pixel row of the band's first row
+            // A street name is a dozen rows tall: rows alone would keep a third of the lanes busy.  Cells of one row do not
+            // interact either, so a row is cut into column bins and a lane owns a (row, bin) bucket: it walks the row's crossings
+            // in order and adds only into its own columns.
+            const int nbins = max(1, min(min(255, (W + 1) / 2), 128 / band_rows));
+            const int bin_w = (W + nbins - 1) / nbins;
             // nobody cleared the coverage cells: the band's rows are contiguous
             {
                 const size_t c0 = (size_t)band * (size_t)W, c1 = c0 + (size_t)band_rows * (size_t)W;
@@ -2098,11 +2124,17 @@ __global__ void __launch_bounds__(32) label_cover_kernel(LabelScene ls) {
                 unsigned n_in = 0, units = 0;  // segments / crossings taken into the batch so far
                 while (sc + n_in < nseg && n_in < (unsigned)kCovUnits) {
                     const unsigned j = sc + n_in + lane;
-                    int r0 = 1, r1 = 0;
+                    int r0 = 1, r1 = 0, b0 = 0, b1 = 0;
                     if (j < nseg && n_in + lane < (unsigned)kCovUnits) {
                         const DevSeg sg = segs[j];
                         r0 = max(f64_as_i32(floor(fmin(sg.y0, sg.y1))), row_lo) - row_lo;
                         r1 = min(f64_as_i32(floor(fmax(sg.y0, sg.y1))), row_lo + band_rows - 1) - row_lo;
+                        // column bins the segment can add into: its own x extent, one key of slack on both sides (`s` goes to
+                        // x_to + 1; the interpolated x of a row may leave the segment's extent by a rounding error)
+                        const long long xa = (long long)f64_as_i32(floor(fmin(sg.x0, sg.x1))) - 1 - L.bx0;
+                        const long long xb = (long long)f64_as_i32(floor(fmax(sg.x0, sg.x1))) + 2 - L.bx0;
+                        b0 = (int)(max(0ll, min(xa, (long long)W - 1)) / bin_w);
+                        b1 = (int)(max(0ll, min(xb, (long long)W - 1)) / bin_w);
                     }
                     const unsigned nr = r1 >= r0 ? (unsigned)(r1 - r0 + 1) : 0u;
                     unsigned incl = nr;
@@ -2114,7 +2146,7 @@ __global__ void __launch_bounds__(32) label_cover_kernel(LabelScene ls) {
                     const unsigned fit = __ballot_sync(kFull, units + incl <= (unsigned)kCovUnits && j < nseg && n_in + lane < (unsigned)kCovUnits);
                     const unsigned take = (fit == kFull) ? 32u : (unsigned)(__ffs(~fit) - 1);
                     if (take == 0u) break;
-                    if (lane < take) s_rng[n_in + lane] = nr ? ((unsigned)r0 | (nr << 16)) : 0u;
+                    if (lane < take) s_rng[n_in + lane] = nr ? ((unsigned)r0 | (nr << 7) | ((unsigned)b0 << 15) | ((unsigned)b1 << 23)) : 0u;
                     // count per row: the union of the taken lanes' row ranges is short (a glyph is a few rows tall)
                     const bool mine = lane < take && nr;
                     int lo = mine ? r0 : 0x7fffffff, hi = mine ? r1 : -1;
@@ -2156,7 +2188,7 @@ __global__ void __launch_bounds__(32) label_cover_kernel(LabelScene ls) {
                 for (unsigned base = 0; base < n_in; base += 32) {
                     const unsigned k = base + lane;
                     const unsigned rg = k < n_in ? s_rng[k] : 0u;
-                    const int r0 = (int)(rg & 0xffffu), nr = (int)(rg >> 16);
+                    const int r0 = (int)(rg & 0x7fu), nr = (int)((rg >> 7) & 0xffu);
                     const bool mine = nr != 0;
                     int lo = mine ? r0 : 0x7fffffff, hi = mine ? r0 + nr - 1 : -1;
                     for (int o = 16; o > 0; o >>= 1) {
@@ -2173,58 +2205,62 @@ __global__ void __launch_bounds__(32) label_cover_kernel(LabelScene ls) {
                     }
                 }
                 __syncwarp();
-                // ---- pass 3: a lane per row, its crossings in segment order ----
+                // ---- pass 3: a lane per (row, column bin), the row's crossings in segment order ----
+                const int n_buckets = band_rows * nbins;
 #pragma unroll 1
-                for (int r = (int)lane; r < band_rows; r += 32) {
-                    {
-                        const int y = row_lo + r;
-                        double* a = A + (size_t)(band + r) * W;
-                        double* sacc = S + (size_t)(band + r) * W;
-                        int kmn = s_kmin[r], kmx = s_kmax[r];
-                        const unsigned u1 = s_off[r + 1];
-                        // Consecutive crossings of a row mostly hit the same cell (a curve is ~64 sub-pixel segments): the cell being
-                        // added to is kept in a register and written back when the sum moves on -- the same additions in the same
-                        // order, without a load-add-store round trip through memory per segment.
-                        int ca = -1, cs = -1;   // cached cell of `a` / `s` (-1: none)
-                        double va = 0.0, vs = 0.0;
-                        for (unsigned u = s_off[r]; u < u1; ++u) {
-                            const DevSeg sg = segs[sc + s_unit[u]];
-                            const double slope = (sg.x1 - sg.x0) / (sg.y1 - sg.y0);  // rasterizer.rs:34-35
-                            const double rslope = 1.0 / slope;
-                            cover_segment_row(
-                                sg, slope, rslope, y,
-                                [&](int x, double v) {
-                                    const int cx = x - L.bx0;
-                                    if (cx >= 0 && cx < W) {
-                                        if (cx != ca) {
-                                            if (ca >= 0) a[ca] = va;
-                                            ca = cx;
-                                            va = a[cx];
-                                        }
-                                        va += v;
+                for (int bk = (int)lane; bk < n_buckets; bk += 32) {
+                    const int r = bk / nbins, bin = bk - r * nbins;
+                    const int cx_lo = bin * bin_w, cx_hi = min(W, cx_lo + bin_w) - 1;  // my columns (cells of the label's arrays)
+                    const int y = row_lo + r;
+                    double* a = A + (size_t)(band + r) * W;
+                    double* sacc = S + (size_t)(band + r) * W;
+                    int kmn = 0x7fffffff, kmx = (int)0x80000000;
+                    const unsigned u1 = s_off[r + 1];
+                    // Consecutive crossings mostly hit the same cell (a curve is ~64 sub-pixel segments): the cell being added to
+                    // is kept in a register and written back when the sum moves on -- the same additions in the same order,
+                    // without a load-add-store round trip through memory per segment.
+                    int ca = -1, cs = -1;  // cached cell of `a` / `s` (-1: none)
+                    double va = 0.0, vs = 0.0;
+                    for (unsigned u = s_off[r]; u < u1; ++u) {
+                        const unsigned k = s_unit[u];
+                        const unsigned rg = s_rng[k];
+                        if (bin < (int)((rg >> 15) & 0xffu) || bin > (int)(rg >> 23)) continue;  // cannot add into my columns
+                        const DevSeg sg = segs[sc + k];
+                        const double slope = (sg.x1 - sg.x0) / (sg.y1 - sg.y0);  // rasterizer.rs:34-35
+                        const double rslope = 1.0 / slope;
+                        cover_segment_row(
+                            sg, slope, rslope, y,
+                            [&](int x, double v) {
+                                const int cx = x - L.bx0;
+                                if (cx >= cx_lo && cx <= cx_hi) {
+                                    if (cx != ca) {
+                                        if (ca >= 0) a[ca] = va;
+                                        ca = cx;
+                                        va = a[cx];
                                     }
-                                    kmn = min(kmn, x);
-                                    kmx = max(kmx, x);
-                                },
-                                [&](int x, double v) {
-                                    const int cx = x - L.bx0;
-                                    if (cx >= 0 && cx < W) {
-                                        if (cx != cs) {
-                                            if (cs >= 0) sacc[cs] = vs;
-                                            cs = cx;
-                                            vs = sacc[cx];
-                                        }
-                                        vs += v;
+                                    va += v;
+                                }
+                                kmn = min(kmn, x);  // (every crossing is processed by at least one bin: the row's key range is complete)
+                                kmx = max(kmx, x);
+                            },
+                            [&](int x, double v) {
+                                const int cx = x - L.bx0;
+                                if (cx >= cx_lo && cx <= cx_hi) {
+                                    if (cx != cs) {
+                                        if (cs >= 0) sacc[cs] = vs;
+                                        cs = cx;
+                                        vs = sacc[cx];
                                     }
-                                    kmn = min(kmn, x);
-                                    kmx = max(kmx, x);
-                                });
-                        }
-                        if (ca >= 0) a[ca] = va;
-                        if (cs >= 0) sacc[cs] = vs;
-                        s_kmin[r] = kmn;
-                        s_kmax[r] = kmx;
+                                    vs += v;
+                                }
+                                kmn = min(kmn, x);
+                                kmx = max(kmx, x);
+                            });
                     }
+                    if (ca >= 0) a[ca] = va;
+                    if (cs >= 0) sacc[cs] = vs;
+                    if (kmn != 0x7fffffff) atomicMin(&s_kmin[r], kmn);
+                    if (kmx != (int)0x80000000) atomicMax(&s_kmax[r], kmx);
                 }
                 __syncwarp();
                 sc += n_in;
@@ -2232,21 +2268,19 @@ __global__ void __launch_bounds__(32) label_cover_kernel(LabelScene ls) {
             // ---- sweep (save_to_figure): the lane of a row, left to right over the touched keys ----
 #pragma unroll 1
             for (int r = (int)lane; r < band_rows; r += 32) {
-                {
-                    const int lo = s_kmin[r], hi = s_kmax[r];
-                    ls.kmin[L.row_first + band + r] = lo;
-                    ls.kmax[L.row_first + band + r] = hi;
-                    if (lo <= hi) {
-                        double run = 0.0;
-                        double* a = A + (size_t)(band + r) * W;
-                        const double* sacc = S + (size_t)(band + r) * W;
-                        for (int x = lo; x <= hi; ++x) {
-                            const int c = x - L.bx0;
-                            const bool inside = c >= 0 && c < W;  // the bbox covers every key; defensive
-                            run += inside ? sacc[c] : 0.0;
-                            const double total = fmin((inside ? a[c] : 0.0) + run, 1.0);
-                            if (inside) a[c] = total;
-                        }
+                const int lo = s_kmin[r], hi = s_kmax[r];
+                ls.kmin[L.row_first + band + r] = lo;
+                ls.kmax[L.row_first + band + r] = hi;
+                if (lo <= hi) {
+                    double run = 0.0;
+                    double* a = A + (size_t)(band + r) * W;
+                    const double* sacc = S + (size_t)(band + r) * W;
+                    for (int x = lo; x <= hi; ++x) {
+                        const int c = x - L.bx0;
+                        const bool inside = c >= 0 && c < W;  // the bbox covers every key; defensive
+                        run += inside ? sacc[c] : 0.0;
+                        const double total = fmin((inside ? a[c] : 0.0) + run, 1.0);
+                        if (inside) a[c] = total;
                     }
                 }
             }

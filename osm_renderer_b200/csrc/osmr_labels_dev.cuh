@@ -792,28 +792,61 @@ struct EmitSink {
         near_tie = true;  // only libm's hypot can decide: the call goes to the host path
         return true;
     }
-    // the reference recurses (first half, then second half); an explicit stack keeps the same emission order
+    // The reference recurses (first half, then second half).  Here the subdivision tree is walked in the same order WITHOUT a
+    // stack: the current node is (depth, path bits); descending to the first half is one midpoint step from the current points,
+    // and after a leaf the next node -- the second half of the nearest ancestor whose first half was just finished -- gets its
+    // control points by repeating the midpoint steps from the root along its path.  Same operations on the same operands as the
+    // recursion, so the points are bit-identical; the explicit stack this replaces lived in local memory and its loads were
+    // half of the kernel's stall samples.
     __device__ void quad(double x0, double y0, double x1, double y1, double x2, double y2) {
-        constexpr int kStack = 20;
-        double st[kStack][6];
-        int sp = 0;
-        st[sp][0] = x0; st[sp][1] = y0; st[sp][2] = x1; st[sp][3] = y1; st[sp][4] = x2; st[sp][5] = y2;
-        ++sp;
-        while (sp > 0) {
-            --sp;
-            const double a0 = st[sp][0], b0 = st[sp][1], a1 = st[sp][2], b1 = st[sp][3], a2 = st[sp][4], b2 = st[sp][5];
-            if (flat_enough(a0, b0, a1, b1, a2, b2) || sp + 2 > kStack) {
-                if (sp + 2 > kStack) near_tie = true;  // absurd depth: not something the device decides
-                line(a0, b0, a2, b2);
+        constexpr int kMaxDepth = 30;
+        unsigned path = 0u;
+        int depth = 0;
+        double a0 = x0, b0 = y0, a1 = x1, b1 = y1, a2 = x2, b2 = y2;
+        for (;;) {
+            bool flat = flat_enough(a0, b0, a1, b1, a2, b2);
+            if (!flat && depth >= kMaxDepth) {  // absurd depth: not something the device decides
+                near_tie = true;
+                flat = true;
+            }
+            if (!flat) {  // first half: (p0, (p0 + p1) / 2, m)
+                const double ax = (a0 + a1) / 2.0, ay = (b0 + b1) / 2.0, bx = (a1 + a2) / 2.0, by = (b1 + b2) / 2.0;
+                a2 = (ax + bx) / 2.0;
+                b2 = (ay + by) / 2.0;
+                a1 = ax;
+                b1 = ay;
+                path <<= 1;
+                ++depth;
                 continue;
             }
-            const double ax = (a0 + a1) / 2.0, ay = (b0 + b1) / 2.0, bx = (a1 + a2) / 2.0, by = (b1 + b2) / 2.0;
-            const double mx = (ax + bx) / 2.0, my = (ay + by) / 2.0;
-            // push the second half first so that the first half is processed next
-            st[sp][0] = mx; st[sp][1] = my; st[sp][2] = bx; st[sp][3] = by; st[sp][4] = a2; st[sp][5] = b2;
-            ++sp;
-            st[sp][0] = a0; st[sp][1] = b0; st[sp][2] = ax; st[sp][3] = ay; st[sp][4] = mx; st[sp][5] = my;
-            ++sp;
+            line(a0, b0, a2, b2);
+            while (depth > 0 && (path & 1u)) {  // both halves of this ancestor are done
+                path >>= 1;
+                --depth;
+            }
+            if (depth == 0) return;
+            path |= 1u;  // the second half of that ancestor: (m, (p1 + p2) / 2, p2)
+            a0 = x0;
+            b0 = y0;
+            a1 = x1;
+            b1 = y1;
+            a2 = x2;
+            b2 = y2;
+            for (int l = depth - 1; l >= 0; --l) {
+                const double ax = (a0 + a1) / 2.0, ay = (b0 + b1) / 2.0, bx = (a1 + a2) / 2.0, by = (b1 + b2) / 2.0;
+                const double mx = (ax + bx) / 2.0, my = (ay + by) / 2.0;
+                if ((path >> l) & 1u) {
+                    a0 = mx;
+                    b0 = my;
+                    a1 = bx;
+                    b1 = by;
+                } else {
+                    a2 = mx;
+                    b2 = my;
+                    a1 = ax;
+                    b1 = ay;
+                }
+            }
         }
     }
 };
