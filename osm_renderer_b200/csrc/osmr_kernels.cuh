@@ -1130,9 +1130,7 @@ struct SegConst {
 // draw_one_perpendicular (line.rs:89-131): evaluates the walk from its start until the first pixel that is not in the
 // line (or until it has left the tile for good on its monotone axis) and appends every in-line, in-tile step with a positive
 // alpha as a fragment (pixel, alpha) to the list of its 16x16 block.  Returns the number of fragments stored.
-constexpr int kRunCap = 12;  // fragments of one walk inside one block that are buffered before they are appended together
-
-struct FragSink {  // where the fragments of one line op go: its (block -> bin entry) pair table and the runs in flight
+struct FragSink {  // where the fragments of one line op go: its (block -> bin entry) pair table, the last entry looked up
     const unsigned* pair;   // the op's pair table (Scene.pair + VisOp.mask_off)
     const BinEntry* entries;
     unsigned* frag_cnt;
@@ -1140,67 +1138,36 @@ struct FragSink {  // where the fragments of one line op go: its (block -> bin e
     unsigned char* frag_pix;
     unsigned* counters;
     int bx0, by0, nbx, nby; // block rectangle of the op's reach bbox
-    // Two runs (consecutive fragments of one walk inside one block): `cur` is being collected; the other one has been counted
-    // in (its atomicAdd is in flight) and is written out when the next run is handed over -- by then the atomic has long
-    // returned, so no walk ever waits for the round trip of an atomic (13 % of the kernel's stall samples when every fragment
-    // took its own).
-    int cur;                // index of the run being collected
-    int run_block;          // its block (by * 4096 + bx), -1: none
-    int run_n[2];
-    unsigned pend_pos;      // position of the pending run in its list (the atomic's return value, consumed one run later)
-    unsigned pend_off, pend_cap;
-    double run_alpha[2][kRunCap];
-    unsigned char run_pix[2][kRunCap];
+    int last_block;         // block (by * 4096 + bx) of last_entry, -1: none yet
+    unsigned last_entry, last_off, last_cap;
 };
 
-__device__ __forceinline__ void frag_write_pending(FragSink& fs) {
-    const int p = fs.cur ^ 1;
-    const int n = fs.run_n[p];
-    if (n == 0) return;
-    fs.run_n[p] = 0;
-    if (fs.pend_pos + (unsigned)n > fs.pend_cap) {  // the capacity is a proven bound; if it ever fails the draw is refused, not clipped
+__device__ __forceinline__ void frag_put(FragSink& fs, int px, int py, double alpha) {
+    const int bx = px / kBW, by = py / kBH;  // px, py are inside the tile
+    const int key = by * 4096 + bx;
+    if (key != fs.last_block) {
+        const int cx = bx - fs.bx0, cy = by - fs.by0;
+        unsigned e = 0xffffffffu;
+        if (cx >= 0 && cx < fs.nbx && cy >= 0 && cy < fs.nby) e = fs.pair[cy * fs.nbx + cx];
+        fs.last_block = key;
+        fs.last_entry = e;
+        if (e != 0xffffffffu) {
+            const BinEntry be = fs.entries[e];
+            fs.last_off = be.frag_off;
+            fs.last_cap = be.frag_cap;
+        }
+    }
+    if (fs.last_entry == 0xffffffffu) {  // the binning proved that no segment of this op reaches this block: a logic error, never silent
+        atomicOr(&fs.counters[CNT_WALK_TRUNC], 2u);
+        return;
+    }
+    const unsigned pos = atomicAdd(&fs.frag_cnt[fs.last_entry], 1u);
+    if (pos >= fs.last_cap) {  // the capacity is a proven bound; if it ever fails the draw is refused, not clipped
         atomicOr(&fs.counters[CNT_OVERFLOW], 256u);
         return;
     }
-    double* fa = fs.frag_alpha + (size_t)fs.pend_off + fs.pend_pos;
-    unsigned char* fp = fs.frag_pix + (size_t)fs.pend_off + fs.pend_pos;
-    for (int i = 0; i < n; ++i) {
-        fa[i] = fs.run_alpha[p][i];
-        fp[i] = fs.run_pix[p][i];
-    }
-}
-
-// hands the collected run over: the previous pending run is written, this one is counted in (one atomic for the whole run)
-__device__ __forceinline__ void frag_flush(FragSink& fs) {
-    const int n = fs.run_n[fs.cur];
-    if (n == 0) return;
-    frag_write_pending(fs);
-    const int bx = fs.run_block & 4095, by = fs.run_block >> 12;
-    const int cx = bx - fs.bx0, cy = by - fs.by0;
-    unsigned e = 0xffffffffu;
-    if (cx >= 0 && cx < fs.nbx && cy >= 0 && cy < fs.nby) e = fs.pair[cy * fs.nbx + cx];
-    if (e == 0xffffffffu) {  // the binning proved that no segment of this op reaches this block: a logic error, never silent
-        atomicOr(&fs.counters[CNT_WALK_TRUNC], 2u);
-        fs.run_n[fs.cur] = 0;
-        return;
-    }
-    const BinEntry be = fs.entries[e];
-    fs.pend_off = be.frag_off;
-    fs.pend_cap = be.frag_cap;
-    fs.pend_pos = atomicAdd(&fs.frag_cnt[e], (unsigned)n);
-    fs.cur ^= 1;  // (the run that was pending is empty now)
-}
-
-__device__ __forceinline__ void frag_put(FragSink& fs, int px, int py, double alpha) {
-    const int key = (py / kBH) * 4096 + px / kBW;  // px, py are inside the tile
-    if (key != fs.run_block || fs.run_n[fs.cur] == kRunCap) {
-        frag_flush(fs);
-        fs.run_block = key;
-    }
-    const int i = fs.run_n[fs.cur];
-    fs.run_alpha[fs.cur][i] = alpha;
-    fs.run_pix[fs.cur][i] = (unsigned char)((py % kBH) * kBW + (px % kBW));
-    fs.run_n[fs.cur] = i + 1;
+    fs.frag_alpha[(size_t)fs.last_off + pos] = alpha;
+    fs.frag_pix[(size_t)fs.last_off + pos] = (unsigned char)((py % kBH) * kBW + (px % kBW));
 }
 
 __device__ __forceinline__ unsigned cover_walk(FragSink& fs, unsigned S, const WalkItem& w, const SegConst& sc, const OpacityCalc& calc,
@@ -1279,7 +1246,6 @@ __device__ __forceinline__ unsigned cover_walk(FragSink& fs, unsigned S, const W
         p_mx += step;
         if (sc.small) fraw += f_step; else raw += d_step;
     }
-    frag_flush(fs);
     return n_put;
 }
 
@@ -1343,10 +1309,9 @@ __global__ void __launch_bounds__(kCoverThreads, OSMR_COVER_MIN_BLOCKS) line_cov
         fs.frag_pix = s.frag_pix;
         fs.counters = s.counters;
         op_block_rect(op.x0, op.y0, op.x1, op.y1, D, fs.bx0, fs.by0, fs.nbx, fs.nby);
-        fs.cur = 0;
-        fs.run_block = -1;
-        fs.run_n[0] = fs.run_n[1] = 0;
-        fs.pend_pos = fs.pend_off = fs.pend_cap = 0;
+        fs.last_block = -1;
+        fs.last_entry = 0xffffffffu;
+        fs.last_off = fs.last_cap = 0;
         __syncwarp();  // the previous op's walks are done with sm.calc
         {  // the op's opacity calculators (built by style_calc_kernel), 16 bytes per lane and step
             const uint4* src = s.calc_table + (size_t)(2u * ar.style + (pass - 1u)) * kCalcEntryUnits;
@@ -1416,8 +1381,6 @@ __global__ void __launch_bounds__(kCoverThreads, OSMR_COVER_MIN_BLOCKS) line_cov
                 OSMR_COUNT("cover.walks", (len0 != 0) + (len1 != 0));
             }
         }
-        frag_flush(fs);          // the run being collected (cover_walk has handed over every finished walk already) ...
-        frag_write_pending(fs);  // ... and the one whose atomic is in flight
         for (int o = 16; o > 0; o >>= 1) steps_stored += __shfl_xor_sync(0xffffffffu, steps_stored, o);
         if (lane == 0 && steps_stored)
             atomicAdd(reinterpret_cast<unsigned long long*>(&s.counters[CNT_WALK_STEPS]), (unsigned long long)steps_stored);
@@ -2036,7 +1999,7 @@ struct LabelScene {
 // (Round 1 gave a warp 32 rows and made it scan ALL segments of the label per row group: 21 ms per C2 batch; an intermediate
 // version parallelised over segments and committed the additions lane by lane: 12.7 ms.)
 // ------------------------------------------------------------------------------------------------------
-constexpr int kCovUnits = 2048;  // (segment, row) crossings per batch
+constexpr int kCovUnits = 4096;  // (segment, row, column bin) crossings per batch
 constexpr int kCovRows = 128;    // rows per band (a taller label is processed band by band)
 
 // draw_line of one segment restricted to pixel row y (rasterizer.rs:52-83); calls add_a(x, value) for every touched cell of `a`
@@ -2074,10 +2037,11 @@ __device__ __forceinline__ void cover_segment_row(const DevSeg& sg, double slope
 
 __global__ void __launch_bounds__(32) label_cover_kernel(LabelScene ls) {
     constexpr unsigned kFull = 0xffffffffu;
-    __shared__ unsigned s_unit[kCovUnits];  // segment (index inside the batch) of every crossing, bucketed by row, in segment order
-    __shared__ unsigned s_rng[kCovUnits];   // per segment of the batch: first row (7 bits) | rows (8) | first column bin (8) | last bin (8)
-    __shared__ unsigned s_off[kCovRows + 1];
-    __shared__ unsigned s_cur[kCovRows];
+    constexpr int kBuckets = kCovRows;      // (row, column bin) buckets of a band: rows * bins <= kCovRows
+    __shared__ unsigned short s_unit[kCovUnits];  // segment (index inside the batch) of every crossing, bucketed, in segment order
+    __shared__ unsigned s_rng[kCovUnits / 2];     // per segment of the batch: first row (7 bits) | rows (8) | first bin (8) | bins - 1 (8)
+    __shared__ unsigned s_off[kBuckets + 1];
+    __shared__ unsigned s_cur[kBuckets];
     __shared__ int s_kmin[kCovRows], s_kmax[kCovRows];  // touched key range per row of the band
     if (ls.skip_flags && (ls.skip_flags[0] | ls.skip_flags[1])) return;
     const unsigned n_cover = ls.n_cover_dev ? *ls.n_cover_dev : ls.n_cover;
@@ -2099,10 +2063,10 @@ __global__ void __launch_bounds__(32) label_cover_kernel(LabelScene ls) {
             const int band_rows = min(kCovRows, R - band);
             const int row_lo = L.ry0 + band;  // pixel row of the band's first row
             // A street name is a dozen rows tall: rows alone would keep a third of the lanes busy.  Cells of one row do not
-            // interact either, so a row is cut into column bins and a lane owns a (row, bin) bucket: it walks the row's crossings
-            // in order and adds only into its own columns.
-            const int nbins = max(1, min(min(255, (W + 1) / 2), 128 / band_rows));
+            // interact either, so a row is cut into column bins and a lane owns a (row, bin) bucket.
+            const int nbins = max(1, min(min(255, (W + 1) / 2), kBuckets / band_rows));
             const int bin_w = (W + nbins - 1) / nbins;
+            const int n_buckets = band_rows * nbins;
             // nobody cleared the coverage cells: the band's rows are contiguous
             {
                 const size_t c0 = (size_t)band * (size_t)W, c1 = c0 + (size_t)band_rows * (size_t)W;
@@ -2118,14 +2082,15 @@ __global__ void __launch_bounds__(32) label_cover_kernel(LabelScene ls) {
             __syncwarp();
             unsigned sc = 0;  // first segment of the current batch
             while (sc < nseg) {
-                // ---- pass 1: row ranges of the batch's segments, crossings per row ----
-                for (int r = (int)lane; r < band_rows; r += 32) s_cur[r] = 0u;
+                // ---- pass 1: (row, bin) rectangles of the batch's segments, crossings per bucket ----
+                for (int k = (int)lane; k < n_buckets; k += 32) s_cur[k] = 0u;
                 __syncwarp();
                 unsigned n_in = 0, units = 0;  // segments / crossings taken into the batch so far
-                while (sc + n_in < nseg && n_in < (unsigned)kCovUnits) {
+                while (sc + n_in < nseg && n_in < (unsigned)(kCovUnits / 2)) {
                     const unsigned j = sc + n_in + lane;
                     int r0 = 1, r1 = 0, b0 = 0, b1 = 0;
-                    if (j < nseg && n_in + lane < (unsigned)kCovUnits) {
+                    const bool in_range = j < nseg && n_in + lane < (unsigned)(kCovUnits / 2);
+                    if (in_range) {
                         const DevSeg sg = segs[j];
                         r0 = max(f64_as_i32(floor(fmin(sg.y0, sg.y1))), row_lo) - row_lo;
                         r1 = min(f64_as_i32(floor(fmax(sg.y0, sg.y1))), row_lo + band_rows - 1) - row_lo;
@@ -2137,94 +2102,110 @@ __global__ void __launch_bounds__(32) label_cover_kernel(LabelScene ls) {
                         b1 = (int)(max(0ll, min(xb, (long long)W - 1)) / bin_w);
                     }
                     const unsigned nr = r1 >= r0 ? (unsigned)(r1 - r0 + 1) : 0u;
-                    unsigned incl = nr;
+                    const unsigned ne = nr * (unsigned)(b1 - b0 + 1);  // one crossing per (row, bin) of the rectangle
+                    unsigned incl = ne;
                     for (int o = 1; o < 32; o <<= 1) {
                         const unsigned y = __shfl_up_sync(kFull, incl, o);
                         if ((int)lane >= o) incl += y;
                     }
-                    // the lanes whose crossings still fit into the batch (a prefix; a segment has at most kCovRows crossings)
-                    const unsigned fit = __ballot_sync(kFull, units + incl <= (unsigned)kCovUnits && j < nseg && n_in + lane < (unsigned)kCovUnits);
+                    // the lanes whose crossings still fit into the batch (a prefix); a single oversized segment is taken alone
+                    const unsigned fit = __ballot_sync(kFull, in_range && (units + incl <= (unsigned)kCovUnits || (units == 0u && lane == 0u && n_in == 0u)));
                     const unsigned take = (fit == kFull) ? 32u : (unsigned)(__ffs(~fit) - 1);
                     if (take == 0u) break;
-                    if (lane < take) s_rng[n_in + lane] = nr ? ((unsigned)r0 | (nr << 7) | ((unsigned)b0 << 15) | ((unsigned)b1 << 23)) : 0u;
-                    // count per row: the union of the taken lanes' row ranges is short (a glyph is a few rows tall)
+                    if (lane < take) s_rng[n_in + lane] = nr ? ((unsigned)r0 | (nr << 7) | ((unsigned)b0 << 15) | ((unsigned)(b1 - b0) << 23)) : 0u;
                     const bool mine = lane < take && nr;
-                    int lo = mine ? r0 : 0x7fffffff, hi = mine ? r1 : -1;
+                    int rlo = mine ? r0 : 0x7fffffff, rhi = mine ? r1 : -1, blo = mine ? b0 : 0x7fffffff, bhi = mine ? b1 : -1;
                     for (int o = 16; o > 0; o >>= 1) {
-                        lo = min(lo, __shfl_xor_sync(kFull, lo, o));
-                        hi = max(hi, __shfl_xor_sync(kFull, hi, o));
+                        rlo = min(rlo, __shfl_xor_sync(kFull, rlo, o));
+                        rhi = max(rhi, __shfl_xor_sync(kFull, rhi, o));
+                        blo = min(blo, __shfl_xor_sync(kFull, blo, o));
+                        bhi = max(bhi, __shfl_xor_sync(kFull, bhi, o));
                     }
-                    for (int r = lo; r <= hi; ++r) {
-                        const unsigned m = __ballot_sync(kFull, mine && r0 <= r && r <= r1);
-                        if (lane == 0 && m) s_cur[r] += (unsigned)__popc(m);
-                    }
+                    for (int r = rlo; r <= rhi; ++r)
+                        for (int bb = blo; bb <= bhi; ++bb) {
+                            const unsigned m = __ballot_sync(kFull, mine && r0 <= r && r <= r1 && b0 <= bb && bb <= b1);
+                            if (lane == 0 && m) s_cur[r * nbins + bb] += (unsigned)__popc(m);
+                        }
                     __syncwarp();
                     units += __shfl_sync(kFull, incl, (int)take - 1);
                     n_in += take;
-                    if (take < 32u) break;
+                    if (take < 32u || units > (unsigned)kCovUnits) break;
                 }
-                if (n_in == 0u) break;  // (cannot happen: one segment always fits)
-                // ---- exclusive scan of the per-row counts ----
+                if (n_in == 0u) break;  // (cannot happen: one segment is always taken)
+                const bool oversized = units > (unsigned)kCovUnits;  // one segment with more crossings than a batch holds (a huge label)
+                // ---- exclusive scan of the per-bucket counts ----
                 {
                     unsigned carry = 0;
-                    for (int base = 0; base < band_rows; base += 32) {
-                        const int r = base + (int)lane;
-                        const unsigned v = r < band_rows ? s_cur[r] : 0u;
+                    for (int base = 0; base < n_buckets; base += 32) {
+                        const int k = base + (int)lane;
+                        const unsigned v = k < n_buckets ? s_cur[k] : 0u;
                         unsigned incl = v;
                         for (int o = 1; o < 32; o <<= 1) {
                             const unsigned y = __shfl_up_sync(kFull, incl, o);
                             if ((int)lane >= o) incl += y;
                         }
-                        if (r < band_rows) {
-                            s_off[r] = carry + incl - v;
-                            s_cur[r] = carry + incl - v;
+                        if (k < n_buckets) {
+                            s_off[k] = carry + incl - v;
+                            s_cur[k] = carry + incl - v;
                         }
                         carry += __shfl_sync(kFull, incl, 31);
                     }
-                    if (lane == 0) s_off[band_rows] = carry;
+                    if (lane == 0) s_off[n_buckets] = carry;
                 }
                 __syncwarp();
-                // ---- pass 2: stable scatter of the crossings into their row buckets ----
-                for (unsigned base = 0; base < n_in; base += 32) {
-                    const unsigned k = base + lane;
-                    const unsigned rg = k < n_in ? s_rng[k] : 0u;
-                    const int r0 = (int)(rg & 0x7fu), nr = (int)((rg >> 7) & 0xffu);
-                    const bool mine = nr != 0;
-                    int lo = mine ? r0 : 0x7fffffff, hi = mine ? r0 + nr - 1 : -1;
-                    for (int o = 16; o > 0; o >>= 1) {
-                        lo = min(lo, __shfl_xor_sync(kFull, lo, o));
-                        hi = max(hi, __shfl_xor_sync(kFull, hi, o));
-                    }
-                    for (int r = lo; r <= hi; ++r) {
-                        const bool in = mine && r0 <= r && r < r0 + nr;
-                        const unsigned m = __ballot_sync(kFull, in);
-                        if (in) s_unit[s_cur[r] + (unsigned)__popc(m & ((1u << lane) - 1u))] = k;
-                        __syncwarp();
-                        if (lane == 0 && m) s_cur[r] += (unsigned)__popc(m);
-                        __syncwarp();
+                // ---- pass 2: stable scatter of the crossings into their buckets ----
+                if (!oversized) {
+                    for (unsigned base = 0; base < n_in; base += 32) {
+                        const unsigned k = base + lane;
+                        const unsigned rg = k < n_in ? s_rng[k] : 0u;
+                        const int r0 = (int)(rg & 0x7fu), nr = (int)((rg >> 7) & 0xffu), b0 = (int)((rg >> 15) & 0xffu), b1 = b0 + (int)(rg >> 23);
+                        const bool mine = nr != 0;
+                        int rlo = mine ? r0 : 0x7fffffff, rhi = mine ? r0 + nr - 1 : -1, blo = mine ? b0 : 0x7fffffff, bhi = mine ? b1 : -1;
+                        for (int o = 16; o > 0; o >>= 1) {
+                            rlo = min(rlo, __shfl_xor_sync(kFull, rlo, o));
+                            rhi = max(rhi, __shfl_xor_sync(kFull, rhi, o));
+                            blo = min(blo, __shfl_xor_sync(kFull, blo, o));
+                            bhi = max(bhi, __shfl_xor_sync(kFull, bhi, o));
+                        }
+                        for (int r = rlo; r <= rhi; ++r)
+                            for (int bb = blo; bb <= bhi; ++bb) {
+                                const bool in = mine && r0 <= r && r < r0 + nr && b0 <= bb && bb <= b1;
+                                const unsigned m = __ballot_sync(kFull, in);
+                                if (!m) continue;
+                                const unsigned at = s_cur[r * nbins + bb];
+                                if (in) s_unit[at + (unsigned)__popc(m & ((1u << lane) - 1u))] = (unsigned short)k;
+                                __syncwarp();
+                                if (lane == 0) s_cur[r * nbins + bb] = at + (unsigned)__popc(m);
+                                __syncwarp();
+                            }
                     }
                 }
                 __syncwarp();
-                // ---- pass 3: a lane per (row, column bin), the row's crossings in segment order ----
-                const int n_buckets = band_rows * nbins;
+                // ---- pass 3: a lane per bucket, every lane walks ITS OWN list (no lane waits for another one's crossing) ----
 #pragma unroll 1
-                for (int bk = (int)lane; bk < n_buckets; bk += 32) {
-                    const int r = bk / nbins, bin = bk - r * nbins;
+                for (int bk0 = 0; bk0 < n_buckets; bk0 += 32) {
+                    const int bk = bk0 + (int)lane;
+                    const bool live = bk < n_buckets;
+                    const int r = live ? bk / nbins : 0, bin = live ? bk - r * nbins : 0;
                     const int cx_lo = bin * bin_w, cx_hi = min(W, cx_lo + bin_w) - 1;  // my columns (cells of the label's arrays)
                     const int y = row_lo + r;
                     double* a = A + (size_t)(band + r) * W;
                     double* sacc = S + (size_t)(band + r) * W;
                     int kmn = 0x7fffffff, kmx = (int)0x80000000;
-                    const unsigned u1 = s_off[r + 1];
                     // Consecutive crossings mostly hit the same cell (a curve is ~64 sub-pixel segments): the cell being added to
                     // is kept in a register and written back when the sum moves on -- the same additions in the same order,
                     // without a load-add-store round trip through memory per segment.
                     int ca = -1, cs = -1;  // cached cell of `a` / `s` (-1: none)
                     double va = 0.0, vs = 0.0;
-                    for (unsigned u = s_off[r]; u < u1; ++u) {
-                        const unsigned k = s_unit[u];
-                        const unsigned rg = s_rng[k];
-                        if (bin < (int)((rg >> 15) & 0xffu) || bin > (int)(rg >> 23)) continue;  // cannot add into my columns
+                    unsigned u = live ? (oversized ? 0u : s_off[bk]) : 0u;
+                    const unsigned u1 = live ? (oversized ? 1u : s_off[bk + 1]) : 0u;
+                    for (; u < u1; ++u) {
+                        const unsigned k = oversized ? 0u : (unsigned)s_unit[u];
+                        if (oversized) {  // the single huge segment: every bucket of its rectangle looks at it
+                            const unsigned rg = s_rng[0];
+                            const int r0 = (int)(rg & 0x7fu), nr = (int)((rg >> 7) & 0xffu), b0 = (int)((rg >> 15) & 0xffu), b1 = b0 + (int)(rg >> 23);
+                            if (r < r0 || r >= r0 + nr || bin < b0 || bin > b1) continue;
+                        }
                         const DevSeg sg = segs[sc + k];
                         const double slope = (sg.x1 - sg.x0) / (sg.y1 - sg.y0);  // rasterizer.rs:34-35
                         const double rslope = 1.0 / slope;

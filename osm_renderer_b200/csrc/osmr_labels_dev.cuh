@@ -762,25 +762,34 @@ struct EmitSink {
             out[n] = sg;
         }
         ++n;
-        // NaN-ignoring min / max (f64::min / max)
-        min_x = fmin(min_x, fmin(x0, x1));
-        max_x = fmax(max_x, fmax(x0, x1));
-        min_y = fmin(min_y, fmin(y0, y1));
-        max_y = fmax(max_y, fmax(y0, y1));
+    }
+    // Bounds of everything a vertex draws, without looking at the segments: a subdivided curve stays inside the convex hull of
+    // its control points (every new point is a midpoint of two old ones, and a rounded midpoint of two doubles lies between
+    // them), so the control points bound it.  The bounds only size the coverage window of the label; one pixel of slack is
+    // added where they are turned into a pixel box.
+    __device__ void bound(double x, double y) {
+        min_x = fmin(min_x, x);  // NaN-ignoring min / max (f64::min / max)
+        max_x = fmax(max_x, x);
+        min_y = fmin(min_y, y);
+        max_y = fmax(max_y, y);
     }
     // draw_quad's flatness test (rasterizer.rs:86-107): hypot(p0-p1) + hypot(p1-p2) <= 1.0001 * hypot(p0-p2)
     __device__ bool flat_enough(double x0, double y0, double x1, double y1, double x2, double y2) {
         const double ax = fabs(x0 - x1), ay = fabs(y0 - y1), bx = fabs(x1 - x2), by = fabs(y1 - y2);
         const double cx = fabs(x0 - x2), cy = fabs(y0 - y2);
         {
-            // (|a| + |b|)^2 = A + B + 2 sqrt(A B) against 1.0001^2 C: one square root instead of three.  Both sides carry a few ulp
-            // of error, the decision is taken only with a 1e-11 relative margin -- far outside anything the rounding of the
-            // reference's own hypot sum could flip -- and everything closer goes to the three-root form below.
+            // |a| + |b| <= 1.0001 |c|  <=>  2 sqrt(A B) <= T with T = 1.0001^2 C - A - B  <=>  T >= 0 and 4 A B <= T^2 (A, B, C the
+            // squared lengths): no square root at all.  Both sides carry a few ulp of error; the decision is taken only with a
+            // 1e-10 relative margin -- far outside anything the rounding of the reference's own hypot sum could flip -- and
+            // everything closer goes to the three-root form below.
             const double A = ax * ax + ay * ay, B = bx * bx + by * by, C = cx * cx + cy * cy;
-            const double X = A + B + 2.0 * sqrt(A * B), Y = 1.00020001 * C;
-            if (X < 1e290 && Y < 1e290 && X > 1e-290 && Y > 1e-290) {
-                if (X < Y * (1.0 - 1e-11)) return true;
-                if (X > Y * (1.0 + 1e-11)) return false;
+            const double Y = 1.00020001 * C, T = Y - A - B, P = 4.0 * A * B, Q = T * T;
+            if (Y < 1e140 && Y > 1e-140 && A > 1e-140 && B > 1e-140) {
+                if (T < -1e-10 * Y) return false;
+                if (T > 1e-10 * Y) {
+                    if (P < Q * (1.0 - 1e-10)) return true;
+                    if (P > Q * (1.0 + 1e-10)) return false;
+                }
             }
         }
         const double lhs = sqrt(ax * ax + ay * ay) + sqrt(bx * bx + by * by);
@@ -890,12 +899,21 @@ __device__ __forceinline__ unsigned emit_vertex(const LabelDev& ld, const GlyphP
         tr(fx, fy, p1x, p1y);
         tr(tx, ty, p0x, p0y);
         sink.line(p0x, p0y, p1x, p1y);
+        if (sink.n) {
+            sink.bound(p0x, p0y);
+            sink.bound(p1x, p1y);
+        }
     } else {
         double p2x, p2y, p1x, p1y, p0x, p0y;
         tr(fx, fy, p2x, p2y);
         tr((double)v.cx * scale, (double)v.cy * scale, p1x, p1y);
         tr(tx, ty, p0x, p0y);
         sink.quad(p0x, p0y, p1x, p1y, p2x, p2y);
+        if (sink.n) {
+            sink.bound(p0x, p0y);
+            sink.bound(p1x, p1y);
+            sink.bound(p2x, p2y);
+        }
     }
     min_x = sink.min_x;
     max_x = sink.max_x;
@@ -1074,10 +1092,11 @@ __global__ void __launch_bounds__(128) label_finish_kernel(Scene s, LabelDev ld)
                 }
                 L.seg_begin = sb;
                 L.seg_count = n_segs;
-                L.bx0 = f64_as_i32(floor(min_x));
-                L.bx1 = f64_as_i32(floor(max_x)) + 1;  // the `s` column is one past the last `a` column
-                L.by0 = f64_as_i32(floor(min_y));
-                L.by1 = f64_as_i32(floor(max_y));
+                // (conservative bounds from the control points, one pixel of slack; the `s` column is one past the last `a` column)
+                L.bx0 = f64_as_i32(floor(min_x)) - 1;
+                L.bx1 = f64_as_i32(floor(max_x)) + 2;
+                L.by0 = f64_as_i32(floor(min_y)) - 1;
+                L.by1 = f64_as_i32(floor(max_y)) + 1;
                 // rows outside the label canvas cannot collide or draw; columns stay complete (the sweep is a prefix sum)
                 L.ry0 = max(L.by0, -D);
                 const long long rows = (long long)min(L.by1, 2 * D - 1) - L.ry0 + 1;
