@@ -1803,7 +1803,7 @@ static int labels_via_host(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_til
     if (!cover_list.empty())
         CK(cudaMemcpyAsync(ctx->d_cover_list.p, cover_list.data(), cover_list.size() * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_label_begin.p, lbegin.data(), (n_tiles + 1) * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemsetAsync(ctx->d_cover_cursor.p, 0, sizeof(unsigned), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_cover_cursor.p, 0, 2 * sizeof(unsigned), ctx->stream));
     LabelScene ls{};
     ls.labels = ctx->d_labels.p;
     ls.label_begin = ctx->d_label_begin.p;
@@ -1819,6 +1819,7 @@ static int labels_via_host(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_til
     ls.plane = ctx->label_plane.p;
     ls.D = D;
     ls.cover_cursor = ctx->d_cover_cursor.p;
+    ls.err_flag = ctx->d_cover_cursor.p + 1;
     if (ls.n_cover) {
         label_cover_kernel<<<std::min<unsigned>(ls.n_cover, (unsigned)ctx->num_sms * 16u), 32, 0, ctx->stream>>>(ls);
         CK(cudaGetLastError());
@@ -1826,7 +1827,10 @@ static int labels_via_host(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_til
     label_commit_kernel<<<n_tiles, kLabelThreads, 0, ctx->stream>>>(ls);
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev_label1, ctx->stream));
+    unsigned cover_err = 0;
+    CK(cudaMemcpyAsync(&cover_err, ctx->d_cover_cursor.p + 1, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));  // recs / segs live on this stack frame
+    if (cover_err) return ctx->fail(OSMR_E_CUDA, "internal error: a label coverage term fell outside its proven window");
     CK(cudaEventElapsedTime(&ctx->stats_label_device_ms, ctx->ev_label0, ctx->ev_label1));
     return OSMR_OK;
 }
@@ -2137,13 +2141,14 @@ static int label_device_enqueue(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t 
     label_vline_write_kernel<<<wide, 128, 0, st>>>(ld);
     label_curve_write_kernel<<<wide, 128, 0, st>>>(ld);
     CK(cudaGetLastError());
-    CK(cudaMemsetAsync(ctx->d_cover_cursor.p, 0, sizeof(unsigned), st));
+    CK(cudaMemsetAsync(ctx->d_cover_cursor.p, 0, 2 * sizeof(unsigned), st));
     LabelScene ls{};
     ls.labels = ctx->d_labels.p;
     ls.label_begin = ctx->d_label_begin.p;
     ls.segs = ctx->d_label_segs.p;
     ls.cover_list = ctx->d_cover_list.p;
     ls.cover_cursor = ctx->d_cover_cursor.p;
+    ls.err_flag = ctx->l_counters.p + LCNT_COVER_ERR;
     ls.icons = ctx->label_icons.p;
     ls.occ = ctx->label_occ.p;
     ls.acc_a = ctx->label_acc.p;
@@ -2168,6 +2173,7 @@ static int label_device_enqueue(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t 
 static int label_device_judge(osmr_ctx* ctx) {
     const unsigned* c = ctx->h_lcnt.p;
     if (c[LCNT_BAD]) return ctx->fail(OSMR_E_INVALID, "label references an entity, style or icon that does not exist");
+    if (c[LCNT_COVER_ERR]) return ctx->fail(OSMR_E_CUDA, "internal error: a label coverage term fell outside its proven window");
     if (c[LCNT_FALLBACK]) return 2;
     if (c[LCNT_OVERFLOW]) {
         unsigned long long cells;

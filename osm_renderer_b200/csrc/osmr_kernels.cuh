@@ -1983,6 +1983,7 @@ struct LabelScene {
     const unsigned* label_cnt;
     const unsigned* skip_flags;  // device layout: [0] overflow, [1] fallback -- nonzero: this attempt is abandoned
     unsigned* cover_cursor;      // work distribution of label_cover_kernel (zeroed before the launch)
+    unsigned* err_flag;          // raised when a pair falls outside its proven window (a logic error: the call fails loudly)
 };
 
 // ------------------------------------------------------------------------------------------------------
@@ -1991,16 +1992,20 @@ struct LabelScene {
 // save_to_figure (rasterizer.rs:109-148).
 //
 // The reference's flatness rule (1.0001) turns every curve into ~64 sub-pixel segments, so a label is thousands of segments that
-// each touch one or two cells of one pixel row.  f64 addition does not commute with reordering: a cell must receive its
-// contributions in segment order.  Cells of different ROWS never interact, so the unit of parallelism is the row: one warp owns
-// a label, takes its segments in batches, buckets the (segment, row) crossings of a batch by row with a STABLE counting sort
-// (shared memory; a few instructions per segment), and then every lane walks the bucket of its own rows in order, doing the area
-// arithmetic and adding straight into its private row of the coverage arrays -- no conflicts, no ordering protocol.
-// (Round 1 gave a warp 32 rows and made it scan ALL segments of the label per row group: 21 ms per C2 batch; an intermediate
-// version parallelised over segments and committed the additions lane by lane: 12.7 ms.)
+// each add into one or two cells.  f64 addition does not commute with reordering: a cell must receive its contributions in
+// segment order -- but only the ADDITIONS into one cell are ordered; the area arithmetic in front of them is not, and different
+// cells do not interact.  One warp owns a label and takes its segments in batches:
+//   A  lanes = (segment, row) crossings: the area arithmetic, fully parallel; every `+=` of draw_line becomes a pair
+//      (cell, value) in shared memory, in the reference's order
+//   B  stable counting sort of the pairs by cell (the batch's cells are a small window of the label: a glyph or two)
+//   C  lanes = cells: each lane adds the pairs of its cell, in order, to the cell's running value
+// Measured history of this kernel on the C2 batch: a warp per 32 rows scanning all segments 21 ms; ordered commit lane by lane
+// 12.7 ms; a lane per row 13.1 ms (3.7 of 32 lanes busy: a street name is a dozen rows); a lane per (row, column bin) 17.5 ms
+// (the crossings of a glyph pile up in a few buckets: 5 lanes busy).
 // ------------------------------------------------------------------------------------------------------
-constexpr int kCovUnits = 4096;  // (segment, row, column bin) crossings per batch
-constexpr int kCovRows = 128;    // rows per band (a taller label is processed band by band)
+constexpr int kCovPairs = 1024;  // pairs per batch
+constexpr int kCovKeys = 512;    // cells (x 2 arrays) of the batch's window
+constexpr int kCovRows = 128;    // rows whose key range is tracked in shared memory (a taller label is processed band by band)
 
 // draw_line of one segment restricted to pixel row y (rasterizer.rs:52-83); calls add_a(x, value) for every touched cell of `a`
 // and add_s(x, value) once
@@ -2037,12 +2042,15 @@ __device__ __forceinline__ void cover_segment_row(const DevSeg& sg, double slope
 
 __global__ void __launch_bounds__(32) label_cover_kernel(LabelScene ls) {
     constexpr unsigned kFull = 0xffffffffu;
-    constexpr int kBuckets = kCovRows;      // (row, column bin) buckets of a band: rows * bins <= kCovRows
-    __shared__ unsigned short s_unit[kCovUnits];  // segment (index inside the batch) of every crossing, bucketed, in segment order
-    __shared__ unsigned s_rng[kCovUnits / 2];     // per segment of the batch: first row (7 bits) | rows (8) | first bin (8) | bins - 1 (8)
-    __shared__ unsigned s_off[kBuckets + 1];
-    __shared__ unsigned s_cur[kBuckets];
-    __shared__ int s_kmin[kCovRows], s_kmax[kCovRows];  // touched key range per row of the band
+    __shared__ double s_val[kCovPairs];
+    __shared__ unsigned short s_key[kCovPairs];    // window-local key: (row * win_w + column) * 2 + (0: `a`, 1: `s`); 0xffff: unused slot
+    __shared__ unsigned short s_order[kCovPairs];  // pair positions sorted by key, stable
+    __shared__ unsigned short s_cnt[kCovKeys];
+    __shared__ unsigned short s_off[kCovKeys + 1];
+    __shared__ unsigned s_seg[32];  // per lane of a chunk: first row inside the band (8 bits) | rows (8) | pair slots per row (16)
+    __shared__ unsigned s_pre[33];  // prefix of crossings (rows) over the chunk's segments
+    __shared__ unsigned s_slot[32]; // first pair slot of every segment of the chunk
+    __shared__ int s_kmin[kCovRows], s_kmax[kCovRows];
     if (ls.skip_flags && (ls.skip_flags[0] | ls.skip_flags[1])) return;
     const unsigned n_cover = ls.n_cover_dev ? *ls.n_cover_dev : ls.n_cover;
     const unsigned lane = threadIdx.x;
@@ -2059,14 +2067,11 @@ __global__ void __launch_bounds__(32) label_cover_kernel(LabelScene ls) {
         double* S = ls.acc_s + L.cell_off;
         const DevSeg* segs = ls.segs + L.seg_begin;
         const unsigned nseg = L.seg_count;
+        OSMR_COUNT("lcover.labels", lane == 0);
+        OSMR_COUNT("lcover.segments", lane == 0 ? nseg : 0);
         for (int band = 0; band < R; band += kCovRows) {
             const int band_rows = min(kCovRows, R - band);
             const int row_lo = L.ry0 + band;  // pixel row of the band's first row
-            // A street name is a dozen rows tall: rows alone would keep a third of the lanes busy.  Cells of one row do not
-            // interact either, so a row is cut into column bins and a lane owns a (row, bin) bucket.
-            const int nbins = max(1, min(min(255, (W + 1) / 2), kBuckets / band_rows));
-            const int bin_w = (W + nbins - 1) / nbins;
-            const int n_buckets = band_rows * nbins;
             // nobody cleared the coverage cells: the band's rows are contiguous
             {
                 const size_t c0 = (size_t)band * (size_t)W, c1 = c0 + (size_t)band_rows * (size_t)W;
@@ -2080,168 +2085,260 @@ __global__ void __launch_bounds__(32) label_cover_kernel(LabelScene ls) {
                 s_kmax[r] = (int)0x80000000;
             }
             __syncwarp();
-            unsigned sc = 0;  // first segment of the current batch
+            unsigned sc = 0;  // next segment
             while (sc < nseg) {
-                // ---- pass 1: (row, bin) rectangles of the batch's segments, crossings per bucket ----
-                for (int k = (int)lane; k < n_buckets; k += 32) s_cur[k] = 0u;
+                // ================= a batch: chunks of 32 segments until the pair slots or the cell window are full =================
+                unsigned n_pairs = 0;  // pair slots handed out
+                int win_r0 = 0x7fffffff, win_r1 = -1, win_c0 = 0x7fffffff, win_c1 = -1;  // the batch's window (rows of the band, columns)
+                int win_w = 0;  // set when the window is frozen (the first chunk that does not fit ends the batch)
+                // ---- first sweep: which segments go into the batch, their window ----
+                unsigned n_in = 0;
+                {
+                    unsigned slots = 0;
+                    int r0w = 0x7fffffff, r1w = -1, c0w = 0x7fffffff, c1w = -1;
+                    while (sc + n_in < nseg) {
+                        const unsigned j = sc + n_in + lane;
+                        int r0 = 1, r1 = 0, c0 = 0, c1 = -1;
+                        if (j < nseg) {
+                            const DevSeg sg = segs[j];
+                            r0 = max(f64_as_i32(floor(fmin(sg.y0, sg.y1))), row_lo) - row_lo;
+                            r1 = min(f64_as_i32(floor(fmax(sg.y0, sg.y1))), row_lo + band_rows - 1) - row_lo;
+                            // columns the segment can add into: its own x extent, one key of slack on both sides (`s` goes to
+                            // x_to + 1; the interpolated x of a row may leave the segment's extent by a rounding error).  Keys
+                            // outside the label's columns are dropped when the pair is made.
+                            const long long xa = (long long)f64_as_i32(floor(fmin(sg.x0, sg.x1))) - 1 - L.bx0;
+                            const long long xb = (long long)f64_as_i32(floor(fmax(sg.x0, sg.x1))) + 2 - L.bx0;
+                            c0 = (int)max(0ll, min(xa, (long long)W - 1));
+                            c1 = (int)max(0ll, min(xb, (long long)W - 1));
+                        }
+                        const bool has = j < nseg && r1 >= r0;
+                        const unsigned need = has ? (unsigned)(r1 - r0 + 1) * (unsigned)(c1 - c0 + 2) : 0u;  // per row: the `a` cells + one `s`
+                        // the chunk is taken as a whole or not at all (except when it is the batch's first: then lane by lane)
+                        unsigned tot = need;
+                        int a0 = has ? r0 : 0x7fffffff, a1 = has ? r1 : -1, b0 = has ? c0 : 0x7fffffff, b1 = has ? c1 : -1;
+                        for (int o = 16; o > 0; o >>= 1) {
+                            tot += __shfl_xor_sync(kFull, tot, o);
+                            a0 = min(a0, __shfl_xor_sync(kFull, a0, o));
+                            a1 = max(a1, __shfl_xor_sync(kFull, a1, o));
+                            b0 = min(b0, __shfl_xor_sync(kFull, b0, o));
+                            b1 = max(b1, __shfl_xor_sync(kFull, b1, o));
+                        }
+                        const int nr0 = min(r0w, a0), nr1 = max(r1w, a1), nc0 = min(c0w, b0), nc1 = max(c1w, b1);
+                        const long long keys = (nr1 >= nr0) ? 2ll * (nr1 - nr0 + 1) * (nc1 - nc0 + 1) : 0ll;
+                        const unsigned n_lanes = min(32u, nseg - (sc + n_in));
+                        if (slots + tot <= (unsigned)kCovPairs && keys <= (long long)kCovKeys) {
+                            slots += tot;
+                            r0w = nr0;
+                            r1w = nr1;
+                            c0w = nc0;
+                            c1w = nc1;
+                            n_in += n_lanes;
+                            continue;
+                        }
+                        if (n_in) break;  // the batch is what fitted so far
+                        // the very first chunk does not fit: take its longest prefix of lanes that does (at least one lane: a
+                        // single segment that is too large for a batch is processed by the slow path below)
+                        unsigned take = 0;
+                        for (unsigned t = 1; t <= n_lanes; ++t) {
+                            unsigned ts = 0;
+                            int p0 = 0x7fffffff, p1 = -1, q0 = 0x7fffffff, q1 = -1;
+                            const bool in = lane < t;
+                            unsigned nd = in ? need : 0u;
+                            int x0 = in && has ? r0 : 0x7fffffff, x1 = in && has ? r1 : -1, y0 = in && has ? c0 : 0x7fffffff, y1 = in && has ? c1 : -1;
+                            for (int o = 16; o > 0; o >>= 1) {
+                                nd += __shfl_xor_sync(kFull, nd, o);
+                                x0 = min(x0, __shfl_xor_sync(kFull, x0, o));
+                                x1 = max(x1, __shfl_xor_sync(kFull, x1, o));
+                                y0 = min(y0, __shfl_xor_sync(kFull, y0, o));
+                                y1 = max(y1, __shfl_xor_sync(kFull, y1, o));
+                            }
+                            ts = nd;
+                            p0 = x0;
+                            p1 = x1;
+                            q0 = y0;
+                            q1 = y1;
+                            const long long kk = (p1 >= p0) ? 2ll * (p1 - p0 + 1) * (q1 - q0 + 1) : 0ll;
+                            if (ts <= (unsigned)kCovPairs && kk <= (long long)kCovKeys) {
+                                take = t;
+                                r0w = p0;
+                                r1w = p1;
+                                c0w = q0;
+                                c1w = q1;
+                            } else {
+                                break;
+                            }
+                        }
+                        n_in = take;
+                        break;
+                    }
+                    win_r0 = r0w;
+                    win_r1 = r1w;
+                    win_c0 = c0w;
+                    win_c1 = c1w;
+                }
+                if (n_in == 0u) {
+                    // ---- slow path: ONE segment larger than a batch (a very long edge): lane 0 adds it straight into the arrays ----
+                    if (lane == 0) {
+                        const DevSeg sg = segs[sc];
+                        const double slope = (sg.x1 - sg.x0) / (sg.y1 - sg.y0), rslope = 1.0 / slope;
+                        const int r0 = max(f64_as_i32(floor(fmin(sg.y0, sg.y1))), row_lo), r1 = min(f64_as_i32(floor(fmax(sg.y0, sg.y1))), row_lo + band_rows - 1);
+                        for (int y = r0; y <= r1; ++y) {
+                            const int r = y - row_lo;
+                            double* a = A + (size_t)(band + r) * W;
+                            double* sacc = S + (size_t)(band + r) * W;
+                            cover_segment_row(
+                                sg, slope, rslope, y,
+                                [&](int x, double v) {
+                                    const int cx = x - L.bx0;
+                                    if (cx >= 0 && cx < W) a[cx] += v;
+                                    s_kmin[r] = min(s_kmin[r], x);
+                                    s_kmax[r] = max(s_kmax[r], x);
+                                },
+                                [&](int x, double v) {
+                                    const int cx = x - L.bx0;
+                                    if (cx >= 0 && cx < W) sacc[cx] += v;
+                                    s_kmin[r] = min(s_kmin[r], x);
+                                    s_kmax[r] = max(s_kmax[r], x);
+                                });
+                        }
+                    }
+                    __syncwarp();
+                    sc += 1;
+                    continue;
+                }
+                OSMR_COUNT("lcover.batches", lane == 0);
+                win_w = win_c1 >= win_c0 ? win_c1 - win_c0 + 1 : 1;
+                const int n_keys = (win_r1 >= win_r0) ? 2 * (win_r1 - win_r0 + 1) * win_w : 0;
+                for (int k = (int)lane; k < n_keys; k += 32) s_cnt[k] = 0;
                 __syncwarp();
-                unsigned n_in = 0, units = 0;  // segments / crossings taken into the batch so far
-                while (sc + n_in < nseg && n_in < (unsigned)(kCovUnits / 2)) {
-                    const unsigned j = sc + n_in + lane;
-                    int r0 = 1, r1 = 0, b0 = 0, b1 = 0;
-                    const bool in_range = j < nseg && n_in + lane < (unsigned)(kCovUnits / 2);
-                    if (in_range) {
+                // ---- A: the area arithmetic, a lane per (segment, row) crossing; pairs land in order ----
+                for (unsigned base = 0; base < n_in; base += 32) {
+                    const unsigned j = sc + base + lane;
+                    int r0 = 1, r1 = 0, c0 = 0, c1 = -1;
+                    if (base + lane < n_in) {
                         const DevSeg sg = segs[j];
                         r0 = max(f64_as_i32(floor(fmin(sg.y0, sg.y1))), row_lo) - row_lo;
                         r1 = min(f64_as_i32(floor(fmax(sg.y0, sg.y1))), row_lo + band_rows - 1) - row_lo;
-                        // column bins the segment can add into: its own x extent, one key of slack on both sides (`s` goes to
-                        // x_to + 1; the interpolated x of a row may leave the segment's extent by a rounding error)
                         const long long xa = (long long)f64_as_i32(floor(fmin(sg.x0, sg.x1))) - 1 - L.bx0;
                         const long long xb = (long long)f64_as_i32(floor(fmax(sg.x0, sg.x1))) + 2 - L.bx0;
-                        b0 = (int)(max(0ll, min(xa, (long long)W - 1)) / bin_w);
-                        b1 = (int)(max(0ll, min(xb, (long long)W - 1)) / bin_w);
+                        c0 = (int)max(0ll, min(xa, (long long)W - 1));
+                        c1 = (int)max(0ll, min(xb, (long long)W - 1));
                     }
                     const unsigned nr = r1 >= r0 ? (unsigned)(r1 - r0 + 1) : 0u;
-                    const unsigned ne = nr * (unsigned)(b1 - b0 + 1);  // one crossing per (row, bin) of the rectangle
-                    unsigned incl = ne;
+                    const unsigned per_row = (unsigned)(c1 - c0 + 2);
+                    unsigned incl = nr;
                     for (int o = 1; o < 32; o <<= 1) {
                         const unsigned y = __shfl_up_sync(kFull, incl, o);
                         if ((int)lane >= o) incl += y;
                     }
-                    // the lanes whose crossings still fit into the batch (a prefix); a single oversized segment is taken alone
-                    const unsigned fit = __ballot_sync(kFull, in_range && (units + incl <= (unsigned)kCovUnits || (units == 0u && lane == 0u && n_in == 0u)));
-                    const unsigned take = (fit == kFull) ? 32u : (unsigned)(__ffs(~fit) - 1);
-                    if (take == 0u) break;
-                    if (lane < take) s_rng[n_in + lane] = nr ? ((unsigned)r0 | (nr << 7) | ((unsigned)b0 << 15) | ((unsigned)(b1 - b0) << 23)) : 0u;
-                    const bool mine = lane < take && nr;
-                    int rlo = mine ? r0 : 0x7fffffff, rhi = mine ? r1 : -1, blo = mine ? b0 : 0x7fffffff, bhi = mine ? b1 : -1;
-                    for (int o = 16; o > 0; o >>= 1) {
-                        rlo = min(rlo, __shfl_xor_sync(kFull, rlo, o));
-                        rhi = max(rhi, __shfl_xor_sync(kFull, rhi, o));
-                        blo = min(blo, __shfl_xor_sync(kFull, blo, o));
-                        bhi = max(bhi, __shfl_xor_sync(kFull, bhi, o));
-                    }
-                    for (int r = rlo; r <= rhi; ++r)
-                        for (int bb = blo; bb <= bhi; ++bb) {
-                            const unsigned m = __ballot_sync(kFull, mine && r0 <= r && r <= r1 && b0 <= bb && bb <= b1);
-                            if (lane == 0 && m) s_cur[r * nbins + bb] += (unsigned)__popc(m);
-                        }
                     __syncwarp();
-                    units += __shfl_sync(kFull, incl, (int)take - 1);
-                    n_in += take;
-                    if (take < 32u || units > (unsigned)kCovUnits) break;
+                    s_seg[lane] = nr ? ((unsigned)r0 | (nr << 8) | (per_row << 16)) : 0u;
+                    s_pre[lane] = incl - nr;
+                    if (lane == 31) s_pre[32] = incl;
+                    // pair slots of the chunk's crossings: unit u of segment q starts at base_slot + (slots of the segments
+                    // before q) + (u's row index inside q) * per_row(q): a second prefix, over slots
+                    unsigned slot_incl = nr * per_row;
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const unsigned y = __shfl_up_sync(kFull, slot_incl, o);
+                        if ((int)lane >= o) slot_incl += y;
+                    }
+                    s_slot[lane] = n_pairs + slot_incl - nr * per_row;
+                    const unsigned chunk_slots = __shfl_sync(kFull, slot_incl, 31);
+                    __syncwarp();
+                    const unsigned n_units = s_pre[32];
+                    for (unsigned ub = 0; ub < n_units; ub += 32) {
+                        const unsigned un = ub + lane;
+                        if (un < n_units) {
+                            int lo = 0, hi = 32;  // largest q with s_pre[q] <= un
+                            while (hi - lo > 1) {
+                                const int mid = (lo + hi) >> 1;
+                                if (s_pre[mid] <= un)
+                                    lo = mid;
+                                else
+                                    hi = mid;
+                            }
+                            const unsigned sgw = s_seg[lo];
+                            const int q_r0 = (int)(sgw & 0xffu);
+                            const unsigned q_per = sgw >> 16;
+                            const unsigned row_i = un - s_pre[lo];
+                            const int r = q_r0 + (int)row_i;
+                            const unsigned slot0 = s_slot[lo] + row_i * q_per;
+                            const DevSeg sg = segs[sc + base + (unsigned)lo];
+                            const double slope = (sg.x1 - sg.x0) / (sg.y1 - sg.y0);  // rasterizer.rs:34-35
+                            const double rslope = 1.0 / slope;
+                            unsigned w = 0;  // slots written
+                            int kmn = 0x7fffffff, kmx = (int)0x80000000;
+                            auto put = [&](int x, double v, unsigned arr) {
+                                const int cx = x - L.bx0;
+                                kmn = min(kmn, x);
+                                kmx = max(kmx, x);
+                                if (cx < 0 || cx >= W) return;  // a key outside the label's columns: tracked, never stored
+                                if (cx < win_c0 || cx > win_c1 || w >= q_per) {  // outside the proven window: never silent
+                                    atomicOr(ls.err_flag, 1u);
+                                    return;
+                                }
+                                const unsigned key = (unsigned)(((r - win_r0) * win_w + (cx - win_c0)) * 2) + arr;
+                                s_val[slot0 + w] = v;
+                                s_key[slot0 + w] = (unsigned short)key;
+                                atomicAdd(reinterpret_cast<unsigned*>(&s_cnt[key & ~1u]), (key & 1u) ? 0x10000u : 1u);  // two 16-bit counters per word
+                                ++w;
+                            };
+                            cover_segment_row(
+                                sg, slope, rslope, row_lo + r, [&](int x, double v) { put(x, v, 0u); }, [&](int x, double v) { put(x, v, 1u); });
+                            for (; w < q_per; ++w) s_key[slot0 + w] = 0xffffu;
+                            if (kmn != 0x7fffffff) atomicMin(&s_kmin[r], kmn);
+                            if (kmx != (int)0x80000000) atomicMax(&s_kmax[r], kmx);
+                        }
+                    }
+                    n_pairs += chunk_slots;
+                    __syncwarp();
                 }
-                if (n_in == 0u) break;  // (cannot happen: one segment is always taken)
-                const bool oversized = units > (unsigned)kCovUnits;  // one segment with more crossings than a batch holds (a huge label)
-                // ---- exclusive scan of the per-bucket counts ----
+                OSMR_COUNT("lcover.pairs", lane == 0 ? n_pairs : 0);
+                // ---- B: stable counting sort of the pairs by key ----
                 {
                     unsigned carry = 0;
-                    for (int base = 0; base < n_buckets; base += 32) {
-                        const int k = base + (int)lane;
-                        const unsigned v = k < n_buckets ? s_cur[k] : 0u;
+                    for (int kb = 0; kb < n_keys; kb += 32) {
+                        const int k = kb + (int)lane;
+                        const unsigned v = k < n_keys ? s_cnt[k] : 0u;
                         unsigned incl = v;
                         for (int o = 1; o < 32; o <<= 1) {
                             const unsigned y = __shfl_up_sync(kFull, incl, o);
                             if ((int)lane >= o) incl += y;
                         }
-                        if (k < n_buckets) {
-                            s_off[k] = carry + incl - v;
-                            s_cur[k] = carry + incl - v;
+                        if (k < n_keys) {
+                            s_off[k] = (unsigned short)(carry + incl - v);
+                            s_cnt[k] = (unsigned short)(carry + incl - v);  // becomes the running cursor
                         }
                         carry += __shfl_sync(kFull, incl, 31);
                     }
-                    if (lane == 0) s_off[n_buckets] = carry;
+                    if (lane == 0) s_off[n_keys] = (unsigned short)carry;
                 }
                 __syncwarp();
-                // ---- pass 2: stable scatter of the crossings into their buckets ----
-                if (!oversized) {
-                    for (unsigned base = 0; base < n_in; base += 32) {
-                        const unsigned k = base + lane;
-                        const unsigned rg = k < n_in ? s_rng[k] : 0u;
-                        const int r0 = (int)(rg & 0x7fu), nr = (int)((rg >> 7) & 0xffu), b0 = (int)((rg >> 15) & 0xffu), b1 = b0 + (int)(rg >> 23);
-                        const bool mine = nr != 0;
-                        int rlo = mine ? r0 : 0x7fffffff, rhi = mine ? r0 + nr - 1 : -1, blo = mine ? b0 : 0x7fffffff, bhi = mine ? b1 : -1;
-                        for (int o = 16; o > 0; o >>= 1) {
-                            rlo = min(rlo, __shfl_xor_sync(kFull, rlo, o));
-                            rhi = max(rhi, __shfl_xor_sync(kFull, rhi, o));
-                            blo = min(blo, __shfl_xor_sync(kFull, blo, o));
-                            bhi = max(bhi, __shfl_xor_sync(kFull, bhi, o));
-                        }
-                        for (int r = rlo; r <= rhi; ++r)
-                            for (int bb = blo; bb <= bhi; ++bb) {
-                                const bool in = mine && r0 <= r && r < r0 + nr && b0 <= bb && bb <= b1;
-                                const unsigned m = __ballot_sync(kFull, in);
-                                if (!m) continue;
-                                const unsigned at = s_cur[r * nbins + bb];
-                                if (in) s_unit[at + (unsigned)__popc(m & ((1u << lane) - 1u))] = (unsigned short)k;
-                                __syncwarp();
-                                if (lane == 0) s_cur[r * nbins + bb] = at + (unsigned)__popc(m);
-                                __syncwarp();
-                            }
-                    }
+                for (unsigned pb = 0; pb < n_pairs; pb += 32) {
+                    const unsigned p = pb + lane;
+                    const unsigned key = p < n_pairs ? (unsigned)s_key[p] : 0xffffu;
+                    const bool live = key != 0xffffu;
+                    // lanes with the same key, in lane (= reference) order; dead lanes get keys of their own
+                    const unsigned peers = __match_any_sync(kFull, live ? key : (0x10000u + lane));
+                    if (live) s_order[(unsigned)s_cnt[key] + (unsigned)__popc(peers & ((1u << lane) - 1u))] = (unsigned short)p;
+                    __syncwarp();
+                    if (live && (peers & ((1u << lane) - 1u)) == 0u) s_cnt[key] = (unsigned short)(s_cnt[key] + __popc(peers));
+                    __syncwarp();
                 }
-                __syncwarp();
-                // ---- pass 3: a lane per bucket, every lane walks ITS OWN list (no lane waits for another one's crossing) ----
-#pragma unroll 1
-                for (int bk0 = 0; bk0 < n_buckets; bk0 += 32) {
-                    const int bk = bk0 + (int)lane;
-                    const bool live = bk < n_buckets;
-                    const int r = live ? bk / nbins : 0, bin = live ? bk - r * nbins : 0;
-                    const int cx_lo = bin * bin_w, cx_hi = min(W, cx_lo + bin_w) - 1;  // my columns (cells of the label's arrays)
-                    const int y = row_lo + r;
-                    double* a = A + (size_t)(band + r) * W;
-                    double* sacc = S + (size_t)(band + r) * W;
-                    int kmn = 0x7fffffff, kmx = (int)0x80000000;
-                    // Consecutive crossings mostly hit the same cell (a curve is ~64 sub-pixel segments): the cell being added to
-                    // is kept in a register and written back when the sum moves on -- the same additions in the same order,
-                    // without a load-add-store round trip through memory per segment.
-                    int ca = -1, cs = -1;  // cached cell of `a` / `s` (-1: none)
-                    double va = 0.0, vs = 0.0;
-                    unsigned u = live ? (oversized ? 0u : s_off[bk]) : 0u;
-                    const unsigned u1 = live ? (oversized ? 1u : s_off[bk + 1]) : 0u;
-                    for (; u < u1; ++u) {
-                        const unsigned k = oversized ? 0u : (unsigned)s_unit[u];
-                        if (oversized) {  // the single huge segment: every bucket of its rectangle looks at it
-                            const unsigned rg = s_rng[0];
-                            const int r0 = (int)(rg & 0x7fu), nr = (int)((rg >> 7) & 0xffu), b0 = (int)((rg >> 15) & 0xffu), b1 = b0 + (int)(rg >> 23);
-                            if (r < r0 || r >= r0 + nr || bin < b0 || bin > b1) continue;
+                // ---- C: a lane per cell, its pairs in order ----
+                for (int kb = 0; kb < n_keys; kb += 32) {
+                    const int k = kb + (int)lane;
+                    if (k < n_keys) {
+                        const unsigned u0 = s_off[k], u1 = s_off[k + 1];
+                        if (u1 > u0) {
+                            const int cell = k >> 1;
+                            const int r = win_r0 + cell / win_w, cx = win_c0 + cell % win_w;
+                            double* dst = ((k & 1) ? S : A) + (size_t)(band + r) * W + cx;
+                            double acc = *dst;
+                            for (unsigned u = u0; u < u1; ++u) acc += s_val[s_order[u]];
+                            *dst = acc;
                         }
-                        const DevSeg sg = segs[sc + k];
-                        const double slope = (sg.x1 - sg.x0) / (sg.y1 - sg.y0);  // rasterizer.rs:34-35
-                        const double rslope = 1.0 / slope;
-                        cover_segment_row(
-                            sg, slope, rslope, y,
-                            [&](int x, double v) {
-                                const int cx = x - L.bx0;
-                                if (cx >= cx_lo && cx <= cx_hi) {
-                                    if (cx != ca) {
-                                        if (ca >= 0) a[ca] = va;
-                                        ca = cx;
-                                        va = a[cx];
-                                    }
-                                    va += v;
-                                }
-                                kmn = min(kmn, x);  // (every crossing is processed by at least one bin: the row's key range is complete)
-                                kmx = max(kmx, x);
-                            },
-                            [&](int x, double v) {
-                                const int cx = x - L.bx0;
-                                if (cx >= cx_lo && cx <= cx_hi) {
-                                    if (cx != cs) {
-                                        if (cs >= 0) sacc[cs] = vs;
-                                        cs = cx;
-                                        vs = sacc[cx];
-                                    }
-                                    vs += v;
-                                }
-                                kmn = min(kmn, x);
-                                kmx = max(kmx, x);
-                            });
                     }
-                    if (ca >= 0) a[ca] = va;
-                    if (cs >= 0) sacc[cs] = vs;
-                    if (kmn != 0x7fffffff) atomicMin(&s_kmin[r], kmn);
-                    if (kmx != (int)0x80000000) atomicMax(&s_kmax[r], kmx);
                 }
                 __syncwarp();
                 sc += n_in;

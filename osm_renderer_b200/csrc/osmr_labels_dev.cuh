@@ -62,6 +62,7 @@ enum {
     LCNT_COVER = 12,    // labels whose text coverage label_cover_kernel computes
     LCNT_VERTS = 13,    // outline vertex instances handed out (one per vertex of every placed glyph)
     LCNT_CURVES = 14,   // of those, curves (the expensive ones: they get a compact work list of their own)
+    LCNT_COVER_ERR = 3,  // label_cover_kernel: a pair fell outside its proven window (a logic error, never silent)
     LCNT_SCAN_OVF = 15,  // (overflow word of the block-sum scan: segment counts beyond 2^32 also trip the capacity check)
     LCNT_COUNT = 16
 };

@@ -365,6 +365,14 @@ inline T shfl(int site, T v, int src) {
     memcpy(&out, &got, sizeof(T));
     return out;
 }
+inline unsigned match_any(int site, unsigned long long v) {
+    Rendezvous& r = cur_warp();
+    const int b = rendezvous(r, cur_lane(), site, v, "warp collective");
+    unsigned m = 0;
+    for (int i = 0; i < 32; ++i)
+        if (((r.arrived_mask[b][0] >> i) & 1u) && r.val[b][i] == v) m |= 1u << i;
+    return m;
+}
 inline void syncwarp(int site) { rendezvous(cur_warp(), cur_lane(), site, 0, "__syncwarp"); }
 inline void syncthreads(int site) { rendezvous(E().block, E().cur, site, 0, "__syncthreads"); }
 
@@ -377,6 +385,7 @@ inline void syncthreads(int site) { rendezvous(E().block, E().cur, site, 0, "__s
 #define __shfl_up_sync(m, v, d) emu::shfl(__LINE__, (v), emu::cur_lane() >= (int)(d) ? emu::cur_lane() - (int)(d) : emu::cur_lane())
 #define __shfl_down_sync(m, v, d) emu::shfl(__LINE__, (v), emu::cur_lane() + (int)(d) < 32 ? emu::cur_lane() + (int)(d) : emu::cur_lane())
 #define __shfl_xor_sync(m, v, x) emu::shfl(__LINE__, (v), emu::cur_lane() ^ (int)(x))
+#define __match_any_sync(m, v) emu::match_any(__LINE__, (unsigned long long)(v))
 #define __syncwarp() emu::syncwarp(__LINE__)
 #define __syncthreads() emu::syncthreads(__LINE__)
 
