@@ -160,6 +160,7 @@ struct osmr_ctx {
     DevBuf<GlyphPlace> l_gplace;
     DevBuf<unsigned> l_place_vinst, l_vinst_place, l_vcnt, l_curve_list, l_scan_blocks;
     DevBuf<double4> l_vbox;
+    DevBuf<unsigned long long> l_curve_shape;
     size_t l_verts_cap = 0;
     DevBuf<double2> l_ring_pts;
     DevBuf<unsigned char> l_heap;
@@ -216,6 +217,9 @@ struct osmr_ctx {
         }
     } scrB;
     cudaStream_t stream2 = nullptr;
+    cudaStream_t label_stream = nullptr;  // the label pass runs beside the area passes; raster_kernel waits for label_done
+    cudaEvent_t label_done = nullptr, label_go = nullptr;
+    bool label_async = false;             // the label plane of this draw is produced on label_stream
     cudaEvent_t ev_wall0 = nullptr, ev_wall1 = nullptr, join2 = nullptr;  // device wall time of a draw across both streams
     cudaEvent_t prep_done = nullptr;  // upload + style calculators on `stream`: what stream2's first chunk waits for
     bool two_streams = true;          // debug key "two_streams"
@@ -309,6 +313,9 @@ int osmr_ctx_create(int device, osmr_ctx** out_ctx) try {
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->label_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->label_done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->label_go, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->prep_done, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->join2, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_wall0);
@@ -409,6 +416,9 @@ void osmr_ctx_destroy(osmr_ctx* ctx) {
     if (ctx->ev_wall0) cudaEventDestroy(ctx->ev_wall0);
     if (ctx->ev_wall1) cudaEventDestroy(ctx->ev_wall1);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+    if (ctx->label_stream) cudaStreamDestroy(ctx->label_stream);
+    if (ctx->label_done) cudaEventDestroy(ctx->label_done);
+    if (ctx->label_go) cudaEventDestroy(ctx->label_go);
     ctx->calc_table.release();
     ctx->out.release();
     for (auto& e : ctx->ev)
@@ -1032,6 +1042,7 @@ static int launch_chunk(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t fla
     launches += 5;
     CK(cudaEventRecord(ev[1], st));
     const unsigned blocks = (unsigned)((D / kBW) * (D / kBH));
+    if (ctx->label_async && ctx->label_plane_active) CK(cudaStreamWaitEvent(st, ctx->label_done, 0));
     raster_kernel<<<tc * blocks, kRasterThreads, 0, st>>>(s);
     ++launches;
     CK(cudaGetLastError());
@@ -2026,7 +2037,11 @@ static int label_device_enqueue(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t 
         }
     }
     const uint32_t n_labels = label_begin[n_tiles];
-    cudaStream_t st = ctx->stream;
+    // The label pass has its own stream: it only meets the area passes at raster_kernel's export, so its kernels (long, latency
+    // bound, few warps per SM) run beside plan / geometry / fill rows / bin / line cover instead of in front of them.
+    cudaStream_t st = ctx->label_stream;
+    CK(cudaEventRecord(ctx->label_go, ctx->stream));  // (the batch description -- tiles -- was uploaded on the compute stream)
+    CK(cudaStreamWaitEvent(st, ctx->label_go, 0));
     // first guesses of the bump-allocated scratch (grown by label_device_judge)
     if (!ctx->l_places_cap) ctx->l_places_cap = 1u << 18;
     if (!ctx->l_segs_cap) ctx->l_segs_cap = 1u << 21;
@@ -2050,6 +2065,7 @@ static int label_device_enqueue(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t 
     CK(ctx->l_vcnt.reserve(ctx->l_verts_cap + 8));
     CK(ctx->l_vbox.reserve(ctx->l_verts_cap + 8));
     CK(ctx->l_curve_list.reserve(ctx->l_verts_cap + 8));
+    CK(ctx->l_curve_shape.reserve(4 * ctx->l_verts_cap + 8));
     CK(ctx->l_scan_blocks.reserve(n_scan_blocks + 8));
     CK(ctx->d_label_segs.reserve(ctx->l_segs_cap));
     CK(ctx->d_cover_list.reserve((size_t)n_labels + 1));
@@ -2113,6 +2129,7 @@ static int label_device_enqueue(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t 
     ld.vcnt = ctx->l_vcnt.p;
     ld.vbox = ctx->l_vbox.p;
     ld.curve_list = ctx->l_curve_list.p;
+    ld.curve_shape = ctx->l_curve_shape.p;
     ld.verts_cap = (unsigned)std::min<size_t>(ctx->l_verts_cap, 0xfffffff0u);
     ld.scan_blocks = ctx->l_scan_blocks.p;
     ld.n_scan_blocks = n_scan_blocks;
@@ -2165,6 +2182,8 @@ static int label_device_enqueue(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t 
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev_label1, st));
     CK(cudaMemcpyAsync(ctx->h_lcnt.p, ctx->l_counters.p, LCNT_COUNT * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(ctx->label_done, st));
+    ctx->label_async = true;
     return OSMR_OK;
 }
 
@@ -2229,8 +2248,10 @@ int osmr_draw_tiles_labeled(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_ti
         }
         const float enqueue_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_host0).count();
         ctx->label_plane_active = true;
-        rc = osmr_batch_draw(ctx, canvas_rgb, flags, out, nullptr);  // synchronises the stream
+        rc = osmr_batch_draw(ctx, canvas_rgb, flags, out, nullptr);  // synchronises the compute streams (which waited for label_done)
         ctx->label_plane_active = false;
+        ctx->label_async = false;
+        cudaStreamSynchronize(ctx->label_stream);  // the counters' copy is the last thing on it
         if (rc) return rc;
         const int verdict = label_device_judge(ctx);
         if (verdict < 0) return verdict;

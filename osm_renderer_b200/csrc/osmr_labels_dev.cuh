@@ -122,6 +122,7 @@ struct LabelDev {
     unsigned* vcnt;         // per vertex instance: segments it draws; after the scan: offset of its first segment ([n]: total)
     double4* vbox;          // per vertex instance: bounds of its segments (min x, max x, min y, max y)
     unsigned* curve_list;   // vertex instances that are curves
+    unsigned long long* curve_shape;  // per curve: 4 words, the shape of its subdivision tree (EmitSink::quad)
     unsigned verts_cap;
     unsigned* scan_blocks;  // block sums of the segment-offset scan
     unsigned n_scan_blocks;
@@ -808,19 +809,49 @@ struct EmitSink {
     // control points by repeating the midpoint steps from the root along its path.  Same operations on the same operands as the
     // recursion, so the points are bit-identical; the explicit stack this replaces lived in local memory and its loads were
     // half of the kernel's stall samples.
+    // shape of the subdivision tree, one bit per visited node in visiting order (1: subdivided).  The counting sweep records it
+    // (shape_out), the writing sweep replays it (shape_in) and never evaluates a flatness test again.
+    unsigned long long* shape_out;
+    const unsigned long long* shape_in;
     __device__ void quad(double x0, double y0, double x1, double y1, double x2, double y2) {
         constexpr int kMaxDepth = 30;
+        constexpr unsigned kShapeBits = 256;
         unsigned path = 0u;
         int depth = 0;
         double a0 = x0, b0 = y0, a1 = x1, b1 = y1, a2 = x2, b2 = y2;
+        // (p1, p2) of the current node's parent, valid while the current node is a first half reached by descending: its
+        // second half then follows without walking down from the root again
+        double pa1 = 0.0, pb1 = 0.0, pa2 = 0.0, pb2 = 0.0;
+        unsigned node = 0;  // visited nodes so far
+        unsigned long long word = 0ull;
+        const bool replay = shape_in != nullptr && (shape_in[3] >> 63) == 0ull;  // bit 255: the tree has more than 255 nodes
+        if (shape_in) word = shape_in[0];
         for (;;) {
-            bool flat = flat_enough(a0, b0, a1, b1, a2, b2);
-            if (!flat && depth >= kMaxDepth) {  // absurd depth: not something the device decides
-                near_tie = true;
-                flat = true;
+            bool flat;
+            if (replay) {
+                flat = ((word >> (node & 63u)) & 1ull) == 0ull;
+            } else {
+                flat = flat_enough(a0, b0, a1, b1, a2, b2);
+                if (!flat && depth >= kMaxDepth) {  // absurd depth: not something the device decides
+                    near_tie = true;
+                    flat = true;
+                }
+                if (shape_out && node < kShapeBits - 1u) {
+                    if (!flat) word |= 1ull << (node & 63u);
+                    if ((node & 63u) == 63u) {
+                        shape_out[node >> 6] = word;
+                        word = 0ull;
+                    }
+                }
             }
+            ++node;
+            if (replay && (node & 63u) == 0u && node < kShapeBits) word = shape_in[node >> 6];
             if (!flat) {  // first half: (p0, (p0 + p1) / 2, m)
                 const double ax = (a0 + a1) / 2.0, ay = (b0 + b1) / 2.0, bx = (a1 + a2) / 2.0, by = (b1 + b2) / 2.0;
+                pa1 = a1;
+                pb1 = b1;
+                pa2 = a2;
+                pb2 = b2;
                 a2 = (ax + bx) / 2.0;
                 b2 = (ay + by) / 2.0;
                 a1 = ax;
@@ -830,12 +861,22 @@ struct EmitSink {
                 continue;
             }
             line(a0, b0, a2, b2);
+            if (depth > 0 && !(path & 1u)) {  // a first half (always reached by descending): its second half is (m, (p1 + p2) / 2, p2)
+                a0 = a2;
+                b0 = b2;
+                a1 = (pa1 + pa2) / 2.0;
+                b1 = (pb1 + pb2) / 2.0;
+                a2 = pa2;
+                b2 = pb2;
+                path |= 1u;
+                continue;
+            }
             while (depth > 0 && (path & 1u)) {  // both halves of this ancestor are done
                 path >>= 1;
                 --depth;
             }
-            if (depth == 0) return;
-            path |= 1u;  // the second half of that ancestor: (m, (p1 + p2) / 2, p2)
+            if (depth == 0) break;
+            path |= 1u;  // the second half of that ancestor: walk down from the root along its path
             a0 = x0;
             b0 = y0;
             a1 = x1;
@@ -858,12 +899,21 @@ struct EmitSink {
                 }
             }
         }
+        if (shape_out) {
+            if (node >= kShapeBits - 1u) {
+                shape_out[3] = 1ull << 63;  // too many nodes for the record: the writing sweep decides again
+            } else {
+                shape_out[node >> 6] = word;                               // the partial word (bits above `node` are zero)
+                if ((node >> 6) < 3u) shape_out[3] = 0ull;                 // (word 3 carries the overflow mark: always written)
+            }
+        }
     }
 };
 
 // One outline vertex -> its draw_line calls (count, bounds, optionally the segments themselves at out[0..)).
 __device__ __forceinline__ unsigned emit_vertex(const LabelDev& ld, const GlyphPlace& gp, const LabelPlace& lp, unsigned vi, unsigned v0, DevSeg* out,
-                                                double& min_x, double& max_x, double& min_y, double& max_y, bool& near_tie) {
+                                                double& min_x, double& max_x, double& min_y, double& max_y, bool& near_tie,
+                                                unsigned long long* shape_out = nullptr, const unsigned long long* shape_in = nullptr) {
     const DevVertex v = ld.verts[vi];
     if (v.type != 2 && v.type != 3) return 0u;  // a move draws nothing
     const double scale = lp.scale;
@@ -895,6 +945,8 @@ __device__ __forceinline__ unsigned emit_vertex(const LabelDev& ld, const GlyphP
     sink.min_y = min_y;
     sink.max_y = max_y;
     sink.near_tie = false;
+    sink.shape_out = shape_out;
+    sink.shape_in = shape_in;
     if (v.type == 2) {
         double p1x, p1y, p0x, p0y;
         tr(fx, fy, p1x, p1y);
@@ -950,7 +1002,8 @@ __global__ void __launch_bounds__(128) label_vfill_kernel(LabelDev ld) {
 }
 
 template <bool WRITE>
-__device__ __forceinline__ void label_vertex_instance(const LabelDev& ld, unsigned inst) {
+__device__ __forceinline__ void label_vertex_instance(const LabelDev& ld, unsigned inst, unsigned curve = 0xffffffffu) {
+    unsigned long long* shape = curve != 0xffffffffu ? ld.curve_shape + (size_t)curve * 4u : nullptr;
     const unsigned gi = ld.vinst_place[inst];
     const GlyphPlace gp = ld.gplace[gi];
     const LabelPlace lp = ld.place[gp.label];
@@ -961,9 +1014,9 @@ __device__ __forceinline__ void label_vertex_instance(const LabelDev& ld, unsign
     bool tie = false;
     if (WRITE) {
         const unsigned off = ld.vcnt[inst], n = ld.vcnt[inst + 1] - off;
-        if (n) emit_vertex(ld, gp, lp, vi, v0, ld.segs + off, mnx, mxx, mny, mxy, tie);
+        if (n) emit_vertex(ld, gp, lp, vi, v0, ld.segs + off, mnx, mxx, mny, mxy, tie, nullptr, shape);
     } else {
-        const unsigned n = emit_vertex(ld, gp, lp, vi, v0, nullptr, mnx, mxx, mny, mxy, tie);
+        const unsigned n = emit_vertex(ld, gp, lp, vi, v0, nullptr, mnx, mxx, mny, mxy, tie, shape, nullptr);
         ld.vcnt[inst] = n;
         ld.vbox[inst] = make_double4(mnx, mxx, mny, mxy);
         if (tie) atomicOr(&ld.counters[LCNT_FALLBACK], 1u);
@@ -987,7 +1040,7 @@ __device__ __forceinline__ void label_curve_body(const LabelDev& ld) {
     const unsigned n_curves = min(ld.counters[LCNT_CURVES], ld.verts_cap);
     if (ld.counters[LCNT_OVERFLOW] & 65u) return;
     if (WRITE && (ld.counters[LCNT_OVERFLOW] || ld.counters[LCNT_FALLBACK])) return;
-    for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < n_curves; k += gridDim.x * blockDim.x) label_vertex_instance<WRITE>(ld, ld.curve_list[k]);
+    for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < n_curves; k += gridDim.x * blockDim.x) label_vertex_instance<WRITE>(ld, ld.curve_list[k], k);
 }
 __global__ void __launch_bounds__(128) label_vline_count_kernel(LabelDev ld) { label_vline_body<false>(ld); }
 __global__ void __launch_bounds__(128) label_vline_write_kernel(LabelDev ld) { label_vline_body<true>(ld); }
