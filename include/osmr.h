@@ -111,6 +111,12 @@ typedef struct osmr_ctx osmr_ctx;
 
 /* replaces Drawer::new + TilePixels::new (drawer.rs:33, tile_pixels.rs:57): scratch + CUDA stream on `device` */
 int osmr_ctx_create(int device, osmr_ctx** out_ctx);
+/* A worker context that SHARES the parent's resident dataset (reference: src/http_server.rs:42-48,69-72 -- GeodataReader, Styler
+ * and Drawer are shared immutably by all worker threads, only TilePixels is per thread).  Own streams, scratch, style / icon /
+ * label tables and zoom classes; the geodata uploaded by osmr_set_geodata on the parent is used by reference (no second copy in
+ * HBM, no second upload).  The dataset is immutable: osmr_set_geodata on either context gives that context a dataset of its own.
+ * Each context is still used by one host thread at a time; different contexts may run on different threads concurrently. */
+int osmr_ctx_create_shared(const osmr_ctx* parent, osmr_ctx** out_ctx);
 void osmr_ctx_destroy(osmr_ctx* ctx);
 const char* osmr_last_error(const osmr_ctx* ctx);
 

@@ -41,6 +41,7 @@ EXPORTS = [
     "osmr_draw_tiles_png",
     "osmr_rgb_to_png",
     "osmr_draw_tiles_auto_png",
+    "osmr_ctx_create_shared",
 ]
 
 _lib = None
@@ -114,6 +115,8 @@ def load():
     L.osmr_draw_tiles_png.argtypes = [vp, vp, u32, vp, vp, vp, u32, vp, sz, vp]
     L.osmr_rgb_to_png.restype = C.c_int
     L.osmr_rgb_to_png.argtypes = [vp, vp, u32, u32, vp, sz, vp]
+    L.osmr_ctx_create_shared.restype = C.c_int
+    L.osmr_ctx_create_shared.argtypes = [vp, C.POINTER(vp)]
     L.osmr_draw_tiles_auto_png.restype = C.c_int
     L.osmr_draw_tiles_auto_png.argtypes = [vp, vp, u32, vp, u32, vp, sz, vp]
     _lib = L

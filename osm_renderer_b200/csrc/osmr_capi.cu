@@ -24,6 +24,7 @@
 #include "osmr_labels_host.hpp"
 #include "osmr_labels_dev.cuh"
 #include <map>
+#include <memory>
 #include <unordered_map>
 
 using namespace osmr;
@@ -91,6 +92,26 @@ struct LabelWorkItem {  // a run of consecutive labels of one tile, laid out by 
 
 }  // namespace
 
+struct Dataset {
+    int device = 0;
+    bool has_geo = false;
+    unsigned n_nodes = 0, n_ways = 0, n_polys = 0, n_mps = 0, n_ints = 0;
+    DevBuf<double2> merc;
+    DevBuf<EntBox> way_box, mp_box;
+    DevBuf<uint2> ways, polys, mps;
+    DevBuf<unsigned> ints;
+    std::vector<unsigned> h_way_len, h_mp_pts;  // node counts per entity (host copy, for scratch sizing)
+    std::vector<uint8_t> h_bin;                 // host copy of the geodata image: tags and coordinates for the label tables
+    osmr_host::BinView h_view;
+    std::vector<double2> h_merc;                // host copy of the Mercator factors (direction tables of the label layout)
+    // f3: the tile index and what the device-side lookup derives from it
+    std::string auto_unavailable;  // why the tile index of the image cannot drive the device-side lookup ("" = it can)
+    unsigned n_idx = 0;
+    DevBuf<uint2> idx_xy, idx_w, idx_m, way_min_tile, mp_min_tile;
+    DevBuf<unsigned> way_rank, mp_rank, rank_entity;
+    ~Dataset() { cudaSetDevice(device); }  // (the buffers free themselves right after, on this device)
+};
+
 struct osmr_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -106,17 +127,10 @@ struct osmr_ctx {
     std::string err;
     int num_sms = 0;
 
-    // dataset
-    bool has_geo = false;
-    unsigned n_nodes = 0, n_ways = 0, n_polys = 0, n_mps = 0, n_ints = 0;
-    DevBuf<double2> merc;
-    DevBuf<EntBox> way_box, mp_box;
-    DevBuf<uint2> ways, polys, mps;
-    DevBuf<unsigned> ints;
-    std::vector<unsigned> h_way_len, h_mp_pts;  // node counts per entity (host copy, for scratch sizing)
+    // dataset: immutable once osmr_set_geodata has returned, shared read-only between the contexts made by
+    // osmr_ctx_create_shared (reference: one GeodataReader behind an Arc for all worker threads, http_server.rs:42-48)
+    std::shared_ptr<Dataset> ds;
     // label pass (host half: osmr_labels_host.hpp)
-    std::vector<uint8_t> h_bin;  // host copy of the geodata image: tags and coordinates for label layout
-    osmr_host::BinView h_view;
     osmr_host::TrueType font;
     std::vector<osmr_host::LabelStyleHost> label_styles;
     std::vector<osmr_host::IconDim> label_icon_dims;
@@ -152,7 +166,6 @@ struct osmr_ctx {
             DevBuf<double2> sc;
         } angle[19];
     } lres;
-    std::vector<double2> h_merc;  // host copy of the Mercator factors (direction tables of the label layout)
     DevBuf<osmr_label> d_label_list;
     DevBuf<ActLabel> l_act;
     DevBuf<unsigned> l_act_cnt, l_counters;
@@ -235,10 +248,6 @@ struct osmr_ctx {
         bool set = false;
     };
     ZoomTable zoom_tables[19];
-    std::string auto_unavailable;  // why the tile index of the image cannot drive the device-side lookup ("" = it can)
-    unsigned n_idx = 0;
-    DevBuf<uint2> idx_xy, idx_w, idx_m, way_min_tile, mp_min_tile;
-    DevBuf<unsigned> way_rank, mp_rank, rank_entity;
     DevBuf<unsigned> auto_bound, auto_cand, auto_cand_cnt, auto_inst;
     DevBuf<unsigned long long> auto_big_keys;
     // f4: PNG encode on the device (osmr_png.cuh)
@@ -308,6 +317,8 @@ int osmr_ctx_create(int device, osmr_ctx** out_ctx) try {
     osmr_ctx* ctx = new (std::nothrow) osmr_ctx();
     if (!ctx) return OSMR_E_NOMEM;
     ctx->device = device;
+    ctx->ds = std::make_shared<Dataset>();
+    ctx->ds->device = device;
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
@@ -348,13 +359,6 @@ void osmr_ctx_destroy(osmr_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    ctx->merc.release();
-    ctx->way_box.release();
-    ctx->mp_box.release();
-    ctx->ways.release();
-    ctx->polys.release();
-    ctx->mps.release();
-    ctx->ints.release();
     ctx->styles.release();
     ctx->dashes.release();
     ctx->icons.release();
@@ -375,14 +379,6 @@ void osmr_ctx_destroy(osmr_ctx* ctx) {
         z.class_styles.release();
         z.class_reach.release();
     }
-    ctx->idx_xy.release();
-    ctx->idx_w.release();
-    ctx->idx_m.release();
-    ctx->way_min_tile.release();
-    ctx->mp_min_tile.release();
-    ctx->way_rank.release();
-    ctx->mp_rank.release();
-    ctx->rank_entity.release();
     ctx->auto_bound.release();
     ctx->auto_cand.release();
     ctx->auto_cand_cnt.release();
@@ -437,6 +433,24 @@ void osmr_ctx_destroy(osmr_ctx* ctx) {
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
+
+// A worker context over the parent's resident dataset (reference: src/http_server.rs:42-48,69-72 -- reader, styler and drawer are
+// shared immutably by all worker threads, each thread owns only its TilePixels).  The new context has its own streams, scratch,
+// style / icon / label tables and zoom classes; the geodata (Mercator factors, entity tables and boxes, tile index, the host
+// copy behind the label tables) is the parent's, by reference.  The dataset is immutable: osmr_set_geodata on either context
+// gives THAT context a dataset of its own and leaves the other one untouched.  Contexts may be used from different host threads
+// (one thread per context, as before).
+int osmr_ctx_create_shared(const osmr_ctx* parent, osmr_ctx** out_ctx) try {
+    if (!out_ctx) return OSMR_E_INVALID;
+    *out_ctx = nullptr;
+    if (!parent) return OSMR_E_INVALID;
+    osmr_ctx* ctx = nullptr;
+    int rc = osmr_ctx_create(parent->device, &ctx);
+    if (rc) return rc;
+    ctx->ds = parent->ds;
+    *out_ctx = ctx;
+    return OSMR_OK;
+} OSMR_CATCH_INT(nullptr)
 
 const char* osmr_last_error(const osmr_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
@@ -531,18 +545,24 @@ int osmr_set_geodata(osmr_ctx* ctx, const void* bin, size_t len) try {
         pos += (size_t)cnt[i] * rec[i];
     }
     const uint32_t n_nodes = cnt[0], n_ways = cnt[1], n_polys = cnt[2], n_mps = cnt[3], n_ints = cnt[5];
+    // a fresh dataset object: contexts that share the previous one (osmr_ctx_create_shared) keep it
+    {
+        std::shared_ptr<Dataset> fresh = std::make_shared<Dataset>();
+        fresh->device = ctx->device;
+        ctx->ds.swap(fresh);
+    }
     std::vector<uint32_t> ints(n_ints);
     if (n_ints) memcpy(ints.data(), base[5], (size_t)n_ints * 4);
     std::vector<uint2> ways(n_ways), polys(n_polys), mps(n_mps);
-    ctx->h_way_len.assign(n_ways, 0);
-    ctx->h_mp_pts.assign(n_mps, 0);
+    ctx->ds->h_way_len.assign(n_ways, 0);
+    ctx->ds->h_mp_pts.assign(n_mps, 0);
     auto range_ok = [&](uint32_t off, uint32_t l) { return (uint64_t)off + l <= n_ints; };
     for (uint32_t i = 0; i < n_ways; ++i) {
         ways[i] = make_uint2(rd_u32(base[1] + (size_t)i * 24 + 8), rd_u32(base[1] + (size_t)i * 24 + 12));
         if (!range_ok(ways[i].x, ways[i].y)) return ctx->fail(OSMR_E_INVALID, "way node list out of range");
         for (uint32_t k = 0; k < ways[i].y; ++k)
             if (ints[ways[i].x + k] >= n_nodes) return ctx->fail(OSMR_E_INVALID, "way references a missing node");
-        ctx->h_way_len[i] = ways[i].y;
+        ctx->ds->h_way_len[i] = ways[i].y;
     }
     for (uint32_t i = 0; i < n_polys; ++i) {
         polys[i] = make_uint2(rd_u32(base[2] + (size_t)i * 8), rd_u32(base[2] + (size_t)i * 8 + 4));
@@ -556,29 +576,29 @@ int osmr_set_geodata(osmr_ctx* ctx, const void* bin, size_t len) try {
         for (uint32_t k = 0; k < mps[i].y; ++k) {
             uint32_t pid = ints[mps[i].x + k];
             if (pid >= n_polys) return ctx->fail(OSMR_E_INVALID, "multipolygon references a missing polygon");
-            ctx->h_mp_pts[i] += polys[pid].y;
+            ctx->ds->h_mp_pts[i] += polys[pid].y;
         }
     }
-    ctx->has_geo = false;
+    ctx->ds->has_geo = false;
     DevBuf<unsigned char> raw_nodes;
     CK(raw_nodes.reserve((size_t)n_nodes * 32 + 16));
-    CK(ctx->merc.reserve(n_nodes + 1));
-    CK(ctx->ways.reserve(n_ways + 1));
-    CK(ctx->polys.reserve(n_polys + 1));
-    CK(ctx->mps.reserve(n_mps + 1));
-    CK(ctx->ints.reserve(n_ints + 1));
+    CK(ctx->ds->merc.reserve(n_nodes + 1));
+    CK(ctx->ds->ways.reserve(n_ways + 1));
+    CK(ctx->ds->polys.reserve(n_polys + 1));
+    CK(ctx->ds->mps.reserve(n_mps + 1));
+    CK(ctx->ds->ints.reserve(n_ints + 1));
     if (n_nodes) CK(cudaMemcpyAsync(raw_nodes.p, base[0], (size_t)n_nodes * 32, cudaMemcpyHostToDevice, ctx->stream));
-    if (n_ways) CK(cudaMemcpyAsync(ctx->ways.p, ways.data(), (size_t)n_ways * 8, cudaMemcpyHostToDevice, ctx->stream));
-    if (n_polys) CK(cudaMemcpyAsync(ctx->polys.p, polys.data(), (size_t)n_polys * 8, cudaMemcpyHostToDevice, ctx->stream));
-    if (n_mps) CK(cudaMemcpyAsync(ctx->mps.p, mps.data(), (size_t)n_mps * 8, cudaMemcpyHostToDevice, ctx->stream));
-    if (n_ints) CK(cudaMemcpyAsync(ctx->ints.p, ints.data(), (size_t)n_ints * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (n_ways) CK(cudaMemcpyAsync(ctx->ds->ways.p, ways.data(), (size_t)n_ways * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (n_polys) CK(cudaMemcpyAsync(ctx->ds->polys.p, polys.data(), (size_t)n_polys * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (n_mps) CK(cudaMemcpyAsync(ctx->ds->mps.p, mps.data(), (size_t)n_mps * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (n_ints) CK(cudaMemcpyAsync(ctx->ds->ints.p, ints.data(), (size_t)n_ints * 4, cudaMemcpyHostToDevice, ctx->stream));
     // a1, transcendental half (tile.rs:88-101 up to the zoom-independent factor), once per dataset.  By default on the HOST with
     // the platform libm -- glibc's tan / log are what the reference (Rust f64::tan / ln on Linux) calls, so the factors are the
     // reference's to the last bit; the device's tan / log differ from glibc's in the last place for a few arguments, which
     // could flip the integer pixel of a node that sits within ~1e-9 px of an exact .5 tie.  Debug key "device_merc" selects
     // project_nodes_kernel instead (0.02 ms for 1.9 M nodes; the host loop takes ~20 ms on 16 threads).
     std::vector<double2> h_merc;
-    ctx->h_merc.clear();
+    ctx->ds->h_merc.clear();
     if (n_nodes && !ctx->device_merc) {
         h_merc.resize(n_nodes);
         const unsigned n_thr = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
@@ -599,38 +619,38 @@ int osmr_set_geodata(osmr_ctx* ctx, const void* bin, size_t len) try {
         for (unsigned t = 1; t < n_thr; ++t) pool.emplace_back(work, t);
         work(0);
         for (auto& th : pool) th.join();
-        CK(cudaMemcpyAsync(ctx->merc.p, h_merc.data(), (size_t)n_nodes * sizeof(double2), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->ds->merc.p, h_merc.data(), (size_t)n_nodes * sizeof(double2), cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
-        ctx->h_merc.swap(h_merc);
+        ctx->ds->h_merc.swap(h_merc);
     } else if (n_nodes) {
         const unsigned char* raw_p = raw_nodes.p;
-        project_nodes_kernel<<<(n_nodes + 255) / 256, 256, 0, ctx->stream>>>(raw_p, n_nodes, ctx->merc.p);
+        project_nodes_kernel<<<(n_nodes + 255) / 256, 256, 0, ctx->stream>>>(raw_p, n_nodes, ctx->ds->merc.p);
         CK(cudaGetLastError());
     }
-    CK(ctx->way_box.reserve(n_ways + 1));
-    CK(ctx->mp_box.reserve(n_mps + 1));
+    CK(ctx->ds->way_box.reserve(n_ways + 1));
+    CK(ctx->ds->mp_box.reserve(n_mps + 1));
     if (n_ways + n_mps) {
         Scene gs{};
-        gs.merc = ctx->merc.p;
-        gs.ways = ctx->ways.p;
-        gs.polys = ctx->polys.p;
-        gs.mps = ctx->mps.p;
-        gs.ints = ctx->ints.p;
+        gs.merc = ctx->ds->merc.p;
+        gs.ways = ctx->ds->ways.p;
+        gs.polys = ctx->ds->polys.p;
+        gs.mps = ctx->ds->mps.p;
+        gs.ints = ctx->ds->ints.p;
         gs.n_ways = n_ways;
         gs.n_mps = n_mps;
-        entity_box_kernel<<<(n_ways + n_mps + 127) / 128, 128, 0, ctx->stream>>>(gs, ctx->way_box.p, ctx->mp_box.p);
+        entity_box_kernel<<<(n_ways + n_mps + 127) / 128, 128, 0, ctx->stream>>>(gs, ctx->ds->way_box.p, ctx->ds->mp_box.p);
         CK(cudaGetLastError());
     }
     CK(cudaStreamSynchronize(ctx->stream));
     raw_nodes.release();
-    ctx->h_bin.assign(p, p + len);
-    if (!ctx->h_view.parse(ctx->h_bin.data(), ctx->h_bin.size())) return ctx->fail(OSMR_E_INVALID, "geodata image truncated");
-    ctx->n_nodes = n_nodes;
-    ctx->n_ways = n_ways;
-    ctx->n_polys = n_polys;
-    ctx->n_mps = n_mps;
-    ctx->n_ints = n_ints;
-    ctx->has_geo = true;
+    ctx->ds->h_bin.assign(p, p + len);
+    if (!ctx->ds->h_view.parse(ctx->ds->h_bin.data(), ctx->ds->h_bin.size())) return ctx->fail(OSMR_E_INVALID, "geodata image truncated");
+    ctx->ds->n_nodes = n_nodes;
+    ctx->ds->n_ways = n_ways;
+    ctx->ds->n_polys = n_polys;
+    ctx->ds->n_mps = n_mps;
+    ctx->ds->n_ints = n_ints;
+    ctx->ds->has_geo = true;
     ctx->has_batch = false;
     ctx->lres.valid = false;
     for (auto& a : ctx->lres.angle) a.set = false;
@@ -639,25 +659,25 @@ int osmr_set_geodata(osmr_ctx* ctx, const void* bin, size_t len) try {
     // ---- f3: the tile index (reader.rs:135-180) + what the device-side lookup derives from it ----
     {
         const uint32_t n_idx = cnt[4];
-        ctx->n_idx = n_idx;
-        ctx->auto_unavailable.clear();
+        ctx->ds->n_idx = n_idx;
+        ctx->ds->auto_unavailable.clear();
         std::vector<uint2> ixy(n_idx), iw(n_idx), im(n_idx);
         struct Ext {
             uint32_t x0 = 0xffffffffu, y0 = 0xffffffffu, x1 = 0, y1 = 0, n = 0;
         };
         std::vector<Ext> wext(n_ways), mext(n_mps);
-        for (uint32_t i = 0; i < n_idx && ctx->auto_unavailable.empty(); ++i) {
+        for (uint32_t i = 0; i < n_idx && ctx->ds->auto_unavailable.empty(); ++i) {
             const uint8_t* r = base[4] + (size_t)i * 32;
             ixy[i] = make_uint2(rd_u32(r), rd_u32(r + 4));
             iw[i] = make_uint2(rd_u32(r + 16), rd_u32(r + 20));
             im[i] = make_uint2(rd_u32(r + 24), rd_u32(r + 28));
             if (i && !(ixy[i - 1].x < ixy[i].x || (ixy[i - 1].x == ixy[i].x && ixy[i - 1].y < ixy[i].y)))
-                ctx->auto_unavailable = "tile index is not sorted by (x, y)";
-            if (!range_ok(iw[i].x, iw[i].y) || !range_ok(im[i].x, im[i].y)) ctx->auto_unavailable = "tile index id list out of range";
-            if (!ctx->auto_unavailable.empty()) break;
+                ctx->ds->auto_unavailable = "tile index is not sorted by (x, y)";
+            if (!range_ok(iw[i].x, iw[i].y) || !range_ok(im[i].x, im[i].y)) ctx->ds->auto_unavailable = "tile index id list out of range";
+            if (!ctx->ds->auto_unavailable.empty()) break;
             auto note = [&](std::vector<Ext>& ext, uint32_t e) {
                 if (e >= ext.size()) {
-                    ctx->auto_unavailable = "tile index references a missing entity";
+                    ctx->ds->auto_unavailable = "tile index references a missing entity";
                     return;
                 }
                 Ext& x = ext[e];
@@ -677,9 +697,9 @@ int osmr_set_geodata(osmr_ctx* ctx, const void* bin, size_t len) try {
                 if (x.n && (uint64_t)(x.x1 - x.x0 + 1) * (uint64_t)(x.y1 - x.y0 + 1) != x.n) return false;
             return true;
         };
-        if (ctx->auto_unavailable.empty() && !(rectangular(wext) && rectangular(mext)))
-            ctx->auto_unavailable = "tile index does not list every entity in the full rectangle of its z18 tiles";
-        if (ctx->auto_unavailable.empty()) {
+        if (ctx->ds->auto_unavailable.empty() && !(rectangular(wext) && rectangular(mext)))
+            ctx->ds->auto_unavailable = "tile index does not list every entity in the full rectangle of its z18 tiles";
+        if (ctx->ds->auto_unavailable.empty()) {
             std::vector<uint2> wmin(n_ways), mmin(n_mps);
             for (uint32_t i = 0; i < n_ways; ++i) wmin[i] = make_uint2(wext[i].x0, wext[i].y0);
             for (uint32_t i = 0; i < n_mps; ++i) mmin[i] = make_uint2(mext[i].x0, mext[i].y0);
@@ -714,25 +734,25 @@ int osmr_set_geodata(osmr_ctx* ctx, const void* bin, size_t len) try {
                     rank_entity[r] = keys[r].loc | OSMR_AREA_MULTIPOLYGON;
                 }
             }
-            CK(ctx->idx_xy.reserve(n_idx + 1));
-            CK(ctx->idx_w.reserve(n_idx + 1));
-            CK(ctx->idx_m.reserve(n_idx + 1));
-            CK(ctx->way_min_tile.reserve(n_ways + 1));
-            CK(ctx->mp_min_tile.reserve(n_mps + 1));
-            CK(ctx->way_rank.reserve(n_ways + 1));
-            CK(ctx->mp_rank.reserve(n_mps + 1));
-            CK(ctx->rank_entity.reserve(keys.size() + 1));
+            CK(ctx->ds->idx_xy.reserve(n_idx + 1));
+            CK(ctx->ds->idx_w.reserve(n_idx + 1));
+            CK(ctx->ds->idx_m.reserve(n_idx + 1));
+            CK(ctx->ds->way_min_tile.reserve(n_ways + 1));
+            CK(ctx->ds->mp_min_tile.reserve(n_mps + 1));
+            CK(ctx->ds->way_rank.reserve(n_ways + 1));
+            CK(ctx->ds->mp_rank.reserve(n_mps + 1));
+            CK(ctx->ds->rank_entity.reserve(keys.size() + 1));
             auto up = [&](void* d, const void* h, size_t bytes) {
                 return bytes ? cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->stream) : cudaSuccess;
             };
-            CK(up(ctx->idx_xy.p, ixy.data(), (size_t)n_idx * 8));
-            CK(up(ctx->idx_w.p, iw.data(), (size_t)n_idx * 8));
-            CK(up(ctx->idx_m.p, im.data(), (size_t)n_idx * 8));
-            CK(up(ctx->way_min_tile.p, wmin.data(), (size_t)n_ways * 8));
-            CK(up(ctx->mp_min_tile.p, mmin.data(), (size_t)n_mps * 8));
-            CK(up(ctx->way_rank.p, wrank.data(), (size_t)n_ways * 4));
-            CK(up(ctx->mp_rank.p, mrank.data(), (size_t)n_mps * 4));
-            CK(up(ctx->rank_entity.p, rank_entity.data(), keys.size() * 4));
+            CK(up(ctx->ds->idx_xy.p, ixy.data(), (size_t)n_idx * 8));
+            CK(up(ctx->ds->idx_w.p, iw.data(), (size_t)n_idx * 8));
+            CK(up(ctx->ds->idx_m.p, im.data(), (size_t)n_idx * 8));
+            CK(up(ctx->ds->way_min_tile.p, wmin.data(), (size_t)n_ways * 8));
+            CK(up(ctx->ds->mp_min_tile.p, mmin.data(), (size_t)n_mps * 8));
+            CK(up(ctx->ds->way_rank.p, wrank.data(), (size_t)n_ways * 4));
+            CK(up(ctx->ds->mp_rank.p, mrank.data(), (size_t)n_mps * 4));
+            CK(up(ctx->ds->rank_entity.p, rank_entity.data(), keys.size() * 4));
             CK(cudaStreamSynchronize(ctx->stream));
         }
     }
@@ -809,7 +829,7 @@ int osmr_set_styles(osmr_ctx* ctx, const osmr_style* styles, uint32_t n_styles, 
 
 // ---------------------------------------------------------------------------------------------------------
 static int validate_batch(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, const uint32_t* area_begin) {
-    if (!ctx->has_geo) return ctx->fail(OSMR_E_STATE, "osmr_set_geodata has not been called");
+    if (!ctx->ds->has_geo) return ctx->fail(OSMR_E_STATE, "osmr_set_geodata has not been called");
     if (n_tiles == 0) return ctx->fail(OSMR_E_INVALID, "empty batch");
     if (!tiles || !area_begin) return ctx->fail(OSMR_E_INVALID, "null batch arrays");
     uint32_t scale = tiles[0].scale;
@@ -945,18 +965,18 @@ static int launch_chunk(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t fla
     const unsigned area_base = ctx->h_area_begin[tb];
     const unsigned n_areas = ctx->h_area_begin[tb + tc] - area_base;
     Scene s{};
-    s.merc = ctx->merc.p;
-    s.way_box = ctx->way_box.p;
-    s.mp_box = ctx->mp_box.p;
-    s.ways = ctx->ways.p;
-    s.polys = ctx->polys.p;
-    s.mps = ctx->mps.p;
-    s.ints = ctx->ints.p;
-    s.n_nodes = ctx->n_nodes;
-    s.n_ways = ctx->n_ways;
-    s.n_polys = ctx->n_polys;
-    s.n_mps = ctx->n_mps;
-    s.n_ints = ctx->n_ints;
+    s.merc = ctx->ds->merc.p;
+    s.way_box = ctx->ds->way_box.p;
+    s.mp_box = ctx->ds->mp_box.p;
+    s.ways = ctx->ds->ways.p;
+    s.polys = ctx->ds->polys.p;
+    s.mps = ctx->ds->mps.p;
+    s.ints = ctx->ds->ints.p;
+    s.n_nodes = ctx->ds->n_nodes;
+    s.n_ways = ctx->ds->n_ways;
+    s.n_polys = ctx->ds->n_polys;
+    s.n_mps = ctx->ds->n_mps;
+    s.n_ints = ctx->ds->n_ints;
     s.styles = ctx->styles.p;
     s.dashes = ctx->dashes.p;
     s.n_styles = ctx->n_styles;
@@ -1300,9 +1320,9 @@ static int encode_png_from_device(osmr_ctx* ctx, const unsigned char* rgb_dev, u
 int osmr_set_zoom_styles(osmr_ctx* ctx, uint32_t zoom, const uint32_t* way_class, const uint32_t* mp_class, const uint32_t* class_begin,
                          const osmr_class_style* class_styles, uint32_t n_classes) try {
     if (!ctx) return OSMR_E_INVALID;
-    if (!ctx->has_geo) return ctx->fail(OSMR_E_STATE, "osmr_set_geodata has not been called");
+    if (!ctx->ds->has_geo) return ctx->fail(OSMR_E_STATE, "osmr_set_geodata has not been called");
     if (zoom > 18) return ctx->fail(OSMR_E_INVALID, "zoom must be <= 18 (tile.rs:5 MAX_ZOOM)");
-    if ((ctx->n_ways && !way_class) || (ctx->n_mps && !mp_class) || !class_begin) return ctx->fail(OSMR_E_INVALID, "null class table");
+    if ((ctx->ds->n_ways && !way_class) || (ctx->ds->n_mps && !mp_class) || !class_begin) return ctx->fail(OSMR_E_INVALID, "null class table");
     if (class_begin[0] != 0) return ctx->fail(OSMR_E_INVALID, "class_begin[0] must be 0");
     for (uint32_t c = 0; c < n_classes; ++c) {
         if (class_begin[c + 1] < class_begin[c]) return ctx->fail(OSMR_E_INVALID, "class_begin must be non-decreasing");
@@ -1315,13 +1335,13 @@ int osmr_set_zoom_styles(osmr_ctx* ctx, uint32_t zoom, const uint32_t* way_class
     cudaSetDevice(ctx->device);
     osmr_ctx::ZoomTable& z = ctx->zoom_tables[zoom];
     z.set = false;
-    CK(z.way_class.reserve(ctx->n_ways + 1));
-    CK(z.mp_class.reserve(ctx->n_mps + 1));
+    CK(z.way_class.reserve(ctx->ds->n_ways + 1));
+    CK(z.mp_class.reserve(ctx->ds->n_mps + 1));
     CK(z.class_begin.reserve(n_classes + 1));
     CK(z.class_styles.reserve(n_cs + 1));
     CK(z.class_reach.reserve(n_classes + 1));
-    if (ctx->n_ways) CK(cudaMemcpyAsync(z.way_class.p, way_class, (size_t)ctx->n_ways * 4, cudaMemcpyHostToDevice, ctx->stream));
-    if (ctx->n_mps) CK(cudaMemcpyAsync(z.mp_class.p, mp_class, (size_t)ctx->n_mps * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->ds->n_ways) CK(cudaMemcpyAsync(z.way_class.p, way_class, (size_t)ctx->ds->n_ways * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->ds->n_mps) CK(cudaMemcpyAsync(z.mp_class.p, mp_class, (size_t)ctx->ds->n_mps * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(z.class_begin.p, class_begin, (size_t)(n_classes + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
     if (n_cs) CK(cudaMemcpyAsync(z.class_styles.p, class_styles, (size_t)n_cs * sizeof(osmr_class_style), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1335,8 +1355,8 @@ int osmr_set_zoom_styles(osmr_ctx* ctx, uint32_t zoom, const uint32_t* way_class
 // On success ctx holds the batch (tiles, area_begin, areas) exactly as osmr_batch_upload would have left it and the events
 // ctx->ev[0] / ev[1] bracket the stage.
 static int auto_prepare(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, const uint8_t canvas_rgb[3], uint32_t flags) {
-    if (!ctx->has_geo) return ctx->fail(OSMR_E_STATE, "osmr_set_geodata has not been called");
-    if (!ctx->auto_unavailable.empty()) return ctx->fail(OSMR_E_STATE, ctx->auto_unavailable.c_str());
+    if (!ctx->ds->has_geo) return ctx->fail(OSMR_E_STATE, "osmr_set_geodata has not been called");
+    if (!ctx->ds->auto_unavailable.empty()) return ctx->fail(OSMR_E_STATE, ctx->ds->auto_unavailable.c_str());
     if (n_tiles == 0 || !tiles) return ctx->fail(OSMR_E_INVALID, "empty batch");
     const uint32_t zoom = tiles[0].zoom, scale = tiles[0].scale;
     if (scale < 1 || scale > 8) return ctx->fail(OSMR_E_INVALID, "scale must be 1..8");
@@ -1364,18 +1384,18 @@ static int auto_prepare(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles,
     CK(cudaMemcpyAsync(ctx->tiles.p, tiles, (size_t)n_tiles * sizeof(osmr_tile), cudaMemcpyHostToDevice, st));
 
     Scene s{};
-    s.merc = ctx->merc.p;
-    s.way_box = ctx->way_box.p;
-    s.mp_box = ctx->mp_box.p;
-    s.ways = ctx->ways.p;
-    s.polys = ctx->polys.p;
-    s.mps = ctx->mps.p;
-    s.ints = ctx->ints.p;
-    s.n_nodes = ctx->n_nodes;
-    s.n_ways = ctx->n_ways;
-    s.n_polys = ctx->n_polys;
-    s.n_mps = ctx->n_mps;
-    s.n_ints = ctx->n_ints;
+    s.merc = ctx->ds->merc.p;
+    s.way_box = ctx->ds->way_box.p;
+    s.mp_box = ctx->ds->mp_box.p;
+    s.ways = ctx->ds->ways.p;
+    s.polys = ctx->ds->polys.p;
+    s.mps = ctx->ds->mps.p;
+    s.ints = ctx->ds->ints.p;
+    s.n_nodes = ctx->ds->n_nodes;
+    s.n_ways = ctx->ds->n_ways;
+    s.n_polys = ctx->ds->n_polys;
+    s.n_mps = ctx->ds->n_mps;
+    s.n_ints = ctx->ds->n_ints;
     s.styles = ctx->styles.p;
     s.dashes = ctx->dashes.p;
     s.n_styles = ctx->n_styles;
@@ -1390,15 +1410,15 @@ static int auto_prepare(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles,
     unsigned* h_auto = ctx->h_cnt.p + (size_t)kMaxChunks * CNT_COUNT;
     s.counters = auto_counters;
     AutoScene a{};
-    a.idx_xy = ctx->idx_xy.p;
-    a.idx_w = ctx->idx_w.p;
-    a.idx_m = ctx->idx_m.p;
-    a.n_idx = ctx->n_idx;
-    a.way_min_tile = ctx->way_min_tile.p;
-    a.mp_min_tile = ctx->mp_min_tile.p;
-    a.way_rank = ctx->way_rank.p;
-    a.mp_rank = ctx->mp_rank.p;
-    a.rank_entity = ctx->rank_entity.p;
+    a.idx_xy = ctx->ds->idx_xy.p;
+    a.idx_w = ctx->ds->idx_w.p;
+    a.idx_m = ctx->ds->idx_m.p;
+    a.n_idx = ctx->ds->n_idx;
+    a.way_min_tile = ctx->ds->way_min_tile.p;
+    a.mp_min_tile = ctx->ds->mp_min_tile.p;
+    a.way_rank = ctx->ds->way_rank.p;
+    a.mp_rank = ctx->ds->mp_rank.p;
+    a.rank_entity = ctx->ds->rank_entity.p;
     a.way_class = z.way_class.p;
     a.mp_class = z.mp_class.p;
     a.class_begin = z.class_begin.p;
@@ -1612,17 +1632,17 @@ int osmr_get_stats(osmr_ctx* ctx, osmr_stats* out) try {
 
 int osmr_project_nodes(osmr_ctx* ctx, const osmr_tile* tile, int32_t* out_xy) try {
     if (!ctx) return OSMR_E_INVALID;
-    if (!ctx->has_geo) return ctx->fail(OSMR_E_STATE, "osmr_set_geodata has not been called");
+    if (!ctx->ds->has_geo) return ctx->fail(OSMR_E_STATE, "osmr_set_geodata has not been called");
     if (!tile || !out_xy) return ctx->fail(OSMR_E_INVALID, "null argument");
     if (tile->scale < 1 || tile->scale > 8 || tile->zoom > 22) return ctx->fail(OSMR_E_INVALID, "bad tile");
     cudaSetDevice(ctx->device);
-    if (ctx->n_nodes == 0) return OSMR_OK;
+    if (ctx->ds->n_nodes == 0) return OSMR_OK;
     DevBuf<int2> tmp;
-    CK(tmp.reserve(ctx->n_nodes));
+    CK(tmp.reserve(ctx->ds->n_nodes));
     int2* tmp_p = tmp.p;
-    project_all_kernel<<<(ctx->n_nodes + 255) / 256, 256, 0, ctx->stream>>>(ctx->merc.p, ctx->n_nodes, *tile, tmp_p);
+    project_all_kernel<<<(ctx->ds->n_nodes + 255) / 256, 256, 0, ctx->stream>>>(ctx->ds->merc.p, ctx->ds->n_nodes, *tile, tmp_p);
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(out_xy, tmp.p, (size_t)ctx->n_nodes * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(out_xy, tmp.p, (size_t)ctx->ds->n_nodes * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     tmp.release();
     return OSMR_OK;
@@ -1706,7 +1726,7 @@ static int labels_via_host(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_til
         if (label_begin[t + 1] < label_begin[t]) return ctx->fail(OSMR_E_INVALID, "label_begin must be non-decreasing");
         if (label_begin[t + 1] > label_begin[t] && !labels) return ctx->fail(OSMR_E_INVALID, "null label list");
     }
-    osmr_host::LayoutEnv env{&ctx->h_view, &ctx->font, &ctx->label_styles, &ctx->label_icon_dims};
+    osmr_host::LayoutEnv env{&ctx->ds->h_view, &ctx->font, &ctx->label_styles, &ctx->label_icon_dims};
     // work items: runs of <= kLabelRun consecutive labels of a tile (the layout of a label does not depend on the others)
     constexpr uint32_t kLabelRun = 96;
     std::vector<LabelWorkItem>& items = ctx->label_items;
@@ -1853,7 +1873,7 @@ static int labels_via_host(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_til
 static int build_label_tables(osmr_ctx* ctx) {
     auto& R = ctx->lres;
     R.valid = false;
-    const osmr_host::BinView& g = ctx->h_view;
+    const osmr_host::BinView& g = ctx->ds->h_view;
     const osmr_host::TrueType& font = ctx->font;
     // distinct text keys
     R.keys.clear();
@@ -1976,19 +1996,19 @@ static int build_angle_table(osmr_ctx* ctx, unsigned zoom, int scale) {
     auto& R = ctx->lres;
     auto& A = R.angle[zoom];
     A.set = false;
-    const uint32_t n_ways = ctx->h_view.n_ways;
-    if (ctx->h_merc.size() != ctx->n_nodes) return ctx->fail(OSMR_E_STATE, "no host copy of the Mercator factors (debug key device_merc)");
+    const uint32_t n_ways = ctx->ds->h_view.n_ways;
+    if (ctx->ds->h_merc.size() != ctx->ds->n_nodes) return ctx->fail(OSMR_E_STATE, "no host copy of the Mercator factors (debug key device_merc)");
     std::vector<unsigned> off(n_ways, 0xffffffffu);
     std::vector<double2> sc;
     const double dim = (double)(unsigned)(256u * (1u << zoom)), fscale = (double)scale;
     std::vector<osmr_host::IPoint> pts;
     for (uint32_t w = 0; w < n_ways; ++w) {
         if (!R.way_has_text[w]) continue;
-        const uint32_t o = osmr_host::BinView::u32(ctx->h_view.ways + (size_t)w * 24 + 8), len = osmr_host::BinView::u32(ctx->h_view.ways + (size_t)w * 24 + 12);
+        const uint32_t o = osmr_host::BinView::u32(ctx->ds->h_view.ways + (size_t)w * 24 + 8), len = osmr_host::BinView::u32(ctx->ds->h_view.ways + (size_t)w * 24 + 12);
         if (len < 2) continue;
         pts.clear();
         for (uint32_t i = 0; i < len; ++i) {
-            const double2 m = ctx->h_merc[ctx->h_view.int_at(o + i)];
+            const double2 m = ctx->ds->h_merc[ctx->ds->h_view.int_at(o + i)];
             volatile double x = m.x * dim, y = m.y * dim;  // project_point with the tile origin at 0 (exact IEEE steps)
             volatile double xs = x * fscale, ys = y * fscale;
             pts.push_back(osmr_host::IPoint{osmr_host::f64_as_i32(std::round(xs)), osmr_host::f64_as_i32(std::round(ys))});
@@ -2011,7 +2031,7 @@ static int build_angle_table(osmr_ctx* ctx, unsigned zoom, int scale) {
 }
 
 static bool label_device_path_allowed(const osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles) {
-    if (ctx->label_host_only || ctx->h_merc.size() != ctx->n_nodes) return false;
+    if (ctx->label_host_only || ctx->ds->h_merc.size() != ctx->ds->n_nodes) return false;
     const uint32_t scale = tiles[0].scale;
     if (scale != 1 && scale != 2 && scale != 4 && scale != 8) return false;  // `* scale` must be exact (osmr_labels_dev.cuh)
     for (uint32_t t = 0; t < n_tiles; ++t)
@@ -2081,16 +2101,16 @@ static int label_device_enqueue(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t 
     CK(cudaMemcpyAsync(ctx->d_label_begin.p, label_begin, (size_t)(n_tiles + 1) * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemsetAsync(ctx->l_counters.p, 0, LCNT_COUNT * sizeof(unsigned), st));
     Scene s{};
-    s.merc = ctx->merc.p;
-    s.ways = ctx->ways.p;
-    s.polys = ctx->polys.p;
-    s.mps = ctx->mps.p;
-    s.ints = ctx->ints.p;
-    s.n_nodes = ctx->n_nodes;
-    s.n_ways = ctx->n_ways;
-    s.n_polys = ctx->n_polys;
-    s.n_mps = ctx->n_mps;
-    s.n_ints = ctx->n_ints;
+    s.merc = ctx->ds->merc.p;
+    s.ways = ctx->ds->ways.p;
+    s.polys = ctx->ds->polys.p;
+    s.mps = ctx->ds->mps.p;
+    s.ints = ctx->ds->ints.p;
+    s.n_nodes = ctx->ds->n_nodes;
+    s.n_ways = ctx->ds->n_ways;
+    s.n_polys = ctx->ds->n_polys;
+    s.n_mps = ctx->ds->n_mps;
+    s.n_ints = ctx->ds->n_ints;
     s.tiles = ctx->tiles.p;
     s.n_tiles = n_tiles;
     s.D = D;

@@ -58,13 +58,20 @@ class OsmEntities:
 class GpuContext:
     """Thin RAII wrapper of osmr_ctx."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, share_dataset_of: "GpuContext | None" = None):
+        """share_dataset_of: another context whose resident geodata this one uses by reference (osmr_ctx_create_shared: the
+        reference shares its GeodataReader between worker threads, http_server.rs:42-48)."""
         self.L = _lib.load()
         h = C.c_void_p()
-        rc = self.L.osmr_ctx_create(device, C.byref(h))
+        if share_dataset_of is not None:
+            rc = self.L.osmr_ctx_create_shared(share_dataset_of.h, C.byref(h))
+        else:
+            rc = self.L.osmr_ctx_create(device, C.byref(h))
         if rc != 0:
             raise _lib.OsmrError(f"osmr_ctx_create(device={device}) failed with {rc}: no usable CUDA device (no CPU fallback)")
         self.h = h
+        if share_dataset_of is not None:
+            self.n_nodes = getattr(share_dataset_of, "n_nodes", 0)
         self._geodata_id = None
         # what this context holds on the device: (identity of the table, rows, icons).  A context is one worker's scratch
         # (TilePixels); several of them may serve one shared Drawer, and a Drawer may be replaced by another with equally

@@ -23,6 +23,10 @@
 #include <cstring>
 #include <functional>
 #include <limits>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <system_error>
 #include <mutex>
 #include <new>
 #include <shared_mutex>

@@ -206,3 +206,53 @@ def test_opacity_outside_the_exact_range_is_refused(fx):
     t.rows[0]["flags"] |= OSMR_STYLE_OPACITY
     ctx.set_table(t)
     ctx.close()
+
+
+def test_worker_contexts_share_one_resident_dataset(fx):
+    """osmr_ctx_create_shared: the reference shares reader / styler / drawer between worker threads and gives each thread only
+    its own TilePixels (http_server.rs:42-48,69-72).  A worker context draws from the parent's geodata without uploading it
+    again, from its own host thread, and replacing the dataset of one context leaves the other one alone."""
+    import threading
+
+    from osm_renderer_b200.drawer import GpuContext
+    from osm_renderer_b200.upstream import synth
+
+    tiles, begins, areas = fx.batches["17"]
+    want = np.stack(oracle.draw_tiles(fx.bin, fx.table, tiles, begins, areas, fx.canvas_rgb, True, n_threads=8))
+    parent = GpuContext(0)
+    parent.set_geodata(fx.bin)
+    parent.set_table(fx.table)
+    workers = [GpuContext(0, share_dataset_of=parent) for _ in range(3)]
+    results = [None] * len(workers)
+
+    def run(i):
+        w = workers[i]
+        w.set_table(fx.table)  # style tables are per context
+        results[i] = w.draw_tiles(tiles, begins, areas, fx.canvas_rgb, True)
+
+    import os
+
+    if os.environ.get("OSMR_TEST_EMU") == "1":  # the host emulator is a single fiber engine: one context at a time
+        for i in range(len(workers)):
+            run(i)
+        mine = parent.draw_tiles(tiles, begins, areas, fx.canvas_rgb, True)
+    else:
+        threads = [threading.Thread(target=run, args=(i,)) for i in range(len(workers))]
+        for t in threads:
+            t.start()
+        mine = parent.draw_tiles(tiles, begins, areas, fx.canvas_rgb, True)  # the parent draws at the same time
+        for t in threads:
+            t.join()
+    assert (mine == want).all()
+    for r in results:
+        assert r is not None and (r == want).all()
+    # a new dataset on one worker: the others (and the parent) keep drawing the old one
+    other = synth.make_metro(n=1)
+    workers[0].set_geodata(other)
+    assert (workers[1].draw_tiles(tiles, begins, areas, fx.canvas_rgb, True) == want).all()
+    assert (parent.draw_tiles(tiles, begins, areas, fx.canvas_rgb, True) == want).all()
+    # the parent goes away first: the shared dataset lives as long as a context uses it
+    parent.close()
+    assert (workers[2].draw_tiles(tiles, begins, areas, fx.canvas_rgb, True) == want).all()
+    for w in workers:
+        w.close()
