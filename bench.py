@@ -17,10 +17,11 @@ One "step" = one pass of the draw path over the batch on every rank.  --scaling 
 full batch (request i of the interleaved global list goes to rank i mod N).  --scaling strong: ONE list of 8 x batch requests
 is dealt i mod N, so the work per rank shrinks with N.  Tiles are independent; no collective touches the data path.
 
-JSON line: `value` = tiles/s of the area passes with the batch description resident in HBM and the output left in HBM (wall
-clock between barriers; `device_only` is the CUDA-event figure); `e2e` = the reference-facing call with pinned HOST buffers,
-copies inside the timed region; siblings `e2e_labeled` (the whole Drawer::draw_to_pixels: area passes + label pass),
-`e2e_auto` (tile list in), `e2e_png` / `e2e_auto_png` (PNG files out), `latency_ms` (p50 of single small calls);
+JSON line: `value` = tiles/s of the whole Drawer::draw_to_pixels (area passes + label pass) with the batch description resident
+in HBM and the output left in HBM (wall clock between barriers; `device_only` is the CUDA-event figure); `e2e` = the same through
+the reference-facing call osmr_draw_tiles_labeled with pinned HOST buffers, copies inside the timed region; siblings
+`value_area_only` / `e2e_area_only` (Fill, Casing, Stroke passes only: round 1's headline), `e2e_auto` (tile list in),
+`e2e_png` / `e2e_auto_png` (PNG files out), `latency_ms` (p50 of single small calls);
 `sustained` = the resident leg repeated for >= --min-seconds with median / min per step; `roofline` = dominant kernel against
 the measured HBM peak with SURVEY 8(d)'s B_tile next to the kernel-local byte count; `cpu_baseline` = the oracle (C++
 restatement of the reference CPU path) on this box's host cores, T = nproc and T = 1.
@@ -51,7 +52,8 @@ WORKLOADS = {
                metro={"zoom": 16, "x0": 9888 * 4 + 56, "y0": 5104 * 4 + 56, "n": 16, "extra_footprints": 100000, "coastline_nodes": 50000}),
 }
 STYLES = {"mapnik": "mapnik_rules.json.gz", "osmosnimki": "osmosnimki_rules.json.gz"}
-HEADLINE_LABELED = False  # `e2e` is osmr_draw_tiles (area passes); the labelled call is reported as e2e_labeled
+HEADLINE_LABELED = True  # `value` / `e2e` are the WHOLE Drawer::draw_to_pixels (area passes + label pass, drawer.rs:60-131), as the
+# reference always runs it; the area passes alone (round 1's headline) are reported as value_area_only / e2e_area_only
 
 
 def log(*a):
@@ -383,12 +385,12 @@ def run_reference(args, rank):
     (oracle/osmr_oracle.cpp), all host threads, tiles dealt to the threads like src/http_server.rs:50-83,105-108."""
     if rank != 0:
         return
-    w = build_workload(args.workload, args.style, labels=True)
+    labeled = HEADLINE_LABELED and args.workload != "C4"
+    w = build_workload(args.workload, args.style, labels=True if args.workload != "C4" else False)
     threads = host_threads()
     n_tiles = len(w["tiles"])
     sample = args.cpu_sample or min(n_tiles, max(16 * threads, 256))  # several tiles per thread: the threads stay busy
     sel = spread(n_tiles, sample)
-    labeled = HEADLINE_LABELED
     for _ in range(max(0, min(args.warmup, 1))):
         cpu_port_throughput(w, spread(n_tiles, threads), threads, labeled)
     t_tot, n_tot = 0.0, 0
@@ -398,7 +400,7 @@ def run_reference(args, rank):
         n_tot += len(sel)
     value = n_tot / t_tot
     # the other variant once, as a sibling
-    tps_other, dt_other, _ = cpu_port_throughput(w, sel, threads, not labeled)
+    tps_other, dt_other, _ = cpu_port_throughput(w, sel, threads, (not labeled) and args.workload != "C4")
     tps_1, _, _ = cpu_port_throughput(w, spread(n_tiles, max(4, len(sel) // threads)), 1, labeled)
     sib = {"value": tps_other, "unit": "tiles/s", "sample": f"{len(sel)} tiles, one pass"}
     line = {
@@ -539,22 +541,38 @@ def main():
     if args.resident_chunks:
         ctx.debug_set("resident_chunks", args.resident_chunks)
     single = len(calls) == 1
-    if single:
-        ctx.batch_upload(calls[0][1], calls[0][2], calls[0][3])
+    headline_labeled = HEADLINE_LABELED and labeled
+    if labeled:
+        ctx.set_font(w["font"])
+        ctx.set_label_table(w["ltable"])
+        call_labels = [sub_batch(w, c[4], True)[3:] for c in calls]
 
-    def resident_step(acc=None):
+    def upload(i, with_labels):
+        z, t, b, a, s = calls[i]
+        if with_labels:
+            ctx.batch_upload_labeled(t, b, a, call_labels[i][0], call_labels[i][1])
+        else:
+            ctx.batch_upload(t, b, a)
+
+    if single:
+        upload(0, headline_labeled)
+
+    def resident_step(acc=None, with_labels=None):
+        with_labels = headline_labeled if with_labels is None else with_labels
         ev = 0.0
-        for z, t, b, a, s in calls:
+        for i, (z, t, b, a, s) in enumerate(calls):
             if not single:
-                ctx.batch_upload(t, b, a)  # (several calls per step: the description is re-sent; C4 / strong scaling only)
-            ms = ctx.batch_draw(w["canvas"], w["caps"])
+                upload(i, with_labels)  # (several calls per step: the description is re-sent; C4 / strong scaling only)
+            ms = ctx.batch_draw_labeled(w["canvas"], w["caps"]) if with_labels else ctx.batch_draw(w["canvas"], w["caps"])
             ev += ms
             if acc is not None:
                 st = ctx.stats()
                 acc.setdefault("zoom_ms", {}).setdefault(z, []).append(ms)
                 acc.setdefault("zoom_tiles", {})[z] = acc.setdefault("zoom_tiles", {}).get(z, 0) + len(t)
-                for k in ("ms_raster", "ms_plan", "ms_cover"):
+                for k in ("ms_raster", "ms_plan", "ms_cover", "ms_label_device", "ms_label_cover"):
                     acc[k] = acc.get(k, 0.0) + st[k]
+                for k in ("n_labels_active", "n_label_segments", "n_label_cells"):
+                    acc.setdefault("lstats", {})[k] = acc.setdefault("lstats", {}).get(k, 0) + int(st[k])
                 acc["launches"] = acc.get("launches", 0) + st["kernel_launches"]
                 for k in ("n_tiles", "n_areas", "n_visible_ops", "n_node_refs", "geom_bytes", "mask_bytes", "walk_bytes", "walk_steps"):
                     acc.setdefault("stats", {})[k] = acc.setdefault("stats", {}).get(k, 0) + int(st[k])
@@ -577,7 +595,27 @@ def main():
     raster_ms = acc["ms_raster"] / args.steps
     plan_ms = acc["ms_plan"] / args.steps
     cover_ms = acc["ms_cover"] / args.steps
+    label_ms = acc["ms_label_device"] / args.steps
+    label_cover_ms = acc["ms_label_cover"] / args.steps
+    lstats = {k: v // args.steps for k, v in acc.get("lstats", {}).items()}
     launches = acc["launches"]
+
+    # ---- value_area_only: the Fill / Casing / Stroke passes alone (round 1's headline), same protocol ----
+    area_only = None
+    if headline_labeled:
+        if single:
+            upload(0, False)
+        for _ in range(3):
+            resident_step(None, False)
+        barrier()
+        t0a = time.perf_counter()
+        for _ in range(args.steps):
+            resident_step(None, False)
+        barrier()
+        area_wall = time.perf_counter() - t0a
+        area_only = {"wall": area_wall}
+        if single:
+            upload(0, True)
 
     # ---- sustained: the same step repeated for >= min_seconds (power / thermal behaviour, median and min per step) ----
     sustained = None
@@ -691,8 +729,6 @@ def main():
     lab = None
     lab_wall = None
     if labeled:
-        ctx.set_font(w["font"])
-        ctx.set_label_table(w["ltable"])
         lab_calls = []
         lab_h2d = 0
         for (z, t, b, a, s), (_, n, pt, pb, pa, nt) in zip(calls, e2e_calls):
@@ -787,6 +823,11 @@ def main():
             leg["d2h_gbs_per_rank"] = leg["d2h_bytes_per_step"] * args.steps / lw / 1e9
     raster_mean_ms, _ = red(raster_ms)
     cover_mean_ms, _ = red(cover_ms)
+    label_cover_mean_ms, _ = red(label_cover_ms)
+    if area_only is not None:
+        aw, at = red(area_only["wall"])
+        area_only = {"value": at / aw, "unit": "tiles/s", "ms_per_step": 1000.0 * aw / args.steps,
+                     "path": "Fill, Casing and Stroke passes only (osmr_batch_draw), resident: round 1's headline leg"}
     if sustained is not None:
         sw, stl = sharding.reduce_job(dist, sustained["seconds"], tiles_per_step * sustained["steps"], device="cuda")
         sustained["tiles_per_s"] = stl / sw
@@ -821,6 +862,16 @@ def main():
     else:
         dom, dom_ms, local_bytes = "raster_kernel", raster_mean_ms, raster_local
     algo_bytes = b_step if b_step is not None else local_bytes - walk_alpha_bytes
+    area_dom = {"kernel": dom, "kernel_ms": dom_ms, "kernel_local_bytes": int(local_bytes), "algorithmic_bytes_B_tile": None if b_step is None else int(b_step),
+                "frac_B_tile": None if b_step is None else b_step / (dom_ms / 1000.0) / 1e9 / peak, "kernel_local_frac": local_bytes / (dom_ms / 1000.0) / 1e9 / peak}
+    if headline_labeled and label_cover_mean_ms > dom_ms:
+        # the longest kernel of a labelled step is the glyph coverage: it reads every outline segment once (32 B, the reference's
+        # draw_line call stream) and writes / sweeps the coverage cells (2 x 8 B); SURVEY 8(d)'s B_tile has no label term, so the
+        # label inputs are added to it: 8 B per label generation listed + 32 B per segment + 16 B per coverage cell
+        dom, dom_ms = "label_cover_kernel", label_cover_mean_ms
+        local_bytes = 32 * lstats.get("n_label_segments", 0) + 16 * lstats.get("n_label_cells", 0)
+        algo_bytes = local_bytes
+        walk_alpha_bytes = 0
     achieved = algo_bytes / (dom_ms / 1000.0) / 1e9
     traffic = None
     prof_json = os.path.join(ROOT, "profiles", "roofline_traffic.json")
@@ -853,6 +904,7 @@ def main():
         "whole_step_frac": (b_step / (step_ms / 1000.0) / 1e9 / peak) if b_step is not None else None,
         # the write-only variant north_star quotes: whole-path tiles/s x 4*D^2 output bytes against the HBM peak
         "north_star_write_frac": (value / world) * (4.0 * D * D) / (peak * 1e9),
+        "area_passes_dominant_kernel": area_dom,
         "note": "the path is FP64/integer-issue and latency bound, not HBM bound (SURVEY.md F6); see profiles/",
     }
 
@@ -875,11 +927,18 @@ def main():
         # second half of BASELINE.json's metric: max |dRGB| of the GPU tiles (e2e output) against the CPU render
         max_abs_diff = int(max(np.abs(gpu_last[i].astype(np.int16) - im.astype(np.int16)).max() for i, im in zip(pick, imgs)))
         if lab is not None:
-            pickl = spread(n_last, max(threads, n_sample // 4))
+            pickl = spread(n_last, max(threads, n_sample // 2))
             tpsl, dtl, imgsl = cpu_port_throughput(w, last_sel[pickl], threads, labeled=True)
-            cpu["value_labeled"] = tpsl
-            cpu["sample_labeled"] = f"{len(pickl)} tiles, {dtl:.1f}s, draw_to_pixels with the label pass"
             max_abs_diff_lab = int(max(np.abs(gpu_lab_last[i].astype(np.int16) - im.astype(np.int16)).max() for i, im in zip(pickl, imgsl)))
+            if headline_labeled:  # the headline path is the whole draw_to_pixels: its CPU figure is `value`
+                tps1l, dt1l, _ = cpu_port_throughput(w, last_sel[pick1], 1, labeled=True)
+                cpu = {"value": tpsl, "unit": "tiles/s", "cores": threads, "kind": "port",
+                       "sample": f"{len(pickl)} tiles spread over the same batch, {dtl:.1f}s, C++ restatement of the reference CPU path (draw_to_pixels with the label pass), tiles dealt to the threads round-robin",
+                       "value_1_thread": tps1l, "sample_1_thread": f"{len(pick1)} tiles, {dt1l:.1f}s",
+                       "value_area_only": tps, "value_area_only_1_thread": tps1}
+            else:
+                cpu["value_labeled"] = tpsl
+                cpu["sample_labeled"] = f"{len(pickl)} tiles, {dtl:.1f}s, draw_to_pixels with the label pass"
 
     per_zoom = None
     if args.workload == "C4":
@@ -912,7 +971,10 @@ def main():
         "device_only": {"value": total_tiles / dev_s_max, "ms_per_step": 1000.0 * dev_s_max / args.steps,
                         "note": "sum of the per-call CUDA-event times; `value` is wall clock between barriers"},
         "sustained": sustained,
-        "stage_ms": {"plan+geometry+fill_rows": plan_ms, "line_cover": cover_ms, "raster": raster_ms},
+        "stage_ms": {"plan+geometry+fill_rows+bin": plan_ms, "line_cover": cover_ms, "raster": raster_ms,
+                     "label_pass (own stream, beside the area stages)": label_ms, "label_cover (inside label_pass)": label_cover_ms},
+        "value_area_only": area_only,
+        "label_stats": lstats,
         # the reference's perf-stats stage names (drawer.rs:51-123) where a stage is separable on the device
         "perf_stats": {"Style areas": (auto or {}).get("ms_auto_stage_last_call"), "Fill areas + Draw areas": plan_ms + cover_ms + raster_ms,
                        "Resetting TilePixels / Blend after areas / RGB export": "fused into raster_kernel",
@@ -935,9 +997,13 @@ def main():
         "max_abs_diff_rgb_vs_cpu": max_abs_diff,
         "max_abs_diff_rgb_vs_cpu_labeled": max_abs_diff_lab,
     }
-    if HEADLINE_LABELED and lab is not None:
+    if headline_labeled and lab is not None:
         line["e2e_area_only"] = e2e_line
-        line["e2e"] = {k: lab[k] for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step", "ms_per_step", "api")}
+        line["e2e"] = lab
+        del line["e2e_labeled"]
+        line["path"] = "the whole Drawer::draw_to_pixels (drawer.rs:60-131): Fill, Casing, Stroke passes + label pass"
+    else:
+        line["path"] = "Fill, Casing and Stroke passes of Drawer::draw_to_pixels (no label lists in this workload)"
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

@@ -173,6 +173,9 @@ typedef struct osmr_stats {
     uint32_t n_labels_active;    /* device layout: label generations with an icon or an existing text */
     uint32_t n_labels_polylabel; /* device layout: of those, areas whose anchor is the pole of inaccessibility (labelable.rs:125-189) */
     uint32_t label_attempts;     /* device layout: attempts of this call (> 1: scratch was grown and the call redone) */
+    float ms_label_cover;        /* device layout: label_cover_kernel alone (the longest kernel of a labelled draw) */
+    uint32_t n_label_segments;   /* device layout: glyph outline segments (draw_line calls of the reference's rasteriser) */
+    uint64_t n_label_cells;      /* device layout: coverage cells of the labels that touch the label canvas */
 } osmr_stats;
 int osmr_get_stats(osmr_ctx* ctx, osmr_stats* out);
 
@@ -231,6 +234,12 @@ int osmr_set_label_styles(osmr_ctx* ctx, const osmr_label_style* styles, uint32_
 int osmr_draw_tiles_labeled(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, const uint32_t* area_begin,
                             const osmr_styled_area* areas, const uint32_t* label_begin, const osmr_label* labels,
                             const uint8_t canvas_rgb[3], uint32_t flags, uint8_t* out);
+
+/* The same call with everything resident in HBM (benchmark "value" leg of the whole draw_to_pixels): upload once, draw any number
+ * of times; `out` / `gpu_ms` as in osmr_batch_draw.  Needs the device label layout (scale 1, 2, 4 or 8; zoom <= 18). */
+int osmr_batch_upload_labeled(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, const uint32_t* area_begin,
+                              const osmr_styled_area* areas, const uint32_t* label_begin, const osmr_label* labels);
+int osmr_batch_draw_labeled(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t flags, uint8_t* out, float* gpu_ms);
 
 /* ------------------------------------------------------------------------------------------------------------
  * the step BEFORE the draw path on the device -- tile -> candidate entities -> ordered styled areas.
@@ -301,7 +310,7 @@ void osmr_free_pinned(void* p);
  *                           host libm, i.e. the reference's own values to the last bit). */
 int osmr_debug_set(osmr_ctx* ctx, const char* key, int value);
 
-uint32_t osmr_abi_version(void); /* 3: osmr_stats gained the label_* fields; osmr_draw_tiles_auto_png; label layout on the device */
+uint32_t osmr_abi_version(void); /* 4: osmr_stats gained the label_* fields; osmr_draw_tiles_auto_png, osmr_ctx_create_shared, osmr_batch_*_labeled */
 
 #ifdef __cplusplus
 }

@@ -42,6 +42,8 @@ EXPORTS = [
     "osmr_rgb_to_png",
     "osmr_draw_tiles_auto_png",
     "osmr_ctx_create_shared",
+    "osmr_batch_upload_labeled",
+    "osmr_batch_draw_labeled",
 ]
 
 _lib = None
@@ -115,6 +117,10 @@ def load():
     L.osmr_draw_tiles_png.argtypes = [vp, vp, u32, vp, vp, vp, u32, vp, sz, vp]
     L.osmr_rgb_to_png.restype = C.c_int
     L.osmr_rgb_to_png.argtypes = [vp, vp, u32, u32, vp, sz, vp]
+    L.osmr_batch_upload_labeled.restype = C.c_int
+    L.osmr_batch_upload_labeled.argtypes = [vp, vp, u32, vp, vp, vp, vp]
+    L.osmr_batch_draw_labeled.restype = C.c_int
+    L.osmr_batch_draw_labeled.argtypes = [vp, vp, u32, vp, C.POINTER(C.c_float)]
     L.osmr_ctx_create_shared.restype = C.c_int
     L.osmr_ctx_create_shared.argtypes = [vp, C.POINTER(vp)]
     L.osmr_draw_tiles_auto_png.restype = C.c_int

@@ -144,7 +144,7 @@ struct osmr_ctx {
     DevBuf<unsigned> d_cover_list, d_cover_cursor;
     std::vector<LabelWorkItem> label_items;  // kept between calls: their vectors' capacity is the layout arena
     PinnedBuf<osmr_host::Seg> h_label_segs;
-    cudaEvent_t ev_label0 = nullptr, ev_label1 = nullptr;
+    cudaEvent_t ev_label0 = nullptr, ev_label1 = nullptr, ev_lcov0 = nullptr, ev_lcov1 = nullptr;
     float stats_label_layout_ms = 0.f, stats_label_device_ms = 0.f;
     unsigned label_threads = 32;
     DevBuf<LabelPix> label_plane;
@@ -179,8 +179,12 @@ struct osmr_ctx {
     DevBuf<unsigned char> l_heap;
     PinnedBuf<unsigned> h_lcnt;
     size_t l_places_cap = 0, l_segs_cap = 0, l_rowrecs_cap = 0, l_cells_cap = 0, l_ring_cap = 0, l_heap_slots = 0;
+    std::vector<osmr_tile> h_batch_tiles;     // resident labelled batch: host copies for the table look-ups of the label pass
+    std::vector<uint32_t> h_label_begin;
+    bool batch_has_labels = false;
     bool label_host_only = false;  // debug key "label_host": always lay labels out on the host (round-1 path)
-    unsigned stats_label_active = 0, stats_label_poly = 0;
+    unsigned stats_label_active = 0, stats_label_poly = 0, stats_label_segs = 0;
+    unsigned long long stats_label_cells = 0;
     // styles / icons
     unsigned n_styles = 0, n_dashes = 0, n_icons = 0;
     DevBuf<osmr_style> styles;
@@ -307,7 +311,7 @@ static inline uint32_t rd_u32(const uint8_t* p) {
 
 extern "C" {
 
-uint32_t osmr_abi_version(void) { return 3; }
+uint32_t osmr_abi_version(void) { return 4; }
 
 int osmr_ctx_create(int device, osmr_ctx** out_ctx) try {
     if (!out_ctx) return OSMR_E_INVALID;
@@ -338,6 +342,8 @@ int osmr_ctx_create(int device, osmr_ctx** out_ctx) try {
     for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_label0);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_label1);
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_lcov0);
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_lcov1);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) {
         double lut[256];
@@ -429,6 +435,8 @@ void osmr_ctx_destroy(osmr_ctx* ctx) {
     if (ctx->areas_ready) cudaEventDestroy(ctx->areas_ready);
     if (ctx->ev_label0) cudaEventDestroy(ctx->ev_label0);
     if (ctx->ev_label1) cudaEventDestroy(ctx->ev_label1);
+    if (ctx->ev_lcov0) cudaEventDestroy(ctx->ev_lcov0);
+    if (ctx->ev_lcov1) cudaEventDestroy(ctx->ev_lcov1);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -908,6 +916,7 @@ static int batch_upload_impl(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_t
     uint32_t n_areas = area_begin[n_tiles];
     if (n_areas && !areas) return ctx->fail(OSMR_E_INVALID, "null area list");
     ctx->has_batch = false;
+    ctx->batch_has_labels = false;
     CK(ctx->tiles.reserve(n_tiles));
     CK(ctx->area_begin.reserve(n_tiles + 1));
     CK(ctx->areas.reserve(n_areas + 1));
@@ -2042,7 +2051,8 @@ static bool label_device_path_allowed(const osmr_ctx* ctx, const osmr_tile* tile
 // Enqueues the whole label pass on the compute stream (nothing here waits for the device): layout kernels, glyph coverage,
 // greedy collisions -> ctx->label_plane.  The counters land in page-locked memory; label_device_judge reads them after the
 // draw has synchronised the stream.
-static int label_device_enqueue(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, const uint32_t* label_begin, const osmr_label* labels) {
+static int label_device_enqueue(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, const uint32_t* label_begin, const osmr_label* labels,
+                                bool resident = false) {
     auto& R = ctx->lres;
     const int D = 256 * ctx->scale, E = 3 * D;
     if (!R.valid) {
@@ -2097,8 +2107,10 @@ static int label_device_enqueue(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t 
     CK(ctx->label_occ.reserve((size_t)n_tiles * ((size_t)E * E / 32)));
     CK(ctx->label_plane.reserve((size_t)n_tiles * D * D));
     CK(cudaEventRecord(ctx->ev_label0, st));
-    if (n_labels) CK(cudaMemcpyAsync(ctx->d_label_list.p, labels, (size_t)n_labels * sizeof(osmr_label), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(ctx->d_label_begin.p, label_begin, (size_t)(n_tiles + 1) * 4, cudaMemcpyHostToDevice, st));
+    if (!resident) {
+        if (n_labels) CK(cudaMemcpyAsync(ctx->d_label_list.p, labels, (size_t)n_labels * sizeof(osmr_label), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->d_label_begin.p, label_begin, (size_t)(n_tiles + 1) * 4, cudaMemcpyHostToDevice, st));
+    }
     CK(cudaMemsetAsync(ctx->l_counters.p, 0, LCNT_COUNT * sizeof(unsigned), st));
     Scene s{};
     s.merc = ctx->ds->merc.p;
@@ -2197,7 +2209,9 @@ static int label_device_enqueue(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t 
     ls.n_cover_dev = ctx->l_counters.p + LCNT_COVER;
     ls.label_cnt = ctx->l_act_cnt.p;
     ls.skip_flags = ctx->l_counters.p + LCNT_OVERFLOW;
+    CK(cudaEventRecord(ctx->ev_lcov0, st));
     label_cover_kernel<<<(unsigned)ctx->num_sms * 16u, 32, 0, st>>>(ls);
+    CK(cudaEventRecord(ctx->ev_lcov1, st));
     label_commit_kernel<<<n_tiles, kLabelThreads, 0, st>>>(ls);
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev_label1, st));
@@ -2233,6 +2247,12 @@ static int label_device_judge(osmr_ctx* ctx) {
     }
     ctx->stats_label_active = c[LCNT_ACTIVE];
     ctx->stats_label_poly = c[LCNT_POLY];
+    ctx->stats_label_segs = c[LCNT_SEGS];
+    {
+        unsigned long long cells;
+        memcpy(&cells, &c[LCNT_CELLS_LO], 8);
+        ctx->stats_label_cells = cells;
+    }
     if (getenv("OSMR_LABEL_DEBUG")) {
         unsigned long long cells;
         memcpy(&cells, &c[LCNT_CELLS_LO], 8);
@@ -2241,6 +2261,79 @@ static int label_device_judge(osmr_ctx* ctx) {
     }
     return 0;
 }
+
+// The resident form of osmr_draw_tiles_labeled (benchmark "value" leg): batch description AND label lists uploaded once ...
+int osmr_batch_upload_labeled(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, const uint32_t* area_begin, const osmr_styled_area* areas,
+                              const uint32_t* label_begin, const osmr_label* labels) try {
+    if (!ctx) return OSMR_E_INVALID;
+    if (!label_begin) return ctx->fail(OSMR_E_INVALID, "null label_begin");
+    if (!ctx->font.loaded()) return ctx->fail(OSMR_E_STATE, "osmr_set_font has not been called");
+    ctx->batch_has_labels = false;
+    int rc = batch_upload_impl(ctx, tiles, n_tiles, area_begin, areas, false, nullptr);
+    if (rc) return rc;
+    if (label_begin[0] != 0) return ctx->fail(OSMR_E_INVALID, "label_begin[0] must be 0");
+    for (uint32_t t = 0; t < n_tiles; ++t) {
+        if (label_begin[t + 1] < label_begin[t]) return ctx->fail(OSMR_E_INVALID, "label_begin must be non-decreasing");
+        if (label_begin[t + 1] > label_begin[t] && !labels) return ctx->fail(OSMR_E_INVALID, "null label list");
+    }
+    if (!label_device_path_allowed(ctx, tiles, n_tiles))
+        return ctx->fail(OSMR_E_STATE, "the resident labelled draw needs the device label layout (scale 1, 2, 4 or 8, zoom <= 18); use osmr_draw_tiles_labeled");
+    cudaSetDevice(ctx->device);
+    const uint32_t n_labels = label_begin[n_tiles];
+    CK(ctx->d_label_list.reserve((size_t)n_labels + 1));
+    CK(ctx->d_label_begin.reserve(n_tiles + 1));
+    if (n_labels) CK(cudaMemcpyAsync(ctx->d_label_list.p, labels, (size_t)n_labels * sizeof(osmr_label), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_label_begin.p, label_begin, (size_t)(n_tiles + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->h_batch_tiles.assign(tiles, tiles + n_tiles);
+    ctx->h_label_begin.assign(label_begin, label_begin + n_tiles + 1);
+    ctx->batch_has_labels = true;
+    return OSMR_OK;
+} OSMR_CATCH_INT(ctx)
+
+// ... then drawn any number of times: area passes + label pass, everything on the device.  `out` / `gpu_ms` as in osmr_batch_draw.
+int osmr_batch_draw_labeled(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t flags, uint8_t* out, float* gpu_ms) try {
+    if (!ctx) return OSMR_E_INVALID;
+    if (!ctx->has_batch || !ctx->batch_has_labels) return ctx->fail(OSMR_E_STATE, "no labelled batch uploaded (osmr_batch_upload_labeled)");
+    cudaSetDevice(ctx->device);
+    for (int attempt = 0; attempt < 12; ++attempt) {
+        int rc = label_device_enqueue(ctx, ctx->h_batch_tiles.data(), ctx->n_tiles, ctx->h_label_begin.data(), nullptr, true);
+        if (rc) {
+            cudaStreamSynchronize(ctx->label_stream);
+            return rc;
+        }
+        ctx->label_plane_active = true;
+        rc = osmr_batch_draw(ctx, canvas_rgb, flags, out, gpu_ms);
+        ctx->label_plane_active = false;
+        ctx->label_async = false;
+        cudaStreamSynchronize(ctx->label_stream);
+        if (rc) return rc;
+        const int verdict = label_device_judge(ctx);
+        if (verdict < 0) return verdict;
+        if (verdict == 0) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ctx->ev_label0, ctx->ev_label1);
+            ctx->stats.ms_label_layout = 0.f;
+            ctx->stats.ms_label_device = ms;
+            ctx->stats.kernel_launches += 13;
+            ctx->stats.label_path = 1;
+            ctx->stats.n_labels_active = ctx->stats_label_active;
+            ctx->stats.n_labels_polylabel = ctx->stats_label_poly;
+            ctx->stats.label_attempts = (uint32_t)attempt + 1;
+            {
+                float mc = 0.f;
+                cudaEventElapsedTime(&mc, ctx->ev_lcov0, ctx->ev_lcov1);
+                ctx->stats.ms_label_cover = mc;
+                ctx->stats.n_label_segments = ctx->stats_label_segs;
+                ctx->stats.n_label_cells = ctx->stats_label_cells;
+            }
+            return OSMR_OK;
+        }
+        if (verdict == 2)
+            return ctx->fail(OSMR_E_STATE, "this batch needs the host label layout (a flatness near-tie or an oversized polylabel); use osmr_draw_tiles_labeled");
+    }
+    return ctx->fail(OSMR_E_NOMEM, "label scratch kept overflowing");
+} OSMR_CATCH_INT(ctx)
 
 int osmr_draw_tiles_labeled(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, const uint32_t* area_begin,
                             const osmr_styled_area* areas, const uint32_t* label_begin, const osmr_label* labels,
@@ -2286,6 +2379,13 @@ int osmr_draw_tiles_labeled(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_ti
             ctx->stats.n_labels_active = ctx->stats_label_active;
             ctx->stats.n_labels_polylabel = ctx->stats_label_poly;
             ctx->stats.label_attempts = (uint32_t)attempt + 1;
+            {
+                float mc = 0.f;
+                cudaEventElapsedTime(&mc, ctx->ev_lcov0, ctx->ev_lcov1);
+                ctx->stats.ms_label_cover = mc;
+                ctx->stats.n_label_segments = ctx->stats_label_segs;
+                ctx->stats.n_label_cells = ctx->stats_label_cells;
+            }
             return OSMR_OK;
         }
         if (verdict == 2) on_device = false;

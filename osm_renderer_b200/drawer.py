@@ -172,6 +172,29 @@ class GpuContext:
         self._check(self.L.osmr_batch_draw(self.h, canvas.ctypes.data, flags, ptr, C.byref(ms)), "osmr_batch_draw")
         return float(ms.value)
 
+    def batch_upload_labeled(self, tiles, area_begin, areas, label_begin, labels):
+        from .wire import LABEL_DTYPE
+
+        tiles = np.ascontiguousarray(tiles, dtype=TILE_DTYPE)
+        area_begin = np.ascontiguousarray(area_begin, dtype=np.uint32)
+        areas = np.ascontiguousarray(areas, dtype=AREA_DTYPE)
+        label_begin = np.ascontiguousarray(label_begin, dtype=np.uint32)
+        labels = np.ascontiguousarray(labels, dtype=LABEL_DTYPE)
+        self._check(
+            self.L.osmr_batch_upload_labeled(self.h, tiles.ctypes.data, len(tiles), area_begin.ctypes.data, areas.ctypes.data,
+                                             label_begin.ctypes.data, labels.ctypes.data),
+            "osmr_batch_upload_labeled",
+        )
+        self._batch_shape = (len(tiles), 256 * int(tiles["scale"][0]))
+
+    def batch_draw_labeled(self, canvas_rgb, use_caps_for_dashes=True, rgba=False, out=None) -> float:
+        """Draw the resident labelled batch (area passes + label pass); returns device milliseconds."""
+        flags, canvas = self._flags(canvas_rgb, use_caps_for_dashes, rgba)
+        ms = C.c_float(0.0)
+        ptr = out.ctypes.data if out is not None else None
+        self._check(self.L.osmr_batch_draw_labeled(self.h, canvas.ctypes.data, flags, ptr, C.byref(ms)), "osmr_batch_draw_labeled")
+        return float(ms.value)
+
     def stats(self) -> dict:
         st = StatsStruct()
         self._check(self.L.osmr_get_stats(self.h, C.byref(st)), "osmr_get_stats")

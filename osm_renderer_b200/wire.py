@@ -103,6 +103,9 @@ class StatsStruct(C.Structure):
         ("n_labels_active", C.c_uint32),
         ("n_labels_polylabel", C.c_uint32),
         ("label_attempts", C.c_uint32),
+        ("ms_label_cover", C.c_float),
+        ("n_label_segments", C.c_uint32),
+        ("n_label_cells", C.c_uint64),
     ]
 
 

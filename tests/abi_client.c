@@ -45,7 +45,8 @@ SA(offsetof(osmr_stats, ms_plan) == 72 && offsetof(osmr_stats, ms_raster) == 76 
 SA(offsetof(osmr_stats, ms_label_layout) == 84 && offsetof(osmr_stats, ms_label_device) == 88 && offsetof(osmr_stats, ms_cover) == 92, stats_ms2);
 SA(offsetof(osmr_stats, ms_auto) == 96 && offsetof(osmr_stats, ms_png) == 100, stats_ms3);
 SA(offsetof(osmr_stats, label_path) == 104 && offsetof(osmr_stats, n_labels_active) == 108, stats_label);
-SA(offsetof(osmr_stats, n_labels_polylabel) == 112 && offsetof(osmr_stats, label_attempts) == 116 && sizeof(osmr_stats) == 120, stats_label2);
+SA(offsetof(osmr_stats, n_labels_polylabel) == 112 && offsetof(osmr_stats, label_attempts) == 116, stats_label2);
+SA(offsetof(osmr_stats, ms_label_cover) == 120 && offsetof(osmr_stats, n_label_segments) == 124 && offsetof(osmr_stats, n_label_cells) == 128 && sizeof(osmr_stats) == 136, stats_label3);
 
 int main(void) {
     osmr_ctx* ctx = (osmr_ctx*)1;

@@ -12,11 +12,12 @@ summ() { python - "$1" <<'PY'
 import json,sys
 d=json.load(open(sys.argv[1]))
 g=lambda k:(d.get(k) or {}).get('value')
+d.setdefault('e2e_labeled', d.get('e2e') if 'labeled' in (d.get('e2e') or {}).get('api','') else None)
 r=lambda v:None if v is None else round(v)
-print('value',r(d['value']),'ms',round(d['ms_per_step'],3),'stages',{k:round(v,3) for k,v in d['stage_ms'].items()},'e2e',r(g('e2e')),'lab',r(g('e2e_labeled')),
+print('value',r(d['value']),'ms',round(d['ms_per_step'],3),'stages',{k:round(v,3) for k,v in d['stage_ms'].items()},'e2e',r(g('e2e')),'area_only',r(g('value_area_only')),r(g('e2e_area_only')),
       'auto',r(g('e2e_auto')),'png',r(g('e2e_png')),'auto_png',r(g('e2e_auto_png')),'cpu',d.get('cpu_baseline'),'diff',d.get('max_abs_diff_rgb_vs_cpu'),d.get('max_abs_diff_rgb_vs_cpu_labeled'))
 print(' sustained',d.get('sustained'),'clocks',d.get('clocks'))
-print(' lab',d.get('e2e_labeled'))
+print(' e2e',d.get('e2e'))
 print(' latency',d.get('latency_ms'),'roofline frac',d['roofline']['frac'],'local',d['roofline']['kernel_local_frac'])
 PY
 }
