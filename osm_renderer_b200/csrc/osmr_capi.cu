@@ -118,7 +118,7 @@ struct osmr_ctx {
     cudaStream_t copy_stream = nullptr;
     cudaStream_t d2h_stream = nullptr;
     cudaEvent_t chunk_done[kMaxChunks] = {};
-    cudaEvent_t cev[kMaxChunks][4] = {};   // per draw chunk: start, after cover, after raster, before cover
+    cudaEvent_t cev[kMaxChunks][5] = {};   // per draw chunk: start, after cover, after raster, before cover, raster start (after the wait for the labels)
     unsigned chunk_launches[kMaxChunks] = {};
     PinnedBuf<unsigned> h_cnt;             // per draw chunk: its counters, copied back asynchronously
     cudaEvent_t areas_ready = nullptr;
@@ -337,7 +337,7 @@ int osmr_ctx_create(int device, osmr_ctx** out_ctx) try {
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_wall1);
     for (unsigned i = 0; i < kMaxChunks && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->chunk_done[i], cudaEventDisableTiming);
     for (unsigned i = 0; i < kMaxChunks; ++i)
-        for (int j = 0; j < 4 && e == cudaSuccess; ++j) e = cudaEventCreate(&ctx->cev[i][j]);
+        for (int j = 0; j < 5 && e == cudaSuccess; ++j) e = cudaEventCreate(&ctx->cev[i][j]);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->areas_ready, cudaEventDisableTiming);
     for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_label0);
@@ -1072,6 +1072,7 @@ static int launch_chunk(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t fla
     CK(cudaEventRecord(ev[1], st));
     const unsigned blocks = (unsigned)((D / kBW) * (D / kBH));
     if (ctx->label_async && ctx->label_plane_active) CK(cudaStreamWaitEvent(st, ctx->label_done, 0));
+    CK(cudaEventRecord(ev[4], st));  // (after the wait: the stage time of raster_kernel does not include the label pass)
     raster_kernel<<<tc * blocks, kRasterThreads, 0, st>>>(s);
     ++launches;
     CK(cudaGetLastError());
@@ -1155,7 +1156,7 @@ static int collect_chunk(osmr_ctx* ctx, unsigned slot, unsigned tb, unsigned tc,
     float ms_plan = 0, ms_cover = 0, ms_raster = 0;
     cudaEventElapsedTime(&ms_plan, ev[0], ev[3]);
     cudaEventElapsedTime(&ms_cover, ev[3], ev[1]);
-    cudaEventElapsedTime(&ms_raster, ev[1], ev[2]);
+    cudaEventElapsedTime(&ms_raster, ev[4], ev[2]);
     unsigned long long used_alpha, steps;
     memcpy(&used_alpha, &h_cnt[CNT_WALK_ALPHA], 8);
     memcpy(&steps, &h_cnt[CNT_WALK_STEPS], 8);
