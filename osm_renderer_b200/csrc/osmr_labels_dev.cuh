@@ -63,8 +63,10 @@ enum {
     LCNT_VERTS = 13,    // outline vertex instances handed out (one per vertex of every placed glyph)
     LCNT_CURVES = 14,   // of those, curves (the expensive ones: they get a compact work list of their own)
     LCNT_COVER_ERR = 3,  // label_cover_kernel: a pair fell outside its proven window (a logic error, never silent)
+    LCNT_CURVE_CURSOR_C = 16,  // work distribution of the curve kernels (counting / writing sweep)
+    LCNT_CURVE_CURSOR_W = 17,
     LCNT_SCAN_OVF = 15,  // (overflow word of the block-sum scan: segment counts beyond 2^32 also trip the capacity check)
-    LCNT_COUNT = 16
+    LCNT_COUNT = 20
 };
 
 struct ActLabel {  // a label generation that can draw or collide
@@ -1035,12 +1037,218 @@ __device__ __forceinline__ void label_vline_body(const LabelDev& ld) {
         label_vertex_instance<WRITE>(ld, i);
     }
 }
+// The curve kernels.  draw_quad (rasterizer.rs:86-107) is a recursion whose shape differs from curve to curve (8 .. 128
+// draw_line calls): a thread per curve left half of the lanes idle while the longest curve of the warp finished, and the walk
+// from the root to the next second half ran with four lanes.  Here the recursion is a state machine and the warp runs it in
+// lock step: every iteration every lane does at most one flatness decision and exactly one midpoint step of ITS curve -- a
+// descent into a first half and a step of the walk from the root towards a second half are the same operation -- and a lane
+// whose curve is finished takes the next curve of the list straight away.  Same operations on the same operands as the
+// recursion, in the same order per curve.
+struct CurveState {
+    double x0, y0, x1, y1, x2, y2;  // control points of the curve (the root of the subdivision tree)
+    double a0, b0, a1, b1, a2, b2;  // control points of the current node
+    double pa1, pb1, pa2, pb2;      // (p1, p2) of the current node's parent while the node is a first half reached by descending
+    unsigned path, node, n_segs, inst, curve;
+    int depth, target;              // target > depth: walking from the root to the node (path, target)
+    unsigned long long word;        // shape bits being collected / replayed
+    bool replay, tie;
+};
+
 template <bool WRITE>
 __device__ __forceinline__ void label_curve_body(const LabelDev& ld) {
+    constexpr unsigned kFull = 0xffffffffu;
+    constexpr int kMaxDepth = 30;
+    constexpr unsigned kShapeBits = 256;
     const unsigned n_curves = min(ld.counters[LCNT_CURVES], ld.verts_cap);
     if (ld.counters[LCNT_OVERFLOW] & 65u) return;
     if (WRITE && (ld.counters[LCNT_OVERFLOW] || ld.counters[LCNT_FALLBACK])) return;
-    for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < n_curves; k += gridDim.x * blockDim.x) label_vertex_instance<WRITE>(ld, ld.curve_list[k], k);
+    unsigned* cursor = &ld.counters[WRITE ? LCNT_CURVE_CURSOR_W : LCNT_CURVE_CURSOR_C];
+    const unsigned lane = lane_id();
+    CurveState c;
+    bool active = false, exhausted = false;
+    DevSeg* out = nullptr;
+    const EmitSink tester{};  // (only its flatness test is used)
+    for (;;) {
+        // ---- lanes without a curve take the next ones of the list ----
+        {
+            const unsigned need = __ballot_sync(kFull, !active && !exhausted);
+            if (need) {
+                unsigned base = 0;
+                if (lane == (unsigned)(__ffs(need) - 1)) base = atomicAdd(cursor, (unsigned)__popc(need));
+                base = __shfl_sync(kFull, base, __ffs(need) - 1);
+                if (!active && !exhausted) {
+                    const unsigned k = base + (unsigned)__popc(need & ((1u << lane) - 1u));
+                    if (k >= n_curves) {
+                        exhausted = true;
+                    } else {
+                        c.curve = k;
+                        c.inst = ld.curve_list[k];
+                        const unsigned gi = ld.vinst_place[c.inst];
+                        const GlyphPlace gp = ld.gplace[gi];
+                        const LabelPlace lp = ld.place[gp.label];
+                        const unsigned v0 = ld.glyph_vbegin[gp.slot];
+                        const unsigned vi = v0 + (c.inst - ld.place_vinst[gi]);
+                        const DevVertex v = ld.verts[vi];
+                        const double scale = lp.scale;
+                        const bool on_line = lp.mode == 1;
+                        const double wx = gp.a, wy = gp.b, sn = gp.c, cs = gp.d, gcx = gp.e, gcy = lp.gcy;
+                        auto tr = [&](double px, double py, double& ox, double& oy) {
+                            if (on_line) {  // text_placer.rs:76-93
+                                const double tx = px - gcx, ty = py - gcy;
+                                ox = wx + (tx * cs - ty * sn);
+                                oy = wy - (ty * cs + tx * sn);
+                            } else {  // text_placer.rs:150-160
+                                ox = wx + px;
+                                oy = wy - py;
+                            }
+                        };
+                        double fx = 0.0, fy = 0.0;  // `from`: the previous vertex's point ((0, 0) before the first one)
+                        if (vi > v0) {
+                            const DevVertex pv = ld.verts[vi - 1];
+                            fx = (double)pv.x * scale;
+                            fy = (double)pv.y * scale;
+                        }
+                        // Glyph::rasterize (text_placer.rs:211-231): draw_quad(to, control, from)
+                        tr((double)v.x * scale, (double)v.y * scale, c.x0, c.y0);
+                        tr((double)v.cx * scale, (double)v.cy * scale, c.x1, c.y1);
+                        tr(fx, fy, c.x2, c.y2);
+                        c.a0 = c.x0; c.b0 = c.y0; c.a1 = c.x1; c.b1 = c.y1; c.a2 = c.x2; c.b2 = c.y2;
+                        c.pa1 = c.pb1 = c.pa2 = c.pb2 = 0.0;
+                        c.path = 0u;
+                        c.node = 0u;
+                        c.n_segs = 0u;
+                        c.depth = 0;
+                        c.target = 0;
+                        c.word = 0ull;
+                        c.tie = false;
+                        c.replay = false;
+                        if (WRITE) {
+                            const unsigned long long* shape = ld.curve_shape + (size_t)k * 4u;
+                            c.replay = (shape[3] >> 63) == 0ull;
+                            c.word = shape[0];
+                            out = ld.segs + ld.vcnt[c.inst];
+                        }
+                        active = true;
+                    }
+                }
+            }
+        }
+        if (__all_sync(kFull, !active)) break;
+        if (active) {
+            bool do_mid = false, go_right = false;
+            if (c.depth < c.target) {  // walking from the root: one level per iteration
+                do_mid = true;
+                go_right = ((c.path >> (c.target - 1 - c.depth)) & 1u) != 0u;
+            } else {
+                // ---- the current node: flat? ----
+                bool flat;
+                if (c.replay) {
+                    flat = ((c.word >> (c.node & 63u)) & 1ull) == 0ull;
+                } else {
+                    EmitSink t2 = tester;
+                    t2.near_tie = false;
+                    flat = t2.flat_enough(c.a0, c.b0, c.a1, c.b1, c.a2, c.b2);
+                    if (t2.near_tie) c.tie = true;
+                    if (!flat && c.depth >= kMaxDepth) {  // absurd depth: not something the device decides
+                        c.tie = true;
+                        flat = true;
+                    }
+                    if (!WRITE && c.node < kShapeBits - 1u) {
+                        if (!flat) c.word |= 1ull << (c.node & 63u);
+                        if ((c.node & 63u) == 63u) {
+                            ld.curve_shape[(size_t)c.curve * 4u + (c.node >> 6)] = c.word;
+                            c.word = 0ull;
+                        }
+                    }
+                }
+                ++c.node;
+                if (WRITE && c.replay && (c.node & 63u) == 0u && c.node < kShapeBits) c.word = ld.curve_shape[(size_t)c.curve * 4u + (c.node >> 6)];
+                if (!flat) {  // descend into the first half
+                    c.pa1 = c.a1;
+                    c.pb1 = c.b1;
+                    c.pa2 = c.a2;
+                    c.pb2 = c.b2;
+                    do_mid = true;
+                    go_right = false;
+                    c.path <<= 1;
+                    c.target = c.depth + 1;
+                } else {
+                    // draw_line(p0, p2) of this leaf (rasterizer.rs:30-32: nothing happens when y does not change)
+                    if (c.b2 - c.b0 != 0.0) {
+                        if (WRITE) {
+                            DevSeg sg;
+                            sg.x0 = c.a0;
+                            sg.y0 = c.b0;
+                            sg.x1 = c.a2;
+                            sg.y1 = c.b2;
+                            out[c.n_segs] = sg;
+                        }
+                        ++c.n_segs;
+                    }
+                    if (c.depth > 0 && !(c.path & 1u)) {  // a first half: its second half is (m, (p1 + p2) / 2, p2)
+                        c.a0 = c.a2;
+                        c.b0 = c.b2;
+                        c.a1 = (c.pa1 + c.pa2) / 2.0;
+                        c.b1 = (c.pb1 + c.pb2) / 2.0;
+                        c.a2 = c.pa2;
+                        c.b2 = c.pb2;
+                        c.path |= 1u;
+                    } else {
+                        while (c.depth > 0 && (c.path & 1u)) {  // both halves of this ancestor are done
+                            c.path >>= 1;
+                            --c.depth;
+                        }
+                        if (c.depth == 0) {
+                            // ---- the curve is finished ----
+                            if (!WRITE) {
+                                ld.vcnt[c.inst] = c.n_segs;
+                                // bounds from the control points (a subdivided curve stays inside their hull; EmitSink::bound)
+                                const double inf = __longlong_as_double(0x7ff0000000000000LL);
+                                double4 bb = make_double4(inf, -inf, inf, -inf);
+                                if (c.n_segs) {
+                                    bb.x = fmin(fmin(c.x0, c.x1), c.x2);
+                                    bb.y = fmax(fmax(c.x0, c.x1), c.x2);
+                                    bb.z = fmin(fmin(c.y0, c.y1), c.y2);
+                                    bb.w = fmax(fmax(c.y0, c.y1), c.y2);
+                                }
+                                ld.vbox[c.inst] = bb;
+                                unsigned long long* shape = ld.curve_shape + (size_t)c.curve * 4u;
+                                if (c.node >= kShapeBits - 1u) {
+                                    shape[3] = 1ull << 63;  // too many nodes for the record: the writing sweep decides again
+                                } else {
+                                    shape[c.node >> 6] = c.word;
+                                    if ((c.node >> 6) < 3u) shape[3] = 0ull;
+                                }
+                                if (c.tie) atomicOr(&ld.counters[LCNT_FALLBACK], 1u);
+                            }
+                            active = false;
+                        } else {
+                            c.path |= 1u;  // the second half of that ancestor: walk down from the root along its path
+                            c.target = c.depth;
+                            c.depth = 0;
+                            c.a0 = c.x0; c.b0 = c.y0; c.a1 = c.x1; c.b1 = c.y1; c.a2 = c.x2; c.b2 = c.y2;
+                        }
+                    }
+                }
+            }
+            if (do_mid) {  // one midpoint step: into the first ((p0, a, m)) or the second half ((m, b, p2)) of the current node
+                const double ax = (c.a0 + c.a1) / 2.0, ay = (c.b0 + c.b1) / 2.0, bx = (c.a1 + c.a2) / 2.0, by = (c.b1 + c.b2) / 2.0;
+                const double mx = (ax + bx) / 2.0, my = (ay + by) / 2.0;
+                if (go_right) {
+                    c.a0 = mx;
+                    c.b0 = my;
+                    c.a1 = bx;
+                    c.b1 = by;
+                } else {
+                    c.a2 = mx;
+                    c.b2 = my;
+                    c.a1 = ax;
+                    c.b1 = ay;
+                }
+                ++c.depth;
+            }
+        }
+    }
 }
 __global__ void __launch_bounds__(128) label_vline_count_kernel(LabelDev ld) { label_vline_body<false>(ld); }
 __global__ void __launch_bounds__(128) label_vline_write_kernel(LabelDev ld) { label_vline_body<true>(ld); }
