@@ -174,6 +174,7 @@ struct osmr_ctx {
     DevBuf<unsigned> l_place_vinst, l_vinst_place, l_vcnt, l_curve_list, l_scan_blocks;
     DevBuf<double4> l_vbox;
     DevBuf<unsigned long long> l_curve_shape;
+    DevBuf<CurveRoot> l_curve_root;
     size_t l_verts_cap = 0;
     DevBuf<double2> l_ring_pts;
     DevBuf<unsigned char> l_heap;
@@ -2097,6 +2098,7 @@ static int label_device_enqueue(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t 
     CK(ctx->l_vbox.reserve(ctx->l_verts_cap + 8));
     CK(ctx->l_curve_list.reserve(ctx->l_verts_cap + 8));
     CK(ctx->l_curve_shape.reserve(4 * ctx->l_verts_cap + 8));
+    CK(ctx->l_curve_root.reserve(ctx->l_verts_cap + 8));
     CK(ctx->l_scan_blocks.reserve(n_scan_blocks + 8));
     CK(ctx->d_label_segs.reserve(ctx->l_segs_cap));
     CK(ctx->d_cover_list.reserve((size_t)n_labels + 1));
@@ -2163,6 +2165,7 @@ static int label_device_enqueue(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t 
     ld.vbox = ctx->l_vbox.p;
     ld.curve_list = ctx->l_curve_list.p;
     ld.curve_shape = ctx->l_curve_shape.p;
+    ld.curve_root = ctx->l_curve_root.p;
     ld.verts_cap = (unsigned)std::min<size_t>(ctx->l_verts_cap, 0xfffffff0u);
     ld.scan_blocks = ctx->l_scan_blocks.p;
     ld.n_scan_blocks = n_scan_blocks;

@@ -2050,6 +2050,8 @@ __global__ void __launch_bounds__(32) label_cover_kernel(LabelScene ls) {
     __shared__ unsigned s_seg[32];  // per lane of a chunk: first row inside the band (8 bits) | rows (8) | pair slots per row (16)
     __shared__ unsigned s_pre[33];  // prefix of crossings (rows) over the chunk's segments
     __shared__ unsigned s_slot[32]; // first pair slot of every segment of the chunk
+    __shared__ unsigned short s_live[kCovKeys];  // the keys of the batch that received pairs, ascending
+    __shared__ unsigned s_retry;    // a crossing needed more pair slots than the tight estimate: the batch is redone with the safe one
     __shared__ int s_kmin[kCovRows], s_kmax[kCovRows];
     if (ls.skip_flags && (ls.skip_flags[0] | ls.skip_flags[1])) return;
     const unsigned n_cover = ls.n_cover_dev ? *ls.n_cover_dev : ls.n_cover;
@@ -2086,7 +2088,13 @@ __global__ void __launch_bounds__(32) label_cover_kernel(LabelScene ls) {
             }
             __syncwarp();
             unsigned sc = 0;  // next segment
+            // Pair slots per crossing: the `a` cells it can touch + one `s`.  The tight estimate (pixel extent of the segment + 2)
+            // is exact unless a rounding error pushes an interpolated x across a pixel border; the safe one adds a cell on each
+            // side.  A batch is formed with the tight estimate (2-3 slots per crossing instead of 5: twice the segments per batch)
+            // and redone with the safe one in the rare case that a crossing ran out of slots.
+            bool tight = true;
             while (sc < nseg) {
+                if (lane == 0) s_retry = 0u;
                 // ================= a batch: chunks of 32 segments until the pair slots or the cell window are full =================
                 unsigned n_pairs = 0;  // pair slots handed out
                 int win_r0 = 0x7fffffff, win_r1 = -1, win_c0 = 0x7fffffff, win_c1 = -1;  // the batch's window (rows of the band, columns)
@@ -2099,6 +2107,9 @@ __global__ void __launch_bounds__(32) label_cover_kernel(LabelScene ls) {
                     while (sc + n_in < nseg) {
                         const unsigned j = sc + n_in + lane;
                         int r0 = 1, r1 = 0, c0 = 0, c1 = -1;
+#ifndef OSMR_EMULATED
+                        if (j + 64 < nseg) asm volatile("prefetch.global.L2 [%0];" ::"l"(segs + j + 64));  // the chunk after the next one
+#endif
                         if (j < nseg) {
                             const DevSeg sg = segs[j];
                             r0 = max(f64_as_i32(floor(fmin(sg.y0, sg.y1))), row_lo) - row_lo;
@@ -2112,7 +2123,7 @@ __global__ void __launch_bounds__(32) label_cover_kernel(LabelScene ls) {
                             c1 = (int)max(0ll, min(xb, (long long)W - 1));
                         }
                         const bool has = j < nseg && r1 >= r0;
-                        const unsigned need = has ? (unsigned)(r1 - r0 + 1) * (unsigned)(c1 - c0 + 2) : 0u;  // per row: the `a` cells + one `s`
+                        const unsigned need = has ? (unsigned)(r1 - r0 + 1) * (unsigned)(tight ? max(c1 - c0 - 1, 2) : c1 - c0 + 2) : 0u;  // per row: the `a` cells + one `s`
                         // the chunk is taken as a whole or not at all (except when it is the batch's first: then lane by lane)
                         unsigned tot = need;
                         int a0 = has ? r0 : 0x7fffffff, a1 = has ? r1 : -1, b0 = has ? c0 : 0x7fffffff, b1 = has ? c1 : -1;
@@ -2225,7 +2236,7 @@ __global__ void __launch_bounds__(32) label_cover_kernel(LabelScene ls) {
                         c1 = (int)max(0ll, min(xb, (long long)W - 1));
                     }
                     const unsigned nr = r1 >= r0 ? (unsigned)(r1 - r0 + 1) : 0u;
-                    const unsigned per_row = (unsigned)(c1 - c0 + 2);
+                    const unsigned per_row = (unsigned)(tight ? max(c1 - c0 - 1, 2) : c1 - c0 + 2);
                     unsigned incl = nr;
                     for (int o = 1; o < 32; o <<= 1) {
                         const unsigned y = __shfl_up_sync(kFull, incl, o);
@@ -2273,6 +2284,10 @@ __global__ void __launch_bounds__(32) label_cover_kernel(LabelScene ls) {
                                 kmn = min(kmn, x);
                                 kmx = max(kmx, x);
                                 if (cx < 0 || cx >= W) return;  // a key outside the label's columns: tracked, never stored
+                                if (w >= q_per && tight) {  // the tight slot estimate was one short: redo the batch with the safe one
+                                    s_retry = 1u;
+                                    return;
+                                }
                                 if (cx < win_c0 || cx > win_c1 || w >= q_per) {  // outside the proven window: never silent
                                     atomicOr(ls.err_flag, 1u);
                                     return;
@@ -2294,7 +2309,14 @@ __global__ void __launch_bounds__(32) label_cover_kernel(LabelScene ls) {
                     __syncwarp();
                 }
                 OSMR_COUNT("lcover.pairs", lane == 0 ? n_pairs : 0);
+                __syncwarp();
+                if (tight && s_retry) {  // (kmin / kmax updates are idempotent; everything else of the batch is rebuilt)
+                    OSMR_COUNT("lcover.retries", lane == 0);
+                    tight = false;
+                    continue;
+                }
                 // ---- B: stable counting sort of the pairs by key ----
+                unsigned n_live = 0;
                 {
                     unsigned carry = 0;
                     for (int kb = 0; kb < n_keys; kb += 32) {
@@ -2310,6 +2332,9 @@ __global__ void __launch_bounds__(32) label_cover_kernel(LabelScene ls) {
                             s_cnt[k] = (unsigned short)(carry + incl - v);  // becomes the running cursor
                         }
                         carry += __shfl_sync(kFull, incl, 31);
+                        const unsigned lv = __ballot_sync(kFull, v != 0u);
+                        if (v) s_live[n_live + (unsigned)__popc(lv & ((1u << lane) - 1u))] = (unsigned short)k;
+                        n_live += (unsigned)__popc(lv);
                     }
                     if (lane == 0) s_off[n_keys] = (unsigned short)carry;
                 }
@@ -2325,23 +2350,23 @@ __global__ void __launch_bounds__(32) label_cover_kernel(LabelScene ls) {
                     if (live && (peers & ((1u << lane) - 1u)) == 0u) s_cnt[key] = (unsigned short)(s_cnt[key] + __popc(peers));
                     __syncwarp();
                 }
-                // ---- C: a lane per cell, its pairs in order ----
-                for (int kb = 0; kb < n_keys; kb += 32) {
-                    const int k = kb + (int)lane;
-                    if (k < n_keys) {
+                // ---- C: a lane per cell that received pairs, its pairs in order ----
+                for (unsigned kb = 0; kb < n_live; kb += 32) {
+                    const unsigned i = kb + lane;
+                    if (i < n_live) {
+                        const int k = (int)s_live[i];
                         const unsigned u0 = s_off[k], u1 = s_off[k + 1];
-                        if (u1 > u0) {
-                            const int cell = k >> 1;
-                            const int r = win_r0 + cell / win_w, cx = win_c0 + cell % win_w;
-                            double* dst = ((k & 1) ? S : A) + (size_t)(band + r) * W + cx;
-                            double acc = *dst;
-                            for (unsigned u = u0; u < u1; ++u) acc += s_val[s_order[u]];
-                            *dst = acc;
-                        }
+                        const int cell = k >> 1;
+                        const int r = win_r0 + cell / win_w, cx = win_c0 + cell % win_w;
+                        double* dst = ((k & 1) ? S : A) + (size_t)(band + r) * W + cx;
+                        double acc = *dst;
+                        for (unsigned u = u0; u < u1; ++u) acc += s_val[s_order[u]];
+                        *dst = acc;
                     }
                 }
                 __syncwarp();
                 sc += n_in;
+                tight = true;
             }
             // ---- sweep (save_to_figure): the lane of a row, left to right over the touched keys ----
 #pragma unroll 1

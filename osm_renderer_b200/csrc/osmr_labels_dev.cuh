@@ -93,6 +93,9 @@ struct LabelPlace {  // layout result of an active label
 };
 // (GlyphOut -- a glyph's segment range and bounds -- is declared in osmr_kernels.cuh next to its reader, label_cover_kernel)
 
+struct CurveRoot {  // draw_quad(to, control, from) of a placed glyph's curve vertex (text_placer.rs:211-231)
+    double x0, y0, x1, y1, x2, y2;
+};
 struct LabelDev {
     // resident tables
     const DevLabelStyle* styles;
@@ -124,6 +127,7 @@ struct LabelDev {
     unsigned* vcnt;         // per vertex instance: segments it draws; after the scan: offset of its first segment ([n]: total)
     double4* vbox;          // per vertex instance: bounds of its segments (min x, max x, min y, max y)
     unsigned* curve_list;   // vertex instances that are curves
+    CurveRoot* curve_root;  // per curve: its control points in pixel space (label_vfill_kernel)
     unsigned long long* curve_shape;  // per curve: 4 words, the shape of its subdivision tree (EmitSink::quad)
     unsigned verts_cap;
     unsigned* scan_blocks;  // block sums of the segment-offset scan
@@ -996,9 +1000,42 @@ __global__ void __launch_bounds__(128) label_vfill_kernel(LabelDev ld) {
         if (lp.mode == 0) continue;  // the label lost its vertex block to an overflow
         const unsigned v0 = ld.glyph_vbegin[gp.slot], v1 = ld.glyph_vbegin[gp.slot + 1];
         const unsigned vo = ld.place_vinst[gi];
+        const double scale = lp.scale;
+        const bool on_line = lp.mode == 1;
+        const double wx = gp.a, wy = gp.b, sn = gp.c, cs = gp.d, gcx = gp.e, gcy = lp.gcy;
+        auto tr = [&](double px, double py, double& ox, double& oy) {
+            if (on_line) {  // text_placer.rs:76-93
+                const double tx = px - gcx, ty = py - gcy;
+                ox = wx + (tx * cs - ty * sn);
+                oy = wy - (ty * cs + tx * sn);
+            } else {  // text_placer.rs:150-160
+                ox = wx + px;
+                oy = wy - py;
+            }
+        };
+        double fx = 0.0, fy = 0.0;  // `from`: the previous vertex's point ((0, 0) before the first one)
         for (unsigned vi = v0; vi < v1; ++vi) {
-            ld.vinst_place[vo + (vi - v0)] = gi;
-            if (ld.verts[vi].type == 3) ld.curve_list[atomicAdd(&ld.counters[LCNT_CURVES], 1u)] = vo + (vi - v0);
+            const unsigned inst = vo + (vi - v0);
+            ld.vinst_place[inst] = gi;
+            const DevVertex v = ld.verts[vi];
+            const double tx = (double)v.x * scale, ty = (double)v.y * scale;
+            if (v.type == 3) {
+                // the curve's work item: Glyph::rasterize (text_placer.rs:211-231) calls draw_quad(to, control, from); the
+                // curve kernels start from these points without walking the placement tables again
+                const unsigned k = atomicAdd(&ld.counters[LCNT_CURVES], 1u);
+                CurveRoot r;
+                tr(tx, ty, r.x0, r.y0);
+                tr((double)v.cx * scale, (double)v.cy * scale, r.x1, r.y1);
+                tr(fx, fy, r.x2, r.y2);
+                ld.curve_list[k] = inst;
+                ld.curve_root[k] = r;
+                // bounds from the control points (a subdivided curve stays inside their hull; EmitSink::bound).  The counting
+                // sweep empties them again for a curve that draws nothing.
+                ld.vbox[inst] = make_double4(fmin(fmin(r.x0, r.x1), r.x2), fmax(fmax(r.x0, r.x1), r.x2), fmin(fmin(r.y0, r.y1), r.y2),
+                                             fmax(fmax(r.y0, r.y1), r.y2));
+            }
+            fx = tx;
+            fy = ty;
         }
     }
 }
@@ -1038,32 +1075,35 @@ __device__ __forceinline__ void label_vline_body(const LabelDev& ld) {
     }
 }
 // The curve kernels.  draw_quad (rasterizer.rs:86-107) is a recursion whose shape differs from curve to curve (8 .. 128
-// draw_line calls): a thread per curve left half of the lanes idle while the longest curve of the warp finished, and the walk
-// from the root to the next second half ran with four lanes.  Here the recursion is a state machine and the warp runs it in
-// lock step: every iteration every lane does at most one flatness decision and exactly one midpoint step of ITS curve -- a
-// descent into a first half and a step of the walk from the root towards a second half are the same operation -- and a lane
-// whose curve is finished takes the next curve of the list straight away.  Same operations on the same operands as the
-// recursion, in the same order per curve.
+// draw_line calls).  Here it is a state machine and the warp runs it in lock step: every iteration every lane visits one node of
+// ITS curve's subdivision tree -- a flatness decision (or its recorded bit), then either the midpoint step into the first half
+// or the leaf's draw_line and the move to the next second half -- and a lane whose curve is finished takes the next curve of the
+// list straight away (control points precomputed by label_vfill_kernel: one independent load, no walk through the placement
+// tables while 31 lanes wait).  The recursion's stack is (p1, p2) per level in shared memory, so the second half of ANY ancestor
+// follows its first half in one step: it starts where the last leaf ended (the midpoint is handed down unchanged) and its
+// control point is (p1 + p2) / 2 -- the operations of the recursion on the same operands, per curve in the same order.
+constexpr int kCurveStackLevels = 6;  // levels of the subdivision stack kept in shared memory (a 90 degree curve needs 6; 8 CTAs per SM fit)
+constexpr int kCurveMaxDepth = 30;
 struct CurveState {
-    double x0, y0, x1, y1, x2, y2;  // control points of the curve (the root of the subdivision tree)
     double a0, b0, a1, b1, a2, b2;  // control points of the current node
-    double pa1, pb1, pa2, pb2;      // (p1, p2) of the current node's parent while the node is a first half reached by descending
     unsigned path, node, n_segs, inst, curve;
-    int depth, target;              // target > depth: walking from the root to the node (path, target)
-    unsigned long long word;        // shape bits being collected / replayed
+    int depth;
+    unsigned long long word;  // shape bits being collected / replayed
     bool replay, tie;
 };
 
+// `stk`: [4][kCurveStackLevels][128] doubles of shared memory -- (p1, p2) of the ancestors of the current node, by depth.
 template <bool WRITE>
-__device__ __forceinline__ void label_curve_body(const LabelDev& ld) {
+__device__ __forceinline__ void label_curve_body(const LabelDev& ld, double* stk) {
     constexpr unsigned kFull = 0xffffffffu;
-    constexpr int kMaxDepth = 30;
     constexpr unsigned kShapeBits = 256;
     const unsigned n_curves = min(ld.counters[LCNT_CURVES], ld.verts_cap);
     if (ld.counters[LCNT_OVERFLOW] & 65u) return;
     if (WRITE && (ld.counters[LCNT_OVERFLOW] || ld.counters[LCNT_FALLBACK])) return;
     unsigned* cursor = &ld.counters[WRITE ? LCNT_CURVE_CURSOR_W : LCNT_CURVE_CURSOR_C];
     const unsigned lane = lane_id();
+    double* my_stk = stk + threadIdx.x;
+    double deep[(kCurveMaxDepth + 1 - kCurveStackLevels) * 4];  // absurdly deep trees only (local memory, never touched otherwise)
     CurveState c;
     bool active = false, exhausted = false;
     DevSeg* out = nullptr;
@@ -1081,44 +1121,14 @@ __device__ __forceinline__ void label_curve_body(const LabelDev& ld) {
                     if (k >= n_curves) {
                         exhausted = true;
                     } else {
+                        const CurveRoot r = ld.curve_root[k];
                         c.curve = k;
                         c.inst = ld.curve_list[k];
-                        const unsigned gi = ld.vinst_place[c.inst];
-                        const GlyphPlace gp = ld.gplace[gi];
-                        const LabelPlace lp = ld.place[gp.label];
-                        const unsigned v0 = ld.glyph_vbegin[gp.slot];
-                        const unsigned vi = v0 + (c.inst - ld.place_vinst[gi]);
-                        const DevVertex v = ld.verts[vi];
-                        const double scale = lp.scale;
-                        const bool on_line = lp.mode == 1;
-                        const double wx = gp.a, wy = gp.b, sn = gp.c, cs = gp.d, gcx = gp.e, gcy = lp.gcy;
-                        auto tr = [&](double px, double py, double& ox, double& oy) {
-                            if (on_line) {  // text_placer.rs:76-93
-                                const double tx = px - gcx, ty = py - gcy;
-                                ox = wx + (tx * cs - ty * sn);
-                                oy = wy - (ty * cs + tx * sn);
-                            } else {  // text_placer.rs:150-160
-                                ox = wx + px;
-                                oy = wy - py;
-                            }
-                        };
-                        double fx = 0.0, fy = 0.0;  // `from`: the previous vertex's point ((0, 0) before the first one)
-                        if (vi > v0) {
-                            const DevVertex pv = ld.verts[vi - 1];
-                            fx = (double)pv.x * scale;
-                            fy = (double)pv.y * scale;
-                        }
-                        // Glyph::rasterize (text_placer.rs:211-231): draw_quad(to, control, from)
-                        tr((double)v.x * scale, (double)v.y * scale, c.x0, c.y0);
-                        tr((double)v.cx * scale, (double)v.cy * scale, c.x1, c.y1);
-                        tr(fx, fy, c.x2, c.y2);
-                        c.a0 = c.x0; c.b0 = c.y0; c.a1 = c.x1; c.b1 = c.y1; c.a2 = c.x2; c.b2 = c.y2;
-                        c.pa1 = c.pb1 = c.pa2 = c.pb2 = 0.0;
+                        c.a0 = r.x0; c.b0 = r.y0; c.a1 = r.x1; c.b1 = r.y1; c.a2 = r.x2; c.b2 = r.y2;
                         c.path = 0u;
                         c.node = 0u;
                         c.n_segs = 0u;
                         c.depth = 0;
-                        c.target = 0;
                         c.word = 0ull;
                         c.tie = false;
                         c.replay = false;
@@ -1135,125 +1145,120 @@ __device__ __forceinline__ void label_curve_body(const LabelDev& ld) {
         }
         if (__all_sync(kFull, !active)) break;
         if (active) {
-            bool do_mid = false, go_right = false;
-            if (c.depth < c.target) {  // walking from the root: one level per iteration
-                do_mid = true;
-                go_right = ((c.path >> (c.target - 1 - c.depth)) & 1u) != 0u;
+            // ---- the current node: flat? ----
+            bool flat;
+            if (c.replay) {
+                flat = ((c.word >> (c.node & 63u)) & 1ull) == 0ull;
             } else {
-                // ---- the current node: flat? ----
-                bool flat;
-                if (c.replay) {
-                    flat = ((c.word >> (c.node & 63u)) & 1ull) == 0ull;
-                } else {
-                    EmitSink t2 = tester;
-                    t2.near_tie = false;
-                    flat = t2.flat_enough(c.a0, c.b0, c.a1, c.b1, c.a2, c.b2);
-                    if (t2.near_tie) c.tie = true;
-                    if (!flat && c.depth >= kMaxDepth) {  // absurd depth: not something the device decides
-                        c.tie = true;
-                        flat = true;
-                    }
-                    if (!WRITE && c.node < kShapeBits - 1u) {
-                        if (!flat) c.word |= 1ull << (c.node & 63u);
-                        if ((c.node & 63u) == 63u) {
-                            ld.curve_shape[(size_t)c.curve * 4u + (c.node >> 6)] = c.word;
-                            c.word = 0ull;
-                        }
-                    }
+                EmitSink t2 = tester;
+                t2.near_tie = false;
+                flat = t2.flat_enough(c.a0, c.b0, c.a1, c.b1, c.a2, c.b2);
+                if (t2.near_tie) c.tie = true;
+                if (!flat && c.depth >= kCurveMaxDepth) {  // absurd depth: not something the device decides
+                    c.tie = true;
+                    flat = true;
                 }
-                ++c.node;
-                if (WRITE && c.replay && (c.node & 63u) == 0u && c.node < kShapeBits) c.word = ld.curve_shape[(size_t)c.curve * 4u + (c.node >> 6)];
-                if (!flat) {  // descend into the first half
-                    c.pa1 = c.a1;
-                    c.pb1 = c.b1;
-                    c.pa2 = c.a2;
-                    c.pb2 = c.b2;
-                    do_mid = true;
-                    go_right = false;
-                    c.path <<= 1;
-                    c.target = c.depth + 1;
-                } else {
-                    // draw_line(p0, p2) of this leaf (rasterizer.rs:30-32: nothing happens when y does not change)
-                    if (c.b2 - c.b0 != 0.0) {
-                        if (WRITE) {
-                            DevSeg sg;
-                            sg.x0 = c.a0;
-                            sg.y0 = c.b0;
-                            sg.x1 = c.a2;
-                            sg.y1 = c.b2;
-                            out[c.n_segs] = sg;
-                        }
-                        ++c.n_segs;
-                    }
-                    if (c.depth > 0 && !(c.path & 1u)) {  // a first half: its second half is (m, (p1 + p2) / 2, p2)
-                        c.a0 = c.a2;
-                        c.b0 = c.b2;
-                        c.a1 = (c.pa1 + c.pa2) / 2.0;
-                        c.b1 = (c.pb1 + c.pb2) / 2.0;
-                        c.a2 = c.pa2;
-                        c.b2 = c.pb2;
-                        c.path |= 1u;
-                    } else {
-                        while (c.depth > 0 && (c.path & 1u)) {  // both halves of this ancestor are done
-                            c.path >>= 1;
-                            --c.depth;
-                        }
-                        if (c.depth == 0) {
-                            // ---- the curve is finished ----
-                            if (!WRITE) {
-                                ld.vcnt[c.inst] = c.n_segs;
-                                // bounds from the control points (a subdivided curve stays inside their hull; EmitSink::bound)
-                                const double inf = __longlong_as_double(0x7ff0000000000000LL);
-                                double4 bb = make_double4(inf, -inf, inf, -inf);
-                                if (c.n_segs) {
-                                    bb.x = fmin(fmin(c.x0, c.x1), c.x2);
-                                    bb.y = fmax(fmax(c.x0, c.x1), c.x2);
-                                    bb.z = fmin(fmin(c.y0, c.y1), c.y2);
-                                    bb.w = fmax(fmax(c.y0, c.y1), c.y2);
-                                }
-                                ld.vbox[c.inst] = bb;
-                                unsigned long long* shape = ld.curve_shape + (size_t)c.curve * 4u;
-                                if (c.node >= kShapeBits - 1u) {
-                                    shape[3] = 1ull << 63;  // too many nodes for the record: the writing sweep decides again
-                                } else {
-                                    shape[c.node >> 6] = c.word;
-                                    if ((c.node >> 6) < 3u) shape[3] = 0ull;
-                                }
-                                if (c.tie) atomicOr(&ld.counters[LCNT_FALLBACK], 1u);
-                            }
-                            active = false;
-                        } else {
-                            c.path |= 1u;  // the second half of that ancestor: walk down from the root along its path
-                            c.target = c.depth;
-                            c.depth = 0;
-                            c.a0 = c.x0; c.b0 = c.y0; c.a1 = c.x1; c.b1 = c.y1; c.a2 = c.x2; c.b2 = c.y2;
-                        }
+                if (!WRITE && c.node < kShapeBits - 1u) {
+                    if (!flat) c.word |= 1ull << (c.node & 63u);
+                    if ((c.node & 63u) == 63u) {
+                        ld.curve_shape[(size_t)c.curve * 4u + (c.node >> 6)] = c.word;
+                        c.word = 0ull;
                     }
                 }
             }
-            if (do_mid) {  // one midpoint step: into the first ((p0, a, m)) or the second half ((m, b, p2)) of the current node
-                const double ax = (c.a0 + c.a1) / 2.0, ay = (c.b0 + c.b1) / 2.0, bx = (c.a1 + c.a2) / 2.0, by = (c.b1 + c.b2) / 2.0;
-                const double mx = (ax + bx) / 2.0, my = (ay + by) / 2.0;
-                if (go_right) {
-                    c.a0 = mx;
-                    c.b0 = my;
-                    c.a1 = bx;
-                    c.b1 = by;
+            ++c.node;
+            if (WRITE && c.replay && (c.node & 63u) == 0u && c.node < kShapeBits) c.word = ld.curve_shape[(size_t)c.curve * 4u + (c.node >> 6)];
+            if (!flat) {
+                // descend into the first half (p0, (p0 + p1) / 2, m); (p1, p2) stay behind for the second half
+                if (c.depth < kCurveStackLevels) {
+                    double* q = my_stk + c.depth * 128;
+                    q[0] = c.a1;
+                    q[kCurveStackLevels * 128] = c.b1;
+                    q[2 * kCurveStackLevels * 128] = c.a2;
+                    q[3 * kCurveStackLevels * 128] = c.b2;
                 } else {
-                    c.a2 = mx;
-                    c.b2 = my;
-                    c.a1 = ax;
-                    c.b1 = ay;
+                    double* q = deep + (c.depth - kCurveStackLevels) * 4;
+                    q[0] = c.a1; q[1] = c.b1; q[2] = c.a2; q[3] = c.b2;
                 }
+                const double ax = (c.a0 + c.a1) / 2.0, ay = (c.b0 + c.b1) / 2.0, bx = (c.a1 + c.a2) / 2.0, by = (c.b1 + c.b2) / 2.0;
+                c.a2 = (ax + bx) / 2.0;
+                c.b2 = (ay + by) / 2.0;
+                c.a1 = ax;
+                c.b1 = ay;
+                c.path <<= 1;
                 ++c.depth;
+            } else {
+                // draw_line(p0, p2) of this leaf (rasterizer.rs:30-32: nothing happens when y does not change)
+                if (c.b2 - c.b0 != 0.0) {
+                    if (WRITE) {
+                        DevSeg sg;
+                        sg.x0 = c.a0;
+                        sg.y0 = c.b0;
+                        sg.x1 = c.a2;
+                        sg.y1 = c.b2;
+                        out[c.n_segs] = sg;
+                    }
+                    ++c.n_segs;
+                }
+                // second halves that are finished take their ancestors with them
+                const int up = min(__ffs((int)~c.path) - 1, c.depth);
+                c.path >>= up;
+                c.depth -= up;
+                if (c.depth == 0) {
+                    // ---- the curve is finished ----
+                    if (!WRITE) {
+                        ld.vcnt[c.inst] = c.n_segs;
+                        if (!c.n_segs) {
+                            const double inf = __longlong_as_double(0x7ff0000000000000LL);
+                            ld.vbox[c.inst] = make_double4(inf, -inf, inf, -inf);
+                        }
+                        unsigned long long* shape = ld.curve_shape + (size_t)c.curve * 4u;
+                        if (c.node >= kShapeBits - 1u) {
+                            shape[3] = 1ull << 63;  // too many nodes for the record: the writing sweep decides again
+                        } else {
+                            shape[c.node >> 6] = c.word;
+                            if ((c.node >> 6) < 3u) shape[3] = 0ull;
+                        }
+                        if (c.tie) atomicOr(&ld.counters[LCNT_FALLBACK], 1u);
+                    }
+                    active = false;
+                } else {
+                    // The node is a first half whose subtree is complete: the leaf just drawn ends in the parent's midpoint m
+                    // (second halves hand p2 down unchanged), and the parent's second half is (m, (p1 + p2) / 2, p2).
+                    double p1x, p1y, p2x, p2y;
+                    const int lv = c.depth - 1;
+                    if (lv < kCurveStackLevels) {
+                        const double* q = my_stk + lv * 128;
+                        p1x = q[0];
+                        p1y = q[kCurveStackLevels * 128];
+                        p2x = q[2 * kCurveStackLevels * 128];
+                        p2y = q[3 * kCurveStackLevels * 128];
+                    } else {
+                        const double* q = deep + (lv - kCurveStackLevels) * 4;
+                        p1x = q[0]; p1y = q[1]; p2x = q[2]; p2y = q[3];
+                    }
+                    c.a0 = c.a2;
+                    c.b0 = c.b2;
+                    c.a1 = (p1x + p2x) / 2.0;
+                    c.b1 = (p1y + p2y) / 2.0;
+                    c.a2 = p2x;
+                    c.b2 = p2y;
+                    c.path |= 1u;
+                }
             }
         }
     }
 }
 __global__ void __launch_bounds__(128) label_vline_count_kernel(LabelDev ld) { label_vline_body<false>(ld); }
 __global__ void __launch_bounds__(128) label_vline_write_kernel(LabelDev ld) { label_vline_body<true>(ld); }
-__global__ void __launch_bounds__(128) label_curve_count_kernel(LabelDev ld) { label_curve_body<false>(ld); }
-__global__ void __launch_bounds__(128) label_curve_write_kernel(LabelDev ld) { label_curve_body<true>(ld); }
+__global__ void __launch_bounds__(128) label_curve_count_kernel(LabelDev ld) {
+    __shared__ double stk[4 * kCurveStackLevels * 128];
+    label_curve_body<false>(ld, stk);
+}
+__global__ void __launch_bounds__(128) label_curve_write_kernel(LabelDev ld) {
+    __shared__ double stk[4 * kCurveStackLevels * 128];
+    label_curve_body<true>(ld, stk);
+}
 
 // exclusive scan of vcnt[0 .. n) in place (n = the vertex instance counter), vcnt[n] = total = the number of segments.
 // Three launches: sums of blocks of 1024 elements, auto_scan_kernel over the block sums, local scans + block offsets.
