@@ -1082,7 +1082,7 @@ __device__ __forceinline__ void label_vline_body(const LabelDev& ld) {
 // tables while 31 lanes wait).  The recursion's stack is (p1, p2) per level in shared memory, so the second half of ANY ancestor
 // follows its first half in one step: it starts where the last leaf ended (the midpoint is handed down unchanged) and its
 // control point is (p1 + p2) / 2 -- the operations of the recursion on the same operands, per curve in the same order.
-constexpr int kCurveStackLevels = 6;  // levels of the subdivision stack kept in shared memory (a 90 degree curve needs 6; 8 CTAs per SM fit)
+constexpr int kCurveStackLevels = 7;  // levels of the subdivision stack kept in shared memory (a 90 degree curve needs 6; 7 CTAs per SM fit)
 constexpr int kCurveMaxDepth = 30;
 struct CurveState {
     double a0, b0, a1, b1, a2, b2;  // control points of the current node
@@ -1091,6 +1091,20 @@ struct CurveState {
     unsigned long long word;  // shape bits being collected / replayed
     bool replay, tie;
 };
+
+// levels beyond the shared-memory stack (out of line: real glyph curves never get here, and the common path pays nothing for them)
+__device__ __noinline__ void curve_deep_push(double* q, double a1, double b1, double a2, double b2) {
+    q[0] = a1;
+    q[1] = b1;
+    q[2] = a2;
+    q[3] = b2;
+}
+__device__ __noinline__ void curve_deep_pop(const double* q, double& p1x, double& p1y, double& p2x, double& p2y) {
+    p1x = q[0];
+    p1y = q[1];
+    p2x = q[2];
+    p2y = q[3];
+}
 
 // `stk`: [4][kCurveStackLevels][128] doubles of shared memory -- (p1, p2) of the ancestors of the current node, by depth.
 template <bool WRITE>
@@ -1105,45 +1119,80 @@ __device__ __forceinline__ void label_curve_body(const LabelDev& ld, double* stk
     double* my_stk = stk + threadIdx.x;
     double deep[(kCurveMaxDepth + 1 - kCurveStackLevels) * 4];  // absurdly deep trees only (local memory, never touched otherwise)
     CurveState c;
-    bool active = false, exhausted = false;
+    bool active = false;
     DevSeg* out = nullptr;
     const EmitSink tester{};  // (only its flatness test is used)
+    // The warp takes 32 curves of the list with ONE atomic and keeps them staged, one per lane; a lane whose curve is finished gets
+    // the next staged one by shuffle.  The loads of a freshly taken chunk are in flight while the warp works on: nobody waits
+    // for them until the first of its curves is handed out.
+    CurveRoot st_r = {};
+    unsigned st_inst = 0, st_off = 0;
+    unsigned long long st_word = 0ull;
+    int st_flags = 0;          // bit 0: a curve is staged here, bit 1: its recorded shape can be replayed
+    unsigned pool_pos = 32;    // lanes pool_pos .. 31 hold staged curves that nobody has taken yet
+    unsigned pool_base = 0;    // list index of lane 0's staged curve
+    bool list_done = false;
     for (;;) {
-        // ---- lanes without a curve take the next ones of the list ----
-        {
-            const unsigned need = __ballot_sync(kFull, !active && !exhausted);
-            if (need) {
+        const unsigned need = __ballot_sync(kFull, !active);
+        if (need) {
+            if (pool_pos < 32u) {
+                const unsigned rank = (unsigned)__popc(need & ((1u << lane) - 1u));
+                const unsigned take = min((unsigned)__popc(need), 32u - pool_pos);
+                const bool taker = !active && rank < take;
+                const int src = taker ? (int)(pool_pos + rank) : (int)lane;
+                const double x0 = __shfl_sync(kFull, st_r.x0, src), y0 = __shfl_sync(kFull, st_r.y0, src);
+                const double x1 = __shfl_sync(kFull, st_r.x1, src), y1 = __shfl_sync(kFull, st_r.y1, src);
+                const double x2 = __shfl_sync(kFull, st_r.x2, src), y2 = __shfl_sync(kFull, st_r.y2, src);
+                const unsigned inst = __shfl_sync(kFull, st_inst, src), curve = pool_base + (unsigned)src;
+                const int flags = __shfl_sync(kFull, st_flags, src);
+                unsigned off = 0;
+                unsigned long long word = 0ull;
+                if (WRITE) {
+                    off = __shfl_sync(kFull, st_off, src);
+                    word = (unsigned long long)__double_as_longlong(__shfl_sync(kFull, __longlong_as_double((long long)st_word), src));
+                }
+                if (taker && (flags & 1)) {
+                    c.curve = curve;
+                    c.inst = inst;
+                    c.a0 = x0; c.b0 = y0; c.a1 = x1; c.b1 = y1; c.a2 = x2; c.b2 = y2;
+                    c.path = 0u;
+                    c.node = 0u;
+                    c.n_segs = 0u;
+                    c.depth = 0;
+                    c.word = WRITE ? word : 0ull;
+                    c.tie = false;
+                    c.replay = WRITE && (flags & 2);
+                    if (WRITE) out = ld.segs + off;
+                    active = true;
+                }
+                pool_pos += take;
+            }
+            if (pool_pos == 32u && !list_done) {
                 unsigned base = 0;
-                if (lane == (unsigned)(__ffs(need) - 1)) base = atomicAdd(cursor, (unsigned)__popc(need));
-                base = __shfl_sync(kFull, base, __ffs(need) - 1);
-                if (!active && !exhausted) {
-                    const unsigned k = base + (unsigned)__popc(need & ((1u << lane) - 1u));
-                    if (k >= n_curves) {
-                        exhausted = true;
-                    } else {
-                        const CurveRoot r = ld.curve_root[k];
-                        c.curve = k;
-                        c.inst = ld.curve_list[k];
-                        c.a0 = r.x0; c.b0 = r.y0; c.a1 = r.x1; c.b1 = r.y1; c.a2 = r.x2; c.b2 = r.y2;
-                        c.path = 0u;
-                        c.node = 0u;
-                        c.n_segs = 0u;
-                        c.depth = 0;
-                        c.word = 0ull;
-                        c.tie = false;
-                        c.replay = false;
+                if (lane == 0) base = atomicAdd(cursor, 32u);
+                base = __shfl_sync(kFull, base, 0);
+                if (base >= n_curves) {
+                    list_done = true;
+                } else {
+                    pool_base = base;
+                    pool_pos = 0u;
+                    const unsigned k = base + lane;
+                    st_flags = 0;
+                    if (k < n_curves) {
+                        st_r = ld.curve_root[k];
+                        st_inst = ld.curve_list[k];
+                        st_flags = 1;
                         if (WRITE) {
                             const unsigned long long* shape = ld.curve_shape + (size_t)k * 4u;
-                            c.replay = (shape[3] >> 63) == 0ull;
-                            c.word = shape[0];
-                            out = ld.segs + ld.vcnt[c.inst];
+                            if ((shape[3] >> 63) == 0ull) st_flags = 3;
+                            st_word = shape[0];
+                            st_off = ld.vcnt[st_inst];
                         }
-                        active = true;
                     }
                 }
             }
         }
-        if (__all_sync(kFull, !active)) break;
+        if (pool_pos == 32u && list_done && __all_sync(kFull, !active)) break;
         if (active) {
             // ---- the current node: flat? ----
             bool flat;
@@ -1177,8 +1226,7 @@ __device__ __forceinline__ void label_curve_body(const LabelDev& ld, double* stk
                     q[2 * kCurveStackLevels * 128] = c.a2;
                     q[3 * kCurveStackLevels * 128] = c.b2;
                 } else {
-                    double* q = deep + (c.depth - kCurveStackLevels) * 4;
-                    q[0] = c.a1; q[1] = c.b1; q[2] = c.a2; q[3] = c.b2;
+                    curve_deep_push(deep + (c.depth - kCurveStackLevels) * 4, c.a1, c.b1, c.a2, c.b2);
                 }
                 const double ax = (c.a0 + c.a1) / 2.0, ay = (c.b0 + c.b1) / 2.0, bx = (c.a1 + c.a2) / 2.0, by = (c.b1 + c.b2) / 2.0;
                 c.a2 = (ax + bx) / 2.0;
@@ -1234,8 +1282,7 @@ __device__ __forceinline__ void label_curve_body(const LabelDev& ld, double* stk
                         p2x = q[2 * kCurveStackLevels * 128];
                         p2y = q[3 * kCurveStackLevels * 128];
                     } else {
-                        const double* q = deep + (lv - kCurveStackLevels) * 4;
-                        p1x = q[0]; p1y = q[1]; p2x = q[2]; p2y = q[3];
+                        curve_deep_pop(deep + (lv - kCurveStackLevels) * 4, p1x, p1y, p2x, p2y);
                     }
                     c.a0 = c.a2;
                     c.b0 = c.b2;
