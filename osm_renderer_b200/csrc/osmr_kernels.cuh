@@ -1960,7 +1960,7 @@ struct DevLabel {  // == osmr_host::LabelRec
     unsigned range_off;
     unsigned long long cell_off;
 };
-struct DevSeg {
+struct alignas(16) DevSeg {  // (16-byte aligned: moved with two 128-bit accesses)
     double x0, y0, x1, y1;
 };
 struct LabelScene {

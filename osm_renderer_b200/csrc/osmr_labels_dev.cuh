@@ -93,7 +93,7 @@ struct LabelPlace {  // layout result of an active label
 };
 // (GlyphOut -- a glyph's segment range and bounds -- is declared in osmr_kernels.cuh next to its reader, label_cover_kernel)
 
-struct CurveRoot {  // draw_quad(to, control, from) of a placed glyph's curve vertex (text_placer.rs:211-231)
+struct alignas(16) CurveRoot {  // draw_quad(to, control, from) of a placed glyph's curve vertex (text_placer.rs:211-231)
     double x0, y0, x1, y1, x2, y2;
 };
 struct LabelDev {
@@ -1106,9 +1106,9 @@ __device__ __noinline__ void curve_deep_pop(const double* q, double& p1x, double
     p2y = q[3];
 }
 
-// `stk`: [4][kCurveStackLevels][128] doubles of shared memory -- (p1, p2) of the ancestors of the current node, by depth.
+// `stk`: [2][kCurveStackLevels][128] double2 of shared memory -- (p1, p2) of the ancestors of the current node, by depth.
 template <bool WRITE>
-__device__ __forceinline__ void label_curve_body(const LabelDev& ld, double* stk) {
+__device__ __forceinline__ void label_curve_body(const LabelDev& ld, double2* stk) {
     constexpr unsigned kFull = 0xffffffffu;
     constexpr unsigned kShapeBits = 256;
     const unsigned n_curves = min(ld.counters[LCNT_CURVES], ld.verts_cap);
@@ -1116,7 +1116,7 @@ __device__ __forceinline__ void label_curve_body(const LabelDev& ld, double* stk
     if (WRITE && (ld.counters[LCNT_OVERFLOW] || ld.counters[LCNT_FALLBACK])) return;
     unsigned* cursor = &ld.counters[WRITE ? LCNT_CURVE_CURSOR_W : LCNT_CURVE_CURSOR_C];
     const unsigned lane = lane_id();
-    double* my_stk = stk + threadIdx.x;
+    double2* my_stk = stk + threadIdx.x;
     double deep[(kCurveMaxDepth + 1 - kCurveStackLevels) * 4];  // absurdly deep trees only (local memory, never touched otherwise)
     CurveState c;
     bool active = false;
@@ -1220,11 +1220,9 @@ __device__ __forceinline__ void label_curve_body(const LabelDev& ld, double* stk
             if (!flat) {
                 // descend into the first half (p0, (p0 + p1) / 2, m); (p1, p2) stay behind for the second half
                 if (c.depth < kCurveStackLevels) {
-                    double* q = my_stk + c.depth * 128;
-                    q[0] = c.a1;
-                    q[kCurveStackLevels * 128] = c.b1;
-                    q[2 * kCurveStackLevels * 128] = c.a2;
-                    q[3 * kCurveStackLevels * 128] = c.b2;
+                    double2* q = my_stk + c.depth * 128;
+                    q[0] = make_double2(c.a1, c.b1);
+                    q[kCurveStackLevels * 128] = make_double2(c.a2, c.b2);
                 } else {
                     curve_deep_push(deep + (c.depth - kCurveStackLevels) * 4, c.a1, c.b1, c.a2, c.b2);
                 }
@@ -1276,11 +1274,12 @@ __device__ __forceinline__ void label_curve_body(const LabelDev& ld, double* stk
                     double p1x, p1y, p2x, p2y;
                     const int lv = c.depth - 1;
                     if (lv < kCurveStackLevels) {
-                        const double* q = my_stk + lv * 128;
-                        p1x = q[0];
-                        p1y = q[kCurveStackLevels * 128];
-                        p2x = q[2 * kCurveStackLevels * 128];
-                        p2y = q[3 * kCurveStackLevels * 128];
+                        const double2* q = my_stk + lv * 128;
+                        const double2 p1 = q[0], p2 = q[kCurveStackLevels * 128];
+                        p1x = p1.x;
+                        p1y = p1.y;
+                        p2x = p2.x;
+                        p2y = p2.y;
                     } else {
                         curve_deep_pop(deep + (lv - kCurveStackLevels) * 4, p1x, p1y, p2x, p2y);
                     }
@@ -1299,11 +1298,11 @@ __device__ __forceinline__ void label_curve_body(const LabelDev& ld, double* stk
 __global__ void __launch_bounds__(128) label_vline_count_kernel(LabelDev ld) { label_vline_body<false>(ld); }
 __global__ void __launch_bounds__(128) label_vline_write_kernel(LabelDev ld) { label_vline_body<true>(ld); }
 __global__ void __launch_bounds__(128) label_curve_count_kernel(LabelDev ld) {
-    __shared__ double stk[4 * kCurveStackLevels * 128];
+    __shared__ double2 stk[2 * kCurveStackLevels * 128];
     label_curve_body<false>(ld, stk);
 }
 __global__ void __launch_bounds__(128) label_curve_write_kernel(LabelDev ld) {
-    __shared__ double stk[4 * kCurveStackLevels * 128];
+    __shared__ double2 stk[2 * kCurveStackLevels * 128];
     label_curve_body<true>(ld, stk);
 }
 
