@@ -1863,7 +1863,7 @@ static int labels_via_host(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_til
     ls.cover_cursor = ctx->d_cover_cursor.p;
     ls.err_flag = ctx->d_cover_cursor.p + 1;
     if (ls.n_cover) {
-        label_cover_kernel<<<std::min<unsigned>(ls.n_cover, (unsigned)ctx->num_sms * 16u), 32, 0, ctx->stream>>>(ls);
+        label_cover_kernel<<<std::min<unsigned>(ls.n_cover, (unsigned)ctx->num_sms * kCovCtasPerSm), 32, 0, ctx->stream>>>(ls);
         CK(cudaGetLastError());
     }
     label_commit_kernel<<<n_tiles, kLabelThreads, 0, ctx->stream>>>(ls);
@@ -2214,7 +2214,7 @@ static int label_device_enqueue(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t 
     ls.label_cnt = ctx->l_act_cnt.p;
     ls.skip_flags = ctx->l_counters.p + LCNT_OVERFLOW;
     CK(cudaEventRecord(ctx->ev_lcov0, st));
-    label_cover_kernel<<<(unsigned)ctx->num_sms * 16u, 32, 0, st>>>(ls);
+    label_cover_kernel<<<(unsigned)ctx->num_sms * kCovCtasPerSm, 32, 0, st>>>(ls);
     CK(cudaEventRecord(ctx->ev_lcov1, st));
     label_commit_kernel<<<n_tiles, kLabelThreads, 0, st>>>(ls);
     CK(cudaGetLastError());

@@ -2003,8 +2003,16 @@ struct LabelScene {
 // 12.7 ms; a lane per row 13.1 ms (3.7 of 32 lanes busy: a street name is a dozen rows); a lane per (row, column bin) 17.5 ms
 // (the crossings of a glyph pile up in a few buckets: 5 lanes busy).
 // ------------------------------------------------------------------------------------------------------
-constexpr int kCovPairs = 1024;  // pairs per batch
-constexpr int kCovKeys = 512;    // cells (x 2 arrays) of the batch's window
+#ifndef OSMR_COV_PAIRS
+#define OSMR_COV_PAIRS 1024
+#endif
+#ifndef OSMR_COV_CTAS
+#define OSMR_COV_CTAS 16
+#endif
+constexpr int kCovPairs = OSMR_COV_PAIRS;     // pairs per batch
+constexpr int kCovKeys = OSMR_COV_PAIRS / 2;  // cells (x 2 arrays) of the batch's window
+constexpr unsigned kCovCtasPerSm = OSMR_COV_CTAS;
+constexpr int kCovDirectUnits = 96;
 constexpr int kCovRows = 128;    // rows whose key range is tracked in shared memory (a taller label is processed band by band)
 
 // draw_line of one segment restricted to pixel row y (rasterizer.rs:52-83); calls add_a(x, value) for every touched cell of `a`
@@ -2050,6 +2058,7 @@ __global__ void __launch_bounds__(32) label_cover_kernel(LabelScene ls) {
     __shared__ unsigned s_seg[32];  // per lane of a chunk: first row inside the band (8 bits) | rows (8) | pair slots per row (16)
     __shared__ unsigned s_pre[33];  // prefix of crossings (rows) over the chunk's segments
     __shared__ unsigned s_slot[32]; // first pair slot of every segment of the chunk
+    __shared__ unsigned char s_umap[kCovDirectUnits];  // crossing of the chunk -> its segment (chunks of few crossings)
     __shared__ unsigned short s_live[kCovKeys];  // the keys of the batch that received pairs, ascending
     __shared__ unsigned s_retry;    // a crossing needed more pair slots than the tight estimate: the batch is redone with the safe one
     __shared__ int s_kmin[kCovRows], s_kmax[kCovRows];
@@ -2255,18 +2264,28 @@ __global__ void __launch_bounds__(32) label_cover_kernel(LabelScene ls) {
                     }
                     s_slot[lane] = n_pairs + slot_incl - nr * per_row;
                     const unsigned chunk_slots = __shfl_sync(kFull, slot_incl, 31);
+                    // crossing -> segment: the usual chunk (glyph segments cross one or two rows) gets a direct map, a chunk with
+                    // long segments a binary search in the prefix
+                    const unsigned n_units = __shfl_sync(kFull, incl, 31);
+                    const bool direct = n_units <= (unsigned)kCovDirectUnits;
+                    if (direct)
+                        for (unsigned i = 0; i < nr; ++i) s_umap[incl - nr + i] = (unsigned char)lane;
                     __syncwarp();
-                    const unsigned n_units = s_pre[32];
                     for (unsigned ub = 0; ub < n_units; ub += 32) {
                         const unsigned un = ub + lane;
                         if (un < n_units) {
-                            int lo = 0, hi = 32;  // largest q with s_pre[q] <= un
-                            while (hi - lo > 1) {
-                                const int mid = (lo + hi) >> 1;
-                                if (s_pre[mid] <= un)
-                                    lo = mid;
-                                else
-                                    hi = mid;
+                            int lo = 0;  // largest q with s_pre[q] <= un
+                            if (direct) {
+                                lo = (int)s_umap[un];
+                            } else {
+                                int hi = 32;
+                                while (hi - lo > 1) {
+                                    const int mid = (lo + hi) >> 1;
+                                    if (s_pre[mid] <= un)
+                                        lo = mid;
+                                    else
+                                        hi = mid;
+                                }
                             }
                             const unsigned sgw = s_seg[lo];
                             const int q_r0 = (int)(sgw & 0xffu);

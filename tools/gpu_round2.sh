@@ -26,7 +26,7 @@ if has tests; then echo "== pytest -m gpu"; timeout 1800 python -m pytest tests 
 if has bench; then echo "== bench N=1 C2"; timeout 900 python bench.py --gpus 1 --steps 20 --warmup 5 ${BENCH_FLAGS:-} > gpurun_out/bench_${TAG}.json 2> gpurun_out/bench_${TAG}.err; tail -2 gpurun_out/bench_${TAG}.err; summ gpurun_out/bench_${TAG}.json; fi
 if has ref; then echo "== reference arm"; timeout 900 python bench.py --impl reference --gpus 1 --steps 5 --warmup 1 > gpurun_out/bench_ref_${TAG}.json 2> gpurun_out/bench_ref_${TAG}.err; tail -1 gpurun_out/bench_ref_${TAG}.err; cut -c1-600 gpurun_out/bench_ref_${TAG}.json; fi
 for v in ${VARIANTS:-}; do
-  echo "== variant $v"; timeout 400 python bench.py --steps 10 --warmup 3 --skip-cpu-baseline --skip-auto --skip-labeled --min-seconds 0.5 --lib tools/dev/variants/$v.so > gpurun_out/bench_$v.json 2> gpurun_out/bench_$v.err; tail -1 gpurun_out/bench_$v.err
+  echo "== variant $v"; timeout 400 python bench.py --steps 10 --warmup 3 --skip-cpu-baseline ${VARIANT_FLAGS:---skip-auto --skip-labeled} --min-seconds 0.5 --lib tools/dev/variants/$v.so > gpurun_out/bench_$v.json 2> gpurun_out/bench_$v.err; tail -1 gpurun_out/bench_$v.err
   summ gpurun_out/bench_$v.json
 done
 for w in c2r1 c3 c4 c5; do
