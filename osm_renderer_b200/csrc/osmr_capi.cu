@@ -173,7 +173,9 @@ struct osmr_ctx {
     DevBuf<GlyphPlace> l_gplace;
     DevBuf<unsigned> l_place_vinst, l_vinst_place, l_vcnt, l_curve_list, l_scan_blocks;
     DevBuf<double4> l_vbox;
-    DevBuf<unsigned long long> l_curve_shape;
+    DevBuf<unsigned long long> l_curve_codes;
+    DevBuf<unsigned char> l_curve_deep;
+    size_t l_curves_cap = 0;
     DevBuf<CurveRoot> l_curve_root;
     size_t l_verts_cap = 0;
     DevBuf<double2> l_ring_pts;
@@ -2078,6 +2080,7 @@ static int label_device_enqueue(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t 
     if (!ctx->l_places_cap) ctx->l_places_cap = 1u << 18;
     if (!ctx->l_segs_cap) ctx->l_segs_cap = 1u << 21;
     if (!ctx->l_verts_cap) ctx->l_verts_cap = 1u << 20;
+    if (!ctx->l_curves_cap) ctx->l_curves_cap = 1u << 19;
     if (!ctx->l_rowrecs_cap) ctx->l_rowrecs_cap = 1u << 19;
     if (!ctx->l_cells_cap) ctx->l_cells_cap = 1u << 23;
     if (!ctx->l_ring_cap) ctx->l_ring_cap = 1u << 16;
@@ -2096,9 +2099,10 @@ static int label_device_enqueue(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t 
     CK(ctx->l_vinst_place.reserve(ctx->l_verts_cap + 8));
     CK(ctx->l_vcnt.reserve(ctx->l_verts_cap + 8));
     CK(ctx->l_vbox.reserve(ctx->l_verts_cap + 8));
-    CK(ctx->l_curve_list.reserve(ctx->l_verts_cap + 8));
-    CK(ctx->l_curve_shape.reserve(4 * ctx->l_verts_cap + 8));
-    CK(ctx->l_curve_root.reserve(ctx->l_verts_cap + 8));
+    CK(ctx->l_curve_list.reserve(ctx->l_curves_cap + 8));
+    CK(ctx->l_curve_codes.reserve((kCurveLeafCap / 4u) * ctx->l_curves_cap + 8));
+    CK(ctx->l_curve_deep.reserve(ctx->l_curves_cap + 8));
+    CK(ctx->l_curve_root.reserve(ctx->l_curves_cap + 8));
     CK(ctx->l_scan_blocks.reserve(n_scan_blocks + 8));
     CK(ctx->d_label_segs.reserve(ctx->l_segs_cap));
     CK(ctx->d_cover_list.reserve((size_t)n_labels + 1));
@@ -2164,7 +2168,9 @@ static int label_device_enqueue(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t 
     ld.vcnt = ctx->l_vcnt.p;
     ld.vbox = ctx->l_vbox.p;
     ld.curve_list = ctx->l_curve_list.p;
-    ld.curve_shape = ctx->l_curve_shape.p;
+    ld.curve_codes = ctx->l_curve_codes.p;
+    ld.curve_deep = ctx->l_curve_deep.p;
+    ld.curves_cap = (unsigned)std::min<size_t>(ctx->l_curves_cap, 0xfffffff0u);
     ld.curve_root = ctx->l_curve_root.p;
     ld.verts_cap = (unsigned)std::min<size_t>(ctx->l_verts_cap, 0xfffffff0u);
     ld.scan_blocks = ctx->l_scan_blocks.p;
@@ -2192,7 +2198,7 @@ static int label_device_enqueue(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t 
     label_scan_apply_kernel<<<n_scan_blocks, 256, 0, st>>>(ld);
     label_finish_kernel<<<n_tiles, 128, 0, st>>>(s, ld);
     label_vline_write_kernel<<<wide, 128, 0, st>>>(ld);
-    label_curve_write_kernel<<<wide, 128, 0, st>>>(ld);
+    label_curve_expand_kernel<<<(unsigned)ctx->num_sms * 8u, 256, 0, st>>>(ld);
     CK(cudaGetLastError());
     CK(cudaMemsetAsync(ctx->d_cover_cursor.p, 0, 2 * sizeof(unsigned), st));
     LabelScene ls{};
@@ -2244,6 +2250,7 @@ static int label_device_judge(osmr_ctx* ctx) {
         if (c[LCNT_OVERFLOW] & 16u) ctx->l_ring_cap = std::max(grow(c[LCNT_RING_PTS]), ctx->l_ring_cap * 2);
         if (c[LCNT_OVERFLOW] & 32u) ctx->l_heap_slots = std::max(grow(c[LCNT_POLY]), ctx->l_heap_slots * 2);
         if (c[LCNT_OVERFLOW] & 64u) ctx->l_verts_cap = std::max(grow(c[LCNT_VERTS]), ctx->l_verts_cap * 2);
+        if (c[LCNT_OVERFLOW] & 128u) ctx->l_curves_cap = std::max(grow(c[LCNT_CURVES]), ctx->l_curves_cap * 2);
         if (ctx->l_places_cap >= 0xfffffff0ull || ctx->l_segs_cap >= 0xfffffff0ull || ctx->l_rowrecs_cap >= 0x7ffffff0ull ||
             ctx->l_cells_cap > (1ull << 33) || ctx->l_ring_cap >= 0xfffffff0ull)
             return ctx->fail(OSMR_E_NOMEM, "label scratch too large; split the batch");

@@ -2004,10 +2004,10 @@ struct LabelScene {
 // (the crossings of a glyph pile up in a few buckets: 5 lanes busy).
 // ------------------------------------------------------------------------------------------------------
 #ifndef OSMR_COV_PAIRS
-#define OSMR_COV_PAIRS 1024
+#define OSMR_COV_PAIRS 512
 #endif
 #ifndef OSMR_COV_CTAS
-#define OSMR_COV_CTAS 16
+#define OSMR_COV_CTAS 24
 #endif
 constexpr int kCovPairs = OSMR_COV_PAIRS;     // pairs per batch
 constexpr int kCovKeys = OSMR_COV_PAIRS / 2;  // cells (x 2 arrays) of the batch's window
@@ -2329,7 +2329,9 @@ __global__ void __launch_bounds__(32) label_cover_kernel(LabelScene ls) {
                 }
                 OSMR_COUNT("lcover.pairs", lane == 0 ? n_pairs : 0);
                 __syncwarp();
-                if (tight && s_retry) {  // (kmin / kmax updates are idempotent; everything else of the batch is rebuilt)
+                const unsigned retry = s_retry;
+                __syncwarp();  // (lane 0 clears the flag at the top of the loop: everybody has read it by then)
+                if (tight && retry) {  // (kmin / kmax updates are idempotent; everything else of the batch is rebuilt)
                     OSMR_COUNT("lcover.retries", lane == 0);
                     tight = false;
                     continue;

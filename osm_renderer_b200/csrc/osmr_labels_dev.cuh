@@ -53,7 +53,7 @@ enum {
     LCNT_SEGS = 1,      // segments handed out
     LCNT_ROWRECS = 2,   // (label, row) work items handed out (multiple of 32)
     LCNT_CELLS_LO = 4,  // 64-bit (4,5): coverage cells handed out
-    LCNT_OVERFLOW = 6,  // bit0 places, bit1 segments, bit2 rows, bit3 cells, bit4 polylabel rings, bit5 polylabel heap, bit6 vertex instances
+    LCNT_OVERFLOW = 6,  // bit0 places, bit1 segments, bit2 rows, bit3 cells, bit4 polylabel rings, bit5 polylabel heap, bit6 vertex instances, bit7 curves
     LCNT_FALLBACK = 7,  // bit0: flatness near-tie (needs libm hypot); bit1: input the device path does not take
     LCNT_BAD = 8,       // label references an entity / style / icon that does not exist
     LCNT_RING_PTS = 9,  // polylabel ring points handed out
@@ -128,7 +128,9 @@ struct LabelDev {
     double4* vbox;          // per vertex instance: bounds of its segments (min x, max x, min y, max y)
     unsigned* curve_list;   // vertex instances that are curves
     CurveRoot* curve_root;  // per curve: its control points in pixel space (label_vfill_kernel)
-    unsigned long long* curve_shape;  // per curve: 4 words, the shape of its subdivision tree (EmitSink::quad)
+    unsigned long long* curve_codes;  // per curve: kCurveLeafCap 16-bit leaf codes ((1 << depth) | path) of the segments it draws, in order
+    unsigned char* curve_deep;        // per curve: 1 when the codes do not describe it (too many leaves, too deep): flattened again
+    unsigned curves_cap;
     unsigned verts_cap;
     unsigned* scan_blocks;  // block sums of the segment-offset scan
     unsigned n_scan_blocks;
@@ -1023,6 +1025,12 @@ __global__ void __launch_bounds__(128) label_vfill_kernel(LabelDev ld) {
                 // the curve's work item: Glyph::rasterize (text_placer.rs:211-231) calls draw_quad(to, control, from); the
                 // curve kernels start from these points without walking the placement tables again
                 const unsigned k = atomicAdd(&ld.counters[LCNT_CURVES], 1u);
+                if (k >= ld.curves_cap) {  // (the counter keeps counting: the redo knows what to allocate)
+                    atomicOr(&ld.counters[LCNT_OVERFLOW], 128u);
+                    fx = tx;
+                    fy = ty;
+                    continue;
+                }
                 CurveRoot r;
                 tr(tx, ty, r.x0, r.y0);
                 tr((double)v.cx * scale, (double)v.cy * scale, r.x1, r.y1);
@@ -1041,8 +1049,7 @@ __global__ void __launch_bounds__(128) label_vfill_kernel(LabelDev ld) {
 }
 
 template <bool WRITE>
-__device__ __forceinline__ void label_vertex_instance(const LabelDev& ld, unsigned inst, unsigned curve = 0xffffffffu) {
-    unsigned long long* shape = curve != 0xffffffffu ? ld.curve_shape + (size_t)curve * 4u : nullptr;
+__device__ __forceinline__ void label_vertex_instance(const LabelDev& ld, unsigned inst) {
     const unsigned gi = ld.vinst_place[inst];
     const GlyphPlace gp = ld.gplace[gi];
     const LabelPlace lp = ld.place[gp.label];
@@ -1053,9 +1060,9 @@ __device__ __forceinline__ void label_vertex_instance(const LabelDev& ld, unsign
     bool tie = false;
     if (WRITE) {
         const unsigned off = ld.vcnt[inst], n = ld.vcnt[inst + 1] - off;
-        if (n) emit_vertex(ld, gp, lp, vi, v0, ld.segs + off, mnx, mxx, mny, mxy, tie, nullptr, shape);
+        if (n) emit_vertex(ld, gp, lp, vi, v0, ld.segs + off, mnx, mxx, mny, mxy, tie);
     } else {
-        const unsigned n = emit_vertex(ld, gp, lp, vi, v0, nullptr, mnx, mxx, mny, mxy, tie, shape, nullptr);
+        const unsigned n = emit_vertex(ld, gp, lp, vi, v0, nullptr, mnx, mxx, mny, mxy, tie);
         ld.vcnt[inst] = n;
         ld.vbox[inst] = make_double4(mnx, mxx, mny, mxy);
         if (tie) atomicOr(&ld.counters[LCNT_FALLBACK], 1u);
@@ -1065,7 +1072,7 @@ __device__ __forceinline__ void label_vertex_instance(const LabelDev& ld, unsign
 template <bool WRITE>
 __device__ __forceinline__ void label_vline_body(const LabelDev& ld) {
     const unsigned n_verts = min(ld.counters[LCNT_VERTS], ld.verts_cap);
-    if (ld.counters[LCNT_OVERFLOW] & 65u) return;
+    if (ld.counters[LCNT_OVERFLOW] & 193u) return;
     if (WRITE && (ld.counters[LCNT_OVERFLOW] || ld.counters[LCNT_FALLBACK])) return;
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n_verts; i += gridDim.x * blockDim.x) {
         const unsigned gi = ld.vinst_place[i];
@@ -1075,21 +1082,31 @@ __device__ __forceinline__ void label_vline_body(const LabelDev& ld) {
     }
 }
 // The curve kernels.  draw_quad (rasterizer.rs:86-107) is a recursion whose shape differs from curve to curve (8 .. 128
-// draw_line calls).  Here it is a state machine and the warp runs it in lock step: every iteration every lane visits one node of
-// ITS curve's subdivision tree -- a flatness decision (or its recorded bit), then either the midpoint step into the first half
-// or the leaf's draw_line and the move to the next second half -- and a lane whose curve is finished takes the next curve of the
-// list straight away (control points precomputed by label_vfill_kernel: one independent load, no walk through the placement
-// tables while 31 lanes wait).  The recursion's stack is (p1, p2) per level in shared memory, so the second half of ANY ancestor
-// follows its first half in one step: it starts where the last leaf ended (the midpoint is handed down unchanged) and its
-// control point is (p1 + p2) / 2 -- the operations of the recursion on the same operands, per curve in the same order.
+// draw_line calls), decided by a flatness test per node.
+//
+// label_curve_count_kernel runs the recursion as a state machine, the warp in lock step: every iteration every lane visits one
+// node of ITS curve's subdivision tree -- the flatness decision, then either the midpoint step into the first half or the leaf
+// and the move to the next second half -- and a lane whose curve is finished takes the next one.  The recursion's stack is
+// (p1, p2) per level in shared memory, so the second half of ANY ancestor follows its first half in one step: it starts where
+// the last leaf ended (the midpoint is handed down unchanged) and its control point is (p1 + p2) / 2.  The warp takes 32 curves
+// of the list with ONE atomic and keeps them staged, one per lane (control points precomputed by label_vfill_kernel); a lane
+// gets its next curve by shuffle, and the loads of a freshly taken chunk are in flight while the warp works on.  Besides the
+// count, every leaf that draws leaves its CODE behind: (1 << depth) | path, 16 bits.
+//
+// label_curve_expand_kernel then writes the segments without any tree walk: a lane per leaf goes from the curve's control points
+// down the leaf's path (depth midpoint steps in registers) and stores its segment at the scanned offset -- no stack, no
+// divergence, coalesced stores.  Every node's points come from its parent's by the same midpoint operations whatever the
+// traversal order, so the leaves are bit-identical to the recursion's.  A curve with more leaves than the code record holds (or
+// deeper than 15 levels) is flattened again by one lane, flatness tests included.
 constexpr int kCurveStackLevels = 7;  // levels of the subdivision stack kept in shared memory (a 90 degree curve needs 6; 7 CTAs per SM fit)
 constexpr int kCurveMaxDepth = 30;
+constexpr unsigned kCurveLeafCap = 128;  // leaf codes per curve
 struct CurveState {
     double a0, b0, a1, b1, a2, b2;  // control points of the current node
-    unsigned path, node, n_segs, inst, curve;
+    unsigned path, n_segs, inst, curve;
     int depth;
-    unsigned long long word;  // shape bits being collected / replayed
-    bool replay, tie;
+    unsigned long long pack;  // leaf codes not yet stored (four per word)
+    bool deep, tie;
 };
 
 // levels beyond the shared-memory stack (out of line: real glyph curves never get here, and the common path pays nothing for them)
@@ -1106,31 +1123,23 @@ __device__ __noinline__ void curve_deep_pop(const double* q, double& p1x, double
     p2y = q[3];
 }
 
-// `stk`: [2][kCurveStackLevels][128] double2 of shared memory -- (p1, p2) of the ancestors of the current node, by depth.
-template <bool WRITE>
-__device__ __forceinline__ void label_curve_body(const LabelDev& ld, double2* stk) {
+__global__ void __launch_bounds__(128) label_curve_count_kernel(LabelDev ld) {
+    __shared__ double2 stk[2 * kCurveStackLevels * 128];  // [2][level][thread]: (p1, p2) of the ancestors of the current node
     constexpr unsigned kFull = 0xffffffffu;
-    constexpr unsigned kShapeBits = 256;
-    const unsigned n_curves = min(ld.counters[LCNT_CURVES], ld.verts_cap);
-    if (ld.counters[LCNT_OVERFLOW] & 65u) return;
-    if (WRITE && (ld.counters[LCNT_OVERFLOW] || ld.counters[LCNT_FALLBACK])) return;
-    unsigned* cursor = &ld.counters[WRITE ? LCNT_CURVE_CURSOR_W : LCNT_CURVE_CURSOR_C];
+    const unsigned n_curves = min(ld.counters[LCNT_CURVES], ld.curves_cap);
+    if (ld.counters[LCNT_OVERFLOW] & 193u) return;
+    unsigned* cursor = &ld.counters[LCNT_CURVE_CURSOR_C];
     const unsigned lane = lane_id();
     double2* my_stk = stk + threadIdx.x;
     double deep[(kCurveMaxDepth + 1 - kCurveStackLevels) * 4];  // absurdly deep trees only (local memory, never touched otherwise)
     CurveState c;
     bool active = false;
-    DevSeg* out = nullptr;
     const EmitSink tester{};  // (only its flatness test is used)
-    // The warp takes 32 curves of the list with ONE atomic and keeps them staged, one per lane; a lane whose curve is finished gets
-    // the next staged one by shuffle.  The loads of a freshly taken chunk are in flight while the warp works on: nobody waits
-    // for them until the first of its curves is handed out.
     CurveRoot st_r = {};
-    unsigned st_inst = 0, st_off = 0;
-    unsigned long long st_word = 0ull;
-    int st_flags = 0;          // bit 0: a curve is staged here, bit 1: its recorded shape can be replayed
-    unsigned pool_pos = 32;    // lanes pool_pos .. 31 hold staged curves that nobody has taken yet
-    unsigned pool_base = 0;    // list index of lane 0's staged curve
+    unsigned st_inst = 0;
+    bool st_valid = false;
+    unsigned pool_pos = 32;  // lanes pool_pos .. 31 hold staged curves that nobody has taken yet
+    unsigned pool_base = 0;  // list index of lane 0's staged curve
     bool list_done = false;
     for (;;) {
         const unsigned need = __ballot_sync(kFull, !active);
@@ -1143,26 +1152,18 @@ __device__ __forceinline__ void label_curve_body(const LabelDev& ld, double2* st
                 const double x0 = __shfl_sync(kFull, st_r.x0, src), y0 = __shfl_sync(kFull, st_r.y0, src);
                 const double x1 = __shfl_sync(kFull, st_r.x1, src), y1 = __shfl_sync(kFull, st_r.y1, src);
                 const double x2 = __shfl_sync(kFull, st_r.x2, src), y2 = __shfl_sync(kFull, st_r.y2, src);
-                const unsigned inst = __shfl_sync(kFull, st_inst, src), curve = pool_base + (unsigned)src;
-                const int flags = __shfl_sync(kFull, st_flags, src);
-                unsigned off = 0;
-                unsigned long long word = 0ull;
-                if (WRITE) {
-                    off = __shfl_sync(kFull, st_off, src);
-                    word = (unsigned long long)__double_as_longlong(__shfl_sync(kFull, __longlong_as_double((long long)st_word), src));
-                }
-                if (taker && (flags & 1)) {
-                    c.curve = curve;
+                const unsigned inst = __shfl_sync(kFull, st_inst, src);
+                const bool valid = __shfl_sync(kFull, (int)st_valid, src) != 0;
+                if (taker && valid) {
+                    c.curve = pool_base + (unsigned)src;
                     c.inst = inst;
                     c.a0 = x0; c.b0 = y0; c.a1 = x1; c.b1 = y1; c.a2 = x2; c.b2 = y2;
                     c.path = 0u;
-                    c.node = 0u;
                     c.n_segs = 0u;
                     c.depth = 0;
-                    c.word = WRITE ? word : 0ull;
+                    c.pack = 0ull;
+                    c.deep = false;
                     c.tie = false;
-                    c.replay = WRITE && (flags & 2);
-                    if (WRITE) out = ld.segs + off;
                     active = true;
                 }
                 pool_pos += take;
@@ -1177,17 +1178,10 @@ __device__ __forceinline__ void label_curve_body(const LabelDev& ld, double2* st
                     pool_base = base;
                     pool_pos = 0u;
                     const unsigned k = base + lane;
-                    st_flags = 0;
-                    if (k < n_curves) {
+                    st_valid = k < n_curves;
+                    if (st_valid) {
                         st_r = ld.curve_root[k];
                         st_inst = ld.curve_list[k];
-                        st_flags = 1;
-                        if (WRITE) {
-                            const unsigned long long* shape = ld.curve_shape + (size_t)k * 4u;
-                            if ((shape[3] >> 63) == 0ull) st_flags = 3;
-                            st_word = shape[0];
-                            st_off = ld.vcnt[st_inst];
-                        }
                     }
                 }
             }
@@ -1195,28 +1189,14 @@ __device__ __forceinline__ void label_curve_body(const LabelDev& ld, double2* st
         if (pool_pos == 32u && list_done && __all_sync(kFull, !active)) break;
         if (active) {
             // ---- the current node: flat? ----
-            bool flat;
-            if (c.replay) {
-                flat = ((c.word >> (c.node & 63u)) & 1ull) == 0ull;
-            } else {
-                EmitSink t2 = tester;
-                t2.near_tie = false;
-                flat = t2.flat_enough(c.a0, c.b0, c.a1, c.b1, c.a2, c.b2);
-                if (t2.near_tie) c.tie = true;
-                if (!flat && c.depth >= kCurveMaxDepth) {  // absurd depth: not something the device decides
-                    c.tie = true;
-                    flat = true;
-                }
-                if (!WRITE && c.node < kShapeBits - 1u) {
-                    if (!flat) c.word |= 1ull << (c.node & 63u);
-                    if ((c.node & 63u) == 63u) {
-                        ld.curve_shape[(size_t)c.curve * 4u + (c.node >> 6)] = c.word;
-                        c.word = 0ull;
-                    }
-                }
+            EmitSink t2 = tester;
+            t2.near_tie = false;
+            bool flat = t2.flat_enough(c.a0, c.b0, c.a1, c.b1, c.a2, c.b2);
+            if (t2.near_tie) c.tie = true;
+            if (!flat && c.depth >= kCurveMaxDepth) {  // absurd depth: not something the device decides
+                c.tie = true;
+                flat = true;
             }
-            ++c.node;
-            if (WRITE && c.replay && (c.node & 63u) == 0u && c.node < kShapeBits) c.word = ld.curve_shape[(size_t)c.curve * 4u + (c.node >> 6)];
             if (!flat) {
                 // descend into the first half (p0, (p0 + p1) / 2, m); (p1, p2) stay behind for the second half
                 if (c.depth < kCurveStackLevels) {
@@ -1236,13 +1216,14 @@ __device__ __forceinline__ void label_curve_body(const LabelDev& ld, double2* st
             } else {
                 // draw_line(p0, p2) of this leaf (rasterizer.rs:30-32: nothing happens when y does not change)
                 if (c.b2 - c.b0 != 0.0) {
-                    if (WRITE) {
-                        DevSeg sg;
-                        sg.x0 = c.a0;
-                        sg.y0 = c.b0;
-                        sg.x1 = c.a2;
-                        sg.y1 = c.b2;
-                        out[c.n_segs] = sg;
+                    if (c.n_segs < kCurveLeafCap && c.depth <= 15) {
+                        c.pack |= (unsigned long long)((1u << c.depth) | c.path) << (16u * (c.n_segs & 3u));
+                        if ((c.n_segs & 3u) == 3u) {
+                            ld.curve_codes[(size_t)c.curve * (kCurveLeafCap / 4u) + (c.n_segs >> 2)] = c.pack;
+                            c.pack = 0ull;
+                        }
+                    } else {
+                        c.deep = true;
                     }
                     ++c.n_segs;
                 }
@@ -1252,21 +1233,14 @@ __device__ __forceinline__ void label_curve_body(const LabelDev& ld, double2* st
                 c.depth -= up;
                 if (c.depth == 0) {
                     // ---- the curve is finished ----
-                    if (!WRITE) {
-                        ld.vcnt[c.inst] = c.n_segs;
-                        if (!c.n_segs) {
-                            const double inf = __longlong_as_double(0x7ff0000000000000LL);
-                            ld.vbox[c.inst] = make_double4(inf, -inf, inf, -inf);
-                        }
-                        unsigned long long* shape = ld.curve_shape + (size_t)c.curve * 4u;
-                        if (c.node >= kShapeBits - 1u) {
-                            shape[3] = 1ull << 63;  // too many nodes for the record: the writing sweep decides again
-                        } else {
-                            shape[c.node >> 6] = c.word;
-                            if ((c.node >> 6) < 3u) shape[3] = 0ull;
-                        }
-                        if (c.tie) atomicOr(&ld.counters[LCNT_FALLBACK], 1u);
+                    ld.vcnt[c.inst] = c.n_segs;
+                    if (!c.n_segs) {  // (label_vfill_kernel wrote the hull of the control points)
+                        const double inf = __longlong_as_double(0x7ff0000000000000LL);
+                        ld.vbox[c.inst] = make_double4(inf, -inf, inf, -inf);
                     }
+                    if ((c.n_segs & 3u) && c.n_segs < kCurveLeafCap) ld.curve_codes[(size_t)c.curve * (kCurveLeafCap / 4u) + (c.n_segs >> 2)] = c.pack;
+                    ld.curve_deep[c.curve] = c.deep ? 1 : 0;
+                    if (c.tie) atomicOr(&ld.counters[LCNT_FALLBACK], 1u);
                     active = false;
                 } else {
                     // The node is a first half whose subtree is complete: the leaf just drawn ends in the parent's midpoint m
@@ -1295,16 +1269,63 @@ __device__ __forceinline__ void label_curve_body(const LabelDev& ld, double2* st
         }
     }
 }
+
+// a curve the leaf codes do not describe: the recursion itself, flatness tests included (EmitSink::quad)
+__device__ __noinline__ void curve_flatten_again(const CurveRoot& r, DevSeg* out) {
+    EmitSink sink;
+    sink.out = out;
+    sink.n = 0;
+    sink.near_tie = false;
+    sink.shape_out = nullptr;
+    sink.shape_in = nullptr;
+    sink.quad(r.x0, r.y0, r.x1, r.y1, r.x2, r.y2);
+}
+
+// a warp per curve, a lane per leaf
+__global__ void __launch_bounds__(256, 4) label_curve_expand_kernel(LabelDev ld) {
+    const unsigned n_curves = min(ld.counters[LCNT_CURVES], ld.curves_cap);
+    if (ld.counters[LCNT_OVERFLOW] || ld.counters[LCNT_FALLBACK]) return;
+    const unsigned lane = lane_id();
+    const unsigned n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (unsigned k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < n_curves; k += n_warps) {
+        const unsigned inst = ld.curve_list[k];
+        const unsigned off = ld.vcnt[inst], n = ld.vcnt[inst + 1] - off;
+        if (!n) continue;
+        const CurveRoot r = ld.curve_root[k];
+        if (ld.curve_deep[k]) {
+            if (lane == 0) curve_flatten_again(r, ld.segs + off);
+            continue;
+        }
+        const unsigned short* codes = reinterpret_cast<const unsigned short*>(ld.curve_codes + (size_t)k * (kCurveLeafCap / 4u));
+        for (unsigned i = lane; i < n; i += 32) {
+            const unsigned code = codes[i];
+            double a0 = r.x0, b0 = r.y0, a1 = r.x1, b1 = r.y1, a2 = r.x2, b2 = r.y2;
+            for (int lv = 30 - __clz(code); lv >= 0; --lv) {
+                const double ax = (a0 + a1) / 2.0, ay = (b0 + b1) / 2.0, bx = (a1 + a2) / 2.0, by = (b1 + b2) / 2.0;
+                const double mx = (ax + bx) / 2.0, my = (ay + by) / 2.0;
+                if ((code >> lv) & 1u) {  // the second half (m, b, p2)
+                    a0 = mx;
+                    b0 = my;
+                    a1 = bx;
+                    b1 = by;
+                } else {  // the first half (p0, a, m)
+                    a2 = mx;
+                    b2 = my;
+                    a1 = ax;
+                    b1 = ay;
+                }
+            }
+            DevSeg sg;
+            sg.x0 = a0;
+            sg.y0 = b0;
+            sg.x1 = a2;
+            sg.y1 = b2;
+            ld.segs[off + i] = sg;
+        }
+    }
+}
 __global__ void __launch_bounds__(128) label_vline_count_kernel(LabelDev ld) { label_vline_body<false>(ld); }
 __global__ void __launch_bounds__(128) label_vline_write_kernel(LabelDev ld) { label_vline_body<true>(ld); }
-__global__ void __launch_bounds__(128) label_curve_count_kernel(LabelDev ld) {
-    __shared__ double2 stk[2 * kCurveStackLevels * 128];
-    label_curve_body<false>(ld, stk);
-}
-__global__ void __launch_bounds__(128) label_curve_write_kernel(LabelDev ld) {
-    __shared__ double2 stk[2 * kCurveStackLevels * 128];
-    label_curve_body<true>(ld, stk);
-}
 
 // exclusive scan of vcnt[0 .. n) in place (n = the vertex instance counter), vcnt[n] = total = the number of segments.
 // Three launches: sums of blocks of 1024 elements, auto_scan_kernel over the block sums, local scans + block offsets.
@@ -1370,7 +1391,7 @@ __global__ void __launch_bounds__(128) label_finish_kernel(Scene s, LabelDev ld)
     const unsigned first = ld.label_begin[t];
     const unsigned n_act = ld.act_cnt[t];
     const int D = s.D;
-    if (ld.counters[LCNT_OVERFLOW] & 67u) return;
+    if (ld.counters[LCNT_OVERFLOW] & 195u) return;
     for (unsigned ai = threadIdx.x; ai < n_act; ai += blockDim.x) {
         const LabelPlace lp = ld.place[first + ai];
         DevLabel L;

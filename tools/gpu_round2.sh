@@ -53,7 +53,7 @@ tail -1 gpurun_out/ncu_labels_${TAG}.log | cut -c1-200
 fi
 if has full_labels; then
 echo "== ncu full (label kernels)"
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"${FULL_LABEL_KERNELS:-label_cover_kernel|label_curve_count_kernel|label_curve_write_kernel}" -s 6 -c 3 -f -o gpurun_out/prof_labels_${TAG} \
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"${FULL_LABEL_KERNELS:-label_cover_kernel|label_curve_count_kernel|label_curve_expand_kernel}" -s 6 -c 3 -f -o gpurun_out/prof_labels_${TAG} \
     python bench.py --steps 2 --warmup 1 --skip-cpu-baseline --skip-auto --min-seconds 0 > gpurun_out/ncu_full_labels_${TAG}.log 2>&1
 tail -2 gpurun_out/ncu_full_labels_${TAG}.log | cut -c1-200
 fi
