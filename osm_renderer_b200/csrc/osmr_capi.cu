@@ -144,7 +144,11 @@ struct osmr_ctx {
     DevBuf<unsigned> d_cover_list, d_cover_cursor;
     std::vector<LabelWorkItem> label_items;  // kept between calls: their vectors' capacity is the layout arena
     PinnedBuf<osmr_host::Seg> h_label_segs;
-    cudaEvent_t ev_label0 = nullptr, ev_label1 = nullptr, ev_lcov0 = nullptr, ev_lcov1 = nullptr;
+    cudaEvent_t ev_label0 = nullptr, ev_label1 = nullptr;
+    // the label pass runs chunk by chunk (the draw's host-output schedule): a draw chunk waits only for the label chunks under it
+    unsigned n_lchunks = 0;
+    unsigned lchunk_tb[kMaxChunks] = {}, lchunk_tc[kMaxChunks] = {};
+    cudaEvent_t lchunk_done[kMaxChunks] = {}, lchunk_up[kMaxChunks] = {}, ev_lcov0[kMaxChunks] = {}, ev_lcov1[kMaxChunks] = {};
     float stats_label_layout_ms = 0.f, stats_label_device_ms = 0.f;
     unsigned label_threads = 32;
     DevBuf<LabelPix> label_plane;
@@ -176,6 +180,9 @@ struct osmr_ctx {
     DevBuf<unsigned long long> l_curve_codes;
     DevBuf<unsigned char> l_curve_deep;
     size_t l_curves_cap = 0;
+    // the capacities the last attempt ran with
+    size_t l_places_used_cap = 0, l_segs_used_cap = 0, l_rowrecs_used_cap = 0, l_cells_used_cap = 0, l_ring_used_cap = 0, l_heap_used_slots = 0,
+           l_verts_used_cap = 0, l_curves_used_cap = 0;
     DevBuf<CurveRoot> l_curve_root;
     size_t l_verts_cap = 0;
     DevBuf<double2> l_ring_pts;
@@ -185,6 +192,7 @@ struct osmr_ctx {
     std::vector<osmr_tile> h_batch_tiles;     // resident labelled batch: host copies for the table look-ups of the label pass
     std::vector<uint32_t> h_label_begin;
     bool batch_has_labels = false;
+    unsigned label_chunks = 0;     // debug key "label_chunks"
     bool label_host_only = false;  // debug key "label_host": always lay labels out on the host (round-1 path)
     unsigned stats_label_active = 0, stats_label_poly = 0, stats_label_segs = 0;
     unsigned long long stats_label_cells = 0;
@@ -345,8 +353,12 @@ int osmr_ctx_create(int device, osmr_ctx** out_ctx) try {
     for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_label0);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_label1);
-    if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_lcov0);
-    if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_lcov1);
+    for (unsigned i = 0; i < kMaxChunks && e == cudaSuccess; ++i) {
+        e = cudaEventCreate(&ctx->ev_lcov0[i]);
+        if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev_lcov1[i]);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->lchunk_done[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->lchunk_up[i], cudaEventDisableTiming);
+    }
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) {
         double lut[256];
@@ -438,8 +450,12 @@ void osmr_ctx_destroy(osmr_ctx* ctx) {
     if (ctx->areas_ready) cudaEventDestroy(ctx->areas_ready);
     if (ctx->ev_label0) cudaEventDestroy(ctx->ev_label0);
     if (ctx->ev_label1) cudaEventDestroy(ctx->ev_label1);
-    if (ctx->ev_lcov0) cudaEventDestroy(ctx->ev_lcov0);
-    if (ctx->ev_lcov1) cudaEventDestroy(ctx->ev_lcov1);
+    for (unsigned i = 0; i < kMaxChunks; ++i) {
+        if (ctx->ev_lcov0[i]) cudaEventDestroy(ctx->ev_lcov0[i]);
+        if (ctx->ev_lcov1[i]) cudaEventDestroy(ctx->ev_lcov1[i]);
+        if (ctx->lchunk_done[i]) cudaEventDestroy(ctx->lchunk_done[i]);
+        if (ctx->lchunk_up[i]) cudaEventDestroy(ctx->lchunk_up[i]);
+    }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -474,6 +490,11 @@ int osmr_debug_set(osmr_ctx* ctx, const char* key, int value) try {
     }
     if (strcmp(key, "label_host") == 0) {  // 1: label layout on the host for every call (the round-1 path; A/B and tests)
         ctx->label_host_only = value != 0;
+        return OSMR_OK;
+    }
+    if (strcmp(key, "label_chunks") == 0) {  // n > 0: the label pass in n equal chunks whatever the batch (tests); 0: the draw's schedule
+        if (value < 0 || value > (int)kMaxChunks) return ctx->fail(OSMR_E_INVALID, "label_chunks must be 0..16");
+        ctx->label_chunks = (unsigned)value;
         return OSMR_OK;
     }
     if (strcmp(key, "direct_out") == 0) {  // 0: always stage the tiles in HBM and copy them back (A/B measurements)
@@ -1074,7 +1095,9 @@ static int launch_chunk(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t fla
     launches += 5;
     CK(cudaEventRecord(ev[1], st));
     const unsigned blocks = (unsigned)((D / kBW) * (D / kBH));
-    if (ctx->label_async && ctx->label_plane_active) CK(cudaStreamWaitEvent(st, ctx->label_done, 0));
+    if (ctx->label_async && ctx->label_plane_active)
+        for (unsigned i = 0; i < ctx->n_lchunks; ++i)
+            if (ctx->lchunk_tb[i] < tb + tc && tb < ctx->lchunk_tb[i] + ctx->lchunk_tc[i]) CK(cudaStreamWaitEvent(st, ctx->lchunk_done[i], 0));
     CK(cudaEventRecord(ev[4], st));  // (after the wait: the stage time of raster_kernel does not include the label pass)
     raster_kernel<<<tc * blocks, kRasterThreads, 0, st>>>(s);
     ++launches;
@@ -1835,7 +1858,7 @@ static int labels_via_host(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_til
     CK(ctx->d_labels.reserve(recs.size() + 1));
     CK(ctx->d_label_segs.reserve(n_segs + 1));
     CK(ctx->d_cover_list.reserve(cover_list.size() + 1));
-    CK(ctx->d_cover_cursor.reserve(4));
+    CK(ctx->d_cover_cursor.reserve(2 * kMaxChunks));
     CK(ctx->d_label_begin.reserve(n_tiles + 1));
     CK(ctx->label_occ.reserve((size_t)n_tiles * ((size_t)E * E / 32)));
     CK(ctx->label_acc.reserve(2 * (size_t)cells + 2));
@@ -2056,7 +2079,7 @@ static bool label_device_path_allowed(const osmr_ctx* ctx, const osmr_tile* tile
 // greedy collisions -> ctx->label_plane.  The counters land in page-locked memory; label_device_judge reads them after the
 // draw has synchronised the stream.
 static int label_device_enqueue(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, const uint32_t* label_begin, const osmr_label* labels,
-                                bool resident = false) {
+                                bool resident, bool chunked) {
     auto& R = ctx->lres;
     const int D = 256 * ctx->scale, E = 3 * D;
     if (!R.valid) {
@@ -2091,8 +2114,6 @@ static int label_device_enqueue(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t 
     CK(ctx->l_place.reserve((size_t)n_labels + 1));
     CK(ctx->d_labels.reserve((size_t)n_labels + 1));
     CK(ctx->l_act_cnt.reserve(n_tiles + 1));
-    CK(ctx->l_counters.reserve(LCNT_COUNT));
-    CK(ctx->h_lcnt.reserve(LCNT_COUNT));
     CK(ctx->l_gplace.reserve(ctx->l_places_cap));
     CK(ctx->l_place_vinst.reserve(ctx->l_places_cap));
     const unsigned n_scan_blocks = (unsigned)((ctx->l_verts_cap + kScanBlock) / kScanBlock) + 1u;
@@ -2106,19 +2127,57 @@ static int label_device_enqueue(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t 
     CK(ctx->l_scan_blocks.reserve(n_scan_blocks + 8));
     CK(ctx->d_label_segs.reserve(ctx->l_segs_cap));
     CK(ctx->d_cover_list.reserve((size_t)n_labels + 1));
-    CK(ctx->d_cover_cursor.reserve(4));
+    CK(ctx->d_cover_cursor.reserve(2 * kMaxChunks));
     CK(ctx->label_row_keys.reserve(2 * ctx->l_rowrecs_cap + 2));
     CK(ctx->label_acc.reserve(2 * ctx->l_cells_cap + 2));
     CK(ctx->l_ring_pts.reserve(ctx->l_ring_cap));
     CK(ctx->l_heap.reserve(ctx->l_heap_slots * (size_t)kPolyHeapCap * sizeof(PolyCell)));
     CK(ctx->label_occ.reserve((size_t)n_tiles * ((size_t)E * E / 32)));
     CK(ctx->label_plane.reserve((size_t)n_tiles * D * D));
+    ctx->l_places_used_cap = ctx->l_places_cap;
+    ctx->l_segs_used_cap = ctx->l_segs_cap;
+    ctx->l_rowrecs_used_cap = ctx->l_rowrecs_cap;
+    ctx->l_cells_used_cap = ctx->l_cells_cap;
+    ctx->l_ring_used_cap = ctx->l_ring_cap;
+    ctx->l_heap_used_slots = ctx->l_heap_slots;
+    ctx->l_verts_used_cap = ctx->l_verts_cap;
+    ctx->l_curves_used_cap = ctx->l_curves_cap;
     CK(cudaEventRecord(ctx->ev_label0, st));
-    if (!resident) {
-        if (n_labels) CK(cudaMemcpyAsync(ctx->d_label_list.p, labels, (size_t)n_labels * sizeof(osmr_label), cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(ctx->d_label_begin.p, label_begin, (size_t)(n_tiles + 1) * 4, cudaMemcpyHostToDevice, st));
+    CK(ctx->l_counters.reserve((size_t)kMaxChunks * LCNT_COUNT));
+    CK(ctx->h_lcnt.reserve((size_t)kMaxChunks * LCNT_COUNT));
+    // The chunks of the label pass: the draw's host-output schedule when the tiles go to the host (a draw chunk then waits only
+    // for the label chunk under it, and its tiles travel while the next label chunk is computed), one chunk otherwise.  The
+    // scratch is reused chunk after chunk (stream order); what outlives a chunk is indexed by tile or by label.
+    {
+        unsigned sizes[kMaxChunks];
+        unsigned n = chunked ? plan_chunks(n_tiles, true, false, ctx->host_chunks, 1, sizes) : 1u;
+        if (!chunked) sizes[0] = n_tiles;
+        if (ctx->label_chunks) {
+            n = std::min<unsigned>(ctx->label_chunks, n_tiles);
+            for (unsigned i = 0; i < n; ++i) sizes[i] = n_tiles / n + (i < n_tiles % n ? 1u : 0u);
+        }
+        ctx->n_lchunks = n;
+        unsigned tb = 0;
+        for (unsigned i = 0; i < n; ++i) {
+            ctx->lchunk_tb[i] = tb;
+            ctx->lchunk_tc[i] = sizes[i];
+            tb += sizes[i];
+        }
+        if (tb != n_tiles) return ctx->fail(OSMR_E_STATE, "internal error: bad label chunk plan");
     }
-    CK(cudaMemsetAsync(ctx->l_counters.p, 0, LCNT_COUNT * sizeof(unsigned), st));
+    if (!resident) {
+        CK(cudaMemcpyAsync(ctx->d_label_begin.p, label_begin, (size_t)(n_tiles + 1) * 4, cudaMemcpyHostToDevice, st));
+        // the label lists: the first chunk's right here, the others behind the styled areas on the copy stream
+        for (unsigned i = 0; i < ctx->n_lchunks; ++i) {
+            const uint32_t l0 = label_begin[ctx->lchunk_tb[i]], l1 = label_begin[ctx->lchunk_tb[i] + ctx->lchunk_tc[i]];
+            if (l1 == l0) continue;
+            cudaStream_t cs = i == 0 ? st : ctx->copy_stream;
+            CK(cudaMemcpyAsync(ctx->d_label_list.p + l0, labels + l0, (size_t)(l1 - l0) * sizeof(osmr_label), cudaMemcpyHostToDevice, cs));
+            if (i) CK(cudaEventRecord(ctx->lchunk_up[i], ctx->copy_stream));
+        }
+    }
+    CK(cudaMemsetAsync(ctx->l_counters.p, 0, (size_t)kMaxChunks * LCNT_COUNT * sizeof(unsigned), st));
+    CK(cudaMemsetAsync(ctx->d_cover_cursor.p, 0, 2 * sizeof(unsigned) * kMaxChunks, st));
     Scene s{};
     s.merc = ctx->ds->merc.p;
     s.ways = ctx->ds->ways.p;
@@ -2188,44 +2247,58 @@ static int label_device_enqueue(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t 
     ld.heap_slots = (unsigned)ctx->l_heap_slots;
     ld.counters = ctx->l_counters.p;
     const unsigned wide = (unsigned)ctx->num_sms * 8u;
-    label_select_kernel<<<n_tiles, kLabelSelThreads, 0, st>>>(s, ld);
-    label_layout_kernel<<<n_tiles, kLayoutThreads, 0, st>>>(s, ld);
-    label_vfill_kernel<<<wide, 128, 0, st>>>(ld);
-    label_vline_count_kernel<<<wide, 128, 0, st>>>(ld);
-    label_curve_count_kernel<<<wide, 128, 0, st>>>(ld);
-    label_scan_sums_kernel<<<n_scan_blocks, 256, 0, st>>>(ld);
-    auto_scan_kernel<<<1, 1024, 0, st>>>(ctx->l_scan_blocks.p, n_scan_blocks, ctx->l_counters.p + LCNT_SCAN_OVF);
-    label_scan_apply_kernel<<<n_scan_blocks, 256, 0, st>>>(ld);
-    label_finish_kernel<<<n_tiles, 128, 0, st>>>(s, ld);
-    label_vline_write_kernel<<<wide, 128, 0, st>>>(ld);
-    label_curve_expand_kernel<<<(unsigned)ctx->num_sms * 8u, 256, 0, st>>>(ld);
-    CK(cudaGetLastError());
-    CK(cudaMemsetAsync(ctx->d_cover_cursor.p, 0, 2 * sizeof(unsigned), st));
-    LabelScene ls{};
-    ls.labels = ctx->d_labels.p;
-    ls.label_begin = ctx->d_label_begin.p;
-    ls.segs = ctx->d_label_segs.p;
-    ls.cover_list = ctx->d_cover_list.p;
-    ls.cover_cursor = ctx->d_cover_cursor.p;
-    ls.err_flag = ctx->l_counters.p + LCNT_COVER_ERR;
-    ls.icons = ctx->label_icons.p;
-    ls.occ = ctx->label_occ.p;
-    ls.acc_a = ctx->label_acc.p;
-    ls.acc_s = ctx->label_acc.p + ctx->l_cells_cap;
-    ls.kmin = ctx->label_row_keys.p;
-    ls.kmax = ctx->label_row_keys.p + ctx->l_rowrecs_cap;
-    ls.plane = ctx->label_plane.p;
-    ls.D = D;
-    ls.n_cover_dev = ctx->l_counters.p + LCNT_COVER;
-    ls.label_cnt = ctx->l_act_cnt.p;
-    ls.skip_flags = ctx->l_counters.p + LCNT_OVERFLOW;
-    CK(cudaEventRecord(ctx->ev_lcov0, st));
-    label_cover_kernel<<<(unsigned)ctx->num_sms * kCovCtasPerSm, 32, 0, st>>>(ls);
-    CK(cudaEventRecord(ctx->ev_lcov1, st));
-    label_commit_kernel<<<n_tiles, kLabelThreads, 0, st>>>(ls);
-    CK(cudaGetLastError());
+    const Scene s_all = s;
+    const LabelDev ld_all = ld;
+    for (unsigned ch = 0; ch < ctx->n_lchunks; ++ch) {
+        const unsigned tb = ctx->lchunk_tb[ch], tc = ctx->lchunk_tc[ch];
+        if (!resident && ch && label_begin[tb + tc] > label_begin[tb]) CK(cudaStreamWaitEvent(st, ctx->lchunk_up[ch], 0));
+        s = s_all;
+        ld = ld_all;
+        s.tiles = s_all.tiles + tb;
+        s.n_tiles = tc;
+        ld.label_begin = ld_all.label_begin + tb;
+        ld.act_cnt = ld_all.act_cnt + tb;
+        ld.n_tiles = tc;
+        ld.counters = ctx->l_counters.p + (size_t)ch * LCNT_COUNT;
+        label_select_kernel<<<tc, kLabelSelThreads, 0, st>>>(s, ld);
+        label_layout_kernel<<<tc, kLayoutThreads, 0, st>>>(s, ld);
+        label_vfill_kernel<<<wide, 128, 0, st>>>(ld);
+        label_vline_count_kernel<<<wide, 128, 0, st>>>(ld);
+        label_curve_count_kernel<<<wide, 128, 0, st>>>(ld);
+        label_scan_sums_kernel<<<n_scan_blocks, 256, 0, st>>>(ld);
+        auto_scan_kernel<<<1, 1024, 0, st>>>(ctx->l_scan_blocks.p, n_scan_blocks, ld.counters + LCNT_SCAN_OVF);
+        label_scan_apply_kernel<<<n_scan_blocks, 256, 0, st>>>(ld);
+        label_finish_kernel<<<tc, 128, 0, st>>>(s, ld);
+        label_vline_write_kernel<<<wide, 128, 0, st>>>(ld);
+        label_curve_expand_kernel<<<(unsigned)ctx->num_sms * 8u, 256, 0, st>>>(ld);
+        CK(cudaGetLastError());
+        LabelScene ls{};
+        ls.labels = ctx->d_labels.p;
+        ls.label_begin = ctx->d_label_begin.p + tb;
+        ls.segs = ctx->d_label_segs.p;
+        ls.cover_list = ctx->d_cover_list.p;
+        ls.cover_cursor = ctx->d_cover_cursor.p + 2 * ch;
+        ls.err_flag = ld.counters + LCNT_COVER_ERR;
+        ls.icons = ctx->label_icons.p;
+        ls.occ = ctx->label_occ.p + (size_t)tb * ((size_t)E * E / 32);
+        ls.acc_a = ctx->label_acc.p;
+        ls.acc_s = ctx->label_acc.p + ctx->l_cells_cap;
+        ls.kmin = ctx->label_row_keys.p;
+        ls.kmax = ctx->label_row_keys.p + ctx->l_rowrecs_cap;
+        ls.plane = ctx->label_plane.p + (size_t)tb * D * D;
+        ls.D = D;
+        ls.n_cover_dev = ld.counters + LCNT_COVER;
+        ls.label_cnt = ctx->l_act_cnt.p + tb;
+        ls.skip_flags = ld.counters + LCNT_OVERFLOW;
+        CK(cudaEventRecord(ctx->ev_lcov0[ch], st));
+        label_cover_kernel<<<(unsigned)ctx->num_sms * kCovCtasPerSm, 32, 0, st>>>(ls);
+        CK(cudaEventRecord(ctx->ev_lcov1[ch], st));
+        label_commit_kernel<<<tc, kLabelThreads, 0, st>>>(ls);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(ctx->lchunk_done[ch], st));
+    }
     CK(cudaEventRecord(ctx->ev_label1, st));
-    CK(cudaMemcpyAsync(ctx->h_lcnt.p, ctx->l_counters.p, LCNT_COUNT * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ctx->h_lcnt.p, ctx->l_counters.p, (size_t)ctx->n_lchunks * LCNT_COUNT * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(ctx->label_done, st));
     ctx->label_async = true;
     return OSMR_OK;
@@ -2234,41 +2307,60 @@ static int label_device_enqueue(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t 
 // After the stream has been synchronised: 0 = the label plane of this attempt is good, 1 = scratch grown, redo the call,
 // 2 = this call needs the host layout, < 0 = error.
 static int label_device_judge(osmr_ctx* ctx) {
-    const unsigned* c = ctx->h_lcnt.p;
-    if (c[LCNT_BAD]) return ctx->fail(OSMR_E_INVALID, "label references an entity, style or icon that does not exist");
-    if (c[LCNT_COVER_ERR]) return ctx->fail(OSMR_E_CUDA, "internal error: a label coverage term fell outside its proven window");
-    if (c[LCNT_FALLBACK]) return 2;
-    if (c[LCNT_OVERFLOW]) {
+    auto cells_of = [](const unsigned* c) {
         unsigned long long cells;
         memcpy(&cells, &c[LCNT_CELLS_LO], 8);
+        return cells;
+    };
+    unsigned overflow = 0, fallback = 0;
+    for (unsigned ch = 0; ch < ctx->n_lchunks; ++ch) {
+        const unsigned* c = ctx->h_lcnt.p + (size_t)ch * LCNT_COUNT;
+        if (c[LCNT_BAD]) return ctx->fail(OSMR_E_INVALID, "label references an entity, style or icon that does not exist");
+        if (c[LCNT_COVER_ERR]) return ctx->fail(OSMR_E_CUDA, "internal error: a label coverage term fell outside its proven window");
+        fallback |= c[LCNT_FALLBACK];
+        overflow |= c[LCNT_OVERFLOW];
+    }
+    if (fallback) return 2;
+    if (overflow) {
         auto grow = [](size_t used) { return used + used / 4 + 1024; };
-        // (a counter is an upper bound of what the attempt wanted only up to the first overflow: later stages were skipped)
-        if (c[LCNT_OVERFLOW] & 1u) ctx->l_places_cap = std::max(grow(c[LCNT_PLACES]), ctx->l_places_cap * 2);
-        if (c[LCNT_OVERFLOW] & 2u) ctx->l_segs_cap = std::max(grow(c[LCNT_SEGS]), ctx->l_segs_cap * 2);
-        if (c[LCNT_OVERFLOW] & 4u) ctx->l_rowrecs_cap = std::max(grow(c[LCNT_ROWRECS]), ctx->l_rowrecs_cap * 2);
-        if (c[LCNT_OVERFLOW] & 8u) ctx->l_cells_cap = std::max(grow((size_t)cells), ctx->l_cells_cap * 2);
-        if (c[LCNT_OVERFLOW] & 16u) ctx->l_ring_cap = std::max(grow(c[LCNT_RING_PTS]), ctx->l_ring_cap * 2);
-        if (c[LCNT_OVERFLOW] & 32u) ctx->l_heap_slots = std::max(grow(c[LCNT_POLY]), ctx->l_heap_slots * 2);
-        if (c[LCNT_OVERFLOW] & 64u) ctx->l_verts_cap = std::max(grow(c[LCNT_VERTS]), ctx->l_verts_cap * 2);
-        if (c[LCNT_OVERFLOW] & 128u) ctx->l_curves_cap = std::max(grow(c[LCNT_CURVES]), ctx->l_curves_cap * 2);
+        for (unsigned ch = 0; ch < ctx->n_lchunks; ++ch) {
+            const unsigned* c = ctx->h_lcnt.p + (size_t)ch * LCNT_COUNT;
+            // (a counter is an upper bound of what the attempt wanted only up to the first overflow: later stages were skipped)
+            if (c[LCNT_OVERFLOW] & 1u) ctx->l_places_cap = std::max(grow(c[LCNT_PLACES]), ctx->l_places_cap);
+            if (c[LCNT_OVERFLOW] & 2u) ctx->l_segs_cap = std::max(grow(c[LCNT_SEGS]), ctx->l_segs_cap);
+            if (c[LCNT_OVERFLOW] & 4u) ctx->l_rowrecs_cap = std::max(grow(c[LCNT_ROWRECS]), ctx->l_rowrecs_cap);
+            if (c[LCNT_OVERFLOW] & 8u) ctx->l_cells_cap = std::max(grow((size_t)cells_of(c)), ctx->l_cells_cap);
+            if (c[LCNT_OVERFLOW] & 16u) ctx->l_ring_cap = std::max(grow(c[LCNT_RING_PTS]), ctx->l_ring_cap);
+            if (c[LCNT_OVERFLOW] & 32u) ctx->l_heap_slots = std::max(grow(c[LCNT_POLY]), ctx->l_heap_slots);
+            if (c[LCNT_OVERFLOW] & 64u) ctx->l_verts_cap = std::max(grow(c[LCNT_VERTS]), ctx->l_verts_cap);
+            if (c[LCNT_OVERFLOW] & 128u) ctx->l_curves_cap = std::max(grow(c[LCNT_CURVES]), ctx->l_curves_cap);
+        }
+        // (a counter that stopped short of its real demand -- a stage skipped after an earlier overflow -- still doubles)
+        if (overflow & 1u) ctx->l_places_cap = std::max(ctx->l_places_cap, ctx->l_places_used_cap * 2);
+        if (overflow & 2u) ctx->l_segs_cap = std::max(ctx->l_segs_cap, ctx->l_segs_used_cap * 2);
+        if (overflow & 4u) ctx->l_rowrecs_cap = std::max(ctx->l_rowrecs_cap, ctx->l_rowrecs_used_cap * 2);
+        if (overflow & 8u) ctx->l_cells_cap = std::max(ctx->l_cells_cap, ctx->l_cells_used_cap * 2);
+        if (overflow & 16u) ctx->l_ring_cap = std::max(ctx->l_ring_cap, ctx->l_ring_used_cap * 2);
+        if (overflow & 32u) ctx->l_heap_slots = std::max(ctx->l_heap_slots, ctx->l_heap_used_slots * 2);
+        if (overflow & 64u) ctx->l_verts_cap = std::max(ctx->l_verts_cap, ctx->l_verts_used_cap * 2);
+        if (overflow & 128u) ctx->l_curves_cap = std::max(ctx->l_curves_cap, ctx->l_curves_used_cap * 2);
         if (ctx->l_places_cap >= 0xfffffff0ull || ctx->l_segs_cap >= 0xfffffff0ull || ctx->l_rowrecs_cap >= 0x7ffffff0ull ||
             ctx->l_cells_cap > (1ull << 33) || ctx->l_ring_cap >= 0xfffffff0ull)
             return ctx->fail(OSMR_E_NOMEM, "label scratch too large; split the batch");
         return 1;
     }
-    ctx->stats_label_active = c[LCNT_ACTIVE];
-    ctx->stats_label_poly = c[LCNT_POLY];
-    ctx->stats_label_segs = c[LCNT_SEGS];
-    {
-        unsigned long long cells;
-        memcpy(&cells, &c[LCNT_CELLS_LO], 8);
-        ctx->stats_label_cells = cells;
-    }
-    if (getenv("OSMR_LABEL_DEBUG")) {
-        unsigned long long cells;
-        memcpy(&cells, &c[LCNT_CELLS_LO], 8);
-        fprintf(stderr, "[osmr labels] active %u places %u segs %u rows %u cells %llu ring_pts %u polylabel %u covered %u\n", c[LCNT_ACTIVE], c[LCNT_PLACES],
-                c[LCNT_SEGS], c[LCNT_ROWRECS], cells, c[LCNT_RING_PTS], c[LCNT_POLY], c[LCNT_COVER]);
+    ctx->stats_label_active = ctx->stats_label_poly = ctx->stats_label_segs = 0;
+    ctx->stats_label_cells = 0;
+    for (unsigned ch = 0; ch < ctx->n_lchunks; ++ch) {
+        const unsigned* c = ctx->h_lcnt.p + (size_t)ch * LCNT_COUNT;
+        ctx->stats_label_active += c[LCNT_ACTIVE];
+        ctx->stats_label_poly += c[LCNT_POLY];
+        ctx->stats_label_segs += c[LCNT_SEGS];
+        ctx->stats_label_cells += cells_of(c);
+        if (getenv("OSMR_LABEL_DEBUG"))
+            fprintf(stderr, "[osmr labels] chunk %u (%u tiles): active %u places %u segs %u rows %u cells %llu ring_pts %u polylabel %u covered %u curves %u\n", ch,
+                    ctx->lchunk_tc[ch], c[LCNT_ACTIVE], c[LCNT_PLACES], c[LCNT_SEGS], c[LCNT_ROWRECS], cells_of(c), c[LCNT_RING_PTS], c[LCNT_POLY], c[LCNT_COVER],
+                    c[LCNT_CURVES]);
     }
     return 0;
 }
@@ -2308,7 +2400,8 @@ int osmr_batch_draw_labeled(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t
     if (!ctx->has_batch || !ctx->batch_has_labels) return ctx->fail(OSMR_E_STATE, "no labelled batch uploaded (osmr_batch_upload_labeled)");
     cudaSetDevice(ctx->device);
     for (int attempt = 0; attempt < 12; ++attempt) {
-        int rc = label_device_enqueue(ctx, ctx->h_batch_tiles.data(), ctx->n_tiles, ctx->h_label_begin.data(), nullptr, true);
+        int rc = label_device_enqueue(ctx, ctx->h_batch_tiles.data(), ctx->n_tiles, ctx->h_label_begin.data(), nullptr, true,
+                                      out != nullptr && !(flags & OSMR_DRAW_OUT_DEVICE));
         if (rc) {
             cudaStreamSynchronize(ctx->label_stream);
             return rc;
@@ -2333,7 +2426,11 @@ int osmr_batch_draw_labeled(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t
             ctx->stats.label_attempts = (uint32_t)attempt + 1;
             {
                 float mc = 0.f;
-                cudaEventElapsedTime(&mc, ctx->ev_lcov0, ctx->ev_lcov1);
+                for (unsigned ch = 0; ch < ctx->n_lchunks; ++ch) {
+                    float m1 = 0.f;
+                    cudaEventElapsedTime(&m1, ctx->ev_lcov0[ch], ctx->ev_lcov1[ch]);
+                    mc += m1;
+                }
                 ctx->stats.ms_label_cover = mc;
                 ctx->stats.n_label_segments = ctx->stats_label_segs;
                 ctx->stats.n_label_cells = ctx->stats_label_cells;
@@ -2353,19 +2450,31 @@ int osmr_draw_tiles_labeled(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_ti
     if (!out) return ctx->fail(OSMR_E_INVALID, "null output buffer");
     if (!label_begin) return ctx->fail(OSMR_E_INVALID, "null label_begin");
     if (!ctx->font.loaded()) return ctx->fail(OSMR_E_STATE, "osmr_set_font has not been called");
-    int rc = batch_upload_impl(ctx, tiles, n_tiles, area_begin, areas, false, nullptr);
+    int rc = validate_batch(ctx, tiles, n_tiles, area_begin);
     if (rc) return rc;
     for (uint32_t t = 0; t < n_tiles; ++t) {
         if (label_begin[t + 1] < label_begin[t]) return ctx->fail(OSMR_E_INVALID, "label_begin must be non-decreasing");
         if (label_begin[t + 1] > label_begin[t] && !labels) return ctx->fail(OSMR_E_INVALID, "null label list");
     }
     if (label_begin[0] != 0) return ctx->fail(OSMR_E_INVALID, "label_begin[0] must be 0");
+    // (as osmr_draw_tiles: the styled areas behind the first chunk's travel on the copy stream while the first chunk is drawn;
+    // the caller's arrays stay alive until this call returns)
+    struct TailGuard {
+        osmr_ctx* c;
+        ~TailGuard() {  // whatever the way out: no copy of the caller's memory stays in flight
+            cudaStreamSynchronize(c->copy_stream);
+            cudaStreamSynchronize(c->label_stream);
+            c->areas_deferred = false;
+        }
+    } tail_guard{ctx};
+    rc = batch_upload_impl(ctx, tiles, n_tiles, area_begin, areas, !(flags & OSMR_DRAW_OUT_DEVICE), out);
+    if (rc) return rc;
     cudaSetDevice(ctx->device);
     // ---- label layout on the device: everything is enqueued behind the upload, the draw follows without a host round trip ----
     bool on_device = label_device_path_allowed(ctx, tiles, n_tiles);
     for (int attempt = 0; on_device && attempt < 12; ++attempt) {
         const auto t_host0 = std::chrono::steady_clock::now();
-        rc = label_device_enqueue(ctx, tiles, n_tiles, label_begin, labels);
+        rc = label_device_enqueue(ctx, tiles, n_tiles, label_begin, labels, false, !(flags & OSMR_DRAW_OUT_DEVICE));
         if (rc) {
             cudaStreamSynchronize(ctx->stream);
             return rc;
@@ -2392,7 +2501,11 @@ int osmr_draw_tiles_labeled(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_ti
             ctx->stats.label_attempts = (uint32_t)attempt + 1;
             {
                 float mc = 0.f;
-                cudaEventElapsedTime(&mc, ctx->ev_lcov0, ctx->ev_lcov1);
+                for (unsigned ch = 0; ch < ctx->n_lchunks; ++ch) {
+                    float m1 = 0.f;
+                    cudaEventElapsedTime(&m1, ctx->ev_lcov0[ch], ctx->ev_lcov1[ch]);
+                    mc += m1;
+                }
                 ctx->stats.ms_label_cover = mc;
                 ctx->stats.n_label_segments = ctx->stats_label_segs;
                 ctx->stats.n_label_cells = ctx->stats_label_cells;

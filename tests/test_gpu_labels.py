@@ -143,3 +143,23 @@ def test_device_layout_equals_host_layout(fx, label_ctx, name):
     finally:
         ctx.debug_set("label_host", 0)
     assert (dev == host).all()
+
+
+@pytest.mark.parametrize("n_chunks", [2, 5])
+def test_chunked_label_pass_equals_golden(fx, label_ctx, n_chunks):
+    """A host-output call runs the label pass chunk by chunk (the draw's schedule: a draw chunk waits only for the label chunk
+    under it, scratch reused chunk after chunk); debug key "label_chunks" forces that on a small batch."""
+    ctx, per = label_ctx
+    tiles, begins, areas = fx.batches["17"]
+    lb, labels = per["17"]
+    try:
+        ctx.debug_set("label_chunks", n_chunks)
+        got = ctx.draw_tiles_labeled(tiles, begins, areas, lb, labels, fx.canvas_rgb, True)
+        assert ctx.stats()["label_path"] == 1
+    finally:
+        ctx.debug_set("label_chunks", 0)
+    golden, _ = fx.golden("17")
+    diff = (got != golden).any(axis=-1)
+    diff[:, 0, :] = False
+    diff[:, :, 255] = False
+    assert diff.sum() == 0

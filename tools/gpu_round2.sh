@@ -47,13 +47,13 @@ tail -2 gpurun_out/ncu_full_${TAG}.log | cut -c1-300
 fi
 if has labels_ncu; then
 echo "== ncu launch list of the label kernels"
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:label_ -c 40 --csv --log-file gpurun_out/launches_labels_${TAG}.csv \
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:label_ -c ${LABELS_NCU_COUNT:-90} --csv --log-file gpurun_out/launches_labels_${TAG}.csv \
     python bench.py --steps 2 --warmup 1 --skip-cpu-baseline --skip-auto --min-seconds 0 > gpurun_out/ncu_labels_${TAG}.log 2>&1
 tail -1 gpurun_out/ncu_labels_${TAG}.log | cut -c1-200
 fi
 if has full_labels; then
 echo "== ncu full (label kernels)"
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"${FULL_LABEL_KERNELS:-label_cover_kernel|label_curve_count_kernel|label_curve_expand_kernel}" -s 6 -c 3 -f -o gpurun_out/prof_labels_${TAG} \
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"${FULL_LABEL_KERNELS:-label_cover_kernel|label_curve_count_kernel|label_curve_expand_kernel}" -s ${FULL_LABEL_SKIP:-9} -c 3 -f -o gpurun_out/prof_labels_${TAG} \
     python bench.py --steps 2 --warmup 1 --skip-cpu-baseline --skip-auto --min-seconds 0 > gpurun_out/ncu_full_labels_${TAG}.log 2>&1
 tail -2 gpurun_out/ncu_full_labels_${TAG}.log | cut -c1-200
 fi
