@@ -2145,13 +2145,16 @@ static int label_device_enqueue(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t 
     CK(cudaEventRecord(ctx->ev_label0, st));
     CK(ctx->l_counters.reserve((size_t)kMaxChunks * LCNT_COUNT));
     CK(ctx->h_lcnt.reserve((size_t)kMaxChunks * LCNT_COUNT));
-    // The chunks of the label pass: the draw's host-output schedule when the tiles go to the host (a draw chunk then waits only
-    // for the label chunk under it, and its tiles travel while the next label chunk is computed), one chunk otherwise.  The
-    // scratch is reused chunk after chunk (stream order); what outlives a chunk is indexed by tile or by label.
+    // The label pass can run chunk by chunk (debug key "label_chunks"; a draw chunk then waits only for the label chunks under it
+    // and the scratch is reused chunk after chunk), but it does NOT by default: label_select / label_layout / label_commit are one
+    // CTA per tile and serial inside a tile (greedy collisions, polylabel), so every chunk pays the latency of its slowest tile --
+    // measured on the C2 batch (B200) 1 chunk 16.6 ms end to end, 2 chunks 17.7, 3 chunks 18.2, the draw's 5-chunk schedule 20.0.
+    // One pass over the whole batch beside the area passes hides those latencies best.
+    (void)chunked;
     {
         unsigned sizes[kMaxChunks];
-        unsigned n = chunked ? plan_chunks(n_tiles, true, false, ctx->host_chunks, 1, sizes) : 1u;
-        if (!chunked) sizes[0] = n_tiles;
+        unsigned n = 1u;
+        sizes[0] = n_tiles;
         if (ctx->label_chunks) {
             n = std::min<unsigned>(ctx->label_chunks, n_tiles);
             for (unsigned i = 0; i < n; ++i) sizes[i] = n_tiles / n + (i < n_tiles % n ? 1u : 0u);

@@ -785,8 +785,8 @@ struct EmitSink {
     }
     // draw_quad's flatness test (rasterizer.rs:86-107): hypot(p0-p1) + hypot(p1-p2) <= 1.0001 * hypot(p0-p2)
     __device__ bool flat_enough(double x0, double y0, double x1, double y1, double x2, double y2) {
-        const double ax = fabs(x0 - x1), ay = fabs(y0 - y1), bx = fabs(x1 - x2), by = fabs(y1 - y2);
-        const double cx = fabs(x0 - x2), cy = fabs(y0 - y2);
+        const double ax = x0 - x1, ay = y0 - y1, bx = x1 - x2, by = y1 - y2;  // (only their squares are used)
+        const double cx = x0 - x2, cy = y0 - y2;
         {
             // |a| + |b| <= 1.0001 |c|  <=>  2 sqrt(A B) <= T with T = 1.0001^2 C - A - B  <=>  T >= 0 and 4 A B <= T^2 (A, B, C the
             // squared lengths): no square root at all.  Both sides carry a few ulp of error; the decision is taken only with a
@@ -1281,46 +1281,74 @@ __device__ __noinline__ void curve_flatten_again(const CurveRoot& r, DevSeg* out
     sink.quad(r.x0, r.y0, r.x1, r.y1, r.x2, r.y2);
 }
 
-// a warp per curve, a lane per leaf
+// a warp per group of 8 curves of the list, a lane per leaf of the group (a curve alone would leave a third of the lanes idle)
+constexpr unsigned kExpandGroup = 8;
 __global__ void __launch_bounds__(256, 4) label_curve_expand_kernel(LabelDev ld) {
+    constexpr unsigned kFull = 0xffffffffu;
     const unsigned n_curves = min(ld.counters[LCNT_CURVES], ld.curves_cap);
     if (ld.counters[LCNT_OVERFLOW] || ld.counters[LCNT_FALLBACK]) return;
     const unsigned lane = lane_id();
     const unsigned n_warps = (gridDim.x * blockDim.x) >> 5;
-    for (unsigned k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < n_curves; k += n_warps) {
-        const unsigned inst = ld.curve_list[k];
-        const unsigned off = ld.vcnt[inst], n = ld.vcnt[inst + 1] - off;
-        if (!n) continue;
-        const CurveRoot r = ld.curve_root[k];
-        if (ld.curve_deep[k]) {
-            if (lane == 0) curve_flatten_again(r, ld.segs + off);
-            continue;
-        }
-        const unsigned short* codes = reinterpret_cast<const unsigned short*>(ld.curve_codes + (size_t)k * (kCurveLeafCap / 4u));
-        for (unsigned i = lane; i < n; i += 32) {
-            const unsigned code = codes[i];
-            double a0 = r.x0, b0 = r.y0, a1 = r.x1, b1 = r.y1, a2 = r.x2, b2 = r.y2;
-            for (int lv = 30 - __clz(code); lv >= 0; --lv) {
-                const double ax = (a0 + a1) / 2.0, ay = (b0 + b1) / 2.0, bx = (a1 + a2) / 2.0, by = (b1 + b2) / 2.0;
-                const double mx = (ax + bx) / 2.0, my = (ay + by) / 2.0;
-                if ((code >> lv) & 1u) {  // the second half (m, b, p2)
-                    a0 = mx;
-                    b0 = my;
-                    a1 = bx;
-                    b1 = by;
-                } else {  // the first half (p0, a, m)
-                    a2 = mx;
-                    b2 = my;
-                    a1 = ax;
-                    b1 = ay;
-                }
+    const unsigned n_groups = (n_curves + kExpandGroup - 1) / kExpandGroup;
+    for (unsigned g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < n_groups; g += n_warps) {
+        const unsigned k0 = g * kExpandGroup;
+        // lanes 0 .. 7: the curves of the group
+        unsigned off = 0, n = 0;
+        bool deep = false;
+        if (lane < kExpandGroup && k0 + lane < n_curves) {
+            const unsigned inst = ld.curve_list[k0 + lane];
+            off = ld.vcnt[inst];
+            n = ld.vcnt[inst + 1] - off;
+            deep = n != 0u && ld.curve_deep[k0 + lane] != 0;
+            if (deep) {  // not described by its codes: flattened again, by this lane alone
+                curve_flatten_again(ld.curve_root[k0 + lane], ld.segs + off);
+                n = 0;
             }
-            DevSeg sg;
-            sg.x0 = a0;
-            sg.y0 = b0;
-            sg.x1 = a2;
-            sg.y1 = b2;
-            ld.segs[off + i] = sg;
+        }
+        unsigned incl = n;
+        for (int o = 1; o < (int)kExpandGroup; o <<= 1) {
+            const unsigned y = __shfl_up_sync(kFull, incl, o);
+            if ((int)lane >= o) incl += y;
+        }
+        const unsigned pre = incl - n;  // leaves of the group before this curve's
+        const unsigned total = __shfl_sync(kFull, incl, kExpandGroup - 1);
+        for (unsigned tb = 0; tb < total; tb += 32) {
+            const unsigned t = tb + lane;
+            // the curve of leaf t: the last one whose first leaf is not behind t
+            unsigned j = 0;
+            for (unsigned step = kExpandGroup / 2; step; step >>= 1) {
+                const unsigned pj = __shfl_sync(kFull, pre, j + step);
+                if (pj <= t) j += step;
+            }
+            const unsigned pj = __shfl_sync(kFull, pre, j), oj = __shfl_sync(kFull, off, j);
+            if (t < total) {
+                const unsigned i = t - pj;
+                const unsigned k = k0 + j;
+                const unsigned code = reinterpret_cast<const unsigned short*>(ld.curve_codes + (size_t)k * (kCurveLeafCap / 4u))[i];
+                const CurveRoot r = ld.curve_root[k];
+                double a0 = r.x0, b0 = r.y0, a1 = r.x1, b1 = r.y1, a2 = r.x2, b2 = r.y2;
+                for (int lv = 30 - __clz(code); lv >= 0; --lv) {
+                    const double ax = (a0 + a1) / 2.0, ay = (b0 + b1) / 2.0, bx = (a1 + a2) / 2.0, by = (b1 + b2) / 2.0;
+                    const double mx = (ax + bx) / 2.0, my = (ay + by) / 2.0;
+                    if ((code >> lv) & 1u) {  // the second half (m, b, p2)
+                        a0 = mx;
+                        b0 = my;
+                        a1 = bx;
+                        b1 = by;
+                    } else {  // the first half (p0, a, m)
+                        a2 = mx;
+                        b2 = my;
+                        a1 = ax;
+                        b1 = ay;
+                    }
+                }
+                DevSeg sg;
+                sg.x0 = a0;
+                sg.y0 = b0;
+                sg.x1 = a2;
+                sg.y1 = b2;
+                ld.segs[oj + i] = sg;
+            }
         }
     }
 }
