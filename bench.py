@@ -609,11 +609,14 @@ def main():
             resident_step(None, False)
         barrier()
         t0a = time.perf_counter()
+        acc_a = {}
         for _ in range(args.steps):
-            resident_step(None, False)
+            resident_step(acc_a, False)
         barrier()
         area_wall = time.perf_counter() - t0a
-        area_only = {"wall": area_wall}
+        # (stage times of the area kernels WITHOUT the label stream beside them: what their roofline is quoted on)
+        area_only = {"wall": area_wall, "ms_cover": acc_a["ms_cover"] / args.steps, "ms_raster": acc_a["ms_raster"] / args.steps,
+                     "ms_plan": acc_a["ms_plan"] / args.steps}
         if single:
             upload(0, True)
 
@@ -827,7 +830,9 @@ def main():
     if area_only is not None:
         aw, at = red(area_only["wall"])
         area_only = {"value": at / aw, "unit": "tiles/s", "ms_per_step": 1000.0 * aw / args.steps,
-                     "path": "Fill, Casing and Stroke passes only (osmr_batch_draw), resident: round 1's headline leg"}
+                     "path": "Fill, Casing and Stroke passes only (osmr_batch_draw), resident: round 1's headline leg",
+                     "ms_cover": area_only["ms_cover"], "ms_raster": area_only["ms_raster"], "ms_plan": area_only["ms_plan"],
+                     "stage_ms_note": "this rank's CUDA-event stage times with no label stream beside the area kernels"}
     if sustained is not None:
         sw, stl = sharding.reduce_job(dist, sustained["seconds"], tiles_per_step * sustained["steps"], device="cuda")
         sustained["tiles_per_s"] = stl / sw
@@ -857,10 +862,13 @@ def main():
     walk_alpha_bytes = 8 * stats["walk_steps"]
     raster_local = tiles_per_step * D * D * 3 + 32 * G + stats["geom_bytes"] + stats["mask_bytes"] + walk_alpha_bytes
     cover_local = stats["geom_bytes"] + walk_alpha_bytes + stats["walk_bytes"] // (8 * 4)
-    if cover_mean_ms > raster_mean_ms:
-        dom, dom_ms, local_bytes = "line_cover_kernel", cover_mean_ms, cover_local
+    # (in a labelled step the area kernels share the SMs with the label stream: their own durations come from the area-only leg)
+    a_cover_ms = area_only["ms_cover"] if area_only else cover_mean_ms
+    a_raster_ms = area_only["ms_raster"] if area_only else raster_mean_ms
+    if a_cover_ms > a_raster_ms:
+        dom, dom_ms, local_bytes = "line_cover_kernel", a_cover_ms, cover_local
     else:
-        dom, dom_ms, local_bytes = "raster_kernel", raster_mean_ms, raster_local
+        dom, dom_ms, local_bytes = "raster_kernel", a_raster_ms, raster_local
     algo_bytes = b_step if b_step is not None else local_bytes - walk_alpha_bytes
     area_dom = {"kernel": dom, "kernel_ms": dom_ms, "kernel_local_bytes": int(local_bytes), "algorithmic_bytes_B_tile": None if b_step is None else int(b_step),
                 "frac_B_tile": None if b_step is None else b_step / (dom_ms / 1000.0) / 1e9 / peak, "kernel_local_frac": local_bytes / (dom_ms / 1000.0) / 1e9 / peak}
