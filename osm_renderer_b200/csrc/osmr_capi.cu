@@ -193,6 +193,7 @@ struct osmr_ctx {
     std::vector<uint32_t> h_label_begin;
     bool batch_has_labels = false;
     unsigned label_chunks = 0;     // debug key "label_chunks"
+    unsigned curve_leaf_cap = 0;   // debug key "curve_leaf_cap" (tests: curves with more leaves are flattened again by one lane)
     bool label_host_only = false;  // debug key "label_host": always lay labels out on the host (round-1 path)
     unsigned stats_label_active = 0, stats_label_poly = 0, stats_label_segs = 0;
     unsigned long long stats_label_cells = 0;
@@ -246,6 +247,7 @@ struct osmr_ctx {
     } scrB;
     cudaStream_t stream2 = nullptr;
     cudaStream_t label_stream = nullptr;  // the label pass runs beside the area passes; raster_kernel waits for label_done
+    cudaStream_t label_stream_normal = nullptr, label_stream_high = nullptr;  // (debug key "label_priority" picks one)
     cudaEvent_t label_done = nullptr, label_go = nullptr;
     bool label_async = false;             // the label plane of this draw is produced on label_stream
     cudaEvent_t ev_wall0 = nullptr, ev_wall1 = nullptr, join2 = nullptr;  // device wall time of a draw across both streams
@@ -339,7 +341,13 @@ int osmr_ctx_create(int device, osmr_ctx** out_ctx) try {
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->label_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->label_stream_normal, cudaStreamNonBlocking);
+    if (e == cudaSuccess) {
+        int lo = 0, hi = 0;
+        e = cudaDeviceGetStreamPriorityRange(&lo, &hi);  // (hi is the numerically smallest = most urgent)
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->label_stream_high, cudaStreamNonBlocking, hi);
+    }
+    ctx->label_stream = ctx->label_stream_normal;
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->label_done, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->label_go, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->prep_done, cudaEventDisableTiming);
@@ -433,7 +441,8 @@ void osmr_ctx_destroy(osmr_ctx* ctx) {
     if (ctx->ev_wall0) cudaEventDestroy(ctx->ev_wall0);
     if (ctx->ev_wall1) cudaEventDestroy(ctx->ev_wall1);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
-    if (ctx->label_stream) cudaStreamDestroy(ctx->label_stream);
+    if (ctx->label_stream_normal) cudaStreamDestroy(ctx->label_stream_normal);
+    if (ctx->label_stream_high) cudaStreamDestroy(ctx->label_stream_high);
     if (ctx->label_done) cudaEventDestroy(ctx->label_done);
     if (ctx->label_go) cudaEventDestroy(ctx->label_go);
     ctx->calc_table.release();
@@ -490,6 +499,16 @@ int osmr_debug_set(osmr_ctx* ctx, const char* key, int value) try {
     }
     if (strcmp(key, "label_host") == 0) {  // 1: label layout on the host for every call (the round-1 path; A/B and tests)
         ctx->label_host_only = value != 0;
+        return OSMR_OK;
+    }
+    if (strcmp(key, "label_priority") == 0) {  // 1: the label stream's CTAs are scheduled before the area kernels' (A/B)
+        cudaStreamSynchronize(ctx->label_stream);
+        ctx->label_stream = value ? ctx->label_stream_high : ctx->label_stream_normal;
+        return OSMR_OK;
+    }
+    if (strcmp(key, "curve_leaf_cap") == 0) {  // tests: leaf codes per curve (0: the build's 128)
+        if (value < 0) return ctx->fail(OSMR_E_INVALID, "curve_leaf_cap must be >= 0");
+        ctx->curve_leaf_cap = (unsigned)value;
         return OSMR_OK;
     }
     if (strcmp(key, "label_chunks") == 0) {  // n > 0: the label pass in n equal chunks whatever the batch (tests); 0: the draw's schedule
@@ -2232,6 +2251,7 @@ static int label_device_enqueue(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t 
     ld.curve_list = ctx->l_curve_list.p;
     ld.curve_codes = ctx->l_curve_codes.p;
     ld.curve_deep = ctx->l_curve_deep.p;
+    ld.leaf_cap = ctx->curve_leaf_cap ? std::min(ctx->curve_leaf_cap, kCurveLeafCap) : kCurveLeafCap;
     ld.curves_cap = (unsigned)std::min<size_t>(ctx->l_curves_cap, 0xfffffff0u);
     ld.curve_root = ctx->l_curve_root.p;
     ld.verts_cap = (unsigned)std::min<size_t>(ctx->l_verts_cap, 0xfffffff0u);

@@ -131,6 +131,7 @@ struct LabelDev {
     unsigned long long* curve_codes;  // per curve: kCurveLeafCap 16-bit leaf codes ((1 << depth) | path) of the segments it draws, in order
     unsigned char* curve_deep;        // per curve: 1 when the codes do not describe it (too many leaves, too deep): flattened again
     unsigned curves_cap;
+    unsigned leaf_cap;                // <= kCurveLeafCap (smaller only in tests: forces the flatten-again path)
     unsigned verts_cap;
     unsigned* scan_blocks;  // block sums of the segment-offset scan
     unsigned n_scan_blocks;
@@ -1216,7 +1217,7 @@ __global__ void __launch_bounds__(128) label_curve_count_kernel(LabelDev ld) {
             } else {
                 // draw_line(p0, p2) of this leaf (rasterizer.rs:30-32: nothing happens when y does not change)
                 if (c.b2 - c.b0 != 0.0) {
-                    if (c.n_segs < kCurveLeafCap && c.depth <= 15) {
+                    if (c.n_segs < ld.leaf_cap && c.depth <= 15) {
                         c.pack |= (unsigned long long)((1u << c.depth) | c.path) << (16u * (c.n_segs & 3u));
                         if ((c.n_segs & 3u) == 3u) {
                             ld.curve_codes[(size_t)c.curve * (kCurveLeafCap / 4u) + (c.n_segs >> 2)] = c.pack;

@@ -471,6 +471,13 @@ static inline cudaError_t cudaDeviceGetAttribute(int* v, int, int) {
     *v = 2;  // "SMs": persistent kernels launch a handful of blocks
     return cudaSuccess;
 }
+static inline cudaError_t cudaDeviceGetStreamPriorityRange(int* lo, int* hi) {
+    *lo = 0;
+    *hi = -1;
+    return cudaSuccess;
+}
+static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned);
+static inline cudaError_t cudaStreamCreateWithPriority(cudaStream_t* s, unsigned f, int) { return cudaStreamCreateWithFlags(s, f); }
 static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) {
     *s = (cudaStream_t)(uintptr_t)1;
     return cudaSuccess;

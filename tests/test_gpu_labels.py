@@ -163,3 +163,23 @@ def test_chunked_label_pass_equals_golden(fx, label_ctx, n_chunks):
     diff[:, 0, :] = False
     diff[:, :, 255] = False
     assert diff.sum() == 0
+
+
+def test_curves_beyond_the_leaf_code_record_are_flattened_again(fx, label_ctx):
+    """label_curve_expand_kernel writes a curve's segments from its recorded leaf codes; a curve with more leaves than the record
+    holds is flattened again (flatness tests included) by one lane.  Debug key "curve_leaf_cap" shrinks the record so that
+    nearly every curve takes that path."""
+    ctx, per = label_ctx
+    tiles, begins, areas = fx.batches["16"]
+    lb, labels = per["16"]
+    try:
+        ctx.debug_set("curve_leaf_cap", 6)
+        got = ctx.draw_tiles_labeled(tiles, begins, areas, lb, labels, fx.canvas_rgb, True)
+        assert ctx.stats()["label_path"] == 1
+    finally:
+        ctx.debug_set("curve_leaf_cap", 0)
+    golden, _ = fx.golden("16")
+    diff = (got != golden).any(axis=-1)
+    diff[:, 0, :] = False
+    diff[:, :, 255] = False
+    assert diff.sum() == 0
