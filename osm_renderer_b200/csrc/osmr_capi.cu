@@ -347,7 +347,9 @@ int osmr_ctx_create(int device, osmr_ctx** out_ctx) try {
         e = cudaDeviceGetStreamPriorityRange(&lo, &hi);  // (hi is the numerically smallest = most urgent)
         if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->label_stream_high, cudaStreamNonBlocking, hi);
     }
-    ctx->label_stream = ctx->label_stream_normal;
+    // The label pass is the longer of the two and has the latency-bound kernels (one CTA per tile, serial inside): its CTAs go first
+    // when both streams have work pending; the area kernels fill what is left (C2 batch: 13.6 -> 13.2 ms per labelled step).
+    ctx->label_stream = ctx->label_stream_high;
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->label_done, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->label_go, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->prep_done, cudaEventDisableTiming);
@@ -501,7 +503,7 @@ int osmr_debug_set(osmr_ctx* ctx, const char* key, int value) try {
         ctx->label_host_only = value != 0;
         return OSMR_OK;
     }
-    if (strcmp(key, "label_priority") == 0) {  // 1: the label stream's CTAs are scheduled before the area kernels' (A/B)
+    if (strcmp(key, "label_priority") == 0) {  // 0: the label stream at normal priority (A/B; default 1: its CTAs are scheduled first)
         cudaStreamSynchronize(ctx->label_stream);
         ctx->label_stream = value ? ctx->label_stream_high : ctx->label_stream_normal;
         return OSMR_OK;
