@@ -250,6 +250,9 @@ struct osmr_ctx {
     cudaStream_t label_stream_normal = nullptr, label_stream_high = nullptr;  // (debug key "label_priority" picks one)
     cudaEvent_t label_done = nullptr, label_go = nullptr;
     bool label_async = false;             // the label plane of this draw is produced on label_stream
+    const osmr_styled_area* tail_src = nullptr;  // styled areas behind the first draw chunk, not yet on their way (flush_area_tail)
+    osmr_styled_area* tail_dst = nullptr;
+    size_t tail_bytes = 0;
     cudaEvent_t ev_wall0 = nullptr, ev_wall1 = nullptr, join2 = nullptr;  // device wall time of a draw across both streams
     cudaEvent_t prep_done = nullptr;  // upload + style calculators on `stream`: what stream2's first chunk waits for
     bool two_streams = true;          // debug key "two_streams"
@@ -952,8 +955,16 @@ static unsigned plan_chunks(unsigned n_tiles, bool to_host, bool direct, unsigne
     return n;
 }
 
+static int flush_area_tail(osmr_ctx* ctx) {
+    if (!ctx->tail_src) return OSMR_OK;
+    CK(cudaMemcpyAsync(ctx->tail_dst, ctx->tail_src, ctx->tail_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+    CK(cudaEventRecord(ctx->areas_ready, ctx->copy_stream));
+    ctx->tail_src = nullptr;
+    return OSMR_OK;
+}
+
 static int batch_upload_impl(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, const uint32_t* area_begin,
-                             const osmr_styled_area* areas, bool defer_tail, const void* host_out) {
+                             const osmr_styled_area* areas, bool defer_tail, const void* host_out, bool hold_tail = false) {
     if (!ctx) return OSMR_E_INVALID;
     int rc = validate_batch(ctx, tiles, n_tiles, area_begin);
     if (rc) return rc;
@@ -979,10 +990,17 @@ static int batch_upload_impl(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_t
         }
     }
     if (head) CK(cudaMemcpyAsync(ctx->areas.p, areas, head * sizeof(osmr_styled_area), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->tail_src = nullptr;
     if (head < n_areas) {
-        CK(cudaMemcpyAsync(ctx->areas.p + head, areas + head, (n_areas - head) * sizeof(osmr_styled_area), cudaMemcpyHostToDevice,
-                           ctx->copy_stream));
-        CK(cudaEventRecord(ctx->areas_ready, ctx->copy_stream));
+        if (hold_tail) {  // the caller has something more urgent for the copy engine first (the label lists): flush_area_tail later
+            ctx->tail_src = areas + head;
+            ctx->tail_dst = ctx->areas.p + head;
+            ctx->tail_bytes = (n_areas - head) * sizeof(osmr_styled_area);
+        } else {
+            CK(cudaMemcpyAsync(ctx->areas.p + head, areas + head, (n_areas - head) * sizeof(osmr_styled_area), cudaMemcpyHostToDevice,
+                               ctx->copy_stream));
+            CK(cudaEventRecord(ctx->areas_ready, ctx->copy_stream));
+        }
         ctx->areas_deferred = true;
     }
     ctx->n_tiles = n_tiles;
@@ -2490,9 +2508,11 @@ int osmr_draw_tiles_labeled(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_ti
             cudaStreamSynchronize(c->copy_stream);
             cudaStreamSynchronize(c->label_stream);
             c->areas_deferred = false;
+            c->tail_src = nullptr;
         }
     } tail_guard{ctx};
-    rc = batch_upload_impl(ctx, tiles, n_tiles, area_begin, areas, !(flags & OSMR_DRAW_OUT_DEVICE), out);
+    // (copy order: the first draw chunk's styled areas, the label lists -- the label pass is the critical path --, then the rest)
+    rc = batch_upload_impl(ctx, tiles, n_tiles, area_begin, areas, !(flags & OSMR_DRAW_OUT_DEVICE), out, true);
     if (rc) return rc;
     cudaSetDevice(ctx->device);
     // ---- label layout on the device: everything is enqueued behind the upload, the draw follows without a host round trip ----
@@ -2505,6 +2525,8 @@ int osmr_draw_tiles_labeled(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_ti
             return rc;
         }
         const float enqueue_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_host0).count();
+        rc = flush_area_tail(ctx);
+        if (rc) return rc;
         ctx->label_plane_active = true;
         rc = osmr_batch_draw(ctx, canvas_rgb, flags, out, nullptr);  // synchronises the compute streams (which waited for label_done)
         ctx->label_plane_active = false;
@@ -2540,6 +2562,8 @@ int osmr_draw_tiles_labeled(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_ti
         if (verdict == 2) on_device = false;
     }
     // ---- host layout ----
+    rc = flush_area_tail(ctx);
+    if (rc) return rc;
     rc = labels_via_host(ctx, tiles, n_tiles, label_begin, labels);
     if (rc) return rc;
     ctx->label_plane_active = true;

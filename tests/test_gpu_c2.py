@@ -98,3 +98,24 @@ def test_c2_second_stylesheet_equals_oracle(ctx):
     got = ctx.draw_tiles(tiles, begins, areas, w["canvas"], w["caps"])
     assert (got == want).all()
     assert len(np.unique(want.reshape(-1, 3), axis=0)) > 3  # something was drawn
+
+
+def test_c2_labeled_big_call_equals_small_calls(ctx):
+    """192 labelled tiles in ONE call take the pipelined route (draw chunks, styled-area tail and label lists on their own copy
+    streams, tiles copied back chunk by chunk); the same tiles in calls of 48 take the simple one.  Same pixels."""
+    import bench
+
+    w = bench.build_workload("C2", "mapnik", labels=True, max_tiles=192)
+    n = len(w["tiles"])
+    assert n >= 128
+    ctx.set_table(w["table"])
+    ctx.set_font(w["font"])
+    ctx.set_label_table(w["ltable"])
+    t, b, a, lb, ln = bench.sub_batch(w, np.arange(n), True)
+    big = ctx.draw_tiles_labeled(t, b, a, lb, ln, w["canvas"], w["caps"])
+    assert ctx.stats()["label_path"] == 1
+    for first in range(0, n, 48):
+        sel = np.arange(first, min(n, first + 48))
+        ts, bs, as_, lbs, lns = bench.sub_batch(w, sel, True)
+        small = ctx.draw_tiles_labeled(ts, bs, as_, lbs, lns, w["canvas"], w["caps"])
+        assert (small == big[sel]).all(), first
