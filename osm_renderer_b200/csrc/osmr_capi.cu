@@ -184,6 +184,21 @@ struct osmr_ctx {
     size_t l_places_used_cap = 0, l_segs_used_cap = 0, l_rowrecs_used_cap = 0, l_cells_used_cap = 0, l_ring_used_cap = 0, l_heap_used_slots = 0,
            l_verts_used_cap = 0, l_curves_used_cap = 0;
     DevBuf<CurveRoot> l_curve_root;
+    // the second set of the label pass's per-chunk scratch: odd label chunks run on their own stream beside the even ones
+    struct LabelScratchB {
+        DevBuf<DevSeg> segs;
+        DevBuf<double> acc;
+        DevBuf<int> row_keys;
+        DevBuf<unsigned> cover_list, place_vinst, vinst_place, vcnt, curve_list, scan_blocks;
+        DevBuf<GlyphPlace> gplace;
+        DevBuf<double4> vbox;
+        DevBuf<unsigned long long> curve_codes;
+        DevBuf<unsigned char> curve_deep, heap;
+        DevBuf<CurveRoot> curve_root;
+        DevBuf<double2> ring_pts;
+    } lscrB;
+    cudaStream_t label_stream2 = nullptr, label_stream2_normal = nullptr, label_stream2_high = nullptr;
+    cudaEvent_t label_join = nullptr, label_prep = nullptr;
     size_t l_verts_cap = 0;
     DevBuf<double2> l_ring_pts;
     DevBuf<unsigned char> l_heap;
@@ -349,7 +364,12 @@ int osmr_ctx_create(int device, osmr_ctx** out_ctx) try {
         int lo = 0, hi = 0;
         e = cudaDeviceGetStreamPriorityRange(&lo, &hi);  // (hi is the numerically smallest = most urgent)
         if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->label_stream_high, cudaStreamNonBlocking, hi);
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->label_stream2_high, cudaStreamNonBlocking, hi);
     }
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->label_stream2_normal, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->label_join, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->label_prep, cudaEventDisableTiming);
+    ctx->label_stream2 = ctx->label_stream2_high;
     // The label pass is the longer of the two and has the latency-bound kernels (one CTA per tile, serial inside): its CTAs go first
     // when both streams have work pending; the area kernels fill what is left (C2 batch: 13.6 -> 13.2 ms per labelled step).
     ctx->label_stream = ctx->label_stream_high;
@@ -448,6 +468,10 @@ void osmr_ctx_destroy(osmr_ctx* ctx) {
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->label_stream_normal) cudaStreamDestroy(ctx->label_stream_normal);
     if (ctx->label_stream_high) cudaStreamDestroy(ctx->label_stream_high);
+    if (ctx->label_stream2_normal) cudaStreamDestroy(ctx->label_stream2_normal);
+    if (ctx->label_stream2_high) cudaStreamDestroy(ctx->label_stream2_high);
+    if (ctx->label_join) cudaEventDestroy(ctx->label_join);
+    if (ctx->label_prep) cudaEventDestroy(ctx->label_prep);
     if (ctx->label_done) cudaEventDestroy(ctx->label_done);
     if (ctx->label_go) cudaEventDestroy(ctx->label_go);
     ctx->calc_table.release();
@@ -508,7 +532,9 @@ int osmr_debug_set(osmr_ctx* ctx, const char* key, int value) try {
     }
     if (strcmp(key, "label_priority") == 0) {  // 0: the label stream at normal priority (A/B; default 1: its CTAs are scheduled first)
         cudaStreamSynchronize(ctx->label_stream);
+        cudaStreamSynchronize(ctx->label_stream2);
         ctx->label_stream = value ? ctx->label_stream_high : ctx->label_stream_normal;
+        ctx->label_stream2 = value ? ctx->label_stream2_high : ctx->label_stream2_normal;
         return OSMR_OK;
     }
     if (strcmp(key, "curve_leaf_cap") == 0) {  // tests: leaf codes per curve (0: the build's 128)
@@ -2184,16 +2210,17 @@ static int label_device_enqueue(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t 
     CK(cudaEventRecord(ctx->ev_label0, st));
     CK(ctx->l_counters.reserve((size_t)kMaxChunks * LCNT_COUNT));
     CK(ctx->h_lcnt.reserve((size_t)kMaxChunks * LCNT_COUNT));
-    // The label pass can run chunk by chunk (debug key "label_chunks"; a draw chunk then waits only for the label chunks under it
-    // and the scratch is reused chunk after chunk), but it does NOT by default: label_select / label_layout / label_commit are one
-    // CTA per tile and serial inside a tile (greedy collisions, polylabel), so every chunk pays the latency of its slowest tile --
-    // measured on the C2 batch (B200) 1 chunk 16.6 ms end to end, 2 chunks 17.7, 3 chunks 18.2, the draw's 5-chunk schedule 20.0.
-    // One pass over the whole batch beside the area passes hides those latencies best.
-    (void)chunked;
+    // The label pass runs chunk by chunk on the draw's host-output schedule when the tiles go to the host: a draw chunk waits only
+    // for the label chunks under it, so its tiles travel while later label chunks are computed.  label_select / label_layout /
+    // label_commit are one CTA per tile and serial inside a tile (greedy collisions, polylabel): on ONE stream every chunk would
+    // pay the latency of its slowest tile (measured on the C2 batch: 1 chunk 16.6 ms end to end, 2 chunks 17.7, 5 chunks 20.0), so
+    // the chunks alternate between two streams with a scratch set each and the latency of one hides behind the other's work.
+    // Resident output: one chunk.  Debug key "label_chunks" = n forces n equal chunks.
     {
         unsigned sizes[kMaxChunks];
         unsigned n = 1u;
         sizes[0] = n_tiles;
+        if (chunked && !ctx->label_chunks) n = plan_chunks(n_tiles, true, false, ctx->host_chunks, 1, sizes);
         if (ctx->label_chunks) {
             n = std::min<unsigned>(ctx->label_chunks, n_tiles);
             for (unsigned i = 0; i < n; ++i) sizes[i] = n_tiles / n + (i < n_tiles % n ? 1u : 0u);
@@ -2206,6 +2233,27 @@ static int label_device_enqueue(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t 
             tb += sizes[i];
         }
         if (tb != n_tiles) return ctx->fail(OSMR_E_STATE, "internal error: bad label chunk plan");
+    }
+    const bool two = ctx->n_lchunks > 1;
+    cudaStream_t st2 = ctx->label_stream2;
+    auto& B = ctx->lscrB;
+    if (two) {
+        CK(B.gplace.reserve(ctx->l_places_cap));
+        CK(B.place_vinst.reserve(ctx->l_places_cap));
+        CK(B.vinst_place.reserve(ctx->l_verts_cap + 8));
+        CK(B.vcnt.reserve(ctx->l_verts_cap + 8));
+        CK(B.vbox.reserve(ctx->l_verts_cap + 8));
+        CK(B.curve_list.reserve(ctx->l_curves_cap + 8));
+        CK(B.curve_codes.reserve((kCurveLeafCap / 4u) * ctx->l_curves_cap + 8));
+        CK(B.curve_deep.reserve(ctx->l_curves_cap + 8));
+        CK(B.curve_root.reserve(ctx->l_curves_cap + 8));
+        CK(B.scan_blocks.reserve(n_scan_blocks + 8));
+        CK(B.segs.reserve(ctx->l_segs_cap));
+        CK(B.cover_list.reserve((size_t)n_labels + 1));
+        CK(B.row_keys.reserve(2 * ctx->l_rowrecs_cap + 2));
+        CK(B.acc.reserve(2 * ctx->l_cells_cap + 2));
+        CK(B.ring_pts.reserve(ctx->l_ring_cap));
+        CK(B.heap.reserve(ctx->l_heap_slots * (size_t)kPolyHeapCap * sizeof(PolyCell)));
     }
     if (!resident) {
         CK(cudaMemcpyAsync(ctx->d_label_begin.p, label_begin, (size_t)(n_tiles + 1) * 4, cudaMemcpyHostToDevice, st));
@@ -2220,6 +2268,10 @@ static int label_device_enqueue(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t 
     }
     CK(cudaMemsetAsync(ctx->l_counters.p, 0, (size_t)kMaxChunks * LCNT_COUNT * sizeof(unsigned), st));
     CK(cudaMemsetAsync(ctx->d_cover_cursor.p, 0, 2 * sizeof(unsigned) * kMaxChunks, st));
+    if (two) {  // the second stream starts behind the batch description and the cleared counters
+        CK(cudaEventRecord(ctx->label_prep, st));
+        CK(cudaStreamWaitEvent(st2, ctx->label_prep, 0));
+    }
     Scene s{};
     s.merc = ctx->ds->merc.p;
     s.ways = ctx->ds->ways.p;
@@ -2292,11 +2344,30 @@ static int label_device_enqueue(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t 
     const unsigned wide = (unsigned)ctx->num_sms * 8u;
     const Scene s_all = s;
     const LabelDev ld_all = ld;
+    cudaStream_t const st_a = st;
     for (unsigned ch = 0; ch < ctx->n_lchunks; ++ch) {
         const unsigned tb = ctx->lchunk_tb[ch], tc = ctx->lchunk_tc[ch];
+        const bool setb = two && (ch & 1u);
+        st = setb ? st2 : st_a;
         if (!resident && ch && label_begin[tb + tc] > label_begin[tb]) CK(cudaStreamWaitEvent(st, ctx->lchunk_up[ch], 0));
         s = s_all;
         ld = ld_all;
+        if (setb) {
+            ld.gplace = B.gplace.p;
+            ld.place_vinst = B.place_vinst.p;
+            ld.vinst_place = B.vinst_place.p;
+            ld.vcnt = B.vcnt.p;
+            ld.vbox = B.vbox.p;
+            ld.curve_list = B.curve_list.p;
+            ld.curve_codes = B.curve_codes.p;
+            ld.curve_deep = B.curve_deep.p;
+            ld.curve_root = B.curve_root.p;
+            ld.scan_blocks = B.scan_blocks.p;
+            ld.segs = B.segs.p;
+            ld.cover_list = B.cover_list.p;
+            ld.ring_pts = B.ring_pts.p;
+            ld.heap = B.heap.p;
+        }
         s.tiles = s_all.tiles + tb;
         s.n_tiles = tc;
         ld.label_begin = ld_all.label_begin + tb;
@@ -2309,7 +2380,7 @@ static int label_device_enqueue(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t 
         label_vline_count_kernel<<<wide, 128, 0, st>>>(ld);
         label_curve_count_kernel<<<wide, 128, 0, st>>>(ld);
         label_scan_sums_kernel<<<n_scan_blocks, 256, 0, st>>>(ld);
-        auto_scan_kernel<<<1, 1024, 0, st>>>(ctx->l_scan_blocks.p, n_scan_blocks, ld.counters + LCNT_SCAN_OVF);
+        auto_scan_kernel<<<1, 1024, 0, st>>>(ld.scan_blocks, n_scan_blocks, ld.counters + LCNT_SCAN_OVF);
         label_scan_apply_kernel<<<n_scan_blocks, 256, 0, st>>>(ld);
         label_finish_kernel<<<tc, 128, 0, st>>>(s, ld);
         label_vline_write_kernel<<<wide, 128, 0, st>>>(ld);
@@ -2318,16 +2389,16 @@ static int label_device_enqueue(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t 
         LabelScene ls{};
         ls.labels = ctx->d_labels.p;
         ls.label_begin = ctx->d_label_begin.p + tb;
-        ls.segs = ctx->d_label_segs.p;
-        ls.cover_list = ctx->d_cover_list.p;
+        ls.segs = ld.segs;
+        ls.cover_list = ld.cover_list;
         ls.cover_cursor = ctx->d_cover_cursor.p + 2 * ch;
         ls.err_flag = ld.counters + LCNT_COVER_ERR;
         ls.icons = ctx->label_icons.p;
         ls.occ = ctx->label_occ.p + (size_t)tb * ((size_t)E * E / 32);
-        ls.acc_a = ctx->label_acc.p;
-        ls.acc_s = ctx->label_acc.p + ctx->l_cells_cap;
-        ls.kmin = ctx->label_row_keys.p;
-        ls.kmax = ctx->label_row_keys.p + ctx->l_rowrecs_cap;
+        ls.acc_a = setb ? B.acc.p : ctx->label_acc.p;
+        ls.acc_s = ls.acc_a + ctx->l_cells_cap;
+        ls.kmin = setb ? B.row_keys.p : ctx->label_row_keys.p;
+        ls.kmax = ls.kmin + ctx->l_rowrecs_cap;
         ls.plane = ctx->label_plane.p + (size_t)tb * D * D;
         ls.D = D;
         ls.n_cover_dev = ld.counters + LCNT_COVER;
@@ -2339,9 +2410,14 @@ static int label_device_enqueue(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t 
         label_commit_kernel<<<tc, kLabelThreads, 0, st>>>(ls);
         CK(cudaGetLastError());
         CK(cudaEventRecord(ctx->lchunk_done[ch], st));
+        CK(cudaMemcpyAsync(ctx->h_lcnt.p + (size_t)ch * LCNT_COUNT, ld.counters, LCNT_COUNT * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    }
+    st = st_a;
+    if (two) {  // the first stream ends behind the second one: synchronising it is synchronising the label pass
+        CK(cudaEventRecord(ctx->label_join, st2));
+        CK(cudaStreamWaitEvent(st, ctx->label_join, 0));
     }
     CK(cudaEventRecord(ctx->ev_label1, st));
-    CK(cudaMemcpyAsync(ctx->h_lcnt.p, ctx->l_counters.p, (size_t)ctx->n_lchunks * LCNT_COUNT * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(ctx->label_done, st));
     ctx->label_async = true;
     return OSMR_OK;
@@ -2462,7 +2538,7 @@ int osmr_batch_draw_labeled(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t
             cudaEventElapsedTime(&ms, ctx->ev_label0, ctx->ev_label1);
             ctx->stats.ms_label_layout = 0.f;
             ctx->stats.ms_label_device = ms;
-            ctx->stats.kernel_launches += 13;
+            ctx->stats.kernel_launches += 13 * ctx->n_lchunks;
             ctx->stats.label_path = 1;
             ctx->stats.n_labels_active = ctx->stats_label_active;
             ctx->stats.n_labels_polylabel = ctx->stats_label_poly;
@@ -2541,7 +2617,7 @@ int osmr_draw_tiles_labeled(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_ti
             ctx->stats.ms_label_layout = enqueue_ms;  // host time spent on labels: table look-ups and launches only
             ctx->stats.ms_label_device = ms;
             ctx->stats.ms_total += ms;
-            ctx->stats.kernel_launches += 13;
+            ctx->stats.kernel_launches += 13 * ctx->n_lchunks;
             ctx->stats.label_path = 1;
             ctx->stats.n_labels_active = ctx->stats_label_active;
             ctx->stats.n_labels_polylabel = ctx->stats_label_poly;
