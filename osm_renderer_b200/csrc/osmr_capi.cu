@@ -120,6 +120,7 @@ struct osmr_ctx {
     cudaEvent_t chunk_done[kMaxChunks] = {};
     cudaEvent_t cev[kMaxChunks][5] = {};   // per draw chunk: start, after cover, after raster, before cover, raster start (after the wait for the labels)
     unsigned chunk_launches[kMaxChunks] = {};
+    unsigned last_draw_chunks = 0;  // draw chunks of the last draw (diagnostics)
     PinnedBuf<unsigned> h_cnt;             // per draw chunk: its counters, copied back asynchronously
     cudaEvent_t areas_ready = nullptr;
     bool areas_deferred = false;
@@ -197,7 +198,7 @@ struct osmr_ctx {
         DevBuf<CurveRoot> curve_root;
         DevBuf<double2> ring_pts;
     } lscrB;
-    cudaStream_t label_stream2 = nullptr, label_stream2_normal = nullptr, label_stream2_high = nullptr;
+    cudaStream_t label_stream2 = nullptr;
     cudaEvent_t label_join = nullptr, label_prep = nullptr;
     size_t l_verts_cap = 0;
     DevBuf<double2> l_ring_pts;
@@ -262,7 +263,6 @@ struct osmr_ctx {
     } scrB;
     cudaStream_t stream2 = nullptr;
     cudaStream_t label_stream = nullptr;  // the label pass runs beside the area passes; raster_kernel waits for label_done
-    cudaStream_t label_stream_normal = nullptr, label_stream_high = nullptr;  // (debug key "label_priority" picks one)
     cudaEvent_t label_done = nullptr, label_go = nullptr;
     bool label_async = false;             // the label plane of this draw is produced on label_stream
     const osmr_styled_area* tail_src = nullptr;  // styled areas behind the first draw chunk, not yet on their way (flush_area_tail)
@@ -359,20 +359,21 @@ int osmr_ctx_create(int device, osmr_ctx** out_ctx) try {
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->label_stream_normal, cudaStreamNonBlocking);
     if (e == cudaSuccess) {
+        // The label pass is the longer of the two and has the latency-bound kernels (one CTA per tile, serial inside): its CTAs go
+        // first when both kinds of stream have work pending, the area kernels fill what is left (C2 batch: 13.6 -> 13.2 ms per
+        // labelled step).  OSMR_LABEL_PRIORITY=0 in the environment keeps the default priority (A/B).  Six streams per context:
+        // the device maps streams onto CUDA_DEVICE_MAX_CONNECTIONS (default 8) hardware queues, and two streams that share a queue
+        // wait for each other's launches -- measured: with ten streams a draw chunk started 9 ms late behind the label pass.
         int lo = 0, hi = 0;
         e = cudaDeviceGetStreamPriorityRange(&lo, &hi);  // (hi is the numerically smallest = most urgent)
-        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->label_stream_high, cudaStreamNonBlocking, hi);
-        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->label_stream2_high, cudaStreamNonBlocking, hi);
+        const char* lp = getenv("OSMR_LABEL_PRIORITY");
+        const int prio = (lp && lp[0] == '0') ? lo : hi;
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->label_stream, cudaStreamNonBlocking, prio);
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->label_stream2, cudaStreamNonBlocking, prio);
     }
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->label_stream2_normal, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->label_join, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->label_prep, cudaEventDisableTiming);
-    ctx->label_stream2 = ctx->label_stream2_high;
-    // The label pass is the longer of the two and has the latency-bound kernels (one CTA per tile, serial inside): its CTAs go first
-    // when both streams have work pending; the area kernels fill what is left (C2 batch: 13.6 -> 13.2 ms per labelled step).
-    ctx->label_stream = ctx->label_stream_high;
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->label_done, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->label_go, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->prep_done, cudaEventDisableTiming);
@@ -466,10 +467,8 @@ void osmr_ctx_destroy(osmr_ctx* ctx) {
     if (ctx->ev_wall0) cudaEventDestroy(ctx->ev_wall0);
     if (ctx->ev_wall1) cudaEventDestroy(ctx->ev_wall1);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
-    if (ctx->label_stream_normal) cudaStreamDestroy(ctx->label_stream_normal);
-    if (ctx->label_stream_high) cudaStreamDestroy(ctx->label_stream_high);
-    if (ctx->label_stream2_normal) cudaStreamDestroy(ctx->label_stream2_normal);
-    if (ctx->label_stream2_high) cudaStreamDestroy(ctx->label_stream2_high);
+    if (ctx->label_stream) cudaStreamDestroy(ctx->label_stream);
+    if (ctx->label_stream2) cudaStreamDestroy(ctx->label_stream2);
     if (ctx->label_join) cudaEventDestroy(ctx->label_join);
     if (ctx->label_prep) cudaEventDestroy(ctx->label_prep);
     if (ctx->label_done) cudaEventDestroy(ctx->label_done);
@@ -528,13 +527,6 @@ int osmr_debug_set(osmr_ctx* ctx, const char* key, int value) try {
     }
     if (strcmp(key, "label_host") == 0) {  // 1: label layout on the host for every call (the round-1 path; A/B and tests)
         ctx->label_host_only = value != 0;
-        return OSMR_OK;
-    }
-    if (strcmp(key, "label_priority") == 0) {  // 0: the label stream at normal priority (A/B; default 1: its CTAs are scheduled first)
-        cudaStreamSynchronize(ctx->label_stream);
-        cudaStreamSynchronize(ctx->label_stream2);
-        ctx->label_stream = value ? ctx->label_stream_high : ctx->label_stream_normal;
-        ctx->label_stream2 = value ? ctx->label_stream2_high : ctx->label_stream2_normal;
         return OSMR_OK;
     }
     if (strcmp(key, "curve_leaf_cap") == 0) {  // tests: leaf codes per curve (0: the build's 128)
@@ -1381,6 +1373,7 @@ int osmr_batch_draw(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t flags, 
         }
         if (redo) continue;  // (copies of the incomplete images are simply overwritten by the second round, in stream order)
         if (staged) CK(cudaStreamSynchronize(ctx->d2h_stream));
+        ctx->last_draw_chunks = n_chunks;
         if (gpu_ms) {  // device wall time of the draw (with several chunks on two streams the stage times overlap)
             float wall = 0.f;
             cudaEventElapsedTime(&wall, ctx->ev_wall0, ctx->ev_wall1);
@@ -2614,6 +2607,19 @@ int osmr_draw_tiles_labeled(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_ti
         if (verdict == 0) {
             float ms = 0.f;
             cudaEventElapsedTime(&ms, ctx->ev_label0, ctx->ev_label1);
+            if (getenv("OSMR_TIMELINE")) {  // (diagnostics: when did what happen, relative to the start of the label pass)
+                auto at = [&](cudaEvent_t e) {
+                    float t = -1.f;
+                    cudaEventElapsedTime(&t, ctx->ev_label0, e);
+                    return t;
+                };
+                fprintf(stderr, "[osmr timeline] label pass end %.2f ms\n", at(ctx->ev_label1));
+                for (unsigned ch = 0; ch < ctx->n_lchunks; ++ch)
+                    fprintf(stderr, "[osmr timeline]   label chunk %u (%u tiles): cover %.2f .. %.2f\n", ch, ctx->lchunk_tc[ch], at(ctx->ev_lcov0[ch]), at(ctx->ev_lcov1[ch]));
+                for (unsigned c = 0; c < ctx->last_draw_chunks; ++c)
+                    fprintf(stderr, "[osmr timeline]   draw chunk %u: start %.2f, bin done %.2f, cover done %.2f, raster %.2f .. %.2f\n", c, at(ctx->cev[c][0]),
+                            at(ctx->cev[c][3]), at(ctx->cev[c][1]), at(ctx->cev[c][4]), at(ctx->cev[c][2]));
+            }
             ctx->stats.ms_label_layout = enqueue_ms;  // host time spent on labels: table look-ups and launches only
             ctx->stats.ms_label_device = ms;
             ctx->stats.ms_total += ms;
