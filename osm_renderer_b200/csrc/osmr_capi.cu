@@ -941,6 +941,24 @@ static unsigned char* pinned_device_alias(const void* p) {
 //   launch tails).  Debug key "host_chunks" = n > 0 forces n equal chunks.
 //   direct (debug key "direct_out", page-locked `out`): a small first chunk hides the upload of the remaining styled
 //   areas, raster_kernel stores the tiles straight into host memory (PCIe-bound stores, 26 GB/s: slower than staging).
+// Counters go home by a store into page-locked host memory, not by a copy: a cudaMemcpyAsync issued early waits in the copy
+// engine's queue until its stream gets there and holds up the copies that other streams issue behind it (the tile images, the
+// styled-area tail) -- seen as draw chunks that started 10 ms late behind the label pass.
+__global__ void export_words_kernel(const unsigned* src, unsigned* dst, unsigned n) {
+    for (unsigned i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+    __threadfence_system();
+}
+static int export_words(osmr_ctx* ctx, const unsigned* src, unsigned* host_dst, unsigned n, cudaStream_t st) {
+    unsigned* alias = reinterpret_cast<unsigned*>(pinned_device_alias(host_dst));
+    if (!alias) {
+        CK(cudaMemcpyAsync(host_dst, src, (size_t)n * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+        return OSMR_OK;
+    }
+    export_words_kernel<<<1, 64, 0, st>>>(src, alias, n);
+    CK(cudaGetLastError());
+    return OSMR_OK;
+}
+
 static unsigned plan_chunks(unsigned n_tiles, bool to_host, bool direct, unsigned host_chunks, unsigned resident_chunks,
                             unsigned sizes[kMaxChunks]) {
     unsigned n = 0;
@@ -1160,7 +1178,11 @@ static int launch_chunk(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t fla
     ++launches;
     CK(cudaGetLastError());
     CK(cudaEventRecord(ev[2], st));
-    CK(cudaMemcpyAsync(ctx->h_cnt.p + (size_t)slot * CNT_COUNT, s.counters, CNT_COUNT * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    {
+        int rc = export_words(ctx, s.counters, ctx->h_cnt.p + (size_t)slot * CNT_COUNT, CNT_COUNT, st);
+        if (rc) return rc;
+        ++launches;
+    }
     ctx->chunk_launches[slot] = launches;
     return OSMR_OK;
 }
@@ -2403,7 +2425,6 @@ static int label_device_enqueue(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t 
         label_commit_kernel<<<tc, kLabelThreads, 0, st>>>(ls);
         CK(cudaGetLastError());
         CK(cudaEventRecord(ctx->lchunk_done[ch], st));
-        CK(cudaMemcpyAsync(ctx->h_lcnt.p + (size_t)ch * LCNT_COUNT, ld.counters, LCNT_COUNT * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
     }
     st = st_a;
     if (two) {  // the first stream ends behind the second one: synchronising it is synchronising the label pass
@@ -2411,6 +2432,10 @@ static int label_device_enqueue(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t 
         CK(cudaStreamWaitEvent(st, ctx->label_join, 0));
     }
     CK(cudaEventRecord(ctx->ev_label1, st));
+    {
+        int rc = export_words(ctx, ctx->l_counters.p, ctx->h_lcnt.p, ctx->n_lchunks * LCNT_COUNT, st);
+        if (rc) return rc;
+    }
     CK(cudaEventRecord(ctx->label_done, st));
     ctx->label_async = true;
     return OSMR_OK;
@@ -2531,7 +2556,7 @@ int osmr_batch_draw_labeled(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t
             cudaEventElapsedTime(&ms, ctx->ev_label0, ctx->ev_label1);
             ctx->stats.ms_label_layout = 0.f;
             ctx->stats.ms_label_device = ms;
-            ctx->stats.kernel_launches += 13 * ctx->n_lchunks;
+            ctx->stats.kernel_launches += 13 * ctx->n_lchunks + 1;
             ctx->stats.label_path = 1;
             ctx->stats.n_labels_active = ctx->stats_label_active;
             ctx->stats.n_labels_polylabel = ctx->stats_label_poly;
@@ -2623,7 +2648,7 @@ int osmr_draw_tiles_labeled(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_ti
             ctx->stats.ms_label_layout = enqueue_ms;  // host time spent on labels: table look-ups and launches only
             ctx->stats.ms_label_device = ms;
             ctx->stats.ms_total += ms;
-            ctx->stats.kernel_launches += 13 * ctx->n_lchunks;
+            ctx->stats.kernel_launches += 13 * ctx->n_lchunks + 1;
             ctx->stats.label_path = 1;
             ctx->stats.n_labels_active = ctx->stats_label_active;
             ctx->stats.n_labels_polylabel = ctx->stats_label_poly;

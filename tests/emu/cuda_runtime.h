@@ -117,6 +117,7 @@ static inline int __double2int_rz(double v) {  // cvt.rzi.s32.f64: saturating, N
     if (v <= -2147483648.0) return (int)0x80000000;
     return (int)v;
 }
+static inline void __threadfence_system() {}
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 static inline int __clz(unsigned v) { return v ? __builtin_clz(v) : 32; }

@@ -45,7 +45,7 @@ def test_resident_batch_api_equals_one_shot(fx, gpu_ctx):
     ms2 = gpu_ctx.batch_draw(fx.canvas_rgb, True)  # output stays in HBM
     assert (out == one).all() and ms1 > 0 and ms2 > 0
     st = gpu_ctx.stats()
-    assert st["n_tiles"] == len(tiles) and st["n_areas"] == len(areas) and st["kernel_launches"] == 7  # style_calc, plan, geometry, fill_rows, bin, cover, raster
+    assert st["n_tiles"] == len(tiles) and st["n_areas"] == len(areas) and st["kernel_launches"] == 8  # style_calc, plan, geometry, fill_rows, bin, cover, raster, counters export
 
 
 def test_huge_coordinates_take_the_exact_i64_path():
