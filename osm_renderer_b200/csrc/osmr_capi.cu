@@ -2225,17 +2225,21 @@ static int label_device_enqueue(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t 
     CK(cudaEventRecord(ctx->ev_label0, st));
     CK(ctx->l_counters.reserve((size_t)kMaxChunks * LCNT_COUNT));
     CK(ctx->h_lcnt.reserve((size_t)kMaxChunks * LCNT_COUNT));
-    // The label pass runs chunk by chunk on the draw's host-output schedule when the tiles go to the host: a draw chunk waits only
-    // for the label chunks under it, so its tiles travel while later label chunks are computed.  label_select / label_layout /
-    // label_commit are one CTA per tile and serial inside a tile (greedy collisions, polylabel): on ONE stream every chunk would
-    // pay the latency of its slowest tile (measured on the C2 batch: 1 chunk 16.6 ms end to end, 2 chunks 17.7, 5 chunks 20.0), so
-    // the chunks alternate between two streams with a scratch set each and the latency of one hides behind the other's work.
+    // The label pass of a host-output call runs in TWO halves on two streams with a scratch set each: a draw chunk waits only for
+    // the label half above it, so the first tiles travel while the second half is still computed.  More chunks lose: label_select /
+    // label_layout / label_commit are one CTA per tile and serial inside a tile (greedy collisions, polylabel), so every chunk
+    // pays the latency of its slowest tile, and thirteen kernels per chunk have thirteen tails.  Measured end to end on the C2 batch
+    // (B200, ms per call): 1 chunk 16.1, 2 chunks 15.8, 3 chunks 16.4, the draw's own 5-chunk schedule 17.7 (one stream: 20.0).
     // Resident output: one chunk.  Debug key "label_chunks" = n forces n equal chunks.
     {
         unsigned sizes[kMaxChunks];
         unsigned n = 1u;
         sizes[0] = n_tiles;
-        if (chunked && !ctx->label_chunks) n = plan_chunks(n_tiles, true, false, ctx->host_chunks, 1, sizes);
+        if (chunked && !ctx->label_chunks && n_tiles >= 256) {
+            n = 2;
+            sizes[0] = n_tiles / 2;
+            sizes[1] = n_tiles - sizes[0];
+        }
         if (ctx->label_chunks) {
             n = std::min<unsigned>(ctx->label_chunks, n_tiles);
             for (unsigned i = 0; i < n; ++i) sizes[i] = n_tiles / n + (i < n_tiles % n ? 1u : 0u);
