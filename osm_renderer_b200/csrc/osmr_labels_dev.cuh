@@ -1313,20 +1313,28 @@ __global__ void __launch_bounds__(256, 4) label_curve_expand_kernel(LabelDev ld)
         }
         const unsigned pre = incl - n;  // leaves of the group before this curve's
         const unsigned total = __shfl_sync(kFull, incl, kExpandGroup - 1);
-        for (unsigned tb = 0; tb < total; tb += 32) {
-            const unsigned t = tb + lane;
-            // the curve of leaf t: the last one whose first leaf is not behind t
-            unsigned j = 0;
+        // leaf t of the group -> (curve j, leaf i of that curve) and its code; the NEXT round's code is loaded before this round's
+        // midpoint steps (the 16-bit load and the count-leading-zeros behind it were 43 % of the kernel's stall samples)
+        auto locate = [&](unsigned t, unsigned& k, unsigned& slot, unsigned& code) {
+            unsigned j = 0;  // the last curve whose first leaf is not behind t
             for (unsigned step = kExpandGroup / 2; step; step >>= 1) {
                 const unsigned pj = __shfl_sync(kFull, pre, j + step);
                 if (pj <= t) j += step;
             }
             const unsigned pj = __shfl_sync(kFull, pre, j), oj = __shfl_sync(kFull, off, j);
-            if (t < total) {
-                const unsigned i = t - pj;
-                const unsigned k = k0 + j;
-                const unsigned code = reinterpret_cast<const unsigned short*>(ld.curve_codes + (size_t)k * (kCurveLeafCap / 4u))[i];
-                const CurveRoot r = ld.curve_root[k];
+            k = k0 + j;
+            slot = oj + (t - pj);
+            code = 0u;
+            if (t < total) code = reinterpret_cast<const unsigned short*>(ld.curve_codes + (size_t)k * (kCurveLeafCap / 4u))[t - pj];
+        };
+        unsigned k_cur = 0, slot_cur = 0, code_cur = 0;
+        if (total) locate(lane, k_cur, slot_cur, code_cur);
+        for (unsigned tb = 0; tb < total; tb += 32) {
+            unsigned k_nxt = 0, slot_nxt = 0, code_nxt = 0;
+            if (tb + 32 < total) locate(tb + 32 + lane, k_nxt, slot_nxt, code_nxt);
+            if (tb + lane < total) {
+                const unsigned code = code_cur;
+                const CurveRoot r = ld.curve_root[k_cur];
                 double a0 = r.x0, b0 = r.y0, a1 = r.x1, b1 = r.y1, a2 = r.x2, b2 = r.y2;
                 for (int lv = 30 - __clz(code); lv >= 0; --lv) {
                     const double ax = (a0 + a1) / 2.0, ay = (b0 + b1) / 2.0, bx = (a1 + a2) / 2.0, by = (b1 + b2) / 2.0;
@@ -1348,8 +1356,11 @@ __global__ void __launch_bounds__(256, 4) label_curve_expand_kernel(LabelDev ld)
                 sg.y0 = b0;
                 sg.x1 = a2;
                 sg.y1 = b2;
-                ld.segs[oj + i] = sg;
+                ld.segs[slot_cur] = sg;
             }
+            k_cur = k_nxt;
+            slot_cur = slot_nxt;
+            code_cur = code_nxt;
         }
     }
 }
