@@ -2013,6 +2013,7 @@ constexpr int kCovPairs = OSMR_COV_PAIRS;     // pairs per batch
 constexpr int kCovKeys = OSMR_COV_PAIRS / 2;  // cells (x 2 arrays) of the batch's window
 constexpr unsigned kCovCtasPerSm = OSMR_COV_CTAS;
 constexpr int kCovDirectUnits = 96;
+constexpr int kCovSegs = 256;  // segments per batch (their row / slot words stay in shared memory between the two sweeps)
 constexpr int kCovRows = 128;    // rows whose key range is tracked in shared memory (a taller label is processed band by band)
 
 // draw_line of one segment restricted to pixel row y (rasterizer.rs:52-83); calls add_a(x, value) for every touched cell of `a`
@@ -2058,6 +2059,7 @@ __global__ void __launch_bounds__(32) label_cover_kernel(LabelScene ls) {
     __shared__ unsigned s_seg[32];  // per lane of a chunk: first row inside the band (8 bits) | rows (8) | pair slots per row (16)
     __shared__ unsigned s_pre[33];  // prefix of crossings (rows) over the chunk's segments
     __shared__ unsigned s_slot[32]; // first pair slot of every segment of the chunk
+    __shared__ unsigned s_segw[kCovSegs];  // per segment of the batch: first row | rows << 8 | pair slots per row << 16 (0: no crossing in the band)
     __shared__ unsigned char s_umap[kCovDirectUnits];  // crossing of the chunk -> its segment (chunks of few crossings)
     __shared__ unsigned short s_live[kCovKeys];  // the keys of the batch that received pairs, ascending
     __shared__ unsigned s_retry;    // a crossing needed more pair slots than the tight estimate: the batch is redone with the safe one
@@ -2134,19 +2136,16 @@ __global__ void __launch_bounds__(32) label_cover_kernel(LabelScene ls) {
                         const bool has = j < nseg && r1 >= r0;
                         const unsigned need = has ? (unsigned)(r1 - r0 + 1) * (unsigned)(tight ? max(c1 - c0 - 1, 2) : c1 - c0 + 2) : 0u;  // per row: the `a` cells + one `s`
                         // the chunk is taken as a whole or not at all (except when it is the batch's first: then lane by lane)
-                        unsigned tot = need;
-                        int a0 = has ? r0 : 0x7fffffff, a1 = has ? r1 : -1, b0 = has ? c0 : 0x7fffffff, b1 = has ? c1 : -1;
-                        for (int o = 16; o > 0; o >>= 1) {
-                            tot += __shfl_xor_sync(kFull, tot, o);
-                            a0 = min(a0, __shfl_xor_sync(kFull, a0, o));
-                            a1 = max(a1, __shfl_xor_sync(kFull, a1, o));
-                            b0 = min(b0, __shfl_xor_sync(kFull, b0, o));
-                            b1 = max(b1, __shfl_xor_sync(kFull, b1, o));
-                        }
+                        const unsigned per_row_w = has ? (unsigned)(tight ? max(c1 - c0 - 1, 2) : c1 - c0 + 2) : 0u;
+                        const unsigned segw = has ? ((unsigned)r0 | ((unsigned)(r1 - r0 + 1) << 8) | (per_row_w << 16)) : 0u;
+                        const unsigned tot = __reduce_add_sync(kFull, need);
+                        const int a0 = __reduce_min_sync(kFull, has ? r0 : 0x7fffffff), a1 = __reduce_max_sync(kFull, has ? r1 : -1);
+                        const int b0 = __reduce_min_sync(kFull, has ? c0 : 0x7fffffff), b1 = __reduce_max_sync(kFull, has ? c1 : -1);
                         const int nr0 = min(r0w, a0), nr1 = max(r1w, a1), nc0 = min(c0w, b0), nc1 = max(c1w, b1);
                         const long long keys = (nr1 >= nr0) ? 2ll * (nr1 - nr0 + 1) * (nc1 - nc0 + 1) : 0ll;
                         const unsigned n_lanes = min(32u, nseg - (sc + n_in));
-                        if (slots + tot <= (unsigned)kCovPairs && keys <= (long long)kCovKeys) {
+                        if (slots + tot <= (unsigned)kCovPairs && keys <= (long long)kCovKeys && n_in + n_lanes <= (unsigned)kCovSegs) {
+                            if (lane < n_lanes) s_segw[n_in + lane] = segw;
                             slots += tot;
                             r0w = nr0;
                             r1w = nr1;
@@ -2189,6 +2188,7 @@ __global__ void __launch_bounds__(32) label_cover_kernel(LabelScene ls) {
                             }
                         }
                         n_in = take;
+                        if (lane < take) s_segw[lane] = segw;
                         break;
                     }
                     win_r0 = r0w;
@@ -2233,35 +2233,22 @@ __global__ void __launch_bounds__(32) label_cover_kernel(LabelScene ls) {
                 __syncwarp();
                 // ---- A: the area arithmetic, a lane per (segment, row) crossing; pairs land in order ----
                 for (unsigned base = 0; base < n_in; base += 32) {
-                    const unsigned j = sc + base + lane;
-                    int r0 = 1, r1 = 0, c0 = 0, c1 = -1;
-                    if (base + lane < n_in) {
-                        const DevSeg sg = segs[j];
-                        r0 = max(f64_as_i32(floor(fmin(sg.y0, sg.y1))), row_lo) - row_lo;
-                        r1 = min(f64_as_i32(floor(fmax(sg.y0, sg.y1))), row_lo + band_rows - 1) - row_lo;
-                        const long long xa = (long long)f64_as_i32(floor(fmin(sg.x0, sg.x1))) - 1 - L.bx0;
-                        const long long xb = (long long)f64_as_i32(floor(fmax(sg.x0, sg.x1))) + 2 - L.bx0;
-                        c0 = (int)max(0ll, min(xa, (long long)W - 1));
-                        c1 = (int)max(0ll, min(xb, (long long)W - 1));
-                    }
-                    const unsigned nr = r1 >= r0 ? (unsigned)(r1 - r0 + 1) : 0u;
-                    const unsigned per_row = (unsigned)(tight ? max(c1 - c0 - 1, 2) : c1 - c0 + 2);
-                    unsigned incl = nr;
+                    // (rows and pair slots of the chunk's segments: the words of the first sweep)
+                    const unsigned segw = base + lane < n_in ? s_segw[base + lane] : 0u;
+                    const unsigned nr = (segw >> 8) & 0xffu, per_row = segw >> 16;
+                    // two prefix sums in one: crossings (rows) in the low half, pair slots in the high half (a chunk has at most
+                    // 32 * 128 crossings and kCovPairs slots).  Unit u of segment q starts at base_slot + (slots of the segments
+                    // before q) + (u's row index inside q) * per_row(q).
+                    unsigned both = nr | ((nr * per_row) << 16);
                     for (int o = 1; o < 32; o <<= 1) {
-                        const unsigned y = __shfl_up_sync(kFull, incl, o);
-                        if ((int)lane >= o) incl += y;
+                        const unsigned y = __shfl_up_sync(kFull, both, o);
+                        if ((int)lane >= o) both += y;
                     }
+                    const unsigned incl = both & 0xffffu, slot_incl = both >> 16;
                     __syncwarp();
-                    s_seg[lane] = nr ? ((unsigned)r0 | (nr << 8) | (per_row << 16)) : 0u;
+                    s_seg[lane] = segw;
                     s_pre[lane] = incl - nr;
                     if (lane == 31) s_pre[32] = incl;
-                    // pair slots of the chunk's crossings: unit u of segment q starts at base_slot + (slots of the segments
-                    // before q) + (u's row index inside q) * per_row(q): a second prefix, over slots
-                    unsigned slot_incl = nr * per_row;
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const unsigned y = __shfl_up_sync(kFull, slot_incl, o);
-                        if ((int)lane >= o) slot_incl += y;
-                    }
                     s_slot[lane] = n_pairs + slot_incl - nr * per_row;
                     const unsigned chunk_slots = __shfl_sync(kFull, slot_incl, 31);
                     // crossing -> segment: the usual chunk (glyph segments cross one or two rows) gets a direct map, a chunk with

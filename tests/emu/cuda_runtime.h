@@ -392,6 +392,28 @@ inline void syncthreads(int site) { rendezvous(E().block, E().cur, site, 0, "__s
 #define __shfl_xor_sync(m, v, x) emu::shfl(__LINE__, (v), emu::cur_lane() ^ (int)(x))
 #define __match_any_sync(m, v) emu::match_any(__LINE__, (unsigned long long)(v))
 #define __syncwarp() emu::syncwarp(__LINE__)
+// REDUX (sm_80+): warp reductions of 32-bit integers
+static inline unsigned emu_reduce_add(unsigned v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+static inline int emu_reduce_min(int v) {
+    for (int o = 16; o > 0; o >>= 1) {
+        const int y = __shfl_xor_sync(0xffffffffu, v, o);
+        v = y < v ? y : v;
+    }
+    return v;
+}
+static inline int emu_reduce_max(int v) {
+    for (int o = 16; o > 0; o >>= 1) {
+        const int y = __shfl_xor_sync(0xffffffffu, v, o);
+        v = y > v ? y : v;
+    }
+    return v;
+}
+#define __reduce_add_sync(m, v) emu_reduce_add(v)
+#define __reduce_min_sync(m, v) emu_reduce_min(v)
+#define __reduce_max_sync(m, v) emu_reduce_max(v)
 #define __syncthreads() emu::syncthreads(__LINE__)
 
 template <typename T>
