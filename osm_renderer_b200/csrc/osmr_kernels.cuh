@@ -2448,18 +2448,23 @@ __global__ void __launch_bounds__(kLabelThreads) label_commit_kernel(LabelScene 
         const int* kmax = ls.kmax + L.row_first;
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         if (has_text) {  // a warp per stored row, lanes over the stripe's key range (nothing is set outside it)
-            for (int r = warp; r < R && !fail; r += kLabelThreads / 32) {
+            // (a warp stops at its own first collision; the shared flag is only written here and read behind the barrier)
+            bool mine = false;
+            for (int r = warp; r < R && !mine; r += kLabelThreads / 32) {
                 const int y = L.ry0 + r;
                 const int lo = max(kmin[r], max(L.bx0, -D)), hi = min(kmax[r], min(L.bx0 + W - 1, 2 * D - 1));
                 if (lo > hi) continue;  // untouched stripe (kmin = INT_MAX)
                 const double* row = tot + (size_t)r * W - L.bx0;
+                bool hit = false;
                 for (int x = lo + lane; x <= hi; x += 32) {
                     if (row[x] > 0.0) {
                         size_t b = occ_index(x, y);
-                        if (occ[b >> 5] & (1u << (b & 31))) fail = 1;
+                        if (occ[b >> 5] & (1u << (b & 31))) hit = true;
                     }
                 }
+                mine = __any_sync(0xffffffffu, hit);
             }
+            if (mine && lane == 0) fail = 1;
         }
         __syncthreads();
         if (!fail) {  // bump_label_generation(true): the label's pixels become final
