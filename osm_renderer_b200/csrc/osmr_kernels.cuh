@@ -2409,7 +2409,9 @@ __global__ void __launch_bounds__(32) label_cover_kernel(LabelScene ls) {
 constexpr int kLabelThreads = 256;
 
 __global__ void __launch_bounds__(kLabelThreads) label_commit_kernel(LabelScene ls) {
-    __shared__ volatile int fail;
+    // (two flags: the icon's is written before the barrier that the text phase reads it behind, the text's is written while other
+    // warps may still be reading the icon's -- one flag would race)
+    __shared__ volatile int fail, fail_text;
     const unsigned tile = blockIdx.x;
     const int D = ls.D, E = 3 * D;
     const unsigned occ_words = (unsigned)((size_t)E * E / 32);
@@ -2426,7 +2428,10 @@ __global__ void __launch_bounds__(kLabelThreads) label_commit_kernel(LabelScene 
     const unsigned li_end = abandoned ? li_begin : (ls.label_cnt ? li_begin + ls.label_cnt[tile] : ls.label_begin[tile + 1]);
     for (unsigned li = li_begin; li < li_end; ++li) {
         const DevLabel L = ls.labels[li];
-        if (threadIdx.x == 0) fail = 0;
+        if (threadIdx.x == 0) {
+            fail = 0;
+            fail_text = 0;
+        }
         __syncthreads();
         int iw = 0, ih = 0;
         if (L.icon >= 0) {  // labeler.rs:94-103: every texel (transparent ones too) claims its pixel
@@ -2464,10 +2469,10 @@ __global__ void __launch_bounds__(kLabelThreads) label_commit_kernel(LabelScene 
                 }
                 mine = __any_sync(0xffffffffu, hit);
             }
-            if (mine && lane == 0) fail = 1;
+            if (mine && lane == 0) fail_text = 1;
         }
         __syncthreads();
-        if (!fail) {  // bump_label_generation(true): the label's pixels become final
+        if (!fail && !fail_text) {  // bump_label_generation(true): the label's pixels become final
             if (L.icon >= 0) {
                 const unsigned tex0 = ls.icons[L.icon].off;
                 for (int p = threadIdx.x; p < iw * ih; p += kLabelThreads) {
