@@ -21,7 +21,7 @@ JSON line: `value` = tiles/s of the whole Drawer::draw_to_pixels (area passes + 
 in HBM and the output left in HBM (wall clock between barriers; `device_only` is the CUDA-event figure); `e2e` = the same through
 the reference-facing call osmr_draw_tiles_labeled with pinned HOST buffers, copies inside the timed region; siblings
 `value_area_only` / `e2e_area_only` (Fill, Casing, Stroke passes only: round 1's headline), `e2e_auto` (tile list in),
-`e2e_png` / `e2e_auto_png` (PNG files out), `latency_ms` (p50 of single small calls);
+`e2e_png` / `e2e_auto_png` (PNG files out), `e2e_auto_labeled` / `e2e_auto_labeled_png` (tile list in, label pass included), `latency_ms` (p50 of single small calls);
 `sustained` = the resident leg repeated for >= --min-seconds with median / min per step; `roofline` = dominant kernel against
 the measured HBM peak with SURVEY 8(d)'s B_tile next to the kernel-local byte count; `cpu_baseline` = the oracle (C++
 restatement of the reference CPU path) on this box's host cores, T = nproc and T = 1.
@@ -761,8 +761,8 @@ def main():
                "pixels_changed_by_labels_in_last_call": int((gpu_lab_last != gpu_last).any(axis=-1).sum())}
 
     # ---- e2e_auto / e2e_png / e2e_auto_png (f3, f4): tile list in and / or PNG files out ----
-    auto = png = auto_png = None
-    auto_wall = png_wall = auto_png_wall = None
+    auto = png = auto_png = auto_lab = auto_lab_png = None
+    auto_wall = png_wall = auto_png_wall = auto_lab_wall = auto_lab_png_wall = None
     if not args.skip_auto:
         from osm_renderer_b200.upstream import pipeline
 
@@ -812,6 +812,38 @@ def main():
         auto_png = {"unit": "tiles/s", "h2d_bytes_per_step": int(sum(c[5] for c in e2e_calls)), "d2h_bytes_per_step": png_bytes[0],
                     "api": "osmr_draw_tiles_auto_png (tile list in, PNG files out = Drawer::draw_tile behind the server's lookup)"}
 
+        # ---- e2e_auto_labeled{,_png}: the whole draw_to_pixels / draw_tile from a tile list (f3 for the label lists as well) ----
+        if labeled:
+            t_lcls = time.perf_counter()
+            for z in sorted({c[0] for c in calls}):
+                nc_, wc_, mc_, cb_, cs_ = pipeline.zoom_label_class_tables(w["builder"], z, w["ltable"])
+                ctx.set_label_table(w["ltable"])
+                ctx.set_zoom_label_styles(z, nc_, wc_, mc_, cb_, cs_)
+            t_lcls = time.perf_counter() - t_lcls
+
+            def auto_lab_step():
+                for z, n, pt, pb, pa, _ in e2e_calls:
+                    check(L.osmr_draw_tiles_auto_labeled(ctx.h, pt, n, canvas.ctypes.data, flags, pin_auto))
+
+            auto_lab_wall = timed(auto_lab_step)
+            alst = ctx.stats()
+            same = bool((np.frombuffer((C.c_uint8 * gpu_lab_last.size).from_address(pin_auto), dtype=np.uint8) == gpu_lab_last.reshape(-1)).all())
+            auto_lab = {"unit": "tiles/s", "h2d_bytes_per_step": int(sum(c[5] for c in e2e_calls)), "d2h_bytes_per_step": d2h,
+                        "api": "osmr_draw_tiles_auto_labeled (tile list only; styled-area AND label lists built on the device, then the whole draw_to_pixels)",
+                        "ms_auto_stage_last_call": float(alst["ms_auto"]), "live_label_generations_last_call": int(alst["n_labels_active"]),
+                        "label_path_last_call": int(alst["label_path"]), "identical_to_e2e_labeled_output": same, "label_class_tables_host_s": t_lcls}
+
+            def auto_lab_png_step():
+                png_bytes[0] = 0
+                for z, n, pt, pb, pa, _ in e2e_calls:
+                    check(L.osmr_draw_tiles_auto_labeled_png(ctx.h, pt, n, canvas.ctypes.data, flags, pin_png, cap, offs.ctypes.data))
+                    png_bytes[0] += int(offs[n])
+
+            auto_lab_png_wall = timed(auto_lab_png_step)
+            auto_lab_png = {"unit": "tiles/s", "h2d_bytes_per_step": int(sum(c[5] for c in e2e_calls)), "d2h_bytes_per_step": png_bytes[0],
+                            "mean_png_bytes": png_bytes[0] / tiles_per_step,
+                            "api": "osmr_draw_tiles_auto_labeled_png (tile list in, PNG files out, label pass included = Drawer::draw_tile complete)"}
+
     # ---- max over ranks (time), sum over ranks (tiles): the only collectives of the whole job ----
     job_tiles = tiles_per_step * args.steps
     red = lambda secs: sharding.reduce_job(dist, secs, job_tiles, device="cuda")
@@ -819,7 +851,7 @@ def main():
     wall, _ = red(wall)
     e2e_wall_max, _ = red(e2e_wall)
     per_rank_d2h_gbs = d2h * args.steps / e2e_wall / 1e9  # this rank's own rate (rank 0 prints its own)
-    for leg, lw in ((lab, lab_wall), (auto, auto_wall), (png, png_wall), (auto_png, auto_png_wall)):
+    for leg, lw in ((lab, lab_wall), (auto, auto_wall), (png, png_wall), (auto_png, auto_png_wall), (auto_lab, auto_lab_wall), (auto_lab_png, auto_lab_png_wall)):
         if leg is not None:  # whole-job numbers for every leg: max wall over ranks, tiles of all ranks
             mw, mt = red(lw)
             leg["value"], leg["ms_per_step"] = mt / mw, 1000.0 * mw / args.steps
@@ -999,6 +1031,8 @@ def main():
         "e2e_auto": auto,
         "e2e_png": png,
         "e2e_auto_png": auto_png,
+        "e2e_auto_labeled": auto_lab,
+        "e2e_auto_labeled_png": auto_lab_png,
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": cpu,

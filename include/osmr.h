@@ -266,6 +266,25 @@ int osmr_draw_tiles_auto(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles
 /* the styled-area lists of the last osmr_draw_tiles_auto call (tests): area_begin[n_tiles + 1], areas[area_begin[n_tiles]] */
 int osmr_auto_readback(osmr_ctx* ctx, uint32_t* area_begin, osmr_styled_area* areas, uint32_t areas_cap);
 
+/* f3 for the LABEL pass: what the reference does between the area passes and draw_labels (src/draw/drawer.rs:106-119) --
+ * Styler::style_areas(.., for_labels = true) (src/mapcss/styler.rs:168-203) and Styler::style_entities(nodes) (styler.rs:115-166)
+ * over the entities of GeodataReader::get_entities_in_tile_with_neighbors (src/geodata/reader.rs:60-100, nodes included) -- on the
+ * device.  As for the area passes the host provides the StyleCache contents per zoom: for every node, way and multipolygon of
+ * the `.bin` the id of its style list (0xffffffff = none), per class its styles as (index into the table of
+ * osmr_set_label_styles, order) with `order` (< 2^19) the dense rank of (layer.unwrap_or(0), z_index) -- compare_styled_entities
+ * ignores is_foreground_fill when for_labels is set (styler.rs:263).  The library appends (global id, multipolygon before way,
+ * local id, position in the style list) and lists the styled nodes behind the styled areas. */
+int osmr_set_zoom_label_styles(osmr_ctx* ctx, uint32_t zoom, const uint32_t* node_class /* n_nodes */, const uint32_t* way_class /* n_ways */,
+                               const uint32_t* mp_class /* n_multipolygons */, const uint32_t* class_begin /* n_classes + 1 */,
+                               const osmr_class_style* class_styles, uint32_t n_classes);
+/* The whole Drawer::draw_to_pixels (src/draw/drawer.rs:60-131) from a tile list: styled-area lists AND label lists are built on
+ * the device, then osmr_draw_tiles_labeled's kernels run on them.  Needs osmr_set_zoom_styles, osmr_set_zoom_label_styles,
+ * osmr_set_font and the label tables; conditions as osmr_draw_tiles_auto.  Label generations that cannot draw or collide (no
+ * icon, no text for the entity) are not listed -- the reference draws nothing for them (src/draw/labeler.rs:16-37). */
+int osmr_draw_tiles_auto_labeled(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, const uint8_t canvas_rgb[3], uint32_t flags, uint8_t* out);
+/* the label lists of the last osmr_draw_tiles_auto_labeled* call (tests): label_begin[n_tiles + 1], labels[label_begin[n_tiles]] */
+int osmr_auto_readback_labels(osmr_ctx* ctx, uint32_t* label_begin, osmr_label* labels, uint32_t labels_cap);
+
 /* ------------------------------------------------------------------------------------------------------------
  * the step AFTER the draw path -- PNG files instead of RGB triples.
  * Replaces Drawer::draw_tile = draw_to_pixels + rgb_triples_to_png (src/draw/drawer.rs:40-58, src/draw/png_writer.rs:4-21:
@@ -285,6 +304,9 @@ int osmr_draw_tiles_png(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles,
  * osmr_draw_tiles_auto (one zoom and one scale per call, osmr_set_zoom_styles first), output as osmr_draw_tiles_png. */
 int osmr_draw_tiles_auto_png(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, const uint8_t canvas_rgb[3], uint32_t flags,
                              uint8_t* png_out, size_t png_cap, uint64_t* png_offset /* n_tiles + 1 */);
+/* the same with the label pass (osmr_draw_tiles_auto_labeled in front of the encoder): Drawer::draw_tile complete */
+int osmr_draw_tiles_auto_labeled_png(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, const uint8_t canvas_rgb[3], uint32_t flags,
+                                     uint8_t* png_out, size_t png_cap, uint64_t* png_offset /* n_tiles + 1 */);
 
 /* rgb_triples_to_png itself (png_writer.rs:4-21) for images the caller already holds: n_images RGB images of
  * (256 * scale)^2 pixels, tightly packed in host memory -> packed PNG files as in osmr_draw_tiles_png. */
@@ -310,7 +332,8 @@ void osmr_free_pinned(void* p);
  *                           host libm, i.e. the reference's own values to the last bit). */
 int osmr_debug_set(osmr_ctx* ctx, const char* key, int value);
 
-uint32_t osmr_abi_version(void); /* 4: osmr_stats gained the label_* fields; osmr_draw_tiles_auto_png, osmr_ctx_create_shared, osmr_batch_*_labeled */
+uint32_t osmr_abi_version(void); /* 5: osmr_set_zoom_label_styles, osmr_draw_tiles_auto_labeled{,_png}, osmr_auto_readback_labels (4: osmr_stats gained the
+                                    label_* fields; osmr_draw_tiles_auto_png, osmr_ctx_create_shared, osmr_batch_*_labeled) */
 
 #ifdef __cplusplus
 }

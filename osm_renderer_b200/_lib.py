@@ -44,6 +44,10 @@ EXPORTS = [
     "osmr_ctx_create_shared",
     "osmr_batch_upload_labeled",
     "osmr_batch_draw_labeled",
+    "osmr_set_zoom_label_styles",
+    "osmr_draw_tiles_auto_labeled",
+    "osmr_draw_tiles_auto_labeled_png",
+    "osmr_auto_readback_labels",
 ]
 
 _lib = None
@@ -125,5 +129,13 @@ def load():
     L.osmr_ctx_create_shared.argtypes = [vp, C.POINTER(vp)]
     L.osmr_draw_tiles_auto_png.restype = C.c_int
     L.osmr_draw_tiles_auto_png.argtypes = [vp, vp, u32, vp, u32, vp, sz, vp]
+    L.osmr_set_zoom_label_styles.restype = C.c_int
+    L.osmr_set_zoom_label_styles.argtypes = [vp, u32, vp, vp, vp, vp, vp, u32]
+    L.osmr_draw_tiles_auto_labeled.restype = C.c_int
+    L.osmr_draw_tiles_auto_labeled.argtypes = [vp, vp, u32, vp, u32, vp]
+    L.osmr_draw_tiles_auto_labeled_png.restype = C.c_int
+    L.osmr_draw_tiles_auto_labeled_png.argtypes = [vp, vp, u32, vp, u32, vp, sz, vp]
+    L.osmr_auto_readback_labels.restype = C.c_int
+    L.osmr_auto_readback_labels.argtypes = [vp, vp, vp, u32]
     _lib = L
     return L

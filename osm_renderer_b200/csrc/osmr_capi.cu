@@ -23,6 +23,7 @@
 #include "osmr_png.cuh"
 #include "osmr_labels_host.hpp"
 #include "osmr_labels_dev.cuh"
+#include "osmr_auto_labels.cuh"
 #include <map>
 #include <memory>
 #include <unordered_map>
@@ -109,6 +110,10 @@ struct Dataset {
     unsigned n_idx = 0;
     DevBuf<uint2> idx_xy, idx_w, idx_m, way_min_tile, mp_min_tile;
     DevBuf<unsigned> way_rank, mp_rank, rank_entity;
+    // f3 for the label pass (osmr_auto_labels.cuh): node lists of the index records, rank of (global id, local id) among the nodes
+    std::string auto_labels_unavailable;
+    DevBuf<uint2> idx_n;
+    DevBuf<unsigned> node_rank, node_rank_entity;
     ~Dataset() { cudaSetDevice(device); }  // (the buffers free themselves right after, on this device)
 };
 
@@ -208,6 +213,7 @@ struct osmr_ctx {
     std::vector<osmr_tile> h_batch_tiles;     // resident labelled batch: host copies for the table look-ups of the label pass
     std::vector<uint32_t> h_label_begin;
     bool batch_has_labels = false;
+    bool resident_needs_host_layout = false;  // osmr_batch_draw_labeled's last verdict (osmr_draw_tiles_auto_labeled falls back on it)
     unsigned label_chunks = 0;     // debug key "label_chunks"
     unsigned curve_leaf_cap = 0;   // debug key "curve_leaf_cap" (tests: curves with more leaves are flattened again by one lane)
     bool label_host_only = false;  // debug key "label_host": always lay labels out on the host (round-1 path)
@@ -281,6 +287,11 @@ struct osmr_ctx {
         DevBuf<int> class_reach;
         unsigned n_classes = 0, n_class_styles = 0;
         bool set = false;
+        // label classes (osmr_set_zoom_label_styles)
+        DevBuf<unsigned> l_node_class, l_way_class, l_mp_class, l_class_begin;
+        DevBuf<osmr_class_style> l_class_styles;
+        unsigned l_n_classes = 0;
+        bool l_set = false;
     };
     ZoomTable zoom_tables[19];
     DevBuf<unsigned> auto_bound, auto_cand, auto_cand_cnt, auto_inst;
@@ -342,7 +353,7 @@ static inline uint32_t rd_u32(const uint8_t* p) {
 
 extern "C" {
 
-uint32_t osmr_abi_version(void) { return 4; }
+uint32_t osmr_abi_version(void) { return 5; }
 
 int osmr_ctx_create(int device, osmr_ctx** out_ctx) try {
     if (!out_ctx) return OSMR_E_INVALID;
@@ -728,14 +739,16 @@ int osmr_set_geodata(osmr_ctx* ctx, const void* bin, size_t len) try {
     ctx->has_batch = false;
     ctx->lres.valid = false;
     for (auto& a : ctx->lres.angle) a.set = false;
-    for (auto& z : ctx->zoom_tables) z.set = false;  // classes are per dataset
+    for (auto& z : ctx->zoom_tables) z.set = z.l_set = false;  // classes are per dataset
 
     // ---- f3: the tile index (reader.rs:135-180) + what the device-side lookup derives from it ----
     {
         const uint32_t n_idx = cnt[4];
         ctx->ds->n_idx = n_idx;
         ctx->ds->auto_unavailable.clear();
-        std::vector<uint2> ixy(n_idx), iw(n_idx), im(n_idx);
+        std::vector<uint2> ixy(n_idx), iw(n_idx), im(n_idx), in_(n_idx);
+        std::vector<uint8_t> node_seen(n_nodes, 0);
+        ctx->ds->auto_labels_unavailable.clear();
         struct Ext {
             uint32_t x0 = 0xffffffffu, y0 = 0xffffffffu, x1 = 0, y1 = 0, n = 0;
         };
@@ -745,6 +758,24 @@ int osmr_set_geodata(osmr_ctx* ctx, const void* bin, size_t len) try {
             ixy[i] = make_uint2(rd_u32(r), rd_u32(r + 4));
             iw[i] = make_uint2(rd_u32(r + 16), rd_u32(r + 20));
             im[i] = make_uint2(rd_u32(r + 24), rd_u32(r + 28));
+            in_[i] = make_uint2(rd_u32(r + 8), rd_u32(r + 12));
+            // a node belongs to one z18 tile (saver.rs:170-173): the device-side label lookup emits it without a dedup step
+            if (!range_ok(in_[i].x, in_[i].y)) {
+                ctx->ds->auto_labels_unavailable = "tile index node list out of range";
+            } else if (ctx->ds->auto_labels_unavailable.empty()) {
+                for (uint32_t k = 0; k < in_[i].y; ++k) {
+                    const uint32_t nd = ints[in_[i].x + k];
+                    if (nd >= n_nodes) {
+                        ctx->ds->auto_labels_unavailable = "tile index references a missing node";
+                        break;
+                    }
+                    if (node_seen[nd]) {
+                        ctx->ds->auto_labels_unavailable = "tile index lists a node in more than one record";
+                        break;
+                    }
+                    node_seen[nd] = 1;
+                }
+            }
             if (i && !(ixy[i - 1].x < ixy[i].x || (ixy[i - 1].x == ixy[i].x && ixy[i - 1].y < ixy[i].y)))
                 ctx->ds->auto_unavailable = "tile index is not sorted by (x, y)";
             if (!range_ok(iw[i].x, iw[i].y) || !range_ok(im[i].x, im[i].y)) ctx->ds->auto_unavailable = "tile index id list out of range";
@@ -827,6 +858,28 @@ int osmr_set_geodata(osmr_ctx* ctx, const void* bin, size_t len) try {
             CK(up(ctx->ds->way_rank.p, wrank.data(), (size_t)n_ways * 4));
             CK(up(ctx->ds->mp_rank.p, mrank.data(), (size_t)n_mps * 4));
             CK(up(ctx->ds->rank_entity.p, rank_entity.data(), keys.size() * 4));
+            if (n_nodes >= OSMR_LABEL_NODE) ctx->ds->auto_labels_unavailable = "too many nodes for osmr_label.entity";
+            if (ctx->ds->auto_labels_unavailable.empty()) {
+                // stable order of the styled nodes behind (layer, z_index): global id, then the reader's local-id order
+                std::vector<std::pair<uint64_t, uint32_t>> nk(n_nodes);
+                for (uint32_t i = 0; i < n_nodes; ++i) {
+                    uint64_t g;
+                    memcpy(&g, base[0] + (size_t)i * 32, 8);
+                    nk[i] = {g, i};
+                }
+                std::sort(nk.begin(), nk.end());
+                std::vector<unsigned> nrank(n_nodes), nrank_entity(n_nodes);
+                for (uint32_t r = 0; r < n_nodes; ++r) {
+                    nrank[nk[r].second] = r;
+                    nrank_entity[r] = nk[r].second;
+                }
+                CK(ctx->ds->idx_n.reserve(n_idx + 1));
+                CK(ctx->ds->node_rank.reserve(n_nodes + 1));
+                CK(ctx->ds->node_rank_entity.reserve(n_nodes + 1));
+                CK(up(ctx->ds->idx_n.p, in_.data(), (size_t)n_idx * 8));
+                CK(up(ctx->ds->node_rank.p, nrank.data(), (size_t)n_nodes * 4));
+                CK(up(ctx->ds->node_rank_entity.p, nrank_entity.data(), (size_t)n_nodes * 4));
+            }
             CK(cudaStreamSynchronize(ctx->stream));
         }
     }
@@ -2540,6 +2593,7 @@ int osmr_batch_draw_labeled(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t
     if (!ctx) return OSMR_E_INVALID;
     if (!ctx->has_batch || !ctx->batch_has_labels) return ctx->fail(OSMR_E_STATE, "no labelled batch uploaded (osmr_batch_upload_labeled)");
     cudaSetDevice(ctx->device);
+    ctx->resident_needs_host_layout = false;
     for (int attempt = 0; attempt < 12; ++attempt) {
         int rc = label_device_enqueue(ctx, ctx->h_batch_tiles.data(), ctx->n_tiles, ctx->h_label_begin.data(), nullptr, true,
                                       out != nullptr && !(flags & OSMR_DRAW_OUT_DEVICE));
@@ -2578,6 +2632,7 @@ int osmr_batch_draw_labeled(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t
             }
             return OSMR_OK;
         }
+        if (verdict == 2) ctx->resident_needs_host_layout = true;
         if (verdict == 2)
             return ctx->fail(OSMR_E_STATE, "this batch needs the host label layout (a flatness near-tie or an oversized polylabel); use osmr_draw_tiles_labeled");
     }
@@ -2684,6 +2739,220 @@ int osmr_draw_tiles_labeled(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_ti
     ctx->stats.ms_label_device = ctx->stats_label_device_ms;
     ctx->stats.label_path = 2;
     return rc;
+} OSMR_CATCH_INT(ctx)
+
+// ---------------------------------------------------------------------------------------------------------
+// f3 for the label pass: label classes per zoom + device-side listing of the label generations (osmr_auto_labels.cuh)
+// ---------------------------------------------------------------------------------------------------------
+int osmr_set_zoom_label_styles(osmr_ctx* ctx, uint32_t zoom, const uint32_t* node_class, const uint32_t* way_class, const uint32_t* mp_class,
+                               const uint32_t* class_begin, const osmr_class_style* class_styles, uint32_t n_classes) try {
+    if (!ctx) return OSMR_E_INVALID;
+    if (!ctx->ds->has_geo) return ctx->fail(OSMR_E_STATE, "osmr_set_geodata has not been called");
+    if (zoom > 18) return ctx->fail(OSMR_E_INVALID, "zoom must be <= 18 (tile.rs:5 MAX_ZOOM)");
+    if ((ctx->ds->n_nodes && !node_class) || (ctx->ds->n_ways && !way_class) || (ctx->ds->n_mps && !mp_class) || !class_begin)
+        return ctx->fail(OSMR_E_INVALID, "null class table");
+    if (class_begin[0] != 0) return ctx->fail(OSMR_E_INVALID, "class_begin[0] must be 0");
+    for (uint32_t c = 0; c < n_classes; ++c) {
+        if (class_begin[c + 1] < class_begin[c]) return ctx->fail(OSMR_E_INVALID, "class_begin must be non-decreasing");
+        if (class_begin[c + 1] - class_begin[c] >= (1u << kAutoWithinBits)) return ctx->fail(OSMR_E_INVALID, "more than 4095 styles in one class");
+    }
+    const uint32_t n_cs = class_begin[n_classes];
+    if (n_cs && !class_styles) return ctx->fail(OSMR_E_INVALID, "null class style list");
+    for (uint32_t i = 0; i < n_cs; ++i)
+        if (class_styles[i].order >= kAutoLabelNodeOrder) return ctx->fail(OSMR_E_INVALID, "label style order rank must be below 2^19");
+    cudaSetDevice(ctx->device);
+    osmr_ctx::ZoomTable& z = ctx->zoom_tables[zoom];
+    z.l_set = false;
+    CK(z.l_node_class.reserve(ctx->ds->n_nodes + 1));
+    CK(z.l_way_class.reserve(ctx->ds->n_ways + 1));
+    CK(z.l_mp_class.reserve(ctx->ds->n_mps + 1));
+    CK(z.l_class_begin.reserve(n_classes + 1));
+    CK(z.l_class_styles.reserve(n_cs + 1));
+    if (ctx->ds->n_nodes) CK(cudaMemcpyAsync(z.l_node_class.p, node_class, (size_t)ctx->ds->n_nodes * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->ds->n_ways) CK(cudaMemcpyAsync(z.l_way_class.p, way_class, (size_t)ctx->ds->n_ways * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->ds->n_mps) CK(cudaMemcpyAsync(z.l_mp_class.p, mp_class, (size_t)ctx->ds->n_mps * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(z.l_class_begin.p, class_begin, (size_t)(n_classes + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (n_cs) CK(cudaMemcpyAsync(z.l_class_styles.p, class_styles, (size_t)n_cs * sizeof(osmr_class_style), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    z.l_n_classes = n_classes;
+    z.l_set = true;
+    return OSMR_OK;
+} OSMR_CATCH_INT(ctx)
+
+// Behind auto_prepare (the styled areas of the batch are resident): the label lists of the same tiles, built on the device and
+// left where osmr_batch_upload_labeled would have put them.  ctx->ev[0] / ev[1] bracket the stage.
+static int auto_prepare_labels(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles) {
+    if (!ctx->ds->auto_labels_unavailable.empty()) return ctx->fail(OSMR_E_STATE, ctx->ds->auto_labels_unavailable.c_str());
+    const uint32_t zoom = tiles[0].zoom;
+    osmr_ctx::ZoomTable& z = ctx->zoom_tables[zoom];
+    if (!z.l_set) return ctx->fail(OSMR_E_STATE, "osmr_set_zoom_label_styles has not been called for this zoom");
+    auto& R = ctx->lres;
+    if (!R.valid) {
+        int rc = build_label_tables(ctx);
+        if (rc) return rc;
+    }
+    cudaStream_t st = ctx->stream;
+    ctx->batch_has_labels = false;
+    CK(ctx->auto_bound.reserve(n_tiles + 2));
+    CK(ctx->auto_cand_cnt.reserve(n_tiles + 1));
+    CK(ctx->auto_inst.reserve(n_tiles + 2));
+    CK(ctx->d_label_begin.reserve(n_tiles + 1));
+    Scene s{};
+    s.mps = ctx->ds->mps.p;
+    s.ints = ctx->ds->ints.p;
+    s.n_nodes = ctx->ds->n_nodes;
+    s.n_ways = ctx->ds->n_ways;
+    s.n_mps = ctx->ds->n_mps;
+    s.n_ints = ctx->ds->n_ints;
+    s.tiles = ctx->tiles.p;
+    s.n_tiles = n_tiles;
+    unsigned* auto_counters = ctx->counters.p + (size_t)kMaxChunks * CNT_COUNT;
+    unsigned* h_auto = ctx->h_cnt.p + (size_t)kMaxChunks * CNT_COUNT;
+    s.counters = auto_counters;
+    AutoLabelScene a{};
+    a.idx_xy = ctx->ds->idx_xy.p;
+    a.idx_n = ctx->ds->idx_n.p;
+    a.idx_w = ctx->ds->idx_w.p;
+    a.idx_m = ctx->ds->idx_m.p;
+    a.n_idx = ctx->ds->n_idx;
+    a.way_min_tile = ctx->ds->way_min_tile.p;
+    a.mp_min_tile = ctx->ds->mp_min_tile.p;
+    a.way_rank = ctx->ds->way_rank.p;
+    a.mp_rank = ctx->ds->mp_rank.p;
+    a.rank_entity = ctx->ds->rank_entity.p;
+    a.node_rank = ctx->ds->node_rank.p;
+    a.node_rank_entity = ctx->ds->node_rank_entity.p;
+    a.node_class = z.l_node_class.p;
+    a.way_class = z.l_way_class.p;
+    a.mp_class = z.l_mp_class.p;
+    a.class_begin = z.l_class_begin.p;
+    a.class_styles = z.l_class_styles.p;
+    a.n_classes = z.l_n_classes;
+    a.lstyles = R.styles.p;
+    a.n_lstyles = (unsigned)ctx->label_styles.size();
+    a.text_id = R.text_id.p;
+    a.ent_total = R.ent_total;
+    a.way_base = R.way_base;
+    a.mp_base = R.mp_base;
+    a.bound = ctx->auto_bound.p;
+    a.cand_cnt = ctx->auto_cand_cnt.p;
+    a.inst_cnt = ctx->auto_inst.p;
+
+    CK(cudaEventRecord(ctx->ev[0], st));
+    CK(cudaMemsetAsync(auto_counters, 0, CNT_COUNT * sizeof(unsigned), st));
+    autol_bound_kernel<<<n_tiles, kAutoThreads, 0, st>>>(s, a);
+    auto_scan_kernel<<<1, 1024, 0, st>>>(ctx->auto_bound.p, n_tiles, &auto_counters[CNT_OVERFLOW]);
+    unsigned total_bound = 0;
+    CK(cudaMemcpyAsync(&total_bound, ctx->auto_bound.p + n_tiles, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_auto, auto_counters, CNT_COUNT * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (h_auto[CNT_OVERFLOW]) return ctx->fail(OSMR_E_NOMEM, "more than 2^32 label candidate references; split the batch");
+    CK(ctx->auto_cand.reserve((size_t)total_bound + 1));
+    a.cand = ctx->auto_cand.p;
+    autol_gather_kernel<<<n_tiles, kAutoThreads, 0, st>>>(s, a);
+    auto_scan_kernel<<<1, 1024, 0, st>>>(ctx->auto_inst.p, n_tiles, &auto_counters[CNT_OVERFLOW]);
+    CK(cudaMemcpyAsync(ctx->d_label_begin.p, ctx->auto_inst.p, (size_t)(n_tiles + 1) * 4, cudaMemcpyDeviceToDevice, st));
+    ctx->h_label_begin.resize(n_tiles + 1);
+    CK(cudaMemcpyAsync(ctx->h_label_begin.data(), ctx->auto_inst.p, (size_t)(n_tiles + 1) * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_auto, auto_counters, CNT_COUNT * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (h_auto[CNT_OVERFLOW]) return ctx->fail(OSMR_E_NOMEM, "more than 2^32 label generations; split the batch");
+    if (h_auto[CNT_BAD_INPUT] & 1u) return ctx->fail(OSMR_E_INVALID, "label class style list references a label style that does not exist");
+    if (h_auto[CNT_BAD_INPUT]) return ctx->fail(OSMR_E_INVALID, "tile index references an entity that does not exist");
+    const uint32_t n_labels = ctx->h_label_begin[n_tiles];
+    CK(ctx->d_label_list.reserve((size_t)n_labels + 1));
+    a.labels_out = ctx->d_label_list.p;
+    for (int attempt = 0;; ++attempt) {
+        a.big_keys = ctx->auto_big_keys.p;
+        a.big_cap = ctx->auto_big_keys.cap;
+        CK(cudaMemsetAsync(auto_counters, 0, CNT_COUNT * sizeof(unsigned), st));
+        autol_sort_kernel<<<n_tiles, kAutoThreads, 0, st>>>(s, a);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(h_auto, auto_counters, CNT_COUNT * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (!(h_auto[CNT_OVERFLOW] & 8u)) break;
+        if (attempt >= 2) return ctx->fail(OSMR_E_NOMEM, "sort scratch kept overflowing");
+        unsigned long long need;
+        memcpy(&need, &h_auto[CNT_WALK_ALPHA], 8);
+        CK(ctx->auto_big_keys.reserve((size_t)need + 1024));
+    }
+    CK(cudaEventRecord(ctx->ev[1], st));
+    ctx->h_batch_tiles.assign(tiles, tiles + n_tiles);
+    ctx->batch_has_labels = true;
+    return OSMR_OK;
+}
+
+// tile list in, finished tiles out: f3 for both halves of draw_to_pixels (drawer.rs:60-131) in front of the draw path
+static int auto_labeled_draw(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, const uint8_t canvas_rgb[3], uint32_t flags, uint8_t* out) {
+    if (!ctx->font.loaded()) return ctx->fail(OSMR_E_STATE, "osmr_set_font has not been called");
+    int rc = auto_prepare(ctx, tiles, n_tiles, canvas_rgb, flags);
+    if (rc) return rc;
+    float ms_areas = 0.f, ms_labels = 0.f;  // (the stage's events are reused: read them before the next stage)
+    cudaEventSynchronize(ctx->ev[1]);
+    cudaEventElapsedTime(&ms_areas, ctx->ev[0], ctx->ev[1]);
+    rc = auto_prepare_labels(ctx, tiles, n_tiles);
+    if (rc) return rc;
+    cudaEventSynchronize(ctx->ev[1]);
+    cudaEventElapsedTime(&ms_labels, ctx->ev[0], ctx->ev[1]);
+    const uint32_t n_labels = ctx->h_label_begin[n_tiles];
+    bool host_layout = !label_device_path_allowed(ctx, tiles, n_tiles);
+    if (!host_layout) {
+        rc = osmr_batch_draw_labeled(ctx, canvas_rgb, flags, out, nullptr);
+        if (rc && !ctx->resident_needs_host_layout) return rc;
+        host_layout = rc != OSMR_OK;
+    }
+    if (host_layout) {  // the lists come back once and the host lays the labels out (same pixels, osmr_stats.label_path = 2)
+        std::vector<osmr_label> h_labels((size_t)n_labels + 1);
+        if (n_labels) CK(cudaMemcpyAsync(h_labels.data(), ctx->d_label_list.p, (size_t)n_labels * sizeof(osmr_label), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        const std::vector<uint32_t> h_begin = ctx->h_label_begin;
+        ctx->batch_has_labels = false;  // (labels_via_host reuses the device label arrays)
+        rc = labels_via_host(ctx, tiles, n_tiles, h_begin.data(), h_labels.data());
+        if (rc) return rc;
+        ctx->label_plane_active = true;
+        rc = osmr_batch_draw(ctx, canvas_rgb, flags, out, nullptr);
+        ctx->label_plane_active = false;
+        if (rc) return rc;
+        ctx->stats.ms_label_layout = ctx->stats_label_layout_ms;
+        ctx->stats.ms_label_device = ctx->stats_label_device_ms;
+        ctx->stats.label_path = 2;
+    }
+    ctx->stats.ms_auto = ms_areas + ms_labels;
+    ctx->stats.ms_total += ms_areas + ms_labels;
+    ctx->stats.kernel_launches += 5;
+    return OSMR_OK;
+}
+
+int osmr_draw_tiles_auto_labeled(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, const uint8_t canvas_rgb[3], uint32_t flags, uint8_t* out) try {
+    if (!ctx) return OSMR_E_INVALID;
+    if (!out && !(flags & OSMR_DRAW_OUT_DEVICE)) return ctx->fail(OSMR_E_INVALID, "null output buffer");
+    return auto_labeled_draw(ctx, tiles, n_tiles, canvas_rgb, flags, out);
+} OSMR_CATCH_INT(ctx)
+
+// Drawer::draw_tile with its label pass for a tile list (drawer.rs:40-58 behind http_server.rs:150-177): tile list in, PNG files out
+int osmr_draw_tiles_auto_labeled_png(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, const uint8_t canvas_rgb[3], uint32_t flags,
+                                     uint8_t* png_out, size_t png_cap, uint64_t* png_offset) try {
+    if (!ctx) return OSMR_E_INVALID;
+    if (!png_out || !png_offset) return ctx->fail(OSMR_E_INVALID, "null output buffer");
+    if (flags & (OSMR_DRAW_OUT_RGBA | OSMR_DRAW_OUT_DEVICE)) return ctx->fail(OSMR_E_INVALID, "osmr_draw_tiles_auto_labeled_png encodes RGB into host memory");
+    int rc = auto_labeled_draw(ctx, tiles, n_tiles, canvas_rgb, flags, nullptr);  // the RGB tiles stay in HBM (ctx->out)
+    if (rc) return rc;
+    return encode_png_from_device(ctx, ctx->out.p, n_tiles, (unsigned)ctx->scale, png_out, png_cap, png_offset);
+} OSMR_CATCH_INT(ctx)
+
+int osmr_auto_readback_labels(osmr_ctx* ctx, uint32_t* label_begin, osmr_label* labels, uint32_t labels_cap) try {
+    if (!ctx || !label_begin) return OSMR_E_INVALID;
+    if (!ctx->has_batch || ctx->h_label_begin.size() != (size_t)ctx->n_tiles + 1) return ctx->fail(OSMR_E_STATE, "no device-built label lists");
+    cudaSetDevice(ctx->device);
+    memcpy(label_begin, ctx->h_label_begin.data(), (size_t)(ctx->n_tiles + 1) * 4);
+    if (labels) {
+        const uint32_t n = ctx->h_label_begin[ctx->n_tiles];
+        if (!ctx->batch_has_labels) return ctx->fail(OSMR_E_STATE, "the device label lists were replaced by the host layout");
+        if (labels_cap < n) return ctx->fail(OSMR_E_INVALID, "labels_cap too small");
+        if (n) CK(cudaMemcpyAsync(labels, ctx->d_label_list.p, (size_t)n * sizeof(osmr_label), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return OSMR_OK;
 } OSMR_CATCH_INT(ctx)
 
 // pinned host memory for callers that want full-speed transfers (optional)

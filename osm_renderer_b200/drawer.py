@@ -316,6 +316,60 @@ class GpuContext:
         self._auto_tiles = n
         return [buf[int(offs[i]) : int(offs[i + 1])].tobytes() for i in range(n)]
 
+    # ---- f3 for the label pass: label lists built on the device ---------------------------------------------------------
+    def set_zoom_label_styles(self, zoom: int, node_class, way_class, mp_class, class_begin, class_styles):
+        """osmr_set_zoom_label_styles: per-zoom label style classes of every node / way / multipolygon."""
+        from .wire import CLASS_STYLE_DTYPE
+
+        node_class = np.ascontiguousarray(node_class, dtype=np.uint32)
+        way_class = np.ascontiguousarray(way_class, dtype=np.uint32)
+        mp_class = np.ascontiguousarray(mp_class, dtype=np.uint32)
+        class_begin = np.ascontiguousarray(class_begin, dtype=np.uint32)
+        class_styles = np.ascontiguousarray(class_styles, dtype=CLASS_STYLE_DTYPE)
+        self._check(
+            self.L.osmr_set_zoom_label_styles(self.h, zoom, node_class.ctypes.data, way_class.ctypes.data, mp_class.ctypes.data,
+                                              class_begin.ctypes.data, class_styles.ctypes.data, len(class_begin) - 1),
+            "osmr_set_zoom_label_styles",
+        )
+
+    def draw_tiles_auto_labeled(self, tiles, canvas_rgb, use_caps_for_dashes=True, rgba=False, out=None):
+        """osmr_draw_tiles_auto_labeled: the whole draw_to_pixels from a tile list (area AND label lists built on the device)."""
+        tiles = np.ascontiguousarray(tiles, dtype=TILE_DTYPE)
+        n = len(tiles)
+        d = 256 * int(tiles["scale"][0]) if n else 256
+        if out is None:
+            out = np.empty((n, d, d, 4 if rgba else 3), dtype=np.uint8)
+        flags, canvas = self._flags(canvas_rgb, use_caps_for_dashes, rgba)
+        self._check(self.L.osmr_draw_tiles_auto_labeled(self.h, tiles.ctypes.data, n, canvas.ctypes.data, flags, out.ctypes.data),
+                    "osmr_draw_tiles_auto_labeled")
+        self._auto_tiles = n
+        return out
+
+    def auto_readback_labels(self):
+        """(label_begin, labels) of the last draw_tiles_auto_labeled* call."""
+        from .wire import LABEL_DTYPE
+
+        begins = np.zeros(self._auto_tiles + 1, dtype=np.uint32)
+        self._check(self.L.osmr_auto_readback_labels(self.h, begins.ctypes.data, None, 0), "osmr_auto_readback_labels")
+        labels = np.zeros(int(begins[-1]), dtype=LABEL_DTYPE)
+        self._check(self.L.osmr_auto_readback_labels(self.h, begins.ctypes.data, labels.ctypes.data, len(labels)), "osmr_auto_readback_labels")
+        return begins, labels
+
+    def draw_tiles_auto_labeled_png(self, tiles, canvas_rgb, use_caps_for_dashes=True):
+        """osmr_draw_tiles_auto_labeled_png: tile list in, one PNG file per tile out, label pass included (Drawer::draw_tile)."""
+        tiles = np.ascontiguousarray(tiles, dtype=TILE_DTYPE)
+        n = len(tiles)
+        cap = n * int(self.L.osmr_png_bound(int(tiles["scale"][0]))) if n else 0
+        buf = np.empty(cap, dtype=np.uint8)
+        offs = np.zeros(n + 1, dtype=np.uint64)
+        flags, canvas = self._flags(canvas_rgb, use_caps_for_dashes, False)
+        self._check(
+            self.L.osmr_draw_tiles_auto_labeled_png(self.h, tiles.ctypes.data, n, canvas.ctypes.data, flags, buf.ctypes.data, cap, offs.ctypes.data),
+            "osmr_draw_tiles_auto_labeled_png",
+        )
+        self._auto_tiles = n
+        return [buf[int(offs[i]) : int(offs[i + 1])].tobytes() for i in range(n)]
+
     def rgb_to_png(self, images):
         """osmr_rgb_to_png: uint8 [n, D, D, 3] (D = 256 * scale) -> list of PNG files (png_writer.rs:4-21)."""
         images = np.ascontiguousarray(images, dtype=np.uint8)

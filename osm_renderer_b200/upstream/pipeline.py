@@ -295,6 +295,7 @@ def _label_methods():
         idx = offs[rep] + (np.arange(tot) - start[rep])
         return np.unique(rd.ints[idx]).astype(np.int64)
 
+    _label_methods.label_lists = _label_lists
     return labels_array, _candidate_nodes
 
 
@@ -338,6 +339,50 @@ def zoom_class_tables(fb: "FastBatchBuilder", zoom: int):
         cs["style"] = sid
         cs["order"] = np.asarray(order).reshape(-1)
     return way_class, mp_class, class_begin, cs
+
+
+def zoom_label_class_tables(fb: "FastBatchBuilder", zoom: int, ltable):
+    """The per-zoom LABEL style classes osmr_set_zoom_label_styles takes: the StyleCache contents (style_cache.rs:68-87) for
+    every node, way and multipolygon at `zoom`, with the styles interned in `ltable` (a wire.LabelStyleTable).
+
+    Returns (node_class, way_class, mp_class, class_begin, class_styles); `order` is the dense rank of (layer, z_index) --
+    compare_styled_entities with for_labels = true (styler.rs:246-272)."""
+    from ..wire import CLASS_STYLE_DTYPE, NO_CLASS
+    from .styler import KIND_NODE
+
+    lists = []  # per class: (label style ids, layer, z)
+    label_lists = _label_methods.label_lists
+
+    def classes_of(kinds, tagkeys):
+        out = np.full(len(kinds), NO_CLASS, dtype=np.uint32)
+        for kind in np.unique(kinds):
+            m = np.nonzero(kinds == kind)[0]
+            inv, ls = label_lists(fb, zoom, int(kind), tagkeys[m], ltable)
+            base = len(lists)
+            lists.extend(ls)
+            out[m] = (base + inv).astype(np.uint32)
+        return out
+
+    rd = fb.rd
+    ntl = rd.nodes["tags_len"].astype(np.int64)
+    ntk = np.where(ntl > 0, (rd.nodes["tags_off"].astype(np.int64) << 32) | ntl, 0)  # untagged nodes: one class
+    node_class = classes_of(np.full(len(ntk), KIND_NODE, dtype=np.int64), ntk)
+    way_class = classes_of(fb.way_kind, fb.way_tagkey)
+    mp_class = classes_of(np.full(len(fb.mp_gid), KIND_MULTIPOLYGON, dtype=np.int64), fb.mp_tagkey)
+    counts = np.array([len(l[0]) for l in lists], dtype=np.int64)
+    class_begin = np.zeros(len(lists) + 1, dtype=np.uint32)
+    class_begin[1:] = np.cumsum(counts)
+    n = int(class_begin[-1])
+    cs = np.zeros(n, dtype=CLASS_STYLE_DTYPE)
+    if n:
+        sid = np.concatenate([l[0] for l in lists])
+        lay = np.concatenate([l[1] for l in lists])
+        zi = np.concatenate([l[2] for l in lists])
+        pair = np.stack([lay.astype(np.float64), zi], axis=1)
+        _, order = np.unique(pair, axis=0, return_inverse=True)
+        cs["style"] = sid
+        cs["order"] = np.asarray(order).reshape(-1)
+    return node_class, way_class, mp_class, class_begin, cs
 
 
 class LabelListBuilder:

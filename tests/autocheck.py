@@ -7,8 +7,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
-def fixture_builder():
-    """nano_moscow.bin + the committed mapnik rules -> (image, reader, styler, style table, FastBatchBuilder)"""
+def fixture_builder(icon_loader=None):
+    """nano_moscow.bin + the committed mapnik rules -> (image, reader, styler, style table, FastBatchBuilder);
+    `icon_loader` (name -> (w, h, rgba) or None) resolves fill-image patterns (without one they fail to load, which the
+    reference treats as "no fill")"""
     from osm_renderer_b200.upstream import geodata, mapcss, pipeline, styler as st
     from osm_renderer_b200.wire import StyleTable
 
@@ -17,7 +19,7 @@ def fixture_builder():
     rd = geodata.GeodataReader(data)
     rules = mapcss.load_rules_json(os.path.join(GOLDEN, "mapnik_rules.json.gz"))
     S = st.Styler(rules, "josm", None)
-    table = StyleTable(None)
+    table = StyleTable(None, icon_loader=icon_loader)
     return data, rd, S, table, pipeline.FastBatchBuilder(rd, S, table)
 
 

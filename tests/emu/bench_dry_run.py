@@ -66,6 +66,9 @@ def main():
     assert d["max_abs_diff_rgb_vs_cpu"] == 0 and d["e2e_auto"]["identical_to_e2e_output"] and d["e2e_png"]["mean_png_bytes"] > 0
     assert d["max_abs_diff_rgb_vs_cpu_labeled"] == 0 and d["e2e_area_only"]["value"] > 0 and d["e2e_auto_png"]["value"] > 0
     assert "draw_tiles_labeled" in d["e2e"]["api"] and d["value_area_only"]["value"] > 0 and d["cpu_baseline"]["value_area_only"] > 0
+    assert d["e2e_auto_labeled"]["identical_to_e2e_labeled_output"] and d["e2e_auto_labeled"]["label_path_last_call"] == 1
+    assert d["e2e_auto_labeled"]["live_label_generations_last_call"] > 0 and d["e2e_auto_labeled_png"]["mean_png_bytes"] > 0
+    print("e2e_auto_labeled:", d["e2e_auto_labeled"])
     assert d["sustained"]["steps"] >= 5 and d["latency_ms"] and d["roofline"]["B_tile_terms"]["sum_U"] > 0
     print("bench dry run ok:", {k: d[k] for k in ("metric", "n_gpus", "gpu_launches", "max_abs_diff_rgb_vs_cpu")})
 

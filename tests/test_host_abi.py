@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), n
     assert set(names) == set(_lib.EXPORTS)
-    assert lib.osmr_abi_version() == 4
+    assert lib.osmr_abi_version() == 5
 
 
 def test_context_creation_fails_loudly_without_a_gpu():
