@@ -1520,10 +1520,8 @@ int osmr_set_zoom_styles(osmr_ctx* ctx, uint32_t zoom, const uint32_t* way_class
     return OSMR_OK;
 } OSMR_CATCH_INT(ctx)
 
-// f3 up to "an ordinary resident batch": candidate lookup, ownership dedup, culling and the painter's order on the device.
-// On success ctx holds the batch (tiles, area_begin, areas) exactly as osmr_batch_upload would have left it and the events
-// ctx->ev[0] / ev[1] bracket the stage.
-static int auto_prepare(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, const uint8_t canvas_rgb[3], uint32_t flags) {
+// (validation, the per-call arrays and the tile upload: the part both halves of f3 need first)
+static int auto_begin(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, const uint8_t canvas_rgb[3], uint32_t flags) {
     if (!ctx->ds->has_geo) return ctx->fail(OSMR_E_STATE, "osmr_set_geodata has not been called");
     if (!ctx->ds->auto_unavailable.empty()) return ctx->fail(OSMR_E_STATE, ctx->ds->auto_unavailable.c_str());
     if (n_tiles == 0 || !tiles) return ctx->fail(OSMR_E_INVALID, "empty batch");
@@ -1551,6 +1549,21 @@ static int auto_prepare(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles,
     CK(ctx->auto_cand_cnt.reserve(n_tiles + 1));
     CK(ctx->auto_inst.reserve(n_tiles + 2));
     CK(cudaMemcpyAsync(ctx->tiles.p, tiles, (size_t)n_tiles * sizeof(osmr_tile), cudaMemcpyHostToDevice, st));
+    ctx->scale = (int)scale;
+    return OSMR_OK;
+}
+
+// f3 up to "an ordinary resident batch": candidate lookup, ownership dedup, culling and the painter's order on the device.
+// On success ctx holds the batch (tiles, area_begin, areas) exactly as osmr_batch_upload would have left it and the events
+// ctx->ev[0] / ev[1] bracket the stage.
+static int auto_prepare(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, const uint8_t canvas_rgb[3], uint32_t flags, bool begun = false) {
+    if (!begun) {
+        int rc = auto_begin(ctx, tiles, n_tiles, canvas_rgb, flags);
+        if (rc) return rc;
+    }
+    const uint32_t zoom = tiles[0].zoom, scale = tiles[0].scale;
+    osmr_ctx::ZoomTable& z = ctx->zoom_tables[zoom];
+    cudaStream_t st = ctx->stream;
 
     Scene s{};
     s.merc = ctx->ds->merc.p;
@@ -2559,6 +2572,28 @@ static int label_device_judge(osmr_ctx* ctx) {
     return 0;
 }
 
+// osmr_stats of a resident labelled draw whose label pass was judged good
+static void resident_label_stats(osmr_ctx* ctx, uint32_t attempts) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev_label0, ctx->ev_label1);
+    ctx->stats.ms_label_layout = 0.f;
+    ctx->stats.ms_label_device = ms;
+    ctx->stats.kernel_launches += 13 * ctx->n_lchunks + 1;
+    ctx->stats.label_path = 1;
+    ctx->stats.n_labels_active = ctx->stats_label_active;
+    ctx->stats.n_labels_polylabel = ctx->stats_label_poly;
+    ctx->stats.label_attempts = attempts;
+    float mc = 0.f;
+    for (unsigned ch = 0; ch < ctx->n_lchunks; ++ch) {
+        float m1 = 0.f;
+        cudaEventElapsedTime(&m1, ctx->ev_lcov0[ch], ctx->ev_lcov1[ch]);
+        mc += m1;
+    }
+    ctx->stats.ms_label_cover = mc;
+    ctx->stats.n_label_segments = ctx->stats_label_segs;
+    ctx->stats.n_label_cells = ctx->stats_label_cells;
+}
+
 // The resident form of osmr_draw_tiles_labeled (benchmark "value" leg): batch description AND label lists uploaded once ...
 int osmr_batch_upload_labeled(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, const uint32_t* area_begin, const osmr_styled_area* areas,
                               const uint32_t* label_begin, const osmr_label* labels) try {
@@ -2610,26 +2645,7 @@ int osmr_batch_draw_labeled(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t
         const int verdict = label_device_judge(ctx);
         if (verdict < 0) return verdict;
         if (verdict == 0) {
-            float ms = 0.f;
-            cudaEventElapsedTime(&ms, ctx->ev_label0, ctx->ev_label1);
-            ctx->stats.ms_label_layout = 0.f;
-            ctx->stats.ms_label_device = ms;
-            ctx->stats.kernel_launches += 13 * ctx->n_lchunks + 1;
-            ctx->stats.label_path = 1;
-            ctx->stats.n_labels_active = ctx->stats_label_active;
-            ctx->stats.n_labels_polylabel = ctx->stats_label_poly;
-            ctx->stats.label_attempts = (uint32_t)attempt + 1;
-            {
-                float mc = 0.f;
-                for (unsigned ch = 0; ch < ctx->n_lchunks; ++ch) {
-                    float m1 = 0.f;
-                    cudaEventElapsedTime(&m1, ctx->ev_lcov0[ch], ctx->ev_lcov1[ch]);
-                    mc += m1;
-                }
-                ctx->stats.ms_label_cover = mc;
-                ctx->stats.n_label_segments = ctx->stats_label_segs;
-                ctx->stats.n_label_cells = ctx->stats_label_cells;
-            }
+            resident_label_stats(ctx, (uint32_t)attempt + 1);
             return OSMR_OK;
         }
         if (verdict == 2) ctx->resident_needs_host_layout = true;
@@ -2885,21 +2901,54 @@ static int auto_prepare_labels(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n
 // tile list in, finished tiles out: f3 for both halves of draw_to_pixels (drawer.rs:60-131) in front of the draw path
 static int auto_labeled_draw(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_tiles, const uint8_t canvas_rgb[3], uint32_t flags, uint8_t* out) {
     if (!ctx->font.loaded()) return ctx->fail(OSMR_E_STATE, "osmr_set_font has not been called");
-    int rc = auto_prepare(ctx, tiles, n_tiles, canvas_rgb, flags);
+    // The label pass is the long pole of a labelled draw and runs on its own stream: its lists are built FIRST, the pass is
+    // enqueued, and the styled-area lists (three host round trips) are built beside it.
+    int rc = auto_begin(ctx, tiles, n_tiles, canvas_rgb, flags);
     if (rc) return rc;
-    float ms_areas = 0.f, ms_labels = 0.f;  // (the stage's events are reused: read them before the next stage)
-    cudaEventSynchronize(ctx->ev[1]);
-    cudaEventElapsedTime(&ms_areas, ctx->ev[0], ctx->ev[1]);
+    float ms_areas = 0.f, ms_labels = 0.f;  // (the stages share their events: read them before the next stage)
     rc = auto_prepare_labels(ctx, tiles, n_tiles);
     if (rc) return rc;
     cudaEventSynchronize(ctx->ev[1]);
     cudaEventElapsedTime(&ms_labels, ctx->ev[0], ctx->ev[1]);
     const uint32_t n_labels = ctx->h_label_begin[n_tiles];
+    const bool chunked = out != nullptr && !(flags & OSMR_DRAW_OUT_DEVICE);
     bool host_layout = !label_device_path_allowed(ctx, tiles, n_tiles);
+    bool drawn = false;
+    ctx->resident_needs_host_layout = false;
     if (!host_layout) {
-        rc = osmr_batch_draw_labeled(ctx, canvas_rgb, flags, out, nullptr);
-        if (rc && !ctx->resident_needs_host_layout) return rc;
-        host_layout = rc != OSMR_OK;
+        rc = label_device_enqueue(ctx, tiles, n_tiles, ctx->h_label_begin.data(), nullptr, true, chunked);
+        if (rc) {
+            cudaStreamSynchronize(ctx->label_stream);
+            return rc;
+        }
+    }
+    rc = auto_prepare(ctx, tiles, n_tiles, canvas_rgb, flags, true);
+    if (rc) {
+        ctx->label_async = false;
+        cudaStreamSynchronize(ctx->label_stream);
+        return rc;
+    }
+    cudaEventSynchronize(ctx->ev[1]);
+    cudaEventElapsedTime(&ms_areas, ctx->ev[0], ctx->ev[1]);
+    if (!host_layout) {
+        ctx->label_plane_active = true;
+        rc = osmr_batch_draw(ctx, canvas_rgb, flags, out, nullptr);
+        ctx->label_plane_active = false;
+        ctx->label_async = false;
+        cudaStreamSynchronize(ctx->label_stream);
+        if (rc) return rc;
+        const int verdict = label_device_judge(ctx);
+        if (verdict < 0) return verdict;
+        if (verdict == 0) {
+            resident_label_stats(ctx, 1);
+            drawn = true;
+        } else if (verdict == 1) {  // label scratch grown: the plain resident loop redoes the call
+            rc = osmr_batch_draw_labeled(ctx, canvas_rgb, flags, out, nullptr);
+            if (rc && !ctx->resident_needs_host_layout) return rc;
+            drawn = rc == OSMR_OK;
+            if (drawn) ctx->stats.label_attempts += 1;
+        }
+        host_layout = !drawn;
     }
     if (host_layout) {  // the lists come back once and the host lays the labels out (same pixels, osmr_stats.label_path = 2)
         std::vector<osmr_label> h_labels((size_t)n_labels + 1);
