@@ -254,8 +254,12 @@ struct osmr_ctx {
         DevBuf<double> walk_alpha;
         DevBuf<unsigned char> walk_len;
         DevBuf<BinEntry> bin_entries;
-        DevBuf<unsigned> frag_cnt, pair_table;
+        DevBuf<unsigned> frag_cnt, pair_table, plan_slice_base, bin_cnt_ent;
+        DevBuf<unsigned long long> bin_cnt_cap;
         void release() {
+            plan_slice_base.release();
+            bin_cnt_ent.release();
+            bin_cnt_cap.release();
             bin_entries.release();
             frag_cnt.release();
             pair_table.release();
@@ -277,6 +281,10 @@ struct osmr_ctx {
     cudaEvent_t ev_wall0 = nullptr, ev_wall1 = nullptr, join2 = nullptr;  // device wall time of a draw across both streams
     cudaEvent_t prep_done = nullptr;  // upload + style calculators on `stream`: what stream2's first chunk waits for
     bool two_streams = true;          // debug key "two_streams"
+    DevBuf<unsigned> plan_slice_base;  // per (tile, pass, slice) of a chunk: plan_count_kernel's counts, then their scan
+    DevBuf<unsigned> bin_cnt_ent;      // per (block area, slice, block) of a chunk: bin_count_kernel's counts, then bin_scan_kernel's offsets
+    DevBuf<unsigned long long> bin_cnt_cap;
+    unsigned plan_slice_areas = 0;     // debug key "plan_slice_areas": styled areas per plan slice (0: the default, 32768)
     size_t geom_cap_units = 0, mask_cap_words = 0, walk_alpha_cap = 0, walk_len_cap = 0, entries_cap = 0, pair_cap = 0;
     DevBuf<unsigned char> out;
     size_t out_bytes = 0;
@@ -575,6 +583,11 @@ int osmr_debug_set(osmr_ctx* ctx, const char* key, int value) try {
     if (strcmp(key, "work_items") == 0) {
         if (value < 1) return ctx->fail(OSMR_E_INVALID, "work_items must be positive");
         ctx->work_items_limit = (unsigned)value;
+        return OSMR_OK;
+    }
+    if (strcmp(key, "plan_slice_areas") == 0) {
+        if (value < 0) return ctx->fail(OSMR_E_INVALID, "plan_slice_areas must not be negative");
+        ctx->plan_slice_areas = (unsigned)value;
         return OSMR_OK;
     }
     if (strcmp(key, "fill_cap") == 0) {
@@ -1211,12 +1224,53 @@ static int launch_chunk(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t fla
         ++launches;
     }
     if (slot == 0) CK(cudaEventRecord(ctx->prep_done, st));  // batch description + calculators are in place
-    plan_ops_kernel<<<3 * tc, kPlanThreads, 0, st>>>(s);
+    {
+        // (tile, pass) lists longer than plan_slice_areas styled areas are cut into slices with a CTA each (low zooms, C4)
+        unsigned max_n = 0;
+        for (unsigned t = tb; t < tb + tc; ++t) max_n = std::max(max_n, ctx->h_area_begin[t + 1] - ctx->h_area_begin[t]);
+        const unsigned per = ctx->plan_slice_areas ? ctx->plan_slice_areas : 32768u;
+        const unsigned slices = std::min(256u, std::max(1u, (max_n + per - 1u) / per));
+        s.plan_slices = slices;
+        s.plan_slice_base = nullptr;
+        if (slices > 1u) {
+            auto& psb = set ? ctx->scrB.plan_slice_base : ctx->plan_slice_base;
+            CK(psb.reserve((size_t)3u * tc * slices + 1));
+            s.plan_slice_base = psb.p;
+            plan_count_kernel<<<3 * tc * slices, kPlanThreads, 0, st>>>(s);
+            plan_scan_kernel<<<(3 * tc + 127) / 128, 128, 0, st>>>(s);
+            launches += 2;
+        }
+        plan_ops_kernel<<<3 * tc * slices, kPlanThreads, 0, st>>>(s);
+    }
     build_geometry_kernel<<<ctx->num_sms * 8, kGeomThreads, 0, st>>>(s);
     fill_rows_kernel<<<ctx->num_sms * 16, kFillThreads, 0, st>>>(s);
     {
         const unsigned nblk = (unsigned)((D / kBW) * (D / kBH));
-        bin_ops_kernel<<<tc * ((nblk + kBinThreads - 1) / kBinThreads), kBinThreads, 0, st>>>(s);
+        const unsigned bin_ctas = tc * ((nblk + kBinThreads - 1) / kBinThreads);
+        // long op lists (the tiles that got plan slices) are binned slice by slice: count, scan, write
+        unsigned bslices = 1u;
+        if (s.plan_slices > 1u) {
+            unsigned max_n = 0;
+            for (unsigned t = tb; t < tb + tc; ++t) max_n = std::max(max_n, ctx->h_area_begin[t + 1] - ctx->h_area_begin[t]);
+            const unsigned per = std::max(1u, (ctx->plan_slice_areas ? ctx->plan_slice_areas : 32768u) / 4u);
+            bslices = std::min(256u, std::max(1u, (max_n + per - 1u) / per));
+            while (bslices > 1u && (size_t)bin_ctas * bslices * kBinThreads * 12u > ((size_t)1 << 30)) bslices /= 2u;
+        }
+        s.bin_slices = bslices;
+        if (bslices > 1u) {
+            auto& bce = set ? ctx->scrB.bin_cnt_ent : ctx->bin_cnt_ent;
+            auto& bcc = set ? ctx->scrB.bin_cnt_cap : ctx->bin_cnt_cap;
+            CK(bce.reserve((size_t)bin_ctas * bslices * kBinThreads + 1));
+            CK(bcc.reserve((size_t)bin_ctas * bslices * kBinThreads + 1));
+            s.bin_cnt_ent = bce.p;
+            s.bin_cnt_cap = bcc.p;
+            bin_count_kernel<<<bin_ctas * bslices, kBinThreads, 0, st>>>(s);
+            bin_scan_kernel<<<bin_ctas, kBinThreads, 0, st>>>(s);
+            bin_write_kernel<<<bin_ctas * bslices, kBinThreads, 0, st>>>(s);
+            launches += 2;
+        } else {
+            bin_ops_kernel<<<bin_ctas, kBinThreads, 0, st>>>(s);
+        }
     }
     CK(cudaEventRecord(ev[3], st));
     line_cover_kernel<<<ctx->num_sms * 8, kCoverThreads, 0, st>>>(s);

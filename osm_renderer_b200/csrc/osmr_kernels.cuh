@@ -151,6 +151,8 @@ struct Scene {
     RasterOp* rop;         // same indexing as vis
     short4* vis_bbox;      // reach bbox of vis[i] (8 bytes; what the raster warps scan)
     unsigned* vis_count;   // per tile
+    unsigned plan_slices;       // CTAs per (tile, pass) of plan_ops_kernel (1: the whole sub-list in one CTA)
+    unsigned* plan_slice_base;  // [3 * tile + pass][slice]: visible ops of the slice (plan_count_kernel), then their exclusive scan
     unsigned* work;        // global indices into vis (all visible ops)
     uint2* fill_work;      // (global index into vis, chunk of 32 mask rows): work items of fill_rows_kernel
     uint2* line_work;      // (global index into vis, batch of 32 segment records): work items of line_cover_kernel
@@ -165,6 +167,9 @@ struct Scene {
     unsigned entries_cap;
     uint2* blk_range;          // per (tile, block): first entry, number of entries
     unsigned* pair;            // per line op: entry index of every block of its bbox rectangle (0xffffffff: no segment reaches it)
+    unsigned bin_slices;               // > 1: the ops of a block area are cut into slices with a CTA each (bin_count / bin_scan / bin_write)
+    unsigned* bin_cnt_ent;             // [block area][slice][thread]: entries of the slice (bin_count_kernel), then its first entry
+    unsigned long long* bin_cnt_cap;   // same indexing: fragment capacity, then the first fragment slot
     unsigned pair_cap;
     const uint4* calc_table;  // kCalcEntryUnits per (style, pass-1), built by style_calc_kernel
     uint4* geom;           // geometry scratch, 16-byte units
@@ -428,23 +433,38 @@ __global__ void style_calc_kernel(Scene s, uint4* table) {
 // raster_kernel walks one after the other: three times the CTAs of a per-tile kernel (a chunk of 256 tiles no longer
 // leaves half of the SMs without a plan CTA) and no dependency between the passes.
 // ------------------------------------------------------------------------------------------------------
+// Low zooms over a large image put millions of styled areas into a handful of tiles (C4: z10-z12).  The host then cuts every
+// (tile, pass) sub-list into `plan_slices` slices of whole 256-generation steps with a CTA each: plan_count_kernel counts the
+// visible generations per slice, plan_scan_kernel turns the counts into the slices' first list positions, and the slices
+// compact into the same ordered list a single CTA would have written.  (In an attempt that overflows a scratch allocator an op
+// is dropped AFTER it was counted and leaves a hole -- such an attempt is discarded by the host and its consumers stop at the
+// overflow flag.)
+// ------------------------------------------------------------------------------------------------------
 constexpr int kPlanThreads = 256;
 
-__global__ void __launch_bounds__(kPlanThreads) plan_ops_kernel(Scene s) {
+template <bool kCountOnly>
+__device__ __forceinline__ void plan_ops_body(const Scene& s) {
     __shared__ unsigned warp_cnt[kPlanThreads / 32];
     __shared__ unsigned running;
-    const unsigned t = blockIdx.x / 3u, the_pass = blockIdx.x % 3u;
+    const unsigned S = s.plan_slices, list_id = blockIdx.x / S, slice = blockIdx.x % S;
+    const unsigned t = list_id / 3u, the_pass = list_id % 3u;
     unsigned base = s.area_begin[t];
     unsigned n = s.area_begin[t + 1] - base;
     const unsigned g_begin = the_pass * n, total = g_begin + n;
+    // the slice's generations: whole steps of kPlanThreads, so that the steps of all slices are the steps of the single-CTA loop
+    const unsigned steps = (n + kPlanThreads - 1u) / kPlanThreads, steps_per_slice = (steps + S - 1u) / S;
+    const unsigned long long s_lo = (unsigned long long)g_begin + (unsigned long long)slice * steps_per_slice * kPlanThreads;
+    const unsigned long long s_hi = min((unsigned long long)total, s_lo + (unsigned long long)steps_per_slice * kPlanThreads);
     const unsigned long long list0 = 3ull * base + (unsigned long long)the_pass * n;  // first slot of this pass's sub-list
     VisOp* vis = s.vis + list0;
     const int D = s.D;
     const TileXform xf = make_xform(s.tiles[t]);
     unsigned long long refs_total = 0;
-    if (threadIdx.x == 0) running = 0;
+    const unsigned first_pos = (S > 1u && !kCountOnly) ? s.plan_slice_base[blockIdx.x] : 0u;
+    if (threadIdx.x == 0) running = first_pos;
     __syncthreads();
-    for (unsigned start = g_begin; start < total; start += kPlanThreads) {
+    for (unsigned long long start64 = s_lo; start64 < s_hi; start64 += kPlanThreads) {
+        const unsigned start = (unsigned)start64;
         unsigned g = start + threadIdx.x;
         bool visible = false;
         unsigned long long refs = 0;
@@ -545,6 +565,11 @@ __global__ void __launch_bounds__(kPlanThreads) plan_ops_kernel(Scene s) {
                 }
             }
         }
+        if (kCountOnly) {  // (block-uniform: every thread of the CTA takes this branch)
+            const unsigned bal = __ballot_sync(0xffffffffu, visible);
+            if (lane_id() == 0 && bal) atomicAdd(&running, (unsigned)__popc(bal));
+            continue;
+        }
         // scratch allocation (order irrelevant); failure marks the op invisible and raises the overflow flag.  Every allocator sees
         // the requests of ALL visible ops even when an earlier one has already failed: one attempt then reports the full need
         // of each, and the host grows them all before the redo.
@@ -628,6 +653,11 @@ __global__ void __launch_bounds__(kPlanThreads) plan_ops_kernel(Scene s) {
         }
         __syncthreads();
     }
+    if (kCountOnly) {
+        __syncthreads();
+        if (threadIdx.x == 0) s.plan_slice_base[blockIdx.x] = running;
+        return;
+    }
     if (the_pass == 0) {
         for (int o = 16; o > 0; o >>= 1) refs_total += __shfl_down_sync(0xffffffffu, refs_total, o);
         if (lane_id() == 0 && refs_total) {
@@ -638,8 +668,24 @@ __global__ void __launch_bounds__(kPlanThreads) plan_ops_kernel(Scene s) {
         }
     }
     if (threadIdx.x == 0) {
-        s.vis_count[blockIdx.x] = running;  // [3 * tile + pass]
-        atomicAdd(&s.counters[CNT_VISIBLE], running);
+        if (slice == S - 1u) s.vis_count[list_id] = running;  // [3 * tile + pass]: the last slice ends where the list ends
+        atomicAdd(&s.counters[CNT_VISIBLE], running - first_pos);
+    }
+}
+
+__global__ void __launch_bounds__(kPlanThreads) plan_ops_kernel(Scene s) { plan_ops_body<false>(s); }
+__global__ void __launch_bounds__(kPlanThreads) plan_count_kernel(Scene s) { plan_ops_body<true>(s); }
+
+// one thread per (tile, pass): counts of its slices -> first list positions
+__global__ void plan_scan_kernel(Scene s) {
+    const unsigned l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= 3u * s.n_tiles) return;
+    unsigned* c = s.plan_slice_base + (size_t)l * s.plan_slices;
+    unsigned acc = 0;
+    for (unsigned k = 0; k < s.plan_slices; ++k) {
+        const unsigned v = c[k];
+        c[k] = acc;
+        acc += v;
     }
 }
 
@@ -1435,7 +1481,13 @@ __device__ __forceinline__ unsigned seg_block_steps(const int4 sr, int reach, in
     return kb >= ka ? (unsigned)(kb - ka + 1) : 0u;
 }
 
-__global__ void __launch_bounds__(kBinThreads) bin_ops_kernel(Scene s) {
+// kMode 0: a CTA per block area runs both sweeps (bin_ops_kernel).  Low zooms put millions of visible ops into a handful of
+// tiles (C4: z10-z12); the host then cuts the chunk sequence of a block area (the 256-op chunks of the Fill, Casing and Stroke
+// lists, in that order) into `bin_slices` slices with a CTA each: kMode 1 = the counting sweep of a slice (bin_count_kernel),
+// bin_scan_kernel = per block the slices' counts -> first entry / first fragment slot plus the block area's one bump allocation,
+// kMode 2 = the writing sweep (bin_write_kernel).  A block's entries stay contiguous and in generation order: slice after slice.
+template <int kMode>
+__device__ __forceinline__ void bin_ops_body(const Scene& s) {
     __shared__ short4 s_bb[kBinThreads];
     __shared__ uint4 s_rop[kBinThreads];  // first half of the RasterOp: a, b, (y0, y1), (kind, rgb)
     __shared__ unsigned s_reach[kBinThreads];
@@ -1453,7 +1505,9 @@ __global__ void __launch_bounds__(kBinThreads) bin_ops_kernel(Scene s) {
     static_assert(kBinThreads == 256, "area layout");
     const unsigned areas_x = (unsigned)bpr / 16u;
     const unsigned groups = areas_x * ((unsigned)bpc / 16u);
-    const unsigned tile = blockIdx.x / groups, grp = blockIdx.x % groups;
+    const unsigned S = kMode == 0 ? 1u : s.bin_slices;
+    const unsigned cta = blockIdx.x / S, slice = blockIdx.x % S;
+    const unsigned tile = cta / groups, grp = cta % groups;
     const unsigned warp_in = threadIdx.x >> 5, lane_in = threadIdx.x & 31u;
     const int rbx = (int)((grp % areas_x) * 16u + (warp_in & 1u) * 8u), rby = (int)((grp / areas_x) * 16u + (warp_in >> 1) * 4u);
     const int bxi = rbx + (int)(lane_in & 7u), byi = rby + (int)(lane_in >> 3);
@@ -1468,13 +1522,32 @@ __global__ void __launch_bounds__(kBinThreads) bin_ops_kernel(Scene s) {
     const unsigned n_areas_tile = s.area_begin[tile + 1] - base;
     unsigned out_ent = 0;
     unsigned long long out_cap = 0;
-    for (int sweep = 0; sweep < 2; ++sweep) {
+    // the slice's chunks of the concatenated chunk sequence (kMode 0: all of them)
+    unsigned c_lo = 0, c_hi = 0xffffffffu;
+    if (kMode != 0) {
+        unsigned total_chunks = 0;
+        for (unsigned p = 0; p < 3u; ++p) total_chunks += (s.vis_count[3u * tile + p] + kBinThreads - 1u) / kBinThreads;
+        const unsigned per = (total_chunks + S - 1u) / S;
+        c_lo = min(total_chunks, slice * per);
+        c_hi = min(total_chunks, c_lo + per);
+    }
+    if (kMode == 2) {
+        out_ent = s.bin_cnt_ent[(size_t)blockIdx.x * kBinThreads + threadIdx.x];
+        out_cap = s.bin_cnt_cap[(size_t)blockIdx.x * kBinThreads + threadIdx.x];
+    }
+    for (int sweep = (kMode == 2 ? 1 : 0); sweep < (kMode == 1 ? 1 : 2); ++sweep) {
         unsigned n_ent = 0;
         unsigned long long cap_sum = 0;
+        unsigned chunk_base = 0;
         for (unsigned the_pass = 0; the_pass < 3u; ++the_pass) {
             const unsigned long long list0 = 3ull * base + (unsigned long long)the_pass * n_areas_tile;
             const unsigned n_vis = s.vis_count[3u * tile + the_pass];
-            for (unsigned chunk = 0; chunk < n_vis; chunk += kBinThreads) {
+            const unsigned n_chunks = (n_vis + kBinThreads - 1u) / kBinThreads;
+            const unsigned ci_lo = c_lo > chunk_base ? min(n_chunks, c_lo - chunk_base) : 0u;
+            const unsigned ci_hi = c_hi > chunk_base ? min(n_chunks, c_hi - chunk_base) : 0u;
+            chunk_base += n_chunks;
+            for (unsigned ci = ci_lo; ci < ci_hi; ++ci) {
+                const unsigned chunk = ci * kBinThreads;
                 __syncthreads();
                 const unsigned vi = chunk + threadIdx.x;
                 if (vi < n_vis) {
@@ -1542,6 +1615,11 @@ __global__ void __launch_bounds__(kBinThreads) bin_ops_kernel(Scene s) {
                 }
             }
         }
+        if (kMode == 1) {  // the slice's counts; bin_scan_kernel turns them into offsets
+            s.bin_cnt_ent[(size_t)blockIdx.x * kBinThreads + threadIdx.x] = n_ent;
+            s.bin_cnt_cap[(size_t)blockIdx.x * kBinThreads + threadIdx.x] = cap_sum;
+            return;
+        }
         if (sweep == 0) {
             // exclusive scan over the CTA's threads, one global bump allocation per CTA
             unsigned incl_e = n_ent;
@@ -1587,6 +1665,91 @@ __global__ void __launch_bounds__(kBinThreads) bin_ops_kernel(Scene s) {
             if (!s_go) return;
             if (live) s.blk_range[(size_t)tile * nblk + b] = make_uint2(out_ent, n_ent);
         }
+    }
+}
+
+__global__ void __launch_bounds__(kBinThreads) bin_ops_kernel(Scene s) { bin_ops_body<0>(s); }
+__global__ void __launch_bounds__(kBinThreads) bin_count_kernel(Scene s) { bin_ops_body<1>(s); }
+__global__ void __launch_bounds__(kBinThreads) bin_write_kernel(Scene s) { bin_ops_body<2>(s); }
+
+// one CTA per block area, a thread per block (bin_ops_body's thread layout): the slices' counts of the block -> the slices' first
+// entry and first fragment slot; the CTA scan and the one bump allocation per CTA are bin_ops_body's own
+__global__ void __launch_bounds__(kBinThreads) bin_scan_kernel(Scene s) {
+    __shared__ unsigned w_ent[kBinThreads / 32];
+    __shared__ unsigned long long w_cap[kBinThreads / 32];
+    __shared__ unsigned base_ent;
+    __shared__ unsigned long long base_cap;
+    __shared__ int s_go;
+    const int D = s.D;
+    const int bpr = D / kBW, bpc = D / kBH, nblk = bpr * bpc;
+    const unsigned areas_x = (unsigned)bpr / 16u;
+    const unsigned groups = areas_x * ((unsigned)bpc / 16u);
+    const unsigned S = s.bin_slices, cta = blockIdx.x;
+    const unsigned tile = cta / groups, grp = cta % groups;
+    const unsigned warp_in = threadIdx.x >> 5, lane_in = threadIdx.x & 31u;
+    const int rbx = (int)((grp % areas_x) * 16u + (warp_in & 1u) * 8u), rby = (int)((grp / areas_x) * 16u + (warp_in >> 1) * 4u);
+    const int bxi = rbx + (int)(lane_in & 7u), byi = rby + (int)(lane_in >> 3);
+    const unsigned b = (unsigned)(byi * bpr + bxi);
+    if (threadIdx.x == 0) s_go = s.counters[CNT_OVERFLOW] == 0u;
+    __syncthreads();
+    if (!s_go) return;
+    unsigned n_ent = 0;
+    unsigned long long cap_sum = 0;
+    for (unsigned k = 0; k < S; ++k) {
+        const size_t idx = ((size_t)cta * S + k) * kBinThreads + threadIdx.x;
+        n_ent += s.bin_cnt_ent[idx];
+        cap_sum += s.bin_cnt_cap[idx];
+    }
+    unsigned incl_e = n_ent;
+    unsigned long long incl_c = cap_sum;
+    for (int off = 1; off < 32; off <<= 1) {
+        const unsigned ye = __shfl_up_sync(0xffffffffu, incl_e, off);
+        const unsigned long long yc = __shfl_up_sync(0xffffffffu, incl_c, off);
+        if ((int)lane_id() >= off) {
+            incl_e += ye;
+            incl_c += yc;
+        }
+    }
+    const unsigned w = threadIdx.x >> 5;
+    if (lane_id() == 31) {
+        w_ent[w] = incl_e;
+        w_cap[w] = incl_c;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long te = 0, tc = 0;
+        for (unsigned k = 0; k < kBinThreads / 32; ++k) {
+            te += w_ent[k];
+            tc += w_cap[k];
+        }
+        const bool te_ok = te <= 0xfffffff0ull;
+        base_ent = (te && te_ok) ? atomicAdd(&s.counters[CNT_BIN_ENTRIES], (unsigned)te) : 0u;
+        base_cap = tc ? atomicAdd(reinterpret_cast<unsigned long long*>(&s.counters[CNT_WALK_ALPHA]), tc) : 0ull;
+        const bool ent_fits = te_ok && (unsigned long long)base_ent + te <= s.entries_cap;
+        const bool cap_fits = base_cap + tc <= s.frag_cap && base_cap + tc <= 0xfffffff0ull;
+        if (!ent_fits) atomicOr(&s.counters[CNT_OVERFLOW], 64u);
+        if (!cap_fits) atomicOr(&s.counters[CNT_OVERFLOW], 4u);
+        s_go = ent_fits && cap_fits;
+    }
+    __syncthreads();
+    if (!s_go) return;  // (bin_write_kernel and everything behind it stop at the overflow flag)
+    unsigned e = base_ent;
+    unsigned long long c = base_cap;
+    for (unsigned k = 0; k < w; ++k) {
+        e += w_ent[k];
+        c += w_cap[k];
+    }
+    e += incl_e - n_ent;
+    c += incl_c - cap_sum;
+    s.blk_range[(size_t)tile * nblk + b] = make_uint2(e, n_ent);
+    for (unsigned k = 0; k < S; ++k) {
+        const size_t idx = ((size_t)cta * S + k) * kBinThreads + threadIdx.x;
+        const unsigned ve = s.bin_cnt_ent[idx];
+        const unsigned long long vc = s.bin_cnt_cap[idx];
+        s.bin_cnt_ent[idx] = e;
+        s.bin_cnt_cap[idx] = c;
+        e += ve;
+        c += vc;
     }
 }
 

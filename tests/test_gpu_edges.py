@@ -36,6 +36,36 @@ def test_scratch_overflow_grows_and_redoes_the_batch(fx):
     assert (got == want).all()
 
 
+def test_sliced_plan_lists_equal_the_single_cta_lists(fx):
+    """debug key plan_slice_areas: every (tile, pass) list is cut into slices with a CTA each (the low-zoom form of
+    plan_ops_kernel, C4) -- same tiles as the oracle's, also through the grow-and-redo path and the chunked host pipeline"""
+    from osm_renderer_b200.drawer import GpuContext
+
+    for name, per in (("14", 300), ("17", 256), ("16", 1000), ("18_2x", 200)):
+        tiles, begins, areas = fx.batches[name]
+        if name == "18_2x":  # @2x: four block areas per tile; six tiles are enough
+            tiles, begins = tiles[30:36], begins[30:37] - begins[30]
+            areas = areas[fx.batches[name][1][30] : fx.batches[name][1][36]]
+        want = np.stack(oracle.draw_tiles(fx.bin, fx.table, tiles, begins, areas, fx.canvas_rgb, True, n_threads=8))
+        ctx = GpuContext(0)
+        try:
+            ctx.set_geodata(fx.bin)
+            ctx.set_table(fx.table)
+            ctx.debug_set("plan_slice_areas", per)
+            got = ctx.draw_tiles(tiles, begins, areas, fx.canvas_rgb, True)
+            assert (got == want).all(), name
+            assert ctx.stats()["kernel_launches"] > 8  # plan_count_kernel + plan_scan_kernel ran
+            ctx.debug_set("scratch_units", 64)
+            ctx.debug_set("work_items", 16)
+            got = ctx.draw_tiles(tiles, begins, areas, fx.canvas_rgb, True)
+            assert (got == want).all(), name + " (redo)"
+            ctx.debug_set("host_chunks", 3)
+            got = ctx.draw_tiles(tiles, begins, areas, fx.canvas_rgb, True)
+            assert (got == want).all(), name + " (chunks)"
+        finally:
+            ctx.close()
+
+
 def test_resident_batch_api_equals_one_shot(fx, gpu_ctx):
     tiles, begins, areas = fx.batches["16"]
     one = gpu_ctx.draw_tiles(tiles, begins, areas, fx.canvas_rgb, True)
