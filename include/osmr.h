@@ -323,7 +323,7 @@ void osmr_free_pinned(void* p);
  *                           of the even-odd rule is exercised on ordinary data (also switches the row-parallel path off);
  *   "scratch_units" (n)     restarts the bump-allocated geometry / mask / walk-cache scratch at n units and "work_items" (n)
  *                           pretends the per-op work lists hold n items, so the grow-and-redo paths run;
- *   "plan_slice_areas" (n)  styled areas per slice of plan_ops_kernel's (tile, pass) lists (0: default 32768; small values
+ *   "plan_slice_areas" (n)  styled areas per slice of plan_ops_kernel's (tile, pass) lists (0: default 16384; small values
  *                           exercise the sliced form on ordinary tiles);
  *   "label_threads" (1..256) host threads of the label layout;
  *   "host_chunks" (0..16)   equal draw chunks of a host-output call (0: the tapered default schedule);

@@ -284,7 +284,7 @@ struct osmr_ctx {
     DevBuf<unsigned> plan_slice_base;  // per (tile, pass, slice) of a chunk: plan_count_kernel's counts, then their scan
     DevBuf<unsigned> bin_cnt_ent;      // per (block area, slice, block) of a chunk: bin_count_kernel's counts, then bin_scan_kernel's offsets
     DevBuf<unsigned long long> bin_cnt_cap;
-    unsigned plan_slice_areas = 0;     // debug key "plan_slice_areas": styled areas per plan slice (0: the default, 32768)
+    unsigned plan_slice_areas = 0;     // debug key "plan_slice_areas": styled areas per plan slice (0: the default, 16384)
     size_t geom_cap_units = 0, mask_cap_words = 0, walk_alpha_cap = 0, walk_len_cap = 0, entries_cap = 0, pair_cap = 0;
     DevBuf<unsigned char> out;
     size_t out_bytes = 0;
@@ -1228,7 +1228,7 @@ static int launch_chunk(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t fla
         // (tile, pass) lists longer than plan_slice_areas styled areas are cut into slices with a CTA each (low zooms, C4)
         unsigned max_n = 0;
         for (unsigned t = tb; t < tb + tc; ++t) max_n = std::max(max_n, ctx->h_area_begin[t + 1] - ctx->h_area_begin[t]);
-        const unsigned per = ctx->plan_slice_areas ? ctx->plan_slice_areas : 32768u;
+        const unsigned per = ctx->plan_slice_areas ? ctx->plan_slice_areas : 16384u;
         const unsigned slices = std::min(256u, std::max(1u, (max_n + per - 1u) / per));
         s.plan_slices = slices;
         s.plan_slice_base = nullptr;
@@ -1252,7 +1252,7 @@ static int launch_chunk(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t fla
         if (s.plan_slices > 1u) {
             unsigned max_n = 0;
             for (unsigned t = tb; t < tb + tc; ++t) max_n = std::max(max_n, ctx->h_area_begin[t + 1] - ctx->h_area_begin[t]);
-            const unsigned per = std::max(1u, (ctx->plan_slice_areas ? ctx->plan_slice_areas : 32768u) / 4u);
+            const unsigned per = std::max(1u, (ctx->plan_slice_areas ? ctx->plan_slice_areas : 16384u) / 4u);
             bslices = std::min(256u, std::max(1u, (max_n + per - 1u) / per));
             while (bslices > 1u && (size_t)bin_ctas * bslices * kBinThreads * 12u > ((size_t)1 << 30)) bslices /= 2u;
         }

@@ -1,5 +1,5 @@
 """Dry run of bench.py's whole flow in the GPU-less container: torch.cuda is stubbed, the library is the emulated one and
-the C2 workload is cut to 4x4 tiles.  Checks that the script assembles its JSON line (every key the driver reads) --
+the C2 workload is cut to 3x3 tiles.  Checks that the script assembles its JSON line (every key the driver reads) --
 the numbers mean nothing.
 
     python tests/emu/bench_dry_run.py
@@ -46,7 +46,7 @@ def main():
     torch.empty = empty
     import bench
 
-    bench.WORKLOADS["C2"] = dict(zoom=14, x0=9900, y0=5118, n=4, scale=1, metro={})  # 16 tiles around the fixture tile
+    bench.WORKLOADS["C2"] = dict(zoom=14, x0=9900, y0=5118, n=3, scale=1, metro={})  # 9 tiles around the fixture tile
     sys.argv = ["bench.py", "--steps", "1", "--warmup", "1", "--lib", lib, "--cpu-sample", "4", "--min-seconds", "0.01", "--no-affinity"]
     buf = io.StringIO()
     with redirect_stdout(buf):
