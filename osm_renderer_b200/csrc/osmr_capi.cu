@@ -214,6 +214,7 @@ struct osmr_ctx {
     std::vector<uint32_t> h_label_begin;
     bool batch_has_labels = false;
     bool resident_needs_host_layout = false;  // osmr_batch_draw_labeled's last verdict (osmr_draw_tiles_auto_labeled falls back on it)
+    bool label_cull = true;        // debug key "label_cull": labels that cannot reach the tile get no outlines and no coverage
     unsigned label_chunks = 0;     // debug key "label_chunks"
     unsigned curve_leaf_cap = 0;   // debug key "curve_leaf_cap" (tests: curves with more leaves are flattened again by one lane)
     bool label_host_only = false;  // debug key "label_host": always lay labels out on the host (round-1 path)
@@ -583,6 +584,10 @@ int osmr_debug_set(osmr_ctx* ctx, const char* key, int value) try {
     if (strcmp(key, "work_items") == 0) {
         if (value < 1) return ctx->fail(OSMR_E_INVALID, "work_items must be positive");
         ctx->work_items_limit = (unsigned)value;
+        return OSMR_OK;
+    }
+    if (strcmp(key, "label_cull") == 0) {
+        ctx->label_cull = value != 0;
         return OSMR_OK;
     }
     if (strcmp(key, "plan_slice_areas") == 0) {
@@ -2480,6 +2485,7 @@ static int label_device_enqueue(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t 
     ld.heap = ctx->l_heap.p;
     ld.heap_slots = (unsigned)ctx->l_heap_slots;
     ld.counters = ctx->l_counters.p;
+    ld.cull = ctx->label_cull ? 1u : 0u;
     const unsigned wide = (unsigned)ctx->num_sms * 8u;
     const Scene s_all = s;
     const LabelDev ld_all = ld;
@@ -2515,6 +2521,7 @@ static int label_device_enqueue(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t 
         ld.counters = ctx->l_counters.p + (size_t)ch * LCNT_COUNT;
         label_select_kernel<<<tc, kLabelSelThreads, 0, st>>>(s, ld);
         label_layout_kernel<<<tc, kLayoutThreads, 0, st>>>(s, ld);
+        label_cull_kernel<<<tc, kCullThreads, 0, st>>>(s, ld);
         label_vfill_kernel<<<wide, 128, 0, st>>>(ld);
         label_vline_count_kernel<<<wide, 128, 0, st>>>(ld);
         label_curve_count_kernel<<<wide, 128, 0, st>>>(ld);
@@ -2622,6 +2629,7 @@ static int label_device_judge(osmr_ctx* ctx) {
             fprintf(stderr, "[osmr labels] chunk %u (%u tiles): active %u places %u segs %u rows %u cells %llu ring_pts %u polylabel %u covered %u curves %u\n", ch,
                     ctx->lchunk_tc[ch], c[LCNT_ACTIVE], c[LCNT_PLACES], c[LCNT_SEGS], c[LCNT_ROWRECS], cells_of(c), c[LCNT_RING_PTS], c[LCNT_POLY], c[LCNT_COVER],
                     c[LCNT_CURVES]);
+        if (getenv("OSMR_LABEL_DEBUG")) fprintf(stderr, "[osmr labels]   culled %u of %u active labels\n", c[LCNT_CULLED], c[LCNT_ACTIVE]);
     }
     return 0;
 }
@@ -2632,7 +2640,7 @@ static void resident_label_stats(osmr_ctx* ctx, uint32_t attempts) {
     cudaEventElapsedTime(&ms, ctx->ev_label0, ctx->ev_label1);
     ctx->stats.ms_label_layout = 0.f;
     ctx->stats.ms_label_device = ms;
-    ctx->stats.kernel_launches += 13 * ctx->n_lchunks + 1;
+    ctx->stats.kernel_launches += 14 * ctx->n_lchunks + 1;
     ctx->stats.label_path = 1;
     ctx->stats.n_labels_active = ctx->stats_label_active;
     ctx->stats.n_labels_polylabel = ctx->stats_label_poly;
@@ -2777,7 +2785,7 @@ int osmr_draw_tiles_labeled(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_ti
             ctx->stats.ms_label_layout = enqueue_ms;  // host time spent on labels: table look-ups and launches only
             ctx->stats.ms_label_device = ms;
             ctx->stats.ms_total += ms;
-            ctx->stats.kernel_launches += 13 * ctx->n_lchunks + 1;
+            ctx->stats.kernel_launches += 14 * ctx->n_lchunks + 1;
             ctx->stats.label_path = 1;
             ctx->stats.n_labels_active = ctx->stats_label_active;
             ctx->stats.n_labels_polylabel = ctx->stats_label_poly;

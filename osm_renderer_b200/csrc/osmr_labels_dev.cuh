@@ -66,6 +66,7 @@ enum {
     LCNT_CURVE_CURSOR_C = 16,  // work distribution of the curve kernels (counting / writing sweep)
     LCNT_CURVE_CURSOR_W = 17,
     LCNT_SCAN_OVF = 15,  // (overflow word of the block-sum scan: segment counts beyond 2^32 also trip the capacity check)
+    LCNT_CULLED = 18,    // statistics: active labels label_cull_kernel took out
     LCNT_COUNT = 20
 };
 
@@ -85,7 +86,7 @@ struct LabelPlace {  // layout result of an active label
     unsigned place_off;  // first GlyphPlace
     unsigned n_places;
     unsigned rgb;
-    unsigned pad;
+    unsigned dead;  // label_cull_kernel: the label cannot reach the tile, directly or through a chain of collisions
     double scale;  // font units -> pixels
     double gcy;    // (descent + ascent) / 2 (text on a line)
     unsigned vinst_off;  // first outline vertex instance of the label (its glyphs' vertices, glyph after glyph)
@@ -146,6 +147,7 @@ struct LabelDev {
     unsigned char* heap;  // polylabel heaps: kPolyHeapCap cells per label that needs one
     unsigned heap_slots;
     unsigned* counters;  // LCNT_*
+    unsigned cull;       // 0: every active label gets its outlines and coverage (debug key "label_cull")
 };
 
 // ------------------------------------------------------------------------------------------------------
@@ -496,7 +498,7 @@ __global__ void __launch_bounds__(kLayoutThreads) label_layout_kernel(Scene s, L
         lp.place_off = 0;
         lp.n_places = 0;
         lp.rgb = st.rgb;
-        lp.pad = 0;
+        lp.dead = 0;
         lp.scale = 0.0;
         lp.gcy = 0.0;
         lp.vinst_off = 0;
@@ -985,6 +987,121 @@ __device__ __forceinline__ unsigned emit_vertex(const LabelDev& ld, const GlyphP
     return sink.n;
 }
 
+// ------------------------------------------------------------------------------------------------------
+// label_cull_kernel: one CTA per tile, between the layout and the outline pass.
+// The reference lays out and rasterises every label of the 3x3 neighbourhood, but a tile shows only its own 256 x 256 pixels: a
+// label matters if its pixels can reach the tile, or if it can block -- directly or through a chain -- a label that does.  A
+// label g fails exactly when one of its pixels is held by an EARLIER successful label (tile_pixels.rs:131-148), so with
+// conservative pixel boxes B:   needed(g) = B(g) meets the tile  or  B(g) meets B(g') of a needed LATER label g'.
+// One backward sweep decides it (needed(g) depends on later labels only).  Everything else is marked dead: no outlines, no
+// coverage, no pixels claimed -- no needed label can tell the difference.  B = the icon rectangle + the hull of every outline
+// point of every glyph (the bounds label_finish_kernel derives its proven coverage window from, two pixels wider).
+// The neighbourhood is nine times the tile, so most labels of a tile's list are dead.
+// ------------------------------------------------------------------------------------------------------
+constexpr unsigned kCullCap = 1024;  // labels of a tile decided in shared memory; a longer list is not culled
+constexpr int kCullThreads = 128;
+
+__global__ void __launch_bounds__(kCullThreads) label_cull_kernel(Scene s, LabelDev ld) {
+    __shared__ int4 box[kCullCap];  // x0, y0, x1, y1 (x0 > x1: no pixels)
+    __shared__ unsigned char needed[kCullCap];
+    const unsigned t = blockIdx.x;
+    const unsigned first = ld.label_begin[t];
+    const unsigned n_act = ld.act_cnt[t];
+    const int D = s.D;
+    if (!ld.cull || n_act > kCullCap || n_act == 0) return;
+    if (ld.counters[LCNT_OVERFLOW] & 65u) return;  // (places or vertex instances overflowed: the attempt is redone)
+    const double lim = 1.0e9;
+    for (unsigned ai = threadIdx.x; ai < n_act; ai += blockDim.x) {
+        const LabelPlace lp = ld.place[first + ai];
+        long long x0 = 0x7fffffff, y0 = 0x7fffffff, x1 = -0x7fffffff, y1 = -0x7fffffff;
+        bool everywhere = false;  // coordinates beyond any canvas or not finite: never culled, meets everything
+        if (lp.icon >= 0 && (unsigned)lp.icon < ld.n_icons) {
+            const DevIcon ic = ld.icons[lp.icon];
+            x0 = lp.ix;
+            y0 = lp.iy;
+            x1 = (long long)lp.ix + (long long)ic.w - 1;
+            y1 = (long long)lp.iy + (long long)ic.h - 1;
+            if (lp.ix > 1000000000 || lp.ix < -1000000000 || lp.iy > 1000000000 || lp.iy < -1000000000) everywhere = true;
+        }
+        if (lp.mode != 0) {
+            const double inf = __longlong_as_double(0x7ff0000000000000LL);
+            double mnx = inf, mxx = -inf, mny = inf, mxy = -inf;
+            const bool on_line = lp.mode == 1;
+            const double scale = lp.scale, gcy = lp.gcy;
+            for (unsigned gi = lp.place_off; gi < lp.place_off + lp.n_places; ++gi) {
+                const GlyphPlace gp = ld.gplace[gi];
+                if (gp.slot < 0) continue;
+                const double wx = gp.a, wy = gp.b, sn = gp.c, cs = gp.d, gcx = gp.e;
+                auto bound = [&](double px, double py) {  // emit_vertex's transform
+                    double ox, oy;
+                    if (on_line) {
+                        const double tx = px - gcx, ty = py - gcy;
+                        ox = wx + (tx * cs - ty * sn);
+                        oy = wy - (ty * cs + tx * sn);
+                    } else {
+                        ox = wx + px;
+                        oy = wy - py;
+                    }
+                    if (!(ox > -lim && ox < lim && oy > -lim && oy < lim)) everywhere = true;  // (NaN included)
+                    mnx = fmin(mnx, ox);
+                    mxx = fmax(mxx, ox);
+                    mny = fmin(mny, oy);
+                    mxy = fmax(mxy, oy);
+                };
+                const unsigned v0 = ld.glyph_vbegin[gp.slot], v1 = ld.glyph_vbegin[gp.slot + 1];
+                if (v1 > v0) bound(0.0, 0.0);  // `from` of the first vertex
+                for (unsigned vi = v0; vi < v1; ++vi) {
+                    const DevVertex v = ld.verts[vi];
+                    bound((double)v.x * scale, (double)v.y * scale);
+                    if (v.type == 3) bound((double)v.cx * scale, (double)v.cy * scale);
+                }
+            }
+            if (mnx <= mxx && !everywhere) {  // label_finish_kernel's window (floor - 1 .. floor + 2), two pixels wider
+                x0 = min(x0, (long long)floor(mnx) - 3);
+                y0 = min(y0, (long long)floor(mny) - 3);
+                x1 = max(x1, (long long)floor(mxx) + 4);
+                y1 = max(y1, (long long)floor(mxy) + 4);
+            }
+        }
+        if (everywhere) {
+            x0 = y0 = -0x7fffffff;
+            x1 = y1 = 0x7fffffff;
+        }
+        box[ai] = make_int4((int)x0, (int)y0, (int)x1, (int)y1);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {  // the backward sweep: one warp, a label at a time, the lanes over the later labels
+        const unsigned lane = threadIdx.x;
+        for (int g = (int)n_act - 1; g >= 0; --g) {
+            const int4 b = box[g];
+            bool need = false;
+            if (b.x <= b.z && b.y <= b.w) {
+                need = b.x <= D - 1 && b.z >= 0 && b.y <= D - 1 && b.w >= 0;
+                for (unsigned h = (unsigned)g + 1u + lane; !need && h - lane < n_act; h += 32) {
+                    bool hit = false;
+                    if (h < n_act && needed[h]) {
+                        const int4 o = box[h];
+                        hit = o.x <= o.z && b.x <= o.z && b.z >= o.x && b.y <= o.w && b.w >= o.y;
+                    }
+                    need = __any_sync(0xffffffffu, hit);
+                }
+            }
+            need = __shfl_sync(0xffffffffu, need ? 1 : 0, 0) != 0;  // (uniform already; keeps the warp converged for the store)
+            if (lane == 0) needed[g] = need ? 1 : 0;
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    unsigned culled = 0;
+    for (unsigned ai = threadIdx.x; ai < n_act; ai += blockDim.x) {
+        if (!needed[ai]) {
+            ld.place[first + ai].dead = 1u;
+            ++culled;
+        }
+    }
+    if (culled) atomicAdd(&ld.counters[LCNT_CULLED], culled);
+}
+
 // The outline pass.  A glyph is ~30 vertices: straight lines (one draw_line each) and quadratic curves (~64 draw_line calls each
 // under the 1.0001 flatness rule, ~20k instructions).  Lanes that hold lines would idle next to lanes that hold curves, so the
 // curves get a compact work list of their own and every lane of the curve kernels flattens a curve:
@@ -1003,6 +1120,13 @@ __global__ void __launch_bounds__(128) label_vfill_kernel(LabelDev ld) {
         if (lp.mode == 0) continue;  // the label lost its vertex block to an overflow
         const unsigned v0 = ld.glyph_vbegin[gp.slot], v1 = ld.glyph_vbegin[gp.slot + 1];
         const unsigned vo = ld.place_vinst[gi];
+        if (lp.dead) {  // label_cull_kernel: its vertex instances draw nothing and belong to no glyph
+            for (unsigned vi = v0; vi < v1; ++vi) {
+                ld.vinst_place[vo + (vi - v0)] = 0xffffffffu;
+                ld.vcnt[vo + (vi - v0)] = 0u;
+            }
+            continue;
+        }
         const double scale = lp.scale;
         const bool on_line = lp.mode == 1;
         const double wx = gp.a, wy = gp.b, sn = gp.c, cs = gp.d, gcx = gp.e, gcy = lp.gcy;
@@ -1077,6 +1201,7 @@ __device__ __forceinline__ void label_vline_body(const LabelDev& ld) {
     if (WRITE && (ld.counters[LCNT_OVERFLOW] || ld.counters[LCNT_FALLBACK])) return;
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n_verts; i += gridDim.x * blockDim.x) {
         const unsigned gi = ld.vinst_place[i];
+        if (gi == 0xffffffffu) continue;  // a culled label's instance
         const unsigned vi = ld.glyph_vbegin[ld.gplace[gi].slot] + (i - ld.place_vinst[gi]);
         if (ld.verts[vi].type == 3) continue;  // curves: label_curve_kernel
         label_vertex_instance<WRITE>(ld, i);
@@ -1452,7 +1577,8 @@ __global__ void __launch_bounds__(128) label_finish_kernel(Scene s, LabelDev ld)
         L.n_ranges = 0;
         L.range_off = 0;
         L.cell_off = 0;
-        if (lp.mode != 0 && lp.n_vinst) {
+        if (lp.dead) L.icon = -2;  // (no icon, no segments: label_commit_kernel passes over it)
+        if (lp.mode != 0 && lp.n_vinst && !lp.dead) {
             const unsigned sb = ld.vcnt[lp.vinst_off], n_segs = ld.vcnt[lp.vinst_off + lp.n_vinst] - sb;
             if (n_segs) {
                 double min_x = __longlong_as_double(0x7ff0000000000000LL), min_y = min_x;

@@ -183,3 +183,23 @@ def test_curves_beyond_the_leaf_code_record_are_flattened_again(fx, label_ctx):
     diff[:, 0, :] = False
     diff[:, :, 255] = False
     assert diff.sum() == 0
+
+
+def test_label_cull_changes_no_pixel(fx, label_ctx):
+    """label_cull_kernel drops the labels of the 3x3 neighbourhood that cannot reach the tile, directly or through a chain of
+    collisions, before their outlines are flattened: same tiles with and without it, far fewer outline segments with it."""
+    ctx, per = label_ctx
+    for name in ("16", "18_2x"):
+        tiles, begins, areas = fx.batches[name]
+        lb, labels = per[name]
+        culled = ctx.draw_tiles_labeled(tiles, begins, areas, lb, labels, fx.canvas_rgb, True)
+        st1 = ctx.stats()
+        try:
+            ctx.debug_set("label_cull", 0)
+            full = ctx.draw_tiles_labeled(tiles, begins, areas, lb, labels, fx.canvas_rgb, True)
+            st0 = ctx.stats()
+        finally:
+            ctx.debug_set("label_cull", 1)
+        assert (culled == full).all(), name
+        assert st1["label_path"] == 1 and st0["label_path"] == 1
+        assert st1["n_labels_active"] == st0["n_labels_active"] and 0 < st1["n_label_segments"] < st0["n_label_segments"] / 2
