@@ -158,6 +158,7 @@ struct osmr_ctx {
     float stats_label_layout_ms = 0.f, stats_label_device_ms = 0.f;
     unsigned label_threads = 32;
     DevBuf<LabelPix> label_plane;
+    DevBuf<unsigned> label_pmask;  // per tile D*D bits: the pending pixels of label_plane
     bool label_plane_active = false;
     // label layout on the device (osmr_labels_dev.cuh): resident tables + per-call scratch
     struct LabelResident {
@@ -480,6 +481,7 @@ void osmr_ctx_destroy(osmr_ctx* ctx) {
     ctx->label_row_keys.release();
     ctx->h_label_segs.release();
     ctx->label_plane.release();
+    ctx->label_pmask.release();
     ctx->geom.release();
     ctx->scrB.release();
     if (ctx->prep_done) cudaEventDestroy(ctx->prep_done);
@@ -1216,6 +1218,7 @@ static int launch_chunk(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t fla
     s.counters = ctx->counters.p + (size_t)slot * CNT_COUNT;
     s.fill_cap = ctx->fill_cap;
     s.label_plane = ctx->label_plane_active ? ctx->label_plane.p + (size_t)tb * D * D : nullptr;
+    s.label_mask = ctx->label_plane_active ? ctx->label_pmask.p + (size_t)tb * (size_t)(D * D / 32) : nullptr;
     s.label_icon_px = ctx->label_icon_px.p;
     s.out = dev_out;
 
@@ -2069,6 +2072,7 @@ static int labels_via_host(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_til
     CK(ctx->label_acc.reserve(2 * (size_t)cells + 2));
     CK(ctx->label_row_keys.reserve(2 * (size_t)n_rows + 2));
     CK(ctx->label_plane.reserve((size_t)n_tiles * D * D));
+    CK(ctx->label_pmask.reserve((size_t)n_tiles * (size_t)(D * D / 32) + 1));
     CK(cudaEventRecord(ctx->ev_label0, ctx->stream));
     if (!recs.empty()) CK(cudaMemcpyAsync(ctx->d_labels.p, recs.data(), recs.size() * sizeof(DevLabel), cudaMemcpyHostToDevice, ctx->stream));
     if (n_segs) CK(cudaMemcpyAsync(ctx->d_label_segs.p, seg_stage, n_segs * sizeof(DevSeg), cudaMemcpyHostToDevice, ctx->stream));
@@ -2089,6 +2093,7 @@ static int labels_via_host(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_til
     ls.kmin = ctx->label_row_keys.p;
     ls.kmax = ctx->label_row_keys.p + n_rows;
     ls.plane = ctx->label_plane.p;
+    ls.pmask = ctx->label_pmask.p;
     ls.D = D;
     ls.cover_cursor = ctx->d_cover_cursor.p;
     ls.err_flag = ctx->d_cover_cursor.p + 1;
@@ -2339,6 +2344,7 @@ static int label_device_enqueue(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t 
     CK(ctx->l_heap.reserve(ctx->l_heap_slots * (size_t)kPolyHeapCap * sizeof(PolyCell)));
     CK(ctx->label_occ.reserve((size_t)n_tiles * ((size_t)E * E / 32)));
     CK(ctx->label_plane.reserve((size_t)n_tiles * D * D));
+    CK(ctx->label_pmask.reserve((size_t)n_tiles * (size_t)(D * D / 32) + 1));
     ctx->l_places_used_cap = ctx->l_places_cap;
     ctx->l_segs_used_cap = ctx->l_segs_cap;
     ctx->l_rowrecs_used_cap = ctx->l_rowrecs_cap;
@@ -2546,6 +2552,7 @@ static int label_device_enqueue(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t 
         ls.kmin = setb ? B.row_keys.p : ctx->label_row_keys.p;
         ls.kmax = ls.kmin + ctx->l_rowrecs_cap;
         ls.plane = ctx->label_plane.p + (size_t)tb * D * D;
+        ls.pmask = ctx->label_pmask.p + (size_t)tb * (size_t)(D * D / 32);
         ls.D = D;
         ls.n_cover_dev = ld.counters + LCNT_COVER;
         ls.label_cnt = ctx->l_act_cnt.p + tb;

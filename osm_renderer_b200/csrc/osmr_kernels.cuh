@@ -179,6 +179,7 @@ struct Scene {
     unsigned* counters;
     int fill_cap;          // <= kFillCap; lowered by tests to force the streaming path
     const struct LabelPix* label_plane;  // per tile D*D entries written by label_kernel, or nullptr (no label pass)
+    const unsigned* label_mask;          // per tile D*D bits: the pixels of label_plane that hold a pending label pixel
     const double4* label_icon_px;        // premultiplied texels of the label icons
     unsigned char* out;
 };
@@ -2043,9 +2044,13 @@ __global__ void __launch_bounds__(kRasterThreads, OSMR_RASTER_MIN_BLOCKS) raster
     __syncwarp();
     // label pass result (drawer.rs:124 blend_unfinished_pixels(true)): one more premultiplied over per labelled pixel
     if (s.label_plane) {
+        // (a tile has a few hundred labelled pixels: the warp reads the block's 256 mask bits, not 4 KB of LabelPix records)
         const LabelPix* plane = s.label_plane + (size_t)tile * D * D;
+        const unsigned* pmask = s.label_mask + (size_t)tile * (size_t)(D * D / 32);
         for (int i = (int)lane; i < kBP; i += 32) {
-            const LabelPix lp = plane[(size_t)(by0 + i / kBW) * D + bx0 + i % kBW];
+            const size_t pix = (size_t)(by0 + i / kBW) * D + bx0 + i % kBW;
+            if (!((pmask[pix >> 5] >> (pix & 31)) & 1u)) continue;
+            const LabelPix lp = plane[pix];
             if (!lp.src) continue;
             double c0, c1, c2, a;
             if (lp.src & 0x80000000u) {
@@ -2139,6 +2144,7 @@ struct LabelScene {
     int* kmin;       // per (label, row): smallest / largest touched key
     int* kmax;
     LabelPix* plane;  // per tile D*D
+    unsigned* pmask;  // per tile D*D bits: which entries of `plane` are pending pixels of this draw (the rest is stale)
     int D;
     // device-side layout (osmr_labels_dev.cuh): the counts live in device memory and the labels of a tile are label_cnt[tile]
     // records starting at label_begin[tile]; nullptr: host-side layout (n_cover, label_begin is a prefix sum)
@@ -2581,7 +2587,8 @@ __global__ void __launch_bounds__(kLabelThreads) label_commit_kernel(LabelScene 
     unsigned* occ = ls.occ + (size_t)tile * occ_words;
     LabelPix* plane = ls.plane + (size_t)tile * D * D;
     for (unsigned i = threadIdx.x; i < occ_words; i += kLabelThreads) occ[i] = 0u;
-    for (int i = threadIdx.x; i < D * D; i += kLabelThreads) plane[i].src = 0u;
+    unsigned* pmask = ls.pmask + (size_t)tile * (size_t)(D * D / 32);
+    for (int i = threadIdx.x; i < D * D / 32; i += kLabelThreads) pmask[i] = 0u;  // (the plane itself keeps stale records)
     __syncthreads();
     auto in_canvas = [&](int x, int y) { return x >= -D && x <= 2 * D - 1 && y >= -D && y <= 2 * D - 1; };  // labels_bb
     auto occ_index = [&](int x, int y) { return (size_t)(y + D) * E + (size_t)(x + D); };
@@ -2650,6 +2657,7 @@ __global__ void __launch_bounds__(kLabelThreads) label_commit_kernel(LabelScene 
                         px.src = 0x80000000u | (tex0 + (unsigned)(yo * iw + xo));
                         px.pad = 0;
                         plane[(size_t)y * D + x] = px;
+                        atomicOr(&pmask[((size_t)y * D + x) >> 5], 1u << (((size_t)y * D + x) & 31));
                     }
                 }
             }
@@ -2671,6 +2679,7 @@ __global__ void __launch_bounds__(kLabelThreads) label_commit_kernel(LabelScene 
                             px.src = 0x40000000u | (L.rgb & 0xffffffu);
                             px.pad = 0;
                             plane[(size_t)y * D + x] = px;
+                            atomicOr(&pmask[((size_t)y * D + x) >> 5], 1u << (((size_t)y * D + x) & 31));
                         }
                     }
                 }
