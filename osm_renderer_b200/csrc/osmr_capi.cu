@@ -169,6 +169,7 @@ struct osmr_ctx {
         DevBuf<DevGlyphRec> glyphs;
         DevBuf<DevVertex> verts;
         unsigned n_keys = 0, ent_total = 0, way_base = 0, mp_base = 0, n_texts = 0;
+        int font_reach = 0;  // font units: how far an outline point can lie from its glyph's pen position (label_precull_kernel)
         std::vector<uint8_t> way_has_text;  // ways whose text may run along the line: they get direction tables
         struct Angle {
             bool set = false;
@@ -179,6 +180,7 @@ struct osmr_ctx {
     } lres;
     DevBuf<osmr_label> d_label_list;
     DevBuf<ActLabel> l_act;
+    DevBuf<unsigned char> l_predead;  // label_precull_kernel's verdict per active label slot
     DevBuf<unsigned> l_act_cnt, l_counters;
     DevBuf<LabelPlace> l_place;
     DevBuf<GlyphPlace> l_gplace;
@@ -2220,6 +2222,15 @@ static int build_label_tables(osmr_ctx* ctx) {
     CK(R.text_begin.reserve(text_begin.size() + 1));
     CK(R.glyphs.reserve(glyphs.size() + 1));
     CK(R.glyph_vbegin.reserve(glyph_vbegin.size() + 1));
+    {  // bound of label_precull_kernel: outline extents (twice: a glyph on a way turns around its centre), advances, ascent, descent
+        long long max_coord = 0, max_adv = 0;
+        for (const DevVertex& v : verts)
+            max_coord = std::max<long long>(max_coord, std::max(std::max(std::abs((long long)v.x), std::abs((long long)v.y)),
+                                                                std::max(std::abs((long long)v.cx), std::abs((long long)v.cy))));
+        for (const DevGlyphRec& g : glyphs) max_adv = std::max<long long>(max_adv, std::abs((long long)g.advance) + std::abs((long long)g.kern));
+        const long long reach = 2 * max_coord + max_adv + std::abs((long long)ctx->font.ascent()) + std::abs((long long)ctx->font.descent());
+        R.font_reach = (int)std::min<long long>(reach, 0x3fffffff);
+    }
     CK(R.verts.reserve(verts.size() + 1));
     auto up = [&](void* d, const void* h, size_t bytes) { return bytes ? cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, st) : cudaSuccess; };
     CK(up(R.styles.p, dstyles.data(), dstyles.size() * sizeof(DevLabelStyle)));
@@ -2321,6 +2332,7 @@ static int label_device_enqueue(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t 
     CK(ctx->d_label_list.reserve((size_t)n_labels + 1));
     CK(ctx->d_label_begin.reserve(n_tiles + 1));
     CK(ctx->l_act.reserve((size_t)n_labels + 1));
+    CK(ctx->l_predead.reserve((size_t)n_labels + 1));
     CK(ctx->l_place.reserve((size_t)n_labels + 1));
     CK(ctx->d_labels.reserve((size_t)n_labels + 1));
     CK(ctx->l_act_cnt.reserve(n_tiles + 1));
@@ -2433,6 +2445,8 @@ static int label_device_enqueue(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t 
     s.n_polys = ctx->ds->n_polys;
     s.n_mps = ctx->ds->n_mps;
     s.n_ints = ctx->ds->n_ints;
+    s.way_box = ctx->ds->way_box.p;
+    s.mp_box = ctx->ds->mp_box.p;
     s.tiles = ctx->tiles.p;
     s.n_tiles = n_tiles;
     s.D = D;
@@ -2492,6 +2506,8 @@ static int label_device_enqueue(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t 
     ld.heap_slots = (unsigned)ctx->l_heap_slots;
     ld.counters = ctx->l_counters.p;
     ld.cull = ctx->label_cull ? 1u : 0u;
+    ld.predead = ctx->l_predead.p;
+    ld.font_reach = R.font_reach;
     const unsigned wide = (unsigned)ctx->num_sms * 8u;
     const Scene s_all = s;
     const LabelDev ld_all = ld;
@@ -2526,6 +2542,7 @@ static int label_device_enqueue(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t 
         ld.n_tiles = tc;
         ld.counters = ctx->l_counters.p + (size_t)ch * LCNT_COUNT;
         label_select_kernel<<<tc, kLabelSelThreads, 0, st>>>(s, ld);
+        label_precull_kernel<<<tc, kCullThreads, 0, st>>>(s, ld);
         label_layout_kernel<<<tc, kLayoutThreads, 0, st>>>(s, ld);
         label_cull_kernel<<<tc, kCullThreads, 0, st>>>(s, ld);
         label_vfill_kernel<<<wide, 128, 0, st>>>(ld);
@@ -2636,7 +2653,7 @@ static int label_device_judge(osmr_ctx* ctx) {
             fprintf(stderr, "[osmr labels] chunk %u (%u tiles): active %u places %u segs %u rows %u cells %llu ring_pts %u polylabel %u covered %u curves %u\n", ch,
                     ctx->lchunk_tc[ch], c[LCNT_ACTIVE], c[LCNT_PLACES], c[LCNT_SEGS], c[LCNT_ROWRECS], cells_of(c), c[LCNT_RING_PTS], c[LCNT_POLY], c[LCNT_COVER],
                     c[LCNT_CURVES]);
-        if (getenv("OSMR_LABEL_DEBUG")) fprintf(stderr, "[osmr labels]   culled %u of %u active labels\n", c[LCNT_CULLED], c[LCNT_ACTIVE]);
+        if (getenv("OSMR_LABEL_DEBUG")) fprintf(stderr, "[osmr labels]   culled %u of %u active labels (%u before the layout)\n", c[LCNT_CULLED], c[LCNT_ACTIVE], c[LCNT_PRECULLED]);
     }
     return 0;
 }
@@ -2647,7 +2664,7 @@ static void resident_label_stats(osmr_ctx* ctx, uint32_t attempts) {
     cudaEventElapsedTime(&ms, ctx->ev_label0, ctx->ev_label1);
     ctx->stats.ms_label_layout = 0.f;
     ctx->stats.ms_label_device = ms;
-    ctx->stats.kernel_launches += 14 * ctx->n_lchunks + 1;
+    ctx->stats.kernel_launches += 15 * ctx->n_lchunks + 1;
     ctx->stats.label_path = 1;
     ctx->stats.n_labels_active = ctx->stats_label_active;
     ctx->stats.n_labels_polylabel = ctx->stats_label_poly;
@@ -2792,7 +2809,7 @@ int osmr_draw_tiles_labeled(osmr_ctx* ctx, const osmr_tile* tiles, uint32_t n_ti
             ctx->stats.ms_label_layout = enqueue_ms;  // host time spent on labels: table look-ups and launches only
             ctx->stats.ms_label_device = ms;
             ctx->stats.ms_total += ms;
-            ctx->stats.kernel_launches += 14 * ctx->n_lchunks + 1;
+            ctx->stats.kernel_launches += 15 * ctx->n_lchunks + 1;
             ctx->stats.label_path = 1;
             ctx->stats.n_labels_active = ctx->stats_label_active;
             ctx->stats.n_labels_polylabel = ctx->stats_label_poly;

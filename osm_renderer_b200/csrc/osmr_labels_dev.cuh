@@ -67,6 +67,7 @@ enum {
     LCNT_CURVE_CURSOR_W = 17,
     LCNT_SCAN_OVF = 15,  // (overflow word of the block-sum scan: segment counts beyond 2^32 also trip the capacity check)
     LCNT_CULLED = 18,    // statistics: active labels label_cull_kernel took out
+    LCNT_PRECULLED = 19, // of those, taken out before the layout (label_precull_kernel)
     LCNT_COUNT = 20
 };
 
@@ -148,6 +149,9 @@ struct LabelDev {
     unsigned heap_slots;
     unsigned* counters;  // LCNT_*
     unsigned cull;       // 0: every active label gets its outlines and coverage (debug key "label_cull")
+    unsigned char* predead;  // same indexing as act: label_precull_kernel's verdict (1: no layout either)
+    int font_reach;          // font units: no outline point of a placed glyph lies farther from the glyph's anchor on the way /
+                             // its pen position than font_reach * scale (outline extents, advances, ascent, descent)
 };
 
 // ------------------------------------------------------------------------------------------------------
@@ -503,6 +507,11 @@ __global__ void __launch_bounds__(kLayoutThreads) label_layout_kernel(Scene s, L
         lp.gcy = 0.0;
         lp.vinst_off = 0;
         lp.n_vinst = 0;
+        if (ld.cull && ld.predead[first + ai]) {  // label_precull_kernel: cannot matter whatever its exact layout
+            lp.dead = 1u;
+            ld.place[first + ai] = lp;
+            continue;
+        }
         // label anchor (labelable.rs), lazily: polylabel is expensive
         bool anchor_done = false, anchor_ok = false;
         double anx = 0.0, any = 0.0;
@@ -1001,6 +1010,133 @@ __device__ __forceinline__ unsigned emit_vertex(const LabelDev& ld, const GlyphP
 constexpr unsigned kCullCap = 1024;  // labels of a tile decided in shared memory; a longer list is not culled
 constexpr int kCullThreads = 128;
 
+// the backward sweep of the cull kernels: one warp, a label at a time, the lanes over the later labels
+__device__ __forceinline__ void cull_sweep(const int4* box, unsigned char* needed, unsigned n_act, int D) {
+    const unsigned lane = threadIdx.x & 31u;
+    for (int g = (int)n_act - 1; g >= 0; --g) {
+        const int4 b = box[g];
+        bool need = false;
+        if (b.x <= b.z && b.y <= b.w) {
+            need = b.x <= D - 1 && b.z >= 0 && b.y <= D - 1 && b.w >= 0;
+            for (unsigned h = (unsigned)g + 1u + lane; !need && h - lane < n_act; h += 32) {
+                bool hit = false;
+                if (h < n_act && needed[h]) {
+                    const int4 o = box[h];
+                    hit = o.x <= o.z && b.x <= o.z && b.z >= o.x && b.y <= o.w && b.w >= o.y;
+                }
+                need = __any_sync(0xffffffffu, hit);
+            }
+        }
+        if (lane == 0) needed[g] = need ? 1 : 0;
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// label_precull_kernel: the same decision BEFORE the layout, from boxes that need no layout: where the label's anchor can be
+// (the node's pixel; for ways and multipolygons the pixel box of the entity -- text along a way sits on the way, polylabel's
+// point inside the polygon's box) widened by what the text can add (along a way: font_reach * scale around a point of the way;
+// centred rows: the summed |advance| to either side, one row height per possible row, font_reach * scale around every pen
+// position) and by the icon.  These boxes contain the exact ones, so every label the exact sweep would keep is kept here;
+// the rest skips label_layout_kernel (glyph placement along the way, polylabel) as well.  label_cull_kernel then decides
+// among the survivors with the exact boxes.
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kCullThreads) label_precull_kernel(Scene s, LabelDev ld) {
+    __shared__ int4 box[kCullCap];
+    __shared__ unsigned char needed[kCullCap];
+    const unsigned t = blockIdx.x;
+    const unsigned first = ld.label_begin[t];
+    const unsigned n_act = ld.act_cnt[t];
+    const int D = s.D;
+    if (!ld.cull) return;
+    if (n_act > kCullCap) {
+        for (unsigned ai = threadIdx.x; ai < n_act; ai += blockDim.x) ld.predead[first + ai] = 0;
+        return;
+    }
+    if (n_act == 0) return;
+    const osmr_tile tile = s.tiles[t];
+    const TileXform xf = make_xform(tile);
+    const double gscale = (double)tile.scale;
+    for (unsigned ai = threadIdx.x; ai < n_act; ai += blockDim.x) {
+        const ActLabel a = ld.act[first + ai];
+        const DevLabelStyle st = ld.styles[a.style];
+        const bool is_mp = (a.entity & OSMR_AREA_MULTIPOLYGON) != 0;
+        const bool is_node = !is_mp && (a.entity & OSMR_LABEL_NODE) != 0;
+        const unsigned idx = a.entity & ~(OSMR_AREA_MULTIPOLYGON | OSMR_LABEL_NODE);
+        // where the anchor / the way's points can be
+        long long ax0, ay0, ax1, ay1;
+        bool everywhere = false, has_anchor = true;
+        if (is_node) {
+            const int2 p = project_point(s.merc[idx], xf);
+            ax0 = ax1 = p.x;
+            ay0 = ay1 = p.y;
+        } else {
+            int x0, y0, x1, y1;
+            entity_pixel_bbox((is_mp ? s.mp_box : s.way_box)[idx], xf, x0, y0, x1, y1);
+            has_anchor = x0 <= x1 && y0 <= y1;
+            ax0 = (long long)x0 - 1;  // (polylabel works on the unrounded coordinates: half a pixel off the integer box)
+            ay0 = (long long)y0 - 1;
+            ax1 = (long long)x1 + 1;
+            ay1 = (long long)y1 + 1;
+        }
+        long long bx0 = 0x7fffffff, by0 = 0x7fffffff, bx1 = -0x7fffffff, by1 = -0x7fffffff;
+        auto widen = [&](double l, double r, double u, double d) {  // anchor box widened by l, r, u, d pixels
+            if (!(l >= 0.0 && l < 1.0e8 && r >= 0.0 && r < 1.0e8 && u >= 0.0 && u < 1.0e8 && d >= 0.0 && d < 1.0e8)) {
+                everywhere = true;
+                return;
+            }
+            bx0 = min(bx0, ax0 - (long long)ceil(l) - 4);
+            bx1 = max(bx1, ax1 + (long long)ceil(r) + 4);
+            by0 = min(by0, ay0 - (long long)ceil(u) - 4);
+            by1 = max(by1, ay1 + (long long)ceil(d) + 4);
+        };
+        unsigned icon_h = 0;
+        if (has_anchor && st.icon >= 0 && (unsigned)st.icon < ld.n_icons) {
+            const DevIcon ic = ld.icons[st.icon];
+            icon_h = ic.h;
+            widen((double)ic.w, (double)ic.w, (double)ic.h, (double)ic.h);
+        }
+        if (has_anchor && a.text != 0xffffffffu) {
+            const double font_size = st.font_size * gscale;
+            const float fs = (float)font_size;
+            const float fscale = fs / (float)(ld.ascent - ld.descent);
+            const double scale = fabs((double)fscale);
+            const double reach = (double)ld.font_reach * scale;
+            const unsigned pos = st.text_position ? st.text_position : ((is_node || is_mp) ? (unsigned)OSMR_TEXT_POS_CENTER : (unsigned)OSMR_TEXT_POS_LINE);
+            if (pos == OSMR_TEXT_POS_LINE) {
+                if (!is_node && !is_mp) widen(reach, reach, reach, reach);
+            } else {
+                const DevGlyphRec* gl = ld.glyphs + ld.text_begin[a.text];
+                double tw = 0.0;
+                unsigned rows = 1;
+                for (unsigned k = 0; k < a.n_glyphs; ++k) {
+                    tw += (fabs((double)gl[k].advance) + fabs((double)gl[k].kern)) * scale;
+                    rows += gl[k].ws ? 1u : 0u;
+                }
+                const double row_h = (fabs((double)ld.ascent) + fabs((double)ld.descent) + fabs((double)ld.line_gap)) * scale;
+                const double v = row_h * (double)(rows + 1u) + (double)icon_h + reach;
+                widen(tw + reach, tw + reach, v, v);
+            }
+        }
+        if (everywhere || !(ax0 > -1000000000ll && ax1 < 1000000000ll && ay0 > -1000000000ll && ay1 < 1000000000ll)) {
+            if (bx0 <= bx1 || everywhere) {
+                bx0 = by0 = -0x7fffffff;
+                bx1 = by1 = 0x7fffffff;
+            }
+        }
+        box[ai] = make_int4((int)max(bx0, -0x7fffffffll), (int)max(by0, -0x7fffffffll), (int)min(bx1, 0x7fffffffll), (int)min(by1, 0x7fffffffll));
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) cull_sweep(box, needed, n_act, D);
+    __syncthreads();
+    unsigned pre = 0;
+    for (unsigned ai = threadIdx.x; ai < n_act; ai += blockDim.x) {
+        ld.predead[first + ai] = needed[ai] ? 0 : 1;
+        pre += needed[ai] ? 0u : 1u;
+    }
+    if (pre) atomicAdd(&ld.counters[LCNT_PRECULLED], pre);
+}
+
 __global__ void __launch_bounds__(kCullThreads) label_cull_kernel(Scene s, LabelDev ld) {
     __shared__ int4 box[kCullCap];  // x0, y0, x1, y1 (x0 > x1: no pixels)
     __shared__ unsigned char needed[kCullCap];
@@ -1015,6 +1151,10 @@ __global__ void __launch_bounds__(kCullThreads) label_cull_kernel(Scene s, Label
         const LabelPlace lp = ld.place[first + ai];
         long long x0 = 0x7fffffff, y0 = 0x7fffffff, x1 = -0x7fffffff, y1 = -0x7fffffff;
         bool everywhere = false;  // coordinates beyond any canvas or not finite: never culled, meets everything
+        if (lp.dead) {  // label_precull_kernel took it out: no box, it stays dead
+            box[ai] = make_int4(1, 1, 0, 0);
+            continue;
+        }
         if (lp.icon >= 0 && (unsigned)lp.icon < ld.n_icons) {
             const DevIcon ic = ld.icons[lp.icon];
             x0 = lp.ix;
@@ -1070,27 +1210,7 @@ __global__ void __launch_bounds__(kCullThreads) label_cull_kernel(Scene s, Label
         box[ai] = make_int4((int)x0, (int)y0, (int)x1, (int)y1);
     }
     __syncthreads();
-    if (threadIdx.x < 32) {  // the backward sweep: one warp, a label at a time, the lanes over the later labels
-        const unsigned lane = threadIdx.x;
-        for (int g = (int)n_act - 1; g >= 0; --g) {
-            const int4 b = box[g];
-            bool need = false;
-            if (b.x <= b.z && b.y <= b.w) {
-                need = b.x <= D - 1 && b.z >= 0 && b.y <= D - 1 && b.w >= 0;
-                for (unsigned h = (unsigned)g + 1u + lane; !need && h - lane < n_act; h += 32) {
-                    bool hit = false;
-                    if (h < n_act && needed[h]) {
-                        const int4 o = box[h];
-                        hit = o.x <= o.z && b.x <= o.z && b.z >= o.x && b.y <= o.w && b.w >= o.y;
-                    }
-                    need = __any_sync(0xffffffffu, hit);
-                }
-            }
-            need = __shfl_sync(0xffffffffu, need ? 1 : 0, 0) != 0;  // (uniform already; keeps the warp converged for the store)
-            if (lane == 0) needed[g] = need ? 1 : 0;
-            __syncwarp();
-        }
-    }
+    if (threadIdx.x < 32) cull_sweep(box, needed, n_act, D);
     __syncthreads();
     unsigned culled = 0;
     for (unsigned ai = threadIdx.x; ai < n_act; ai += blockDim.x) {
