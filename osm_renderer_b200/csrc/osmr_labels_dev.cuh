@@ -612,9 +612,26 @@ __global__ void __launch_bounds__(kLayoutThreads) label_layout_kernel(Scene s, L
                             atomicOr(&ld.counters[LCNT_FALLBACK], 2u);  // no direction table for this way: host path
                         } else {
                             const double2* sc = ld.sincos[tile.zoom] + aoff;
-                            const int2 pf = project_point(s.merc[s.ints[wr.x]], xf), pb = project_point(s.merc[s.ints[wr.x + len - 1]], xf);
+                            // The way's pixels once, into a per-thread cache: compute_way_position walks the way again for every
+                            // glyph, and a point is two dependent loads away (node id, Mercator factors) -- that chain, glyphs x
+                            // segments long, was the whole duration of this kernel (0.87 ms for the slowest label of a batch).
+                            constexpr unsigned kWayCache = 40;
+                            int2 cache[kWayCache];
+                            const bool cached = len <= kWayCache;
+                            // The direction table holds sin / cos of the INTEGER pixel differences as seen from tile (0, 0).  They
+                            // are the same in every tile except when a coordinate sits on an exact half pixel left of / above the
+                            // tile origin (round-half-away-from-zero mirrors there): such a way is laid out by the host.
+                            for (unsigned i = 0; i < len; ++i) {
+                                const double2 m = s.merc[s.ints[wr.x + i]];
+                                if (cached) cache[i] = project_point(m, xf);
+                                const double2 r = tile_rel(m, xf);
+                                if ((r.x < 0.0 && r.x - floor(r.x) == 0.5) || (r.y < 0.0 && r.y - floor(r.y) == 0.5))
+                                    atomicOr(&ld.counters[LCNT_FALLBACK], 2u);
+                            }
+                            auto raw_pt = [&](unsigned j) { return cached ? cache[j] : project_point(s.merc[s.ints[wr.x + j]], xf); };
+                            const int2 pf = raw_pt(0), pb = raw_pt(len - 1);
                             const bool rev = pf.x > pb.x;
-                            auto pt = [&](unsigned i) { return project_point(s.merc[s.ints[wr.x + (rev ? len - 1 - i : i)]], xf); };
+                            auto pt = [&](unsigned i) { return raw_pt(rev ? len - 1 - i : i); };
                             double way_len = 0.0;
                             {
                                 int2 prev = pt(0);
@@ -623,14 +640,6 @@ __global__ void __launch_bounds__(kLayoutThreads) label_layout_kernel(Scene s, L
                                     way_len += point_dist(prev.x, prev.y, cur.x, cur.y);
                                     prev = cur;
                                 }
-                            }
-                            // The direction table holds sin / cos of the INTEGER pixel differences as seen from tile (0, 0).  They
-                            // are the same in every tile except when a coordinate sits on an exact half pixel left of / above the
-                            // tile origin (round-half-away-from-zero mirrors there): such a way is laid out by the host.
-                            for (unsigned i = 0; i < len; ++i) {
-                                const double2 r = tile_rel(s.merc[s.ints[wr.x + i]], xf);
-                                if ((r.x < 0.0 && r.x - floor(r.x) == 0.5) || (r.y < 0.0 && r.y - floor(r.y) == 0.5))
-                                    atomicOr(&ld.counters[LCNT_FALLBACK], 2u);
                             }
                             if (!(total_width > way_len) && take_block()) {
                                 double cur = (way_len - total_width) / 2.0;
