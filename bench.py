@@ -600,6 +600,23 @@ def main():
     lstats = {k: v // args.steps for k, v in acc.get("lstats", {}).items()}
     launches = acc["launches"]
 
+    # ---- the label kernels with nothing beside them (debug key label_serial): in the headline step they share the SMs with the
+    # area kernels, so their event times there are not their own durations ----
+    label_alone = None
+    if headline_labeled:
+        ctx.debug_set("label_serial", 1)
+        try:
+            for _ in range(2):
+                resident_step()
+            acc_s = {}
+            n_serial = max(3, min(args.steps, 10))
+            for _ in range(n_serial):
+                resident_step(acc_s)
+            label_alone = {"ms_label_pass": acc_s["ms_label_device"] / n_serial, "ms_label_cover": acc_s["ms_label_cover"] / n_serial,
+                           "note": "label pass finished before the area passes start; not part of any timed leg"}
+        finally:
+            ctx.debug_set("label_serial", 0)
+
     # ---- value_area_only: the Fill / Casing / Stroke passes alone (round 1's headline), same protocol ----
     area_only = None
     if headline_labeled:
@@ -858,7 +875,7 @@ def main():
             leg["d2h_gbs_per_rank"] = leg["d2h_bytes_per_step"] * args.steps / lw / 1e9
     raster_mean_ms, _ = red(raster_ms)
     cover_mean_ms, _ = red(cover_ms)
-    label_cover_mean_ms, _ = red(label_cover_ms)
+    label_cover_mean_ms, _ = red(label_alone["ms_label_cover"] if label_alone else label_cover_ms)
     if area_only is not None:
         aw, at = red(area_only["wall"])
         area_only = {"value": at / aw, "unit": "tiles/s", "ms_per_step": 1000.0 * aw / args.steps,
@@ -1013,6 +1030,7 @@ def main():
         "sustained": sustained,
         "stage_ms": {"plan+geometry+fill_rows+bin": plan_ms, "line_cover": cover_ms, "raster": raster_ms,
                      "label_pass (own stream, beside the area stages)": label_ms, "label_cover (inside label_pass)": label_cover_ms},
+        "label_kernels_alone": label_alone,
         "value_area_only": area_only,
         "label_stats": lstats,
         # the reference's perf-stats stage names (drawer.rs:51-123) where a stage is separable on the device

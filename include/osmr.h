@@ -325,6 +325,9 @@ void osmr_free_pinned(void* p);
  *                           pretends the per-op work lists hold n items, so the grow-and-redo paths run;
  *   "plan_slice_areas" (n)  styled areas per slice of plan_ops_kernel's (tile, pass) lists (0: default 16384; small values
  *                           exercise the sliced form on ordinary tiles);
+ *   "label_cull" (0/1)      labels that cannot reach the tile get no layout, outlines or coverage (default 1; same pixels);
+ *   "label_serial" (0/1)    a resident labelled draw finishes its label pass before the area passes start (timing of the label
+ *                           kernels with nothing beside them; default 0);
  *   "label_threads" (1..256) host threads of the label layout;
  *   "host_chunks" (0..16)   equal draw chunks of a host-output call (0: the tapered default schedule);
  *   "two_streams" (0/1)     draw chunks alternate between two compute streams (default 1);

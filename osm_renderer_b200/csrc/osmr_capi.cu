@@ -217,6 +217,7 @@ struct osmr_ctx {
     std::vector<uint32_t> h_label_begin;
     bool batch_has_labels = false;
     bool resident_needs_host_layout = false;  // osmr_batch_draw_labeled's last verdict (osmr_draw_tiles_auto_labeled falls back on it)
+    bool label_serial = false;     // debug key "label_serial": the label pass finishes before the area passes start (measurement only)
     bool label_cull = true;        // debug key "label_cull": labels that cannot reach the tile get no outlines and no coverage
     unsigned label_chunks = 0;     // debug key "label_chunks"
     unsigned curve_leaf_cap = 0;   // debug key "curve_leaf_cap" (tests: curves with more leaves are flattened again by one lane)
@@ -588,6 +589,10 @@ int osmr_debug_set(osmr_ctx* ctx, const char* key, int value) try {
     if (strcmp(key, "work_items") == 0) {
         if (value < 1) return ctx->fail(OSMR_E_INVALID, "work_items must be positive");
         ctx->work_items_limit = (unsigned)value;
+        return OSMR_OK;
+    }
+    if (strcmp(key, "label_serial") == 0) {
+        ctx->label_serial = value != 0;
         return OSMR_OK;
     }
     if (strcmp(key, "label_cull") == 0) {
@@ -2722,6 +2727,7 @@ int osmr_batch_draw_labeled(osmr_ctx* ctx, const uint8_t canvas_rgb[3], uint32_t
             cudaStreamSynchronize(ctx->label_stream);
             return rc;
         }
+        if (ctx->label_serial) cudaStreamSynchronize(ctx->label_stream);  // (the label kernels' own durations: nothing beside them)
         ctx->label_plane_active = true;
         rc = osmr_batch_draw(ctx, canvas_rgb, flags, out, gpu_ms);
         ctx->label_plane_active = false;

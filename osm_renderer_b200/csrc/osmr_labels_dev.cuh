@@ -473,7 +473,9 @@ __device__ bool poly_label_anchor(double2* pts, unsigned* off, unsigned n_rings,
 // ------------------------------------------------------------------------------------------------------
 // label_layout_kernel: one thread per active label (persistent grid over (tile, label) pairs)
 // ------------------------------------------------------------------------------------------------------
-constexpr int kLayoutThreads = 64;
+// A label is one thread's serial work (a few thousand instructions, a different path for every label), so a warp that holds
+// many labels executes the SUM of their paths: consecutive labels of a tile go to different warps (label ai -> warp ai % 8).
+constexpr int kLayoutThreads = 256;
 
 __device__ __forceinline__ double2 tile_rel(const double2 m, const TileXform& t) {  // coords_to_xy_tile_relative * scale
     double2 r;
@@ -489,7 +491,7 @@ __global__ void __launch_bounds__(kLayoutThreads) label_layout_kernel(Scene s, L
     const osmr_tile tile = s.tiles[t];
     const TileXform xf = make_xform(tile);
     const double gscale = (double)tile.scale;
-    for (unsigned ai = threadIdx.x; ai < n_act; ai += kLayoutThreads) {
+    for (unsigned ai = (threadIdx.x & 31u) * (kLayoutThreads / 32) + (threadIdx.x >> 5); ai < n_act; ai += kLayoutThreads) {
         const ActLabel a = ld.act[first + ai];
         const DevLabelStyle st = ld.styles[a.style];
         const bool is_mp = (a.entity & OSMR_AREA_MULTIPOLYGON) != 0;
