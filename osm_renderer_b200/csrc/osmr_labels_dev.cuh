@@ -473,9 +473,7 @@ __device__ bool poly_label_anchor(double2* pts, unsigned* off, unsigned n_rings,
 // ------------------------------------------------------------------------------------------------------
 // label_layout_kernel: one thread per active label (persistent grid over (tile, label) pairs)
 // ------------------------------------------------------------------------------------------------------
-// A label is one thread's serial work (a few thousand instructions, a different path for every label), so a warp that holds
-// many labels executes the SUM of their paths: consecutive labels of a tile go to different warps (label ai -> warp ai % 8).
-constexpr int kLayoutThreads = 256;
+constexpr int kLayoutThreads = 64;
 
 __device__ __forceinline__ double2 tile_rel(const double2 m, const TileXform& t) {  // coords_to_xy_tile_relative * scale
     double2 r;
@@ -491,7 +489,7 @@ __global__ void __launch_bounds__(kLayoutThreads) label_layout_kernel(Scene s, L
     const osmr_tile tile = s.tiles[t];
     const TileXform xf = make_xform(tile);
     const double gscale = (double)tile.scale;
-    for (unsigned ai = (threadIdx.x & 31u) * (kLayoutThreads / 32) + (threadIdx.x >> 5); ai < n_act; ai += kLayoutThreads) {
+    for (unsigned ai = threadIdx.x; ai < n_act; ai += kLayoutThreads) {
         const ActLabel a = ld.act[first + ai];
         const DevLabelStyle st = ld.styles[a.style];
         const bool is_mp = (a.entity & OSMR_AREA_MULTIPOLYGON) != 0;
@@ -614,26 +612,9 @@ __global__ void __launch_bounds__(kLayoutThreads) label_layout_kernel(Scene s, L
                             atomicOr(&ld.counters[LCNT_FALLBACK], 2u);  // no direction table for this way: host path
                         } else {
                             const double2* sc = ld.sincos[tile.zoom] + aoff;
-                            // The way's pixels once, into a per-thread cache: compute_way_position walks the way again for every
-                            // glyph, and a point is two dependent loads away (node id, Mercator factors) -- that chain, glyphs x
-                            // segments long, was the whole duration of this kernel (0.87 ms for the slowest label of a batch).
-                            constexpr unsigned kWayCache = 40;
-                            int2 cache[kWayCache];
-                            const bool cached = len <= kWayCache;
-                            // The direction table holds sin / cos of the INTEGER pixel differences as seen from tile (0, 0).  They
-                            // are the same in every tile except when a coordinate sits on an exact half pixel left of / above the
-                            // tile origin (round-half-away-from-zero mirrors there): such a way is laid out by the host.
-                            for (unsigned i = 0; i < len; ++i) {
-                                const double2 m = s.merc[s.ints[wr.x + i]];
-                                if (cached) cache[i] = project_point(m, xf);
-                                const double2 r = tile_rel(m, xf);
-                                if ((r.x < 0.0 && r.x - floor(r.x) == 0.5) || (r.y < 0.0 && r.y - floor(r.y) == 0.5))
-                                    atomicOr(&ld.counters[LCNT_FALLBACK], 2u);
-                            }
-                            auto raw_pt = [&](unsigned j) { return cached ? cache[j] : project_point(s.merc[s.ints[wr.x + j]], xf); };
-                            const int2 pf = raw_pt(0), pb = raw_pt(len - 1);
+                            const int2 pf = project_point(s.merc[s.ints[wr.x]], xf), pb = project_point(s.merc[s.ints[wr.x + len - 1]], xf);
                             const bool rev = pf.x > pb.x;
-                            auto pt = [&](unsigned i) { return raw_pt(rev ? len - 1 - i : i); };
+                            auto pt = [&](unsigned i) { return project_point(s.merc[s.ints[wr.x + (rev ? len - 1 - i : i)]], xf); };
                             double way_len = 0.0;
                             {
                                 int2 prev = pt(0);
@@ -642,6 +623,14 @@ __global__ void __launch_bounds__(kLayoutThreads) label_layout_kernel(Scene s, L
                                     way_len += point_dist(prev.x, prev.y, cur.x, cur.y);
                                     prev = cur;
                                 }
+                            }
+                            // The direction table holds sin / cos of the INTEGER pixel differences as seen from tile (0, 0).  They
+                            // are the same in every tile except when a coordinate sits on an exact half pixel left of / above the
+                            // tile origin (round-half-away-from-zero mirrors there): such a way is laid out by the host.
+                            for (unsigned i = 0; i < len; ++i) {
+                                const double2 r = tile_rel(s.merc[s.ints[wr.x + i]], xf);
+                                if ((r.x < 0.0 && r.x - floor(r.x) == 0.5) || (r.y < 0.0 && r.y - floor(r.y) == 0.5))
+                                    atomicOr(&ld.counters[LCNT_FALLBACK], 2u);
                             }
                             if (!(total_width > way_len) && take_block()) {
                                 double cur = (way_len - total_width) / 2.0;
