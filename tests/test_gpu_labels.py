@@ -203,3 +203,20 @@ def test_label_cull_changes_no_pixel(fx, label_ctx):
         assert (culled == full).all(), name
         assert st1["label_path"] == 1 and st0["label_path"] == 1
         assert st1["n_labels_active"] == st0["n_labels_active"] and 0 < st1["n_label_segments"] < st0["n_label_segments"] / 2
+
+
+def test_label_serial_key_changes_no_pixel(fx, label_ctx):
+    """debug key label_serial (bench.py's `label_kernels_alone` leg): the resident labelled draw waits for its label pass before
+    the area passes start -- a scheduling change only"""
+    ctx, per = label_ctx
+    tiles, begins, areas = fx.batches["15"]
+    lb, labels = per["15"]
+    want = ctx.draw_tiles_labeled(tiles, begins, areas, lb, labels, fx.canvas_rgb, True)
+    ctx.batch_upload_labeled(tiles, begins, areas, lb, labels)
+    out = np.empty_like(want)
+    try:
+        ctx.debug_set("label_serial", 1)
+        ms = ctx.batch_draw_labeled(fx.canvas_rgb, True, out=out)
+    finally:
+        ctx.debug_set("label_serial", 0)
+    assert ms > 0 and (out == want).all() and ctx.stats()["ms_label_cover"] > 0
