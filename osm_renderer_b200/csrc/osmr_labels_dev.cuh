@@ -1034,8 +1034,7 @@ __device__ __forceinline__ void cull_sweep(const int4* box, unsigned char* neede
 
 // ------------------------------------------------------------------------------------------------------
 // label_precull_kernel: the same decision BEFORE the layout, from boxes that need no layout: where the label's anchor can be
-// (the node's pixel; for ways and multipolygons the pixel box of the entity -- text along a way sits on the way, polylabel's
-// point inside the polygon's box) widened by what the text can add (along a way: font_reach * scale around a point of the way;
+// (the node's pixel; for text along a way the pixel box of the way -- the glyphs sit on it) widened by what the text can add (along a way: font_reach * scale around a point of the way;
 // centred rows: the summed |advance| to either side, one row height per possible row, font_reach * scale around every pen
 // position) and by the icon.  These boxes contain the exact ones, so every label the exact sweep would keep is kept here;
 // the rest skips label_layout_kernel (glyph placement along the way, polylabel) as well.  label_cull_kernel then decides
@@ -1090,6 +1089,14 @@ __global__ void __launch_bounds__(kCullThreads) label_precull_kernel(Scene s, La
             by0 = min(by0, ay0 - (long long)ceil(u) - 4);
             by1 = max(by1, ay1 + (long long)ceil(d) + 4);
         };
+        {
+            // An anchor that comes from polylabel cannot be bounded without running it: for a degenerate ring (no interior, or a
+            // signed area that cancels) the answer is the ring's centroid (labelable.rs:163), which need not lie in any box of the
+            // entity -- or is not a number at all.  Such a label is decided by label_cull_kernel, from its real position.
+            const bool has_icon = st.icon >= 0 && (unsigned)st.icon < ld.n_icons;
+            const unsigned tpos = st.text_position ? st.text_position : ((is_node || is_mp) ? (unsigned)OSMR_TEXT_POS_CENTER : (unsigned)OSMR_TEXT_POS_LINE);
+            if (!is_node && (has_icon || (a.text != 0xffffffffu && tpos != OSMR_TEXT_POS_LINE))) everywhere = true;
+        }
         unsigned icon_h = 0;
         if (has_anchor && st.icon >= 0 && (unsigned)st.icon < ld.n_icons) {
             const DevIcon ic = ld.icons[st.icon];
